@@ -1,0 +1,124 @@
+"""GPU numerics: every hand-written kernel vs a plain PyTorch fp32 reference of the same op.
+
+Mirrors the reference's CPU-oracle strategy (unit_tests/cuda_dense_ops_test.cpp,
+cuda_conv2d_nchw_ops_test.cpp, cuda_batchnorm_ops_test.cpp, cuda_loss_funcs_test.cpp).
+"""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def _rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+# ----------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 256), (200, 100, 72), (1000, 512, 768),
+                                   (4096, 768, 3072), (37, 24, 40)])
+def test_linear_fwd(M, N, K):
+    from tnn_b200.ops import gemm
+    torch.manual_seed(0)
+    x = torch.randn(M, K, device=_dev()).bfloat16()
+    w = (torch.randn(N, K, device=_dev()) / math.sqrt(K)).bfloat16()
+    b = torch.randn(N, device=_dev())
+    y = gemm.linear_fwd(x, w, b)
+    ref = x.float() @ w.float().t() + b
+    assert _rel_err(y, ref) < 1e-2
+    y2 = gemm.linear_fwd(x, w, b, act="relu")
+    assert _rel_err(y2, torch.relu(ref)) < 1e-2
+    y3 = gemm.linear_fwd(x, w, None, act="gelu")
+    assert _rel_err(y3, torch.nn.functional.gelu(x.float() @ w.float().t(), approximate="tanh")) < 1e-2
+    res = torch.randn(M, N, device=_dev()).bfloat16()
+    y4 = gemm.linear_fwd(x, w, b, residual=res)
+    assert _rel_err(y4, ref + res.float()) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 128, 128), (512, 768, 3072), (200, 104, 72)])
+def test_linear_dgrad_wgrad(M, N, K):
+    from tnn_b200.ops import gemm
+    torch.manual_seed(1)
+    x = torch.randn(M, K, device=_dev()).bfloat16()
+    w = (torch.randn(N, K, device=_dev()) / math.sqrt(K)).bfloat16()
+    dy = torch.randn(M, N, device=_dev()).bfloat16()
+    dx = gemm.linear_dgrad(dy, w)
+    assert _rel_err(dx, dy.float() @ w.float()) < 1e-2
+    dw = torch.zeros(N, K, device=_dev())
+    gemm.linear_wgrad(dy, x, dw)
+    ref = dy.float().t() @ x.float()
+    assert _rel_err(dw, ref) < 1e-2
+    gemm.linear_wgrad(dy, x, dw)  # accumulate (beta = 1)
+    assert _rel_err(dw, 2 * ref) < 1e-2
+    db = torch.zeros(N, device=_dev())
+    gemm.bias_grad(dy, db)
+    assert _rel_err(db, dy.float().sum(0)) < 1e-2
+
+
+# ----------------------------------------------------------------------------- Conv
+CONV_CASES = [
+    # N, H, W, C, K, R, stride, pad
+    (8, 32, 32, 16, 128, 3, 1, 1),
+    (8, 32, 32, 128, 128, 3, 1, 1),
+    (8, 16, 16, 256, 256, 3, 1, 1),
+    (8, 8, 8, 512, 512, 3, 1, 1),
+    (8, 32, 32, 128, 256, 3, 2, 1),
+    (8, 16, 16, 256, 512, 3, 2, 1),
+    (8, 32, 32, 16, 128, 1, 1, 0),
+    (8, 32, 32, 128, 256, 1, 2, 0),
+    (6, 4, 4, 512, 512, 3, 1, 1),
+    (4, 32, 32, 3, 16, 3, 1, 1),      # direct path
+    (4, 28, 28, 8, 16, 5, 1, 0),      # im2col path
+]
+
+
+@pytest.mark.parametrize("N,H,W,C,K,R,stride,pad", CONV_CASES)
+def test_conv2d(N, H, W, C, K, R, stride, pad):
+    from tnn_b200.ops import conv
+    torch.manual_seed(2)
+    dev = _dev()
+    x = torch.randn(N, H, W, C, device=dev).bfloat16()
+    w = torch.randn(K, R, R, C, device=dev) / math.sqrt(R * R * C)
+    w = w.bfloat16().float()
+    b = torch.randn(K, device=dev)
+    plan = conv.make_plan(N, H, W, C, K, R, R, stride, pad, dev)
+    st = conv.ConvState()
+    cache = {}
+    y = conv.conv2d_fwd(plan, x, w, w.bfloat16(), b, cache=cache)
+    ref = conv.conv2d_fwd_ref(x, w, b, stride, pad)
+    assert y.shape == ref.shape
+    assert _rel_err(y, ref) < 1e-2, plan.path
+    dy = torch.randn_like(ref).bfloat16()
+    if plan.path != "direct":
+        dx = conv.conv2d_dgrad(plan, dy, w, st)
+        dref = conv.conv2d_dgrad_ref(dy, w, (N, H, W, C), stride, pad)
+        assert _rel_err(dx, dref) < 1e-2, plan.path
+        res = torch.randn(N, H, W, C, device=dev).bfloat16()
+        dx2 = conv.conv2d_dgrad(plan, dy, w, st, residual=res)
+        assert _rel_err(dx2, dref + res.float()) < 1e-2, plan.path
+    dw = torch.zeros(K, R, R, C, device=dev)
+    db = torch.zeros(K, device=dev)
+    conv.conv2d_wgrad(plan, dy, x, dw, db, cache=cache)
+    wref = conv.conv2d_wgrad_ref(dy, x, (K, R, R, C), stride, pad)
+    assert _rel_err(dw, wref) < 1e-2, plan.path
+    assert _rel_err(db, dy.float().sum((0, 1, 2))) < 1e-2
+
+
+def test_conv_residual_relu_epilogue():
+    from tnn_b200.ops import conv
+    dev = _dev()
+    N, H, W, C, K = 8, 16, 16, 128, 128
+    x = torch.randn(N, H, W, C, device=dev).bfloat16()
+    w = (torch.randn(K, 3, 3, C, device=dev) / math.sqrt(9 * C)).bfloat16().float()
+    res = torch.randn(N, H, W, K, device=dev).bfloat16()
+    plan = conv.make_plan(N, H, W, C, K, 3, 3, 1, 1, dev)
+    assert plan.path == "tma"
+    y = conv.conv2d_fwd(plan, x, w, w.bfloat16(), None, residual=res, act="relu")
+    ref = torch.relu(conv.conv2d_fwd_ref(x, w, None, 1, 1) + res.float())
+    assert _rel_err(y, ref) < 1e-2

@@ -1,0 +1,327 @@
+// Python bindings (pybind11 through torch/extension.h).  Every function takes torch tensors
+// only as typed pointer carriers; all work happens in the hand-written kernels on the
+// CURRENT torch CUDA stream, so they compose with torch streams / events / CUDA graphs.
+#include <ATen/cuda/CUDAContext.h>
+#include <torch/extension.h>
+
+#include <optional>
+#include <vector>
+
+#include "kernels/simt_ops.cuh"
+#include "kernels/umma_gemm.cuh"
+#include "runtime/runtime.hpp"
+
+namespace py = pybind11;
+using torch::Tensor;
+using OptT = std::optional<Tensor>;
+
+namespace tnn {
+void attention_bind(py::module_& m);  // attention.cpp
+}
+
+static cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+static void* vp(const Tensor& t) { return t.data_ptr(); }
+static void* vp(const OptT& t) { return t.has_value() ? t->data_ptr() : nullptr; }
+static float* fp(const Tensor& t) {
+  TORCH_CHECK(t.scalar_type() == torch::kFloat32, "expected fp32 tensor");
+  return t.data_ptr<float>();
+}
+static float* fp(const OptT& t) { return t.has_value() ? fp(*t) : nullptr; }
+static void check_cuda(const Tensor& t) { TORCH_CHECK(t.is_cuda(), "expected a CUDA tensor"); }
+
+static tnn::Epilogue make_epi(const Tensor& out, int out_mode, int act, double alpha, const OptT& bias,
+                              const OptT& residual, int64_t ldc, const std::vector<int64_t>& grid) {
+  tnn::Epilogue e;
+  e.out = vp(out);
+  e.out_mode = out_mode;
+  e.act = act;
+  e.alpha = (float)alpha;
+  e.bias = fp(bias);
+  e.residual = vp(residual);
+  e.ldc = ldc;
+  if (!grid.empty()) {
+    // {OH, OW, sN, sH, sW, base}
+    TORCH_CHECK(grid.size() == 6, "grid spec = {OH, OW, sN, sH, sW, base}");
+    e.grid_mode = 1;
+    e.OH = (int)grid[0];
+    e.OW = (int)grid[1];
+    e.sN = grid[2];
+    e.sH = grid[3];
+    e.sW = grid[4];
+    e.base = grid[5];
+  }
+  return e;
+}
+
+static tnn::ConvGeom make_geom(const std::vector<int64_t>& g, const std::vector<int64_t>& taps) {
+  TORCH_CHECK(g.size() == 7, "geom = {IN, IH, IW, C, ON, OH, OW}");
+  TORCH_CHECK(taps.size() % 4 == 0 && taps.size() / 4 <= tnn::kMaxTaps, "taps = flat {dh,dw,nb,koff}*");
+  tnn::ConvGeom cg{};
+  cg.IN = (int)g[0];
+  cg.IH = (int)g[1];
+  cg.IW = (int)g[2];
+  cg.C = (int)g[3];
+  cg.ON = (int)g[4];
+  cg.OH = (int)g[5];
+  cg.OW = (int)g[6];
+  cg.ntaps = (int)(taps.size() / 4);
+  for (int t = 0; t < cg.ntaps; ++t)
+    cg.taps[t] = tnn::ConvTap{(int)taps[4 * t], (int)taps[4 * t + 1], (int)taps[4 * t + 2], (int)taps[4 * t + 3]};
+  return cg;
+}
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "tnn_b200 native kernels (sm_100a) and C++ runtime";
+
+  // ------------------------------------------------------------------ tcgen05 GEMM / conv
+  m.def("gemm", [](const Tensor& A, const Tensor& B, int64_t M, int64_t N, int64_t K, int64_t lda,
+                   int64_t ldb, bool a_mn, bool b_mn, const Tensor& out, int64_t ldc, int out_mode,
+                   int act, double alpha, const OptT& bias, const OptT& residual, int splits) {
+    check_cuda(A);
+    TORCH_CHECK(A.scalar_type() == torch::kBFloat16 && B.scalar_type() == torch::kBFloat16, "bf16 operands");
+    tnn::Epilogue e = make_epi(out, out_mode, act, alpha, bias, residual, ldc, {});
+    tnn::gemm_bf16(vp(A), vp(B), (int)M, (int)N, (int)K, lda, ldb, a_mn, b_mn, e, splits, cur_stream());
+  });
+  m.def("conv_fprop", [](const Tensor& X, const Tensor& Wt, int64_t ldw, int64_t N,
+                         const std::vector<int64_t>& geom, const std::vector<int64_t>& taps,
+                         const Tensor& out, int64_t ldc, const std::vector<int64_t>& grid, int out_mode,
+                         int act, double alpha, const OptT& bias, const OptT& residual) {
+    check_cuda(X);
+    tnn::ConvGeom g = make_geom(geom, taps);
+    tnn::Epilogue e = make_epi(out, out_mode, act, alpha, bias, residual, ldc, grid);
+    tnn::conv_fprop_bf16(vp(X), vp(Wt), ldw, (int)N, g, e, cur_stream());
+  });
+  m.def("conv_wgrad", [](const Tensor& dY, int64_t ldy, int64_t Kout, const Tensor& X,
+                         const std::vector<int64_t>& geom, const std::vector<int64_t>& taps,
+                         const Tensor& dW, int64_t ldw, double alpha) {
+    check_cuda(X);
+    tnn::ConvGeom g = make_geom(geom, taps);
+    tnn::conv_wgrad_bf16(vp(dY), ldy, (int)Kout, vp(X), g, fp(dW), ldw, (float)alpha, cur_stream());
+  });
+  m.def("conv_geom_supported", [](const std::vector<int64_t>& geom, const std::vector<int64_t>& taps) {
+    return tnn::conv_geom_supported(make_geom(geom, taps));
+  });
+
+  // ------------------------------------------------------------------ elementwise
+  m.def("cast_f32_to_bf16", [](const Tensor& x, const Tensor& y) {
+    tnn::cast_f32_to_bf16(fp(x), vp(y), x.numel(), cur_stream());
+  });
+  m.def("cast_bf16_to_f32", [](const Tensor& x, const Tensor& y) {
+    tnn::cast_bf16_to_f32(vp(x), fp(y), x.numel(), cur_stream());
+  });
+  m.def("add_bf16", [](const Tensor& a, const Tensor& b, const Tensor& o, bool relu) {
+    tnn::add_bf16(vp(a), vp(b), vp(o), a.numel(), relu, cur_stream());
+  });
+  m.def("binary_bf16", [](const Tensor& a, const Tensor& b, const Tensor& o, int op) {
+    tnn::binary_bf16(vp(a), vp(b), vp(o), a.numel(), op, cur_stream());
+  });
+  m.def("act_fwd", [](const Tensor& x, const Tensor& y, int kind, double slope) {
+    tnn::act_fwd(vp(x), vp(y), x.numel(), kind, (float)slope, x.scalar_type() == torch::kFloat32, cur_stream());
+  });
+  m.def("act_bwd", [](const Tensor& x, const Tensor& dy, const Tensor& dx, int kind, double slope) {
+    tnn::act_bwd(vp(x), vp(dy), vp(dx), x.numel(), kind, (float)slope, x.scalar_type() == torch::kFloat32,
+                 cur_stream());
+  });
+  m.def("dropout_fwd", [](const Tensor& x, const Tensor& y, double p, uint64_t seed) {
+    tnn::dropout_fwd(vp(x), vp(y), x.numel(), (float)p, seed, cur_stream());
+  });
+  m.def("fill_f32", [](const Tensor& x, double v) { tnn::fill_f32(fp(x), x.numel(), (float)v, cur_stream()); });
+  m.def("axpy_f32", [](const Tensor& y, const Tensor& x, double a) {
+    tnn::axpy_f32(fp(y), fp(x), (float)a, x.numel(), cur_stream());
+  });
+  m.def("scale_f32", [](const Tensor& x, double a) { tnn::scale_f32(fp(x), (float)a, x.numel(), cur_stream()); });
+  m.def("colsum_bf16", [](const Tensor& x, int64_t M, int64_t N, double alpha, const Tensor& out) {
+    tnn::colsum_bf16(vp(x), M, (int)N, (float)alpha, fp(out), cur_stream());
+  });
+  m.def("phase_split", [](const Tensor& x, const Tensor& xp, int N, int H, int W, int C) {
+    tnn::phase_split(vp(x), vp(xp), N, H, W, C, cur_stream());
+  });
+  m.def("phase_merge", [](const Tensor& xp, const Tensor& x, int N, int H, int W, int C) {
+    tnn::phase_merge(vp(xp), vp(x), N, H, W, C, cur_stream());
+  });
+  m.def("nchw_to_nhwc", [](const Tensor& x, const Tensor& y, int N, int C, int H, int W) {
+    tnn::nchw_to_nhwc(vp(x), vp(y), N, C, H, W, x.scalar_type() == torch::kFloat32, cur_stream());
+  });
+  m.def("nhwc_to_nchw", [](const Tensor& x, const Tensor& y, int N, int C, int H, int W) {
+    tnn::nhwc_to_nchw(vp(x), vp(y), N, C, H, W, x.scalar_type() == torch::kFloat32, cur_stream());
+  });
+  m.def("transpose_bf16", [](const Tensor& x, const Tensor& y, int rows, int cols) {
+    tnn::transpose_bf16(vp(x), vp(y), rows, cols, cur_stream());
+  });
+  m.def("conv_weight_prep", [](const Tensor& w, const OptT& wb, const OptT& wt, int K, int R, int S, int C) {
+    tnn::conv_weight_prep(fp(w), vp(wb), vp(wt), K, R, S, C, cur_stream());
+  });
+  m.def("philox_uniform", [](const Tensor& x, double lo, double hi, uint64_t seed) {
+    tnn::philox_uniform_f32(fp(x), x.numel(), (float)lo, (float)hi, seed, cur_stream());
+  });
+  m.def("philox_normal", [](const Tensor& x, double mean, double std, uint64_t seed) {
+    tnn::philox_normal_f32(fp(x), x.numel(), (float)mean, (float)std, seed, cur_stream());
+  });
+
+  // ------------------------------------------------------------------ normalisation
+  m.def("bn_train_stats", [](const Tensor& x, int64_t M, int C, const OptT& gamma, const OptT& beta,
+                             double eps, double momentum, const OptT& rmean, const OptT& rvar,
+                             const Tensor& smean, const Tensor& sinvstd, const Tensor& ss, const Tensor& ws) {
+    tnn::bn_train_stats(vp(x), M, C, fp(gamma), fp(beta), (float)eps, (float)momentum, fp(rmean), fp(rvar),
+                        fp(smean), fp(sinvstd), fp(ss), fp(ws), cur_stream());
+  });
+  m.def("bn_eval_scale_shift", [](int C, const OptT& gamma, const OptT& beta, const Tensor& rmean,
+                                  const Tensor& rvar, double eps, const Tensor& ss) {
+    tnn::bn_eval_scale_shift(C, fp(gamma), fp(beta), fp(rmean), fp(rvar), (float)eps, fp(ss), cur_stream());
+  });
+  m.def("bn_apply", [](const Tensor& x, const Tensor& y, int64_t M, int C, const Tensor& ss, bool relu,
+                       double drop_p, uint64_t seed) {
+    tnn::bn_apply(vp(x), vp(y), M, C, fp(ss), relu, (float)drop_p, seed, cur_stream());
+  });
+  m.def("bn_bwd_reduce", [](const Tensor& dy, const Tensor& x, const OptT& y, int64_t M, int C,
+                            const OptT& gamma, const Tensor& smean, const Tensor& sinvstd, bool masked,
+                            double drop_p, const OptT& dgamma, const OptT& dbeta, const Tensor& coef,
+                            const Tensor& ws) {
+    tnn::bn_bwd_reduce(vp(dy), vp(x), vp(y), M, C, fp(gamma), fp(smean), fp(sinvstd), masked, (float)drop_p,
+                       fp(dgamma), fp(dbeta), fp(coef), fp(ws), cur_stream());
+  });
+  m.def("bn_bwd_apply", [](const Tensor& dy, const Tensor& x, const OptT& y, const OptT& extra,
+                           const Tensor& dx, int64_t M, int C, const Tensor& smean, const Tensor& sinvstd,
+                           const Tensor& coef, bool masked, double drop_p) {
+    tnn::bn_bwd_apply(vp(dy), vp(x), vp(y), vp(extra), vp(dx), M, C, fp(smean), fp(sinvstd), fp(coef), masked,
+                      (float)drop_p, cur_stream());
+  });
+  m.def("layernorm_fwd", [](const Tensor& x, const OptT& res, const Tensor& y, const OptT& sum_out,
+                            int64_t rows, int C, const OptT& gamma, const OptT& beta, double eps,
+                            const OptT& mean, const OptT& rstd) {
+    tnn::layernorm_fwd(vp(x), vp(res), vp(y), vp(sum_out), rows, C, fp(gamma), fp(beta), (float)eps, fp(mean),
+                       fp(rstd), cur_stream());
+  });
+  m.def("layernorm_bwd", [](const Tensor& dy, const Tensor& x, int64_t rows, int C, const OptT& gamma,
+                            const Tensor& mean, const Tensor& rstd, const Tensor& dx, const OptT& dgamma,
+                            const OptT& dbeta) {
+    tnn::layernorm_bwd(vp(dy), vp(x), rows, C, fp(gamma), fp(mean), fp(rstd), vp(dx), fp(dgamma), fp(dbeta),
+                       cur_stream());
+  });
+  m.def("groupnorm_fwd", [](const Tensor& x, const Tensor& y, int N, int HW, int C, int G, const OptT& gamma,
+                            const OptT& beta, double eps, const Tensor& mean, const Tensor& rstd) {
+    tnn::groupnorm_fwd(vp(x), vp(y), N, HW, C, G, fp(gamma), fp(beta), (float)eps, fp(mean), fp(rstd),
+                       cur_stream());
+  });
+  m.def("groupnorm_bwd", [](const Tensor& dy, const Tensor& x, int N, int HW, int C, int G, const OptT& gamma,
+                            const Tensor& mean, const Tensor& rstd, const Tensor& dx, const OptT& dgamma,
+                            const OptT& dbeta) {
+    tnn::groupnorm_bwd(vp(dy), vp(x), N, HW, C, G, fp(gamma), fp(mean), fp(rstd), vp(dx), fp(dgamma),
+                       fp(dbeta), cur_stream());
+  });
+
+  // ------------------------------------------------------------------ pooling
+  m.def("maxpool_fwd", [](const Tensor& x, const Tensor& y, const OptT& mask, std::vector<int> d) {
+    TORCH_CHECK(d.size() == 12, "dims = {N,H,W,C,kh,kw,sh,sw,ph,pw,OH,OW}");
+    tnn::maxpool_fwd(vp(x), vp(y), (uint8_t*)vp(mask), d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8],
+                     d[9], d[10], d[11], cur_stream());
+  });
+  m.def("maxpool_bwd", [](const Tensor& dy, const Tensor& mask, const Tensor& dx, std::vector<int> d) {
+    tnn::maxpool_bwd(vp(dy), (const uint8_t*)vp(mask), vp(dx), d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7],
+                     d[8], d[9], d[10], d[11], cur_stream());
+  });
+  m.def("avgpool_fwd", [](const Tensor& x, const Tensor& y, std::vector<int> d) {
+    tnn::avgpool_fwd(vp(x), vp(y), d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9], d[10], d[11],
+                     cur_stream());
+  });
+  m.def("avgpool_bwd", [](const Tensor& dy, const Tensor& dx, std::vector<int> d) {
+    tnn::avgpool_bwd(vp(dy), vp(dx), d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9], d[10], d[11],
+                     cur_stream());
+  });
+
+  // ------------------------------------------------------------------ loss
+  m.def("softmax_ce", [](const Tensor& logits, int64_t ld, const Tensor& labels, int64_t rows, int V,
+                         double loss_scale, double grad_scale, const OptT& grad, const Tensor& out) {
+    TORCH_CHECK(labels.scalar_type() == torch::kInt32, "labels must be int32");
+    tnn::softmax_ce(vp(logits), logits.scalar_type() == torch::kFloat32, ld, labels.data_ptr<int>(), rows, V,
+                    (float)loss_scale, (float)grad_scale, vp(grad), fp(out), cur_stream());
+  });
+  m.def("regression_loss", [](const Tensor& pred, const Tensor& target, int kind, double delta,
+                              double grad_scale, const OptT& grad, const Tensor& out) {
+    tnn::regression_loss(vp(pred), vp(target), pred.scalar_type() == torch::kFloat32, pred.numel(), kind,
+                         (float)delta, (float)grad_scale, vp(grad), fp(out), cur_stream());
+  });
+
+  // ------------------------------------------------------------------ optimizers
+  m.def("adam_step_flat", [](const Tensor& p, const Tensor& g, const Tensor& mm, const Tensor& v,
+                             const OptT& pb, double lr, double b1, double b2, double eps, double wd,
+                             bool decoupled, int64_t step, double grad_scale, bool zero_grad) {
+    tnn::AdamHyper h{(float)lr, (float)b1, (float)b2, (float)eps, (float)wd, decoupled ? 1 : 0,
+                     (float)(1.0 - std::pow(b1, (double)step)), (float)(1.0 - std::pow(b2, (double)step)),
+                     (float)grad_scale};
+    tnn::adam_step_flat(fp(p), fp(g), fp(mm), fp(v), vp(pb), p.numel(), h, zero_grad, cur_stream());
+  });
+  m.def("sgd_step_flat", [](const Tensor& p, const Tensor& g, const OptT& mom, const OptT& pb, double lr,
+                            double momentum, double wd, double grad_scale, bool zero_grad) {
+    tnn::sgd_step_flat(fp(p), fp(g), fp(mom), vp(pb), p.numel(), (float)lr, (float)momentum, (float)wd,
+                       (float)grad_scale, zero_grad, cur_stream());
+  });
+  m.def("dp_fused_step", [](int world, int rank, int64_t n, int64_t chunk, std::vector<int64_t> g_peers,
+                            std::vector<int64_t> p_peers, std::vector<int64_t> pb_peers,
+                            std::vector<int64_t> flag_peers, int64_t g_mc, int64_t p_mc, int64_t pb_mc,
+                            const Tensor& mm, const OptT& v, const Tensor& sync, uint32_t epoch,
+                            uint32_t grid_base, bool use_adam, double lr, double b1, double b2, double eps,
+                            double wd, bool decoupled, int64_t step, double grad_scale, double momentum,
+                            int ctas) {
+    TORCH_CHECK((int)g_peers.size() == world && (int)p_peers.size() == world &&
+                (int)pb_peers.size() == world && (int)flag_peers.size() == world, "peer lists");
+    std::vector<float*> g(world), p(world);
+    std::vector<void*> pb(world);
+    std::vector<uint32_t*> fl(world);
+    for (int r = 0; r < world; ++r) {
+      g[r] = reinterpret_cast<float*>(g_peers[r]);
+      p[r] = reinterpret_cast<float*>(p_peers[r]);
+      pb[r] = reinterpret_cast<void*>(pb_peers[r]);
+      fl[r] = reinterpret_cast<uint32_t*>(flag_peers[r]);
+    }
+    tnn::AdamHyper h{(float)lr, (float)b1, (float)b2, (float)eps, (float)wd, decoupled ? 1 : 0,
+                     (float)(1.0 - std::pow(b1, (double)step)), (float)(1.0 - std::pow(b2, (double)step)),
+                     (float)grad_scale};
+    uint32_t* s32 = reinterpret_cast<uint32_t*>(sync.data_ptr());
+    tnn::dp_fused_step(world, rank, n, chunk, g.data(), p.data(), pb.data(), fl.data(),
+                       reinterpret_cast<const float*>(g_mc), reinterpret_cast<float*>(p_mc),
+                       reinterpret_cast<void*>(pb_mc), fp(mm), fp(v), s32, s32 + 1, epoch, grid_base,
+                       use_adam ? 1 : 0, h, (float)momentum, ctas, cur_stream());
+  });
+  m.def("p2p_barrier", [](const Tensor& flag_ptrs, int world, int rank, uint32_t epoch) {
+    tnn::p2p_barrier(reinterpret_cast<uint32_t* const*>(flag_ptrs.data_ptr()), world, rank, epoch, cur_stream());
+  });
+
+  // ------------------------------------------------------------------ conv helpers
+  m.def("conv_direct_fwd", [](const Tensor& x, const Tensor& w, const OptT& bias, const Tensor& y,
+                              std::vector<int> d) {
+    TORCH_CHECK(d.size() == 11, "dims = {N,H,W,C,K,R,S,stride,pad,OH,OW}");
+    tnn::conv_direct_fwd(vp(x), fp(w), fp(bias), vp(y), d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8],
+                         d[9], d[10], cur_stream());
+  });
+  m.def("conv_direct_wgrad", [](const Tensor& x, const Tensor& dy, const Tensor& dw, const OptT& dbias,
+                                std::vector<int> d) {
+    tnn::conv_direct_wgrad(vp(x), vp(dy), fp(dw), fp(dbias), d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7],
+                           d[8], d[9], d[10], cur_stream());
+  });
+  m.def("im2col_nhwc", [](const Tensor& x, const Tensor& col, int64_t ldcol, std::vector<int> d) {
+    TORCH_CHECK(d.size() == 10, "dims = {N,H,W,C,R,S,stride,pad,OH,OW}");
+    tnn::im2col_nhwc(vp(x), vp(col), ldcol, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9],
+                     cur_stream());
+  });
+  m.def("col2im_nhwc", [](const Tensor& col, int64_t ldcol, const Tensor& dx, std::vector<int> d) {
+    tnn::col2im_nhwc(vp(col), ldcol, vp(dx), d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9],
+                     cur_stream());
+  });
+
+  // ------------------------------------------------------------------ embedding
+  m.def("embedding_fwd", [](const Tensor& ids, const Tensor& table, const OptT& pos, const Tensor& y,
+                            int64_t T, int L, int D, int V) {
+    tnn::embedding_fwd(ids.data_ptr<int>(), fp(table), fp(pos), vp(y), T, L, D, V, cur_stream());
+  });
+  m.def("embedding_bwd", [](const Tensor& ids, const Tensor& dy, const OptT& dtable, const OptT& dpos,
+                            int64_t T, int L, int D, int V) {
+    tnn::embedding_bwd(ids.data_ptr<int>(), vp(dy), fp(dtable), fp(dpos), T, L, D, V, cur_stream());
+  });
+  m.def("argmax_rows", [](const Tensor& x, int64_t ld, int64_t rows, int V, const Tensor& out) {
+    tnn::argmax_rows(vp(x), x.scalar_type() == torch::kFloat32, ld, rows, V, out.data_ptr<int>(), cur_stream());
+  });
+
+  tnn::attention_bind(m);
+  tnn::runtime_bind(m);
+}

@@ -1,0 +1,111 @@
+// Shared device helpers for the SIMT kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+namespace tnn {
+
+#define TNN_CHECK_LAUNCH()                                                                    \
+  do {                                                                                        \
+    cudaError_t e_ = cudaGetLastError();                                                      \
+    if (e_ != cudaSuccess) {                                                                  \
+      fprintf(stderr, "[tnn_b200] launch error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, \
+              __LINE__);                                                                      \
+      abort();                                                                                \
+    }                                                                                         \
+  } while (0)
+
+static constexpr int kSMs = 148;
+typedef __nv_bfloat16 bf16;
+
+__host__ inline int grid_for(long long n, int block, int max_blocks = kSMs * 16) {
+  long long g = (n + block - 1) / block;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return (int)g;
+}
+
+// 8 bf16 <-> 8 floats through one 16-byte register quad
+struct alignas(16) BF8 {
+  uint4 q;
+};
+__device__ __forceinline__ void bf8_unpack(const uint4& q, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 bf8_pack(const float (&f)[8]) {
+  uint4 q;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return q;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum; `red` is >= 32 floats of shared memory.  All threads get the result.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : -INFINITY;
+  t = warp_max(t);
+  return t;
+}
+
+// Philox4x32-10 counter RNG: (seed, counter) -> 4 x uint32.
+__device__ __forceinline__ uint4 philox4(uint64_t seed, uint64_t ctr) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x2B7E1516u, c3 = 0x3C6EF372u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ float u32_to_unit(uint32_t x) {  // (0,1)
+  return ((x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+}
+// keep-mask for 8 consecutive elements starting at index 8*vec_idx
+__device__ __forceinline__ void dropout_keep8(uint64_t seed, long long vec_idx, float p, bool (&keep)[8]) {
+  uint4 a = philox4(seed, (uint64_t)vec_idx * 2);
+  uint4 b = philox4(seed, (uint64_t)vec_idx * 2 + 1);
+  const uint32_t r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) keep[i] = u32_to_unit(r[i]) >= p;
+}
+
+}  // namespace tnn

@@ -1,0 +1,224 @@
+// SIMT convolution helpers.
+//  * direct first-layer convolution (C_in < 8 cannot be described by a 16-byte-aligned TMA
+//    tensor map and has K = R*S*C_in <= 75, far below one UMMA tile)
+//  * im2col / col2im for geometries outside the TMA window path (odd widths, 5x5/7x7,
+//    stride > 2); the GEMM itself still runs on tcgen05.
+#include "common.cuh"
+#include "simt_ops.cuh"
+
+namespace tnn {
+
+struct DConvP {
+  int N, H, W, C, K, R, S, stride, pad, OH, OW;
+};
+
+// thread = (output pixel, group of 8 output channels)
+__global__ void __launch_bounds__(256)
+    k_conv_direct_fwd(const bf16* __restrict__ x, const float* __restrict__ w,
+                      const float* __restrict__ bias, bf16* __restrict__ y, DConvP p) {
+  extern __shared__ float sw[];  // [R*S*C][K]  (k fastest so a thread reads 8 consecutive)
+  const int rsc = p.R * p.S * p.C;
+  for (int i = threadIdx.x; i < rsc * p.K; i += blockDim.x) {
+    int k = i / rsc, j = i - k * rsc;
+    sw[j * p.K + k] = w[i];
+  }
+  __syncthreads();
+  const int kg = p.K / 8;
+  const long long total = (long long)p.N * p.OH * p.OW * kg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int g = (int)(i % kg);
+    long long t = i / kg;
+    int ow = (int)(t % p.OW);
+    t /= p.OW;
+    int oh = (int)(t % p.OH);
+    int n = (int)(t / p.OH);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[g * 8 + j] : 0.f;
+    for (int r = 0; r < p.R; ++r) {
+      int h = oh * p.stride - p.pad + r;
+      if (h < 0 || h >= p.H) continue;
+      for (int s = 0; s < p.S; ++s) {
+        int ww = ow * p.stride - p.pad + s;
+        if (ww < 0 || ww >= p.W) continue;
+        const bf16* xp = x + (((long long)n * p.H + h) * p.W + ww) * p.C;
+        for (int c = 0; c < p.C; ++c) {
+          float xv = __bfloat162float(xp[c]);
+          const float* wp = sw + ((r * p.S + s) * p.C + c) * p.K + g * 8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += xv * wp[j];
+        }
+      }
+    }
+    reinterpret_cast<uint4*>(y)[i] = bf8_pack(acc);
+  }
+}
+void conv_direct_fwd(const void* x, const float* w, const float* bias, void* y, int N, int H, int W,
+                     int C, int K, int R, int S, int stride, int pad, int OH, int OW, cudaStream_t s) {
+  if (K % 8 != 0) {
+    fprintf(stderr, "[tnn_b200] conv_direct_fwd needs K %% 8 == 0\n");
+    abort();
+  }
+  DConvP p{N, H, W, C, K, R, S, stride, pad, OH, OW};
+  size_t smem = (size_t)R * S * C * K * sizeof(float);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    cudaFuncSetAttribute(k_conv_direct_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  long long total = (long long)N * OH * OW * (K / 8);
+  k_conv_direct_fwd<<<grid_for(total, 256), 256, smem, s>>>((const bf16*)x, w, bias, (bf16*)y, p);
+  TNN_CHECK_LAUNCH();
+}
+
+// wgrad: block stages PIX pixels of dy and the matching input patches in smem, every thread
+// owns outputs o = tid, tid+256, ... of dW[K][R*S*C]; block partials go out by atomicAdd.
+static constexpr int DW_PIX = 32;
+__global__ void __launch_bounds__(256)
+    k_conv_direct_wgrad(const bf16* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw,
+                        float* __restrict__ dbias, DConvP p, int pix_per_block) {
+  extern __shared__ float sm[];
+  const int rsc = p.R * p.S * p.C;
+  float* s_dy = sm;                   // [DW_PIX][K]
+  float* s_x = sm + DW_PIX * p.K;     // [DW_PIX][rsc]
+  const int nout = p.K * rsc;
+  const int per = (nout + 255) / 256;
+  float acc[8];                        // supports nout <= 2048
+  float bacc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const long long npix = (long long)p.N * p.OH * p.OW;
+  const long long p_begin = (long long)blockIdx.x * pix_per_block;
+  const long long p_end = min(npix, p_begin + pix_per_block);
+  for (long long p0 = p_begin; p0 < p_end; p0 += DW_PIX) {
+    const int np = (int)min((long long)DW_PIX, p_end - p0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < DW_PIX * p.K; i += blockDim.x) {
+      int pp = i / p.K, k = i - pp * p.K;
+      s_dy[i] = pp < np ? __bfloat162float(dy[(p0 + pp) * p.K + k]) : 0.f;
+    }
+    for (int i = threadIdx.x; i < DW_PIX * rsc; i += blockDim.x) {
+      int pp = i / rsc, j = i - pp * rsc;
+      float v = 0.f;
+      if (pp < np) {
+        long long pix = p0 + pp;
+        int ow = (int)(pix % p.OW);
+        long long t = pix / p.OW;
+        int oh = (int)(t % p.OH);
+        int n = (int)(t / p.OH);
+        int c = j % p.C, rs = j / p.C, s = rs % p.S, r = rs / p.S;
+        int h = oh * p.stride - p.pad + r, ww = ow * p.stride - p.pad + s;
+        if (h >= 0 && h < p.H && ww >= 0 && ww < p.W)
+          v = __bfloat162float(x[(((long long)n * p.H + h) * p.W + ww) * p.C + c]);
+      }
+      s_x[i] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (q >= per) break;
+      int o = threadIdx.x + q * 256;
+      if (o < nout) {
+        int k = o / rsc, j = o - k * rsc;
+        float a = 0.f;
+        for (int pp = 0; pp < DW_PIX; ++pp) a += s_dy[pp * p.K + k] * s_x[pp * rsc + j];
+        acc[q] += a;
+      }
+    }
+    if (dbias && threadIdx.x < p.K) {
+      for (int pp = 0; pp < DW_PIX; ++pp) bacc += s_dy[pp * p.K + threadIdx.x];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    int o = threadIdx.x + q * 256;
+    if (q < per && o < nout) atomicAdd(dw + o, acc[q]);
+  }
+  if (dbias && threadIdx.x < p.K) atomicAdd(dbias + threadIdx.x, bacc);
+}
+void conv_direct_wgrad(const void* x, const void* dy, float* dw, float* dbias, int N, int H, int W,
+                       int C, int K, int R, int S, int stride, int pad, int OH, int OW,
+                       cudaStream_t s) {
+  const int rsc = R * S * C;
+  if (K * rsc > 2048 || K > 256) {
+    fprintf(stderr, "[tnn_b200] conv_direct_wgrad: K*R*S*C too large (%d)\n", K * rsc);
+    abort();
+  }
+  DConvP p{N, H, W, C, K, R, S, stride, pad, OH, OW};
+  long long npix = (long long)N * OH * OW;
+  int blocks = (int)min((long long)kSMs * 4, (npix + DW_PIX - 1) / DW_PIX);
+  int ppb = (int)((npix + blocks - 1) / blocks);
+  ppb = (ppb + DW_PIX - 1) / DW_PIX * DW_PIX;
+  blocks = (int)((npix + ppb - 1) / ppb);
+  size_t smem = (size_t)DW_PIX * (K + rsc) * sizeof(float);
+  k_conv_direct_wgrad<<<blocks, 256, smem, s>>>((const bf16*)x, (const bf16*)dy, dw, dbias, p, ppb);
+  TNN_CHECK_LAUNCH();
+}
+
+// --------------------------------------------------------------------------- im2col / col2im
+__global__ void __launch_bounds__(256)
+    k_im2col(const bf16* __restrict__ x, bf16* __restrict__ col, long long ldcol, DConvP p) {
+  const int rsc = p.R * p.S * p.C;
+  const long long total = (long long)p.N * p.OH * p.OW * rsc;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int j = (int)(i % rsc);
+    long long pix = i / rsc;
+    int ow = (int)(pix % p.OW);
+    long long t = pix / p.OW;
+    int oh = (int)(t % p.OH);
+    int n = (int)(t / p.OH);
+    int c = j % p.C, rs = j / p.C, s = rs % p.S, r = rs / p.S;
+    int h = oh * p.stride - p.pad + r, w = ow * p.stride - p.pad + s;
+    bf16 v = __float2bfloat16(0.f);
+    if (h >= 0 && h < p.H && w >= 0 && w < p.W) v = x[(((long long)n * p.H + h) * p.W + w) * p.C + c];
+    col[pix * ldcol + j] = v;
+  }
+}
+void im2col_nhwc(const void* x, void* col, long long ldcol, int N, int H, int W, int C, int R, int S,
+                 int stride, int pad, int OH, int OW, cudaStream_t s) {
+  DConvP p{N, H, W, C, 0, R, S, stride, pad, OH, OW};
+  long long total = (long long)N * OH * OW * R * S * C;
+  k_im2col<<<grid_for(total, 256), 256, 0, s>>>((const bf16*)x, (bf16*)col, ldcol, p);
+  TNN_CHECK_LAUNCH();
+}
+// gather formulation: one thread per input element sums the col entries that map onto it
+__global__ void __launch_bounds__(256)
+    k_col2im(const bf16* __restrict__ col, long long ldcol, bf16* __restrict__ dx, DConvP p) {
+  const long long total = (long long)p.N * p.H * p.W * p.C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % p.C);
+    long long t = i / p.C;
+    int w = (int)(t % p.W);
+    t /= p.W;
+    int h = (int)(t % p.H);
+    int n = (int)(t / p.H);
+    float acc = 0.f;
+    for (int r = 0; r < p.R; ++r) {
+      int hh = h + p.pad - r;
+      if (hh < 0 || hh % p.stride) continue;
+      int oh = hh / p.stride;
+      if (oh >= p.OH) continue;
+      for (int s = 0; s < p.S; ++s) {
+        int ww = w + p.pad - s;
+        if (ww < 0 || ww % p.stride) continue;
+        int ow = ww / p.stride;
+        if (ow >= p.OW) continue;
+        long long pix = ((long long)n * p.OH + oh) * p.OW + ow;
+        acc += __bfloat162float(col[pix * ldcol + (r * p.S + s) * p.C + c]);
+      }
+    }
+    dx[i] = __float2bfloat16(acc);
+  }
+}
+void col2im_nhwc(const void* col, long long ldcol, void* dx, int N, int H, int W, int C, int R, int S,
+                 int stride, int pad, int OH, int OW, cudaStream_t s) {
+  DConvP p{N, H, W, C, 0, R, S, stride, pad, OH, OW};
+  long long total = (long long)N * H * W * C;
+  k_col2im<<<grid_for(total, 256), 256, 0, s>>>((const bf16*)col, ldcol, (bf16*)dx, p);
+  TNN_CHECK_LAUNCH();
+}
+
+}  // namespace tnn

@@ -1,0 +1,307 @@
+// Optimizer kernels.
+//
+// (1) Flat single-GPU Adam/AdamW/SGD: ONE launch over the whole parameter slab (the
+//     reference launches one kernel per parameter tensor, src/nn/optimizers_impl/cuda/
+//     adam_kernels.cu:19-130), fused with the bf16 compute-copy refresh and grad zeroing.
+//
+// (2) The data-parallel product path: a single kernel per step that
+//        barrier(all ranks' grads complete)                      [peer flags, .sys scope]
+//     -> reduce my 1/W slice of the gradient across all W GPUs   [NVLink peer loads, or one
+//                                                                  multimem.ld_reduce via NVLS]
+//     -> scale (1/W, 1/accum) -> Adam/SGD update of my slice     [optimizer state is sharded:
+//                                                                  m, v exist only for my slice]
+//     -> broadcast new fp32 + bf16 params to every replica       [peer stores / multimem.st]
+//     -> barrier(all ranks done) -> zero my gradient slab.
+//     No NCCL call, no scale/cast/optimizer/memset kernels on that path.
+#include "common.cuh"
+#include "simt_ops.cuh"
+
+namespace tnn {
+
+__device__ __forceinline__ float adam_update(float& p, float g, float& m, float& v, const AdamHyper& h) {
+  if (h.weight_decay != 0.f && h.decoupled) p -= h.weight_decay * h.lr * p;
+  m = h.beta1 * m + (1.f - h.beta1) * g;
+  v = h.beta2 * v + (1.f - h.beta2) * g * g;
+  float mh = m / h.bias_c1, vh = v / h.bias_c2;
+  float upd = h.lr * mh / (sqrtf(vh) + h.eps);
+  if (h.weight_decay != 0.f && !h.decoupled) upd += h.weight_decay * h.lr * p;
+  p -= upd;
+  return p;
+}
+
+__global__ void __launch_bounds__(256)
+    k_adam_flat(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                float* __restrict__ v, bf16* __restrict__ pb, long long n, AdamHyper h, int zero_grad) {
+  const long long nv = n / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 P = reinterpret_cast<float4*>(p)[i], G = reinterpret_cast<float4*>(g)[i];
+    float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+    adam_update(P.x, G.x * h.grad_scale, M.x, V.x, h);
+    adam_update(P.y, G.y * h.grad_scale, M.y, V.y, h);
+    adam_update(P.z, G.z * h.grad_scale, M.z, V.z, h);
+    adam_update(P.w, G.w * h.grad_scale, M.w, V.w, h);
+    reinterpret_cast<float4*>(p)[i] = P;
+    reinterpret_cast<float4*>(m)[i] = M;
+    reinterpret_cast<float4*>(v)[i] = V;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pb) {
+      uint2 o;
+      __nv_bfloat162 a = __floats2bfloat162_rn(P.x, P.y), b = __floats2bfloat162_rn(P.z, P.w);
+      o.x = *reinterpret_cast<uint32_t*>(&a);
+      o.y = *reinterpret_cast<uint32_t*>(&b);
+      reinterpret_cast<uint2*>(pb)[i] = o;
+    }
+  }
+  for (long long i = nv * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float P = p[i], M = m[i], V = v[i];
+    adam_update(P, g[i] * h.grad_scale, M, V, h);
+    p[i] = P;
+    m[i] = M;
+    v[i] = V;
+    if (zero_grad) g[i] = 0.f;
+    if (pb) pb[i] = __float2bfloat16(P);
+  }
+}
+void adam_step_flat(float* p, float* g, float* m, float* v, void* p_bf16, long long n,
+                    const AdamHyper& h, int zero_grad, cudaStream_t s) {
+  if (n <= 0) return;
+  k_adam_flat<<<grid_for(n / 4 + 1, 256, kSMs * 8), 256, 0, s>>>(p, g, m, v, (bf16*)p_bf16, n, h, zero_grad);
+  TNN_CHECK_LAUNCH();
+}
+
+__global__ void __launch_bounds__(256)
+    k_sgd_flat(float* __restrict__ p, float* __restrict__ g, float* __restrict__ mom,
+               bf16* __restrict__ pb, long long n, float lr, float momentum, float wd, float gs,
+               int zero_grad) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float P = p[i], G = g[i] * gs + wd * P;
+    if (mom) {
+      float V = momentum * mom[i] - lr * G;
+      mom[i] = V;
+      P += V;
+    } else {
+      P -= lr * G;
+    }
+    p[i] = P;
+    if (zero_grad) g[i] = 0.f;
+    if (pb) pb[i] = __float2bfloat16(P);
+  }
+}
+void sgd_step_flat(float* p, float* g, float* mom, void* p_bf16, long long n, float lr,
+                   float momentum, float weight_decay, float grad_scale, int zero_grad,
+                   cudaStream_t s) {
+  if (n <= 0) return;
+  k_sgd_flat<<<grid_for(n, 256, kSMs * 8), 256, 0, s>>>(p, g, mom, (bf16*)p_bf16, n, lr, momentum,
+                                                      weight_decay, grad_scale, zero_grad);
+  TNN_CHECK_LAUNCH();
+}
+
+// =====================================================================================
+// Fused data-parallel step over NVLink peer memory
+// =====================================================================================
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_peer_v4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 multimem_ld_reduce_v4(const float* mc) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_v4(float* mc, float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void multimem_st_bf16x4(bf16* mc, uint32_t lo, uint32_t hi) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.bf16x2 [%0], {%1, %2};" ::"l"(mc), "r"(lo), "r"(hi)
+               : "memory");
+}
+
+static constexpr int kMaxWorld = 16;
+struct DpArgs {
+  int world, rank;
+  long long n;          // total parameters
+  long long chunk;      // per-rank slice length (multiple of 4)
+  float* g_peers[kMaxWorld];    // every rank's gradient slab (peer mapped), [rank] is local
+  float* p_peers[kMaxWorld];    // every rank's fp32 parameter slab
+  bf16* pb_peers[kMaxWorld];    // every rank's bf16 parameter copy
+  uint32_t* flag_peers[kMaxWorld];  // every rank's flag array (world words)
+  const float* g_mc;    // multicast views (NVLS) or null
+  float* p_mc;
+  bf16* pb_mc;
+  float* m;             // optimizer state for MY slice only (length chunk)
+  float* v;
+  uint32_t* grid_ctr;   // local grid barrier counter / go flag
+  uint32_t* go_flag;
+  uint32_t epoch;       // 2 cross-rank barriers per launch: epoch*2+1, epoch*2+2
+  uint32_t grid_base;   // grid_ctr value at launch = launches so far * 2 * gridDim.x
+  int use_adam;
+  AdamHyper h;
+  float sgd_momentum;
+};
+
+__device__ __forceinline__ void dp_barrier(const DpArgs& a, uint32_t epoch, uint32_t grid_target) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) atomicAdd(a.grid_ctr, 1u);
+  if (blockIdx.x == 0) {
+    if (threadIdx.x == 0)
+      while (ld_acquire_gpu(a.grid_ctr) < grid_target) {
+      }
+    __syncthreads();
+    if (threadIdx.x < a.world) {
+      __threadfence_system();
+      st_release_sys(a.flag_peers[threadIdx.x] + a.rank, epoch);
+      while (ld_acquire_sys(a.flag_peers[a.rank] + threadIdx.x) < epoch) {
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_gpu(a.go_flag, epoch);
+  }
+  if (threadIdx.x == 0)
+    while (ld_acquire_gpu(a.go_flag) < epoch) {
+    }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(512) k_dp_step(const DpArgs a) {
+  const uint32_t G = gridDim.x;
+  dp_barrier(a, a.epoch * 2 + 1, a.grid_base + G);
+
+  const long long lo = (long long)a.rank * a.chunk;
+  const long long hi = min(a.n, lo + a.chunk);
+  const long long nv = hi > lo ? (hi - lo + 3) / 4 : 0;   // slab is padded to a multiple of 4
+  const AdamHyper h = a.h;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long e = lo + i * 4;
+    float4 g;
+    if (a.g_mc) {
+      g = multimem_ld_reduce_v4(a.g_mc + e);
+    } else {
+      g = ld_peer_v4(a.g_peers[0] + e);
+      for (int r = 1; r < a.world; ++r) {
+        float4 t = ld_peer_v4(a.g_peers[r] + e);
+        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+      }
+    }
+    g.x *= h.grad_scale; g.y *= h.grad_scale; g.z *= h.grad_scale; g.w *= h.grad_scale;
+    float4 P = *reinterpret_cast<const float4*>(a.p_peers[a.rank] + e);
+    float4 M = reinterpret_cast<float4*>(a.m)[i];
+    if (a.use_adam) {
+      float4 V = reinterpret_cast<float4*>(a.v)[i];
+      adam_update(P.x, g.x, M.x, V.x, h);
+      adam_update(P.y, g.y, M.y, V.y, h);
+      adam_update(P.z, g.z, M.z, V.z, h);
+      adam_update(P.w, g.w, M.w, V.w, h);
+      reinterpret_cast<float4*>(a.v)[i] = V;
+    } else {
+      const float mu = a.sgd_momentum, lr = h.lr, wd = h.weight_decay;
+      g.x += wd * P.x; g.y += wd * P.y; g.z += wd * P.z; g.w += wd * P.w;
+      M.x = mu * M.x - lr * g.x; M.y = mu * M.y - lr * g.y;
+      M.z = mu * M.z - lr * g.z; M.w = mu * M.w - lr * g.w;
+      P.x += M.x; P.y += M.y; P.z += M.z; P.w += M.w;
+    }
+    reinterpret_cast<float4*>(a.m)[i] = M;
+    __nv_bfloat162 b0 = __floats2bfloat162_rn(P.x, P.y), b1 = __floats2bfloat162_rn(P.z, P.w);
+    const uint32_t u0 = *reinterpret_cast<uint32_t*>(&b0), u1 = *reinterpret_cast<uint32_t*>(&b1);
+    if (a.p_mc) {
+      multimem_st_v4(a.p_mc + e, P);
+      multimem_st_bf16x4(a.pb_mc + e, u0, u1);
+    } else {
+      for (int r = 0; r < a.world; ++r) {
+        *reinterpret_cast<float4*>(a.p_peers[r] + e) = P;
+        *reinterpret_cast<uint2*>(a.pb_peers[r] + e) = make_uint2(u0, u1);
+      }
+    }
+  }
+
+  dp_barrier(a, a.epoch * 2 + 2, a.grid_base + 2 * G);
+
+  // every rank is done reading my gradients: clear them for the next accumulation
+  float4* gz = reinterpret_cast<float4*>(a.g_peers[a.rank]);
+  const long long nz = (a.n + 3) / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nz;
+       i += (long long)gridDim.x * blockDim.x)
+    gz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// Raw-argument entry used by the binding layer (keeps DpArgs private to this TU).
+void dp_fused_step(int world, int rank, long long n, long long chunk, float* const* g_peers,
+                   float* const* p_peers, void* const* pb_peers, uint32_t* const* flag_peers,
+                   const float* g_mc, float* p_mc, void* pb_mc, float* m, float* v,
+                   uint32_t* grid_ctr, uint32_t* go_flag, uint32_t epoch, uint32_t grid_base,
+                   int use_adam, const AdamHyper& h, float sgd_momentum, int ctas, cudaStream_t s) {
+  if (world > kMaxWorld) {
+    fprintf(stderr, "[tnn_b200] dp_fused_step: world %d > %d\n", world, kMaxWorld);
+    abort();
+  }
+  DpArgs a{};
+  a.world = world;
+  a.rank = rank;
+  a.n = n;
+  a.chunk = chunk;
+  for (int r = 0; r < world; ++r) {
+    a.g_peers[r] = g_peers[r];
+    a.p_peers[r] = p_peers[r];
+    a.pb_peers[r] = (bf16*)pb_peers[r];
+    a.flag_peers[r] = flag_peers[r];
+  }
+  a.g_mc = g_mc;
+  a.p_mc = p_mc;
+  a.pb_mc = (bf16*)pb_mc;
+  a.m = m;
+  a.v = v;
+  a.grid_ctr = grid_ctr;
+  a.go_flag = go_flag;
+  a.epoch = epoch;
+  a.grid_base = grid_base;
+  a.use_adam = use_adam;
+  a.h = h;
+  a.sgd_momentum = sgd_momentum;
+  k_dp_step<<<ctas, 512, 0, s>>>(a);
+  TNN_CHECK_LAUNCH();
+}
+
+// Stand-alone cross-rank barrier (used by tests and by the pipeline runtime).
+__global__ void k_p2p_barrier(uint32_t* const* flags, int world, int rank, uint32_t epoch) {
+  if (threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(flags[threadIdx.x] + rank, epoch);
+    while (ld_acquire_sys(flags[rank] + threadIdx.x) < epoch) {
+    }
+  }
+}
+void p2p_barrier(uint32_t* const* flags, int world, int rank, uint32_t epoch, cudaStream_t s) {
+  k_p2p_barrier<<<1, 32, 0, s>>>(flags, world, rank, epoch);
+  TNN_CHECK_LAUNCH();
+}
+
+}  // namespace tnn

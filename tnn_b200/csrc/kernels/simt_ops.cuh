@@ -1,0 +1,155 @@
+// Host launchers of the SIMT (non tensor-core) kernels.  All activation tensors are
+// NHWC / row-major with the channel (feature) dimension contiguous; "bf16" buffers are
+// __nv_bfloat16, parameters / statistics / gradients of parameters are fp32.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tnn {
+
+// ---- elementwise (elementwise.cu) ------------------------------------------------
+enum ActKind : int {
+  AK_NONE = 0, AK_RELU = 1, AK_LEAKY_RELU = 2, AK_SIGMOID = 3, AK_TANH = 4, AK_ELU = 5, AK_GELU = 6
+};
+void cast_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t s);
+void cast_bf16_to_f32(const void* in, float* out, long long n, cudaStream_t s);
+// out = a + b (bf16), optional relu
+void add_bf16(const void* a, const void* b, void* out, long long n, int relu, cudaStream_t s);
+// N-ary elementwise on bf16 arrays: op 0 add, 1 sub, 2 mul
+void binary_bf16(const void* a, const void* b, void* out, long long n, int op, cudaStream_t s);
+void act_fwd(const void* x, void* y, long long n, int kind, float slope, int is_f32, cudaStream_t s);
+// dx = dy * act'(x)   (x = pre-activation input)
+void act_bwd(const void* x, const void* dy, void* dx, long long n, int kind, float slope, int is_f32,
+             cudaStream_t s);
+// inverted dropout with a counter-based RNG: the mask is a pure function of (seed, index), so
+// backward recomputes it instead of storing it.
+void dropout_fwd(const void* x, void* y, long long n, float p, uint64_t seed, cudaStream_t s);
+void dropout_bwd(const void* dy, void* dx, long long n, float p, uint64_t seed, cudaStream_t s);
+void fill_f32(float* x, long long n, float v, cudaStream_t s);
+void axpy_f32(float* y, const float* x, float a, long long n, cudaStream_t s);
+void scale_f32(float* x, float a, long long n, cudaStream_t s);
+// column sums of a [M, N] bf16 matrix accumulated into fp32 out[N] (bias gradient)
+void colsum_bf16(const void* x, long long M, int N, float alpha, float* out, cudaStream_t s);
+// stride-2 phase split: X[N,H,W,C] -> Xp[4][N,H/2,W/2,C] (phase = (h&1)*2 + (w&1)) and inverse
+void phase_split(const void* x, void* xp, int N, int H, int W, int C, cudaStream_t s);
+void phase_merge(const void* xp, void* x, int N, int H, int W, int C, cudaStream_t s);
+void nchw_to_nhwc(const void* x, void* y, int N, int C, int H, int W, int is_f32, cudaStream_t s);
+void nhwc_to_nchw(const void* x, void* y, int N, int C, int H, int W, int is_f32, cudaStream_t s);
+// conv weights: fp32 [K,R,S,C] -> bf16 [K,R,S,C] and bf16 [C,R,S,K] with (r,s) flipped (dgrad)
+void conv_weight_prep(const float* w, void* w_bf16, void* wt_bf16, int K, int R, int S, int C,
+                      cudaStream_t s);
+void philox_uniform_f32(float* x, long long n, float lo, float hi, uint64_t seed, cudaStream_t s);
+void philox_normal_f32(float* x, long long n, float mean, float std, uint64_t seed, cudaStream_t s);
+// generic [rows, cols] transposes (bf16)
+void transpose_bf16(const void* x, void* y, int rows, int cols, cudaStream_t s);
+
+// ---- normalisation (norm.cu) -------------------------------------------------------
+// BatchNorm over a [M, C] bf16 view.  ws is a persistent fp32 workspace of 2*C+4 floats
+// (zero-initialised once); scale_shift receives [2*C] = {gamma*invstd, beta - mean*gamma*invstd}.
+void bn_train_stats(const void* x, long long M, int C, const float* gamma, const float* beta,
+                    float eps, float momentum, float* running_mean, float* running_var,
+                    float* save_mean, float* save_invstd, float* scale_shift, float* ws,
+                    cudaStream_t s);
+void bn_eval_scale_shift(int C, const float* gamma, const float* beta, const float* running_mean,
+                         const float* running_var, float eps, float* scale_shift, cudaStream_t s);
+// y = act(x*scale + shift) [* dropout]; residual-free.  drop_p == 0 disables dropout.
+void bn_apply(const void* x, void* y, long long M, int C, const float* scale_shift, int relu,
+              float drop_p, uint64_t seed, cudaStream_t s);
+// Backward.  g = dy * mask(y) (mask = y != 0 when relu/dropout were fused, scaled by 1/(1-p)).
+// Accumulates dgamma/dbeta (fp32, +=) and writes coef[3*C] for bn_bwd_apply.
+void bn_bwd_reduce(const void* dy, const void* x, const void* y, long long M, int C,
+                   const float* gamma, const float* save_mean, const float* save_invstd,
+                   int masked, float drop_p, float* dgamma, float* dbeta, float* coef, float* ws,
+                   cudaStream_t s);
+// dx = coef0*(g - coef1 - xhat*coef2) (+ extra, an optional residual gradient to add)
+void bn_bwd_apply(const void* dy, const void* x, const void* y, const void* extra, void* dx,
+                  long long M, int C, const float* save_mean, const float* save_invstd,
+                  const float* coef, int masked, float drop_p, cudaStream_t s);
+// LayerNorm over rows of length C (bf16 io, fp32 affine).  One warp per row.
+void layernorm_fwd(const void* x, const void* residual, void* y, void* sum_out, long long rows, int C,
+                   const float* gamma, const float* beta, float eps, float* mean, float* rstd,
+                   cudaStream_t s);
+void layernorm_bwd(const void* dy, const void* x, long long rows, int C, const float* gamma,
+                   const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
+                   cudaStream_t s);
+// GroupNorm on NHWC [N, HW, C] with G groups.
+void groupnorm_fwd(const void* x, void* y, int N, int HW, int C, int G, const float* gamma,
+                   const float* beta, float eps, float* mean, float* rstd, cudaStream_t s);
+void groupnorm_bwd(const void* dy, const void* x, int N, int HW, int C, int G, const float* gamma,
+                   const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
+                   cudaStream_t s);
+
+// ---- pooling (pool.cu) -----------------------------------------------------------
+void maxpool_fwd(const void* x, void* y, uint8_t* mask, int N, int H, int W, int C, int kh, int kw,
+                 int sh, int sw, int ph, int pw, int OH, int OW, cudaStream_t s);
+void maxpool_bwd(const void* dy, const uint8_t* mask, void* dx, int N, int H, int W, int C, int kh,
+                 int kw, int sh, int sw, int ph, int pw, int OH, int OW, cudaStream_t s);
+void avgpool_fwd(const void* x, void* y, int N, int H, int W, int C, int kh, int kw, int sh, int sw,
+                 int ph, int pw, int OH, int OW, cudaStream_t s);
+void avgpool_bwd(const void* dy, void* dx, int N, int H, int W, int C, int kh, int kw, int sh, int sw,
+                 int ph, int pw, int OH, int OW, cudaStream_t s);
+
+// ---- loss / accuracy (loss.cu) ------------------------------------------------------
+// Fused log-softmax cross entropy.  logits bf16 or fp32 [rows, V] (row stride ld), labels int32.
+// out[0] += sum of per-row losses * loss_scale; out[1] += #correct (argmax == label).
+// grad (same dtype/stride as logits, may be null) = (softmax - onehot) * grad_scale.
+void softmax_ce(const void* logits, int is_f32, long long ld, const int* labels, long long rows, int V,
+                float loss_scale, float grad_scale, void* grad, float* out, cudaStream_t s);
+// regression losses on fp32/bf16 flattened tensors: kind 0 mse, 1 mae, 2 huber(delta)
+void regression_loss(const void* pred, const void* target, int is_f32, long long n, int kind,
+                     float delta, float grad_scale, void* grad, float* out, cudaStream_t s);
+
+// ---- optimizers (optim.cu) ----------------------------------------------------------
+struct AdamHyper {
+  float lr, beta1, beta2, eps, weight_decay;
+  int decoupled;
+  float bias_c1, bias_c2;  // 1 - beta^t
+  float grad_scale;        // applied to the gradient before use (1/world, 1/accum)
+};
+// One launch over the whole parameter slab.  Also refreshes the bf16 compute copy and zeroes
+// the gradient slab (so no separate memset / cast kernels exist on the step path).
+void adam_step_flat(float* p, float* g, float* m, float* v, void* p_bf16, long long n,
+                    const AdamHyper& h, int zero_grad, cudaStream_t s);
+void sgd_step_flat(float* p, float* g, float* mom, void* p_bf16, long long n, float lr,
+                   float momentum, float weight_decay, float grad_scale, int zero_grad,
+                   cudaStream_t s);
+// Fused data-parallel step (the product path): barrier -> reduce my 1/W gradient slice over
+// NVLink peer pointers (or one multimem.ld_reduce through NVLS when *_mc are given) -> scale ->
+// Adam/SGD on my slice (sharded optimizer state) -> broadcast fp32 + bf16 params to every
+// replica -> barrier -> zero my gradient slab.  All pointer arrays are HOST arrays of device
+// pointers (they are copied into the kernel argument block).
+void dp_fused_step(int world, int rank, long long n, long long chunk, float* const* g_peers,
+                   float* const* p_peers, void* const* pb_peers, uint32_t* const* flag_peers,
+                   const float* g_mc, float* p_mc, void* pb_mc, float* m, float* v,
+                   uint32_t* grid_ctr, uint32_t* go_flag, uint32_t epoch, uint32_t grid_base,
+                   int use_adam, const AdamHyper& h, float sgd_momentum, int ctas, cudaStream_t s);
+// Device-side barrier across ranks through peer-mapped flag words (st.release.sys /
+// ld.acquire.sys).  `flags` is a DEVICE array of pointers; flags[r] points at rank r's flag
+// array (world uint32 each); `epoch` must increase on every call.
+void p2p_barrier(uint32_t* const* flags, int world, int rank, uint32_t epoch, cudaStream_t s);
+// Zero a gradient slab (used after the post-step barrier in the fused DP path).
+void zero_f32(float* x, long long n, cudaStream_t s);
+
+// ---- direct / fallback convolution (conv_simt.cu) -----------------------------------
+// Small-C_in direct convolution (first layer, C_in < 8): x bf16 NHWC, w fp32 [K,R,S,C].
+void conv_direct_fwd(const void* x, const float* w, const float* bias, void* y, int N, int H, int W,
+                     int C, int K, int R, int S, int stride, int pad, int OH, int OW, cudaStream_t s);
+void conv_direct_wgrad(const void* x, const void* dy, float* dw, float* dbias, int N, int H, int W,
+                       int C, int K, int R, int S, int stride, int pad, int OH, int OW,
+                       cudaStream_t s);
+// im2col / col2im for geometries the TMA window path does not cover (bf16, NHWC):
+// col is [N*OH*OW, R*S*C] with row stride ldcol.
+void im2col_nhwc(const void* x, void* col, long long ldcol, int N, int H, int W, int C, int R, int S,
+                 int stride, int pad, int OH, int OW, cudaStream_t s);
+void col2im_nhwc(const void* col, long long ldcol, void* dx, int N, int H, int W, int C, int R, int S,
+                 int stride, int pad, int OH, int OW, cudaStream_t s);
+
+// ---- embedding & friends (embed.cu) ---------------------------------------------------
+void embedding_fwd(const int* ids, const float* table, const float* pos_table, void* y, long long T,
+                   int L, int D, int V, cudaStream_t s);
+void embedding_bwd(const int* ids, const void* dy, float* dtable, float* dpos, long long T, int L,
+                   int D, int V, cudaStream_t s);
+void argmax_rows(const void* x, int is_f32, long long ld, long long rows, int V, int* out,
+                 cudaStream_t s);
+
+}  // namespace tnn

@@ -1,0 +1,699 @@
+// tcgen05 GEMM + implicit-GEMM convolution kernels for sm_100a.
+//
+// One warp-specialised CTA computes a 128 x BLOCK_N fp32 tile in TMEM:
+//   warp 0      : TMA producer (one elected lane) -> 128B-swizzled smem ring
+//   warp 1      : TMEM allocator + tcgen05.mma issuer (one elected lane)
+//   warps 2..5  : epilogue, tcgen05.ld TMEM -> registers -> fused epilogue -> global
+// Two CTAs are co-resident per SM (<= 256 TMEM columns, <= ~100 KB smem each) so one
+// CTA's epilogue overlaps the other's main loop without a persistent scheduler.
+//
+// The same main loop serves
+//   * Dense fwd / dgrad / wgrad  (any K-major / MN-major operand combination),
+//   * Conv2d fprop and dgrad as implicit GEMM: the activation operand is fetched by
+//     4-D TMA boxes shifted per filter tap, the zero halo comes from TMA OOB fill, no
+//     im2col buffer exists (reference: im2col + cuBLAS, src/nn/layers_impl/
+//     legacy_conv2d_layer.cpp:137-227, or cuDNN graphs, cuda/cudnn_conv2d_ops.cu),
+//   * Conv2d wgrad (second kernel): both operands MN-major, K = pixels, one TMEM
+//     accumulator per filter tap, split-K over pixel blocks with fp32 red.add
+//     (beta = 1 accumulate semantics of the reference, conv2d_nchw_ops.cu:85-87).
+#include "umma_gemm.cuh"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "sm100.cuh"
+
+namespace tnn {
+using namespace sm100;
+
+#define TNN_CUDA_CHECK(x)                                                              \
+  do {                                                                                 \
+    cudaError_t e_ = (x);                                                              \
+    if (e_ != cudaSuccess) {                                                           \
+      fprintf(stderr, "[tnn_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_),   \
+              __FILE__, __LINE__);                                                     \
+      abort();                                                                         \
+    }                                                                                  \
+  } while (0)
+
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
+static constexpr int kThreads = 192;
+static constexpr int ATOM_BYTES = 64 * 128;  // 64 rows x 128 B
+
+struct KParams {
+  int M, N, K;
+  int kc_per_tap;
+  int kb_total;
+  int kb_per_split;
+  int OH, OW;       // output grid (conv) for tile -> (n, h) mapping
+  int BH, BN;       // TMA window box: {64, OW, BH, BN}
+  int ntaps;
+  int vec_ok;       // 16-byte vector stores legal
+  ConvTap taps[kMaxTaps];
+  Epilogue epi;
+};
+
+// ---------------------------------------------------------------------------
+// epilogue helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ long long epi_row_offset(const Epilogue& e, int m) {
+  if (e.grid_mode) {
+    int hw = e.OH * e.OW;
+    int n = m / hw;
+    int r = m - n * hw;
+    int oh = r / e.OW;
+    int ow = r - oh * e.OW;
+    return e.base + (long long)n * e.sN + (long long)oh * e.sH + (long long)ow * e.sW;
+  }
+  return e.base + (long long)m * e.ldc;
+}
+
+// Processes 32 consecutive columns [n, n+32) of one output row held in r[].
+__device__ __forceinline__ void epi_store_32(const KParams& p, const uint32_t (&r)[32], bool row_ok,
+                                             long long row_off, int n) {
+  const Epilogue& e = p.epi;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * e.alpha;
+  if (e.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n + j < p.N) v[j] += __ldg(e.bias + n + j);
+  }
+  if (!row_ok) return;
+  const bool full = (n + 32 <= p.N) && p.vec_ok;
+  if (e.residual != nullptr) {
+    const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(e.residual) + row_off + n;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 q = __ldg(reinterpret_cast<const uint4*>(res) + j);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float2 f = __bfloat1622float2(h[t]);
+          v[j * 8 + t * 2] += f.x;
+          v[j * 8 + t * 2 + 1] += f.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n + j < p.N) v[j] += __bfloat162float(res[j]);
+    }
+  }
+  if (e.act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (e.act == ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+  }
+  if (e.out_mode == OUT_BF16) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out) + row_off + n;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 q;
+        q.x = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]);
+        q.y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
+        q.z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]);
+        q.w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
+        reinterpret_cast<uint4*>(o)[j] = q;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n + j < p.N) o[j] = __float2bfloat16(v[j]);
+    }
+  } else if (e.out_mode == OUT_F32) {
+    float* o = reinterpret_cast<float*>(e.out) + row_off + n;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        reinterpret_cast<float4*>(o)[j] = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n + j < p.N) o[j] = v[j];
+    }
+  } else {  // OUT_F32_ATOMIC
+    float* o = reinterpret_cast<float*>(e.out) + row_off + n;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n + j < p.N) atomicAdd(o + j, v[j]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// GEMM / conv-fprop kernel
+// ---------------------------------------------------------------------------
+template <int BLOCK_N, bool A_MN, bool B_MN, bool CONV_A, int STAGES>
+__global__ void __launch_bounds__(kThreads)
+    umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+                     const __grid_constant__ CUtensorMap tmB, const KParams p) {
+  constexpr int A_BYTES = BLOCK_M * 128;
+  constexpr int B_BYTES = BLOCK_N * 128;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  static_assert(!(CONV_A && A_MN), "conv window operand is K-major");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BLOCK_M;
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int kb_begin = blockIdx.z * p.kb_per_split;
+  const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
+  const int nkb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ----------------------------- TMA producer -----------------------------
+      int img0 = 0, h0 = 0;
+      if (CONV_A) {
+        const int hw = p.OH * p.OW;
+        if (p.BN > 1) {
+          img0 = blockIdx.x * p.BN;
+        } else {
+          img0 = m0 / hw;
+          h0 = (m0 - img0 * hw) / p.OW;
+        }
+      }
+      for (int i = 0; i < nkb; ++i) {
+        const int kb = kb_begin + i;
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        int kB;
+        if (CONV_A) {
+          const int t = kb / p.kc_per_tap;
+          const int kc = kb - t * p.kc_per_tap;
+          const ConvTap tap = p.taps[t];
+          tma_load_4d(sa, &tmA, &full[s], kc * BLOCK_K, tap.dw, h0 + tap.dh, img0 + tap.nb);
+          kB = tap.koff + kc * BLOCK_K;
+        } else {
+          kB = kb * BLOCK_K;
+          if (A_MN) {
+            tma_load_2d(sa, &tmA, &full[s], m0, kB);
+            tma_load_2d(sa + ATOM_BYTES, &tmA, &full[s], m0 + 64, kB);
+          } else {
+            tma_load_2d(sa, &tmA, &full[s], kB, m0);
+          }
+        }
+        if (B_MN) {
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_load_2d(sb + j * ATOM_BYTES, &tmB, &full[s], n0 + j * 64, kB);
+        } else {
+          tma_load_2d(sb, &tmB, &full[s], kB, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ----------------------------- MMA issuer -----------------------------
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          const uint64_t ad = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, ATOM_BYTES, 1024)
+                                   : make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
+          const uint64_t bd = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, ATOM_BYTES, 1024)
+                                   : make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+          umma_f16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ----------------------------- epilogue -----------------------------
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    const bool row_ok = m < p.M;
+    const long long row_off = row_ok ? epi_row_offset(p.epi, m) : 0;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+      if (n0 + c >= p.N) break;
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+      tmem_ld_wait();
+      epi_store_32(p, r, row_ok, row_off, n0 + c);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------
+// conv wgrad kernel: M = Kout tile (128), N = 64 input channels per tap, T taps
+// ---------------------------------------------------------------------------
+template <int T, int STAGES>
+__global__ void __launch_bounds__(kThreads)
+    umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmA,
+                      const __grid_constant__ CUtensorMap tmB, const KParams p, int c_tiles,
+                      float* __restrict__ dW, long long ldw) {
+  constexpr int A_BYTES = 2 * ATOM_BYTES;
+  constexpr int B_BYTES = T * ATOM_BYTES;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = (T * 64 <= 64) ? 64 : ((T * 64 <= 128) ? 128 : ((T * 64 <= 256) ? 256 : 512));
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kout0 = (blockIdx.y / c_tiles) * BLOCK_M;
+  const int c0 = (blockIdx.y % c_tiles) * 64;
+  const int tap0 = blockIdx.z * T;
+  const int kb_begin = blockIdx.x * p.kb_per_split;
+  const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
+  const int nkb = kb_end - kb_begin;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (elect_one()) {
+        const int hw = p.OH * p.OW;
+        for (int i = 0; i < nkb; ++i) {
+          const int kb = kb_begin + i;
+          const int s = i % STAGES;
+          const uint32_t ph = (i / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_expect_tx(&full[s], STAGE_BYTES);
+          const int pix0 = kb * BLOCK_K;
+          int img0, h0;
+          if (p.BN > 1) {
+            img0 = kb * p.BN;
+            h0 = 0;
+          } else {
+            img0 = pix0 / hw;
+            h0 = (pix0 - img0 * hw) / p.OW;
+          }
+          tma_load_2d(sa, &tmA, &full[s], kout0, pix0);
+          tma_load_2d(sa + ATOM_BYTES, &tmA, &full[s], kout0 + 64, pix0);
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const ConvTap tap = p.taps[tap0 + t];
+            tma_load_4d(sb + t * ATOM_BYTES, &tmB, &full[s], c0, tap.dw, h0 + tap.dh,
+                        img0 + tap.nb);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (elect_one()) {
+        constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, 64, 1u, 1u);
+        for (int i = 0; i < nkb; ++i) {
+          const int s = i % STAGES;
+          const uint32_t ph = (i / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              const uint64_t ad = make_smem_desc_sw128(a_addr + k * 2048, ATOM_BYTES, 1024);
+              const uint64_t bd =
+                  make_smem_desc_sw128(b_addr + t * ATOM_BYTES + k * 2048, ATOM_BYTES, 1024);
+              umma_f16(tmem_base + t * 64, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(tmem_full);
+      }
+    } else {
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      const int q = warp & 3;
+      const int row = q * 32 + lane;
+      const int ko = kout0 + row;
+      const bool row_ok = ko < p.M;
+#pragma unroll 1
+      for (int t = 0; t < T; ++t) {
+        const int koff = p.taps[tap0 + t].koff;
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 32) {
+          if (c0 + c >= p.N) break;
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + t * 64 + c, r);
+          tmem_ld_wait();
+          if (row_ok) {
+            float* o = dW + (long long)ko * ldw + koff + c0 + c;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + c + j < p.N) atomicAdd(o + j, __uint_as_float(r[j]) * p.epi.alpha);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    TNN_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    if (p == nullptr || qres != cudaDriverEntryPointSuccess) {
+      fprintf(stderr, "[tnn_b200] cuTensorMapEncodeTiled unavailable\n");
+      abort();
+    }
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+// dims / box innermost-first; strides (bytes) for dims 1..rank-1.
+static CUtensorMap make_tmap_bf16(const void* ptr, int rank, const uint64_t* dims,
+                                  const uint64_t* strides_bytes, const uint32_t* box) {
+  CUtensorMap m;
+  cuuint64_t gdims[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr),
+                               gdims, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr,
+            "[tnn_b200] cuTensorMapEncodeTiled failed (%d): rank=%d ptr=%p dims=[%llu,%llu,%llu,%llu] "
+            "stride1=%llu box=[%u,%u,%u,%u]\n",
+            (int)r, rank, ptr, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+            (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+            (unsigned long long)(rank > 1 ? strides_bytes[0] : 0), box[0], rank > 1 ? box[1] : 0,
+            rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    abort();
+  }
+  return m;
+}
+
+// 2-D operand map.  K-major: global [rows, K] -> dims {K, rows}, box {64, box_rows}.
+// MN-major: global [K, mn] -> dims {mn, K}, box {64, 64}.
+static CUtensorMap make_operand_map(const void* ptr, long long rows, long long cols, long long ld,
+                                    uint32_t box_rows) {
+  uint64_t dims[2] = {(uint64_t)cols, (uint64_t)rows};
+  uint64_t str[1] = {(uint64_t)ld * 2};
+  uint32_t box[2] = {64, box_rows};
+  return make_tmap_bf16(ptr, 2, dims, str, box);
+}
+
+static CUtensorMap make_window_map(const void* X, const ConvGeom& g, int BH, int BN) {
+  uint64_t dims[4] = {(uint64_t)g.C, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.IN};
+  uint64_t str[3] = {(uint64_t)g.C * 2, (uint64_t)g.IW * g.C * 2, (uint64_t)g.IH * g.IW * g.C * 2};
+  uint32_t box[4] = {64, (uint32_t)g.OW, (uint32_t)BH, (uint32_t)BN};
+  return make_tmap_bf16(X, 4, dims, str, box);
+}
+
+static bool pick_window(const ConvGeom& g, int rows, int* BH, int* BN) {
+  // window of `rows` output pixels = BN images x BH rows x OW columns
+  if (g.OW <= 0 || rows % g.OW != 0) return false;
+  int r = rows / g.OW;  // rows of width OW
+  if (r <= g.OH) {
+    if (g.OH % r != 0) return false;
+    *BH = r;
+    *BN = 1;
+  } else {
+    if (r % g.OH != 0) return false;
+    *BH = g.OH;
+    *BN = r / g.OH;
+  }
+  return *BH <= 256 && *BN <= 256 && g.OW <= 256;
+}
+
+bool conv_geom_supported(const ConvGeom& g) {
+  int bh, bn;
+  if (g.C % 8 != 0) return false;
+  if (g.ntaps < 1 || g.ntaps > kMaxTaps) return false;
+  return pick_window(g, 128, &bh, &bn) && pick_window(g, 64, &bh, &bn);
+}
+
+template <typename Kern>
+static void set_smem(Kern k, int bytes) {
+  TNN_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, bool CONV_A>
+static void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, dim3 grid,
+                        cudaStream_t stream) {
+  constexpr int STAGES = (BLOCK_N <= 64) ? 4 : ((BLOCK_N <= 128) ? 3 : 4);
+  constexpr int smem = STAGES * (BLOCK_M * 128 + BLOCK_N * 128) + 1024 + 256;
+  auto kern = umma_gemm_kernel<BLOCK_N, A_MN, B_MN, CONV_A, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    set_smem(kern, smem);
+    configured = true;
+  }
+  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  TNN_CUDA_CHECK(cudaGetLastError());
+}
+
+static int pick_block_n(int N) {
+  const char* e = getenv("TNN_GEMM_BLOCK_N");
+  if (e != nullptr) {
+    int v = atoi(e);
+    if (v == 64 || v == 128 || v == 256) return v;
+  }
+  if (N <= 64) return 64;
+  return 128;
+}
+
+static int epi_vec_ok(const Epilogue& e, int N) {
+  bool ok = (N % 8 == 0) && (e.base % 8 == 0);
+  if (e.grid_mode)
+    ok = ok && (e.sN % 8 == 0) && (e.sH % 8 == 0) && (e.sW % 8 == 0);
+  else
+    ok = ok && (e.ldc % 8 == 0);
+  ok = ok && ((reinterpret_cast<uintptr_t>(e.out) & 15) == 0);
+  if (e.residual) ok = ok && ((reinterpret_cast<uintptr_t>(e.residual) & 15) == 0);
+  return ok ? 1 : 0;
+}
+
+#define TNN_DISPATCH_BN(BN_, ...)            \
+  if (BN_ == 64) {                           \
+    constexpr int BNc = 64;                  \
+    __VA_ARGS__                              \
+  } else if (BN_ == 128) {                   \
+    constexpr int BNc = 128;                 \
+    __VA_ARGS__                              \
+  } else {                                   \
+    constexpr int BNc = 256;                 \
+    __VA_ARGS__                              \
+  }
+
+void gemm_bf16(const void* A, const void* B, int M, int N, int K, long long lda, long long ldb,
+               bool a_mn, bool b_mn, const Epilogue& epi, int splits, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return;
+  if (lda % 8 != 0 || ldb % 8 != 0 || (reinterpret_cast<uintptr_t>(A) & 15) ||
+      (reinterpret_cast<uintptr_t>(B) & 15)) {
+    fprintf(stderr, "[tnn_b200] gemm_bf16: operands must be 16-byte aligned with ld %% 8 == 0\n");
+    abort();
+  }
+  const int bn = pick_block_n(N);
+  KParams p{};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.kc_per_tap = (K + BLOCK_K - 1) / BLOCK_K;
+  p.kb_total = p.kc_per_tap;
+  if (splits < 1) splits = 1;
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+  if (splits > 1 && epi.out_mode != OUT_F32_ATOMIC) {
+    fprintf(stderr, "[tnn_b200] gemm_bf16: split-K requires OUT_F32_ATOMIC\n");
+    abort();
+  }
+  p.ntaps = 1;
+  p.epi = epi;
+  p.vec_ok = epi_vec_ok(epi, N);
+  CUtensorMap tmA = a_mn ? make_operand_map(A, K, M, lda, 64) : make_operand_map(A, M, K, lda, BLOCK_M);
+  CUtensorMap tmB = b_mn ? make_operand_map(B, K, N, ldb, 64) : make_operand_map(B, N, K, ldb, bn);
+  dim3 grid((M + BLOCK_M - 1) / BLOCK_M, (N + bn - 1) / bn, splits);
+  TNN_DISPATCH_BN(bn, {
+    if (!a_mn && !b_mn) launch_gemm<BNc, false, false, false>(tmA, tmB, p, grid, stream);
+    else if (!a_mn && b_mn) launch_gemm<BNc, false, true, false>(tmA, tmB, p, grid, stream);
+    else if (a_mn && !b_mn) launch_gemm<BNc, true, false, false>(tmA, tmB, p, grid, stream);
+    else launch_gemm<BNc, true, true, false>(tmA, tmB, p, grid, stream);
+  })
+}
+
+void conv_fprop_bf16(const void* X, const void* Wt, long long ldw, int N, const ConvGeom& g,
+                     const Epilogue& epi, cudaStream_t stream) {
+  int BH, BN;
+  if (!pick_window(g, BLOCK_M, &BH, &BN) || g.C % 8 != 0 || ldw % 8 != 0) {
+    fprintf(stderr, "[tnn_b200] conv_fprop_bf16: unsupported geometry OH=%d OW=%d C=%d\n", g.OH,
+            g.OW, g.C);
+    abort();
+  }
+  const int M = g.ON * g.OH * g.OW;
+  const int bn = pick_block_n(N);
+  KParams p{};
+  p.M = M;
+  p.N = N;
+  p.K = g.C;
+  p.kc_per_tap = (g.C + BLOCK_K - 1) / BLOCK_K;
+  p.kb_total = p.kc_per_tap * g.ntaps;
+  p.kb_per_split = p.kb_total;
+  p.OH = g.OH;
+  p.OW = g.OW;
+  p.BH = BH;
+  p.BN = BN;
+  p.ntaps = g.ntaps;
+  for (int t = 0; t < g.ntaps; ++t) p.taps[t] = g.taps[t];
+  p.epi = epi;
+  p.vec_ok = epi_vec_ok(epi, N);
+  CUtensorMap tmA = make_window_map(X, g, BH, BN);
+  // weight matrix [N, Ktot]: the last tap may read past koff+C; the extent is ldw
+  CUtensorMap tmB = make_operand_map(Wt, N, ldw, ldw, bn);
+  dim3 grid((M + BLOCK_M - 1) / BLOCK_M, (N + bn - 1) / bn, 1);
+  TNN_DISPATCH_BN(bn, { launch_gemm<BNc, false, false, true>(tmA, tmB, p, grid, stream); })
+}
+
+void conv_wgrad_bf16(const void* dY, long long ldy, int Kout, const void* X, const ConvGeom& g,
+                     float* dW, long long ldw, float alpha, cudaStream_t stream) {
+  int BH, BN;
+  if (!pick_window(g, BLOCK_K, &BH, &BN) || g.C % 8 != 0 || ldy % 8 != 0 ||
+      (g.ntaps != 1 && g.ntaps % 3 != 0)) {
+    fprintf(stderr, "[tnn_b200] conv_wgrad_bf16: unsupported geometry OH=%d OW=%d C=%d taps=%d\n",
+            g.OH, g.OW, g.C, g.ntaps);
+    abort();
+  }
+  const int Mpix = g.ON * g.OH * g.OW;
+  KParams p{};
+  p.M = Kout;
+  p.N = g.C;
+  p.K = Mpix;
+  p.kb_total = (Mpix + BLOCK_K - 1) / BLOCK_K;
+  p.OH = g.OH;
+  p.OW = g.OW;
+  p.BH = BH;
+  p.BN = BN;
+  p.ntaps = g.ntaps;
+  for (int t = 0; t < g.ntaps; ++t) p.taps[t] = g.taps[t];
+  p.epi.alpha = alpha;
+  const int T = (g.ntaps == 1) ? 1 : 3;
+  const int groups = g.ntaps / T;
+  const int c_tiles = (g.C + 63) / 64;
+  const int k_tiles = (Kout + BLOCK_M - 1) / BLOCK_M;
+  const int tiles = c_tiles * k_tiles * groups;
+  int splits = (2 * 148 + tiles - 1) / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > p.kb_total) splits = p.kb_total;
+  p.kb_per_split = (p.kb_total + splits - 1) / splits;
+  splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
+
+  CUtensorMap tmA = make_operand_map(dY, Mpix, Kout, ldy, 64);
+  uint64_t dims[4] = {(uint64_t)g.C, (uint64_t)g.IW, (uint64_t)g.IH, (uint64_t)g.IN};
+  uint64_t str[3] = {(uint64_t)g.C * 2, (uint64_t)g.IW * g.C * 2, (uint64_t)g.IH * g.IW * g.C * 2};
+  uint32_t box[4] = {64, (uint32_t)g.OW, (uint32_t)BH, (uint32_t)BN};
+  CUtensorMap tmB = make_tmap_bf16(X, 4, dims, str, box);
+  dim3 grid(splits, k_tiles * c_tiles, groups);
+  if (T == 1) {
+    constexpr int STAGES = 6;
+    constexpr int smem = STAGES * (2 * ATOM_BYTES + ATOM_BYTES) + 1024 + 256;
+    auto kern = umma_wgrad_kernel<1, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+      set_smem(kern, smem);
+      configured = true;
+    }
+    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p, c_tiles, dW, ldw);
+  } else {
+    constexpr int STAGES = 4;
+    constexpr int smem = STAGES * (2 * ATOM_BYTES + 3 * ATOM_BYTES) + 1024 + 256;
+    auto kern = umma_wgrad_kernel<3, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+      set_smem(kern, smem);
+      configured = true;
+    }
+    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p, c_tiles, dW, ldw);
+  }
+  TNN_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace tnn
