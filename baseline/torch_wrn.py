@@ -1,0 +1,81 @@
+"""torch + cuDNN + NCCL re-creation of the reference WRN-16-8 / CIFAR-100 training config
+(mirrors /root/reference/torch/torch_wrn16_8_cifar100.py semantics: pre-activation wide blocks,
+dropout 0.3, Adam).  Used only as the MEASURED library baseline (bench.py --impl torch)."""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class WideBlock(nn.Module):
+    def __init__(self, cin, cout, stride, p):
+        super().__init__()
+        self.bn1 = nn.BatchNorm2d(cin, eps=1e-2)
+        self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=True)
+        self.bn2 = nn.BatchNorm2d(cout, eps=1e-2)
+        self.drop = nn.Dropout(p)
+        self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=True)
+        self.short = nn.Conv2d(cin, cout, 1, stride, 0, bias=False) if (stride != 1 or cin != cout) else None
+
+    def forward(self, x):
+        o = self.conv1(F.relu(self.bn1(x)))
+        o = self.conv2(self.drop(F.relu(self.bn2(o))))
+        return o + (self.short(x) if self.short is not None else x)
+
+
+class WRN16_8(nn.Module):
+    def __init__(self, classes=100, p=0.3):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, 16, 3, 1, 1)
+        cfg = [(16, 128, 1), (128, 128, 1), (128, 256, 2), (256, 256, 1), (256, 512, 2), (512, 512, 1)]
+        self.blocks = nn.Sequential(*[WideBlock(a, b, s, p) for a, b, s in cfg])
+        self.bn = nn.BatchNorm2d(512, eps=1e-2)
+        self.fc = nn.Linear(512, classes)
+
+    def forward(self, x):
+        x = self.blocks(self.conv1(x))
+        x = F.relu(self.bn(x))
+        return self.fc(F.adaptive_avg_pool2d(x, 1).flatten(1))
+
+
+def bench_torch_wrn(B, steps, warmup, local, world):
+    import torch.distributed as dist
+    dev = torch.device("cuda", local)
+    torch.backends.cudnn.benchmark = True
+    model = WRN16_8().to(dev).to(memory_format=torch.channels_last)
+    if world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, eps=1e-3, weight_decay=3e-4, fused=True)
+    xs = [torch.rand(B, 3, 32, 32, device=dev).to(memory_format=torch.channels_last) for _ in range(4)]
+    ys = [torch.randint(0, 100, (B,), device=dev) for _ in range(4)]
+
+    def step(i):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = F.cross_entropy(model(xs[i % 4]), ys[i % 4])
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for i in range(max(warmup, 3)):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = step(i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    return {"metric": "WRN-16-8 CIFAR-100 training throughput", "value": world * B * steps / (ms / 1e3), "unit": "img/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
+            "scaling": "weak", "dtype": "bf16", "data": "synthetic",
+            "config": {"model": "cifar100_wrn16_8", "global_batch": world * B, "parallelism": f"ddp{world}",
+                       "stack": "torch autocast bf16 + cuDNN channels_last + NCCL"}, "final_loss": float(loss)}

@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""Headline benchmark: WRN-16-8 / CIFAR-100 bf16 training throughput (images/s), data parallel
+over N B200s of one node (weak scaling, per-GPU batch 256) -- the metric/config named by
+BASELINE.json; BASELINE.md's published number is ~2480 img/s (TNN 2-stage pipeline, 2 GPUs).
+
+  python bench.py --gpus N --steps K --warmup W [--impl tnn|reference|torch] [--dp fused|nccl]
+
+For N > 1 launch with ``python -m torch.distributed.run --nnodes=1 --nproc-per-node N
+--master-addr 127.0.0.1 --master-port P bench.py --gpus N ...``.
+
+Timing: W warm-up steps, then exactly K steps bracketed by barrier + cuda synchronize, CUDA
+events on the compute stream, MAX over ranks.  ``value`` = device-resident inputs;
+``e2e.value`` = the same K steps through the public training API with, every step, an H2D copy of
+that step's batch from pinned host memory and a D2H read of a step's loss.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BASELINE_IMG_S = 2480.0      # 256 / 0.103 s (TNN C++ pipeline, WRN-16-8 / CIFAR-100)
+PER_GPU_BATCH = 256
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="tnn", choices=["tnn", "reference", "torch"])
+    ap.add_argument("--dp", default="fused", choices=["fused", "nccl"])
+    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
+    ap.add_argument("--model", default="cifar100_wrn16_8")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons, power = [], 0, set(), []
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def emit(d):
+    print(json.dumps(d), flush=True)
+
+
+def run_reference(args):
+    # The reference is a CMake/C++ tree with no setup.py / pyproject.toml; the one allowed offline
+    # install (`pip install --no-index ... --target baseline/_ref /root/reference`) fails with
+    # "Neither 'setup.py' nor 'pyproject.toml' found" (recorded in DESIGN.md), and its CMake build
+    # needs network FetchContent + libibverbs + TBB and a header that is missing from the snapshot.
+    emit({"impl": "reference", "unavailable": "reference is a C++/CMake tree: pip install fails (no setup.py/pyproject.toml) "
+          "and the CMake build needs network FetchContent, libibverbs, TBB and a missing header (device/engine.hpp)"})
+
+
+def dist_setup(n):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, local, world
+
+
+def max_over_ranks(ms: float, world: int, dev) -> float:
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return ms
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def barrier(world):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def run_tnn(args):
+    import torch
+    from tnn_b200.models import ExampleModels, load_or_create_model
+    from tnn_b200.nn import LossFactory, OptimizerFactory
+    from tnn_b200.nn.train import DevicePrefetcher, TrainStep
+    from tnn_b200.ops import native
+
+    rank, local, world = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    Cx = native.require()
+    B = args.batch
+    # reference trainer hyper-parameters: Adam(lr, 0.9, 0.999, eps 1e-3, wd 3e-4) (examples/trainer.cpp:67-71)
+    opt = OptimizerFactory.create_adam(1e-3, 0.9, 0.999, 1e-3, 3e-4)
+    dp = None
+    if world > 1 and args.dp == "fused":
+        from tnn_b200.parallel.dp import FusedDataParallel
+        dp = FusedDataParallel(opt)
+        graph = dp.build_graph(ExampleModels.create(args.model), dev, seed=1234, name=args.model)
+        parallelism = f"dp{world}-fused-p2p" + ("-nvls" if dp.mc else "")
+    else:
+        graph = load_or_create_model(args.model, device=dev, seed=1234)
+        opt.attach(graph.context())
+        if world > 1:
+            from tnn_b200.parallel.dp import AllReduceDataParallel
+            dp = AllReduceDataParallel(graph, opt)
+        parallelism = f"dp{world}" + ("-nccl-allreduce" if world > 1 else "")
+    crit = LossFactory.create_logsoftmax_crossentropy()
+    step = TrainStep(graph, crit, opt, None, 1, dp)
+
+    g = torch.Generator().manual_seed(100 + rank)
+    NB = 4
+    host = [(torch.rand((B, 32, 32, 3), generator=g).pin_memory(), torch.randint(0, 100, (B,), generator=g, dtype=torch.int32).pin_memory())
+            for _ in range(NB)]
+    devb = [(x.to(dev), y.to(dev)) for x, y in host]
+
+    # ---------------- device-resident timing
+    for i in range(args.warmup):
+        step(*devb[i % NB])
+    barrier(world)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = Cx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        stats = step(*devb[i % NB])
+    e1.record()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    launches = Cx.launch_count() - l0
+    clocks = sampler.stop()
+    loss_val = float(stats[0])
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---------------- end to end: pinned host -> device every step, loss read back every step
+    e2e = None
+    if not args.no_e2e:
+        pre = DevicePrefetcher(dev)
+        loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        copy_done = torch.cuda.Event()
+
+        def run(n):
+            staged = pre.stage(*host[0])
+            last = 0.0
+            for i in range(n):
+                dx, dy, slot = staged
+                pre.acquire(slot)
+                st = step(dx, dy)
+                pre.release(slot)
+                staged = pre.stage(*host[(i + 1) % NB])
+                if i > 0:
+                    copy_done.synchronize()          # D2H read of the previous step's loss
+                    last = float(loss_host[0])
+                loss_host.copy_(st, non_blocking=True)
+                copy_done.record()
+            copy_done.synchronize()
+            return float(loss_host[0]) + 0.0 * last
+
+        run(max(3, args.warmup))
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        run(args.steps)
+        e1.record()
+        barrier(world)
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms2 = max_over_ranks(max(e0.elapsed_time(e1), wall_ms), world, dev)
+        e2e = {"value": world * B * args.steps / (ms2 / 1e3), "unit": "img/s", "ms_per_step": ms2 / args.steps,
+               "h2d_bytes_per_step": B * 32 * 32 * 3 * 4 + B * 4, "d2h_bytes_per_step": 8}
+
+    if rank == 0:
+        out = {
+            "metric": "WRN-16-8 CIFAR-100 training throughput", "value": value, "unit": "img/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": value / BASELINE_IMG_S, "dtype": "bf16", "data": "synthetic",
+            "impl": "tnn_b200",
+            "config": {"model": args.model, "global_batch": world * B, "per_gpu_batch": B, "seq_len": None,
+                       "image": [32, 32, 3], "classes": 100, "optimizer": "adam(lr1e-3,eps1e-3,wd3e-4)",
+                       "parallelism": parallelism,
+                       "l2": "inputs rotate over 4 batches; per-step activation working set (~2 GB) >> 126 MB L2"},
+            "clocks": clocks, "gpu_launches": int(launches), "launches_per_step": launches / max(1, args.steps),
+            "final_loss": loss_val,
+        }
+        if e2e:
+            out["e2e"] = e2e
+        emit(out)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_torch(args):
+    """torch + cuDNN + NCCL re-creation of the same config (the 'reference-equivalent' measured
+    baseline of BASELINE.md): bf16 autocast, channels_last, DDP for N > 1."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    from torch_wrn import bench_torch_wrn
+    rank, local, world = dist_setup(args.gpus)
+    res = bench_torch_wrn(args.batch, args.steps, args.warmup, local, world)
+    if rank == 0:
+        res.update({"impl": "torch", "vs_baseline": res["value"] / BASELINE_IMG_S})
+        emit(res)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    elif a.impl == "torch":
+        run_torch(a)
+    else:
+        run_tnn(a)

@@ -322,6 +322,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     tnn::argmax_rows(vp(x), x.scalar_type() == torch::kFloat32, ld, rows, V, out.data_ptr<int>(), cur_stream());
   });
 
+  m.def("launch_count", []() { return tnn::g_launch_count; });
   tnn::attention_bind(m);
   tnn::runtime_bind(m);
 }

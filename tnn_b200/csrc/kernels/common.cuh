@@ -8,8 +8,12 @@
 
 namespace tnn {
 
+// number of kernels launched by this library in the current process (bench.py reports it)
+extern unsigned long long g_launch_count;
+
 #define TNN_CHECK_LAUNCH()                                                                    \
   do {                                                                                        \
+    ++::tnn::g_launch_count;                                                                  \
     cudaError_t e_ = cudaGetLastError();                                                      \
     if (e_ != cudaSuccess) {                                                                  \
       fprintf(stderr, "[tnn_b200] launch error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, \

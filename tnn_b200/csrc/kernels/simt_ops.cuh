@@ -7,6 +7,8 @@
 
 namespace tnn {
 
+extern unsigned long long g_launch_count;
+
 // ---- elementwise (elementwise.cu) ------------------------------------------------
 enum ActKind : int {
   AK_NONE = 0, AK_RELU = 1, AK_LEAKY_RELU = 2, AK_SIGMOID = 3, AK_TANH = 4, AK_ELU = 5, AK_GELU = 6

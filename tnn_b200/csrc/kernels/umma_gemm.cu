@@ -29,6 +29,7 @@
 
 namespace tnn {
 using namespace sm100;
+extern unsigned long long g_launch_count;
 
 #define TNN_CUDA_CHECK(x)                                                              \
   do {                                                                                 \
@@ -528,6 +529,7 @@ static void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const KP
     configured = true;
   }
   kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  ++g_launch_count;
   TNN_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -682,6 +684,7 @@ void conv_wgrad_bf16(const void* dY, long long ldy, int Kout, const void* X, con
       configured = true;
     }
     kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p, c_tiles, dW, ldw);
+    ++g_launch_count;
   } else {
     constexpr int STAGES = 4;
     constexpr int smem = STAGES * (2 * ATOM_BYTES + 3 * ATOM_BYTES) + 1024 + 256;
@@ -692,6 +695,7 @@ void conv_wgrad_bf16(const void* dY, long long ldy, int Kout, const void* X, con
       configured = true;
     }
     kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p, c_tiles, dW, ldw);
+    ++g_launch_count;
   }
   TNN_CUDA_CHECK(cudaGetLastError());
 }

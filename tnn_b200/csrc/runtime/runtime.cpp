@@ -1,4 +1,300 @@
+// pybind11 surface of the C++ host runtime: archiver (wire/checkpoint format), offset
+// allocators, native data path, tokenizer, profiler event store.
 #include "runtime.hpp"
+
+#include <pybind11/numpy.h>
+#include <pybind11/stl.h>
+
+#include <chrono>
+#include <memory>
+#include <mutex>
+
+#include "allocator.hpp"
+#include "archiver.hpp"
+#include "data_loader.hpp"
+#include "tokenizer.hpp"
+
+namespace py = pybind11;
+
 namespace tnn {
-void runtime_bind(pybind11::module_& m) { (void)m; }
+
+// ------------------------------------------------------------------------------ profiler
+// Reference: include/profiling/event.hpp:11-62, profiler.hpp:13-157.
+struct ProfEvent {
+  int type;  // 0 COMPUTE, 1 COMMUNICATION, 2 OTHER
+  int64_t start_ns, end_ns;
+  std::string name, source;
+};
+class Profiler {
+ public:
+  void init_start_time() {
+    start_ns_ = now_ns();
+  }
+  static int64_t now_ns() {
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(
+               std::chrono::system_clock::now().time_since_epoch())
+        .count();
+  }
+  void add_event(int type, int64_t s, int64_t e, const std::string& name, const std::string& src) {
+    std::lock_guard<std::mutex> g(mu_);
+    events_.push_back(ProfEvent{type, s, e, name, src});
+  }
+  // merge another profiler's events, re-basing them by the difference of the start times
+  void merge(const Profiler& o) {
+    std::lock_guard<std::mutex> g(mu_);
+    const int64_t delta = start_ns_ - o.start_ns_;
+    for (const auto& ev : o.events_) events_.push_back(ProfEvent{ev.type, ev.start_ns + delta, ev.end_ns + delta, ev.name, ev.source});
+  }
+  void sort() {
+    std::lock_guard<std::mutex> g(mu_);
+    std::sort(events_.begin(), events_.end(), [](const ProfEvent& a, const ProfEvent& b) { return a.start_ns < b.start_ns; });
+  }
+  void clear() {
+    std::lock_guard<std::mutex> g(mu_);
+    events_.clear();
+  }
+  py::bytes serialize() const {
+    Writer w;
+    w.prim<int64_t>(start_ns_);
+    w.prim<uint64_t>(events_.size());
+    for (const auto& e : events_) {
+      w.prim<uint8_t>((uint8_t)e.type);
+      w.prim<int64_t>(e.start_ns);
+      w.prim<int64_t>(e.end_ns);
+      w.str(e.name);
+      w.str(e.source);
+    }
+    return py::bytes(reinterpret_cast<const char*>(w.buffer().data()), w.size());
+  }
+  static std::shared_ptr<Profiler> deserialize(const std::string& b) {
+    auto p = std::make_shared<Profiler>();
+    Reader r(reinterpret_cast<const uint8_t*>(b.data()), b.size());
+    p->start_ns_ = r.prim<int64_t>();
+    uint64_t n = r.prim<uint64_t>();
+    for (uint64_t i = 0; i < n; ++i) {
+      ProfEvent e;
+      e.type = r.prim<uint8_t>();
+      e.start_ns = r.prim<int64_t>();
+      e.end_ns = r.prim<int64_t>();
+      e.name = r.str();
+      e.source = r.str();
+      p->events_.push_back(std::move(e));
+    }
+    return p;
+  }
+  std::vector<py::tuple> events() const {
+    std::vector<py::tuple> out;
+    for (const auto& e : events_) out.push_back(py::make_tuple(e.type, e.start_ns, e.end_ns, e.name, e.source));
+    return out;
+  }
+  int64_t start_ns() const { return start_ns_; }
+
+ private:
+  int64_t start_ns_ = 0;
+  std::vector<ProfEvent> events_;
+  mutable std::mutex mu_;
+};
+
+static const uint8_t* as_ptr(int64_t p) { return reinterpret_cast<const uint8_t*>(p); }
+
+void runtime_bind(py::module_& m) {
+  // ---------------------------------------------------------------- archiver
+  py::class_<Sizer>(m, "Sizer")
+      .def(py::init<>())
+      .def("size", &Sizer::size)
+      .def("u8", [](Sizer& s, uint8_t v) { s.prim(v); })
+      .def("u16", [](Sizer& s, uint16_t v) { s.prim(v); })
+      .def("u32", [](Sizer& s, uint32_t v) { s.prim(v); })
+      .def("u64", [](Sizer& s, uint64_t v) { s.prim(v); })
+      .def("i64", [](Sizer& s, int64_t v) { s.prim(v); })
+      .def("f32", [](Sizer& s, float v) { s.prim(v); })
+      .def("f64", [](Sizer& s, double v) { s.prim(v); })
+      .def("boolean", [](Sizer& s, bool v) { s.prim<uint8_t>(v); })
+      .def("string", [](Sizer& s, const std::string& v) { s.str(v); })
+      .def("sizes", [](Sizer& s, const std::vector<uint64_t>& v) { s.sizes(v); })
+      .def("raw", [](Sizer& s, const py::bytes& b) { s.bytes(nullptr, std::string(b).size()); })
+      .def("tensor", [](Sizer& s, uint32_t dt, const std::vector<uint64_t>& shape, uint64_t nbytes) { s.tensor(dt, shape, nbytes); });
+  py::class_<Writer>(m, "Writer")
+      .def(py::init<size_t>(), py::arg("reserve") = 0)
+      .def("size", &Writer::size)
+      .def("u8", [](Writer& w, uint8_t v) { w.prim(v); })
+      .def("u16", [](Writer& w, uint16_t v) { w.prim(v); })
+      .def("u32", [](Writer& w, uint32_t v) { w.prim(v); })
+      .def("u64", [](Writer& w, uint64_t v) { w.prim(v); })
+      .def("i64", [](Writer& w, int64_t v) { w.prim(v); })
+      .def("f32", [](Writer& w, float v) { w.prim(v); })
+      .def("f64", [](Writer& w, double v) { w.prim(v); })
+      .def("boolean", [](Writer& w, bool v) { w.prim<uint8_t>(v); })
+      .def("string", [](Writer& w, const std::string& v) { w.str(v); })
+      .def("sizes", [](Writer& w, const std::vector<uint64_t>& v) { w.sizes(v); })
+      .def("raw", [](Writer& w, const py::bytes& b) { std::string s = b; w.bytes(s.data(), s.size()); })
+      .def("raw_ptr", [](Writer& w, int64_t ptr, uint64_t n) { w.bytes(as_ptr(ptr), n); })
+      .def("tensor", [](Writer& w, uint32_t dt, const std::vector<uint64_t>& shape, int64_t ptr, uint64_t nbytes) {
+        w.tensor(dt, shape, as_ptr(ptr), nbytes);
+      })
+      .def("packet_header", [](Writer& w, uint8_t type, uint64_t packet_len, uint64_t msg_len, uint64_t serial,
+                               uint64_t offset, uint32_t total) {
+        PacketHeader h;
+        h.type = type;
+        h.endianness = host_is_little_endian() ? 1 : 0;
+        h.packet_length = packet_len;
+        h.msg_length = msg_len;
+        h.msg_serial_id = serial;
+        h.packet_offset = offset;
+        h.total_packets = total;
+        h.write(w);
+      })
+      .def("getvalue", [](const Writer& w) { return py::bytes(reinterpret_cast<const char*>(w.buffer().data()), w.size()); });
+  struct PyReader {
+    std::string data;
+    std::unique_ptr<Reader> r;
+  };
+  py::class_<PyReader>(m, "Reader")
+      .def(py::init([](const py::bytes& b, bool swap) {
+             auto p = std::make_unique<PyReader>();
+             p->data = b;
+             p->r = std::make_unique<Reader>(reinterpret_cast<const uint8_t*>(p->data.data()), p->data.size(), swap);
+             return p;
+           }),
+           py::arg("data"), py::arg("swap") = false)
+      .def("offset", [](PyReader& r) { return r.r->offset(); })
+      .def("remaining", [](PyReader& r) { return r.r->remaining(); })
+      .def("u8", [](PyReader& r) { return r.r->prim<uint8_t>(); })
+      .def("u16", [](PyReader& r) { return r.r->prim<uint16_t>(); })
+      .def("u32", [](PyReader& r) { return r.r->prim<uint32_t>(); })
+      .def("u64", [](PyReader& r) { return r.r->prim<uint64_t>(); })
+      .def("i64", [](PyReader& r) { return r.r->prim<int64_t>(); })
+      .def("f32", [](PyReader& r) { return r.r->prim<float>(); })
+      .def("f64", [](PyReader& r) { return r.r->prim<double>(); })
+      .def("boolean", [](PyReader& r) { return r.r->prim<uint8_t>() != 0; })
+      .def("string", [](PyReader& r) { return py::bytes(r.r->str()); })
+      .def("sizes", [](PyReader& r) { return r.r->sizes(); })
+      .def("raw", [](PyReader& r, uint64_t n) {
+        const uint8_t* p = r.r->bytes(n);
+        return py::bytes(reinterpret_cast<const char*>(p), n);
+      })
+      .def("raw_into", [](PyReader& r, int64_t dst, uint64_t n, uint32_t elem_size) {
+        const uint8_t* p = r.r->bytes(n);
+        uint8_t* d = reinterpret_cast<uint8_t*>(dst);
+        std::memcpy(d, p, n);
+        if (r.r->swap() && elem_size > 1)
+          for (uint64_t i = 0; i + elem_size <= n; i += elem_size) std::reverse(d + i, d + i + elem_size);
+      })
+      .def("packet_header", [](PyReader& r) {
+        const uint8_t* p = r.r->bytes(PacketHeader::kBytes);
+        PacketHeader h = PacketHeader::read(p, PacketHeader::kBytes);
+        return py::make_tuple(h.version, h.type, h.endianness, h.packet_length, h.msg_length, h.msg_serial_id,
+                              h.packet_offset, h.total_packets, h.compression);
+      });
+  m.attr("PACKET_HEADER_BYTES") = (int)PacketHeader::kBytes;
+  m.def("host_is_little_endian", &host_is_little_endian);
+
+  // ---------------------------------------------------------------- allocators
+  py::class_<DELAllocator>(m, "DELAllocator")
+      .def(py::init<uint64_t, uint64_t>(), py::arg("slab_bytes") = (64ull << 20), py::arg("align") = 256)
+      .def("allocate", [](DELAllocator& a, uint64_t n) {
+        Block b = a.allocate(n);
+        return py::make_tuple(b.slab, b.offset, b.size);
+      })
+      .def("free", &DELAllocator::free)
+      .def("flip", &DELAllocator::flip)
+      .def("set_side", &DELAllocator::set_side)
+      .def("side", &DELAllocator::side)
+      .def("reserve", &DELAllocator::reserve)
+      .def("clear", &DELAllocator::clear)
+      .def("num_slabs", &DELAllocator::num_slabs)
+      .def("slab_size", &DELAllocator::slab_size)
+      .def("total_allocated", &DELAllocator::total_allocated)
+      .def("peak_allocated", &DELAllocator::peak_allocated)
+      .def("reset_peak", &DELAllocator::reset_peak)
+      .def("total_reserved", &DELAllocator::total_reserved);
+  py::class_<PoolAllocator>(m, "PoolAllocatorCore")
+      .def(py::init<>())
+      .def("acquire", &PoolAllocator::acquire)
+      .def("add", &PoolAllocator::add)
+      .def("release", &PoolAllocator::release)
+      .def("block_size", &PoolAllocator::block_size)
+      .def("total_bytes", &PoolAllocator::total_bytes)
+      .def("cached_bytes", &PoolAllocator::cached_bytes);
+
+  // ---------------------------------------------------------------- data path
+  py::class_<RecordImageDataset>(m, "RecordImageDataset")
+      .def(py::init<int, int, int, int>(), py::arg("C"), py::arg("H"), py::arg("W"), py::arg("label_bytes"))
+      .def("add_file", &RecordImageDataset::add_file)
+      .def("add_records", [](RecordImageDataset& d, const py::bytes& b) {
+        std::string s = b;
+        d.add_records(reinterpret_cast<const uint8_t*>(s.data()), s.size() / d.record_bytes());
+      })
+      .def("add_mnist_csv", [](RecordImageDataset& d, const std::string& path) {
+        size_t n = 0;
+        std::vector<uint8_t> recs = parse_mnist_csv(path, &n);
+        d.add_records(recs.data(), n);
+        return n;
+      })
+      .def("size", &RecordImageDataset::size)
+      .def("assemble", [](const RecordImageDataset& d, py::array_t<int64_t, py::array::c_style> idx, int64_t out_ptr,
+                          int64_t label_ptr, const py::dict& aug, uint64_t seed, int nthreads) {
+        AugmentParams a;
+        auto geti = [&](const char* k, int dflt) { return aug.contains(k) ? aug[k].cast<int>() : dflt; };
+        auto getf = [&](const char* k, float dflt) { return aug.contains(k) ? aug[k].cast<float>() : dflt; };
+        a.random_crop_pad = geti("random_crop_pad", 0);
+        a.hflip_p = getf("hflip_p", 0.f);
+        a.vflip_p = getf("vflip_p", 0.f);
+        a.brightness = getf("brightness", 0.f);
+        a.contrast = getf("contrast", 0.f);
+        a.noise_std = getf("noise_std", 0.f);
+        a.cutout = geti("cutout", 0);
+        if (aug.contains("mean") && aug.contains("std")) {
+          a.normalize = 1;
+          auto mv = aug["mean"].cast<std::vector<float>>(), sv = aug["std"].cast<std::vector<float>>();
+          for (int i = 0; i < 3; ++i) {
+            a.mean[i] = mv[i % mv.size()];
+            a.stdv[i] = sv[i % sv.size()];
+          }
+        }
+        const int B = (int)idx.size();
+        py::gil_scoped_release rel;
+        d.assemble(idx.data(), B, reinterpret_cast<float*>(out_ptr), reinterpret_cast<int32_t*>(label_ptr), a, seed,
+                   nthreads);
+      });
+  py::class_<TokenDataset>(m, "TokenDataset")
+      .def(py::init<const std::string&>())
+      .def("num_tokens", &TokenDataset::num_tokens)
+      .def("sample", [](const TokenDataset& d, int B, int L, uint64_t seed, int64_t x_ptr, int64_t y_ptr) {
+        d.sample(B, L, seed, reinterpret_cast<int32_t*>(x_ptr), reinterpret_cast<int32_t*>(y_ptr));
+      })
+      .def("window", [](const TokenDataset& d, uint64_t start, int L, int64_t x_ptr) {
+        d.window(start, L, reinterpret_cast<int32_t*>(x_ptr));
+      });
+
+  // ---------------------------------------------------------------- tokenizer
+  py::class_<Tokenizer>(m, "Tokenizer")
+      .def(py::init<>())
+      .def("load", &Tokenizer::load)
+      .def("save", &Tokenizer::save)
+      .def("set_vocab", [](Tokenizer& t, const std::vector<py::bytes>& v) {
+        std::vector<std::string> s;
+        for (auto& b : v) s.emplace_back(std::string(b));
+        t.set_vocab(std::move(s));
+      })
+      .def("vocab_size", &Tokenizer::vocab_size)
+      .def("decode", [](const Tokenizer& t, const std::vector<int32_t>& ids) { return py::bytes(t.decode(ids)); })
+      .def("decode_one", [](const Tokenizer& t, int32_t id) { return py::bytes(t.decode_one(id)); })
+      .def("encode", [](const Tokenizer& t, const std::string& s) { return t.encode(s); });
+
+  // ---------------------------------------------------------------- profiler
+  py::class_<Profiler, std::shared_ptr<Profiler>>(m, "ProfilerCore")
+      .def(py::init<>())
+      .def("init_start_time", &Profiler::init_start_time)
+      .def_static("now_ns", &Profiler::now_ns)
+      .def("add_event", &Profiler::add_event)
+      .def("merge", &Profiler::merge)
+      .def("sort", &Profiler::sort)
+      .def("clear", &Profiler::clear)
+      .def("serialize", &Profiler::serialize)
+      .def_static("deserialize", [](const py::bytes& b) { return Profiler::deserialize(std::string(b)); })
+      .def("events", &Profiler::events)
+      .def("start_ns", &Profiler::start_ns);
+}
+
 }  // namespace tnn

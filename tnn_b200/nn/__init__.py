@@ -1,0 +1,8 @@
+from .layer import Layer, LayerFactory, ParamDescriptor  # noqa: F401
+from .layers import *  # noqa: F401,F403
+from .blocks import Sequential, MSequential, ResidualBlock, AttentionBlock, FlashAttentionBlock, SDPALayer  # noqa: F401
+from .builder import LayerBuilder  # noqa: F401
+from .graph import Graph, GraphBuilder, GraphContext, GraphExecutor, graph_from_sequential  # noqa: F401
+from .loss import LossFactory, CrossEntropyLoss, compute_class_corrects  # noqa: F401
+from .optimizers import OptimizerFactory, SGD, Adam  # noqa: F401
+from .schedulers import SchedulerFactory  # noqa: F401
