@@ -142,7 +142,7 @@ def run_tnn(args):
     import torch
     from tnn_b200.models import ExampleModels, load_or_create_model
     from tnn_b200.nn import LossFactory, OptimizerFactory
-    from tnn_b200.nn.train import DevicePrefetcher, TrainStep
+    from tnn_b200.nn.train import TrainStep
     from tnn_b200.ops import native
 
     rank, local, world = dist_setup(args.gpus)
@@ -180,6 +180,7 @@ def run_tnn(args):
     sampler = ClockSampler(local)
     sampler.start()
     l0 = Cx.launch_count()
+    r0 = step.replays
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
@@ -187,7 +188,7 @@ def run_tnn(args):
     e1.record()
     barrier(world)
     ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
-    launches = Cx.launch_count() - l0
+    launches = (Cx.launch_count() - l0) + (step.replays - r0) * step.captured_launches
     clocks = sampler.stop()
     loss_val = float(stats[0])
     value = world * B * args.steps / (ms / 1e3)
@@ -195,19 +196,14 @@ def run_tnn(args):
     # ---------------- end to end: pinned host -> device every step, loss read back every step
     e2e = None
     if not args.no_e2e:
-        pre = DevicePrefetcher(dev)
         loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
         copy_done = torch.cuda.Event()
 
         def run(n):
-            staged = pre.stage(*host[0])
             last = 0.0
             for i in range(n):
-                dx, dy, slot = staged
-                pre.acquire(slot)
-                st = step(dx, dy)
-                pre.release(slot)
-                staged = pre.stage(*host[(i + 1) % NB])
+                hx, hy = host[i % NB]
+                st = step(hx, hy)                    # pinned host batch -> H2D inside the step
                 if i > 0:
                     copy_done.synchronize()          # D2H read of the previous step's loss
                     last = float(loss_host[0])
@@ -239,7 +235,7 @@ def run_tnn(args):
                        "image": [32, 32, 3], "classes": 100, "optimizer": "adam(lr1e-3,eps1e-3,wd3e-4)",
                        "parallelism": parallelism,
                        "l2": "inputs rotate over 4 batches; per-step activation working set (~2 GB) >> 126 MB L2"},
-            "clocks": clocks, "gpu_launches": int(launches), "launches_per_step": launches / max(1, args.steps),
+            "clocks": clocks, "gpu_launches": int(launches), "cuda_graph": bool(step.use_graph), "launches_per_step": launches / max(1, args.steps),
             "final_loss": loss_val,
         }
         if e2e:

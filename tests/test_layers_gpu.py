@@ -1,0 +1,142 @@
+"""Layer CPU<->GPU parity ("device agnosticity", reference: unit_tests/layer_device_agnosticity_test.cpp):
+the same layer with the same parameters must produce the same forward/backward on the fp32
+CPU reference path and on the sm_100a kernel path (bf16 tolerance)."""
+import copy
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from tnn_b200.nn import layers as L  # noqa: E402
+from tnn_b200.nn import blocks as B  # noqa: E402
+from tnn_b200.nn.builder import LayerBuilder  # noqa: E402
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def _pair(make, seed=3):
+    cpu = make().init("cpu", seed)
+    gpu = make().init("cpu", seed).to("cuda")
+    return cpu, gpu
+
+
+def _check(make, x, tol=2e-2, train=True, int_input=False):
+    cpu, gpu = _pair(make)
+    cpu.set_training(train), gpu.set_training(train)
+    xq = x if int_input else x.bfloat16().float()
+    yc = cpu.forward(xq)
+    yg = gpu.forward(xq.cuda() if int_input else xq.cuda().bfloat16())
+    assert yc.shape == yg.shape
+    assert _rel(yg, yc) < tol, f"forward mismatch {_rel(yg, yc)}"
+    if not train:
+        return
+    dy = torch.randn_like(yc).bfloat16().float()
+    dc = cpu.backward(dy)
+    dg = gpu.backward(dy.cuda().bfloat16())
+    if dc is not None and dg is not None:
+        assert _rel(dg, dc) < tol, f"dgrad mismatch {_rel(dg, dc)}"
+    pc = dict(cpu.parameters())
+    for (n, _), lc, lg in zip(cpu.parameters(), cpu.all_layers(), gpu.all_layers()):
+        pass
+    for lc, lg in zip(cpu.all_layers(), gpu.all_layers()):
+        for k in lc.grads:
+            gc, gg = lc.grads[k], lg.grads[k]
+            if gc.abs().max() > 0:
+                assert _rel(gg, gc) < 6e-2, f"{lc.name}.{k} grad mismatch {_rel(gg, gc)}"
+
+
+def test_dense():
+    _check(lambda: L.DenseLayer(96, 100, True, "fc"), torch.randn(64, 96))
+
+
+def test_conv_3x3():
+    _check(lambda: L.Conv2DLayer(32, 64, 3, 3, 1, 1, 1, 1, True, "c"), torch.randn(4, 16, 16, 32))
+
+
+def test_conv_first_layer_direct():
+    _check(lambda: L.Conv2DLayer(3, 16, 3, 3, 1, 1, 1, 1, True, "c"), torch.randn(4, 32, 32, 3))
+
+
+@pytest.mark.parametrize("relu", [False, True])
+@pytest.mark.parametrize("C", [16, 128, 24])
+def test_batchnorm(relu, C):
+    _check(lambda: L.BatchNormLayer(C, 1e-5, 0.1, True, relu, "bn"), torch.randn(8, 8, 8, C) * 2 + 0.5)
+
+
+def test_batchnorm_eval():
+    _check(lambda: L.BatchNormLayer(64, 1e-5, 0.1, True, True, "bn"), torch.randn(4, 4, 4, 64), train=False)
+
+
+def test_batchnorm_running_stats():
+    cpu, gpu = _pair(lambda: L.BatchNormLayer(32, 1e-5, 0.1, True, False, "bn"))
+    x = (torch.randn(16, 4, 4, 32) * 3 + 1).bfloat16().float()
+    cpu.forward(x), gpu.forward(x.cuda().bfloat16())
+    assert _rel(gpu.params["running_mean"], cpu.params["running_mean"]) < 1e-2
+    assert _rel(gpu.params["running_var"], cpu.params["running_var"]) < 1e-2
+
+
+def test_maxpool_avgpool():
+    _check(lambda: L.MaxPool2DLayer(2, 2, 2, 2, 0, 0, "mp"), torch.randn(4, 8, 8, 16))
+    _check(lambda: L.MaxPool2DLayer(3, 3, 2, 2, 1, 1, "mp"), torch.randn(2, 9, 9, 8))
+    _check(lambda: L.AvgPool2DLayer(8, 8, 1, 1, 0, 0, "ap"), torch.randn(4, 8, 8, 32))
+    _check(lambda: L.AvgPool2DLayer(2, 2, 2, 2, 0, 0, "ap"), torch.randn(4, 8, 8, 16))
+
+
+@pytest.mark.parametrize("act", ["relu", "leaky_relu", "sigmoid", "tanh", "elu", "gelu"])
+def test_activations(act):
+    _check(lambda: L.ActivationLayer(act, act), torch.randn(4, 33, 7))
+
+
+def test_layernorm_groupnorm():
+    _check(lambda: L.LayerNormLayer(96, 1e-5, True, "ln"), torch.randn(6, 10, 96))
+    _check(lambda: L.GroupNormLayer(4, 32, 1e-5, True, "gn"), torch.randn(3, 5, 5, 32))
+
+
+def test_embedding():
+    ids = torch.randint(0, 50, (4, 12))
+    _check(lambda: L.EmbeddingLayer(50, 32, -1, "emb"), ids, int_input=True)
+
+
+def test_residual_block_fused():
+    def make():
+        b = LayerBuilder([[8, 8, 32]])
+        b.wide_residual_block(32, 64, 2, 0.0, "wrb")
+        return b.build()[0]
+    _check(make, torch.randn(4, 8, 8, 32), tol=3e-2)
+
+    def make2():
+        b = LayerBuilder([[8, 8, 32]])
+        b.basic_residual_block(32, 32, 1, "brb")
+        return b.build()[0]
+    _check(make2, torch.randn(4, 8, 8, 32), tol=3e-2)
+
+
+def test_softmax_ce_and_adam():
+    from tnn_b200.nn import LossFactory
+    crit = LossFactory.create_logsoftmax_crossentropy()
+    logits = torch.randn(64, 100).bfloat16().float()
+    y = torch.randint(0, 100, (64,))
+    sc, gc = crit.loss_and_grad(logits, y)
+    sg, gg = crit.loss_and_grad(logits.cuda().bfloat16(), y.cuda().int())
+    assert abs(float(sc[0]) - float(sg[0])) < 2e-2
+    assert float(sc[1]) == float(sg[1])
+    assert _rel(gg, gc) < 2e-2
+    # flat Adam kernel vs reference math
+    from tnn_b200.ops import native
+    Cx = native.require()
+    n = 10007
+    p = torch.randn(n); g = torch.randn(n); m = torch.zeros(n); v = torch.zeros(n)
+    pg, gg2, mg, vg = p.cuda(), g.cuda(), m.cuda(), v.cuda()
+    lp = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    for t in range(1, 4):
+        Cx.adam_step_flat(pg, gg2, mg, vg, lp, 1e-2, 0.9, 0.999, 1e-3, 3e-4, False, t, 1.0, False)
+        m = 0.9 * m + 0.1 * g
+        v = 0.999 * v + 0.001 * g * g
+        upd = 1e-2 * (m / (1 - 0.9 ** t)) / ((v / (1 - 0.999 ** t)).sqrt() + 1e-3) + 3e-4 * 1e-2 * p
+        p = p - upd
+    assert _rel(pg, p) < 1e-5
+    assert _rel(lp, p) < 1e-2

@@ -22,7 +22,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 CSRC = ROOT / "csrc"
-BUILD = ROOT.parent / "build" / "tnn_b200_C"
+BUILD = ROOT / "_build"   # travels with the tree (gpurun) so the GPU box does not rebuild
 TARGET = ROOT / "_C.so"
 
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -60,6 +60,11 @@ def _headers_digest() -> str:
     return h.hexdigest()
 
 
+def _flag_sig(cmd: list[str]) -> str:
+    """Flags that affect code generation, minus absolute paths (the tree is relocated on the GPU box)."""
+    return " ".join(c for c in cmd[1:] if not c.startswith("-I") and not c.startswith("/"))
+
+
 def _compile_one(src: Path, cmd: list[str], obj: Path, stamp: str) -> tuple[Path, bool, str]:
     stamp_file = obj.with_suffix(".stamp")
     if obj.exists() and stamp_file.exists() and stamp_file.read_text() == stamp:
@@ -91,10 +96,10 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = True) ->
     ]
     tasks = []
     for s in cu:
-        stamp = hashlib.sha256(s.read_bytes() + hdr.encode() + " ".join(nvcc).encode()).hexdigest()
+        stamp = hashlib.sha256(s.read_bytes() + hdr.encode() + _flag_sig(nvcc).encode()).hexdigest()
         tasks.append((s, nvcc, BUILD / (s.stem + ".cu.o"), "" if force else stamp, stamp))
     for s in cpp:
-        stamp = hashlib.sha256(s.read_bytes() + hdr.encode() + " ".join(gxx).encode()).hexdigest()
+        stamp = hashlib.sha256(s.read_bytes() + hdr.encode() + _flag_sig(gxx).encode()).hexdigest()
         tasks.append((s, gxx, BUILD / (s.stem + ".cpp.o"), "" if force else stamp, stamp))
     objs, rebuilt = [], False
     with cf.ThreadPoolExecutor(max_workers=jobs or min(8, os.cpu_count() or 4)) as ex:

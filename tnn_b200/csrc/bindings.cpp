@@ -122,16 +122,18 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     tnn::act_bwd(vp(x), vp(dy), vp(dx), x.numel(), kind, (float)slope, x.scalar_type() == torch::kFloat32,
                  cur_stream());
   });
-  m.def("dropout_fwd", [](const Tensor& x, const Tensor& y, double p, uint64_t seed) {
-    tnn::dropout_fwd(vp(x), vp(y), x.numel(), (float)p, seed, cur_stream());
+  m.def("dropout_fwd", [](const Tensor& x, const Tensor& y, double p, uint64_t seed, const OptT& state) {
+    // `state` = the fp32[16] device step-state tensor; its uint64 seed counter lives at floats 12..13
+    const uint64_t* sp = state.has_value() ? reinterpret_cast<const uint64_t*>(state->data_ptr<float>() + 12) : nullptr;
+    tnn::dropout_fwd(vp(x), vp(y), x.numel(), (float)p, seed, sp, cur_stream());
   });
   m.def("fill_f32", [](const Tensor& x, double v) { tnn::fill_f32(fp(x), x.numel(), (float)v, cur_stream()); });
   m.def("axpy_f32", [](const Tensor& y, const Tensor& x, double a) {
     tnn::axpy_f32(fp(y), fp(x), (float)a, x.numel(), cur_stream());
   });
   m.def("scale_f32", [](const Tensor& x, double a) { tnn::scale_f32(fp(x), (float)a, x.numel(), cur_stream()); });
-  m.def("colsum_bf16", [](const Tensor& x, int64_t M, int64_t N, double alpha, const Tensor& out) {
-    tnn::colsum_bf16(vp(x), M, (int)N, (float)alpha, fp(out), cur_stream());
+  m.def("colsum_bf16", [](const Tensor& x, int64_t M, int64_t N, int64_t ld, double alpha, const Tensor& out) {
+    tnn::colsum_bf16(vp(x), M, (int)N, ld, (float)alpha, fp(out), cur_stream());
   });
   m.def("phase_split", [](const Tensor& x, const Tensor& xp, int N, int H, int W, int C) {
     tnn::phase_split(vp(x), vp(xp), N, H, W, C, cur_stream());
@@ -170,8 +172,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     tnn::bn_eval_scale_shift(C, fp(gamma), fp(beta), fp(rmean), fp(rvar), (float)eps, fp(ss), cur_stream());
   });
   m.def("bn_apply", [](const Tensor& x, const Tensor& y, int64_t M, int C, const Tensor& ss, bool relu,
-                       double drop_p, uint64_t seed) {
-    tnn::bn_apply(vp(x), vp(y), M, C, fp(ss), relu, (float)drop_p, seed, cur_stream());
+                       double drop_p, uint64_t seed, const OptT& state) {
+    const uint64_t* sp = state.has_value() ? reinterpret_cast<const uint64_t*>(state->data_ptr<float>() + 12) : nullptr;
+    tnn::bn_apply(vp(x), vp(y), M, C, fp(ss), relu, (float)drop_p, seed, sp, cur_stream());
   });
   m.def("bn_bwd_reduce", [](const Tensor& dy, const Tensor& x, const OptT& y, int64_t M, int C,
                             const OptT& gamma, const Tensor& smean, const Tensor& sinvstd, bool masked,
@@ -256,13 +259,19 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     tnn::sgd_step_flat(fp(p), fp(g), fp(mom), vp(pb), p.numel(), (float)lr, (float)momentum, (float)wd,
                        (float)grad_scale, zero_grad, cur_stream());
   });
+  m.def("adam_step_flat_dev", [](const Tensor& p, const Tensor& g, const Tensor& mm, const Tensor& v,
+                                 const OptT& pb, const Tensor& state, bool zero_grad) {
+    tnn::adam_step_flat_dev(fp(p), fp(g), fp(mm), fp(v), vp(pb), p.numel(), fp(state), zero_grad, cur_stream());
+  });
+  m.def("sgd_step_flat_dev", [](const Tensor& p, const Tensor& g, const OptT& mom, const OptT& pb,
+                                const Tensor& state, bool zero_grad) {
+    tnn::sgd_step_flat_dev(fp(p), fp(g), fp(mom), vp(pb), p.numel(), fp(state), zero_grad, cur_stream());
+  });
   m.def("dp_fused_step", [](int world, int rank, int64_t n, int64_t chunk, std::vector<int64_t> g_peers,
                             std::vector<int64_t> p_peers, std::vector<int64_t> pb_peers,
                             std::vector<int64_t> flag_peers, int64_t g_mc, int64_t p_mc, int64_t pb_mc,
-                            const Tensor& mm, const OptT& v, const Tensor& sync, uint32_t epoch,
-                            uint32_t grid_base, bool use_adam, double lr, double b1, double b2, double eps,
-                            double wd, bool decoupled, int64_t step, double grad_scale, double momentum,
-                            int ctas) {
+                            const Tensor& mm, const OptT& v, const Tensor& sync, const Tensor& state,
+                            bool use_adam, int ctas) {
     TORCH_CHECK((int)g_peers.size() == world && (int)p_peers.size() == world &&
                 (int)pb_peers.size() == world && (int)flag_peers.size() == world, "peer lists");
     std::vector<float*> g(world), p(world);
@@ -274,14 +283,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       pb[r] = reinterpret_cast<void*>(pb_peers[r]);
       fl[r] = reinterpret_cast<uint32_t*>(flag_peers[r]);
     }
-    tnn::AdamHyper h{(float)lr, (float)b1, (float)b2, (float)eps, (float)wd, decoupled ? 1 : 0,
-                     (float)(1.0 - std::pow(b1, (double)step)), (float)(1.0 - std::pow(b2, (double)step)),
-                     (float)grad_scale};
-    uint32_t* s32 = reinterpret_cast<uint32_t*>(sync.data_ptr());
     tnn::dp_fused_step(world, rank, n, chunk, g.data(), p.data(), pb.data(), fl.data(),
                        reinterpret_cast<const float*>(g_mc), reinterpret_cast<float*>(p_mc),
-                       reinterpret_cast<void*>(pb_mc), fp(mm), fp(v), s32, s32 + 1, epoch, grid_base,
-                       use_adam ? 1 : 0, h, (float)momentum, ctas, cur_stream());
+                       reinterpret_cast<void*>(pb_mc), fp(mm), fp(v), reinterpret_cast<uint32_t*>(sync.data_ptr()),
+                       fp(state), use_adam ? 1 : 0, ctas, cur_stream());
   });
   m.def("p2p_barrier", [](const Tensor& flag_ptrs, int world, int rank, uint32_t epoch) {
     tnn::p2p_barrier(reinterpret_cast<uint32_t* const*>(flag_ptrs.data_ptr()), world, rank, epoch, cur_stream());

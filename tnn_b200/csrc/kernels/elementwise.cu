@@ -200,7 +200,8 @@ void act_bwd(const void* x, const void* dy, void* dx, long long n, int kind, flo
 
 // ---------------------------------------------------------------- dropout
 __global__ void k_dropout(const bf16* __restrict__ x, bf16* __restrict__ y, long long n, float p,
-                          float scale, uint64_t seed) {
+                          float scale, uint64_t seed, const uint64_t* __restrict__ seed_ptr) {
+  if (seed_ptr) seed ^= (*seed_ptr) * 0x9E3779B97F4A7C15ull;
   long long nv = (n + 7) / 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv;
        i += (long long)gridDim.x * blockDim.x) {
@@ -218,13 +219,12 @@ __global__ void k_dropout(const bf16* __restrict__ x, bf16* __restrict__ y, long
     }
   }
 }
-void dropout_fwd(const void* x, void* y, long long n, float p, uint64_t seed, cudaStream_t s) {
+void dropout_fwd(const void* x, void* y, long long n, float p, uint64_t seed, const uint64_t* seed_ptr,
+                 cudaStream_t s) {
   if (n <= 0) return;
-  k_dropout<<<grid_for((n + 7) / 8, 256), 256, 0, s>>>((const bf16*)x, (bf16*)y, n, p, 1.f / (1.f - p), seed);
+  k_dropout<<<grid_for((n + 7) / 8, 256), 256, 0, s>>>((const bf16*)x, (bf16*)y, n, p, 1.f / (1.f - p), seed,
+                                                      seed_ptr);
   TNN_CHECK_LAUNCH();
-}
-void dropout_bwd(const void* dy, void* dx, long long n, float p, uint64_t seed, cudaStream_t s) {
-  dropout_fwd(dy, dx, n, p, seed, s);  // same mask, same scale
 }
 
 // ---------------------------------------------------------------- fp32 vector ops
@@ -262,26 +262,42 @@ void scale_f32(float* x, float a, long long n, cudaStream_t s) {
 
 // ---------------------------------------------------------------- column sums (bias grad)
 // block = 256 threads = (256/LPR) row-lanes x LPR column-groups of 8 channels.
-__global__ void k_colsum_bf16(const bf16* __restrict__ x, long long M, int N, float alpha,
+__global__ void k_colsum_bf16(const bf16* __restrict__ x, long long M, int N, long long ld, float alpha,
                               float* __restrict__ out) {
   extern __shared__ float sm[];
   const int groups = (N + 7) / 8;            // 8-wide column groups
   const int lpr = min(groups, 256);          // column groups handled per row pass
   const int rpb = 256 / lpr;                 // rows in flight per block
   const int cg = threadIdx.x % lpr, rl = threadIdx.x / lpr;
-  const bool vec = (N % 8 == 0);
+  const bool vec = (N % 8 == 0) && (ld % 8 == 0);
   for (int g0 = 0; g0 < groups; g0 += lpr) {
     const int g = g0 + cg;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (g < groups && rl < rpb) {
-      for (long long r = (long long)blockIdx.x * rpb + rl; r < M; r += (long long)gridDim.x * rpb) {
+      const long long stride = (long long)gridDim.x * rpb;
+      long long r = (long long)blockIdx.x * rpb + rl;
+      if (vec) {
+        for (; r + 3 * stride < M; r += 4 * stride) {
+          uint4 q[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(x + (r + u * stride) * ld + g * 8));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float f[8];
+            bf8_unpack(q[u], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+          }
+        }
+      }
+      for (; r < M; r += stride) {
         if (vec) {
           float f[8];
-          bf8_unpack(*reinterpret_cast<const uint4*>(x + r * N + g * 8), f);
+          bf8_unpack(*reinterpret_cast<const uint4*>(x + r * ld + g * 8), f);
 #pragma unroll
           for (int j = 0; j < 8; ++j) acc[j] += f[j];
         } else {
-          for (int j = 0; j < 8 && g * 8 + j < N; ++j) acc[j] += __bfloat162float(x[r * N + g * 8 + j]);
+          for (int j = 0; j < 8 && g * 8 + j < N; ++j) acc[j] += __bfloat162float(x[r * ld + g * 8 + j]);
         }
       }
     }
@@ -299,14 +315,15 @@ __global__ void k_colsum_bf16(const bf16* __restrict__ x, long long M, int N, fl
     }
   }
 }
-void colsum_bf16(const void* x, long long M, int N, float alpha, float* out, cudaStream_t s) {
+void colsum_bf16(const void* x, long long M, int N, long long ld, float alpha, float* out, cudaStream_t s) {
   if (M <= 0 || N <= 0) return;
   int groups = (N + 7) / 8;
   int lpr = groups < 256 ? groups : 256;
   int rpb = 256 / lpr;
-  int blocks = (int)((M + rpb - 1) / rpb);
-  if (blocks > kSMs * 4) blocks = kSMs * 4;
-  k_colsum_bf16<<<blocks, 256, 256 * 8 * sizeof(float), s>>>((const bf16*)x, M, N, alpha, out);
+  int blocks = (int)((M + rpb * 4 - 1) / (rpb * 4));
+  if (blocks > kSMs * 8) blocks = kSMs * 8;
+  if (blocks < 1) blocks = 1;
+  k_colsum_bf16<<<blocks, 256, 256 * 8 * sizeof(float), s>>>((const bf16*)x, M, N, ld, alpha, out);
   TNN_CHECK_LAUNCH();
 }
 

@@ -11,37 +11,65 @@
 
 namespace tnn {
 
-// Generic "per-channel sums of K quantities over M rows" skeleton.
-// Each functor call yields K values per channel for one 8-wide vector.
-template <int K, typename F>
-__device__ __forceinline__ void channel_reduce(long long M, int C, float* ws, float* sm, F f) {
-  const int groups = (C + 7) / 8;
-  const int lpr = min(groups, 256);
-  const int rpb = 256 / lpr;
-  const int cg = threadIdx.x % lpr, rl = threadIdx.x / lpr;
-  for (int g0 = 0; g0 < groups; g0 += lpr) {
-    const int g = g0 + cg;
-    float acc[K][8];
+// ---------------------------------------------------------------------------------------
+// Mapping shared by all four BatchNorm kernels: a thread owns ONE group of 8 consecutive
+// channels (so every per-channel coefficient sits in registers) and strides over rows, UNROLL
+// rows in flight per iteration (UNROLL x 2-3 independent 16-byte loads per thread keep enough
+// bytes in flight to saturate HBM3e).  block = 256 threads = lpr channel-groups x rpb row-lanes.
+// ---------------------------------------------------------------------------------------
+static constexpr int BN_UNROLL = 4;
+
+struct BnMap {
+  int groups, lpr, rpb, cg, rl;
+  __device__ __forceinline__ BnMap(int C) {
+    groups = (C + 7) / 8;
+    lpr = min(groups, 256);
+    rpb = 256 / lpr;
+    cg = threadIdx.x % lpr;
+    rl = threadIdx.x / lpr;
+  }
+};
+
+__device__ __forceinline__ void load8(const bf16* x, long long r, int C, int g, float (&f)[8]) {
+  if ((C & 7) == 0) {
+    bf8_unpack(__ldg(reinterpret_cast<const uint4*>(x + r * C + g * 8)), f);
+  } else {
 #pragma unroll
-    for (int k = 0; k < K; ++k)
+    for (int j = 0; j < 8; ++j) f[j] = (g * 8 + j < C) ? __bfloat162float(x[r * C + g * 8 + j]) : 0.f;
+  }
+}
+__device__ __forceinline__ uint4 load8raw(const bf16* x, long long r, int C, int g) {
+  return __ldg(reinterpret_cast<const uint4*>(x + r * C + g * 8));
+}
+__device__ __forceinline__ void store8(bf16* y, long long r, int C, int g, const float (&f)[8]) {
+  if ((C & 7) == 0) {
+    *reinterpret_cast<uint4*>(y + r * C + g * 8) = bf8_pack(f);
+  } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
-    if (g < groups && rl < rpb) {
-      for (long long r = (long long)blockIdx.x * rpb + rl; r < M; r += (long long)gridDim.x * rpb)
-        f(r, g, acc);
-    }
+    for (int j = 0; j < 8; ++j)
+      if (g * 8 + j < C) y[r * C + g * 8 + j] = __float2bfloat16(f[j]);
+  }
+}
+__device__ __forceinline__ void load_coef8(const float* p, int C, int g, float (&f)[8]) {
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      __syncthreads();
+  for (int j = 0; j < 8; ++j) f[j] = (p != nullptr && g * 8 + j < C) ? __ldg(p + g * 8 + j) : 0.f;
+}
+
+// cross-row-lane reduction of K x 8 per-thread partials -> atomicAdd into ws[k*C + c]
+template <int K>
+__device__ __forceinline__ void block_channel_reduce(const BnMap& m, int g, int C, float (&acc)[K][8], float* ws,
+                                                     float* sm) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sm[(rl * lpr + cg) * 8 + j] = (rl < rpb) ? acc[k][j] : 0.f;
-      __syncthreads();
-      if (rl == 0 && g < groups) {
-        for (int j = 0; j < 8 && g * 8 + j < C; ++j) {
-          float t = 0.f;
-          for (int q = 0; q < rpb; ++q) t += sm[(q * lpr + cg) * 8 + j];
-          atomicAdd(ws + k * C + g * 8 + j, t);
-        }
+  for (int k = 0; k < K; ++k) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm[(m.rl * m.lpr + m.cg) * 8 + j] = (m.rl < m.rpb) ? acc[k][j] : 0.f;
+    __syncthreads();
+    if (m.rl == 0 && g < m.groups) {
+      for (int j = 0; j < 8 && g * 8 + j < C; ++j) {
+        float t = 0.f;
+        for (int q = 0; q < m.rpb; ++q) t += sm[(q * m.lpr + m.cg) * 8 + j];
+        atomicAdd(ws + k * C + g * 8 + j, t);
       }
     }
   }
@@ -61,22 +89,14 @@ __device__ __forceinline__ bool last_block_done(unsigned int* counter) {
   return is_last;
 }
 
-__device__ __forceinline__ void load8(const bf16* x, long long r, int C, int g, float (&f)[8]) {
-  if ((C & 7) == 0) {
-    bf8_unpack(*reinterpret_cast<const uint4*>(x + r * C + g * 8), f);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = (g * 8 + j < C) ? __bfloat162float(x[r * C + g * 8 + j]) : 0.f;
-  }
-}
-__device__ __forceinline__ void store8(bf16* y, long long r, int C, int g, const float (&f)[8]) {
-  if ((C & 7) == 0) {
-    *reinterpret_cast<uint4*>(y + r * C + g * 8) = bf8_pack(f);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (g * 8 + j < C) y[r * C + g * 8 + j] = __float2bfloat16(f[j]);
-  }
+static int bn_blocks(long long M, int C) {
+  int groups = (C + 7) / 8;
+  int lpr = groups < 256 ? groups : 256;
+  int rpb = 256 / lpr;
+  long long b = (M + (long long)rpb * BN_UNROLL - 1) / ((long long)rpb * BN_UNROLL);
+  if (b > kSMs * 8) b = kSMs * 8;
+  if (b < 1) b = 1;
+  return (int)b;
 }
 
 // ------------------------------------------------------------------ BN forward statistics
@@ -85,15 +105,45 @@ __global__ void __launch_bounds__(256)
                const float* __restrict__ beta, float eps, float momentum, float* running_mean,
                float* running_var, float* save_mean, float* save_invstd, float* scale_shift, float* ws) {
   extern __shared__ float sm[];
-  channel_reduce<2>(M, C, ws, sm, [&](long long r, int g, float (&acc)[2][8]) {
-    float f[8];
-    load8(x, r, C, g, f);
+  const BnMap m(C);
+  const bool vec = (C & 7) == 0;
+  for (int g0 = 0; g0 < m.groups; g0 += m.lpr) {
+    const int g = g0 + m.cg;
+    float acc[2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[0][j] += f[j];
-      acc[1][j] += f[j] * f[j];
+    for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+    if (g < m.groups && m.rl < m.rpb) {
+      const long long stride = (long long)gridDim.x * m.rpb;
+      long long r = (long long)blockIdx.x * m.rpb + m.rl;
+      if (vec) {
+        for (; r + (BN_UNROLL - 1) * stride < M; r += BN_UNROLL * stride) {
+          uint4 q[BN_UNROLL];
+#pragma unroll
+          for (int u = 0; u < BN_UNROLL; ++u) q[u] = load8raw(x, r + u * stride, C, g);
+#pragma unroll
+          for (int u = 0; u < BN_UNROLL; ++u) {
+            float f[8];
+            bf8_unpack(q[u], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              acc[0][j] += f[j];
+              acc[1][j] += f[j] * f[j];
+            }
+          }
+        }
+      }
+      for (; r < M; r += stride) {
+        float f[8];
+        load8(x, r, C, g, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0][j] += f[j];
+          acc[1][j] += f[j] * f[j];
+        }
+      }
     }
-  });
+    block_channel_reduce<2>(m, g, C, acc, ws, sm);
+  }
   if (last_block_done(reinterpret_cast<unsigned int*>(ws + 2 * C))) {
     const float inv_m = 1.f / (float)M;
     const float unbias = M > 1 ? (float)M / (float)(M - 1) : 1.f;
@@ -116,15 +166,6 @@ __global__ void __launch_bounds__(256)
     }
     if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(ws + 2 * C) = 0u;
   }
-}
-static int bn_blocks(long long M, int C) {
-  int groups = (C + 7) / 8;
-  int lpr = groups < 256 ? groups : 256;
-  int rpb = 256 / lpr;
-  long long b = (M + rpb - 1) / rpb;
-  if (b > kSMs * 4) b = kSMs * 4;
-  if (b < 1) b = 1;
-  return (int)b;
 }
 void bn_train_stats(const void* x, long long M, int C, const float* gamma, const float* beta,
                     float eps, float momentum, float* running_mean, float* running_var,
@@ -153,42 +194,65 @@ void bn_eval_scale_shift(int C, const float* gamma, const float* beta, const flo
 }
 
 // ------------------------------------------------------------------ BN apply
+// The dropout mask index is the element's 8-wide vector index r*groups + g (stable across
+// thread mappings), so forward and any recomputation agree.
 template <bool RELU, bool DROP>
 __global__ void __launch_bounds__(256)
     k_bn_apply(const bf16* __restrict__ x, bf16* __restrict__ y, long long M, int C,
-               const float* __restrict__ ss, float p, float dscale, uint64_t seed) {
-  const int groups = (C + 7) / 8;
-  const long long total = M * groups;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / groups;
-    const int g = (int)(i - r * groups);
-    float f[8];
-    load8(x, r, C, g, f);
-    bool keep[8];
-    if (DROP) dropout_keep8(seed, i, p, keep);
+               const float* __restrict__ ss, float p, float dscale, uint64_t seed,
+               const uint64_t* __restrict__ seed_ptr) {
+  if (DROP && seed_ptr) seed ^= (*seed_ptr) * 0x9E3779B97F4A7C15ull;
+  const BnMap m(C);
+  for (int g0 = 0; g0 < m.groups; g0 += m.lpr) {
+    const int g = g0 + m.cg;
+    if (g >= m.groups || m.rl >= m.rpb) continue;
+    float sc[8], sh[8];
+    load_coef8(ss, C, g, sc);
+    load_coef8(ss + C, C, g, sh);
+    const long long stride = (long long)gridDim.x * m.rpb;
+    long long r = (long long)blockIdx.x * m.rpb + m.rl;
+    auto one = [&](long long row, float (&f)[8]) {
+      bool keep[8];
+      if (DROP) dropout_keep8(seed, row * m.groups + g, p, keep);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int c = min(g * 8 + j, C - 1);
-      float v = f[j] * __ldg(ss + c) + __ldg(ss + C + c);
-      if (RELU) v = fmaxf(v, 0.f);
-      if (DROP) v = keep[j] ? v * dscale : 0.f;
-      f[j] = v;
+      for (int j = 0; j < 8; ++j) {
+        float v = f[j] * sc[j] + sh[j];
+        if (RELU) v = fmaxf(v, 0.f);
+        if (DROP) v = keep[j] ? v * dscale : 0.f;
+        f[j] = v;
+      }
+      store8(y, row, C, g, f);
+    };
+    if ((C & 7) == 0) {
+      for (; r + (BN_UNROLL - 1) * stride < M; r += BN_UNROLL * stride) {
+        uint4 q[BN_UNROLL];
+#pragma unroll
+        for (int u = 0; u < BN_UNROLL; ++u) q[u] = load8raw(x, r + u * stride, C, g);
+#pragma unroll
+        for (int u = 0; u < BN_UNROLL; ++u) {
+          float f[8];
+          bf8_unpack(q[u], f);
+          one(r + u * stride, f);
+        }
+      }
     }
-    store8(y, r, C, g, f);
+    for (; r < M; r += stride) {
+      float f[8];
+      load8(x, r, C, g, f);
+      one(r, f);
+    }
   }
 }
 void bn_apply(const void* x, void* y, long long M, int C, const float* scale_shift, int relu,
-              float drop_p, uint64_t seed, cudaStream_t s) {
-  long long total = M * ((C + 7) / 8);
-  int g = grid_for(total, 256);
+              float drop_p, uint64_t seed, const uint64_t* seed_ptr, cudaStream_t s) {
+  int g = bn_blocks(M, C);
   float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const bf16* xi = (const bf16*)x;
   bf16* yo = (bf16*)y;
-  if (relu && drop_p > 0.f) k_bn_apply<true, true><<<g, 256, 0, s>>>(xi, yo, M, C, scale_shift, drop_p, ds, seed);
-  else if (relu) k_bn_apply<true, false><<<g, 256, 0, s>>>(xi, yo, M, C, scale_shift, drop_p, ds, seed);
-  else if (drop_p > 0.f) k_bn_apply<false, true><<<g, 256, 0, s>>>(xi, yo, M, C, scale_shift, drop_p, ds, seed);
-  else k_bn_apply<false, false><<<g, 256, 0, s>>>(xi, yo, M, C, scale_shift, drop_p, ds, seed);
+  if (relu && drop_p > 0.f) k_bn_apply<true, true><<<g, 256, 0, s>>>(xi, yo, M, C, scale_shift, drop_p, ds, seed, seed_ptr);
+  else if (relu) k_bn_apply<true, false><<<g, 256, 0, s>>>(xi, yo, M, C, scale_shift, drop_p, ds, seed, seed_ptr);
+  else if (drop_p > 0.f) k_bn_apply<false, true><<<g, 256, 0, s>>>(xi, yo, M, C, scale_shift, drop_p, ds, seed, seed_ptr);
+  else k_bn_apply<false, false><<<g, 256, 0, s>>>(xi, yo, M, C, scale_shift, drop_p, ds, seed, seed_ptr);
   TNN_CHECK_LAUNCH();
 }
 
@@ -199,21 +263,57 @@ __global__ void __launch_bounds__(256)
                     const float* __restrict__ mean, const float* __restrict__ invstd, int masked,
                     float dscale, float* dgamma, float* dbeta, float* coef, float* ws) {
   extern __shared__ float sm[];
-  channel_reduce<2>(M, C, ws, sm, [&](long long r, int g, float (&acc)[2][8]) {
-    float d[8], xv[8], yv[8];
-    load8(dy, r, C, g, d);
-    load8(x, r, C, g, xv);
-    if (masked) load8(y, r, C, g, yv);
+  const BnMap m(C);
+  const bool vec = (C & 7) == 0;
+  for (int g0 = 0; g0 < m.groups; g0 += m.lpr) {
+    const int g = g0 + m.cg;
+    float acc[2][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int c = min(g * 8 + j, C - 1);
-      float gg = d[j];
-      if (masked) gg = (yv[j] != 0.f) ? gg * dscale : 0.f;
-      float xh = (xv[j] - __ldg(mean + c)) * __ldg(invstd + c);
-      acc[0][j] += gg;
-      acc[1][j] += gg * xh;
+    for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+    if (g < m.groups && m.rl < m.rpb) {
+      float mu[8], is[8];
+      load_coef8(mean, C, g, mu);
+      load_coef8(invstd, C, g, is);
+      const long long stride = (long long)gridDim.x * m.rpb;
+      long long r = (long long)blockIdx.x * m.rpb + m.rl;
+      auto one = [&](const float (&d)[8], const float (&xv)[8], const float (&yv)[8]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float gg = d[j];
+          if (masked) gg = (yv[j] != 0.f) ? gg * dscale : 0.f;
+          acc[0][j] += gg;
+          acc[1][j] += gg * (xv[j] - mu[j]) * is[j];
+        }
+      };
+      if (vec) {
+        for (; r + (BN_UNROLL - 1) * stride < M; r += BN_UNROLL * stride) {
+          uint4 qd[BN_UNROLL], qx[BN_UNROLL], qy[BN_UNROLL];
+#pragma unroll
+          for (int u = 0; u < BN_UNROLL; ++u) {
+            qd[u] = load8raw(dy, r + u * stride, C, g);
+            qx[u] = load8raw(x, r + u * stride, C, g);
+            if (masked) qy[u] = load8raw(y, r + u * stride, C, g);
+          }
+#pragma unroll
+          for (int u = 0; u < BN_UNROLL; ++u) {
+            float d[8], xv[8], yv[8];
+            bf8_unpack(qd[u], d);
+            bf8_unpack(qx[u], xv);
+            if (masked) bf8_unpack(qy[u], yv);
+            one(d, xv, yv);
+          }
+        }
+      }
+      for (; r < M; r += stride) {
+        float d[8], xv[8], yv[8];
+        load8(dy, r, C, g, d);
+        load8(x, r, C, g, xv);
+        if (masked) load8(y, r, C, g, yv);
+        one(d, xv, yv);
+      }
     }
-  });
+    block_channel_reduce<2>(m, g, C, acc, ws, sm);
+  }
   if (last_block_done(reinterpret_cast<unsigned int*>(ws + 2 * C))) {
     const float inv_m = 1.f / (float)M;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -246,38 +346,69 @@ __global__ void __launch_bounds__(256)
                    const bf16* __restrict__ extra, bf16* __restrict__ dx, long long M, int C,
                    const float* __restrict__ mean, const float* __restrict__ invstd,
                    const float* __restrict__ coef, int masked, float dscale) {
-  const int groups = (C + 7) / 8;
-  const long long total = M * groups;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / groups;
-    const int g = (int)(i - r * groups);
-    float d[8], xv[8], yv[8], ev[8];
-    load8(dy, r, C, g, d);
-    load8(x, r, C, g, xv);
-    if (masked) load8(y, r, C, g, yv);
-    if (extra) load8(extra, r, C, g, ev);
+  const BnMap m(C);
+  const bool vec = (C & 7) == 0;
+  for (int g0 = 0; g0 < m.groups; g0 += m.lpr) {
+    const int g = g0 + m.cg;
+    if (g >= m.groups || m.rl >= m.rpb) continue;
+    float mu[8], is[8], c0[8], c1[8], c2[8];
+    load_coef8(mean, C, g, mu);
+    load_coef8(invstd, C, g, is);
+    load_coef8(coef, C, g, c0);
+    load_coef8(coef + C, C, g, c1);
+    load_coef8(coef + 2 * C, C, g, c2);
+    const long long stride = (long long)gridDim.x * m.rpb;
+    long long r = (long long)blockIdx.x * m.rpb + m.rl;
+    auto one = [&](long long row, float (&d)[8], const float (&xv)[8], const float (&yv)[8], const float (&ev)[8]) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int c = min(g * 8 + j, C - 1);
-      float gg = d[j];
-      if (masked) gg = (yv[j] != 0.f) ? gg * dscale : 0.f;
-      float xh = (xv[j] - __ldg(mean + c)) * __ldg(invstd + c);
-      float v = __ldg(coef + c) * (gg - __ldg(coef + C + c) - xh * __ldg(coef + 2 * C + c));
-      if (extra) v += ev[j];
-      d[j] = v;
+      for (int j = 0; j < 8; ++j) {
+        float gg = d[j];
+        if (masked) gg = (yv[j] != 0.f) ? gg * dscale : 0.f;
+        float xh = (xv[j] - mu[j]) * is[j];
+        float v = c0[j] * (gg - c1[j] - xh * c2[j]);
+        if (extra) v += ev[j];
+        d[j] = v;
+      }
+      store8(dx, row, C, g, d);
+    };
+    if (vec) {
+      for (; r + (BN_UNROLL - 1) * stride < M; r += BN_UNROLL * stride) {
+        uint4 qd[BN_UNROLL], qx[BN_UNROLL], qy[BN_UNROLL], qe[BN_UNROLL];
+#pragma unroll
+        for (int u = 0; u < BN_UNROLL; ++u) {
+          qd[u] = load8raw(dy, r + u * stride, C, g);
+          qx[u] = load8raw(x, r + u * stride, C, g);
+          if (masked) qy[u] = load8raw(y, r + u * stride, C, g);
+          if (extra) qe[u] = load8raw(extra, r + u * stride, C, g);
+        }
+#pragma unroll
+        for (int u = 0; u < BN_UNROLL; ++u) {
+          float d[8], xv[8], yv[8], ev[8];
+          bf8_unpack(qd[u], d);
+          bf8_unpack(qx[u], xv);
+          if (masked) bf8_unpack(qy[u], yv);
+          if (extra) bf8_unpack(qe[u], ev);
+          one(r + u * stride, d, xv, yv, ev);
+        }
+      }
     }
-    store8(dx, r, C, g, d);
+    for (; r < M; r += stride) {
+      float d[8], xv[8], yv[8], ev[8];
+      load8(dy, r, C, g, d);
+      load8(x, r, C, g, xv);
+      if (masked) load8(y, r, C, g, yv);
+      if (extra) load8(extra, r, C, g, ev);
+      one(r, d, xv, yv, ev);
+    }
   }
 }
 void bn_bwd_apply(const void* dy, const void* x, const void* y, const void* extra, void* dx,
                   long long M, int C, const float* save_mean, const float* save_invstd,
                   const float* coef, int masked, float drop_p, cudaStream_t s) {
-  long long total = M * ((C + 7) / 8);
   float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  k_bn_bwd_apply<<<grid_for(total, 256), 256, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y,
-                                                      (const bf16*)extra, (bf16*)dx, M, C, save_mean,
-                                                      save_invstd, coef, masked, ds);
+  k_bn_bwd_apply<<<bn_blocks(M, C), 256, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y,
+                                                  (const bf16*)extra, (bf16*)dx, M, C, save_mean,
+                                                  save_invstd, coef, masked, ds);
   TNN_CHECK_LAUNCH();
 }
 

@@ -64,6 +64,78 @@ __global__ void __launch_bounds__(256)
     if (pb) pb[i] = __float2bfloat16(P);
   }
 }
+// Step state in device memory (written by the host once per step OUTSIDE any CUDA graph):
+//   [0] lr [1] beta1 [2] beta2 [3] eps [4] weight_decay [5] decoupled [6] grad_scale [7] momentum
+//   [8] 1-beta1^t [9] 1-beta2^t   [12..13] uint64 seed counter
+__device__ __forceinline__ AdamHyper hyper_from_state(const float* st) {
+  AdamHyper h;
+  h.lr = st[0]; h.beta1 = st[1]; h.beta2 = st[2]; h.eps = st[3]; h.weight_decay = st[4];
+  h.decoupled = st[5] != 0.f; h.grad_scale = st[6]; h.bias_c1 = st[8]; h.bias_c2 = st[9];
+  return h;
+}
+__global__ void __launch_bounds__(256)
+    k_adam_flat_dev(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                    float* __restrict__ v, bf16* __restrict__ pb, long long n, const float* __restrict__ st,
+                    int zero_grad) {
+  const AdamHyper h = hyper_from_state(st);
+  const long long nv = (n + 3) / 4;   // slabs are padded to a multiple of 64 elements
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv;
+       i += (long long)gridDim.x * blockDim.x) {
+    float4 P = reinterpret_cast<float4*>(p)[i], G = reinterpret_cast<float4*>(g)[i];
+    float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+    adam_update(P.x, G.x * h.grad_scale, M.x, V.x, h);
+    adam_update(P.y, G.y * h.grad_scale, M.y, V.y, h);
+    adam_update(P.z, G.z * h.grad_scale, M.z, V.z, h);
+    adam_update(P.w, G.w * h.grad_scale, M.w, V.w, h);
+    reinterpret_cast<float4*>(p)[i] = P;
+    reinterpret_cast<float4*>(m)[i] = M;
+    reinterpret_cast<float4*>(v)[i] = V;
+    if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pb) {
+      uint2 o;
+      __nv_bfloat162 a = __floats2bfloat162_rn(P.x, P.y), b = __floats2bfloat162_rn(P.z, P.w);
+      o.x = *reinterpret_cast<uint32_t*>(&a);
+      o.y = *reinterpret_cast<uint32_t*>(&b);
+      reinterpret_cast<uint2*>(pb)[i] = o;
+    }
+  }
+}
+void adam_step_flat_dev(float* p, float* g, float* m, float* v, void* p_bf16, long long n,
+                        const float* state, int zero_grad, cudaStream_t s) {
+  if (n <= 0) return;
+  if (n % 4 != 0) {
+    fprintf(stderr, "[tnn_b200] adam_step_flat_dev: slab length must be a multiple of 4\n");
+    abort();
+  }
+  k_adam_flat_dev<<<grid_for(n / 4 + 1, 256, kSMs * 8), 256, 0, s>>>(p, g, m, v, (bf16*)p_bf16, n, state, zero_grad);
+  TNN_CHECK_LAUNCH();
+}
+__global__ void __launch_bounds__(256)
+    k_sgd_flat_dev(float* __restrict__ p, float* __restrict__ g, float* __restrict__ mom,
+                   bf16* __restrict__ pb, long long n, const float* __restrict__ st, int zero_grad) {
+  const float lr = st[0], wd = st[4], gs = st[6], momentum = st[7];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float P = p[i], G = g[i] * gs + wd * P;
+    if (mom) {
+      float V = momentum * mom[i] - lr * G;
+      mom[i] = V;
+      P += V;
+    } else {
+      P -= lr * G;
+    }
+    p[i] = P;
+    if (zero_grad) g[i] = 0.f;
+    if (pb) pb[i] = __float2bfloat16(P);
+  }
+}
+void sgd_step_flat_dev(float* p, float* g, float* mom, void* p_bf16, long long n, const float* state,
+                       int zero_grad, cudaStream_t s) {
+  if (n <= 0) return;
+  k_sgd_flat_dev<<<grid_for(n, 256, kSMs * 8), 256, 0, s>>>(p, g, mom, (bf16*)p_bf16, n, state, zero_grad);
+  TNN_CHECK_LAUNCH();
+}
+
 void adam_step_flat(float* p, float* g, float* m, float* v, void* p_bf16, long long n,
                     const AdamHyper& h, int zero_grad, cudaStream_t s) {
   if (n <= 0) return;
@@ -158,13 +230,11 @@ struct DpArgs {
   bf16* pb_mc;
   float* m;             // optimizer state for MY slice only (length chunk)
   float* v;
-  uint32_t* grid_ctr;   // local grid barrier counter / go flag
-  uint32_t* go_flag;
-  uint32_t epoch;       // 2 cross-rank barriers per launch: epoch*2+1, epoch*2+2
-  uint32_t grid_base;   // grid_ctr value at launch = launches so far * 2 * gridDim.x
+  uint32_t* grid_ctr;   // sync[0]: local grid barrier counter
+  uint32_t* go_flag;    // sync[1]: local release flag
+  uint32_t* epoch_ctr;  // sync[2]: launches so far (device resident so the kernel is graph-replayable)
+  const float* state;   // device step state (hyper-parameters, see hyper_from_state)
   int use_adam;
-  AdamHyper h;
-  float sgd_momentum;
 };
 
 __device__ __forceinline__ void dp_barrier(const DpArgs& a, uint32_t epoch, uint32_t grid_target) {
@@ -193,12 +263,16 @@ __device__ __forceinline__ void dp_barrier(const DpArgs& a, uint32_t epoch, uint
 
 __global__ void __launch_bounds__(512) k_dp_step(const DpArgs a) {
   const uint32_t G = gridDim.x;
-  dp_barrier(a, a.epoch * 2 + 1, a.grid_base + G);
+  const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(a.epoch_ctr);
+  const uint32_t grid_base = epoch * 2u * G;
+  dp_barrier(a, epoch * 2 + 1, grid_base + G);
 
   const long long lo = (long long)a.rank * a.chunk;
   const long long hi = min(a.n, lo + a.chunk);
   const long long nv = hi > lo ? (hi - lo + 3) / 4 : 0;   // slab is padded to a multiple of 4
-  const AdamHyper h = a.h;
+  AdamHyper h = hyper_from_state(a.state);
+  h.grad_scale /= (float)a.world;
+  const float sgd_momentum = a.state[7];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv;
        i += (long long)gridDim.x * blockDim.x) {
     const long long e = lo + i * 4;
@@ -223,7 +297,7 @@ __global__ void __launch_bounds__(512) k_dp_step(const DpArgs a) {
       adam_update(P.w, g.w, M.w, V.w, h);
       reinterpret_cast<float4*>(a.v)[i] = V;
     } else {
-      const float mu = a.sgd_momentum, lr = h.lr, wd = h.weight_decay;
+      const float mu = sgd_momentum, lr = h.lr, wd = h.weight_decay;
       g.x += wd * P.x; g.y += wd * P.y; g.z += wd * P.z; g.w += wd * P.w;
       M.x = mu * M.x - lr * g.x; M.y = mu * M.y - lr * g.y;
       M.z = mu * M.z - lr * g.z; M.w = mu * M.w - lr * g.w;
@@ -243,7 +317,7 @@ __global__ void __launch_bounds__(512) k_dp_step(const DpArgs a) {
     }
   }
 
-  dp_barrier(a, a.epoch * 2 + 2, a.grid_base + 2 * G);
+  dp_barrier(a, epoch * 2 + 2, grid_base + 2 * G);
 
   // every rank is done reading my gradients: clear them for the next accumulation
   float4* gz = reinterpret_cast<float4*>(a.g_peers[a.rank]);
@@ -251,14 +325,15 @@ __global__ void __launch_bounds__(512) k_dp_step(const DpArgs a) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nz;
        i += (long long)gridDim.x * blockDim.x)
     gz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // every thread of this launch read `epoch` before the first barrier; safe to advance it now
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.epoch_ctr = epoch + 1;
 }
 
 // Raw-argument entry used by the binding layer (keeps DpArgs private to this TU).
 void dp_fused_step(int world, int rank, long long n, long long chunk, float* const* g_peers,
                    float* const* p_peers, void* const* pb_peers, uint32_t* const* flag_peers,
                    const float* g_mc, float* p_mc, void* pb_mc, float* m, float* v,
-                   uint32_t* grid_ctr, uint32_t* go_flag, uint32_t epoch, uint32_t grid_base,
-                   int use_adam, const AdamHyper& h, float sgd_momentum, int ctas, cudaStream_t s) {
+                   uint32_t* sync, const float* state, int use_adam, int ctas, cudaStream_t s) {
   if (world > kMaxWorld) {
     fprintf(stderr, "[tnn_b200] dp_fused_step: world %d > %d\n", world, kMaxWorld);
     abort();
@@ -279,13 +354,11 @@ void dp_fused_step(int world, int rank, long long n, long long chunk, float* con
   a.pb_mc = (bf16*)pb_mc;
   a.m = m;
   a.v = v;
-  a.grid_ctr = grid_ctr;
-  a.go_flag = go_flag;
-  a.epoch = epoch;
-  a.grid_base = grid_base;
+  a.grid_ctr = sync;
+  a.go_flag = sync + 1;
+  a.epoch_ctr = sync + 2;
+  a.state = state;
   a.use_adam = use_adam;
-  a.h = h;
-  a.sgd_momentum = sgd_momentum;
   k_dp_step<<<ctas, 512, 0, s>>>(a);
   TNN_CHECK_LAUNCH();
 }

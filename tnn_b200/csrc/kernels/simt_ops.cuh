@@ -25,13 +25,14 @@ void act_bwd(const void* x, const void* dy, void* dx, long long n, int kind, flo
              cudaStream_t s);
 // inverted dropout with a counter-based RNG: the mask is a pure function of (seed, index), so
 // backward recomputes it instead of storing it.
-void dropout_fwd(const void* x, void* y, long long n, float p, uint64_t seed, cudaStream_t s);
-void dropout_bwd(const void* dy, void* dx, long long n, float p, uint64_t seed, cudaStream_t s);
+// effective seed = seed ^ (*seed_ptr * golden) when seed_ptr != null (device-resident step counter)
+void dropout_fwd(const void* x, void* y, long long n, float p, uint64_t seed, const uint64_t* seed_ptr,
+                 cudaStream_t s);
 void fill_f32(float* x, long long n, float v, cudaStream_t s);
 void axpy_f32(float* y, const float* x, float a, long long n, cudaStream_t s);
 void scale_f32(float* x, float a, long long n, cudaStream_t s);
 // column sums of a [M, N] bf16 matrix accumulated into fp32 out[N] (bias gradient)
-void colsum_bf16(const void* x, long long M, int N, float alpha, float* out, cudaStream_t s);
+void colsum_bf16(const void* x, long long M, int N, long long ld, float alpha, float* out, cudaStream_t s);
 // stride-2 phase split: X[N,H,W,C] -> Xp[4][N,H/2,W/2,C] (phase = (h&1)*2 + (w&1)) and inverse
 void phase_split(const void* x, void* xp, int N, int H, int W, int C, cudaStream_t s);
 void phase_merge(const void* xp, void* x, int N, int H, int W, int C, cudaStream_t s);
@@ -56,7 +57,7 @@ void bn_eval_scale_shift(int C, const float* gamma, const float* beta, const flo
                          const float* running_var, float eps, float* scale_shift, cudaStream_t s);
 // y = act(x*scale + shift) [* dropout]; residual-free.  drop_p == 0 disables dropout.
 void bn_apply(const void* x, void* y, long long M, int C, const float* scale_shift, int relu,
-              float drop_p, uint64_t seed, cudaStream_t s);
+              float drop_p, uint64_t seed, const uint64_t* seed_ptr, cudaStream_t s);
 // Backward.  g = dy * mask(y) (mask = y != 0 when relu/dropout were fused, scaled by 1/(1-p)).
 // Accumulates dgamma/dbeta (fp32, +=) and writes coef[3*C] for bn_bwd_apply.
 void bn_bwd_reduce(const void* dy, const void* x, const void* y, long long M, int C,
@@ -123,8 +124,13 @@ void sgd_step_flat(float* p, float* g, float* mom, void* p_bf16, long long n, fl
 void dp_fused_step(int world, int rank, long long n, long long chunk, float* const* g_peers,
                    float* const* p_peers, void* const* pb_peers, uint32_t* const* flag_peers,
                    const float* g_mc, float* p_mc, void* pb_mc, float* m, float* v,
-                   uint32_t* grid_ctr, uint32_t* go_flag, uint32_t epoch, uint32_t grid_base,
-                   int use_adam, const AdamHyper& h, float sgd_momentum, int ctas, cudaStream_t s);
+                   uint32_t* sync, const float* state, int use_adam, int ctas, cudaStream_t s);
+// Graph-replayable variants: hyper-parameters come from a 16-float device "step state" that the
+// host refreshes with one small H2D copy per step (outside the captured region).
+void adam_step_flat_dev(float* p, float* g, float* m, float* v, void* p_bf16, long long n,
+                        const float* state, int zero_grad, cudaStream_t s);
+void sgd_step_flat_dev(float* p, float* g, float* mom, void* p_bf16, long long n, const float* state,
+                       int zero_grad, cudaStream_t s);
 // Device-side barrier across ranks through peer-mapped flag words (st.release.sys /
 // ld.acquire.sys).  `flags` is a DEVICE array of pointers; flags[r] points at rank r's flag
 // array (world uint32 each); `epoch` must increase on every call.

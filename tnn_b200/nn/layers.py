@@ -13,6 +13,7 @@ import math
 import torch
 import torch.nn.functional as F
 
+from ..core import stepstate
 from ..core.config import TConfig
 from ..ops import conv as conv_ops
 from ..ops import gemm as gemm_ops
@@ -299,12 +300,11 @@ class BatchNormLayer(Layer):
             if self.training:
                 Cx.bn_train_stats(x, M, C, gamma, beta, self.epsilon, self.momentum, self.params["running_mean"],
                                   self.params["running_var"], b["mean"], b["invstd"], b["ss"], b["ws"])
-                self._step += 1
-                seed = (self.seed * 1000003 + self._step * 7919 + mb_id) & 0x7FFFFFFFFFFFFFFF
+                seed = (self.seed * 1000003 + (hash(self.name) & 0xFFFFFF) * 7919 + mb_id) & 0x7FFFFFFFFFFFFFFF
             else:
                 Cx.bn_eval_scale_shift(C, gamma, beta, self.params["running_mean"], self.params["running_var"],
                                        self.epsilon, b["ss"])
-            Cx.bn_apply(x, y, M, C, b["ss"], self.use_relu, p_drop, seed)
+            Cx.bn_apply(x, y, M, C, b["ss"], self.use_relu, p_drop, seed, stepstate.get(x.device).dev if p_drop > 0 else None)
             if self.training:
                 c = self.cache(mb_id)
                 c["x"] = x
@@ -424,10 +424,9 @@ class MaxPool2DLayer(_Pool2D):
                 self.cache(mb_id).update(mask=mask, d=d)
             return y
         xf = x.permute(0, 3, 1, 2).float()
-        y, idx = F.max_pool2d(xf, (self.pool_h, self.pool_w), (self.stride_h, self.stride_w), (self.pad_h, self.pad_w),
-                              return_indices=True)
+        y = F.max_pool2d(xf, (self.pool_h, self.pool_w), (self.stride_h, self.stride_w), (self.pad_h, self.pad_w))
         if self.training:
-            self.cache(mb_id).update(idx=idx, shape=xf.shape)
+            self.cache(mb_id).update(xf=xf)
         return y.permute(0, 2, 3, 1).contiguous().to(x.dtype)
 
     def backward_impl(self, dy, mb_id):
@@ -439,10 +438,10 @@ class MaxPool2DLayer(_Pool2D):
             dx = torch.empty((d[0], d[1], d[2], d[3]), dtype=torch.bfloat16, device=dy.device)
             Cx.maxpool_bwd(dy, c["mask"], dx, d)
             return dx
-        g = dy.permute(0, 3, 1, 2).float()
-        dx = F.max_unpool2d(g, c["idx"], (self.pool_h, self.pool_w), (self.stride_h, self.stride_w),
-                            (self.pad_h, self.pad_w), output_size=c["shape"][2:])
-        return dx.permute(0, 2, 3, 1).contiguous().to(dy.dtype)
+        xx = c["xf"].detach().clone().requires_grad_(True)
+        y = F.max_pool2d(xx, (self.pool_h, self.pool_w), (self.stride_h, self.stride_w), (self.pad_h, self.pad_w))
+        (gx,) = torch.autograd.grad(y, xx, dy.permute(0, 3, 1, 2).float())
+        return gx.permute(0, 2, 3, 1).contiguous().to(dy.dtype)
 
 
 @register()
@@ -577,9 +576,10 @@ class DropoutLayer(Layer):
         self._step += 1
         seed = (self.seed * 1000003 + self._step * 7919 + mb_id) & 0x7FFFFFFFFFFFFFFF
         if x.is_cuda:
+            seed = (self.seed * 1000003 + (hash(self.name) & 0xFFFFFF) * 7919 + mb_id) & 0x7FFFFFFFFFFFFFFF
             x = to_bf16(x).contiguous()
             y = torch.empty_like(x)
-            native.require().dropout_fwd(x, y, self.dropout_rate, seed)
+            native.require().dropout_fwd(x, y, self.dropout_rate, seed, stepstate.get(x.device).dev)
             self.cache(mb_id)["seed"] = seed
             return y
         g = torch.Generator().manual_seed(seed & 0x7FFFFFFF)
@@ -594,7 +594,7 @@ class DropoutLayer(Layer):
         if dy.is_cuda:
             dy = to_bf16(dy).contiguous()
             dx = torch.empty_like(dy)
-            native.require().dropout_fwd(dy, dx, self.dropout_rate, c["seed"])
+            native.require().dropout_fwd(dy, dx, self.dropout_rate, c["seed"], stepstate.get(dy.device).dev)
             return dx
         return dy * c["keep"]
 

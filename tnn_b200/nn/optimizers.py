@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import torch
 
+from ..core import stepstate
 from ..core.config import TConfig
 from ..ops import native
 
@@ -23,6 +24,12 @@ class Optimizer:
         self.step_count = 0
         self.grad_scale = 1.0
         self.fused_zero_grad = True
+        self.external_state = False     # True: the caller (TrainStep) already pushed the step state
+
+    def _push_state(self, device):
+        if not self.external_state:
+            stepstate.get(device).advance(self)
+        return stepstate.get(device).dev
 
     def attach(self, ctx):
         self.ctx = ctx
@@ -84,8 +91,10 @@ class SGD(Optimizer):
         self.step_count += 1
         p, g = ctx.param_slab, ctx.grad_slab
         if p.is_cuda:
-            native.require().sgd_step_flat(p, g, self.velocity, ctx.lp_slab, self.lr, self.momentum,
-                                           self.weight_decay, self.grad_scale, self.fused_zero_grad)
+            self.step_count -= 1
+            st = self._push_state(p.device)
+            self.step_count += 1
+            native.require().sgd_step_flat_dev(p, g, self.velocity, ctx.lp_slab, st, self.fused_zero_grad)
         else:
             gg = g * self.grad_scale + self.weight_decay * p
             if self.velocity is not None:
@@ -131,9 +140,10 @@ class Adam(Optimizer):
         t = self.step_count
         p, g = ctx.param_slab, ctx.grad_slab
         if p.is_cuda:
-            native.require().adam_step_flat(p, g, self.m, self.v, ctx.lp_slab, self.lr, self.beta1, self.beta2,
-                                            self.epsilon, self.weight_decay, self.decoupled, t, self.grad_scale,
-                                            self.fused_zero_grad)
+            self.step_count -= 1
+            st = self._push_state(p.device)
+            self.step_count += 1
+            native.require().adam_step_flat_dev(p, g, self.m, self.v, ctx.lp_slab, st, self.fused_zero_grad)
         else:
             gg = g * self.grad_scale
             if self.weight_decay != 0 and self.decoupled:

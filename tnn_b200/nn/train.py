@@ -15,6 +15,7 @@ from dataclasses import asdict, dataclass, field
 
 import torch
 
+from ..core import stepstate
 from ..core.dtype import dtype_to_string, string_to_dtype, to_torch
 from ..utils.env import Env
 from .graph import Graph, GraphExecutor
@@ -96,32 +97,105 @@ class TrainingConfig:
 class TrainStep:
     """One optimisation step through the public API: forward, fused loss+grad, backward,
     (every ``accum`` calls) optimizer update + scheduler step.  Returns the device-resident
-    [loss, n_correct] tensor; nothing here synchronises the host."""
+    [loss, n_correct] tensor; nothing here synchronises the host.
+
+    On a GPU (and ``accum == 1``) the whole step is captured into ONE CUDA graph after two eager
+    warm-up calls and replayed afterwards: per-step scalars (lr, Adam bias corrections, dropout
+    seed counter) live in the device step state that the host refreshes with a single 64-byte
+    H2D copy before each replay, so schedules and dropout masks keep evolving under replay.
+    ``x`` / ``y`` may be device tensors or PINNED host tensors (copied straight into the graph's
+    static input buffers)."""
 
     def __init__(self, graph: Graph, criterion: Loss, optimizer: Optimizer, scheduler=None, accum: int = 1,
-                 dp=None):
+                 dp=None, use_graph: bool | None = None):
         self.graph, self.criterion, self.optimizer, self.scheduler = graph, criterion, optimizer, scheduler
         self.executor = GraphExecutor(graph)
         self.accum = max(1, int(accum))
-        self.dp = dp                      # parallel.dp.FusedDataParallel or None
+        self.dp = dp                      # parallel.dp.FusedDataParallel / AllReduceDataParallel or None
         self._micro = 0
         if optimizer.ctx is None:
             optimizer.attach(graph.context())
         optimizer.grad_scale = 1.0 / self.accum
+        self.device = graph.device()
+        if use_graph is None:
+            use_graph = os.environ.get("TNN_CUDA_GRAPH", "1") == "1"
+        # NCCL collectives are not captured here: the all-reduce baseline stays eager
+        self.use_graph = bool(use_graph) and self.device.type == "cuda" and self.accum == 1 and \
+            not type(dp).__name__.startswith("AllReduce")
+        self._cg = None
+        self._warm = 0
+        self.captured_launches = 0
+        self.replays = 0
+        self._sx = self._sy = self._sstats = None
+        self._state = stepstate.get(self.device)
 
-    def __call__(self, x: torch.Tensor, y: torch.Tensor, mb_id: int = 0) -> torch.Tensor:
+    # ---- the work itself (capturable: no host sync, no Python-visible per-step scalars)
+    def _core(self, x, y, mb_id=0):
         out = self.executor.forward({"input": x}, mb_id=mb_id)["output"]
         stats, grad = self.criterion.loss_and_grad(out, y)
         self.executor.backward({"output": grad}, mb_id=mb_id)
-        self._micro += 1
-        if self._micro % self.accum == 0:
+        return stats
+
+    def _update(self):
+        self.optimizer.external_state = True
+        try:
             if self.dp is not None:
                 self.dp.step()
             else:
                 self.optimizer.update()
+        finally:
+            self.optimizer.external_state = False
+
+    def _eager(self, x, y, mb_id=0):
+        if x.device != self.device:
+            x, y = x.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True)
+        self._micro += 1
+        do_update = self._micro % self.accum == 0
+        self._state.advance(self.optimizer if do_update else None)
+        stats = self._core(x, y, mb_id)
+        if do_update:
+            self._update()
             if self.scheduler is not None:
                 self.scheduler.step()
         return stats
+
+    def __call__(self, x: torch.Tensor, y: torch.Tensor, mb_id: int = 0) -> torch.Tensor:
+        if not self.use_graph:
+            return self._eager(x, y, mb_id)
+        if self._cg is None:
+            if self._warm < 2:
+                self._warm += 1
+                return self._eager(x, y, mb_id)
+            self._capture(x, y)
+        elif tuple(x.shape) != tuple(self._sx.shape):
+            return self._eager(x, y, mb_id)      # ragged last batch: run it eagerly
+        self._sx.copy_(x, non_blocking=True)
+        self._sy.copy_(y, non_blocking=True)
+        self._micro += 1
+        self._state.advance(self.optimizer)
+        self._cg.replay()
+        self.replays += 1
+        self.optimizer.step_count += 1
+        if self.scheduler is not None:
+            self.scheduler.step()
+        return self._sstats
+
+    def _capture(self, x, y):
+        self._sx = torch.empty(x.shape, dtype=x.dtype, device=self.device)
+        self._sy = torch.empty(y.shape, dtype=y.dtype, device=self.device)
+        self._sx.copy_(x, non_blocking=True)
+        self._sy.copy_(y, non_blocking=True)
+        torch.cuda.synchronize(self.device)
+        count = self.optimizer.step_count
+        from ..ops import native
+        l0 = native.require().launch_count()
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(cg):
+            self._sstats = self._core(self._sx, self._sy, 0)
+            self._update()
+        self.captured_launches = int(native.require().launch_count() - l0)   # kernels per replay
+        self.optimizer.step_count = count     # capture does not execute; replays advance it
+        self._cg = cg
 
 
 class DevicePrefetcher:

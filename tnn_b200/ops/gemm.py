@@ -83,7 +83,8 @@ def bias_grad(dy: torch.Tensor, db: torch.Tensor, alpha: float = 1.0) -> None:
     if not native.use_native(dy):
         db.add_(alpha * dy.float().sum(0))
         return
-    native.require().colsum_bf16(dy, dy.shape[0], dy.shape[1], float(alpha), db)
+    assert dy.stride(1) == 1
+    native.require().colsum_bf16(dy, dy.shape[0], dy.shape[1], dy.stride(0), float(alpha), db)
 
 
 def matmul_nt(a: torch.Tensor, b: torch.Tensor, alpha: float = 1.0) -> torch.Tensor:

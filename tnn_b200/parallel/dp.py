@@ -22,6 +22,7 @@ import os
 import torch
 import torch.distributed as dist
 
+from ..core import stepstate
 from ..nn.graph import ALIGN_ELEMS, Graph, graph_from_sequential
 from ..nn.optimizers import SGD, Adam, Optimizer
 from ..ops import native
@@ -130,19 +131,16 @@ class FusedDataParallel:
     # ---------------------------------------------------------------- one fused step
     def step(self):
         opt = self.optimizer
+        dev = self.graph.device()
+        if not opt.external_state:
+            stepstate.get(dev).advance(opt)
         opt.step_count += 1
         Cx = native.require()
-        adam = isinstance(opt, Adam)
-        G = self.ctas
         Cx.dp_fused_step(
             self.world, self.rank, self.n, self.chunk, self.g_peers, self.p_peers, self.pb_peers, self.flag_peers,
             (self.mc + self.off_g) if self.mc else 0, (self.mc + self.off_p) if self.mc else 0,
-            (self.mc + self.off_lp) if self.mc else 0, self.m, self.v, self.sync, self.epoch, self.launches * 2 * G,
-            adam, opt.lr, getattr(opt, "beta1", 0.9), getattr(opt, "beta2", 0.999), getattr(opt, "epsilon", 1e-8),
-            opt.weight_decay, getattr(opt, "decoupled", False), opt.step_count, opt.grad_scale / self.world,
-            getattr(opt, "momentum", 0.0), G)
-        self.epoch += 1
-        self.launches += 1
+            (self.mc + self.off_lp) if self.mc else 0, self.m, self.v, self.sync, stepstate.get(dev).dev,
+            isinstance(opt, Adam), self.ctas)
         for layer in self.graph.ctx.layers:
             layer.mark_lp_fresh()
 
