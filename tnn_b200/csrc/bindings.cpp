@@ -185,10 +185,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   });
   m.def("bn_bwd_apply", [](const Tensor& dy, const Tensor& x, const OptT& y, const OptT& extra,
                            const Tensor& dx, int64_t M, int C, const Tensor& smean, const Tensor& sinvstd,
-                           const Tensor& coef, bool masked, double drop_p) {
+                           const Tensor& coef, bool masked, double drop_p, const OptT& colsum_out,
+                           const OptT& colsum_ws) {
     tnn::bn_bwd_apply(vp(dy), vp(x), vp(y), vp(extra), vp(dx), M, C, fp(smean), fp(sinvstd), fp(coef), masked,
-                      (float)drop_p, cur_stream());
+                      (float)drop_p, fp(colsum_out), fp(colsum_ws), cur_stream());
   });
+  m.def("bn_ws_floats", &tnn::bn_ws_floats);
   m.def("layernorm_fwd", [](const Tensor& x, const OptT& res, const Tensor& y, const OptT& sum_out,
                             int64_t rows, int C, const OptT& gamma, const OptT& beta, double eps,
                             const OptT& mean, const OptT& rstd) {

@@ -321,7 +321,7 @@ void colsum_bf16(const void* x, long long M, int N, long long ld, float alpha, f
   int lpr = groups < 256 ? groups : 256;
   int rpb = 256 / lpr;
   int blocks = (int)((M + rpb * 4 - 1) / (rpb * 4));
-  if (blocks > kSMs * 8) blocks = kSMs * 8;
+  if (blocks > kSMs) blocks = kSMs;   // same-address atomics: keep the CTA count low
   if (blocks < 1) blocks = 1;
   k_colsum_bf16<<<blocks, 256, 256 * 8 * sizeof(float), s>>>((const bf16*)x, M, N, ld, alpha, out);
   TNN_CHECK_LAUNCH();

@@ -18,6 +18,10 @@ namespace tnn {
 // bytes in flight to saturate HBM3e).  block = 256 threads = lpr channel-groups x rpb row-lanes.
 // ---------------------------------------------------------------------------------------
 static constexpr int BN_UNROLL = 4;
+// Partial sums go to one of BN_REPL replica rows (same-address L2 atomics from ~600 CTAs
+// serialise badly; 64 replicas 1 KB apart cut the contention to ~9 CTAs per address) and the
+// last CTA folds the replicas.
+static constexpr int BN_REPL = 64;
 
 struct BnMap {
   int groups, lpr, rpb, cg, rl;
@@ -69,10 +73,22 @@ __device__ __forceinline__ void block_channel_reduce(const BnMap& m, int g, int 
       for (int j = 0; j < 8 && g * 8 + j < C; ++j) {
         float t = 0.f;
         for (int q = 0; q < m.rpb; ++q) t += sm[(q * m.lpr + m.cg) * 8 + j];
-        atomicAdd(ws + k * C + g * 8 + j, t);
+        atomicAdd(ws + ((size_t)(blockIdx.x % BN_REPL) * K + k) * C + g * 8 + j, t);
       }
     }
   }
+}
+// sum of replica rows for quantity k, channel c (called by the last CTA), and reset
+template <int K>
+__device__ __forceinline__ float fold_replicas(float* ws, int k, int C, int c) {
+  float t = 0.f;
+#pragma unroll 8
+  for (int r = 0; r < BN_REPL; ++r) {
+    float* p = ws + ((size_t)r * K + k) * C + c;
+    t += __ldcg(p);
+    *p = 0.f;
+  }
+  return t;
 }
 
 // returns true in exactly one CTA: the last one to arrive (all partial sums visible)
@@ -94,10 +110,12 @@ static int bn_blocks(long long M, int C) {
   int lpr = groups < 256 ? groups : 256;
   int rpb = 256 / lpr;
   long long b = (M + (long long)rpb * BN_UNROLL - 1) / ((long long)rpb * BN_UNROLL);
-  if (b > kSMs * 8) b = kSMs * 8;
+  if (b > kSMs * 4) b = kSMs * 4;
   if (b < 1) b = 1;
   return (int)b;
 }
+
+int bn_ws_floats(int C) { return BN_REPL * 2 * C + 4; }
 
 // ------------------------------------------------------------------ BN forward statistics
 __global__ void __launch_bounds__(256)
@@ -144,11 +162,11 @@ __global__ void __launch_bounds__(256)
     }
     block_channel_reduce<2>(m, g, C, acc, ws, sm);
   }
-  if (last_block_done(reinterpret_cast<unsigned int*>(ws + 2 * C))) {
+  if (last_block_done(reinterpret_cast<unsigned int*>(ws + (size_t)BN_REPL * 2 * C))) {
     const float inv_m = 1.f / (float)M;
     const float unbias = M > 1 ? (float)M / (float)(M - 1) : 1.f;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float s = __ldcg(ws + c), ss = __ldcg(ws + C + c);
+      float s = fold_replicas<2>(ws, 0, C, c), ss = fold_replicas<2>(ws, 1, C, c);
       float mean = s * inv_m;
       float var = fmaxf(ss * inv_m - mean * mean, 0.f);
       float invstd = rsqrtf(var + eps);
@@ -161,10 +179,8 @@ __global__ void __launch_bounds__(256)
         running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
         running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * unbias;
       }
-      ws[c] = 0.f;
-      ws[C + c] = 0.f;
     }
-    if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(ws + 2 * C) = 0u;
+    if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(ws + (size_t)BN_REPL * 2 * C) = 0u;
   }
 }
 void bn_train_stats(const void* x, long long M, int C, const float* gamma, const float* beta,
@@ -314,20 +330,18 @@ __global__ void __launch_bounds__(256)
     }
     block_channel_reduce<2>(m, g, C, acc, ws, sm);
   }
-  if (last_block_done(reinterpret_cast<unsigned int*>(ws + 2 * C))) {
+  if (last_block_done(reinterpret_cast<unsigned int*>(ws + (size_t)BN_REPL * 2 * C))) {
     const float inv_m = 1.f / (float)M;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float db = __ldcg(ws + c), dg = __ldcg(ws + C + c);
+      float db = fold_replicas<2>(ws, 0, C, c), dg = fold_replicas<2>(ws, 1, C, c);
       if (dbeta) dbeta[c] += db;
       if (dgamma) dgamma[c] += dg;
       float gm = gamma ? gamma[c] : 1.f;
       coef[c] = gm * invstd[c];
       coef[C + c] = db * inv_m;
       coef[2 * C + c] = dg * inv_m;
-      ws[c] = 0.f;
-      ws[C + c] = 0.f;
     }
-    if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(ws + 2 * C) = 0u;
+    if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(ws + (size_t)BN_REPL * 2 * C) = 0u;
   }
 }
 void bn_bwd_reduce(const void* dy, const void* x, const void* y, long long M, int C,
@@ -345,12 +359,17 @@ __global__ void __launch_bounds__(256)
     k_bn_bwd_apply(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ y,
                    const bf16* __restrict__ extra, bf16* __restrict__ dx, long long M, int C,
                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                   const float* __restrict__ coef, int masked, float dscale) {
+                   const float* __restrict__ coef, int masked, float dscale, float* colsum_out,
+                   float* colsum_ws) {
+  extern __shared__ float sm[];
   const BnMap m(C);
   const bool vec = (C & 7) == 0;
   for (int g0 = 0; g0 < m.groups; g0 += m.lpr) {
     const int g = g0 + m.cg;
-    if (g >= m.groups || m.rl >= m.rpb) continue;
+    float csum[1][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) csum[0][j] = 0.f;
+    if (g < m.groups && m.rl < m.rpb) {
     float mu[8], is[8], c0[8], c1[8], c2[8];
     load_coef8(mean, C, g, mu);
     load_coef8(invstd, C, g, is);
@@ -368,6 +387,7 @@ __global__ void __launch_bounds__(256)
         float v = c0[j] * (gg - c1[j] - xh * c2[j]);
         if (extra) v += ev[j];
         d[j] = v;
+        csum[0][j] += v;
       }
       store8(dx, row, C, g, d);
     };
@@ -400,15 +420,23 @@ __global__ void __launch_bounds__(256)
       if (extra) load8(extra, r, C, g, ev);
       one(r, d, xv, yv, ev);
     }
+    }
+    if (colsum_out) block_channel_reduce<1>(m, g, C, csum, colsum_ws, sm);
+  }
+  // fused bias gradient of the producer convolution: column sums of dx
+  if (colsum_out && last_block_done(reinterpret_cast<unsigned int*>(colsum_ws + (size_t)BN_REPL * C))) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) colsum_out[c] = fold_replicas<1>(colsum_ws, 0, C, c);
+    if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(colsum_ws + (size_t)BN_REPL * C) = 0u;
   }
 }
 void bn_bwd_apply(const void* dy, const void* x, const void* y, const void* extra, void* dx,
                   long long M, int C, const float* save_mean, const float* save_invstd,
-                  const float* coef, int masked, float drop_p, cudaStream_t s) {
+                  const float* coef, int masked, float drop_p, float* colsum_out, float* colsum_ws,
+                  cudaStream_t s) {
   float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  k_bn_bwd_apply<<<bn_blocks(M, C), 256, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y,
-                                                  (const bf16*)extra, (bf16*)dx, M, C, save_mean,
-                                                  save_invstd, coef, masked, ds);
+  k_bn_bwd_apply<<<bn_blocks(M, C), 256, 256 * 8 * sizeof(float), s>>>(
+      (const bf16*)dy, (const bf16*)x, (const bf16*)y, (const bf16*)extra, (bf16*)dx, M, C, save_mean,
+      save_invstd, coef, masked, ds, colsum_out, colsum_ws);
   TNN_CHECK_LAUNCH();
 }
 

@@ -67,7 +67,10 @@ void bn_bwd_reduce(const void* dy, const void* x, const void* y, long long M, in
 // dx = coef0*(g - coef1 - xhat*coef2) (+ extra, an optional residual gradient to add)
 void bn_bwd_apply(const void* dy, const void* x, const void* y, const void* extra, void* dx,
                   long long M, int C, const float* save_mean, const float* save_invstd,
-                  const float* coef, int masked, float drop_p, cudaStream_t s);
+                  const float* coef, int masked, float drop_p, float* colsum_out, float* colsum_ws,
+                  cudaStream_t s);
+// floats needed by the `ws` / `colsum_ws` workspaces of the BN kernels (zero-initialised once)
+int bn_ws_floats(int C);
 // LayerNorm over rows of length C (bf16 io, fp32 affine).  One warp per row.
 void layernorm_fwd(const void* x, const void* residual, void* y, void* sum_out, long long rows, int C,
                    const float* gamma, const float* beta, float eps, float* mean, float* rstd,

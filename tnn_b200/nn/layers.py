@@ -225,11 +225,16 @@ class Conv2DLayer(Layer):
                 self.grads["bias"].add_(dy.float().sum((0, 1, 2)))
             dx = gx.permute(0, 2, 3, 1).contiguous().to(dy.dtype)
             return dx + residual if residual is not None else dx
+        colsum = getattr(dy, "_tnn_colsum", None)
         if dy.is_cuda:
             dy = to_bf16(dy).contiguous()
         else:
             dy = dy.float()
-        conv_ops.conv2d_wgrad(plan, dy, x, self.grads["weight"], self.grads.get("bias"), cache=c)
+        db = self.grads.get("bias")
+        if db is not None and colsum is not None and dy.is_cuda and plan.path != "direct":
+            native.require().axpy_f32(db, colsum, 1.0)       # bias grad came fused out of the BN backward
+            db = None
+        conv_ops.conv2d_wgrad(plan, dy, x, self.grads["weight"], db, cache=c)
         if not need_dx or plan.path == "direct":
             return None
         return conv_ops.conv2d_dgrad(plan, dy, w, self._state, self.param_version, residual=residual)
@@ -281,7 +286,8 @@ class BatchNormLayer(Layer):
         if self._gpu is None or self._gpu["ws"].device != dev:
             C = self.num_features
             z = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)  # noqa: E731
-            self._gpu = dict(ws=z(2 * C + 4), mean=z(C), invstd=z(C), ss=z(2 * C), coef=z(3 * C))
+            nws = native.require().bn_ws_floats(C)
+            self._gpu = dict(ws=z(nws), cws=z(nws), mean=z(C), invstd=z(C), ss=z(2 * C), coef=z(3 * C))
         return self._gpu
 
     def forward_impl(self, x, mb_id):
@@ -351,8 +357,12 @@ class BatchNormLayer(Layer):
             Cx.bn_bwd_reduce(dy, x, y, M, C, gamma, c["mean"], c["invstd"], masked, c["p"], self.grads.get("gamma"),
                              self.grads.get("beta"), b["coef"], b["ws"])
             dx = torch.empty_like(x)
-            Cx.bn_bwd_apply(dy, x, y, extra, dx, M, C, c["mean"], c["invstd"], b["coef"], masked, c["p"])
-            return dx.reshape(dy.shape)
+            colsum = torch.empty(C, dtype=torch.float32, device=dy.device)
+            Cx.bn_bwd_apply(dy, x, y, extra, dx, M, C, c["mean"], c["invstd"], b["coef"], masked, c["p"], colsum,
+                            b["cws"])
+            dx = dx.reshape(dy.shape)
+            dx._tnn_colsum = colsum      # column sums of dx = bias gradient of the producing conv/dense
+            return dx
         g = dy.float().reshape(-1, C)
         xf, y = c["x"], c["y"]
         if masked:
