@@ -78,16 +78,18 @@ __device__ __forceinline__ void block_channel_reduce(const BnMap& m, int g, int 
     }
   }
 }
-// sum of replica rows for quantity k, channel c (called by the last CTA), and reset
+// sum of replica rows for quantity k, channel c (called by the last CTA), and reset.  All
+// BN_REPL loads are issued before any store so they overlap (one L2 round trip, not 64).
 template <int K>
 __device__ __forceinline__ float fold_replicas(float* ws, int k, int C, int c) {
+  float v[BN_REPL];
+#pragma unroll
+  for (int r = 0; r < BN_REPL; ++r) v[r] = __ldcg(ws + ((size_t)r * K + k) * C + c);
   float t = 0.f;
-#pragma unroll 8
-  for (int r = 0; r < BN_REPL; ++r) {
-    float* p = ws + ((size_t)r * K + k) * C + c;
-    t += __ldcg(p);
-    *p = 0.f;
-  }
+#pragma unroll
+  for (int r = 0; r < BN_REPL; ++r) t += v[r];
+#pragma unroll
+  for (int r = 0; r < BN_REPL; ++r) ws[((size_t)r * K + k) * C + c] = 0.f;
   return t;
 }
 
@@ -355,7 +357,7 @@ void bn_bwd_reduce(const void* dy, const void* x, const void* y, long long M, in
   TNN_CHECK_LAUNCH();
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
     k_bn_bwd_apply(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ y,
                    const bf16* __restrict__ extra, bf16* __restrict__ dx, long long M, int C,
                    const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -392,17 +394,18 @@ __global__ void __launch_bounds__(256)
       store8(dx, row, C, g, d);
     };
     if (vec) {
-      for (; r + (BN_UNROLL - 1) * stride < M; r += BN_UNROLL * stride) {
-        uint4 qd[BN_UNROLL], qx[BN_UNROLL], qy[BN_UNROLL], qe[BN_UNROLL];
+      constexpr int U = 2;
+      for (; r + (U - 1) * stride < M; r += U * stride) {
+        uint4 qd[U], qx[U], qy[U], qe[U];
 #pragma unroll
-        for (int u = 0; u < BN_UNROLL; ++u) {
+        for (int u = 0; u < U; ++u) {
           qd[u] = load8raw(dy, r + u * stride, C, g);
           qx[u] = load8raw(x, r + u * stride, C, g);
           if (masked) qy[u] = load8raw(y, r + u * stride, C, g);
           if (extra) qe[u] = load8raw(extra, r + u * stride, C, g);
         }
 #pragma unroll
-        for (int u = 0; u < BN_UNROLL; ++u) {
+        for (int u = 0; u < U; ++u) {
           float d[8], xv[8], yv[8], ev[8];
           bf8_unpack(qd[u], d);
           bf8_unpack(qx[u], xv);
