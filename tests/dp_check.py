@@ -58,27 +58,59 @@ def main():
         return g, losses, step, dp
 
     ok = True
+
+    # ---- (1) exact check of ONE fused step on deterministic gradients vs all-gather + torch Adam
+    for mc in (False, True):
+        stepstate._STATES.clear()
+        opt = OptimizerFactory.create_adam(1e-2, 0.9, 0.999, 1e-3, 3e-4)
+        dp = FusedDataParallel(opt, use_multicast=mc)
+        g = dp.build_graph(ExampleModels.create(model), dev, seed=99, name=model)
+        ctx = g.ctx
+        n = ctx.numel
+        p_ref = ctx.param_slab[:n].clone()
+        m_ref = torch.zeros_like(p_ref)
+        v_ref = torch.zeros_like(p_ref)
+        for t in range(1, 4):
+            gg = torch.Generator(device=dev).manual_seed(77 * t + rank)
+            ctx.grad_slab[:n].copy_(torch.randn(n, device=dev, generator=gg) * 0.05)
+            allg = [torch.empty(n, device=dev) for _ in range(world)]
+            dist.all_gather(allg, ctx.grad_slab[:n].clone())
+            gsum = torch.stack(allg).sum(0) / world
+            dp.step()
+            torch.cuda.synchronize()
+            m_ref = 0.9 * m_ref + 0.1 * gsum
+            v_ref = 0.999 * v_ref + 0.001 * gsum * gsum
+            upd = 1e-2 * (m_ref / (1 - 0.9 ** t)) / ((v_ref / (1 - 0.999 ** t)).sqrt() + 1e-3) + 3e-4 * 1e-2 * p_ref
+            p_ref = p_ref - upd
+            err = float((ctx.param_slab[:n] - p_ref).abs().max())
+            zeroed = bool((ctx.grad_slab[:n] == 0).all())
+            lp_ok = bool(torch.allclose(ctx.lp_slab[:n].float(), p_ref, rtol=1e-2, atol=1e-3))
+            good = err < 2e-5 and zeroed and lp_ok
+            ok &= good
+            if rank == 0:
+                print(f"unit step {t} (multicast={'on' if dp.mc else 'off'}): max|p - ref|={err:.3e} grads_zeroed={zeroed} "
+                      f"bf16_ok={lp_ok} -> {'OK' if good else 'FAIL'}", flush=True)
+        mine = ctx.param_slab[:n].clone()
+        other = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(other, mine)
+        same = all(torch.equal(o, other[0]) for o in other)
+        ok &= same
+        if rank == 0:
+            print(f"replicas bit-identical across ranks: {same}", flush=True)
+        del g, dp
+        torch.cuda.empty_cache()
+
+    # ---- (2) training-level agreement with the NCCL all-reduce baseline (loose: fp32 atomics +
+    #          bf16 make individual runs differ at the 1e-2 level after a few Adam steps)
     gb, lb, _, _ = run("nccl", 6, False)
-    pb = gb.ctx.param_slab.clone()
     for mc in (False, True):
         for graph in (False, True):
             gf, lf, _, dp = run("fused", 6, graph, multicast=mc)
-            pf = gf.ctx.param_slab
-            n = min(pf.numel(), pb.numel())
-            err = float((pf[:n] - pb[:n]).abs().max())
-            rel = float((pf[:n] - pb[:n]).norm() / pb[:n].norm())
-            # replicas identical across ranks
-            mine = pf[:n].clone()
-            other = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(other, mine)
-            same = all(torch.equal(o, other[0]) for o in other)
-            lp_ok = bool(torch.allclose(gf.ctx.lp_slab[:n].float(), pf[:n], rtol=1e-2, atol=1e-3))
-            good = rel < 2e-3 and same and lp_ok and all(abs(a - b) < 5e-2 for a, b in zip(lb, lf))
+            good = all(abs(a - b) < 6e-2 for a, b in zip(lb, lf)) and all(v == v for v in lf)
             ok &= good
             if rank == 0:
-                print(f"fused(multicast={'on' if dp.mc else 'off'}, graph={graph}): max|dp|={err:.3e} rel={rel:.3e} "
-                      f"replicas_identical={same} bf16_copy_ok={lp_ok} losses_f={['%.4f' % v for v in lf[:3]]} "
-                      f"losses_b={['%.4f' % v for v in lb[:3]]} -> {'OK' if good else 'FAIL'}", flush=True)
+                print(f"train fused(multicast={'on' if dp.mc else 'off'}, graph={graph}): losses {['%.4f' % v for v in lf]} "
+                      f"vs nccl {['%.4f' % v for v in lb]} -> {'OK' if good else 'FAIL'}", flush=True)
             del gf, dp
             torch.cuda.empty_cache()
 
@@ -110,4 +142,11 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except SystemExit:
+        raise
+    except BaseException:  # noqa: BLE001
+        import traceback
+        print(f"[rank {os.environ.get('RANK')}] " + traceback.format_exc(), flush=True)
+        raise
