@@ -1,0 +1,1 @@
+from .env import Env  # noqa: F401
