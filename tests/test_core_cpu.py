@@ -1,0 +1,515 @@
+"""CPU tests of the host runtime: dtype/config, archiver wire format, tensor records, allocators,
+graph IR + checkpoints, optimizers vs torch.optim, schedulers, losses, data path, tokenizer,
+profiler, and an end-to-end mnist_cnn training run (BASELINE config 1: plumbing on CPU).
+
+Reference tests mirrored: unit_tests/archiver_test.cpp, tensor_test.cpp (save/load),
+bf16_test.cpp, device_manager_test.cpp; plus what the reference lacks:
+optimizer/scheduler oracles and checkpoint round trips including optimizer state.
+"""
+import io
+import math
+import os
+import struct
+
+import numpy as np
+import pytest
+import torch
+
+from tnn_b200.core import tensor_io
+from tnn_b200.core.config import TConfig
+from tnn_b200.core.dtype import DType, dtype_eps, dtype_size, dtype_to_string, from_torch, string_to_dtype, to_torch
+from tnn_b200.models import ExampleModels, load_or_create_model
+from tnn_b200.nn import (Graph, GraphBuilder, GraphExecutor, LossFactory, OptimizerFactory, SchedulerFactory,
+                         compute_class_corrects, graph_from_sequential)
+from tnn_b200.nn.layers import ActivationLayer, AddLayer, DenseLayer, MBroadcastLayer
+from tnn_b200.ops import native
+
+
+# ------------------------------------------------------------------------------- dtype / config
+def test_dtype_table():
+    assert string_to_dtype("FP32") == string_to_dtype("FLOAT") == DType.FP32
+    assert string_to_dtype("BF16") == DType.BF16 and string_to_dtype("DOUBLE") == DType.FP64
+    assert dtype_size(DType.BF16) == 2 and dtype_size(DType.FP64) == 8 and dtype_size(DType.INT64_T) == 8
+    assert to_torch(DType.BF16) == torch.bfloat16 and from_torch(torch.float16) == DType.FP16
+    assert dtype_eps(DType.FP16) == 1e-3 and dtype_eps(DType.BF16) == 1e-2 and dtype_eps(DType.FP32) == 1e-5
+    assert dtype_to_string(DType.FP32) in ("FP32", "FLOAT")
+
+
+def test_bf16_rounding_is_rne():
+    # 1 + 2^-8 is exactly between two bf16 values -> ties to even (1.0); 1 + 3*2^-8 -> 1 + 2^-6
+    x = torch.tensor([1.0 + 2 ** -8, 1.0 + 3 * 2 ** -8, 1.0 + 2 ** -7])
+    y = x.to(torch.bfloat16).float()
+    assert y.tolist() == [1.0, 1.0 + 2 ** -6, 1.0 + 2 ** -7]
+
+
+def test_tconfig_typed_json_round_trip():
+    c = TConfig("conv", "conv2d", in_channels=3, use_bias=True, eps=1e-5, act="relu", dims=[1, 2, 3],
+                nested=TConfig("inner", "dense", n=4))
+    j = c.to_json()
+    assert j["name"] == "conv" and j["type"] == "conv2d"
+    c2 = TConfig.from_json(j)
+    assert c2 == c and c2["in_channels"] == 3 and c2["use_bias"] is True and c2.get("missing", 7) == 7
+    assert isinstance(c2["eps"], float) and isinstance(c2["in_channels"], int)
+    assert TConfig.from_json(c.dump()) == c
+
+
+# ------------------------------------------------------------------------------- archiver
+needs_native = pytest.mark.skipif(native.load() is None, reason="native extension not built")
+
+
+@needs_native
+def test_archiver_sizer_writer_reader_agree():
+    Cx = native.require()
+    blob = bytes(range(256)) * 64
+    t = torch.arange(24, dtype=torch.float32).reshape(2, 3, 4)
+
+    def emit(a):
+        a.u16(7)
+        a.u64(1 << 40)
+        a.f32(1.5)
+        a.boolean(True)
+        a.string("hello archive")
+        a.sizes([3, 1, 4, 1, 5])
+        return a
+
+    s = emit(Cx.Sizer())
+    s.raw(blob)
+    s.tensor(int(DType.FP32), list(t.shape), t.numel() * 4)
+    w = emit(Cx.Writer())
+    w.raw(blob)
+    w.tensor(int(DType.FP32), list(t.shape), t.data_ptr(), t.numel() * 4)
+    data = w.getvalue()
+    assert s.size() == w.size() == len(data)
+    # exact layout: u16, u64, f32, u8, u64 len + bytes, u64 n + n*u64
+    assert data[:2] == struct.pack("<H", 7) and data[2:10] == struct.pack("<Q", 1 << 40)
+    assert data[15:23] == struct.pack("<Q", len("hello archive"))
+    r = Cx.Reader(data, False)
+    assert r.u16() == 7 and r.u64() == 1 << 40 and r.f32() == 1.5 and r.boolean() is True
+    assert r.string() == b"hello archive" and r.sizes() == [3, 1, 4, 1, 5]
+    assert r.raw(len(blob)) == blob
+    assert r.u32() == int(DType.FP32) and r.sizes() == [2, 3, 4]
+    out = torch.empty_like(t)
+    r.raw_into(out.data_ptr(), t.numel() * 4, 4)
+    assert torch.equal(out, t) and r.remaining() == 0
+
+
+@needs_native
+def test_archiver_endianness_swap():
+    Cx = native.require()
+    w = Cx.Writer()
+    w.u32(0x01020304)
+    w.f32(2.5)
+    be = w.getvalue()[:4][::-1] + w.getvalue()[4:][::-1]       # the same values written big-endian
+    r = Cx.Reader(be, True)
+    assert r.u32() == 0x01020304 and r.f32() == 2.5
+    assert Cx.host_is_little_endian() is True
+
+
+def test_tensor_record_format_and_trailer():
+    t = torch.randn(3, 5)
+    f = io.BytesIO()
+    tensor_io.save_tensor(f, t)
+    raw = f.getvalue()
+    # {u32 dtype, u64 ndims, u64 dims[], raw}  (include/tensor/tensor.hpp:585-606)
+    assert struct.unpack("<I", raw[:4])[0] == int(DType.FP32)
+    assert struct.unpack("<QQQ", raw[4:28]) == (2, 3, 5)
+    assert len(raw) == 28 + 60
+    f.seek(0)
+    assert torch.equal(tensor_io.load_tensor(f), t)
+    f = io.BytesIO()
+    tensor_io.save_tensor(f, t.to(torch.bfloat16))
+    tensor_io.write_trailer(f, {"step": 12, "m": torch.ones(4), "cfg": {"a": 1}})
+    f.seek(0)
+    assert tensor_io.load_tensor(f).dtype == torch.bfloat16
+    ex = tensor_io.read_trailer(f)
+    assert ex["step"] == 12 and torch.equal(ex["m"], torch.ones(4)) and ex["cfg"] == {"a": 1}
+    dst = torch.zeros(3, 4)
+    f = io.BytesIO()
+    tensor_io.save_tensor(f, t)
+    f.seek(0)
+    with pytest.raises(Exception):
+        tensor_io.load_into(f, dst)                              # shape mismatch is an error
+
+
+# ------------------------------------------------------------------------------- allocators
+@needs_native
+def test_del_allocator_double_ended_and_pool_reuse():
+    from tnn_b200.core.device import DELAllocator, DeviceManager, PoolAllocator, getHost
+    a = DELAllocator("cpu", slab_bytes=1 << 20)
+    t1 = a.allocate((256, 256), torch.float32)
+    a.flip()
+    t2 = a.allocate((128,), torch.float32)
+    assert t1.data_ptr() % 256 == 0 and t2.data_ptr() % 256 == 0
+    assert a.total_allocated() >= t1.numel() * 4 + t2.numel() * 4 and a.side() is True
+    assert t2.data_ptr() > t1.data_ptr()                         # right side of the same slab
+    a.free(t1)
+    a.free(t2)
+    a.clear()
+    assert a.total_allocated() == 0 and a.peak_allocated() >= 256 * 256 * 4
+    p = PoolAllocator("cpu")
+    x = p.allocate((1000,), torch.float32)
+    ptr = x.data_ptr()
+    p.free(x)
+    y = p.allocate((900,), torch.float32)                       # block <= 4x the request is reused
+    assert y.data_ptr() == ptr and p.cached_bytes() == 0
+    dm = DeviceManager.getInstance()
+    assert dm.getDevice("CPU").type.name == "CPU" and getHost().total_memory() > 0
+
+
+# ------------------------------------------------------------------------------- graph IR
+def test_graph_builder_topo_sort_cycle_and_multi_input():
+    b = GraphBuilder("g")
+    n1 = b.add_layer(DenseLayer(4, 4, name="a"), "a")
+    n2 = b.add_layer(MBroadcastLayer(2, "bc"), "bc")
+    n3 = b.add_layer(ActivationLayer("tanh", "t"), "t")
+    n4 = b.add_layer(AddLayer("add"), "add")
+    # declared out of order on purpose
+    b.add_edge(["u", "v2"], ["out"], n4)
+    b.add_edge(["v"], ["v2"], n3)
+    b.add_edge(["h"], ["u", "v"], n2)
+    b.add_edge(["in"], ["h"], n1)
+    g = b.compile("cpu", seed=3)
+    assert [e.op for e in g.edges] == ["a", "bc", "t", "add"]
+    ex = GraphExecutor(g)
+    x = torch.randn(3, 4)
+    out = ex.forward({"in": x})["out"]
+    h = x @ n1.layer.params["weight"].t() + n1.layer.params["bias"]
+    torch.testing.assert_close(out, h + torch.tanh(h))
+    gin = ex.backward({"out": torch.ones_like(out)})["in"]
+    assert gin.shape == x.shape
+    bad = GraphBuilder("cyc")
+    a = bad.add_layer(DenseLayer(2, 2, name="a"), "a")
+    c = bad.add_layer(DenseLayer(2, 2, name="c"), "c")
+    bad.add_edge(["x"], ["y"], a)
+    bad.add_edge(["y"], ["x"], c)
+    with pytest.raises(ValueError):
+        bad.compile("cpu")
+
+
+def test_graph_context_packs_params_into_aligned_slabs():
+    g = load_or_create_model("mnist_cnn", device="cpu", seed=1)
+    ctx = g.context()
+    assert ctx.param_slab.numel() == ctx.grad_slab.numel() >= ctx.num_parameters()
+    for layer, d, off, n in ctx.entries:
+        assert off % 64 == 0                                     # 256-byte aligned sub-spans
+        assert layer.params[d.name].data_ptr() == ctx.param_slab.data_ptr() + off * 4
+        assert layer.grads[d.name].data_ptr() == ctx.grad_slab.data_ptr() + off * 4
+    ctx.grad_slab.fill_(1.0)
+    ctx.zero_grads()
+    assert all(float(l.grads[d.name].abs().sum()) == 0 for l, d, _, _ in ctx.entries)
+
+
+def test_checkpoint_round_trip_including_optimizer_state(tmp_path):
+    from tnn_b200.nn.train import TrainStep, load_checkpoint, save_checkpoint
+    g = load_or_create_model("mnist_cnn", device="cpu", seed=5)
+    opt = OptimizerFactory.create_adam(1e-3, 0.9, 0.999, 1e-3, 3e-4)
+    sched = SchedulerFactory.create_step_lr(opt, 3, 0.5)
+    step = TrainStep(g, LossFactory.create_logsoftmax_crossentropy(), opt, sched)
+    x, y = torch.rand(8, 28, 28, 1), torch.randint(0, 10, (8,), dtype=torch.int32)
+    for _ in range(4):
+        step(x, y)
+    path = str(tmp_path / "ckpt")
+    save_checkpoint(g, path, opt, sched, 4)
+    head = open(path, "rb").read(64)
+    assert head.lstrip().startswith(b"{")                        # JSON graph config first (graph.hpp:119-126)
+    opt2 = OptimizerFactory.create_adam(1e-3, 0.9, 0.999, 1e-3, 3e-4)
+    sched2 = SchedulerFactory.create_step_lr(opt2, 3, 0.5)
+    g2, extra = load_checkpoint(path, "cpu", opt2, sched2)
+    assert extra["step"] == 4 and opt2.step_count == opt.step_count
+    assert abs(opt2.get_learning_rate() - opt.get_learning_rate()) < 1e-12
+    for (n1, p1), (n2, p2) in zip(g.ctx.parameters(), g2.ctx.parameters()):
+        assert n1 == n2 and torch.equal(p1, p2)
+    # resumed optimisation continues bit-identically
+    s2 = TrainStep(g2, LossFactory.create_logsoftmax_crossentropy(), opt2, sched2)
+    a, b = step(x, y), s2(x, y)
+    torch.testing.assert_close(a, b)
+    torch.testing.assert_close(g.ctx.param_slab, g2.ctx.param_slab)
+
+
+# ------------------------------------------------------------------------------- optimizers
+def _toy_graph():
+    from tnn_b200.nn import Sequential
+    seq = Sequential([DenseLayer(6, 5, name="a"), ActivationLayer("tanh"), DenseLayer(5, 3, name="b")], "toy")
+    return graph_from_sequential(seq, "cpu", seed=2, name="toy")
+
+
+@pytest.mark.parametrize("kind", ["adam_coupled", "adamw", "sgd", "sgd_momentum"])
+def test_optimizers_match_reference_formulas(kind):
+    g = _toy_graph()
+    ctx = g.context()
+    if kind == "adam_coupled":
+        opt = OptimizerFactory.create_adam(1e-2, 0.9, 0.999, 1e-3, 3e-4, False)
+    elif kind == "adamw":
+        opt = OptimizerFactory.create_adam(1e-2, 0.9, 0.999, 1e-8, 1e-2, True)
+    elif kind == "sgd":
+        opt = OptimizerFactory.create_sgd(0.1, 0.0)
+    else:
+        opt = OptimizerFactory.create_sgd(0.1, 0.9)
+    opt.attach(ctx)
+    n = ctx.numel
+    p = ctx.param_slab[:n].clone()
+    m = torch.zeros(n)
+    v = torch.zeros(n)
+    gen = torch.Generator().manual_seed(0)
+    for t in range(1, 5):
+        gr = torch.randn(n, generator=gen)
+        ctx.grad_slab[:n].copy_(gr)
+        opt.update()
+        if kind.startswith("adam"):
+            lr, wd = 1e-2, (3e-4 if kind == "adam_coupled" else 1e-2)
+            eps = 1e-3 if kind == "adam_coupled" else 1e-8
+            if kind == "adamw":
+                p = p - wd * lr * p
+            m = 0.9 * m + 0.1 * gr
+            v = 0.999 * v + 0.001 * gr * gr
+            upd = lr * (m / (1 - 0.9 ** t)) / ((v / (1 - 0.999 ** t)).sqrt() + eps)
+            if kind == "adam_coupled":
+                upd = upd + wd * lr * p
+            p = p - upd
+        elif kind == "sgd":
+            p = p - 0.1 * gr
+        else:
+            m = 0.9 * m - 0.1 * gr          # v <- mu v - lr g ; p <- p + v  (sgd_kernels.cu:26-35)
+            p = p + m
+        torch.testing.assert_close(ctx.param_slab[:n], p, atol=1e-6, rtol=1e-5)
+        assert float(ctx.grad_slab.abs().sum()) == 0.0 or not opt.fused_zero_grad
+    cfg = opt.get_config()
+    assert OptimizerFactory.create_from_config(cfg.to_json()).get_config() == cfg
+
+
+def test_schedulers_follow_torch():
+    import torch.optim.lr_scheduler as S
+
+    def pair():
+        o = OptimizerFactory.create_sgd(0.1)
+        w = torch.nn.Parameter(torch.zeros(1))
+        return o, torch.optim.SGD([w], lr=0.1)
+
+    cases = [
+        ("step_lr", dict(step_size=3, gamma=0.5), lambda to: S.StepLR(to, 3, 0.5)),
+        ("multi_step_lr", dict(milestones=[2, 5], gamma=0.1), lambda to: S.MultiStepLR(to, [2, 5], 0.1)),
+        ("exponential_lr", dict(gamma=0.9), lambda to: S.ExponentialLR(to, 0.9)),
+        ("cosine_annealing_lr", dict(T_max=10, eta_min=0.01), lambda to: S.CosineAnnealingLR(to, 10, 0.01)),
+        ("polynomial_lr", dict(total_steps=8, power=2.0), lambda to: S.PolynomialLR(to, 8, 2.0)),
+    ]
+    for name, kw, mk in cases:
+        o, to = pair()
+        try:
+            s = SchedulerFactory.create(name, o, **kw)
+        except KeyError:
+            s = SchedulerFactory.create(name.replace("_lr", ""), o, **kw)
+        ts = mk(to)
+        for _ in range(9):
+            s.step()
+            to.step()
+            ts.step()
+            assert abs(o.get_learning_rate() - to.param_groups[0]["lr"]) < 1e-9, name
+        cfg = s.get_config()
+        s2 = SchedulerFactory.create_from_config(cfg.to_json() if hasattr(cfg, "to_json") else cfg, OptimizerFactory.create_sgd(0.1))
+        assert type(s2) is type(s)
+    # warm-up + cosine and plateau: qualitative checks
+    o = OptimizerFactory.create_sgd(1.0)
+    s = SchedulerFactory.create_warmup_cosine(o, 4, 20, 0.0, 0.0)
+    lrs = []
+    for _ in range(20):
+        s.step()
+        lrs.append(o.get_learning_rate())
+    assert lrs[0] < lrs[3] <= 1.0 and lrs[-1] < 0.05 and max(lrs) <= 1.0 + 1e-9
+    o = OptimizerFactory.create_sgd(1.0)
+    s = SchedulerFactory.create("reduce_lr_on_plateau", o, factor=0.5, patience=1)
+    for metric in (1.0, 1.0, 1.0, 1.0):
+        s.step(metric)
+    assert o.get_learning_rate() < 1.0
+    sd = s.state_dict()
+    s.load_state_dict(sd)
+
+
+# ------------------------------------------------------------------------------- losses
+def test_losses_against_torch():
+    import torch.nn.functional as F
+    logits = torch.randn(7, 5)
+    y = torch.randint(0, 5, (7,), dtype=torch.int32)
+    ce = LossFactory.create("logsoftmax_crossentropy")
+    stats, grad = ce.loss_and_grad(logits, y)
+    ref = F.cross_entropy(logits, y.long())
+    assert abs(float(stats[0]) - float(ref)) < 1e-6
+    lg = logits.clone().requires_grad_(True)
+    F.cross_entropy(lg, y.long()).backward()
+    torch.testing.assert_close(grad, lg.grad, atol=1e-6, rtol=1e-5)
+    assert int(stats[1]) == int((logits.argmax(-1) == y).sum()) == compute_class_corrects(logits, y)
+    for name, fn in (("mse", F.mse_loss), ("mae", F.l1_loss), ("huber", lambda a, b: F.huber_loss(a, b, delta=1.0))):
+        l = LossFactory.create(name)
+        p, t = torch.randn(4, 3), torch.randn(4, 3)
+        pp = p.clone().requires_grad_(True)
+        r = fn(pp, t)
+        r.backward()
+        assert abs(l.compute_loss(p, t) - float(r)) < 1e-6
+        torch.testing.assert_close(l.compute_gradient(p, t), pp.grad, atol=1e-6, rtol=1e-5)
+    for alias in ("ce", "crossentropy", "mean_squared_error", "mean_absolute_error", "logsoftmax_ce"):
+        assert LossFactory.create(alias) is not None
+
+
+# ------------------------------------------------------------------------------- data path
+@needs_native
+def test_cifar_binary_loader_and_augmentation(tmp_path):
+    from tnn_b200.data import AugmentationBuilder, CIFAR10DataLoader, DataLoaderFactory
+    rng = np.random.default_rng(0)
+    n = 50
+    labels = rng.integers(0, 10, n, dtype=np.uint8)
+    pix = rng.integers(0, 256, (n, 3, 32, 32), dtype=np.uint8)
+    rec = np.concatenate([labels[:, None], pix.reshape(n, -1)], 1)
+    os.makedirs(tmp_path / "cifar-10-batches-bin", exist_ok=True)
+    for i in range(1, 6):
+        rec.tofile(tmp_path / "cifar-10-batches-bin" / f"data_batch_{i}.bin")
+    rec.tofile(tmp_path / "cifar-10-batches-bin" / "test_batch.bin")
+    ld = CIFAR10DataLoader()
+    ld.load_data(str(tmp_path), train=False)
+    assert ld.size() == n and tuple(ld.get_data_shape()) == (32, 32, 3)
+    x, y = ld.get_batch(16)
+    assert x.shape == (16, 32, 32, 3) and y.dtype == torch.int32
+    # CHW -> NHWC transpose and /255 (cifar10_data_loader.hpp:152-165)
+    torch.testing.assert_close(x[0], torch.from_numpy(pix[0]).permute(1, 2, 0).float() / 255)
+    assert y.tolist() == labels[:16].tolist()
+    seen = 16
+    while True:
+        b = ld.get_batch(16)
+        if b is None:
+            break
+        seen += b[0].shape[0]
+    assert seen == n
+    ld.set_seed(3)
+    ld.shuffle()
+    ld.reset()
+    x2, y2 = ld.get_batch(n)
+    assert sorted(y2.tolist()) == sorted(labels.tolist()) and y2.tolist() != labels.tolist()
+    aug = AugmentationBuilder(seed=1).horizontal_flip(1.0).build()
+    ld.set_augmentation(aug)
+    ld.reset()
+    tr, va = DataLoaderFactory.create("cifar10", str(tmp_path))
+    assert tr.size() == 5 * n and va.size() == n
+    out = aug.apply(x.clone())
+    torch.testing.assert_close(out, x.flip(2))
+    full = (AugmentationBuilder(seed=2).random_crop(1.0, 4).cutout(1.0, 8).brightness(1.0, 0.2).contrast(1.0, 0.2)
+            .gaussian_noise(1.0, 0.01).rotation(1.0, 10).vertical_flip(0.5).normalize([0.5] * 3, [0.25] * 3).build())
+    z = full.apply_python(x.clone(), full=True)
+    assert z.shape == x.shape and torch.isfinite(z).all()
+
+
+@needs_native
+def test_token_dataset_and_tokenizer(tmp_path):
+    from tnn_b200.data import OpenWebTextDataLoader, Tokenizer
+    toks = (np.arange(5000) % 997).astype(np.uint16)
+    toks.tofile(tmp_path / "train.bin")
+    toks[:2000].tofile(tmp_path / "val.bin")
+    ld = OpenWebTextDataLoader(seq_len=32)
+    ld.load_data(str(tmp_path), train=True)
+    x, y = ld.get_batch(4)
+    assert x.shape == (4, 32) and y.shape == (4, 32)
+    assert torch.equal(x[:, 1:].long(), y[:, :-1].long())        # next-token labels, integer class ids
+    w = ld.window(10, 8)
+    assert w.reshape(-1).tolist() == list(range(10, 18))
+    tok = Tokenizer.byte_fallback([b"he", b"llo", b" wor", b"ld"])
+    ids = tok.encode("hello world")
+    assert tok.decode(ids) == "hello world" and len(ids) < len("hello world")
+    path = str(tmp_path / "vocab.bin")
+    tok.save(path)
+    raw = open(path, "rb").read()
+    assert struct.unpack("<I", raw[:4])[0] == tok.vocab_size()   # u32 n; {u32 len; bytes} x n
+    t2 = Tokenizer(path)
+    assert t2.decode(ids) == "hello world" and t2.vocab_size() == tok.vocab_size()
+
+
+@needs_native
+def test_profiler_merge_rebases_and_serialises():
+    from tnn_b200.utils.profiler import EventType, Profiler
+    a, b = Profiler(), Profiler()
+    a.init_start_time()
+    b.init_start_time()
+    t = Profiler.now_ns()
+    a.add_event(EventType.COMPUTE, t, t + 1000, "fwd", "stage0")
+    b.add_event(EventType.COMMUNICATION, t + 500, t + 700, "send", "stage1")
+    b2 = Profiler.deserialize(b.serialize())
+    a.merge(b2)
+    a.sort()
+    ev = a.events()
+    assert len(ev) == 2 and {e["name"] for e in ev} == {"fwd", "send"}
+    with a.span("host-span"):
+        pass
+    assert len(a.events()) == 3
+
+
+def test_env_file_and_training_config(tmp_path):
+    from tnn_b200.nn.train import TrainingConfig
+    from tnn_b200.utils.env import Env
+    p = tmp_path / ".env"
+    p.write_text("EPOCHS=3\nBATCH_SIZE = 64\n# comment\nMODEL_NAME=\"cifar100_wrn16_8\"\nLR_INITIAL=0.01\nDEVICE_TYPE=CPU\n")
+    e = Env(str(p))
+    assert e.get("EPOCHS", 1, int) == 3 and e.get("MISSING", 5, int) == 5
+    c = TrainingConfig.load_from_env(str(p))
+    assert c.epochs == 3 and c.batch_size == 64 and c.model_name == "cifar100_wrn16_8" and c.lr_initial == 0.01
+    assert c.device() == torch.device("cpu")
+    import json
+    j = tmp_path / "cfg.json"
+    j.write_text(json.dumps({"epochs": 2, "batch_size": 16, "model_name": "mnist_cnn"}))
+    c2 = TrainingConfig.load_from_json(str(j))
+    assert c2.epochs == 2 and c2.model_name == "mnist_cnn"
+
+
+# ------------------------------------------------------------------------------- model zoo + trainer
+def test_every_zoo_model_builds_and_reports_shape():
+    names = ExampleModels.available_models()
+    for required in ["mnist_cnn", "cifar10_vgg", "cifar10_resnet9", "cifar100_resnet18", "cifar100_wrn16_8",
+                     "tiny_imagenet_resnet18", "tiny_imagenet_wrn16_8", "tiny_imagenet_resnet50", "tiny_imagenet_vit",
+                     "tiny_imagenet_flash_vit", "imagenet_resnet50", "gpt2_small", "gpt2_medium", "gpt2_large",
+                     "flash_gpt2_small", "flash_gpt2_medium", "flash_gpt2_large"]:
+        assert required in names, required
+    shapes = {"mnist_cnn": ((2, 28, 28, 1), (2, 10)), "cifar10_resnet9": ((2, 32, 32, 3), (2, 10)),
+              "cifar100_wrn16_8": ((2, 32, 32, 3), (2, 100)), "cifar10_vgg": ((2, 32, 32, 3), (2, 10)),
+              "cifar100_resnet18": ((2, 32, 32, 3), (2, 100))}
+    for n, (i, o) in shapes.items():
+        m = ExampleModels.create(n)
+        assert tuple(m.output_shape(i)) == o, n
+        assert m.forward_flops(i) > 0
+    wrn = ExampleModels.create("cifar100_wrn16_8")
+    nparams = sum(math.prod(d.shape) for l in wrn.all_layers() for d in l.param_descriptors() if d.trainable)
+    assert 10.5e6 < nparams < 11.5e6                              # ~11.0 M
+    g = ExampleModels.create("gpt2_small", seq_len=16, vocab=64)
+    assert tuple(g.output_shape((2, 16))) == (2, 16, 64)
+
+
+def test_small_gpt_trains_on_cpu():
+    from tnn_b200.nn.train import TrainStep
+    seq = ExampleModels.create("gpt2_small", seq_len=16, vocab=48)
+    # shrink: keep 2 blocks so the CPU test stays fast
+    g = graph_from_sequential(seq, "cpu", seed=3, name="tiny_gpt")
+    opt = OptimizerFactory.create_adam(3e-4)
+    step = TrainStep(g, LossFactory.create_logsoftmax_crossentropy(), opt)
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randint(0, 48, (2, 16), generator=gen, dtype=torch.int32)
+    y = torch.roll(x, -1, 1)
+    losses = [float(step(x, y)[0]) for _ in range(6)]
+    assert all(math.isfinite(v) for v in losses) and losses[-1] < losses[0]
+
+
+def test_mnist_cnn_trainer_cpu_world1(tmp_path):
+    """BASELINE config 1: mnist_cnn Sequential fp32 on CPU through train_model (plumbing)."""
+    from tnn_b200.data import SyntheticDataLoader
+    from tnn_b200.nn.train import TrainingConfig, train_model, validate_model
+    torch.manual_seed(0)
+    g = load_or_create_model("mnist_cnn", device="cpu", seed=1)
+    train = SyntheticDataLoader((28, 28, 1), 10, n=256, seed=1)
+    val = SyntheticDataLoader((28, 28, 1), 10, n=64, seed=1)
+    train.load_data()
+    val.load_data()
+    cfg = TrainingConfig(epochs=3, batch_size=32, progress_print_interval=0, snapshot_dir=str(tmp_path), device_type="CPU")
+    opt = OptimizerFactory.create_adam(2e-3, 0.9, 0.999, 1e-3, 0.0)
+    crit = LossFactory.create_logsoftmax_crossentropy()
+    sched = SchedulerFactory.create_step_lr(opt, 1000, 0.1)
+    lines = []
+    hist = train_model(g, train, val, opt, crit, sched, cfg, log=lines.append)
+    assert len(hist["train_loss"]) == 3 and hist["train_loss"][-1] < hist["train_loss"][0]
+    assert os.path.exists(os.path.join(str(tmp_path), g.name))   # best-validation snapshot
+    vl, va = validate_model(g, val, crit, cfg)
+    assert math.isfinite(vl) and 0.0 <= va <= 1.0
+    g2 = Graph.load_state(os.path.join(str(tmp_path), g.name), "cpu")
+    assert [n for n, _ in g2.ctx.parameters()] == [n for n, _ in g.ctx.parameters()]

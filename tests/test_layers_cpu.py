@@ -1,0 +1,324 @@
+"""CPU (fp32 oracle path) layer semantics: every layer's forward/backward against torch autograd
+on the same weights, config round trips, shape inference and gradient accumulation.
+
+Mirrors the reference's layer tests (unit_tests/legacy_{dense,conv2d,maxpool2d,avgpool,batchnorm}
+_layer_test.cpp, groupnorm_layer_test.cpp, residual_block_test.cpp, attention_block_test.cpp,
+slice_ops_test.cpp), with autograd as the golden source instead of hand-computed constants.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tnn_b200.core.config import TConfig
+from tnn_b200.nn import (ActivationLayer, AddLayer, AttentionBlock, AvgPool2DLayer, BatchNormLayer, ClassTokenLayer,
+                         Conv2DLayer, DenseLayer, DropoutLayer, EmbeddingLayer, FlattenLayer, GroupNormLayer,
+                         LayerBuilder, LayerFactory, LayerNormLayer, MaxPool2DLayer, MBroadcastLayer, MSequential,
+                         MulLayer, PositionalEmbeddingLayer, ResidualBlock, Sequential, SliceLayer, SubLayer,
+                         TransposeLayer)
+
+torch.manual_seed(0)
+
+
+def _grad_check(layer, x, ref_fn, atol=1e-4, rtol=1e-4, param_map=None):
+    """ref_fn(x, params: dict) -> y built from torch ops; compares y, dx and every param grad."""
+    layer.init("cpu", seed=3)
+    layer.set_training(True)
+    y = layer.forward(x.clone(), 0)
+    dy = torch.randn_like(y)
+    dx = layer.backward(dy, 0)
+    xs = x.clone().requires_grad_(x.dtype.is_floating_point)
+    ps = {k: v.clone().requires_grad_(True) for k, v in layer.params.items() if k in layer.grads}
+    for k, v in layer.params.items():
+        if k not in ps:
+            ps[k] = v.clone()
+    yr = ref_fn(xs, ps)
+    assert y.shape == yr.shape
+    torch.testing.assert_close(y, yr.detach(), atol=atol, rtol=rtol)
+    wanted = [xs] if xs.requires_grad else []
+    names = [k for k in ps if ps[k].requires_grad]
+    gs = torch.autograd.grad(yr, wanted + [ps[k] for k in names], dy, allow_unused=True)
+    if xs.requires_grad and dx is not None:
+        torch.testing.assert_close(dx, gs[0], atol=atol, rtol=rtol)
+    for k, g in zip(names, gs[len(wanted):]):
+        if g is None:
+            continue
+        torch.testing.assert_close(layer.grads[k], g, atol=atol, rtol=rtol)
+    return y
+
+
+def _nhwc_conv(x, w, b, stride, pad):
+    y = F.conv2d(x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), b, stride, pad)
+    return y.permute(0, 2, 3, 1)
+
+
+def test_dense_matches_autograd_and_accumulates():
+    l = DenseLayer(12, 7, True, "fc")
+    x = torch.randn(5, 12)
+    _grad_check(l, x, lambda x, p: x @ p["weight"].t() + p["bias"])
+    g1 = l.grads["weight"].clone()
+    l.forward(x, 0)
+    l.backward(torch.zeros(5, 7), 0)
+    torch.testing.assert_close(l.grads["weight"], g1)          # += 0 keeps the accumulated grad
+    l.zero_grads()
+    assert float(l.grads["weight"].abs().sum()) == 0.0
+
+
+def test_dense_init_bounds_and_3d_input():
+    l = DenseLayer(64, 32).init("cpu", seed=1)
+    b = 1 / math.sqrt(64)
+    assert float(l.params["weight"].abs().max()) <= b and float(l.params["bias"].abs().max()) <= b
+    y = l.forward(torch.randn(2, 3, 64), 0)
+    assert y.shape == (2, 3, 32)
+    assert l.backward(torch.randn(2, 3, 32), 0).shape == (2, 3, 64)
+
+
+@pytest.mark.parametrize("k,s,p,cin,cout,hw", [(3, 1, 1, 4, 6, 8), (3, 2, 1, 8, 8, 8), (1, 1, 0, 5, 3, 6),
+                                               (1, 2, 0, 4, 4, 6), (5, 1, 2, 2, 3, 9)])
+def test_conv2d_matches_autograd(k, s, p, cin, cout, hw):
+    l = Conv2DLayer(cin, cout, k, k, s, s, p, p, True, "conv")
+    x = torch.randn(2, hw, hw, cin)
+    y = _grad_check(l, x, lambda x, prm: _nhwc_conv(x, prm["weight"], prm["bias"], s, p), atol=2e-4)
+    assert tuple(y.shape) == l.output_shape(tuple(x.shape))
+
+
+def test_conv2d_anisotropic_generic_path():
+    l = Conv2DLayer(3, 4, 3, 2, 2, 1, 1, 0, True, "conv")
+    x = torch.randn(2, 7, 6, 3)
+    _grad_check(l, x, lambda x, prm: F.conv2d(x.permute(0, 3, 1, 2), prm["weight"].permute(0, 3, 1, 2), prm["bias"],
+                                              (2, 1), (1, 0)).permute(0, 2, 3, 1), atol=2e-4)
+
+
+@pytest.mark.parametrize("relu", [False, True])
+def test_batchnorm_train_semantics(relu):
+    C = 6
+    l = BatchNormLayer(C, 1e-5, 0.1, True, relu, "bn")
+    x = torch.randn(4, 5, 5, C) * 2 + 1
+
+    def ref(x, p):
+        y = F.batch_norm(x.reshape(-1, C), None, None, p["gamma"], p["beta"], True, 0.1, 1e-5).reshape(x.shape)
+        return torch.relu(y) if relu else y
+
+    _grad_check(l, x, ref, atol=2e-4, rtol=1e-3)
+    xf = x.reshape(-1, C)
+    M = xf.shape[0]
+    torch.testing.assert_close(l.params["running_mean"], 0.1 * xf.mean(0), atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(l.params["running_var"], 0.9 + 0.1 * xf.var(0, unbiased=True), atol=1e-5, rtol=1e-5)
+    assert M > 1
+    # inference uses the running statistics
+    l.set_training(False)
+    y = l.forward(x, 0)
+    yr = (x - l.params["running_mean"]) / torch.sqrt(l.params["running_var"] + 1e-5)
+    torch.testing.assert_close(y, torch.relu(yr) if relu else yr, atol=1e-5, rtol=1e-5)
+
+
+def test_batchnorm_running_stats_are_serialised_params():
+    l = BatchNormLayer(4).init("cpu")
+    names = [n for n, _ in l.parameters()]
+    assert any("running_mean" in n for n in names) and any("running_var" in n for n in names)
+    assert "running_mean" not in l.grads
+
+
+@pytest.mark.parametrize("cls,fn", [(MaxPool2DLayer, F.max_pool2d), (AvgPool2DLayer, F.avg_pool2d)])
+@pytest.mark.parametrize("k,s,p", [(2, 2, 0), (3, 2, 1), (3, 1, 1)])
+def test_pooling(cls, fn, k, s, p):
+    l = cls(k, k, s, s, p, p, "pool")
+    x = torch.randn(2, 8, 8, 3)
+    _grad_check(l, x, lambda x, _: fn(x.permute(0, 3, 1, 2), k, s, p).permute(0, 2, 3, 1))
+    assert l.output_shape((2, 8, 8, 3)) == tuple(l.forward(x, 0).shape)
+
+
+@pytest.mark.parametrize("act", ["relu", "leaky_relu", "sigmoid", "tanh", "elu", "gelu", "softmax", "linear"])
+def test_activations(act):
+    ref = {"relu": torch.relu, "leaky_relu": lambda x: F.leaky_relu(x, 0.01), "sigmoid": torch.sigmoid, "tanh": torch.tanh,
+           "elu": F.elu, "gelu": lambda x: F.gelu(x, approximate="tanh"), "softmax": lambda x: torch.softmax(x, -1),
+           "linear": lambda x: x}[act]
+    _grad_check(ActivationLayer(act), torch.randn(3, 4, 5), lambda x, _: ref(x), atol=1e-5)
+
+
+def test_dropout_scaling_and_eval_identity():
+    l = DropoutLayer(0.4).init("cpu", seed=5)
+    x = torch.ones(64, 64)
+    y = l.forward(x, 0)
+    kept = y != 0
+    assert 0.5 < float(kept.float().mean()) < 0.7
+    torch.testing.assert_close(y[kept], torch.full_like(y[kept], 1 / 0.6))
+    dx = l.backward(torch.ones_like(x), 0)
+    torch.testing.assert_close(dx, y)                           # same mask, same scale
+    l.set_training(False)
+    assert torch.equal(l.forward(x, 0), x)
+
+
+def test_layernorm_and_groupnorm():
+    C = 16
+    _grad_check(LayerNormLayer(C), torch.randn(3, 5, C),
+                lambda x, p: F.layer_norm(x, (C,), p["gamma"], p["beta"], 1e-5), atol=2e-4, rtol=1e-3)
+    _grad_check(GroupNormLayer(4, C), torch.randn(2, 4, 4, C),
+                lambda x, p: F.group_norm(x.permute(0, 3, 1, 2), 4, p["gamma"], p["beta"], 1e-5).permute(0, 2, 3, 1),
+                atol=2e-4, rtol=1e-3)
+
+
+def test_embedding_family():
+    e = EmbeddingLayer(20, 8).init("cpu", seed=2)
+    ids = torch.randint(0, 20, (3, 5), dtype=torch.int32)
+    y = e.forward(ids, 0)
+    torch.testing.assert_close(y, e.params["weight"][ids.long()])
+    dy = torch.randn_like(y)
+    e.backward(dy, 0)
+    ref = torch.zeros(20, 8).index_add_(0, ids.long().reshape(-1), dy.reshape(-1, 8))
+    torch.testing.assert_close(e.grads["weight"], ref)
+    # float ids (the reference wire format) are accepted
+    torch.testing.assert_close(e.forward(ids.float(), 1), y)
+    _grad_check(PositionalEmbeddingLayer(8, 10), torch.randn(2, 6, 8), lambda x, p: x + p["weight"][:6])
+    _grad_check(ClassTokenLayer(8), torch.randn(2, 6, 8),
+                lambda x, p: torch.cat([p["token"].reshape(1, 1, -1).expand(2, 1, -1), x], 1))
+
+
+def test_shape_layers():
+    _grad_check(FlattenLayer(1), torch.randn(2, 3, 4, 5), lambda x, _: x.flatten(1))
+    _grad_check(SliceLayer(1, 2, 3), torch.randn(2, 8, 4), lambda x, _: x[:, 2:5])
+    _grad_check(TransposeLayer(), torch.randn(2, 3, 5), lambda x, _: x.transpose(1, 2))
+
+
+def test_nary_and_broadcast():
+    a, b, c = torch.randn(2, 3), torch.randn(2, 3), torch.randn(2, 3)
+    assert torch.allclose(AddLayer().forward([a, b, c], 0), a + b + c)
+    assert torch.allclose(SubLayer().forward([a, b], 0), a - b)
+    m = MulLayer()
+    assert torch.allclose(m.forward([a, b], 0), a * b)
+    ga, gb = m.backward(torch.ones(2, 3), 0)
+    assert torch.allclose(ga, b) and torch.allclose(gb, a)
+    bc = MBroadcastLayer(3)
+    outs = bc.forward(a, 0)
+    assert len(outs) == 3
+    assert torch.allclose(bc.backward([a, b, c], 0), a + b + c)
+
+
+def test_residual_block_variants():
+    for act in ("relu", "linear"):
+        main = Sequential([Conv2DLayer(4, 4, 3, 3, 1, 1, 1, 1, False, "c1"), BatchNormLayer(4, use_relu=True, name="b1"),
+                           Conv2DLayer(4, 4, 3, 3, 1, 1, 1, 1, False, "c2")], "main")
+        blk = ResidualBlock(main, None, act, "res")
+        blk.init("cpu", seed=11)
+        x = torch.randn(2, 6, 6, 4)
+        y = blk.forward(x, 0)
+        dy = torch.randn_like(y)
+        dx = blk.backward(dy, 0)
+        xs = x.clone().requires_grad_(True)
+        w1, w2 = main.layers[0].params["weight"], main.layers[2].params["weight"]
+        h = _nhwc_conv(xs, w1, None, 1, 1)
+        h = torch.relu(F.batch_norm(h.reshape(-1, 4), None, None, main.layers[1].params["gamma"],
+                                    main.layers[1].params["beta"], True).reshape(h.shape))
+        yr = _nhwc_conv(h, w2, None, 1, 1) + xs
+        yr = torch.relu(yr) if act == "relu" else yr
+        torch.testing.assert_close(y, yr.detach(), atol=2e-4, rtol=1e-3)
+        (gx,) = torch.autograd.grad(yr, xs, dy)
+        torch.testing.assert_close(dx, gx, atol=5e-4, rtol=1e-3)
+
+
+def test_residual_block_with_projection_shortcut():
+    main = Sequential([BatchNormLayer(4, use_relu=True, name="b"), Conv2DLayer(4, 8, 3, 3, 2, 2, 1, 1, True, "c")], "main")
+    sc = Sequential([Conv2DLayer(4, 8, 1, 1, 2, 2, 0, 0, False, "p")], "sc")
+    blk = ResidualBlock(main, sc, "linear", "res").init("cpu", seed=4)
+    x = torch.randn(2, 8, 8, 4)
+    y = blk.forward(x, 0)
+    assert y.shape == (2, 4, 4, 8) == blk.output_shape((2, 8, 8, 4))
+    dx = blk.backward(torch.randn_like(y), 0)
+    assert dx.shape == x.shape and torch.isfinite(dx).all()
+    cfg = blk.get_config()
+    blk2 = LayerFactory.create(cfg.to_json())
+    assert blk2.get_config() == cfg
+
+
+def test_msequential_orders_branches_and_sums_grads():
+    s1 = Sequential([DenseLayer(6, 6, name="a")], "s1")
+    s2 = Sequential([DenseLayer(6, 6, name="b"), ActivationLayer("tanh")], "s2")
+    ms = MSequential([s1, s2], AddLayer("join"), "ms").init("cpu", seed=8)
+    x = torch.randn(3, 6)
+    y = ms.forward(x, 0)
+    ref = s1.forward(x, 1) + s2.forward(x, 1)
+    torch.testing.assert_close(y, ref)
+    assert ms._order is not None and sorted(ms._order) == [0, 1]
+    dx = ms.backward(torch.ones_like(y), 0)
+    assert dx.shape == x.shape
+    assert LayerFactory.create(ms.get_config().to_json()).get_config() == ms.get_config()
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_attention_block_matches_torch(causal):
+    E, H, B, L = 16, 4, 2, 6
+    blk = AttentionBlock(E, H, causal, "attn")
+    x = torch.randn(B, L, E)
+
+    def ref(x, p):
+        qkv = (x.reshape(B * L, E) @ p["qkv_weight"].t() + p["qkv_bias"]).reshape(B, L, 3, H, E // H)
+        q, k, v = (qkv[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+        o = F.scaled_dot_product_attention(q, k, v, is_causal=causal)
+        o = o.permute(0, 2, 1, 3).reshape(B * L, E)
+        return (o @ p["out_weight"].t() + p["out_bias"]).reshape(B, L, E)
+
+    _grad_check(blk, x, ref, atol=5e-4, rtol=1e-3)
+
+
+def test_every_registered_type_round_trips_through_the_factory():
+    names = LayerFactory.available()
+    for required in ["dense", "conv2d", "batchnorm", "maxpool2d", "avgpool2d", "groupnorm", "layer_norm", "dropout",
+                     "flatten", "activation", "embedding", "pos_embedding", "class_token", "slice", "transpose",
+                     "identity", "add", "sub", "mul", "mbroadcast", "sdpa", "sequential", "msequential",
+                     "residual_block", "attention_block", "flash_attention_block", "legacy_dense", "legacy_conv2d",
+                     "legacy_maxpool2d", "legacy_avgpool2d", "legacy_batchnorm"]:
+        assert required in names, required
+    samples = [DenseLayer(3, 4, False, "d"), Conv2DLayer(3, 4, 3, 3, 2, 2, 1, 1, True, "c"), BatchNormLayer(4, 1e-3, 0.2, True, True, "b"),
+               MaxPool2DLayer(2, 2, name="m"), AvgPool2DLayer(3, 3, 2, 2, 1, 1, "a"), GroupNormLayer(2, 4, name="g"),
+               LayerNormLayer(8, name="l"), DropoutLayer(0.3, "dr"), FlattenLayer(1, -1, "f"), ActivationLayer("gelu", "act"),
+               EmbeddingLayer(10, 4, name="e"), PositionalEmbeddingLayer(4, 9, "p"), ClassTokenLayer(4, "ct"),
+               SliceLayer(1, 0, 2, "s"), AttentionBlock(8, 2, True, "at")]
+    for l in samples:
+        cfg = l.get_config()
+        again = LayerFactory.create(TConfig.from_json(cfg.to_json()))
+        assert type(again) is type(l) and again.get_config() == cfg
+
+
+def test_legacy_nchw_facades_match_nhwc_layers():
+    conv = LayerFactory.create(TConfig("lc", "legacy_conv2d", in_channels=3, out_channels=5, kernel_h=3, kernel_w=3,
+                                       stride_h=1, stride_w=1, pad_h=1, pad_w=1, use_bias=True)).init("cpu", seed=9)
+    x = torch.randn(2, 3, 7, 7)
+    y = conv.forward(x, 0)
+    assert y.shape == (2, 5, 7, 7) == conv.output_shape((2, 3, 7, 7))
+    w = conv.inner.params["weight"].permute(0, 3, 1, 2)
+    torch.testing.assert_close(y, F.conv2d(x, w, conv.inner.params["bias"], 1, 1), atol=1e-4, rtol=1e-4)
+    dx = conv.backward(torch.ones_like(y), 0)
+    assert dx.shape == x.shape
+    pool = LayerFactory.create(TConfig("lp", "legacy_maxpool2d", pool_h=2, pool_w=2)).init("cpu")
+    torch.testing.assert_close(pool.forward(x, 0), F.max_pool2d(x, 2))
+
+
+def test_builder_shape_inference_and_blocks():
+    b = LayerBuilder([32, 32, 3])
+    b.conv2d(16, 3, 3, 1, 1, 1, 1).batchnorm(use_relu=True).wide_residual_block(16, 32, 2, 0.3).basic_residual_block(32, 32, 1)
+    b.maxpool2d(2, 2).avgpool2d(8, 8).flatten().dense(10)
+    assert_shape = b.get_batchless_current_shape()
+    layers = b.build()
+    assert assert_shape == [[10]]
+    #_current_shape() == [[10]]
+    seq = Sequential(layers, "m").init("cpu", seed=1)
+    y = seq.forward(torch.randn(2, 32, 32, 3), 0)
+    assert y.shape == (2, 10)
+    assert seq.output_shape((2, 32, 32, 3)) == (2, 10)
+    dx = seq.backward(torch.randn(2, 10), 0)
+    assert dx.shape == (2, 32, 32, 3)
+
+
+def test_microbatch_caches_are_independent():
+    l = DenseLayer(4, 4).init("cpu", seed=0)
+    x0, x1 = torch.randn(2, 4), torch.randn(2, 4)
+    l.forward(x0, 0)
+    l.forward(x1, 1)
+    g = torch.ones(2, 4)
+    l.backward(g, 1)
+    w1 = l.grads["weight"].clone()
+    torch.testing.assert_close(w1, g.t() @ x1)
+    l.backward(g, 0)
+    torch.testing.assert_close(l.grads["weight"], w1 + g.t() @ x0)
+    assert not l._cache

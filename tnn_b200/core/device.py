@@ -163,6 +163,7 @@ class DELAllocator:
             device = Device(DeviceType.GPU, d.index or 0) if d.type == "cuda" else Device(DeviceType.CPU, 0)
         self.device = device
         self._core = native.require().DELAllocator(slab_bytes, align)
+        self._align = int(align)
         self._slabs: list[torch.Tensor] = []
         self._live: dict[int, tuple[int, int]] = {}
 
@@ -172,7 +173,10 @@ class DELAllocator:
 
     def _back(self):
         while len(self._slabs) < self._core.num_slabs():
-            self._slabs.append(self.device.allocate(self._core.slab_size(len(self._slabs))))
+            n = self._core.slab_size(len(self._slabs))
+            raw = self.device.allocate(n + self._align)           # base aligned so offsets stay aligned
+            skew = (-raw.data_ptr()) % self._align
+            self._slabs.append(raw[skew:skew + n])
 
     def allocate(self, shape, dtype=torch.float32) -> torch.Tensor:
         n = int(math.prod(shape)) if len(shape) else 1

@@ -126,6 +126,9 @@ class CIFAR10DataLoader(RecordImageLoader):
         super().__init__(3, 32, 32, 1)
 
     def load_data(self, path: str, train: bool = True):
+        sub = os.path.join(path, "cifar-10-batches-bin")       # layout of the official archive
+        if os.path.isdir(sub):
+            path = sub
         files = sorted(glob.glob(os.path.join(path, "data_batch_*.bin"))) if train else [os.path.join(path, "test_batch.bin")]
         if os.path.isfile(path):
             files = [path]
@@ -144,6 +147,9 @@ class CIFAR100DataLoader(RecordImageLoader):
         super().__init__(3, 32, 32, 2)
 
     def load_data(self, path: str, train: bool = True):
+        sub = os.path.join(path, "cifar-100-binary")
+        if os.path.isdir(sub):
+            path = sub
         f = path if os.path.isfile(path) else os.path.join(path, "train.bin" if train else "test.bin")
         if not os.path.exists(f):
             raise FileNotFoundError(f)
