@@ -12,6 +12,7 @@
 #include "allocator.hpp"
 #include "archiver.hpp"
 #include "data_loader.hpp"
+#include "tcp_bus.hpp"
 #include "tokenizer.hpp"
 
 namespace py = pybind11;
@@ -188,6 +189,46 @@ void runtime_bind(py::module_& m) {
       });
   m.attr("PACKET_HEADER_BYTES") = (int)PacketHeader::kBytes;
   m.def("host_is_little_endian", &host_is_little_endian);
+
+  // ---------------------------------------------------------------- TCP message bus
+  py::class_<TcpBus>(m, "TcpBus")
+      .def(py::init<int, int, size_t>(), py::arg("listen_port"), py::arg("sockets_per_peer") = 4,
+           py::arg("max_packet") = (size_t)(4u << 20))
+      .def("start", &TcpBus::start)
+      .def("stop", [](TcpBus& b) { py::gil_scoped_release rel; b.stop(); })
+      .def("port", &TcpBus::port)
+      .def("connect", [](TcpBus& b, const std::string& host, int port, int timeout_ms) {
+        py::gil_scoped_release rel;
+        b.connect(host, port, timeout_ms);
+      }, py::arg("host"), py::arg("port"), py::arg("timeout_ms") = 10000)
+      .def("has_peer", &TcpBus::has_peer)
+      .def("peers", &TcpBus::peers)
+      .def("send", [](TcpBus& b, const std::string& key, const py::bytes& msg) {
+        std::string s = msg;
+        py::gil_scoped_release rel;
+        b.send(key, reinterpret_cast<const uint8_t*>(s.data()), s.size());
+      })
+      .def("recv", [](TcpBus& b, int timeout_ms) -> py::object {
+        std::string from;
+        std::vector<uint8_t> msg;
+        bool ok;
+        {
+          py::gil_scoped_release rel;
+          ok = b.recv(timeout_ms, &from, &msg);
+        }
+        if (!ok) return py::none();
+        return py::make_tuple(from, py::bytes(reinterpret_cast<const char*>(msg.data()), msg.size()));
+      }, py::arg("timeout_ms") = -1)
+      .def("stats", [](const TcpBus& b) {
+        auto s = b.stats();
+        py::dict d;
+        d["bytes_sent"] = s.bytes_sent;
+        d["bytes_received"] = s.bytes_received;
+        d["messages_sent"] = s.messages_sent;
+        d["messages_received"] = s.messages_received;
+        d["packets_sent"] = s.packets_sent;
+        return d;
+      });
 
   // ---------------------------------------------------------------- allocators
   py::class_<DELAllocator>(m, "DELAllocator")

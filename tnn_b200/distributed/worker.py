@@ -1,0 +1,218 @@
+"""Pipeline-stage worker: a blocking event loop that executes coordinator commands.
+
+Reference: include/distributed/worker.hpp:41-346 (event loop :64-89, set_config :98-130,
+FORWARD_JOB :145-167, BACKWARD_JOB :168-193, UPDATE_PARAMETERS :194-207, profiling :226-236,
+SAVE_TO_FILE :287-304, ERROR_REPORT :317-328).  Commands the reference declares but leaves as
+``throw "Not implemented"`` (HEALTH_CHECK, STATUS_REQUEST, LOAD_PARAMS, SEND_PARAMS,
+CHECKPOINT_REQUEST, BARRIER_SYNC, REPORT_LOAD) are implemented here.
+"""
+from __future__ import annotations
+
+import json
+import threading
+import time
+import traceback
+
+import torch
+
+from ..core.config import TConfig
+from ..nn.graph import Graph, graph_from_sequential
+from ..nn.layer import LayerFactory
+from ..nn.optimizers import OptimizerFactory
+from ..nn.schedulers import SchedulerFactory
+from ..utils.profiler import EventType, GlobalProfiler, Profiler
+from .communicator import Communicator, InProcessCommunicator, TCPCommunicator
+from .message import CommandType, Endpoint, Job, Message, StageConfig
+
+
+class Worker:
+    def __init__(self, communicator: Communicator, device="cpu", name: str = "worker"):
+        self.comm = communicator
+        self.comm._owner = self
+        self.device = torch.device(device)
+        self.name = name
+        self.graph: Graph | None = None
+        self.model = None
+        self.optimizer = None
+        self.scheduler = None
+        self.config: StageConfig | None = None
+        self.next_ep = self.prev_ep = self.coord_ep = Endpoint("NONE")
+        self.should_stop = False
+        self.training = True
+        self._thread: threading.Thread | None = None
+        self.stage_id = -1
+        self._busy_ns = 0
+        self._jobs = 0
+        self.fault_inject = None          # callable(Message) -> None; tests use it to drop / delay / raise
+
+    # ------------------------------------------------------------------ lifecycle
+    def start(self, background: bool = False):
+        self.comm.start()
+        if background:
+            self._thread = threading.Thread(target=self.run, name=f"{self.name}-loop", daemon=True)
+            self._thread.start()
+            return self
+        self.run()
+        return self
+
+    def run(self):
+        while not self.should_stop:
+            msg = self.comm.dequeue_input_message(timeout=0.25)
+            if msg is None:
+                continue
+            try:
+                if self.fault_inject is not None:
+                    self.fault_inject(msg)
+                self.process_message(msg)
+            except Exception as e:  # noqa: BLE001
+                err = f"[{self.name} stage {self.stage_id}] {type(e).__name__}: {e}\n{traceback.format_exc(limit=4)}"
+                if self.coord_ep:
+                    try:
+                        self.comm.send_message(Message(CommandType.ERROR_REPORT, err), self.coord_ep)
+                    except Exception:  # noqa: BLE001
+                        pass
+
+    def stop(self):
+        self.should_stop = True
+        if self._thread is not None:
+            self._thread.join(timeout=3)
+        self.comm.stop()
+
+    # ------------------------------------------------------------------ configuration
+    def set_config(self, cfg: StageConfig):
+        self.config = cfg
+        self.stage_id = cfg.stage_id
+        if cfg.device:
+            self.device = torch.device(cfg.device)
+        seq = LayerFactory.create(TConfig.from_json(cfg.model_config))
+        self.model = seq
+        self.graph = graph_from_sequential(seq, self.device, cfg.seed, name=f"stage{cfg.stage_id}")
+        self.graph.set_training(True)
+        if cfg.optimizer_config:
+            self.optimizer = OptimizerFactory.create_from_config(cfg.optimizer_config)
+            self.optimizer.attach(self.graph.context())
+        if cfg.scheduler_config and self.optimizer is not None:
+            self.scheduler = SchedulerFactory.create_from_config(cfg.scheduler_config, self.optimizer)
+        self.coord_ep, self.next_ep, self.prev_ep = cfg.coordinator_endpoint, cfg.next_stage_endpoint, cfg.prev_stage_endpoint
+        for ep in (self.coord_ep, self.next_ep, self.prev_ep):
+            if ep and ep.type != Endpoint.IN_PROCESS:
+                self.comm.connect(ep)
+
+    # ------------------------------------------------------------------ dispatch
+    def _reply(self, cmd: CommandType, payload=None, to: Endpoint | None = None):
+        self.comm.send_message(Message(cmd, payload), to or self.coord_ep)
+
+    def process_message(self, msg: Message):
+        c = msg.command_type
+        if c == CommandType.FORWARD_JOB:
+            job: Job = msg.get(Job)
+            t0 = Profiler.now_ns()
+            x = job.data.to(self.device, non_blocking=True) if job.data.device != self.device else job.data
+            y = self.model.forward(x, job.mb_id)
+            GlobalProfiler.add_event(EventType.COMPUTE, t0, Profiler.now_ns(), f"forward mb {job.mb_id}", self.name)
+            self._busy_ns += Profiler.now_ns() - t0
+            self._jobs += 1
+            self._reply(CommandType.FORWARD_JOB, Job(y, job.mb_id), self.next_ep if self.next_ep else self.coord_ep)
+        elif c == CommandType.BACKWARD_JOB:
+            job = msg.get(Job)
+            t0 = Profiler.now_ns()
+            g = job.data.to(self.device, non_blocking=True) if job.data.device != self.device else job.data
+            dx = self.model.backward(g, job.mb_id)
+            GlobalProfiler.add_event(EventType.COMPUTE, t0, Profiler.now_ns(), f"backward mb {job.mb_id}", self.name)
+            self._busy_ns += Profiler.now_ns() - t0
+            if self.prev_ep and dx is not None:
+                self._reply(CommandType.BACKWARD_JOB, Job(dx, job.mb_id), self.prev_ep)
+            else:
+                self._reply(CommandType.BACKWARD_COMPLETE, None)
+        elif c == CommandType.UPDATE_PARAMETERS:
+            t0 = Profiler.now_ns()
+            if self.optimizer is not None:
+                self.optimizer.update()
+                self.optimizer.zero_grads()
+                if self.scheduler is not None:
+                    self.scheduler.step()
+            GlobalProfiler.add_event(EventType.COMPUTE, t0, Profiler.now_ns(), "update", self.name)
+            self._reply(CommandType.PARAMETERS_UPDATED, True)
+        elif c == CommandType.TRAIN_MODE:
+            self.training = True
+            if self.graph is not None:
+                self.graph.set_training(True)
+        elif c == CommandType.EVAL_MODE:
+            self.training = False
+            if self.graph is not None:
+                self.graph.set_training(False)
+        elif c == CommandType.CONFIG_TRANSFER:
+            self.set_config(msg.get(StageConfig))
+            self._reply(CommandType.CONFIG_RECEIVED, True)
+        elif c == CommandType.SHUTDOWN:
+            self.should_stop = True
+        elif c == CommandType.START_PROFILING:
+            GlobalProfiler.get_profiler().clear()
+            GlobalProfiler.init_start_time()
+            self._reply(CommandType.PROFILING_STARTED, True)
+        elif c == CommandType.REPORT_PROFILING:
+            self._reply(CommandType.PROFILING_REPORTED, GlobalProfiler.get_profiler())
+        elif c == CommandType.CLEAR_PROFILING:
+            GlobalProfiler.get_profiler().clear()
+            self._reply(CommandType.PROFILING_CLEARED, True)
+        elif c == CommandType.PRINT_PROFILING:
+            for e in GlobalProfiler.get_profiler().events():
+                print(f"[{self.name}] {e['type']} {e['name']} {(e['end_ns'] - e['start_ns']) / 1e6:.3f} ms")
+            self._reply(CommandType.PROFILING_PRINTED, True)
+        elif c == CommandType.SAVE_TO_FILE:
+            path = msg.get(str)
+            self.graph.save_state(path + f".stage{self.stage_id}" if not path.endswith(f".stage{self.stage_id}") else path)
+        elif c == CommandType.LOAD_PARAMS:
+            path = msg.get(str)
+            with open(path, "rb") as f:
+                data = f.read()
+            _, end = json.JSONDecoder().raw_decode(data.decode("latin-1"))
+            import io
+            self.graph.load_state_tensors(io.BytesIO(data[end:]))
+            self._reply(CommandType.PARAMS_LOADED, True)
+        elif c == CommandType.SEND_PARAMS:
+            self._reply(CommandType.PARAMS_TRANSFER, Job(self.graph.ctx.param_slab.detach().clone(), self.stage_id))
+        elif c == CommandType.PARAMS_TRANSFER:
+            job = msg.get(Job)
+            self.graph.ctx.param_slab.copy_(job.data.to(self.device))
+            self.graph.ctx.refresh_lp()
+            self._reply(CommandType.PARAMS_LOADED, True)
+        elif c in (CommandType.HEALTH_CHECK, CommandType.STATUS_REQUEST):
+            status = {"name": self.name, "stage": self.stage_id, "configured": self.graph is not None, "training": self.training,
+                      "jobs": self._jobs, "device": str(self.device), "time": time.time()}
+            self._reply(CommandType.STATUS_RESPONSE, json.dumps(status))
+        elif c == CommandType.CHECKPOINT_REQUEST:
+            path = msg.get(str)
+            from ..nn.train import save_checkpoint
+            save_checkpoint(self.graph, f"{path}.stage{self.stage_id}", self.optimizer, self.scheduler,
+                            self.optimizer.step_count if self.optimizer else 0)
+            self._reply(CommandType.CHECKPOINT_COMPLETE, f"{path}.stage{self.stage_id}")
+        elif c == CommandType.BARRIER_SYNC:
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
+            self._reply(CommandType.BARRIER_SYNC, True)
+        elif c == CommandType.REPORT_LOAD:
+            avg_ms = self._busy_ns / 1e6 / max(1, self._jobs)
+            self._reply(CommandType.LOAD_REPORT, json.dumps({"stage": self.stage_id, "avg_forward_backward_ms": avg_ms,
+                                                             "jobs": self._jobs}))
+        elif c == CommandType.HANDSHAKE:
+            self._reply(CommandType.HANDSHAKE_ACK, self.name, Endpoint.from_json(json.loads(msg.get(str))) if msg.has_type(str) else None)
+        else:
+            raise NotImplementedError(f"worker does not handle {c.name}")
+
+
+class InProcessWorker(Worker):
+    def __init__(self, device="cpu", name="local-worker"):
+        super().__init__(InProcessCommunicator(name), device, name)
+
+
+class TCPWorker(Worker):
+    """``tcp_worker <port> [--gpu]`` of the reference (examples/tcp_worker.cpp:121-141)."""
+
+    def __init__(self, host="127.0.0.1", port=0, use_gpu=False, gpu_index=0, io_threads=4, name=None):
+        dev = torch.device("cuda", gpu_index) if use_gpu and torch.cuda.is_available() else torch.device("cpu")
+        comm = TCPCommunicator(host, port, io_threads, device=dev, name=name or f"tcp-worker-{port}")
+        super().__init__(comm, dev, name or f"tcp-worker-{port}")
+
+
+RoCEWorker = TCPWorker
