@@ -328,3 +328,43 @@ def test_data_parallel_mode_averages_replica_gradients():
         co.stop()
         for w in workers:
             w.stop()
+
+
+# ------------------------------------------------------------------------------- NCCL-style 1F1B engine (gloo on CPU)
+def _pp_rank(rank, world, port, seed, M, out_q):
+    import torch.distributed as dist
+    torch.set_num_threads(1)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tnn_b200.parallel.pipeline import PipelineParallel
+    batches = _batches(3)
+    B = batches[0][0].shape[0]
+    pp = PipelineParallel(_model(), NaivePipelinePartitioner([1] * world), OptimizerFactory.create_sgd(0.05, 0.9),
+                          LossFactory.create_logsoftmax_crossentropy(), M, (B // M, 8, 8, 4), "cpu", seed=seed)
+    losses = []
+    for x, y in batches:
+        st = pp.broadcast_stats(pp.train_batch(x, y))
+        losses.append(float(st[0]))
+    if rank == 0:
+        out_q.put((losses, pp.p2p_bytes))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,M", [(2, 2), (3, 4)])
+def test_1f1b_pipeline_engine_equals_single_device(world, M):
+    seed = 4242
+    ref, _ = _reference_losses(_batches(3), M, seed)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 21000 + (os.getpid() % 10000) + world
+    procs = [ctx.Process(target=_pp_rank, args=(r, world, port, seed, M, q), daemon=True) for r in range(world)]
+    for p in procs:
+        p.start()
+    losses, nbytes = q.get(timeout=120)
+    for p in procs:
+        p.join(30)
+    for a, b in zip(ref, losses):
+        assert abs(a - b) < 1e-5, (ref, losses)
+    assert nbytes > 0

@@ -1,0 +1,179 @@
+"""Pipeline parallelism over NCCL p2p: one process per GPU (torchrun), one stage per rank, 1F1B.
+
+This is the B200-native replacement for the reference's data path between pipeline stages
+(serialise -> TCP/RoCE -> deserialise on every hop): activations and their
+gradients move device-to-device with ``ncclSend/ncclRecv`` (``torch.distributed`` p2p, backend
+``nccl``; ``gloo`` in the CPU tests), shapes and dtypes are static per schedule so no metadata
+travels, and the receive for the next microbatch is posted before the current one is computed so
+the NVLink transfer overlaps compute.  The schedule is non-interleaved 1F1B (the reference
+injects all forwards first -- GPipe with eager backward, coordinator.hpp:165-223 -- which holds
+M microbatches of activations on stage 0; 1F1B holds at most S - rank).
+
+The model is split by a ``Partitioner`` exactly as the coordinator does (fresh layers from
+config, per-stage seed => identical initial weights to the single-device model), every stage
+owns its optimizer (worker.hpp:194-207) and the last stage computes loss and gradient scaled
+by 1/M (coordinator.hpp:198,206).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from ..nn.blocks import Sequential
+from ..nn.graph import Graph, graph_from_sequential
+from ..nn.loss import Loss
+from ..nn.optimizers import Optimizer, OptimizerFactory
+from .partitioner import Partitioner, flatten_pipeline_layers
+
+
+class PipelineParallel:
+    def __init__(self, model: Sequential, partitioner: Partitioner, optimizer: Optimizer, criterion: Loss,
+                 num_microbatches: int, microbatch_shape: tuple, device, seed: int = 123456, group=None,
+                 scheduler_factory=None):
+        assert dist.is_initialized(), "init torch.distributed first (nccl on GPUs, gloo on CPU)"
+        self.group = group or dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self.device = torch.device(device)
+        self.M = int(num_microbatches)
+        self.criterion = criterion
+        layers = flatten_pipeline_layers(model)
+        self.partitions = partitioner.partition_model(layers)
+        if len(self.partitions) != self.world:
+            raise ValueError(f"{len(self.partitions)} partitions for world size {self.world}")
+        part = self.partitions[self.rank]
+        mine = Partitioner.split(layers, [part], fresh=True)[0]
+        self.stage = Sequential(mine, f"stage_{self.rank}")
+        self.graph: Graph = graph_from_sequential(self.stage, self.device, seed, name=f"stage{self.rank}")
+        self.optimizer = OptimizerFactory.create_from_config(optimizer.get_config())
+        self.optimizer.attach(self.graph.context())
+        self.scheduler = scheduler_factory(self.optimizer) if scheduler_factory else None
+        # static boundary shapes for this microbatch size
+        s = tuple(microbatch_shape)
+        self.in_shape = self.out_shape = None
+        for i, p in enumerate(self.partitions):
+            if i == self.rank:
+                self.in_shape = s
+            for l in layers[p.start_offset:p.end]:
+                s = tuple(l.output_shape(s))
+            if i == self.rank:
+                self.out_shape = s
+        self.act_dtype = torch.bfloat16 if self.device.type == "cuda" else torch.float32
+        self.is_first, self.is_last = self.rank == 0, self.rank == self.world - 1
+        self.prev, self.next = self.rank - 1, self.rank + 1
+        self.steps = 0
+        self.p2p_bytes = 0
+
+    # ------------------------------------------------------------------ p2p helpers
+    def _ops(self, send_next=None, send_prev=None, recv_prev=False, recv_next=False):
+        ops, rp, rn = [], None, None
+        if send_prev is not None:
+            ops.append(dist.P2POp(dist.isend, send_prev, self.prev, self.group))
+        if recv_prev:
+            rp = torch.empty(self.in_shape, dtype=self.act_dtype, device=self.device)
+            ops.append(dist.P2POp(dist.irecv, rp, self.prev, self.group))
+        if send_next is not None:
+            ops.append(dist.P2POp(dist.isend, send_next, self.next, self.group))
+        if recv_next:
+            rn = torch.empty(self.out_shape, dtype=self.act_dtype, device=self.device)
+            ops.append(dist.P2POp(dist.irecv, rn, self.next, self.group))
+        if ops:
+            for t in (send_next, send_prev):
+                if t is not None:
+                    self.p2p_bytes += t.numel() * t.element_size()
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()          # NCCL: orders the CURRENT stream after the transfer; the host does not block
+        return rp, rn
+
+    def _boundary(self, t: torch.Tensor) -> torch.Tensor:
+        return t.to(self.act_dtype).contiguous()
+
+    # ------------------------------------------------------------------ one microbatch of work
+    def _forward(self, x, mb, labels, stats):
+        y = self.stage.forward(x, mb)
+        if self.is_last:
+            st, grad = self.criterion.loss_and_grad(y, labels[mb], scale=1.0 / self.M)
+            stats += st.to(stats.dtype) * torch.tensor([1.0 / self.M, 1.0], device=stats.device, dtype=stats.dtype)
+            return grad
+        return self._boundary(y)
+
+    def _backward(self, g, mb):
+        dx = self.stage.backward(g, mb)
+        return None if (self.is_first or dx is None) else self._boundary(dx)
+
+    # ------------------------------------------------------------------ schedule
+    def train_batch(self, x: torch.Tensor | None, y: torch.Tensor | None, update: bool = True) -> torch.Tensor:
+        """1F1B over ``M`` microbatches.  ``x`` is consumed on the first stage, ``y`` on the last.
+        Returns the device tensor [mean loss, #correct] (meaningful on the last stage)."""
+        M, S, r = self.M, self.world, self.rank
+        xs = list(torch.tensor_split(x.to(self.device, non_blocking=True), M, 0)) if self.is_first else None
+        ys = list(torch.tensor_split(y.to(self.device, non_blocking=True), M, 0)) if self.is_last else None
+        stats = torch.zeros(2, dtype=torch.float32, device=self.device)
+        warm = min(S - r - 1, M)
+        remaining = M - warm
+        pending = []                      # forward results waiting for their backward (last stage: grads)
+        fwd_i = bwd_i = 0
+
+        def next_input(recv):
+            return xs[fwd_i] if self.is_first else recv
+
+        # warm-up forwards
+        for _ in range(warm):
+            inp, _ = self._ops(recv_prev=not self.is_first)
+            out = self._forward(next_input(inp), fwd_i, ys, stats)
+            fwd_i += 1
+            self._ops(send_next=out)
+        inp = None
+        if remaining > 0 and not self.is_first:
+            inp, _ = self._ops(recv_prev=True)
+        # steady state: one forward, one backward
+        for k in range(remaining):
+            out = self._forward(next_input(inp), fwd_i, ys, stats)
+            fwd_i += 1
+            if self.is_last:
+                gout = out
+            else:
+                _, gout = self._ops(send_next=out, recv_next=True)
+            gin = self._backward(gout, bwd_i)
+            bwd_i += 1
+            last = k == remaining - 1
+            if self.is_first:
+                inp = None
+            elif last:
+                self._ops(send_prev=gin)
+                inp = None
+            else:
+                inp, _ = self._ops(send_prev=gin, recv_prev=True)
+        # cool-down backwards
+        for _ in range(warm):
+            _, gout = self._ops(recv_next=True)
+            gin = self._backward(gout, bwd_i)
+            bwd_i += 1
+            if not self.is_first:
+                self._ops(send_prev=gin)
+        if update:
+            self.optimizer.update()
+            self.optimizer.zero_grads()
+            if self.scheduler is not None:
+                self.scheduler.step()
+        self.steps += 1
+        return stats
+
+    def eval_batch(self, x, y):
+        self.graph.set_training(False)
+        inp, _ = self._ops(recv_prev=not self.is_first)
+        out = self.stage.forward(x.to(self.device) if self.is_first else inp, 0)
+        stats = torch.zeros(2, dtype=torch.float32, device=self.device)
+        if self.is_last:
+            st, _ = self.criterion.loss_and_grad(out, y.to(self.device), want_grad=False)
+            stats += st
+        else:
+            self._ops(send_next=self._boundary(out))
+        self.graph.set_training(True)
+        return stats
+
+    def broadcast_stats(self, stats: torch.Tensor) -> torch.Tensor:
+        """Make the last stage's [loss, corrects] visible on every rank."""
+        s = stats.clone()
+        dist.broadcast(s, self.world - 1, group=self.group)
+        return s
