@@ -122,3 +122,42 @@ def test_conv_residual_relu_epilogue():
     y = conv.conv2d_fwd(plan, x, w, w.bfloat16(), None, residual=res, act="relu")
     ref = torch.relu(conv.conv2d_fwd_ref(x, w, None, 1, 1) + res.float())
     assert _rel_err(y, ref) < 1e-2
+
+
+# ----------------------------------------------------------------------------- attention (tcgen05 flash fwd + decode)
+@pytest.mark.parametrize("B,L,H,causal", [(2, 128, 2, False), (2, 128, 2, True), (1, 384, 3, True), (2, 200, 4, True),
+                                          (2, 200, 4, False), (1, 1024, 12, True), (3, 72, 1, True)])
+def test_attention_fwd_matches_reference(B, L, H, causal):
+    from tnn_b200.ops import attention as A
+    from tnn_b200.ops import native
+    assert hasattr(native.require(), "attention_fwd")
+    torch.manual_seed(1)
+    qkv = (torch.randn(B, L, 3, H, 64, device=_dev()) * 0.8).bfloat16()
+    o, lse = A.attention_fwd(qkv, causal)
+    oref, lref = A.attention_ref(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], causal)
+    assert o.shape == (B, L, H * 64) and o.dtype == torch.bfloat16
+    assert _rel_err(o.reshape(B, L, H, 64), oref) < 2e-2
+    assert (lse - lref).abs().max().item() < 2e-2
+
+
+def test_attention_kv_cache_prefill_and_decode():
+    from tnn_b200.ops import attention as A
+    torch.manual_seed(2)
+    B, H, Lp, Lmax = 2, 3, 150, 256
+    cache = A.KVCache(B, Lmax, H, 64, _dev(), torch.bfloat16)
+    full = (torch.randn(B, Lp + 5, 3, H, 64, device=_dev()) * 0.7).bfloat16()
+    o, _ = A.attention_fwd(full[:, :Lp], True, kv_cache=cache, pos=0)
+    oref, _ = A.attention_ref(full[:, :Lp, 0], full[:, :Lp, 1], full[:, :Lp, 2], True)
+    assert _rel_err(o.reshape(B, Lp, H, 64), oref) < 2e-2
+    for t in range(5):
+        pos = Lp + t
+        step = full[:, pos:pos + 1]
+        o1, _ = A.attention_fwd(step, True, kv_cache=cache, pos=pos)
+        ref, _ = A.attention_ref(step[:, :, 0], full[:, :pos + 1, 1], full[:, :pos + 1, 2], True, q_offset=pos)
+        assert o1.shape == (B, 1, H * 64)
+        assert _rel_err(o1.reshape(B, 1, H, 64), ref) < 2e-2
+    # chunked prefill continuation (L_q > 1 with an offset) goes through the tensor-core kernel
+    cache2 = A.KVCache(B, Lmax, H, 64, _dev(), torch.bfloat16)
+    A.attention_fwd(full[:, :100], True, kv_cache=cache2, pos=0)
+    o2, _ = A.attention_fwd(full[:, 100:Lp], True, kv_cache=cache2, pos=100)
+    assert _rel_err(o2.reshape(B, Lp - 100, H, 64), oref[:, 100:]) < 2e-2

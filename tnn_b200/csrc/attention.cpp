@@ -1,4 +1,51 @@
-#include <pybind11/pybind11.h>
+// Python bindings of the fused attention kernels.
+#include <ATen/cuda/CUDAContext.h>
+#include <torch/extension.h>
+
+#include "kernels/attention.cuh"
+
+namespace py = pybind11;
+using torch::Tensor;
+
 namespace tnn {
-void attention_bind(pybind11::module_& m) { (void)m; }
+
+static void check_head_view(const Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kBFloat16, name, ": expected a CUDA bf16 tensor");
+  TORCH_CHECK(t.dim() == 4 && t.size(3) == 64 && t.stride(3) == 1 && t.stride(2) == 64, name,
+              ": expected a [B, L, H, 64] view with contiguous heads");
+}
+
+void attention_bind(py::module_& m) {
+  m.def("attention_fwd", [](const Tensor& q, const Tensor& k, const Tensor& v, const Tensor& out,
+                            const std::optional<Tensor>& lse, bool causal, int64_t q_offset) {
+    check_head_view(q, "q");
+    check_head_view(k, "k");
+    check_head_view(v, "v");
+    const int B = (int)q.size(0), Lq = (int)q.size(1), H = (int)q.size(2), Lk = (int)k.size(1);
+    TORCH_CHECK(k.size(0) == B && v.size(0) == B && k.size(2) == H && v.size(2) == H && v.size(1) == Lk, "q/k/v shape mismatch");
+    TORCH_CHECK(out.is_cuda() && out.scalar_type() == torch::kBFloat16 && out.is_contiguous() &&
+                    out.numel() == (int64_t)B * Lq * H * 64, "out must be contiguous bf16 [B, Lq, H*64]");
+    float* lp = nullptr;
+    if (lse.has_value()) {
+      TORCH_CHECK(lse->scalar_type() == torch::kFloat32 && lse->is_contiguous() && lse->numel() == (int64_t)B * H * Lq,
+                  "lse must be contiguous fp32 [B, H, Lq]");
+      lp = lse->data_ptr<float>();
+    }
+    attention_fwd_bf16(q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0), v.data_ptr(),
+                       v.stride(1), v.stride(0), out.data_ptr(), lp, B, H, Lq, Lk, causal ? 1 : 0, (int)q_offset,
+                       at::cuda::getCurrentCUDAStream().stream());
+  });
+  m.def("attention_decode", [](const Tensor& q, const Tensor& kc, const Tensor& vc, const Tensor& out, int64_t len) {
+    TORCH_CHECK(q.is_cuda() && q.scalar_type() == torch::kBFloat16, "q: CUDA bf16");
+    check_head_view(kc, "k cache");
+    check_head_view(vc, "v cache");
+    const int B = (int)kc.size(0), H = (int)kc.size(2);
+    TORCH_CHECK(q.numel() == (int64_t)B * H * 64, "q must hold one token per batch row");
+    TORCH_CHECK(kc.stride(0) == vc.stride(0) && kc.stride(1) == vc.stride(1), "k/v cache strides differ");
+    const int64_t q_batch = q.dim() >= 2 ? q.stride(0) : (int64_t)H * 64;
+    attention_decode_bf16(q.data_ptr(), q_batch, kc.data_ptr(), vc.data_ptr(), kc.stride(1), kc.stride(0), out.data_ptr(),
+                          B, H, (int)len, at::cuda::getCurrentCUDAStream().stream());
+  });
+}
+
 }  // namespace tnn

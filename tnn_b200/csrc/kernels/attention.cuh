@@ -1,0 +1,20 @@
+// Host interface of the fused attention kernels (attention.cu).  All strides are in elements.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace tnn {
+
+// q/k/v: bf16 views [B, L, H, 64] with token stride *_tok and batch stride *_batch (so the packed
+// QKV projection [B, L, 3, H, 64] and the KV cache [B, Lmax, H, 64] are both addressed in place).
+// out: bf16 [B, Lq, H*64]; lse: fp32 [B, H, Lq] or null.  q_offset = absolute position of query 0.
+void attention_fwd_bf16(const void* q, long long q_tok, long long q_batch, const void* k, long long k_tok,
+                        long long k_batch, const void* v, long long v_tok, long long v_batch, void* out,
+                        float* lse, int B, int H, int Lq, int Lk, int causal, int q_offset, cudaStream_t stream);
+
+// Single-token decode: q bf16 [B, H*64] (batch stride q_batch), caches [B, Lmax, H, 64], attends to
+// the first `len` cached positions.  out: bf16 [B, H*64].
+void attention_decode_bf16(const void* q, long long q_batch, const void* kcache, const void* vcache,
+                           long long tok_stride, long long batch_stride, void* out, int B, int H, int len,
+                           cudaStream_t stream);
+
+}  // namespace tnn
