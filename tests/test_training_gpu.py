@@ -44,3 +44,30 @@ def test_loss_decreases_and_checkpoint_roundtrip():
     g2 = Graph.load_state(buf, device="cuda")
     for (n1, p1), (n2, p2) in zip(g.ctx.parameters(), g2.ctx.parameters()):
         assert n1 == n2 and torch.equal(p1, p2)
+
+
+def test_gpt2_engine_cached_decode_matches_full_forward_gpu():
+    """bf16 kernels: KV-cached prefill + decode vs the uncached full forward of the same model."""
+    from tnn_b200.inference import GPT2InferenceEngine
+    from tnn_b200.models.zoo import _gpt2
+    from tnn_b200.nn import graph_from_sequential
+    dev = torch.device("cuda", 0)
+    seq = _gpt2(256, 4, 3, False, "mini_gpt", None, seq_len=320, vocab=1000, dropout=0.1)
+    g = graph_from_sequential(seq, dev, 5, "mini_gpt")
+    eng = GPT2InferenceEngine(g, max_batch=4)
+    gen = torch.Generator().manual_seed(0)
+    ids = torch.randint(0, 1000, (4, 200), generator=gen, dtype=torch.int32).to(dev)
+    nxt, logits = eng.prefill(ids, return_logits=True)
+    full = eng.full_forward_logits(ids)[:, -1, :].float()
+    err = (logits.float()[:, :1000] - full[:, :1000]).abs().max().item()
+    assert err < 0.15 * max(1.0, full.abs().max().item()), err
+    seq_ids = ids
+    tok = nxt
+    agree = 0
+    for _ in range(6):
+        seq_ids = torch.cat([seq_ids, tok.reshape(-1, 1)], 1)
+        tok, lg = eng.decode(tok, return_logits=True)
+        ref = eng.full_forward_logits(seq_ids)[:, -1, :].float()
+        assert (lg.float()[:, :1000] - ref[:, :1000]).abs().max().item() < 0.15 * max(1.0, ref.abs().max().item())
+        agree += int((tok.long() == ref[:, :1000].argmax(-1)).sum())
+    assert agree >= 20                                            # greedy tokens agree (bf16 ties aside)
