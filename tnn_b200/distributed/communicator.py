@@ -14,6 +14,7 @@ IN_PROCESS short-circuit, profile counters), tcp_communicator.hpp, roce_communic
 """
 from __future__ import annotations
 
+import atexit
 import threading
 import time
 from collections import deque
@@ -141,6 +142,8 @@ class TCPCommunicator(Communicator):
         self._running = True
         self._pump = threading.Thread(target=self._receive_loop, name=f"{self.name}-rx", daemon=True)
         self._pump.start()
+        # a daemon thread parked inside the C++ bus (GIL released) must not outlive the interpreter
+        atexit.register(self.stop)
         return self
 
     start_server = start

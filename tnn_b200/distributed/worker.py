@@ -52,7 +52,10 @@ class Worker:
             self._thread = threading.Thread(target=self.run, name=f"{self.name}-loop", daemon=True)
             self._thread.start()
             return self
-        self.run()
+        try:
+            self.run()
+        finally:
+            self.comm.stop()
         return self
 
     def run(self):
