@@ -161,3 +161,46 @@ def test_attention_kv_cache_prefill_and_decode():
     A.attention_fwd(full[:, :100], True, kv_cache=cache2, pos=0)
     o2, _ = A.attention_fwd(full[:, 100:Lp], True, kv_cache=cache2, pos=100)
     assert _rel_err(o2.reshape(B, Lp - 100, H, 64), oref[:, 100:]) < 2e-2
+
+
+# ----------------------------------------------------------------------------- generic tensor op family
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n", [8, 1000, 4099, 1 << 20])
+def test_tensor_op_family_matches_cpu_oracle(dtype, n):
+    from tnn_b200.ops import tensor_ops as ops
+    torch.manual_seed(n)
+    a = torch.randn(n).to(dtype)
+    b = (torch.randn(n).abs() + 0.5).to(dtype)
+    c = torch.randn(n).to(dtype)
+    A, B, Cc = a.to(_dev()), b.to(_dev()), c.to(_dev())
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    for f in (ops.add, ops.sub, ops.mul, ops.div, ops.minimum, ops.maximum, ops.greater):
+        torch.testing.assert_close(f(A, B).cpu().float(), f(a, b).float(), atol=tol, rtol=tol)
+    for f in (ops.sqrt, ops.rsqrt, ops.rcp):
+        torch.testing.assert_close(f(B).cpu().float(), f(b).float(), atol=tol, rtol=tol)
+    torch.testing.assert_close(ops.abs(A).cpu(), a.abs())
+    torch.testing.assert_close(ops.clamp(A, -0.5, 0.5).cpu(), a.clamp(-0.5, 0.5))
+    torch.testing.assert_close(ops.mul_scalar(A, 1.5).cpu().float(), (a.float() * 1.5).to(dtype).float(), atol=tol, rtol=tol)
+    torch.testing.assert_close(ops.fmadd(A, B, Cc).cpu().float(), (a.float() * b.float() + c.float()), atol=4 * tol, rtol=4 * tol)
+    ref = a.double().sum().item()
+    assert abs(float(ops.sum(A)) - ref) < 1e-3 * max(1.0, abs(ref)) + 1e-2 * (n ** 0.5) * (dtype == torch.bfloat16)
+    refd = (a.double() * b.double()).sum().item()
+    assert abs(float(ops.dot_product(A, B)) - refd) < 2e-3 * max(1.0, abs(refd)) + 1e-3 * n ** 0.5
+    refs = ((a.double() - 0.25) ** 2).sum().item()
+    assert abs(float(ops.sum_squared_diff(A, 0.25)) - refs) < 2e-3 * refs + 1e-3
+
+
+def test_layout_and_softmax_kernels():
+    from tnn_b200.ops import tensor_ops as ops
+    x = torch.randn(3, 6, 7, 16)
+    for dt in (torch.float32, torch.bfloat16):
+        xc, xg = x.to(dt), x.to(dt).to(_dev())
+        torch.testing.assert_close(ops.pad(xg, 2, 1, 0.0).cpu(), ops.pad(xc, 2, 1, 0.0))
+        torch.testing.assert_close(ops.unpad(xg, 1, 2).cpu(), ops.unpad(xc, 1, 2))
+        torch.testing.assert_close(ops.crop(xg, 1, 2, 3, 4).cpu(), ops.crop(xc, 1, 2, 3, 4))
+        s = ops.softmax(xg)
+        assert _rel_err(s.cpu(), torch.softmax(x, -1)) < (1e-5 if dt == torch.float32 else 1e-2)
+        g = torch.randn_like(x).to(dt)
+        assert _rel_err(ops.softmax_backward(s, g.to(_dev())).cpu(), ops.softmax_backward(s.cpu(), g)) < 2e-2
+    w = torch.tensor([1, 256, 65536], dtype=torch.int32).to(_dev())
+    assert ops.bswap(w).cpu().tolist() == [1 << 24, 1 << 16, 1 << 8]

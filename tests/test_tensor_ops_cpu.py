@@ -1,0 +1,105 @@
+"""Tensor facade + ops family on CPU (the oracle path; the GPU kernels are compared against the
+same functions in tests/test_kernels_gpu.py).  Mirrors unit_tests/tensor_test.cpp and the op
+coverage of gpu_tensor_ops_test.cpp."""
+import io
+
+import torch
+
+from tnn_b200.core import tensor as T
+from tnn_b200.core.dtype import DType
+from tnn_b200.ops import tensor_ops as ops
+
+
+def test_factories_and_record_round_trip(tmp_path):
+    t = T.make_tensor(DType.FP32, [2, 3, 4])
+    assert t.shape == (2, 3, 4) and t.dtype == torch.float32 and float(t.abs().sum()) == 0
+    assert T.make_tensor([5]).shape == (5,)
+    assert T.make_tensor("BF16", [2, 2]).dtype == torch.bfloat16
+    T.fill_random_uniform(t, -1, 1, seed=3)
+    assert -1 <= float(t.min()) and float(t.max()) <= 1 and float(t.abs().sum()) > 0
+    u = T.create_like(t)
+    assert u.shape == t.shape and float(u.abs().sum()) == 0
+    T.save(t, tmp_path / "t.bin")
+    assert torch.equal(T.load(tmp_path / "t.bin"), t)
+    buf = io.BytesIO()
+    T.save(t, buf)
+    buf.seek(0)
+    assert torch.equal(T.load_into(buf, torch.empty(2, 3, 4)), t)
+    assert T.dtype_cast(t, "BF16").dtype == torch.bfloat16
+    s = T.stats(t)
+    assert abs(s["mean"] - float(t.mean())) < 1e-6 and abs(s["variance"] - float(t.var(unbiased=False))) < 1e-6
+    assert len(T.head(t, 5)) == 5 and T.span(t, 1, 1).shape == (1, 3, 4) and T.nbytes(t) == 96
+    d = torch.zeros(3, 4)
+    T.copy_batch(d, 2, torch.ones(2, 4), 1)
+    assert float(d[2].sum()) == 4
+
+
+def test_allocator_backed_tensor():
+    from tnn_b200.core.device import DELAllocator
+    from tnn_b200.ops import native
+    if native.load() is None:
+        return
+    a = DELAllocator("cpu", slab_bytes=1 << 20)
+    t = T.make_tensor(a, DType.FP32, [16, 16])
+    assert T.aligned(t) and float(t.abs().sum()) == 0
+
+
+def test_elementwise_family():
+    a, b, c = torch.randn(37), torch.randn(37).abs() + 0.5, torch.randn(37)
+    torch.testing.assert_close(ops.add(a, b), a + b)
+    torch.testing.assert_close(ops.sub(a, b), a - b)
+    torch.testing.assert_close(ops.mul(a, b), a * b)
+    torch.testing.assert_close(ops.div(a, b), a / b)
+    torch.testing.assert_close(ops.minimum(a, b), torch.minimum(a, b))
+    torch.testing.assert_close(ops.maximum(a, b), torch.maximum(a, b))
+    torch.testing.assert_close(ops.greater(a, b), (a > b).float())
+    torch.testing.assert_close(ops.equal(a, a), torch.ones(37))
+    torch.testing.assert_close(ops.mul_scalar(a, 2.5), a * 2.5)
+    torch.testing.assert_close(ops.add_scalar(a, -1.0), a - 1.0)
+    torch.testing.assert_close(ops.sqrt(b), b.sqrt())
+    torch.testing.assert_close(ops.rsqrt(b), b.rsqrt())
+    torch.testing.assert_close(ops.rcp(b), 1 / b)
+    torch.testing.assert_close(ops.abs(a), a.abs())
+    torch.testing.assert_close(ops.clamp(a, -0.5, 0.5), a.clamp(-0.5, 0.5))
+    torch.testing.assert_close(ops.fmadd(a, b, c), a * b + c)
+    torch.testing.assert_close(ops.fmsub(a, b, c), a * b - c)
+    torch.testing.assert_close(ops.fnmadd(a, b, c), c - a * b)
+    y = c.clone()
+    torch.testing.assert_close(ops.axpy(y, a, 0.5), c + 0.5 * a)
+    assert abs(float(ops.sum(a)) - float(a.sum())) < 1e-4
+    assert abs(float(ops.dot_product(a, b)) - float((a * b).sum())) < 1e-4
+    assert abs(float(ops.sum_squared_diff(a, 0.25)) - float(((a - 0.25) ** 2).sum())) < 1e-4
+    z = torch.zeros(8)
+    assert float(ops.set_scalar(z, 3.0).sum()) == 24
+    assert ops.cast(a, torch.bfloat16).dtype == torch.bfloat16
+    w = torch.tensor([1, 256], dtype=torch.int32)
+    ops.bswap(w)
+    assert w.tolist() == [1 << 24, 1 << 16]
+    n1 = ops.fill_random_normal(torch.empty(1000), 1.0, 2.0, 7)
+    n2 = ops.fill_random_normal(torch.empty(1000), 1.0, 2.0, 7)
+    assert torch.equal(n1, n2) and abs(float(n1.mean()) - 1.0) < 0.3
+
+
+def test_layout_ops():
+    x = torch.arange(2 * 4 * 5 * 3, dtype=torch.float32).reshape(2, 4, 5, 3)
+    p = ops.pad(x, 1, 2, -1.0)
+    assert p.shape == (2, 6, 9, 3) and float(p[0, 0, 0, 0]) == -1.0
+    torch.testing.assert_close(p[:, 1:5, 2:7], x)
+    torch.testing.assert_close(ops.unpad(p, 1, 2), x)
+    torch.testing.assert_close(ops.crop(x, 1, 2, 2, 3), x[:, 1:3, 2:5])
+    torch.testing.assert_close(ops.nhwc_to_nchw(x), x.permute(0, 3, 1, 2))
+    torch.testing.assert_close(ops.nchw_to_nhwc(ops.nhwc_to_nchw(x)), x)
+    torch.testing.assert_close(ops.transpose_2d(x.reshape(8, 15)), x.reshape(8, 15).t())
+    assert [t.shape[0] for t in ops.split(x, 2)] == [1, 1] and ops.slice_batch(x, 1, 1).shape[0] == 1
+    # im2col agrees with a conv expressed as a GEMM
+    w = torch.randn(6, 3, 3, 3)                                   # [K, R, S, C]
+    col = ops.im2col(x, 3, 3, 1, 1)
+    y = (col @ w.reshape(6, -1).t()).reshape(2, 4, 5, 6)
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)
+    torch.testing.assert_close(y, ref, atol=1e-3, rtol=1e-4)
+    s = ops.softmax(x)
+    torch.testing.assert_close(s, torch.softmax(x, -1))
+    g = torch.randn_like(x)
+    xx = x.clone().requires_grad_(True)
+    torch.softmax(xx, -1).backward(g)
+    torch.testing.assert_close(ops.softmax_backward(s, g), xx.grad, atol=1e-6, rtol=1e-4)

@@ -329,6 +329,37 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     tnn::argmax_rows(vp(x), x.scalar_type() == torch::kFloat32, ld, rows, V, out.data_ptr<int>(), cur_stream());
   });
 
+  // ---- generic tensor op family (tensor_ops.cu)
+  auto is32 = [](const Tensor& t) {
+    TORCH_CHECK(t.is_cuda() && (t.scalar_type() == torch::kFloat32 || t.scalar_type() == torch::kBFloat16),
+                "tensor ops take CUDA fp32 / bf16 tensors");
+    return t.scalar_type() == torch::kFloat32 ? 1 : 0;
+  };
+  m.def("tensor_binary", [is32](const Tensor& a, const OptT& b, double scalar, const Tensor& out, int op) {
+    tnn::tensor_binary(vp(a), vp(b), (float)scalar, vp(out), a.numel(), op, is32(a), cur_stream());
+  });
+  m.def("tensor_unary", [is32](const Tensor& a, const Tensor& out, int op, double lo, double hi) {
+    tnn::tensor_unary(vp(a), vp(out), a.numel(), op, (float)lo, (float)hi, is32(a), cur_stream());
+  });
+  m.def("tensor_ternary", [is32](const Tensor& a, const Tensor& b, const Tensor& c, const Tensor& out, int op) {
+    tnn::tensor_ternary(vp(a), vp(b), vp(c), vp(out), a.numel(), op, is32(a), cur_stream());
+  });
+  m.def("tensor_reduce", [is32](const Tensor& a, const OptT& b, double mu, int mode, const Tensor& out) {
+    tnn::tensor_reduce(vp(a), vp(b), (float)mu, a.numel(), mode, is32(a), fp(out), cur_stream());
+  });
+  m.def("tensor_window_copy", [is32](const Tensor& src, const Tensor& dst, int N, int SH, int SW, int DH, int DW, int C,
+                                     int off_h, int off_w, double fill) {
+    tnn::tensor_window_copy(vp(src), vp(dst), N, SH, SW, DH, DW, C, off_h, off_w, (float)fill, is32(src), cur_stream());
+  });
+  m.def("softmax_rows", [is32](const Tensor& x, const Tensor& y, int64_t rows, int C) {
+    tnn::softmax_rows(vp(x), vp(y), rows, C, is32(x), cur_stream());
+  });
+  m.def("softmax_rows_bwd", [is32](const Tensor& y, const Tensor& dy, const Tensor& dx, int64_t rows, int C) {
+    tnn::softmax_rows_bwd(vp(y), vp(dy), vp(dx), rows, C, is32(y), cur_stream());
+  });
+  m.def("tensor_bswap", [](const Tensor& t) {
+    tnn::tensor_bswap(t.data_ptr(), t.numel(), (int)t.element_size(), cur_stream());
+  });
   m.def("launch_count", []() { return tnn::g_launch_count; });
   tnn::attention_bind(m);
   tnn::runtime_bind(m);

@@ -46,6 +46,23 @@ void philox_normal_f32(float* x, long long n, float mean, float std, uint64_t se
 // generic [rows, cols] transposes (bf16)
 void transpose_bf16(const void* x, void* y, int rows, int cols, cudaStream_t s);
 
+// ---- generic tensor ops (tensor_ops.cu) -------------------------------------------
+enum TensorBinaryOp : int { TOP_ADD = 0, TOP_SUB = 1, TOP_MUL = 2, TOP_DIV = 3, TOP_MIN = 4, TOP_MAX = 5, TOP_EQ = 6, TOP_GT = 7 };
+enum TensorUnaryOp : int { UOP_SQRT = 0, UOP_RSQRT = 1, UOP_RCP = 2, UOP_ABS = 3, UOP_CLAMP = 4, UOP_NEG = 5, UOP_EXP = 6, UOP_LOG = 7, UOP_SQUARE = 8 };
+// out = a (op) b  (b == nullptr: a (op) scalar); fp32 or bf16
+void tensor_binary(const void* a, const void* b, float scalar, void* out, long long n, int op, int is_f32, cudaStream_t s);
+void tensor_unary(const void* a, void* out, long long n, int op, float lo, float hi, int is_f32, cudaStream_t s);
+// op 0 fmadd a*b+c, 1 fmsub a*b-c, 2 fnmadd -(a*b)+c
+void tensor_ternary(const void* a, const void* b, const void* c, void* out, long long n, int op, int is_f32, cudaStream_t s);
+// mode 0 sum(a), 1 dot(a,b), 2 sum((a-mu)^2); *out (device fp32) is overwritten; finishes on the device
+void tensor_reduce(const void* a, const void* b, float mu, long long n, int mode, int is_f32, float* out, cudaStream_t s);
+// dst[n,h,w,c] = src[n,h+off_h,w+off_w,c] or fill outside (pad: negative offsets; crop/unpad: positive)
+void tensor_window_copy(const void* src, void* dst, int N, int SH, int SW, int DH, int DW, int C, int off_h, int off_w,
+                        float fill, int is_f32, cudaStream_t s);
+void softmax_rows(const void* x, void* y, long long rows, int C, int is_f32, cudaStream_t s);
+void softmax_rows_bwd(const void* y, const void* dy, void* dx, long long rows, int C, int is_f32, cudaStream_t s);
+void tensor_bswap(void* p, long long n_elems, int elem_size, cudaStream_t s);
+
 // ---- normalisation (norm.cu) -------------------------------------------------------
 // BatchNorm over a [M, C] bf16 view.  ws is a persistent fp32 workspace of 2*C+4 floats
 // (zero-initialised once); scale_shift receives [2*C] = {gamma*invstd, beta - mean*gamma*invstd}.
