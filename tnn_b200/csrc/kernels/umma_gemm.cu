@@ -290,6 +290,133 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ---------------------------------------------------------------------------
+// CTA-pair GEMM / conv-fprop kernel (cta_group::2): a (2,1,1) cluster computes a 256 x BLOCK_N
+// tile.  Each CTA TMA-loads its own 128 rows of A (or its own conv window) and its own
+// BLOCK_N/2 rows of B, so per-SM shared-memory traffic per MMA halves compared with the
+// single-CTA kernel (the SS-mode 128x128 tile is smem-bandwidth bound at ~50% of tensor peak).
+// The leader issues tcgen05.mma.cta_group::2 with M = 256; accumulator rows 0..127 sit in the
+// leader's TMEM, 128..255 in the peer's; commits are multicast to both CTAs' barriers.
+// K-major A (plain or conv window) x K-major B only (dense fwd, conv fprop, conv dgrad).
+// ---------------------------------------------------------------------------
+template <int BLOCK_N, bool CONV_A, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads)
+    umma_gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const KParams p) {
+  constexpr int A_BYTES = BLOCK_M * 128;
+  constexpr int B_BYTES = (BLOCK_N / 2) * 128;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = BLOCK_N;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int m0 = blockIdx.x * BLOCK_M;                 // this CTA's 128 rows (pair = 256 rows)
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int nkb = p.kb_total;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ----------------------------- TMA producer (both CTAs; bytes land on the leader's barrier)
+      int img0 = 0, h0 = 0;
+      if (CONV_A) {
+        const int hw = p.OH * p.OW;
+        if (p.BN > 1) {
+          img0 = blockIdx.x * p.BN;
+        } else {
+          img0 = m0 / hw;
+          h0 = (m0 - img0 * hw) / p.OW;
+        }
+      }
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* sa = smem + s * STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        if (leader) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);
+        int kB;
+        if (CONV_A) {
+          const int t = i / p.kc_per_tap;
+          const int kc = i - t * p.kc_per_tap;
+          const ConvTap tap = p.taps[t];
+          tma_load_4d_2sm(sa, &tmA, &full[s], kc * BLOCK_K, tap.dw, h0 + tap.dh, img0 + tap.nb);
+          kB = tap.koff + kc * BLOCK_K;
+        } else {
+          kB = i * BLOCK_K;
+          tma_load_2d_2sm(sa, &tmA, &full[s], kB, m0);
+        }
+        tma_load_2d_2sm(sb, &tmB, &full[s], kB, n0 + (int)rank * (BLOCK_N / 2));
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      // ----------------------------- MMA issuer (leader CTA only)
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BLOCK_N, 0u, 0u);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k)
+          umma_f16_2sm(tmem_base, make_smem_desc_sw128(a_addr + k * 32, 0, 1024),
+                       make_smem_desc_sw128(b_addr + k * 32, 0, 1024), idesc, (i > 0 || k > 0) ? 1u : 0u);
+        umma_commit_2sm(&empty[s]);
+      }
+      umma_commit_2sm(tmem_full);
+    }
+  } else {
+    // ----------------------------- epilogue (each CTA drains its own 128 accumulator rows)
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    const bool row_ok = m < p.M;
+    const long long row_off = row_ok ? epi_row_offset(p.epi, m) : 0;
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+      if (n0 + c >= p.N) break;
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+      tmem_ld_wait();
+      epi_store_32(p, r, row_ok, row_off, n0 + c);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2sm<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------
 // conv wgrad kernel: M = Kout tile (128), N = 64 input channels per tap, T taps
 // ---------------------------------------------------------------------------
 template <int T, int STAGES>
@@ -533,6 +660,32 @@ static void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const KP
   TNN_CUDA_CHECK(cudaGetLastError());
 }
 
+template <int BLOCK_N, bool CONV_A>
+static void launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, dim3 grid,
+                         cudaStream_t stream) {
+  constexpr int STAGES = (BLOCK_N <= 128) ? 4 : 3;
+  constexpr int smem = STAGES * (BLOCK_M * 128 + (BLOCK_N / 2) * 128) + 1024 + 256;
+  auto kern = umma_gemm2_kernel<BLOCK_N, CONV_A, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    set_smem(kern, smem);
+    configured = true;
+  }
+  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);   // cluster dims are a kernel attribute
+  ++g_launch_count;
+  TNN_CUDA_CHECK(cudaGetLastError());
+}
+
+// CTA-pair path: opt-in with TNN_GEMM_2CTA=1 (default decided by measurement)
+static bool use_2cta(int M, int N, bool a_mn, bool b_mn, int splits) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("TNN_GEMM_2CTA");
+    mode = (e != nullptr) ? atoi(e) : 0;
+  }
+  return mode > 0 && !a_mn && !b_mn && splits <= 1 && M >= 256 && N >= 128;
+}
+
 static int pick_block_n(int N) {
   const char* e = getenv("TNN_GEMM_BLOCK_N");
   if (e != nullptr) {
@@ -573,6 +726,25 @@ void gemm_bf16(const void* A, const void* B, int M, int N, int K, long long lda,
       (reinterpret_cast<uintptr_t>(B) & 15)) {
     fprintf(stderr, "[tnn_b200] gemm_bf16: operands must be 16-byte aligned with ld %% 8 == 0\n");
     abort();
+  }
+  if (use_2cta(M, N, a_mn, b_mn, splits)) {
+    const int bn2 = N >= 256 ? 256 : 128;
+    KParams p{};
+    p.M = M;
+    p.N = N;
+    p.K = K;
+    p.kc_per_tap = (K + BLOCK_K - 1) / BLOCK_K;
+    p.kb_total = p.kc_per_tap;
+    p.kb_per_split = p.kb_total;
+    p.ntaps = 1;
+    p.epi = epi;
+    p.vec_ok = epi_vec_ok(epi, N);
+    CUtensorMap tmA = make_operand_map(A, M, K, lda, BLOCK_M);
+    CUtensorMap tmB = make_operand_map(B, N, K, ldb, bn2 / 2);
+    dim3 grid(2 * ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)), (N + bn2 - 1) / bn2, 1);
+    if (bn2 == 256) launch_gemm2<256, false>(tmA, tmB, p, grid, stream);
+    else launch_gemm2<128, false>(tmA, tmB, p, grid, stream);
+    return;
   }
   const int bn = pick_block_n(N);
   KParams p{};
@@ -629,6 +801,14 @@ void conv_fprop_bf16(const void* X, const void* Wt, long long ldw, int N, const 
   p.epi = epi;
   p.vec_ok = epi_vec_ok(epi, N);
   CUtensorMap tmA = make_window_map(X, g, BH, BN);
+  if (use_2cta(M, N, false, false, 1)) {
+    const int bn2 = N >= 256 ? 256 : 128;
+    CUtensorMap tmB2 = make_operand_map(Wt, N, ldw, ldw, bn2 / 2);
+    dim3 grid2(2 * ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)), (N + bn2 - 1) / bn2, 1);
+    if (bn2 == 256) launch_gemm2<256, true>(tmA, tmB2, p, grid2, stream);
+    else launch_gemm2<128, true>(tmA, tmB2, p, grid2, stream);
+    return;
+  }
   // weight matrix [N, Ktot]: the last tap may read past koff+C; the extent is ldw
   CUtensorMap tmB = make_operand_map(Wt, N, ldw, ldw, bn);
   dim3 grid((M + BLOCK_M - 1) / BLOCK_M, (N + bn - 1) / bn, 1);
