@@ -147,14 +147,17 @@ void runtime_bind(py::module_& m) {
       })
       .def("getvalue", [](const Writer& w) { return py::bytes(reinterpret_cast<const char*>(w.buffer().data()), w.size()); });
   struct PyReader {
-    std::string data;
+    py::bytes data;   // keeps the buffer alive; the reader parses it in place (no copy)
     std::unique_ptr<Reader> r;
   };
   py::class_<PyReader>(m, "Reader")
       .def(py::init([](const py::bytes& b, bool swap) {
              auto p = std::make_unique<PyReader>();
              p->data = b;
-             p->r = std::make_unique<Reader>(reinterpret_cast<const uint8_t*>(p->data.data()), p->data.size(), swap);
+             char* buf = nullptr;
+             Py_ssize_t len = 0;
+             if (PyBytes_AsStringAndSize(p->data.ptr(), &buf, &len) != 0) throw py::error_already_set();
+             p->r = std::make_unique<Reader>(reinterpret_cast<const uint8_t*>(buf), (size_t)len, swap);
              return p;
            }),
            py::arg("data"), py::arg("swap") = false)
@@ -204,9 +207,11 @@ void runtime_bind(py::module_& m) {
       .def("has_peer", &TcpBus::has_peer)
       .def("peers", &TcpBus::peers)
       .def("send", [](TcpBus& b, const std::string& key, const py::bytes& msg) {
-        std::string s = msg;
-        py::gil_scoped_release rel;
-        b.send(key, reinterpret_cast<const uint8_t*>(s.data()), s.size());
+        char* buf = nullptr;
+        Py_ssize_t len = 0;
+        if (PyBytes_AsStringAndSize(msg.ptr(), &buf, &len) != 0) throw py::error_already_set();
+        py::gil_scoped_release rel;   // `msg` stays referenced by the caller for the duration of the call
+        b.send(key, reinterpret_cast<const uint8_t*>(buf), (size_t)len);
       })
       .def("recv", [](TcpBus& b, int timeout_ms) -> py::object {
         std::string from;

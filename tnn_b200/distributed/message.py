@@ -255,7 +255,7 @@ class Message:
         return s.size()
 
     def serialize(self) -> bytes:
-        w = native.require().Writer(0)
+        w = native.require().Writer(self.byte_size())
         self._emit(w, False)
         return w.getvalue()
 
