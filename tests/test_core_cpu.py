@@ -513,3 +513,22 @@ def test_mnist_cnn_trainer_cpu_world1(tmp_path):
     assert math.isfinite(vl) and 0.0 <= va <= 1.0
     g2 = Graph.load_state(os.path.join(str(tmp_path), g.name), "cpu")
     assert [n for n, _ in g2.ctx.parameters()] == [n for n, _ in g.ctx.parameters()]
+
+
+@needs_native
+def test_native_cpu_gemm_and_thread_pool():
+    from tnn_b200.utils.threading import ThreadWrapper, cpu_gemm, parallel_for, parallel_for_2d
+    a, b = torch.randn(130, 70), torch.randn(70, 45)
+    ref = a @ b
+    for ta, tb, aa, bb in ((False, False, a, b), (True, False, a.t().contiguous(), b), (False, True, a, b.t().contiguous()),
+                           (True, True, a.t().contiguous(), b.t().contiguous())):
+        torch.testing.assert_close(cpu_gemm(aa, bb, ta, tb), ref, atol=1e-4, rtol=1e-4)
+    c = torch.ones(130, 45)
+    torch.testing.assert_close(cpu_gemm(a, b, alpha=2.0, beta=0.5, out=c), 2 * ref + 0.5, atol=1e-4, rtol=1e-4)   # beta accumulate
+    hits = [0] * 11
+    parallel_for(11, lambda s, e: [hits.__setitem__(i, hits[i] + 1) for i in range(s, e)], grain=3)
+    assert hits == [1] * 11
+    tiles = []
+    parallel_for_2d(70, 40, lambda r0, r1, c0, c1: tiles.append((r1 - r0) * (c1 - c0)))
+    assert sum(tiles) == 70 * 40
+    assert ThreadWrapper(2).execute(torch.get_num_threads) == 2

@@ -11,6 +11,7 @@
 
 #include "allocator.hpp"
 #include "archiver.hpp"
+#include "cpu_math.hpp"
 #include "data_loader.hpp"
 #include "tcp_bus.hpp"
 #include "tokenizer.hpp"
@@ -192,6 +193,24 @@ void runtime_bind(py::module_& m) {
       });
   m.attr("PACKET_HEADER_BYTES") = (int)PacketHeader::kBytes;
   m.def("host_is_little_endian", &host_is_little_endian);
+
+  // ---------------------------------------------------------------- CPU math / threading
+  m.def("cpu_sgemm", [](int64_t a, int64_t b, int64_t c, int64_t M, int64_t N, int64_t K, bool ta, bool tb, double alpha,
+                        double beta, int64_t lda, int64_t ldb, int64_t ldc, int threads) {
+    py::gil_scoped_release rel;
+    cpu_sgemm(reinterpret_cast<const float*>(a), reinterpret_cast<const float*>(b), reinterpret_cast<float*>(c), M, N, K, ta, tb,
+              (float)alpha, (float)beta, lda, ldb, ldc, threads);
+  }, py::arg("a"), py::arg("b"), py::arg("c"), py::arg("M"), py::arg("N"), py::arg("K"), py::arg("trans_a") = false,
+     py::arg("trans_b") = false, py::arg("alpha") = 1.0, py::arg("beta") = 0.0, py::arg("lda") = 0, py::arg("ldb") = 0,
+     py::arg("ldc") = 0, py::arg("threads") = 0);
+  m.def("parallel_for", [](int64_t n, int64_t grain, const py::function& fn, int threads) {
+    // Python callables run under the GIL; this is for API parity and for callables that release it
+    global_pool(threads).parallel_for(n, grain, [&](int64_t b, int64_t e) {
+      py::gil_scoped_acquire acq;
+      fn(b, e);
+    });
+  }, py::arg("n"), py::arg("grain"), py::arg("fn"), py::arg("threads") = 0, py::call_guard<py::gil_scoped_release>());
+  m.def("pool_threads", [](int threads) { return global_pool(threads).size(); }, py::arg("threads") = 0);
 
   // ---------------------------------------------------------------- TCP message bus
   py::class_<TcpBus>(m, "TcpBus")
