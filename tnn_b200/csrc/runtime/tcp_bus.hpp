@@ -56,36 +56,39 @@ class TcpBus {
 
   void start() {
     if (running_.exchange(true)) return;
-    lfd_ = ::socket(AF_INET, SOCK_STREAM, 0);
-    if (lfd_ < 0) throw std::runtime_error("TcpBus: socket() failed");
+    const int lfd = ::socket(AF_INET, SOCK_STREAM, 0);
+    if (lfd < 0) throw std::runtime_error("TcpBus: socket() failed");
+    lfd_ = lfd;
     int one = 1;
-    setsockopt(lfd_, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
+    setsockopt(lfd, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
     sockaddr_in addr{};
     addr.sin_family = AF_INET;
     addr.sin_addr.s_addr = htonl(INADDR_ANY);
     addr.sin_port = htons((uint16_t)port_);
-    if (::bind(lfd_, reinterpret_cast<sockaddr*>(&addr), sizeof(addr)) != 0) {
-      ::close(lfd_);
+    if (::bind(lfd, reinterpret_cast<sockaddr*>(&addr), sizeof(addr)) != 0) {
+      ::close(lfd);
+      lfd_ = -1;
       running_ = false;
       throw std::runtime_error("TcpBus: bind() failed on port " + std::to_string(port_));
     }
     if (port_ == 0) {
       socklen_t len = sizeof(addr);
-      getsockname(lfd_, reinterpret_cast<sockaddr*>(&addr), &len);
+      getsockname(lfd, reinterpret_cast<sockaddr*>(&addr), &len);
       port_ = ntohs(addr.sin_port);
     }
-    ::listen(lfd_, 64);
+    ::listen(lfd, 64);
     acceptor_ = std::thread([this] { accept_loop(); });
   }
 
   void stop() {
     if (!running_.exchange(false)) return;
-    if (lfd_ >= 0) {
-      ::shutdown(lfd_, SHUT_RDWR);
-      ::close(lfd_);
+    const int lfd = lfd_.load();
+    if (lfd >= 0) ::shutdown(lfd, SHUT_RDWR);
+    if (acceptor_.joinable()) acceptor_.join();   // the acceptor polls running_; close only after it left
+    if (lfd >= 0) {
+      ::close(lfd);
       lfd_ = -1;
     }
-    if (acceptor_.joinable()) acceptor_.join();
     std::vector<std::thread> readers;
     {
       std::lock_guard<std::mutex> g(mu_);
@@ -293,13 +296,14 @@ class TcpBus {
   }
 
   void accept_loop() {
+    const int lfd = lfd_.load();
     while (running_) {
-      pollfd pfd{lfd_, POLLIN, 0};
+      pollfd pfd{lfd, POLLIN, 0};
       int r = ::poll(&pfd, 1, 200);
       if (r <= 0) continue;
       sockaddr_in peer_addr{};
       socklen_t len = sizeof(peer_addr);
-      int fd = ::accept(lfd_, reinterpret_cast<sockaddr*>(&peer_addr), &len);
+      int fd = ::accept(lfd, reinterpret_cast<sockaddr*>(&peer_addr), &len);
       if (fd < 0) continue;
       tune(fd);
       uint32_t hello[3];
@@ -377,7 +381,7 @@ class TcpBus {
   int port_;
   int spp_;
   size_t max_packet_;
-  int lfd_ = -1;
+  std::atomic<int> lfd_{-1};
   std::atomic<bool> running_{false};
   std::thread acceptor_;
   std::mutex mu_;
