@@ -37,16 +37,45 @@ class WRN16_8(nn.Module):
         return self.fc(F.adaptive_avg_pool2d(x, 1).flatten(1))
 
 
-def bench_torch_wrn(B, steps, warmup, local, world):
+class ResNet9(nn.Module):
+    """torch mirror of the zoo's cifar10_resnet9 (reference: torch/torch_resnet9_deepspeed.py model)."""
+
+    def __init__(self, classes=10):
+        super().__init__()
+
+        def cb(i, o):
+            return nn.Sequential(nn.Conv2d(i, o, 3, 1, 1, bias=False), nn.BatchNorm2d(o, eps=1e-2), nn.ReLU(inplace=True))
+
+        class Res(nn.Module):
+            def __init__(self, c):
+                super().__init__()
+                self.c1 = nn.Conv2d(c, c, 3, 1, 1, bias=False)
+                self.b1 = nn.BatchNorm2d(c, eps=1e-2)
+                self.c2 = nn.Conv2d(c, c, 3, 1, 1, bias=False)
+                self.b2 = nn.BatchNorm2d(c, eps=1e-2)
+
+            def forward(self, x):
+                return F.relu(x + self.b2(self.c2(F.relu(self.b1(self.c1(x))))))
+
+        self.net = nn.Sequential(cb(3, 64), cb(64, 128), nn.MaxPool2d(2), Res(128), Res(128), cb(128, 256), nn.MaxPool2d(2),
+                                 Res(256), Res(256), cb(256, 512), nn.MaxPool2d(2), Res(512), nn.AvgPool2d(4), nn.Flatten(),
+                                 nn.Linear(512, classes))
+
+    def forward(self, x):
+        return self.net(x)
+
+
+def bench_torch_wrn(B, steps, warmup, local, world, model_name="cifar100_wrn16_8"):
     import torch.distributed as dist
     dev = torch.device("cuda", local)
     torch.backends.cudnn.benchmark = True
-    model = WRN16_8().to(dev).to(memory_format=torch.channels_last)
+    classes = 10 if "cifar10_" in model_name else 100
+    model = (ResNet9(classes) if "resnet9" in model_name else WRN16_8(classes)).to(dev).to(memory_format=torch.channels_last)
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, eps=1e-3, weight_decay=3e-4, fused=True)
     xs = [torch.rand(B, 3, 32, 32, device=dev).to(memory_format=torch.channels_last) for _ in range(4)]
-    ys = [torch.randint(0, 100, (B,), device=dev) for _ in range(4)]
+    ys = [torch.randint(0, classes, (B,), device=dev) for _ in range(4)]
 
     def step(i):
         with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -74,8 +103,8 @@ def bench_torch_wrn(B, steps, warmup, local, world):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
-    return {"metric": "WRN-16-8 CIFAR-100 training throughput", "value": world * B * steps / (ms / 1e3), "unit": "img/s",
+    return {"metric": ("WRN-16-8 CIFAR-100" if "wrn" in model_name else model_name) + " training throughput", "value": world * B * steps / (ms / 1e3), "unit": "img/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
             "scaling": "weak", "dtype": "bf16", "data": "synthetic",
-            "config": {"model": "cifar100_wrn16_8", "global_batch": world * B, "parallelism": f"ddp{world}",
+            "config": {"model": model_name, "global_batch": world * B, "parallelism": f"ddp{world}",
                        "stack": "torch autocast bf16 + cuDNN channels_last + NCCL"}, "final_loss": float(loss)}

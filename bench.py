@@ -55,7 +55,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -169,7 +169,8 @@ def run_tnn(args):
 
     g = torch.Generator().manual_seed(100 + rank)
     NB = 4
-    host = [(torch.rand((B, 32, 32, 3), generator=g).pin_memory(), torch.randint(0, 100, (B,), generator=g, dtype=torch.int32).pin_memory())
+    classes = 10 if "cifar10_" in args.model else 100
+    host = [(torch.rand((B, 32, 32, 3), generator=g).pin_memory(), torch.randint(0, classes, (B,), generator=g, dtype=torch.int32).pin_memory())
             for _ in range(NB)]
     devb = [(x.to(dev), y.to(dev)) for x, y in host]
 
@@ -227,12 +228,12 @@ def run_tnn(args):
 
     if rank == 0:
         out = {
-            "metric": "WRN-16-8 CIFAR-100 training throughput", "value": value, "unit": "img/s", "n_gpus": world,
+            "metric": ("WRN-16-8 CIFAR-100" if args.model == "cifar100_wrn16_8" else args.model) + " training throughput", "value": value, "unit": "img/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": value / BASELINE_IMG_S, "dtype": "bf16", "data": "synthetic",
             "impl": "tnn_b200",
             "config": {"model": args.model, "global_batch": world * B, "per_gpu_batch": B, "seq_len": None,
-                       "image": [32, 32, 3], "classes": 100, "optimizer": "adam(lr1e-3,eps1e-3,wd3e-4)",
+                       "image": [32, 32, 3], "classes": classes, "optimizer": "adam(lr1e-3,eps1e-3,wd3e-4)",
                        "parallelism": parallelism,
                        "l2": "inputs rotate over 4 batches; per-step activation working set (~2 GB) >> 126 MB L2"},
             "clocks": clocks, "gpu_launches": int(launches), "cuda_graph": bool(step.use_graph), "launches_per_step": launches / max(1, args.steps),
@@ -253,7 +254,7 @@ def run_torch(args):
     sys.path.insert(0, os.path.join(ROOT, "baseline"))
     from torch_wrn import bench_torch_wrn
     rank, local, world = dist_setup(args.gpus)
-    res = bench_torch_wrn(args.batch, args.steps, args.warmup, local, world)
+    res = bench_torch_wrn(args.batch, args.steps, args.warmup, local, world, args.model)
     if rank == 0:
         res.update({"impl": "torch", "vs_baseline": res["value"] / BASELINE_IMG_S})
         emit(res)
