@@ -140,3 +140,46 @@ def test_softmax_ce_and_adam():
         p = p - upd
     assert _rel(pg, p) < 1e-5
     assert _rel(lp, p) < 1e-2
+
+
+def test_batchnorm_statistics_fused_into_conv_epilogue():
+    """conv -> BN: after the first step the conv epilogue accumulates the BN statistics; results must
+    match the stand-alone statistics kernel (and the running averages must keep evolving)."""
+    import os
+    from tnn_b200.nn import BatchNormLayer, Conv2DLayer, ResidualBlock, Sequential
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    for (N, H, C, K, st) in [(8, 16, 64, 128, 1), (4, 32, 128, 256, 2), (16, 8, 256, 512, 1)]:
+        def build():
+            conv = Conv2DLayer(C, K, 3, 3, st, st, 1, 1, True, "c").init(dev, 3)
+            bn = BatchNormLayer(K, 1e-2, 0.1, True, True, "b").init(dev, 3)
+            return conv, bn
+        x = torch.randn(N, H, H, C, device=dev).bfloat16()
+        outs = {}
+        for mode in ("0", "1"):
+            os.environ["TNN_BN_FUSE_STATS"] = mode
+            conv, bn = build()
+            for it in range(3):
+                y = bn.forward(conv.forward(x, 0), 0)
+            outs[mode] = (y.float(), bn.params["running_mean"].clone(), bn.params["running_var"].clone(), conv._stats_ws)
+        os.environ["TNN_BN_FUSE_STATS"] = "1"
+        assert outs["1"][3] is not None and outs["0"][3] is not None      # requested in both, used only in mode 1
+        assert (outs["1"][0] - outs["0"][0]).abs().max().item() < 3e-2
+        torch.testing.assert_close(outs["1"][1], outs["0"][1], atol=2e-3, rtol=2e-3)
+        torch.testing.assert_close(outs["1"][2], outs["0"][2], atol=2e-3, rtol=2e-3)
+    # residual block output (conv epilogue with residual add) feeding the next block's BatchNorm
+    main = Sequential([BatchNormLayer(128, 1e-2, use_relu=True, name="b1"), Conv2DLayer(128, 128, 3, 3, 1, 1, 1, 1, True, "c1")], "m")
+    blk = ResidualBlock(main, None, "linear", "r").init(dev, 5)
+    nxt = BatchNormLayer(128, 1e-2, use_relu=True, name="b2").init(dev, 5)
+    x = torch.randn(8, 16, 16, 128, device=dev).bfloat16()
+    ref = None
+    for it in range(3):
+        out = blk.forward(x, 0)
+        used = getattr(out, "_tnn_bn_stats", None) is not None
+        y = nxt.forward(out, 0)
+        if it == 0:
+            assert not used
+            ref = y.float()
+        else:
+            assert used
+            assert (y.float() - ref).abs().max().item() < 3e-2

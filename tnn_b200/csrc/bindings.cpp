@@ -85,12 +85,26 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv_fprop", [](const Tensor& X, const Tensor& Wt, int64_t ldw, int64_t N,
                          const std::vector<int64_t>& geom, const std::vector<int64_t>& taps,
                          const Tensor& out, int64_t ldc, const std::vector<int64_t>& grid, int out_mode,
-                         int act, double alpha, const OptT& bias, const OptT& residual) {
+                         int act, double alpha, const OptT& bias, const OptT& residual, const OptT& col_stats) {
     check_cuda(X);
     tnn::ConvGeom g = make_geom(geom, taps);
     tnn::Epilogue e = make_epi(out, out_mode, act, alpha, bias, residual, ldc, grid);
+    if (col_stats.has_value()) {
+      TORCH_CHECK(col_stats->numel() >= (int64_t)tnn::bn_stat_replicas() * 2 * N, "col_stats workspace too small");
+      e.col_sum = fp(*col_stats);
+      e.col_repl = tnn::bn_stat_replicas();
+    }
     tnn::conv_fprop_bf16(vp(X), vp(Wt), ldw, (int)N, g, e, cur_stream());
+  }, py::arg("X"), py::arg("Wt"), py::arg("ldw"), py::arg("N"), py::arg("geom"), py::arg("taps"), py::arg("out"),
+     py::arg("ldc"), py::arg("grid"), py::arg("out_mode"), py::arg("act"), py::arg("alpha"), py::arg("bias"),
+     py::arg("residual"), py::arg("col_stats") = py::none());
+  m.def("bn_finalize_stats", [](const Tensor& ws, int64_t M, int C, const OptT& gamma, const OptT& beta, double eps,
+                                double momentum, const OptT& rmean, const OptT& rvar, const Tensor& smean,
+                                const Tensor& sinvstd, const Tensor& ss) {
+    tnn::bn_finalize_stats(fp(ws), M, C, fp(gamma), fp(beta), (float)eps, (float)momentum, fp(rmean), fp(rvar),
+                           fp(smean), fp(sinvstd), fp(ss), cur_stream());
   });
+  m.def("bn_stat_replicas", &tnn::bn_stat_replicas);
   m.def("conv_wgrad", [](const Tensor& dY, int64_t ldy, int64_t Kout, const Tensor& X,
                          const std::vector<int64_t>& geom, const std::vector<int64_t>& taps,
                          const Tensor& dW, int64_t ldw, double alpha) {

@@ -195,6 +195,40 @@ void bn_train_stats(const void* x, long long M, int C, const float* gamma, const
   TNN_CHECK_LAUNCH();
 }
 
+// Statistics that were accumulated by a producer kernel's epilogue (conv / GEMM `col_sum`
+// workspace, replica layout [BN_REPL][2][C]): fold the replicas, derive mean / invstd /
+// (scale, shift), update the running averages and reset the workspace.  One small CTA.
+__global__ void __launch_bounds__(256)
+    k_bn_finalize(float* ws, long long M, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                  float eps, float momentum, float* running_mean, float* running_var, float* save_mean,
+                  float* save_invstd, float* scale_shift) {
+  const float inv_m = 1.f / (float)M;
+  const float unbias = M > 1 ? (float)M / (float)(M - 1) : 1.f;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    float s = fold_replicas<2>(ws, 0, C, c), ss = fold_replicas<2>(ws, 1, C, c);
+    float mean = s * inv_m;
+    float var = fmaxf(ss * inv_m - mean * mean, 0.f);
+    float invstd = rsqrtf(var + eps);
+    save_mean[c] = mean;
+    save_invstd[c] = invstd;
+    float gm = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+    scale_shift[c] = gm * invstd;
+    scale_shift[C + c] = bt - mean * gm * invstd;
+    if (running_mean) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * unbias;
+    }
+  }
+}
+void bn_finalize_stats(float* ws, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                       float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                       float* scale_shift, cudaStream_t s) {
+  k_bn_finalize<<<(C + 255) / 256, 256, 0, s>>>(ws, M, C, gamma, beta, eps, momentum, running_mean, running_var, save_mean,
+                                             save_invstd, scale_shift);
+  TNN_CHECK_LAUNCH();
+}
+int bn_stat_replicas() { return BN_REPL; }
+
 __global__ void k_bn_eval_ss(int C, const float* gamma, const float* beta, const float* rm,
                              const float* rv, float eps, float* ss) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;

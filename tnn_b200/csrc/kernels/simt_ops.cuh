@@ -70,6 +70,11 @@ void bn_train_stats(const void* x, long long M, int C, const float* gamma, const
                     float eps, float momentum, float* running_mean, float* running_var,
                     float* save_mean, float* save_invstd, float* scale_shift, float* ws,
                     cudaStream_t s);
+// finalize statistics accumulated by a producer epilogue into ws = [replicas][2][C] (see umma_gemm.cuh)
+void bn_finalize_stats(float* ws, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
+                       float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                       float* scale_shift, cudaStream_t s);
+int bn_stat_replicas();
 void bn_eval_scale_shift(int C, const float* gamma, const float* beta, const float* running_mean,
                          const float* running_var, float eps, float* scale_shift, cudaStream_t s);
 // y = act(x*scale + shift) [* dropout]; residual-free.  drop_p == 0 disables dropout.

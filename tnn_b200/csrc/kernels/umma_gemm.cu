@@ -86,9 +86,8 @@ __device__ __forceinline__ void epi_store_32(const KParams& p, const uint32_t (&
     for (int j = 0; j < 32; ++j)
       if (n + j < p.N) v[j] += __ldg(e.bias + n + j);
   }
-  if (!row_ok) return;
   const bool full = (n + 32 <= p.N) && p.vec_ok;
-  if (e.residual != nullptr) {
+  if (row_ok && e.residual != nullptr) {
     const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(e.residual) + row_off + n;
     if (full) {
 #pragma unroll
@@ -115,6 +114,39 @@ __device__ __forceinline__ void epi_store_32(const KParams& p, const uint32_t (&
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
   }
+  if (e.col_sum != nullptr) {
+    // BatchNorm statistics of the STORED tile (sum and sum of squares per output channel), so the
+    // consumer BatchNorm never re-reads this activation: a butterfly transpose-reduce over the
+    // warp's 32 rows leaves column (n + lane) in lane `lane` after 31 shuffles per quantity, then
+    // one fp32 atomic per lane into a replica row (same replica layout as norm.cu).
+    float a[32], b[32];
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float t = v[j];
+      if (e.out_mode == OUT_BF16) t = __bfloat162float(__float2bfloat16(t));
+      t = row_ok ? t : 0.f;
+      a[j] = t;
+      b[j] = t * t;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int j = 0; j < off; ++j) {
+        const float sa = upper ? a[j] : a[j + off], ka = upper ? a[j + off] : a[j];
+        const float sb = upper ? b[j] : b[j + off], kb = upper ? b[j + off] : b[j];
+        a[j] = ka + __shfl_xor_sync(0xffffffffu, sa, off);
+        b[j] = kb + __shfl_xor_sync(0xffffffffu, sb, off);
+      }
+    }
+    if (n + lane < p.N) {
+      float* ws = e.col_sum + (size_t)(blockIdx.x % e.col_repl) * 2 * p.N;
+      atomicAdd(ws + n + lane, a[0]);
+      atomicAdd(ws + p.N + n + lane, b[0]);
+    }
+  }
+  if (!row_ok) return;
   if (e.out_mode == OUT_BF16) {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out) + row_off + n;
     if (full) {

@@ -24,8 +24,10 @@ struct Epilogue {
   int grid_mode = 0;                    // 1: rows are (n, oh, ow) of an output grid
   int OH = 1, OW = 1;
   long long sN = 0, sH = 0, sW = 0, base = 0;
-  float* col_sum = nullptr;             // optional per-column sum / sum of squares of the
-  float* col_sumsq = nullptr;           // stored value (BatchNorm statistics fusion)
+  // BatchNorm statistics fusion: fp32 workspace [col_repl][2][N] (sum, sum of squares of the stored
+  // values per column), replica row = blockIdx.x % col_repl; folded by bn_finalize_stats (norm.cu)
+  float* col_sum = nullptr;
+  int col_repl = 1;
 };
 
 struct ConvTap {

@@ -9,6 +9,7 @@ sdpa}_layer.cpp and include/nn/activations.hpp.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -167,6 +168,10 @@ class Conv2DLayer(Layer):
             self._generic = False
         self._plans = {}
         self._state = conv_ops.ConvState()
+        # BatchNorm statistics fusion: a consumer BatchNorm that finds this layer as the producer of
+        # its input asks for the statistics to be accumulated in the conv epilogue from then on
+        self._stats_ws = None
+        self._stats_requested = False
 
     def param_descriptors(self):
         fan_in = self.in_channels * self.kernel_h * self.kernel_w
@@ -201,8 +206,17 @@ class Conv2DLayer(Layer):
                 y = y + residual
         elif x.is_cuda:
             x = to_bf16(x).contiguous()
+            ws = None
+            if self.training and self._stats_requested and plan.path == "tma":
+                if self._stats_ws is None or self._stats_ws.device != x.device:
+                    self._stats_ws = torch.zeros(native.require().bn_ws_floats(self.out_channels), dtype=torch.float32,
+                                                 device=x.device)
+                ws = self._stats_ws
             y = conv_ops.conv2d_fwd(plan, x, self.params["weight"], self.lp("weight"), self.params.get("bias"),
-                                    residual=residual, act=act, cache=c)
+                                    residual=residual, act=act, cache=c, stats_ws=ws)
+            if self.training:
+                y._tnn_producer = self
+                y._tnn_bn_stats = ws          # None until a BatchNorm consumer asked for them
         else:
             y = conv_ops.conv2d_fwd(plan, x.float(), self.params["weight"], None, self.params.get("bias"),
                                     residual=residual, act=act)
@@ -298,12 +312,21 @@ class BatchNormLayer(Layer):
         p_drop = self.fused_dropout_p if self.training else 0.0
         if x.is_cuda:
             Cx = native.require()
+            fused_ws = getattr(x, "_tnn_bn_stats", None)
+            producer = getattr(x, "_tnn_producer", None)
             x = to_bf16(x).contiguous()
             M = x.numel() // C
             b = self._bufs(x.device)
             y = torch.empty_like(x)
             seed = 0
-            if self.training:
+            if self.training and fused_ws is not None and os.environ.get("TNN_BN_FUSE_STATS", "1") == "1":
+                # the producing convolution already accumulated sum / sum-of-squares in its epilogue
+                Cx.bn_finalize_stats(fused_ws, M, C, gamma, beta, self.epsilon, self.momentum, self.params["running_mean"],
+                                     self.params["running_var"], b["mean"], b["invstd"], b["ss"])
+                x._tnn_bn_stats = None                    # the workspace is reset by the fold: single consumer
+            elif self.training:
+                if producer is not None and getattr(producer, "out_channels", -1) == C:
+                    producer._stats_requested = True      # takes effect from the next forward on
                 Cx.bn_train_stats(x, M, C, gamma, beta, self.epsilon, self.momentum, self.params["running_mean"],
                                   self.params["running_var"], b["mean"], b["invstd"], b["ss"], b["ws"])
                 seed = (self.seed * 1000003 + (hash(self.name) & 0xFFFFFF) * 7919 + mb_id) & 0x7FFFFFFFFFFFFFFF

@@ -153,8 +153,11 @@ class ConvState:
         self.w_pad = None         # padded bf16 weight matrix for the im2col path
 
 
-def conv2d_fwd(plan: ConvPlan, x, w, w_bf16, bias, residual=None, act=None, cache: dict | None = None):
-    """x [N,H,W,C]; w fp32 [K,R,S,C]; w_bf16 bf16 view of w (or None).  Returns y [N,OH,OW,K]."""
+def conv2d_fwd(plan: ConvPlan, x, w, w_bf16, bias, residual=None, act=None, cache: dict | None = None,
+               stats_ws: torch.Tensor | None = None):
+    """x [N,H,W,C]; w fp32 [K,R,S,C]; w_bf16 bf16 view of w (or None).  Returns y [N,OH,OW,K].
+    ``stats_ws`` (tma path only): fp32 workspace the epilogue accumulates per-channel sum / sum of
+    squares of y into (BatchNorm statistics fusion, finalised by ``bn_finalize_stats``)."""
     if plan.path == "ref":
         y = conv2d_fwd_ref(x, w, bias, plan.stride, plan.pad)
         if residual is not None:
@@ -179,7 +182,8 @@ def conv2d_fwd(plan: ConvPlan, x, w, w_bf16, bias, residual=None, act=None, cach
             Cx.phase_split(x, xin, N, plan.H, plan.W, plan.C)
             if cache is not None:
                 cache["x_ps"] = xin
-        Cx.conv_fprop(xin, w_bf16, rsc, K, plan.f_geom, plan.f_taps, y, K, [], OUT_BF16, ACT[act], 1.0, bias, residual)
+        Cx.conv_fprop(xin, w_bf16, rsc, K, plan.f_geom, plan.f_taps, y, K, [], OUT_BF16, ACT[act], 1.0, bias, residual,
+                      stats_ws)
         return y
     # im2col fallback
     ld = (rsc + 7) // 8 * 8
