@@ -366,6 +366,7 @@ __global__ void __launch_bounds__(DEC_THREADS)
   float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const unsigned gmask = 0xFFu << (threadIdx.x & 24);
   for (int j = g; j < len; j += DEC_GROUPS) {
     float kf[8], vf[8];
     bf8_unpack(__ldg(reinterpret_cast<const uint4*>(kb + (long long)j * tok_stride)), kf);
@@ -373,9 +374,10 @@ __global__ void __launch_bounds__(DEC_THREADS)
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += qf[i] * kf[i];
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    // the 4 key groups of a warp run different trip counts: shuffle inside the 8-lane group only
+    s += __shfl_xor_sync(gmask, s, 1);
+    s += __shfl_xor_sync(gmask, s, 2);
+    s += __shfl_xor_sync(gmask, s, 4);
     const float mn = fmaxf(m, s);
     const float a = exp2f(m - mn), e = exp2f(s - mn);
     l = l * a + e;
