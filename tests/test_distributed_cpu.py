@@ -368,3 +368,24 @@ def test_1f1b_pipeline_engine_equals_single_device(world, M):
     for a, b in zip(ref, losses):
         assert abs(a - b) < 1e-5, (ref, losses)
     assert nbytes > 0
+
+
+def test_env_fault_injection_drop_and_delay(monkeypatch):
+    monkeypatch.setenv("TNN_FAULT_INJECT", "0:FORWARD_JOB:drop:2")
+    w = InProcessWorker("cpu", "w0")
+    cfg = CoordinatorConfig(ParallelMode.PIPELINE, _model(), OptimizerFactory.create_sgd(0.05), None,
+                            NaivePipelinePartitioner([1]), local_worker=w, seed=1)
+    co = Coordinator(cfg).start()
+    crit = LossFactory.create_logsoftmax_crossentropy()
+    x, y = _batches(1)[0]
+    try:
+        co.timeout_job = 1.0
+        l, _ = co.async_train_batch([x], [y], crit)             # 1st FORWARD_JOB passes
+        assert l > 0
+        with pytest.raises(DistributedError, match="timed out"):
+            co.async_train_batch([x], [y], crit)                 # 2nd one is dropped by the injected fault
+        co.timeout_job = 30.0
+        assert co.async_train_batch([x], [y], crit)[0] > 0       # later ones pass again
+    finally:
+        co.stop()
+        w.stop()

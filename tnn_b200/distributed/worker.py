@@ -9,6 +9,7 @@ CHECKPOINT_REQUEST, BARRIER_SYNC, REPORT_LOAD) are implemented here.
 from __future__ import annotations
 
 import json
+import os
 import threading
 import time
 import traceback
@@ -23,6 +24,15 @@ from ..nn.schedulers import SchedulerFactory
 from ..utils.profiler import EventType, GlobalProfiler, Profiler
 from .communicator import Communicator, InProcessCommunicator, TCPCommunicator
 from .message import CommandType, Endpoint, Job, Message, StageConfig
+
+
+def _parse_fault_env(spec: str):
+    if not spec:
+        return None
+    p = spec.split(":")
+    if len(p) < 3:
+        return None
+    return {"stage": p[0], "cmd": p[1].upper(), "action": p[2], "nth": int(p[3]) if len(p) > 3 else 0, "seen": 0}
 
 
 class Worker:
@@ -44,6 +54,7 @@ class Worker:
         self._busy_ns = 0
         self._jobs = 0
         self.fault_inject = None          # callable(Message) -> None; tests use it to drop / delay / raise
+        self._env_fault = _parse_fault_env(os.environ.get("TNN_FAULT_INJECT", ""))
 
     # ------------------------------------------------------------------ lifecycle
     def start(self, background: bool = False):
@@ -66,6 +77,8 @@ class Worker:
             try:
                 if self.fault_inject is not None:
                     self.fault_inject(msg)
+                if self._env_fault and self._apply_env_fault(msg):
+                    continue
                 self.process_message(msg)
             except Exception as e:  # noqa: BLE001
                 err = f"[{self.name} stage {self.stage_id}] {type(e).__name__}: {e}\n{traceback.format_exc(limit=4)}"
@@ -74,6 +87,25 @@ class Worker:
                         self.comm.send_message(Message(CommandType.ERROR_REPORT, err), self.coord_ep)
                     except Exception:  # noqa: BLE001
                         pass
+
+    def _apply_env_fault(self, msg: Message) -> bool:
+        """TNN_FAULT_INJECT="<stage|*>:<COMMAND>:<drop|delay=SEC|raise|kill>[:<nth>]" (SURVEY 5.3).
+        Returns True when the message must be dropped."""
+        f = self._env_fault
+        if f["stage"] not in ("*", str(self.stage_id)) or msg.command_type.name != f["cmd"]:
+            return False
+        f["seen"] += 1
+        if f["nth"] and f["seen"] != f["nth"]:
+            return False
+        act = f["action"]
+        if act == "drop":
+            return True
+        if act.startswith("delay="):
+            time.sleep(float(act.split("=", 1)[1]))
+            return False
+        if act == "kill":
+            os._exit(17)
+        raise RuntimeError(f"TNN_FAULT_INJECT raised on {msg.command_type.name}")
 
     def stop(self):
         self.should_stop = True
