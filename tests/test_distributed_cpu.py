@@ -379,9 +379,9 @@ def test_env_fault_injection_drop_and_delay(monkeypatch):
     crit = LossFactory.create_logsoftmax_crossentropy()
     x, y = _batches(1)[0]
     try:
-        co.timeout_job = 1.0
         l, _ = co.async_train_batch([x], [y], crit)             # 1st FORWARD_JOB passes
         assert l > 0
+        co.timeout_job = 2.0
         with pytest.raises(DistributedError, match="timed out"):
             co.async_train_batch([x], [y], crit)                 # 2nd one is dropped by the injected fault
         co.timeout_job = 30.0
