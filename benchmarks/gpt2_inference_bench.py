@@ -56,7 +56,19 @@ def run_tnn(a, dev):
     e1.record()
     torch.cuda.synchronize()
     ms_decode = e0.elapsed_time(e1) / a.decode
-    return {"impl": "tnn_b200", "prefill_ms": ms_prefill, "prefill_tok_s": a.batch * a.seq / ms_prefill * 1e3,
+    # the same decode as replays of one captured CUDA graph (tokens + position stay on the device)
+    eng.prefill(prompt[:, :start])
+    eng.decode_graph(tok, 2)
+    eng.prefill(prompt[:, :start])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.decode_graph(tok, a.decode)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_graph = e0.elapsed_time(e1) / a.decode
+    return {"impl": "tnn_b200", "decode_graph_ms_per_step": ms_graph, "decode_graph_tok_s": a.batch / ms_graph * 1e3,
+            "prefill_ms": ms_prefill, "prefill_tok_s": a.batch * a.seq / ms_prefill * 1e3,
             "decode_ms_per_step": ms_decode, "decode_tok_s": a.batch / ms_decode * 1e3,
             "launches_prefill": int(launches_prefill), "launches_per_decode_step": (Cx.launch_count() - l0) / a.decode}
 

@@ -71,3 +71,29 @@ def test_gpt2_engine_cached_decode_matches_full_forward_gpu():
         assert (lg.float()[:, :1000] - ref[:, :1000]).abs().max().item() < 0.15 * max(1.0, ref.abs().max().item())
         agree += int((tok.long() == ref[:, :1000].argmax(-1)).sum())
     assert agree >= 20                                            # greedy tokens agree (bf16 ties aside)
+
+
+def test_gpt2_graph_decode_matches_eager_decode():
+    from tnn_b200.inference import GPT2InferenceEngine
+    from tnn_b200.models.zoo import _gpt2
+    from tnn_b200.nn import graph_from_sequential
+    dev = torch.device("cuda", 0)
+    seq = _gpt2(256, 4, 3, False, "mini_gpt", None, seq_len=320, vocab=1000, dropout=0.0)
+    g = graph_from_sequential(seq, dev, 5, "mini_gpt")
+    eng = GPT2InferenceEngine(g, max_batch=4)
+    ids = torch.randint(0, 1000, (4, 37), generator=torch.Generator().manual_seed(1), dtype=torch.int32).to(dev)
+    first = eng.prefill(ids)
+    eager = []
+    tok = first
+    for _ in range(12):
+        tok = eng.decode(tok)
+        eager.append(tok)
+    eager = torch.stack(eager, 1)
+    eng.prefill(ids)
+    graph = eng.decode_graph(first, 12)
+    assert graph.shape == (4, 12) and eng.cur_len == 37 + 12
+    assert (graph == eager).float().mean().item() > 0.9          # identical kernels; bf16 ties may flip a token
+    # a second call reuses the captured graph from a different position
+    eng.prefill(ids[:, :20])
+    again = eng.decode_graph(eng.prefill(ids[:, :20]), 5)
+    assert again.shape == (4, 5)

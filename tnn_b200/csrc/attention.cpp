@@ -46,6 +46,29 @@ void attention_bind(py::module_& m) {
     attention_decode_bf16(q.data_ptr(), q_batch, kc.data_ptr(), vc.data_ptr(), kc.stride(1), kc.stride(0), out.data_ptr(),
                           B, H, (int)len, at::cuda::getCurrentCUDAStream().stream());
   });
+  m.def("attention_decode_append", [](const Tensor& qkv, const Tensor& kc, const Tensor& vc, const Tensor& out,
+                                      const Tensor& pos) {
+    check_head_view(kc, "k cache");
+    check_head_view(vc, "v cache");
+    const int B = (int)kc.size(0), H = (int)kc.size(2);
+    TORCH_CHECK(qkv.is_cuda() && qkv.scalar_type() == torch::kBFloat16 && qkv.is_contiguous() &&
+                    qkv.numel() == (int64_t)B * 3 * H * 64, "qkv must be contiguous bf16 [B, 3*H*64]");
+    TORCH_CHECK(pos.is_cuda() && pos.scalar_type() == torch::kInt32, "pos: CUDA int32 scalar");
+    attention_decode_append_bf16(qkv.data_ptr(), kc.data_ptr(), vc.data_ptr(), kc.stride(1), kc.stride(0), out.data_ptr(), B, H,
+                                 pos.data_ptr<int>(), at::cuda::getCurrentCUDAStream().stream());
+  });
+  m.def("embed_decode", [](const Tensor& tok, const Tensor& wte, const Tensor& wpe, const Tensor& x, const Tensor& pos) {
+    TORCH_CHECK(tok.scalar_type() == torch::kInt32 && pos.scalar_type() == torch::kInt32, "int32 ids / pos");
+    TORCH_CHECK(wte.scalar_type() == torch::kFloat32 && wpe.scalar_type() == torch::kFloat32, "fp32 tables");
+    embed_decode(tok.data_ptr<int>(), wte.data_ptr<float>(), wpe.data_ptr<float>(), x.data_ptr(), (int)tok.numel(),
+                 (int)wte.size(1), (int)wte.size(0), pos.data_ptr<int>(), at::cuda::getCurrentCUDAStream().stream());
+  });
+  m.def("decode_epilogue", [](const Tensor& next, const Tensor& tok, const Tensor& history, const Tensor& pos,
+                              const Tensor& step) {
+    const int B = (int)tok.numel();
+    decode_epilogue(next.data_ptr<int>(), tok.data_ptr<int>(), history.data_ptr<int>(), B, (int)(history.numel() / B),
+                    pos.data_ptr<int>(), step.data_ptr<int>(), at::cuda::getCurrentCUDAStream().stream());
+  });
 }
 
 }  // namespace tnn

@@ -406,6 +406,124 @@ __global__ void __launch_bounds__(DEC_THREADS)
   }
 }
 
+// Decode step with the position held in DEVICE memory (so the whole step is CUDA-graph
+// replayable): appends this token's K / V rows to the cache at *pos_ptr, then attends over
+// positions [0, *pos_ptr].  qkv is the packed projection of the current token [B, 3, H, 64].
+__global__ void __launch_bounds__(DEC_THREADS)
+    attn_decode_append_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc, bf16* __restrict__ vc,
+                              long long tok_stride, long long batch_stride, bf16* __restrict__ out, int H,
+                              const int* __restrict__ pos_ptr, float scale_log2) {
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int pos = *pos_ptr;
+  const int len = pos + 1;
+  const bf16* row = qkv + (long long)b * 3 * H * AT_D;
+  // threads 0..7 append K, 8..15 append V (16 bytes each)
+  if (threadIdx.x < 16) {
+    const int which = threadIdx.x >> 3, sub8 = threadIdx.x & 7;
+    const uint4 val = *reinterpret_cast<const uint4*>(row + (long long)(1 + which) * H * AT_D + h * AT_D + sub8 * 8);
+    bf16* dst = (which ? vc : kc) + (long long)b * batch_stride + (long long)pos * tok_stride + h * AT_D + sub8 * 8;
+    *reinterpret_cast<uint4*>(dst) = val;
+  }
+  __syncthreads();
+  const int g = threadIdx.x >> 3;
+  const int sub = threadIdx.x & 7;
+  float qf[8];
+  bf8_unpack(*reinterpret_cast<const uint4*>(row + h * AT_D + sub * 8), qf);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) qf[i] *= scale_log2;
+  const bf16* kb = kc + (long long)b * batch_stride + h * AT_D + sub * 8;
+  const bf16* vb = vc + (long long)b * batch_stride + h * AT_D + sub * 8;
+  float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const unsigned gmask = 0xFFu << (threadIdx.x & 24);
+  for (int j = g; j < len; j += DEC_GROUPS) {
+    float kf[8], vf[8];
+    // plain loads: row `pos` was written by this CTA just above (not via the read-only path)
+    bf8_unpack(*reinterpret_cast<const uint4*>(kb + (long long)j * tok_stride), kf);
+    bf8_unpack(*reinterpret_cast<const uint4*>(vb + (long long)j * tok_stride), vf);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += qf[i] * kf[i];
+    s += __shfl_xor_sync(gmask, s, 1);
+    s += __shfl_xor_sync(gmask, s, 2);
+    s += __shfl_xor_sync(gmask, s, 4);
+    const float mn = fmaxf(m, s);
+    const float a = exp2f(m - mn), e = exp2f(s - mn);
+    l = l * a + e;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = acc[i] * a + e * vf[i];
+    m = mn;
+  }
+  __shared__ float sm_m[DEC_GROUPS], sm_l[DEC_GROUPS], sm_o[DEC_GROUPS][AT_D];
+  if (sub == 0) {
+    sm_m[g] = m;
+    sm_l[g] = l;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm_o[g][sub * 8 + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < AT_D) {
+    float M = -INFINITY;
+    for (int i = 0; i < DEC_GROUPS; ++i) M = fmaxf(M, sm_m[i]);
+    float L = 0.f, O = 0.f;
+    for (int i = 0; i < DEC_GROUPS; ++i) {
+      const float w = (sm_m[i] == -INFINITY) ? 0.f : exp2f(sm_m[i] - M);
+      L += sm_l[i] * w;
+      O += sm_o[i][threadIdx.x] * w;
+    }
+    out[((long long)b * H + h) * AT_D + threadIdx.x] = __float2bfloat16(L > 0.f ? O / L : 0.f);
+  }
+}
+
+void attention_decode_append_bf16(const void* qkv, void* kcache, void* vcache, long long tok_stride,
+                                  long long batch_stride, void* out, int B, int H, const int* pos_ptr,
+                                  cudaStream_t stream) {
+  if (B <= 0 || H <= 0) return;
+  dim3 grid(H, B);
+  attn_decode_append_kernel<<<grid, DEC_THREADS, 0, stream>>>(
+      reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(kcache), reinterpret_cast<bf16*>(vcache), tok_stride,
+      batch_stride, reinterpret_cast<bf16*>(out), H, pos_ptr, 1.4426950408889634f / sqrtf((float)AT_D));
+  TNN_CHECK_LAUNCH();
+}
+
+// x[b, :] = wte[tok[b], :] + wpe[*pos, :]  (bf16 out), one CTA per sequence
+__global__ void __launch_bounds__(256)
+    k_embed_decode(const int* __restrict__ tok, const float* __restrict__ wte, const float* __restrict__ wpe,
+                   bf16* __restrict__ x, int D, int V, const int* __restrict__ pos_ptr) {
+  const int b = blockIdx.x;
+  const int pos = *pos_ptr;
+  int id = tok[b];
+  id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+  for (int d = threadIdx.x; d < D; d += blockDim.x)
+    x[(long long)b * D + d] = __float2bfloat16(wte[(long long)id * D + d] + wpe[(long long)pos * D + d]);
+}
+void embed_decode(const int* tok, const float* wte, const float* wpe, void* x, int B, int D, int V, const int* pos_ptr,
+                  cudaStream_t stream) {
+  k_embed_decode<<<B, 256, 0, stream>>>(tok, wte, wpe, reinterpret_cast<bf16*>(x), D, V, pos_ptr);
+  TNN_CHECK_LAUNCH();
+}
+
+// end of a decode step: publish the sampled tokens, log them, advance the device position
+__global__ void k_decode_epilogue(const int* __restrict__ next, int* __restrict__ tok, int* __restrict__ history,
+                                  int B, int hist_cap, int* pos_ptr, int* step_ptr) {
+  const int step = *step_ptr;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    tok[b] = next[b];
+    if (step < hist_cap) history[(long long)step * B + b] = next[b];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *pos_ptr += 1;
+    *step_ptr = step + 1;
+  }
+}
+void decode_epilogue(const int* next, int* tok, int* history, int B, int hist_cap, int* pos_ptr, int* step_ptr,
+                     cudaStream_t stream) {
+  k_decode_epilogue<<<1, 256, 0, stream>>>(next, tok, history, B, hist_cap, pos_ptr, step_ptr);
+  TNN_CHECK_LAUNCH();
+}
+
 void attention_decode_bf16(const void* q, long long q_batch, const void* kcache, const void* vcache,
                            long long tok_stride, long long batch_stride, void* out, int B, int H, int len,
                            cudaStream_t stream) {

@@ -17,4 +17,13 @@ void attention_decode_bf16(const void* q, long long q_batch, const void* kcache,
                            long long tok_stride, long long batch_stride, void* out, int B, int H, int len,
                            cudaStream_t stream);
 
+// Graph-replayable decode step pieces: the position lives in device memory.
+void attention_decode_append_bf16(const void* qkv, void* kcache, void* vcache, long long tok_stride,
+                                  long long batch_stride, void* out, int B, int H, const int* pos_ptr,
+                                  cudaStream_t stream);
+void embed_decode(const int* tok, const float* wte, const float* wpe, void* x, int B, int D, int V, const int* pos_ptr,
+                  cudaStream_t stream);
+void decode_epilogue(const int* next, int* tok, int* history, int B, int hist_cap, int* pos_ptr, int* step_ptr,
+                     cudaStream_t stream);
+
 }  // namespace tnn

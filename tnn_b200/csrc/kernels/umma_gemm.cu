@@ -322,6 +322,180 @@ __global__ void __launch_bounds__(kThreads)
 }
 
 // ---------------------------------------------------------------------------
+// Persistent variant of the kernel above: grid = min(#tiles, 2 x #SMs); every CTA walks tiles
+// t = blockIdx.x, blockIdx.x + gridDim.x, ... with
+//   * the TMA producer running ahead across tile boundaries (one smem ring for all tiles),
+//   * TWO accumulator buffers in TMEM (2 x BLOCK_N columns): the MMA warp fills buffer it&1 while
+//     the epilogue warps drain the other one, so the epilogue (and the launch / TMEM-alloc /
+//     descriptor-fetch prologue, paid once per CTA instead of once per tile) is off the tensor
+//     core's critical path.  Short-K shapes (GPT-2: K = 768, early conv layers) were dominated
+//     by exactly those per-tile costs.
+// Tile order is n-fastest so concurrently running CTAs share the A row block through L2.
+// ---------------------------------------------------------------------------
+template <int BLOCK_N, bool A_MN, bool B_MN, bool CONV_A, int STAGES>
+__global__ void __launch_bounds__(kThreads)
+    umma_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                             const KParams p, int m_tiles, int n_tiles, int num_tiles) {
+  constexpr int A_BYTES = BLOCK_M * 128;
+  constexpr int B_BYTES = BLOCK_N * 128;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
+  static_assert(TMEM_COLS <= 512, "two accumulator buffers must fit in TMEM");
+  static_assert(!(CONV_A && A_MN), "conv window operand is K-major");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;    // [2]
+  uint64_t* tmem_empty = tmem_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ----------------------------- TMA producer -----------------------------
+      int kit = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int tile_n = t % n_tiles;
+        const int tile_m = (t / n_tiles) % m_tiles;
+        const int z = t / (n_tiles * m_tiles);
+        const int m0 = tile_m * BLOCK_M, n0 = tile_n * BLOCK_N;
+        const int kb_begin = z * p.kb_per_split;
+        const int kb_end = min(kb_begin + p.kb_per_split, p.kb_total);
+        int img0 = 0, h0 = 0;
+        if (CONV_A) {
+          const int hw = p.OH * p.OW;
+          if (p.BN > 1) {
+            img0 = tile_m * p.BN;
+          } else {
+            img0 = m0 / hw;
+            h0 = (m0 - img0 * hw) / p.OW;
+          }
+        }
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++kit) {
+          const int s = kit % STAGES;
+          const uint32_t ph = (kit / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_expect_tx(&full[s], STAGE_BYTES);
+          int kB;
+          if (CONV_A) {
+            const int tp = kb / p.kc_per_tap;
+            const int kc = kb - tp * p.kc_per_tap;
+            const ConvTap tap = p.taps[tp];
+            tma_load_4d(sa, &tmA, &full[s], kc * BLOCK_K, tap.dw, h0 + tap.dh, img0 + tap.nb);
+            kB = tap.koff + kc * BLOCK_K;
+          } else {
+            kB = kb * BLOCK_K;
+            if (A_MN) {
+              tma_load_2d(sa, &tmA, &full[s], m0, kB);
+              tma_load_2d(sa + ATOM_BYTES, &tmA, &full[s], m0 + 64, kB);
+            } else {
+              tma_load_2d(sa, &tmA, &full[s], kB, m0);
+            }
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(sb + j * ATOM_BYTES, &tmB, &full[s], n0 + j * 64, kB);
+          } else {
+            tma_load_2d(sb, &tmB, &full[s], kB, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ----------------------------- MMA issuer -----------------------------
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      int kit = 0, it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int z = t / (n_tiles * m_tiles);
+        const int kb_begin = z * p.kb_per_split;
+        const int nkb = min(kb_begin + p.kb_per_split, p.kb_total) - kb_begin;
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);      // epilogue drained this buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+        for (int i = 0; i < nkb; ++i, ++kit) {
+          const int s = kit % STAGES;
+          const uint32_t ph = (kit / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t ad = A_MN ? make_smem_desc_sw128(a_addr + k * 2048, ATOM_BYTES, 1024)
+                                     : make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
+            const uint64_t bd = B_MN ? make_smem_desc_sw128(b_addr + k * 2048, ATOM_BYTES, 1024)
+                                     : make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+            umma_f16(d_tmem, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ----------------------------- epilogue -----------------------------
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int tile_n = t % n_tiles;
+      const int tile_m = (t / n_tiles) % m_tiles;
+      const int m0 = tile_m * BLOCK_M, n0 = tile_n * BLOCK_N;
+      const int acc = it & 1;
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const int m = m0 + row;
+      const bool row_ok = m < p.M;
+      const long long row_off = row_ok ? epi_row_offset(p.epi, m) : 0;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        if (n0 + c >= p.N) break;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS + c, r);
+        tmem_ld_wait();
+        epi_store_32(p, r, row_ok, row_off, n0 + c);
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------
 // CTA-pair GEMM / conv-fprop kernel (cta_group::2): a (2,1,1) cluster computes a 256 x BLOCK_N
 // tile.  Each CTA TMA-loads its own 128 rows of A (or its own conv window) and its own
 // BLOCK_N/2 rows of B, so per-SM shared-memory traffic per MMA halves compared with the
@@ -718,6 +892,33 @@ static bool use_2cta(int M, int N, bool a_mn, bool b_mn, int splits) {
   return mode > 0 && !a_mn && !b_mn && splits <= 1 && M >= 256 && N >= 128;
 }
 
+static bool use_persistent() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("TNN_GEMM_PERSIST");
+    mode = (e != nullptr) ? atoi(e) : 1;
+  }
+  return mode > 0;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, bool CONV_A>
+static void launch_gemm_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, int m_tiles,
+                                int n_tiles, int splits, cudaStream_t stream) {
+  constexpr int STAGES = (BLOCK_N <= 64) ? 4 : 3;
+  constexpr int smem = STAGES * (BLOCK_M * 128 + BLOCK_N * 128) + 1024 + 256;
+  auto kern = umma_gemm_persist_kernel<BLOCK_N, A_MN, B_MN, CONV_A, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    set_smem(kern, smem);
+    configured = true;
+  }
+  const int num_tiles = m_tiles * n_tiles * splits;
+  const int grid = num_tiles < 2 * 148 ? num_tiles : 2 * 148;
+  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p, m_tiles, n_tiles, num_tiles);
+  ++g_launch_count;
+  TNN_CUDA_CHECK(cudaGetLastError());
+}
+
 static int pick_block_n(int N) {
   const char* e = getenv("TNN_GEMM_BLOCK_N");
   if (e != nullptr) {
@@ -799,6 +1000,21 @@ void gemm_bf16(const void* A, const void* B, int M, int N, int K, long long lda,
   CUtensorMap tmA = a_mn ? make_operand_map(A, K, M, lda, 64) : make_operand_map(A, M, K, lda, BLOCK_M);
   CUtensorMap tmB = b_mn ? make_operand_map(B, K, N, ldb, 64) : make_operand_map(B, N, K, ldb, bn);
   dim3 grid((M + BLOCK_M - 1) / BLOCK_M, (N + bn - 1) / bn, splits);
+  if (use_persistent() && bn <= 128) {
+    const int mt = (int)grid.x, nt = (int)grid.y;
+    if (bn == 64) {
+      if (!a_mn && !b_mn) launch_gemm_persist<64, false, false, false>(tmA, tmB, p, mt, nt, splits, stream);
+      else if (!a_mn && b_mn) launch_gemm_persist<64, false, true, false>(tmA, tmB, p, mt, nt, splits, stream);
+      else if (a_mn && !b_mn) launch_gemm_persist<64, true, false, false>(tmA, tmB, p, mt, nt, splits, stream);
+      else launch_gemm_persist<64, true, true, false>(tmA, tmB, p, mt, nt, splits, stream);
+    } else {
+      if (!a_mn && !b_mn) launch_gemm_persist<128, false, false, false>(tmA, tmB, p, mt, nt, splits, stream);
+      else if (!a_mn && b_mn) launch_gemm_persist<128, false, true, false>(tmA, tmB, p, mt, nt, splits, stream);
+      else if (a_mn && !b_mn) launch_gemm_persist<128, true, false, false>(tmA, tmB, p, mt, nt, splits, stream);
+      else launch_gemm_persist<128, true, true, false>(tmA, tmB, p, mt, nt, splits, stream);
+    }
+    return;
+  }
   TNN_DISPATCH_BN(bn, {
     if (!a_mn && !b_mn) launch_gemm<BNc, false, false, false>(tmA, tmB, p, grid, stream);
     else if (!a_mn && b_mn) launch_gemm<BNc, false, true, false>(tmA, tmB, p, grid, stream);
@@ -844,6 +1060,11 @@ void conv_fprop_bf16(const void* X, const void* Wt, long long ldw, int N, const 
   // weight matrix [N, Ktot]: the last tap may read past koff+C; the extent is ldw
   CUtensorMap tmB = make_operand_map(Wt, N, ldw, ldw, bn);
   dim3 grid((M + BLOCK_M - 1) / BLOCK_M, (N + bn - 1) / bn, 1);
+  if (use_persistent() && bn <= 128) {
+    if (bn == 64) launch_gemm_persist<64, false, false, true>(tmA, tmB, p, (int)grid.x, (int)grid.y, 1, stream);
+    else launch_gemm_persist<128, false, false, true>(tmA, tmB, p, (int)grid.x, (int)grid.y, 1, stream);
+    return;
+  }
   TNN_DISPATCH_BN(bn, { launch_gemm<BNc, false, false, true>(tmA, tmB, p, grid, stream); })
 }
 

@@ -71,6 +71,8 @@ class GPT2InferenceEngine:
                        for _ in self.blocks]
         self.cur_len = 0
         self.cur_batch = 0
+        self._dev = None
+        self._graph = None
 
     # ------------------------------------------------------------------ building blocks
     def _embed(self, ids: torch.Tensor, pos: int) -> torch.Tensor:
@@ -163,6 +165,65 @@ class GPT2InferenceEngine:
             tok = self.decode(tok)
             out.append(tok)
         return torch.stack(out, 1)
+
+    # ------------------------------------------------------------------ CUDA-graph decode (GPU)
+    def _decode_step_device(self):
+        """One decode step whose position / tokens live in device memory (graph replayable)."""
+        Cx = native.require()
+        B, E = self.cur_batch, self.E
+        st = self._dev
+        x = torch.empty((B, E), dtype=torch.bfloat16, device=self.device)
+        Cx.embed_decode(st["tok"], self.embed.params["weight"], self.pos.params["weight"], x, st["pos"])
+        for b, cache in zip(self.blocks, self.caches):
+            y = b.ln1.forward_impl(x, 0)
+            qkv = b.attn._qkv(y)                                         # [B, 3E]
+            o = torch.empty((B, E), dtype=torch.bfloat16, device=self.device)
+            Cx.attention_decode_append(qkv, cache.k[:B], cache.v[:B], o, st["pos"])
+            x = b.attn._out(o, x)
+            x = self._mlp(b, x)
+        logits = self._logits_last(x).reshape(B, -1)
+        nxt = self._argmax(logits)
+        Cx.decode_epilogue(nxt, st["tok"], st["history"], st["pos"], st["step"])
+
+    @torch.no_grad()
+    def decode_graph(self, tokens: torch.Tensor, steps: int) -> torch.Tensor:
+        """``steps`` greedy decode steps as replays of ONE captured CUDA graph: token ids and the
+        position stay on the device between steps (no host round trip, no per-step launches from
+        Python).  Returns the generated ids [B, steps]."""
+        if not self.cuda:
+            out, tok = [], tokens
+            for _ in range(steps):
+                tok = self.decode(tok)
+                out.append(tok)
+            return torch.stack(out, 1)
+        B = self.cur_batch
+        steps = min(int(steps), self.max_len - self.cur_len)
+        dev = self.device
+        if getattr(self, "_dev", None) is None or self._dev["tok"].numel() != B or self._dev["history"].shape[0] < steps:
+            self._dev = dict(tok=torch.zeros(B, dtype=torch.int32, device=dev), pos=torch.zeros(1, dtype=torch.int32, device=dev),
+                             step=torch.zeros(1, dtype=torch.int32, device=dev),
+                             history=torch.zeros((max(steps, 64), B), dtype=torch.int32, device=dev))
+            self._graph = None
+        st = self._dev
+        st["tok"].copy_(tokens.to(dev).to(torch.int32).reshape(B))
+        st["pos"].fill_(self.cur_len)
+        st["step"].zero_()
+        if self._graph is None:
+            self._decode_step_device()                                   # warm-up (allocator, plans) ...
+            st["tok"].copy_(tokens.to(dev).to(torch.int32).reshape(B))   # ... then rewind its side effects
+            st["pos"].fill_(self.cur_len)
+            st["step"].zero_()
+            torch.cuda.synchronize(dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._decode_step_device()
+            self._graph = g
+        for _ in range(steps):
+            self._graph.replay()
+        self.cur_len += steps
+        for c in self.caches:
+            c.len = self.cur_len
+        return st["history"][:steps].t().contiguous()
 
     def full_forward_logits(self, ids: torch.Tensor) -> torch.Tensor:
         """Reference path: the whole model over the whole sequence, no cache (what the reference

@@ -328,6 +328,16 @@ class AttentionBlock(Block):
             self.cache(mb_id).update(x=x2, qkv=qkv, o=o2, lse=lse)
         return y.reshape(B, L, E)
 
+    # inference helpers (inference/gpt2.py): the two projections without the attention in between
+    def _qkv(self, x2: torch.Tensor) -> torch.Tensor:
+        if x2.is_cuda:
+            return gemm_ops.linear_fwd(_aligned_rows(to_bf16(x2)), self.lp("qkv_weight"), self.params["qkv_bias"])
+        return gemm_ops.linear_fwd(x2.float(), self.params["qkv_weight"], self.params["qkv_bias"])
+
+    def _out(self, o2: torch.Tensor, residual: torch.Tensor | None = None) -> torch.Tensor:
+        w = self.lp("out_weight") if o2.is_cuda else self.params["out_weight"]
+        return gemm_ops.linear_fwd(o2, w, self.params["out_bias"], residual=residual)
+
     def backward_impl(self, dy, mb_id):
         c = self.cache(mb_id)
         x2, qkv, o2 = c["x"], c["qkv"], c["o"]
