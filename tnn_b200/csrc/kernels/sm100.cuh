@@ -224,6 +224,11 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t a_desc, u
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// arrive on the LEADER CTA's copy of a barrier from either CTA of the pair
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask)
+               : "memory");
+}
 // arrives (once all MMAs issued so far retired) on the barrier at this smem offset in BOTH CTAs
 __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
   asm volatile(

@@ -623,6 +623,156 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads)
 }
 
 // ---------------------------------------------------------------------------
+// Persistent CTA-pair kernel: the (2,1,1) cluster walks 256 x BLOCK_N tiles, double-buffered
+// accumulators in both CTAs' TMEM.  The leader may only overwrite accumulator buffer `acc` once
+// BOTH CTAs' epilogues drained their 128 rows of it, so all 256 epilogue threads of the pair
+// arrive on the LEADER's tmem_empty barrier (remote mbarrier arrive through the cluster window).
+// ---------------------------------------------------------------------------
+template <int BLOCK_N, bool CONV_A, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads)
+    umma_gemm2_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                              const KParams p, int m_tiles /* 256-row tiles */, int n_tiles, int num_tiles) {
+  constexpr int A_BYTES = BLOCK_M * 128;
+  constexpr int B_BYTES = (BLOCK_N / 2) * 128;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
+  static_assert(TMEM_COLS <= 512, "two accumulator buffers must fit in TMEM");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;    // [2]
+  uint64_t* tmem_empty = tmem_full + 2;    // [2] (only the leader's copy is used)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int nkb = p.kb_total;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 256);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int kit = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs) {
+        const int tile_n = t % n_tiles;
+        const int tile_m = t / n_tiles;
+        const int m0 = (tile_m * 2 + (int)rank) * BLOCK_M;
+        const int n0 = tile_n * BLOCK_N;
+        int img0 = 0, h0 = 0;
+        if (CONV_A) {
+          const int hw = p.OH * p.OW;
+          if (p.BN > 1) {
+            img0 = (tile_m * 2 + (int)rank) * p.BN;
+          } else {
+            img0 = m0 / hw;
+            h0 = (m0 - img0 * hw) / p.OW;
+          }
+        }
+        for (int i = 0; i < nkb; ++i, ++kit) {
+          const int s = kit % STAGES;
+          const uint32_t ph = (kit / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          if (leader) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);
+          int kB;
+          if (CONV_A) {
+            const int tp = i / p.kc_per_tap;
+            const int kc = i - tp * p.kc_per_tap;
+            const ConvTap tap = p.taps[tp];
+            tma_load_4d_2sm(sa, &tmA, &full[s], kc * BLOCK_K, tap.dw, h0 + tap.dh, img0 + tap.nb);
+            kB = tap.koff + kc * BLOCK_K;
+          } else {
+            kB = i * BLOCK_K;
+            tma_load_2d_2sm(sa, &tmA, &full[s], kB, m0);
+          }
+          tma_load_2d_2sm(sb, &tmB, &full[s], kB, n0 + (int)rank * (BLOCK_N / 2));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BLOCK_M, BLOCK_N, 0u, 0u);
+      int kit = 0, it = 0;
+      for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int i = 0; i < nkb; ++i, ++kit) {
+          const int s = kit % STAGES;
+          const uint32_t ph = (kit / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            umma_f16_2sm(d_tmem, make_smem_desc_sw128(a_addr + k * 32, 0, 1024),
+                         make_smem_desc_sw128(b_addr + k * 32, 0, 1024), idesc, (i > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(&empty[s]);
+        }
+        umma_commit_2sm(&tmem_full[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int t = pair; t < num_tiles; t += num_pairs, ++it) {
+      const int tile_n = t % n_tiles;
+      const int tile_m = t / n_tiles;
+      const int m0 = (tile_m * 2 + (int)rank) * BLOCK_M;
+      const int n0 = tile_n * BLOCK_N;
+      const int acc = it & 1;
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const int m = m0 + row;
+      const bool row_ok = m < p.M;
+      const long long row_off = row_ok ? epi_row_offset(p.epi, m) : 0;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        if (n0 + c >= p.N) break;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + c, r);
+        tmem_ld_wait();
+        epi_store_32(p, r, row_ok, row_off, n0 + c);
+      }
+      tc_fence_before();
+      mbar_arrive_leader(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2sm<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------
 // conv wgrad kernel: M = Kout tile (128), N = 64 input channels per tap, T taps
 // ---------------------------------------------------------------------------
 template <int T, int STAGES>
@@ -882,6 +1032,25 @@ static void launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const K
   TNN_CUDA_CHECK(cudaGetLastError());
 }
 
+template <int BLOCK_N, bool CONV_A>
+static void launch_gemm2_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, int m_tiles256,
+                                 int n_tiles, cudaStream_t stream) {
+  constexpr int STAGES = (BLOCK_N <= 128) ? 4 : 6;     // BLOCK_N = 256 owns the SM (TMEM full): deeper ring
+  constexpr int smem = STAGES * (BLOCK_M * 128 + (BLOCK_N / 2) * 128) + 1024 + 256;
+  auto kern = umma_gemm2_persist_kernel<BLOCK_N, CONV_A, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    set_smem(kern, smem);
+    configured = true;
+  }
+  const int num_tiles = m_tiles256 * n_tiles;
+  const int max_pairs = (BLOCK_N <= 128) ? 148 : 74;   // 2 resident CTAs per SM, or 1
+  const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
+  kern<<<2 * pairs, kThreads, smem, stream>>>(tmA, tmB, p, m_tiles256, n_tiles, num_tiles);
+  ++g_launch_count;
+  TNN_CUDA_CHECK(cudaGetLastError());
+}
+
 // CTA-pair path: opt-in with TNN_GEMM_2CTA=1 (default decided by measurement)
 static bool use_2cta(int M, int N, bool a_mn, bool b_mn, int splits) {
   static int mode = -1;
@@ -890,6 +1059,11 @@ static bool use_2cta(int M, int N, bool a_mn, bool b_mn, int splits) {
     mode = (e != nullptr) ? atoi(e) : 0;
   }
   return mode > 0 && !a_mn && !b_mn && splits <= 1 && M >= 256 && N >= 128;
+}
+static bool use_2cta_persist() {
+  const char* e = getenv("TNN_GEMM_2CTA");
+  static int mode = (e != nullptr) ? atoi(e) : 0;
+  return mode >= 2;
 }
 
 static bool use_persistent() {
@@ -975,6 +1149,11 @@ void gemm_bf16(const void* A, const void* B, int M, int N, int K, long long lda,
     CUtensorMap tmA = make_operand_map(A, M, K, lda, BLOCK_M);
     CUtensorMap tmB = make_operand_map(B, N, K, ldb, bn2 / 2);
     dim3 grid(2 * ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)), (N + bn2 - 1) / bn2, 1);
+    if (use_2cta_persist()) {
+      if (bn2 == 256) launch_gemm2_persist<256, false>(tmA, tmB, p, (int)grid.x / 2, (int)grid.y, stream);
+      else launch_gemm2_persist<128, false>(tmA, tmB, p, (int)grid.x / 2, (int)grid.y, stream);
+      return;
+    }
     if (bn2 == 256) launch_gemm2<256, false>(tmA, tmB, p, grid, stream);
     else launch_gemm2<128, false>(tmA, tmB, p, grid, stream);
     return;
@@ -1053,6 +1232,11 @@ void conv_fprop_bf16(const void* X, const void* Wt, long long ldw, int N, const 
     const int bn2 = N >= 256 ? 256 : 128;
     CUtensorMap tmB2 = make_operand_map(Wt, N, ldw, ldw, bn2 / 2);
     dim3 grid2(2 * ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)), (N + bn2 - 1) / bn2, 1);
+    if (use_2cta_persist()) {
+      if (bn2 == 256) launch_gemm2_persist<256, true>(tmA, tmB2, p, (int)grid2.x / 2, (int)grid2.y, stream);
+      else launch_gemm2_persist<128, true>(tmA, tmB2, p, (int)grid2.x / 2, (int)grid2.y, stream);
+      return;
+    }
     if (bn2 == 256) launch_gemm2<256, true>(tmA, tmB2, p, grid2, stream);
     else launch_gemm2<128, true>(tmA, tmB2, p, grid2, stream);
     return;
