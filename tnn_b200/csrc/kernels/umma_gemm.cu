@@ -851,7 +851,10 @@ __global__ void __launch_bounds__(kThreads)
       }
     } else if (warp == 1) {
       if (elect_one()) {
-        constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, 64, 1u, 1u);
+        // ONE MMA of N = T*64 per k-step: the T tap tiles are consecutive 64-wide MN-major atoms
+        // (LBO = ATOM_BYTES), so the dY operand is fetched from shared memory once per k-step
+        // instead of once per tap -- the kernel was shared-memory-bandwidth bound.
+        constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, T * 64, 1u, 1u);
         for (int i = 0; i < nkb; ++i) {
           const int s = i % STAGES;
           const uint32_t ph = (i / STAGES) & 1;
@@ -860,14 +863,10 @@ __global__ void __launch_bounds__(kThreads)
           const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
 #pragma unroll
-          for (int t = 0; t < T; ++t) {
-#pragma unroll
-            for (int k = 0; k < BLOCK_K / 16; ++k) {
-              const uint64_t ad = make_smem_desc_sw128(a_addr + k * 2048, ATOM_BYTES, 1024);
-              const uint64_t bd =
-                  make_smem_desc_sw128(b_addr + t * ATOM_BYTES + k * 2048, ATOM_BYTES, 1024);
-              umma_f16(tmem_base + t * 64, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
-            }
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 2048, ATOM_BYTES, 1024);
+            const uint64_t bd = make_smem_desc_sw128(b_addr + k * 2048, ATOM_BYTES, 1024);
+            umma_f16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty[s]);
         }
