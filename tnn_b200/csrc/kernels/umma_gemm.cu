@@ -1050,20 +1050,25 @@ static void launch_gemm2_persist(const CUtensorMap& tmA, const CUtensorMap& tmB,
   TNN_CUDA_CHECK(cudaGetLastError());
 }
 
-// CTA-pair path: opt-in with TNN_GEMM_2CTA=1 (default decided by measurement)
-static bool use_2cta(int M, int N, bool a_mn, bool b_mn, int splits) {
-  static int mode = -1;
-  if (mode < 0) {
+// CTA-pair path.  TNN_GEMM_2CTA: unset/-1 = auto (measured on B200, profiles/gemm2_check_r1.log and
+// gemm_persist_check_r1.log: the persistent pair kernel wins for N >= 256 with >= 32 k-blocks, i.e. the
+// 16x16x256 and 8x8x512 conv layers (+9..17%), and loses on short-K GEMMs where two resident 1-CTA
+// persistent CTAs per SM overlap better), 0 = never, 1 = non-persistent pair kernel, 2 = persistent pair.
+static int mode_2cta() {
+  static int mode = -2;
+  if (mode == -2) {
     const char* e = getenv("TNN_GEMM_2CTA");
-    mode = (e != nullptr) ? atoi(e) : 0;
+    mode = (e != nullptr) ? atoi(e) : -1;
   }
-  return mode > 0 && !a_mn && !b_mn && splits <= 1 && M >= 256 && N >= 128;
+  return mode;
 }
-static bool use_2cta_persist() {
-  const char* e = getenv("TNN_GEMM_2CTA");
-  static int mode = (e != nullptr) ? atoi(e) : 0;
-  return mode >= 2;
+static bool use_2cta(int M, int N, bool a_mn, bool b_mn, int splits, int kb_total) {
+  const int mode = mode_2cta();
+  if (mode == 0 || a_mn || b_mn || splits > 1 || M < 256 || N < 128) return false;
+  if (mode < 0) return N >= 256 && kb_total >= 32;
+  return true;
 }
+static bool use_2cta_persist() { return mode_2cta() != 1; }
 
 static bool use_persistent() {
   static int mode = -1;
@@ -1133,7 +1138,7 @@ void gemm_bf16(const void* A, const void* B, int M, int N, int K, long long lda,
     fprintf(stderr, "[tnn_b200] gemm_bf16: operands must be 16-byte aligned with ld %% 8 == 0\n");
     abort();
   }
-  if (use_2cta(M, N, a_mn, b_mn, splits)) {
+  if (use_2cta(M, N, a_mn, b_mn, splits, (K + BLOCK_K - 1) / BLOCK_K)) {
     const int bn2 = N >= 256 ? 256 : 128;
     KParams p{};
     p.M = M;
@@ -1227,7 +1232,7 @@ void conv_fprop_bf16(const void* X, const void* Wt, long long ldw, int N, const 
   p.epi = epi;
   p.vec_ok = epi_vec_ok(epi, N);
   CUtensorMap tmA = make_window_map(X, g, BH, BN);
-  if (use_2cta(M, N, false, false, 1)) {
+  if (use_2cta(M, N, false, false, 1, p.kb_total)) {
     const int bn2 = N >= 256 ? 256 : 128;
     CUtensorMap tmB2 = make_operand_map(Wt, N, ldw, ldw, bn2 / 2);
     dim3 grid2(2 * ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)), (N + bn2 - 1) / bn2, 1);
