@@ -186,3 +186,32 @@ def test_batchnorm_statistics_fused_into_conv_epilogue():
         else:
             assert used
             assert (y.float() - ref).abs().max().item() < 3e-2
+
+
+@pytest.mark.parametrize("relu,p", [(True, 0.0), (True, 0.3), (False, 0.3)])
+def test_batchnorm_backward_mask_recompute_equals_stored_mask(relu, p):
+    """Backward rebuilds the ReLU/dropout mask from x + statistics + the dropout counter; it must give
+    the same gradients as reading the mask from the stored forward output."""
+    import os
+    from tnn_b200.nn import BatchNormLayer
+    dev = torch.device("cuda", 0)
+    x = (torch.randn(16, 12, 12, 64, device=dev) * 1.5 + 0.3).bfloat16()
+    dy = torch.randn(16, 12, 12, 64, device=dev).bfloat16()
+    res = {}
+    for mode in ("0", "1"):
+        os.environ["TNN_BN_RECOMPUTE_MASK"] = mode
+        bn = BatchNormLayer(64, 1e-2, 0.1, True, relu, "bn").init(dev, 7)
+        bn.params["gamma"].uniform_(0.5, 1.5)
+        bn.params["beta"].uniform_(-0.5, 0.5)
+        bn.fused_dropout_p = p
+        y = bn.forward(x, 0)
+        assert (bn.cache(0)["y"] is None) == (mode == "1")
+        dx = bn.backward(dy, 0)
+        res[mode] = (y.float(), dx.float(), bn.grads["gamma"].clone(), bn.grads["beta"].clone())
+    os.environ["TNN_BN_RECOMPUTE_MASK"] = "1"
+    assert torch.equal(res["0"][0], res["1"][0])
+    assert (res["0"][1] - res["1"][1]).abs().max().item() <= 2e-2 * res["0"][1].abs().max().item()
+    # at most a handful of elements sit exactly on the ReLU boundary
+    assert ((res["0"][1] - res["1"][1]).abs() > 1e-6).float().mean().item() < 1e-3
+    torch.testing.assert_close(res["0"][2], res["1"][2], atol=5e-2, rtol=1e-2)
+    torch.testing.assert_close(res["0"][3], res["1"][3], atol=5e-2, rtol=1e-2)

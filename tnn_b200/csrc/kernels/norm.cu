@@ -309,30 +309,64 @@ void bn_apply(const void* x, void* y, long long M, int C, const float* scale_shi
 }
 
 // ------------------------------------------------------------------ BN backward
+// Mask recomputation (y == nullptr with masked != 0): instead of re-reading the forward output to
+// find which elements survived ReLU / dropout, the mask is rebuilt from x and the saved statistics
+// (v = x*gamma*invstd + beta - mean*gamma*invstd, the exact forward expression) and from the
+// counter-based dropout generator -- one tensor less to read in each of the two backward passes.
+struct BnMaskArgs {
+  const float* beta;
+  int relu;
+  float p;
+  uint64_t seed;
+  const uint64_t* seed_ptr;
+};
+
 __global__ void __launch_bounds__(256)
     k_bn_bwd_reduce(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ y,
                     long long M, int C, const float* __restrict__ gamma,
                     const float* __restrict__ mean, const float* __restrict__ invstd, int masked,
-                    float dscale, float* dgamma, float* dbeta, float* coef, float* ws) {
+                    float dscale, float* dgamma, float* dbeta, float* coef, float* ws, BnMaskArgs ma) {
   extern __shared__ float sm[];
   const BnMap m(C);
   const bool vec = (C & 7) == 0;
+  const bool recompute = masked && (y == nullptr);
+  uint64_t seed = ma.seed;
+  if (recompute && ma.p > 0.f && ma.seed_ptr) seed ^= (*ma.seed_ptr) * 0x9E3779B97F4A7C15ull;
   for (int g0 = 0; g0 < m.groups; g0 += m.lpr) {
     const int g = g0 + m.cg;
     float acc[2][8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
     if (g < m.groups && m.rl < m.rpb) {
-      float mu[8], is[8];
+      float mu[8], is[8], sc[8], sh[8];
       load_coef8(mean, C, g, mu);
       load_coef8(invstd, C, g, is);
+      if (recompute) {
+        float gm[8], bt[8];
+        load_coef8(gamma, C, g, gm);
+        load_coef8(ma.beta, C, g, bt);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (gamma == nullptr) gm[j] = 1.f;
+          sc[j] = gm[j] * is[j];
+          sh[j] = bt[j] - mu[j] * gm[j] * is[j];
+        }
+      }
       const long long stride = (long long)gridDim.x * m.rpb;
       long long r = (long long)blockIdx.x * m.rpb + m.rl;
-      auto one = [&](const float (&d)[8], const float (&xv)[8], const float (&yv)[8]) {
+      auto one = [&](long long row, const float (&d)[8], const float (&xv)[8], const float (&yv)[8]) {
+        bool keep[8];
+        if (recompute && ma.p > 0.f) dropout_keep8(seed, row * m.groups + g, ma.p, keep);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float gg = d[j];
-          if (masked) gg = (yv[j] != 0.f) ? gg * dscale : 0.f;
+          if (recompute) {
+            bool on = ma.relu ? (xv[j] * sc[j] + sh[j] > 0.f) : true;
+            if (ma.p > 0.f) on = on && keep[j];
+            gg = on ? gg * dscale : 0.f;
+          } else if (masked) {
+            gg = (yv[j] != 0.f) ? gg * dscale : 0.f;
+          }
           acc[0][j] += gg;
           acc[1][j] += gg * (xv[j] - mu[j]) * is[j];
         }
@@ -344,15 +378,15 @@ __global__ void __launch_bounds__(256)
           for (int u = 0; u < BN_UNROLL; ++u) {
             qd[u] = load8raw(dy, r + u * stride, C, g);
             qx[u] = load8raw(x, r + u * stride, C, g);
-            if (masked) qy[u] = load8raw(y, r + u * stride, C, g);
+            if (masked && !recompute) qy[u] = load8raw(y, r + u * stride, C, g);
           }
 #pragma unroll
           for (int u = 0; u < BN_UNROLL; ++u) {
             float d[8], xv[8], yv[8];
             bf8_unpack(qd[u], d);
             bf8_unpack(qx[u], xv);
-            if (masked) bf8_unpack(qy[u], yv);
-            one(d, xv, yv);
+            if (masked && !recompute) bf8_unpack(qy[u], yv);
+            one(r + u * stride, d, xv, yv);
           }
         }
       }
@@ -360,8 +394,8 @@ __global__ void __launch_bounds__(256)
         float d[8], xv[8], yv[8];
         load8(dy, r, C, g, d);
         load8(x, r, C, g, xv);
-        if (masked) load8(y, r, C, g, yv);
-        one(d, xv, yv);
+        if (masked && !recompute) load8(y, r, C, g, yv);
+        one(r, d, xv, yv);
       }
     }
     block_channel_reduce<2>(m, g, C, acc, ws, sm);
@@ -383,11 +417,12 @@ __global__ void __launch_bounds__(256)
 void bn_bwd_reduce(const void* dy, const void* x, const void* y, long long M, int C,
                    const float* gamma, const float* save_mean, const float* save_invstd,
                    int masked, float drop_p, float* dgamma, float* dbeta, float* coef, float* ws,
-                   cudaStream_t s) {
+                   const float* beta, int relu, uint64_t seed, const uint64_t* seed_ptr, cudaStream_t s) {
   float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  BnMaskArgs ma{beta, relu, drop_p, seed, seed_ptr};
   k_bn_bwd_reduce<<<bn_blocks(M, C), 256, 256 * 8 * sizeof(float), s>>>(
       (const bf16*)dy, (const bf16*)x, (const bf16*)y, M, C, gamma, save_mean, save_invstd, masked,
-      ds, dgamma, dbeta, coef, ws);
+      ds, dgamma, dbeta, coef, ws, ma);
   TNN_CHECK_LAUNCH();
 }
 
@@ -396,29 +431,49 @@ __global__ void __launch_bounds__(256, 2)
                    const bf16* __restrict__ extra, bf16* __restrict__ dx, long long M, int C,
                    const float* __restrict__ mean, const float* __restrict__ invstd,
                    const float* __restrict__ coef, int masked, float dscale, float* colsum_out,
-                   float* colsum_ws) {
+                   float* colsum_ws, const float* __restrict__ gamma, BnMaskArgs ma) {
   extern __shared__ float sm[];
   const BnMap m(C);
   const bool vec = (C & 7) == 0;
+  const bool recompute = masked && (y == nullptr);
+  uint64_t seed = ma.seed;
+  if (recompute && ma.p > 0.f && ma.seed_ptr) seed ^= (*ma.seed_ptr) * 0x9E3779B97F4A7C15ull;
   for (int g0 = 0; g0 < m.groups; g0 += m.lpr) {
     const int g = g0 + m.cg;
     float csum[1][8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) csum[0][j] = 0.f;
     if (g < m.groups && m.rl < m.rpb) {
-    float mu[8], is[8], c0[8], c1[8], c2[8];
+    float mu[8], is[8], c0[8], c1[8], c2[8], sc[8], sh[8];
     load_coef8(mean, C, g, mu);
     load_coef8(invstd, C, g, is);
     load_coef8(coef, C, g, c0);
     load_coef8(coef + C, C, g, c1);
     load_coef8(coef + 2 * C, C, g, c2);
+    if (recompute) {
+      float gm[8], bt[8];
+      load_coef8(gamma, C, g, gm);
+      load_coef8(ma.beta, C, g, bt);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (gamma == nullptr) gm[j] = 1.f;
+        sc[j] = gm[j] * is[j];
+        sh[j] = bt[j] - mu[j] * gm[j] * is[j];
+      }
+    }
     const long long stride = (long long)gridDim.x * m.rpb;
     long long r = (long long)blockIdx.x * m.rpb + m.rl;
     auto one = [&](long long row, float (&d)[8], const float (&xv)[8], const float (&yv)[8], const float (&ev)[8]) {
+      bool keep[8];
+      if (recompute && ma.p > 0.f) dropout_keep8(seed, row * m.groups + g, ma.p, keep);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float gg = d[j];
-        if (masked) gg = (yv[j] != 0.f) ? gg * dscale : 0.f;
+        if (recompute) {
+          bool on = ma.relu ? (xv[j] * sc[j] + sh[j] > 0.f) : true;
+          if (ma.p > 0.f) on = on && keep[j];
+          gg = on ? gg * dscale : 0.f;
+        } else if (masked) gg = (yv[j] != 0.f) ? gg * dscale : 0.f;
         float xh = (xv[j] - mu[j]) * is[j];
         float v = c0[j] * (gg - c1[j] - xh * c2[j]);
         if (extra) v += ev[j];
@@ -435,7 +490,7 @@ __global__ void __launch_bounds__(256, 2)
         for (int u = 0; u < U; ++u) {
           qd[u] = load8raw(dy, r + u * stride, C, g);
           qx[u] = load8raw(x, r + u * stride, C, g);
-          if (masked) qy[u] = load8raw(y, r + u * stride, C, g);
+          if (masked && !recompute) qy[u] = load8raw(y, r + u * stride, C, g);
           if (extra) qe[u] = load8raw(extra, r + u * stride, C, g);
         }
 #pragma unroll
@@ -443,7 +498,7 @@ __global__ void __launch_bounds__(256, 2)
           float d[8], xv[8], yv[8], ev[8];
           bf8_unpack(qd[u], d);
           bf8_unpack(qx[u], xv);
-          if (masked) bf8_unpack(qy[u], yv);
+          if (masked && !recompute) bf8_unpack(qy[u], yv);
           if (extra) bf8_unpack(qe[u], ev);
           one(r + u * stride, d, xv, yv, ev);
         }
@@ -453,7 +508,7 @@ __global__ void __launch_bounds__(256, 2)
       float d[8], xv[8], yv[8], ev[8];
       load8(dy, r, C, g, d);
       load8(x, r, C, g, xv);
-      if (masked) load8(y, r, C, g, yv);
+      if (masked && !recompute) load8(y, r, C, g, yv);
       if (extra) load8(extra, r, C, g, ev);
       one(r, d, xv, yv, ev);
     }
@@ -469,11 +524,13 @@ __global__ void __launch_bounds__(256, 2)
 void bn_bwd_apply(const void* dy, const void* x, const void* y, const void* extra, void* dx,
                   long long M, int C, const float* save_mean, const float* save_invstd,
                   const float* coef, int masked, float drop_p, float* colsum_out, float* colsum_ws,
+                  const float* gamma, const float* beta, int relu, uint64_t seed, const uint64_t* seed_ptr,
                   cudaStream_t s) {
   float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  BnMaskArgs ma{beta, relu, drop_p, seed, seed_ptr};
   k_bn_bwd_apply<<<bn_blocks(M, C), 256, 256 * 8 * sizeof(float), s>>>(
       (const bf16*)dy, (const bf16*)x, (const bf16*)y, (const bf16*)extra, (bf16*)dx, M, C, save_mean,
-      save_invstd, coef, masked, ds, colsum_out, colsum_ws);
+      save_invstd, coef, masked, ds, colsum_out, colsum_ws, gamma, ma);
   TNN_CHECK_LAUNCH();
 }
 

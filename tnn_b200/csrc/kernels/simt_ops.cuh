@@ -85,11 +85,12 @@ void bn_apply(const void* x, void* y, long long M, int C, const float* scale_shi
 void bn_bwd_reduce(const void* dy, const void* x, const void* y, long long M, int C,
                    const float* gamma, const float* save_mean, const float* save_invstd,
                    int masked, float drop_p, float* dgamma, float* dbeta, float* coef, float* ws,
-                   cudaStream_t s);
+                   const float* beta, int relu, uint64_t seed, const uint64_t* seed_ptr, cudaStream_t s);
 // dx = coef0*(g - coef1 - xhat*coef2) (+ extra, an optional residual gradient to add)
 void bn_bwd_apply(const void* dy, const void* x, const void* y, const void* extra, void* dx,
                   long long M, int C, const float* save_mean, const float* save_invstd,
                   const float* coef, int masked, float drop_p, float* colsum_out, float* colsum_ws,
+                  const float* gamma, const float* beta, int relu, uint64_t seed, const uint64_t* seed_ptr,
                   cudaStream_t s);
 // floats needed by the `ws` / `colsum_ws` workspaces of the BN kernels (zero-initialised once)
 int bn_ws_floats(int C);

@@ -337,9 +337,13 @@ class BatchNormLayer(Layer):
             if self.training:
                 c = self.cache(mb_id)
                 c["x"] = x
-                c["y"] = y if (self.use_relu or p_drop > 0) else None
+                # backward rebuilds the ReLU / dropout mask from x + statistics + the dropout counter
+                # (TNN_BN_RECOMPUTE_MASK=0: keep y and read the mask from it instead)
+                keep_y = os.environ.get("TNN_BN_RECOMPUTE_MASK", "1") != "1"
+                c["y"] = y if ((self.use_relu or p_drop > 0) and keep_y) else None
                 c["mean"], c["invstd"] = b["mean"].clone(), b["invstd"].clone()
                 c["p"] = p_drop
+                c["seed"] = seed
             return y
         xf = x.float().reshape(-1, C)
         if self.training:
@@ -377,12 +381,14 @@ class BatchNormLayer(Layer):
             x, y = c["x"], c["y"]
             M = x.numel() // C
             b = self._bufs(dy.device)
+            state = stepstate.get(dy.device).dev if c["p"] > 0 else None
+            beta = self.params.get("beta")
             Cx.bn_bwd_reduce(dy, x, y, M, C, gamma, c["mean"], c["invstd"], masked, c["p"], self.grads.get("gamma"),
-                             self.grads.get("beta"), b["coef"], b["ws"])
+                             self.grads.get("beta"), b["coef"], b["ws"], beta, self.use_relu, c.get("seed", 0), state)
             dx = torch.empty_like(x)
             colsum = torch.empty(C, dtype=torch.float32, device=dy.device)
             Cx.bn_bwd_apply(dy, x, y, extra, dx, M, C, c["mean"], c["invstd"], b["coef"], masked, c["p"], colsum,
-                            b["cws"])
+                            b["cws"], gamma, beta, self.use_relu, c.get("seed", 0), state)
             dx = dx.reshape(dy.shape)
             dx._tnn_colsum = colsum      # column sums of dx = bias gradient of the producing conv/dense
             return dx
