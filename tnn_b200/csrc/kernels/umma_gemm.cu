@@ -74,11 +74,11 @@ __device__ __forceinline__ long long epi_row_offset(const Epilogue& e, int m) {
   return e.base + (long long)m * e.ldc;
 }
 
-// Processes 32 consecutive columns [n, n+32) of one output row held in r[].
-__device__ __forceinline__ void epi_store_32(const KParams& p, const uint32_t (&r)[32], bool row_ok,
-                                             long long row_off, int n) {
+// Epilogue math for 32 consecutive columns [n, n+32) of one output row held in r[]: alpha, bias,
+// residual, activation and (optionally) the fused BatchNorm column statistics.  Result in v[].
+__device__ __forceinline__ void epi_compute_32(const KParams& p, const uint32_t (&r)[32], bool row_ok,
+                                               long long row_off, int n, float (&v)[32]) {
   const Epilogue& e = p.epi;
-  float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * e.alpha;
   if (e.bias != nullptr) {
@@ -146,6 +146,13 @@ __device__ __forceinline__ void epi_store_32(const KParams& p, const uint32_t (&
       atomicAdd(ws + p.N + n + lane, b[0]);
     }
   }
+}
+
+// Direct (per-thread) global store of the 32 values computed above.
+__device__ __forceinline__ void epi_write_32(const KParams& p, const float (&v)[32], bool row_ok, long long row_off,
+                                             int n) {
+  const Epilogue& e = p.epi;
+  const bool full = (n + 32 <= p.N) && p.vec_ok;
   if (!row_ok) return;
   if (e.out_mode == OUT_BF16) {
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(e.out) + row_off + n;
@@ -181,6 +188,13 @@ __device__ __forceinline__ void epi_store_32(const KParams& p, const uint32_t (&
     for (int j = 0; j < 32; ++j)
       if (n + j < p.N) atomicAdd(o + j, v[j]);
   }
+}
+
+__device__ __forceinline__ void epi_store_32(const KParams& p, const uint32_t (&r)[32], bool row_ok,
+                                             long long row_off, int n) {
+  float v[32];
+  epi_compute_32(p, r, row_ok, row_off, n, v);
+  epi_write_32(p, v, row_ok, row_off, n);
 }
 
 // ---------------------------------------------------------------------------
@@ -332,22 +346,29 @@ __global__ void __launch_bounds__(kThreads)
 //     by exactly those per-tile costs.
 // Tile order is n-fastest so concurrently running CTAs share the A row block through L2.
 // ---------------------------------------------------------------------------
-template <int BLOCK_N, bool A_MN, bool B_MN, bool CONV_A, int STAGES>
+template <int BLOCK_N, bool A_MN, bool B_MN, bool CONV_A, int STAGES, bool TMA_STORE>
 __global__ void __launch_bounds__(kThreads)
     umma_gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                             const KParams p, int m_tiles, int n_tiles, int num_tiles) {
+                             const __grid_constant__ CUtensorMap tmC, const KParams p, int m_tiles, int n_tiles,
+                             int num_tiles) {
   constexpr int A_BYTES = BLOCK_M * 128;
   constexpr int B_BYTES = BLOCK_N * 128;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  // TMA_STORE: the epilogue stages a [128 rows x 64 cols] bf16 sub-tile in 128B-swizzled shared
+  // memory and one thread issues a coalesced TMA store (cp.async.bulk.tensor ... global.shared::cta);
+  // the per-thread 16-byte row stores of the direct path cost one LSU wavefront each and, for
+  // short-K tiles, the store stream was as long as the MMA main loop.
+  constexpr int STORE_BYTES = TMA_STORE ? BLOCK_M * 128 : 0;
   constexpr uint32_t ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
   static_assert(TMEM_COLS <= 512, "two accumulator buffers must fit in TMEM");
   static_assert(!(CONV_A && A_MN), "conv window operand is K-major");
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  // two CTAs per SM only fit without alignment slack: the window itself is declared 1024-byte aligned
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0u) __trap();
+  uint8_t* sC = smem + STAGES * STAGE_BYTES;      // store staging (TMA_STORE only)
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + STORE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;    // [2]
@@ -359,6 +380,7 @@ __global__ void __launch_bounds__(kThreads)
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (TMA_STORE) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -477,17 +499,53 @@ __global__ void __launch_bounds__(kThreads)
       const int m = m0 + row;
       const bool row_ok = m < p.M;
       const long long row_off = row_ok ? epi_row_offset(p.epi, m) : 0;
+      if (TMA_STORE) {
+        const bool store_thread = (threadIdx.x == 64);          // first lane of the first epilogue warp
+        uint8_t* srow = sC + row * 128;
+        const int sw = row & 7;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        if (n0 + c >= p.N) break;
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS + c, r);
-        tmem_ld_wait();
-        epi_store_32(p, r, row_ok, row_off, n0 + c);
+        for (int h = 0; h < BLOCK_N; h += 64) {
+          if (n0 + h >= p.N) break;
+          if (store_thread) tma_store_wait_read();              // previous sub-tile left the staging buffer
+          named_bar_sync(1, 128);
+#pragma unroll 1
+          for (int c = 0; c < 64; c += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS + h + c, r);
+            tmem_ld_wait();
+            float v[32];
+            epi_compute_32(p, r, row_ok, row_off, n0 + h + c, v);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              uint4 o;
+              o.x = pack_bf16(v[t * 8 + 0], v[t * 8 + 1]);
+              o.y = pack_bf16(v[t * 8 + 2], v[t * 8 + 3]);
+              o.z = pack_bf16(v[t * 8 + 4], v[t * 8 + 5]);
+              o.w = pack_bf16(v[t * 8 + 6], v[t * 8 + 7]);
+              *reinterpret_cast<uint4*>(srow + ((((c >> 3) + t) ^ sw) << 4)) = o;
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (store_thread) {
+            tma_store_2d(&tmC, sC, n0 + h, m0);                 // rows >= M / cols >= N are clipped by TMA
+            tma_store_commit();
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          if (n0 + c >= p.N) break;
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS + c, r);
+          tmem_ld_wait();
+          epi_store_32(p, r, row_ok, row_off, n0 + c);
+        }
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
     }
+    if (TMA_STORE && threadIdx.x == 64) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -1079,12 +1137,29 @@ static bool use_persistent() {
   return mode > 0;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, bool CONV_A>
-static void launch_gemm_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, int m_tiles,
-                                int n_tiles, int splits, cudaStream_t stream) {
+// TMA-store epilogue is legal for a plain row-major bf16 output with 16-byte aligned rows
+static bool tma_store_ok(const Epilogue& e, int N) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* env = getenv("TNN_GEMM_TMA_STORE");
+    mode = (env != nullptr) ? atoi(env) : 1;
+  }
+  return mode > 0 && e.out_mode == OUT_BF16 && e.grid_mode == 0 && e.base == 0 && (e.ldc % 8) == 0 && (N % 8) == 0 &&
+         (reinterpret_cast<uintptr_t>(e.out) & 15) == 0;
+}
+static CUtensorMap make_store_map(const Epilogue& e, int M, int N) {
+  uint64_t dims[2] = {(uint64_t)N, (uint64_t)M};
+  uint64_t str[1] = {(uint64_t)e.ldc * 2};
+  uint32_t box[2] = {64, (uint32_t)BLOCK_M};
+  return make_tmap_bf16(e.out, 2, dims, str, box);
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, bool CONV_A, bool TMA_STORE>
+static void launch_gemm_persist_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const KParams& p,
+                                  int m_tiles, int n_tiles, int splits, cudaStream_t stream) {
   constexpr int STAGES = (BLOCK_N <= 64) ? 4 : 3;
-  constexpr int smem = STAGES * (BLOCK_M * 128 + BLOCK_N * 128) + 1024 + 256;
-  auto kern = umma_gemm_persist_kernel<BLOCK_N, A_MN, B_MN, CONV_A, STAGES>;
+  constexpr int smem = STAGES * (BLOCK_M * 128 + BLOCK_N * 128) + (TMA_STORE ? BLOCK_M * 128 : 0) + 128;
+  auto kern = umma_gemm_persist_kernel<BLOCK_N, A_MN, B_MN, CONV_A, STAGES, TMA_STORE>;
   static bool configured = false;
   if (!configured) {
     set_smem(kern, smem);
@@ -1092,9 +1167,19 @@ static void launch_gemm_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, 
   }
   const int num_tiles = m_tiles * n_tiles * splits;
   const int grid = num_tiles < 2 * 148 ? num_tiles : 2 * 148;
-  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p, m_tiles, n_tiles, num_tiles);
+  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmC, p, m_tiles, n_tiles, num_tiles);
   ++g_launch_count;
   TNN_CUDA_CHECK(cudaGetLastError());
+}
+template <int BLOCK_N, bool A_MN, bool B_MN, bool CONV_A>
+static void launch_gemm_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, int m_tiles,
+                                int n_tiles, int splits, cudaStream_t stream) {
+  if (splits == 1 && tma_store_ok(p.epi, p.N)) {
+    CUtensorMap tmC = make_store_map(p.epi, p.M, p.N);
+    launch_gemm_persist_t<BLOCK_N, A_MN, B_MN, CONV_A, true>(tmA, tmB, tmC, p, m_tiles, n_tiles, splits, stream);
+  } else {
+    launch_gemm_persist_t<BLOCK_N, A_MN, B_MN, CONV_A, false>(tmA, tmB, tmA, p, m_tiles, n_tiles, splits, stream);
+  }
 }
 
 static int pick_block_n(int N) {
