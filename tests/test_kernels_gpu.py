@@ -204,3 +204,16 @@ def test_layout_and_softmax_kernels():
         assert _rel_err(ops.softmax_backward(s, g.to(_dev())).cpu(), ops.softmax_backward(s.cpu(), g)) < 2e-2
     w = torch.tensor([1, 256, 65536], dtype=torch.int32).to(_dev())
     assert ops.bswap(w).cpu().tolist() == [1 << 24, 1 << 16, 1 << 8]
+
+
+@pytest.mark.parametrize("M,N,K", [(32, 2304, 768), (32, 768, 3072), (1, 768, 768), (7, 100, 72), (32, 50257 // 8 * 8, 768), (20, 136, 1032)])
+def test_skinny_decode_gemm(M, N, K):
+    from tnn_b200.ops import gemm
+    x = torch.randn(M, K, device=_dev()).bfloat16()
+    w = (torch.randn(N, K, device=_dev()) / math.sqrt(K)).bfloat16()
+    b = torch.randn(N, device=_dev())
+    res = torch.randn(M, N, device=_dev()).bfloat16()
+    ref = x.float() @ w.float().t() + b
+    assert _rel_err(gemm.linear_fwd(x, w, b), ref) < 1e-2
+    assert _rel_err(gemm.linear_fwd(x, w, b, act="gelu"), torch.nn.functional.gelu(ref, approximate="tanh")) < 1e-2
+    assert _rel_err(gemm.linear_fwd(x, w, None, act="relu", residual=res), torch.relu(ref - b + res.float())) < 1e-2

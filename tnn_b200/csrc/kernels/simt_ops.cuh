@@ -63,6 +63,11 @@ void softmax_rows(const void* x, void* y, long long rows, int C, int is_f32, cud
 void softmax_rows_bwd(const void* y, const void* dy, void* dx, long long rows, int C, int is_f32, cudaStream_t s);
 void tensor_bswap(void* p, long long n_elems, int elem_size, cudaStream_t s);
 
+// ---- skinny GEMM for decode (skinny_gemm.cu): out[M<=32,N] = act(x W^T + bias (+ residual)), act 0/1 relu/2 gelu
+void skinny_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, const float* bias,
+                      const void* residual, long long ldr, void* out, long long ldo, int M, int N, int K, int act,
+                      cudaStream_t s);
+
 // ---- normalisation (norm.cu) -------------------------------------------------------
 // BatchNorm over a [M, C] bf16 view.  ws is a persistent fp32 workspace of 2*C+4 floats
 // (zero-initialised once); scale_shift receives [2*C] = {gamma*invstd, beta - mean*gamma*invstd}.

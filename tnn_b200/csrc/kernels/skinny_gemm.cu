@@ -1,0 +1,147 @@
+// Skinny GEMM for decode: out[M <= 32, N] = act(x[M, K] . W[N, K]^T + bias (+ residual)), bf16.
+//
+// With one token per sequence the M dimension is the batch (32): the tcgen05 tile kernel would
+// run N/128 CTAs, each wasting 3/4 of its 128-row tile, and the step is bound by how fast the
+// WEIGHTS stream from HBM.  This kernel is weight-streaming: every warp owns 8 output columns and
+// the full K range, lanes fetch 16 contiguous bytes of their weight row (UNROLL loads in flight
+// per lane, no shared-memory staging of W), x (tiny, L2 resident) is staged once per K chunk in
+// padded shared memory, and the products run on mma.sync m16n8k16 (two m16 tiles = 32 rows).
+// The k index inside each 32-wide step is permuted consistently for both operands so that a
+// lane's 16-byte weight load IS its B fragment for two MMAs -- no shuffles, no transposes.
+// (tcgen05 needs M = 64/128 rows per instruction; at M = 32 the legacy warp-level MMA is the
+// right tool and the kernel is HBM-bound, not tensor-bound.)
+#include "common.cuh"
+#include "simt_ops.cuh"
+
+namespace tnn {
+
+static constexpr int SK_WARPS = 8;             // 64 output columns per CTA
+static constexpr int SK_KC = 1024;             // K chunk staged in smem
+static constexpr int SK_PAD = 32;              // +64 bytes per row: conflict-free 16-byte fragment loads
+static constexpr int SK_UNROLL = 4;            // 32-wide k steps in flight per lane
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(SK_WARPS * 32)
+    k_skinny_gemm(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ w, long long ldw,
+                  const float* __restrict__ bias, const bf16* __restrict__ residual, long long ldr,
+                  bf16* __restrict__ out, long long ldo, int M, int N, int K, int act) {
+  extern __shared__ __align__(16) uint8_t sk_smem[];
+  bf16* sx = reinterpret_cast<bf16*>(sk_smem);             // [32][SK_KC + SK_PAD]
+  constexpr int LDS = SK_KC + SK_PAD;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_base = (blockIdx.x * SK_WARPS + warp) * 8;
+  const int nrow = n_base + (lane >> 2);                   // this lane's weight row (B column)
+  const int kq = (lane & 3) * 8;                           // this lane's 8-element slice of a 32-wide k step
+  const bool n_ok = nrow < N;
+  const bf16* wrow = w + (long long)(n_ok ? nrow : 0) * ldw;
+  float acc[2][4];
+#pragma unroll
+  for (int t = 0; t < 2; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[t][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += SK_KC) {
+    const int kc = min(SK_KC, K - k0);
+    __syncthreads();
+    // stage x[:, k0:k0+kc] (zero rows >= M and the k tail so no masking is needed below)
+    for (int i = threadIdx.x; i < 32 * (SK_KC / 8); i += blockDim.x) {
+      const int r = i / (SK_KC / 8), c8 = (i % (SK_KC / 8)) * 8;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (r < M && c8 < kc) {
+        if (c8 + 8 <= kc) {
+          v = *reinterpret_cast<const uint4*>(x + (long long)r * ldx + k0 + c8);
+        } else {
+          bf16 tmp[8];
+          for (int j = 0; j < 8; ++j) tmp[j] = (c8 + j < kc) ? x[(long long)r * ldx + k0 + c8 + j] : __float2bfloat16(0.f);
+          v = *reinterpret_cast<uint4*>(tmp);
+        }
+      }
+      *reinterpret_cast<uint4*>(sx + r * LDS + c8) = v;
+    }
+    __syncthreads();
+    const int steps = (kc + 31) / 32;
+    for (int s0 = 0; s0 < steps; s0 += SK_UNROLL) {
+      uint4 wq[SK_UNROLL];
+#pragma unroll
+      for (int u = 0; u < SK_UNROLL; ++u) {
+        const int kk = (s0 + u) * 32 + kq;
+        wq[u] = make_uint4(0, 0, 0, 0);
+        if (n_ok && s0 + u < steps && kk + 8 <= kc)
+          wq[u] = __ldg(reinterpret_cast<const uint4*>(wrow + k0 + kk));
+        else if (n_ok && s0 + u < steps && kk < kc) {
+          bf16 tmp[8];
+          for (int j = 0; j < 8; ++j) tmp[j] = (kk + j < kc) ? wrow[k0 + kk + j] : __float2bfloat16(0.f);
+          wq[u] = *reinterpret_cast<uint4*>(tmp);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < SK_UNROLL; ++u) {
+        if (s0 + u >= steps) break;
+        const int kk = (s0 + u) * 32 + kq;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int r0 = t * 16 + (lane >> 2);
+          const uint4 xa = *reinterpret_cast<const uint4*>(sx + r0 * LDS + kk);
+          const uint4 xb = *reinterpret_cast<const uint4*>(sx + (r0 + 8) * LDS + kk);
+          // logical k (lane%4)*2+{0,1} <-> elements 0,1 ; logical k+8 <-> elements 2,3 (first MMA);
+          // elements 4..7 feed the second MMA the same way
+          const uint32_t a1[4] = {xa.x, xb.x, xa.y, xb.y};
+          const uint32_t a2[4] = {xa.z, xb.z, xa.w, xb.w};
+          mma_bf16_16816(acc[t], a1, wq[u].x, wq[u].y);
+          mma_bf16_16816(acc[t], a2, wq[u].z, wq[u].w);
+        }
+      }
+    }
+  }
+  // C fragment: rows lane/4 (+8), columns n_base + (lane%4)*2 + {0,1}
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int row = t * 16 + h * 8 + (lane >> 2);
+      if (row >= M) continue;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int col = n_base + (lane & 3) * 2 + j;
+        if (col >= N) continue;
+        float v = acc[t][h * 2 + j];
+        if (bias) v += bias[col];
+        if (residual) v += __bfloat162float(residual[(long long)row * ldr + col]);
+        if (act == 1) v = fmaxf(v, 0.f);
+        else if (act == 2) {
+          const float k0c = 0.7978845608028654f, k1c = 0.044715f;
+          v = 0.5f * v * (1.f + tanhf(k0c * (v + k1c * v * v * v)));
+        }
+        out[(long long)row * ldo + col] = __float2bfloat16(v);
+      }
+    }
+  }
+}
+
+void skinny_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, const float* bias,
+                      const void* residual, long long ldr, void* out, long long ldo, int M, int N, int K, int act,
+                      cudaStream_t s) {
+  if (M <= 0 || N <= 0 || K <= 0) return;
+  if (M > 32 || (ldx % 8) || (ldw % 8) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) {
+    fprintf(stderr, "[tnn_b200] skinny_gemm_bf16: needs M <= 32 and 16-byte aligned rows\n");
+    abort();
+  }
+  constexpr int smem = 32 * (SK_KC + SK_PAD) * 2;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_skinny_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    configured = true;
+  }
+  const int grid = (N + SK_WARPS * 8 - 1) / (SK_WARPS * 8);
+  k_skinny_gemm<<<grid, SK_WARPS * 32, smem, s>>>((const bf16*)x, ldx, (const bf16*)w, ldw, bias, (const bf16*)residual, ldr,
+                                                  (bf16*)out, ldo, M, N, K, act);
+  TNN_CHECK_LAUNCH();
+}
+
+}  // namespace tnn

@@ -12,6 +12,9 @@ import torch
 
 from . import native
 
+import os
+
+_SKINNY = os.environ.get("TNN_SKINNY_GEMM", "1") == "1"
 ACT = {"none": 0, "linear": 0, None: 0, "relu": 1, "gelu": 2}
 OUT_BF16, OUT_F32, OUT_F32_ATOMIC = 0, 1, 2
 
@@ -45,6 +48,11 @@ def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = Non
     assert x.stride(1) == 1 and w.stride(1) == 1
     if out is None:
         out = torch.empty((M, N), device=x.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    if M <= 32 and out.dtype == torch.bfloat16 and _SKINNY and x.stride(0) % 8 == 0 and w.stride(0) % 8 == 0 and \
+            (residual is None or (residual.dtype == torch.bfloat16 and residual.stride(-1) == 1)):
+        # decode-sized batch: weight-streaming kernel (HBM bound) instead of a 3/4-empty 128-row tile
+        C.skinny_gemm(x, w, bias, residual, out, ACT[act])
+        return out
     C.gemm(x, w, M, N, K, x.stride(0), w.stride(0), False, False, out, out.stride(0),
            OUT_F32 if out.dtype == torch.float32 else OUT_BF16, ACT[act], 1.0, bias, residual, 1)
     return out
