@@ -289,6 +289,11 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
          ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
+// 16-byte vector reduction to global memory (one L2 transaction for four fp32 adds)
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // ---------------------------------------------------------------------------
 // small numeric helpers for epilogues
 // ---------------------------------------------------------------------------

@@ -184,9 +184,14 @@ __device__ __forceinline__ void epi_write_32(const KParams& p, const float (&v)[
     }
   } else {  // OUT_F32_ATOMIC
     float* o = reinterpret_cast<float*>(e.out) + row_off + n;
+    if ((n + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (n + j < p.N) atomicAdd(o + j, v[j]);
+      for (int j = 0; j < 32; j += 4) red_add_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n + j < p.N) atomicAdd(o + j, v[j]);
+    }
   }
 }
 
@@ -948,9 +953,18 @@ __global__ void __launch_bounds__(kThreads)
           tmem_ld_wait();
           if (row_ok) {
             float* o = dW + (long long)ko * ldw + koff + c0 + c;
+            const float al = p.epi.alpha;
+            if ((c0 + c + 32 <= p.N) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+              // split-K partial sums: 8 vector reductions instead of 32 scalar atomics per thread
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (c0 + c + j < p.N) atomicAdd(o + j, __uint_as_float(r[j]) * p.epi.alpha);
+              for (int j = 0; j < 32; j += 4)
+                red_add_v4(o + j, __uint_as_float(r[j]) * al, __uint_as_float(r[j + 1]) * al,
+                           __uint_as_float(r[j + 2]) * al, __uint_as_float(r[j + 3]) * al);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (c0 + c + j < p.N) atomicAdd(o + j, __uint_as_float(r[j]) * al);
+            }
           }
         }
       }
