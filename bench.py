@@ -44,29 +44,70 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason sampling DURING the timed region."""
+    """SM clock / throttle-reason sampling DURING the timed region: NVML polled every 10 ms from a
+    thread (nvidia-smi -lms as a fallback when pynvml is unavailable)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+        self.idx, self.rows, self.proc, self.t = gpu_index, [], None, None
+        self.samples, self.stop_flag, self.nvml = [], False, None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.idx]) if vis and vis.split(",")[self.idx].isdigit() else self.idx
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:  # noqa: BLE001
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:  # noqa: BLE001
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                pw = n.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((sm, mx, pw, rs))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.01)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            n = self.nvml
+            names = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            sm = sorted(s[0] for s in self.samples)
+            reasons = sorted(k for k, bit in names.items() if any(s[3] & bit for s in self.samples))
+            return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": float(max((s[1] for s in self.samples), default=0)) or None,
+                    "reasons": reasons, "samples": len(sm), "power_w_max": max((s[2] for s in self.samples), default=None),
+                    "source": "nvml@10ms"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -90,7 +131,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(power) if power else None}
+                "samples": len(sm), "power_w_max": max(power) if power else None, "source": "nvidia-smi@100ms"}
 
 
 def emit(d):
