@@ -918,6 +918,8 @@ __global__ void __launch_bounds__(kThreads)
         // (LBO = ATOM_BYTES), so the dY operand is fetched from shared memory once per k-step
         // instead of once per tap -- the kernel was shared-memory-bandwidth bound.
         constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, T * 64, 1u, 1u);
+        constexpr uint32_t idesc1 = make_idesc_bf16(BLOCK_M, 64, 1u, 1u);
+        const bool wide = p.vec_ok != 0;      // host switch (TNN_WGRAD_WIDE): one N = T*64 MMA vs T MMAs of N = 64
         for (int i = 0; i < nkb; ++i) {
           const int s = i % STAGES;
           const uint32_t ph = (i / STAGES) & 1;
@@ -925,11 +927,23 @@ __global__ void __launch_bounds__(kThreads)
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t b_addr = a_addr + A_BYTES;
+          if (wide) {
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 2048, ATOM_BYTES, 1024);
-            const uint64_t bd = make_smem_desc_sw128(b_addr + k * 2048, ATOM_BYTES, 1024);
-            umma_f16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              const uint64_t ad = make_smem_desc_sw128(a_addr + k * 2048, ATOM_BYTES, 1024);
+              const uint64_t bd = make_smem_desc_sw128(b_addr + k * 2048, ATOM_BYTES, 1024);
+              umma_f16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / 16; ++k) {
+                const uint64_t ad = make_smem_desc_sw128(a_addr + k * 2048, ATOM_BYTES, 1024);
+                const uint64_t bd = make_smem_desc_sw128(b_addr + t * ATOM_BYTES + k * 2048, ATOM_BYTES, 1024);
+                umma_f16(tmem_base + t * 64, ad, bd, idesc1, (i > 0 || k > 0) ? 1u : 0u);
+              }
+            }
           }
           umma_commit(&empty[s]);
         }
@@ -1377,6 +1391,14 @@ void conv_wgrad_bf16(const void* dY, long long ldy, int Kout, const void* X, con
   p.ntaps = g.ntaps;
   for (int t = 0; t < g.ntaps; ++t) p.taps[t] = g.taps[t];
   p.epi.alpha = alpha;
+  {
+    static int wide = -1;
+    if (wide < 0) {
+      const char* e = getenv("TNN_WGRAD_WIDE");
+      wide = (e != nullptr) ? atoi(e) : 1;
+    }
+    p.vec_ok = wide;          // reused as the wide-MMA switch by the wgrad kernel
+  }
   const int T = (g.ntaps == 1) ? 1 : 3;
   const int groups = g.ntaps / T;
   const int c_tiles = (g.C + 63) / 64;
