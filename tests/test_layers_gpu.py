@@ -109,13 +109,13 @@ def test_residual_block_fused():
         b = LayerBuilder([[8, 8, 32]])
         b.wide_residual_block(32, 64, 2, 0.0, "wrb")
         return b.build()[0]
-    _check(make, torch.randn(4, 8, 8, 32), tol=6e-2)
+    _check(make, torch.randn(4, 8, 8, 32), tol=8e-2)
 
     def make2():
         b = LayerBuilder([[8, 8, 32]])
         b.basic_residual_block(32, 32, 1, "brb")
         return b.build()[0]
-    _check(make2, torch.randn(4, 8, 8, 32), tol=6e-2)
+    _check(make2, torch.randn(4, 8, 8, 32), tol=8e-2)
 
 
 def test_softmax_ce_and_adam():
