@@ -295,7 +295,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                             std::vector<int64_t> p_peers, std::vector<int64_t> pb_peers,
                             std::vector<int64_t> flag_peers, int64_t g_mc, int64_t p_mc, int64_t pb_mc,
                             const Tensor& mm, const OptT& v, const Tensor& sync, const Tensor& state,
-                            bool use_adam, int ctas) {
+                            bool use_adam, int ctas, int64_t lo0, int64_t hi0, int64_t st_off) {
     TORCH_CHECK((int)g_peers.size() == world && (int)p_peers.size() == world &&
                 (int)pb_peers.size() == world && (int)flag_peers.size() == world, "peer lists");
     std::vector<float*> g(world), p(world);
@@ -310,8 +310,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     tnn::dp_fused_step(world, rank, n, chunk, g.data(), p.data(), pb.data(), fl.data(),
                        reinterpret_cast<const float*>(g_mc), reinterpret_cast<float*>(p_mc),
                        reinterpret_cast<void*>(pb_mc), fp(mm), fp(v), reinterpret_cast<uint32_t*>(sync.data_ptr()),
-                       fp(state), use_adam ? 1 : 0, ctas, cur_stream());
-  });
+                       fp(state), use_adam ? 1 : 0, ctas, lo0, hi0, st_off, cur_stream());
+  }, py::arg("world"), py::arg("rank"), py::arg("n"), py::arg("chunk"), py::arg("g_peers"), py::arg("p_peers"),
+     py::arg("pb_peers"), py::arg("flag_peers"), py::arg("g_mc"), py::arg("p_mc"), py::arg("pb_mc"), py::arg("m"),
+     py::arg("v"), py::arg("sync"), py::arg("state"), py::arg("use_adam"), py::arg("ctas"), py::arg("lo0") = 0,
+     py::arg("hi0") = -1, py::arg("st_off") = 0);
   m.def("p2p_barrier", [](const Tensor& flag_ptrs, int world, int rank, uint32_t epoch) {
     tnn::p2p_barrier(reinterpret_cast<uint32_t* const*>(flag_ptrs.data_ptr()), world, rank, epoch, cur_stream());
   });

@@ -221,6 +221,9 @@ struct DpArgs {
   int world, rank;
   long long n;          // total parameters
   long long chunk;      // per-rank slice length (multiple of 4)
+  long long lo0, hi0;   // element range [lo0, hi0) handled by this launch (a gradient bucket); the range is
+                        // split W ways; optimizer state is indexed by (element - rank slice start) + st_off
+  long long st_off;
   float* g_peers[kMaxWorld];    // every rank's gradient slab (peer mapped), [rank] is local
   float* p_peers[kMaxWorld];    // every rank's fp32 parameter slab
   bf16* pb_peers[kMaxWorld];    // every rank's bf16 parameter copy
@@ -267,8 +270,8 @@ __global__ void __launch_bounds__(512) k_dp_step(const DpArgs a) {
   const uint32_t grid_base = epoch * 2u * G;
   dp_barrier(a, epoch * 2 + 1, grid_base + G);
 
-  const long long lo = (long long)a.rank * a.chunk;
-  const long long hi = min(a.n, lo + a.chunk);
+  const long long lo = a.lo0 + (long long)a.rank * a.chunk;
+  const long long hi = min(a.hi0, lo + a.chunk);
   const long long nv = hi > lo ? (hi - lo + 3) / 4 : 0;   // slab is padded to a multiple of 4
   AdamHyper h = hyper_from_state(a.state);
   h.grad_scale /= (float)a.world;
@@ -288,14 +291,14 @@ __global__ void __launch_bounds__(512) k_dp_step(const DpArgs a) {
     }
     g.x *= h.grad_scale; g.y *= h.grad_scale; g.z *= h.grad_scale; g.w *= h.grad_scale;
     float4 P = *reinterpret_cast<const float4*>(a.p_peers[a.rank] + e);
-    float4 M = reinterpret_cast<float4*>(a.m)[i];
+    float4 M = reinterpret_cast<float4*>(a.m + a.st_off)[i];
     if (a.use_adam) {
-      float4 V = reinterpret_cast<float4*>(a.v)[i];
+      float4 V = reinterpret_cast<float4*>(a.v + a.st_off)[i];
       adam_update(P.x, g.x, M.x, V.x, h);
       adam_update(P.y, g.y, M.y, V.y, h);
       adam_update(P.z, g.z, M.z, V.z, h);
       adam_update(P.w, g.w, M.w, V.w, h);
-      reinterpret_cast<float4*>(a.v)[i] = V;
+      reinterpret_cast<float4*>(a.v + a.st_off)[i] = V;
     } else {
       const float mu = sgd_momentum, lr = h.lr, wd = h.weight_decay;
       g.x += wd * P.x; g.y += wd * P.y; g.z += wd * P.z; g.w += wd * P.w;
@@ -303,7 +306,7 @@ __global__ void __launch_bounds__(512) k_dp_step(const DpArgs a) {
       M.z = mu * M.z - lr * g.z; M.w = mu * M.w - lr * g.w;
       P.x += M.x; P.y += M.y; P.z += M.z; P.w += M.w;
     }
-    reinterpret_cast<float4*>(a.m)[i] = M;
+    reinterpret_cast<float4*>(a.m + a.st_off)[i] = M;
     __nv_bfloat162 b0 = __floats2bfloat162_rn(P.x, P.y), b1 = __floats2bfloat162_rn(P.z, P.w);
     const uint32_t u0 = *reinterpret_cast<uint32_t*>(&b0), u1 = *reinterpret_cast<uint32_t*>(&b1);
     if (a.p_mc) {
@@ -320,8 +323,8 @@ __global__ void __launch_bounds__(512) k_dp_step(const DpArgs a) {
   dp_barrier(a, epoch * 2 + 2, grid_base + 2 * G);
 
   // every rank is done reading my gradients: clear them for the next accumulation
-  float4* gz = reinterpret_cast<float4*>(a.g_peers[a.rank]);
-  const long long nz = (a.n + 3) / 4;
+  float4* gz = reinterpret_cast<float4*>(a.g_peers[a.rank] + a.lo0);
+  const long long nz = (a.hi0 - a.lo0 + 3) / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nz;
        i += (long long)gridDim.x * blockDim.x)
     gz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -333,7 +336,8 @@ __global__ void __launch_bounds__(512) k_dp_step(const DpArgs a) {
 void dp_fused_step(int world, int rank, long long n, long long chunk, float* const* g_peers,
                    float* const* p_peers, void* const* pb_peers, uint32_t* const* flag_peers,
                    const float* g_mc, float* p_mc, void* pb_mc, float* m, float* v,
-                   uint32_t* sync, const float* state, int use_adam, int ctas, cudaStream_t s) {
+                   uint32_t* sync, const float* state, int use_adam, int ctas, long long lo0, long long hi0,
+                   long long st_off, cudaStream_t s) {
   if (world > kMaxWorld) {
     fprintf(stderr, "[tnn_b200] dp_fused_step: world %d > %d\n", world, kMaxWorld);
     abort();
@@ -343,6 +347,9 @@ void dp_fused_step(int world, int rank, long long n, long long chunk, float* con
   a.rank = rank;
   a.n = n;
   a.chunk = chunk;
+  a.lo0 = lo0;
+  a.hi0 = hi0 < 0 ? n : hi0;
+  a.st_off = st_off;
   for (int r = 0; r < world; ++r) {
     a.g_peers[r] = g_peers[r];
     a.p_peers[r] = p_peers[r];

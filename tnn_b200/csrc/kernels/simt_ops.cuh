@@ -155,7 +155,8 @@ void sgd_step_flat(float* p, float* g, float* mom, void* p_bf16, long long n, fl
 void dp_fused_step(int world, int rank, long long n, long long chunk, float* const* g_peers,
                    float* const* p_peers, void* const* pb_peers, uint32_t* const* flag_peers,
                    const float* g_mc, float* p_mc, void* pb_mc, float* m, float* v,
-                   uint32_t* sync, const float* state, int use_adam, int ctas, cudaStream_t s);
+                   uint32_t* sync, const float* state, int use_adam, int ctas, long long lo0, long long hi0, long long st_off,
+                   cudaStream_t s);
 // Graph-replayable variants: hyper-parameters come from a 16-float device "step state" that the
 // host refreshes with one small H2D copy per step (outside the captured region).
 void adam_step_flat_dev(float* p, float* g, float* m, float* v, void* p_bf16, long long n,

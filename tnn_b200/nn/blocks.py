@@ -92,10 +92,16 @@ class Sequential(Block):
                 x = layer.forward(x, mb_id)
         return x
 
+    backward_hook = None        # optional callable(layer_index), fired after each layer's backward (DP overlap)
+
     def backward_impl(self, dy, mb_id, first_extra=None):
+        hook = self.backward_hook
         for i in range(len(self.layers) - 1, -1, -1):
             layer = self.layers[i]
             if dy is None:
+                if hook is not None:
+                    for j in range(i, -1, -1):
+                        hook(j)
                 break
             if i == 0 and first_extra is not None:
                 if isinstance(layer, BatchNormLayer):
@@ -104,6 +110,8 @@ class Sequential(Block):
                     first_extra = None
                     continue
             dy = layer.backward(dy, mb_id)
+            if hook is not None:
+                hook(i)
         if first_extra is not None and dy is not None:
             dy = _add(dy, first_extra)
         return dy

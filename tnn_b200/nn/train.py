@@ -128,6 +128,11 @@ class TrainStep:
         self.replays = 0
         self._sx = self._sy = self._sstats = None
         self._state = stepstate.get(self.device)
+        # fused DP with bucket overlap: the top-level Sequential reports per-layer backward completion
+        if dp is not None and getattr(dp, "side", None) is not None and self.accum == 1:
+            top = graph.get_layers()[0]
+            if hasattr(top, "backward_hook"):
+                top.backward_hook = dp.backward_hook
 
     # ---- the work itself (capturable: no host sync, no Python-visible per-step scalars)
     def _core(self, x, y, mb_id=0):

@@ -1,6 +1,9 @@
 """Data parallelism.
 
-``FusedDataParallel`` is the product path: parameters, gradients and bf16
+``FusedDataParallel`` is the product path; with ``overlap`` (default) the slab is cut
+into gradient buckets (groups of top-level layers) and each bucket's fused reduce+update kernel is
+queued on a side stream as soon as backward has produced it, so the NVLink traffic and the optimizer
+math overlap the rest of backward.  Summary: parameters, gradients and bf16
 compute copies of every replica live in ONE NVLink peer-mapped symmetric slab per GPU
 (``torch.distributed._symmetric_memory`` provides the allocation + handle exchange, i.e. the
 plumbing); each optimisation step is a single hand-written kernel
@@ -72,7 +75,8 @@ class FusedDataParallel:
 
     FLAG_BYTES = 4096
 
-    def __init__(self, optimizer: Optimizer, group=None, ctas: int | None = None, use_multicast: bool | None = None):
+    def __init__(self, optimizer: Optimizer, group=None, ctas: int | None = None, use_multicast: bool | None = None,
+                 overlap: bool | None = None, bucket_elems: int | None = None):
         assert dist.is_initialized(), "init torch.distributed (nccl) first"
         self.group = group or dist.group.WORLD
         self.world = dist.get_world_size(self.group)
@@ -83,6 +87,12 @@ class FusedDataParallel:
         self.graph: Graph | None = None
         self.epoch = 0
         self.launches = 0
+        # overlap: gradient buckets (groups of top-level layers, in backward-completion order) are
+        # reduced + updated by the same kernel on a SIDE stream while backward continues
+        self.overlap = overlap if overlap is not None else os.environ.get("TNN_DP_OVERLAP", "1") == "1"
+        self.bucket_elems = int(bucket_elems or os.environ.get("TNN_DP_BUCKET_ELEMS", 2 << 20))
+        self.buckets: list[dict] = []
+        self.side = None
 
     # ---------------------------------------------------------------- construction
     def build_graph(self, seq, device, seed=None, name=None) -> Graph:
@@ -122,25 +132,105 @@ class FusedDataParallel:
         self.sync = torch.zeros(4, dtype=torch.int32, device=device)
         opt = self.optimizer
         opt.ctx = self.graph.context()
-        self.m = torch.zeros(chunk, dtype=torch.float32, device=device)
-        self.v = torch.zeros(chunk, dtype=torch.float32, device=device) if isinstance(opt, Adam) else None
+        self._plan_buckets(seq)
+        nstate = max(chunk, sum(b["chunk"] for b in self.buckets)) if self.buckets else chunk
+        self.m = torch.zeros(nstate, dtype=torch.float32, device=device)
+        self.v = torch.zeros(nstate, dtype=torch.float32, device=device) if isinstance(opt, Adam) else None
+        if self.overlap and self.buckets and device.type == "cuda":
+            self.side = torch.cuda.Stream(device)
         dist.barrier(self.group)
         torch.cuda.synchronize(device)
         return self.graph
 
+    # ---------------------------------------------------------------- gradient buckets
+    def _plan_buckets(self, seq):
+        """Contiguous slab ranges per group of top-level layers (the model is a Sequential whose
+        parameters were packed in layer order), grouped from the END so that a bucket is complete as
+        soon as backward has passed its first layer."""
+        self.buckets = []
+        top = getattr(seq, "layers", None)
+        if not top or self.world < 2:
+            return
+        owner = {}
+        for i, l in enumerate(top):
+            for sub in l.all_layers():
+                owner[id(sub)] = i
+        ranges = {}
+        for layer, d, off, numel in self.graph.ctx.entries:
+            i = owner.get(id(layer))
+            if i is None:
+                return
+            end = off + (numel + ALIGN_ELEMS - 1) // ALIGN_ELEMS * ALIGN_ELEMS
+            lo, hi = ranges.get(i, (off, end))
+            ranges[i] = (min(lo, off), max(hi, end))
+        groups, hi, first, lo = [], None, None, None
+        for i in sorted(ranges, reverse=True):          # last layer first = backward completion order
+            lo_i, hi_i = ranges[i]
+            if hi is None:
+                hi = hi_i
+            first, lo = i, lo_i
+            if hi - lo >= self.bucket_elems:
+                groups.append((first, lo, hi))
+                hi = None
+        if hi is not None:
+            groups.append((first, lo, hi))
+        # the groups must tile [0, n) exactly
+        covered = sum(h - l for _, l, h in groups)
+        if covered != self.n or len(groups) < 2:
+            self.buckets = []
+            return
+        st = 0
+        for first, lo, hi in groups:
+            c = ((hi - lo + self.world - 1) // self.world + 3) // 4 * 4
+            self.buckets.append(dict(first_layer=first, lo=lo, hi=hi, chunk=c, st_off=st))
+            st += c
+
+    def _launch(self, lo0=0, hi0=-1, chunk=None, st_off=0):
+        opt = self.optimizer
+        dev = self.graph.device()
+        native.require().dp_fused_step(
+            self.world, self.rank, self.n, chunk if chunk is not None else self.chunk, self.g_peers, self.p_peers, self.pb_peers,
+            self.flag_peers, (self.mc + self.off_g) if self.mc else 0, (self.mc + self.off_p) if self.mc else 0,
+            (self.mc + self.off_lp) if self.mc else 0, self.m, self.v, self.sync, stepstate.get(dev).dev,
+            isinstance(opt, Adam), self.ctas, lo0, hi0, st_off)
+        self.launches += 1
+
+    def backward_hook(self, layer_index: int):
+        """Called by the top-level Sequential right after layer `layer_index` finished its backward:
+        when that completes a bucket, its fused reduce+update is queued on the side stream."""
+        if self.side is None:
+            return
+        for b in self.buckets:
+            if b["first_layer"] == layer_index:
+                main = torch.cuda.current_stream(self.graph.device())
+                self.side.wait_stream(main)
+                with torch.cuda.stream(self.side):
+                    self._launch(b["lo"], b["hi"], b["chunk"], b["st_off"])
+                self._pending = True
+
+    def step_overlapped_finish(self):
+        """End of the step: join the side stream (all buckets reduced and updated everywhere)."""
+        # (the step state was advanced by TrainStep BEFORE forward: the bucket kernels already used it)
+        self.optimizer.step_count += 1
+        torch.cuda.current_stream(self.graph.device()).wait_stream(self.side)
+        self._pending = False
+        for layer in self.graph.ctx.layers:
+            layer.mark_lp_fresh()
+
     # ---------------------------------------------------------------- one fused step
     def step(self):
+        if self.side is not None and getattr(self, "_pending", False):
+            return self.step_overlapped_finish()
         opt = self.optimizer
         dev = self.graph.device()
         if not opt.external_state:
             stepstate.get(dev).advance(opt)
         opt.step_count += 1
-        Cx = native.require()
-        Cx.dp_fused_step(
-            self.world, self.rank, self.n, self.chunk, self.g_peers, self.p_peers, self.pb_peers, self.flag_peers,
-            (self.mc + self.off_g) if self.mc else 0, (self.mc + self.off_p) if self.mc else 0,
-            (self.mc + self.off_lp) if self.mc else 0, self.m, self.v, self.sync, stepstate.get(dev).dev,
-            isinstance(opt, Adam), self.ctas)
+        if self.buckets:
+            for b in self.buckets:          # same bucket layout (and optimizer-state layout) without overlap
+                self._launch(b["lo"], b["hi"], b["chunk"], b["st_off"])
+        else:
+            self._launch()
         for layer in self.graph.ctx.layers:
             layer.mark_lp_fresh()
 
