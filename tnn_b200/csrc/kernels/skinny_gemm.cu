@@ -15,10 +15,11 @@
 
 namespace tnn {
 
-static constexpr int SK_WARPS = 8;             // 64 output columns per CTA
-static constexpr int SK_KC = 1024;             // K chunk staged in smem
+static constexpr int SK_WARPS = 8;             // 2 column groups (8 columns each) x 4 K-slices
+static constexpr int SK_COLS = 16;             // output columns per CTA -> N/16 CTAs stream the weights
+static constexpr int SK_KC = 1024;             // K chunk staged in smem (256 per K-slice warp)
 static constexpr int SK_PAD = 32;              // +64 bytes per row: conflict-free 16-byte fragment loads
-static constexpr int SK_UNROLL = 4;            // 32-wide k steps in flight per lane
+static constexpr int SK_UNROLL = 8;            // 32-wide k steps (16-byte weight loads) in flight per lane
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -35,7 +36,9 @@ __global__ void __launch_bounds__(SK_WARPS * 32)
   bf16* sx = reinterpret_cast<bf16*>(sk_smem);             // [32][SK_KC + SK_PAD]
   constexpr int LDS = SK_KC + SK_PAD;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_base = (blockIdx.x * SK_WARPS + warp) * 8;
+  const int cg = warp & 1;                                 // column group inside the CTA
+  const int ks = warp >> 1;                                // K-slice 0..3 (256 of every 1024-chunk)
+  const int n_base = blockIdx.x * SK_COLS + cg * 8;
   const int nrow = n_base + (lane >> 2);                   // this lane's weight row (B column)
   const int kq = (lane & 3) * 8;                           // this lane's 8-element slice of a 32-wide k step
   const bool n_ok = nrow < N;
@@ -49,7 +52,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32)
   for (int k0 = 0; k0 < K; k0 += SK_KC) {
     const int kc = min(SK_KC, K - k0);
     __syncthreads();
-    // stage x[:, k0:k0+kc] (zero rows >= M and the k tail so no masking is needed below)
+    // stage x[:, k0:k0+kc] (rows >= M and the k tail are zero filled so no masking is needed below)
     for (int i = threadIdx.x; i < 32 * (SK_KC / 8); i += blockDim.x) {
       const int r = i / (SK_KC / 8), c8 = (i % (SK_KC / 8)) * 8;
       uint4 v = make_uint4(0, 0, 0, 0);
@@ -65,40 +68,57 @@ __global__ void __launch_bounds__(SK_WARPS * 32)
       *reinterpret_cast<uint4*>(sx + r * LDS + c8) = v;
     }
     __syncthreads();
-    const int steps = (kc + 31) / 32;
-    for (int s0 = 0; s0 < steps; s0 += SK_UNROLL) {
-      uint4 wq[SK_UNROLL];
+    // this warp's slice of the chunk: k in [ks*256, ks*256 + 256) = 8 steps of 32, all loads issued first
+    const int kb = ks * (SK_KC / 4);
+    uint4 wq[SK_UNROLL];
 #pragma unroll
-      for (int u = 0; u < SK_UNROLL; ++u) {
-        const int kk = (s0 + u) * 32 + kq;
-        wq[u] = make_uint4(0, 0, 0, 0);
-        if (n_ok && s0 + u < steps && kk + 8 <= kc)
-          wq[u] = __ldg(reinterpret_cast<const uint4*>(wrow + k0 + kk));
-        else if (n_ok && s0 + u < steps && kk < kc) {
-          bf16 tmp[8];
-          for (int j = 0; j < 8; ++j) tmp[j] = (kk + j < kc) ? wrow[k0 + kk + j] : __float2bfloat16(0.f);
-          wq[u] = *reinterpret_cast<uint4*>(tmp);
-        }
+    for (int u = 0; u < SK_UNROLL; ++u) {
+      const int kk = kb + u * 32 + kq;
+      wq[u] = make_uint4(0, 0, 0, 0);
+      if (n_ok && kk + 8 <= kc) {
+        wq[u] = __ldg(reinterpret_cast<const uint4*>(wrow + k0 + kk));
+      } else if (n_ok && kk < kc) {
+        bf16 tmp[8];
+        for (int j = 0; j < 8; ++j) tmp[j] = (kk + j < kc) ? wrow[k0 + kk + j] : __float2bfloat16(0.f);
+        wq[u] = *reinterpret_cast<uint4*>(tmp);
       }
+    }
 #pragma unroll
-      for (int u = 0; u < SK_UNROLL; ++u) {
-        if (s0 + u >= steps) break;
-        const int kk = (s0 + u) * 32 + kq;
+    for (int u = 0; u < SK_UNROLL; ++u) {
+      const int kk = kb + u * 32 + kq;
+      if (kb + u * 32 >= kc) break;
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const int r0 = t * 16 + (lane >> 2);
-          const uint4 xa = *reinterpret_cast<const uint4*>(sx + r0 * LDS + kk);
-          const uint4 xb = *reinterpret_cast<const uint4*>(sx + (r0 + 8) * LDS + kk);
-          // logical k (lane%4)*2+{0,1} <-> elements 0,1 ; logical k+8 <-> elements 2,3 (first MMA);
-          // elements 4..7 feed the second MMA the same way
-          const uint32_t a1[4] = {xa.x, xb.x, xa.y, xb.y};
-          const uint32_t a2[4] = {xa.z, xb.z, xa.w, xb.w};
-          mma_bf16_16816(acc[t], a1, wq[u].x, wq[u].y);
-          mma_bf16_16816(acc[t], a2, wq[u].z, wq[u].w);
-        }
+      for (int t = 0; t < 2; ++t) {
+        const int r0 = t * 16 + (lane >> 2);
+        const uint4 xa = *reinterpret_cast<const uint4*>(sx + r0 * LDS + kk);
+        const uint4 xb = *reinterpret_cast<const uint4*>(sx + (r0 + 8) * LDS + kk);
+        // logical k (lane%4)*2+{0,1} <-> elements 0,1 ; logical k+8 <-> elements 2,3 (first MMA);
+        // elements 4..7 feed the second MMA the same way
+        const uint32_t a1[4] = {xa.x, xb.x, xa.y, xb.y};
+        const uint32_t a2[4] = {xa.z, xb.z, xa.w, xb.w};
+        mma_bf16_16816(acc[t], a1, wq[u].x, wq[u].y);
+        mma_bf16_16816(acc[t], a2, wq[u].z, wq[u].w);
       }
     }
   }
+  // reduce the 4 K-slices of each column group through shared memory (reuse the x staging area)
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(sk_smem);          // [4 ks][2 cg][32 lanes][8]
+#pragma unroll
+  for (int t = 0; t < 2; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[(((ks * 2 + cg) * 32) + lane) * 8 + t * 4 + j] = acc[t][j];
+  __syncthreads();
+  if (ks != 0) return;
+#pragma unroll
+  for (int t = 0; t < 2; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v += red[(((q * 2 + cg) * 32) + lane) * 8 + t * 4 + j];
+      acc[t][j] = v;
+    }
   // C fragment: rows lane/4 (+8), columns n_base + (lane%4)*2 + {0,1}
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
@@ -138,7 +158,7 @@ void skinny_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw
     cudaFuncSetAttribute(k_skinny_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     configured = true;
   }
-  const int grid = (N + SK_WARPS * 8 - 1) / (SK_WARPS * 8);
+  const int grid = (N + SK_COLS - 1) / SK_COLS;
   k_skinny_gemm<<<grid, SK_WARPS * 32, smem, s>>>((const bf16*)x, ldx, (const bf16*)w, ldw, bias, (const bf16*)residual, ldr,
                                                   (bf16*)out, ldo, M, N, K, act);
   TNN_CHECK_LAUNCH();

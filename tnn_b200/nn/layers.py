@@ -337,9 +337,10 @@ class BatchNormLayer(Layer):
             if self.training:
                 c = self.cache(mb_id)
                 c["x"] = x
-                # backward rebuilds the ReLU / dropout mask from x + statistics + the dropout counter
-                # (TNN_BN_RECOMPUTE_MASK=0: keep y and read the mask from it instead)
-                keep_y = os.environ.get("TNN_BN_RECOMPUTE_MASK", "1") != "1"
+                # TNN_BN_RECOMPUTE_MASK=1: backward rebuilds the ReLU / dropout mask from x + statistics +
+                # the dropout counter instead of reading y (saves the y activation; measured 2.8% SLOWER
+                # per WRN step on B200 -- the extra ALU work costs more than the saved read -- so off by default)
+                keep_y = os.environ.get("TNN_BN_RECOMPUTE_MASK", "0") != "1"
                 c["y"] = y if ((self.use_relu or p_drop > 0) and keep_y) else None
                 c["mean"], c["invstd"] = b["mean"].clone(), b["invstd"].clone()
                 c["p"] = p_drop
