@@ -58,10 +58,15 @@ class AllReduceDataParallel:
         if self._base_scale is None:
             self._base_scale = opt.grad_scale
         if self.world > 1:
-            dist.all_reduce(self.graph.ctx.grad_slab, group=self.group)
-        opt.grad_scale = self._base_scale / self.world
+            g = self.graph.ctx.grad_slab
+            # average (not sum): the optimizer's grad_scale lives in the device step state that TrainStep
+            # pushed before the step, so the 1/world factor has to be applied to the gradients themselves
+            if g.is_cuda:
+                dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(g, group=self.group)
+                g.mul_(1.0 / self.world)
         opt.update()
-        opt.grad_scale = self._base_scale
 
     def broadcast_parameters(self, src: int = 0):
         if self.world > 1:
