@@ -25,6 +25,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly ONE JSON line: NCCL's own banner / debug lines ("NCCL version ...") go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 BASELINE_IMG_S = 2480.0      # 256 / 0.103 s (TNN C++ pipeline, WRN-16-8 / CIFAR-100)
 PER_GPU_BATCH = 256
