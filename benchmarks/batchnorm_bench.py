@@ -15,8 +15,11 @@ from tnn_b200.nn.layers import BatchNormLayer  # noqa: E402
 if __name__ == "__main__":
     _, hbm, how = peaks()
     dev = torch.device("cuda", 0)
+    only = sys.argv[1:]
     for name, N, H, C in [("wrn_g1", 256, 32, 128), ("wrn_g2", 256, 16, 256), ("wrn_g3", 256, 8, 512), ("r9_64", 256, 32, 64),
                           ("pipeline_224", 32, 224, 64)]:
+        if only and name not in only:
+            continue
         l = BatchNormLayer(C, 1e-2, 0.1, True, True, name).init(dev, 0)
         x = torch.randn(N, H, H, C, device=dev).bfloat16()
         dy = torch.randn_like(x)
