@@ -18,10 +18,11 @@ namespace tnn {
 // bytes in flight to saturate HBM3e).  block = 256 threads = lpr channel-groups x rpb row-lanes.
 // ---------------------------------------------------------------------------------------
 static constexpr int BN_UNROLL = 4;
-// Partial sums go to one of BN_REPL replica rows (same-address L2 atomics from ~600 CTAs
-// serialise badly; 64 replicas 1 KB apart cut the contention to ~9 CTAs per address) and the
-// last CTA folds the replicas.
-static constexpr int BN_REPL = 64;
+// Partial sums go to one of BN_REPL replica rows and the last CTA folds the replicas.  Each atomic
+// instruction touches 32 different channels, so per-address contention is one lane per CTA; 8
+// replicas keep it at ~74 CTAs per address while the single-CTA fold at the end of every BN
+// kernel (a serial tail that was ~half of the small-tensor kernels' time with 64 replicas) stays short.
+static constexpr int BN_REPL = 8;
 
 struct BnMap {
   int groups, lpr, rpb, cg, rl;
