@@ -1404,7 +1404,7 @@ void conv_wgrad_bf16(const void* dY, long long ldy, int Kout, const void* X, con
   const int c_tiles = (g.C + 63) / 64;
   const int k_tiles = (Kout + BLOCK_M - 1) / BLOCK_M;
   const int tiles = c_tiles * k_tiles * groups;
-  int splits = (2 * 148 + tiles - 1) / tiles;
+  int splits = (2 * 148 + tiles - 1) / tiles;      // ~2 CTAs per SM
   if (splits < 1) splits = 1;
   if (splits > p.kb_total) splits = p.kb_total;
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
@@ -1428,15 +1428,34 @@ void conv_wgrad_bf16(const void* dY, long long ldy, int Kout, const void* X, con
     kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p, c_tiles, dW, ldw);
     ++g_launch_count;
   } else {
-    constexpr int STAGES = 4;
-    constexpr int smem = STAGES * (2 * ATOM_BYTES + 3 * ATOM_BYTES) + 1024 + 256;
-    auto kern = umma_wgrad_kernel<3, STAGES>;
-    static bool configured = false;
-    if (!configured) {
-      set_smem(kern, smem);
-      configured = true;
+    // 4 stages = 160 KB = ONE CTA per SM (its atomic epilogue is then fully exposed); 2 stages = 80 KB
+    // lets two CTAs share an SM so one's split-K epilogue overlaps the other's main loop.
+    static int stages = -1;
+    if (stages < 0) {
+      const char* e = getenv("TNN_WGRAD_STAGES");
+      stages = (e != nullptr) ? atoi(e) : 2;
     }
-    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p, c_tiles, dW, ldw);
+    if (stages == 2) {
+      constexpr int STAGES = 2;
+      constexpr int smem = STAGES * (2 * ATOM_BYTES + 3 * ATOM_BYTES) + 1024 + 256;
+      auto kern = umma_wgrad_kernel<3, STAGES>;
+      static bool configured = false;
+      if (!configured) {
+        set_smem(kern, smem);
+        configured = true;
+      }
+      kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p, c_tiles, dW, ldw);
+    } else {
+      constexpr int STAGES = 4;
+      constexpr int smem = STAGES * (2 * ATOM_BYTES + 3 * ATOM_BYTES) + 1024 + 256;
+      auto kern = umma_wgrad_kernel<3, STAGES>;
+      static bool configured = false;
+      if (!configured) {
+        set_smem(kern, smem);
+        configured = true;
+      }
+      kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p, c_tiles, dW, ldw);
+    }
     ++g_launch_count;
   }
   TNN_CUDA_CHECK(cudaGetLastError());
