@@ -691,20 +691,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads)
 // BOTH CTAs' epilogues drained their 128 rows of it, so all 256 epilogue threads of the pair
 // arrive on the LEADER's tmem_empty barrier (remote mbarrier arrive through the cluster window).
 // ---------------------------------------------------------------------------
-template <int BLOCK_N, bool CONV_A, int STAGES>
+template <int BLOCK_N, bool CONV_A, int STAGES, bool TMA_STORE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads)
     umma_gemm2_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                              const KParams p, int m_tiles /* 256-row tiles */, int n_tiles, int num_tiles) {
+                              const __grid_constant__ CUtensorMap tmC, const KParams p,
+                              int m_tiles /* 256-row tiles */, int n_tiles, int num_tiles) {
   constexpr int A_BYTES = BLOCK_M * 128;
   constexpr int B_BYTES = (BLOCK_N / 2) * 128;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STORE_BYTES = TMA_STORE ? BLOCK_M * 128 : 0;
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;
   static_assert(TMEM_COLS <= 512, "two accumulator buffers must fit in TMEM");
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0u) __trap();
+  uint8_t* sC = smem + STAGES * STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + STORE_BYTES);
   uint64_t* empty = full + STAGES;
   uint64_t* tmem_full = empty + STAGES;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;    // [2] (only the leader's copy is used)
@@ -721,6 +723,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads)
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (TMA_STORE) tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
@@ -817,17 +820,53 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads)
       const int m = m0 + row;
       const bool row_ok = m < p.M;
       const long long row_off = row_ok ? epi_row_offset(p.epi, m) : 0;
+      if (TMA_STORE) {
+        const bool store_thread = (threadIdx.x == 64);
+        uint8_t* srow = sC + row * 128;
+        const int sw = row & 7;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        if (n0 + c >= p.N) break;
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + c, r);
-        tmem_ld_wait();
-        epi_store_32(p, r, row_ok, row_off, n0 + c);
+        for (int h = 0; h < BLOCK_N; h += 64) {
+          if (n0 + h >= p.N) break;
+          if (store_thread) tma_store_wait_read();
+          named_bar_sync(1, 128);
+#pragma unroll 1
+          for (int c = 0; c < 64; c += 32) {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + h + c, r);
+            tmem_ld_wait();
+            float v[32];
+            epi_compute_32(p, r, row_ok, row_off, n0 + h + c, v);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              uint4 o;
+              o.x = pack_bf16(v[t * 8 + 0], v[t * 8 + 1]);
+              o.y = pack_bf16(v[t * 8 + 2], v[t * 8 + 3]);
+              o.z = pack_bf16(v[t * 8 + 4], v[t * 8 + 5]);
+              o.w = pack_bf16(v[t * 8 + 6], v[t * 8 + 7]);
+              *reinterpret_cast<uint4*>(srow + ((((c >> 3) + t) ^ sw) << 4)) = o;
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (store_thread) {
+            tma_store_2d(&tmC, sC, n0 + h, m0);
+            tma_store_commit();
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          if (n0 + c >= p.N) break;
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + c, r);
+          tmem_ld_wait();
+          epi_store_32(p, r, row_ok, row_off, n0 + c);
+        }
       }
       tc_fence_before();
       mbar_arrive_leader(&tmem_empty[acc]);
     }
+    if (TMA_STORE && threadIdx.x == 64) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -1117,12 +1156,12 @@ static void launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const K
   TNN_CUDA_CHECK(cudaGetLastError());
 }
 
-template <int BLOCK_N, bool CONV_A>
-static void launch_gemm2_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, int m_tiles256,
-                                 int n_tiles, cudaStream_t stream) {
+template <int BLOCK_N, bool CONV_A, bool TMA_STORE>
+static void launch_gemm2_persist_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                                   const KParams& p, int m_tiles256, int n_tiles, cudaStream_t stream) {
   constexpr int STAGES = (BLOCK_N <= 128) ? 4 : 6;     // BLOCK_N = 256 owns the SM (TMEM full): deeper ring
-  constexpr int smem = STAGES * (BLOCK_M * 128 + (BLOCK_N / 2) * 128) + 1024 + 256;
-  auto kern = umma_gemm2_persist_kernel<BLOCK_N, CONV_A, STAGES>;
+  constexpr int smem = STAGES * (BLOCK_M * 128 + (BLOCK_N / 2) * 128) + (TMA_STORE ? BLOCK_M * 128 : 0) + 128;
+  auto kern = umma_gemm2_persist_kernel<BLOCK_N, CONV_A, STAGES, TMA_STORE>;
   static bool configured = false;
   if (!configured) {
     set_smem(kern, smem);
@@ -1131,7 +1170,7 @@ static void launch_gemm2_persist(const CUtensorMap& tmA, const CUtensorMap& tmB,
   const int num_tiles = m_tiles256 * n_tiles;
   const int max_pairs = (BLOCK_N <= 128) ? 148 : 74;   // 2 resident CTAs per SM, or 1
   const int pairs = num_tiles < max_pairs ? num_tiles : max_pairs;
-  kern<<<2 * pairs, kThreads, smem, stream>>>(tmA, tmB, p, m_tiles256, n_tiles, num_tiles);
+  kern<<<2 * pairs, kThreads, smem, stream>>>(tmA, tmB, tmC, p, m_tiles256, n_tiles, num_tiles);
   ++g_launch_count;
   TNN_CUDA_CHECK(cudaGetLastError());
 }
@@ -1180,6 +1219,17 @@ static CUtensorMap make_store_map(const Epilogue& e, int M, int N) {
   uint64_t str[1] = {(uint64_t)e.ldc * 2};
   uint32_t box[2] = {64, (uint32_t)BLOCK_M};
   return make_tmap_bf16(e.out, 2, dims, str, box);
+}
+
+template <int BLOCK_N, bool CONV_A>
+static void launch_gemm2_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const KParams& p, int m_tiles256,
+                                 int n_tiles, cudaStream_t stream) {
+  if (tma_store_ok(p.epi, p.N)) {
+    CUtensorMap tmC = make_store_map(p.epi, p.M, p.N);
+    launch_gemm2_persist_t<BLOCK_N, CONV_A, true>(tmA, tmB, tmC, p, m_tiles256, n_tiles, stream);
+  } else {
+    launch_gemm2_persist_t<BLOCK_N, CONV_A, false>(tmA, tmB, tmA, p, m_tiles256, n_tiles, stream);
+  }
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, bool CONV_A, bool TMA_STORE>
