@@ -1235,7 +1235,7 @@ static void launch_gemm2_persist(const CUtensorMap& tmA, const CUtensorMap& tmB,
 template <int BLOCK_N, bool A_MN, bool B_MN, bool CONV_A, bool TMA_STORE>
 static void launch_gemm_persist_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const KParams& p,
                                   int m_tiles, int n_tiles, int splits, cudaStream_t stream) {
-  constexpr int STAGES = (BLOCK_N <= 64) ? 4 : 3;
+  constexpr int STAGES = (BLOCK_N <= 64) ? 4 : ((BLOCK_N <= 128) ? 3 : 4);
   constexpr int smem = STAGES * (BLOCK_M * 128 + BLOCK_N * 128) + (TMA_STORE ? BLOCK_M * 128 : 0) + 128;
   auto kern = umma_gemm_persist_kernel<BLOCK_N, A_MN, B_MN, CONV_A, STAGES, TMA_STORE>;
   static bool configured = false;
@@ -1244,7 +1244,8 @@ static void launch_gemm_persist_t(const CUtensorMap& tmA, const CUtensorMap& tmB
     configured = true;
   }
   const int num_tiles = m_tiles * n_tiles * splits;
-  const int grid = num_tiles < 2 * 148 ? num_tiles : 2 * 148;
+  const int max_ctas = (BLOCK_N <= 128) ? 2 * 148 : 148;
+  const int grid = num_tiles < max_ctas ? num_tiles : max_ctas;
   kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmC, p, m_tiles, n_tiles, num_tiles);
   ++g_launch_count;
   TNN_CUDA_CHECK(cudaGetLastError());
@@ -1346,6 +1347,11 @@ void gemm_bf16(const void* A, const void* B, int M, int N, int K, long long lda,
   CUtensorMap tmA = a_mn ? make_operand_map(A, K, M, lda, 64) : make_operand_map(A, M, K, lda, BLOCK_M);
   CUtensorMap tmB = b_mn ? make_operand_map(B, K, N, ldb, 64) : make_operand_map(B, N, K, ldb, bn);
   dim3 grid((M + BLOCK_M - 1) / BLOCK_M, (N + bn - 1) / bn, splits);
+  if (use_persistent() && bn == 256 && !a_mn && !b_mn && splits == 1) {
+    // 128 x 256 tiles, one CTA per SM (both TMEM accumulator buffers = all 512 columns)
+    launch_gemm_persist<256, false, false, false>(tmA, tmB, p, (int)grid.x, (int)grid.y, 1, stream);
+    return;
+  }
   if (use_persistent() && bn <= 128) {
     const int mt = (int)grid.x, nt = (int)grid.y;
     if (bn == 64) {
