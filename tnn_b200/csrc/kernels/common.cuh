@@ -85,12 +85,14 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   return t;
 }
 
-// Philox4x32-10 counter RNG: (seed, counter) -> 4 x uint32.
+// Philox4x32-R counter RNG: (seed, counter) -> 4 x uint32.  R = 10 is the standard strength;
+// R = 7 is the shortest variant that still passes BigCrush and is what the dropout masks use.
+template <int ROUNDS = 10>
 __device__ __forceinline__ uint4 philox4(uint64_t seed, uint64_t ctr) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x2B7E1516u, c3 = 0x3C6EF372u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
@@ -103,13 +105,17 @@ __device__ __forceinline__ uint4 philox4(uint64_t seed, uint64_t ctr) {
 __device__ __forceinline__ float u32_to_unit(uint32_t x) {  // (0,1)
   return ((x >> 8) + 0.5f) * (1.0f / 16777216.0f);
 }
-// keep-mask for 8 consecutive elements starting at index 8*vec_idx
+// keep-mask for 8 consecutive elements starting at index 8*vec_idx: ONE Philox block per vector,
+// 16 random bits per element (drop probability resolved to 1/65536).
 __device__ __forceinline__ void dropout_keep8(uint64_t seed, long long vec_idx, float p, bool (&keep)[8]) {
-  uint4 a = philox4(seed, (uint64_t)vec_idx * 2);
-  uint4 b = philox4(seed, (uint64_t)vec_idx * 2 + 1);
-  const uint32_t r[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  const uint4 a = philox4<7>(seed, (uint64_t)vec_idx);
+  const uint32_t thr = (uint32_t)(p * 65536.0f + 0.5f);
+  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) keep[i] = u32_to_unit(r[i]) >= p;
+  for (int i = 0; i < 4; ++i) {
+    keep[2 * i] = (w[i] & 0xFFFFu) >= thr;
+    keep[2 * i + 1] = (w[i] >> 16) >= thr;
+  }
 }
 
 }  // namespace tnn
