@@ -25,6 +25,21 @@ if __name__ == "__main__":
         t_ref = time_cuda(lambda: F.scaled_dot_product_attention(q, k, v, is_causal=causal), 20)
         emit(bench="attention_fwd", shape=name, B=B, L=L, H=H, causal=causal, ms=t, tflops=flops / t / 1e9, sdpa_ms=t_ref,
              sdpa_tflops=flops / t_ref / 1e9, frac_of_peak=flops / t / 1e9 / peak, peak=how)
+        # backward: tcgen05 flash backward vs the op-by-op recompute it replaces vs SDPA autograd
+        o, lse = A.attention_fwd(qkv, causal)
+        do = torch.randn_like(o)
+        tb = time_cuda(lambda: A.attention_bwd(qkv, do, o, lse, causal), 10)
+        row = dict(bench="attention_bwd", shape=name, B=B, L=L, H=H, causal=causal, ms=tb, tflops=2.5 * flops / tb / 1e9,
+                   frac_of_peak=2.5 * flops / tb / 1e9 / peak)
+        if B * H * L * L * 4 * 6 < (40 << 30):
+            os.environ["TNN_ATTN_BWD_KERNEL"] = "0"
+            row["fallback_ms"] = time_cuda(lambda: A.attention_bwd(qkv, do, o, lse, causal), 3)
+            os.environ["TNN_ATTN_BWD_KERNEL"] = "1"
+        qg, kg, vg = (t_.detach().clone().requires_grad_(True) for t_ in (q, k, v))
+        og = F.scaled_dot_product_attention(qg, kg, vg, is_causal=causal)
+        dog = torch.randn_like(og)
+        row["sdpa_bwd_ms"] = time_cuda(lambda: torch.autograd.grad(og, (qg, kg, vg), dog, retain_graph=True), 10)
+        emit(**row)
     B, H, Lmax = 32, 12, 1024
     cache = A.KVCache(B, Lmax, H, 64, dev, torch.bfloat16)
     cache.k.normal_()

@@ -140,6 +140,32 @@ def test_attention_fwd_matches_reference(B, L, H, causal):
     assert (lse - lref).abs().max().item() < 2e-2
 
 
+@pytest.mark.parametrize("causal", [True, False])
+@pytest.mark.parametrize("B,L,H", [(2, 128, 2), (1, 200, 3), (2, 384, 2), (1, 1024, 2)])
+def test_attention_bwd_matches_reference(B, L, H, causal, monkeypatch):
+    """tcgen05 flash backward vs the fp32 recompute-everything formula (autograd of attention_ref)."""
+    from tnn_b200.ops import attention as A
+    from tnn_b200.ops import native
+    assert hasattr(native.require(), "attention_bwd")
+    torch.manual_seed(3)
+    qkv = (torch.randn(B, L, 3, H, 64, device=_dev()) * 0.8).bfloat16()
+    do = (torch.randn(B, L, H * 64, device=_dev()) * 0.5).bfloat16()
+    o, lse = A.attention_fwd(qkv, causal)
+    got = A.attention_bwd(qkv, do, o, lse, causal)
+    ref_in = qkv.float().requires_grad_(True)
+    oref, _ = A.attention_ref(ref_in[:, :, 0], ref_in[:, :, 1], ref_in[:, :, 2], causal)
+    (oref.reshape(B, L, H * 64) * do.float()).sum().backward()
+    ref = ref_in.grad
+    assert got.shape == qkv.shape and got.dtype == torch.bfloat16
+    for i, name in enumerate(("dq", "dk", "dv")):
+        err = _rel_err(got[:, :, i], ref[:, :, i])
+        assert err < 3e-2, f"{name} rel err {err}"
+    # and it agrees with the op-by-op fallback it replaces
+    monkeypatch.setenv("TNN_ATTN_BWD_KERNEL", "0")
+    slow = A.attention_bwd(qkv, do, o, lse, causal)
+    assert _rel_err(got, slow.float()) < 3e-2
+
+
 def test_attention_kv_cache_prefill_and_decode():
     from tnn_b200.ops import attention as A
     torch.manual_seed(2)

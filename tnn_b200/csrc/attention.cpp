@@ -35,6 +35,26 @@ void attention_bind(py::module_& m) {
                        v.stride(1), v.stride(0), out.data_ptr(), lp, B, H, Lq, Lk, causal ? 1 : 0, (int)q_offset,
                        at::cuda::getCurrentCUDAStream().stream());
   });
+  m.def("attention_bwd", [](const Tensor& qkv, const Tensor& dout, const Tensor& out, const Tensor& lse,
+                            const Tensor& dqkv, const Tensor& delta, const Tensor& dq_acc, bool causal) {
+    TORCH_CHECK(qkv.is_cuda() && qkv.scalar_type() == torch::kBFloat16 && qkv.dim() == 5 && qkv.size(2) == 3 &&
+                    qkv.size(4) == 64 && qkv.is_contiguous(), "qkv must be contiguous bf16 [B, L, 3, H, 64]");
+    TORCH_CHECK(dqkv.is_cuda() && dqkv.scalar_type() == torch::kBFloat16 && dqkv.is_contiguous() &&
+                    dqkv.sizes() == qkv.sizes(), "dqkv must match qkv");
+    const int B = (int)qkv.size(0), L = (int)qkv.size(1), H = (int)qkv.size(3);
+    const int64_t E = (int64_t)H * 64, n = (int64_t)B * L * E;
+    TORCH_CHECK(dout.scalar_type() == torch::kBFloat16 && dout.is_contiguous() && dout.numel() == n, "dout: contiguous bf16 [B, L, H*64]");
+    TORCH_CHECK(out.scalar_type() == torch::kBFloat16 && out.is_contiguous() && out.numel() == n, "out: contiguous bf16 [B, L, H*64]");
+    TORCH_CHECK(lse.scalar_type() == torch::kFloat32 && lse.is_contiguous() && lse.numel() == (int64_t)B * H * L, "lse: fp32 [B, H, L]");
+    TORCH_CHECK(delta.scalar_type() == torch::kFloat32 && delta.is_contiguous() && delta.numel() == (int64_t)B * H * L, "delta: fp32 [B, H, L]");
+    TORCH_CHECK(dq_acc.scalar_type() == torch::kFloat32 && dq_acc.is_contiguous() && dq_acc.numel() == n, "dq_acc: fp32 [B, L, H*64]");
+    auto* base = reinterpret_cast<at::BFloat16*>(qkv.data_ptr());
+    auto* dbase = reinterpret_cast<at::BFloat16*>(dqkv.data_ptr());
+    attention_bwd_bf16(base, base + E, base + 2 * E, 3 * E, (int64_t)L * 3 * E, dout.data_ptr(), out.data_ptr(),
+                       lse.data_ptr<float>(), delta.data_ptr<float>(), dq_acc.data_ptr<float>(), dbase, dbase + E,
+                       dbase + 2 * E, 3 * E, (int64_t)L * 3 * E, B, H, L, causal ? 1 : 0,
+                       at::cuda::getCurrentCUDAStream().stream());
+  });
   m.def("attention_decode", [](const Tensor& q, const Tensor& kc, const Tensor& vc, const Tensor& out, int64_t len) {
     TORCH_CHECK(q.is_cuda() && q.scalar_type() == torch::kBFloat16, "q: CUDA bf16");
     check_head_view(kc, "k cache");

@@ -288,7 +288,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 attn_encode_fn() {
 }
 
 // [B, L, H, 64] view with arbitrary token / batch strides (elements): dims {64, H, L, B}.
-static CUtensorMap make_head_map(const void* ptr, int B, int L, int H, long long tok_stride, long long batch_stride) {
+CUtensorMap make_head_map(const void* ptr, int B, int L, int H, long long tok_stride, long long batch_stride) {
   CUtensorMap m;
   cuuint64_t dims[4] = {(cuuint64_t)AT_D, (cuuint64_t)H, (cuuint64_t)L, (cuuint64_t)B};
   cuuint64_t str[3] = {(cuuint64_t)AT_D * 2, (cuuint64_t)tok_stride * 2, (cuuint64_t)batch_stride * 2};

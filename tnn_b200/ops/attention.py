@@ -8,12 +8,14 @@ or cuDNN SDPA in cudnn_flash_attention_ops.cu:123,209).
 GPU: tcgen05 flash-attention forward (csrc/kernels/attention.cu): S = QK^T and O += PV on the
 tensor cores with S / PV tiles in TMEM, one softmax thread per query row, online softmax,
 causal tile skipping; decode (L_q = 1) uses a split-KV SIMT kernel over the KV cache.
-Backward recomputes P from the saved log-sum-exp.
+Backward: tcgen05 flash backward (attention_bwd.cu) recomputing P tile by tile from the saved
+log-sum-exp; dQ accumulates in fp32 through vector reductions.
 CPU: fp32 reference.
 """
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 
@@ -71,6 +73,15 @@ def attention_fwd(qkv: torch.Tensor, causal: bool, kv_cache: KVCache | None = No
 def attention_bwd(qkv: torch.Tensor, do: torch.Tensor, o: torch.Tensor, lse: torch.Tensor, causal: bool):
     """dqkv [B, L, 3, H, D] from do [B, L, H*D]; P is recomputed from the saved lse."""
     B, L, _, H, D = qkv.shape
+    if qkv.is_cuda and D == 64 and qkv.dtype == torch.bfloat16 and os.environ.get("TNN_ATTN_BWD_KERNEL", "1") != "0":
+        # tcgen05 flash backward (csrc/kernels/attention_bwd.cu): five MMAs per (key tile, query tile)
+        Cx = native.require()
+        dqkv = torch.empty_like(qkv, memory_format=torch.contiguous_format)
+        delta = torch.empty((B, H, L), device=qkv.device, dtype=torch.float32)
+        dq_acc = torch.empty((B, L, H * D), device=qkv.device, dtype=torch.float32)
+        Cx.attention_bwd(qkv.contiguous(), do.reshape(B, L, H * D).to(torch.bfloat16).contiguous(),
+                         o.reshape(B, L, H * D).contiguous(), lse.contiguous(), dqkv, delta, dq_acc, bool(causal))
+        return dqkv
     q, k, v = (qkv[:, :, i].float().permute(0, 2, 1, 3) for i in range(3))   # [B,H,L,D]
     dof = do.float().reshape(B, L, H, D).permute(0, 2, 1, 3)
     of = o.float().reshape(B, L, H, D).permute(0, 2, 1, 3)
