@@ -27,6 +27,14 @@ class Block(nn.Module):
         return x + self.fc2(F.gelu(self.fc1(self.ln2(x)), approximate="tanh"))
 
 
+def _block_train(blk: "Block", x, p_drop: float):
+    B, L, E = x.shape
+    q, k, v = blk.qkv(blk.ln1(x)).view(B, L, 3, blk.H, E // blk.H).unbind(2)
+    o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True)
+    x = x + F.dropout(blk.proj(o.transpose(1, 2).reshape(B, L, E)), p_drop)
+    return x + F.dropout(blk.fc2(F.gelu(blk.fc1(blk.ln2(x)), approximate="tanh")), p_drop)
+
+
 class GPT2(nn.Module):
     def __init__(self, V=50257, E=768, H=12, layers=12, Lmax=1024):
         super().__init__()
@@ -46,3 +54,11 @@ class GPT2(nn.Module):
         for b, c in zip(self.blocks, caches):
             x = b(x, c, pos)
         return self.head(self.ln_f(x[:, -1:])).argmax(-1).reshape(B)
+
+    def forward_train(self, ids, p_drop: float = 0.1):
+        """Training forward over the whole sequence -> logits [B, L, V] (flash SDPA, no cache)."""
+        B, L = ids.shape
+        x = F.dropout(self.wte(ids) + self.wpe(torch.arange(L, device=ids.device)), p_drop)
+        for b in self.blocks:
+            x = _block_train(b, x, p_drop)
+        return self.head(self.ln_f(x))

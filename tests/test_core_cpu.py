@@ -532,3 +532,35 @@ def test_native_cpu_gemm_and_thread_pool():
     parallel_for_2d(70, 40, lambda r0, r1, c0, c1: tiles.append((r1 - r0) * (c1 - c0)))
     assert sum(tiles) == 70 * 40
     assert ThreadWrapper(2).execute(torch.get_num_threads) == 2
+
+
+def test_legacy_matrix_value_semantics():
+    """matrix.hpp surface: element-wise +,-, scalar *,/, product, clone/reshape/resize, fills."""
+    import pytest
+    import torch
+    from tnn_b200.core import Matrix
+    a = Matrix(3, 4).fill(2.0)
+    b = Matrix(3, 4, torch.arange(12, dtype=torch.float32))
+    c = a + b
+    assert torch.equal(c.data(), b.data() + 2)
+    c -= a
+    assert torch.equal(c.data(), b.data())
+    assert torch.allclose((b * 0.5).data(), b.data() * 0.5) and torch.allclose((b / 4).data(), b.data() / 4)
+    with pytest.raises(ZeroDivisionError):
+        b / 0
+    with pytest.raises(ValueError):
+        a + Matrix(4, 3)
+    w = Matrix(4, 2).fill_random_normal(0.0, 1.0, seed=5)
+    assert torch.allclose((b * w).data(), b.data() @ w.data(), atol=1e-5)
+    assert (b @ w).rows() == 3 and (b @ w).cols() == 2
+    with pytest.raises(ValueError):
+        a * Matrix(3, 4)
+    d = b.clone()
+    d[0, 0] = 100.0
+    assert b[0, 0] == 0.0                                     # clone owns its storage
+    assert b.reshape(2, 6).data().shape == (2, 6)
+    assert torch.equal(b.transpose().data(), b.data().t())
+    d.resize(5, 5)
+    assert d.size() == 25 and float(d.data().abs().sum()) == 0.0
+    u = Matrix(64, 64).fill_random_uniform(0.25, seed=9)
+    assert float(u.data().abs().max()) <= 0.25 and float(u.data().std()) > 0.05
