@@ -1460,9 +1460,48 @@ void conv_wgrad_bf16(const void* dY, long long ldy, int Kout, const void* X, con
   const int c_tiles = (g.C + 63) / 64;
   const int k_tiles = (Kout + BLOCK_M - 1) / BLOCK_M;
   const int tiles = c_tiles * k_tiles * groups;
-  int splits = (2 * 148 + tiles - 1) / tiles;      // ~2 CTAs per SM
-  if (splits < 1) splits = 1;
-  if (splits > p.kb_total) splits = p.kb_total;
+  // Split-K plan.  The kernel is not persistent, so the grid must FIT the resident slots: with the
+  // 4-stage ring (160 KB) one CTA lives on an SM (148 slots), with the 2-stage ring two do (296).
+  // tiles*splits just above a multiple of the slot count costs a whole extra wave (the old
+  // ceil(296/tiles) rule launched 300 / 312 / 384 CTAs for the three WRN stages = 3 waves of 148),
+  // so splits = floor(slots / tiles) and the ring depth whose slot count is filled best wins.
+  static int forced_stages = -1;
+  if (forced_stages < 0) {
+    const char* e = getenv("TNN_WGRAD_STAGES");
+    forced_stages = (e != nullptr) ? atoi(e) : 0;
+  }
+  int stages = 4, splits = 1;
+  {
+    double best = -1.0;
+    for (int st : {4, 2}) {
+      if (T == 1 && st == 2) continue;                   // the 1-tap kernel has one (6-stage) variant
+      if (forced_stages != 0 && T != 1 && st != forced_stages) continue;
+      const int slots = (st == 2) ? 296 : 148;
+      int sp = slots / tiles;
+      if (sp < 1) sp = 1;
+      if (sp > p.kb_total) sp = p.kb_total;
+      const int ctas = tiles * sp;
+      const int waves = (ctas + slots - 1) / slots;
+      const double eff = (double)ctas / ((double)waves * slots) * (st == 2 ? 0.96 : 1.0);
+      if (eff > best) {
+        best = eff;
+        stages = st;
+        splits = sp;
+      }
+    }
+  }
+  {
+    static int legacy = -1;                 // A/B switch: the previous ceil(296 / tiles) rule
+    if (legacy < 0) {
+      const char* e = getenv("TNN_WGRAD_LEGACY_SPLITS");
+      legacy = (e != nullptr) ? atoi(e) : 0;
+    }
+    if (legacy) {
+      stages = 4;
+      splits = (2 * 148 + tiles - 1) / tiles;
+      if (splits > p.kb_total) splits = p.kb_total;
+    }
+  }
   p.kb_per_split = (p.kb_total + splits - 1) / splits;
   splits = (p.kb_total + p.kb_per_split - 1) / p.kb_per_split;
 
@@ -1484,14 +1523,6 @@ void conv_wgrad_bf16(const void* dY, long long ldy, int Kout, const void* X, con
     kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p, c_tiles, dW, ldw);
     ++g_launch_count;
   } else {
-    // 4 stages = 160 KB = ONE CTA per SM; 2 stages = 80 KB lets two CTAs share an SM so one's split-K
-    // epilogue overlaps the other's main loop.  Measured in the same run on WRN-16-8 (B200):
-    // 4 stages 5.69 ms/step, 2 stages 5.83 ms/step -> the deeper ring wins, 2 stays as a switch.
-    static int stages = -1;
-    if (stages < 0) {
-      const char* e = getenv("TNN_WGRAD_STAGES");
-      stages = (e != nullptr) ? atoi(e) : 4;
-    }
     if (stages == 2) {
       constexpr int STAGES = 2;
       constexpr int smem = STAGES * (2 * ATOM_BYTES + 3 * ATOM_BYTES) + 1024 + 256;

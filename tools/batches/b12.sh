@@ -5,10 +5,11 @@ timeout 150 python -m pytest tests/test_kernels_gpu.py -m gpu -q -k attention_bw
 tail -25 gpurun_out/pytest_attn_bwd.log | cut -c1-300
 timeout 600 python -m pytest tests -m gpu -q --timeout=90 --timeout-method=thread --deselect tests/test_kernels_gpu.py::test_attention_bwd_matches_reference > gpurun_out/pytest_gpu_b12.log 2>&1
 tail -3 gpurun_out/pytest_gpu_b12.log
-for v in base recompute base2; do
+for v in base recompute legacy_wgrad base2; do
   case $v in
     base|base2) env="";;
     recompute) env="TNN_BN_RECOMPUTE_MASK=1";;
+    legacy_wgrad) env="TNN_WGRAD_LEGACY_SPLITS=1";;
   esac
   env $env timeout 300 python bench.py --steps 60 --warmup 10 > gpurun_out/b12_bench_$v.json 2> gpurun_out/b12_bench_$v.err
   python -c "import json;d=json.loads(open('gpurun_out/b12_bench_$v.json').read().strip().splitlines()[-1]);print('$v',d['ms_per_step'],d['value'],d.get('e2e'),d.get('clocks'))"
