@@ -15,16 +15,24 @@ _STATES: dict = {}
 
 
 class StepState:
+    RING = 2048
+
     def __init__(self, device: torch.device):
         self.device = device
-        self.host = torch.zeros(16, dtype=torch.float32, pin_memory=(device.type == "cuda"))
+        # The H2D copy is asynchronous and the host may run many replays ahead of the device, so every
+        # step gets its OWN pinned source row (a ring far deeper than the driver's launch queue lets
+        # the host get ahead): a single reused row could be rewritten before an earlier copy reads it.
+        self.ring = torch.zeros((self.RING, 16), dtype=torch.float32, pin_memory=(device.type == "cuda"))
+        self.host = self.ring[0]
         self.dev = torch.zeros(16, dtype=torch.float32, device=device)
         self.counter = 0
 
     def advance(self, optimizer=None):
         """Bump the seed counter, refresh optimizer scalars, push to the device (async)."""
         self.counter += 1
-        h = self.host
+        h = self.ring[self.counter % self.RING]
+        h.copy_(self.host)                      # scalars persist from step to step unless refreshed
+        self.host = h
         h[12:14].view(torch.int64)[0] = self.counter
         if optimizer is not None:
             t = optimizer.step_count + 1

@@ -166,6 +166,9 @@ class Worker:
                 self.optimizer.zero_grads()
                 if self.scheduler is not None:
                     self.scheduler.step()
+            if self.graph is not None and self.graph.device().type == "cuda":
+                from ..core import stepstate
+                stepstate.get(self.graph.device()).advance(None)     # fresh dropout masks for the next batch
             GlobalProfiler.add_event(EventType.COMPUTE, t0, Profiler.now_ns(), "update", self.name)
             self._reply(CommandType.PARAMETERS_UPDATED, True)
         elif c == CommandType.TRAIN_MODE:

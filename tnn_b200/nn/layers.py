@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import math
 import os
+import zlib
 
 import torch
 import torch.nn.functional as F
@@ -319,6 +320,8 @@ class BatchNormLayer(Layer):
             b = self._bufs(x.device)
             y = torch.empty_like(x)
             seed = 0
+            if self.training:
+                seed = (self.seed * 1000003 + (zlib.crc32(self.name.encode()) & 0xFFFFFF) * 7919 + mb_id) & 0x7FFFFFFFFFFFFFFF
             if self.training and fused_ws is not None and os.environ.get("TNN_BN_FUSE_STATS", "1") == "1":
                 # the producing convolution already accumulated sum / sum-of-squares in its epilogue
                 Cx.bn_finalize_stats(fused_ws, M, C, gamma, beta, self.epsilon, self.momentum, self.params["running_mean"],
@@ -329,7 +332,6 @@ class BatchNormLayer(Layer):
                     producer._stats_requested = True      # takes effect from the next forward on
                 Cx.bn_train_stats(x, M, C, gamma, beta, self.epsilon, self.momentum, self.params["running_mean"],
                                   self.params["running_var"], b["mean"], b["invstd"], b["ss"], b["ws"])
-                seed = (self.seed * 1000003 + (hash(self.name) & 0xFFFFFF) * 7919 + mb_id) & 0x7FFFFFFFFFFFFFFF
             else:
                 Cx.bn_eval_scale_shift(C, gamma, beta, self.params["running_mean"], self.params["running_var"],
                                        self.epsilon, b["ss"])
@@ -616,7 +618,7 @@ class DropoutLayer(Layer):
         self._step += 1
         seed = (self.seed * 1000003 + self._step * 7919 + mb_id) & 0x7FFFFFFFFFFFFFFF
         if x.is_cuda:
-            seed = (self.seed * 1000003 + (hash(self.name) & 0xFFFFFF) * 7919 + mb_id) & 0x7FFFFFFFFFFFFFFF
+            seed = (self.seed * 1000003 + (zlib.crc32(self.name.encode()) & 0xFFFFFF) * 7919 + mb_id) & 0x7FFFFFFFFFFFFFFF
             x = to_bf16(x).contiguous()
             y = torch.empty_like(x)
             native.require().dropout_fwd(x, y, self.dropout_rate, seed, stepstate.get(x.device).dev)

@@ -13,12 +13,24 @@ The model is split by a ``Partitioner`` exactly as the coordinator does (fresh l
 config, per-stage seed => identical initial weights to the single-device model), every stage
 owns its optimizer (worker.hpp:194-207) and the last stage computes loss and gradient scaled
 by 1/M (coordinator.hpp:198,206).
+
+Launch overhead: a stage runs ~150 small kernels per microbatch; issued one by one from Python the
+stage is launch-bound long before the GPU is busy.  On a GPU every (forward, microbatch) and
+(backward, microbatch) unit is therefore captured ONCE into a CUDA graph (after two eager
+iterations) and replayed from then on: activations arrive by ``ncclRecv`` straight into the
+graph's static input buffer, the graph's output buffer is what ``ncclSend`` reads, all graphs share
+one memory pool and are captured -- and always replayed -- in schedule order, so a unit's scratch
+memory can be reused by later units while the per-microbatch layer caches stay alive between a
+forward and its backward.  ``TNN_PP_GRAPH=0`` keeps the eager path.
 """
 from __future__ import annotations
+
+import os
 
 import torch
 import torch.distributed as dist
 
+from ..core import stepstate
 from ..nn.blocks import Sequential
 from ..nn.graph import Graph, graph_from_sequential
 from ..nn.loss import Loss
@@ -63,6 +75,16 @@ class PipelineParallel:
         self.prev, self.next = self.rank - 1, self.rank + 1
         self.steps = 0
         self.p2p_bytes = 0
+        self._fwd_i = self._bwd_i = 0
+        self._rbufs = {"prev": {}, "next": {}}      # persistent receive buffers per microbatch slot
+        self.use_graphs = self.device.type == "cuda" and os.environ.get("TNN_PP_GRAPH", "1") == "1"
+        self._graph_mode = False
+        self._graphs: dict = {}
+        self._statics: dict = {}
+        self._pool = None
+        self._gstats = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self._stat_scale = torch.tensor([1.0 / self.M, 1.0], dtype=torch.float32).to(self.device)
+        self.graph_replays = 0
 
     # ------------------------------------------------------------------ p2p helpers
     def _ops(self, send_next=None, send_prev=None, recv_prev=False, recv_next=False):
@@ -70,12 +92,12 @@ class PipelineParallel:
         if send_prev is not None:
             ops.append(dist.P2POp(dist.isend, send_prev, self.prev, self.group))
         if recv_prev:
-            rp = torch.empty(self.in_shape, dtype=self.act_dtype, device=self.device)
+            rp = self._recv_buf("prev", self._fwd_i, self.in_shape)
             ops.append(dist.P2POp(dist.irecv, rp, self.prev, self.group))
         if send_next is not None:
             ops.append(dist.P2POp(dist.isend, send_next, self.next, self.group))
         if recv_next:
-            rn = torch.empty(self.out_shape, dtype=self.act_dtype, device=self.device)
+            rn = self._recv_buf("next", self._bwd_i, self.out_shape)
             ops.append(dist.P2POp(dist.irecv, rn, self.next, self.group))
         if ops:
             for t in (send_next, send_prev):
@@ -85,19 +107,71 @@ class PipelineParallel:
                 r.wait()          # NCCL: orders the CURRENT stream after the transfer; the host does not block
         return rp, rn
 
+    def _recv_buf(self, side: str, mb: int, shape) -> torch.Tensor:
+        """The receive buffer of microbatch slot ``mb`` (the same storage every iteration: it is the
+        static input of that slot's CUDA graph and it is what the layer caches of the slot refer to)."""
+        d = self._rbufs[side]
+        b = d.get(mb)
+        if b is None:
+            b = d[mb] = torch.empty(shape, dtype=self.act_dtype, device=self.device)
+        return b
+
     def _boundary(self, t: torch.Tensor) -> torch.Tensor:
         return t.to(self.act_dtype).contiguous()
 
+    # ------------------------------------------------------------------ CUDA-graph units
+    def _static(self, kind: str, mb: int, src: torch.Tensor) -> torch.Tensor:
+        """A fixed-address copy of a per-iteration input (first stage's images, last stage's labels)."""
+        key = (kind, mb)
+        b = self._statics.get(key)
+        if b is None or b.shape != src.shape or b.dtype != src.dtype:
+            if b is not None:
+                raise ValueError(f"pipeline graphs were captured for {tuple(b.shape)} {b.dtype}, got {tuple(src.shape)} {src.dtype}")
+            b = self._statics[key] = torch.empty_like(src, memory_format=torch.contiguous_format)
+        b.copy_(src, non_blocking=True)
+        return b
+
+    def _run_graph(self, key, body):
+        ent = self._graphs.get(key)
+        if ent is None:
+            if self._pool is None:
+                self._pool = torch.cuda.graph_pool_handle()
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg, pool=self._pool, capture_error_mode="thread_local"):
+                out = body()
+            ent = self._graphs[key] = (cg, out)
+        ent[0].replay()
+        self.graph_replays += 1
+        return ent[1]
+
     # ------------------------------------------------------------------ one microbatch of work
     def _forward(self, x, mb, labels, stats):
+        if self._graph_mode:
+            sx = self._static("x", mb, x) if self.is_first else x         # non-first: x IS the slot's receive buffer
+            sl = self._static("y", mb, labels[mb]) if self.is_last else None
+
+            def body():
+                y = self.stage.forward(sx, mb)
+                if self.is_last:
+                    st, grad = self.criterion.loss_and_grad(y, sl, scale=1.0 / self.M)
+                    self._gstats.add_(st.to(torch.float32) * self._stat_scale)
+                    return grad
+                return self._boundary(y)
+            return self._run_graph(("f", mb), body)
         y = self.stage.forward(x, mb)
         if self.is_last:
             st, grad = self.criterion.loss_and_grad(y, labels[mb], scale=1.0 / self.M)
-            stats += st.to(stats.dtype) * torch.tensor([1.0 / self.M, 1.0], device=stats.device, dtype=stats.dtype)
+            stats += st.to(stats.dtype) * self._stat_scale.to(stats.dtype)
             return grad
         return self._boundary(y)
 
     def _backward(self, g, mb):
+        if self._graph_mode:
+            # g is the slot's receive buffer (or, on the last stage, the forward graph's own output)
+            def body():
+                dx = self.stage.backward(g, mb)
+                return None if (self.is_first or dx is None) else self._boundary(dx)
+            return self._run_graph(("b", mb), body)
         dx = self.stage.backward(g, mb)
         return None if (self.is_first or dx is None) else self._boundary(dx)
 
@@ -108,34 +182,42 @@ class PipelineParallel:
         M, S, r = self.M, self.world, self.rank
         xs = list(torch.tensor_split(x.to(self.device, non_blocking=True), M, 0)) if self.is_first else None
         ys = list(torch.tensor_split(y.to(self.device, non_blocking=True), M, 0)) if self.is_last else None
-        stats = torch.zeros(2, dtype=torch.float32, device=self.device)
+        if self.device.type == "cuda":
+            stepstate.get(self.device).advance(None)         # new dropout masks every iteration
+        # two eager iterations first: lazy workspaces, bf16 weight copies and the conv->BN statistics
+        # fusion (which switches on from the second forward) must be settled before capture
+        self._graph_mode = self.use_graphs and self.steps >= 2 and self.graph.training
+        if self._graph_mode:
+            stats = self._gstats
+            stats.zero_()
+        else:
+            stats = torch.zeros(2, dtype=torch.float32, device=self.device)
         warm = min(S - r - 1, M)
         remaining = M - warm
-        pending = []                      # forward results waiting for their backward (last stage: grads)
-        fwd_i = bwd_i = 0
+        self._fwd_i = self._bwd_i = 0
 
         def next_input(recv):
-            return xs[fwd_i] if self.is_first else recv
+            return xs[self._fwd_i] if self.is_first else recv
 
         # warm-up forwards
         for _ in range(warm):
             inp, _ = self._ops(recv_prev=not self.is_first)
-            out = self._forward(next_input(inp), fwd_i, ys, stats)
-            fwd_i += 1
+            out = self._forward(next_input(inp), self._fwd_i, ys, stats)
+            self._fwd_i += 1
             self._ops(send_next=out)
         inp = None
         if remaining > 0 and not self.is_first:
             inp, _ = self._ops(recv_prev=True)
         # steady state: one forward, one backward
         for k in range(remaining):
-            out = self._forward(next_input(inp), fwd_i, ys, stats)
-            fwd_i += 1
+            out = self._forward(next_input(inp), self._fwd_i, ys, stats)
+            self._fwd_i += 1
             if self.is_last:
                 gout = out
             else:
                 _, gout = self._ops(send_next=out, recv_next=True)
-            gin = self._backward(gout, bwd_i)
-            bwd_i += 1
+            gin = self._backward(gout, self._bwd_i)
+            self._bwd_i += 1
             last = k == remaining - 1
             if self.is_first:
                 inp = None
@@ -147,8 +229,8 @@ class PipelineParallel:
         # cool-down backwards
         for _ in range(warm):
             _, gout = self._ops(recv_next=True)
-            gin = self._backward(gout, bwd_i)
-            bwd_i += 1
+            gin = self._backward(gout, self._bwd_i)
+            self._bwd_i += 1
             if not self.is_first:
                 self._ops(send_prev=gin)
         if update:
@@ -157,7 +239,7 @@ class PipelineParallel:
             if self.scheduler is not None:
                 self.scheduler.step()
         self.steps += 1
-        return stats
+        return stats.clone() if self._graph_mode else stats
 
     def eval_batch(self, x, y):
         self.graph.set_training(False)
