@@ -178,8 +178,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     uint8_t* dsrow = sdS + half * AB_TILE + row * 128;
     const int kbase = jb * 128 + half * 64;
 
+    // dq_full(it_done) must already have been waited on by the caller (see the loop: the wait sits
+    // BEFORE this thread's pds_full arrival, otherwise the MMA warp could complete the NEXT phase of
+    // dq_full first and a parity wait two phases behind would never return)
     auto flush_dq = [&](int it_done) {
-      mbar_wait(dq_full, it_done & 1);
       tc_fence_after();
       const int qi = (i_start + it_done) * 128 + row;
       uint32_t r[32];
@@ -204,6 +206,9 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       }
       const bool need_mask = (i * 128 + 128 > p.L) || (jb * 128 + 128 > p.L) || (CAUSAL && i == jb);
       mbar_wait(sdp_full, it & 1);
+      // S/dP of tile `it` complete => every earlier MMA (incl. dQ of tile it-1) has completed: this
+      // wait returns at once, and dQ(it) cannot be issued before this thread arrives on pds_full
+      if (it > 0) mbar_wait(dq_full, (it - 1) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < 64; c += 32) {
@@ -250,7 +255,8 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
       }
     }
     if (n_it > 0) {
-      flush_dq(n_it - 1);                // also orders the dK / dV reads after the last MMA
+      mbar_wait(dq_full, (n_it - 1) & 1);   // last commit: dK / dV / dQ accumulators are final
+      flush_dq(n_it - 1);
       const int kj = jb * 128 + row;
       uint32_t rk[32], rv[32];
       tmem_ld_32x32(tmem_dK + lane_off + half * 32, rk);
