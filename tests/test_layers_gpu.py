@@ -219,3 +219,40 @@ def test_batchnorm_backward_mask_recompute_equals_stored_mask(relu, p):
     assert ((res["0"][1] - res["1"][1]).abs() > 1e-6).float().mean().item() < 1e-3
     torch.testing.assert_close(res["0"][2], res["1"][2], atol=5e-2, rtol=1e-2)
     torch.testing.assert_close(res["0"][3], res["1"][3], atol=5e-2, rtol=1e-2)
+
+
+@pytest.mark.parametrize("relu,p,C,K", [(True, 0.0, 64, 128), (True, 0.3, 128, 128), (False, 0.3, 32, 64), (True, 0.3, 256, 256)])
+def test_batchnorm_backward_fused_into_dgrad_epilogue(relu, p, C, K):
+    """BN(+ReLU+dropout) -> conv3x3: the conv's dgrad epilogue does the BatchNorm backward reduction
+    (mask, scale, per-channel sums); gradients must match the separate reduce + apply kernels."""
+    import os
+    from tnn_b200.nn.builder import LayerBuilder
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(5)
+    x = (torch.randn(8, 16, 16, C, device=dev) * 1.5 + 0.3).bfloat16()
+    dy = torch.randn(8, 16, 16, K, device=dev).bfloat16()
+    res = {}
+    for mode in ("0", "1"):
+        os.environ["TNN_BN_FUSE_BWD"] = mode
+        b = LayerBuilder([[16, 16, C]])
+        b.batchnorm(1e-2, 0.1, True, relu, "bn")
+        if p > 0:
+            b.dropout(p, "drop")
+        b.conv2d(K, 3, 3, 1, 1, 1, 1, True, "conv")
+        seq = B.Sequential(b.build(), "s").init(dev, 11)
+        bn, conv = seq.layers[0], seq.layers[-1]
+        assert conv._bn_prev is bn and bn._bwd_consumer is conv
+        torch.manual_seed(99)
+        bn.params["gamma"].uniform_(0.5, 1.5)
+        bn.params["beta"].uniform_(-0.5, 0.5)
+        y = seq.forward(x, 0)
+        assert (bn.cache(0)["y"] is None) == (mode == "1" or not (relu or p > 0))
+        dx = seq.backward(dy, 0)
+        res[mode] = (y.float(), dx.float(), bn.grads["gamma"].clone(), bn.grads["beta"].clone(),
+                     conv.grads["weight"].clone(), conv.grads["bias"].clone())
+    os.environ.pop("TNN_BN_FUSE_BWD", None)
+    a, f = res["0"], res["1"]
+    assert torch.equal(a[0], f[0])
+    assert _rel(f[1], a[1]) < 2e-2, f"dx {_rel(f[1], a[1])}"
+    assert _rel(f[2], a[2]) < 2e-2 and _rel(f[3], a[3]) < 2e-2, f"dgamma {_rel(f[2], a[2])} dbeta {_rel(f[3], a[3])}"
+    assert torch.equal(a[4], f[4]) and torch.equal(a[5], f[5])      # the conv's own grads do not depend on the fusion

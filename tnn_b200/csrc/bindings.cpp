@@ -85,7 +85,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv_fprop", [](const Tensor& X, const Tensor& Wt, int64_t ldw, int64_t N,
                          const std::vector<int64_t>& geom, const std::vector<int64_t>& taps,
                          const Tensor& out, int64_t ldc, const std::vector<int64_t>& grid, int out_mode,
-                         int act, double alpha, const OptT& bias, const OptT& residual, const OptT& col_stats) {
+                         int act, double alpha, const OptT& bias, const OptT& residual, const OptT& col_stats,
+                         const OptT& bnb_x, const OptT& bnb_pack, bool bnb_relu, double bnb_drop, uint64_t bnb_seed,
+                         const OptT& bnb_state) {
     check_cuda(X);
     tnn::ConvGeom g = make_geom(geom, taps);
     tnn::Epilogue e = make_epi(out, out_mode, act, alpha, bias, residual, ldc, grid);
@@ -94,15 +96,39 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       e.col_sum = fp(*col_stats);
       e.col_repl = tnn::bn_stat_replicas();
     }
+    if (bnb_x.has_value()) {
+      // BatchNorm-backward fusion: this launch is the dgrad of the conv that consumes BN(x)
+      TORCH_CHECK(col_stats.has_value() && bnb_pack.has_value(), "bnb_x needs col_stats and bnb_pack");
+      TORCH_CHECK(bnb_x->scalar_type() == torch::kBFloat16 && bnb_x->is_contiguous() && bnb_x->numel() == out.numel(),
+                  "bnb_x must be a contiguous bf16 tensor shaped like out");
+      TORCH_CHECK(bnb_pack->scalar_type() == torch::kFloat32 && bnb_pack->numel() >= 4 * N &&
+                      (reinterpret_cast<uintptr_t>(bnb_pack->data_ptr()) & 15) == 0, "bnb_pack: 16-byte aligned fp32 [N][4]");
+      TORCH_CHECK(out_mode == tnn::OUT_BF16 && N % 8 == 0 && ldc == N, "BN-backward fusion needs a dense bf16 [M, N] output");
+      e.bnb_x = vp(*bnb_x);
+      e.bnb_pack = fp(*bnb_pack);
+      e.bnb_relu = bnb_relu ? 1 : 0;
+      e.bnb_drop = (float)bnb_drop;
+      e.bnb_dscale = bnb_drop > 0.0 ? (float)(1.0 / (1.0 - bnb_drop)) : 1.f;
+      e.bnb_seed = bnb_seed;
+      e.bnb_seed_ptr = bnb_state.has_value()
+          ? reinterpret_cast<const unsigned long long*>(bnb_state->data_ptr<float>() + 12) : nullptr;
+    }
     tnn::conv_fprop_bf16(vp(X), vp(Wt), ldw, (int)N, g, e, cur_stream());
   }, py::arg("X"), py::arg("Wt"), py::arg("ldw"), py::arg("N"), py::arg("geom"), py::arg("taps"), py::arg("out"),
      py::arg("ldc"), py::arg("grid"), py::arg("out_mode"), py::arg("act"), py::arg("alpha"), py::arg("bias"),
-     py::arg("residual"), py::arg("col_stats") = py::none());
+     py::arg("residual"), py::arg("col_stats") = py::none(), py::arg("bnb_x") = py::none(),
+     py::arg("bnb_pack") = py::none(), py::arg("bnb_relu") = false, py::arg("bnb_drop") = 0.0, py::arg("bnb_seed") = 0,
+     py::arg("bnb_state") = py::none());
   m.def("bn_finalize_stats", [](const Tensor& ws, int64_t M, int C, const OptT& gamma, const OptT& beta, double eps,
                                 double momentum, const OptT& rmean, const OptT& rvar, const Tensor& smean,
-                                const Tensor& sinvstd, const Tensor& ss) {
+                                const Tensor& sinvstd, const Tensor& ss, const OptT& pack) {
     tnn::bn_finalize_stats(fp(ws), M, C, fp(gamma), fp(beta), (float)eps, (float)momentum, fp(rmean), fp(rvar),
-                           fp(smean), fp(sinvstd), fp(ss), cur_stream());
+                           fp(smean), fp(sinvstd), fp(ss), fp(pack), cur_stream());
+  }, py::arg("ws"), py::arg("M"), py::arg("C"), py::arg("gamma"), py::arg("beta"), py::arg("eps"), py::arg("momentum"),
+     py::arg("rmean"), py::arg("rvar"), py::arg("smean"), py::arg("sinvstd"), py::arg("ss"), py::arg("pack") = py::none());
+  m.def("bn_bwd_coef", [](const Tensor& ws, int64_t M, int C, const OptT& gamma, const Tensor& sinvstd,
+                          const OptT& dgamma, const OptT& dbeta, const Tensor& coef) {
+    tnn::bn_bwd_coef(fp(ws), M, C, fp(gamma), fp(sinvstd), fp(dgamma), fp(dbeta), fp(coef), cur_stream());
   });
   m.def("bn_stat_replicas", &tnn::bn_stat_replicas);
   m.def("conv_wgrad", [](const Tensor& dY, int64_t ldy, int64_t Kout, const Tensor& X,
@@ -177,10 +203,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   // ------------------------------------------------------------------ normalisation
   m.def("bn_train_stats", [](const Tensor& x, int64_t M, int C, const OptT& gamma, const OptT& beta,
                              double eps, double momentum, const OptT& rmean, const OptT& rvar,
-                             const Tensor& smean, const Tensor& sinvstd, const Tensor& ss, const Tensor& ws) {
+                             const Tensor& smean, const Tensor& sinvstd, const Tensor& ss, const Tensor& ws,
+                             const OptT& pack) {
     tnn::bn_train_stats(vp(x), M, C, fp(gamma), fp(beta), (float)eps, (float)momentum, fp(rmean), fp(rvar),
-                        fp(smean), fp(sinvstd), fp(ss), fp(ws), cur_stream());
-  });
+                        fp(smean), fp(sinvstd), fp(ss), fp(ws), fp(pack), cur_stream());
+  }, py::arg("x"), py::arg("M"), py::arg("C"), py::arg("gamma"), py::arg("beta"), py::arg("eps"), py::arg("momentum"),
+     py::arg("rmean"), py::arg("rvar"), py::arg("smean"), py::arg("sinvstd"), py::arg("ss"), py::arg("ws"),
+     py::arg("pack") = py::none());
   m.def("bn_eval_scale_shift", [](int C, const OptT& gamma, const OptT& beta, const Tensor& rmean,
                                   const Tensor& rvar, double eps, const Tensor& ss) {
     tnn::bn_eval_scale_shift(C, fp(gamma), fp(beta), fp(rmean), fp(rvar), (float)eps, fp(ss), cur_stream());

@@ -124,7 +124,8 @@ int bn_ws_floats(int C) { return BN_REPL * 2 * C + 4; }
 __global__ void __launch_bounds__(256)
     k_bn_stats(const bf16* __restrict__ x, long long M, int C, const float* __restrict__ gamma,
                const float* __restrict__ beta, float eps, float momentum, float* running_mean,
-               float* running_var, float* save_mean, float* save_invstd, float* scale_shift, float* ws) {
+               float* running_var, float* save_mean, float* save_invstd, float* scale_shift, float* ws,
+               float4* pack) {
   extern __shared__ float sm[];
   const BnMap m(C);
   const bool vec = (C & 7) == 0;
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(256)
       float gm = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
       scale_shift[c] = gm * invstd;
       scale_shift[C + c] = bt - mean * gm * invstd;
+      if (pack) pack[c] = make_float4(invstd, -mean * invstd, gm * invstd, bt - mean * gm * invstd);
       if (running_mean) {
         running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
         running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * unbias;
@@ -188,7 +190,7 @@ __global__ void __launch_bounds__(256)
 }
 void bn_train_stats(const void* x, long long M, int C, const float* gamma, const float* beta,
                     float eps, float momentum, float* running_mean, float* running_var,
-                    float* save_mean, float* save_invstd, float* scale_shift, float* ws,
+                    float* save_mean, float* save_invstd, float* scale_shift, float* ws, float* pack,
                     cudaStream_t s) {
   static bool configured = false;
   if (!configured) {
@@ -197,7 +199,7 @@ void bn_train_stats(const void* x, long long M, int C, const float* gamma, const
   }
   k_bn_stats<<<bn_blocks(M, C), 256, 256 * 8 * sizeof(float), s>>>(
       (const bf16*)x, M, C, gamma, beta, eps, momentum, running_mean, running_var, save_mean,
-      save_invstd, scale_shift, ws);
+      save_invstd, scale_shift, ws, reinterpret_cast<float4*>(pack));
   TNN_CHECK_LAUNCH();
 }
 
@@ -207,7 +209,7 @@ void bn_train_stats(const void* x, long long M, int C, const float* gamma, const
 __global__ void __launch_bounds__(256)
     k_bn_finalize(float* ws, long long M, int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                   float eps, float momentum, float* running_mean, float* running_var, float* save_mean,
-                  float* save_invstd, float* scale_shift) {
+                  float* save_invstd, float* scale_shift, float4* pack) {
   const float inv_m = 1.f / (float)M;
   const float unbias = M > 1 ? (float)M / (float)(M - 1) : 1.f;
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
@@ -220,6 +222,7 @@ __global__ void __launch_bounds__(256)
     float gm = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
     scale_shift[c] = gm * invstd;
     scale_shift[C + c] = bt - mean * gm * invstd;
+    if (pack) pack[c] = make_float4(invstd, -mean * invstd, gm * invstd, bt - mean * gm * invstd);
     if (running_mean) {
       running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
       running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * unbias;
@@ -228,9 +231,9 @@ __global__ void __launch_bounds__(256)
 }
 void bn_finalize_stats(float* ws, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
                        float* running_mean, float* running_var, float* save_mean, float* save_invstd,
-                       float* scale_shift, cudaStream_t s) {
+                       float* scale_shift, float* pack, cudaStream_t s) {
   k_bn_finalize<<<(C + 255) / 256, 256, 0, s>>>(ws, M, C, gamma, beta, eps, momentum, running_mean, running_var, save_mean,
-                                             save_invstd, scale_shift);
+                                             save_invstd, scale_shift, reinterpret_cast<float4*>(pack));
   TNN_CHECK_LAUNCH();
 }
 int bn_stat_replicas() { return BN_REPL; }
@@ -532,6 +535,27 @@ __global__ void __launch_bounds__(256, 2)
     if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(colsum_ws + (size_t)BN_REPL * C) = 0u;
   }
 }
+// Backward statistics that a dgrad epilogue accumulated (ws = [BN_REPL][2][C]: sum g, sum g*xhat):
+// fold, add into dgamma / dbeta, write the apply coefficients, reset the workspace.  One small CTA.
+__global__ void __launch_bounds__(256)
+    k_bn_bwd_coef(float* ws, long long M, int C, const float* __restrict__ gamma, const float* __restrict__ invstd,
+                  float* dgamma, float* dbeta, float* coef) {
+  const float inv_m = 1.f / (float)M;
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < C; c += gridDim.x * blockDim.x) {
+    float db = fold_replicas<2>(ws, 0, C, c), dg = fold_replicas<2>(ws, 1, C, c);
+    if (dbeta) dbeta[c] += db;
+    if (dgamma) dgamma[c] += dg;
+    coef[c] = (gamma ? gamma[c] : 1.f) * invstd[c];
+    coef[C + c] = db * inv_m;
+    coef[2 * C + c] = dg * inv_m;
+  }
+}
+void bn_bwd_coef(float* ws, long long M, int C, const float* gamma, const float* save_invstd, float* dgamma,
+                 float* dbeta, float* coef, cudaStream_t s) {
+  k_bn_bwd_coef<<<(C + 255) / 256, 256, 0, s>>>(ws, M, C, gamma, save_invstd, dgamma, dbeta, coef);
+  TNN_CHECK_LAUNCH();
+}
+
 void bn_bwd_apply(const void* dy, const void* x, const void* y, const void* extra, void* dx,
                   long long M, int C, const float* save_mean, const float* save_invstd,
                   const float* coef, int masked, float drop_p, float* colsum_out, float* colsum_ws,

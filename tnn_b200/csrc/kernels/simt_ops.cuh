@@ -73,12 +73,17 @@ void skinny_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw
 // (zero-initialised once); scale_shift receives [2*C] = {gamma*invstd, beta - mean*gamma*invstd}.
 void bn_train_stats(const void* x, long long M, int C, const float* gamma, const float* beta,
                     float eps, float momentum, float* running_mean, float* running_var,
-                    float* save_mean, float* save_invstd, float* scale_shift, float* ws,
+                    float* save_mean, float* save_invstd, float* scale_shift, float* ws, float* pack,
                     cudaStream_t s);
 // finalize statistics accumulated by a producer epilogue into ws = [replicas][2][C] (see umma_gemm.cuh)
 void bn_finalize_stats(float* ws, long long M, int C, const float* gamma, const float* beta, float eps, float momentum,
                        float* running_mean, float* running_var, float* save_mean, float* save_invstd,
-                       float* scale_shift, cudaStream_t s);
+                       float* scale_shift, float* pack, cudaStream_t s);
+// `pack` (nullable, [C][4] fp32 = invstd, -mean*invstd, gamma*invstd, beta - mean*gamma*invstd) is the
+// per-channel record the BatchNorm-backward fusion in the dgrad epilogue reads (umma_gemm.cuh).
+// bn_bwd_coef folds the (sum g, sum g*xhat) statistics such an epilogue left in ws.
+void bn_bwd_coef(float* ws, long long M, int C, const float* gamma, const float* save_invstd, float* dgamma,
+                 float* dbeta, float* coef, cudaStream_t s);
 int bn_stat_replicas();
 void bn_eval_scale_shift(int C, const float* gamma, const float* beta, const float* running_mean,
                          const float* running_var, float eps, float* scale_shift, cudaStream_t s);

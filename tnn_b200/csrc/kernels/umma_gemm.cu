@@ -25,6 +25,7 @@
 
 #include <mutex>
 
+#include "common.cuh"
 #include "sm100.cuh"
 
 namespace tnn {
@@ -114,6 +115,49 @@ __device__ __forceinline__ void epi_compute_32(const KParams& p, const uint32_t 
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
   }
+  float xh[32];
+  const bool bnb = e.bnb_x != nullptr;
+  if (bnb) {
+    // BatchNorm backward fusion (see Epilogue): v is d(BN output) here
+    const __nv_bfloat16* xs = reinterpret_cast<const __nv_bfloat16*>(e.bnb_x) + row_off + n;
+    float xv[32];
+    if (row_ok && full) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 q = __ldg(reinterpret_cast<const uint4*>(xs) + j);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float2 f = __bfloat1622float2(h[t]);
+          xv[j * 8 + t * 2] = f.x;
+          xv[j * 8 + t * 2 + 1] = f.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) xv[j] = (row_ok && n + j < p.N) ? __bfloat162float(xs[j]) : 0.f;
+    }
+    unsigned long long seed = e.bnb_seed;
+    if (e.bnb_drop > 0.f && e.bnb_seed_ptr != nullptr) seed ^= (*e.bnb_seed_ptr) * 0x9E3779B97F4A7C15ull;
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+      bool keep[8];
+      if (e.bnb_drop > 0.f) {
+        // same element -> mask mapping as the forward apply kernel: vector index = element offset / 8
+        dropout_keep8(seed, (row_off + n + j8 * 8) >> 3, e.bnb_drop, keep);
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int j = j8 * 8 + t;
+        const float4 P = (n + j < p.N) ? __ldg(reinterpret_cast<const float4*>(e.bnb_pack) + n + j)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        bool on = e.bnb_relu ? (xv[j] * P.z + P.w > 0.f) : true;
+        if (e.bnb_drop > 0.f) on = on && keep[t];
+        v[j] = on ? v[j] * e.bnb_dscale : 0.f;
+        xh[j] = xv[j] * P.x + P.y;
+      }
+    }
+  }
   if (e.col_sum != nullptr) {
     // BatchNorm statistics of the STORED tile (sum and sum of squares per output channel), so the
     // consumer BatchNorm never re-reads this activation: a butterfly transpose-reduce over the
@@ -127,7 +171,7 @@ __device__ __forceinline__ void epi_compute_32(const KParams& p, const uint32_t 
       if (e.out_mode == OUT_BF16) t = __bfloat162float(__float2bfloat16(t));
       t = row_ok ? t : 0.f;
       a[j] = t;
-      b[j] = t * t;
+      b[j] = bnb ? t * xh[j] : t * t;
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) {
@@ -1160,7 +1204,10 @@ template <int BLOCK_N, bool CONV_A, bool TMA_STORE>
 static void launch_gemm2_persist_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                    const KParams& p, int m_tiles256, int n_tiles, cudaStream_t stream) {
   constexpr int STAGES = (BLOCK_N <= 128) ? 4 : 6;     // BLOCK_N = 256 owns the SM (TMEM full): deeper ring
-  constexpr int smem = STAGES * (BLOCK_M * 128 + (BLOCK_N / 2) * 128) + (TMA_STORE ? BLOCK_M * 128 : 0) + 128;
+  // barriers: (2*STAGES + 4) mbarriers + the TMEM slot = 132 bytes at 6 stages -- 128 was 4 bytes short
+  // (tmem_slot landed past the dynamic window: "illegal memory access" on the first pair launch)
+  constexpr int kBarBytes = ((2 * STAGES + 4) * 8 + 4 + 127) / 128 * 128;
+  constexpr int smem = STAGES * (BLOCK_M * 128 + (BLOCK_N / 2) * 128) + (TMA_STORE ? BLOCK_M * 128 : 0) + kBarBytes;
   auto kern = umma_gemm2_persist_kernel<BLOCK_N, CONV_A, STAGES, TMA_STORE>;
   static bool configured = false;
   if (!configured) {
@@ -1236,7 +1283,8 @@ template <int BLOCK_N, bool A_MN, bool B_MN, bool CONV_A, bool TMA_STORE>
 static void launch_gemm_persist_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const KParams& p,
                                   int m_tiles, int n_tiles, int splits, cudaStream_t stream) {
   constexpr int STAGES = (BLOCK_N <= 64) ? 4 : ((BLOCK_N <= 128) ? 3 : 4);
-  constexpr int smem = STAGES * (BLOCK_M * 128 + BLOCK_N * 128) + (TMA_STORE ? BLOCK_M * 128 : 0) + 128;
+  constexpr int kBarBytes = ((2 * STAGES + 4) * 8 + 4 + 127) / 128 * 128;
+  constexpr int smem = STAGES * (BLOCK_M * 128 + BLOCK_N * 128) + (TMA_STORE ? BLOCK_M * 128 : 0) + kBarBytes;
   auto kern = umma_gemm_persist_kernel<BLOCK_N, A_MN, B_MN, CONV_A, STAGES, TMA_STORE>;
   static bool configured = false;
   if (!configured) {

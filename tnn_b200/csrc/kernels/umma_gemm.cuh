@@ -28,6 +28,18 @@ struct Epilogue {
   // values per column), replica row = blockIdx.x % col_repl; folded by bn_finalize_stats (norm.cu)
   float* col_sum = nullptr;
   int col_repl = 1;
+  // BatchNorm BACKWARD fusion, for the dgrad of a convolution whose input is BN(+ReLU)(+dropout)(x):
+  // the value this GEMM produces is d(BN output); with bnb_x set the epilogue turns it into
+  //   g = mask(x) * dy * bnb_dscale        mask = [x*scale + shift > 0] (ReLU) and the dropout keep bit
+  // stores g, and col_sum receives (sum g, sum g * xhat) per channel -- exactly what the BatchNorm
+  // backward needs, so its two-tensor reduction pass disappears (norm.cu: bn_bwd_coef + bn_bwd_apply).
+  const void* bnb_x = nullptr;          // bf16 BN input, same addressing as out
+  const float* bnb_pack = nullptr;      // [N][4] fp32: invstd, -mean*invstd, scale, shift
+  int bnb_relu = 0;
+  float bnb_drop = 0.f;                 // dropout probability (0 = none)
+  float bnb_dscale = 1.f;               // 1 / (1 - p)
+  unsigned long long bnb_seed = 0;
+  const unsigned long long* bnb_seed_ptr = nullptr;   // device step counter mixed into the seed
 };
 
 struct ConvTap {

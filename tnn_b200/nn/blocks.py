@@ -67,6 +67,17 @@ class Sequential(Block):
             if isinstance(a, BatchNormLayer) and isinstance(b, DropoutLayer) and b.dropout_rate > 0:
                 a.fused_dropout_p = b.dropout_rate
                 b.fused_into_prev = True
+        # BatchNorm(+ReLU) [+ fused Dropout] -> Conv2D: the conv's dgrad epilogue performs the BatchNorm's
+        # backward reduction (the BN output has no other consumer inside a Sequential)
+        for i, a in enumerate(self.layers):
+            if not isinstance(a, BatchNormLayer):
+                continue
+            j = i + 1
+            if j < len(self.layers) and isinstance(self.layers[j], DropoutLayer) and getattr(self.layers[j], "fused_into_prev", False):
+                j += 1
+            if j < len(self.layers) and isinstance(self.layers[j], Conv2DLayer) and not self.layers[j]._generic:
+                self.layers[j]._bn_prev = a
+                a._bwd_consumer = self.layers[j]
 
     def add(self, layer: Layer):
         self.layers.append(layer)

@@ -173,6 +173,7 @@ class Conv2DLayer(Layer):
         # its input asks for the statistics to be accumulated in the conv epilogue from then on
         self._stats_ws = None
         self._stats_requested = False
+        self._bn_prev = None         # set by Sequential: BatchNorm(+ReLU+dropout) whose output is this layer's only input
 
     def param_descriptors(self):
         fan_in = self.in_channels * self.kernel_h * self.kernel_w
@@ -252,6 +253,19 @@ class Conv2DLayer(Layer):
         conv_ops.conv2d_wgrad(plan, dy, x, self.grads["weight"], db, cache=c)
         if not need_dx or plan.path == "direct":
             return None
+        bn = self._bn_prev
+        if bn is not None and dy.is_cuda and residual is None and plan.path == "tma" and plan.stride == 1 and \
+                not plan.d_needs_zero and len(plan.d_launches) == 1 and bn.training and \
+                os.environ.get("TNN_BN_FUSE_BWD", "1") == "1":
+            bc = bn._cache.get(mb_id)
+            if bc is not None and bc.get("pack") is not None and bc["x"].shape == x.shape and self.in_channels % 32 == 0:
+                # dgrad + BatchNorm-backward reduction in one kernel: the epilogue masks / scales the
+                # gradient, stores g and accumulates (sum g, sum g*xhat) into the BatchNorm's workspace
+                bnb = dict(x=bc["x"], pack=bc["pack"], relu=bn.use_relu, p=bc["p"], seed=bc.get("seed", 0),
+                           state=stepstate.get(dy.device).dev if bc["p"] > 0 else None, ws=bn._bufs(dy.device)["ws"])
+                g = conv_ops.conv2d_dgrad(plan, dy, w, self._state, self.param_version, bn_bwd=bnb)
+                g._tnn_bn_g = bn
+                return g
         return conv_ops.conv2d_dgrad(plan, dy, w, self._state, self.param_version, residual=residual)
 
     def output_shape(self, s):
@@ -287,6 +301,7 @@ class BatchNormLayer(Layer):
         self.affine, self.use_relu = bool(affine), bool(use_relu)
         self._gpu = None
         self.fused_dropout_p = 0.0   # set by Sequential when a Dropout layer directly follows
+        self._bwd_consumer = None    # set by Sequential: the Conv2DLayer whose dgrad epilogue does this layer's backward reduction
 
     def param_descriptors(self):
         C = self.num_features
@@ -322,16 +337,21 @@ class BatchNormLayer(Layer):
             seed = 0
             if self.training:
                 seed = (self.seed * 1000003 + (zlib.crc32(self.name.encode()) & 0xFFFFFF) * 7919 + mb_id) & 0x7FFFFFFFFFFFFFFF
+            rec = None
+            if self.training:
+                # this microbatch's statistics record, written by the statistics kernel itself (no clones):
+                # [0:4C] the (invstd, -mean*invstd, scale, shift) pack per channel (16-byte aligned), [4C:5C] mean, [5C:6C] invstd
+                rec = torch.empty(6 * C, dtype=torch.float32, device=x.device)
             if self.training and fused_ws is not None and os.environ.get("TNN_BN_FUSE_STATS", "1") == "1":
                 # the producing convolution already accumulated sum / sum-of-squares in its epilogue
                 Cx.bn_finalize_stats(fused_ws, M, C, gamma, beta, self.epsilon, self.momentum, self.params["running_mean"],
-                                     self.params["running_var"], b["mean"], b["invstd"], b["ss"])
+                                     self.params["running_var"], rec[4 * C:5 * C], rec[5 * C:], b["ss"], rec[:4 * C])
                 x._tnn_bn_stats = None                    # the workspace is reset by the fold: single consumer
             elif self.training:
                 if producer is not None and getattr(producer, "out_channels", -1) == C:
                     producer._stats_requested = True      # takes effect from the next forward on
                 Cx.bn_train_stats(x, M, C, gamma, beta, self.epsilon, self.momentum, self.params["running_mean"],
-                                  self.params["running_var"], b["mean"], b["invstd"], b["ss"], b["ws"])
+                                  self.params["running_var"], rec[4 * C:5 * C], rec[5 * C:], b["ss"], b["ws"], rec[:4 * C])
             else:
                 Cx.bn_eval_scale_shift(C, gamma, beta, self.params["running_mean"], self.params["running_var"],
                                        self.epsilon, b["ss"])
@@ -343,8 +363,11 @@ class BatchNormLayer(Layer):
                 # the dropout counter instead of reading y (saves the y activation; measured 2.8% SLOWER
                 # per WRN step on B200 -- the extra ALU work costs more than the saved read -- so off by default)
                 keep_y = os.environ.get("TNN_BN_RECOMPUTE_MASK", "0") != "1"
-                c["y"] = y if ((self.use_relu or p_drop > 0) and keep_y) else None
-                c["mean"], c["invstd"] = b["mean"].clone(), b["invstd"].clone()
+                # BN-backward fusion (the consumer conv's dgrad epilogue rebuilds the mask from x): y is not
+                # needed by backward at all then -- but keep it unless the consumer is known to fuse
+                fuse_bwd = self._bwd_consumer is not None and os.environ.get("TNN_BN_FUSE_BWD", "1") == "1"
+                c["y"] = y if ((self.use_relu or p_drop > 0) and keep_y and not fuse_bwd) else None
+                c["mean"], c["invstd"], c["pack"] = rec[4 * C:5 * C], rec[5 * C:], rec[:4 * C]
                 c["p"] = p_drop
                 c["seed"] = seed
             return y
@@ -386,6 +409,20 @@ class BatchNormLayer(Layer):
             b = self._bufs(dy.device)
             state = stepstate.get(dy.device).dev if c["p"] > 0 else None
             beta = self.params.get("beta")
+            if getattr(dy, "_tnn_bn_g", None) is self:
+                # dy is already g = mask * d(out) / (1-p) and b["ws"] holds (sum g, sum g*xhat): the
+                # consumer convolution's dgrad epilogue did the reduction pass (umma_gemm.cuh, Epilogue::bnb_*)
+                Cx.bn_bwd_coef(b["ws"], M, C, gamma, c["invstd"], self.grads.get("gamma"), self.grads.get("beta"), b["coef"])
+                dx = torch.empty_like(x)
+                colsum = torch.empty(C, dtype=torch.float32, device=dy.device)
+                Cx.bn_bwd_apply(dy, x, None, extra, dx, M, C, c["mean"], c["invstd"], b["coef"], False, 0.0, colsum,
+                                b["cws"], gamma, beta, False, 0, None)
+                dx = dx.reshape(dy.shape)
+                dx._tnn_colsum = colsum
+                return dx
+            # (y is None with a mask = the forward dropped y expecting the fused backward or
+            # TNN_BN_RECOMPUTE_MASK=1: the kernels below then rebuild the mask from x, the statistics and
+            # the dropout counter)
             Cx.bn_bwd_reduce(dy, x, y, M, C, gamma, c["mean"], c["invstd"], masked, c["p"], self.grads.get("gamma"),
                              self.grads.get("beta"), b["coef"], b["ws"], beta, self.use_relu, c.get("seed", 0), state)
             dx = torch.empty_like(x)

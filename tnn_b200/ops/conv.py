@@ -203,8 +203,11 @@ def conv2d_fwd(plan: ConvPlan, x, w, w_bf16, bias, residual=None, act=None, cach
     return y
 
 
-def conv2d_dgrad(plan: ConvPlan, dy, w, state: ConvState, w_version: int = 0, residual=None):
-    """dx [N,H,W,C] from dy [N,OH,OW,K].  `residual` (same shape as dx) is added in the epilogue."""
+def conv2d_dgrad(plan: ConvPlan, dy, w, state: ConvState, w_version: int = 0, residual=None, bn_bwd: dict | None = None):
+    """dx [N,H,W,C] from dy [N,OH,OW,K].  `residual` (same shape as dx) is added in the epilogue.
+    ``bn_bwd`` (tma path, stride 1): fuse the backward reduction of the BatchNorm(+ReLU+dropout) that
+    produced this convolution's input into the epilogue -- the result is then g = mask * dx / (1-p) and
+    ``bn_bwd["ws"]`` receives per-channel (sum g, sum g * xhat); keys x, pack, relu, p, seed, state, ws."""
     if plan.path == "ref":
         dx = conv2d_dgrad_ref(dy, w, (plan.N, plan.H, plan.W, plan.C), plan.stride, plan.pad)
         if residual is not None:
@@ -225,6 +228,13 @@ def conv2d_dgrad(plan: ConvPlan, dy, w, state: ConvState, w_version: int = 0, re
                 dx.copy_(residual)   # phases without taps keep the residual; others overwrite
         else:
             dx = torch.empty((N, H, W, C), device=dy.device, dtype=torch.bfloat16)
+        if bn_bwd is not None:
+            assert residual is None and len(plan.d_launches) == 1 and not plan.d_needs_zero
+            geom, taps, grid = plan.d_launches[0]
+            Cx.conv_fprop(dy, state.wt, rsk, C, geom, taps, dx, C, grid, OUT_BF16, 0, 1.0, None, None, bn_bwd["ws"],
+                          bn_bwd["x"], bn_bwd["pack"], bool(bn_bwd["relu"]), float(bn_bwd["p"]), int(bn_bwd["seed"]),
+                          bn_bwd["state"])
+            return dx
         for geom, taps, grid in plan.d_launches:
             Cx.conv_fprop(dy, state.wt, rsk, C, geom, taps, dx, C, grid, OUT_BF16, 0, 1.0, None, residual)
         return dx
