@@ -66,6 +66,18 @@ void attention_bind(py::module_& m) {
     attention_decode_bf16(q.data_ptr(), q_batch, kc.data_ptr(), vc.data_ptr(), kc.stride(1), kc.stride(0), out.data_ptr(),
                           B, H, (int)len, at::cuda::getCurrentCUDAStream().stream());
   });
+  m.def("kv_cache_store", [](const Tensor& qkv, const Tensor& kc, const Tensor& vc, int64_t pos) {
+    check_head_view(kc, "k cache");
+    check_head_view(vc, "v cache");
+    TORCH_CHECK(qkv.is_cuda() && qkv.scalar_type() == torch::kBFloat16 && qkv.dim() == 5 && qkv.size(2) == 3 &&
+                    qkv.size(4) == 64 && qkv.is_contiguous(), "qkv must be contiguous bf16 [B, L, 3, H, 64]");
+    const int B = (int)qkv.size(0), L = (int)qkv.size(1), H = (int)qkv.size(3);
+    TORCH_CHECK(kc.size(0) >= B && kc.size(2) == H && pos >= 0 && pos + L <= kc.size(1), "KV cache too small");
+    TORCH_CHECK(kc.stride(0) == vc.stride(0) && kc.stride(1) == vc.stride(1) && kc.stride(1) % 8 == 0 && kc.stride(0) % 8 == 0,
+                "k/v cache strides differ or are not 16-byte multiples");
+    kv_cache_store_bf16(qkv.data_ptr(), kc.data_ptr(), vc.data_ptr(), kc.stride(1), kc.stride(0), B, L, H * 64, (int)pos,
+                        at::cuda::getCurrentCUDAStream().stream());
+  });
   m.def("attention_decode_append", [](const Tensor& qkv, const Tensor& kc, const Tensor& vc, const Tensor& out,
                                       const Tensor& pos) {
     check_head_view(kc, "k cache");

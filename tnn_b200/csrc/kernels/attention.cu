@@ -487,6 +487,33 @@ void attention_decode_append_bf16(const void* qkv, void* kcache, void* vcache, l
   TNN_CHECK_LAUNCH();
 }
 
+// Prefill: copy the K and V slots of the packed projection [B, L, 3, E] into the caches at [pos, pos+L)
+// (16-byte vectors; replaces two strided framework copy kernels per layer, ~55 us each at B=32 L=1024)
+__global__ void __launch_bounds__(256)
+    k_kv_store(const bf16* __restrict__ qkv, bf16* __restrict__ kc, bf16* __restrict__ vc, long long n_vec, int E8,
+               int L, long long tok_stride, long long batch_stride, int pos) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= n_vec) return;
+  const int c = (int)(gid % E8);
+  long long t = gid / E8;
+  const int which = (int)(t & 1);            // 0 = K, 1 = V
+  t >>= 1;
+  const int l = (int)(t % L);
+  const long long b = t / L;
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(qkv + ((b * L + l) * 3 + 1 + which) * (long long)E8 * 8) + c);
+  bf16* dst = (which ? vc : kc) + b * batch_stride + (long long)(pos + l) * tok_stride;
+  reinterpret_cast<uint4*>(dst)[c] = v;
+}
+void kv_cache_store_bf16(const void* qkv, void* kcache, void* vcache, long long tok_stride, long long batch_stride,
+                         int B, int L, int E, int pos, cudaStream_t stream) {
+  if (B <= 0 || L <= 0) return;
+  const long long n_vec = (long long)B * L * 2 * (E / 8);
+  k_kv_store<<<(unsigned)((n_vec + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const bf16*>(qkv), reinterpret_cast<bf16*>(kcache), reinterpret_cast<bf16*>(vcache), n_vec, E / 8, L,
+      tok_stride, batch_stride, pos);
+  TNN_CHECK_LAUNCH();
+}
+
 // x[b, :] = wte[tok[b], :] + wpe[*pos, :]  (bf16 out), one CTA per sequence
 __global__ void __launch_bounds__(256)
     k_embed_decode(const int* __restrict__ tok, const float* __restrict__ wte, const float* __restrict__ wpe,

@@ -26,6 +26,10 @@ void attention_decode_bf16(const void* q, long long q_batch, const void* kcache,
                            long long tok_stride, long long batch_stride, void* out, int B, int H, int len,
                            cudaStream_t stream);
 
+// Prefill: K / V slots of the packed projection qkv [B, L, 3, E] -> caches [B, Lmax, E] at [pos, pos+L)
+void kv_cache_store_bf16(const void* qkv, void* kcache, void* vcache, long long tok_stride, long long batch_stride,
+                         int B, int L, int E, int pos, cudaStream_t stream);
+
 // Graph-replayable decode step pieces: the position lives in device memory.
 void attention_decode_append_bf16(const void* qkv, void* kcache, void* vcache, long long tok_stride,
                                   long long batch_stride, void* out, int B, int H, const int* pos_ptr,

@@ -47,19 +47,45 @@ void embedding_bwd(const int* ids, const void* dy, float* dtable, float* dpos, l
   TNN_CHECK_LAUNCH();
 }
 
+// Row arg-max (greedy decoding over [B, V] logits, V = 50257).  One CTA of 1024 threads per row;
+// bf16 rows whose stride allows it are read as 16-byte vectors (8 logits per load, ~6 loads per thread
+// at GPT-2's vocabulary instead of ~200 dependent 2-byte loads: 97 us -> a few us in the decode graph).
+// Ties resolve to the smallest index.
 template <typename T>
-__global__ void __launch_bounds__(256)
-    k_argmax_rows(const T* __restrict__ x, long long ld, long long rows, int V, int* __restrict__ out) {
+__global__ void __launch_bounds__(1024)
+    k_argmax_rows(const T* __restrict__ x, long long ld, long long rows, int V, int* __restrict__ out, int vec_ok) {
   __shared__ float rv[32];
   __shared__ int ri[32];
   for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
     float mx = -INFINITY;
-    int am = 0;
-    for (int c = threadIdx.x; c < V; c += blockDim.x) {
-      float v = (float)x[r * ld + c];
-      if (v > mx) {
-        mx = v;
-        am = c;
+    int am = 0x7fffffff;
+    const T* row = x + r * ld;
+    if (sizeof(T) == 2 && vec_ok) {
+      const int nv = V >> 3;
+      for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        float f[8];
+        bf8_unpack(__ldg(reinterpret_cast<const uint4*>(row) + i), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (f[j] > mx) {
+            mx = f[j];
+            am = i * 8 + j;
+          }
+      }
+      for (int c = (nv << 3) + threadIdx.x; c < V; c += blockDim.x) {
+        const float v = (float)row[c];
+        if (v > mx || (v == mx && c < am)) {
+          mx = v;
+          am = c;
+        }
+      }
+    } else {
+      for (int c = threadIdx.x; c < V; c += blockDim.x) {
+        const float v = (float)row[c];
+        if (v > mx) {
+          mx = v;
+          am = c;
+        }
       }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -88,16 +114,17 @@ __global__ void __launch_bounds__(256)
           am = oi;
         }
       }
-      if (lane == 0) out[r] = am;
+      if (lane == 0) out[r] = (am == 0x7fffffff) ? 0 : am;
     }
   }
 }
 void argmax_rows(const void* x, int is_f32, long long ld, long long rows, int V, int* out,
                  cudaStream_t s) {
   if (rows <= 0) return;
-  int blocks = (int)(rows < kSMs * 4 ? rows : kSMs * 4);
-  if (is_f32) k_argmax_rows<float><<<blocks, 256, 0, s>>>((const float*)x, ld, rows, V, out);
-  else k_argmax_rows<bf16><<<blocks, 256, 0, s>>>((const bf16*)x, ld, rows, V, out);
+  int blocks = (int)(rows < kSMs * 2 ? rows : kSMs * 2);
+  const int vec_ok = (!is_f32 && (ld % 8) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) ? 1 : 0;
+  if (is_f32) k_argmax_rows<float><<<blocks, 1024, 0, s>>>((const float*)x, ld, rows, V, out, 0);
+  else k_argmax_rows<bf16><<<blocks, 1024, 0, s>>>((const bf16*)x, ld, rows, V, out, vec_ok);
   TNN_CHECK_LAUNCH();
 }
 

@@ -330,28 +330,34 @@ struct BnMaskArgs {
   const uint64_t* seed_ptr;
 };
 
-__global__ void __launch_bounds__(256, 2)
+// MODE 0: dy is used as is (no mask, or dy is already the masked g of the fused dgrad epilogue)
+// MODE 1: mask = (y != 0), scaled by 1/(1-p)        MODE 2: mask rebuilt from x, statistics and RNG
+// The modes are separate instantiations so the common paths do not carry the recompute state in
+// registers: ncu showed the single do-everything kernel at 128 registers = 2 CTAs / SM and 16-22 % of
+// HBM bandwidth (latency bound); these run 3 CTAs / SM with the per-channel constants pre-combined.
+template <int MODE>
+__global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
     k_bn_bwd_reduce(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ y,
                     long long M, int C, const float* __restrict__ gamma,
-                    const float* __restrict__ mean, const float* __restrict__ invstd, int masked,
+                    const float* __restrict__ mean, const float* __restrict__ invstd,
                     float dscale, float* dgamma, float* dbeta, float* coef, float* ws, BnMaskArgs ma) {
   extern __shared__ float sm[];
   const BnMap m(C);
   const bool vec = (C & 7) == 0;
-  const bool recompute = masked && (y == nullptr);
   uint64_t seed = ma.seed;
-  if (recompute && ma.p > 0.f && ma.seed_ptr) seed ^= (*ma.seed_ptr) * 0x9E3779B97F4A7C15ull;
+  if (MODE == 2 && ma.p > 0.f && ma.seed_ptr) seed ^= (*ma.seed_ptr) * 0x9E3779B97F4A7C15ull;
+  constexpr int U = 2;
   for (int g0 = 0; g0 < m.groups; g0 += m.lpr) {
     const int g = g0 + m.cg;
-    float acc[2][8];
+    float acc[2][8];       // sum g, sum g * (x - mean); the invstd factor is applied once at the end
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
     if (g < m.groups && m.rl < m.rpb) {
-      float mu[8], is[8], sc[8], sh[8];
+      float mu[8], sc[8], sh[8];
       load_coef8(mean, C, g, mu);
-      load_coef8(invstd, C, g, is);
-      if (recompute) {
-        float gm[8], bt[8];
+      if (MODE == 2) {
+        float gm[8], bt[8], is[8];
+        load_coef8(invstd, C, g, is);
         load_coef8(gamma, C, g, gm);
         load_coef8(ma.beta, C, g, bt);
 #pragma unroll
@@ -365,36 +371,36 @@ __global__ void __launch_bounds__(256, 2)
       long long r = (long long)blockIdx.x * m.rpb + m.rl;
       auto one = [&](long long row, const float (&d)[8], const float (&xv)[8], const float (&yv)[8]) {
         bool keep[8];
-        if (recompute && ma.p > 0.f) dropout_keep8(seed, row * m.groups + g, ma.p, keep);
+        if (MODE == 2 && ma.p > 0.f) dropout_keep8(seed, row * m.groups + g, ma.p, keep);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float gg = d[j];
-          if (recompute) {
+          if (MODE == 2) {
             bool on = ma.relu ? (xv[j] * sc[j] + sh[j] > 0.f) : true;
             if (ma.p > 0.f) on = on && keep[j];
             gg = on ? gg * dscale : 0.f;
-          } else if (masked) {
+          } else if (MODE == 1) {
             gg = (yv[j] != 0.f) ? gg * dscale : 0.f;
           }
           acc[0][j] += gg;
-          acc[1][j] += gg * (xv[j] - mu[j]) * is[j];
+          acc[1][j] += gg * (xv[j] - mu[j]);
         }
       };
       if (vec) {
-        for (; r + (BN_UNROLL - 1) * stride < M; r += BN_UNROLL * stride) {
-          uint4 qd[BN_UNROLL], qx[BN_UNROLL], qy[BN_UNROLL];
+        for (; r + (U - 1) * stride < M; r += U * stride) {
+          uint4 qd[U], qx[U], qy[U];
 #pragma unroll
-          for (int u = 0; u < BN_UNROLL; ++u) {
+          for (int u = 0; u < U; ++u) {
             qd[u] = load8raw(dy, r + u * stride, C, g);
             qx[u] = load8raw(x, r + u * stride, C, g);
-            if (masked && !recompute) qy[u] = load8raw(y, r + u * stride, C, g);
+            if (MODE == 1) qy[u] = load8raw(y, r + u * stride, C, g);
           }
 #pragma unroll
-          for (int u = 0; u < BN_UNROLL; ++u) {
+          for (int u = 0; u < U; ++u) {
             float d[8], xv[8], yv[8];
             bf8_unpack(qd[u], d);
             bf8_unpack(qx[u], xv);
-            if (masked && !recompute) bf8_unpack(qy[u], yv);
+            if (MODE == 1) bf8_unpack(qy[u], yv);
             one(r + u * stride, d, xv, yv);
           }
         }
@@ -403,7 +409,7 @@ __global__ void __launch_bounds__(256, 2)
         float d[8], xv[8], yv[8];
         load8(dy, r, C, g, d);
         load8(x, r, C, g, xv);
-        if (masked && !recompute) load8(y, r, C, g, yv);
+        if (MODE == 1) load8(y, r, C, g, yv);
         one(r, d, xv, yv);
       }
     }
@@ -412,11 +418,12 @@ __global__ void __launch_bounds__(256, 2)
   if (last_block_done(reinterpret_cast<unsigned int*>(ws + (size_t)BN_REPL * 2 * C))) {
     const float inv_m = 1.f / (float)M;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float db = fold_replicas<2>(ws, 0, C, c), dg = fold_replicas<2>(ws, 1, C, c);
+      const float is = invstd[c];
+      float db = fold_replicas<2>(ws, 0, C, c), dg = fold_replicas<2>(ws, 1, C, c) * is;
       if (dbeta) dbeta[c] += db;
       if (dgamma) dgamma[c] += dg;
       float gm = gamma ? gamma[c] : 1.f;
-      coef[c] = gm * invstd[c];
+      coef[c] = gm * is;
       coef[C + c] = db * inv_m;
       coef[2 * C + c] = dg * inv_m;
     }
@@ -431,101 +438,121 @@ void bn_bwd_reduce(const void* dy, const void* x, const void* y, long long M, in
   BnMaskArgs ma{beta, relu, drop_p, seed, seed_ptr};
   static bool configured = false;
   if (!configured) {   // ncu: the default carveout admitted ONE 8 KB-smem CTA per SM (occupancy limit "shared memory")
-    cudaFuncSetAttribute(k_bn_bwd_reduce, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    cudaFuncSetAttribute(k_bn_bwd_reduce<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    cudaFuncSetAttribute(k_bn_bwd_reduce<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    cudaFuncSetAttribute(k_bn_bwd_reduce<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
     configured = true;
   }
-  k_bn_bwd_reduce<<<bn_blocks(M, C), 256, 256 * 8 * sizeof(float), s>>>(
-      (const bf16*)dy, (const bf16*)x, (const bf16*)y, M, C, gamma, save_mean, save_invstd, masked,
-      ds, dgamma, dbeta, coef, ws, ma);
+  const int mode = !masked ? 0 : (y != nullptr ? 1 : 2);
+  const int grid = bn_blocks(M, C);
+  const size_t smem = 256 * 8 * sizeof(float);
+#define TNN_BN_RED(MODE_)                                                                                         \
+  k_bn_bwd_reduce<MODE_><<<grid, 256, smem, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, M, C, gamma,    \
+                                                 save_mean, save_invstd, ds, dgamma, dbeta, coef, ws, ma)
+  if (mode == 0) TNN_BN_RED(0);
+  else if (mode == 1) TNN_BN_RED(1);
+  else TNN_BN_RED(2);
+#undef TNN_BN_RED
   TNN_CHECK_LAUNCH();
 }
 
-__global__ void __launch_bounds__(256, 2)
+// dx = c0*(g - c1 - xhat*c2) (+ extra) with xhat = (x - mean)*invstd, evaluated as A*g + B*x + D with
+// A = c0, B = -c0*c2*invstd, D = c0*(c2*invstd*mean - c1): three constants per channel instead of five.
+template <int MODE, bool EXTRA>
+__global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
     k_bn_bwd_apply(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ y,
                    const bf16* __restrict__ extra, bf16* __restrict__ dx, long long M, int C,
                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                   const float* __restrict__ coef, int masked, float dscale, float* colsum_out,
+                   const float* __restrict__ coef, float dscale, float* colsum_out,
                    float* colsum_ws, const float* __restrict__ gamma, BnMaskArgs ma) {
   extern __shared__ float sm[];
   const BnMap m(C);
   const bool vec = (C & 7) == 0;
-  const bool recompute = masked && (y == nullptr);
   uint64_t seed = ma.seed;
-  if (recompute && ma.p > 0.f && ma.seed_ptr) seed ^= (*ma.seed_ptr) * 0x9E3779B97F4A7C15ull;
+  if (MODE == 2 && ma.p > 0.f && ma.seed_ptr) seed ^= (*ma.seed_ptr) * 0x9E3779B97F4A7C15ull;
   for (int g0 = 0; g0 < m.groups; g0 += m.lpr) {
     const int g = g0 + m.cg;
     float csum[1][8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) csum[0][j] = 0.f;
     if (g < m.groups && m.rl < m.rpb) {
-    float mu[8], is[8], c0[8], c1[8], c2[8], sc[8], sh[8];
-    load_coef8(mean, C, g, mu);
-    load_coef8(invstd, C, g, is);
-    load_coef8(coef, C, g, c0);
-    load_coef8(coef + C, C, g, c1);
-    load_coef8(coef + 2 * C, C, g, c2);
-    if (recompute) {
-      float gm[8], bt[8];
-      load_coef8(gamma, C, g, gm);
-      load_coef8(ma.beta, C, g, bt);
+      float ca[8], cb[8], cd[8], sc[8], sh[8];
+      {
+        float mu[8], is[8], c1[8], c2[8];
+        load_coef8(mean, C, g, mu);
+        load_coef8(invstd, C, g, is);
+        load_coef8(coef, C, g, ca);
+        load_coef8(coef + C, C, g, c1);
+        load_coef8(coef + 2 * C, C, g, c2);
+        if (MODE == 2) {
+          float gm[8], bt[8];
+          load_coef8(gamma, C, g, gm);
+          load_coef8(ma.beta, C, g, bt);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (gamma == nullptr) gm[j] = 1.f;
-        sc[j] = gm[j] * is[j];
-        sh[j] = bt[j] - mu[j] * gm[j] * is[j];
-      }
-    }
-    const long long stride = (long long)gridDim.x * m.rpb;
-    long long r = (long long)blockIdx.x * m.rpb + m.rl;
-    auto one = [&](long long row, float (&d)[8], const float (&xv)[8], const float (&yv)[8], const float (&ev)[8]) {
-      bool keep[8];
-      if (recompute && ma.p > 0.f) dropout_keep8(seed, row * m.groups + g, ma.p, keep);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float gg = d[j];
-        if (recompute) {
-          bool on = ma.relu ? (xv[j] * sc[j] + sh[j] > 0.f) : true;
-          if (ma.p > 0.f) on = on && keep[j];
-          gg = on ? gg * dscale : 0.f;
-        } else if (masked) gg = (yv[j] != 0.f) ? gg * dscale : 0.f;
-        float xh = (xv[j] - mu[j]) * is[j];
-        float v = c0[j] * (gg - c1[j] - xh * c2[j]);
-        if (extra) v += ev[j];
-        d[j] = v;
-        csum[0][j] += v;
-      }
-      store8(dx, row, C, g, d);
-    };
-    if (vec) {
-      constexpr int U = 2;
-      for (; r + (U - 1) * stride < M; r += U * stride) {
-        uint4 qd[U], qx[U], qy[U], qe[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          qd[u] = load8raw(dy, r + u * stride, C, g);
-          qx[u] = load8raw(x, r + u * stride, C, g);
-          if (masked && !recompute) qy[u] = load8raw(y, r + u * stride, C, g);
-          if (extra) qe[u] = load8raw(extra, r + u * stride, C, g);
+          for (int j = 0; j < 8; ++j) {
+            if (gamma == nullptr) gm[j] = 1.f;
+            sc[j] = gm[j] * is[j];
+            sh[j] = bt[j] - mu[j] * gm[j] * is[j];
+          }
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          float d[8], xv[8], yv[8], ev[8];
-          bf8_unpack(qd[u], d);
-          bf8_unpack(qx[u], xv);
-          if (masked && !recompute) bf8_unpack(qy[u], yv);
-          if (extra) bf8_unpack(qe[u], ev);
-          one(r + u * stride, d, xv, yv, ev);
+        for (int j = 0; j < 8; ++j) {
+          cb[j] = -ca[j] * c2[j] * is[j];
+          cd[j] = ca[j] * (c2[j] * is[j] * mu[j] - c1[j]);
         }
       }
-    }
-    for (; r < M; r += stride) {
-      float d[8], xv[8], yv[8], ev[8];
-      load8(dy, r, C, g, d);
-      load8(x, r, C, g, xv);
-      if (masked && !recompute) load8(y, r, C, g, yv);
-      if (extra) load8(extra, r, C, g, ev);
-      one(r, d, xv, yv, ev);
-    }
+      const long long stride = (long long)gridDim.x * m.rpb;
+      long long r = (long long)blockIdx.x * m.rpb + m.rl;
+      auto one = [&](long long row, float (&d)[8], const float (&xv)[8], const float (&yv)[8], const float (&ev)[8]) {
+        bool keep[8];
+        if (MODE == 2 && ma.p > 0.f) dropout_keep8(seed, row * m.groups + g, ma.p, keep);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float gg = d[j];
+          if (MODE == 2) {
+            bool on = ma.relu ? (xv[j] * sc[j] + sh[j] > 0.f) : true;
+            if (ma.p > 0.f) on = on && keep[j];
+            gg = on ? gg * dscale : 0.f;
+          } else if (MODE == 1) {
+            gg = (yv[j] != 0.f) ? gg * dscale : 0.f;
+          }
+          float v = ca[j] * gg + cb[j] * xv[j] + cd[j];
+          if (EXTRA) v += ev[j];
+          d[j] = v;
+          csum[0][j] += v;
+        }
+        store8(dx, row, C, g, d);
+      };
+      if (vec) {
+        constexpr int U = 2;
+        for (; r + (U - 1) * stride < M; r += U * stride) {
+          uint4 qd[U], qx[U], qy[U], qe[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            qd[u] = load8raw(dy, r + u * stride, C, g);
+            qx[u] = load8raw(x, r + u * stride, C, g);
+            if (MODE == 1) qy[u] = load8raw(y, r + u * stride, C, g);
+            if (EXTRA) qe[u] = load8raw(extra, r + u * stride, C, g);
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            float d[8], xv[8], yv[8], ev[8];
+            bf8_unpack(qd[u], d);
+            bf8_unpack(qx[u], xv);
+            if (MODE == 1) bf8_unpack(qy[u], yv);
+            if (EXTRA) bf8_unpack(qe[u], ev);
+            one(r + u * stride, d, xv, yv, ev);
+          }
+        }
+      }
+      for (; r < M; r += stride) {
+        float d[8], xv[8], yv[8], ev[8];
+        load8(dy, r, C, g, d);
+        load8(x, r, C, g, xv);
+        if (MODE == 1) load8(y, r, C, g, yv);
+        if (EXTRA) load8(extra, r, C, g, ev);
+        one(r, d, xv, yv, ev);
+      }
     }
     if (colsum_out) block_channel_reduce<1>(m, g, C, csum, colsum_ws, sm);
   }
@@ -563,14 +590,30 @@ void bn_bwd_apply(const void* dy, const void* x, const void* y, const void* extr
                   cudaStream_t s) {
   float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   BnMaskArgs ma{beta, relu, drop_p, seed, seed_ptr};
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(k_bn_bwd_apply, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
-    configured = true;
+  const int mode = !masked ? 0 : (y != nullptr ? 1 : 2);
+  const int grid = bn_blocks(M, C);
+  const size_t smem = 256 * 8 * sizeof(float);
+#define TNN_BN_APPLY(MODE_, EXTRA_)                                                                              \
+  do {                                                                                                           \
+    static bool configured = false;                                                                              \
+    if (!configured) {                                                                                           \
+      cudaFuncSetAttribute(k_bn_bwd_apply<MODE_, EXTRA_>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);   \
+      configured = true;                                                                                         \
+    }                                                                                                            \
+    k_bn_bwd_apply<MODE_, EXTRA_><<<grid, 256, smem, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y,       \
+                                                          (const bf16*)extra, (bf16*)dx, M, C, save_mean,        \
+                                                          save_invstd, coef, ds, colsum_out, colsum_ws, gamma, ma); \
+  } while (0)
+  if (extra != nullptr) {
+    if (mode == 0) TNN_BN_APPLY(0, true);
+    else if (mode == 1) TNN_BN_APPLY(1, true);
+    else TNN_BN_APPLY(2, true);
+  } else {
+    if (mode == 0) TNN_BN_APPLY(0, false);
+    else if (mode == 1) TNN_BN_APPLY(1, false);
+    else TNN_BN_APPLY(2, false);
   }
-  k_bn_bwd_apply<<<bn_blocks(M, C), 256, 256 * 8 * sizeof(float), s>>>(
-      (const bf16*)dy, (const bf16*)x, (const bf16*)y, (const bf16*)extra, (bf16*)dx, M, C, save_mean,
-      save_invstd, coef, masked, ds, colsum_out, colsum_ws, gamma, ma);
+#undef TNN_BN_APPLY
   TNN_CHECK_LAUNCH();
 }
 

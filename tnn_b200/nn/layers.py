@@ -256,11 +256,14 @@ class Conv2DLayer(Layer):
         bn = self._bn_prev
         if bn is not None and dy.is_cuda and residual is None and plan.path == "tma" and plan.stride == 1 and \
                 not plan.d_needs_zero and len(plan.d_launches) == 1 and bn.training and \
-                os.environ.get("TNN_BN_FUSE_BWD", "1") == "1":
+                os.environ.get("TNN_BN_FUSE_BWD", "0") == "1":
             bc = bn._cache.get(mb_id)
             if bc is not None and bc.get("pack") is not None and bc["x"].shape == x.shape and self.in_channels % 32 == 0:
                 # dgrad + BatchNorm-backward reduction in one kernel: the epilogue masks / scales the
-                # gradient, stores g and accumulates (sum g, sum g*xhat) into the BatchNorm's workspace
+                # gradient, stores g and accumulates (sum g, sum g*xhat) into the BatchNorm's workspace.
+                # OFF by default (TNN_BN_FUSE_BWD=1 enables): measured in the same run on WRN-16-8 it is
+                # 4.5 % SLOWER per step (5.63 vs 5.38 ms) -- the 4 epilogue warps become the GEMM's
+                # bottleneck (dgrad 107 -> 165 us) and that costs more than the reduction kernel it removes
                 bnb = dict(x=bc["x"], pack=bc["pack"], relu=bn.use_relu, p=bc["p"], seed=bc.get("seed", 0),
                            state=stepstate.get(dy.device).dev if bc["p"] > 0 else None, ws=bn._bufs(dy.device)["ws"])
                 g = conv_ops.conv2d_dgrad(plan, dy, w, self._state, self.param_version, bn_bwd=bnb)
@@ -365,7 +368,7 @@ class BatchNormLayer(Layer):
                 keep_y = os.environ.get("TNN_BN_RECOMPUTE_MASK", "0") != "1"
                 # BN-backward fusion (the consumer conv's dgrad epilogue rebuilds the mask from x): y is not
                 # needed by backward at all then -- but keep it unless the consumer is known to fuse
-                fuse_bwd = self._bwd_consumer is not None and os.environ.get("TNN_BN_FUSE_BWD", "1") == "1"
+                fuse_bwd = self._bwd_consumer is not None and os.environ.get("TNN_BN_FUSE_BWD", "0") == "1"
                 c["y"] = y if ((self.use_relu or p_drop > 0) and keep_y and not fuse_bwd) else None
                 c["mean"], c["invstd"], c["pack"] = rec[4 * C:5 * C], rec[5 * C:], rec[:4 * C]
                 c["p"] = p_drop

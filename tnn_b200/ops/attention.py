@@ -52,8 +52,13 @@ def attention_fwd(qkv: torch.Tensor, causal: bool, kv_cache: KVCache | None = No
     B, L, _, H, D = qkv.shape
     q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
     if kv_cache is not None:
-        kv_cache.k[:, pos:pos + L] = k
-        kv_cache.v[:, pos:pos + L] = v
+        Cx = native.require() if qkv.is_cuda else None
+        if Cx is not None and hasattr(Cx, "kv_cache_store") and D == 64 and qkv.dtype == torch.bfloat16 and \
+                qkv.is_contiguous() and kv_cache.k.dtype == torch.bfloat16:
+            Cx.kv_cache_store(qkv, kv_cache.k, kv_cache.v, int(pos))      # one vectorised kernel for K and V
+        else:
+            kv_cache.k[:, pos:pos + L] = k
+            kv_cache.v[:, pos:pos + L] = v
         kv_cache.len = pos + L
         k, v = kv_cache.k[:, :pos + L], kv_cache.v[:, :pos + L]
     if qkv.is_cuda:
