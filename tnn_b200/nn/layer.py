@@ -14,6 +14,7 @@ from typing import Callable
 
 import torch
 
+from ..core import side_stream
 from ..core.config import TConfig
 from ..core.dtype import DType, dtype_to_string, string_to_dtype, to_torch
 
@@ -180,7 +181,11 @@ class Layer:
             grads = [self._migrate(g) for g in grads]
         else:
             grads = self._migrate(grads)
-        out = self.backward_impl(grads, mb_id)
+        side_stream.enter()
+        try:
+            out = self.backward_impl(grads, mb_id)
+        finally:
+            side_stream.exit_()          # outermost backward: join the side-stream weight gradients
         self._cache.pop(mb_id, None)
         return out
 

@@ -15,7 +15,7 @@ import zlib
 import torch
 import torch.nn.functional as F
 
-from ..core import stepstate
+from ..core import side_stream, stepstate
 from ..core.config import TConfig
 from ..ops import conv as conv_ops
 from ..ops import gemm as gemm_ops
@@ -250,7 +250,12 @@ class Conv2DLayer(Layer):
         if db is not None and colsum is not None and dy.is_cuda and plan.path != "direct":
             native.require().axpy_f32(db, colsum, 1.0)       # bias grad came fused out of the BN backward
             db = None
-        conv_ops.conv2d_wgrad(plan, dy, x, self.grads["weight"], db, cache=c)
+        if dy.is_cuda and plan.path == "tma" and side_stream.enabled():
+            # weight gradient on the side stream: overlaps the dgrad / BatchNorm backward that follow
+            gw = self.grads["weight"]
+            side_stream.run(dy.device, lambda: conv_ops.conv2d_wgrad(plan, dy, x, gw, db, cache=c), keep=(dy, x, c, gw, db))
+        else:
+            conv_ops.conv2d_wgrad(plan, dy, x, self.grads["weight"], db, cache=c)
         if not need_dx or plan.path == "direct":
             return None
         bn = self._bn_prev

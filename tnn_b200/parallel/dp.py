@@ -25,7 +25,7 @@ import os
 import torch
 import torch.distributed as dist
 
-from ..core import stepstate
+from ..core import side_stream, stepstate
 from ..nn.graph import ALIGN_ELEMS, Graph, graph_from_sequential
 from ..nn.optimizers import SGD, Adam, Optimizer
 from ..ops import native
@@ -209,6 +209,8 @@ class FusedDataParallel:
             if b["first_layer"] == layer_index:
                 main = torch.cuda.current_stream(self.graph.device())
                 self.side.wait_stream(main)
+                if side_stream.has_pending(self.graph.device()):
+                    self.side.wait_stream(side_stream.stream(self.graph.device()))   # the bucket's weight gradients
                 with torch.cuda.stream(self.side):
                     self._launch(b["lo"], b["hi"], b["chunk"], b["st_off"])
                 self._pending = True
