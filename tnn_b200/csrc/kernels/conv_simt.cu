@@ -137,10 +137,175 @@ __global__ void __launch_bounds__(256)
   }
   if (dbias && threadIdx.x < p.K) atomicAdd(dbias + threadIdx.x, bacc);
 }
+// Tensor-core variant for the first layer (R*S*C + 1 <= 32, K <= 64): dW^T[j][k] = sum_pix P[pix][j] * dy[pix][k]
+// with P the im2col patch matrix (27 columns for 3x3x3) plus a column of ones whose product is the
+// bias gradient.  A CTA stages 1024 pixels of P and dy TRANSPOSED in shared memory (bf16, the
+// reduction dimension contiguous, rows padded by 16 bytes so fragment loads are conflict free); each of
+// the 8 warps reduces its 128 pixels with mma.sync m16n8k16 (M = 32 patch columns, N = K output
+// channels), warps combine through shared memory and the CTA adds its [K][rsc] block to dW with one
+// atomic per element.  (The scalar kernel above spent ~110 us on the 3->16 WRN stem: two shared-memory
+// loads per FMA and a divide per staged element.)
+static constexpr int DT_PIX = 1024;
+static constexpr int DT_LD = DT_PIX + 8;
+__device__ __forceinline__ void dt_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                       uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+template <int NT>   // NT = K / 8 output-channel tiles
+__global__ void __launch_bounds__(256)
+    k_conv_stem_wgrad(const bf16* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw,
+                      float* __restrict__ dbias, DConvP p) {
+  extern __shared__ __align__(16) uint8_t dt_smem[];
+  bf16* sP = reinterpret_cast<bf16*>(dt_smem);                 // [32][DT_LD]   patch^T (row 31.. rsc = ones / zero)
+  bf16* sD = sP + 32 * DT_LD;                                  // [K][DT_LD]    dy^T
+  float* sAcc = reinterpret_cast<float*>(sD + p.K * DT_LD);    // [32][K]
+  const int rsc = p.R * p.S * p.C;
+  const int K = p.K;
+  const long long npix = (long long)p.N * p.OH * p.OW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 32 * K; i += blockDim.x) sAcc[i] = 0.f;
+  float acc[2][NT][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < NT; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+
+  for (long long p0 = (long long)blockIdx.x * DT_PIX; p0 < npix; p0 += (long long)gridDim.x * DT_PIX) {
+    __syncthreads();
+    // ---- stage patch^T: lanes walk pixels (conflict-free 2-byte stores), each warp owns patch columns
+    //      j = warp, warp + 8, ...; the pixel is decoded once and reused for the warp's 4 columns
+    {
+      int jr[4], js[4], jc[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int j = warp + 8 * q;
+        jc[q] = j % p.C;
+        const int rs = j / p.C;
+        js[q] = rs % p.S;
+        jr[q] = rs / p.S;
+      }
+      for (int pp = lane; pp < DT_PIX; pp += 32) {
+        const long long pix = p0 + pp;
+        const bool ok = pix < npix;
+        int n = 0, oh = 0, ow = 0;
+        if (ok) {
+          ow = (int)(pix % p.OW);
+          const long long t = pix / p.OW;
+          oh = (int)(t % p.OH);
+          n = (int)(t / p.OH);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = warp + 8 * q;
+          float v = 0.f;
+          if (ok) {
+            if (j < rsc) {
+              const int h = oh * p.stride - p.pad + jr[q], ww = ow * p.stride - p.pad + js[q];
+              if (h >= 0 && h < p.H && ww >= 0 && ww < p.W)
+                v = __bfloat162float(x[(((long long)n * p.H + h) * p.W + ww) * p.C + jc[q]]);
+            } else if (j == rsc) {
+              v = 1.f;                                // ones column: its product is the bias gradient
+            }
+          }
+          sP[j * DT_LD + pp] = __float2bfloat16(v);
+        }
+      }
+    }
+    // ---- stage dy^T: one pixel per thread per pass, 16 bytes (8 channels) at a time
+    for (int pp = threadIdx.x; pp < DT_PIX; pp += blockDim.x) {
+      const long long pix = p0 + pp;
+      for (int k8 = 0; k8 < K; k8 += 8) {
+        uint4 q = make_uint4(0, 0, 0, 0);
+        if (pix < npix) q = __ldg(reinterpret_cast<const uint4*>(dy + pix * K + k8));
+        const bf16* h = reinterpret_cast<const bf16*>(&q);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) sD[(k8 + t) * DT_LD + pp] = h[t];
+      }
+    }
+    __syncthreads();
+    // ---- this warp's 128 pixels: 8 k-steps of 16
+    const int pw = warp * 128;
+#pragma unroll 2
+    for (int ks = 0; ks < 8; ++ks) {
+      const int k0 = pw + ks * 16 + (lane & 3) * 2;
+      uint32_t a[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const bf16* base = sP + (mt * 16 + (lane >> 2)) * DT_LD + k0;
+        a[mt][0] = *reinterpret_cast<const uint32_t*>(base);
+        a[mt][1] = *reinterpret_cast<const uint32_t*>(base + 8 * DT_LD);
+        a[mt][2] = *reinterpret_cast<const uint32_t*>(base + 8);
+        a[mt][3] = *reinterpret_cast<const uint32_t*>(base + 8 * DT_LD + 8);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const bf16* bb = sD + (nt * 8 + (lane >> 2)) * DT_LD + k0;
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(bb);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(bb + 8);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) dt_mma(acc[mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
+      }
+    }
+  }
+  // ---- combine the warps, then one atomic per dW element
+  __syncthreads();
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      const int row = mt * 16 + (lane >> 2), col = nt * 8 + (lane & 3) * 2;
+      atomicAdd(&sAcc[row * K + col], acc[mt][nt][0]);
+      atomicAdd(&sAcc[row * K + col + 1], acc[mt][nt][1]);
+      atomicAdd(&sAcc[(row + 8) * K + col], acc[mt][nt][2]);
+      atomicAdd(&sAcc[(row + 8) * K + col + 1], acc[mt][nt][3]);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * K; i += blockDim.x) {
+    const int j = i / K, k = i - j * K;
+    if (j < rsc) atomicAdd(dw + k * rsc + j, sAcc[i]);
+    else if (j == rsc && dbias) atomicAdd(dbias + k, sAcc[i]);
+  }
+}
+
 void conv_direct_wgrad(const void* x, const void* dy, float* dw, float* dbias, int N, int H, int W,
                        int C, int K, int R, int S, int stride, int pad, int OH, int OW,
                        cudaStream_t s) {
   const int rsc = R * S * C;
+  {
+    static int use_tc = -1;
+    if (use_tc < 0) {
+      const char* e = getenv("TNN_STEM_WGRAD_TC");
+      use_tc = (e != nullptr) ? atoi(e) : 1;
+    }
+    const int NT = K / 8;
+    if (use_tc && rsc + 1 <= 32 && K % 8 == 0 && (NT == 1 || NT == 2 || NT == 4 || NT == 8)) {
+      DConvP p{N, H, W, C, K, R, S, stride, pad, OH, OW};
+      const long long npix = (long long)N * OH * OW;
+      const int blocks = (int)min((long long)kSMs * 2, (npix + DT_PIX - 1) / DT_PIX);
+      const int smem = (32 + K) * DT_LD * 2 + 32 * K * 4;
+#define TNN_STEM(NT_)                                                                                          \
+  do {                                                                                                         \
+    static bool configured = false;                                                                            \
+    if (!configured) {                                                                                         \
+      cudaFuncSetAttribute(k_conv_stem_wgrad<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   \
+      configured = true;                                                                                       \
+    }                                                                                                          \
+    k_conv_stem_wgrad<NT_><<<blocks, 256, smem, s>>>((const bf16*)x, (const bf16*)dy, dw, dbias, p);           \
+  } while (0)
+      if (NT == 1) TNN_STEM(1);
+      else if (NT == 2) TNN_STEM(2);
+      else if (NT == 4) TNN_STEM(4);
+      else TNN_STEM(8);
+#undef TNN_STEM
+      TNN_CHECK_LAUNCH();
+      return;
+    }
+  }
   if (K * rsc > 2048 || K > 256) {
     fprintf(stderr, "[tnn_b200] conv_direct_wgrad: K*R*S*C too large (%d)\n", K * rsc);
     abort();
