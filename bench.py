@@ -25,8 +25,12 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly ONE JSON line: NCCL's own banner / debug lines ("NCCL version ...") go to stderr
+# stdout carries exactly ONE JSON line.  NCCL's banner ("NCCL version ...", a bare printf when the box
+# exports NCCL_DEBUG=VERSION) and any other library chatter on fd 1 are sent to stderr: the process keeps
+# a private duplicate of the real stdout for the result line and points fd 1 at fd 2.
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 BASELINE_IMG_S = 2480.0      # 256 / 0.103 s (TNN C++ pipeline, WRN-16-8 / CIFAR-100)
 PER_GPU_BATCH = 256
@@ -137,7 +141,8 @@ class ClockSampler:
 
 
 def emit(d):
-    print(json.dumps(d), flush=True)
+    _RESULT_OUT.write(json.dumps(d) + "\n")
+    _RESULT_OUT.flush()
 
 
 def run_reference(args):
