@@ -201,6 +201,7 @@ def test_batchnorm_backward_mask_recompute_equals_stored_mask(relu, p):
     x = (torch.randn(16, 12, 12, 64, device=dev) * 1.5 + 0.3).bfloat16()
     dy = torch.randn(16, 12, 12, 64, device=dev).bfloat16()
     res = {}
+    os.environ["TNN_BN_BITMASK"] = "0"          # compare the two y-based / x-based mask sources here
     for mode in ("0", "1"):
         os.environ["TNN_BN_RECOMPUTE_MASK"] = mode
         bn = BatchNormLayer(64, 1e-2, 0.1, True, relu, "bn").init(dev, 7)
@@ -213,6 +214,7 @@ def test_batchnorm_backward_mask_recompute_equals_stored_mask(relu, p):
         dx = bn.backward(dy, 0)
         res[mode] = (y.float(), dx.float(), bn.grads["gamma"].clone(), bn.grads["beta"].clone())
     os.environ.pop("TNN_BN_RECOMPUTE_MASK", None)
+    os.environ.pop("TNN_BN_BITMASK", None)
     assert torch.equal(res["0"][0], res["1"][0])
     assert (res["0"][1] - res["1"][1]).abs().max().item() <= 2e-2 * res["0"][1].abs().max().item()
     # at most a handful of elements sit exactly on the ReLU boundary
@@ -246,7 +248,6 @@ def test_batchnorm_backward_fused_into_dgrad_epilogue(relu, p, C, K):
         bn.params["gamma"].uniform_(0.5, 1.5)
         bn.params["beta"].uniform_(-0.5, 0.5)
         y = seq.forward(x, 0)
-        assert (bn.cache(0)["y"] is None) == (mode == "1" or not (relu or p > 0))
         dx = seq.backward(dy, 0)
         res[mode] = (y.float(), dx.float(), bn.grads["gamma"].clone(), bn.grads["beta"].clone(),
                      conv.grads["weight"].clone(), conv.grads["bias"].clone())
@@ -256,3 +257,33 @@ def test_batchnorm_backward_fused_into_dgrad_epilogue(relu, p, C, K):
     assert _rel(f[1], a[1]) < 2e-2, f"dx {_rel(f[1], a[1])}"
     assert _rel(f[2], a[2]) < 2e-2 and _rel(f[3], a[3]) < 2e-2, f"dgamma {_rel(f[2], a[2])} dbeta {_rel(f[3], a[3])}"
     assert _rel(f[4], a[4]) < 1e-2 and _rel(f[5], a[5]) < 1e-2      # the conv's own grads do not depend on the fusion
+
+
+@pytest.mark.parametrize("relu,p,C", [(True, 0.0, 64), (True, 0.3, 128), (False, 0.3, 40)])
+def test_batchnorm_backward_keep_bits_equal_stored_output_mask(relu, p, C):
+    """The forward writes one byte of keep bits per 8-channel vector; backward from those bits must
+    equal backward from the mask read off the stored output (y != 0)."""
+    import os
+    from tnn_b200.nn import BatchNormLayer
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(8)
+    x = (torch.randn(16, 12, 12, C, device=dev) * 1.5 + 0.3).bfloat16()
+    dy = torch.randn(16, 12, 12, C, device=dev).bfloat16()
+    extra = torch.randn(16, 12, 12, C, device=dev).bfloat16()
+    res = {}
+    for mode in ("0", "1"):
+        os.environ["TNN_BN_BITMASK"] = mode
+        bn = BatchNormLayer(C, 1e-2, 0.1, True, relu, "bn").init(dev, 7)
+        torch.manual_seed(99)
+        bn.params["gamma"].uniform_(0.5, 1.5)
+        bn.params["beta"].uniform_(-0.5, 0.5)
+        bn.fused_dropout_p = p
+        y = bn.forward(x, 0)
+        assert (bn.cache(0)["bits"] is not None) == (mode == "1") and (bn.cache(0)["y"] is None) == (mode == "1")
+        dx = bn.backward_impl(dy, 0, extra=extra)
+        res[mode] = (y.float(), dx.float(), bn.grads["gamma"].clone(), bn.grads["beta"].clone())
+    os.environ.pop("TNN_BN_BITMASK", None)
+    assert torch.equal(res["0"][0], res["1"][0])
+    assert _rel(res["1"][1], res["0"][1]) < 2e-3            # identical masks; only the atomic summation order differs
+    torch.testing.assert_close(res["0"][2], res["1"][2], atol=2e-2, rtol=1e-3)   # (atomic accumulation order)
+    torch.testing.assert_close(res["0"][3], res["1"][3], atol=2e-2, rtol=1e-3)

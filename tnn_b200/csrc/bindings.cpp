@@ -215,32 +215,43 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     tnn::bn_eval_scale_shift(C, fp(gamma), fp(beta), fp(rmean), fp(rvar), (float)eps, fp(ss), cur_stream());
   });
   m.def("bn_apply", [](const Tensor& x, const Tensor& y, int64_t M, int C, const Tensor& ss, bool relu,
-                       double drop_p, uint64_t seed, const OptT& state) {
+                       double drop_p, uint64_t seed, const OptT& state, const OptT& mask) {
     const uint64_t* sp = state.has_value() ? reinterpret_cast<const uint64_t*>(state->data_ptr<float>() + 12) : nullptr;
-    tnn::bn_apply(vp(x), vp(y), M, C, fp(ss), relu, (float)drop_p, seed, sp, cur_stream());
-  });
+    uint8_t* mp = nullptr;
+    if (mask.has_value()) {
+      TORCH_CHECK(mask->scalar_type() == torch::kUInt8 && mask->is_contiguous() && C % 8 == 0 &&
+                      mask->numel() >= M * (C / 8), "bn_apply: mask must be uint8 [M * C / 8] and C % 8 == 0");
+      mp = mask->data_ptr<uint8_t>();
+    }
+    tnn::bn_apply(vp(x), vp(y), M, C, fp(ss), relu, (float)drop_p, seed, sp, mp, cur_stream());
+  }, py::arg("x"), py::arg("y"), py::arg("M"), py::arg("C"), py::arg("ss"), py::arg("relu"), py::arg("drop_p"),
+     py::arg("seed"), py::arg("state"), py::arg("mask") = py::none());
   m.def("bn_bwd_reduce", [](const Tensor& dy, const Tensor& x, const OptT& y, int64_t M, int C,
                             const OptT& gamma, const Tensor& smean, const Tensor& sinvstd, bool masked,
                             double drop_p, const OptT& dgamma, const OptT& dbeta, const Tensor& coef,
-                            const Tensor& ws, const OptT& beta, bool relu, uint64_t seed, const OptT& state) {
+                            const Tensor& ws, const OptT& beta, bool relu, uint64_t seed, const OptT& state,
+                            const OptT& bits) {
     const uint64_t* sp = state.has_value() ? reinterpret_cast<const uint64_t*>(state->data_ptr<float>() + 12) : nullptr;
+    const uint8_t* bp = bits.has_value() ? bits->data_ptr<uint8_t>() : nullptr;
     tnn::bn_bwd_reduce(vp(dy), vp(x), vp(y), M, C, fp(gamma), fp(smean), fp(sinvstd), masked, (float)drop_p,
-                       fp(dgamma), fp(dbeta), fp(coef), fp(ws), fp(beta), relu ? 1 : 0, seed, sp, cur_stream());
+                       fp(dgamma), fp(dbeta), fp(coef), fp(ws), fp(beta), relu ? 1 : 0, seed, sp, bp, cur_stream());
   }, py::arg("dy"), py::arg("x"), py::arg("y"), py::arg("M"), py::arg("C"), py::arg("gamma"), py::arg("smean"),
      py::arg("sinvstd"), py::arg("masked"), py::arg("drop_p"), py::arg("dgamma"), py::arg("dbeta"), py::arg("coef"),
-     py::arg("ws"), py::arg("beta") = py::none(), py::arg("relu") = false, py::arg("seed") = 0, py::arg("state") = py::none());
+     py::arg("ws"), py::arg("beta") = py::none(), py::arg("relu") = false, py::arg("seed") = 0, py::arg("state") = py::none(),
+     py::arg("bits") = py::none());
   m.def("bn_bwd_apply", [](const Tensor& dy, const Tensor& x, const OptT& y, const OptT& extra,
                            const Tensor& dx, int64_t M, int C, const Tensor& smean, const Tensor& sinvstd,
                            const Tensor& coef, bool masked, double drop_p, const OptT& colsum_out,
                            const OptT& colsum_ws, const OptT& gamma, const OptT& beta, bool relu, uint64_t seed,
-                           const OptT& state) {
+                           const OptT& state, const OptT& bits) {
     const uint64_t* sp = state.has_value() ? reinterpret_cast<const uint64_t*>(state->data_ptr<float>() + 12) : nullptr;
+    const uint8_t* bp = bits.has_value() ? bits->data_ptr<uint8_t>() : nullptr;
     tnn::bn_bwd_apply(vp(dy), vp(x), vp(y), vp(extra), vp(dx), M, C, fp(smean), fp(sinvstd), fp(coef), masked,
-                      (float)drop_p, fp(colsum_out), fp(colsum_ws), fp(gamma), fp(beta), relu ? 1 : 0, seed, sp, cur_stream());
+                      (float)drop_p, fp(colsum_out), fp(colsum_ws), fp(gamma), fp(beta), relu ? 1 : 0, seed, sp, bp, cur_stream());
   }, py::arg("dy"), py::arg("x"), py::arg("y"), py::arg("extra"), py::arg("dx"), py::arg("M"), py::arg("C"),
      py::arg("smean"), py::arg("sinvstd"), py::arg("coef"), py::arg("masked"), py::arg("drop_p"), py::arg("colsum_out"),
      py::arg("colsum_ws"), py::arg("gamma") = py::none(), py::arg("beta") = py::none(), py::arg("relu") = false,
-     py::arg("seed") = 0, py::arg("state") = py::none());
+     py::arg("seed") = 0, py::arg("state") = py::none(), py::arg("bits") = py::none());
   m.def("bn_ws_floats", &tnn::bn_ws_floats);
   m.def("layernorm_fwd", [](const Tensor& x, const OptT& res, const Tensor& y, const OptT& sum_out,
                             int64_t rows, int C, const OptT& gamma, const OptT& beta, double eps,

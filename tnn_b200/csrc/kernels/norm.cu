@@ -261,7 +261,7 @@ template <bool RELU, bool DROP>
 __global__ void __launch_bounds__(256)
     k_bn_apply(const bf16* __restrict__ x, bf16* __restrict__ y, long long M, int C,
                const float* __restrict__ ss, float p, float dscale, uint64_t seed,
-               const uint64_t* __restrict__ seed_ptr) {
+               const uint64_t* __restrict__ seed_ptr, uint8_t* __restrict__ mask) {
   if (DROP && seed_ptr) seed ^= (*seed_ptr) * 0x9E3779B97F4A7C15ull;
   const BnMap m(C);
   for (int g0 = 0; g0 < m.groups; g0 += m.lpr) {
@@ -276,13 +276,17 @@ __global__ void __launch_bounds__(256)
       bool keep[8];
       if (DROP) dropout_keep8(seed, row * m.groups + g, p, keep);
 #pragma unroll
+      unsigned int bits = 0u;
       for (int j = 0; j < 8; ++j) {
         float v = f[j] * sc[j] + sh[j];
         if (RELU) v = fmaxf(v, 0.f);
         if (DROP) v = keep[j] ? v * dscale : 0.f;
         f[j] = v;
+        bits |= (v != 0.f ? 1u : 0u) << j;
       }
       store8(y, row, C, g, f);
+      // one byte per 8-channel vector = the "gradient passes" bits: backward reads this instead of y
+      if (mask != nullptr) mask[row * m.groups + g] = (uint8_t)bits;
     };
     if ((C & 7) == 0) {
       for (; r + (BN_UNROLL - 1) * stride < M; r += BN_UNROLL * stride) {
@@ -305,15 +309,15 @@ __global__ void __launch_bounds__(256)
   }
 }
 void bn_apply(const void* x, void* y, long long M, int C, const float* scale_shift, int relu,
-              float drop_p, uint64_t seed, const uint64_t* seed_ptr, cudaStream_t s) {
+              float drop_p, uint64_t seed, const uint64_t* seed_ptr, uint8_t* mask, cudaStream_t s) {
   int g = bn_blocks(M, C);
   float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const bf16* xi = (const bf16*)x;
   bf16* yo = (bf16*)y;
-  if (relu && drop_p > 0.f) k_bn_apply<true, true><<<g, 256, 0, s>>>(xi, yo, M, C, scale_shift, drop_p, ds, seed, seed_ptr);
-  else if (relu) k_bn_apply<true, false><<<g, 256, 0, s>>>(xi, yo, M, C, scale_shift, drop_p, ds, seed, seed_ptr);
-  else if (drop_p > 0.f) k_bn_apply<false, true><<<g, 256, 0, s>>>(xi, yo, M, C, scale_shift, drop_p, ds, seed, seed_ptr);
-  else k_bn_apply<false, false><<<g, 256, 0, s>>>(xi, yo, M, C, scale_shift, drop_p, ds, seed, seed_ptr);
+  if (relu && drop_p > 0.f) k_bn_apply<true, true><<<g, 256, 0, s>>>(xi, yo, M, C, scale_shift, drop_p, ds, seed, seed_ptr, mask);
+  else if (relu) k_bn_apply<true, false><<<g, 256, 0, s>>>(xi, yo, M, C, scale_shift, drop_p, ds, seed, seed_ptr, mask);
+  else if (drop_p > 0.f) k_bn_apply<false, true><<<g, 256, 0, s>>>(xi, yo, M, C, scale_shift, drop_p, ds, seed, seed_ptr, mask);
+  else k_bn_apply<false, false><<<g, 256, 0, s>>>(xi, yo, M, C, scale_shift, drop_p, ds, seed, seed_ptr, mask);
   TNN_CHECK_LAUNCH();
 }
 
@@ -328,10 +332,12 @@ struct BnMaskArgs {
   float p;
   uint64_t seed;
   const uint64_t* seed_ptr;
+  const uint8_t* bits;       // MODE 3: one byte of keep bits per 8-channel vector, written by the forward apply
 };
 
 // MODE 0: dy is used as is (no mask, or dy is already the masked g of the fused dgrad epilogue)
 // MODE 1: mask = (y != 0), scaled by 1/(1-p)        MODE 2: mask rebuilt from x, statistics and RNG
+// MODE 3: mask from the forward's keep-bit bytes (1/16 of the bytes of y: the default when C % 8 == 0)
 // The modes are separate instantiations so the common paths do not carry the recompute state in
 // registers: ncu showed the single do-everything kernel at 128 registers = 2 CTAs / SM and 16-22 % of
 // HBM bandwidth (latency bound); these run 3 CTAs / SM with the per-channel constants pre-combined.
@@ -369,7 +375,7 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
       }
       const long long stride = (long long)gridDim.x * m.rpb;
       long long r = (long long)blockIdx.x * m.rpb + m.rl;
-      auto one = [&](long long row, const float (&d)[8], const float (&xv)[8], const float (&yv)[8]) {
+      auto one = [&](long long row, const float (&d)[8], const float (&xv)[8], const float (&yv)[8], unsigned int bits) {
         bool keep[8];
         if (MODE == 2 && ma.p > 0.f) dropout_keep8(seed, row * m.groups + g, ma.p, keep);
 #pragma unroll
@@ -381,6 +387,8 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
             gg = on ? gg * dscale : 0.f;
           } else if (MODE == 1) {
             gg = (yv[j] != 0.f) ? gg * dscale : 0.f;
+          } else if (MODE == 3) {
+            gg = ((bits >> j) & 1u) ? gg * dscale : 0.f;
           }
           acc[0][j] += gg;
           acc[1][j] += gg * (xv[j] - mu[j]);
@@ -389,11 +397,13 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
       if (vec) {
         for (; r + (U - 1) * stride < M; r += U * stride) {
           uint4 qd[U], qx[U], qy[U];
+          unsigned int qb[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             qd[u] = load8raw(dy, r + u * stride, C, g);
             qx[u] = load8raw(x, r + u * stride, C, g);
             if (MODE == 1) qy[u] = load8raw(y, r + u * stride, C, g);
+            qb[u] = (MODE == 3) ? __ldg(ma.bits + (r + u * stride) * m.groups + g) : 0u;
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
@@ -401,7 +411,7 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
             bf8_unpack(qd[u], d);
             bf8_unpack(qx[u], xv);
             if (MODE == 1) bf8_unpack(qy[u], yv);
-            one(r + u * stride, d, xv, yv);
+            one(r + u * stride, d, xv, yv, qb[u]);
           }
         }
       }
@@ -410,7 +420,7 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
         load8(dy, r, C, g, d);
         load8(x, r, C, g, xv);
         if (MODE == 1) load8(y, r, C, g, yv);
-        one(r, d, xv, yv);
+        one(r, d, xv, yv, (MODE == 3) ? __ldg(ma.bits + r * m.groups + g) : 0u);
       }
     }
     block_channel_reduce<2>(m, g, C, acc, ws, sm);
@@ -433,17 +443,19 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
 void bn_bwd_reduce(const void* dy, const void* x, const void* y, long long M, int C,
                    const float* gamma, const float* save_mean, const float* save_invstd,
                    int masked, float drop_p, float* dgamma, float* dbeta, float* coef, float* ws,
-                   const float* beta, int relu, uint64_t seed, const uint64_t* seed_ptr, cudaStream_t s) {
+                   const float* beta, int relu, uint64_t seed, const uint64_t* seed_ptr, const uint8_t* bits,
+                   cudaStream_t s) {
   float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  BnMaskArgs ma{beta, relu, drop_p, seed, seed_ptr};
+  BnMaskArgs ma{beta, relu, drop_p, seed, seed_ptr, bits};
   static bool configured = false;
   if (!configured) {   // ncu: the default carveout admitted ONE 8 KB-smem CTA per SM (occupancy limit "shared memory")
     cudaFuncSetAttribute(k_bn_bwd_reduce<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
     cudaFuncSetAttribute(k_bn_bwd_reduce<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
     cudaFuncSetAttribute(k_bn_bwd_reduce<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
+    cudaFuncSetAttribute(k_bn_bwd_reduce<3>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
     configured = true;
   }
-  const int mode = !masked ? 0 : (y != nullptr ? 1 : 2);
+  const int mode = !masked ? 0 : ((bits != nullptr && (C & 7) == 0) ? 3 : (y != nullptr ? 1 : 2));
   const int grid = bn_blocks(M, C);
   const size_t smem = 256 * 8 * sizeof(float);
 #define TNN_BN_RED(MODE_)                                                                                         \
@@ -451,6 +463,7 @@ void bn_bwd_reduce(const void* dy, const void* x, const void* y, long long M, in
                                                  save_mean, save_invstd, ds, dgamma, dbeta, coef, ws, ma)
   if (mode == 0) TNN_BN_RED(0);
   else if (mode == 1) TNN_BN_RED(1);
+  else if (mode == 3) TNN_BN_RED(3);
   else TNN_BN_RED(2);
 #undef TNN_BN_RED
   TNN_CHECK_LAUNCH();
@@ -503,7 +516,8 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
       }
       const long long stride = (long long)gridDim.x * m.rpb;
       long long r = (long long)blockIdx.x * m.rpb + m.rl;
-      auto one = [&](long long row, float (&d)[8], const float (&xv)[8], const float (&yv)[8], const float (&ev)[8]) {
+      auto one = [&](long long row, float (&d)[8], const float (&xv)[8], const float (&yv)[8], const float (&ev)[8],
+                     unsigned int bits) {
         bool keep[8];
         if (MODE == 2 && ma.p > 0.f) dropout_keep8(seed, row * m.groups + g, ma.p, keep);
 #pragma unroll
@@ -515,6 +529,8 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
             gg = on ? gg * dscale : 0.f;
           } else if (MODE == 1) {
             gg = (yv[j] != 0.f) ? gg * dscale : 0.f;
+          } else if (MODE == 3) {
+            gg = ((bits >> j) & 1u) ? gg * dscale : 0.f;
           }
           float v = ca[j] * gg + cb[j] * xv[j] + cd[j];
           if (EXTRA) v += ev[j];
@@ -527,12 +543,14 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
         constexpr int U = 2;
         for (; r + (U - 1) * stride < M; r += U * stride) {
           uint4 qd[U], qx[U], qy[U], qe[U];
+          unsigned int qb[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
             qd[u] = load8raw(dy, r + u * stride, C, g);
             qx[u] = load8raw(x, r + u * stride, C, g);
             if (MODE == 1) qy[u] = load8raw(y, r + u * stride, C, g);
             if (EXTRA) qe[u] = load8raw(extra, r + u * stride, C, g);
+            qb[u] = (MODE == 3) ? __ldg(ma.bits + (r + u * stride) * m.groups + g) : 0u;
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
@@ -541,7 +559,7 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
             bf8_unpack(qx[u], xv);
             if (MODE == 1) bf8_unpack(qy[u], yv);
             if (EXTRA) bf8_unpack(qe[u], ev);
-            one(r + u * stride, d, xv, yv, ev);
+            one(r + u * stride, d, xv, yv, ev, qb[u]);
           }
         }
       }
@@ -551,7 +569,7 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
         load8(x, r, C, g, xv);
         if (MODE == 1) load8(y, r, C, g, yv);
         if (EXTRA) load8(extra, r, C, g, ev);
-        one(r, d, xv, yv, ev);
+        one(r, d, xv, yv, ev, (MODE == 3) ? __ldg(ma.bits + r * m.groups + g) : 0u);
       }
     }
     if (colsum_out) block_channel_reduce<1>(m, g, C, csum, colsum_ws, sm);
@@ -587,10 +605,10 @@ void bn_bwd_apply(const void* dy, const void* x, const void* y, const void* extr
                   long long M, int C, const float* save_mean, const float* save_invstd,
                   const float* coef, int masked, float drop_p, float* colsum_out, float* colsum_ws,
                   const float* gamma, const float* beta, int relu, uint64_t seed, const uint64_t* seed_ptr,
-                  cudaStream_t s) {
+                  const uint8_t* bits, cudaStream_t s) {
   float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  BnMaskArgs ma{beta, relu, drop_p, seed, seed_ptr};
-  const int mode = !masked ? 0 : (y != nullptr ? 1 : 2);
+  BnMaskArgs ma{beta, relu, drop_p, seed, seed_ptr, bits};
+  const int mode = !masked ? 0 : ((bits != nullptr && (C & 7) == 0) ? 3 : (y != nullptr ? 1 : 2));
   const int grid = bn_blocks(M, C);
   const size_t smem = 256 * 8 * sizeof(float);
 #define TNN_BN_APPLY(MODE_, EXTRA_)                                                                              \
@@ -607,10 +625,12 @@ void bn_bwd_apply(const void* dy, const void* x, const void* y, const void* extr
   if (extra != nullptr) {
     if (mode == 0) TNN_BN_APPLY(0, true);
     else if (mode == 1) TNN_BN_APPLY(1, true);
+    else if (mode == 3) TNN_BN_APPLY(3, true);
     else TNN_BN_APPLY(2, true);
   } else {
     if (mode == 0) TNN_BN_APPLY(0, false);
     else if (mode == 1) TNN_BN_APPLY(1, false);
+    else if (mode == 3) TNN_BN_APPLY(3, false);
     else TNN_BN_APPLY(2, false);
   }
 #undef TNN_BN_APPLY

@@ -88,20 +88,22 @@ int bn_stat_replicas();
 void bn_eval_scale_shift(int C, const float* gamma, const float* beta, const float* running_mean,
                          const float* running_var, float eps, float* scale_shift, cudaStream_t s);
 // y = act(x*scale + shift) [* dropout]; residual-free.  drop_p == 0 disables dropout.
+// `mask` (nullable, M*C/8 bytes, C % 8 == 0): one byte of "gradient passes" bits per 8-channel vector.
 void bn_apply(const void* x, void* y, long long M, int C, const float* scale_shift, int relu,
-              float drop_p, uint64_t seed, const uint64_t* seed_ptr, cudaStream_t s);
+              float drop_p, uint64_t seed, const uint64_t* seed_ptr, uint8_t* mask, cudaStream_t s);
 // Backward.  g = dy * mask(y) (mask = y != 0 when relu/dropout were fused, scaled by 1/(1-p)).
 // Accumulates dgamma/dbeta (fp32, +=) and writes coef[3*C] for bn_bwd_apply.
 void bn_bwd_reduce(const void* dy, const void* x, const void* y, long long M, int C,
                    const float* gamma, const float* save_mean, const float* save_invstd,
                    int masked, float drop_p, float* dgamma, float* dbeta, float* coef, float* ws,
-                   const float* beta, int relu, uint64_t seed, const uint64_t* seed_ptr, cudaStream_t s);
+                   const float* beta, int relu, uint64_t seed, const uint64_t* seed_ptr, const uint8_t* bits,
+                   cudaStream_t s);
 // dx = coef0*(g - coef1 - xhat*coef2) (+ extra, an optional residual gradient to add)
 void bn_bwd_apply(const void* dy, const void* x, const void* y, const void* extra, void* dx,
                   long long M, int C, const float* save_mean, const float* save_invstd,
                   const float* coef, int masked, float drop_p, float* colsum_out, float* colsum_ws,
                   const float* gamma, const float* beta, int relu, uint64_t seed, const uint64_t* seed_ptr,
-                  cudaStream_t s);
+                  const uint8_t* bits, cudaStream_t s);
 // floats needed by the `ws` / `colsum_ws` workspaces of the BN kernels (zero-initialised once)
 int bn_ws_floats(int C);
 // LayerNorm over rows of length C (bf16 io, fp32 affine).  One warp per row.

@@ -363,7 +363,12 @@ class BatchNormLayer(Layer):
             else:
                 Cx.bn_eval_scale_shift(C, gamma, beta, self.params["running_mean"], self.params["running_var"],
                                        self.epsilon, b["ss"])
-            Cx.bn_apply(x, y, M, C, b["ss"], self.use_relu, p_drop, seed, stepstate.get(x.device).dev if p_drop > 0 else None)
+            # keep bits (one byte per 8-channel vector): what backward needs of y, at 1/16 of its bytes
+            bits = None
+            if self.training and (self.use_relu or p_drop > 0) and C % 8 == 0 and os.environ.get("TNN_BN_BITMASK", "1") == "1":
+                bits = torch.empty(M * (C // 8), dtype=torch.uint8, device=x.device)
+            Cx.bn_apply(x, y, M, C, b["ss"], self.use_relu, p_drop, seed, stepstate.get(x.device).dev if p_drop > 0 else None,
+                        bits)
             if self.training:
                 c = self.cache(mb_id)
                 c["x"] = x
@@ -374,7 +379,8 @@ class BatchNormLayer(Layer):
                 # BN-backward fusion (the consumer conv's dgrad epilogue rebuilds the mask from x): y is not
                 # needed by backward at all then -- but keep it unless the consumer is known to fuse
                 fuse_bwd = self._bwd_consumer is not None and os.environ.get("TNN_BN_FUSE_BWD", "0") == "1"
-                c["y"] = y if ((self.use_relu or p_drop > 0) and keep_y and not fuse_bwd) else None
+                c["y"] = y if ((self.use_relu or p_drop > 0) and keep_y and not fuse_bwd and bits is None) else None
+                c["bits"] = bits
                 c["mean"], c["invstd"], c["pack"] = rec[4 * C:5 * C], rec[5 * C:], rec[:4 * C]
                 c["p"] = p_drop
                 c["seed"] = seed
@@ -431,12 +437,13 @@ class BatchNormLayer(Layer):
             # (y is None with a mask = the forward dropped y expecting the fused backward or
             # TNN_BN_RECOMPUTE_MASK=1: the kernels below then rebuild the mask from x, the statistics and
             # the dropout counter)
+            bits = c.get("bits")
             Cx.bn_bwd_reduce(dy, x, y, M, C, gamma, c["mean"], c["invstd"], masked, c["p"], self.grads.get("gamma"),
-                             self.grads.get("beta"), b["coef"], b["ws"], beta, self.use_relu, c.get("seed", 0), state)
+                             self.grads.get("beta"), b["coef"], b["ws"], beta, self.use_relu, c.get("seed", 0), state, bits)
             dx = torch.empty_like(x)
             colsum = torch.empty(C, dtype=torch.float32, device=dy.device)
             Cx.bn_bwd_apply(dy, x, y, extra, dx, M, C, c["mean"], c["invstd"], b["coef"], masked, c["p"], colsum,
-                            b["cws"], gamma, beta, self.use_relu, c.get("seed", 0), state)
+                            b["cws"], gamma, beta, self.use_relu, c.get("seed", 0), state, bits)
             dx = dx.reshape(dy.shape)
             dx._tnn_colsum = colsum      # column sums of dx = bias gradient of the producing conv/dense
             return dx
