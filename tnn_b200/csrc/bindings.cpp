@@ -426,15 +426,16 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     tnn::tensor_bswap(t.data_ptr(), t.numel(), (int)t.element_size(), cur_stream());
   });
   m.def("skinny_gemm", [](const Tensor& x, const Tensor& w, const OptT& bias, const OptT& residual, const Tensor& out,
-                          int act) {
+                          int act, bool static_weights) {
     TORCH_CHECK(x.is_cuda() && x.scalar_type() == torch::kBFloat16 && w.scalar_type() == torch::kBFloat16 &&
                     out.scalar_type() == torch::kBFloat16, "bf16 CUDA tensors");
     TORCH_CHECK(x.dim() == 2 && w.dim() == 2 && x.size(1) == w.size(1) && x.stride(1) == 1 && w.stride(1) == 1 &&
                     out.stride(1) == 1, "x [M,K], w [N,K] row-major");
     tnn::skinny_gemm_bf16(vp(x), x.stride(0), vp(w), w.stride(0), fp(bias), vp(residual),
                           residual.has_value() ? residual->stride(0) : 0, vp(out), out.stride(0), (int)x.size(0),
-                          (int)w.size(0), (int)x.size(1), act, cur_stream());
-  });
+                          (int)w.size(0), (int)x.size(1), act, static_weights ? 1 : 0, cur_stream());
+  }, py::arg("x"), py::arg("w"), py::arg("bias"), py::arg("residual"), py::arg("out"), py::arg("act"),
+     py::arg("static_weights") = false);
   m.def("launch_count", []() { return tnn::g_launch_count; });
   tnn::attention_bind(m);
   tnn::runtime_bind(m);

@@ -413,6 +413,7 @@ __global__ void __launch_bounds__(DEC_THREADS)
     attn_decode_append_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ kc, bf16* __restrict__ vc,
                               long long tok_stride, long long batch_stride, bf16* __restrict__ out, int H,
                               const int* __restrict__ pos_ptr, float scale_log2) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: dependents may start their prologue
   const int h = blockIdx.x, b = blockIdx.y;
   const int pos = *pos_ptr;
   const int len = pos + 1;
@@ -518,6 +519,7 @@ void kv_cache_store_bf16(const void* qkv, void* kcache, void* vcache, long long 
 __global__ void __launch_bounds__(256)
     k_embed_decode(const int* __restrict__ tok, const float* __restrict__ wte, const float* __restrict__ wpe,
                    bf16* __restrict__ x, int D, int V, const int* __restrict__ pos_ptr) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: dependents may start their prologue
   const int b = blockIdx.x;
   const int pos = *pos_ptr;
   int id = tok[b];

@@ -54,6 +54,7 @@ void embedding_bwd(const int* ids, const void* dy, float* dtable, float* dpos, l
 template <typename T>
 __global__ void __launch_bounds__(1024)
     k_argmax_rows(const T* __restrict__ x, long long ld, long long rows, int V, int* __restrict__ out, int vec_ok) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: dependents may start their prologue
   __shared__ float rv[32];
   __shared__ int ri[32];
   for (long long r = blockIdx.x; r < rows; r += gridDim.x) {

@@ -642,6 +642,7 @@ __global__ void __launch_bounds__(256)
     k_ln_fwd(const bf16* __restrict__ x, const bf16* __restrict__ res, bf16* __restrict__ y,
              bf16* __restrict__ sum_out, long long rows, int C, const float* __restrict__ gamma,
              const float* __restrict__ beta, float eps, float* mean, float* rstd) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // PDL: dependents may start their prologue
   const int lane = threadIdx.x & 31;
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;

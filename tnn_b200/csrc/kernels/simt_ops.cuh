@@ -65,7 +65,7 @@ void tensor_bswap(void* p, long long n_elems, int elem_size, cudaStream_t s);
 
 // ---- skinny GEMM for decode (skinny_gemm.cu): out[M<=32,N] = act(x W^T + bias (+ residual)), act 0/1 relu/2 gelu
 void skinny_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, const float* bias,
-                      const void* residual, long long ldr, void* out, long long ldo, int M, int N, int K, int act,
+                      const void* residual, long long ldr, void* out, long long ldo, int M, int N, int K, int act, int static_weights,
                       cudaStream_t s);
 
 // ---- normalisation (norm.cu) -------------------------------------------------------

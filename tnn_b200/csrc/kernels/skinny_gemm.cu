@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(SK_WARPS * 32)
     k_skinny_gemm(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ w, long long ldw,
                   const float* __restrict__ bias, const bf16* __restrict__ residual, long long ldr,
                   bf16* __restrict__ out, long long ldo, int M, int N, int K, int act, int ksplit) {
+  // programmatic dependent launch: let the NEXT kernel of the decode chain start its own prologue now
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(16) uint8_t sk_smem[];
   bf16* sx = reinterpret_cast<bf16*>(sk_smem);                                // [32][SK_KC + SK_PAD]
   float* part = reinterpret_cast<float*>(sk_smem + SK_X_BYTES);               // [ksplit][2][32][8], written by peers
@@ -99,6 +101,9 @@ __global__ void __launch_bounds__(SK_WARPS * 32)
         }
       }
     }
+    // (launched with the PDL attribute when the weights are static: everything above overlapped the
+    //  previous kernel of the stream; its output x is only valid after this wait.  No-op otherwise.)
+    if (k0 == k_beg) asm volatile("griddepcontrol.wait;" ::: "memory");
     __syncthreads();
     // 2) stage x[:, k0:k0+kc] (rows >= M and the k tail up to 4*sub are zero filled: no masking below)
     const int kfill = min(SK_KC, 4 * sub);
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32)
 
 void skinny_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw, const float* bias,
                       const void* residual, long long ldr, void* out, long long ldo, int M, int N, int K, int act,
-                      cudaStream_t s) {
+                      int static_weights, cudaStream_t s) {
   if (M <= 0 || N <= 0 || K <= 0) return;
   if (M > 32 || (ldx % 8) || (ldw % 8) || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) {
     fprintf(stderr, "[tnn_b200] skinny_gemm_bf16: needs M <= 32 and 16-byte aligned rows\n");
@@ -208,11 +213,13 @@ void skinny_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw
   }
   constexpr int smem = SK_X_BYTES + SK_PART_BYTES;
   static bool configured = false;
-  static int forced = -1;
+  static int forced = -1, pdl = 1;
   if (!configured) {
     cudaFuncSetAttribute(k_skinny_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const char* e = getenv("TNN_SKINNY_KSPLIT");
     forced = (e != nullptr) ? atoi(e) : 0;
+    const char* e2 = getenv("TNN_PDL");
+    pdl = (e2 != nullptr) ? atoi(e2) : 1;
     configured = true;
   }
   const int col_ctas = (N + SK_COLS - 1) / SK_COLS;
@@ -225,13 +232,19 @@ void skinny_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw
   cfg.blockDim = dim3(SK_WARPS * 32, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)ksplit;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (static_weights && pdl) {
+    // the weight stream does not depend on the previous kernel: start early, wait inside the kernel
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   cudaError_t err = cudaLaunchKernelEx(&cfg, k_skinny_gemm, (const bf16*)x, ldx, (const bf16*)w, ldw, bias,
                                        (const bf16*)residual, ldr, (bf16*)out, ldo, M, N, K, act, ksplit);
   if (err != cudaSuccess) {

@@ -1237,7 +1237,17 @@ static int mode_2cta() {
 static bool use_2cta(int M, int N, bool a_mn, bool b_mn, int splits, int kb_total) {
   const int mode = mode_2cta();
   if (mode == 0 || a_mn || b_mn || splits > 1 || M < 256 || N < 128) return false;
-  if (mode < 0) return N >= 256 && kb_total >= 32;
+  if (mode < 0) {
+    // auto rule; the two thresholds are tunable for A/B runs (TNN_GEMM_2CTA_MIN_N / _MIN_KB)
+    static int min_n = -1, min_kb = -1;
+    if (min_n < 0) {
+      const char* a = getenv("TNN_GEMM_2CTA_MIN_N");
+      const char* b = getenv("TNN_GEMM_2CTA_MIN_KB");
+      min_n = (a != nullptr) ? atoi(a) : 256;
+      min_kb = (b != nullptr) ? atoi(b) : 32;
+    }
+    return N >= min_n && kb_total >= min_kb;
+  }
   return true;
 }
 static bool use_2cta_persist() { return mode_2cta() != 1; }

@@ -26,6 +26,7 @@ from ..nn.graph import Graph
 from ..nn.layers import (ActivationLayer, DenseLayer, DropoutLayer, EmbeddingLayer, LayerNormLayer,
                          PositionalEmbeddingLayer)
 from ..ops import attention as attn_ops
+from ..ops import gemm as gemm_ops
 from ..ops import native
 
 
@@ -128,11 +129,12 @@ class GPT2InferenceEngine:
         if B > self.max_batch or L > self.max_len:
             raise ValueError(f"prompt [{B}, {L}] exceeds engine capacity [{self.max_batch}, {self.max_len}]")
         self.cur_batch, self.cur_len = B, 0
-        x = self._embed(ids, 0)
-        x = self._layers(x, 0)
-        self.cur_len = L
-        logits = self._logits_last(x[:, -1:, :].contiguous()).reshape(B, -1)
-        nxt = self._argmax(logits)
+        with gemm_ops.static_weights():
+            x = self._embed(ids, 0)
+            x = self._layers(x, 0)
+            self.cur_len = L
+            logits = self._logits_last(x[:, -1:, :].contiguous()).reshape(B, -1)
+            nxt = self._argmax(logits)
         return (nxt, logits) if return_logits else nxt
 
     @torch.no_grad()
@@ -142,11 +144,12 @@ class GPT2InferenceEngine:
         if self.cur_len >= self.max_len:
             raise ValueError("KV cache is full")
         ids = tokens.to(self.device).to(torch.int32).reshape(B, 1)
-        x = self._embed(ids, self.cur_len)
-        x = self._layers(x, self.cur_len)
-        self.cur_len += 1
-        logits = self._logits_last(x).reshape(B, -1)
-        nxt = self._argmax(logits)
+        with gemm_ops.static_weights():
+            x = self._embed(ids, self.cur_len)
+            x = self._layers(x, self.cur_len)
+            self.cur_len += 1
+            logits = self._logits_last(x).reshape(B, -1)
+            nxt = self._argmax(logits)
         return (nxt, logits) if return_logits else nxt
 
     @torch.no_grad()
@@ -174,14 +177,15 @@ class GPT2InferenceEngine:
         st = self._dev
         x = torch.empty((B, E), dtype=torch.bfloat16, device=self.device)
         Cx.embed_decode(st["tok"], self.embed.params["weight"], self.pos.params["weight"], x, st["pos"])
-        for b, cache in zip(self.blocks, self.caches):
-            y = b.ln1.forward_impl(x, 0)
-            qkv = b.attn._qkv(y)                                         # [B, 3E]
-            o = torch.empty((B, E), dtype=torch.bfloat16, device=self.device)
-            Cx.attention_decode_append(qkv, cache.k[:B], cache.v[:B], o, st["pos"])
-            x = b.attn._out(o, x)
-            x = self._mlp(b, x)
-        logits = self._logits_last(x).reshape(B, -1)
+        with gemm_ops.static_weights():
+            for b, cache in zip(self.blocks, self.caches):
+                y = b.ln1.forward_impl(x, 0)
+                qkv = b.attn._qkv(y)                                         # [B, 3E]
+                o = torch.empty((B, E), dtype=torch.bfloat16, device=self.device)
+                Cx.attention_decode_append(qkv, cache.k[:B], cache.v[:B], o, st["pos"])
+                x = b.attn._out(o, x)
+                x = self._mlp(b, x)
+            logits = self._logits_last(x).reshape(B, -1)
         nxt = self._argmax(logits)
         Cx.decode_epilogue(nxt, st["tok"], st["history"], st["pos"], st["step"])
 

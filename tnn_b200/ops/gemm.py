@@ -15,6 +15,24 @@ from . import native
 import os
 
 _SKINNY = os.environ.get("TNN_SKINNY_GEMM", "1") == "1"
+# Set (through ``static_weights()``) while an inference engine runs: the decode GEMMs may then be
+# launched as programmatic dependents that stream their weights before the previous kernel has finished.
+_STATIC_WEIGHTS = False
+
+
+class static_weights:
+    """Context manager: weights are not written by any kernel in flight (inference)."""
+
+    def __enter__(self):
+        global _STATIC_WEIGHTS
+        self.prev, _STATIC_WEIGHTS = _STATIC_WEIGHTS, True
+        return self
+
+    def __exit__(self, *exc):
+        global _STATIC_WEIGHTS
+        _STATIC_WEIGHTS = self.prev
+        return False
+
 ACT = {"none": 0, "linear": 0, None: 0, "relu": 1, "gelu": 2}
 OUT_BF16, OUT_F32, OUT_F32_ATOMIC = 0, 1, 2
 
@@ -51,7 +69,7 @@ def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = Non
     if M <= 32 and out.dtype == torch.bfloat16 and _SKINNY and x.stride(0) % 8 == 0 and w.stride(0) % 8 == 0 and \
             (residual is None or (residual.dtype == torch.bfloat16 and residual.stride(-1) == 1)):
         # decode-sized batch: weight-streaming kernel (HBM bound) instead of a 3/4-empty 128-row tile
-        C.skinny_gemm(x, w, bias, residual, out, ACT[act])
+        C.skinny_gemm(x, w, bias, residual, out, ACT[act], _STATIC_WEIGHTS)
         return out
     C.gemm(x, w, M, N, K, x.stride(0), w.stride(0), False, False, out, out.stride(0),
            OUT_F32 if out.dtype == torch.float32 else OUT_BF16, ACT[act], 1.0, bias, residual, 1)
