@@ -357,7 +357,8 @@ class BatchNormLayer(Layer):
                 x._tnn_bn_stats = None                    # the workspace is reset by the fold: single consumer
             elif self.training:
                 if producer is not None and getattr(producer, "out_channels", -1) == C:
-                    producer._stats_requested = True      # takes effect from the next forward on
+                    # takes effect from the next forward on
+                    producer._stats_requested = os.environ.get("TNN_BN_FUSE_STATS", "1") == "1"
                 Cx.bn_train_stats(x, M, C, gamma, beta, self.epsilon, self.momentum, self.params["running_mean"],
                                   self.params["running_var"], rec[4 * C:5 * C], rec[5 * C:], b["ss"], b["ws"], rec[:4 * C])
             else:
