@@ -138,13 +138,10 @@ __global__ void __launch_bounds__(256)
       const long long stride = (long long)gridDim.x * m.rpb;
       long long r = (long long)blockIdx.x * m.rpb + m.rl;
       if (vec) {
-        // every iteration issues BN_UNROLL independent 16-byte loads; rows past the end load zeros
-        // (a serial one-load-at-a-time tail used to add 2-3 DRAM round trips to every launch)
-        for (; r < M; r += BN_UNROLL * stride) {
+        for (; r + (BN_UNROLL - 1) * stride < M; r += BN_UNROLL * stride) {
           uint4 q[BN_UNROLL];
 #pragma unroll
-          for (int u = 0; u < BN_UNROLL; ++u)
-            q[u] = (r + u * stride < M) ? load8raw(x, r + u * stride, C, g) : make_uint4(0u, 0u, 0u, 0u);
+          for (int u = 0; u < BN_UNROLL; ++u) q[u] = load8raw(x, r + u * stride, C, g);
 #pragma unroll
           for (int u = 0; u < BN_UNROLL; ++u) {
             float f[8];
@@ -292,16 +289,15 @@ __global__ void __launch_bounds__(256)
       if (mask != nullptr) mask[row * m.groups + g] = (uint8_t)bits;
     };
     if ((C & 7) == 0) {
-      for (; r < M; r += BN_UNROLL * stride) {
+      for (; r + (BN_UNROLL - 1) * stride < M; r += BN_UNROLL * stride) {
         uint4 q[BN_UNROLL];
 #pragma unroll
-        for (int u = 0; u < BN_UNROLL; ++u)
-          q[u] = (r + u * stride < M) ? load8raw(x, r + u * stride, C, g) : make_uint4(0u, 0u, 0u, 0u);
+        for (int u = 0; u < BN_UNROLL; ++u) q[u] = load8raw(x, r + u * stride, C, g);
 #pragma unroll
         for (int u = 0; u < BN_UNROLL; ++u) {
           float f[8];
           bf8_unpack(q[u], f);
-          if (r + u * stride < M) one(r + u * stride, f);
+          one(r + u * stride, f);
         }
       }
     }
@@ -399,17 +395,15 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
         }
       };
       if (vec) {
-        for (; r < M; r += U * stride) {
+        for (; r + (U - 1) * stride < M; r += U * stride) {
           uint4 qd[U], qx[U], qy[U];
           unsigned int qb[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const bool in = r + u * stride < M;          // rows past the end: dy = 0 contributes nothing
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            qd[u] = in ? load8raw(dy, r + u * stride, C, g) : z;
-            qx[u] = in ? load8raw(x, r + u * stride, C, g) : z;
-            if (MODE == 1) qy[u] = in ? load8raw(y, r + u * stride, C, g) : z;
-            qb[u] = (MODE == 3 && in) ? __ldg(ma.bits + (r + u * stride) * m.groups + g) : 0u;
+            qd[u] = load8raw(dy, r + u * stride, C, g);
+            qx[u] = load8raw(x, r + u * stride, C, g);
+            if (MODE == 1) qy[u] = load8raw(y, r + u * stride, C, g);
+            qb[u] = (MODE == 3) ? __ldg(ma.bits + (r + u * stride) * m.groups + g) : 0u;
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
@@ -547,18 +541,16 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
       };
       if (vec) {
         constexpr int U = 2;
-        for (; r < M; r += U * stride) {
+        for (; r + (U - 1) * stride < M; r += U * stride) {
           uint4 qd[U], qx[U], qy[U], qe[U];
           unsigned int qb[U];
 #pragma unroll
           for (int u = 0; u < U; ++u) {
-            const bool in = r + u * stride < M;
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-            qd[u] = in ? load8raw(dy, r + u * stride, C, g) : z;
-            qx[u] = in ? load8raw(x, r + u * stride, C, g) : z;
-            if (MODE == 1) qy[u] = in ? load8raw(y, r + u * stride, C, g) : z;
-            if (EXTRA) qe[u] = in ? load8raw(extra, r + u * stride, C, g) : z;
-            qb[u] = (MODE == 3 && in) ? __ldg(ma.bits + (r + u * stride) * m.groups + g) : 0u;
+            qd[u] = load8raw(dy, r + u * stride, C, g);
+            qx[u] = load8raw(x, r + u * stride, C, g);
+            if (MODE == 1) qy[u] = load8raw(y, r + u * stride, C, g);
+            if (EXTRA) qe[u] = load8raw(extra, r + u * stride, C, g);
+            qb[u] = (MODE == 3) ? __ldg(ma.bits + (r + u * stride) * m.groups + g) : 0u;
           }
 #pragma unroll
           for (int u = 0; u < U; ++u) {
@@ -567,7 +559,7 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
             bf8_unpack(qx[u], xv);
             if (MODE == 1) bf8_unpack(qy[u], yv);
             if (EXTRA) bf8_unpack(qe[u], ev);
-            if (r + u * stride < M) one(r + u * stride, d, xv, yv, ev, qb[u]);
+            one(r + u * stride, d, xv, yv, ev, qb[u]);
           }
         }
       }

@@ -543,19 +543,11 @@ __global__ void __launch_bounds__(kThreads)
       const int tile_m = (t / n_tiles) % m_tiles;
       const int m0 = tile_m * BLOCK_M, n0 = tile_n * BLOCK_N;
       const int acc = it & 1;
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after();
       const int m = m0 + row;
       const bool row_ok = m < p.M;
       const long long row_off = row_ok ? epi_row_offset(p.epi, m) : 0;
-      if (p.epi.residual != nullptr && row_ok) {
-        // pull this thread's residual row segment towards L2 while the tile's main loop is still running:
-        // the epilogue's residual loads were fully exposed (+30..35 us on every conv with a fused shortcut add)
-        const char* rp = reinterpret_cast<const char*>(reinterpret_cast<const __nv_bfloat16*>(p.epi.residual) + row_off + n0);
-#pragma unroll
-        for (int b = 0; b < BLOCK_N * 2; b += 128)
-          if (n0 + b / 2 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + b));
-      }
-      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
-      tc_fence_after();
       if (TMA_STORE) {
         const bool store_thread = (threadIdx.x == 64);          // first lane of the first epilogue warp
         uint8_t* srow = sC + row * 128;
@@ -867,19 +859,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads)
       const int m0 = (tile_m * 2 + (int)rank) * BLOCK_M;
       const int n0 = tile_n * BLOCK_N;
       const int acc = it & 1;
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after();
       const int m = m0 + row;
       const bool row_ok = m < p.M;
       const long long row_off = row_ok ? epi_row_offset(p.epi, m) : 0;
-      if (p.epi.residual != nullptr && row_ok) {
-        // pull this thread's residual row segment towards L2 while the tile's main loop is still running:
-        // the epilogue's residual loads were fully exposed (+30..35 us on every conv with a fused shortcut add)
-        const char* rp = reinterpret_cast<const char*>(reinterpret_cast<const __nv_bfloat16*>(p.epi.residual) + row_off + n0);
-#pragma unroll
-        for (int b = 0; b < BLOCK_N * 2; b += 128)
-          if (n0 + b / 2 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + b));
-      }
-      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
-      tc_fence_after();
       if (TMA_STORE) {
         const bool store_thread = (threadIdx.x == 64);
         uint8_t* srow = sC + row * 128;

@@ -350,15 +350,18 @@ class BatchNormLayer(Layer):
                 # this microbatch's statistics record, written by the statistics kernel itself (no clones):
                 # [0:4C] the (invstd, -mean*invstd, scale, shift) pack per channel (16-byte aligned), [4C:5C] mean, [5C:6C] invstd
                 rec = torch.empty(6 * C, dtype=torch.float32, device=x.device)
-            if self.training and fused_ws is not None and os.environ.get("TNN_BN_FUSE_STATS", "1") == "1":
+            if self.training and fused_ws is not None and os.environ.get("TNN_BN_FUSE_STATS", "0") == "1":
                 # the producing convolution already accumulated sum / sum-of-squares in its epilogue
+                # (TNN_BN_FUSE_STATS=1; off by default since the persistent GEMMs became epilogue-bound: the
+                # same conv costs 93-127 us with the statistics epilogue and 67-72 us without, which is more
+                # than the stand-alone statistics kernel -- same-run A/B 4.269 vs 4.284 ms/step)
                 Cx.bn_finalize_stats(fused_ws, M, C, gamma, beta, self.epsilon, self.momentum, self.params["running_mean"],
                                      self.params["running_var"], rec[4 * C:5 * C], rec[5 * C:], b["ss"], rec[:4 * C])
                 x._tnn_bn_stats = None                    # the workspace is reset by the fold: single consumer
             elif self.training:
                 if producer is not None and getattr(producer, "out_channels", -1) == C:
                     # takes effect from the next forward on
-                    producer._stats_requested = os.environ.get("TNN_BN_FUSE_STATS", "1") == "1"
+                    producer._stats_requested = os.environ.get("TNN_BN_FUSE_STATS", "0") == "1"
                 Cx.bn_train_stats(x, M, C, gamma, beta, self.epsilon, self.momentum, self.params["running_mean"],
                                   self.params["running_var"], rec[4 * C:5 * C], rec[5 * C:], b["ss"], b["ws"], rec[:4 * C])
             else:
