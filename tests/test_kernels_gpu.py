@@ -243,3 +243,40 @@ def test_skinny_decode_gemm(M, N, K):
     assert _rel_err(gemm.linear_fwd(x, w, b), ref) < 1e-2
     assert _rel_err(gemm.linear_fwd(x, w, b, act="gelu"), torch.nn.functional.gelu(ref, approximate="tanh")) < 1e-2
     assert _rel_err(gemm.linear_fwd(x, w, None, act="relu", residual=res), torch.relu(ref - b + res.float())) < 1e-2
+
+
+@pytest.mark.parametrize("rows,V", [(64, 5003), (300, 2048), (16, 50257)])
+def test_softmax_ce_vectorised_rows_with_padded_stride(rows, V):
+    """bf16 logits living in rows padded to a multiple of 8 elements (what the Dense layer emits for an
+    odd vocabulary): the 16-byte-vector online-softmax kernel vs the fp32 formula, no copy of the logits."""
+    from tnn_b200.nn import LossFactory
+    torch.manual_seed(4)
+    ld = (V + 7) // 8 * 8
+    buf = torch.zeros(rows, ld, device=_dev(), dtype=torch.bfloat16)
+    logits = buf[:, :V]
+    logits.copy_(torch.randn(rows, V, device=_dev()) * 3)
+    y = torch.randint(0, V, (rows,), device=_dev(), dtype=torch.int32)
+    crit = LossFactory.create_logsoftmax_crossentropy()
+    pred3 = logits.reshape(rows // 4, 4, V) if rows % 4 == 0 else logits
+    stats, grad = crit.loss_and_grad(pred3, y.reshape(pred3.shape[:-1]))
+    assert grad.shape == pred3.shape and grad.stride(-2) == ld          # gradient keeps the padded stride
+    lf = logits.float()
+    ref_loss = torch.nn.functional.cross_entropy(lf, y.long())
+    ref_grad = (torch.softmax(lf, -1) - torch.nn.functional.one_hot(y.long(), V)) / rows
+    assert abs(float(stats[0]) - float(ref_loss)) < 2e-2
+    assert float(stats[1]) == float((lf.argmax(-1) == y.long()).sum())
+    assert _rel_err(grad.reshape(rows, V), ref_grad) < 2e-2
+
+
+@pytest.mark.parametrize("M,N", [(8192, 768), (4096, 1001), (2048, 72)])
+def test_tall_column_sums(M, N):
+    from tnn_b200.ops import gemm
+    torch.manual_seed(6)
+    ld = (N + 7) // 8 * 8
+    buf = torch.zeros(M, ld, device=_dev(), dtype=torch.bfloat16)
+    dy = buf[:, :N]
+    dy.copy_(torch.randn(M, N, device=_dev()))
+    db = torch.full((N,), 0.5, device=_dev())
+    gemm.bias_grad(dy, db, 0.25)
+    ref = 0.5 + 0.25 * dy.float().sum(0)
+    assert _rel_err(db, ref) < 2e-3

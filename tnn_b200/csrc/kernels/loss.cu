@@ -83,9 +83,132 @@ __global__ void k_softmax_ce(const T* __restrict__ logits, long long ld, const i
     __syncthreads();
   }
 }
+// bf16 rows with 16-byte aligned starts (ld % 8 == 0): two passes of 16-byte loads instead of three
+// passes of 2-byte loads.  Pass 1 is an online softmax (running max / rescaled sum / arg-max per
+// thread, merged across the CTA), pass 2 re-reads the row (L2 resident: 100 KB at GPT-2's vocabulary)
+// and writes the gradient as 16-byte vectors.  [8192, 50257] logits: 1.39 ms -> bandwidth bound.
+__global__ void __launch_bounds__(512)
+    k_softmax_ce_bf16v(const bf16* __restrict__ logits, long long ld, const int* __restrict__ labels,
+                       long long rows, int V, float loss_scale, float grad_scale, bf16* __restrict__ grad,
+                       float* __restrict__ out) {
+  __shared__ float s_m[16], s_s[16], s_bv[16];
+  __shared__ int s_bi[16];
+  __shared__ float s_M, s_S;
+  __shared__ int s_A;
+  const int nv = V >> 3;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const bf16* x = logits + r * ld;
+    const int label = labels[r];
+    float m = -INFINITY, sum = 0.f, bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+      float f[8];
+      bf8_unpack(__ldg(reinterpret_cast<const uint4*>(x) + i), f);
+      float lm = f[0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) lm = fmaxf(lm, f[j]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (f[j] > bv) {
+          bv = f[j];
+          bi = i * 8 + j;
+        }
+      const float mn = fmaxf(m, lm);
+      float add = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) add += __expf(f[j] - mn);
+      sum = sum * __expf(m - mn) + add;
+      m = mn;
+    }
+    for (int c = (nv << 3) + threadIdx.x; c < V; c += blockDim.x) {      // ragged tail (V % 8 elements)
+      const float v = __bfloat162float(x[c]);
+      if (v > bv || (v == bv && c < bi)) {
+        bv = v;
+        bi = c;
+      }
+      const float mn = fmaxf(m, v);
+      sum = sum * __expf(m - mn) + __expf(v - mn);
+      m = mn;
+    }
+    // warp merge of (m, sum) and (bv, bi)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mn = fmaxf(m, om);
+      sum = (mn == -INFINITY) ? 0.f : sum * __expf(m - mn) + os * __expf(om - mn);
+      m = mn;
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    __syncthreads();
+    if (lane == 0) {
+      s_m[w] = m;
+      s_s[w] = sum;
+      s_bv[w] = bv;
+      s_bi[w] = bi;
+    }
+    __syncthreads();
+    if (w == 0) {
+      m = lane < nw ? s_m[lane] : -INFINITY;
+      sum = lane < nw ? s_s[lane] : 0.f;
+      bv = lane < nw ? s_bv[lane] : -INFINITY;
+      bi = lane < nw ? s_bi[lane] : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, m, o), os = __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mn = fmaxf(m, om);
+        sum = (mn == -INFINITY) ? 0.f : sum * __expf(m - mn) + os * __expf(om - mn);
+        m = mn;
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      if (lane == 0) {
+        s_M = m;
+        s_S = sum;
+        s_A = bi;
+        const bool valid = label >= 0 && label < V;
+        if (valid) atomicAdd(out, (m + __logf(sum) - __bfloat162float(x[label])) * loss_scale);
+        if (valid && bi == label) atomicAdd(out + 1, 1.f);
+      }
+    }
+    __syncthreads();
+    if (grad != nullptr) {
+      const float M = s_M, inv = 1.f / s_S;
+      bf16* g = grad + r * ld;
+      for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+        float f[8];
+        bf8_unpack(__ldg(reinterpret_cast<const uint4*>(x) + i), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = (__expf(f[j] - M) * inv - ((i * 8 + j) == label ? 1.f : 0.f)) * grad_scale;
+        reinterpret_cast<uint4*>(g)[i] = bf8_pack(f);
+      }
+      for (int c = (nv << 3) + threadIdx.x; c < V; c += blockDim.x)
+        g[c] = __float2bfloat16((__expf(__bfloat162float(x[c]) - M) * inv - (c == label ? 1.f : 0.f)) * grad_scale);
+    }
+    __syncthreads();
+  }
+}
+
 void softmax_ce(const void* logits, int is_f32, long long ld, const int* labels, long long rows, int V,
                 float loss_scale, float grad_scale, void* grad, float* out, cudaStream_t s) {
   if (rows <= 0) return;
+  if (!is_f32 && V >= 2048 && (ld % 8) == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
+      (grad == nullptr || (reinterpret_cast<uintptr_t>(grad) & 15) == 0)) {
+    const int blocks = (int)(rows < kSMs * 4 ? rows : kSMs * 4);
+    k_softmax_ce_bf16v<<<blocks, 512, 0, s>>>((const bf16*)logits, ld, labels, rows, V, loss_scale, grad_scale,
+                                             (bf16*)grad, out);
+    TNN_CHECK_LAUNCH();
+    return;
+  }
   int threads = V <= 1024 ? 128 : 512;
   int blocks = (int)(rows < kSMs * 8 ? rows : kSMs * 8);
   if (is_f32)

@@ -352,7 +352,8 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
   const bool vec = (C & 7) == 0;
   uint64_t seed = ma.seed;
   if (MODE == 2 && ma.p > 0.f && ma.seed_ptr) seed ^= (*ma.seed_ptr) * 0x9E3779B97F4A7C15ull;
-  constexpr int U = 2;
+  // rows in flight per thread: the bit-mask / no-mask modes read two tensors per row and can afford four
+  constexpr int U = (MODE == 0 || MODE == 3) ? 4 : 2;
   for (int g0 = 0; g0 < m.groups; g0 += m.lpr) {
     const int g = g0 + m.cg;
     float acc[2][8];       // sum g, sum g * (x - mean); the invstd factor is applied once at the end
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
         store8(dx, row, C, g, d);
       };
       if (vec) {
-        constexpr int U = 2;
+        constexpr int U = ((MODE == 0 || MODE == 3) && !EXTRA) ? 3 : 2;
         for (; r + (U - 1) * stride < M; r += U * stride) {
           uint4 qd[U], qx[U], qy[U], qe[U];
           unsigned int qb[U];
