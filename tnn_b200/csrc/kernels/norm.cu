@@ -18,6 +18,7 @@ namespace tnn {
 // bytes in flight to saturate HBM3e).  block = 256 threads = lpr channel-groups x rpb row-lanes.
 // ---------------------------------------------------------------------------------------
 static constexpr int BN_UNROLL = 4;
+static constexpr int BN_STATS_UNROLL = 8;     // the statistics pass holds nothing but its accumulators
 // Partial sums go to one of BN_REPL replica rows and the last CTA folds the replicas.  Each atomic
 // instruction touches 32 different channels, so per-address contention is one lane per CTA; 8
 // replicas keep it at ~74 CTAs per address while the single-CTA fold at the end of every BN
@@ -108,12 +109,18 @@ __device__ __forceinline__ bool last_block_done(unsigned int* counter) {
   return is_last;
 }
 
-static int bn_blocks(long long M, int C) {
+// Grid size: at most 4 CTAs per SM, and chosen so that every row-lane gets a WHOLE number of unrolled
+// passes (`unroll` rows each): the rows left over for the one-load-at-a-time tail loop cost a DRAM
+// round trip apiece (ncu: 20-27 us for a 17 MB tensor, long-scoreboard + barrier stalls).
+static int bn_blocks(long long M, int C, int unroll = BN_UNROLL) {
   int groups = (C + 7) / 8;
   int lpr = groups < 256 ? groups : 256;
   int rpb = 256 / lpr;
-  long long b = (M + (long long)rpb * BN_UNROLL - 1) / ((long long)rpb * BN_UNROLL);
-  if (b > kSMs * 4) b = kSMs * 4;
+  const long long cap = kSMs * 4;
+  long long rpl = (M + (long long)rpb * cap - 1) / ((long long)rpb * cap);     // rows per lane at the cap
+  rpl = (rpl + unroll - 1) / unroll * unroll;
+  long long b = (M + (long long)rpb * rpl - 1) / ((long long)rpb * rpl);
+  if (b > cap) b = cap;
   if (b < 1) b = 1;
   return (int)b;
 }
@@ -138,12 +145,12 @@ __global__ void __launch_bounds__(256)
       const long long stride = (long long)gridDim.x * m.rpb;
       long long r = (long long)blockIdx.x * m.rpb + m.rl;
       if (vec) {
-        for (; r + (BN_UNROLL - 1) * stride < M; r += BN_UNROLL * stride) {
-          uint4 q[BN_UNROLL];
+        for (; r + (BN_STATS_UNROLL - 1) * stride < M; r += BN_STATS_UNROLL * stride) {
+          uint4 q[BN_STATS_UNROLL];
 #pragma unroll
-          for (int u = 0; u < BN_UNROLL; ++u) q[u] = load8raw(x, r + u * stride, C, g);
+          for (int u = 0; u < BN_STATS_UNROLL; ++u) q[u] = load8raw(x, r + u * stride, C, g);
 #pragma unroll
-          for (int u = 0; u < BN_UNROLL; ++u) {
+          for (int u = 0; u < BN_STATS_UNROLL; ++u) {
             float f[8];
             bf8_unpack(q[u], f);
 #pragma unroll
@@ -197,7 +204,7 @@ void bn_train_stats(const void* x, long long M, int C, const float* gamma, const
     cudaFuncSetAttribute(k_bn_stats, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
     configured = true;
   }
-  k_bn_stats<<<bn_blocks(M, C), 256, 256 * 8 * sizeof(float), s>>>(
+  k_bn_stats<<<bn_blocks(M, C, BN_STATS_UNROLL), 256, 256 * 8 * sizeof(float), s>>>(
       (const bf16*)x, M, C, gamma, beta, eps, momentum, running_mean, running_var, save_mean,
       save_invstd, scale_shift, ws, reinterpret_cast<float4*>(pack));
   TNN_CHECK_LAUNCH();
@@ -457,7 +464,7 @@ void bn_bwd_reduce(const void* dy, const void* x, const void* y, long long M, in
     configured = true;
   }
   const int mode = !masked ? 0 : ((bits != nullptr && (C & 7) == 0) ? 3 : (y != nullptr ? 1 : 2));
-  const int grid = bn_blocks(M, C);
+  const int grid = bn_blocks(M, C, (mode == 0 || mode == 3) ? 4 : 2);
   const size_t smem = 256 * 8 * sizeof(float);
 #define TNN_BN_RED(MODE_)                                                                                         \
   k_bn_bwd_reduce<MODE_><<<grid, 256, smem, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, M, C, gamma,    \
@@ -610,7 +617,7 @@ void bn_bwd_apply(const void* dy, const void* x, const void* y, const void* extr
   float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   BnMaskArgs ma{beta, relu, drop_p, seed, seed_ptr, bits};
   const int mode = !masked ? 0 : ((bits != nullptr && (C & 7) == 0) ? 3 : (y != nullptr ? 1 : 2));
-  const int grid = bn_blocks(M, C);
+  const int grid = bn_blocks(M, C, ((mode == 0 || mode == 3) && extra == nullptr) ? 3 : 2);
   const size_t smem = 256 * 8 * sizeof(float);
 #define TNN_BN_APPLY(MODE_, EXTRA_)                                                                              \
   do {                                                                                                           \

@@ -99,7 +99,9 @@ def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, alpha: flo
         return
     C = native.require()
     tiles = ((N + 127) // 128) * ((K + 127) // 128)
-    splits = max(1, min((M + 63) // 64, (2 * 148 + tiles - 1) // tiles))
+    # split-K so that tiles * splits FITS the 2 x 148 resident persistent CTAs (floor, not ceil: 108 tiles
+    # x 3 splits = 324 work items run as two rounds of K/3 each, 108 x 2 = 216 as one round of K/2)
+    splits = max(1, min((M + 63) // 64, (2 * 148) // tiles))
     C.gemm(dy, x, N, K, M, dy.stride(0), x.stride(0), True, True, dw, dw.stride(0), OUT_F32_ATOMIC, 0,
            float(alpha), None, None, splits)
 
