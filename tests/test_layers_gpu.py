@@ -96,6 +96,9 @@ def test_activations(act):
 
 def test_layernorm_groupnorm():
     _check(lambda: L.LayerNormLayer(96, 1e-5, True, "ln"), torch.randn(6, 10, 96))
+    _check(lambda: L.LayerNormLayer(768, 1e-5, True, "ln"), torch.randn(4, 40, 768))      # 3 vectors per lane
+    _check(lambda: L.LayerNormLayer(1280, 1e-5, True, "ln"), torch.randn(2, 33, 1280))    # 5 -> 8-vector variant
+    _check(lambda: L.LayerNormLayer(100, 1e-5, True, "ln"), torch.randn(7, 9, 100))       # scalar fallback (C % 8 != 0)
     _check(lambda: L.GroupNormLayer(4, 32, 1e-5, True, "gn"), torch.randn(3, 5, 5, 32))
 
 
@@ -288,3 +291,14 @@ def test_batchnorm_backward_keep_bits_equal_stored_output_mask(relu, p, C):
     assert _rel(res["1"][1], res["0"][1]) < 1e-2            # identical masks; only the atomic summation order differs
     torch.testing.assert_close(res["0"][2], res["1"][2], atol=2e-2, rtol=1e-3)   # (atomic accumulation order)
     torch.testing.assert_close(res["0"][3], res["1"][3], atol=2e-2, rtol=1e-3)
+
+
+def test_transformer_ffn_residual_block_fuses_shortcut_gradient_into_layernorm_backward():
+    """LN -> Dense -> GELU -> Dense inside a residual block: the shortcut gradient is added by the LayerNorm
+    dx kernel (no separate add); forward / backward must match the fp32 CPU path."""
+    def make():
+        b = LayerBuilder([[24, 256]])
+        fb = b._sub().layernorm(1e-5, True, "ln").dense(512, True, "fc1").activation("gelu", "act").dense(256, True, "fc2")
+        b.residual_block(fb.build(), None, "linear", "res")
+        return b.build()[0]
+    _check(make, torch.randn(4, 24, 256), tol=4e-2, grad_tol=8e-2)

@@ -261,10 +261,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   });
   m.def("layernorm_bwd", [](const Tensor& dy, const Tensor& x, int64_t rows, int C, const OptT& gamma,
                             const Tensor& mean, const Tensor& rstd, const Tensor& dx, const OptT& dgamma,
-                            const OptT& dbeta) {
+                            const OptT& dbeta, const OptT& extra) {
     tnn::layernorm_bwd(vp(dy), vp(x), rows, C, fp(gamma), fp(mean), fp(rstd), vp(dx), fp(dgamma), fp(dbeta),
-                       cur_stream());
-  });
+                       vp(extra), cur_stream());
+  }, py::arg("dy"), py::arg("x"), py::arg("rows"), py::arg("C"), py::arg("gamma"), py::arg("mean"), py::arg("rstd"),
+     py::arg("dx"), py::arg("dgamma"), py::arg("dbeta"), py::arg("extra") = py::none());
   m.def("groupnorm_fwd", [](const Tensor& x, const Tensor& y, int N, int HW, int C, int G, const OptT& gamma,
                             const OptT& beta, double eps, const Tensor& mean, const Tensor& rstd) {
     tnn::groupnorm_fwd(vp(x), vp(y), N, HW, C, G, fp(gamma), fp(beta), (float)eps, fp(mean), fp(rstd),

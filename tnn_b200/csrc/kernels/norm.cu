@@ -688,10 +688,91 @@ __global__ void __launch_bounds__(256)
     }
   }
 }
+// Rows of up to 32 lanes x NV 16-byte vectors (C % 8 == 0, C <= 256 * NV) stay in registers between the
+// statistics and the normalisation: one global read per operand, 16-byte loads and stores
+// (the scalar kernel above re-reads the row with 2-byte loads: 15 us for [8192, 768], 2 TB/s).
+template <int NV>
+__global__ void __launch_bounds__(256)
+    k_ln_fwd_vec(const bf16* __restrict__ x, const bf16* __restrict__ res, bf16* __restrict__ y,
+                 bf16* __restrict__ sum_out, long long rows, int C, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, float* mean, float* rstd) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nvec = C >> 3;
+  for (long long r = warp; r < rows; r += nwarps) {
+    float v[NV][8];
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        bf8_unpack(__ldg(reinterpret_cast<const uint4*>(x + r * C) + vi), v[i]);
+        if (res) {
+          float t[8];
+          bf8_unpack(__ldg(reinterpret_cast<const uint4*>(res + r * C) + vi), t);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i][j] += t[j];
+        }
+        if (sum_out) {
+          const uint4 q = bf8_pack(v[i]);
+          reinterpret_cast<uint4*>(sum_out + r * C)[vi] = q;
+          bf8_unpack(q, v[i]);                       // statistics of the ROUNDED sum, as the scalar path
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s += v[i][j];
+          ss += v[i][j] * v[i][j];
+        }
+      }
+    }
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    const float m = s / C;
+    const float rs = rsqrtf(fmaxf(ss / C - m * m, 0.f) + eps);
+    if (lane == 0) {
+      if (mean) mean[r] = m;
+      if (rstd) rstd[r] = rs;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[j] = (v[i][j] - m) * rs;
+          if (gamma) o[j] = o[j] * __ldg(gamma + vi * 8 + j) + (beta ? __ldg(beta + vi * 8 + j) : 0.f);
+        }
+        reinterpret_cast<uint4*>(y + r * C)[vi] = bf8_pack(o);
+      }
+    }
+  }
+}
+static bool ln_vec_ok(const void* a, const void* b, const void* c, const void* d, int C) {
+  auto al = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return (C % 8) == 0 && C <= 256 * 8 && al(a) && al(b) && al(c) && al(d);
+}
+
 void layernorm_fwd(const void* x, const void* residual, void* y, void* sum_out, long long rows, int C,
                    const float* gamma, const float* beta, float eps, float* mean, float* rstd,
                    cudaStream_t s) {
   if (rows <= 0) return;
+  if (ln_vec_ok(x, residual, y, sum_out, C)) {
+    const int g = grid_for(rows * 32, 256);
+    const int nv = (C / 8 + 31) / 32;
+#define TNN_LN_FWD(NV_)                                                                                      \
+  k_ln_fwd_vec<NV_><<<g, 256, 0, s>>>((const bf16*)x, (const bf16*)residual, (bf16*)y, (bf16*)sum_out, rows, C, \
+                                      gamma, beta, eps, mean, rstd)
+    if (nv <= 1) TNN_LN_FWD(1);
+    else if (nv <= 2) TNN_LN_FWD(2);
+    else if (nv <= 4) TNN_LN_FWD(4);
+    else TNN_LN_FWD(8);
+#undef TNN_LN_FWD
+    TNN_CHECK_LAUNCH();
+    return;
+  }
   int g = grid_for(rows * 32, 256);
   k_ln_fwd<<<g, 256, 0, s>>>((const bf16*)x, (const bf16*)residual, (bf16*)y, (bf16*)sum_out, rows, C,
                              gamma, beta, eps, mean, rstd);
@@ -739,10 +820,134 @@ __global__ void __launch_bounds__(256)
   if (dgamma) atomicAdd(dgamma + c, dg);
   if (dbeta) atomicAdd(dbeta + c, db);
 }
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ extra: the gradient that bypassed this layer through
+// a residual connection, so the block's "main + shortcut" add needs no kernel of its own)
+template <int NV>
+__global__ void __launch_bounds__(256)
+    k_ln_bwd_dx_vec(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ extra,
+                    long long rows, int C, const float* __restrict__ gamma, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, bf16* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int nvec = C >> 3;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const float m = mean[r], rs = rstd[r];
+    float g[NV][8], xh[NV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        bf8_unpack(__ldg(reinterpret_cast<const uint4*>(dy + r * C) + vi), g[i]);
+        bf8_unpack(__ldg(reinterpret_cast<const uint4*>(x + r * C) + vi), xh[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (gamma) g[i][j] *= __ldg(gamma + vi * 8 + j);
+          xh[i][j] = (xh[i][j] - m) * rs;
+          s1 += g[i][j];
+          s2 += g[i][j] * xh[i][j];
+        }
+      }
+    }
+    s1 = warp_sum(s1) / C;
+    s2 = warp_sum(s2) / C;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        float o[8], e[8];
+        if (extra) bf8_unpack(__ldg(reinterpret_cast<const uint4*>(extra + r * C) + vi), e);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[j] = rs * (g[i][j] - s1 - xh[i][j] * s2);
+          if (extra) o[j] += e[j];
+        }
+        reinterpret_cast<uint4*>(dx + r * C)[vi] = bf8_pack(o);
+      }
+    }
+  }
+}
+// dgamma / dbeta: a CTA owns 64 columns (8 vector groups) and a slab of rows; 32 row-lanes x 16-byte loads,
+// shared-memory reduction, one atomic per column and quantity
+__global__ void __launch_bounds__(256)
+    k_ln_bwd_params_vec(const bf16* __restrict__ dy, const bf16* __restrict__ x, long long rows, int C,
+                        const float* __restrict__ mean, const float* __restrict__ rstd, float* dgamma,
+                        float* dbeta, long long rows_per_split) {
+  __shared__ float sg[32][65], sb[32][65];
+  const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * 64 + cg * 8;
+  const long long r_begin = (long long)blockIdx.y * rows_per_split;
+  const long long r_end = min(rows, r_begin + rows_per_split);
+  float ag[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ab[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < C) {
+    for (long long r = r_begin + rl; r < r_end; r += 32) {
+      float g[8], xv[8];
+      bf8_unpack(__ldg(reinterpret_cast<const uint4*>(dy + r * C + c0)), g);
+      bf8_unpack(__ldg(reinterpret_cast<const uint4*>(x + r * C + c0)), xv);
+      const float m = __ldg(mean + r), rs = __ldg(rstd + r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        ag[j] += g[j] * (xv[j] - m) * rs;
+        ab[j] += g[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sg[rl][cg * 8 + j] = ag[j];
+    sb[rl][cg * 8 + j] = ab[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int col = threadIdx.x & 63;
+    const bool is_b = threadIdx.x >= 64;
+    float t = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) t += is_b ? sb[q][col] : sg[q][col];
+    const int c = blockIdx.x * 64 + col;
+    if (c < C) {
+      if (is_b) {
+        if (dbeta) atomicAdd(dbeta + c, t);
+      } else if (dgamma) {
+        atomicAdd(dgamma + c, t);
+      }
+    }
+  }
+}
+
 void layernorm_bwd(const void* dy, const void* x, long long rows, int C, const float* gamma,
                    const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
-                   cudaStream_t s) {
+                   const void* extra, cudaStream_t s) {
   if (rows <= 0) return;
+  if (ln_vec_ok(dy, x, dx, extra, C)) {
+    const int g = grid_for(rows * 32, 256);
+    const int nv = (C / 8 + 31) / 32;
+#define TNN_LN_BWD(NV_)                                                                                          \
+  k_ln_bwd_dx_vec<NV_><<<g, 256, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)extra, rows, C, gamma, mean, \
+                                         rstd, (bf16*)dx)
+    if (nv <= 1) TNN_LN_BWD(1);
+    else if (nv <= 2) TNN_LN_BWD(2);
+    else if (nv <= 4) TNN_LN_BWD(4);
+    else TNN_LN_BWD(8);
+#undef TNN_LN_BWD
+    if (dgamma || dbeta) {
+      const int col_tiles = (C + 63) / 64;
+      int splits = (4 * kSMs + col_tiles - 1) / col_tiles;
+      const long long max_splits = rows / 64 > 0 ? rows / 64 : 1;
+      if (splits > max_splits) splits = (int)max_splits;
+      const long long rps = ((rows + splits - 1) / splits + 31) / 32 * 32;
+      splits = (int)((rows + rps - 1) / rps);
+      k_ln_bwd_params_vec<<<dim3(col_tiles, splits), 256, 0, s>>>((const bf16*)dy, (const bf16*)x, rows, C, mean, rstd,
+                                                                  dgamma, dbeta, rps);
+    }
+    TNN_CHECK_LAUNCH();
+    return;
+  }
+  if (extra != nullptr) {
+    fprintf(stderr, "[tnn_b200] layernorm_bwd: the fused residual-gradient add needs C %% 8 == 0 and 16-byte aligned rows\n");
+    abort();
+  }
   k_ln_bwd_dx<<<grid_for(rows * 32, 256), 256, 0, s>>>((const bf16*)dy, (const bf16*)x, rows, C, gamma,
                                                       mean, rstd, (bf16*)dx);
   if (dgamma || dbeta) {

@@ -112,7 +112,7 @@ void layernorm_fwd(const void* x, const void* residual, void* y, void* sum_out, 
                    cudaStream_t s);
 void layernorm_bwd(const void* dy, const void* x, long long rows, int C, const float* gamma,
                    const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
-                   cudaStream_t s);
+                   const void* extra, cudaStream_t s);
 // GroupNorm on NHWC [N, HW, C] with G groups.
 void groupnorm_fwd(const void* x, void* y, int N, int HW, int C, int G, const float* gamma,
                    const float* beta, float eps, float* mean, float* rstd, cudaStream_t s);

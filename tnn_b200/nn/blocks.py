@@ -16,7 +16,7 @@ from ..ops import attention as attn_ops
 from ..ops import gemm as gemm_ops
 from ..ops import native
 from .layer import Layer, LayerFactory, ParamDescriptor, register
-from .layers import (ActivationLayer, BatchNormLayer, Conv2DLayer, DenseLayer, DropoutLayer, _aligned_rows,
+from .layers import (ActivationLayer, BatchNormLayer, Conv2DLayer, DenseLayer, DropoutLayer, LayerNormLayer, _aligned_rows,
                      _normal_init, _uniform_init, to_bf16)
 
 
@@ -115,10 +115,12 @@ class Sequential(Block):
                         hook(j)
                 break
             if i == 0 and first_extra is not None:
-                if isinstance(layer, BatchNormLayer):
+                if isinstance(layer, (BatchNormLayer, LayerNormLayer)):
                     dy = layer.backward_impl(layer._migrate(dy), mb_id, extra=first_extra)
                     layer._cache.pop(mb_id, None)
                     first_extra = None
+                    if hook is not None:
+                        hook(i)
                     continue
             dy = layer.backward(dy, mb_id)
             if hook is not None:
@@ -128,7 +130,7 @@ class Sequential(Block):
         return dy
 
     def fuses_first_extra(self) -> bool:
-        return len(self.layers) > 0 and isinstance(self.layers[0], BatchNormLayer)
+        return len(self.layers) > 0 and isinstance(self.layers[0], (BatchNormLayer, LayerNormLayer))
 
     def fuses_last_residual(self) -> bool:
         return len(self.layers) > 0 and isinstance(self.layers[-1], (Conv2DLayer, DenseLayer)) and \

@@ -930,7 +930,9 @@ class LayerNormLayer(Layer):
         y = y.to(x.dtype)
         return (y, xf.to(x.dtype)) if return_sum else y
 
-    def backward_impl(self, dy, mb_id):
+    def backward_impl(self, dy, mb_id, extra=None):
+        """``extra``: a gradient to ADD to dx (the residual-branch gradient of the enclosing block), fused
+        into the dx kernel on the GPU."""
         c = self.cache(mb_id)
         C = self.normalized_shape
         gamma = self.params.get("gamma")
@@ -938,8 +940,12 @@ class LayerNormLayer(Layer):
             Cx = native.require()
             dy = to_bf16(dy).contiguous()
             dx = torch.empty_like(dy)
+            fuse = extra is not None and C % 8 == 0 and extra.dtype == torch.bfloat16 and extra.is_contiguous() and \
+                extra.shape == dy.shape
             Cx.layernorm_bwd(dy, c["x"], dy.numel() // C, C, gamma, c["mean"], c["rstd"], dx, self.grads.get("gamma"),
-                             self.grads.get("beta"))
+                             self.grads.get("beta"), extra if fuse else None)
+            if extra is not None and not fuse:
+                dx = dx + extra.to(dx.dtype)
             return dx
         g = dy.float()
         xh = (c["x"] - c["mean"]) * c["rstd"]
@@ -948,6 +954,8 @@ class LayerNormLayer(Layer):
             self.grads["beta"].add_(g.reshape(-1, C).sum(0))
             g = g * gamma
         dx = c["rstd"] * (g - g.mean(-1, keepdim=True) - xh * (g * xh).mean(-1, keepdim=True))
+        if extra is not None:
+            dx = dx + extra.float()
         return dx.to(dy.dtype)
 
     def config_params(self):
