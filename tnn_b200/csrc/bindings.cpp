@@ -162,11 +162,15 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     tnn::act_bwd(vp(x), vp(dy), vp(dx), x.numel(), kind, (float)slope, x.scalar_type() == torch::kFloat32,
                  cur_stream());
   });
-  m.def("dropout_fwd", [](const Tensor& x, const Tensor& y, double p, uint64_t seed, const OptT& state) {
+  m.def("dropout_fwd", [](const Tensor& x, const Tensor& y, double p, uint64_t seed, const OptT& state,
+                          const OptT& residual) {
     // `state` = the fp32[16] device step-state tensor; its uint64 seed counter lives at floats 12..13
     const uint64_t* sp = state.has_value() ? reinterpret_cast<const uint64_t*>(state->data_ptr<float>() + 12) : nullptr;
-    tnn::dropout_fwd(vp(x), vp(y), x.numel(), (float)p, seed, sp, cur_stream());
-  });
+    if (residual.has_value())
+      TORCH_CHECK(residual->scalar_type() == torch::kBFloat16 && residual->is_contiguous() && residual->numel() == x.numel(),
+                  "dropout_fwd: residual must be a contiguous bf16 tensor shaped like x");
+    tnn::dropout_fwd(vp(x), vp(y), x.numel(), (float)p, seed, sp, vp(residual), cur_stream());
+  }, py::arg("x"), py::arg("y"), py::arg("p"), py::arg("seed"), py::arg("state"), py::arg("residual") = py::none());
   m.def("fill_f32", [](const Tensor& x, double v) { tnn::fill_f32(fp(x), x.numel(), (float)v, cur_stream()); });
   m.def("axpy_f32", [](const Tensor& y, const Tensor& x, double a) {
     tnn::axpy_f32(fp(y), fp(x), (float)a, x.numel(), cur_stream());

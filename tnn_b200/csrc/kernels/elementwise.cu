@@ -199,8 +199,10 @@ void act_bwd(const void* x, const void* dy, void* dx, long long n, int kind, flo
 }
 
 // ---------------------------------------------------------------- dropout
+// y = dropout(x) (+ res: the residual branch of the enclosing block, so "x + dropout(f(x))" is one kernel)
 __global__ void k_dropout(const bf16* __restrict__ x, bf16* __restrict__ y, long long n, float p,
-                          float scale, uint64_t seed, const uint64_t* __restrict__ seed_ptr) {
+                          float scale, uint64_t seed, const uint64_t* __restrict__ seed_ptr,
+                          const bf16* __restrict__ res) {
   if (seed_ptr) seed ^= (*seed_ptr) * 0x9E3779B97F4A7C15ull;
   long long nv = (n + 7) / 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv;
@@ -212,18 +214,27 @@ __global__ void k_dropout(const bf16* __restrict__ x, bf16* __restrict__ y, long
       bf8_unpack(reinterpret_cast<const uint4*>(x)[i], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = keep[j] ? f[j] * scale : 0.f;
+      if (res != nullptr) {
+        float r[8];
+        bf8_unpack(__ldg(reinterpret_cast<const uint4*>(res) + i), r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += r[j];
+      }
       reinterpret_cast<uint4*>(y)[i] = bf8_pack(f);
     } else {
-      for (int j = 0; j < 8 && i * 8 + j < n; ++j)
-        y[i * 8 + j] = __float2bfloat16(keep[j] ? __bfloat162float(x[i * 8 + j]) * scale : 0.f);
+      for (int j = 0; j < 8 && i * 8 + j < n; ++j) {
+        float v = keep[j] ? __bfloat162float(x[i * 8 + j]) * scale : 0.f;
+        if (res != nullptr) v += __bfloat162float(res[i * 8 + j]);
+        y[i * 8 + j] = __float2bfloat16(v);
+      }
     }
   }
 }
 void dropout_fwd(const void* x, void* y, long long n, float p, uint64_t seed, const uint64_t* seed_ptr,
-                 cudaStream_t s) {
+                 const void* residual, cudaStream_t s) {
   if (n <= 0) return;
   k_dropout<<<grid_for((n + 7) / 8, 256), 256, 0, s>>>((const bf16*)x, (bf16*)y, n, p, 1.f / (1.f - p), seed,
-                                                      seed_ptr);
+                                                      seed_ptr, (const bf16*)residual);
   TNN_CHECK_LAUNCH();
 }
 

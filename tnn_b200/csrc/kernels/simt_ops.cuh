@@ -27,7 +27,7 @@ void act_bwd(const void* x, const void* dy, void* dx, long long n, int kind, flo
 // backward recomputes it instead of storing it.
 // effective seed = seed ^ (*seed_ptr * golden) when seed_ptr != null (device-resident step counter)
 void dropout_fwd(const void* x, void* y, long long n, float p, uint64_t seed, const uint64_t* seed_ptr,
-                 cudaStream_t s);
+                 const void* residual, cudaStream_t s);
 void fill_f32(float* x, long long n, float v, cudaStream_t s);
 void axpy_f32(float* y, const float* x, float a, long long n, cudaStream_t s);
 void scale_f32(float* x, float a, long long n, cudaStream_t s);

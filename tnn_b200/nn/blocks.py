@@ -99,6 +99,7 @@ class Sequential(Block):
             if i == n - 1 and (last_residual is not None or last_act is not None):
                 x = layer.forward_impl(layer._migrate(x), mb_id, residual=last_residual, act=last_act) \
                     if isinstance(layer, Conv2DLayer) else layer.forward_impl(layer._migrate(x), mb_id, residual=last_residual)
+                # (Dense / Conv2D add it in the GEMM epilogue, Dropout in its own kernel)
             else:
                 x = layer.forward(x, mb_id)
         return x
@@ -133,8 +134,8 @@ class Sequential(Block):
         return len(self.layers) > 0 and isinstance(self.layers[0], (BatchNormLayer, LayerNormLayer))
 
     def fuses_last_residual(self) -> bool:
-        return len(self.layers) > 0 and isinstance(self.layers[-1], (Conv2DLayer, DenseLayer)) and \
-            not getattr(self.layers[-1], "_generic", False)
+        return len(self.layers) > 0 and isinstance(self.layers[-1], (Conv2DLayer, DenseLayer, DropoutLayer)) and \
+            not getattr(self.layers[-1], "_generic", False) and not getattr(self.layers[-1], "fused_into_prev", False)
 
     def output_shape(self, s):
         for layer in self.layers:
@@ -184,10 +185,14 @@ class ResidualBlock(Block):
     def forward_impl(self, x, mb_id):
         short = self.shortcut.forward(x, mb_id) if self.shortcut is not None else x
         act = self.activation
-        fuse = self.main.fuses_last_residual() and act in ("linear", "none", "relu") and \
-            isinstance(self.main.layers[-1], Conv2DLayer)
+        last = self.main.layers[-1] if len(self.main.layers) else None
+        fuse = self.main.fuses_last_residual() and (
+            (isinstance(last, Conv2DLayer) and act in ("linear", "none", "relu")) or
+            (isinstance(last, (DenseLayer, DropoutLayer)) and act in ("linear", "none") and x.is_cuda and
+             short.shape == self.main.output_shape(tuple(x.shape))))
         if fuse:
-            y = self.main.forward_impl(x, mb_id, last_residual=short if short.is_cuda else short,
+            # Conv2D / Dense add the shortcut in the GEMM epilogue, Dropout in its own kernel
+            y = self.main.forward_impl(x, mb_id, last_residual=short,
                                        last_act="relu" if act == "relu" else None)
         else:
             y = _add(self.main.forward(x, mb_id), short, relu=(act == "relu"))

@@ -657,6 +657,14 @@ class ActivationFactory:
 
 
 # =============================================================================== Dropout
+def _residual_add(x, residual):
+    if x.is_cuda and x.dtype == torch.bfloat16 and residual.dtype == torch.bfloat16 and x.shape == residual.shape:
+        o = torch.empty_like(x)
+        native.require().add_bf16(x.contiguous(), residual.contiguous(), o, False)
+        return o
+    return x + residual.to(x.dtype)
+
+
 @register()
 class DropoutLayer(Layer):
     """Inverted dropout, scale 1/(1-p); the GPU mask is a pure function of (seed, index) and is
@@ -668,22 +676,29 @@ class DropoutLayer(Layer):
         self.dropout_rate = float(dropout_rate)
         self.fused_into_prev = False   # set by Sequential when the preceding BatchNorm applies it
 
-    def forward_impl(self, x, mb_id):
+    def forward_impl(self, x, mb_id, residual=None):
+        """``residual`` (the shortcut of the enclosing residual block) is added in the same kernel."""
         if not self.training or self.dropout_rate <= 0 or self.fused_into_prev:
-            return x
+            return x if residual is None else _residual_add(x, residual)
         self._step += 1
         seed = (self.seed * 1000003 + self._step * 7919 + mb_id) & 0x7FFFFFFFFFFFFFFF
         if x.is_cuda:
             seed = (self.seed * 1000003 + (zlib.crc32(self.name.encode()) & 0xFFFFFF) * 7919 + mb_id) & 0x7FFFFFFFFFFFFFFF
             x = to_bf16(x).contiguous()
             y = torch.empty_like(x)
-            native.require().dropout_fwd(x, y, self.dropout_rate, seed, stepstate.get(x.device).dev)
+            res = None
+            if residual is not None:
+                res = to_bf16(residual).contiguous()
+                if res.shape != x.shape:
+                    res = res.expand_as(x).contiguous()
+            native.require().dropout_fwd(x, y, self.dropout_rate, seed, stepstate.get(x.device).dev, res)
             self.cache(mb_id)["seed"] = seed
             return y
         g = torch.Generator().manual_seed(seed & 0x7FFFFFFF)
         keep = (torch.rand(x.shape, generator=g) >= self.dropout_rate).to(x.dtype) / (1 - self.dropout_rate)
         self.cache(mb_id)["keep"] = keep
-        return x * keep
+        y = x * keep
+        return y if residual is None else y + residual.to(y.dtype)
 
     def backward_impl(self, dy, mb_id):
         if not self.training or self.dropout_rate <= 0 or self.fused_into_prev:
