@@ -564,3 +564,41 @@ def test_legacy_matrix_value_semantics():
     assert d.size() == 25 and float(d.data().abs().sum()) == 0.0
     u = Matrix(64, 64).fill_random_uniform(0.25, seed=9)
     assert float(u.data().abs().max()) <= 0.25 and float(u.data().std()) > 0.05
+
+
+def test_step_state_ring_gives_every_step_its_own_source_row():
+    """The async H2D copy of the step state must not share its pinned source with later steps."""
+    import torch
+    from tnn_b200.core import stepstate
+    st = stepstate.StepState(torch.device("cpu"))
+
+    class _Opt:
+        step_count, lr, beta1, beta2, epsilon, weight_decay, decoupled, grad_scale, momentum = 0, 0.1, 0.9, 0.999, 1e-8, 0.0, False, 1.0, 0.0
+    rows = set()
+    for i in range(5):
+        _Opt.step_count = i
+        st.advance(_Opt)
+        rows.add(st.host.data_ptr())
+        assert int(st.host[12:14].view(torch.int64)[0]) == i + 1            # seed counter
+        assert abs(float(st.dev[8]) - (1.0 - 0.9 ** (i + 1))) < 1e-6        # Adam bias correction of THIS step
+    assert len(rows) == 5
+    st.advance(None)                                                        # scalars persist when not refreshed
+    assert abs(float(st.dev[0]) - 0.1) < 1e-7 and int(st.host[12:14].view(torch.int64)[0]) == 6
+
+
+def test_side_stream_bookkeeping_is_a_noop_without_pending_work():
+    from tnn_b200.core import side_stream
+    side_stream.enter()
+    side_stream.enter()
+    side_stream.exit_()
+    side_stream.exit_()
+    side_stream.exit_()          # unbalanced exit must not underflow the depth counter
+    assert side_stream._depth == 0
+    from tnn_b200.ops import gemm
+    assert gemm._STATIC_WEIGHTS is False
+    with gemm.static_weights():
+        assert gemm._STATIC_WEIGHTS is True
+        with gemm.static_weights():
+            pass
+        assert gemm._STATIC_WEIGHTS is True
+    assert gemm._STATIC_WEIGHTS is False
