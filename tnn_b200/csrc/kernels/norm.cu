@@ -195,10 +195,125 @@ __global__ void __launch_bounds__(256)
     if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(ws + (size_t)BN_REPL * 2 * C) = 0u;
   }
 }
+// "Tall" layout of the statistics pass: a CTA owns 64 channels (8 vector groups) and a slab of rows,
+// 32 row-lanes x 8 rows in flight per thread, one shared-memory reduction and 128 atomics per CTA straight
+// into ws[0:2C] (no replicas: a column is touched once per row slab).  The generic kernel above gives
+// every CTA ALL channels, i.e. 2*C atomics per CTA -- 0.5 M atomics and a 16-way replica fold for the
+// 512-channel WRN stage, which is why it needs 20-27 us whatever the tensor size (ncu: long-scoreboard +
+// barrier stalls, 7 % DRAM utilisation).
+__global__ void __launch_bounds__(256)
+    k_bn_stats_tall(const bf16* __restrict__ x, long long M, int C, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float eps, float momentum, float* running_mean,
+                    float* running_var, float* save_mean, float* save_invstd, float* scale_shift, float* ws,
+                    float4* pack, long long rows_per_split, unsigned int total_ctas) {
+  __shared__ float s1[32][65], s2[32][65];
+  const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * 64 + cg * 8;
+  const long long r_begin = (long long)blockIdx.y * rows_per_split;
+  const long long r_end = min(M, r_begin + rows_per_split);
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < C) {
+    long long r = r_begin + rl;
+    for (; r + 7 * 32 < r_end; r += 8 * 32) {
+      uint4 q[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) q[u] = __ldg(reinterpret_cast<const uint4*>(x + (r + u * 32) * C + c0));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        float f[8];
+        bf8_unpack(q[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a[j] += f[j];
+          b[j] += f[j] * f[j];
+        }
+      }
+    }
+    for (; r < r_end; r += 32) {
+      float f[8];
+      bf8_unpack(__ldg(reinterpret_cast<const uint4*>(x + r * C + c0)), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a[j] += f[j];
+        b[j] += f[j] * f[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s1[rl][cg * 8 + j] = a[j];
+    s2[rl][cg * 8 + j] = b[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int col = threadIdx.x & 63;
+    const bool sq = threadIdx.x >= 64;
+    float t = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) t += sq ? s2[q][col] : s1[q][col];
+    const int c = blockIdx.x * 64 + col;
+    if (c < C) atomicAdd(ws + (sq ? C : 0) + c, t);
+  }
+  // last CTA: derive the statistics, reset the accumulators
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* counter = reinterpret_cast<unsigned int*>(ws + (size_t)BN_REPL * 2 * C);
+    is_last = (atomicAdd(counter, 1u) == total_ctas - 1);
+    if (is_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const float inv_m = 1.f / (float)M;
+  const float unbias = M > 1 ? (float)M / (float)(M - 1) : 1.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float s = __ldcg(ws + c), ss = __ldcg(ws + C + c);
+    ws[c] = 0.f;
+    ws[C + c] = 0.f;
+    const float mean = s * inv_m;
+    const float var = fmaxf(ss * inv_m - mean * mean, 0.f);
+    const float invstd = rsqrtf(var + eps);
+    save_mean[c] = mean;
+    save_invstd[c] = invstd;
+    const float gm = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+    scale_shift[c] = gm * invstd;
+    scale_shift[C + c] = bt - mean * gm * invstd;
+    if (pack) pack[c] = make_float4(invstd, -mean * invstd, gm * invstd, bt - mean * gm * invstd);
+    if (running_mean) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * unbias;
+    }
+  }
+}
+
 void bn_train_stats(const void* x, long long M, int C, const float* gamma, const float* beta,
                     float eps, float momentum, float* running_mean, float* running_var,
                     float* save_mean, float* save_invstd, float* scale_shift, float* ws, float* pack,
                     cudaStream_t s) {
+  {
+    static int tall = -1;
+    if (tall < 0) {
+      const char* e = getenv("TNN_BN_STATS_TALL");
+      tall = (e != nullptr) ? atoi(e) : 1;
+    }
+    if (tall && (C % 8) == 0 && M >= 256 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+      const int col_tiles = (C + 63) / 64;
+      int splits = (4 * kSMs + col_tiles - 1) / col_tiles;
+      const long long max_splits = M / 256 > 0 ? M / 256 : 1;              // >= one 8-deep pass per thread
+      if (splits > max_splits) splits = (int)max_splits;
+      if (splits < 1) splits = 1;
+      const long long rps = ((M + splits - 1) / splits + 31) / 32 * 32;
+      splits = (int)((M + rps - 1) / rps);
+      dim3 grid(col_tiles, splits);
+      k_bn_stats_tall<<<grid, 256, 0, s>>>((const bf16*)x, M, C, gamma, beta, eps, momentum, running_mean, running_var,
+                                           save_mean, save_invstd, scale_shift, ws, reinterpret_cast<float4*>(pack), rps,
+                                           (unsigned int)(col_tiles * splits));
+      TNN_CHECK_LAUNCH();
+      return;
+    }
+  }
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(k_bn_stats, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
