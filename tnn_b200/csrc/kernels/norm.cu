@@ -563,6 +563,94 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 3)
     if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(ws + (size_t)BN_REPL * 2 * C) = 0u;
   }
 }
+// Tall layout of the backward reduction (same scheme as k_bn_stats_tall): 64 channels x a slab of rows per
+// CTA, 4 rows (dy, x, keep bits) in flight per thread, 128 atomics per CTA into ws[0:2C].
+template <int MODE>     // 0: dy as is, 3: keep bits
+__global__ void __launch_bounds__(256)
+    k_bn_bwd_reduce_tall(const bf16* __restrict__ dy, const bf16* __restrict__ x, long long M, int C,
+                         const float* __restrict__ gamma, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, float dscale, float* dgamma, float* dbeta, float* coef,
+                         float* ws, const uint8_t* __restrict__ bits, long long rows_per_split, unsigned int total_ctas) {
+  __shared__ float s1[32][65], s2[32][65];
+  const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * 64 + cg * 8;
+  const int groups = C >> 3, g = c0 >> 3;
+  const long long r_begin = (long long)blockIdx.y * rows_per_split;
+  const long long r_end = min(M, r_begin + rows_per_split);
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < C) {
+    float mu[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mu[j] = __ldg(mean + c0 + j);
+    auto one = [&](const uint4& qd, const uint4& qx, unsigned int kb) {
+      float d[8], xv[8];
+      bf8_unpack(qd, d);
+      bf8_unpack(qx, xv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float gg = d[j];
+        if (MODE == 3) gg = ((kb >> j) & 1u) ? gg * dscale : 0.f;
+        a[j] += gg;
+        b[j] += gg * (xv[j] - mu[j]);
+      }
+    };
+    long long r = r_begin + rl;
+    for (; r + 3 * 32 < r_end; r += 4 * 32) {
+      uint4 qd[4], qx[4];
+      unsigned int kb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        qd[u] = __ldg(reinterpret_cast<const uint4*>(dy + (r + u * 32) * C + c0));
+        qx[u] = __ldg(reinterpret_cast<const uint4*>(x + (r + u * 32) * C + c0));
+        kb[u] = (MODE == 3) ? __ldg(bits + (r + u * 32) * groups + g) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) one(qd[u], qx[u], kb[u]);
+    }
+    for (; r < r_end; r += 32)
+      one(__ldg(reinterpret_cast<const uint4*>(dy + r * C + c0)), __ldg(reinterpret_cast<const uint4*>(x + r * C + c0)),
+          (MODE == 3) ? __ldg(bits + r * groups + g) : 0u);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s1[rl][cg * 8 + j] = a[j];
+    s2[rl][cg * 8 + j] = b[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int col = threadIdx.x & 63;
+    const bool second = threadIdx.x >= 64;
+    float t = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) t += second ? s2[q][col] : s1[q][col];
+    const int c = blockIdx.x * 64 + col;
+    if (c < C) atomicAdd(ws + (second ? C : 0) + c, t);
+  }
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* counter = reinterpret_cast<unsigned int*>(ws + (size_t)BN_REPL * 2 * C);
+    is_last = (atomicAdd(counter, 1u) == total_ctas - 1);
+    if (is_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const float inv_m = 1.f / (float)M;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float is = invstd[c];
+    const float db = __ldcg(ws + c), dg = __ldcg(ws + C + c) * is;
+    ws[c] = 0.f;
+    ws[C + c] = 0.f;
+    if (dbeta) dbeta[c] += db;
+    if (dgamma) dgamma[c] += dg;
+    coef[c] = (gamma ? gamma[c] : 1.f) * is;
+    coef[C + c] = db * inv_m;
+    coef[2 * C + c] = dg * inv_m;
+  }
+}
+
 void bn_bwd_reduce(const void* dy, const void* x, const void* y, long long M, int C,
                    const float* gamma, const float* save_mean, const float* save_invstd,
                    int masked, float drop_p, float* dgamma, float* dbeta, float* coef, float* ws,
@@ -579,6 +667,33 @@ void bn_bwd_reduce(const void* dy, const void* x, const void* y, long long M, in
     configured = true;
   }
   const int mode = !masked ? 0 : ((bits != nullptr && (C & 7) == 0) ? 3 : (y != nullptr ? 1 : 2));
+  {
+    static int tall = -1;
+    if (tall < 0) {
+      const char* e = getenv("TNN_BN_STATS_TALL");
+      tall = (e != nullptr) ? atoi(e) : 1;
+    }
+    if (tall && (mode == 0 || mode == 3) && (C % 8) == 0 && M >= 256 &&
+        ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x)) & 15) == 0) {
+      const int col_tiles = (C + 63) / 64;
+      int splits = (4 * kSMs + col_tiles - 1) / col_tiles;
+      const long long max_splits = M / 128 > 0 ? M / 128 : 1;              // >= one 4-deep pass per thread
+      if (splits > max_splits) splits = (int)max_splits;
+      if (splits < 1) splits = 1;
+      const long long rps = ((M + splits - 1) / splits + 31) / 32 * 32;
+      splits = (int)((M + rps - 1) / rps);
+      dim3 grid2(col_tiles, splits);
+      const unsigned int total = (unsigned int)(col_tiles * splits);
+      if (mode == 0)
+        k_bn_bwd_reduce_tall<0><<<grid2, 256, 0, s>>>((const bf16*)dy, (const bf16*)x, M, C, gamma, save_mean, save_invstd, ds,
+                                                     dgamma, dbeta, coef, ws, bits, rps, total);
+      else
+        k_bn_bwd_reduce_tall<3><<<grid2, 256, 0, s>>>((const bf16*)dy, (const bf16*)x, M, C, gamma, save_mean, save_invstd, ds,
+                                                     dgamma, dbeta, coef, ws, bits, rps, total);
+      TNN_CHECK_LAUNCH();
+      return;
+    }
+  }
   const int grid = bn_blocks(M, C, (mode == 0 || mode == 3) ? 4 : 2);
   const size_t smem = 256 * 8 * sizeof(float);
 #define TNN_BN_RED(MODE_)                                                                                         \
