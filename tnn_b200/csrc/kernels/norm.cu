@@ -839,6 +839,98 @@ void bn_bwd_coef(float* ws, long long M, int C, const float* gamma, const float*
   TNN_CHECK_LAUNCH();
 }
 
+// Tall layout of the backward apply (see k_bn_stats_tall): 64 channels x a slab of rows per CTA; the
+// per-channel constants are loaded once per thread, the fused bias-gradient column sums cost 64 atomics
+// per CTA instead of C.
+template <int MODE, bool EXTRA>     // MODE 0: dy as is, 3: keep bits
+__global__ void __launch_bounds__(256)
+    k_bn_bwd_apply_tall(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ extra,
+                        bf16* __restrict__ dx, long long M, int C, const float* __restrict__ mean,
+                        const float* __restrict__ invstd, const float* __restrict__ coef, float dscale,
+                        float* colsum_out, float* colsum_ws, const uint8_t* __restrict__ bits,
+                        long long rows_per_split, unsigned int total_ctas) {
+  __shared__ float s1[32][65];
+  const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * 64 + cg * 8;
+  const int groups = C >> 3, g = c0 >> 3;
+  const long long r_begin = (long long)blockIdx.y * rows_per_split;
+  const long long r_end = min(M, r_begin + rows_per_split);
+  float csum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < C) {
+    float ca[8], cb[8], cd[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float mu = __ldg(mean + c0 + j), is = __ldg(invstd + c0 + j);
+      const float c1 = __ldg(coef + C + c0 + j), c2 = __ldg(coef + 2 * C + c0 + j);
+      ca[j] = __ldg(coef + c0 + j);
+      cb[j] = -ca[j] * c2 * is;
+      cd[j] = ca[j] * (c2 * is * mu - c1);
+    }
+    auto one = [&](long long row, const uint4& qd, const uint4& qx, const uint4& qe, unsigned int kb) {
+      float d[8], xv[8], ev[8];
+      bf8_unpack(qd, d);
+      bf8_unpack(qx, xv);
+      if (EXTRA) bf8_unpack(qe, ev);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float gg = d[j];
+        if (MODE == 3) gg = ((kb >> j) & 1u) ? gg * dscale : 0.f;
+        float v = ca[j] * gg + cb[j] * xv[j] + cd[j];
+        if (EXTRA) v += ev[j];
+        d[j] = v;
+        csum[j] += v;
+      }
+      *reinterpret_cast<uint4*>(dx + row * C + c0) = bf8_pack(d);
+    };
+    constexpr int U = (EXTRA || MODE == 3) ? 2 : 4;
+    long long r = r_begin + rl;
+    for (; r + (U - 1) * 32 < r_end; r += U * 32) {
+      uint4 qd[U], qx[U], qe[U];
+      unsigned int kb[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        qd[u] = __ldg(reinterpret_cast<const uint4*>(dy + (r + u * 32) * C + c0));
+        qx[u] = __ldg(reinterpret_cast<const uint4*>(x + (r + u * 32) * C + c0));
+        if (EXTRA) qe[u] = __ldg(reinterpret_cast<const uint4*>(extra + (r + u * 32) * C + c0));
+        kb[u] = (MODE == 3) ? __ldg(bits + (r + u * 32) * groups + g) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) one(r + u * 32, qd[u], qx[u], qe[u], kb[u]);
+    }
+    for (; r < r_end; r += 32) {
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      one(r, __ldg(reinterpret_cast<const uint4*>(dy + r * C + c0)), __ldg(reinterpret_cast<const uint4*>(x + r * C + c0)),
+          EXTRA ? __ldg(reinterpret_cast<const uint4*>(extra + r * C + c0)) : z, (MODE == 3) ? __ldg(bits + r * groups + g) : 0u);
+    }
+  }
+  if (colsum_out == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[rl][cg * 8 + j] = csum[j];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) t += s1[q][threadIdx.x];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < C) atomicAdd(colsum_ws + c, t);
+  }
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* counter = reinterpret_cast<unsigned int*>(colsum_ws + (size_t)BN_REPL * C);
+    is_last = (atomicAdd(counter, 1u) == total_ctas - 1);
+    if (is_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    colsum_out[c] = __ldcg(colsum_ws + c);
+    colsum_ws[c] = 0.f;
+  }
+}
+
 void bn_bwd_apply(const void* dy, const void* x, const void* y, const void* extra, void* dx,
                   long long M, int C, const float* save_mean, const float* save_invstd,
                   const float* coef, int masked, float drop_p, float* colsum_out, float* colsum_ws,
@@ -847,6 +939,39 @@ void bn_bwd_apply(const void* dy, const void* x, const void* y, const void* extr
   float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   BnMaskArgs ma{beta, relu, drop_p, seed, seed_ptr, bits};
   const int mode = !masked ? 0 : ((bits != nullptr && (C & 7) == 0) ? 3 : (y != nullptr ? 1 : 2));
+  {
+    static int tall = -1;
+    if (tall < 0) {
+      const char* e = getenv("TNN_BN_STATS_TALL");
+      tall = (e != nullptr) ? atoi(e) : 1;
+    }
+    auto al = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (tall && (mode == 0 || mode == 3) && (C % 8) == 0 && M >= 256 && al(dy) && al(x) && al(extra) && al(dx)) {
+      const int col_tiles = (C + 63) / 64;
+      int splits = (4 * kSMs + col_tiles - 1) / col_tiles;
+      const long long max_splits = M / 128 > 0 ? M / 128 : 1;
+      if (splits > max_splits) splits = (int)max_splits;
+      if (splits < 1) splits = 1;
+      const long long rps = ((M + splits - 1) / splits + 31) / 32 * 32;
+      splits = (int)((M + rps - 1) / rps);
+      dim3 grid2(col_tiles, splits);
+      const unsigned int total = (unsigned int)(col_tiles * splits);
+#define TNN_BN_APPLY_TALL(MODE_, EXTRA_)                                                                          \
+  k_bn_bwd_apply_tall<MODE_, EXTRA_><<<grid2, 256, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)extra,   \
+                                                           (bf16*)dx, M, C, save_mean, save_invstd, coef, ds,      \
+                                                           colsum_out, colsum_ws, bits, rps, total)
+      if (extra != nullptr) {
+        if (mode == 0) TNN_BN_APPLY_TALL(0, true);
+        else TNN_BN_APPLY_TALL(3, true);
+      } else {
+        if (mode == 0) TNN_BN_APPLY_TALL(0, false);
+        else TNN_BN_APPLY_TALL(3, false);
+      }
+#undef TNN_BN_APPLY_TALL
+      TNN_CHECK_LAUNCH();
+      return;
+    }
+  }
   const int grid = bn_blocks(M, C, 2);
   const size_t smem = 256 * 8 * sizeof(float);
 #define TNN_BN_APPLY(MODE_, EXTRA_)                                                                              \
