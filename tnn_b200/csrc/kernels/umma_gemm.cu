@@ -1397,13 +1397,14 @@ void gemm_bf16(const void* A, const void* B, int M, int N, int K, long long lda,
   }
   int bn = pick_block_n(N);
   {
-    // wide K-major GEMMs (QKV / FC1 / LM head forward): 128 x 256 tiles, one CTA per SM -- half the B-operand
-    // shared-memory traffic per MMA of the 128 x 128 tile (gemm_bench, B200: qkv 1110 -> 1180, fc1 1144 -> 1237,
-    // 4k square 1188 -> 1459 TFLOP/s).  TNN_GEMM_AUTO_BN256=0 disables, TNN_GEMM_BLOCK_N overrides.
+    // wide K-major GEMMs (QKV / FC1 / LM head forward) as 128 x 256 tiles, one CTA per SM: faster in the
+    // isolated gemm_bench (qkv 1110 -> 1180, fc1 1144 -> 1237 TFLOP/s) but SLOWER inside the models in a
+    // same-run A/B (GPT-2 prefill 11.6 -> 12.9 ms, training step 14.5 -> 15.3 ms: bias/GELU epilogues of a
+    // 256-wide tile on 4 warps, one CTA per SM) -> opt-in with TNN_GEMM_AUTO_BN256=1.
     static int auto256 = -1;
     if (auto256 < 0) {
       const char* e = getenv("TNN_GEMM_AUTO_BN256");
-      auto256 = (e != nullptr) ? atoi(e) : 1;
+      auto256 = (e != nullptr) ? atoi(e) : 0;
     }
     if (auto256 && getenv("TNN_GEMM_BLOCK_N") == nullptr && !a_mn && !b_mn && splits <= 1 && N >= 1024 &&
         (long long)((M + BLOCK_M - 1) / BLOCK_M) * ((N + 255) / 256) >= 2 * 148)
