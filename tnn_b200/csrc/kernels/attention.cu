@@ -170,59 +170,69 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
       tc_fence_after();
       const int kbase = j * AT_BN;
       const bool need_mask = (kbase + AT_BN > p.Lk) || (CAUSAL && (kbase + AT_BN - 1 > q0 + p.q_offset));
-      // pass 1: row maximum
-      float mx = m;
+      // Probabilities for this tile.  One sweep over S: p = exp2(s*c - m_ref), written as bf16 into the
+      // swizzled P tile, summed in fp32, while the tile's own row maximum is tracked on the side.  m_ref is
+      // the running maximum; only when a row's tile maximum exceeds it by more than 2^16 (never after the
+      // first tiles in practice) does the warp take the classic second sweep with the new maximum and
+      // rescale O / l.  The first tile (m_ref = -inf) always takes both sweeps.  (The separate max sweep
+      // over TMEM cost a quarter of the softmax warps' instructions, and they are the kernel's bottleneck.)
+      auto sweep = [&](float m_ref, float& lsum_out, float& mx_out, bool write) {
+        float lsum = 0.f, mx = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < AT_BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_S + lane_off + c, r);
-        tmem_ld_wait();
-        if (need_mask) {
+        for (int c = 0; c < AT_BN; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_S + lane_off + c, r);
+          tmem_ld_wait();
+          float pr[32];
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
-            const int kj = kbase + c + t;
-            const bool ok = (kj < p.Lk) && (!CAUSAL || kj <= qi);
-            mx = fmaxf(mx, ok ? __uint_as_float(r[t]) * p.scale_log2 : -INFINITY);
+            float sv = __uint_as_float(r[t]) * p.scale_log2;
+            if (need_mask) {
+              const int kj = kbase + c + t;
+              const bool ok = (kj < p.Lk) && (!CAUSAL || kj <= qi);
+              sv = ok ? sv : -INFINITY;
+            }
+            mx = fmaxf(mx, sv);
+            pr[t] = exp2f(sv - m_ref);            // exp2(-inf) = 0 for masked columns
           }
-        } else {
+          if (write) {
+            uint8_t* atom = prow + (c >> 6) * AT_TILE;
+            const int cc0 = ((c >> 5) & 1) * 4;
 #pragma unroll
-          for (int t = 0; t < 32; ++t) mx = fmaxf(mx, __uint_as_float(r[t]) * p.scale_log2);
+            for (int t = 0; t < 4; ++t) {
+              uint4 v;
+              v.x = pack_bf16(pr[t * 8 + 0], pr[t * 8 + 1]);
+              v.y = pack_bf16(pr[t * 8 + 2], pr[t * 8 + 3]);
+              v.z = pack_bf16(pr[t * 8 + 4], pr[t * 8 + 5]);
+              v.w = pack_bf16(pr[t * 8 + 6], pr[t * 8 + 7]);
+              *reinterpret_cast<uint4*>(atom + (((cc0 + t) ^ sw) << 4)) = v;
+            }
+#pragma unroll
+            for (int t = 0; t < 32; ++t) lsum += pr[t];
+          }
         }
+        lsum_out = lsum;
+        mx_out = mx;
+      };
+      float lsum = 0.f, mx_tile = -INFINITY, alpha = 1.f, m_use = m;
+      bool resweep = true;
+      if (j > 0) {
+        // every lane of the warp has a finite running maximum after the first tile unless its row is fully
+        // masked so far (m == -inf is represented by m_use = 0 below, with l = 0)
+        // (a row that has been fully masked so far has m = -inf: sweep against 0 and let the test below
+        //  send the warp through the second sweep as soon as the row sees a finite score)
+        sweep((m == -INFINITY) ? 0.f : m, lsum, mx_tile, true);
+        resweep = __any_sync(0xffffffffu, mx_tile > m + 16.f) != 0;
+      } else {
+        float dummy;
+        sweep(0.f, dummy, mx_tile, false);         // first tile: maximum only
       }
-      const float m_use = (mx == -INFINITY) ? 0.f : mx;
-      const float alpha = exp2f(m - m_use);        // m = -inf on the first tile -> 0
-      // pass 2: probabilities -> bf16 -> swizzled smem, row sum
-      float lsum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < AT_BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_S + lane_off + c, r);
-        tmem_ld_wait();
-        float pr[32];
-#pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          float e = exp2f(__uint_as_float(r[t]) * p.scale_log2 - m_use);
-          if (need_mask) {
-            const int kj = kbase + c + t;
-            const bool ok = (kj < p.Lk) && (!CAUSAL || kj <= qi);
-            e = ok ? e : 0.f;
-          }
-          pr[t] = e;
-        }
-        uint8_t* atom = prow + (c >> 6) * AT_TILE;
-        const int cc0 = ((c >> 5) & 1) * 4;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          uint4 v;
-          v.x = pack_bf16(pr[t * 8 + 0], pr[t * 8 + 1]);
-          v.y = pack_bf16(pr[t * 8 + 2], pr[t * 8 + 3]);
-          v.z = pack_bf16(pr[t * 8 + 4], pr[t * 8 + 5]);
-          v.w = pack_bf16(pr[t * 8 + 6], pr[t * 8 + 7]);
-          *reinterpret_cast<uint4*>(atom + (((cc0 + t) ^ sw) << 4)) = v;
-        }
-        // the sum uses the bf16-rounded values the tensor core will see
-#pragma unroll
-        for (int t = 0; t < 32; ++t) lsum += __bfloat162float(__float2bfloat16(pr[t]));
+      if (resweep) {
+        const float mx = fmaxf(m, mx_tile);
+        m_use = (mx == -INFINITY) ? 0.f : mx;
+        alpha = (m == -INFINITY) ? 0.f : exp2f(m - m_use);      // first tile: nothing accumulated yet
+        float unused;
+        sweep(m_use, lsum, unused, true);
       }
       tc_fence_before();
       mbar_arrive(s_free);               // S columns may be overwritten by the next Q K^T
