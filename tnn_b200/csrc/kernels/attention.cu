@@ -186,14 +186,14 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
           float pr[32];
 #pragma unroll
           for (int t = 0; t < 32; ++t) {
-            float sv = __uint_as_float(r[t]) * p.scale_log2;
+            float raw = __uint_as_float(r[t]);
             if (need_mask) {
               const int kj = kbase + c + t;
               const bool ok = (kj < p.Lk) && (!CAUSAL || kj <= qi);
-              sv = ok ? sv : -INFINITY;
+              raw = ok ? raw : -INFINITY;
             }
-            mx = fmaxf(mx, sv);
-            pr[t] = exp2f(sv - m_ref);            // exp2(-inf) = 0 for masked columns
+            mx = fmaxf(mx, raw);                                   // maximum of the RAW scores (scale > 0)
+            pr[t] = exp2f(fmaf(raw, p.scale_log2, -m_ref));        // exp2(-inf) = 0 for masked columns
           }
           if (write) {
             uint8_t* atom = prow + (c >> 6) * AT_TILE;
@@ -212,7 +212,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
           }
         }
         lsum_out = lsum;
-        mx_out = mx;
+        mx_out = mx * p.scale_log2;          // (-inf stays -inf)
       };
       float lsum = 0.f, mx_tile = -INFINITY, alpha = 1.f, m_use = m;
       bool resweep = true;
