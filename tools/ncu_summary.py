@@ -53,6 +53,26 @@ def main(path):
             except ValueError:
                 vals.append(v)
         print(f"| {name} | {r[gi]} | {r[bi]} | " + " | ".join(vals) + " |")
+    # ---- top warp-stall reasons per distinct kernel (cycles a warp waits per issued instruction)
+    stall_cols = [i for i, h in enumerate(hdr) if h.startswith("smsp__average_warp") and "issue_stalled_" in h and h.endswith(".ratio")]
+    if stall_cols:
+        print("\nTop stall reasons per kernel (warp cycles per issued instruction; first instance of each kernel):\n")
+        print("| kernel | reasons |")
+        print("|---|---|")
+        seen = set()
+        for r in rows[2:]:
+            name = r[ki].split("(")[0].replace("void ", "").replace("tnn::", "")[:60]
+            if name in seen:
+                continue
+            seen.add(name)
+            vals = []
+            for i in stall_cols:
+                try:
+                    vals.append((float(r[i].replace(",", "")), hdr[i].split("issue_stalled_")[1].split(".")[0].replace("_per_issue_active", "")))
+                except ValueError:
+                    pass
+            vals.sort(reverse=True)
+            print(f"| {name} | " + ", ".join(f"{b} {a:.2f}" for a, b in vals[:5]) + " |")
 
 
 if __name__ == "__main__":
