@@ -195,6 +195,18 @@ __global__ void __launch_bounds__(256)
     if (threadIdx.x == 0) *reinterpret_cast<unsigned int*>(ws + (size_t)BN_REPL * 2 * C) = 0u;
   }
 }
+// ---- per-thread asynchronous rings (cp.async): every thread streams ITS OWN rows through a private ring of
+// 16-byte shared-memory slots, RING stages deep, so 2..3 x RING x 16 bytes per thread are in flight without
+// holding them in registers (ncu on the register-staged tall kernels: 30-43 % of DRAM bandwidth,
+// long-scoreboard stalls, 3 CTAs/SM by registers).  No barrier is involved: a thread only ever reads the
+// slots it filled itself, after cp.async.wait_group.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // "Tall" layout of the statistics pass: a CTA owns 64 channels (8 vector groups) and a slab of rows,
 // 32 row-lanes x 8 rows in flight per thread, one shared-memory reduction and 128 atomics per CTA straight
 // into ws[0:2C] (no replicas: a column is touched once per row slab).  The generic kernel above gives
@@ -288,6 +300,100 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// cp.async version of k_bn_stats_tall (same grid, same outputs)
+template <int RING>
+__global__ void __launch_bounds__(256)
+    k_bn_stats_async(const bf16* __restrict__ x, long long M, int C, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float eps, float momentum, float* running_mean,
+                     float* running_var, float* save_mean, float* save_invstd, float* scale_shift, float* ws,
+                     float4* pack, long long rows_per_split, unsigned int total_ctas) {
+  extern __shared__ __align__(16) uint8_t bn_dyn[];
+  uint4* ring = reinterpret_cast<uint4*>(bn_dyn);                        // [RING][256]
+  const int tid = threadIdx.x, cg = tid & 7, rl = tid >> 3;
+  const int c0 = blockIdx.x * 64 + cg * 8;
+  const long long r_begin = (long long)blockIdx.y * rows_per_split;
+  const long long r_end = min(M, r_begin + rows_per_split);
+  const long long r0 = r_begin + rl;
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < C && r0 < r_end) {
+    const int n = (int)((r_end - r0 + 31) / 32);
+#pragma unroll
+    for (int st = 0; st < RING; ++st) {
+      if (st < n) cp_async16(&ring[st * 256 + tid], x + (r0 + 32LL * st) * C + c0);
+      cp_async_commit();
+    }
+    for (int base = 0; base < n; base += RING) {
+#pragma unroll
+      for (int st = 0; st < RING; ++st) {
+        const int i = base + st;
+        cp_async_wait<RING - 1>();
+        if (i < n) {
+          float f[8];
+          bf8_unpack(ring[st * 256 + tid], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            a[j] += f[j];
+            b[j] += f[j] * f[j];
+          }
+        }
+        if (i + RING < n) cp_async16(&ring[st * 256 + tid], x + (r0 + 32LL * (i + RING)) * C + c0);
+        cp_async_commit();
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  float* s1 = reinterpret_cast<float*>(bn_dyn);             // [32][65] (the ring is at least 2 * 32 * 65 floats)
+  float* s2 = s1 + 32 * 65;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s1[rl * 65 + cg * 8 + j] = a[j];
+    s2[rl * 65 + cg * 8 + j] = b[j];
+  }
+  __syncthreads();
+  if (tid < 128) {
+    const int col = tid & 63;
+    const bool sq = tid >= 64;
+    const float* src = sq ? s2 : s1;
+    float t = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) t += src[q * 65 + col];
+    const int c = blockIdx.x * 64 + col;
+    if (c < C) atomicAdd(ws + (sq ? C : 0) + c, t);
+  }
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned int* counter = reinterpret_cast<unsigned int*>(ws + (size_t)BN_REPL * 2 * C);
+    is_last = (atomicAdd(counter, 1u) == total_ctas - 1);
+    if (is_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const float inv_m = 1.f / (float)M;
+  const float unbias = M > 1 ? (float)M / (float)(M - 1) : 1.f;
+  for (int c = tid; c < C; c += blockDim.x) {
+    const float sm_ = __ldcg(ws + c), ss = __ldcg(ws + C + c);
+    ws[c] = 0.f;
+    ws[C + c] = 0.f;
+    const float mean = sm_ * inv_m;
+    const float var = fmaxf(ss * inv_m - mean * mean, 0.f);
+    const float invstd = rsqrtf(var + eps);
+    save_mean[c] = mean;
+    save_invstd[c] = invstd;
+    const float gm = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
+    scale_shift[c] = gm * invstd;
+    scale_shift[C + c] = bt - mean * gm * invstd;
+    if (pack) pack[c] = make_float4(invstd, -mean * invstd, gm * invstd, bt - mean * gm * invstd);
+    if (running_mean) {
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * unbias;
+    }
+  }
+}
+
 void bn_train_stats(const void* x, long long M, int C, const float* gamma, const float* beta,
                     float eps, float momentum, float* running_mean, float* running_var,
                     float* save_mean, float* save_invstd, float* scale_shift, float* ws, float* pack,
@@ -307,6 +413,25 @@ void bn_train_stats(const void* x, long long M, int C, const float* gamma, const
       const long long rps = ((M + splits - 1) / splits + 31) / 32 * 32;
       splits = (int)((M + rps - 1) / rps);
       dim3 grid(col_tiles, splits);
+      static int use_async = -1;
+      if (use_async < 0) {
+        const char* e = getenv("TNN_BN_ASYNC");
+        use_async = (e != nullptr) ? atoi(e) : 1;
+      }
+      if (use_async) {
+        constexpr int RING = 8;
+        constexpr int dyn = RING * 256 * 16;                    // 32 KB
+        static bool cfg = false;
+        if (!cfg) {
+          cudaFuncSetAttribute(k_bn_stats_async<RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+          cfg = true;
+        }
+        k_bn_stats_async<RING><<<grid, 256, dyn, s>>>((const bf16*)x, M, C, gamma, beta, eps, momentum, running_mean,
+                                                      running_var, save_mean, save_invstd, scale_shift, ws,
+                                                      reinterpret_cast<float4*>(pack), rps, (unsigned int)(col_tiles * splits));
+        TNN_CHECK_LAUNCH();
+        return;
+      }
       k_bn_stats_tall<<<grid, 256, 0, s>>>((const bf16*)x, M, C, gamma, beta, eps, momentum, running_mean, running_var,
                                            save_mean, save_invstd, scale_shift, ws, reinterpret_cast<float4*>(pack), rps,
                                            (unsigned int)(col_tiles * splits));
@@ -651,6 +776,113 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// cp.async version of k_bn_bwd_reduce_tall (same grid, same outputs)
+template <int MODE, int RING>
+__global__ void __launch_bounds__(256)
+    k_bn_bwd_reduce_async(const bf16* __restrict__ dy, const bf16* __restrict__ x, long long M, int C,
+                          const float* __restrict__ gamma, const float* __restrict__ mean,
+                          const float* __restrict__ invstd, float dscale, float* dgamma, float* dbeta, float* coef,
+                          float* ws, const uint8_t* __restrict__ bits, long long rows_per_split, unsigned int total_ctas) {
+  extern __shared__ __align__(16) uint8_t bn_dyn[];
+  uint4* ring = reinterpret_cast<uint4*>(bn_dyn);                        // [RING][2][256]
+  const int tid = threadIdx.x, cg = tid & 7, rl = tid >> 3;
+  const int c0 = blockIdx.x * 64 + cg * 8;
+  const int groups = C >> 3, g = c0 >> 3;
+  const long long r_begin = (long long)blockIdx.y * rows_per_split;
+  const long long r_end = min(M, r_begin + rows_per_split);
+  const long long r0 = r_begin + rl;
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, b[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < C && r0 < r_end) {
+    const int n = (int)((r_end - r0 + 31) / 32);
+    float mu[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mu[j] = __ldg(mean + c0 + j);
+    unsigned int kbr[RING];
+#pragma unroll
+    for (int st = 0; st < RING; ++st) {
+      kbr[st] = 0u;
+      if (st < n) {
+        const long long row = r0 + 32LL * st;
+        cp_async16(&ring[(st * 2 + 0) * 256 + tid], dy + row * C + c0);
+        cp_async16(&ring[(st * 2 + 1) * 256 + tid], x + row * C + c0);
+        if (MODE == 3) kbr[st] = __ldg(bits + row * groups + g);
+      }
+      cp_async_commit();
+    }
+    for (int base = 0; base < n; base += RING) {
+#pragma unroll
+      for (int st = 0; st < RING; ++st) {
+        const int i = base + st;
+        cp_async_wait<RING - 1>();
+        if (i < n) {
+          float d[8], xv[8];
+          bf8_unpack(ring[(st * 2 + 0) * 256 + tid], d);
+          bf8_unpack(ring[(st * 2 + 1) * 256 + tid], xv);
+          const unsigned int kb = kbr[st];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float gg = d[j];
+            if (MODE == 3) gg = ((kb >> j) & 1u) ? gg * dscale : 0.f;
+            a[j] += gg;
+            b[j] += gg * (xv[j] - mu[j]);
+          }
+        }
+        const int nx = i + RING;
+        if (nx < n) {
+          const long long row = r0 + 32LL * nx;
+          cp_async16(&ring[(st * 2 + 0) * 256 + tid], dy + row * C + c0);
+          cp_async16(&ring[(st * 2 + 1) * 256 + tid], x + row * C + c0);
+          if (MODE == 3) kbr[st] = __ldg(bits + row * groups + g);
+        }
+        cp_async_commit();
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();                                          // every thread is done with its ring: reuse it
+  float* s1 = reinterpret_cast<float*>(bn_dyn);             // [32][65]
+  float* s2 = s1 + 32 * 65;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s1[rl * 65 + cg * 8 + j] = a[j];
+    s2[rl * 65 + cg * 8 + j] = b[j];
+  }
+  __syncthreads();
+  if (tid < 128) {
+    const int col = tid & 63;
+    const bool second = tid >= 64;
+    const float* src = second ? s2 : s1;
+    float t = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) t += src[q * 65 + col];
+    const int c = blockIdx.x * 64 + col;
+    if (c < C) atomicAdd(ws + (second ? C : 0) + c, t);
+  }
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned int* counter = reinterpret_cast<unsigned int*>(ws + (size_t)BN_REPL * 2 * C);
+    is_last = (atomicAdd(counter, 1u) == total_ctas - 1);
+    if (is_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const float inv_m = 1.f / (float)M;
+  for (int c = tid; c < C; c += blockDim.x) {
+    const float is = invstd[c];
+    const float db = __ldcg(ws + c), dg = __ldcg(ws + C + c) * is;
+    ws[c] = 0.f;
+    ws[C + c] = 0.f;
+    if (dbeta) dbeta[c] += db;
+    if (dgamma) dgamma[c] += dg;
+    coef[c] = (gamma ? gamma[c] : 1.f) * is;
+    coef[C + c] = db * inv_m;
+    coef[2 * C + c] = dg * inv_m;
+  }
+}
+
 void bn_bwd_reduce(const void* dy, const void* x, const void* y, long long M, int C,
                    const float* gamma, const float* save_mean, const float* save_invstd,
                    int masked, float drop_p, float* dgamma, float* dbeta, float* coef, float* ws,
@@ -684,6 +916,29 @@ void bn_bwd_reduce(const void* dy, const void* x, const void* y, long long M, in
       splits = (int)((M + rps - 1) / rps);
       dim3 grid2(col_tiles, splits);
       const unsigned int total = (unsigned int)(col_tiles * splits);
+      static int use_async = -1;
+      if (use_async < 0) {
+        const char* e = getenv("TNN_BN_ASYNC");
+        use_async = (e != nullptr) ? atoi(e) : 1;
+      }
+      if (use_async) {
+        constexpr int RING = 8;
+        constexpr int dyn = RING * 2 * 256 * 16;                  // 64 KB: three CTAs per SM
+        static bool cfg = false;
+        if (!cfg) {
+          cudaFuncSetAttribute(k_bn_bwd_reduce_async<0, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+          cudaFuncSetAttribute(k_bn_bwd_reduce_async<3, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+          cfg = true;
+        }
+        if (mode == 0)
+          k_bn_bwd_reduce_async<0, RING><<<grid2, 256, dyn, s>>>((const bf16*)dy, (const bf16*)x, M, C, gamma, save_mean,
+                                                                 save_invstd, ds, dgamma, dbeta, coef, ws, bits, rps, total);
+        else
+          k_bn_bwd_reduce_async<3, RING><<<grid2, 256, dyn, s>>>((const bf16*)dy, (const bf16*)x, M, C, gamma, save_mean,
+                                                                 save_invstd, ds, dgamma, dbeta, coef, ws, bits, rps, total);
+        TNN_CHECK_LAUNCH();
+        return;
+      }
       if (mode == 0)
         k_bn_bwd_reduce_tall<0><<<grid2, 256, 0, s>>>((const bf16*)dy, (const bf16*)x, M, C, gamma, save_mean, save_invstd, ds,
                                                      dgamma, dbeta, coef, ws, bits, rps, total);
@@ -931,6 +1186,113 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// cp.async version of k_bn_bwd_apply_tall (same grid, same outputs)
+template <int MODE, bool EXTRA, int RING>
+__global__ void __launch_bounds__(256)
+    k_bn_bwd_apply_async(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ extra,
+                         bf16* __restrict__ dx, long long M, int C, const float* __restrict__ mean,
+                         const float* __restrict__ invstd, const float* __restrict__ coef, float dscale,
+                         float* colsum_out, float* colsum_ws, const uint8_t* __restrict__ bits,
+                         long long rows_per_split, unsigned int total_ctas) {
+  constexpr int NT = EXTRA ? 3 : 2;
+  extern __shared__ __align__(16) uint8_t bn_dyn[];
+  uint4* ring = reinterpret_cast<uint4*>(bn_dyn);                        // [RING][NT][256]
+  const int tid = threadIdx.x, cg = tid & 7, rl = tid >> 3;
+  const int c0 = blockIdx.x * 64 + cg * 8;
+  const int groups = C >> 3, g = c0 >> 3;
+  const long long r_begin = (long long)blockIdx.y * rows_per_split;
+  const long long r_end = min(M, r_begin + rows_per_split);
+  const long long r0 = r_begin + rl;
+  float csum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < C && r0 < r_end) {
+    const int n = (int)((r_end - r0 + 31) / 32);
+    float ca[8], cb[8], cd[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float mu = __ldg(mean + c0 + j), is = __ldg(invstd + c0 + j);
+      const float c1 = __ldg(coef + C + c0 + j), c2 = __ldg(coef + 2 * C + c0 + j);
+      ca[j] = __ldg(coef + c0 + j);
+      cb[j] = -ca[j] * c2 * is;
+      cd[j] = ca[j] * (c2 * is * mu - c1);
+    }
+    unsigned int kbr[RING];
+    auto issue = [&](int st, int i) {
+      const long long row = r0 + 32LL * i;
+      cp_async16(&ring[(st * NT + 0) * 256 + tid], dy + row * C + c0);
+      cp_async16(&ring[(st * NT + 1) * 256 + tid], x + row * C + c0);
+      if (EXTRA) cp_async16(&ring[(st * NT + 2) * 256 + tid], extra + row * C + c0);
+    };
+#pragma unroll
+    for (int st = 0; st < RING; ++st) {
+      kbr[st] = 0u;
+      if (st < n) {
+        issue(st, st);
+        if (MODE == 3) kbr[st] = __ldg(bits + (r0 + 32LL * st) * groups + g);
+      }
+      cp_async_commit();
+    }
+    for (int base = 0; base < n; base += RING) {
+#pragma unroll
+      for (int st = 0; st < RING; ++st) {
+        const int i = base + st;
+        cp_async_wait<RING - 1>();
+        if (i < n) {
+          float d[8], xv[8], ev[8];
+          bf8_unpack(ring[(st * NT + 0) * 256 + tid], d);
+          bf8_unpack(ring[(st * NT + 1) * 256 + tid], xv);
+          if (EXTRA) bf8_unpack(ring[(st * NT + 2) * 256 + tid], ev);
+          const unsigned int kb = kbr[st];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float gg = d[j];
+            if (MODE == 3) gg = ((kb >> j) & 1u) ? gg * dscale : 0.f;
+            float v = ca[j] * gg + cb[j] * xv[j] + cd[j];
+            if (EXTRA) v += ev[j];
+            d[j] = v;
+            csum[j] += v;
+          }
+          *reinterpret_cast<uint4*>(dx + (r0 + 32LL * i) * C + c0) = bf8_pack(d);
+        }
+        const int nx = i + RING;
+        if (nx < n) {
+          issue(st, nx);
+          if (MODE == 3) kbr[st] = __ldg(bits + (r0 + 32LL * nx) * groups + g);
+        }
+        cp_async_commit();
+      }
+    }
+  }
+  cp_async_wait<0>();
+  if (colsum_out == nullptr) return;
+  __syncthreads();
+  float* s1 = reinterpret_cast<float*>(bn_dyn);             // [32][65]
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[rl * 65 + cg * 8 + j] = csum[j];
+  __syncthreads();
+  if (tid < 64) {
+    float t = 0.f;
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) t += s1[q * 65 + tid];
+    const int c = blockIdx.x * 64 + tid;
+    if (c < C) atomicAdd(colsum_ws + c, t);
+  }
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned int* counter = reinterpret_cast<unsigned int*>(colsum_ws + (size_t)BN_REPL * C);
+    is_last = (atomicAdd(counter, 1u) == total_ctas - 1);
+    if (is_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int c = tid; c < C; c += blockDim.x) {
+    colsum_out[c] = __ldcg(colsum_ws + c);
+    colsum_ws[c] = 0.f;
+  }
+}
+
 void bn_bwd_apply(const void* dy, const void* x, const void* y, const void* extra, void* dx,
                   long long M, int C, const float* save_mean, const float* save_invstd,
                   const float* coef, int masked, float drop_p, float* colsum_out, float* colsum_ws,
@@ -956,6 +1318,35 @@ void bn_bwd_apply(const void* dy, const void* x, const void* y, const void* extr
       splits = (int)((M + rps - 1) / rps);
       dim3 grid2(col_tiles, splits);
       const unsigned int total = (unsigned int)(col_tiles * splits);
+      static int use_async = -1;
+      if (use_async < 0) {
+        const char* e = getenv("TNN_BN_ASYNC");
+        use_async = (e != nullptr) ? atoi(e) : 1;
+      }
+      if (use_async) {
+#define TNN_BN_APPLY_ASYNC(MODE_, EXTRA_, RING_)                                                                     \
+  do {                                                                                                               \
+    constexpr int dyn = RING_ * ((EXTRA_) ? 3 : 2) * 256 * 16;                                                       \
+    static bool cfg = false;                                                                                         \
+    if (!cfg) {                                                                                                      \
+      cudaFuncSetAttribute(k_bn_bwd_apply_async<MODE_, EXTRA_, RING_>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn); \
+      cfg = true;                                                                                                    \
+    }                                                                                                                \
+    k_bn_bwd_apply_async<MODE_, EXTRA_, RING_><<<grid2, 256, dyn, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)extra, \
+                                                                       (bf16*)dx, M, C, save_mean, save_invstd, coef, ds, \
+                                                                       colsum_out, colsum_ws, bits, rps, total);      \
+  } while (0)
+        if (extra != nullptr) {
+          if (mode == 0) TNN_BN_APPLY_ASYNC(0, true, 5);
+          else TNN_BN_APPLY_ASYNC(3, true, 5);
+        } else {
+          if (mode == 0) TNN_BN_APPLY_ASYNC(0, false, 8);
+          else TNN_BN_APPLY_ASYNC(3, false, 8);
+        }
+#undef TNN_BN_APPLY_ASYNC
+        TNN_CHECK_LAUNCH();
+        return;
+      }
 #define TNN_BN_APPLY_TALL(MODE_, EXTRA_)                                                                          \
   k_bn_bwd_apply_tall<MODE_, EXTRA_><<<grid2, 256, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)extra,   \
                                                            (bf16*)dx, M, C, save_mean, save_invstd, coef, ds,      \
