@@ -555,8 +555,99 @@ __global__ void __launch_bounds__(256)
     }
   }
 }
+// Tall / cp.async version of k_bn_apply (no reduction): a CTA owns 64 channels x a slab of rows, every thread
+// streams its x rows through a private ring and writes y (+ the keep-bit byte) straight to global memory.
+template <bool RELU, bool DROP, int RING>
+__global__ void __launch_bounds__(256)
+    k_bn_apply_async(const bf16* __restrict__ x, bf16* __restrict__ y, long long M, int C,
+                     const float* __restrict__ ss, float p, float dscale, uint64_t seed,
+                     const uint64_t* __restrict__ seed_ptr, uint8_t* __restrict__ mask, long long rows_per_split) {
+  extern __shared__ __align__(16) uint8_t bn_dyn[];
+  uint4* ring = reinterpret_cast<uint4*>(bn_dyn);                        // [RING][256]
+  if (DROP && seed_ptr) seed ^= (*seed_ptr) * 0x9E3779B97F4A7C15ull;
+  const int tid = threadIdx.x, cg = tid & 7, rl = tid >> 3;
+  const int c0 = blockIdx.x * 64 + cg * 8;
+  const int groups = C >> 3, g = c0 >> 3;
+  const long long r_begin = (long long)blockIdx.y * rows_per_split;
+  const long long r_end = min(M, r_begin + rows_per_split);
+  const long long r0 = r_begin + rl;
+  if (c0 >= C || r0 >= r_end) return;
+  const int n = (int)((r_end - r0 + 31) / 32);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(ss + c0 + j);
+    sh[j] = __ldg(ss + C + c0 + j);
+  }
+#pragma unroll
+  for (int st = 0; st < RING; ++st) {
+    if (st < n) cp_async16(&ring[st * 256 + tid], x + (r0 + 32LL * st) * C + c0);
+    cp_async_commit();
+  }
+  for (int base = 0; base < n; base += RING) {
+#pragma unroll
+    for (int st = 0; st < RING; ++st) {
+      const int i = base + st;
+      cp_async_wait<RING - 1>();
+      if (i < n) {
+        const long long row = r0 + 32LL * i;
+        float f[8];
+        bf8_unpack(ring[st * 256 + tid], f);
+        bool keep[8];
+        if (DROP) dropout_keep8(seed, row * groups + g, p, keep);
+        unsigned int bits = 0u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v = f[j] * sc[j] + sh[j];
+          if (RELU) v = fmaxf(v, 0.f);
+          if (DROP) v = keep[j] ? v * dscale : 0.f;
+          f[j] = v;
+          bits |= (v != 0.f ? 1u : 0u) << j;
+        }
+        *reinterpret_cast<uint4*>(y + row * C + c0) = bf8_pack(f);
+        if (mask != nullptr) mask[row * groups + g] = (uint8_t)bits;
+      }
+      if (i + RING < n) cp_async16(&ring[st * 256 + tid], x + (r0 + 32LL * (i + RING)) * C + c0);
+      cp_async_commit();
+    }
+  }
+  cp_async_wait<0>();
+}
+
 void bn_apply(const void* x, void* y, long long M, int C, const float* scale_shift, int relu,
               float drop_p, uint64_t seed, const uint64_t* seed_ptr, uint8_t* mask, cudaStream_t s) {
+  {
+    static int use_async = -1;
+    if (use_async < 0) {
+      const char* e = getenv("TNN_BN_ASYNC");
+      const char* t = getenv("TNN_BN_STATS_TALL");
+      use_async = ((e != nullptr) ? atoi(e) : 1) && ((t != nullptr) ? atoi(t) : 1);
+    }
+    if (use_async && (C % 8) == 0 && M >= 256 &&
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+      constexpr int RING = 8;
+      constexpr int dyn = RING * 256 * 16;
+      const int col_tiles = (C + 63) / 64;
+      int splits = (4 * kSMs + col_tiles - 1) / col_tiles;
+      const long long max_splits = M / 256 > 0 ? M / 256 : 1;
+      if (splits > max_splits) splits = (int)max_splits;
+      if (splits < 1) splits = 1;
+      const long long rps = ((M + splits - 1) / splits + 31) / 32 * 32;
+      splits = (int)((M + rps - 1) / rps);
+      dim3 grid(col_tiles, splits);
+      const float dsc = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+#define TNN_BN_FWD_ASYNC(R_, D_)                                                                                  \
+  k_bn_apply_async<R_, D_, RING><<<grid, 256, dyn, s>>>((const bf16*)x, (bf16*)y, M, C, scale_shift, drop_p, dsc, seed, \
+                                                        seed_ptr, mask, rps)
+      if (relu && drop_p > 0.f) TNN_BN_FWD_ASYNC(true, true);
+      else if (relu) TNN_BN_FWD_ASYNC(true, false);
+      else if (drop_p > 0.f) TNN_BN_FWD_ASYNC(false, true);
+      else TNN_BN_FWD_ASYNC(false, false);
+#undef TNN_BN_FWD_ASYNC
+      TNN_CHECK_LAUNCH();
+      return;
+    }
+  }
   int g = bn_blocks(M, C);
   float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   const bf16* xi = (const bf16*)x;
