@@ -49,8 +49,12 @@ struct AttnParams {
   float* lse;            // [B, H, Lq] natural-log LSE, may be null
 };
 
-template <bool CAUSAL>
-__global__ void __launch_bounds__(AT_THREADS, 2)
+// SPLIT = true: eight softmax warps instead of four (320 threads): warps 2..5 own key columns [0,64) of
+// their TMEM-lane quadrant, warps 6..9 columns [64,128), and each thread keeps 32 of the 64 output
+// columns.  The two threads of a query row agree on the running maximum through a flag + (rarely) an
+// exchange that aliases the dead P tile; their partial row sums meet once at the end.
+template <bool CAUSAL, bool SPLIT>
+__global__ void __launch_bounds__(SPLIT ? 320 : AT_THREADS, 2)
     attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   // 2 CTAs/SM need 2 x (112 KB + barriers) <= 227 KB: no alignment slack, so the dynamic window
@@ -92,10 +96,11 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
       mbar_init(&kv_empty[s], 1);
     }
     mbar_init(s_full, 1);
-    mbar_init(s_free, 128);
-    mbar_init(p_full, 128);
+    mbar_init(s_free, SPLIT ? 256 : 128);
+    mbar_init(p_full, SPLIT ? 256 : 128);
     mbar_init(o_full, 1);
-    mbar_init(o_free, 128);
+    mbar_init(o_free, SPLIT ? 256 : 128);
+    tmem_slot[1] = 0u;                       // SPLIT: "some row needs the second sweep" flag (tile index + 1)
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc<256>(tmem_slot);
@@ -151,6 +156,126 @@ __global__ void __launch_bounds__(AT_THREADS, 2)
         umma_commit(o_full);
         umma_commit(&kv_empty[s]);
       }
+    }
+  } else if (SPLIT) {
+    // ------------------------------------------------------------------ softmax / output warps, two threads per row
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quad * 32 + lane;
+    const int qi = q0 + row + p.q_offset;
+    const uint32_t lane_off = static_cast<uint32_t>(quad * 32) << 16;
+    float o[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) o[i] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    uint8_t* prow = sP + half * AT_TILE + row * 128;        // this thread's 64 key columns = atom `half`
+    const int sw = row & 7;
+    float* ex = reinterpret_cast<float*>(sP);               // [2][128] exchange area; aliases P while P is dead
+    volatile uint32_t* flag = tmem_slot + 1;
+    const int cbase = half * 64;
+
+    for (int j = 0; j < nblk; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int kbase = j * AT_BN;
+      const bool need_mask = (kbase + AT_BN > p.Lk) || (CAUSAL && (kbase + AT_BN - 1 > q0 + p.q_offset));
+      auto sweep = [&](float m_ref, float& lsum_out, float& mx_out, bool write) {
+        float lsum = 0.f, mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_S + lane_off + cbase + c, r);
+          tmem_ld_wait();
+          float pr[32];
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            float raw = __uint_as_float(r[t]);
+            if (need_mask) {
+              const int kj = kbase + cbase + c + t;
+              const bool ok = (kj < p.Lk) && (!CAUSAL || kj <= qi);
+              raw = ok ? raw : -INFINITY;
+            }
+            mx = fmaxf(mx, raw);
+            pr[t] = exp2f(fmaf(raw, p.scale_log2, -m_ref));
+          }
+          if (write) {
+            const int cc0 = (c >> 5) * 4;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              uint4 v;
+              v.x = pack_bf16(pr[t * 8 + 0], pr[t * 8 + 1]);
+              v.y = pack_bf16(pr[t * 8 + 2], pr[t * 8 + 3]);
+              v.z = pack_bf16(pr[t * 8 + 4], pr[t * 8 + 5]);
+              v.w = pack_bf16(pr[t * 8 + 6], pr[t * 8 + 7]);
+              *reinterpret_cast<uint4*>(prow + (((cc0 + t) ^ sw) << 4)) = v;
+            }
+#pragma unroll
+            for (int t = 0; t < 32; ++t) lsum += pr[t];
+          }
+        }
+        lsum_out = lsum;
+        mx_out = mx * p.scale_log2;
+      };
+      float lsum = 0.f, mx_tile = -INFINITY, alpha = 1.f, m_use = m;
+      bool resweep = true;
+      if (j > 0) {
+        sweep((m == -INFINITY) ? 0.f : m, lsum, mx_tile, true);
+        if (mx_tile > m + 16.f) *flag = (uint32_t)(j + 1);
+        named_bar_sync(2, 256);                       // all first sweeps done, flag final for this tile
+        resweep = (*flag == (uint32_t)(j + 1));
+      } else {
+        float dummy;
+        sweep(0.f, dummy, mx_tile, false);            // first tile: maximum only (nothing written)
+      }
+      if (resweep) {
+        // agree on the row maximum with the thread that owns the other 64 columns of this row
+        ex[half * 128 + row] = mx_tile;
+        named_bar_sync(2, 256);
+        const float other = ex[(half ^ 1) * 128 + row];
+        named_bar_sync(2, 256);                       // everybody has read before P overwrites the area
+        const float mx = fmaxf(m, fmaxf(mx_tile, other));
+        m_use = (mx == -INFINITY) ? 0.f : mx;
+        alpha = (m == -INFINITY) ? 0.f : exp2f(m - m_use);
+        float unused;
+        sweep(m_use, lsum, unused, true);
+      }
+      tc_fence_before();
+      mbar_arrive(s_free);
+      fence_proxy_async_smem();
+      mbar_arrive(p_full);
+      l = l * alpha + lsum;
+      m = m_use;
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+      {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_PV + lane_off + half * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) o[t] = o[t] * alpha + __uint_as_float(r[t]);
+      }
+      tc_fence_before();
+      mbar_arrive(o_free);
+    }
+    // the last P V product has completed (o_full): P is dead, use it to add the two partial row sums
+    ex[half * 128 + row] = l;
+    named_bar_sync(2, 256);
+    l += ex[(half ^ 1) * 128 + row];
+    const int qrow = q0 + row;
+    if (qrow < p.Lq) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      bf16* dst = p.O + ((long long)b * p.Lq + qrow) * p.o_row + (long long)h * AT_D + half * 32;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        uint4 v;
+        v.x = pack_bf16(o[t * 8 + 0] * inv, o[t * 8 + 1] * inv);
+        v.y = pack_bf16(o[t * 8 + 2] * inv, o[t * 8 + 3] * inv);
+        v.z = pack_bf16(o[t * 8 + 4] * inv, o[t * 8 + 5] * inv);
+        v.w = pack_bf16(o[t * 8 + 6] * inv, o[t * 8 + 7] * inv);
+        reinterpret_cast<uint4*>(dst)[t] = v;
+      }
+      if (half == 0 && p.lse != nullptr)
+        p.lse[((long long)b * p.H + h) * p.Lq + qrow] = (m + log2f(fmaxf(l, 1e-30f))) * 0.6931471805599453f;
     }
   } else {
     // ------------------------------------------------------------------ softmax / output warps
@@ -340,16 +465,26 @@ void attention_fwd_bf16(const void* q, long long q_tok, long long q_batch, const
   p.o_row = (long long)H * AT_D;
   p.lse = lse;
   static bool configured = false;
+  static int split = 0;
   if (!configured) {
-    cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-    cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    cudaFuncSetAttribute(attn_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    cudaFuncSetAttribute(attn_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    cudaFuncSetAttribute(attn_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    cudaFuncSetAttribute(attn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    const char* e = getenv("TNN_ATTN_SPLIT");
+    split = (e != nullptr) ? atoi(e) : 0;
     configured = true;
   }
   dim3 grid((Lq + AT_BM - 1) / AT_BM, H, B);
-  if (causal)
-    attn_fwd_kernel<true><<<grid, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
+  if (split) {
+    if (causal)
+      attn_fwd_kernel<true, true><<<grid, 320, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
+    else
+      attn_fwd_kernel<false, true><<<grid, 320, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
+  } else if (causal)
+    attn_fwd_kernel<true, false><<<grid, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
   else
-    attn_fwd_kernel<false><<<grid, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
+    attn_fwd_kernel<false, false><<<grid, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
   TNN_CHECK_LAUNCH();
 }
 
