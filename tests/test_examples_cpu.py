@@ -24,3 +24,16 @@ def test_trainer_cli_runs_one_synthetic_epoch_on_cpu(tmp_path):
                          env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "epoch 1 done" in out.stdout and "[trainer] done" in out.stdout
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` must exit 0 with exactly one JSON line (the reference is a C++/CMake tree
+    that cannot be pip-installed offline: the line says so)."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference"], capture_output=True,
+                         text=True, timeout=120)
+    assert out.returncode == 0
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and "unavailable" in d
