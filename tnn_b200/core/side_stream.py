@@ -5,7 +5,9 @@ until the optimizer.  Issued on the compute stream it sits between the layer's d
 BatchNorm backward and everything waits for it; issued on a second stream, the tensor-core-bound
 wgrad kernels (one 160 KB CTA per SM, 192 threads) share the SMs with the memory-bound BatchNorm
 backward kernels and fill the last-wave gaps of the persistent dgrad GEMMs.  Inside a captured
-training step the two streams become parallel branches of the CUDA graph.
+training step the two streams become parallel branches of the CUDA graph.  (Reference: one ``Flow`` = one
+CUDA stream per device context, include/device/flow.hpp:28-65, and every layer's dgrad / wgrad are issued
+back to back on it, e.g. src/nn/layers_impl/conv2d_layer.cpp backward.)
 
 Usage (layers):   side_stream.run(device, fn, keep=(tensors...))
 Joined automatically when the OUTERMOST ``Layer.backward`` returns (``enter``/``exit`` depth

@@ -2,7 +2,9 @@
 its per-step scalars from (learning rate, Adam bias corrections, dropout seed counter).  The host
 refreshes it with ONE small pinned->device copy per step, outside any captured CUDA graph, so a
 captured training step can be replayed while lr schedules, bias corrections and dropout masks
-keep changing.
+keep changing.  (The reference passes these scalars BY VALUE to a kernel per parameter tensor and step --
+src/nn/optimizers_impl/cuda/adam_kernels.cu:22,59 take ``bias_correction1/2`` as arguments -- which is exactly what
+cannot be baked into a CUDA graph.)
 
 layout: [0] lr [1] beta1 [2] beta2 [3] eps [4] weight_decay [5] decoupled [6] grad_scale
         [7] momentum [8] 1-beta1^t [9] 1-beta2^t [12..13] uint64 seed counter
