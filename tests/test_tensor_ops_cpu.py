@@ -103,3 +103,32 @@ def test_layout_ops():
     xx = x.clone().requires_grad_(True)
     torch.softmax(xx, -1).backward(g)
     torch.testing.assert_close(ops.softmax_backward(s, g), xx.grad, atol=1e-6, rtol=1e-4)
+
+
+def test_tensor_facade_remaining_members():
+    """clone / resize / ensure / share_from / same_shape / shape_str / scalar arithmetic / statistics
+    (include/tensor/tensor.hpp)."""
+    import pytest
+    import torch
+    from tnn_b200.core import tensor as T
+    a = T.make_tensor([2, 3, 4])
+    T.fill(a, 1.5)
+    b = T.clone(a)
+    b[0, 0, 0] = 9.0
+    assert float(a[0, 0, 0]) == 1.5 and T.same_shape(a, b) and T.shape_str(a) == "[2, 3, 4]"
+    s = T.share_from(a, [6, 4])
+    s[0, 0] = -2.0
+    assert float(a[0, 0, 0]) == -2.0                                # shared storage
+    assert T.capacity(a) >= 24
+    small = T.ensure(a, [3, 4])
+    assert small.data_ptr() == a.data_ptr() and tuple(small.shape) == (3, 4)     # reuses the buffer
+    big = T.ensure(a, [10, 10])
+    assert big.data_ptr() != a.data_ptr() and tuple(big.shape) == (10, 10)
+    assert tuple(T.resize(a, [4, 6]).shape) == (4, 6) and T.resize(a, [4, 6]).data_ptr() == a.data_ptr()
+    x = torch.arange(12, dtype=torch.float32).reshape(3, 4)
+    assert torch.allclose(T.add_scalar(x, 2.0), x + 2) and torch.allclose(T.sub_scalar(x, 1.0), x - 1)
+    assert torch.allclose(T.mul_scalar(x, 0.5), x * 0.5) and torch.allclose(T.div_scalar(x, 4.0), x / 4)
+    with pytest.raises(ZeroDivisionError):
+        T.div_scalar(x, 0.0)
+    assert T.tmin(x) == 0.0 and T.tmax(x) == 11.0 and abs(T.mean(x) - 5.5) < 1e-6
+    assert abs(T.variance(x) - float(x.var(unbiased=False))) < 1e-4

@@ -145,3 +145,64 @@ def aligned(t: torch.Tensor, alignment: int = DEFAULT_ALIGNMENT) -> bool:
 
 def shape_size(shape) -> int:
     return int(math.prod(shape)) if len(shape) else 1
+
+
+# ---- the remaining members of the reference Tensor (include/tensor/tensor.hpp: clone, resize, ensure,
+# ---- share_from, same_shape, shape_str, the scalar arithmetic and the min / max / mean / variance queries)
+def clone(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().clone()
+
+
+def same_shape(a: torch.Tensor, b: torch.Tensor) -> bool:
+    return tuple(a.shape) == tuple(b.shape)
+
+
+def shape_str(t: torch.Tensor) -> str:
+    return "[" + ", ".join(str(int(d)) for d in t.shape) + "]"
+
+
+def capacity(t: torch.Tensor) -> int:
+    """Elements the underlying storage can hold from this tensor's offset (reference: capacity())."""
+    return (t.untyped_storage().nbytes() // t.element_size()) - t.storage_offset()
+
+
+def ensure(t: torch.Tensor, shape) -> torch.Tensor:
+    """A tensor of ``shape`` that reuses ``t``'s storage when it is large enough (grow-only buffer, the
+    reference's ensure()); otherwise a fresh allocation on the same device.  Contents are unspecified."""
+    n = shape_size(shape)
+    if t.is_contiguous() and capacity(t) >= n:
+        return t.as_strided(tuple(shape), torch.empty(tuple(shape), device="meta").stride())
+    return torch.empty(tuple(shape), dtype=t.dtype, device=t.device)
+
+
+def resize(t: torch.Tensor, shape) -> torch.Tensor:
+    """Reference resize(): new shape, old contents dropped unless the element count is unchanged."""
+    if shape_size(shape) == t.numel() and t.is_contiguous():
+        return t.reshape(tuple(shape))
+    return ensure(t, shape)
+
+
+def share_from(src: torch.Tensor, shape=None) -> torch.Tensor:
+    """A second handle on ``src``'s storage (reference share_from()): writes through either are visible in both."""
+    return src.view(src.shape if shape is None else tuple(shape))
+
+
+def _scalar_like(t: torch.Tensor, v: float) -> torch.Tensor:
+    return torch.full((1,), float(v), dtype=t.dtype, device=t.device).expand_as(t).contiguous()
+
+
+def add_scalar(t, v, out=None): return ops.add(t, _scalar_like(t, v), out=out)          # noqa: E704
+def sub_scalar(t, v, out=None): return ops.sub(t, _scalar_like(t, v), out=out)          # noqa: E704
+def mul_scalar(t, v, out=None): return ops.mul(t, _scalar_like(t, v), out=out)          # noqa: E704
+
+
+def div_scalar(t, v, out=None):
+    if v == 0:
+        raise ZeroDivisionError("Division by zero.")
+    return ops.mul(t, _scalar_like(t, 1.0 / v), out=out)
+
+
+def tmin(t: torch.Tensor) -> float: return stats(t)["min"]        # reference Tensor::min()  # noqa: E704
+def tmax(t: torch.Tensor) -> float: return stats(t)["max"]        # reference Tensor::max()  # noqa: E704
+def mean(t: torch.Tensor) -> float: return stats(t)["mean"]                              # noqa: E704
+def variance(t: torch.Tensor) -> float: return stats(t)["variance"]                      # noqa: E704
