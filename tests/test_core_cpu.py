@@ -602,3 +602,35 @@ def test_side_stream_bookkeeping_is_a_noop_without_pending_work():
             pass
         assert gemm._STATIC_WEIGHTS is True
     assert gemm._STATIC_WEIGHTS is False
+
+
+def test_logger_step_log_and_hardware_info(tmp_path):
+    """utils: console+file logger, JSON-lines step log, hardware / memory / affinity probes
+    (reference: include/logging/logger.hpp, include/utils/hardware_info.hpp, thread_affinity.hpp)."""
+    import json
+    from tnn_b200.utils.hardware_info import HardwareInfo, ThreadAffinity, get_memory_usage_kb, get_shape_hash
+    from tnn_b200.utils.logger import GlobalLogger, Logger, StepLog
+    lf = tmp_path / "run.log"
+    log = Logger("unit", str(lf), "debug")
+    log.info("hello", 1)
+    log.debug("dbg")
+    log.warn("careful")
+    assert GlobalLogger.get() is GlobalLogger.get()
+    text = lf.read_text()
+    assert "hello" in text and "careful" in text and "dbg" in text
+    sl = StepLog(str(tmp_path / "steps.jsonl"))
+    sl.write(step=1, loss=2.5)
+    sl.write(step=2, loss=2.0)
+    sl.close()
+    rows = [json.loads(l) for l in (tmp_path / "steps.jsonl").read_text().splitlines()]
+    assert [r["step"] for r in rows] == [1, 2] and rows[1]["loss"] == 2.0
+    hw = HardwareInfo()
+    s = hw.summary()
+    assert "CPU" in s and "RAM" in s
+    assert get_memory_usage_kb() > 1000
+    assert get_shape_hash((2, 3, 4)) == get_shape_hash([2, 3, 4]) != get_shape_hash((4, 3, 2))
+    cur = ThreadAffinity.current()
+    assert len(cur) >= 1
+    one = sorted(cur)[:1]
+    assert ThreadAffinity.pin(one) and ThreadAffinity.current() == set(one)
+    ThreadAffinity.pin(sorted(cur))
