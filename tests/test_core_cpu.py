@@ -634,3 +634,14 @@ def test_logger_step_log_and_hardware_info(tmp_path):
     one = sorted(cur)[:1]
     assert ThreadAffinity.pin(one) and ThreadAffinity.current() == set(one)
     ThreadAffinity.pin(sorted(cur))
+
+
+def test_native_simd_dot_product():
+    """AVX2/FMA dot product of the C++ runtime (reference: the hand-written assembly in include/utils/simd_asm.hpp)."""
+    import torch
+    from tnn_b200.utils.threading import cpu_dot
+    g = torch.Generator().manual_seed(0)
+    for n in (1, 7, 8, 31, 32, 33, 257, 4096, 100003):
+        a, b = torch.randn(n, generator=g), torch.randn(n, generator=g)
+        ref = float((a.double() * b.double()).sum())
+        assert abs(cpu_dot(a, b) - ref) <= 1e-4 * max(1.0, abs(ref)) + 1e-3 * (n ** 0.5) * 1e-2

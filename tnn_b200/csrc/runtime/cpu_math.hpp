@@ -131,4 +131,40 @@ inline void cpu_sgemm(const float* A, const float* B, float* C, int64_t M, int64
   global_pool(threads).parallel_for(M, MB, panel);
 }
 
+
+// ---- SIMD dot product (reference: include/utils/simd_asm.hpp:13-15, hand-written AVX2 assembly).  Here: AVX2 +
+// FMA intrinsics in a function compiled for that target and selected at run time, four independent
+// accumulators (32 floats per iteration), scalar fallback on CPUs without AVX2.
+#if defined(__x86_64__)
+#include <immintrin.h>
+__attribute__((target("avx2,fma"))) inline float cpu_dot_avx2(const float* a, const float* b, int64_t n) {
+  __m256 s0 = _mm256_setzero_ps(), s1 = _mm256_setzero_ps(), s2 = _mm256_setzero_ps(), s3 = _mm256_setzero_ps();
+  int64_t i = 0;
+  for (; i + 32 <= n; i += 32) {
+    s0 = _mm256_fmadd_ps(_mm256_loadu_ps(a + i), _mm256_loadu_ps(b + i), s0);
+    s1 = _mm256_fmadd_ps(_mm256_loadu_ps(a + i + 8), _mm256_loadu_ps(b + i + 8), s1);
+    s2 = _mm256_fmadd_ps(_mm256_loadu_ps(a + i + 16), _mm256_loadu_ps(b + i + 16), s2);
+    s3 = _mm256_fmadd_ps(_mm256_loadu_ps(a + i + 24), _mm256_loadu_ps(b + i + 24), s3);
+  }
+  for (; i + 8 <= n; i += 8) s0 = _mm256_fmadd_ps(_mm256_loadu_ps(a + i), _mm256_loadu_ps(b + i), s0);
+  __m256 s = _mm256_add_ps(_mm256_add_ps(s0, s1), _mm256_add_ps(s2, s3));
+  __m128 lo = _mm256_castps256_ps128(s), hi = _mm256_extractf128_ps(s, 1);
+  lo = _mm_add_ps(lo, hi);
+  lo = _mm_hadd_ps(lo, lo);
+  lo = _mm_hadd_ps(lo, lo);
+  float r = _mm_cvtss_f32(lo);
+  for (; i < n; ++i) r += a[i] * b[i];
+  return r;
+}
+#endif
+inline float cpu_dot(const float* a, const float* b, int64_t n) {
+#if defined(__x86_64__)
+  static const bool has_avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma");
+  if (has_avx2) return cpu_dot_avx2(a, b, n);
+#endif
+  double r = 0.0;
+  for (int64_t i = 0; i < n; ++i) r += (double)a[i] * b[i];
+  return (float)r;
+}
+
 }  // namespace tnn

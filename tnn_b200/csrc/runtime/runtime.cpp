@@ -203,6 +203,10 @@ void runtime_bind(py::module_& m) {
   }, py::arg("a"), py::arg("b"), py::arg("c"), py::arg("M"), py::arg("N"), py::arg("K"), py::arg("trans_a") = false,
      py::arg("trans_b") = false, py::arg("alpha") = 1.0, py::arg("beta") = 0.0, py::arg("lda") = 0, py::arg("ldb") = 0,
      py::arg("ldc") = 0, py::arg("threads") = 0);
+  m.def("cpu_dot", [](int64_t a, int64_t b, int64_t n) {
+    py::gil_scoped_release rel;
+    return cpu_dot(reinterpret_cast<const float*>(a), reinterpret_cast<const float*>(b), n);
+  });
   m.def("parallel_for", [](int64_t n, int64_t grain, const py::function& fn, int threads) {
     // Python callables run under the GIL; this is for API parity and for callables that release it
     global_pool(threads).parallel_for(n, grain, [&](int64_t b, int64_t e) {

@@ -59,3 +59,11 @@ def cpu_gemm(a: torch.Tensor, b: torch.Tensor, trans_a=False, trans_b=False, alp
     C.cpu_sgemm(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, trans_a, trans_b, float(alpha), float(beta),
                 a.stride(0), b.stride(0), out.stride(0), threads)
     return out
+
+
+def cpu_dot(a: torch.Tensor, b: torch.Tensor) -> float:
+    """fp32 dot product through the native AVX2/FMA kernel (reference: the hand-written assembly
+    ``simd_dot_product_asm``, include/utils/simd_asm.hpp:13-15)."""
+    a, b = a.contiguous().float().reshape(-1), b.contiguous().float().reshape(-1)
+    assert a.numel() == b.numel()
+    return float(native.require().cpu_dot(a.data_ptr(), b.data_ptr(), a.numel()))
