@@ -132,3 +132,31 @@ def test_tensor_facade_remaining_members():
         T.div_scalar(x, 0.0)
     assert T.tmin(x) == 0.0 and T.tmax(x) == 11.0 and abs(T.mean(x) - 5.5) < 1e-6
     assert abs(T.variance(x) - float(x.var(unbiased=False))) < 1e-4
+
+
+def test_tensor_utils_col2im_layout_and_diagnostics(capsys):
+    """col2im is the adjoint of im2col; CNHW transposes; NaN/Inf check; value distribution
+    (include/tensor/tensor_utils.hpp, tensor_ops.hpp)."""
+    import pytest
+    import torch
+    from tnn_b200.ops import tensor_ops as ops
+    x = torch.randn(2, 6, 5, 3)
+    for (R, S, st, pd) in [(3, 3, 1, 1), (2, 2, 2, 0), (3, 3, 2, 1)]:
+        col = ops.im2col(x, R, S, st, pd)
+        g = torch.randn_like(col)
+        back = ops.col2im(g, x.shape, R, S, st, pd)
+        # <im2col(x), g> == <x, col2im(g)>
+        assert abs(float((col * g).sum()) - float((x * back).sum())) < 1e-3 * max(1.0, float((col * g).abs().sum()))
+    y = torch.randn(2, 3, 4, 5)
+    assert torch.equal(ops.cnhw_to_nchw(ops.nchw_to_cnhw(y)), y) and ops.nchw_to_cnhw(y).shape == (3, 2, 4, 5)
+    assert ops.check_nan_and_inf(y, "y")
+    bad = y.clone()
+    bad[0, 0, 0, 0] = float("nan")
+    bad[1, 1, 1, 1] = float("inf")
+    assert not ops.check_nan_and_inf(bad, "bad")
+    assert "1 NaN, 1 Inf" in capsys.readouterr().out
+    with pytest.raises(FloatingPointError):
+        ops.check_nan_and_inf(bad, "bad", raise_on_error=True)
+    edges, counts = ops.buckets(torch.arange(100, dtype=torch.float32), 10)
+    assert counts.tolist() == [10] * 10 and float(edges[0]) == 0.0 and float(edges[-1]) == 99.0
+    assert "distribution over 4 buckets" in ops.print_data_distribution(torch.randn(50), 4, "w")

@@ -260,3 +260,65 @@ def softmax_backward(y: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
         return dx
     yf, g = y.float(), dy.float()
     return (yf * (g - (g * yf).sum(-1, keepdim=True))).to(y.dtype)
+
+
+# ---- remaining utilities of include/tensor/tensor_utils.hpp / tensor_ops.hpp --------------------------------
+def col2im(col: torch.Tensor, x_shape, R: int, S: int, stride: int, pad_: int) -> torch.Tensor:
+    """[N*OH*OW, R*S*C] -> [N,H,W,C]: the adjoint of ``im2col`` (every input element sums the col entries that
+    map onto it; gather formulation on the GPU)."""
+    N, H, W, C = x_shape
+    OH, OW = (H + 2 * pad_ - R) // stride + 1, (W + 2 * pad_ - S) // stride + 1
+    if col.is_cuda and col.dtype == torch.bfloat16 and (R * S * C) % 8 == 0:
+        dx = torch.empty((N, H, W, C), dtype=col.dtype, device=col.device)
+        native.require().col2im_nhwc(col.contiguous(), R * S * C, dx, [N, H, W, C, R, S, stride, pad_, OH, OW])
+        return dx
+    c = col.float().reshape(N, OH * OW, R * S, C).permute(0, 3, 2, 1).reshape(N, C * R * S, OH * OW)
+    x = torch.nn.functional.fold(c, (H, W), (R, S), padding=pad_, stride=stride)      # [N, C, H, W]
+    return x.permute(0, 2, 3, 1).contiguous().to(col.dtype)
+
+
+def nchw_to_cnhw(x: torch.Tensor) -> torch.Tensor:
+    return x.permute(1, 0, 2, 3).contiguous()
+
+
+def cnhw_to_nchw(x: torch.Tensor) -> torch.Tensor:
+    return x.permute(1, 0, 2, 3).contiguous()
+
+
+def check_nan_and_inf(x: torch.Tensor, name: str = "tensor", raise_on_error: bool = False) -> bool:
+    """True when every element is finite; otherwise reports the counts (reference: check_nan_and_inf)."""
+    finite = torch.isfinite(x)
+    if bool(finite.all()):
+        return True
+    n_nan, n_inf = int(torch.isnan(x).sum()), int(torch.isinf(x).sum())
+    msg = f"{name}: {n_nan} NaN, {n_inf} Inf of {x.numel()} elements"
+    if raise_on_error:
+        raise FloatingPointError(msg)
+    print("[tnn_b200] " + msg)
+    return False
+
+
+def buckets(x: torch.Tensor, n: int = 10, lo: float | None = None, hi: float | None = None):
+    """Histogram of the finite values: (edges [n+1], counts [n])."""
+    v = x.detach().float().reshape(-1)
+    v = v[torch.isfinite(v)]
+    if v.numel() == 0:
+        return torch.zeros(n + 1), torch.zeros(n, dtype=torch.int64)
+    lo = float(v.min()) if lo is None else lo
+    hi = float(v.max()) if hi is None else hi
+    if hi <= lo:
+        hi = lo + 1.0
+    counts = torch.histc(v.cpu(), bins=n, min=lo, max=hi).to(torch.int64)
+    return torch.linspace(lo, hi, n + 1), counts
+
+
+def print_data_distribution(x: torch.Tensor, n: int = 10, name: str = "tensor") -> str:
+    edges, counts = buckets(x, n)
+    total = max(1, int(counts.sum()))
+    lines = [f"{name}: {x.numel()} elements, distribution over {n} buckets"]
+    for i in range(n):
+        bar = "#" * int(40 * int(counts[i]) / total)
+        lines.append(f"  [{float(edges[i]):+.4g}, {float(edges[i + 1]):+.4g}) {int(counts[i]):>9d} {bar}")
+    s = "\n".join(lines)
+    print(s)
+    return s
