@@ -645,3 +645,26 @@ def test_native_simd_dot_product():
         a, b = torch.randn(n, generator=g), torch.randn(n, generator=g)
         ref = float((a.double() * b.double()).sum())
         assert abs(cpu_dot(a, b) - ref) <= 1e-4 * max(1.0, abs(ref)) + 1e-3 * (n ** 0.5) * 1e-2
+
+
+def test_misc_helpers():
+    """misc.hpp / parser.hpp counterparts."""
+    import enum
+
+    import pytest
+    from tnn_b200.utils import misc
+
+    class Mode(enum.Enum):
+        SYNC = 0
+        SEMI_ASYNC = 1
+    assert misc.from_str(" 12 ", int) == 12 and misc.from_str("1e-3", float) == 1e-3
+    assert misc.from_str("Yes", bool) is True and misc.from_str("off", bool) is False
+    with pytest.raises(ValueError):
+        misc.from_str("maybe", bool)
+    assert misc.from_str("semi_async", Mode) is Mode.SEMI_ASYNC and misc.from_str("0", Mode) is Mode.SYNC
+    assert misc.get_enum_vector(Mode) == [Mode.SYNC, Mode.SEMI_ASYNC]
+    h1 = misc.hash_combine(misc.hash_combine(0, 3), 5)
+    assert h1 == misc.hash_combine(misc.hash_combine(0, 3), 5) != misc.hash_combine(misc.hash_combine(0, 5), 3)
+    calls = []
+    ms = misc.benchmark(lambda: calls.append(1), iters=5, warmup=2)
+    assert len(calls) == 7 and ms >= 0.0
