@@ -668,3 +668,81 @@ def test_misc_helpers():
     calls = []
     ms = misc.benchmark(lambda: calls.append(1), iters=5, warmup=2)
     assert len(calls) == 7 and ms >= 0.0
+
+
+def test_image_folder_loaders_decode_jpeg_trees_and_cache(tmp_path):
+    """TinyImageNet / ImageNet-100 layouts: lazy threaded JPEG decoding, labels from the directory structure /
+    annotation file, optional one-off decoded cache (tiny_imagenet_data_loader.hpp, imagenet100_data_loader.hpp)."""
+    import numpy as np
+    import torch
+    from PIL import Image
+    from tnn_b200.data import DataLoaderFactory, ImageNet100DataLoader, TinyImageNetDataLoader
+    rng = np.random.default_rng(0)
+
+    def jpeg(path, value, hw=(16, 16)):
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        arr = np.full((*hw, 3), value, dtype=np.uint8)
+        Image.fromarray(arr).save(path, quality=95)
+
+    import os
+    # ---- TinyImageNet layout
+    root = tmp_path / "tiny"
+    wnids = ["n01", "n02", "n03"]
+    os.makedirs(root, exist_ok=True)
+    (root / "wnids.txt").write_text("\n".join(wnids) + "\n")
+    for ci, w in enumerate(wnids):
+        for k in range(4):
+            jpeg(str(root / "train" / w / "images" / f"{w}_{k}.JPEG"), 40 + 80 * ci)
+    ann = []
+    for k in range(6):
+        jpeg(str(root / "val" / "images" / f"val_{k}.JPEG"), 40 + 80 * (k % 3))
+        ann.append(f"val_{k}.JPEG\t{wnids[k % 3]}\t0\t0\t1\t1")
+    (root / "val" / "val_annotations.txt").write_text("\n".join(ann) + "\n")
+    tr, va = DataLoaderFactory.create("tiny_imagenet", str(root))
+    assert tr.size() == 12 and va.size() == 6 and tr.get_data_shape() == (64, 64, 3)
+    x, y = tr.get_batch(12)
+    assert x.shape == (12, 64, 64, 3) and x.dtype == torch.float32 and y.dtype == torch.int32
+    for i in range(12):                                   # the pixel level encodes the class
+        assert abs(float(x[i].mean()) * 255 - (40 + 80 * int(y[i]))) < 3.0
+    xv, yv = va.get_batch(6)
+    assert sorted(yv.tolist()) == [0, 0, 1, 1, 2, 2]
+    # decoded cache: same content through the memory-mapped path
+    cached = TinyImageNetDataLoader().cache(str(root), True)
+    assert cached.x is not None and cached.size() == 12
+    xc, yc = cached.get_batch(12)
+    assert torch.equal(yc.sort().values, y.sort().values) and abs(float(xc.mean()) - float(x.mean())) < 1e-3
+    # ---- class-per-directory layout (ImageNet-100), resized to the requested edge
+    root2 = tmp_path / "in100"
+    for split, n in (("train", 3), ("val", 2)):
+        for ci, cname in enumerate(["cat", "dog"]):
+            for k in range(n):
+                jpeg(str(root2 / split / cname / f"{k}.jpg"), 60 + 100 * ci, hw=(20, 30))
+    ld = ImageNet100DataLoader(size=32).load_data(str(root2), True)
+    x2, y2 = ld.get_batch(6)
+    assert x2.shape == (6, 32, 32, 3) and sorted(y2.tolist()) == [0, 0, 0, 1, 1, 1] and ld.class_names == ["cat", "dog"]
+
+
+def test_wifi_loader_columns_normalisation_and_modes(tmp_path):
+    """wifi_data_loader.hpp: column ranges, header handling, z-score normalisation + de-normalisation,
+    regression and classification targets."""
+    import numpy as np
+    import torch
+    from tnn_b200.data import WiFiDataLoader
+    rng = np.random.default_rng(1)
+    feats = rng.normal(-70, 10, size=(50, 6)).astype(np.float32)
+    xy = rng.normal(100, 20, size=(50, 2)).astype(np.float32)
+    floor = rng.integers(0, 4, size=(50, 1)).astype(np.float32)
+    table = np.concatenate([feats, xy, floor], 1)
+    f = tmp_path / "wifi.csv"
+    np.savetxt(f, table, delimiter=",", header=",".join(f"c{i}" for i in range(9)), comments="")
+    reg = WiFiDataLoader(True).load_data(str(f), 0, 6, 6, 8, True)
+    assert reg.size() == 50 and reg.num_features() == 6 and reg.num_outputs() == 2
+    raw_y = reg.y.clone()
+    reg.normalize_data()
+    assert abs(float(reg.x.mean())) < 1e-4 and abs(float(reg.x.std(unbiased=False)) - 1.0) < 5e-2
+    assert torch.allclose(reg.denormalize_targets(reg.y), raw_y, atol=1e-3)
+    xb, yb = reg.get_batch(16)
+    assert xb.shape == (16, 6) and yb.shape == (16, 2)
+    cls = WiFiDataLoader(False).load_data(str(f), 0, 6, 8, 9, True)
+    assert cls.y.dtype == torch.int32 and cls.num_outputs() == int(floor.max()) + 1
+    assert torch.equal(cls.y, torch.from_numpy(floor[:, 0].astype(np.int32)))

@@ -173,28 +173,110 @@ class MNISTDataLoader(RecordImageLoader):
         return self
 
 
-class TinyImageNetDataLoader(BaseDataLoader):
-    """TinyImageNet / ImageNet-100 directory trees of JPEGs.  JPEG decoding needs an image codec;
-    this image ships none usable offline (no PIL/stb), so the loader consumes the ``.npy`` / raw
-    record caches produced by ``python -m tnn_b200.data.prepare`` and raises a clear error otherwise."""
+class ImageFolderDataLoader(BaseDataLoader):
+    """Directory trees of JPEG / PNG images (reference: image_data_loader.hpp + stb_image decoding,
+    tiny_imagenet_data_loader.hpp, imagenet100_data_loader.hpp).
+
+    Two sources, tried in this order:
+      * decoded caches ``<split>_x.npy`` (uint8 NHWC) + ``<split>_y.npy`` (int32) -- memory mapped;
+      * the image tree itself, decoded lazily per batch by a thread pool (PIL releases the GIL while
+        decoding), resized to ``size`` x ``size``.  ``cache()`` writes the caches once.
+    Layouts: TinyImageNet (``train/<wnid>/images/*.JPEG``, ``val/images`` + ``val_annotations.txt``,
+    ``wnids.txt``) and class-per-directory (``train/<class>/*``, ``val/<class>/*`` -- ImageNet-100)."""
+
+    EXTS = (".jpeg", ".jpg", ".png", ".bmp")
 
     def __init__(self, size: int = 64, classes: int = 200):
         super().__init__()
         self.img, self.classes = size, classes
-        self.x = self.y = None
+        self.x = self.y = None                 # caches (memmap) ...
+        self.files: list[str] = []             # ... or the image tree
+        self.labels: np.ndarray | None = None
+        self.class_names: list[str] = []
+        self._pool = None
+
+    # ------------------------------------------------------------------ discovery
+    def _scan(self, path: str, train: bool):
+        split = "train" if train else "val"
+        root = os.path.join(path, split)
+        if not os.path.isdir(root):
+            raise FileNotFoundError(f"expected {root}/ (image tree) or {split}_x.npy / {split}_y.npy in {path}")
+        wn = os.path.join(path, "wnids.txt")
+        ann = os.path.join(root, "val_annotations.txt")
+        if os.path.exists(wn):
+            names = [l.strip() for l in open(wn) if l.strip()]
+        elif os.path.isdir(os.path.join(path, "train")):
+            names = sorted(d for d in os.listdir(os.path.join(path, "train")) if os.path.isdir(os.path.join(path, "train", d)))
+        else:
+            names = sorted(d for d in os.listdir(root) if os.path.isdir(os.path.join(root, d)))
+        index = {n: i for i, n in enumerate(names)}
+        files, labels = [], []
+        if not train and os.path.exists(ann):                       # TinyImageNet validation: flat dir + annotation file
+            for line in open(ann):
+                parts = line.split()
+                if len(parts) >= 2 and parts[1] in index:
+                    files.append(os.path.join(root, "images", parts[0]))
+                    labels.append(index[parts[1]])
+        else:
+            for n in names:
+                d = os.path.join(root, n)
+                if os.path.isdir(os.path.join(d, "images")):
+                    d = os.path.join(d, "images")
+                if not os.path.isdir(d):
+                    continue
+                for f in sorted(os.listdir(d)):
+                    if f.lower().endswith(self.EXTS):
+                        files.append(os.path.join(d, f))
+                        labels.append(index[n])
+        if not files:
+            raise FileNotFoundError(f"no images under {root}")
+        self.files, self.labels, self.class_names = files, np.asarray(labels, dtype=np.int32), names
 
     def load_data(self, path: str, train: bool = True):
         split = "train" if train else "val"
         xf, yf = os.path.join(path, f"{split}_x.npy"), os.path.join(path, f"{split}_y.npy")
-        if not (os.path.exists(xf) and os.path.exists(yf)):
-            raise FileNotFoundError(f"expected decoded caches {xf} / {yf} (uint8 NHWC + int32 labels)")
-        self.x = np.load(xf, mmap_mode="r")
-        self.y = np.load(yf, mmap_mode="r")
+        if os.path.exists(xf) and os.path.exists(yf):
+            self.x = np.load(xf, mmap_mode="r")
+            self.y = np.load(yf, mmap_mode="r")
+        else:
+            self._scan(path, train)
+        self.order = None
         self.reset()
         return self
 
+    # ------------------------------------------------------------------ decoding
+    def _decode(self, f: str) -> np.ndarray:
+        from PIL import Image
+        with Image.open(f) as im:
+            im = im.convert("RGB")
+            if im.size != (self.img, self.img):
+                im = im.resize((self.img, self.img), Image.BILINEAR)
+            return np.asarray(im, dtype=np.uint8)
+
+    def _decode_many(self, files) -> np.ndarray:
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=max(1, self.num_threads))
+        return np.stack(list(self._pool.map(self._decode, files)))
+
+    def cache(self, path: str, train: bool = True, chunk: int = 1024):
+        """Decode the whole split once into ``<split>_x.npy`` / ``<split>_y.npy`` (uint8 NHWC / int32)."""
+        if not self.files:
+            self._scan(path, train)
+        split = "train" if train else "val"
+        out = np.lib.format.open_memmap(os.path.join(path, f"{split}_x.npy"), mode="w+", dtype=np.uint8,
+                                        shape=(len(self.files), self.img, self.img, 3))
+        for i in range(0, len(self.files), chunk):
+            out[i:i + chunk] = self._decode_many(self.files[i:i + chunk])
+        out.flush()
+        np.save(os.path.join(path, f"{split}_y.npy"), self.labels)
+        return self.load_data(path, train)
+
+    # ------------------------------------------------------------------ BaseDataLoader
     def size(self):
-        return 0 if self.x is None else int(self.x.shape[0])
+        if self.x is not None:
+            return int(self.x.shape[0])
+        return len(self.files)
 
     def get_data_shape(self):
         return (self.img, self.img, 3)
@@ -204,11 +286,29 @@ class TinyImageNetDataLoader(BaseDataLoader):
         if idx is None:
             return None
         order = np.sort(idx)
-        x = torch.from_numpy(np.asarray(self.x[order], dtype=np.float32) / 255.0)
-        y = torch.from_numpy(np.asarray(self.y[order], dtype=np.int32))
+        if self.x is not None:
+            xb, yb = np.asarray(self.x[order]), np.asarray(self.y[order], dtype=np.int32)
+        else:
+            xb, yb = self._decode_many([self.files[i] for i in order]), self.labels[order]
+        x = torch.from_numpy(xb.astype(np.float32) / 255.0)
+        y = torch.from_numpy(np.ascontiguousarray(yb, dtype=np.int32))
         if self.augmentation is not None:
             x = self.augmentation.apply_python(x, full=True)
         return x, y
+
+
+class TinyImageNetDataLoader(ImageFolderDataLoader):
+    """TinyImageNet-200, 64 x 64 (tiny_imagenet_data_loader.hpp)."""
+
+    def __init__(self, size: int = 64, classes: int = 200):
+        super().__init__(size, classes)
+
+
+class ImageNet100DataLoader(ImageFolderDataLoader):
+    """ImageNet-100 subset, class-per-directory, resized to 224 x 224 (imagenet100_data_loader.hpp)."""
+
+    def __init__(self, size: int = 224, classes: int = 100):
+        super().__init__(size, classes)
 
 
 class OpenWebTextDataLoader(BaseDataLoader):
@@ -280,6 +380,77 @@ class RegressionCSVDataLoader(BaseDataLoader):
         return self.x[i], self.y[i]
 
 
+class WiFiDataLoader(BaseDataLoader):
+    """UJIIndoorLoc-style CSV (wifi_data_loader.hpp): a block of feature columns (RSSI readings) and a block
+    of target columns, regression (float targets, optionally z-scored) or classification (integer class per
+    row), with the reference's ``normalize_data`` (feature / target mean and std kept for de-normalisation)."""
+
+    def __init__(self, is_regression: bool = True):
+        super().__init__()
+        self.is_regression = bool(is_regression)
+        self.x = self.y = None
+        self.feature_means = self.feature_stds = self.target_means = self.target_stds = None
+        self.is_normalized = False
+
+    def load_data(self, path: str, feature_start_col: int = 0, feature_end_col: int = 0, target_start_col: int = 0,
+                  target_end_col: int = 0, has_header: bool = True):
+        arr = np.loadtxt(path, delimiter=",", skiprows=1 if has_header else 0, dtype=np.float32, ndmin=2)
+        ncol = arr.shape[1]
+        if feature_end_col <= feature_start_col:             # reference default: all but the last column(s)
+            feature_start_col, feature_end_col = 0, ncol - 1
+        if target_end_col <= target_start_col:
+            target_start_col, target_end_col = feature_end_col, ncol
+        self.x = torch.from_numpy(arr[:, feature_start_col:min(feature_end_col, ncol)].copy())
+        t = arr[:, target_start_col:min(target_end_col, ncol)]
+        if self.is_regression:
+            self.y = torch.from_numpy(t.copy())
+        else:
+            self.y = torch.from_numpy(t[:, 0].astype(np.int32))
+        self.is_normalized = False
+        self.order = None
+        self.reset()
+        return self
+
+    def normalize_data(self):
+        if self.x is None or self.x.shape[0] == 0:
+            raise RuntimeError("no data to normalize")
+        self.feature_means = self.x.mean(0)
+        self.feature_stds = self.x.std(0, unbiased=False).clamp_min(1e-8)
+        self.x = (self.x - self.feature_means) / self.feature_stds
+        if self.is_regression:
+            self.target_means = self.y.mean(0)
+            self.target_stds = self.y.std(0, unbiased=False).clamp_min(1e-8)
+            self.y = (self.y - self.target_means) / self.target_stds
+        self.is_normalized = True
+        return self
+
+    def denormalize_targets(self, pred: torch.Tensor) -> torch.Tensor:
+        if not (self.is_normalized and self.is_regression):
+            return pred
+        return pred * self.target_stds.to(pred.device) + self.target_means.to(pred.device)
+
+    def num_features(self) -> int:
+        return 0 if self.x is None else int(self.x.shape[1])
+
+    def num_outputs(self) -> int:
+        if self.y is None:
+            return 0
+        return int(self.y.shape[1]) if self.is_regression else int(self.y.max()) + 1
+
+    def size(self):
+        return 0 if self.x is None else int(self.x.shape[0])
+
+    def get_data_shape(self):
+        return (self.num_features(),)
+
+    def get_batch(self, batch_size: int):
+        idx = self._next_indices(batch_size)
+        if idx is None:
+            return None
+        i = torch.from_numpy(idx)
+        return self.x[i], self.y[i]
+
+
 class SyntheticDataLoader(BaseDataLoader):
     """Random images / tokens of a given shape (benchmarks, tests, no dataset on disk)."""
 
@@ -330,7 +501,16 @@ class DataLoaderFactory:
         if n in ("tiny_imagenet", "tinyimagenet"):
             return TinyImageNetDataLoader(64, 200).load_data(path, True), TinyImageNetDataLoader(64, 200).load_data(path, False)
         if n in ("imagenet100", "imagenet_100"):
-            return TinyImageNetDataLoader(224, 100).load_data(path, True), TinyImageNetDataLoader(224, 100).load_data(path, False)
+            return ImageNet100DataLoader().load_data(path, True), ImageNet100DataLoader().load_data(path, False)
+        if n in ("wifi", "uji", "uji_indoor_loc"):
+            reg = kw.get("is_regression", True)
+            tr = WiFiDataLoader(reg).load_data(os.path.join(path, kw.get("train_file", "trainingData.csv")), **kw.get("columns", {}))
+            va = WiFiDataLoader(reg).load_data(os.path.join(path, kw.get("val_file", "validationData.csv")), **kw.get("columns", {}))
+            return tr, va
+        if n in ("regression", "regression_csv"):
+            nt = kw.get("n_targets", 1)
+            return (RegressionCSVDataLoader(nt).load_data(os.path.join(path, kw.get("train_file", "train.csv"))),
+                    RegressionCSVDataLoader(nt).load_data(os.path.join(path, kw.get("val_file", "val.csv"))))
         if n in ("open_webtext", "openwebtext"):
             L = kw.get("seq_len", 1024)
             return OpenWebTextDataLoader(L).load_data(path, True), OpenWebTextDataLoader(L).load_data(path, False)
