@@ -181,6 +181,9 @@ def test_in_process_pipeline_equals_single_device():
         co.barrier()
         loads = co.report_load()
         assert len(loads) == 3 and all(l["jobs"] > 0 for l in loads)
+        for l in loads:      # the reference's LoadTracker record (load_tracker.hpp)
+            assert l["avg_forward_time"] > 0 and l["avg_backward_time"] > 0
+            assert l["avg_cpu_utilization"] > 0 and l["max_memory_usage"] > 10
     finally:
         co.stop()
         for w in workers:

@@ -53,6 +53,9 @@ class Worker:
         self.stage_id = -1
         self._busy_ns = 0
         self._jobs = 0
+        self._fwd_ns = self._bwd_ns = 0
+        self._fwd_jobs = self._bwd_jobs = 0
+        self._cpu_t0 = (time.process_time(), time.perf_counter())
         self.fault_inject = None          # callable(Message) -> None; tests use it to drop / delay / raise
         self._env_fault = _parse_fault_env(os.environ.get("TNN_FAULT_INJECT", ""))
 
@@ -133,6 +136,23 @@ class Worker:
             if ep and ep.type != Endpoint.IN_PROCESS:
                 self.comm.connect(ep)
 
+    def load_tracker(self) -> dict:
+        """The reference's LoadTracker record (include/distributed/load_tracker.hpp:10-22): average forward /
+        backward time per job in ms, CPU utilisation of this worker process (0..1 per core since start; -1 when
+        unavailable) and peak memory in MB (host RSS, plus the CUDA allocator peak on a GPU stage)."""
+        cpu0, wall0 = self._cpu_t0
+        wall = time.perf_counter() - wall0
+        cpu = (time.process_time() - cpu0) / wall if wall > 0 else -1.0
+        try:
+            import resource
+            rss_mb = resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1024.0
+        except Exception:  # noqa: BLE001
+            rss_mb = -1.0
+        gpu_mb = torch.cuda.max_memory_allocated(self.device) / 2 ** 20 if self.device.type == "cuda" else 0.0
+        return {"avg_forward_time": self._fwd_ns / 1e6 / max(1, self._fwd_jobs),
+                "avg_backward_time": self._bwd_ns / 1e6 / max(1, self._bwd_jobs),
+                "avg_cpu_utilization": cpu, "max_memory_usage": rss_mb, "max_device_memory_usage": gpu_mb}
+
     # ------------------------------------------------------------------ dispatch
     def _reply(self, cmd: CommandType, payload=None, to: Endpoint | None = None):
         self.comm.send_message(Message(cmd, payload), to or self.coord_ep)
@@ -146,6 +166,8 @@ class Worker:
             y = self.model.forward(x, job.mb_id)
             GlobalProfiler.add_event(EventType.COMPUTE, t0, Profiler.now_ns(), f"forward mb {job.mb_id}", self.name)
             self._busy_ns += Profiler.now_ns() - t0
+            self._fwd_ns += Profiler.now_ns() - t0
+            self._fwd_jobs += 1
             self._jobs += 1
             self._reply(CommandType.FORWARD_JOB, Job(y, job.mb_id), self.next_ep if self.next_ep else self.coord_ep)
         elif c == CommandType.BACKWARD_JOB:
@@ -155,6 +177,8 @@ class Worker:
             dx = self.model.backward(g, job.mb_id)
             GlobalProfiler.add_event(EventType.COMPUTE, t0, Profiler.now_ns(), f"backward mb {job.mb_id}", self.name)
             self._busy_ns += Profiler.now_ns() - t0
+            self._bwd_ns += Profiler.now_ns() - t0
+            self._bwd_jobs += 1
             if self.prev_ep and dx is not None:
                 self._reply(CommandType.BACKWARD_JOB, Job(dx, job.mb_id), self.prev_ep)
             else:
@@ -232,7 +256,7 @@ class Worker:
         elif c == CommandType.REPORT_LOAD:
             avg_ms = self._busy_ns / 1e6 / max(1, self._jobs)
             self._reply(CommandType.LOAD_REPORT, json.dumps({"stage": self.stage_id, "avg_forward_backward_ms": avg_ms,
-                                                             "jobs": self._jobs}))
+                                                             "jobs": self._jobs, **self.load_tracker()}))
         elif c == CommandType.HANDSHAKE:
             self._reply(CommandType.HANDSHAKE_ACK, self.name, Endpoint.from_json(json.loads(msg.get(str))) if msg.has_type(str) else None)
         else:
