@@ -322,3 +322,49 @@ def test_microbatch_caches_are_independent():
     l.backward(g, 0)
     torch.testing.assert_close(l.grads["weight"], w1 + g.t() @ x0)
     assert not l._cache
+
+
+def test_graph_reducer_merges_linear_chains_into_sequentials():
+    """Reducer / SeqReduction (reducer.hpp, seq_reduction.hpp): chains of single-in / single-out ops collapse
+    into Sequential nodes; branches and joins survive; the reduced graph computes the same function."""
+    import torch
+    from tnn_b200.nn import layers as L
+    from tnn_b200.nn.blocks import Sequential
+    from tnn_b200.nn.graph import GraphBuilder, GraphExecutor
+    from tnn_b200.nn.reducer import ReducerBuilder
+
+    def build():
+        b = GraphBuilder("g")
+        a1 = b.add_layer(L.DenseLayer(8, 8, True, "a1"))
+        a2 = b.add_layer(L.ActivationLayer("tanh", "a2"))
+        a3 = b.add_layer(L.DenseLayer(8, 6, True, "a3"))
+        l1 = b.add_layer(L.DenseLayer(6, 6, True, "l1"))
+        l2 = b.add_layer(L.ActivationLayer("relu", "l2"))
+        r1 = b.add_layer(L.DenseLayer(6, 6, True, "r1"))
+        add = b.add_layer(L.AddLayer("join"))
+        t1 = b.add_layer(L.DenseLayer(6, 4, True, "t1"))
+        t2 = b.add_layer(L.ActivationLayer("sigmoid", "t2"))
+        b.add_edge(["input"], ["h1"], a1).add_edge(["h1"], ["h2"], a2).add_edge(["h2"], ["h3"], a3)
+        b.add_edge(["h3"], ["p1"], l1).add_edge(["p1"], ["p2"], l2)          # branch 1 (two ops)
+        b.add_edge(["h3"], ["q1"], r1)                                          # branch 2 (one op)
+        b.add_edge(["p2", "q1"], ["j"], add)
+        b.add_edge(["j"], ["k"], t1).add_edge(["k"], ["output"], t2)
+        return b
+    ref = build().compile("cpu", seed=3)
+    red_b = ReducerBuilder().seq_reduction().build().reduce(build())
+    # input chain (3 ops) -> 1, branch 1 (2 ops) -> 1, tail (2 ops) -> 1; r1 and the join stay
+    assert len(red_b.edges) == 5
+    seqs = [n.layer for n in red_b.op_nodes.values() if isinstance(n.layer, Sequential)]
+    assert sorted(len(s.layers) for s in seqs) == [2, 2, 3]
+    assert "h1" not in red_b.io_nodes and "h3" in red_b.io_nodes and "j" in red_b.io_nodes
+    red = red_b.compile("cpu", seed=3)
+    # same parameters -> same function
+    src = {n: p for n, p in ref.ctx.parameters()}
+    for n, p in red.ctx.parameters():
+        key = [k for k in src if k.split(".")[-2:] == n.split(".")[-2:]]
+        assert key, n
+        p.copy_(src[key[0]])
+    x = torch.randn(5, 8)
+    y0 = GraphExecutor(ref).forward({"input": x})["output"]
+    y1 = GraphExecutor(red).forward({"input": x})["output"]
+    assert torch.allclose(y0, y1, atol=1e-6)

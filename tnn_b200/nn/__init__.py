@@ -6,3 +6,4 @@ from .graph import Graph, GraphBuilder, GraphContext, GraphExecutor, graph_from_
 from .loss import LossFactory, CrossEntropyLoss, compute_class_corrects  # noqa: F401
 from .optimizers import OptimizerFactory, SGD, Adam  # noqa: F401
 from .schedulers import SchedulerFactory  # noqa: F401
+from .reducer import Reducer, ReducerBuilder, ReductionStrategy, SeqReduction  # noqa: F401,E402
