@@ -746,3 +746,29 @@ def test_wifi_loader_columns_normalisation_and_modes(tmp_path):
     cls = WiFiDataLoader(False).load_data(str(f), 0, 6, 8, 9, True)
     assert cls.y.dtype == torch.int32 and cls.num_outputs() == int(floor.max()) + 1
     assert torch.equal(cls.y, torch.from_numpy(floor[:, 0].astype(np.int32)))
+
+
+def test_concurrent_map_semantics_and_thread_safety():
+    """concurrent_map.hpp: emplace / try_get / erase / contains / operator[] / size under concurrent writers."""
+    import threading
+    from tnn_b200.utils.concurrent import ConcurrentMap
+    m = ConcurrentMap(default_factory=int)
+    assert m.emplace("a", 1) and not m.emplace("a", 2)            # emplace keeps the first value
+    assert m.try_get("a") == (True, 1) and m.try_get("zz", -1) == (False, -1)
+    assert m["fresh"] == 0 and m.contains("fresh") and "fresh" in m and m.size() == 2
+    assert m.erase("fresh") and not m.erase("fresh") and len(m) == 1
+
+    def work(tid):
+        for i in range(2000):
+            m.update_with("ctr", lambda v: (v or 0) + 1)
+            m.emplace((tid, i % 50), i)
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert m["ctr"] == 8 * 2000 and m.size() == 2 + 8 * 50
+    strict = ConcurrentMap()
+    try:
+        strict["missing"]
+        assert False
+    except KeyError:
+        pass
