@@ -772,3 +772,18 @@ def test_concurrent_map_semantics_and_thread_safety():
         assert False
     except KeyError:
         pass
+
+
+def test_tasks_on_host_threads_and_flows():
+    """task.hpp: ready() / sync() with an error status, CPU tasks on worker threads, flow-bound tasks."""
+    import time
+    from tnn_b200.core.device import DeviceManager, create_cpu_task, create_cuda_task
+    t = create_cpu_task(lambda a, b: (time.sleep(0.05), a + b)[1], 2, 3)
+    assert t.sync() is None and t.ready() and t.result() == 5
+    bad = create_cpu_task(lambda: 1 / 0)
+    err = bad.sync()
+    assert isinstance(err, ZeroDivisionError) and bad.ready()
+    flow = DeviceManager.getInstance().getHost().getFlow()
+    ft = create_cuda_task(flow, lambda x: x * 2, 21)          # a host flow runs the work inline
+    assert ft.ready() and ft.sync() is None and ft.result() == 42
+    assert isinstance(create_cuda_task(flow, lambda: [][1]).sync(), IndexError)

@@ -67,6 +67,68 @@ class Flow:
             self._ctx.__exit__(*a)
 
 
+class Task:
+    """Handle on a unit of asynchronous work (reference: include/device/task.hpp -- ``ready()`` / ``sync()`` returning
+    an error status; ``create_cpu_task`` / ``create_cuda_task``).  A CPU task runs on the native thread pool's Python
+    side (a ``concurrent.futures`` future); a GPU task is whatever ``fn`` enqueued on its flow plus the event
+    recorded behind it, so ``sync()`` waits for exactly that work and not for the whole device."""
+
+    def __init__(self, future=None, event=None, flow: Flow | None = None, result=None, error: BaseException | None = None):
+        self._future, self._event, self._flow = future, event, flow
+        self._result, self._error = result, error
+
+    def ready(self) -> bool:
+        if self._error is not None:
+            return True
+        if self._future is not None:
+            return self._future.done()
+        if self._event is not None:
+            return bool(self._event.query())
+        return True
+
+    def sync(self) -> BaseException | None:
+        """Block until the work is done; returns None on success or the exception that the work raised."""
+        if self._future is not None:
+            try:
+                self._result = self._future.result()
+            except BaseException as e:  # noqa: BLE001
+                self._error = e
+            self._future = None
+        if self._event is not None:
+            self._event.synchronize()
+        return self._error
+
+    def result(self):
+        err = self.sync()
+        if err is not None:
+            raise err
+        return self._result
+
+
+_TASK_POOL = None
+
+
+def create_cpu_task(fn, *args, **kw) -> Task:
+    """Run ``fn(*args)`` on a host worker thread (task.hpp create_cpu_task)."""
+    global _TASK_POOL
+    if _TASK_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        import os as _os
+        _TASK_POOL = ThreadPoolExecutor(max_workers=max(2, min(8, _os.cpu_count() or 2)), thread_name_prefix="tnn-task")
+    return Task(future=_TASK_POOL.submit(fn, *args, **kw))
+
+
+def create_cuda_task(flow: Flow, fn, *args, **kw) -> Task:
+    """Enqueue ``fn(*args)`` on ``flow`` (its kernels go to the flow's stream) and return a task bound to an event
+    recorded right behind it (task.hpp create_cuda_task).  On a CPU flow the call simply runs."""
+    try:
+        with flow:
+            res = fn(*args, **kw)
+        return Task(event=flow.record_event(), flow=flow, result=res)
+    except BaseException as e:  # noqa: BLE001
+        return Task(error=e)
+
+
 class Device:
     def __init__(self, type: DeviceType, index: int = 0):
         self.type, self.index = type, index
