@@ -120,7 +120,8 @@ def test_batchnorm_running_stats_are_serialised_params():
     assert "running_mean" not in l.grads
 
 
-@pytest.mark.parametrize("cls,fn", [(MaxPool2DLayer, F.max_pool2d), (AvgPool2DLayer, F.avg_pool2d)])
+@pytest.mark.parametrize("cls,fn", [(MaxPool2DLayer, F.max_pool2d),
+                                    (AvgPool2DLayer, lambda x, k, s, p: F.avg_pool2d(x, k, s, p, count_include_pad=False))])
 @pytest.mark.parametrize("k,s,p", [(2, 2, 0), (3, 2, 1), (3, 1, 1)])
 def test_pooling(cls, fn, k, s, p):
     l = cls(k, k, s, s, p, p, "pool")

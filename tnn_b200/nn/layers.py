@@ -544,7 +544,31 @@ class MaxPool2DLayer(_Pool2D):
 
 @register()
 class AvgPool2DLayer(_Pool2D):
+    """Average pooling.  Like the reference's NHWC layer (src/nn/layers_impl/cpu/avgpool_ops.cpp:27-48,75-78)
+    the divisor is the number of IN-BOUNDS pixels of the window, so zero padding does not dilute border
+    outputs; the legacy NCHW layer divides by pool_h*pool_w instead (avgpool_nchw_ops.cpp:19,56) and is
+    served by ``count_include_pad = True``.  The kernel divides by the window size; with padding the
+    per-position ratio window/in-bounds is applied around it (a [OH,OW] table, cached per shape)."""
     TYPE_NAME = "avgpool2d"
+    count_include_pad = False
+
+    def _border_scale(self, d, device, dtype):
+        """[1,OH,OW,1] factor (pool_h*pool_w / in-bounds count), or None when every window is full."""
+        if self.count_include_pad or (self.pad_h == 0 and self.pad_w == 0):
+            return None
+        key = (tuple(d), str(device), dtype)
+        tab = getattr(self, "_border_tab", None)
+        if tab is None or tab[0] != key:
+            H, W, OH, OW = d[1], d[2], d[10], d[11]
+            h0 = torch.arange(OH) * self.stride_h - self.pad_h
+            w0 = torch.arange(OW) * self.stride_w - self.pad_w
+            nh = (torch.clamp(h0 + self.pool_h, max=H) - torch.clamp(h0, min=0)).clamp(min=0)
+            nw = (torch.clamp(w0 + self.pool_w, max=W) - torch.clamp(w0, min=0)).clamp(min=0)
+            cnt = (nh[:, None] * nw[None, :]).float()
+            scale = torch.where(cnt > 0, float(self.pool_h * self.pool_w) / cnt.clamp(min=1), torch.zeros_like(cnt))
+            tab = (key, scale.reshape(1, OH, OW, 1).to(device=device, dtype=dtype))
+            self._border_tab = tab
+        return tab[1]
 
     def forward_impl(self, x, mb_id):
         d = self._dims(x.shape)
@@ -555,24 +579,33 @@ class AvgPool2DLayer(_Pool2D):
             x = to_bf16(x).contiguous()
             y = torch.empty((d[0], d[10], d[11], d[3]), dtype=torch.bfloat16, device=x.device)
             Cx.avgpool_fwd(x, y, d)
-            return y
+            sc = self._border_scale(d, x.device, torch.float32)
+            return y if sc is None else (y.float() * sc).to(torch.bfloat16)
         y = F.avg_pool2d(x.permute(0, 3, 1, 2).float(), (self.pool_h, self.pool_w), (self.stride_h, self.stride_w),
-                         (self.pad_h, self.pad_w), count_include_pad=True)
+                         (self.pad_h, self.pad_w), count_include_pad=self.count_include_pad)
         return y.permute(0, 2, 3, 1).contiguous().to(x.dtype)
 
     def backward_impl(self, dy, mb_id):
         d = self.cache(mb_id)["d"]
         if dy.is_cuda and d[3] % 8 == 0:
             Cx = native.require()
+            sc = self._border_scale(d, dy.device, torch.float32)
+            if sc is not None:
+                dy = dy.float() * sc
             dy = to_bf16(dy).contiguous()
             dx = torch.empty((d[0], d[1], d[2], d[3]), dtype=torch.bfloat16, device=dy.device)
             Cx.avgpool_bwd(dy, dx, d)
             return dx
         x = torch.zeros((d[0], d[3], d[1], d[2]), requires_grad=True)
         y = F.avg_pool2d(x, (self.pool_h, self.pool_w), (self.stride_h, self.stride_w), (self.pad_h, self.pad_w),
-                         count_include_pad=True)
+                         count_include_pad=self.count_include_pad)
         (gx,) = torch.autograd.grad(y, x, dy.permute(0, 3, 1, 2).float().cpu())
         return gx.permute(0, 2, 3, 1).contiguous().to(dy.dtype).to(dy.device)
+
+
+class _AvgPoolFullWindow(AvgPool2DLayer):
+    """Divisor = pool_h*pool_w whatever the padding: the legacy NCHW semantics."""
+    count_include_pad = True
 
 
 # =============================================================================== Activations
@@ -1256,7 +1289,7 @@ class LegacyMaxPool2DLayer(_NCHWFacade):
 @register()
 class LegacyAvgPool2DLayer(_NCHWFacade):
     TYPE_NAME = "legacy_avgpool2d"
-    INNER = AvgPool2DLayer
+    INNER = _AvgPoolFullWindow
 
 
 @register()
