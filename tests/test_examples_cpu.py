@@ -37,3 +37,58 @@ def test_bench_reference_arm_prints_one_json_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and "unavailable" in d
+
+
+def _run(rel, *args, cwd=None, env=None, timeout=300):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, rel), *args], cwd=cwd, env=env, capture_output=True, text=True,
+                         timeout=timeout)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-2500:])
+    return out.stdout
+
+
+def test_small_example_apps_run_on_cpu(tmp_path):
+    """device_manager_example / hardware_info_example / msequential_example / test_del / graph_test twins."""
+    import json
+    assert "Memory access test passed" in _run("examples/device_manager_example.py")
+    out = _run("examples/hardware_info_example.py", "--samples", "1", "--interval", "0.01", "--out-dir", str(tmp_path))
+    assert "NUMA Node 0" in out
+    info = json.load(open(tmp_path / "temp" / "hardware_info.json"))
+    assert info["logical_cores"] >= 1 and "numa" in info
+    assert (tmp_path / "logs" / "cpu_status.csv").read_text().count("\n") == 2
+    out = _run("examples/msequential_example.py")
+    assert "Output shape: (4, 5)" in out and "Output shape: (8, 50)" in out and out.count("Backward pass completed") == 2
+    assert "ptrX: offset    10240" in _run("examples/del_allocator_example.py")
+    out = _run("examples/graph_example.py", "--steps", "2", "--batch", "16", cwd=tmp_path,
+               env=dict(os.environ, DEVICE_TYPE="CPU", MODEL_NAME="mnist_cnn"))
+    assert "op nodes reduced to 1" in out and out.count("Loss:") == 2
+
+
+def test_legacy_zoo_matches_nhwc_zoo_and_legacy_trainer_runs(tmp_path):
+    """legacy::ExampleModels: same network on NCHW tensors built from legacy_* layers (same seed -> same output)."""
+    import torch
+    from tnn_b200.models import ExampleModels, legacy
+    assert "cifar100_wrn16_8" in legacy.ExampleModels.available_models() and "gpt2_small" in legacy.ExampleModels.available_models()
+    a = ExampleModels.create("cifar10_resnet9").init("cpu", seed=1).set_training(False)
+    b = legacy.ExampleModels.create("cifar10_resnet9").init("cpu", seed=1).set_training(False)
+    types = {type(l).__name__ for l in b.layers}
+    assert "LegacyConv2DLayer" in types and "Conv2DLayer" not in types
+    x = torch.randn(2, 32, 32, 3)
+    torch.testing.assert_close(a.forward(x, 0), b.forward(x.permute(0, 3, 1, 2).contiguous(), 0))
+    vit = legacy.ExampleModels.create("tiny_imagenet_vit").init("cpu", seed=2).set_training(True)
+    y = vit.forward(torch.randn(1, 3, 64, 64), 0)
+    assert y.shape == (1, 200) and vit.backward(torch.ones_like(y), 0).shape == (1, 3, 64, 64)
+    env = dict(os.environ, MODEL_NAME="mnist_cnn", DEVICE_TYPE="CPU", BATCH_SIZE="16", EPOCHS="1")
+    out = _run("examples/legacy_trainer.py", "--synthetic", "--samples", "64", cwd=tmp_path, env=env)
+    assert "epoch 1 done" in out and "[legacy_trainer] done" in out
+
+
+def test_cpu_runnable_benchmarks(tmp_path):
+    """dense_benchmark / grad_clear_benchmark / tcp_communicator_benchmark twins on their CPU paths."""
+    import json
+    last = lambda s: json.loads([l for l in s.splitlines() if l.startswith("{")][-1])  # noqa: E731
+    d = last(_run("benchmarks/dense_bench.py", "--in", "512", "--out", "64", "--batch", "8", "--passes", "2"))
+    assert d["max_diff"] == 0.0 and d["max_grad_diff"] == 0.0 and d["max_weight_grad_diff"] == 0.0
+    g = last(_run("benchmarks/grad_clear_bench.py", "mnist_cnn"))
+    assert g["tensors"] > 0 and g["bulk_ms"] > 0
+    t = last(_run("benchmarks/tcp_communicator_bench.py", "--self-test", "--mb", "1", "--seconds", "1"))
+    assert t["messages"] > 0 and t["MBps"] > 0

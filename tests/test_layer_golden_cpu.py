@@ -318,3 +318,40 @@ def test_config_carries_every_constructor_argument(layer, expect):
     assert cfg.name == layer.name and cfg.type == layer.TYPE_NAME
     for k, v in expect.items():
         assert cfg[k] == v, k
+
+
+# ------------------------------------------------------------------------------------- losses (hand-computed)
+def test_loss_values_gradients_and_config_round_trip():
+    """loss.hpp / loss_ops.cpp: means over every element, 2/n MSE gradient, clamped probabilities."""
+    import math
+    from tnn_b200.nn.loss import LossFactory
+    pred, tgt = T(1, 2, 3, 5, shape=(2, 2)), T(0, 2, 5, 1, shape=(2, 2))       # diffs 1 0 -2 4
+    mse = LossFactory.create_mse()
+    assert mse.compute_loss(pred, tgt) == pytest.approx((1 + 0 + 4 + 16) / 4)
+    assert mse.compute_gradient(pred, tgt).tolist() == [[0.5, 0.0], [-1.0, 2.0]]
+    mae = LossFactory.create_mae()
+    assert mae.compute_loss(pred, tgt) == pytest.approx(7 / 4)
+    assert mae.compute_gradient(pred, tgt).tolist() == [[0.25, 0.0], [-0.25, 0.25]]
+    hub = LossFactory.create_huber(1.5)
+    # |d| <= delta: d^2/2 ; else delta*(|d| - delta/2)
+    assert hub.compute_loss(pred, tgt) == pytest.approx((0.5 + 0 + 1.5 * (2 - 0.75) + 1.5 * (4 - 0.75)) / 4)
+    assert hub.compute_gradient(pred, tgt).tolist() == [[0.25, 0.0], [-0.375, 0.375]]
+    # cross entropy on probabilities: -log p[label] averaged over rows, gradient only at the label
+    ce = LossFactory.create_crossentropy(use_logits=False, eps=1e-6)
+    probs = T(0.5, 0.5, 0.0, 1.0, shape=(2, 2))
+    labels = torch.tensor([0, 0], dtype=torch.int32)
+    assert ce.compute_loss(probs, labels) == pytest.approx((math.log(2) - math.log(1e-6)) / 2, rel=1e-4)
+    g = ce.compute_gradient(probs, labels)
+    assert g[0].tolist() == [-1.0, 0.0] and g[1, 1] == 0 and float(g[1, 0]) == pytest.approx(-0.5e6, rel=1e-3)
+    # logits: uniform logits -> log(C); gradient (softmax - onehot)/rows
+    cel = LossFactory.create("ce")
+    assert cel.compute_loss(torch.zeros(3, 4), torch.tensor([0, 1, 2])) == pytest.approx(math.log(4), rel=1e-6)
+    gl = cel.compute_gradient(torch.zeros(1, 4), torch.tensor([2]))
+    torch.testing.assert_close(gl, T(0.25, 0.25, -0.75, 0.25, shape=(1, 4)))
+    for loss in (mse, mae, hub, ce, cel, LossFactory.create_logsoftmax_crossentropy()):
+        cfg = loss.get_config()
+        again = LossFactory.create_from_config(TConfig.from_json(cfg.to_json()))
+        assert type(again) is type(loss) and again.get_config() == cfg and type(loss.clone()) is type(loss)
+    assert hub.get_config()["delta"] == 1.5 and ce.get_config()["epsilon"] == 1e-6 and ce.get_config()["use_logits"] is False
+    with pytest.raises(ValueError):
+        LossFactory.create("hinge")

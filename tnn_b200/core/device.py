@@ -151,6 +151,15 @@ class Device:
         from ..utils.hardware_info import HardwareInfo
         return HardwareInfo().total_ram_kb * 1024
 
+    def available_memory(self) -> int:
+        """Free bytes right now (device.hpp getAvailableMemory)."""
+        if self.type == DeviceType.GPU:
+            return torch.cuda.mem_get_info(self.index)[0]
+        from ..utils.hardware_info import HardwareInfo
+        return HardwareInfo().available_ram_kb * 1024
+
+    getTotalMemory, getAvailableMemory, getName = total_memory, available_memory, name
+
     def allocate(self, nbytes: int, pinned: bool = False) -> torch.Tensor:
         if self.type == DeviceType.GPU:
             return torch.empty(nbytes, dtype=torch.uint8, device=self.torch)
@@ -202,6 +211,17 @@ class DeviceManager:
 
     def available(self) -> list[str]:
         return sorted(self.devices)
+
+    getAvailableDeviceIDs = available
+
+    def hasDevice(self, spec) -> bool:
+        try:
+            self.getDevice(spec)
+            return True
+        except KeyError:
+            return False
+
+    has_device = hasDevice
 
 
 def getHost() -> Device:

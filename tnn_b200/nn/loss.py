@@ -30,8 +30,18 @@ class Loss:
         """Returns (stats device tensor [loss, n_correct], grad).  No host sync."""
         raise NotImplementedError
 
+    def config_params(self) -> dict:
+        return {}
+
     def get_config(self) -> TConfig:
-        return TConfig(self.NAME, self.NAME)
+        """LossConfig (loss.hpp:75-83,376-382): type name + the constructor arguments."""
+        return TConfig(self.NAME, self.NAME, **self.config_params())
+
+    def name(self) -> str:
+        return self.NAME
+
+    def clone(self) -> "Loss":
+        return LossFactory.create_from_config(self.get_config())
 
 
 def _rows_view(pred):
@@ -53,7 +63,10 @@ class CrossEntropyLoss(Loss):
 
     def __init__(self, use_logits: bool = True, eps: float = 1e-15):
         super().__init__()
-        self.use_logits, self.eps = use_logits, eps
+        self.use_logits, self.eps = bool(use_logits), float(eps)
+
+    def config_params(self):
+        return dict(use_logits=self.use_logits, epsilon=self.eps)
 
     def loss_and_grad(self, pred, target, scale: float = 1.0, want_grad: bool = True):
         p2, V = _rows_view(pred)
@@ -73,7 +86,7 @@ class CrossEntropyLoss(Loss):
             logp = torch.log_softmax(x, -1)
             prob = logp.exp()
         else:
-            prob = x.clamp_min(self.eps)
+            prob = x.clamp(self.eps, 1.0 - self.eps)      # loss_ops.cpp:31-34
             logp = prob.log()
         loss = -(logp[torch.arange(rows), labels]).mean()
         correct = (x.argmax(-1) == labels).sum().float()
@@ -100,6 +113,9 @@ class LogSoftmaxCrossEntropyLoss(CrossEntropyLoss):
 
     def __init__(self):
         super().__init__(use_logits=True)
+
+    def config_params(self):
+        return {}
 
 
 class _Regression(Loss):
@@ -150,6 +166,15 @@ class MAELoss(_Regression):
 class HuberLoss(_Regression):
     NAME, KIND = "huber", 2
 
+    def config_params(self):
+        return dict(delta=float(self.delta))
+
+    def set_delta(self, delta: float):
+        self.delta = float(delta)
+
+    def get_delta(self) -> float:
+        return self.delta
+
 
 class LossFactory:
     """loss.hpp:464-523."""
@@ -158,7 +183,7 @@ class LossFactory:
     def create(name: str, **kw) -> Loss:
         n = name.lower()
         if n in ("crossentropy", "ce"):
-            return CrossEntropyLoss(kw.get("use_logits", True), kw.get("eps", 1e-15))
+            return CrossEntropyLoss(kw.get("use_logits", True), kw.get("epsilon", kw.get("eps", 1e-15)))
         if n in ("logsoftmax_crossentropy", "logsoftmax_ce"):
             return LogSoftmaxCrossEntropyLoss()
         if n in ("mse", "mean_squared_error"):
@@ -176,6 +201,18 @@ class LossFactory:
     @staticmethod
     def create_logsoftmax_crossentropy():
         return LogSoftmaxCrossEntropyLoss()
+
+    @staticmethod
+    def create_mse():
+        return MSELoss()
+
+    @staticmethod
+    def create_mae():
+        return MAELoss()
+
+    @staticmethod
+    def create_huber(delta: float = 1.0):
+        return HuberLoss(delta)
 
     @staticmethod
     def create_from_config(cfg: TConfig) -> Loss:

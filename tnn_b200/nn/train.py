@@ -86,6 +86,12 @@ class TrainingConfig:
     def to_json(self) -> dict:
         return asdict(self)
 
+    def print_config(self, out=None):
+        """One ``key: value`` line per field (train.hpp print_config)."""
+        print("Training configuration:", file=out)
+        for k, v in asdict(self).items():
+            print(f"  {k}: {v}", file=out)
+
     def device(self) -> torch.device:
         t = self.device_type.upper()
         if t.startswith("GPU") or t.startswith("CUDA"):

@@ -71,6 +71,103 @@ class HardwareInfo:
         return "\n".join(lines)
 
 
+    # ---- topology / dynamic state (hardware_info.hpp: NUMA map, utilisation, temperature, JSON dump)
+    @staticmethod
+    def _parse_cpulist(txt: str) -> list:
+        out = []
+        for part in txt.strip().split(","):
+            if not part:
+                continue
+            if "-" in part:
+                a, b = part.split("-")
+                out.extend(range(int(a), int(b) + 1))
+            else:
+                out.append(int(part))
+        return out
+
+    def numa_topology(self) -> dict:
+        """{node id: [cpu ids]} from sysfs; one node holding every CPU when the kernel exposes none."""
+        base = "/sys/devices/system/node"
+        nodes = {}
+        if os.path.isdir(base):
+            for d in sorted(os.listdir(base)):
+                if d.startswith("node") and d[4:].isdigit():
+                    try:
+                        nodes[int(d[4:])] = self._parse_cpulist(open(f"{base}/{d}/cpulist").read())
+                    except OSError:
+                        continue
+        return nodes or {0: list(range(self.logical_cores))}
+
+    @staticmethod
+    def _cpu_times():
+        try:
+            with open("/proc/stat") as f:
+                v = [int(x) for x in f.readline().split()[1:]]
+            idle = v[3] + (v[4] if len(v) > 4 else 0)
+            return sum(v), idle
+        except (OSError, ValueError, IndexError):
+            return 0, 0
+
+    def update_dynamic_info(self) -> bool:
+        """Refreshes available RAM, load average, CPU utilisation since the previous call, clock and
+        temperature (when the platform exposes them)."""
+        total, idle = self._cpu_times()
+        prev = getattr(self, "_prev_times", None)
+        self.cpu_utilization = 0.0
+        if prev is not None and total > prev[0]:
+            self.cpu_utilization = 100.0 * (1.0 - (idle - prev[1]) / (total - prev[0]))
+        self._prev_times = (total, idle)
+        try:
+            self.load_average = os.getloadavg()
+        except OSError:
+            self.load_average = (0.0, 0.0, 0.0)
+        try:
+            with open("/proc/meminfo") as f:
+                for l in f:
+                    if l.startswith("MemAvailable"):
+                        self.available_ram_kb = int(l.split()[1])
+        except OSError:
+            pass
+        self.cpu_mhz = 0.0
+        try:
+            self.cpu_mhz = int(open("/sys/devices/system/cpu/cpu0/cpufreq/scaling_cur_freq").read()) / 1000.0
+        except (OSError, ValueError):
+            try:
+                with open("/proc/cpuinfo") as f:
+                    for l in f:
+                        if l.startswith("cpu MHz"):
+                            self.cpu_mhz = float(l.split(":")[1])
+                            break
+            except (OSError, ValueError):
+                pass
+        self.temperature_c = -1.0
+        tz = "/sys/class/thermal"
+        if os.path.isdir(tz):
+            temps = []
+            for d in os.listdir(tz):
+                try:
+                    temps.append(int(open(f"{tz}/{d}/temp").read()) / 1000.0)
+                except (OSError, ValueError):
+                    continue
+            if temps:
+                self.temperature_c = max(temps)
+        return True
+
+    def to_dict(self) -> dict:
+        d = dict(cpu_model=self.cpu_model, sockets=self.sockets, physical_cores=self.physical_cores,
+                 logical_cores=self.logical_cores, caches=dict(self.caches), total_ram_kb=self.total_ram_kb,
+                 available_ram_kb=self.available_ram_kb, gpus=list(self.gpus),
+                 numa={str(k): v for k, v in self.numa_topology().items()})
+        for k in ("cpu_utilization", "load_average", "cpu_mhz", "temperature_c"):
+            if hasattr(self, k):
+                d[k] = getattr(self, k)
+        return d
+
+    def to_json(self, indent: int = 2) -> str:
+        import json
+        return json.dumps(self.to_dict(), indent=indent)
+
+
 def get_memory_usage_kb() -> int:
     try:
         with open("/proc/self/status") as f:
