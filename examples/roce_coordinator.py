@@ -28,6 +28,8 @@ if __name__ == "__main__":
     ap.add_argument("--proportions", default="1,2")
     ap.add_argument("--synthetic", action="store_true")
     ap.add_argument("--gpu", action="store_true")
+    ap.add_argument("--legacy", action="store_true",
+                    help="legacy_tcp_coordinator / legacy_roce_coordinator: NCHW zoo + loaders, Adam eps 1e-5 wd 1e-4")
     a = ap.parse_args()
     env = Env(".env")
     cfg = TrainingConfig.load_from_env()
@@ -39,8 +41,13 @@ if __name__ == "__main__":
         i += 1
     local = TCPWorker(env.get("LOCAL_WORKER_HOST", "127.0.0.1"), env.get("LOCAL_WORKER_PORT", 0, int),
                       use_gpu=a.gpu and torch.cuda.is_available())
-    model = ExampleModels.create(cfg.model_name)
-    opt = OptimizerFactory.create_adam(cfg.lr_initial, 0.9, 0.999, 1e-3, 3e-4)
+    if a.legacy:
+        from tnn_b200.models import legacy
+        model = legacy.ExampleModels.create(cfg.model_name)
+        opt = OptimizerFactory.create_adam(cfg.lr_initial, 0.9, 0.999, 1e-5, 1e-4)
+    else:
+        model = ExampleModels.create(cfg.model_name)
+        opt = OptimizerFactory.create_adam(cfg.lr_initial, 0.9, 0.999, 1e-3, 3e-4)
     ccfg = CoordinatorConfig(ParallelMode.PIPELINE, model, opt, SchedulerFactory.create_step_lr(opt, 10 ** 6, 0.1),
                              NaivePipelinePartitioner(NaivePartitionerConfig(props)), local_worker=local,
                              local_worker_position=env.get("LOCAL_WORKER_POSITION", 0, int), worker_endpoints=workers)
@@ -51,6 +58,10 @@ if __name__ == "__main__":
         train, val = synthetic_for(cfg.model_name, 512)
         train.load_data()
         val.load_data()
+        if a.legacy:
+            train, val = legacy.DataLoaderFactory.wrap(train), legacy.DataLoaderFactory.wrap(val)
+    elif a.legacy:
+        train, val = legacy.DataLoaderFactory.create(cfg.dataset_name, cfg.dataset_path)
     else:
         train, val = DataLoaderFactory.create(cfg.dataset_name, cfg.dataset_path)
     co.start()
