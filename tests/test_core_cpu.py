@@ -525,6 +525,11 @@ def test_native_cpu_gemm_and_thread_pool():
         torch.testing.assert_close(cpu_gemm(aa, bb, ta, tb), ref, atol=1e-4, rtol=1e-4)
     c = torch.ones(130, 45)
     torch.testing.assert_close(cpu_gemm(a, b, alpha=2.0, beta=0.5, out=c), 2 * ref + 0.5, atol=1e-4, rtol=1e-4)   # beta accumulate
+    # shapes that cross the 96-row / 256-deep / 16-column blocking and leave ragged 6x16 edge tiles
+    for M, N, K in ((1, 1, 1), (5, 17, 3), (97, 33, 257), (200, 130, 600)):
+        x, y = torch.randn(M, K), torch.randn(K, N)
+        torch.testing.assert_close(cpu_gemm(x, y), x @ y, atol=2e-4, rtol=1e-4)
+        torch.testing.assert_close(cpu_gemm(x, y, threads=1), cpu_gemm(x, y, threads=4))       # same result on any pool size
     hits = [0] * 11
     parallel_for(11, lambda s, e: [hits.__setitem__(i, hits[i] + 1) for i in range(s, e)], grain=3)
     assert hits == [1] * 11

@@ -3,6 +3,7 @@ same functions in tests/test_kernels_gpu.py).  Mirrors unit_tests/tensor_test.cp
 coverage of gpu_tensor_ops_test.cpp."""
 import io
 
+import pytest
 import torch
 
 from tnn_b200.core import tensor as T
@@ -160,3 +161,53 @@ def test_tensor_utils_col2im_layout_and_diagnostics(capsys):
     edges, counts = ops.buckets(torch.arange(100, dtype=torch.float32), 10)
     assert counts.tolist() == [10] * 10 and float(edges[0]) == 0.0 and float(edges[-1]) == 99.0
     assert "distribution over 4 buckets" in ops.print_data_distribution(torch.randn(50), 4, "w")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_native_cpu_elementwise_family_matches_torch(dtype):
+    """ops/cpu/{s,d}kernels.cpp twin: the native multi-versioned loops behind every ops.* call on contiguous CPU
+    fp32 / fp64 tensors (sizes straddle the per-task grain so the thread-pool path and the tails are covered)."""
+    from tnn_b200.ops import native, tensor_ops as ops
+    C = native.require()
+    assert hasattr(C, "cpu_binary") and hasattr(C, "cpu_reduce")
+    g = torch.Generator().manual_seed(5)
+    tol = dict(rtol=1e-6, atol=1e-6) if dtype == torch.float32 else dict(rtol=1e-12, atol=1e-12)
+    for n in (1, 7, 1000, (1 << 15) + 3, 200_001):
+        a = torch.randn(n, generator=g, dtype=dtype)
+        b = torch.randn(n, generator=g, dtype=dtype) + 0.1
+        c = torch.randn(n, generator=g, dtype=dtype)
+        for name, ref in (("add", a + b), ("sub", a - b), ("mul", a * b), ("div", a / b), ("minimum", torch.minimum(a, b)),
+                          ("maximum", torch.maximum(a, b)), ("equal", (a == b).to(dtype)), ("greater", (a > b).to(dtype))):
+            torch.testing.assert_close(getattr(ops, name)(a, b), ref, **tol)
+        torch.testing.assert_close(ops.add(a, 2.5), a + 2.5, **tol)
+        torch.testing.assert_close(ops.div(a, 4.0), a / 4.0, **tol)
+        torch.testing.assert_close(ops.maximum(a, 0.0), a.clamp_min(0), **tol)
+        p = a.abs() + 0.5
+        for name, ref in (("sqrt", p.sqrt()), ("rsqrt", p.rsqrt()), ("rcp", 1 / p), ("abs", a.abs()), ("neg", -a),
+                          ("exp", a.exp()), ("log", p.log()), ("square", a * a)):
+            src = p if name in ("sqrt", "rsqrt", "rcp", "log") else a
+            torch.testing.assert_close(getattr(ops, name)(src), ref, rtol=tol["rtol"] * 10, atol=tol["atol"] * 10)
+        torch.testing.assert_close(ops.clamp(a, -0.5, 0.25), a.clamp(-0.5, 0.25), **tol)
+        torch.testing.assert_close(ops.fmadd(a, b, c), a * b + c, **tol)
+        torch.testing.assert_close(ops.fmsub(a, b, c), a * b - c, **tol)
+        torch.testing.assert_close(ops.fnmadd(a, b, c), c - a * b, **tol)
+        y = c.clone()
+        ops.axpy(y, a, -1.5)
+        torch.testing.assert_close(y, c - 1.5 * a, **tol)
+        assert float(ops.set_scalar(y, 3.25).min()) == 3.25 == float(y.max())
+        inplace = a.clone()
+        ops.add(inplace, b, out=inplace)                                     # aliasing output
+        torch.testing.assert_close(inplace, a + b, **tol)
+        ad = a.double()
+        assert float(ops.sum(a)) == pytest.approx(float(ad.sum()), rel=1e-6, abs=1e-6)
+        assert float(ops.dot_product(a, b)) == pytest.approx(float((ad * b.double()).sum()), rel=1e-6, abs=1e-5)
+        assert float(ops.sum_squared_diff(a, 0.3)) == pytest.approx(float(((ad - 0.3) ** 2).sum()), rel=1e-6)
+    # thread count does not change a reduction (per-grain partials combined in order)
+    big = torch.randn(500_000, generator=g, dtype=dtype)
+    r1 = C.cpu_reduce(big.data_ptr(), 0, 0.0, big.numel(), 0, dtype == torch.float64, 1)
+    r8 = C.cpu_reduce(big.data_ptr(), 0, 0.0, big.numel(), 0, dtype == torch.float64, 8)
+    assert r1 == r8
+    # strided views and integer tensors keep working through the torch path
+    v = torch.arange(12, dtype=dtype).reshape(3, 4).t()
+    torch.testing.assert_close(ops.add(v, v), v + v)
+    assert ops.add(torch.tensor([1, 2]), torch.tensor([3, 4])).tolist() == [4, 6]

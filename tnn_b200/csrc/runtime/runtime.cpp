@@ -10,6 +10,7 @@
 #include <mutex>
 
 #include "allocator.hpp"
+#include "cpu_ops.hpp"
 #include "archiver.hpp"
 #include "cpu_math.hpp"
 #include "data_loader.hpp"
@@ -207,6 +208,40 @@ void runtime_bind(py::module_& m) {
     py::gil_scoped_release rel;
     return cpu_dot(reinterpret_cast<const float*>(a), reinterpret_cast<const float*>(b), n);
   });
+  // CPU elementwise / reduction family (cpu_ops.hpp); pointers are raw data_ptr()s of contiguous fp32 / fp64 tensors
+  m.def("cpu_binary", [](int64_t a, int64_t b, double s, int64_t o, int64_t n, int op, bool f64, int threads) {
+    py::gil_scoped_release rel;
+    if (f64) cpuops::binary<double>((const double*)a, (const double*)b, s, (double*)o, n, op, threads);
+    else cpuops::binary<float>((const float*)a, (const float*)b, (float)s, (float*)o, n, op, threads);
+  }, py::arg("a"), py::arg("b"), py::arg("scalar"), py::arg("out"), py::arg("n"), py::arg("op"), py::arg("f64") = false,
+     py::arg("threads") = 0);
+  m.def("cpu_unary", [](int64_t a, int64_t o, int64_t n, int op, double lo, double hi, bool f64, int threads) {
+    py::gil_scoped_release rel;
+    if (f64) cpuops::unary<double>((const double*)a, (double*)o, n, op, lo, hi, threads);
+    else cpuops::unary<float>((const float*)a, (float*)o, n, op, (float)lo, (float)hi, threads);
+  }, py::arg("a"), py::arg("out"), py::arg("n"), py::arg("op"), py::arg("lo") = 0.0, py::arg("hi") = 0.0,
+     py::arg("f64") = false, py::arg("threads") = 0);
+  m.def("cpu_ternary", [](int64_t a, int64_t b, int64_t c, int64_t o, int64_t n, int op, bool f64, int threads) {
+    py::gil_scoped_release rel;
+    if (f64) cpuops::ternary<double>((const double*)a, (const double*)b, (const double*)c, (double*)o, n, op, threads);
+    else cpuops::ternary<float>((const float*)a, (const float*)b, (const float*)c, (float*)o, n, op, threads);
+  }, py::arg("a"), py::arg("b"), py::arg("c"), py::arg("out"), py::arg("n"), py::arg("op"), py::arg("f64") = false,
+     py::arg("threads") = 0);
+  m.def("cpu_axpy", [](int64_t y, int64_t x, double alpha, int64_t n, bool f64, int threads) {
+    py::gil_scoped_release rel;
+    if (f64) cpuops::axpy<double>((double*)y, (const double*)x, alpha, n, threads);
+    else cpuops::axpy<float>((float*)y, (const float*)x, (float)alpha, n, threads);
+  }, py::arg("y"), py::arg("x"), py::arg("alpha"), py::arg("n"), py::arg("f64") = false, py::arg("threads") = 0);
+  m.def("cpu_fill", [](int64_t y, double v, int64_t n, bool f64, int threads) {
+    py::gil_scoped_release rel;
+    if (f64) cpuops::fill<double>((double*)y, v, n, threads);
+    else cpuops::fill<float>((float*)y, (float)v, n, threads);
+  }, py::arg("y"), py::arg("value"), py::arg("n"), py::arg("f64") = false, py::arg("threads") = 0);
+  m.def("cpu_reduce", [](int64_t a, int64_t b, double mu, int64_t n, int op, bool f64, int threads) {
+    py::gil_scoped_release rel;
+    return f64 ? cpuops::reduce<double>((const double*)a, (const double*)b, mu, n, op, threads)
+               : cpuops::reduce<float>((const float*)a, (const float*)b, mu, n, op, threads);
+  }, py::arg("a"), py::arg("b"), py::arg("mu"), py::arg("n"), py::arg("op"), py::arg("f64") = false, py::arg("threads") = 0);
   m.def("parallel_for", [](int64_t n, int64_t grain, const py::function& fn, int threads) {
     // Python callables run under the GIL; this is for API parity and for callables that release it
     global_pool(threads).parallel_for(n, grain, [&](int64_t b, int64_t e) {

@@ -1,7 +1,10 @@
 """``ops::`` free-function family (reference: include/ops/ops.hpp:17-835) and the tensor layout ops
 (include/tensor/tensor_ops.hpp:13-354).  GPU fp32 / bf16 tensors run the hand-written kernels of
-csrc/kernels/tensor_ops.cu (128-bit vectorised, reductions finish on the device); anything else
-(CPU, integer dtypes) uses the torch reference math that the tests treat as the oracle.
+csrc/kernels/tensor_ops.cu (128-bit vectorised, reductions finish on the device); contiguous CPU
+fp32 / fp64 tensors run the native multi-versioned (AVX2+FMA | baseline) loops of
+csrc/runtime/cpu_ops.hpp on the shared thread pool (the reference's ops/cpu/skernels.cpp,
+dkernels.cpp); anything else (integer dtypes, strided views) uses the torch reference math that
+the tests treat as the oracle.
 """
 from __future__ import annotations
 
@@ -21,16 +24,34 @@ def _native_ok(*ts) -> bool:
         t is None or (t.is_cuda and t.dtype == t0.dtype and t.is_contiguous() and t.shape == t0.shape) for t in ts)
 
 
+def _cpu_ok(*ts) -> bool:
+    """Contiguous same-shape CPU fp32 / fp64 operands -> the native loops."""
+    t0 = ts[0]
+    return (not t0.is_cuda) and t0.dtype in (torch.float32, torch.float64) and t0.numel() > 0 and all(
+        t is None or ((not t.is_cuda) and t.dtype == t0.dtype and t.is_contiguous() and t.shape == t0.shape) for t in ts)
+
+
+def _cpu():
+    """The native module for the CPU family (None when it could not be built: torch math is used)."""
+    return native.load()
+
+
 def _binary(name, a, b, out=None):
     out = torch.empty_like(a) if out is None else out
     if isinstance(b, torch.Tensor):
         if _native_ok(a, b, out):
             native.require().tensor_binary(a, b, 0.0, out, _BIN[name])
             return out
+        if _cpu_ok(a, b, out) and _cpu() is not None:
+            _cpu().cpu_binary(a.data_ptr(), b.data_ptr(), 0.0, out.data_ptr(), a.numel(), _BIN[name], a.dtype == torch.float64)
+            return out
         out.copy_(_TORCH_BIN[name](a, b))
         return out
     if _native_ok(a, out):
         native.require().tensor_binary(a, None, float(b), out, _BIN[name])
+        return out
+    if _cpu_ok(a, out) and _cpu() is not None:
+        _cpu().cpu_binary(a.data_ptr(), 0, float(b), out.data_ptr(), a.numel(), _BIN[name], a.dtype == torch.float64)
         return out
     bb = torch.full_like(a, b)
     out.copy_(_TORCH_BIN[name](a, bb))
@@ -52,6 +73,9 @@ def _unary(name, a, out=None, lo=0.0, hi=0.0):
     out = torch.empty_like(a) if out is None else out
     if _native_ok(a, out):
         native.require().tensor_unary(a, out, _UN[name], float(lo), float(hi))
+        return out
+    if _cpu_ok(a, out) and _cpu() is not None:
+        _cpu().cpu_unary(a.data_ptr(), out.data_ptr(), a.numel(), _UN[name], float(lo), float(hi), a.dtype == torch.float64)
         return out
     f = {"sqrt": torch.sqrt, "rsqrt": torch.rsqrt, "rcp": torch.reciprocal, "abs": torch.abs,
          "clamp": lambda t: torch.clamp(t, lo, hi), "neg": torch.neg, "exp": torch.exp, "log": torch.log,
@@ -76,6 +100,9 @@ def _ternary(op, a, b, c, out=None):
     if _native_ok(a, b, c, out):
         native.require().tensor_ternary(a, b, c, out, op)
         return out
+    if _cpu_ok(a, b, c, out) and _cpu() is not None:
+        _cpu().cpu_ternary(a.data_ptr(), b.data_ptr(), c.data_ptr(), out.data_ptr(), a.numel(), op, a.dtype == torch.float64)
+        return out
     out.copy_(a * b + c if op == 0 else (a * b - c if op == 1 else c - a * b))
     return out
 
@@ -89,6 +116,9 @@ def set_scalar(a: torch.Tensor, v: float) -> torch.Tensor:
     if a.is_cuda and a.dtype == torch.float32 and a.is_contiguous():
         native.require().fill_f32(a, float(v))
         return a
+    if _cpu_ok(a) and _cpu() is not None:
+        _cpu().cpu_fill(a.data_ptr(), float(v), a.numel(), a.dtype == torch.float64)
+        return a
     return a.fill_(v)
 
 
@@ -96,6 +126,9 @@ def axpy(y: torch.Tensor, x: torch.Tensor, alpha: float) -> torch.Tensor:
     """y += alpha * x."""
     if y.is_cuda and y.dtype == x.dtype == torch.float32 and y.is_contiguous() and x.is_contiguous():
         native.require().axpy_f32(y, x, float(alpha))
+        return y
+    if _cpu_ok(y, x) and _cpu() is not None:
+        _cpu().cpu_axpy(y.data_ptr(), x.data_ptr(), float(alpha), y.numel(), y.dtype == torch.float64)
         return y
     return y.add_(x, alpha=alpha)
 
@@ -106,6 +139,10 @@ def _reduce(mode, a, b=None, mu=0.0) -> torch.Tensor:
         out = torch.empty(1, dtype=torch.float32, device=a.device)
         native.require().tensor_reduce(a, b, float(mu), mode, out)
         return out[0]
+    if (_cpu_ok(a, b) if b is not None else _cpu_ok(a)) and _cpu() is not None:
+        r = _cpu().cpu_reduce(a.data_ptr(), b.data_ptr() if b is not None else 0, float(mu), a.numel(), mode,
+                              a.dtype == torch.float64)
+        return torch.tensor(r, dtype=torch.float32)
     af = a.double()
     if mode == 0:
         return af.sum().float()
