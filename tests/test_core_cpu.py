@@ -792,3 +792,82 @@ def test_tasks_on_host_threads_and_flows():
     ft = create_cuda_task(flow, lambda x: x * 2, 21)          # a host flow runs the work inline
     assert ft.ready() and ft.sync() is None and ft.result() == 42
     assert isinstance(create_cuda_task(flow, lambda: [][1]).sync(), IndexError)
+
+
+def test_native_planner_matches_python_oracles():
+    """csrc/runtime/planner.hpp: graph order, slab layout, buckets, pipeline schedules and partitions, each checked
+    against the straightforward Python twin that stays in the tree as the oracle."""
+    import random
+    from tnn_b200.nn.graph import ALIGN_ELEMS, _plan_slab
+    from tnn_b200.ops import native
+    from tnn_b200.parallel.partitioner import (NaiveDataPartitioner, NaivePipelinePartitioner, SeqPartition,
+                                               _min_bottleneck_split, _min_bottleneck_split_py)
+    C = native.require()
+    rnd = random.Random(7)
+    # --- topological order on random layered DAGs declared in shuffled order
+    for trial in range(20):
+        b = GraphBuilder(f"g{trial}")
+        n_ops = rnd.randint(1, 12)
+        made = ["in"]
+        spec = []
+        for i in range(n_ops):
+            k = rnd.randint(1, min(2, len(made)))
+            ins = rnd.sample(made, k)
+            out = f"t{i}"
+            made.append(out)
+            spec.append((ins, out, k))
+        rnd.shuffle(spec)
+        for ins, out, k in spec:
+            node = b.add_layer(AddLayer(f"add_{out}") if k > 1 else ActivationLayer("tanh", f"act_{out}"), f"op_{out}")
+            b.add_edge(ins, [out], node)
+        fast, slow = b.topo_sort(), b._topo_sort_py()
+        assert [e.op for e in fast] == [e.op for e in slow]
+        pos = {e.outputs[0]: i for i, e in enumerate(fast)}
+        assert all(pos[i] < pos[e.outputs[0]] for e in fast for i in e.inputs if i in pos)
+    with pytest.raises(ValueError, match="cycle"):
+        C.plan_topo_order([[1], [0]], [[0], [1]])
+    two = GraphBuilder("dup")
+    two.add_edge(["a"], ["x"], two.add_layer(ActivationLayer("relu", "r1"), "r1"))
+    two.add_edge(["b"], ["x"], two.add_layer(ActivationLayer("relu", "r2"), "r2"))
+    with pytest.raises(ValueError, match="io node x has two producers"):
+        two.topo_sort()
+    # --- slab layout and buckets
+    sizes = [rnd.randint(1, 5000) for _ in range(50)]
+    off = _plan_slab(sizes)
+    cur = 0
+    for n, o in zip(sizes, off):
+        assert o == cur and o % ALIGN_ELEMS == 0
+        cur += (n + ALIGN_ELEMS - 1) // ALIGN_ELEMS * ALIGN_ELEMS
+    assert off[-1] == cur and _plan_slab([]) == [0]
+    buckets = C.plan_buckets(off, 20000)
+    assert buckets[0][1] == off[-1] and buckets[-1][0] == 0                 # last-produced gradients first, full cover
+    assert all(a[0] == b[1] for a, b in zip(buckets, buckets[1:])) and all(lo in off for lo, _ in buckets)
+    assert all(hi - lo >= 20000 for lo, hi in buckets[:-1])
+    assert C.plan_buckets(off, 0) == [(0, off[-1])]
+    # --- schedules: what parallel/pipeline.PipelineEngine.train_batch walks (warm-up, 1F1B, cool-down)
+    for S in (1, 2, 4, 8):
+        for M in (1, 2, 3, 8):
+            for r in range(S):
+                sch = C.plan_schedule_1f1b(S, r, M)
+                warm = min(S - r - 1, M)
+                assert [m for o, m in sch if o == "F"] == list(range(M)) == [m for o, m in sch if o == "B"]
+                assert [o for o, _ in sch[:warm]] == ["F"] * warm and [o for o, _ in sch[len(sch) - warm:]] == ["B"] * warm
+                assert C.plan_peak_in_flight(sch) == min(S - r, M)
+                done = set()
+                for o, m in sch:                                           # a backward never precedes its forward
+                    assert o == "F" or m in done
+                    done.add(m) if o == "F" else None
+    assert C.plan_peak_in_flight(C.plan_schedule_gpipe(6)) == 6
+    # --- partitions
+    layers = [DenseLayer(4, 4, name=f"l{i}") for i in range(11)]
+    assert [(p.start_offset, p.length) for p in NaivePipelinePartitioner([1, 2, 1]).partition_model(layers)] == [(0, 2), (2, 5), (7, 4)]
+    assert [(p.start_offset, p.length) for p in NaiveDataPartitioner([1, 3]).partition_input(torch.zeros(10, 2))] == [(0, 2), (2, 8)]
+    with pytest.raises(ValueError):
+        NaivePipelinePartitioner([1, 1, 1]).partition_model(layers[:2])
+    for _ in range(30):
+        L, n = rnd.randint(1, 14), rnd.randint(1, 5)
+        cost = [rnd.uniform(0.1, 10) for _ in range(L)]
+        bnd = [rnd.uniform(0, 3) for _ in range(L)] if rnd.random() < 0.5 else None
+        a, bpy = _min_bottleneck_split(cost, n, bnd), _min_bottleneck_split_py(cost, n, bnd)
+        assert a == bpy and all(isinstance(p, SeqPartition) for p in a)
+        assert a[0].start_offset == 0 and a[-1].end == L and all(x.end == y.start_offset for x, y in zip(a, a[1:]))

@@ -11,6 +11,7 @@
 
 #include "allocator.hpp"
 #include "cpu_ops.hpp"
+#include "planner.hpp"
 #include "archiver.hpp"
 #include "cpu_math.hpp"
 #include "data_loader.hpp"
@@ -208,6 +209,30 @@ void runtime_bind(py::module_& m) {
     py::gil_scoped_release rel;
     return cpu_dot(reinterpret_cast<const float*>(a), reinterpret_cast<const float*>(b), n);
   });
+  // ---------------------------------------------------------------- planner (graph order, slabs, schedules, partitions)
+  m.def("plan_topo_order", &planner::topo_order, py::arg("inputs"), py::arg("outputs"));
+  m.def("plan_slab", &planner::plan_slab, py::arg("sizes"), py::arg("align"));
+  m.def("plan_buckets", &planner::plan_buckets, py::arg("offsets"), py::arg("bucket_elems"));
+  m.def("plan_schedule_1f1b", [](int64_t stages, int64_t rank, int64_t mbs) {
+    std::vector<std::pair<std::string, int64_t>> out;
+    for (const auto& st : planner::schedule_1f1b(stages, rank, mbs)) out.emplace_back(std::string(1, st.op), st.mb);
+    return out;
+  }, py::arg("stages"), py::arg("rank"), py::arg("microbatches"));
+  m.def("plan_schedule_gpipe", [](int64_t mbs) {
+    std::vector<std::pair<std::string, int64_t>> out;
+    for (const auto& st : planner::schedule_gpipe(mbs)) out.emplace_back(std::string(1, st.op), st.mb);
+    return out;
+  }, py::arg("microbatches"));
+  m.def("plan_peak_in_flight", [](const std::vector<std::pair<std::string, int64_t>>& steps) {
+    std::vector<planner::Step> s;
+    for (const auto& p : steps) s.push_back({p.first.empty() ? 'F' : p.first[0], p.second});
+    return planner::peak_in_flight(s);
+  });
+  m.def("plan_split_by_proportions", &planner::split_by_proportions, py::arg("total"), py::arg("proportions"),
+        py::arg("at_least_one") = true);
+  m.def("plan_min_bottleneck_split", &planner::min_bottleneck_split, py::arg("cost"), py::arg("n"),
+        py::arg("boundary") = std::vector<double>());
+
   // CPU elementwise / reduction family (cpu_ops.hpp); pointers are raw data_ptr()s of contiguous fp32 / fp64 tensors
   m.def("cpu_binary", [](int64_t a, int64_t b, double s, int64_t o, int64_t n, int op, bool f64, int threads) {
     py::gil_scoped_release rel;

@@ -80,7 +80,30 @@ class GraphBuilder:
         return self
 
     def topo_sort(self) -> list[Edge]:
-        """Kahn's algorithm over edges; raises on cycles (graph_builder.hpp:28-112)."""
+        """Kahn's algorithm over edges; raises on cycles and on io nodes with two producers
+        (graph_builder.hpp:28-112).  The ordering itself is computed by the native planner
+        (csrc/runtime/planner.hpp::topo_order); ``_topo_sort_py`` is the same algorithm kept as the test oracle."""
+        from ..ops import native
+        C = native.load()
+        if C is None or not hasattr(C, "plan_topo_order"):
+            return self._topo_sort_py()
+        ids: dict[str, int] = {}
+
+        def nid(u):
+            return ids.setdefault(u, len(ids))
+
+        ins = [[nid(u) for u in e.inputs] for e in self.edges]
+        outs = [[nid(u) for u in e.outputs] for e in self.edges]
+        try:
+            order = C.plan_topo_order(ins, outs)
+        except (ValueError, RuntimeError) as err:
+            msg = str(err)
+            for u, i in ids.items():                       # report the io node by its name, not its dense id
+                msg = msg.replace(f"io node {i} ", f"io node {u} ")
+            raise ValueError(msg) from None
+        return [self.edges[i] for i in order]
+
+    def _topo_sort_py(self) -> list[Edge]:
         producers = {}
         for e in self.edges:
             for o in e.outputs:
@@ -111,24 +134,36 @@ class GraphBuilder:
         return Graph(self, torch.device(device), seed, alloc_fn)
 
 
+def _plan_slab(sizes: list[int]) -> list[int]:
+    """Element offsets of ``sizes`` packed with ALIGN_ELEMS alignment; the last entry is the slab length."""
+    from ..ops import native
+    C = native.load()
+    if C is not None and hasattr(C, "plan_slab"):
+        return list(C.plan_slab([int(n) for n in sizes], ALIGN_ELEMS))
+    out, cur = [], 0
+    for n in sizes:
+        out.append(cur)
+        cur += (n + ALIGN_ELEMS - 1) // ALIGN_ELEMS * ALIGN_ELEMS
+    return out + [cur]
+
+
 class GraphContext:
     def __init__(self, layers: list[Layer], device: torch.device, alloc_fn=None):
         self.device = device
         self.layers = layers
         alloc = alloc_fn or (lambda n, dt: torch.zeros(n, dtype=dt, device=device))
-        entries, buffers = [], []
-        off = boff = 0
+        train, frozen = [], []
         for layer in layers:
             for d in layer.param_descriptors():
                 n = 1
                 for s in d.shape:
                     n *= s
-                if d.trainable:
-                    entries.append((layer, d, off, n))
-                    off += (n + ALIGN_ELEMS - 1) // ALIGN_ELEMS * ALIGN_ELEMS
-                else:
-                    buffers.append((layer, d, boff, n))
-                    boff += (n + ALIGN_ELEMS - 1) // ALIGN_ELEMS * ALIGN_ELEMS
+                (train if d.trainable else frozen).append((layer, d, n))
+        # aligned back-to-back offsets from the native planner (csrc/runtime/planner.hpp::plan_slab)
+        toff, boffs = _plan_slab([n for _, _, n in train]), _plan_slab([n for _, _, n in frozen])
+        entries = [(layer, d, o, n) for (layer, d, n), o in zip(train, toff)]
+        buffers = [(layer, d, o, n) for (layer, d, n), o in zip(frozen, boffs)]
+        off, boff = toff[-1], boffs[-1]
         self.numel = off
         self.param_slab = alloc(max(off, ALIGN_ELEMS), torch.float32)
         self.grad_slab = alloc(max(off, ALIGN_ELEMS), torch.float32)

@@ -87,6 +87,13 @@ class NaivePipelinePartitioner(Partitioner):
 
     def partition_model(self, layers):
         _check(layers, self.num_partitions)
+        C = _native()
+        if C is not None:
+            try:
+                return [SeqPartition(int(a), int(b)) for a, b in
+                        C.plan_split_by_proportions(len(layers), list(self.config.proportions), True)]
+            except RuntimeError as e:                    # pybind maps std::invalid_argument to ValueError; keep both
+                raise ValueError(str(e)) from None
         total, psum = len(layers), sum(self.config.proportions)
         parts, cur = [], 0
         for i, prop in enumerate(self.config.proportions):
@@ -122,6 +129,10 @@ class NaiveDataPartitioner(Partitioner):
             raise ValueError("number of partitions must be greater than zero")
         if x is None or x.dim() == 0:
             raise ValueError("input tensor is null or has empty shape")
+        C = _native()
+        if C is not None:
+            return [InputPartition(int(a), int(b)) for a, b in
+                    C.plan_split_by_proportions(int(x.shape[0]), list(self.config.proportions), False)]
         B, psum = x.shape[0], sum(self.config.proportions)
         parts, cur = [], 0
         for i, prop in enumerate(self.config.proportions):
@@ -155,9 +166,24 @@ def _nested_flops(layer: Layer, s) -> int:
     return 0
 
 
+def _native():
+    from ..ops import native
+    C = native.load()
+    return C if C is not None and hasattr(C, "plan_min_bottleneck_split") else None
+
+
 def _min_bottleneck_split(cost, n, boundary=None):
     """Contiguous split of len(cost) items into n non-empty groups minimising the largest group
-    cost (+ boundary[j] charged to the group that ends at item j).  O(n * L^2) DP."""
+    cost (+ boundary[j] charged to the group that ends at item j).  O(n * L^2) DP, run by the native
+    planner (csrc/runtime/planner.hpp::min_bottleneck_split); ``_min_bottleneck_split_py`` is the oracle."""
+    C = _native()
+    if C is None:
+        return _min_bottleneck_split_py(cost, n, boundary)
+    parts = C.plan_min_bottleneck_split([float(c) for c in cost], int(n), [float(b) for b in boundary] if boundary is not None else [])
+    return [SeqPartition(int(a), int(b)) for a, b in parts]
+
+
+def _min_bottleneck_split_py(cost, n, boundary=None):
     L = len(cost)
     n = min(n, L)
     pre = [0.0]
