@@ -122,6 +122,51 @@ TNN_MV static double red_loop(const T* a, const T* b, double mu, int64_t n) {
   return ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7])) + tail;
 }
 
+// ---- fused optimizer steps over the flat slabs (reference: include/nn/optimizers_impl/cpu/adam_kernels.hpp,
+// sgd_kernels.hpp).  One pass over p, g (and m, v / velocity) instead of one pass per arithmetic op.
+struct AdamArgs {
+  float lr, beta1, beta2, eps, weight_decay, grad_scale, bias1, bias2;   // bias_k = 1 - beta_k^t
+  bool decoupled, zero_grad;
+};
+TNN_MV static void adam_loop(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                             int64_t n, AdamArgs a) {
+  const float inv_b1 = 1.f / a.bias1, inv_b2 = 1.f / a.bias2;
+  const float decay = (a.weight_decay != 0.f && a.decoupled) ? 1.f - a.weight_decay * a.lr : 1.f;
+  const float l2 = (a.weight_decay != 0.f && !a.decoupled) ? a.weight_decay * a.lr : 0.f;
+  for (int64_t i = 0; i < n; ++i) {
+    const float gg = g[i] * a.grad_scale;
+    const float pi = p[i] * decay;
+    const float mi = a.beta1 * m[i] + (1.f - a.beta1) * gg;
+    const float vi = a.beta2 * v[i] + (1.f - a.beta2) * gg * gg;
+    m[i] = mi;
+    v[i] = vi;
+    const float upd = a.lr * (mi * inv_b1) / (std::sqrt(vi * inv_b2) + a.eps) + l2 * pi;
+    p[i] = pi - upd;
+    if (a.zero_grad) g[i] = 0.f;
+  }
+}
+struct SgdArgs {
+  float lr, momentum, weight_decay, grad_scale;
+  bool zero_grad;
+};
+TNN_MV static void sgd_loop(float* __restrict__ p, float* __restrict__ g, float* vel /*may be null*/, int64_t n, SgdArgs a) {
+  if (vel) {
+    for (int64_t i = 0; i < n; ++i) {
+      const float gg = g[i] * a.grad_scale + a.weight_decay * p[i];
+      const float vi = a.momentum * vel[i] - a.lr * gg;
+      vel[i] = vi;
+      p[i] += vi;
+      if (a.zero_grad) g[i] = 0.f;
+    }
+  } else {
+    for (int64_t i = 0; i < n; ++i) {
+      const float gg = g[i] * a.grad_scale + a.weight_decay * p[i];
+      p[i] -= a.lr * gg;
+      if (a.zero_grad) g[i] = 0.f;
+    }
+  }
+}
+
 template <class F>
 static void for_chunks(int64_t n, int threads, F&& f) {
   if (n <= 0) return;
@@ -180,6 +225,13 @@ void axpy(T* y, const T* x, T alpha, int64_t n, int threads = 0) {
 template <class T>
 void fill(T* y, T v, int64_t n, int threads = 0) {
   for_chunks(n, threads, [&](int64_t l, int64_t h) { fill_loop<T>(y + l, v, h - l); });
+}
+
+inline void adam_step(float* p, float* g, float* m, float* v, int64_t n, AdamArgs a, int threads = 0) {
+  for_chunks(n, threads, [&](int64_t l, int64_t h) { adam_loop(p + l, g + l, m + l, v + l, h - l, a); });
+}
+inline void sgd_step(float* p, float* g, float* vel, int64_t n, SgdArgs a, int threads = 0) {
+  for_chunks(n, threads, [&](int64_t l, int64_t h) { sgd_loop(p + l, g + l, vel ? vel + l : nullptr, h - l, a); });
 }
 
 // sum / dot / sum of squared differences, double accumulation, deterministic in the thread count

@@ -6,6 +6,7 @@
 #include <pybind11/stl.h>
 
 #include <chrono>
+#include <cmath>
 #include <memory>
 #include <mutex>
 
@@ -267,6 +268,22 @@ void runtime_bind(py::module_& m) {
     return f64 ? cpuops::reduce<double>((const double*)a, (const double*)b, mu, n, op, threads)
                : cpuops::reduce<float>((const float*)a, (const float*)b, mu, n, op, threads);
   }, py::arg("a"), py::arg("b"), py::arg("mu"), py::arg("n"), py::arg("op"), py::arg("f64") = false, py::arg("threads") = 0);
+  m.def("cpu_adam_step", [](int64_t p, int64_t g, int64_t mm, int64_t v, int64_t n, double lr, double b1, double b2, double eps,
+                            double wd, bool decoupled, double grad_scale, int64_t t, bool zero_grad, int threads) {
+    py::gil_scoped_release rel;
+    cpuops::AdamArgs a{(float)lr, (float)b1, (float)b2, (float)eps, (float)wd, (float)grad_scale,
+                       (float)(1.0 - std::pow(b1, (double)t)), (float)(1.0 - std::pow(b2, (double)t)), decoupled, zero_grad};
+    cpuops::adam_step((float*)p, (float*)g, (float*)mm, (float*)v, n, a, threads);
+  }, py::arg("p"), py::arg("g"), py::arg("m"), py::arg("v"), py::arg("n"), py::arg("lr"), py::arg("beta1"), py::arg("beta2"),
+     py::arg("eps"), py::arg("weight_decay"), py::arg("decoupled"), py::arg("grad_scale"), py::arg("step"),
+     py::arg("zero_grad") = false, py::arg("threads") = 0);
+  m.def("cpu_sgd_step", [](int64_t p, int64_t g, int64_t vel, int64_t n, double lr, double momentum, double wd, double grad_scale,
+                           bool zero_grad, int threads) {
+    py::gil_scoped_release rel;
+    cpuops::SgdArgs a{(float)lr, (float)momentum, (float)wd, (float)grad_scale, zero_grad};
+    cpuops::sgd_step((float*)p, (float*)g, (float*)vel, n, a, threads);
+  }, py::arg("p"), py::arg("g"), py::arg("velocity"), py::arg("n"), py::arg("lr"), py::arg("momentum"), py::arg("weight_decay"),
+     py::arg("grad_scale"), py::arg("zero_grad") = false, py::arg("threads") = 0);
   m.def("parallel_for", [](int64_t n, int64_t grain, const py::function& fn, int threads) {
     // Python callables run under the GIL; this is for API parity and for callables that release it
     global_pool(threads).parallel_for(n, grain, [&](int64_t b, int64_t e) {

@@ -65,6 +65,17 @@ class Optimizer:
     def clone(self) -> "Optimizer":
         return OptimizerFactory.create_from_config(self.get_config())
 
+    @staticmethod
+    def _cpu_native(*ts) -> bool:
+        """Flat fp32 CPU slabs -> the fused one-pass native step (csrc/runtime/cpu_ops.hpp::adam_step / sgd_step);
+        TNN_CPU_OPT_TORCH=1 keeps the op-by-op torch formulation (the oracle the tests compare against)."""
+        import os
+        if os.environ.get("TNN_CPU_OPT_TORCH", "0") == "1":
+            return False
+        C = native.load()
+        return C is not None and hasattr(C, "cpu_adam_step") and all(
+            t is None or ((not t.is_cuda) and t.dtype == torch.float32 and t.is_contiguous()) for t in ts)
+
     def _after_update(self):
         ctx = self.ctx
         if ctx.lp_slab is not None:
@@ -95,6 +106,9 @@ class SGD(Optimizer):
             st = self._push_state(p.device)
             self.step_count += 1
             native.require().sgd_step_flat_dev(p, g, self.velocity, ctx.lp_slab, st, self.fused_zero_grad)
+        elif self._cpu_native(p, g, self.velocity):
+            native.load().cpu_sgd_step(p.data_ptr(), g.data_ptr(), self.velocity.data_ptr() if self.velocity is not None else 0,
+                                       p.numel(), self.lr, self.momentum, self.weight_decay, self.grad_scale, self.fused_zero_grad)
         else:
             gg = g * self.grad_scale + self.weight_decay * p
             if self.velocity is not None:
@@ -144,6 +158,10 @@ class Adam(Optimizer):
             st = self._push_state(p.device)
             self.step_count += 1
             native.require().adam_step_flat_dev(p, g, self.m, self.v, ctx.lp_slab, st, self.fused_zero_grad)
+        elif self._cpu_native(p, g, self.m, self.v):
+            native.load().cpu_adam_step(p.data_ptr(), g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), p.numel(), self.lr,
+                                        self.beta1, self.beta2, self.epsilon, self.weight_decay, self.decoupled, self.grad_scale,
+                                        t, self.fused_zero_grad)
         else:
             gg = g * self.grad_scale
             if self.weight_decay != 0 and self.decoupled:
