@@ -871,3 +871,39 @@ def test_native_planner_matches_python_oracles():
         a, bpy = _min_bottleneck_split(cost, n, bnd), _min_bottleneck_split_py(cost, n, bnd)
         assert a == bpy and all(isinstance(p, SeqPartition) for p in a)
         assert a[0].start_offset == 0 and a[-1].end == L and all(x.end == y.start_offset for x, y in zip(a, a[1:]))
+
+
+def test_layer_profiler_and_trainer_switches(capsys):
+    """PROFILER_TYPE / PRINT_LAYER_PROFILING / PRINT_LAYER_MEMORY_USAGE: per-layer fwd/bwd table, restored on detach."""
+    from tnn_b200.data import SyntheticDataLoader
+    from tnn_b200.nn.train import TrainingConfig, train_model
+    from tnn_b200.utils.profiler import LayerProfiler
+    g = load_or_create_model("mnist_cnn", device="cpu", seed=2)
+    model = g.get_layers()[0]
+    conv1 = model.layers[0]
+    prof = LayerProfiler("CUMULATIVE").attach(model)
+    assert "forward_impl" in conv1.__dict__
+    g.set_training(True)
+    x = torch.rand(4, 28, 28, 1)
+    for _ in range(2):
+        y = model.forward(x, 0)
+        model.backward(torch.ones_like(y), 0)
+    rows = {r[0]: r for r in prof.rows()}
+    assert rows["mnist_cnn/conv1"][3] == 2 and rows["mnist_cnn/conv1"][4] == 2 and rows["mnist_cnn/conv1"][1] > 0
+    txt = prof.report()
+    assert "mnist_cnn/output" in txt and "share" in txt and prof.rows()[0][3] == 2         # cumulative keeps the counts
+    assert "params KiB" in prof.memory_report()
+    prof.detach()
+    assert "forward_impl" not in conv1.__dict__ and "backward_impl" not in conv1.__dict__
+    cfg = TrainingConfig(epochs=1, batch_size=16, progress_print_interval=0, device_type="CPU", profiler_type="NORMAL",
+                         print_layer_memory_usage=True)
+    train = SyntheticDataLoader((28, 28, 1), 10, 32)
+    train.load_data()
+    import tempfile
+    cfg.snapshot_dir = tempfile.mkdtemp()
+    lines = []
+    hist = train_model(g, train, None, OptimizerFactory.create_sgd(0.01), LossFactory.create_logsoftmax_crossentropy(), None, cfg,
+                       log=lines.append)
+    out = "\n".join(lines)
+    assert "layer profile, epoch 1 (normal)" in out and "layer memory, epoch 1" in out and "mnist_cnn/bn1" in out
+    assert hist["layer_profile"] and "forward_impl" not in conv1.__dict__

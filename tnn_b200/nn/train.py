@@ -282,7 +282,16 @@ def train_model(graph: Graph, train_loader, val_loader, optimizer: Optimizer, cr
     cfg = cfg or TrainingConfig()
     dev = graph.device()
     graph.set_training(True)
-    step_fn = TrainStep(graph, criterion, optimizer, scheduler, cfg.gradient_accumulation_steps, dp)
+    lprof = None
+    if cfg.print_layer_profiling or cfg.print_layer_memory_usage or str(cfg.profiler_type).upper() not in ("", "NONE"):
+        from ..utils.profiler import LayerProfiler
+        mode = str(cfg.profiler_type).upper()
+        lprof = LayerProfiler("NORMAL" if mode in ("", "NONE") else mode)
+        for layer in graph.get_layers():
+            lprof.attach(layer)
+    # per-layer events cannot be recorded inside a replayed CUDA graph: profile the eager step
+    step_fn = TrainStep(graph, criterion, optimizer, scheduler, cfg.gradient_accumulation_steps, dp,
+                        use_graph=False if lprof is not None else None)
     pre = DevicePrefetcher(dev)
     history = {"train_loss": [], "val_acc": [], "step_ms": []}
     best_acc = -1.0
@@ -319,6 +328,11 @@ def train_model(graph: Graph, train_loader, val_loader, optimizer: Optimizer, cr
                 break
         history["train_loss"].append(float(acc[0].cpu()) / max(1, global_step))
         log(f"epoch {epoch + 1} done in {time.time() - t_epoch:.2f}s")
+        if lprof is not None:
+            if cfg.print_layer_profiling or str(cfg.profiler_type).upper() not in ("", "NONE"):
+                log(lprof.report(f"layer profile, epoch {epoch + 1}"))
+            if cfg.print_layer_memory_usage:
+                log(lprof.memory_report(f"layer memory, epoch {epoch + 1}"))
         if val_loader is not None:
             vloss, vacc = validate_model(graph, val_loader, criterion, cfg)
             history["val_acc"].append(vacc)
@@ -329,6 +343,9 @@ def train_model(graph: Graph, train_loader, val_loader, optimizer: Optimizer, cr
         if 0 < cfg.max_steps <= global_step:
             save_checkpoint(graph, os.path.join(cfg.snapshot_dir, graph.name), optimizer, scheduler, global_step)
             break
+    if lprof is not None:
+        history["layer_profile"] = lprof.rows()
+        lprof.detach()
     return history
 
 

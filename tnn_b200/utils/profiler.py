@@ -117,3 +117,123 @@ class GlobalProfiler:
     @classmethod
     def add_event(cls, *a, **k):
         cls.get_profiler().add_event(*a, **k)
+
+
+class LayerProfiler:
+    """Per-layer forward / backward timing and memory table for the single-process trainer -- the
+    ``PROFILER_TYPE = NONE | NORMAL | CUMULATIVE``, ``PRINT_LAYER_PROFILING`` and
+    ``PRINT_LAYER_MEMORY_USAGE`` switches of TrainingConfig (include/nn/train.hpp:31,54-56), which
+    the reference declares without implementing the per-layer part.
+
+    ``attach(model)`` wraps ``forward_impl`` / ``backward_impl`` of every leaf layer INSTANCE (the
+    classes and the un-profiled hot path are untouched); ``detach()`` restores them.  On a GPU each
+    call is bracketed by CUDA events on the launching stream and resolved when the table is
+    built, so profiling adds no synchronisation inside the step (it does need the eager step: the
+    trainer turns CUDA-graph replay off while a profiler is attached).  NORMAL reports the interval
+    since the last report, CUMULATIVE the totals since attach."""
+
+    def __init__(self, mode: str = "NORMAL"):
+        self.mode = (mode or "NORMAL").upper()
+        self._layers = []            # (path, layer)
+        self._saved = {}
+        self._host = {}              # path -> [fwd_ms, bwd_ms, fwd_calls, bwd_calls]
+        self._pending = []           # (path, slot, ev0, ev1)
+
+    @staticmethod
+    def _leaves(layer, prefix=""):
+        kids = layer.children() if hasattr(layer, "children") else []
+        path = f"{prefix}/{layer.name}" if prefix else layer.name
+        if not kids:
+            yield path, layer
+            return
+        for k in kids:
+            yield from LayerProfiler._leaves(k, path)
+
+    def attach(self, model) -> "LayerProfiler":
+        import time
+        for path, layer in self._leaves(model):
+            if id(layer) in self._saved:
+                continue
+            self._layers.append((path, layer))
+            self._host[path] = [0.0, 0.0, 0, 0]
+            self._saved[id(layer)] = (layer, layer.__dict__.get("forward_impl"), layer.__dict__.get("backward_impl"))
+
+            def wrap(fn, slot, path=path):
+                def timed(*a, **k):
+                    t = a[0] if a and isinstance(a[0], torch.Tensor) else (a[0][0] if a and isinstance(a[0], (list, tuple)) and a[0] else None)
+                    if t is not None and t.is_cuda:
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                        out = fn(*a, **k)
+                        e1.record()
+                        self._pending.append((path, slot, e0, e1))
+                    else:
+                        t0 = time.perf_counter()
+                        out = fn(*a, **k)
+                        self._host[path][slot] += (time.perf_counter() - t0) * 1e3
+                    self._host[path][2 + slot] += 1
+                    return out
+                return timed
+
+            layer.forward_impl = wrap(layer.forward_impl, 0)
+            layer.backward_impl = wrap(layer.backward_impl, 1)
+        return self
+
+    def detach(self):
+        for layer, f, b in self._saved.values():
+            for name, orig in (("forward_impl", f), ("backward_impl", b)):
+                if orig is None:
+                    layer.__dict__.pop(name, None)           # fall back to the class method
+                else:
+                    layer.__dict__[name] = orig
+        self._saved.clear()
+        self._layers.clear()
+
+    def _resolve(self):
+        if self._pending:
+            torch.cuda.synchronize()
+            for path, slot, e0, e1 in self._pending:
+                self._host[path][slot] += e0.elapsed_time(e1)
+            self._pending.clear()
+
+    def rows(self):
+        self._resolve()
+        return [(p, *self._host[p]) for p, _ in self._layers]
+
+    def reset(self):
+        self._resolve()
+        for v in self._host.values():
+            v[:] = [0.0, 0.0, 0, 0]
+
+    def report(self, title: str = "layer profile") -> str:
+        rows = self.rows()
+        tot = sum(r[1] + r[2] for r in rows) or 1.0
+        w = max([len(r[0]) for r in rows] + [5])
+        lines = [f"-- {title} ({self.mode.lower()}) --", f"{'layer':<{w}} {'fwd ms':>10} {'bwd ms':>10} {'calls':>7} {'share':>7}"]
+        for p, f, b, nf, nb in rows:
+            lines.append(f"{p:<{w}} {f:>10.3f} {b:>10.3f} {nf:>7d} {100 * (f + b) / tot:>6.1f}%")
+        lines.append(f"{'total':<{w}} {sum(r[1] for r in rows):>10.3f} {sum(r[2] for r in rows):>10.3f}")
+        if self.mode != "CUMULATIVE":
+            self.reset()
+        return "\n".join(lines)
+
+    def memory_report(self, title: str = "layer memory") -> str:
+        """Parameter bytes and the bytes currently held in each layer's per-microbatch caches."""
+        def nbytes(o):
+            if isinstance(o, torch.Tensor):
+                return o.numel() * o.element_size()
+            if isinstance(o, dict):
+                return sum(nbytes(v) for v in o.values())
+            if isinstance(o, (list, tuple)):
+                return sum(nbytes(v) for v in o)
+            return 0
+        w = max([len(p) for p, _ in self._layers] + [5])
+        lines = [f"-- {title} --", f"{'layer':<{w}} {'params KiB':>12} {'cached KiB':>12}"]
+        tp = tc = 0
+        for p, layer in self._layers:
+            pb = sum(nbytes(t) for t in getattr(layer, "params", {}).values())
+            cb = nbytes(getattr(layer, "_cache", {}))
+            tp, tc = tp + pb, tc + cb
+            lines.append(f"{p:<{w}} {pb / 1024:>12.1f} {cb / 1024:>12.1f}")
+        lines.append(f"{'total':<{w}} {tp / 1024:>12.1f} {tc / 1024:>12.1f}")
+        return "\n".join(lines)
