@@ -369,3 +369,93 @@ def test_graph_reducer_merges_linear_chains_into_sequentials():
     y0 = GraphExecutor(ref).forward({"input": x})["output"]
     y1 = GraphExecutor(red).forward({"input": x})["output"]
     assert torch.allclose(y0, y1, atol=1e-6)
+
+
+def test_user_defined_layers_through_the_extension_bases(tmp_path):
+    """siso_layer.hpp / stateless_layer.hpp / parameterized_layer.hpp: a user writes forward_impl / backward_impl (+ the
+    parameter list), registers the type, and gets init, slabs, optimizer, config round trip and checkpoints from the base."""
+    from tnn_b200.nn import (GraphExecutor, OptimizerFactory, ParamDescriptor, ParameterizedLayer, SISOLayer, StatelessLayer,
+                             graph_from_sequential, register)
+    from tnn_b200.nn.graph import Graph
+
+    @register()
+    class ScaleShift(ParameterizedLayer):
+        TYPE_NAME = "test_scale_shift"
+
+        def __init__(self, features, name="scale_shift"):
+            super().__init__(name)
+            self.features = int(features)
+
+        def param_descriptors(self):
+            return [ParamDescriptor("scale", (self.features,), lambda t, g: t.fill_(2.0)),
+                    ParamDescriptor("shift", (self.features,), lambda t, g: t.zero_())]
+
+        def forward_impl(self, x, mb_id):
+            if self.training:
+                self.cache(mb_id)["x"] = x
+            return x * self.params["scale"] + self.params["shift"]
+
+        def backward_impl(self, dy, mb_id):
+            x = self.cache(mb_id)["x"]
+            self.grads["scale"] += (dy * x).reshape(-1, self.features).sum(0)
+            self.grads["shift"] += dy.reshape(-1, self.features).sum(0)
+            return dy * self.params["scale"]
+
+        def config_params(self):
+            return dict(features=self.features)
+
+        @classmethod
+        def create_from_config(cls, c):
+            return cls(c["features"], c.name)
+
+    @register()
+    class Halve(StatelessLayer):
+        TYPE_NAME = "test_halve"
+
+        def forward_impl(self, x, mb_id):
+            return x[..., ::2].contiguous()
+
+        def backward_impl(self, dy, mb_id):
+            dx = torch.zeros(*dy.shape[:-1], dy.shape[-1] * 2)
+            dx[..., ::2] = dy
+            return dx
+
+        def compute_output_shape(self, s):
+            return (*s[:-1], s[-1] // 2)
+
+        @classmethod
+        def create_from_config(cls, c):
+            return cls(c.name)
+
+    seq = Sequential([ScaleShift(6, "ss"), Halve("half"), DenseLayer(3, 2, True, "fc")], "custom")
+    assert seq.output_shape((5, 6)) == (5, 2) and Halve("h").output_shapes([(4, 8)]) == [(4, 4)]
+    assert Halve("h").param_descriptors() == [] and isinstance(Halve("h"), SISOLayer)
+    with pytest.raises(RuntimeError):
+        Halve("h").init("cpu").forward([torch.zeros(1, 2), torch.zeros(1, 2)], 0)
+    with pytest.raises(NotImplementedError):
+        ParameterizedLayer("p").param_descriptors()
+    again = LayerFactory.create(TConfig.from_json(seq.get_config().to_json()))
+    assert [type(l).__name__ for l in again.layers] == ["ScaleShift", "Halve", "DenseLayer"]
+    g = graph_from_sequential(seq, "cpu", seed=4)
+    g.set_training(True)
+    ss = g.get_layers()[0].layers[0]
+    assert ss.params["scale"].data_ptr() >= g.context().param_slab.data_ptr()        # re-homed into the slab
+    opt = OptimizerFactory.create_sgd(0.1)
+    opt.attach(g.context())
+    ex = GraphExecutor(g)
+    x = torch.randn(5, 6)
+    y = ex.forward({"input": x})["output"]
+    ex.backward({"output": torch.ones_like(y)})
+    fc = g.get_layers()[0].layers[2]
+    expect = (torch.ones(5, 2) @ fc.params["weight"])                                   # d/d(halved input)
+    full = torch.zeros(5, 6)
+    full[:, ::2] = expect
+    torch.testing.assert_close(ss.grads["shift"], full.sum(0))
+    before = ss.params["shift"].clone()
+    opt.update()
+    torch.testing.assert_close(ss.params["shift"], before - 0.1 * full.sum(0))
+    path = str(tmp_path / "custom_model")
+    with open(path, "wb") as f:
+        g.save_state(f)
+    g2 = Graph.load_state(path, "cpu")
+    torch.testing.assert_close(g2.get_layers()[0].layers[0].params["shift"], ss.params["shift"])

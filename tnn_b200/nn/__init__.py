@@ -1,4 +1,4 @@
-from .layer import Layer, LayerFactory, ParamDescriptor  # noqa: F401
+from .layer import Layer, LayerFactory, ParamDescriptor, ParameterizedLayer, SISOLayer, StatelessLayer, register  # noqa: F401
 from .layers import *  # noqa: F401,F403
 from .blocks import Sequential, MSequential, ResidualBlock, AttentionBlock, FlashAttentionBlock, SDPALayer  # noqa: F401
 from .builder import LayerBuilder  # noqa: F401

@@ -277,3 +277,46 @@ def register(*aliases):
     def deco(layer_cls):
         return LayerFactory.register_layer(layer_cls, *aliases)
     return deco
+
+
+# ----------------------------------------------------------------------------------------------- extension bases
+class SISOLayer(Layer):
+    """Single-input / single-output layer (reference: include/nn/siso_layer.hpp:9-34).  The base ``Layer`` already
+    unwraps one-element lists; this class makes the contract explicit for user-defined layers: a list of more than
+    one tensor is an error, and the shape rule is ``compute_output_shape`` (``output_shapes`` is the list form)."""
+
+    def forward(self, inputs, mb_id: int = 0):
+        if isinstance(inputs, (list, tuple)) and len(inputs) != 1:
+            raise RuntimeError("SISOLayer only supports single input and single output")
+        return super().forward(inputs, mb_id)
+
+    def backward(self, grads, mb_id: int = 0):
+        if isinstance(grads, (list, tuple)) and len(grads) != 1:
+            raise RuntimeError("SISOLayer only supports single grad output and single grad input")
+        return super().backward(grads, mb_id)
+
+    def compute_output_shape(self, input_shape):
+        return tuple(input_shape)
+
+    def output_shape(self, s):
+        return tuple(self.compute_output_shape(tuple(s)))
+
+    def output_shapes(self, input_shapes):
+        if len(input_shapes) != 1:
+            raise RuntimeError("SISOLayer expects exactly one input shape")
+        return [self.output_shape(input_shapes[0])]
+
+
+class StatelessLayer(SISOLayer):
+    """A SISO layer without parameters (layers_impl/stateless_layer.hpp:16-22): activations, shape ops, ..."""
+
+    def param_descriptors(self):
+        return []
+
+
+class ParameterizedLayer(SISOLayer):
+    """A SISO layer that owns parameters (layers_impl/parameterized_layer.hpp:15-22): subclasses list them in
+    ``param_descriptors`` (name, shape, initialiser) and the base allocates, initialises, slabs and serialises them."""
+
+    def param_descriptors(self):
+        raise NotImplementedError(f"{type(self).__name__} must describe its parameters")
