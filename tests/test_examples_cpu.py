@@ -92,3 +92,21 @@ def test_cpu_runnable_benchmarks(tmp_path):
     assert g["tensors"] > 0 and g["bulk_ms"] > 0
     t = last(_run("benchmarks/tcp_communicator_bench.py", "--self-test", "--mb", "1", "--seconds", "1"))
     assert t["messages"] > 0 and t["MBps"] > 0
+
+
+def test_torch_pipeline_baseline_matches_single_stage(tmp_path):
+    """baseline/torch_pipeline.py (the library arm for the pipeline configs): two gloo stages follow the one-stage loss."""
+    import json
+    script = os.path.join(ROOT, "baseline", "torch_pipeline.py")
+    common = ["--model", "tiny", "--batch", "16", "--microbatches", "4", "--steps", "2", "--warmup", "1", "--print-losses"]
+    one = subprocess.run([sys.executable, script, *common], capture_output=True, text=True, timeout=300, cwd=tmp_path,
+                         env=dict(os.environ, MASTER_PORT="29561"))
+    assert one.returncode == 0, one.stderr[-2000:]
+    two = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29562", script, *common, "--proportions", "1,1"], capture_output=True,
+                         text=True, timeout=300, cwd=tmp_path)
+    assert two.returncode == 0, two.stderr[-2000:]
+    l1 = json.loads([l for l in one.stdout.splitlines() if l.startswith("{")][-1])
+    l2 = json.loads([l for l in two.stdout.splitlines() if l.startswith("{")][-1])
+    assert l2["n_gpus"] == 2 and l2["config"]["parallelism"] == "pp2" and len(l1["losses"]) == 3
+    assert all(abs(a - b) < 1e-4 for a, b in zip(l1["losses"], l2["losses"]))
