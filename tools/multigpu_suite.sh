@@ -13,3 +13,7 @@ timeout 150 $T --master-port 29566 bench.py --gpus $N --dp nccl --steps 40 --war
 cut -c1-200 gpurun_out/mg${N}_bench_tnn_nccl.json
 timeout 150 $T --master-port 29577 bench.py --gpus $N --impl torch --steps 40 --warmup 8 > gpurun_out/mg${N}_bench_torch.json 2>/dev/null
 cut -c1-200 gpurun_out/mg${N}_bench_torch.json
+# library arm for the pipeline configs: torch autograd + cuDNN stages, 1F1B over NCCL p2p (baseline/torch_pipeline.py)
+timeout 200 $T --master-port 29588 baseline/torch_pipeline.py --model cifar100_wrn16_8 --batch 256 --microbatches 4 --steps 30 --warmup 8 \
+  > gpurun_out/mg${N}_torch_pipeline.json 2> gpurun_out/mg${N}_torch_pipeline.err
+cut -c1-300 gpurun_out/mg${N}_torch_pipeline.json; tail -2 gpurun_out/mg${N}_torch_pipeline.err
