@@ -15,7 +15,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from tnn_b200.data import DataLoaderFactory  # noqa: E402
-from tnn_b200.distributed import (CoordinatorConfig, Endpoint, NetworkCoordinator, ParallelMode, TCPWorker,  # noqa: E402
+from tnn_b200.distributed import (CoordinatorConfig, Endpoint, RoCECoordinator, ParallelMode, RoCEWorker,  # noqa: E402
                                   train_model)
 from tnn_b200.models import ExampleModels  # noqa: E402
 from tnn_b200.nn import LossFactory, OptimizerFactory, SchedulerFactory  # noqa: E402
@@ -37,9 +37,9 @@ if __name__ == "__main__":
     workers = []
     i = 1
     while env.has(f"WORKER{i}_PORT") or os.environ.get(f"WORKER{i}_PORT"):
-        workers.append(Endpoint.tcp(env.get(f"WORKER{i}_HOST", "127.0.0.1"), env.get(f"WORKER{i}_PORT", 0, int)))
+        workers.append(Endpoint.roce(env.get(f"WORKER{i}_HOST", "127.0.0.1"), env.get(f"WORKER{i}_PORT", 0, int)))
         i += 1
-    local = TCPWorker(env.get("LOCAL_WORKER_HOST", "127.0.0.1"), env.get("LOCAL_WORKER_PORT", 0, int),
+    local = RoCEWorker(env.get("LOCAL_WORKER_HOST", "127.0.0.1"), env.get("LOCAL_WORKER_PORT", 0, int),
                       use_gpu=a.gpu and torch.cuda.is_available())
     if a.legacy:
         from tnn_b200.models import legacy
@@ -51,7 +51,7 @@ if __name__ == "__main__":
     ccfg = CoordinatorConfig(ParallelMode.PIPELINE, model, opt, SchedulerFactory.create_step_lr(opt, 10 ** 6, 0.1),
                              NaivePipelinePartitioner(NaivePartitionerConfig(props)), local_worker=local,
                              local_worker_position=env.get("LOCAL_WORKER_POSITION", 0, int), worker_endpoints=workers)
-    co = NetworkCoordinator(ccfg, env.get("COORDINATOR_HOST", "127.0.0.1"), env.get("COORDINATOR_PORT", 0, int))
+    co = RoCECoordinator(ccfg, env.get("COORDINATOR_HOST", "127.0.0.1"), env.get("COORDINATOR_PORT", 0, int))
     if a.synthetic:
         sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
         from trainer import synthetic_for

@@ -1,11 +1,11 @@
 #!/usr/bin/env python
 """Pipeline-stage worker process (reference: examples/tcp_worker.cpp:39-141, roce_worker.cpp).
 
-  python examples/tcp_worker.py <port> [--gpu] [--gpu-index N] [--host 127.0.0.1] [--io-threads 4]
+  python examples/roce_worker.py <port> [--gpu] [--gpu-index N] [--host 127.0.0.1] [--io-threads 4]
 
 Waits for a coordinator to send CONFIG_TRANSFER, then serves FORWARD/BACKWARD/UPDATE commands
-until SHUTDOWN.  ``--device/--gid-index`` of the RoCE worker are accepted and ignored (the
-transport here is the TCP bus; on-node tensors move over NVLink).
+until SHUTDOWN.  ``--device/--gid-index`` of the reference RoCE worker are accepted and ignored: the
+transport is the shared-memory rendezvous of tnn_b200/distributed/rendezvous.py (no NIC to pick).
 """
 import argparse
 import os
@@ -13,7 +13,7 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-from tnn_b200.distributed import TCPWorker  # noqa: E402
+from tnn_b200.distributed import RoCEWorker  # noqa: E402
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
@@ -28,7 +28,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     import torch
     torch.set_num_threads(a.num_threads)
-    w = TCPWorker(a.host, a.port, a.gpu, a.gpu_index, a.io_threads)
+    w = RoCEWorker(a.host, a.port, a.gpu, a.gpu_index, a.io_threads)
     print(f"[worker] listening on {a.host}:{a.port} ({'GPU ' + str(a.gpu_index) if a.gpu else 'CPU'})", flush=True)
     w.start()
     print("[worker] shutdown", flush=True)

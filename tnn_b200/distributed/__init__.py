@@ -1,5 +1,7 @@
 """Coordinator / worker distributed runtime (reference: include/distributed/)."""
-from .communicator import Communicator, InProcessCommunicator, RoCECommunicator, TCPCommunicator  # noqa: F401
+from .communicator import Communicator, InProcessCommunicator, TCPCommunicator  # noqa: F401
+from .rendezvous import RendezvousCommunicator, SlabAllocator  # noqa: F401
+RoCECommunicator = RendezvousCommunicator
 from .coordinator import (Coordinator, CoordinatorConfig, DistributedError, NetworkCoordinator,  # noqa: F401
                           RoCECoordinator)
 from .message import CommandType, Endpoint, Job, Message, ParallelMode, StageConfig  # noqa: F401

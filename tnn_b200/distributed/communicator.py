@@ -9,8 +9,10 @@ IN_PROCESS short-circuit, profile counters), tcp_communicator.hpp, roce_communic
 * ``TCPCommunicator`` serialises with the C++ archiver and ships packets through the C++
   ``TcpBus`` (multi-socket, 4 MiB slices, reassembly, priority dequeue).  Every send/receive is
   recorded as a COMMUNICATION event in the global profiler, as the reference does per packet.
-* RoCE endpoints are accepted and carried over the TCP bus (on one NVSwitch node the data path is
-  NVLink: parallel/pipeline.py and parallel/dp.py; there is no ibverbs in this image).
+* The RoCE family (``RoCECommunicator`` / ``RoCEWorker`` / ``RoCECoordinator``) is the one-sided rendezvous
+  transport of ``rendezvous.py``: registered shared-memory slab, PREPARE / READY_TO_WRITE / write + immediate,
+  control frames on the TCP bus.  (The tensor data path of the B200 engines is NVLink: parallel/pipeline.py and
+  parallel/dp.py.)
 """
 from __future__ import annotations
 
@@ -212,5 +214,9 @@ class TCPCommunicator(Communicator):
         return d
 
 
-# RoCE API names of the reference resolve to the TCP bus here (see module docstring).
-RoCECommunicator = TCPCommunicator
+def __getattr__(name):
+    # ``RoCECommunicator`` lives in rendezvous.py (which imports this module): resolve it lazily
+    if name == "RoCECommunicator":
+        from .rendezvous import RendezvousCommunicator
+        return RendezvousCommunicator
+    raise AttributeError(name)

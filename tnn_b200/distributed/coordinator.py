@@ -317,4 +317,13 @@ class NetworkCoordinator(Coordinator):
         super().__init__(config, comm)
 
 
-RoCECoordinator = NetworkCoordinator
+class RoCECoordinator(Coordinator):
+    """Coordinator on the rendezvous transport (examples/roce_coordinator.cpp); every worker of the job must be a
+    ``RoCEWorker`` (the two transports frame their packets differently, as TCP and RoCE binaries do upstream)."""
+
+    def __init__(self, config: CoordinatorConfig, host="127.0.0.1", port=0, device=None, slab_bytes=256 << 20):
+        from .rendezvous import RendezvousCommunicator
+        comm = RendezvousCommunicator(host, port, device=device, name="coordinator", slab_bytes=slab_bytes)
+        comm.start()
+        config.coordinator_endpoint = comm.endpoint()
+        super().__init__(config, comm)

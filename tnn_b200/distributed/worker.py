@@ -277,4 +277,12 @@ class TCPWorker(Worker):
         super().__init__(comm, dev, name or f"tcp-worker-{port}")
 
 
-RoCEWorker = TCPWorker
+class RoCEWorker(Worker):
+    """``roce_worker`` of the reference (examples/roce_worker.cpp): same worker over the one-sided rendezvous
+    transport (``distributed/rendezvous.py`` -- registered slab, PREPARE / READY_TO_WRITE / write + immediate)."""
+
+    def __init__(self, host="127.0.0.1", port=0, use_gpu=False, gpu_index=0, io_threads=4, name=None, slab_bytes=256 << 20):
+        from .rendezvous import RendezvousCommunicator
+        dev = torch.device("cuda", gpu_index) if use_gpu and torch.cuda.is_available() else torch.device("cpu")
+        comm = RendezvousCommunicator(host, port, io_threads, device=dev, name=name or f"roce-worker-{port}", slab_bytes=slab_bytes)
+        super().__init__(comm, dev, name or f"roce-worker-{port}")
