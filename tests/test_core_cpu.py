@@ -907,3 +907,21 @@ def test_layer_profiler_and_trainer_switches(capsys):
     out = "\n".join(lines)
     assert "layer profile, epoch 1 (normal)" in out and "layer memory, epoch 1" in out and "mnist_cnn/bn1" in out
     assert hist["layer_profile"] and "forward_impl" not in conv1.__dict__
+
+
+def test_env_static_and_instance_lookups(tmp_path, monkeypatch):
+    """env.hpp: Env::get<T>(key, default) is static upstream; both spellings work here and the default's type decides."""
+    from tnn_b200.utils.env import Env
+    f = tmp_path / ".env"
+    f.write_text(chr(10).join(["# comment", "EPOCHS=7", "NAME='wrn'", "FLAG=true", "LR=0.5", ""]))
+    e = Env(str(f))
+    assert e.get("EPOCHS", 1) == 7 and e.get("LR", 0.1) == 0.5 and e.get("NAME", "x") == "wrn" and e.get("FLAG", False) is True
+    assert e.get("MISSING", 3) == 3 and e.get("EPOCHS", typ=str) == "7" and e.has("NAME") and not e.has("NOPE_XYZ")
+    monkeypatch.setenv("EPOCHS", "9")                       # the process environment wins over the file
+    assert e.get("EPOCHS", 1) == 9
+    monkeypatch.chdir(tmp_path)
+    Env.reload(".env")
+    assert Env.get("NAME", "") == "wrn" and Env.get("EPOCHS", 0) == 9 and Env.has("LR")
+    monkeypatch.setenv("ONLY_IN_PROCESS", "12")
+    assert Env.get("ONLY_IN_PROCESS", 0) == 12
+    Env.reload("/nonexistent/.env")
