@@ -20,11 +20,12 @@ from common import emit  # noqa: E402
 
 import torch  # noqa: E402
 
-from tnn_b200.distributed import CommandType, Endpoint, Job, Message, TCPCommunicator  # noqa: E402
+from tnn_b200.distributed import CommandType, Endpoint, Job, Message, RoCECommunicator, TCPCommunicator  # noqa: E402
 
 
-def run_side(host, port, peer_host, peer_port, threads, seconds, shape, inflight=4, quiet=False):
-    comm = TCPCommunicator(host, port, num_io_threads=threads, name=f"bench{port}")
+def run_side(host, port, peer_host, peer_port, threads, seconds, shape, inflight=4, quiet=False, transport="tcp"):
+    cls = RoCECommunicator if transport == "roce" else TCPCommunicator      # roce = shared-memory rendezvous (roce_communicator_benchmark.cpp)
+    comm = cls(host, port, num_io_threads=threads, name=f"bench{port}")
     comm.start()
     peer = Endpoint.tcp(peer_host, peer_port)
     for attempt in range(120):
@@ -57,7 +58,7 @@ def run_side(host, port, peer_host, peer_port, threads, seconds, shape, inflight
     time.sleep(0.3)                    # let the peer drain before the sockets close
     stats = comm.stats()
     comm.stop()
-    res = dict(bench="tcp_communicator", port=port, messages=received, bytes=received * nbytes, seconds=round(dt, 3),
+    res = dict(bench=f"{transport}_communicator", port=port, messages=received, bytes=received * nbytes, seconds=round(dt, 3),
                MBps=round(received * nbytes / dt / 1e6, 1), message_MB=round(nbytes / 2 ** 20, 1), io_threads=threads,
                packets_sent=(stats.get("bus") or {}).get("packets_sent"))
     if not quiet:
@@ -66,8 +67,8 @@ def run_side(host, port, peer_host, peer_port, threads, seconds, shape, inflight
     return res
 
 
-def _child(port, peer_port, threads, seconds, shape, q):
-    q.put(run_side("127.0.0.1", port, "127.0.0.1", peer_port, threads, seconds, shape, quiet=True))
+def _child(port, peer_port, threads, seconds, shape, q, transport):
+    q.put(run_side("127.0.0.1", port, "127.0.0.1", peer_port, threads, seconds, shape, quiet=True, transport=transport))
 
 
 def main():
@@ -80,15 +81,17 @@ def main():
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--mb", type=int, default=128, help="message payload in MiB (reference: 128)")
     ap.add_argument("--self-test", action="store_true", help="spawn the peer locally")
+    ap.add_argument("--transport", choices=["tcp", "roce"], default="tcp",
+                    help="roce = the rendezvous transport (reference: roce_communicator_benchmark.cpp)")
     a = ap.parse_args()
     shape = (a.mb * 2, 32, 32, 128)                  # mb MiB of fp32; 128 -> the reference's [256,32,32,128]
     if a.self_test:
         p0 = 24000 + os.getpid() % 3000
         ctx = mp.get_context("spawn")
         q = ctx.Queue()
-        child = ctx.Process(target=_child, args=(p0 + 1, p0, a.num_threads, a.seconds, shape, q), daemon=True)
+        child = ctx.Process(target=_child, args=(p0 + 1, p0, a.num_threads, a.seconds, shape, q, a.transport), daemon=True)
         child.start()
-        mine = run_side("127.0.0.1", p0, "127.0.0.1", p0 + 1, a.num_threads, a.seconds, shape, quiet=True)
+        mine = run_side("127.0.0.1", p0, "127.0.0.1", p0 + 1, a.num_threads, a.seconds, shape, quiet=True, transport=a.transport)
         other = q.get(timeout=a.seconds + 60)
         child.join(10)
         emit(**mine)
@@ -98,7 +101,7 @@ def main():
         ap.error("--port and --peer-port are required (or --self-test)")
     print(f"Communicator Benchmark Configuration\nListen host: {a.host}\nListen port: {a.port}\nPeer host: {a.peer_host}\n"
           f"Peer port: {a.peer_port}\nWorker threads: {a.num_threads}")
-    emit(**run_side(a.host, a.port, a.peer_host, a.peer_port, a.num_threads, a.seconds, shape))
+    emit(**run_side(a.host, a.port, a.peer_host, a.peer_port, a.num_threads, a.seconds, shape, transport=a.transport))
     return 0
 
 

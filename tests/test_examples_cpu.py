@@ -90,8 +90,9 @@ def test_cpu_runnable_benchmarks(tmp_path):
     assert d["max_diff"] == 0.0 and d["max_grad_diff"] == 0.0 and d["max_weight_grad_diff"] == 0.0
     g = last(_run("benchmarks/grad_clear_bench.py", "mnist_cnn"))
     assert g["tensors"] > 0 and g["bulk_ms"] > 0
-    t = last(_run("benchmarks/tcp_communicator_bench.py", "--self-test", "--mb", "1", "--seconds", "1"))
-    assert t["messages"] > 0 and t["MBps"] > 0
+    for transport in ("tcp", "roce"):
+        t = last(_run("benchmarks/tcp_communicator_bench.py", "--self-test", "--mb", "1", "--seconds", "1", "--transport", transport))
+        assert t["bench"] == f"{transport}_communicator" and t["messages"] > 0 and t["MBps"] > 0
 
 
 def test_torch_pipeline_baseline_matches_single_stage(tmp_path):
