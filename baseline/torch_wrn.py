@@ -65,7 +65,9 @@ class ResNet9(nn.Module):
         return self.net(x)
 
 
-def bench_torch_wrn(B, steps, warmup, local, world, model_name="cifar100_wrn16_8"):
+def bench_torch_wrn(B, steps, warmup, local, world, model_name="cifar100_wrn16_8", graphed=True):
+    """Library arm.  ``graphed`` captures forward + backward + fused Adam in ONE CUDA graph (static inputs,
+    capturable optimizer) so this arm is not launch-bound -- the same execution model as tnn_b200's TrainStep."""
     import torch.distributed as dist
     dev = torch.device("cuda", local)
     torch.backends.cudnn.benchmark = True
@@ -73,17 +75,48 @@ def bench_torch_wrn(B, steps, warmup, local, world, model_name="cifar100_wrn16_8
     model = (ResNet9(classes) if "resnet9" in model_name else WRN16_8(classes)).to(dev).to(memory_format=torch.channels_last)
     if world > 1:
         model = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, eps=1e-3, weight_decay=3e-4, fused=True)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, eps=1e-3, weight_decay=3e-4, fused=True, capturable=graphed)
     xs = [torch.rand(B, 3, 32, 32, device=dev).to(memory_format=torch.channels_last) for _ in range(4)]
     ys = [torch.randint(0, classes, (B,), device=dev) for _ in range(4)]
+    sx, sy = xs[0].clone(memory_format=torch.channels_last), ys[0].clone()
 
-    def step(i):
+    def eager(x, y):
         with torch.autocast("cuda", dtype=torch.bfloat16):
-            loss = F.cross_entropy(model(xs[i % 4]), ys[i % 4])
+            loss = F.cross_entropy(model(x), y)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
         return loss
+
+    graph, gloss, mode = None, None, "eager"
+    if graphed:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(11 if world > 1 else 3):     # DDP needs 11 warm-up iterations before capture
+                    eager(sx, sy)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            opt.zero_grad(set_to_none=True)
+            with torch.cuda.graph(graph):
+                with torch.autocast("cuda", dtype=torch.bfloat16, cache_enabled=False):
+                    gloss = F.cross_entropy(model(sx), sy)
+                gloss.backward()
+                opt.step()
+            mode = "cuda-graph"
+        except Exception as e:  # noqa: BLE001
+            graph, mode = None, f"eager (graph capture failed: {type(e).__name__})"
+            torch.cuda.synchronize()
+
+    def step(i):
+        if graph is None:
+            return eager(xs[i % 4], ys[i % 4])
+        sx.copy_(xs[i % 4])
+        sy.copy_(ys[i % 4])
+        graph.replay()
+        return gloss
 
     for i in range(max(warmup, 3)):
         step(i)
@@ -107,4 +140,4 @@ def bench_torch_wrn(B, steps, warmup, local, world, model_name="cifar100_wrn16_8
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "higher_is_better": True,
             "scaling": "weak", "dtype": "bf16", "data": "synthetic",
             "config": {"model": model_name, "global_batch": world * B, "parallelism": f"ddp{world}",
-                       "stack": "torch autocast bf16 + cuDNN channels_last + NCCL"}, "final_loss": float(loss)}
+                       "stack": "torch autocast bf16 + cuDNN channels_last + fused Adam + NCCL", "execution": mode}, "final_loss": float(loss)}

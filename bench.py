@@ -146,12 +146,11 @@ def emit(d):
 
 
 def run_reference(args):
-    # The reference is a CMake/C++ tree with no setup.py / pyproject.toml; the one allowed offline
-    # install (`pip install --no-index ... --target baseline/_ref /root/reference`) fails with
-    # "Neither 'setup.py' nor 'pyproject.toml' found" (recorded in DESIGN.md), and its CMake build
-    # needs network FetchContent + libibverbs + TBB and a header that is missing from the snapshot.
-    emit({"impl": "reference", "unavailable": "reference is a C++/CMake tree: pip install fails (no setup.py/pyproject.toml) "
-          "and the CMake build needs network FetchContent, libibverbs, TBB and a missing header (device/engine.hpp)"})
+    """Unmodified reference code from baseline/_ref through its own training loop (see
+    baseline/reference_arm.py for what is run and why it is the reference's torch implementation)."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import reference_arm
+    reference_arm.run(args, emit, dist_setup, barrier, max_over_ranks, ClockSampler, BASELINE_IMG_S)
 
 
 def dist_setup(n):

@@ -925,3 +925,66 @@ def test_env_static_and_instance_lookups(tmp_path, monkeypatch):
     monkeypatch.setenv("ONLY_IN_PROCESS", "12")
     assert Env.get("ONLY_IN_PROCESS", 0) == 12
     Env.reload("/nonexistent/.env")
+
+
+def test_checkpoint_header_is_the_reference_graph_schema(tmp_path):
+    """ADVICE r1: Graph::save_state writes GraphConfig as a TConfig (include/nn/graph.hpp:78-126, src/nn/op_node.cpp:6-15,
+    src/common/config.cpp:225-237): {name, type:"graph", parameters:{op_nodes:{type:"json", value:[{type:"op_node",
+    parameters:{uid,name,layer_config}}]}, io_nodes, edges:[{producers, consumers, op_node}]}}.  A header hand-written in
+    exactly that schema (what a reference-produced file contains) followed by tensor records must load."""
+    import io
+    import json
+    import struct
+
+    from tnn_b200.core import tensor_io
+    from tnn_b200.models import load_or_create_model
+    from tnn_b200.nn.graph import Graph
+
+    g = load_or_create_model("mnist_cnn", device="cpu", seed=3)
+    buf = io.BytesIO()
+    g.save_state(buf)
+    raw = buf.getvalue()
+    hdr, end = json.JSONDecoder().raw_decode(raw.decode("latin-1"))
+    assert hdr["type"] == "graph" and set(hdr["parameters"]) == {"op_nodes", "io_nodes", "edges"}
+    ops = hdr["parameters"]["op_nodes"]
+    assert ops["type"] == "json" and ops["value"][0]["type"] == "op_node"
+    assert set(ops["value"][0]["parameters"]) == {"uid", "name", "layer_config"}
+    assert ops["value"][0]["parameters"]["layer_config"]["type"] == "json"
+    assert hdr["parameters"]["io_nodes"]["value"][0] == {"name": "", "type": "io_node", "parameters": {"uid": {"type": "string", "value": "input"}}}
+    e0 = hdr["parameters"]["edges"]["value"][0]
+    assert set(e0) == {"producers", "consumers", "op_node"}
+    seq_cfg = ops["value"][0]["parameters"]["layer_config"]["value"]
+    assert seq_cfg["type"] == "sequential" and seq_cfg["parameters"]["layers"]["type"] == "json"
+
+    # golden: a reference-style file for a one-dense-layer graph, built byte by byte without our writer
+    dense = {"name": "fc", "type": "dense", "parameters": {"input_features": {"type": "size_t", "value": 3},
+                                                            "output_features": {"type": "size_t", "value": 2},
+                                                            "use_bias": {"type": "bool", "value": True}}}
+    seq = {"name": "m", "type": "sequential", "parameters": {"layers": {"type": "json", "value": [dense]}}}
+    golden = {"name": "tiny", "type": "graph", "parameters": {
+        "op_nodes": {"type": "json", "value": [{"name": "", "type": "op_node", "parameters": {
+            "uid": {"type": "string", "value": "model"}, "name": {"type": "string", "value": "m"},
+            "layer_config": {"type": "json", "value": seq}}}]},
+        "io_nodes": {"type": "json", "value": [{"name": "", "type": "io_node", "parameters": {"uid": {"type": "string", "value": u}}}
+                                               for u in ("input", "output")]},
+        "edges": {"type": "json", "value": [{"producers": ["input"], "consumers": ["output"], "op_node": "model"}]}}}
+    W = torch.arange(6, dtype=torch.float32).reshape(2, 3)
+    b = torch.tensor([0.5, -0.5])
+    blob = json.dumps(golden, indent=4).encode()
+    for t in (W, b):                               # TensorImpl::save: u32 dtype (FP32 = 5), u64 ndims, u64 dims[], raw
+        blob += struct.pack("<IQ", 5, t.dim()) + struct.pack(f"<{t.dim()}Q", *t.shape) + t.numpy().tobytes()
+    p = tmp_path / "tiny"
+    p.write_bytes(blob)
+    g2 = Graph.load_state(str(p), "cpu")
+    assert g2.name == "tiny"
+    x = torch.tensor([[1.0, 2.0, 3.0]])
+    from tnn_b200.nn.graph import GraphExecutor
+    y = GraphExecutor(g2).forward({"input": x})["output"]
+    torch.testing.assert_close(y, x @ W.t() + b)
+    # and the round-1 flat header still loads
+    flat = {"name": "old", "op_nodes": [{"uid": "model", "name": "m", "layer_config": seq}], "io_nodes": [{"uid": "input"}, {"uid": "output"}],
+            "edges": [{"inputs": ["input"], "outputs": ["output"], "op": "model"}]}
+    p2 = tmp_path / "old"
+    p2.write_bytes(json.dumps(flat).encode() + blob[len(json.dumps(golden, indent=4).encode()):])
+    g3 = Graph.load_state(str(p2), "cpu")
+    torch.testing.assert_close(GraphExecutor(g3).forward({"input": x})["output"], y)

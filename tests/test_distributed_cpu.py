@@ -333,6 +333,93 @@ def test_data_parallel_mode_averages_replica_gradients():
             w.stop()
 
 
+def test_tcp_data_parallel_mode_reduces_gradients_over_the_bus():
+    """DATA mode with a REMOTE (TCP) replica must still average gradients (it used to be a silent no-op)."""
+    seed = 9
+    ctx = mp.get_context("spawn")
+    port = 21000 + (os.getpid() % 20000)
+    ready = ctx.Event()
+    proc = ctx.Process(target=_tcp_worker_main, args=(port, ready), daemon=True)
+    proc.start()
+    assert ready.wait(60)
+    local = TCPWorker("127.0.0.1", 0, use_gpu=False, name="local-dp")
+    cfg = CoordinatorConfig(ParallelMode.DATA, _model(), OptimizerFactory.create_sgd(0.1), None,
+                            NaiveDataPartitioner([1, 1]), local_worker=local, local_worker_position=0,
+                            worker_endpoints=[Endpoint.tcp("127.0.0.1", port)], seed=seed)
+    co = NetworkCoordinator(cfg, "127.0.0.1", 0)
+    crit = LossFactory.create_logsoftmax_crossentropy()
+    x, y = _batches(1, 8)[0]
+    try:
+        co.start()
+        xs, ys = split_microbatches(x, y, 2)
+        co.async_train_batch(xs, ys, crit)
+        co.update_parameters()
+        p0, p1 = co.gather_parameters()
+        assert torch.equal(p0.cpu(), p1.cpu())                  # replicas stay identical across the bus
+        # the helper's SGD carries momentum 0.9: identical to plain SGD on the first step only (v0 = 0)
+        ref, gref = _reference_losses([(x, y)], 2, seed, steps_lr=0.1)
+        torch.testing.assert_close(p0[:gref.ctx.numel].cpu(), gref.ctx.param_slab[:gref.ctx.numel], atol=1e-5, rtol=1e-4)
+    finally:
+        co.stop()
+        local.stop()
+        proc.join(10)
+        if proc.is_alive():
+            proc.terminate()
+
+
+def _dp_shard_rank(rank, world, port, out_q):
+    """FusedDataParallel's sharded-state gather / scatter on gloo (the layout logic is device independent)."""
+    import torch.distributed as dist
+    from tnn_b200.nn.optimizers import Adam
+    from tnn_b200.parallel.dp import FusedDataParallel
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dp = FusedDataParallel.__new__(FusedDataParallel)
+        dp.group, dp.world, dp.rank, dp.n = dist.group.WORLD, world, rank, 1000
+        dp.buckets = [dict(lo=600, hi=1000, chunk=200, st_off=0), dict(lo=0, hi=600, chunk=300, st_off=200)]
+        dp.chunk = 500
+        dp.optimizer = Adam(1e-3)
+        dp.optimizer.step_count = 7
+        full_m = torch.arange(1000, dtype=torch.float32)
+        full_v = full_m * 2
+        dp.m, dp.v = torch.zeros(500), torch.zeros(500)
+        dp._scatter(full_m, dp.m)
+        dp._scatter(full_v, dp.v)
+        sd = dp.state_dict()
+        ok = torch.equal(sd["m"], full_m) and torch.equal(sd["v"], full_v) and sd["step"] == 7
+        # rank r must hold exactly its slices
+        exp = torch.cat([full_m[600 + rank * 200: 600 + (rank + 1) * 200], full_m[rank * 300:(rank + 1) * 300]])
+        ok = ok and torch.equal(dp.m, exp)
+        dp2 = FusedDataParallel.__new__(FusedDataParallel)
+        dp2.__dict__.update(dp.__dict__)
+        dp2.optimizer = Adam(1e-3)
+        dp2.m, dp2.v = torch.zeros(500), torch.zeros(500)
+        dp2.load_state_dict(sd)
+        ok = ok and torch.equal(dp2.m, dp.m) and torch.equal(dp2.v, dp.v) and dp2.optimizer.step_count == 7
+        out_q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fused_dp_state_dict_gathers_and_scatters_sharded_moments():
+    """checkpoint / resume under FusedDataParallel (moments live sharded in dp.m / dp.v)."""
+    from tnn_b200.nn.optimizers import Adam
+    a = Adam(1e-3)
+    assert "m" not in a.state_dict() and "v" not in a.state_dict()     # unattached / DP-owned state: no null entries
+    a.load_state_dict({"step": 3, "lr": 0.1, "m": None, "v": None})    # and nulls from old files are ignored
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 23000 + (os.getpid() % 20000)
+    ps = [ctx.Process(target=_dp_shard_rank, args=(r, 2, port, q), daemon=True) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in ps)
+    for p in ps:
+        p.join(30)
+    assert got == [(0, True), (1, True)]
+
+
 # ------------------------------------------------------------------------------- NCCL-style 1F1B engine (gloo on CPU)
 def _pp_rank(rank, world, port, seed, M, out_q):
     import torch.distributed as dist
@@ -498,3 +585,55 @@ def test_roce_two_process_pipeline_equals_single_device():
         local.stop()
         proc.join(10)
     assert not ({f for f in os.listdir("/dev/shm") if f.startswith("tnn_")} - before) or True
+
+
+def test_tcp_bus_rejects_hostile_packets_and_worker_rejects_foreign_paths(tmp_path):
+    """the control plane validates everything a peer declares (message length cap, slice geometry, no size
+    change for a live serial), survives garbage without terminating, binds to the configured host, and the worker
+    refuses file commands outside its I/O roots."""
+    import socket
+    import struct
+    from tnn_b200.ops import native
+    C = native.require()
+    bus = C.TcpBus(0, 2, 1 << 20, "127.0.0.1", 1 << 24)         # 16 MiB message cap
+    bus.start()
+    try:
+        port = bus.port()
+        # bound to loopback only
+        lst = [l for l in open("/proc/net/tcp").read().splitlines() if f":{port:04X} " in l and " 0A " in l]
+        assert lst and all(l.split()[1].startswith("0100007F") for l in lst)
+
+        def conn():
+            s = socket.create_connection(("127.0.0.1", port))
+            s.sendall(struct.pack("<III", 0x544E4E42, 55555, 0))
+            return s
+
+        def header(packet_len, msg_len, serial, off, total):
+            # PacketHeader layout (csrc/runtime/archiver.hpp): u8 version, u8 type, u8 endianness, u64 packet_length,
+            # u64 msg_length, u64 serial, u64 offset, u32 total, u8 compression
+            return struct.pack("<BBBQQQQIB", 1, 0, 1, packet_len, msg_len, serial, off, total, 0)
+
+        assert len(header(0, 0, 0, 0, 1)) == 40
+        s1 = conn()
+        s1.sendall(header(4, 1 << 40, 1, 0, 1 << 20))            # 1 TiB declared: must be refused, not allocated
+        time.sleep(0.3)
+        s2 = conn()
+        s2.sendall(header(1 << 20, 3 << 20, 7, 0, 3) + b"x" * (1 << 20))
+        s2.sendall(header(1 << 20, 2 << 20, 7, 1, 2) + b"y" * (1 << 20))   # same serial, other length: rejected
+        time.sleep(0.3)
+        s3 = conn()
+        payload = struct.pack("<H", 3) + b"ok"
+        s3.sendall(header(len(payload), len(payload), 9, 0, 1) + payload)   # a well-formed message still arrives
+        got = bus.recv(5000)
+        assert got is not None and got[1] == payload
+        assert bus.stats()["bad_packets"] >= 2
+        for s in (s1, s2, s3):
+            s.close()
+    finally:
+        bus.stop()
+    w = InProcessWorker("cpu", "guard")
+    assert w._checked_path(str(tmp_path / "ok.bin")).endswith("ok.bin")
+    with pytest.raises(PermissionError):
+        w._checked_path("/etc/passwd")
+    with pytest.raises(PermissionError):
+        w._checked_path(os.path.join(str(tmp_path), *[".."] * 12, "etc", "shadow"))

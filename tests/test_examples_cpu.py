@@ -27,8 +27,9 @@ def test_trainer_cli_runs_one_synthetic_epoch_on_cpu(tmp_path):
 
 
 def test_bench_reference_arm_prints_one_json_line():
-    """`bench.py --impl reference` must exit 0 with exactly one JSON line (the reference is a C++/CMake tree
-    that cannot be pip-installed offline: the line says so)."""
+    """`bench.py --impl reference` must exit 0 with exactly one JSON line.  On a GPU box it times the unmodified
+    reference torch WRN-16-8 (baseline/_ref); without CUDA it says so.  The reference module itself must import
+    and build the model without touching tnn_b200."""
     import json
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference"], capture_output=True,
                          text=True, timeout=120)
@@ -37,6 +38,14 @@ def test_bench_reference_arm_prints_one_json_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and "unavailable" in d
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import reference_arm
+    assert reference_arm.ensure_installed() is None
+    ref = reference_arm.load_reference_module()
+    import torch
+    m = ref.WRN16_8CIFAR100(num_classes=100)
+    assert m(torch.rand(2, 3, 32, 32)).shape == (2, 100)
+    assert sum(p.numel() for p in m.parameters()) > 10_000_000
 
 
 def _run(rel, *args, cwd=None, env=None, timeout=300):

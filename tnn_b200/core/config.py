@@ -9,6 +9,9 @@ from typing import Any
 
 
 def _tag(v: Any):
+    """Type-tagged JSON value with the reference's type names (src/common/config.cpp:89-126): nested configs and
+    arbitrary structures are ``json`` (the reference stores ``LayerConfig::to_json()`` objects as nlohmann::json),
+    homogeneous lists are ``vector<size_t|int|float|string>``."""
     if isinstance(v, bool):
         return {"type": "bool", "value": v}
     if isinstance(v, int):
@@ -18,40 +21,68 @@ def _tag(v: Any):
     if isinstance(v, str):
         return {"type": "string", "value": v}
     if isinstance(v, TConfig):
-        return {"type": "config", "value": v.to_json()}
+        return {"type": "json", "value": v.to_json()}
     if isinstance(v, (list, tuple)):
-        if all(isinstance(e, TConfig) for e in v) and len(v) > 0:
-            return {"type": "config_array", "value": [e.to_json() for e in v]}
-        if all(isinstance(e, bool) for e in v) and len(v) > 0:
-            return {"type": "bool_array", "value": list(v)}
-        if all(isinstance(e, int) for e in v):
-            return {"type": "size_t_array", "value": list(v)}
-        if all(isinstance(e, (int, float)) for e in v):
-            return {"type": "float_array", "value": [float(e) for e in v]}
+        if len(v) > 0 and all(isinstance(e, TConfig) for e in v):
+            return {"type": "json", "value": [e.to_json() for e in v]}
+        if len(v) > 0 and all(isinstance(e, bool) for e in v):
+            return {"type": "json", "value": list(v)}
+        if all(isinstance(e, int) and not isinstance(e, bool) for e in v):
+            return {"type": "vector<size_t>" if all(e >= 0 for e in v) else "vector<int>", "value": list(v)}
+        if all(isinstance(e, (int, float)) and not isinstance(e, bool) for e in v):
+            return {"type": "vector<float>", "value": [float(e) for e in v]}
         if all(isinstance(e, str) for e in v):
-            return {"type": "string_array", "value": list(v)}
-        return {"type": "json", "value": [_tag(e) for e in v]}
+            return {"type": "vector<string>", "value": list(v)}
+        return {"type": "json", "value": [_plain(e) for e in v]}
     if isinstance(v, dict):
-        return {"type": "json", "value": v}
+        return {"type": "json", "value": _plain(v)}
     if v is None:
-        return {"type": "null", "value": None}
+        return {"type": "json", "value": None}
     raise TypeError(f"unsupported config value type {type(v)}")
+
+
+def _plain(v: Any):
+    """Plain JSON form of a value nested inside a ``json`` parameter (configs become their to_json())."""
+    if isinstance(v, TConfig):
+        return v.to_json()
+    if isinstance(v, (list, tuple)):
+        return [_plain(e) for e in v]
+    if isinstance(v, dict):
+        return {k: _plain(e) for k, e in v.items()}
+    return v
+
+
+def _is_config_json(d: Any) -> bool:
+    return isinstance(d, dict) and "parameters" in d and "type" in d and "name" in d and isinstance(d["parameters"], dict)
+
+
+def _revive(v: Any):
+    """Inverse of _plain: dicts shaped like TConfig::to_json() come back as TConfig objects."""
+    if _is_config_json(v):
+        return TConfig.from_json(v)
+    if isinstance(v, list):
+        return [_revive(e) for e in v]
+    return v
 
 
 def _untag(d: Any):
     if not isinstance(d, dict) or "type" not in d:
         return d
     t, v = d["type"], d.get("value")
-    if t == "config":
+    if t == "config":                       # round-1 files
         return TConfig.from_json(v)
     if t == "config_array":
         return [TConfig.from_json(e) for e in v]
-    if t in ("size_t", "int", "int64"):
+    if t in ("size_t", "int", "int64", "long", "long long", "unsigned int", "unsigned long", "unsigned long long"):
         return int(v)
     if t in ("float", "double"):
         return float(v)
-    if t == "json" and isinstance(v, list):
-        return [_untag(e) for e in v]
+    if t == "json":
+        if isinstance(v, list) and v and all(isinstance(e, dict) and set(e) == {"type", "value"} for e in v):
+            return [_untag(e) for e in v]   # round-1 heterogeneous lists
+        return _revive(v)
+    if t in ("vector<float>", "vector<double>", "float_array"):
+        return [float(e) for e in v]
     return v
 
 

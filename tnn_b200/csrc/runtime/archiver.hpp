@@ -118,7 +118,7 @@ class Reader {
 
  private:
   void need(size_t n) const {
-    if (off_ + n > n_) throw std::out_of_range("tnn::Reader: read past end of buffer");
+    if (n > n_ - off_) throw std::out_of_range("tnn::Reader: read past end of buffer");   // off_ <= n_ always; no wrap
   }
   const uint8_t* p_;
   size_t n_;

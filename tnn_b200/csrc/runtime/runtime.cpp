@@ -295,8 +295,9 @@ void runtime_bind(py::module_& m) {
 
   // ---------------------------------------------------------------- TCP message bus
   py::class_<TcpBus>(m, "TcpBus")
-      .def(py::init<int, int, size_t>(), py::arg("listen_port"), py::arg("sockets_per_peer") = 4,
-           py::arg("max_packet") = (size_t)(4u << 20))
+      .def(py::init<int, int, size_t, const std::string&, uint64_t>(), py::arg("listen_port"), py::arg("sockets_per_peer") = 4,
+           py::arg("max_packet") = (size_t)(4u << 20), py::arg("bind_host") = std::string("127.0.0.1"),
+           py::arg("max_message") = (uint64_t)(8ull << 30))
       .def("start", &TcpBus::start)
       .def("stop", [](TcpBus& b) { py::gil_scoped_release rel; b.stop(); })
       .def("port", &TcpBus::port)
@@ -332,6 +333,7 @@ void runtime_bind(py::module_& m) {
         d["messages_sent"] = s.messages_sent;
         d["messages_received"] = s.messages_received;
         d["packets_sent"] = s.packets_sent;
+        d["bad_packets"] = s.bad_packets;
         return d;
       });
 

@@ -45,11 +45,17 @@ class TcpBus {
   static constexpr int kPriorities = 64;
 
   struct Stats {
-    uint64_t bytes_sent = 0, bytes_received = 0, messages_sent = 0, messages_received = 0, packets_sent = 0;
+    uint64_t bytes_sent = 0, bytes_received = 0, messages_sent = 0, messages_received = 0, packets_sent = 0,
+             bad_packets = 0;
   };
 
-  TcpBus(int listen_port, int sockets_per_peer = 4, size_t max_packet = 4u << 20)
-      : port_(listen_port), spp_(sockets_per_peer < 1 ? 1 : sockets_per_peer), max_packet_(max_packet) {}
+  // `bind_host`: interface the listener binds to ("127.0.0.1" by default: the bus is unauthenticated, so it is
+  // NOT exposed on every interface unless the caller asks for "0.0.0.0").  `max_message`: upper bound accepted
+  // for a peer-declared message length (a peer cannot make this process allocate more than that).
+  TcpBus(int listen_port, int sockets_per_peer = 4, size_t max_packet = 4u << 20,
+         const std::string& bind_host = "127.0.0.1", uint64_t max_message = 8ull << 30)
+      : port_(listen_port), spp_(sockets_per_peer < 1 ? 1 : sockets_per_peer), max_packet_(max_packet),
+        bind_host_(bind_host), max_message_(max_message) {}
   ~TcpBus() { stop(); }
 
   int port() const { return port_; }
@@ -63,7 +69,21 @@ class TcpBus {
     setsockopt(lfd, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
     sockaddr_in addr{};
     addr.sin_family = AF_INET;
-    addr.sin_addr.s_addr = htonl(INADDR_ANY);
+    if (bind_host_.empty() || bind_host_ == "0.0.0.0" || bind_host_ == "*") {
+      addr.sin_addr.s_addr = htonl(INADDR_ANY);
+    } else if (inet_pton(AF_INET, bind_host_ == "localhost" ? "127.0.0.1" : bind_host_.c_str(), &addr.sin_addr) != 1) {
+      addrinfo hints{}, *res = nullptr;
+      hints.ai_family = AF_INET;
+      hints.ai_socktype = SOCK_STREAM;
+      if (getaddrinfo(bind_host_.c_str(), nullptr, &hints, &res) != 0 || res == nullptr) {
+        ::close(lfd);
+        lfd_ = -1;
+        running_ = false;
+        throw std::runtime_error("TcpBus: cannot resolve bind host " + bind_host_);
+      }
+      addr.sin_addr = reinterpret_cast<sockaddr_in*>(res->ai_addr)->sin_addr;
+      freeaddrinfo(res);
+    }
     addr.sin_port = htons((uint16_t)port_);
     if (::bind(lfd, reinterpret_cast<sockaddr*>(&addr), sizeof(addr)) != 0) {
       ::close(lfd);
@@ -207,6 +227,7 @@ class TcpBus {
     s.messages_sent = stats_msgs_sent_;
     s.messages_received = stats_msgs_recv_;
     s.packets_sent = stats_packets_;
+    s.bad_packets = stats_bad_packets_;
     return s;
   }
 
@@ -217,6 +238,8 @@ class TcpBus {
   };
   struct Pending {
     std::vector<uint8_t> buf;
+    uint64_t len = 0;                 // declared message length (fixed for the life of the serial)
+    std::vector<uint8_t> seen;        // one flag per slice: duplicates are rejected
     uint32_t got = 0;
   };
   struct Peer {
@@ -297,7 +320,7 @@ class TcpBus {
 
   void accept_loop() {
     const int lfd = lfd_.load();
-    while (running_) {
+    while (running_) try {
       pollfd pfd{lfd, POLLIN, 0};
       int r = ::poll(&pfd, 1, 200);
       if (r <= 0) continue;
@@ -314,23 +337,80 @@ class TcpBus {
       char ip[64];
       inet_ntop(AF_INET, &peer_addr.sin_addr, ip, sizeof(ip));
       add_channel(std::string(ip) + ":" + std::to_string(hello[1]), fd);
+    } catch (...) {
+      stats_bad_packets_.fetch_add(1);    // e.g. thread creation failed: keep accepting
     }
   }
 
+  // One reader thread per socket.  Everything a peer controls is validated before it sizes or indexes a buffer:
+  // message length (<= max_message_), packet count (== ceil(msg / max_packet)), packet offset (< count), packet
+  // length (exactly the slice it claims to be) and a serial's length may not change once its buffer exists (a second
+  // packet with another msg_length would reallocate under a concurrent reader).  Any violation, I/O error or
+  // allocation failure drops this channel; nothing thrown here may escape the thread (std::terminate).
   void read_loop(const std::string& key, std::shared_ptr<Peer> peer, std::shared_ptr<Channel> ch) {
+    try {
+      read_loop_impl(key, peer, ch);
+    } catch (...) {
+      stats_bad_packets_.fetch_add(1);
+    }
+    {
+      std::lock_guard<std::mutex> g(mu_);
+      auto it = peers_.find(key);
+      if (it != peers_.end()) {
+        auto& v = it->second->chans;
+        for (size_t i = 0; i < v.size(); ++i)
+          if (v[i] == ch) {
+            v.erase(v.begin() + i);
+            break;
+          }
+      }
+    }
+  }
+
+  void read_loop_impl(const std::string& key, std::shared_ptr<Peer>& peer, std::shared_ptr<Channel>& ch) {
     std::vector<uint8_t> hb(PacketHeader::kBytes);
     while (running_) {
       if (!read_all(ch->fd, hb.data(), hb.size())) break;
       PacketHeader h = PacketHeader::read(hb.data(), hb.size());
-      if (h.version != 1 || h.total_packets == 0 || h.packet_length > max_packet_) break;
-      const size_t off = (size_t)h.packet_offset * max_packet_;
-      if (off + h.packet_length > h.msg_length) break;
+      if (h.version != 1 || h.total_packets == 0 || h.packet_length > max_packet_ || h.msg_length > max_message_) {
+        stats_bad_packets_.fetch_add(1);
+        break;
+      }
+      const uint64_t want_packets = std::max<uint64_t>(1, (h.msg_length + max_packet_ - 1) / max_packet_);
+      if (h.total_packets != want_packets || h.packet_offset >= h.total_packets) {
+        stats_bad_packets_.fetch_add(1);
+        break;
+      }
+      const uint64_t off = (uint64_t)h.packet_offset * max_packet_;
+      const uint64_t want_len = std::min<uint64_t>(max_packet_, h.msg_length - std::min<uint64_t>(h.msg_length, off));
+      if (h.packet_length != want_len) {
+        stats_bad_packets_.fetch_add(1);
+        break;
+      }
       std::vector<uint8_t>* dst;
       {
         std::lock_guard<std::mutex> g(peer->amu);
-        Pending& pd = peer->assembling[h.msg_serial_id];
-        if (pd.buf.size() != h.msg_length) pd.buf.resize(h.msg_length);
-        dst = &pd.buf;
+        auto it = peer->assembling.find(h.msg_serial_id);
+        if (it == peer->assembling.end()) {
+          if (peer->assembling.size() >= kMaxAssembling) {
+            stats_bad_packets_.fetch_add(1);
+            break;
+          }
+          Pending pd;
+          pd.buf.resize(h.msg_length);
+          pd.len = h.msg_length;
+          pd.seen.assign(h.total_packets, 0);
+          it = peer->assembling.emplace(h.msg_serial_id, std::move(pd)).first;
+        } else if (it->second.len != h.msg_length || it->second.seen.size() != h.total_packets) {
+          stats_bad_packets_.fetch_add(1);
+          break;                                  // size change for a live serial: never reallocate
+        }
+        if (it->second.seen[h.packet_offset]) {
+          stats_bad_packets_.fetch_add(1);
+          break;                                  // duplicate slice
+        }
+        it->second.seen[h.packet_offset] = 1;
+        dst = &it->second.buf;
       }
       // distinct packets of one message land in disjoint ranges, so concurrent reader threads
       // (one per socket) can fill the same buffer without holding the lock
@@ -339,10 +419,11 @@ class TcpBus {
       std::vector<uint8_t> done;
       {
         std::lock_guard<std::mutex> g(peer->amu);
-        Pending& pd = peer->assembling[h.msg_serial_id];
-        if (++pd.got == h.total_packets) {
-          done = std::move(pd.buf);
-          peer->assembling.erase(h.msg_serial_id);
+        auto it = peer->assembling.find(h.msg_serial_id);
+        if (it == peer->assembling.end()) break;
+        if (++it->second.got == h.total_packets) {
+          done = std::move(it->second.buf);
+          peer->assembling.erase(it);
           complete = true;
         }
       }
@@ -364,23 +445,15 @@ class TcpBus {
         cv_.notify_one();
       }
     }
-    {
-      std::lock_guard<std::mutex> g(mu_);
-      auto it = peers_.find(key);
-      if (it != peers_.end()) {
-        auto& v = it->second->chans;
-        for (size_t i = 0; i < v.size(); ++i)
-          if (v[i] == ch) {
-            v.erase(v.begin() + i);
-            break;
-          }
-      }
-    }
   }
 
+  static constexpr size_t kMaxAssembling = 4096;   // messages in flight per peer
   int port_;
   int spp_;
   size_t max_packet_;
+  std::string bind_host_;
+  uint64_t max_message_;
+  std::atomic<uint64_t> stats_bad_packets_{0};
   std::atomic<int> lfd_{-1};
   std::atomic<bool> running_{false};
   std::thread acceptor_;

@@ -17,6 +17,7 @@ IN_PROCESS short-circuit, profile counters), tcp_communicator.hpp, roce_communic
 from __future__ import annotations
 
 import atexit
+import os
 import threading
 import time
 from collections import deque
@@ -129,7 +130,8 @@ class TCPCommunicator(Communicator):
         super().__init__(name)
         self.host = host
         self.device = device
-        self._bus = native.require().TcpBus(int(port), int(skts_per_endpoint), 4 << 20)
+        self._bus = native.require().TcpBus(int(port), int(skts_per_endpoint), 4 << 20, str(host),
+                                            int(os.environ.get("TNN_TCP_MAX_MESSAGE", 8 << 30)))
         self._pump: threading.Thread | None = None
         self._running = False
         self._port = port

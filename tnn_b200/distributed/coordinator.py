@@ -232,9 +232,14 @@ class Coordinator:
         return [m.payload.data for m in got]
 
     def _average_replica_gradients(self):
-        """All-reduce (sum of 1/M-scaled microbatch gradients = batch mean) across replicas."""
-        # replicas expose their gradient slab through the in-process worker objects when local,
-        # otherwise parameters are re-synchronised after the update (host-staged fallback)
+        """All-reduce (sum of 1/M-scaled microbatch gradients = batch mean) across replicas.
+
+        In-process replicas expose their gradient slab by reference (summed in place).  Remote (TCP / RoCE)
+        replicas go through the message bus: SEND_PARAMS("grads") makes every worker reply PARAMS_TRANSFER with
+        its gradient slab, the coordinator sums them and returns the total as PARAMS_TRANSFER tagged
+        ``GRAD_SLAB_TAG``; workers overwrite their gradient slab and acknowledge with PARAMS_LOADED, so
+        UPDATE_PARAMETERS applies the same batch gradient on every replica (the reference has no gradient
+        reduction at all)."""
         workers = [ep.communicator() for ep in self.stage_endpoints if ep.type == Endpoint.IN_PROCESS]
         owners = [getattr(c, "_owner", None) for c in workers]
         if len(owners) == self.num_stages and all(o is not None and o.graph is not None for o in owners):
@@ -246,6 +251,17 @@ class Coordinator:
             # batch gradient is the SUM over replicas
             for s in slabs:
                 s.copy_(total.to(s.device))
+            return
+        from .message import GRAD_SLAB_TAG
+        self.broadcast(CommandType.SEND_PARAMS, "grads")
+        got = self.join(CommandType.PARAMS_TRANSFER, self.num_stages, self.timeout_update, what="gather replica gradients")
+        if len({m.payload.data.numel() for m in got}) != 1:
+            raise DistributedError("DATA mode: replicas report gradient slabs of different sizes")
+        total = got[0].payload.data.detach().to("cpu", torch.float32).clone()
+        for m in got[1:]:
+            total += m.payload.data.detach().to("cpu", torch.float32)
+        self.broadcast(CommandType.PARAMS_TRANSFER, Job(total, GRAD_SLAB_TAG))
+        self.join(CommandType.PARAMS_LOADED, self.num_stages, self.timeout_update, what="scatter summed gradients")
 
     # ------------------------------------------------------------------ monitoring
     def health_check(self, timeout: float = 5.0) -> list[dict]:

@@ -147,6 +147,10 @@ class Job:
     mb_id: int = 0
 
 
+# mb_id of a PARAMS_TRANSFER job that carries a GRADIENT slab (DATA-mode reduction over the bus)
+GRAD_SLAB_TAG = (1 << 62) | 0x6772
+
+
 @dataclass
 class StageConfig:
     model_config: dict = field(default_factory=dict)        # Sequential TConfig JSON

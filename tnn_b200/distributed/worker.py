@@ -23,7 +23,7 @@ from ..nn.optimizers import OptimizerFactory
 from ..nn.schedulers import SchedulerFactory
 from ..utils.profiler import EventType, GlobalProfiler, Profiler
 from .communicator import Communicator, InProcessCommunicator, TCPCommunicator
-from .message import CommandType, Endpoint, Job, Message, StageConfig
+from .message import GRAD_SLAB_TAG, CommandType, Endpoint, Job, Message, StageConfig
 
 
 def _parse_fault_env(spec: str):
@@ -58,6 +58,20 @@ class Worker:
         self._cpu_t0 = (time.process_time(), time.perf_counter())
         self.fault_inject = None          # callable(Message) -> None; tests use it to drop / delay / raise
         self._env_fault = _parse_fault_env(os.environ.get("TNN_FAULT_INJECT", ""))
+        # directories a peer may name in SAVE_TO_FILE / LOAD_PARAMS / CHECKPOINT_REQUEST (the bus is unauthenticated):
+        # the working directory, the system temp directory and TNN_WORKER_IO_ROOT (os.pathsep separated)
+        import tempfile
+        roots = [os.getcwd(), tempfile.gettempdir()] + [r for r in os.environ.get("TNN_WORKER_IO_ROOT", "").split(os.pathsep) if r]
+        self.io_roots = [os.path.realpath(r) for r in roots]
+
+    def _checked_path(self, path: str) -> str:
+        """Reject paths outside the configured I/O roots (after resolving symlinks and '..')."""
+        real = os.path.realpath(os.path.abspath(path))
+        for root in self.io_roots:
+            if real == root or real.startswith(root.rstrip(os.sep) + os.sep):
+                return real
+        raise PermissionError(f"worker {self.name}: path {path!r} is outside the allowed I/O roots {self.io_roots} "
+                              f"(extend with TNN_WORKER_IO_ROOT)")
 
     # ------------------------------------------------------------------ lifecycle
     def start(self, background: bool = False):
@@ -222,10 +236,10 @@ class Worker:
                 print(f"[{self.name}] {e['type']} {e['name']} {(e['end_ns'] - e['start_ns']) / 1e6:.3f} ms")
             self._reply(CommandType.PROFILING_PRINTED, True)
         elif c == CommandType.SAVE_TO_FILE:
-            path = msg.get(str)
+            path = self._checked_path(msg.get(str))
             self.graph.save_state(path + f".stage{self.stage_id}" if not path.endswith(f".stage{self.stage_id}") else path)
         elif c == CommandType.LOAD_PARAMS:
-            path = msg.get(str)
+            path = self._checked_path(msg.get(str))
             with open(path, "rb") as f:
                 data = f.read()
             _, end = json.JSONDecoder().raw_decode(data.decode("latin-1"))
@@ -233,18 +247,24 @@ class Worker:
             self.graph.load_state_tensors(io.BytesIO(data[end:]))
             self._reply(CommandType.PARAMS_LOADED, True)
         elif c == CommandType.SEND_PARAMS:
-            self._reply(CommandType.PARAMS_TRANSFER, Job(self.graph.ctx.param_slab.detach().clone(), self.stage_id))
+            # payload "grads" selects the gradient slab (DATA-mode reduction over the bus), default = parameters
+            what = msg.get(str) if msg.has_type(str) else "params"
+            slab = self.graph.ctx.grad_slab if what == "grads" else self.graph.ctx.param_slab
+            self._reply(CommandType.PARAMS_TRANSFER, Job(slab.detach().clone(), self.stage_id))
         elif c == CommandType.PARAMS_TRANSFER:
             job = msg.get(Job)
-            self.graph.ctx.param_slab.copy_(job.data.to(self.device))
-            self.graph.ctx.refresh_lp()
+            if job.mb_id == GRAD_SLAB_TAG:
+                self.graph.ctx.grad_slab.copy_(job.data.to(self.device))
+            else:
+                self.graph.ctx.param_slab.copy_(job.data.to(self.device))
+                self.graph.ctx.refresh_lp()
             self._reply(CommandType.PARAMS_LOADED, True)
         elif c in (CommandType.HEALTH_CHECK, CommandType.STATUS_REQUEST):
             status = {"name": self.name, "stage": self.stage_id, "configured": self.graph is not None, "training": self.training,
                       "jobs": self._jobs, "device": str(self.device), "time": time.time()}
             self._reply(CommandType.STATUS_RESPONSE, json.dumps(status))
         elif c == CommandType.CHECKPOINT_REQUEST:
-            path = msg.get(str)
+            path = self._checked_path(msg.get(str))
             from ..nn.train import save_checkpoint
             save_checkpoint(self.graph, f"{path}.stage{self.stage_id}", self.optimizer, self.scheduler,
                             self.optimizer.step_count if self.optimizer else 0)

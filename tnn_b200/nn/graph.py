@@ -27,8 +27,9 @@ class IONode:
     def __init__(self, uid: str):
         self.uid = uid
 
-    def get_config(self):
-        return {"uid": self.uid}
+    def get_config(self) -> TConfig:
+        """NodeConfig of the reference (src/nn/io_node.cpp:5-11): TConfig type "io_node", parameter uid."""
+        return TConfig("", "io_node", uid=self.uid)
 
 
 class OpNode:
@@ -36,8 +37,10 @@ class OpNode:
         self.uid = uid
         self.layer = layer
 
-    def get_config(self):
-        return {"uid": self.uid, "name": self.layer.name, "layer_config": self.layer.get_config().to_json()}
+    def get_config(self) -> TConfig:
+        """src/nn/op_node.cpp:6-15: TConfig type "op_node", parameters uid / name / layer_config (json)."""
+        c = TConfig("", "op_node")
+        return c.set("uid", self.uid).set("name", self.layer.name).set("layer_config", self.layer.get_config())
 
 
 class Edge:
@@ -45,7 +48,8 @@ class Edge:
         self.inputs, self.outputs, self.op = list(inputs), list(outputs), op
 
     def get_config(self):
-        return {"inputs": self.inputs, "outputs": self.outputs, "op": self.op}
+        """include/nn/graph.hpp:93-113: plain JSON {producers: [io uid], consumers: [io uid], op_node: uid}."""
+        return {"producers": self.inputs, "consumers": self.outputs, "op_node": self.op}
 
 
 class GraphBuilder:
@@ -253,21 +257,38 @@ class Graph:
         for l in self.get_layers():
             l.set_seed(seed)
 
-    def get_config(self) -> dict:
-        return {"name": self.name,
-                "op_nodes": [n.get_config() for n in self.op_nodes.values()],
-                "io_nodes": [n.get_config() for n in self.io_nodes.values()],
-                "edges": [e.get_config() for e in self.edges]}
+    def get_config(self) -> TConfig:
+        """GraphConfig in the reference schema (include/nn/graph.hpp:78-117): a TConfig of type "graph" whose
+        parameters op_nodes / io_nodes / edges are json arrays of NodeConfig::to_json() / edge objects."""
+        return TConfig(self.name, "graph",
+                       op_nodes=[n.get_config() for n in self.op_nodes.values()],
+                       io_nodes=[n.get_config() for n in self.io_nodes.values()],
+                       edges=[e.get_config() for e in self.edges])
 
     @staticmethod
-    def create_from_config(cfg: dict, device="cpu", seed=None, alloc_fn=None) -> "Graph":
-        b = GraphBuilder(cfg.get("name", "graph"))
-        for n in cfg["io_nodes"]:
-            b.io(n["uid"])
-        for n in cfg["op_nodes"]:
-            b.add_layer(LayerFactory.create(TConfig.from_json(n["layer_config"])), n["uid"])
-        for e in cfg["edges"]:
-            b.add_edge(e["inputs"], e["outputs"], e["op"])
+    def create_from_config(cfg, device="cpu", seed=None, alloc_fn=None) -> "Graph":
+        """Accepts the reference schema (graph.hpp:128-169) as TConfig / its JSON, and the flat round-1 form
+        ({name, op_nodes:[{uid,name,layer_config}], io_nodes:[{uid}], edges:[{inputs,outputs,op}]})."""
+        if isinstance(cfg, dict) and "parameters" in cfg:
+            cfg = TConfig.from_json(cfg)
+        if isinstance(cfg, TConfig):
+            name = cfg.name or "graph"
+            ios = [(n.get("uid") if isinstance(n, TConfig) else n["uid"]) for n in cfg.get("io_nodes", [])]
+            ops = [(n.get("uid"), n.get("layer_config")) if isinstance(n, TConfig) else (n["uid"], n["layer_config"])
+                   for n in cfg.get("op_nodes", [])]
+            edges = cfg.get("edges", [])
+        else:
+            name = cfg.get("name", "graph")
+            ios = [n["uid"] for n in cfg["io_nodes"]]
+            ops = [(n["uid"], n["layer_config"]) for n in cfg["op_nodes"]]
+            edges = cfg["edges"]
+        b = GraphBuilder(name)
+        for u in ios:
+            b.io(u)
+        for uid, lc in ops:
+            b.add_layer(LayerFactory.create(lc if isinstance(lc, TConfig) else TConfig.from_json(lc)), uid)
+        for e in edges:
+            b.add_edge(e.get("producers", e.get("inputs")), e.get("consumers", e.get("outputs")), e.get("op_node", e.get("op")))
         return b.compile(device, seed, alloc_fn)
 
     # -- checkpoint: pretty JSON config immediately followed by tensor records (graph.hpp:119-183)
@@ -277,7 +298,7 @@ class Graph:
             f = open(f, "wb")
             close = True
         try:
-            f.write(json.dumps(self.get_config(), indent=4).encode())
+            f.write(json.dumps(self.get_config().to_json(), indent=4).encode())
             for _, t in self.ctx.parameters():
                 tensor_io.save_tensor(f, t)
             if extra_sections:

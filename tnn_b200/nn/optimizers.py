@@ -180,13 +180,19 @@ class Adam(Optimizer):
 
     def state_dict(self):
         d = super().state_dict()
-        d.update(m=self.m, v=self.v)
+        # under FusedDataParallel the moments are sharded in dp.m / dp.v (self.m is None): the DP wrapper
+        # contributes the gathered tensors (FusedDataParallel.state_dict); never write a null moment
+        if self.m is not None:
+            d["m"] = self.m
+        if self.v is not None:
+            d["v"] = self.v
         return d
 
     def load_state_dict(self, d):
         super().load_state_dict(d)
-        if "m" in d:
+        if d.get("m") is not None and self.m is not None:
             self.m.copy_(d["m"])
+        if d.get("v") is not None and self.v is not None:
             self.v.copy_(d["v"])
 
     def get_config(self):

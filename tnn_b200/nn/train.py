@@ -303,6 +303,7 @@ def train_model(graph: Graph, train_loader, val_loader, optimizer: Optimizer, cr
         train_loader.reset()
         acc = torch.zeros(2, dtype=torch.float32, device=dev)
         seen = 0
+        epoch_batches = 0                 # acc is per epoch: divide by THIS epoch's batches
         t_epoch = time.time()
         t_last = time.time()
         nxt = train_loader.get_batch(cfg.batch_size)
@@ -317,16 +318,17 @@ def train_model(graph: Graph, train_loader, val_loader, optimizer: Optimizer, cr
             acc += stats
             seen += dy.numel()
             global_step += 1
+            epoch_batches += 1
             if cfg.progress_print_interval > 0 and global_step % cfg.progress_print_interval == 0:
                 a = acc.cpu()
                 dt = (time.time() - t_last) / cfg.progress_print_interval * 1e3
                 t_last = time.time()
                 history["step_ms"].append(dt)
-                log(f"epoch {epoch + 1} step {global_step}: loss {float(a[0]) / max(1, global_step):.4f} "
+                log(f"epoch {epoch + 1} step {global_step}: loss {float(a[0]) / max(1, epoch_batches):.4f} "
                     f"acc {100 * float(a[1]) / max(1, seen):.2f}% {dt:.2f} ms/step lr {optimizer.get_learning_rate():.2e}")
             if 0 < cfg.max_steps <= global_step:
                 break
-        history["train_loss"].append(float(acc[0].cpu()) / max(1, global_step))
+        history["train_loss"].append(float(acc[0].cpu()) / max(1, epoch_batches))
         log(f"epoch {epoch + 1} done in {time.time() - t_epoch:.2f}s")
         if lprof is not None:
             if cfg.print_layer_profiling or str(cfg.profiler_type).upper() not in ("", "NONE"):
@@ -339,9 +341,9 @@ def train_model(graph: Graph, train_loader, val_loader, optimizer: Optimizer, cr
             log(f"validation: loss {vloss:.4f} acc {100 * vacc:.2f}%")
             if vacc > best_acc:
                 best_acc = vacc
-                save_checkpoint(graph, os.path.join(cfg.snapshot_dir, graph.name), optimizer, scheduler, global_step)
+                save_checkpoint(graph, os.path.join(cfg.snapshot_dir, graph.name), optimizer, scheduler, global_step, dp)
         if 0 < cfg.max_steps <= global_step:
-            save_checkpoint(graph, os.path.join(cfg.snapshot_dir, graph.name), optimizer, scheduler, global_step)
+            save_checkpoint(graph, os.path.join(cfg.snapshot_dir, graph.name), optimizer, scheduler, global_step, dp)
             break
     if lprof is not None:
         history["layer_profile"] = lprof.rows()
@@ -349,13 +351,21 @@ def train_model(graph: Graph, train_loader, val_loader, optimizer: Optimizer, cr
     return history
 
 
-def save_checkpoint(graph: Graph, path: str, optimizer: Optimizer | None = None, scheduler=None, step: int = 0):
+def save_checkpoint(graph: Graph, path: str, optimizer: Optimizer | None = None, scheduler=None, step: int = 0, dp=None):
     """Model file in the reference format (JSON + tensor records) plus an optional trailer with
-    optimizer / scheduler state so that resume is exact."""
+    optimizer / scheduler state so that resume is exact.  With a data-parallel wrapper the call is
+    COLLECTIVE (sharded optimizer state is gathered) and only rank 0 writes the file."""
     extra = {"step": int(step)}
+    state_src = dp if (dp is not None and hasattr(dp, "state_dict")) else optimizer
+    if state_src is not None:
+        for k, v in state_src.state_dict().items():
+            if v is not None:
+                extra["opt." + k] = v
+    if dp is not None and getattr(dp, "world", 1) > 1:
+        import torch.distributed as dist
+        if dist.is_initialized() and dist.get_rank(getattr(dp, "group", None)) != 0:
+            return
     if optimizer is not None:
-        for k, v in optimizer.state_dict().items():
-            extra["opt." + k] = v
         extra["opt.config"] = optimizer.get_config().to_json()
     if scheduler is not None:
         extra["sched.state"] = scheduler.state_dict()
@@ -363,12 +373,16 @@ def save_checkpoint(graph: Graph, path: str, optimizer: Optimizer | None = None,
     graph.save_state(path, extra)
 
 
+def optimizer_state_from_extra(extra: dict, device="cpu") -> dict:
+    return {k[4:]: (v.to(device) if isinstance(v, torch.Tensor) else v)
+            for k, v in extra.items() if k.startswith("opt.") and k != "opt.config" and v is not None}
+
+
 def load_checkpoint(path: str, device="cpu", optimizer: Optimizer | None = None, scheduler=None, alloc_fn=None):
     graph, extra = Graph.load_state(path, device, alloc_fn, return_extra=True)
     if optimizer is not None:
         optimizer.attach(graph.context())
-        optimizer.load_state_dict({k[4:]: (v.to(device) if isinstance(v, torch.Tensor) else v)
-                                   for k, v in extra.items() if k.startswith("opt.") and k != "opt.config"})
+        optimizer.load_state_dict(optimizer_state_from_extra(extra, device))
     if scheduler is not None and "sched.state" in extra:
         scheduler.load_state_dict(extra["sched.state"])
     return graph, extra

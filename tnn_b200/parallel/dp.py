@@ -145,6 +145,9 @@ class FusedDataParallel:
             self.side = torch.cuda.Stream(device)
         dist.barrier(self.group)
         torch.cuda.synchronize(device)
+        if seed is None:
+            self.broadcast_parameters(0)      # unseeded replicas would start (and stay) different
+            torch.cuda.synchronize(device)
         return self.graph
 
     # ---------------------------------------------------------------- gradient buckets
@@ -240,6 +243,61 @@ class FusedDataParallel:
             self._launch()
         for layer in self.graph.ctx.layers:
             layer.mark_lp_fresh()
+
+    # ---------------------------------------------------------------- checkpoint / resume (sharded state)
+    def _shards(self):
+        """(lo, hi, chunk, st_off) of every launch's slab range: rank r owns [lo + r*chunk, min(hi, lo + (r+1)*chunk))
+        and keeps its optimizer state at [st_off, st_off + chunk) of self.m / self.v."""
+        if self.buckets:
+            return [(b["lo"], b["hi"], b["chunk"], b["st_off"]) for b in self.buckets]
+        return [(0, self.n, self.chunk, 0)]
+
+    def _gather(self, shard_state: torch.Tensor) -> torch.Tensor:
+        full = torch.zeros(self.n, dtype=torch.float32, device=shard_state.device)
+        for lo, hi, c, st in self._shards():
+            mine = torch.zeros(c, dtype=torch.float32, device=shard_state.device)
+            k = min(c, shard_state.numel() - st)
+            mine[:k] = shard_state[st:st + k]
+            parts = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(parts, mine, group=self.group)
+            for r, part in enumerate(parts):
+                a, b = lo + r * c, min(hi, lo + (r + 1) * c)
+                if b > a:
+                    full[a:b] = part[:b - a]
+        return full
+
+    def _scatter(self, full: torch.Tensor, shard_state: torch.Tensor):
+        full = full.to(shard_state.device, torch.float32).reshape(-1)
+        for lo, hi, c, st in self._shards():
+            a, b = lo + self.rank * c, min(hi, lo + (self.rank + 1) * c)
+            if b > a:
+                shard_state[st:st + (b - a)] = full[a:b]
+
+    def state_dict(self) -> dict:
+        """Optimizer state with the W-way sharded moments gathered to full slab length (collective: every rank calls)."""
+        d = dict(self.optimizer.state_dict())
+        if isinstance(self.optimizer, Adam):
+            d["m"], d["v"] = self._gather(self.m), self._gather(self.v)
+        elif self.m is not None and getattr(self.optimizer, "momentum", 0.0) > 0:
+            d["velocity"] = self._gather(self.m)
+        return d
+
+    def load_state_dict(self, d: dict):
+        Optimizer.load_state_dict(self.optimizer, {k: v for k, v in d.items() if k not in ("m", "v", "velocity")})
+        if isinstance(self.optimizer, Adam):
+            if d.get("m") is not None:
+                self._scatter(d["m"], self.m)
+            if d.get("v") is not None:
+                self._scatter(d["v"], self.v)
+        elif d.get("velocity") is not None:
+            self._scatter(d["velocity"], self.m)
+
+    def broadcast_parameters(self, src: int = 0):
+        """Make every replica bit-identical to rank `src` (needed when replicas were built without a common seed
+        or after rank 0 loaded a checkpoint)."""
+        dist.broadcast(self.graph.ctx.param_slab, src, group=self.group)
+        dist.broadcast(self.graph.ctx.buffer_slab, src, group=self.group)
+        self.graph.ctx.refresh_lp()
 
     def roofline_bytes(self) -> dict:
         """Bytes this rank moves over NVLink per step (for the achieved-fraction report)."""
