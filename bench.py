@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
     ap.add_argument("--model", default="cifar100_wrn16_8")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gpt2", action="store_true", help="skip the GPT-2 inference block (BASELINE config 4)")
+    ap.add_argument("--gpt2-iters", type=int, default=5)
     return ap.parse_args()
 
 
@@ -151,6 +153,31 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "baseline"))
     import reference_arm
     reference_arm.run(args, emit, dist_setup, barrier, max_over_ranks, ClockSampler, BASELINE_IMG_S)
+
+
+def gpt2_block(args, impl: str, rank: int, world: int, dev) -> dict | None:
+    """GPT-2 small inference bs=32 seq=1024 (BASELINE config 4) on every rank's GPU; tokens/s are the whole-job
+    aggregate (N independent replicas = N x the slowest rank), times are the max over ranks."""
+    if args.no_gpt2:
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+    import gpt2_lib
+    import torch
+    try:
+        r = gpt2_lib.tnn_gpt2(dev, iters=args.gpt2_iters) if impl == "tnn" else gpt2_lib.torch_gpt2(dev, iters=args.gpt2_iters)
+    except Exception as e:  # noqa: BLE001
+        r = {"error": f"{type(e).__name__}: {e}"[:300]}
+    torch.cuda.synchronize()
+    if "error" not in r:
+        for k in [k for k in r if k.endswith("_ms") or k.endswith("ms_per_step")]:
+            r[k] = max_over_ranks(r[k], world, dev)
+        B, L = r["batch"], r["seq"]
+        for k in [k for k in r if k.endswith("tok_s")]:
+            ms_key = k.replace("tok_s", "ms") if k.startswith("prefill") else "decode_ms_per_step"
+            r[k] = world * (B * L if k.startswith("prefill") else B) / r[ms_key] * 1e3
+        r["n_gpus"] = world
+        r["unit"] = "tokens/s (whole job)"
+    return r
 
 
 def dist_setup(n):
@@ -273,6 +300,13 @@ def run_tnn(args):
         e2e = {"value": world * B * args.steps / (ms2 / 1e3), "unit": "img/s", "ms_per_step": ms2 / args.steps,
                "h2d_bytes_per_step": B * 32 * 32 * 3 * 4 + B * 4, "d2h_bytes_per_step": 8}
 
+    launches_wrn = int(launches)
+    used_graph = bool(step.use_graph)
+    del step, graph, devb
+    torch.cuda.empty_cache()
+    l0 = Cx.launch_count()
+    gpt2 = gpt2_block(args, "tnn", rank, world, dev)
+    launches_gpt2 = int(Cx.launch_count() - l0)
     if rank == 0:
         out = {
             "metric": ("WRN-16-8 CIFAR-100" if args.model == "cifar100_wrn16_8" else args.model) + " training throughput", "value": value, "unit": "img/s", "n_gpus": world,
@@ -283,11 +317,14 @@ def run_tnn(args):
                        "image": [32, 32, 3], "classes": classes, "optimizer": "adam(lr1e-3,eps1e-3,wd3e-4)",
                        "parallelism": parallelism,
                        "l2": "inputs rotate over 4 batches; per-step activation working set (~2 GB) >> 126 MB L2"},
-            "clocks": clocks, "gpu_launches": int(launches), "cuda_graph": bool(step.use_graph), "launches_per_step": launches / max(1, args.steps),
+            "clocks": clocks, "gpu_launches": int(launches), "cuda_graph": used_graph, "launches_per_step": launches / max(1, args.steps),
             "final_loss": loss_val,
         }
         if e2e:
             out["e2e"] = e2e
+        if gpt2 is not None:
+            gpt2["gpu_launches_eager"] = launches_gpt2
+            out["gpt2"] = gpt2
         emit(out)
     if world > 1:
         import torch.distributed as dist
@@ -302,9 +339,18 @@ def run_torch(args):
     from torch_wrn import bench_torch_wrn
     rank, local, world = dist_setup(args.gpus)
     res = bench_torch_wrn(args.batch, args.steps, args.warmup, local, world, args.model)
+    import torch
+    torch.cuda.empty_cache()
+    gpt2 = gpt2_block(args, "torch", rank, world, torch.device("cuda", local))
     if rank == 0:
         res.update({"impl": "torch", "vs_baseline": res["value"] / BASELINE_IMG_S})
+        if gpt2 is not None:
+            res["gpt2"] = gpt2
         emit(res)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

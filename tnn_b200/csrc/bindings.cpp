@@ -17,6 +17,7 @@ using OptT = std::optional<Tensor>;
 
 namespace tnn {
 void attention_bind(py::module_& m);  // attention.cpp
+void mxfp8_bind(py::module_& m);      // mxfp8.cpp
 }
 
 static cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
@@ -443,5 +444,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
      py::arg("static_weights") = false);
   m.def("launch_count", []() { return tnn::g_launch_count; });
   tnn::attention_bind(m);
+  tnn::mxfp8_bind(m);
   tnn::runtime_bind(m);
 }

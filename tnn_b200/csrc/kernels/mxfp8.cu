@@ -1,0 +1,629 @@
+// Block-scaled fp8 (MXFP8) for the GPT-2 inference path: quantisers, a LayerNorm that emits MXFP8 and a
+// persistent tcgen05 GEMM that multiplies e4m3 operands with per-32-element ue8m0 scales
+// (`tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale`, SASS: UTCQMMA), scale factors staged global ->
+// shared by bulk copies and shared -> TMEM by `tcgen05.cp.32x128b.warpx4` (SASS: UTCCP).
+//
+// Reference counterpart: the reference runs GPT-2 through cuBLAS GemmEx in fp32/fp16
+// (/root/reference/src/math/cuda/gemm.cu:74, examples/gpt2_inference.cpp:44-121); it has no fp8 path.
+//
+// Tile geometry is byte-identical to the bf16 kernel (umma_gemm.cu): a K block is 128 bytes of one row
+// (= 128 e4m3 values), 128B-swizzled by TMA, K-major UMMA descriptors advance 32 B per MMA (K = 32).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp8.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "mxfp8.cuh"
+#include "sm100.cuh"
+#include "umma_gemm.cuh"
+
+namespace tnn {
+using namespace sm100;
+
+// ---------------------------------------------------------------------------------------------------
+// quantisation helpers
+// ---------------------------------------------------------------------------------------------------
+// ue8m0 exponent byte for a block whose largest magnitude is amax: scale = 2^(floor(log2 amax) - 8)
+__device__ __forceinline__ uint32_t mx_scale_byte(float amax) {
+  if (!(amax > 0.f)) return 127u - 8u;                     // all-zero block: any finite scale
+  const int e = (int)((__float_as_uint(amax) >> 23) & 0xFF) - 127;   // floor(log2(amax)) for normal floats
+  int b = e - 8 + 127;
+  b = b < 0 ? 0 : (b > 254 ? 254 : b);
+  return (uint32_t)b;
+}
+__device__ __forceinline__ float mx_scale_inv(uint32_t byte) {   // 1 / 2^(byte - 127)
+  return __uint_as_float((uint32_t)(254 - (int)byte) << 23);
+}
+__device__ __forceinline__ float mx_scale_val(uint32_t byte) {
+  return byte == 0 ? 5.877471754111438e-39f : __uint_as_float(byte << 23);
+}
+// four floats -> four e4m3 bytes (satfinite), packed little-endian
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+  const __nv_fp8x2_storage_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
+  const __nv_fp8x2_storage_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
+  return (uint32_t)lo | ((uint32_t)hi << 16);
+}
+__device__ __forceinline__ long long sf_offset(long long row, int kgroup, int kblocks) {
+  // kgroup = index of the 32-element group along K; kblocks = K / 128
+  const long long rb = row >> 7;
+  const int r = (int)(row & 127);
+  return (rb * kblocks + (kgroup >> 2)) * 512 + (r & 31) * 16 + (r >> 5) * 4 + (kgroup & 3);
+}
+
+// One thread per 32-element block: rows x (K/32) blocks.  Threads of a warp take consecutive blocks of a
+// row, so the loads are 64 B (bf16) / 128 B (fp32) per thread and fully coalesced across the warp.
+template <typename T>
+__global__ void __launch_bounds__(256) k_mxfp8_quantize(const T* __restrict__ x, long long ldx, long long rows,
+                                                        long long rows_pad, int K, uint8_t* __restrict__ q,
+                                                        long long ldq, uint8_t* __restrict__ sf) {
+  const int groups = K >> 5;
+  const long long total = rows_pad * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / groups;
+    const int g = (int)(i - row * groups);
+    if (row >= rows) {                       // padding rows of the last scale block
+      sf[sf_offset(row, g, K >> 7)] = 127;
+      continue;
+    }
+    float v[32];
+    if (sizeof(T) == 2) {
+      const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(x) + row * ldx + g * 32);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float f[8];
+        bf8_unpack(__ldg(p + j), f);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) v[j * 8 + t] = f[t];
+      }
+    } else {
+      const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + row * ldx + g * 32);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 f = __ldg(p + j);
+        v[j * 4] = f.x; v[j * 4 + 1] = f.y; v[j * 4 + 2] = f.z; v[j * 4 + 3] = f.w;
+      }
+    }
+    float amax = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(v[j]));
+    const uint32_t sb = mx_scale_byte(amax);
+    const float inv = mx_scale_inv(sb);
+    uint4* o = reinterpret_cast<uint4*>(q + row * ldq + g * 32);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      uint4 w;
+      w.x = pack_e4m3x4(v[j * 16 + 0] * inv, v[j * 16 + 1] * inv, v[j * 16 + 2] * inv, v[j * 16 + 3] * inv);
+      w.y = pack_e4m3x4(v[j * 16 + 4] * inv, v[j * 16 + 5] * inv, v[j * 16 + 6] * inv, v[j * 16 + 7] * inv);
+      w.z = pack_e4m3x4(v[j * 16 + 8] * inv, v[j * 16 + 9] * inv, v[j * 16 + 10] * inv, v[j * 16 + 11] * inv);
+      w.w = pack_e4m3x4(v[j * 16 + 12] * inv, v[j * 16 + 13] * inv, v[j * 16 + 14] * inv, v[j * 16 + 15] * inv);
+      o[j] = w;
+    }
+    sf[sf_offset(row, g, K >> 7)] = (uint8_t)sb;
+  }
+}
+
+static void check_quant_args(long long ld, int K, long long ldq, const char* what) {
+  if (K % 128 != 0 || ld % 8 != 0 || ldq % 16 != 0) {
+    fprintf(stderr, "[tnn_b200] %s: K %% 128, ldx %% 8, ldq %% 16 required (K=%d ldx=%lld ldq=%lld)\n", what, K, ld, ldq);
+    abort();
+  }
+}
+void mxfp8_quantize_bf16(const void* x, long long ldx, long long rows, int K, void* q, long long ldq, void* sf,
+                         cudaStream_t s) {
+  check_quant_args(ldx, K, ldq, "mxfp8_quantize_bf16");
+  const long long rows_pad = ((rows + 127) / 128 + 1) * 128;     // includes the spare scale block
+  k_mxfp8_quantize<bf16><<<grid_for(rows_pad * (K / 32), 256), 256, 0, s>>>(
+      reinterpret_cast<const bf16*>(x), ldx, rows, rows_pad, K, reinterpret_cast<uint8_t*>(q), ldq,
+      reinterpret_cast<uint8_t*>(sf));
+  TNN_CHECK_LAUNCH();
+}
+void mxfp8_quantize_f32(const float* x, long long ldx, long long rows, int K, void* q, long long ldq, void* sf,
+                        cudaStream_t s) {
+  check_quant_args(ldx, K, ldq, "mxfp8_quantize_f32");
+  const long long rows_pad = ((rows + 127) / 128 + 1) * 128;
+  k_mxfp8_quantize<float><<<grid_for(rows_pad * (K / 32), 256), 256, 0, s>>>(
+      x, ldx, rows, rows_pad, K, reinterpret_cast<uint8_t*>(q), ldq, reinterpret_cast<uint8_t*>(sf));
+  TNN_CHECK_LAUNCH();
+}
+
+__global__ void __launch_bounds__(256) k_mxfp8_dequantize(const uint8_t* __restrict__ q, long long ldq,
+                                                          const uint8_t* __restrict__ sf, long long rows, int K,
+                                                          float* __restrict__ out) {
+  const long long total = rows * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / K;
+    const int k = (int)(i - row * K);
+    const __half_raw h = __nv_cvt_fp8_to_halfraw(q[row * ldq + k], __NV_E4M3);
+    out[i] = __half2float(__half(h)) * mx_scale_val(sf[sf_offset(row, k >> 5, K >> 7)]);
+  }
+}
+void mxfp8_dequantize(const void* q, long long ldq, const void* sf, long long rows, int K, float* out, cudaStream_t s) {
+  k_mxfp8_dequantize<<<grid_for(rows * K, 256), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(q), ldq,
+                                                               reinterpret_cast<const uint8_t*>(sf), rows, K, out);
+  TNN_CHECK_LAUNCH();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// LayerNorm -> MXFP8.  One warp per row; lane l owns the 16-byte vectors l, l + 32, ... of the row (8 bf16
+// each), so a 32-element scale block is 4 ADJACENT lanes of one vector round: amax via two xor-shuffles.
+// ---------------------------------------------------------------------------------------------------
+template <int VPL>   // vectors per lane: C = VPL * 256
+__global__ void __launch_bounds__(256) k_layernorm_mxfp8(const bf16* __restrict__ x, const bf16* __restrict__ residual,
+                                                         bf16* __restrict__ sum_out, long long rows,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         float eps, uint8_t* __restrict__ q, uint8_t* __restrict__ sf,
+                                                         bf16* __restrict__ y_bf16) {
+  constexpr int C = VPL * 256;
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[VPL][8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const long long off = row * C + (long long)(lane + 32 * j) * 8;
+    bf8_unpack(__ldg(reinterpret_cast<const uint4*>(x + off)), v[j]);
+    if (residual != nullptr) {
+      float r[8];
+      bf8_unpack(__ldg(reinterpret_cast<const uint4*>(residual + off)), r);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) v[j][t] += r[t];
+      if (sum_out != nullptr) {
+        // the residual stream is carried in bf16: normalise what is stored
+        const uint4 pk = bf8_pack(v[j]);
+        *reinterpret_cast<uint4*>(sum_out + off) = pk;
+        bf8_unpack(pk, v[j]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) s += v[j][t];
+  }
+  const float mean = warp_sum(s) * (1.f / C);
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < VPL; ++j)
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const float d = v[j][t] - mean;
+      ss += d * d;
+    }
+  const float rstd = rsqrtf(warp_sum(ss) * (1.f / C) + eps);
+#pragma unroll
+  for (int j = 0; j < VPL; ++j) {
+    const int c0 = (lane + 32 * j) * 8;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float y[8];
+    float amax = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      y[t] = (v[j][t] - mean) * rstd * gg[t] + bb[t];
+      amax = fmaxf(amax, fabsf(y[t]));
+    }
+    if (y_bf16 != nullptr) *reinterpret_cast<uint4*>(y_bf16 + row * C + c0) = bf8_pack(y);
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+    const uint32_t sb = mx_scale_byte(amax);
+    const float inv = mx_scale_inv(sb);
+    uint2 w;
+    w.x = pack_e4m3x4(y[0] * inv, y[1] * inv, y[2] * inv, y[3] * inv);
+    w.y = pack_e4m3x4(y[4] * inv, y[5] * inv, y[6] * inv, y[7] * inv);
+    *reinterpret_cast<uint2*>(q + row * C + c0) = w;
+    if ((lane & 3) == 0) sf[sf_offset(row, c0 >> 5, C >> 7)] = (uint8_t)sb;
+  }
+}
+__global__ void k_sf_pad_rows(uint8_t* sf, long long rows, long long rows_pad, int K) {
+  const int groups = K >> 5;
+  const long long total = (rows_pad - rows) * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = rows + i / groups;
+    sf[sf_offset(row, (int)(i % groups), K >> 7)] = 127;
+  }
+}
+void layernorm_fwd_mxfp8(const void* x, const void* residual, void* sum_out, long long rows, int C, const float* gamma,
+                         const float* beta, float eps, void* q, void* sf, void* y_bf16, cudaStream_t s) {
+  const int wpb = 8;
+  const int grid = (int)((rows + wpb - 1) / wpb);
+#define TNN_LN_FP8(V)                                                                                                  \
+  k_layernorm_mxfp8<V><<<grid, wpb * 32, 0, s>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(residual), \
+                                                 reinterpret_cast<bf16*>(sum_out), rows, gamma, beta, eps,               \
+                                                 reinterpret_cast<uint8_t*>(q), reinterpret_cast<uint8_t*>(sf),          \
+                                                 reinterpret_cast<bf16*>(y_bf16))
+  switch (C) {
+    case 256: TNN_LN_FP8(1); break;
+    case 512: TNN_LN_FP8(2); break;
+    case 768: TNN_LN_FP8(3); break;
+    case 1024: TNN_LN_FP8(4); break;
+    case 1280: TNN_LN_FP8(5); break;
+    default:
+      fprintf(stderr, "[tnn_b200] layernorm_fwd_mxfp8: C must be 256/512/768/1024/1280 (got %d)\n", C);
+      abort();
+  }
+#undef TNN_LN_FP8
+  TNN_CHECK_LAUNCH();
+  const long long rows_pad = ((rows + 127) / 128 + 1) * 128;
+  if (rows_pad > rows) {
+    k_sf_pad_rows<<<grid_for((rows_pad - rows) * (C / 32), 256), 256, 0, s>>>(reinterpret_cast<uint8_t*>(sf), rows, rows_pad, C);
+    TNN_CHECK_LAUNCH();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// MXFP8 GEMM
+// ---------------------------------------------------------------------------------------------------
+static constexpr int F8_BLOCK_M = 128;
+static constexpr int F8_BLOCK_K = 128;      // bytes == elements
+static constexpr int F8_THREADS = 192;      // warp 0 TMA, warp 1 MMA + scale copies, warps 2..5 epilogue
+static constexpr int F8_SF_BYTES = 3 * 512; // per stage: SFA block + two SFB blocks
+
+struct F8Params {
+  int M, N, K;
+  int kblocks;                 // K / 128
+  int sfb_blocks;              // row blocks allocated in sfb (for clamping)
+  int vec_ok;                  // 16-byte epilogue accesses legal (row strides % 8 elements, aligned bases)
+  const uint8_t* sfa;
+  const uint8_t* sfb;
+  Fp8Epilogue epi;
+};
+
+__device__ __forceinline__ void bulk_load(void* smem, const void* gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem)),
+               "l"(reinterpret_cast<uint64_t>(gmem)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// Shared-memory descriptor of a scale-factor image: 32 rows x 16 bytes, K-major, no swizzle
+// (8-row core matrices of 128 B: SBO = 128, LBO unused).
+__device__ __forceinline__ uint64_t make_sf_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((128u >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+// 32 rows x 128 bit from shared memory into 4 TMEM columns, replicated over the four 32-lane quadrants
+__device__ __forceinline__ void tmem_cp_32x128b_warpx4(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+// Instruction descriptor, kind::mxf8f6f4 block-scaled: e4m3 x e4m3, ue8m0 scales, K-major operands.
+//   [4,6) b_sf_id  [7,10) a_format=0 (e4m3)  [10,13) b_format=0  [15] a_major [16] b_major
+//   [17,23) N>>3   [23] scale_format=1 (ue8m0)  [24,29) M>>4      [29,31) a_sf_id
+__host__ __device__ constexpr uint32_t make_idesc_mxf8(uint32_t M, uint32_t N) {
+  return ((N >> 3) << 17) | (1u << 23) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_mxf8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t sfa_tmem, uint32_t sfb_tmem, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t"
+      "}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+      : "memory");
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(F8_THREADS)
+    umma_gemm_mxfp8_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                   const F8Params p, int m_tiles, int n_tiles, int num_tiles) {
+  static_assert(BLOCK_N == 128 || BLOCK_N == 192, "tile widths: 128 or 192 (two accumulators + scales in 512 TMEM columns)");
+  constexpr int A_BYTES = F8_BLOCK_M * 128;
+  constexpr int B_BYTES = BLOCK_N * 128;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t ACC_COLS = BLOCK_N;
+  constexpr uint32_t SF_BASE = 2 * ACC_COLS;       // scale columns: [SF_BASE + 16*b, +4) SFA, [+4, +12) SFB; b = 0/1
+  constexpr uint32_t TMEM_COLS = 512;
+  static_assert(SF_BASE + 32 <= TMEM_COLS, "accumulators + scale buffers exceed TMEM");
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0u) __trap();
+  uint8_t* sSF = smem + STAGES * STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sSF + STAGES * F8_SF_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;    // [2]
+  uint64_t* tmem_empty = tmem_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ----------------------------- producer: TMA tiles + bulk scale images -----------------------------
+      int kit = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int tile_n = t % n_tiles;
+        const int tile_m = t / n_tiles;
+        const int m0 = tile_m * F8_BLOCK_M, n0 = tile_n * BLOCK_N;
+        const int nb0 = n0 >> 7;
+        const int nb1 = min(nb0 + 1, p.sfb_blocks - 1);
+        for (int kb = 0; kb < p.kblocks; ++kb, ++kit) {
+          const int s = kit % STAGES;
+          const uint32_t ph = (kit / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = smem + s * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          uint8_t* sf = sSF + s * F8_SF_BYTES;
+          mbar_expect_tx(&full[s], STAGE_BYTES + F8_SF_BYTES);
+          tma_load_2d(sa, &tmA, &full[s], kb * F8_BLOCK_K, m0);
+          tma_load_2d(sb, &tmB, &full[s], kb * F8_BLOCK_K, n0);
+          bulk_load(sf, p.sfa + ((long long)tile_m * p.kblocks + kb) * 512, 512, &full[s]);
+          bulk_load(sf + 512, p.sfb + ((long long)nb0 * p.kblocks + kb) * 512, 512, &full[s]);
+          bulk_load(sf + 1024, p.sfb + ((long long)nb1 * p.kblocks + kb) * 512, 512, &full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // ----------------------------- MMA issuer -----------------------------
+      constexpr uint32_t idesc0 = make_idesc_mxf8(F8_BLOCK_M, BLOCK_N);
+      int kit = 0, it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int tile_n = t % n_tiles;
+        const int n0 = tile_n * BLOCK_N;
+        const uint32_t sfb_col_off = (uint32_t)((n0 & 127) >> 5);      // tile starts mid scale block (BLOCK_N = 192)
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);      // epilogue drained this buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+        for (int i = 0; i < p.kblocks; ++i, ++kit) {
+          const int s = kit % STAGES;
+          const uint32_t ph = (kit / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+          const uint32_t sf_addr = smem_u32(sSF + s * F8_SF_BYTES);
+          // scale images -> TMEM (alternating buffers; tcgen05.cp and tcgen05.mma execute in issue order)
+          const uint32_t sf_t = tmem_base + SF_BASE + (uint32_t)(kit & 1) * 16;
+          tmem_cp_32x128b_warpx4(sf_t, make_sf_desc(sf_addr));
+          tmem_cp_32x128b_warpx4(sf_t + 4, make_sf_desc(sf_addr + 512));
+          tmem_cp_32x128b_warpx4(sf_t + 8, make_sf_desc(sf_addr + 1024));
+#pragma unroll
+          for (int k = 0; k < F8_BLOCK_K / 32; ++k) {
+            const uint64_t ad = make_smem_desc_sw128(a_addr + k * 32, 0, 1024);
+            const uint64_t bd = make_smem_desc_sw128(b_addr + k * 32, 0, 1024);
+            // byte k of every 32-bit scale word belongs to this 32-wide K slice
+            const uint32_t idesc = idesc0 | ((uint32_t)k << 29) | ((uint32_t)k << 4);
+            umma_mxf8(d_tmem, ad, bd, idesc, sf_t, sf_t + 4 + sfb_col_off, (i > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ----------------------------- epilogue (warps 2..5: TMEM lane quadrant = warp % 4) -----------------------------
+    const Fp8Epilogue& e = p.epi;
+    const int qd = warp & 3;
+    const int row = qd * 32 + lane;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int tile_n = t % n_tiles;
+      const int tile_m = t / n_tiles;
+      const int m0 = tile_m * F8_BLOCK_M, n0 = tile_n * BLOCK_N;
+      const int acc = it & 1;
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const int m = m0 + row;
+      const bool row_ok = m < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        const int n = n0 + c;
+        if (n >= p.N) break;
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(qd * 32) << 16) + acc * ACC_COLS + c, r);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * e.alpha;
+        const bool full = (n + 32 <= p.N) && p.vec_ok;
+        if (e.bias != nullptr) {
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(reinterpret_cast<const float4*>(e.bias + n) + j);
+              v[j * 4] += b.x; v[j * 4 + 1] += b.y; v[j * 4 + 2] += b.z; v[j * 4 + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n + j < p.N) v[j] += __ldg(e.bias + n + j);
+          }
+        }
+        if (e.residual != nullptr) {
+          const bf16* res = reinterpret_cast<const bf16*>(e.residual) + (long long)m * e.ldc + n;
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float f[8];
+              bf8_unpack(__ldg(reinterpret_cast<const uint4*>(res) + j), f);
+#pragma unroll
+              for (int u = 0; u < 8; ++u) v[j * 8 + u] += f[u];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n + j < p.N) v[j] += __bfloat162float(res[j]);
+          }
+        }
+        if (e.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (e.act == ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
+        }
+        if (e.out != nullptr) {
+          bf16* o = reinterpret_cast<bf16*>(e.out) + (long long)m * e.ldc + n;
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 w;
+              w.x = pack_bf16(v[j * 8 + 0], v[j * 8 + 1]);
+              w.y = pack_bf16(v[j * 8 + 2], v[j * 8 + 3]);
+              w.z = pack_bf16(v[j * 8 + 4], v[j * 8 + 5]);
+              w.w = pack_bf16(v[j * 8 + 6], v[j * 8 + 7]);
+              reinterpret_cast<uint4*>(o)[j] = w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n + j < p.N) o[j] = __float2bfloat16(v[j]);
+          }
+        }
+        if (e.out_q != nullptr) {
+          // this thread holds exactly one 32-element scale block of the next GEMM's A operand (K' = N, N % 128 == 0)
+          float amax = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(v[j]));
+          const uint32_t sb = mx_scale_byte(amax);
+          const float inv = mx_scale_inv(sb);
+          uint4* oq = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(e.out_q) + (long long)m * e.ldq + n);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            uint4 w;
+            w.x = pack_e4m3x4(v[j * 16 + 0] * inv, v[j * 16 + 1] * inv, v[j * 16 + 2] * inv, v[j * 16 + 3] * inv);
+            w.y = pack_e4m3x4(v[j * 16 + 4] * inv, v[j * 16 + 5] * inv, v[j * 16 + 6] * inv, v[j * 16 + 7] * inv);
+            w.z = pack_e4m3x4(v[j * 16 + 8] * inv, v[j * 16 + 9] * inv, v[j * 16 + 10] * inv, v[j * 16 + 11] * inv);
+            w.w = pack_e4m3x4(v[j * 16 + 12] * inv, v[j * 16 + 13] * inv, v[j * 16 + 14] * inv, v[j * 16 + 15] * inv);
+            oq[j] = w;
+          }
+          reinterpret_cast<uint8_t*>(e.out_sf)[sf_offset(m, n >> 5, p.N >> 7)] = (uint8_t)sb;
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled_v12000 f8_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || ptr == nullptr || qres != cudaDriverEntryPointSuccess) {
+      fprintf(stderr, "[tnn_b200] cuTensorMapEncodeTiled unavailable\n");
+      abort();
+    }
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  });
+  return fn;
+}
+// [rows, K] bytes, K-major: dims {K, rows}, box {128, box_rows}, 128B swizzle
+static CUtensorMap make_u8_map(const void* ptr, long long rows, long long K, long long ld, uint32_t box_rows) {
+  CUtensorMap m;
+  cuuint64_t gdims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld};
+  cuuint32_t bx[2] = {128, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = f8_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), gdims, gstr, bx, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[tnn_b200] mxfp8 tensor map failed (%d): rows=%lld K=%lld ld=%lld box=%u\n", (int)r, rows, K, ld, box_rows);
+    abort();
+  }
+  return m;
+}
+
+template <int BLOCK_N, int STAGES>
+static void launch_mxfp8(const CUtensorMap& tmA, const CUtensorMap& tmB, const F8Params& p, cudaStream_t stream) {
+  constexpr int smem_bytes = STAGES * (F8_BLOCK_M * 128 + BLOCK_N * 128 + F8_SF_BYTES) + (2 * STAGES + 4) * 8 + 16;
+  static bool attr_set = false;
+  auto kern = umma_gemm_mxfp8_persist_kernel<BLOCK_N, STAGES>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) {
+      fprintf(stderr, "[tnn_b200] mxfp8 smem attribute: %s\n", cudaGetErrorString(e));
+      abort();
+    }
+    attr_set = true;
+  }
+  const int m_tiles = (p.M + F8_BLOCK_M - 1) / F8_BLOCK_M;
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = m_tiles * n_tiles;
+  const int grid = num_tiles < kSMs ? num_tiles : kSMs;
+  kern<<<grid, F8_THREADS, smem_bytes, stream>>>(tmA, tmB, p, m_tiles, n_tiles, num_tiles);
+  TNN_CHECK_LAUNCH();
+}
+
+void gemm_mxfp8(const void* A, long long lda, const void* sfa, const void* B, long long ldb, const void* sfb, int M, int N,
+                int K, const Fp8Epilogue& epi, cudaStream_t stream) {
+  if (K % 128 != 0 || lda % 16 != 0 || ldb % 16 != 0 || M <= 0 || N <= 0) {
+    fprintf(stderr, "[tnn_b200] gemm_mxfp8: K %% 128 == 0 and 16-byte row strides required (M=%d N=%d K=%d)\n", M, N, K);
+    abort();
+  }
+  if (epi.out_q != nullptr && (N % 128 != 0 || epi.ldq % 16 != 0 || epi.out_sf == nullptr)) {
+    fprintf(stderr, "[tnn_b200] gemm_mxfp8: the fp8 output needs N %% 128 == 0, ldq %% 16 == 0 and out_sf\n");
+    abort();
+  }
+  F8Params p{};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.kblocks = K / 128;
+  p.sfb_blocks = (N + 127) / 128 + 1;
+  p.sfa = reinterpret_cast<const uint8_t*>(sfa);
+  p.sfb = reinterpret_cast<const uint8_t*>(sfb);
+  p.epi = epi;
+  p.vec_ok = (epi.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(epi.out) | reinterpret_cast<uintptr_t>(epi.residual)) % 16 == 0) &&
+             (reinterpret_cast<uintptr_t>(epi.bias) % 16 == 0);
+  // 192-wide tiles keep two accumulators + scales inside 512 TMEM columns and divide the GPT-2 widths
+  // (768, 2304, 3072); other widths take 128 when that wastes fewer columns
+  const int waste192 = ((N + 191) / 192) * 192 - N, waste128 = ((N + 127) / 128) * 128 - N;
+  const char* force = getenv("TNN_FP8_BLOCK_N");
+  const bool use192 = force ? atoi(force) == 192 : (waste192 <= waste128);
+  const CUtensorMap tmA = make_u8_map(A, M, K, lda, F8_BLOCK_M);
+  if (use192) {
+    const CUtensorMap tmB = make_u8_map(B, N, K, ldb, 192);
+    launch_mxfp8<192, 5>(tmA, tmB, p, stream);
+  } else {
+    const CUtensorMap tmB = make_u8_map(B, N, K, ldb, 128);
+    launch_mxfp8<128, 6>(tmA, tmB, p, stream);
+  }
+}
+
+}  // namespace tnn

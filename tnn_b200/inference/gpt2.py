@@ -35,7 +35,12 @@ class _Block:
 
 
 class GPT2InferenceEngine:
-    def __init__(self, model: Graph | Sequential, max_batch: int = 1, max_len: int | None = None):
+    """``precision="fp8"`` (GPU only) runs every token GEMM of the transformer blocks in block-scaled fp8
+    (MXFP8: e4m3 + one ue8m0 scale per 32 elements, ``ops/mxfp8.py`` / ``csrc/kernels/mxfp8.cu``): weights are
+    quantised once, LayerNorm writes its output directly as MXFP8, the fc1 epilogue applies GELU and
+    re-quantises for fc2; attention, the residual stream and the LM head stay bf16."""
+
+    def __init__(self, model: Graph | Sequential, max_batch: int = 1, max_len: int | None = None, precision: str = "bf16"):
         seq = model.get_layers()[0] if isinstance(model, Graph) else model
         self.model = seq
         self.device = seq.device
@@ -74,6 +79,53 @@ class GPT2InferenceEngine:
         self.cur_batch = 0
         self._dev = None
         self._graph = None
+        self.precision = "bf16"
+        self._fp8 = None
+        if precision == "fp8":
+            self.enable_fp8()
+        elif precision != "bf16":
+            raise ValueError(f"precision must be bf16 or fp8, not {precision!r}")
+
+    # ------------------------------------------------------------------ block-scaled fp8
+    def enable_fp8(self):
+        """Quantise the block weights to MXFP8 once (offline weight quantiser) and switch prefill to the fp8 path."""
+        if not self.cuda:
+            raise RuntimeError("the fp8 path needs a GPU (tcgen05 block-scaled MMA)")
+        from ..ops import mxfp8
+        self._fp8 = []
+        for b in self.blocks:
+            w = {}
+            for key, layer, wn, bn in (("qkv", b.attn, "qkv_weight", "qkv_bias"), ("out", b.attn, "out_weight", "out_bias"),
+                                       ("fc1", b.fc1, "weight", "bias"), ("fc2", b.fc2, "weight", "bias")):
+                W = layer.params[wn].detach().float().contiguous()
+                q, sf = mxfp8.quantize(W)
+                bias = layer.params[bn].detach().float().contiguous() if bn in layer.params else None
+                w[key] = (q, sf, bias)
+            if b.act != "gelu":
+                raise ValueError("the fp8 MLP epilogue implements GELU (GPT-2); got " + str(b.act))
+            self._fp8.append(w)
+        self.precision = "fp8"
+        return self
+
+    def _layers_fp8(self, x, pos: int):
+        from ..ops import mxfp8
+        B, L, E = x.shape
+        H, D = self.H, self.D
+        x2 = x.reshape(B * L, E).contiguous()
+        for b, w, cache in zip(self.blocks, self._fp8, self.caches):
+            view = attn_ops.KVCache.__new__(attn_ops.KVCache)
+            view.k, view.v, view.len = cache.k[:B], cache.v[:B], cache.len
+            q, sf = mxfp8.layernorm_quant(x2, b.ln1.params["gamma"], b.ln1.params["beta"], b.ln1.epsilon)
+            qkv, _, _ = mxfp8.gemm(q, sf, w["qkv"][0], w["qkv"][1], bias=w["qkv"][2])
+            o, _ = attn_ops.attention_fwd(qkv.reshape(B, L, 3, H, D), b.attn.is_causal, kv_cache=view, pos=pos)
+            cache.len = view.len
+            oq, osf = mxfp8.quantize(o.reshape(B * L, E))
+            x2, _, _ = mxfp8.gemm(oq, osf, w["out"][0], w["out"][1], bias=w["out"][2], residual=x2)
+            q, sf = mxfp8.layernorm_quant(x2, b.ln2.params["gamma"], b.ln2.params["beta"], b.ln2.epsilon)
+            _, hq, hsf = mxfp8.gemm(q, sf, w["fc1"][0], w["fc1"][1], bias=w["fc1"][2], act=mxfp8.ACT_GELU,
+                                    want_bf16=False, want_fp8=True)
+            x2, _, _ = mxfp8.gemm(hq, hsf, w["fc2"][0], w["fc2"][1], bias=w["fc2"][2], residual=x2)
+        return x2.reshape(B, L, E)
 
     # ------------------------------------------------------------------ building blocks
     def _embed(self, ids: torch.Tensor, pos: int) -> torch.Tensor:
@@ -131,7 +183,7 @@ class GPT2InferenceEngine:
         self.cur_batch, self.cur_len = B, 0
         with gemm_ops.static_weights():
             x = self._embed(ids, 0)
-            x = self._layers(x, 0)
+            x = self._layers_fp8(x, 0) if (self.precision == "fp8" and B * L >= 128) else self._layers(x, 0)
             self.cur_len = L
             logits = self._logits_last(x[:, -1:, :].contiguous()).reshape(B, -1)
             nxt = self._argmax(logits)
