@@ -1,0 +1,586 @@
+// tnn_tests: unit tests of the C++ host (reference strategy, SURVEY 4: gtest executables per area -- tensor_test,
+// archiver_test, device_manager_test, layer tests with CPU-vs-GPU parity, partitioner_test ...).  No network deps, so
+// the harness is 30 lines of macros instead of GoogleTest.  GPU cases skip when no device is visible.
+//   tnn_tests [filter-substring]
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <iostream>
+#include <sstream>
+
+#include "runtime/archiver.hpp"
+#include "tnn/example_models.hpp"
+#include "tnn/stepstate.hpp"
+#include "tnn/train.hpp"
+
+using namespace tnn;
+
+struct TestCase {
+  const char* name;
+  std::function<void()> fn;
+};
+static std::vector<TestCase>& registry() {
+  static std::vector<TestCase> r;
+  return r;
+}
+struct Registrar {
+  Registrar(const char* n, std::function<void()> f) { registry().push_back({n, std::move(f)}); }
+};
+struct Skip : std::exception {
+  std::string why;
+  explicit Skip(std::string w) : why(std::move(w)) {}
+};
+#define TEST(name)                                    \
+  static void test_##name();                          \
+  static Registrar reg_##name(#name, test_##name);    \
+  static void test_##name()
+#define CHECK(cond)                                                                                      \
+  do {                                                                                                   \
+    if (!(cond)) throw std::runtime_error(std::string("CHECK failed: " #cond " at line ") + std::to_string(__LINE__)); \
+  } while (0)
+#define CHECK_NEAR(a, b, tol)                                                                                              \
+  do {                                                                                                                     \
+    const double a__ = (a), b__ = (b);                                                                                     \
+    if (!(std::fabs(a__ - b__) <= (tol)))                                                                                  \
+      throw std::runtime_error("CHECK_NEAR failed: " #a " = " + std::to_string(a__) + ", " #b " = " + std::to_string(b__) + \
+                               " (tol " + std::to_string((double)(tol)) + ") at line " + std::to_string(__LINE__));         \
+  } while (0)
+static Device need_gpu() {
+  if (!DeviceManager::getInstance().has_gpu()) throw Skip("no GPU");
+  return getGPU(0);
+}
+
+// ------------------------------------------------------------------------------------- json / config / dtype
+TEST(json_round_trip) {
+  const std::string s = R"({"a": 1, "b": [1.5, true, null, "x\ny"], "c": {"d": -7, "e": 1e-05}})";
+  Json j = Json::parse(s);
+  CHECK(j.at("a").as_int() == 1 && j.at("b")[0].as_double() == 1.5 && j.at("b")[1].as_bool() && j.at("b")[2].is_null());
+  CHECK(j.at("b")[3].as_string() == "x\ny" && j.at("c").at("d").as_int() == -7);
+  CHECK(Json::parse(j.dump(4)) == j && Json::parse(j.dump()) == j);
+  size_t pos = 0;
+  const std::string two = s + "BINARY";
+  Json::parse(two, &pos);
+  CHECK(two.substr(pos) == "BINARY");                  // checkpoint header parsing stops at the end of the value
+}
+TEST(tconfig_reference_schema) {
+  TConfig c("fc", "dense");
+  c.set("input_features", (size_t)512).set("use_bias", true).set("epsilon", 1e-5f).set("activation", "relu").set("dims", std::vector<size_t>{1, 2, 3});
+  const Json j = c.to_json();
+  CHECK(j.at("parameters").at("input_features").at("type").as_string() == "size_t");
+  CHECK(j.at("parameters").at("dims").at("type").as_string() == "vector<size_t>");
+  TConfig seq("m", "sequential");
+  seq.set("layers", std::vector<TConfig>{c, c});
+  CHECK(seq.to_json().at("parameters").at("layers").at("type").as_string() == "json");
+  TConfig back = TConfig::from_string(seq.dump());
+  CHECK(back == seq && back.get_config_array("layers")[1].get<size_t>("input_features") == 512);
+  CHECK(back.get_config_array("layers")[0].get<std::vector<size_t>>("dims").size() == 3);
+  CHECK(back.get<int>("missing", 7) == 7);
+}
+TEST(dtype_helpers) {
+  CHECK(get_dtype_size(DType_t::BF16) == 2 && get_dtype_size(DType_t::FP64) == 8 && string_to_dtype("float") == DType_t::FP32);
+  CHECK(dtype_eps(DType_t::BF16) == 1e-2 && dtype_eps(DType_t::FP16) == 1e-3);
+  CHECK_NEAR(bf16_to_float(float_to_bf16(3.14159f)), 3.140625, 1e-6);
+  CHECK_NEAR(fp16_to_float(float_to_fp16(0.1f)), 0.0999755859375, 1e-9);
+  CHECK(fp16_to_float(float_to_fp16(70000.f)) == INFINITY && fp16_to_float(float_to_fp16(1e-7f)) > 0);
+  CHECK(bf16_to_float(float_to_bf16(1.00390625f)) == 1.0f);     // round to nearest even at the tie
+}
+
+// ------------------------------------------------------------------------------------- archiver (wire format)
+TEST(archiver_byte_layout) {
+  Writer w;
+  w.prim<uint16_t>(0x1234);
+  w.str("hello");
+  std::vector<uint64_t> v{1, 2, 3};
+  w.prim<uint64_t>(v.size());
+  for (auto e : v) w.prim<uint64_t>(e);
+  CHECK(w.size() == 2 + 8 + 5 + 8 + 24);
+  Reader r(w.buffer().data(), w.size(), false);
+  CHECK(r.prim<uint16_t>() == 0x1234 && r.str() == "hello" && r.prim<uint64_t>() == 3);
+  PacketHeader h;
+  h.endianness = 1;            // little-endian sender
+  h.packet_length = 77;
+  h.msg_length = 1234567;
+  h.msg_serial_id = 42;
+  h.packet_offset = 3;
+  h.total_packets = 9;
+  Writer hw;
+  h.write(hw);
+  CHECK(hw.size() == PacketHeader::kBytes);
+  PacketHeader g = PacketHeader::read(hw.buffer().data(), hw.size());
+  CHECK(g.msg_length == 1234567 && g.total_packets == 9 && g.packet_offset == 3 && g.msg_serial_id == 42);
+  bool threw = false;
+  try {
+    Reader bad(w.buffer().data(), 4, false);
+    bad.prim<uint64_t>();
+  } catch (const std::out_of_range&) { threw = true; }
+  CHECK(threw);
+}
+
+// ------------------------------------------------------------------------------------- allocators
+TEST(del_allocator_double_ended) {
+  DELAllocatorV2 a(HostAllocator(), 1 << 20, 256);
+  void* l1 = a.allocate(1000);
+  a.flip();
+  void* r1 = a.allocate(1000);
+  a.flip();
+  void* l2 = a.allocate(5000);
+  CHECK(a.num_slabs() == 1);
+  CHECK((char*)l2 == (char*)l1 + 1024);                       // left end bumps upward
+  CHECK((char*)r1 > (char*)l2);                               // right end comes from the top of the slab
+  CHECK(((uintptr_t)l1 & 255) == 0 && ((uintptr_t)r1 & 255) == 0);
+  a.deallocate(l1);                                           // interior hole on the left
+  void* l3 = a.allocate(512);
+  CHECK(l3 == l1);                                            // first fit reuses it
+  a.deallocate(l2);
+  a.deallocate(l3);
+  a.deallocate(r1);
+  CHECK(a.bytes_in_use() == 0);
+  // same sequence again -> same addresses (what CUDA-graph capture of a step relies on)
+  void* l1b = a.allocate(1000);
+  a.flip();
+  void* r1b = a.allocate(1000);
+  CHECK(l1b == l1 && r1b == r1);
+  a.deallocate(l1b);
+  a.deallocate(r1b);
+  a.reserve(8 << 20);
+  CHECK(a.num_slabs() == 1 && a.bytes_reserved() >= (8u << 20));
+  void* big = a.allocate(6 << 20);
+  CHECK(big != nullptr && a.num_slabs() == 1);
+  a.deallocate(big);
+  a.clear();
+  CHECK(a.num_slabs() == 0);
+}
+TEST(pool_allocator_reuse_rule) {
+  PoolAllocator p(HostAllocator());
+  void* a = p.allocate(10000);
+  p.deallocate(a);
+  void* b = p.allocate(4000);          // 10240 <= 4 * 4096: reused
+  CHECK(b == a);
+  p.deallocate(b);
+  void* c = p.allocate(1000);          // 10240 > 4 * 1024: fresh block
+  CHECK(c != a);
+  p.deallocate(c);
+  CHECK(p.bytes_in_use() == 0 && p.bytes_reserved() > 0);
+  p.release_cached();
+  CHECK(p.bytes_reserved() == 0);
+}
+
+// ------------------------------------------------------------------------------------- tensors
+TEST(tensor_basics_cpu) {
+  Tensor t = make_tensor<float>({2, 3, 4});
+  CHECK(t->size() == 24 && t->stride(0) == 12 && t->stride(1) == 4 && t->dims() == 3);
+  t->fill(2.0);
+  t->at<float>({1, 2, 3}) = 5.f;
+  CHECK_NEAR(t->sum(), 2.0 * 23 + 5, 1e-6);
+  CHECK_NEAR(t->max(), 5.0, 0);
+  Tensor u = t->clone();
+  u->mul_scalar(0.5);
+  t->add(*u);
+  CHECK_NEAR(t->at<float>({0, 0, 0}), 3.0, 1e-6);
+  Tensor v = t->span(12, {3, 4});
+  CHECK_NEAR(v->at<float>({2, 3}), 7.5, 1e-6);
+  v->fill(1.0);                                               // views share storage
+  CHECK_NEAR(t->at<float>({1, 0, 0}), 1.0, 0);
+  Tensor sum = u + u;
+  CHECK_NEAR(sum->at<float>({0, 0, 0}), 2.0, 1e-6);
+  t->fill_random_uniform(-1, 1, 7);
+  CHECK(t->min() >= -1 && t->max() <= 1 && std::fabs(t->mean()) < 0.6);
+  Tensor b = dtype_cast(*t, DType_t::BF16);
+  CHECK(max_abs_diff(*b, *t) < 1e-2);
+}
+TEST(tensor_save_load_record) {
+  Tensor t = make_tensor<float>({3, 5});
+  t->fill_random_normal(0, 1, 3);
+  std::stringstream ss;
+  t->save(ss);
+  CHECK(ss.str().size() == 4 + 8 + 16 + 60);                  // {u32 dtype, u64 ndims, u64 dims[], raw}
+  uint32_t dt;
+  std::memcpy(&dt, ss.str().data(), 4);
+  CHECK(dt == 5);                                             // FP32
+  Tensor u = load(ss, HostAllocator());
+  CHECK(u->shape() == t->shape() && max_abs_diff(*t, *u) == 0);
+}
+TEST(tensor_gpu_round_trip) {
+  const Device g = need_gpu();
+  Tensor h = make_tensor<float>({1000});
+  h->fill_random_uniform(-2, 2, 11);
+  Tensor d = h->to_device(g);
+  CHECK(d->is_gpu());
+  d->mul_scalar(2.0);
+  d->add_scalar(1.0);
+  Tensor back = d->to_host();
+  for (size_t i = 0; i < 1000; i += 97) CHECK_NEAR(back->data_as<float>()[i], 2 * h->data_as<float>()[i] + 1, 1e-5);
+  CHECK_NEAR(d->sum(), 2 * h->sum() + 1000, 1e-1);
+  Tensor b = dtype_cast(*d, DType_t::BF16);
+  CHECK(max_abs_diff(*b, *back) < 5e-2);
+}
+
+// ------------------------------------------------------------------------------------- layers: finite differences (CPU)
+static double loss_of(Layer& l, const Tensor& x, const Tensor& w) {       // L = sum(w * f(x))
+  Tensor y = l.forward(x, 0);
+  double s = 0;
+  for (size_t i = 0; i < y->size(); ++i) s += (double)y->data_as<float>()[i] * w->data_as<float>()[i];
+  return s;
+}
+// analytic derivative vs central AND one-sided differences: at a ReLU / max-pool kink the analytic value equals one of the
+// one-sided derivatives, not their average
+static bool deriv_ok(double l0, double lp, double lm, double eps, double ana, double tol, double* shown) {
+  const double c = (lp - lm) / (2 * eps), f = (lp - l0) / eps, b = (l0 - lm) / eps;
+  *shown = c;
+  for (double num : {c, f, b})
+    if (std::fabs(num - ana) <= tol * (1 + std::fabs(num))) return true;
+  return false;
+}
+static void gradcheck(std::unique_ptr<Layer> layer, const Shape& xs, double tol = 2e-2, bool check_params = true, float eps = 1e-2f) {
+  Layer& l = *layer;
+  l.init(getHost(), 3);
+  l.set_training(true);
+  Tensor x = make_tensor<float>(xs);
+  x->fill_random_normal(0, 1, 5);
+  Tensor y0 = l.forward(x, 0);
+  Tensor w = make_tensor<float>(y0->shape());
+  w->fill_random_normal(0, 1, 9);
+  for (Layer* s : l.all_layers())
+    for (auto& g : s->grads()) g.second->zero();
+  Tensor dx = l.backward(w, 0);
+  const double l0 = loss_of(l, x, w);
+  l.clear_caches();
+  if (dx) {
+    for (size_t i = 0; i < x->size(); i += std::max<size_t>(1, x->size() / 17)) {
+      const float keep = x->data_as<float>()[i];
+      x->data_as<float>()[i] = keep + eps;
+      const double lp = loss_of(l, x, w);
+      l.clear_caches();
+      x->data_as<float>()[i] = keep - eps;
+      const double lm = loss_of(l, x, w);
+      l.clear_caches();
+      x->data_as<float>()[i] = keep;
+      const double ana = dx->data_as<float>()[i];
+      double num;
+      if (!deriv_ok(l0, lp, lm, eps, ana, tol, &num))
+        throw std::runtime_error(l.type() + ": dx[" + std::to_string(i) + "] numeric " + std::to_string(num) + " vs analytic " + std::to_string(ana));
+    }
+  }
+  if (!check_params) return;
+  for (Layer* s : l.all_layers())
+    for (auto& g : s->grads()) {
+      Tensor p = s->param(g.first);
+      for (size_t i = 0; i < p->size(); i += std::max<size_t>(1, p->size() / 7)) {
+        const float keep = p->data_as<float>()[i];
+        p->data_as<float>()[i] = keep + eps;
+        const double lp = loss_of(l, x, w);
+        l.clear_caches();
+        p->data_as<float>()[i] = keep - eps;
+        const double lm = loss_of(l, x, w);
+        l.clear_caches();
+        p->data_as<float>()[i] = keep;
+        const double ana = g.second->data_as<float>()[i];
+        double num;
+        if (!deriv_ok(l0, lp, lm, eps, ana, tol, &num))
+          throw std::runtime_error(s->name() + "." + g.first + "[" + std::to_string(i) + "] numeric " + std::to_string(num) + " vs analytic " + std::to_string(ana));
+      }
+    }
+}
+TEST(gradcheck_dense) { gradcheck(std::make_unique<DenseLayer>(7, 5), {4, 7}); }
+TEST(gradcheck_conv2d) {
+  gradcheck(std::make_unique<Conv2DLayer>(3, 4, 3, 3, 1, 1, 1, 1), {2, 6, 6, 3});
+  gradcheck(std::make_unique<Conv2DLayer>(2, 3, 3, 3, 2, 2, 1, 1, false), {2, 8, 8, 2});
+  gradcheck(std::make_unique<Conv2DLayer>(2, 3, 3, 2, 2, 1, 1, 0), {1, 7, 6, 2});        // anisotropic kernel / stride / pad
+}
+TEST(gradcheck_batchnorm) {
+  gradcheck(std::make_unique<BatchNormLayer>(4, 1e-5, 0.1, true, false), {3, 5, 5, 4});
+  gradcheck(std::make_unique<BatchNormLayer>(4, 1e-5, 0.1, true, true), {3, 5, 5, 4}, 6e-2);
+}
+TEST(gradcheck_pools_acts_norms) {
+  gradcheck(std::make_unique<MaxPool2DLayer>(2, 2), {2, 6, 6, 3});
+  gradcheck(std::make_unique<AvgPool2DLayer>(3, 3, 2, 2, 1, 1), {2, 7, 7, 2});
+  for (const char* a : {"relu", "leaky_relu", "sigmoid", "tanh", "elu", "gelu", "softmax"}) gradcheck(std::make_unique<ActivationLayer>(a), {3, 9});
+  gradcheck(std::make_unique<LayerNormLayer>(8), {5, 8});
+  gradcheck(std::make_unique<GroupNormLayer>(2, 6), {2, 4, 4, 6});
+  gradcheck(std::make_unique<SliceLayer>(1, 1, 2), {3, 5, 4});
+  gradcheck(std::make_unique<TransposeLayer>(), {2, 3, 5});
+  gradcheck(std::make_unique<ClassTokenLayer>(4), {2, 3, 4});
+  gradcheck(std::make_unique<PositionalEmbeddingLayer>(4, 6), {2, 6, 4});
+}
+TEST(gradcheck_attention_and_blocks) {
+  gradcheck(std::make_unique<AttentionBlock>(8, 2, true), {2, 5, 8}, 3e-2);
+  gradcheck(std::make_unique<AttentionBlock>(8, 2, false), {1, 4, 8}, 3e-2);
+  LayerBuilder b({6, 6, 4});
+  b.wide_residual_block(4, 8, 2, 0.0, "w");
+  gradcheck(b.build_sequential("wrn_block"), {2, 6, 6, 4}, 6e-2, true, 2e-3f);
+  LayerBuilder r({6, 6, 4});
+  r.basic_residual_block(4, 4, 1, "r");
+  gradcheck(r.build_sequential("res_block"), {2, 6, 6, 4}, 6e-2, true, 2e-3f);
+  LayerBuilder g({5, 8});
+  g.gpt_block(8, 2, 16, 0.0, true, "gelu", "h0");
+  gradcheck(g.build_sequential("gpt"), {2, 5, 8}, 4e-2);
+}
+TEST(msequential_and_nary) {
+  Vec<std::unique_ptr<Layer>> seqs;
+  for (int i = 0; i < 2; ++i) {
+    LayerBuilder b({6});
+    b.dense(4, true, "fc" + std::to_string(i));
+    seqs.push_back(b.build_sequential("branch" + std::to_string(i)));
+  }
+  auto m = std::make_unique<MSequential>(std::move(seqs), std::make_unique<NAryLayer>(0, "join"), "m");
+  gradcheck(std::move(m), {3, 6});
+}
+
+// ------------------------------------------------------------------------------------- factory / zoo / graph / checkpoint
+TEST(factory_covers_reference_type_names) {
+  const char* names[] = {"dense", "conv2d", "batchnorm", "maxpool2d", "avgpool2d", "groupnorm", "layer_norm", "dropout", "flatten", "activation", "embedding",
+                         "pos_embedding", "class_token", "slice", "transpose", "identity", "add", "sub", "mul", "mbroadcast", "sdpa", "sequential", "msequential",
+                         "residual_block", "attention_block", "flash_attention_block", "legacy_dense", "legacy_conv2d", "legacy_maxpool2d", "legacy_avgpool2d",
+                         "legacy_batchnorm"};
+  for (const char* n : names) CHECK(LayerFactory::has(n));
+  // config round trip through the factory for a composite model
+  auto wrn = ExampleModels::create("cifar100_wrn16_8");
+  const TConfig cfg = wrn->get_config();
+  auto again = LayerFactory::create(cfg);
+  CHECK(again->get_config() == cfg);
+  CHECK(again->output_shape({2, 32, 32, 3}) == Shape({2, 100}));
+  auto legacy = LayerFactory::create(R"({"name":"lc","type":"legacy_conv2d","parameters":{"in_channels":{"type":"size_t","value":3},"out_channels":{"type":"size_t","value":4},
+     "kernel_h":{"type":"size_t","value":3},"kernel_w":{"type":"size_t","value":3},"pad_h":{"type":"size_t","value":1},"pad_w":{"type":"size_t","value":1}}})");
+  CHECK(legacy->type() == "legacy_conv2d" && legacy->output_shape({2, 3, 8, 8}) == Shape({2, 4, 8, 8}));
+  legacy->init(getHost(), 1);
+  Tensor x = make_tensor<float>({2, 3, 8, 8});
+  x->fill_random_normal(0, 1, 1);
+  CHECK(legacy->forward(x, 0)->shape() == Shape({2, 4, 8, 8}));
+}
+TEST(zoo_builds_every_model) {
+  for (const auto& n : ExampleModels::available_models()) {
+    auto m = ExampleModels::create(n);
+    Shape in{2};
+    const Shape s = ExampleModels::input_shape(n);
+    in.insert(in.end(), s.begin(), s.end());
+    const Shape out = m->output_shape(in);
+    CHECK(out.back() == ExampleModels::num_classes(n));
+  }
+  CHECK(ExampleModels::available_models().size() >= 17);
+}
+TEST(graph_topology_and_cycle_detection) {
+  GraphBuilder b("g");
+  OpNode& a = b.add_layer(std::make_unique<DenseLayer>(4, 4, true, "a"), "a");
+  OpNode& c = b.add_layer(std::make_unique<DenseLayer>(4, 2, true, "c"), "c");
+  b.add_edge({"mid"}, {"out"}, c);                            // declared out of order
+  b.add_edge({"in"}, {"mid"}, a);
+  const auto order = b.topo_sort();
+  CHECK(order[0].op == "a" && order[1].op == "c");
+  GraphBuilder cyc("cyc");
+  OpNode& p = cyc.add_layer(std::make_unique<IdentityLayer>("p"), "p");
+  OpNode& q = cyc.add_layer(std::make_unique<IdentityLayer>("q"), "q");
+  cyc.add_edge({"x"}, {"y"}, p).add_edge({"y"}, {"x"}, q);
+  bool threw = false;
+  try { cyc.topo_sort(); } catch (const std::runtime_error&) { threw = true; }
+  CHECK(threw);
+}
+TEST(graph_context_slabs_and_checkpoint_round_trip) {
+  Graph g = load_or_create_model("mnist_cnn", "", getHost(), 7);
+  GraphContext& ctx = g.context();
+  CHECK(ctx.num_parameters() > 1000 && ctx.param_slab()->size() >= ctx.num_parameters());
+  // parameters live inside the slab
+  Layer* conv1 = g.get_layers()[0]->children()[0];
+  const char* base = static_cast<const char*>(ctx.param_slab()->data());
+  const char* wp = static_cast<const char*>(conv1->param("weight")->data());
+  CHECK(wp >= base && wp < base + ctx.param_slab()->nbytes());
+  auto opt = OptimizerFactory::create_adam(1e-2, 0.9, 0.999, 1e-3, 3e-4);
+  auto crit = LossFactory::create_logsoftmax_crossentropy();
+  TrainStep step(g, *crit, *opt);
+  SyntheticDataLoader data({28, 28, 1}, 10, 64, 3);
+  Tensor x, y;
+  data.get_batch(16, x, y);
+  for (int i = 0; i < 3; ++i) step(x, y);
+  const std::string path = "/tmp/tnn_tests_ckpt.bin";
+  save_checkpoint(g, path, opt.get(), nullptr, 3);
+  // header is the reference schema
+  std::ifstream f(path, std::ios::binary);
+  std::stringstream ss;
+  ss << f.rdbuf();
+  size_t pos = 0;
+  const Json hdr = Json::parse(ss.str(), &pos);
+  CHECK(hdr.at("type").as_string() == "graph" && hdr.at("parameters").at("op_nodes").at("type").as_string() == "json");
+  CHECK(hdr.at("parameters").at("edges").at("value")[0].contains("producers"));
+  auto opt2 = OptimizerFactory::create_adam(1e-2, 0.9, 0.999, 1e-3, 3e-4);
+  uint64_t step_no = 0;
+  Graph g2 = load_checkpoint(path, getHost(), opt2.get(), nullptr, &step_no);
+  CHECK(step_no == 3 && opt2->step_count == 3);
+  CHECK(max_abs_diff(*g2.context().param_slab(), *ctx.param_slab()) == 0);
+  CHECK(max_abs_diff(*g2.context().buffer_slab(), *ctx.buffer_slab()) == 0);        // BatchNorm running statistics serialise too
+  CHECK(max_abs_diff(*opt2->state_tensors()["m"], *opt->state_tensors()["m"]) == 0);
+  // resumed training continues identically
+  TrainStep step2(g2, *crit, *opt2);
+  Tensor s1 = step(x, y), s2 = step2(x, y);
+  CHECK_NEAR(s1->data_as<float>()[0], s2->data_as<float>()[0], 1e-6);
+}
+TEST(schedulers_closed_forms) {
+  auto opt = OptimizerFactory::create_sgd(1.0);
+  auto s = SchedulerFactory::create_step_lr(opt.get(), 2, 0.5);
+  s->step(); CHECK_NEAR(opt->get_learning_rate(), 1.0, 0);
+  s->step(); CHECK_NEAR(opt->get_learning_rate(), 0.5, 0);
+  s->step(); s->step(); CHECK_NEAR(opt->get_learning_rate(), 0.25, 0);
+  auto o2 = OptimizerFactory::create_sgd(1.0);
+  auto c = SchedulerFactory::create_cosine_annealing_lr(o2.get(), 10, 0.0);
+  for (int i = 0; i < 5; ++i) c->step();
+  CHECK_NEAR(o2->get_learning_rate(), 0.5, 1e-9);
+  auto o3 = OptimizerFactory::create_sgd(1.0);
+  auto w = SchedulerFactory::create_linear_warmup(o3.get(), 4, 0.0);
+  w->step(); CHECK_NEAR(o3->get_learning_rate(), 0.25, 1e-9);
+  auto o4 = OptimizerFactory::create_sgd(1.0);
+  auto r = SchedulerFactory::create_reduce_lr_on_plateau(o4.get(), 0.1, 1);
+  r->step(1.0); r->step(1.0); r->step(1.0);
+  CHECK_NEAR(o4->get_learning_rate(), 0.1, 1e-12);
+  for (const char* t : {"no_op", "step_lr", "multi_step_lr", "exponential_lr", "cosine_annealing_lr", "cosine_annealing_warm_restarts", "linear_warmup",
+                        "warmup_cosine_annealing", "reduce_lr_on_plateau", "polynomial_lr", "one_cycle_lr"}) {
+    TConfig cfg(t, t);
+    auto sc = SchedulerFactory::create_from_config(cfg, o4.get());
+    CHECK(sc->get_config().type == t || std::string(t) == "no_op");
+    auto sc2 = SchedulerFactory::create_from_config(sc->get_config(), o4.get());
+    CHECK(sc2->name() == sc->name());
+  }
+}
+TEST(losses_match_closed_forms) {
+  Tensor p = make_tensor_from({2.f, 1.f, 0.f, 0.f, 0.f, 3.f}, {2, 3});
+  Tensor y = make_tensor(DType_t::INT32_T, {2});
+  y->data_as<int32_t>()[0] = 0;
+  y->data_as<int32_t>()[1] = 1;
+  auto ce = LossFactory::create("logsoftmax_crossentropy");
+  Tensor stats, grad;
+  ce->loss_and_grad(p, y, stats, &grad);
+  const double l0 = std::log(std::exp(2.) + std::exp(1.) + 1) - 2, l1 = std::log(2 + std::exp(3.)) - 0;
+  CHECK_NEAR(stats->data_as<float>()[0], (l0 + l1) / 2, 1e-5);
+  CHECK_NEAR(stats->data_as<float>()[1], 1.0, 0);              // row 0 correct, row 1 wrong
+  CHECK_NEAR(grad->data_as<float>()[0], (std::exp(2.) / (std::exp(2.) + std::exp(1.) + 1) - 1) / 2, 1e-6);
+  float loss = 0;
+  Tensor t = make_tensor_from({1.f, 1.f, 1.f, 1.f, 1.f, 1.f}, {2, 3});
+  LossFactory::create("mse")->compute_loss(p, t, loss);
+  CHECK_NEAR(loss, (1 + 0 + 1 + 1 + 1 + 4) / 6.0, 1e-6);
+  LossFactory::create("mae")->compute_loss(p, t, loss);
+  CHECK_NEAR(loss, (1 + 0 + 1 + 1 + 1 + 2) / 6.0, 1e-6);
+  LossFactory::create("huber")->compute_loss(p, t, loss);
+  CHECK_NEAR(loss, (0.5 + 0 + 0.5 + 0.5 + 0.5 + 1.5) / 6.0, 1e-6);
+  CHECK(compute_class_corrects(p, y) == 1);
+}
+TEST(training_converges_on_cpu) {
+  Graph g = load_or_create_model("mnist_cnn", "", getHost(), 11);
+  auto opt = OptimizerFactory::create_adam(3e-3, 0.9, 0.999, 1e-3, 0.0);
+  auto crit = LossFactory::create_logsoftmax_crossentropy();
+  SyntheticDataLoader train({28, 28, 1}, 10, 256, 5), val({28, 28, 1}, 10, 128, 5);
+  TrainingConfig cfg;
+  cfg.epochs = 3;
+  cfg.batch_size = 32;
+  cfg.progress_print_interval = 0;
+  cfg.snapshot_dir = "/tmp/tnn_tests_snap";
+  TrainHistory h = train_model(g, train, &val, *opt, *crit, nullptr, cfg, [](const std::string&) {});
+  CHECK(h.train_loss.size() == 3 && h.train_loss.back() < h.train_loss.front() * 0.8);
+  CHECK(h.val_acc.back() > 0.3);
+}
+
+// ------------------------------------------------------------------------------------- GPU: layer parity with the CPU oracle
+static void parity(const std::function<std::unique_ptr<Layer>()>& make, const Shape& xs, double tol, bool train = true) {
+  const Device g = need_gpu();
+  auto lc = make(), lg = make();
+  lc->init(getHost(), 5);
+  lg->init(g, 5);
+  // same parameters on both sides
+  auto cl = lc->all_layers(), gl = lg->all_layers();
+  for (size_t i = 0; i < cl.size(); ++i)
+    for (auto& p : cl[i]->params()) gl[i]->param(p.first)->copy_from(*p.second);
+  for (Layer* l : gl) l->mark_params_dirty();
+  lc->set_training(train);
+  lg->set_training(train);
+  Tensor x = make_tensor<float>(xs);
+  x->fill_random_normal(0, 1, 21);
+  // bf16 inputs on both sides so that the comparison measures the kernels, not the input rounding
+  Tensor xb = dtype_cast(*dtype_cast(*x, DType_t::BF16), DType_t::FP32);
+  Tensor yc = lc->forward(xb, 0);
+  Tensor yg = lg->forward(xb->to_device(g), 0);
+  const double scale = std::max(1.0, yc->max() - yc->min());
+  const double d = max_abs_diff(*yc, *yg);
+  if (!(d <= tol * scale)) throw std::runtime_error(lc->type() + ": forward differs by " + std::to_string(d) + " (scale " + std::to_string(scale) + ")");
+  if (!train) return;
+  Tensor w = make_tensor<float>(yc->shape());
+  w->fill_random_normal(0, 1, 22);
+  Tensor wb = dtype_cast(*dtype_cast(*w, DType_t::BF16), DType_t::FP32);
+  Tensor dc = lc->backward(wb, 0);
+  Tensor dg = lg->backward(wb->to_device(g), 0);
+  side_flow::join(g);
+  if (dc && dg) {
+    const double ds = std::max(1.0, dc->max() - dc->min()), dd = max_abs_diff(*dc, *dg);
+    if (!(dd <= tol * ds)) throw std::runtime_error(lc->type() + ": dx differs by " + std::to_string(dd) + " (scale " + std::to_string(ds) + ")");
+  }
+  for (size_t i = 0; i < cl.size(); ++i)
+    for (auto& gr : cl[i]->grads()) {
+      const double gs = std::max(1.0, gr.second->max() - gr.second->min()), gd = max_abs_diff(*gr.second, *gl[i]->grad(gr.first));
+      if (!(gd <= 2 * tol * gs)) throw std::runtime_error(cl[i]->name() + "." + gr.first + ": gradient differs by " + std::to_string(gd) + " (scale " + std::to_string(gs) + ")");
+    }
+}
+TEST(gpu_parity_dense_conv) {
+  parity([]() -> std::unique_ptr<Layer> { return std::make_unique<DenseLayer>(64, 48); }, {40, 64}, 2e-2);
+  parity([]() -> std::unique_ptr<Layer> { return std::make_unique<DenseLayer>(512, 100); }, {256, 512}, 2e-2);            // classifier head: N % 8 != 0
+  parity([]() -> std::unique_ptr<Layer> { return std::make_unique<Conv2DLayer>(16, 32, 3, 3, 1, 1, 1, 1); }, {4, 16, 16, 16}, 2e-2);
+  parity([]() -> std::unique_ptr<Layer> { return std::make_unique<Conv2DLayer>(32, 64, 3, 3, 2, 2, 1, 1); }, {4, 16, 16, 32}, 2e-2);
+  parity([]() -> std::unique_ptr<Layer> { return std::make_unique<Conv2DLayer>(32, 64, 1, 1, 2, 2, 0, 0, false); }, {4, 16, 16, 32}, 2e-2);
+  parity([]() -> std::unique_ptr<Layer> { return std::make_unique<Conv2DLayer>(3, 16, 3, 3, 1, 1, 1, 1); }, {8, 32, 32, 3}, 2e-2);      // direct first-layer kernel
+  parity([]() -> std::unique_ptr<Layer> { return std::make_unique<Conv2DLayer>(8, 16, 5, 5, 1, 1, 0, 0, false); }, {2, 12, 12, 8}, 2e-2);   // im2col path
+}
+TEST(gpu_parity_norms_pools_acts) {
+  parity([]() -> std::unique_ptr<Layer> { return std::make_unique<BatchNormLayer>(32, 1e-5, 0.1, true, true); }, {8, 8, 8, 32}, 3e-2);
+  parity([]() -> std::unique_ptr<Layer> { return std::make_unique<BatchNormLayer>(64, 1e-5, 0.1, true, false); }, {4, 16, 16, 64}, 3e-2);
+  parity([]() -> std::unique_ptr<Layer> { return std::make_unique<LayerNormLayer>(256); }, {6, 10, 256}, 3e-2);
+  parity([]() -> std::unique_ptr<Layer> { return std::make_unique<GroupNormLayer>(4, 32); }, {2, 8, 8, 32}, 3e-2);
+  parity([]() -> std::unique_ptr<Layer> { return std::make_unique<MaxPool2DLayer>(2, 2); }, {2, 8, 8, 16}, 1e-2);
+  parity([]() -> std::unique_ptr<Layer> { return std::make_unique<AvgPool2DLayer>(8, 8, 1, 1); }, {4, 8, 8, 32}, 1e-2);
+  for (const char* a : {"relu", "leaky_relu", "sigmoid", "tanh", "elu", "gelu"}) parity([a]() -> std::unique_ptr<Layer> { return std::make_unique<ActivationLayer>(a); }, {4, 64}, 2e-2);
+}
+TEST(gpu_parity_blocks) {
+  parity([]() -> std::unique_ptr<Layer> { LayerBuilder b({16, 16, 32}); b.wide_residual_block(32, 64, 2, 0.0, "w"); return b.build_sequential("wrn_block"); }, {4, 16, 16, 32}, 5e-2);
+  parity([]() -> std::unique_ptr<Layer> { LayerBuilder b({8, 8, 32}); b.basic_residual_block(32, 32, 1, "r"); return b.build_sequential("res_block"); }, {4, 8, 8, 32}, 5e-2);
+  parity([]() -> std::unique_ptr<Layer> { return std::make_unique<AttentionBlock>(128, 2, true); }, {2, 64, 128}, 4e-2);
+}
+TEST(gpu_train_step_graph_matches_eager_and_learns) {
+  const Device g = need_gpu();
+  auto run = [&](bool use_graph) {
+    Graph gr = load_or_create_model("cifar10_resnet9", "", g, 3);
+    auto opt = OptimizerFactory::create_adam(1e-3, 0.9, 0.999, 1e-3, 3e-4);
+    auto crit = LossFactory::create_logsoftmax_crossentropy();
+    TrainStep step(gr, *crit, *opt, nullptr, 1, use_graph);
+    SyntheticDataLoader data({32, 32, 3}, 10, 256, 9);
+    data.set_pinned(true);
+    Tensor x, y;
+    data.get_batch(64, x, y);
+    std::vector<float> losses;
+    for (int i = 0; i < 12; ++i) {
+      Tensor st = step(x, y);
+      float h[2];
+      st->copy_to_host(h, 8);
+      losses.push_back(h[0]);
+    }
+    CHECK(use_graph == step.captured());
+    return losses;
+  };
+  const auto eager = run(false), graph = run(true);
+  CHECK(eager.back() < eager.front() * 0.7 && graph.back() < graph.front() * 0.7);
+  for (size_t i = 0; i < eager.size(); ++i) CHECK_NEAR(eager[i], graph[i], 0.05 * std::max(1.f, eager[i]));
+}
+
+int main(int argc, char** argv) {
+  const std::string filter = argc > 1 ? argv[1] : "";
+  int passed = 0, failed = 0, skipped = 0;
+  for (auto& t : registry()) {
+    if (!filter.empty() && std::string(t.name).find(filter) == std::string::npos) continue;
+    try {
+      t.fn();
+      std::cout << "[ OK      ] " << t.name << std::endl;
+      ++passed;
+    } catch (const Skip& s) {
+      std::cout << "[ SKIPPED ] " << t.name << " (" << s.why << ")" << std::endl;
+      ++skipped;
+    } catch (const std::exception& e) {
+      std::cout << "[ FAILED  ] " << t.name << ": " << e.what() << std::endl;
+      ++failed;
+    }
+  }
+  std::cout << passed << " passed, " << failed << " failed, " << skipped << " skipped" << std::endl;
+  return failed ? 1 : 0;
+}

@@ -129,5 +129,69 @@ def build(force: bool = False, jobs: int | None = None, verbose: bool = True) ->
     return TARGET
 
 
+# ----------------------------------------------------------------------------------------------- C++ host
+CPP = ROOT.parent / "cpp"
+
+
+def build_host(force: bool = False, verbose: bool = True) -> dict:
+    """libtnn_b200.so (the C++ framework: cpp/include/tnn + cpp/src, linked with the SAME sm_100a kernel objects as
+    _C.so but with NO torch and NO Python) and its executables: cpp/bin/trainer, cpp/bin/bench_cpp, cpp/bin/tnn_tests.
+    ``ldd cpp/bin/trainer`` shows libtnn_b200, libcudart, libstdc++ -- nothing else."""
+    cuda = _cuda_home()
+    build(force=False, verbose=verbose)                       # kernel objects (tnn_b200/_build/*.cu.o)
+    obj_dir, lib_dir, bin_dir = CPP / "_build", CPP / "lib", CPP / "bin"
+    for d in (obj_dir, lib_dir, bin_dir):
+        d.mkdir(parents=True, exist_ok=True)
+    hdr = hashlib.sha256()
+    for h in sorted(list((CPP / "include").rglob("*.hpp")) + list(CSRC.rglob("*.hpp")) + list(CSRC.rglob("*.cuh"))):
+        hdr.update(h.read_bytes())
+    gxx = ["g++", "-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", f"-I{CPP / 'include'}", f"-I{CSRC}",
+           f"-I{cuda}/include", "-pthread"]
+    tasks = []
+    for s in sorted((CPP / "src").glob("*.cpp")) + sorted((CPP / "examples").glob("*.cpp")) + sorted((CPP / "tests").glob("*.cpp")):
+        stamp = hashlib.sha256(s.read_bytes() + hdr.hexdigest().encode() + _flag_sig(gxx).encode()).hexdigest()
+        tasks.append((s, obj_dir / (s.stem + ".o"), stamp))
+    rebuilt = False
+    with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
+        futs = []
+        for s, obj, stamp in tasks:
+            if force and obj.with_suffix(".stamp").exists():
+                obj.with_suffix(".stamp").unlink()
+            futs.append(ex.submit(_compile_one, s, gxx, obj, stamp))
+        for f in futs:
+            obj, did, _ = f.result()
+            rebuilt |= did
+            if did and verbose:
+                print(f"[tnn_b200.build] compiled cpp/{obj.name}", flush=True)
+    lib = lib_dir / "libtnn_b200.so"
+    lib_objs = [obj_dir / (s.stem + ".o") for s in sorted((CPP / "src").glob("*.cpp"))]
+    cu_objs = sorted(BUILD.glob("*.cu.o"))
+    newest_cu = max(o.stat().st_mtime for o in cu_objs)
+    if rebuilt or not lib.exists() or lib.stat().st_mtime < newest_cu:
+        link = ["g++", "-shared", "-o", str(lib), *map(str, lib_objs), *map(str, cu_objs), f"-L{cuda}/lib64", "-lcudart",
+                f"-Wl,-rpath,{cuda}/lib64", "-pthread", "-ldl"]
+        r = subprocess.run(link, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"libtnn_b200 link failed:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            print(f"[tnn_b200.build] linked {lib}", flush=True)
+        rebuilt = True
+    exes = {}
+    for s in sorted((CPP / "examples").glob("*.cpp")) + sorted((CPP / "tests").glob("*.cpp")):
+        exe = bin_dir / s.stem
+        if rebuilt or not exe.exists():
+            link = ["g++", "-o", str(exe), str(obj_dir / (s.stem + ".o")), f"-L{lib_dir}", "-ltnn_b200", f"-L{cuda}/lib64", "-lcudart",
+                    "-Wl,-rpath,$ORIGIN/../lib", f"-Wl,-rpath,{cuda}/lib64", "-pthread"]
+            r = subprocess.run(link, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"link of {exe.name} failed:\n{r.stdout}\n{r.stderr}")
+            if verbose:
+                print(f"[tnn_b200.build] linked {exe}", flush=True)
+        exes[s.stem] = exe
+    return {"lib": lib, **exes}
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv)
+    if "--no-host" not in sys.argv:
+        build_host(force="--force" in sys.argv)
