@@ -46,6 +46,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH)
     ap.add_argument("--model", default="cifar100_wrn16_8")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host", default="auto", choices=["auto", "cpp", "python"],
+                    help="which host drives the training step: the C++ framework (libtnn_b200 through tnn_b200._host; single GPU) "
+                         "or the Python host (also the data-parallel path)")
     ap.add_argument("--no-gpt2", action="store_true", help="skip the GPT-2 inference block (BASELINE config 4)")
     ap.add_argument("--gpt2-iters", type=int, default=5)
     return ap.parse_args()
@@ -212,7 +215,40 @@ def barrier(world):
     torch.cuda.synchronize()
 
 
+def run_tnn_cpp(args):
+    """Single-GPU arm driven by the C++ host: model, executor, workspace allocator, CUDA-graph capture, optimizer and the
+    timing loop all live in libtnn_b200 (cpp/src/bench.cpp); Python only samples clocks and prints the line."""
+    import torch
+    from tnn_b200 import build as tb
+    tb.build_host(verbose=False)
+    from tnn_b200 import _host
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    sampler = ClockSampler(local)
+    sampler.start()
+    out = json.loads(_host.bench_train(args.model, args.batch, args.steps, args.warmup, local, True))
+    clocks = sampler.stop()
+    out["impl"] = "tnn_b200"
+    out["clocks"] = clocks
+    out["config"]["classes"] = 10 if "cifar10_" in args.model else 100
+    out["config"]["image"] = [32, 32, 3]
+    out["config"]["seq_len"] = None
+    out["config"]["clock_sampling"] = "NVML over the device-timed AND the end-to-end region of the C++ benchmark call"
+    gpt2 = gpt2_block(args, "tnn", 0, 1, dev)
+    if gpt2 is not None:
+        out["gpt2"] = gpt2
+    emit(out)
+
+
 def run_tnn(args):
+    if args.host != "python" and int(os.environ.get("WORLD_SIZE", 1)) == 1 and args.dp == "fused":
+        try:
+            return run_tnn_cpp(args)
+        except Exception as e:  # noqa: BLE001
+            if args.host == "cpp":
+                raise
+            print(f"[bench] C++ host unavailable ({type(e).__name__}: {e}); falling back to the Python host", file=sys.stderr)
     import torch
     from tnn_b200.models import ExampleModels, load_or_create_model
     from tnn_b200.nn import LossFactory, OptimizerFactory

@@ -1,0 +1,190 @@
+// tnn_b200._host: thin pybind11 layer over libtnn_b200 (the C++ framework).  NO torch here: arrays cross as numpy.
+// Python tests drive the C++ layers / graphs / trainer through this module and compare them with torch oracles.
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <sstream>
+
+#include "kernels/simt_ops.cuh"
+#include "tnn/bench.hpp"
+#include "tnn/example_models.hpp"
+#include "tnn/stepstate.hpp"
+#include "tnn/train.hpp"
+
+namespace py = pybind11;
+using namespace tnn;
+
+static Device parse_device(const std::string& s) { return DeviceManager::getInstance().getDevice(s); }
+// numpy (float32 / int32) -> host tensor
+static Tensor from_numpy(const py::array& a) {
+  py::array c = py::array::ensure(a, py::array::c_style | py::array::forcecast);
+  Shape shape;
+  for (py::ssize_t i = 0; i < c.ndim(); ++i) shape.push_back((size_t)c.shape(i));
+  DType_t dt;
+  if (c.dtype().is(py::dtype::of<float>())) dt = DType_t::FP32;
+  else if (c.dtype().is(py::dtype::of<int32_t>())) dt = DType_t::INT32_T;
+  else if (c.dtype().is(py::dtype::of<int64_t>())) dt = DType_t::INT64_T;
+  else if (c.dtype().is(py::dtype::of<double>())) dt = DType_t::FP64;
+  else throw std::invalid_argument("from_numpy: float32 / float64 / int32 / int64 arrays");
+  Tensor t = make_tensor(dt, shape, getHost());
+  std::memcpy(t->data(), c.data(), t->nbytes());
+  if (dt == DType_t::FP64) return dtype_cast(*t, DType_t::FP32);
+  if (dt == DType_t::INT64_T) return dtype_cast(*t, DType_t::INT32_T);
+  return t;
+}
+// any tensor -> numpy float32 (or int32)
+static py::array to_numpy(const Tensor& t) {
+  if (!t) return py::array();
+  std::vector<py::ssize_t> shape(t->shape().begin(), t->shape().end());
+  if (t->data_type() == DType_t::INT32_T) {
+    Tensor h = t->is_gpu() ? t->to_host() : t;
+    py::array_t<int32_t> out(shape);
+    std::memcpy(out.mutable_data(), h->data(), h->nbytes());
+    return std::move(out);
+  }
+  const auto v = to_float_vector(*t);
+  py::array_t<float> out(shape);
+  std::memcpy(out.mutable_data(), v.data(), v.size() * 4);
+  return std::move(out);
+}
+
+struct PyLayer {
+  std::unique_ptr<Layer> layer;
+  Device dev = getHost();
+  void sync() const {
+    if (dev.is_gpu()) {
+      side_flow::join(dev);
+      current_flow(dev).synchronize();
+    }
+  }
+  Tensor put(const py::array& a) const {
+    Tensor h = from_numpy(a);
+    return dev.is_gpu() ? h->to_device(dev) : h;
+  }
+};
+
+struct PyTrainer {
+  std::unique_ptr<Graph> graph;
+  std::unique_ptr<Loss> loss;
+  std::unique_ptr<Optimizer> opt;
+  std::unique_ptr<Scheduler> sched;
+  std::unique_ptr<TrainStep> step;
+};
+
+PYBIND11_MODULE(_host, m) {
+  m.doc() = "tnn_b200 C++ host (libtnn_b200) -- numpy in / numpy out";
+  m.def("num_gpus", [] { return DeviceManager::getInstance().num_gpus(); });
+  m.def("registered_layer_types", [] { return LayerFactory::registered_types(); });
+  m.def("available_models", [] { return ExampleModels::available_models(); });
+  m.def("model_config", [](const std::string& name) { return ExampleModels::create(name)->get_config().dump(-1); });
+  m.def("launch_count", [] { return (unsigned long long)g_launch_count; });
+  // the flagship benchmark, in process (bench.py --host cpp); returns the JSON line as a string
+  m.def("bench_train", [](const std::string& model, size_t batch, int steps, int warmup, int gpu, bool use_graph) {
+    Json j;
+    {
+      py::gil_scoped_release rel;
+      j = bench_train(model, batch, steps, warmup, gpu, use_graph);
+    }
+    return j.dump();
+  }, py::arg("model") = "cifar100_wrn16_8", py::arg("batch") = 256, py::arg("steps") = 30, py::arg("warmup") = 5, py::arg("gpu") = 0,
+     py::arg("use_graph") = true);
+
+  py::class_<PyLayer>(m, "Layer")
+      .def(py::init([](const std::string& config_json, const std::string& device, uint64_t seed) {
+             auto p = std::make_unique<PyLayer>();
+             p->layer = LayerFactory::create(TConfig::from_string(config_json));
+             p->dev = parse_device(device);
+             p->layer->init(p->dev, seed);
+             return p;
+           }), py::arg("config_json"), py::arg("device") = "CPU", py::arg("seed") = 1)
+      .def("type", [](PyLayer& l) { return l.layer->type(); })
+      .def("config", [](PyLayer& l) { return l.layer->get_config().dump(-1); })
+      .def("set_training", [](PyLayer& l, bool f) { l.layer->set_training(f); })
+      .def("output_shape", [](PyLayer& l, const Shape& s) { return l.layer->output_shape(s); })
+      .def("forward", [](PyLayer& l, const py::array& x, size_t mb) {
+        Tensor y = l.layer->forward(l.put(x), mb);
+        l.sync();
+        return to_numpy(y);
+      }, py::arg("x"), py::arg("mb_id") = 0)
+      .def("forward_multi", [](PyLayer& l, const std::vector<py::array>& xs, size_t mb) {
+        Vec<Tensor> in;
+        for (auto& x : xs) in.push_back(l.put(x));
+        Vec<Tensor> out = l.layer->forward(in, mb);
+        l.sync();
+        std::vector<py::array> r;
+        for (auto& t : out) r.push_back(to_numpy(t));
+        return r;
+      }, py::arg("xs"), py::arg("mb_id") = 0)
+      .def("backward", [](PyLayer& l, const py::array& dy, size_t mb) {
+        Tensor dx = l.layer->backward(l.put(dy), mb);
+        l.sync();
+        return to_numpy(dx);
+      }, py::arg("dy"), py::arg("mb_id") = 0)
+      // every parameter / gradient of the layer tree as {"layer_name.param": array}
+      .def("params", [](PyLayer& l) {
+        py::dict d;
+        for (Layer* s : l.layer->all_layers())
+          for (auto& p : s->params()) d[py::str(s->name() + "." + p.first)] = to_numpy(p.second);
+        return d;
+      })
+      .def("grads", [](PyLayer& l) {
+        l.sync();
+        py::dict d;
+        for (Layer* s : l.layer->all_layers())
+          for (auto& p : s->grads()) d[py::str(s->name() + "." + p.first)] = to_numpy(p.second);
+        return d;
+      })
+      .def("set_param", [](PyLayer& l, const std::string& qualified, const py::array& v) {
+        for (Layer* s : l.layer->all_layers())
+          for (auto& p : s->params())
+            if (s->name() + "." + p.first == qualified) {
+              Tensor h = from_numpy(v);
+              if (h->size() != p.second->size()) throw std::invalid_argument("set_param: size mismatch for " + qualified);
+              p.second->copy_from(*h->reshape(p.second->shape()));
+              s->mark_params_dirty();
+              return;
+            }
+        throw std::out_of_range("set_param: no parameter " + qualified);
+      })
+      .def("zero_grads", [](PyLayer& l) {
+        for (Layer* s : l.layer->all_layers())
+          for (auto& g : s->grads()) g.second->zero();
+      });
+
+  py::class_<PyTrainer>(m, "Trainer")
+      .def(py::init([](const std::string& model, const std::string& device, uint64_t seed, const std::string& optimizer_json, const std::string& loss,
+                       bool use_graph, const std::string& checkpoint) {
+             auto t = std::make_unique<PyTrainer>();
+             const Device dev = parse_device(device);
+             t->opt = OptimizerFactory::create_from_config(TConfig::from_string(optimizer_json));
+             if (!checkpoint.empty()) t->graph = std::make_unique<Graph>(load_checkpoint(checkpoint, dev, t->opt.get()));
+             else t->graph = std::make_unique<Graph>(load_or_create_model(model, "", dev, seed));
+             t->loss = LossFactory::create(loss);
+             t->step = std::make_unique<TrainStep>(*t->graph, *t->loss, *t->opt, nullptr, 1, use_graph);
+             return t;
+           }), py::arg("model"), py::arg("device") = "CPU", py::arg("seed") = 1,
+           py::arg("optimizer_json") = R"({"name":"adam","type":"adam","parameters":{"learning_rate":{"type":"double","value":0.001}}})",
+           py::arg("loss") = "logsoftmax_crossentropy", py::arg("use_graph") = true, py::arg("checkpoint") = "")
+      .def("step", [](PyTrainer& t, const py::array& x, const py::array& y) {
+        Tensor hx = from_numpy(x), hy = from_numpy(y);
+        Tensor st = (*t.step)(hx, hy);
+        float h[2];
+        st->copy_to_host(h, 8);
+        return std::make_pair(h[0], h[1]);
+      })
+      .def("num_parameters", [](PyTrainer& t) { return t.graph->context().num_parameters(); })
+      .def("captured", [](PyTrainer& t) { return t.step->captured(); })
+      .def("param_slab", [](PyTrainer& t) { return to_numpy(t.graph->context().param_slab()); })
+      .def("save", [](PyTrainer& t, const std::string& path) { save_checkpoint(*t.graph, path, t.opt.get(), nullptr, t.opt->step_count); })
+      .def("graph_config", [](PyTrainer& t) { return t.graph->get_config().dump(-1); })
+      .def("predict", [](PyTrainer& t, const py::array& x) {
+        t.graph->set_training(false);
+        GraphExecutor ex(*t.graph);
+        Tensor h = from_numpy(x);
+        Tensor out = ex.forward(t.graph->device().is_gpu() ? h->to_device(t.graph->device()) : h, 0);
+        py::array r = to_numpy(out);
+        t.graph->set_training(true);
+        return r;
+      });
+}

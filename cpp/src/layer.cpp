@@ -145,10 +145,10 @@ StepState::StepState(const Device& d) : device_(d) {
 }
 StepState& StepState::get(const Device& d) {
   static std::mutex mu;
-  static std::map<int, std::unique_ptr<StepState>> all;
+  static auto* all = new std::map<int, StepState*>();      // leaked: see DeviceManager::getInstance
   std::lock_guard<std::mutex> g(mu);
-  auto& s = all[d.is_gpu() ? d.id() : -1];
-  if (!s) s = std::make_unique<StepState>(d);
+  auto& s = (*all)[d.is_gpu() ? d.id() : -1];
+  if (!s) s = new StepState(d);
   return *s;
 }
 void StepState::advance(const Optimizer* opt) {
@@ -168,8 +168,8 @@ void StepState::advance(const Optimizer* opt) {
 namespace side_flow {
 static bool g_enabled = true;
 static std::mutex g_mu;
-static std::map<int, std::vector<Tensor>> g_keep;
-static std::map<int, bool> g_pending;
+static std::map<int, std::vector<Tensor>>& g_keep = *new std::map<int, std::vector<Tensor>>();
+static std::map<int, bool>& g_pending = *new std::map<int, bool>();
 bool enabled() { return g_enabled; }
 void set_enabled(bool on) { g_enabled = on; }
 void run(const Device& d, const std::function<void()>& fn, std::vector<Tensor> keep) {

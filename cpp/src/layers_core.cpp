@@ -1151,11 +1151,11 @@ Tensor ResidualBlock::forward_impl(const Tensor& x, size_t mb, const FwdAux&) {
   return y;
 }
 Tensor ResidualBlock::backward_impl(const Tensor& dyin, size_t mb, BwdAux& aux) {
-  Tensor dy = dyin;
+  Tensor dy = as_compute(dyin);          // the identity shortcut hands dy on as `extra`: it must be in the compute dtype
   Tensor colsum = aux.colsum_in;
   if (act_ == "relu") {
     Tensor y = cache(mb).get("y");
-    Tensor d = as_compute(dyin);
+    Tensor d = dy;
     Tensor g = new_tensor(d->data_type(), d->shape());
     if (device_.is_gpu()) act_bwd(y->data(), d->data(), g->data(), (long long)d->size(), AK_RELU, 0.f, 0, stream());
     else {

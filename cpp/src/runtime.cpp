@@ -104,8 +104,10 @@ DeviceManager::DeviceManager() {
   for (int i = 0; i < n; ++i) gpus_.emplace_back(DeviceType::GPU, i);
 }
 DeviceManager& DeviceManager::getInstance() {
-  static DeviceManager m;
-  return m;
+  // intentionally leaked (as every singleton of the runtime): tensors owned by other statics may be released during
+  // process teardown and must still find their allocator, flows and device manager alive
+  static DeviceManager* m = new DeviceManager();
+  return *m;
 }
 const Device& DeviceManager::getGPU(int i) const {
   if (i < 0 || i >= (int)gpus_.size()) throw std::out_of_range("DeviceManager: no GPU " + std::to_string(i) + " (" + std::to_string(gpus_.size()) + " visible)");
@@ -184,15 +186,15 @@ void DeviceAllocator::deallocate(void* p) {
 }
 DeviceAllocator& DeviceAllocator::instance(const Device& d) {
   static std::mutex mu;
-  static std::map<int, std::unique_ptr<DeviceAllocator>> all;
+  static auto* all = new std::map<int, DeviceAllocator*>();
   std::lock_guard<std::mutex> g(mu);
-  auto& a = all[dev_key(d)];
-  if (!a) a = std::make_unique<DeviceAllocator>(d);
+  auto& a = (*all)[dev_key(d)];
+  if (!a) a = new DeviceAllocator(d);
   return *a;
 }
 DeviceAllocator& DeviceAllocator::pinned() {
-  static DeviceAllocator a(getHost(), DeviceManager::getInstance().has_gpu());
-  return a;
+  static DeviceAllocator* a = new DeviceAllocator(getHost(), DeviceManager::getInstance().has_gpu());
+  return *a;
 }
 
 PoolAllocator::~PoolAllocator() { release_cached(); }
@@ -234,10 +236,10 @@ void PoolAllocator::release_cached() {
 }
 PoolAllocator& PoolAllocator::instance(const Device& d, flowHandle_t flow) {
   static std::mutex mu;
-  static std::map<std::pair<int, flowHandle_t>, std::unique_ptr<PoolAllocator>> all;
+  static auto* all = new std::map<std::pair<int, flowHandle_t>, PoolAllocator*>();
   std::lock_guard<std::mutex> g(mu);
-  auto& a = all[{dev_key(d), flow}];
-  if (!a) a = std::make_unique<PoolAllocator>(DeviceAllocator::instance(d));
+  auto& a = (*all)[{dev_key(d), flow}];
+  if (!a) a = new PoolAllocator(DeviceAllocator::instance(d));
   return *a;
 }
 

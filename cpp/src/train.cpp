@@ -219,7 +219,7 @@ void SyntheticDataLoader::fill_sample(size_t index, float* dst, int32_t* label) 
     return;
   }
   std::normal_distribution<float> nd(0.f, 0.5f);
-  std::mt19937_64 cg(seed_ * 7919ull + (uint64_t)cls);   // class prototype
+  std::mt19937_64 cg(7919ull * (uint64_t)(cls + 1) + 12345ull);   // class prototype: shared by every loader (train / val draw different noise)
   std::normal_distribution<float> pd(0.5f, 0.25f);
   for (size_t i = 0; i < per; ++i) dst[i] = pd(cg) + nd(g) * 0.3f;
 }

@@ -1,0 +1,236 @@
+"""The C++ host (libtnn_b200, driven through the torch-free pybind module ``tnn_b200._host``) against plain PyTorch
+fp32 oracles on the CPU, plus format compatibility between the C++ host and the Python host (configs, checkpoints).
+The compiled unit-test binary ``cpp/bin/tnn_tests`` (finite-difference gradient checks, allocators, archiver, graph,
+schedulers ...) runs here as well."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _host():
+    from tnn_b200 import build
+    build.build_host(verbose=False)
+    from tnn_b200 import _host
+    return _host
+
+
+def cfg(type_, name="l", **params):
+    def tag(v):
+        if isinstance(v, bool):
+            return {"type": "bool", "value": v}
+        if isinstance(v, int):
+            return {"type": "size_t", "value": v}
+        if isinstance(v, float):
+            return {"type": "double", "value": v}
+        if isinstance(v, str):
+            return {"type": "string", "value": v}
+        return {"type": "json", "value": v}
+    return json.dumps({"name": name, "type": type_, "parameters": {k: tag(v) for k, v in params.items()}})
+
+
+def t(a):
+    return torch.from_numpy(np.asarray(a)).float()
+
+
+def test_tnn_tests_binary_passes_on_cpu():
+    _host()
+    out = subprocess.run([os.path.join(ROOT, "cpp", "bin", "tnn_tests")], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert " 0 failed" in out.stdout and "gradcheck_conv2d" in out.stdout
+    # the executables do not depend on torch or python
+    ldd = subprocess.run(["ldd", os.path.join(ROOT, "cpp", "bin", "trainer")], capture_output=True, text=True).stdout
+    assert "libtnn_b200" in ldd and "libtorch" not in ldd and "libc10" not in ldd and "libpython" not in ldd
+
+
+def test_factory_registers_every_reference_type_name():
+    H = _host()
+    have = set(H.registered_layer_types())
+    want = {"dense", "conv2d", "batchnorm", "maxpool2d", "avgpool2d", "groupnorm", "layer_norm", "dropout", "flatten", "activation", "embedding",
+            "pos_embedding", "class_token", "slice", "transpose", "identity", "add", "sub", "mul", "mbroadcast", "sdpa", "sequential", "msequential",
+            "residual_block", "attention_block", "flash_attention_block", "legacy_dense", "legacy_conv2d", "legacy_maxpool2d", "legacy_avgpool2d",
+            "legacy_batchnorm"}
+    assert want <= have
+    assert len(H.available_models()) >= 17
+
+
+@pytest.mark.parametrize("stride,pad,bias,R,S", [(1, 1, True, 3, 3), (2, 1, False, 3, 3), (1, 0, True, 1, 1), (2, 0, False, 1, 1), (1, 2, True, 5, 5)])
+def test_conv2d_matches_torch(stride, pad, bias, R, S):
+    H = _host()
+    C, K = 3, 5
+    l = H.Layer(cfg("conv2d", in_channels=C, out_channels=K, kernel_h=R, kernel_w=S, stride_h=stride, stride_w=stride, pad_h=pad, pad_w=pad, use_bias=bias))
+    p = l.params()
+    x = np.random.RandomState(0).randn(2, 9, 8, C).astype("float32")
+    w = t(p["l.weight"]).permute(0, 3, 1, 2).requires_grad_(True)
+    b = t(p["l.bias"]).requires_grad_(True) if bias else None
+    xt = t(x).permute(0, 3, 1, 2).requires_grad_(True)
+    yt = F.conv2d(xt, w, b, stride, pad)
+    y = l.forward(x)
+    np.testing.assert_allclose(y, yt.permute(0, 2, 3, 1).detach().numpy(), rtol=1e-4, atol=1e-4)
+    dy = np.random.RandomState(1).randn(*y.shape).astype("float32")
+    yt.backward(t(dy).permute(0, 3, 1, 2))
+    dx = l.backward(dy)
+    g = l.grads()
+    np.testing.assert_allclose(dx, xt.grad.permute(0, 2, 3, 1).numpy(), rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(g["l.weight"], w.grad.permute(0, 2, 3, 1).numpy(), rtol=1e-3, atol=1e-3)
+    if bias:
+        np.testing.assert_allclose(g["l.bias"], b.grad.numpy(), rtol=1e-3, atol=1e-3)
+
+
+def test_dense_batchnorm_pools_layernorm_groupnorm_match_torch():
+    H = _host()
+    rs = np.random.RandomState(2)
+    # dense
+    l = H.Layer(cfg("dense", input_features=7, output_features=5, use_bias=True))
+    p = l.params()
+    x = rs.randn(4, 7).astype("float32")
+    w, b, xt = t(p["l.weight"]).requires_grad_(True), t(p["l.bias"]).requires_grad_(True), t(x).requires_grad_(True)
+    yt = F.linear(xt, w, b)
+    np.testing.assert_allclose(l.forward(x), yt.detach().numpy(), rtol=1e-5, atol=1e-5)
+    dy = rs.randn(4, 5).astype("float32")
+    yt.backward(t(dy))
+    np.testing.assert_allclose(l.backward(dy), xt.grad.numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(l.grads()["l.weight"], w.grad.numpy(), rtol=1e-4, atol=1e-5)
+    # batchnorm (training statistics, running-stat update with unbiased variance, fused ReLU)
+    for relu in (False, True):
+        l = H.Layer(cfg("batchnorm", num_features=6, epsilon=1e-5, momentum=0.1, affine=True, use_relu=relu))
+        x = rs.randn(3, 4, 5, 6).astype("float32")
+        bn = torch.nn.BatchNorm2d(6, eps=1e-5, momentum=0.1)
+        xt = t(x).permute(0, 3, 1, 2).requires_grad_(True)
+        yt = bn(xt)
+        yt = torch.relu(yt) if relu else yt
+        np.testing.assert_allclose(l.forward(x), yt.permute(0, 2, 3, 1).detach().numpy(), rtol=1e-4, atol=1e-4)
+        dy = rs.randn(*x.shape).astype("float32")
+        yt.backward(t(dy).permute(0, 3, 1, 2))
+        np.testing.assert_allclose(l.backward(dy), xt.grad.permute(0, 2, 3, 1).numpy(), rtol=1e-3, atol=1e-4)
+        g, pp = l.grads(), l.params()
+        np.testing.assert_allclose(g["l.gamma"], bn.weight.grad.numpy(), rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(g["l.beta"], bn.bias.grad.numpy(), rtol=1e-3, atol=1e-4)
+        np.testing.assert_allclose(pp["l.running_mean"], bn.running_mean.numpy(), rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(pp["l.running_var"], bn.running_var.numpy(), rtol=1e-4, atol=1e-5)
+    # pools
+    x = rs.randn(2, 7, 7, 3).astype("float32")
+    for typ, fn in (("maxpool2d", F.max_pool2d), ("avgpool2d", F.avg_pool2d)):
+        l = H.Layer(cfg(typ, pool_h=3, pool_w=3, stride_h=2, stride_w=2, pad_h=0, pad_w=0))
+        xt = t(x).permute(0, 3, 1, 2).requires_grad_(True)
+        yt = fn(xt, 3, 2)
+        y = l.forward(x)
+        np.testing.assert_allclose(y, yt.permute(0, 2, 3, 1).detach().numpy(), rtol=1e-5, atol=1e-6)
+        dy = rs.randn(*y.shape).astype("float32")
+        yt.backward(t(dy).permute(0, 3, 1, 2))
+        np.testing.assert_allclose(l.backward(dy), xt.grad.permute(0, 2, 3, 1).numpy(), rtol=1e-5, atol=1e-6)
+    # layer norm / group norm
+    l = H.Layer(cfg("layer_norm", normalized_shape=8, epsilon=1e-5, affine=True))
+    x = rs.randn(5, 3, 8).astype("float32")
+    xt = t(x).requires_grad_(True)
+    yt = F.layer_norm(xt, (8,))
+    np.testing.assert_allclose(l.forward(x), yt.detach().numpy(), rtol=1e-4, atol=1e-5)
+    dy = rs.randn(*x.shape).astype("float32")
+    yt.backward(t(dy))
+    np.testing.assert_allclose(l.backward(dy), xt.grad.numpy(), rtol=1e-3, atol=1e-4)
+    l = H.Layer(cfg("groupnorm", num_groups=2, num_channels=6, epsilon=1e-5, affine=True))
+    x = rs.randn(2, 4, 4, 6).astype("float32")
+    xt = t(x).permute(0, 3, 1, 2).requires_grad_(True)
+    yt = F.group_norm(xt, 2)
+    np.testing.assert_allclose(l.forward(x), yt.permute(0, 2, 3, 1).detach().numpy(), rtol=1e-4, atol=1e-5)
+    dy = rs.randn(*x.shape).astype("float32")
+    yt.backward(t(dy).permute(0, 3, 1, 2))
+    np.testing.assert_allclose(l.backward(dy), xt.grad.permute(0, 2, 3, 1).numpy(), rtol=1e-3, atol=1e-4)
+
+
+@pytest.mark.parametrize("act", ["relu", "leaky_relu", "sigmoid", "tanh", "elu", "gelu", "softmax"])
+def test_activations_match_torch(act):
+    H = _host()
+    fn = {"relu": torch.relu, "leaky_relu": lambda v: F.leaky_relu(v, 0.01), "sigmoid": torch.sigmoid, "tanh": torch.tanh, "elu": F.elu,
+          "gelu": lambda v: F.gelu(v, approximate="tanh"), "softmax": lambda v: torch.softmax(v, -1)}[act]
+    l = H.Layer(cfg("activation", activation=act))
+    x = np.random.RandomState(3).randn(4, 9).astype("float32")
+    xt = t(x).requires_grad_(True)
+    yt = fn(xt)
+    np.testing.assert_allclose(l.forward(x), yt.detach().numpy(), rtol=1e-5, atol=1e-6)
+    dy = np.random.RandomState(4).randn(4, 9).astype("float32")
+    yt.backward(t(dy))
+    np.testing.assert_allclose(l.backward(dy), xt.grad.numpy(), rtol=1e-4, atol=1e-5)
+
+
+def test_attention_block_matches_torch_sdpa():
+    H = _host()
+    E, Hh, B, L = 16, 2, 2, 6
+    for causal in (True, False):
+        l = H.Layer(cfg("attention_block", embed_dim=E, num_heads=Hh, is_causal=causal))
+        p = {k: t(v) for k, v in l.params().items()}
+        x = np.random.RandomState(5).randn(B, L, E).astype("float32")
+        xt = t(x).requires_grad_(True)
+        qkv = F.linear(xt, p["l.qkv_weight"], p["l.qkv_bias"]).view(B, L, 3, Hh, E // Hh)
+        q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))
+        o = F.scaled_dot_product_attention(q, k, v, is_causal=causal).transpose(1, 2).reshape(B, L, E)
+        yt = F.linear(o, p["l.out_weight"], p["l.out_bias"])
+        np.testing.assert_allclose(l.forward(x), yt.detach().numpy(), rtol=1e-4, atol=1e-5)
+        dy = np.random.RandomState(6).randn(B, L, E).astype("float32")
+        yt.backward(t(dy))
+        np.testing.assert_allclose(l.backward(dy), xt.grad.numpy(), rtol=1e-3, atol=1e-4)
+
+
+def test_zoo_configs_are_identical_in_both_hosts_and_wrn_forward_matches_python_host():
+    """The C++ zoo builds the SAME layer configs as the Python zoo (names, types, keys), and -- with the C++ parameters
+    copied in -- the Python host computes the same WRN-16-8 logits on the CPU."""
+    H = _host()
+    from tnn_b200.core.config import TConfig
+    from tnn_b200.models import ExampleModels
+    for name in ("mnist_cnn", "cifar10_resnet9", "cifar100_wrn16_8", "tiny_imagenet_vit", "gpt2_small"):
+        cj = json.loads(H.model_config(name))
+        pj = ExampleModels.create(name).get_config().to_json()
+
+        def norm(j):                    # numeric type tags differ harmlessly (size_t vs double for eps ...): compare values
+            if isinstance(j, dict):
+                if set(j) == {"type", "value"}:
+                    return norm(j["value"])
+                return {k: norm(v) for k, v in j.items()}
+            if isinstance(j, list):
+                return [norm(v) for v in j]
+            return float(j) if isinstance(j, (int, float)) and not isinstance(j, bool) else j
+        assert norm(cj) == norm(pj), name
+    cpp = H.Layer(H.model_config("cifar100_wrn16_8"), "CPU", 3)
+    cpp.set_training(False)
+    py = ExampleModels.create("cifar100_wrn16_8").init("cpu", seed=1).set_training(False)
+    params = cpp.params()
+    for layer in py.all_layers():
+        for k in list(layer.params):
+            q = f"{layer.name}.{k}"
+            if q in params:
+                layer.params[k].copy_(torch.from_numpy(params[q]).reshape(layer.params[k].shape))
+        layer.mark_params_dirty()
+    x = np.random.RandomState(7).rand(2, 32, 32, 3).astype("float32")
+    np.testing.assert_allclose(cpp.forward(x), py.forward(torch.from_numpy(x), 0).numpy(), rtol=2e-3, atol=2e-3)
+
+
+def test_checkpoints_are_interchangeable_between_the_cpp_and_python_hosts(tmp_path):
+    H = _host()
+    from tnn_b200.nn.graph import Graph, GraphExecutor
+    tr = H.Trainer("mnist_cnn", "CPU", 5)
+    xs = np.random.RandomState(8).rand(16, 28, 28, 1).astype("float32")
+    ys = (np.arange(16) % 10).astype("int32")
+    losses = [tr.step(xs, ys)[0] for _ in range(4)]
+    assert losses[-1] < losses[0]
+    path = str(tmp_path / "cpp_model")
+    tr.save(path)
+    # Python host reads the C++ file (reference schema header + tensor records; the C++ trailer is ignored by the reader)
+    g = Graph.load_state(path, "cpu")
+    g.set_training(False)
+    ref = tr.predict(xs)
+    got = GraphExecutor(g).forward({"input": torch.from_numpy(xs)})["output"].numpy()
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-4)
+    # and the C++ host reads a Python-written file
+    p2 = str(tmp_path / "py_model")
+    g.save_state(p2)
+    tr2 = H.Trainer("mnist_cnn", "CPU", 1, checkpoint=p2)
+    np.testing.assert_allclose(tr2.predict(xs), ref, rtol=1e-4, atol=1e-4)
+    np.testing.assert_array_equal(tr2.param_slab()[:tr.num_parameters()] != 0, tr.param_slab()[:tr.num_parameters()] != 0)

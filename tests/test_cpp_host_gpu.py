@@ -1,0 +1,85 @@
+"""The C++ host on a B200: the compiled GPU unit tests (layer parity with the C++ CPU oracle, CUDA-graph step vs eager
+step), numpy-level parity of GPU layers with PyTorch fp32 oracles, and the in-process flagship benchmark."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from test_cpp_host_cpu import _host, cfg, t  # noqa: E402
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+
+
+def test_tnn_tests_binary_gpu_cases():
+    _need_gpu()
+    _host()
+    out = subprocess.run([os.path.join(ROOT, "cpp", "bin", "tnn_tests"), "gpu"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert " 0 failed" in out.stdout and "0 skipped" in out.stdout
+
+
+def test_gpu_conv_and_batchnorm_layers_match_torch_fp32():
+    _need_gpu()
+    H = _host()
+    rs = np.random.RandomState(0)
+    for (C, K, stride, hw) in ((16, 32, 1, 16), (32, 64, 2, 16), (64, 64, 1, 8)):
+        l = H.Layer(cfg("conv2d", in_channels=C, out_channels=K, kernel_h=3, kernel_w=3, stride_h=stride, stride_w=stride, pad_h=1, pad_w=1, use_bias=True), "GPU:0")
+        p = l.params()
+        x = rs.randn(8, hw, hw, C).astype("float32")
+        xb = torch.from_numpy(x).bfloat16().float()                     # the GPU path computes on bf16 activations
+        w = t(p["l.weight"]).bfloat16().float().permute(0, 3, 1, 2).requires_grad_(True)
+        b = t(p["l.bias"]).requires_grad_(True)
+        xt = xb.permute(0, 3, 1, 2).requires_grad_(True)
+        yt = F.conv2d(xt, w, b, stride, 1)
+        y = l.forward(xb.numpy())
+        ref = yt.permute(0, 2, 3, 1).detach().numpy()
+        assert np.abs(y - ref).max() <= 2e-2 * max(1.0, np.abs(ref).max())
+        dy = torch.from_numpy(rs.randn(*y.shape).astype("float32")).bfloat16().float()
+        yt.backward(dy.permute(0, 3, 1, 2))
+        dx = l.backward(dy.numpy())
+        g = l.grads()
+        rdx = xt.grad.permute(0, 2, 3, 1).numpy()
+        assert np.abs(dx - rdx).max() <= 2e-2 * max(1.0, np.abs(rdx).max())
+        rw = w.grad.permute(0, 2, 3, 1).numpy()
+        assert np.abs(g["l.weight"] - rw).max() <= 2e-2 * max(1.0, np.abs(rw).max())
+        assert np.abs(g["l.bias"] - b.grad.numpy()).max() <= 2e-2 * max(1.0, np.abs(b.grad.numpy()).max())
+    l = H.Layer(cfg("batchnorm", num_features=64, epsilon=1e-5, momentum=0.1, affine=True, use_relu=True), "GPU:0")
+    x = torch.from_numpy(rs.randn(8, 8, 8, 64).astype("float32")).bfloat16().float()
+    bn = torch.nn.BatchNorm2d(64, eps=1e-5, momentum=0.1)
+    xt = x.permute(0, 3, 1, 2).requires_grad_(True)
+    yt = torch.relu(bn(xt))
+    y = l.forward(x.numpy())
+    assert np.abs(y - yt.permute(0, 2, 3, 1).detach().numpy()).max() < 4e-2
+    dy = torch.from_numpy(rs.randn(*y.shape).astype("float32")).bfloat16().float()
+    yt.backward(dy.permute(0, 3, 1, 2))
+    dx = l.backward(dy.numpy())
+    # relative L2: a ReLU mask flips for pre-activations within bf16 rounding of zero
+    r = xt.grad.permute(0, 2, 3, 1).numpy()
+    assert np.linalg.norm(dx - r) / np.linalg.norm(r) < 3e-2
+    assert np.abs(l.params()["l.running_var"] - bn.running_var.numpy()).max() < 2e-2
+
+
+def test_cpp_trainer_learns_and_bench_train_reports_a_graph_captured_step():
+    _need_gpu()
+    H = _host()
+    tr = H.Trainer("cifar10_resnet9", "GPU:0", 3)
+    rs = np.random.RandomState(1)
+    xs = rs.rand(64, 32, 32, 3).astype("float32")
+    ys = (np.arange(64) % 10).astype("int32")
+    losses = [tr.step(xs, ys)[0] for _ in range(12)]
+    assert tr.captured() and losses[-1] < 0.7 * losses[0], losses
+    out = json.loads(H.bench_train("cifar100_wrn16_8", 64, 4, 3, 0, True))
+    assert out["cuda_graph"] and out["gpu_launches"] > 100 and out["value"] > 0 and out["e2e"]["value"] > 0
+    assert out["e2e"]["h2d_bytes_per_step"] == 64 * 32 * 32 * 3 * 4 + 64 * 4

@@ -176,7 +176,23 @@ def build_host(force: bool = False, verbose: bool = True) -> dict:
         if verbose:
             print(f"[tnn_b200.build] linked {lib}", flush=True)
         rebuilt = True
-    exes = {}
+    # Python binding of the C++ host (pybind11 only -- no torch): tnn_b200/_host.so
+    import pybind11
+    host_so = ROOT / "_host.so"
+    bsrc = CPP / "python" / "host_bindings.cpp"
+    bobj = obj_dir / "host_bindings.o"
+    bcmd = gxx + [f"-I{pybind11.get_include()}", f"-I{sysconfig.get_paths()['include']}", "-fvisibility=hidden"]
+    bstamp = hashlib.sha256(bsrc.read_bytes() + hdr.hexdigest().encode() + _flag_sig(bcmd).encode()).hexdigest()
+    _, bdid, _ = _compile_one(bsrc, bcmd, bobj, bstamp)
+    if bdid or rebuilt or not host_so.exists():
+        link = ["g++", "-shared", "-o", str(host_so), str(bobj), f"-L{lib_dir}", "-ltnn_b200", f"-L{cuda}/lib64", "-lcudart",
+                "-Wl,-rpath,$ORIGIN/../cpp/lib", f"-Wl,-rpath,{cuda}/lib64", "-pthread"]
+        r = subprocess.run(link, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"_host.so link failed:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            print(f"[tnn_b200.build] linked {host_so}", flush=True)
+    exes = {"_host": host_so}
     for s in sorted((CPP / "examples").glob("*.cpp")) + sorted((CPP / "tests").glob("*.cpp")):
         exe = bin_dir / s.stem
         if rebuilt or not exe.exists():

@@ -229,14 +229,15 @@ class ResidualBlock(Block):
 
     def get_config(self):
         c = TConfig(self.name, self.TYPE_NAME, activation=self.activation, main_path=self.main.get_config())
-        if self.shortcut is not None:
-            c.set("shortcut_path", self.shortcut.get_config())
+        # the reference writes an EMPTY json object for "no shortcut" (residual_block.cpp:156-161)
+        c.set("shortcut_path", self.shortcut.get_config() if self.shortcut is not None else {})
         return c
 
     @classmethod
     def create_from_config(cls, c):
         main = LayerFactory.create(c["main_path"])
-        sc = LayerFactory.create(c["shortcut_path"]) if c.has("shortcut_path") else None
+        sp = c.get("shortcut_path")
+        sc = LayerFactory.create(sp) if isinstance(sp, TConfig) else None
         return cls(main, sc, c.get("activation", "relu"), c.name)
 
 
