@@ -1,0 +1,117 @@
+// Profiler: host wall-clock spans {type, start, end, name, source}, mergeable across ranks with start-time re-basing
+// and serialisable as a message payload (reference: include/profiling/event.hpp:11-62, profiler.hpp:13-157).
+// Byte-compatible with the Python host's ProfilerCore (tnn_b200/csrc/runtime/runtime.cpp).
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <cstdint>
+#include <fstream>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "runtime/archiver.hpp"
+
+namespace tnn {
+
+enum class EventType : int { COMPUTE = 0, COMMUNICATION = 1, OTHER = 2 };
+struct Event_t {
+  EventType type;
+  int64_t start_ns, end_ns;
+  std::string name, source;
+};
+
+class Profiler {
+ public:
+  Profiler() = default;
+  Profiler(const Profiler& o) : start_ns_(o.start_ns_), events_(o.events_) {}
+  Profiler& operator=(const Profiler& o) {
+    if (this != &o) {
+      start_ns_ = o.start_ns_;
+      events_ = o.events_;
+    }
+    return *this;
+  }
+  static int64_t now_ns() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::system_clock::now().time_since_epoch()).count(); }
+  void init_start_time() { start_ns_ = now_ns(); }
+  int64_t start_ns() const { return start_ns_; }
+  void add_event(EventType t, int64_t s, int64_t e, const std::string& name, const std::string& source) {
+    std::lock_guard<std::mutex> g(mu_);
+    events_.push_back(Event_t{t, s, e, name, source});
+  }
+  void merge(const Profiler& o) {                 // re-base the other profiler's events by the start-time difference
+    std::lock_guard<std::mutex> g(mu_);
+    const int64_t delta = start_ns_ - o.start_ns_;
+    for (const auto& ev : o.events_) events_.push_back(Event_t{ev.type, ev.start_ns + delta, ev.end_ns + delta, ev.name, ev.source});
+  }
+  void sort() {
+    std::lock_guard<std::mutex> g(mu_);
+    std::sort(events_.begin(), events_.end(), [](const Event_t& a, const Event_t& b) { return a.start_ns < b.start_ns; });
+  }
+  void clear() {
+    std::lock_guard<std::mutex> g(mu_);
+    events_.clear();
+  }
+  std::vector<Event_t> events() const {
+    std::lock_guard<std::mutex> g(mu_);
+    return events_;
+  }
+  std::string serialize() const {
+    std::lock_guard<std::mutex> g(mu_);
+    Writer w;
+    w.prim<int64_t>(start_ns_);
+    w.prim<uint64_t>(events_.size());
+    for (const auto& e : events_) {
+      w.prim<uint8_t>((uint8_t)e.type);
+      w.prim<int64_t>(e.start_ns);
+      w.prim<int64_t>(e.end_ns);
+      w.str(e.name);
+      w.str(e.source);
+    }
+    return std::string(reinterpret_cast<const char*>(w.buffer().data()), w.size());
+  }
+  static Profiler deserialize(const std::string& b) {
+    Profiler p;
+    Reader r(reinterpret_cast<const uint8_t*>(b.data()), b.size());
+    p.start_ns_ = r.prim<int64_t>();
+    const uint64_t n = r.prim<uint64_t>();
+    for (uint64_t i = 0; i < n; ++i) {
+      Event_t e;
+      e.type = (EventType)r.prim<uint8_t>();
+      e.start_ns = r.prim<int64_t>();
+      e.end_ns = r.prim<int64_t>();
+      e.name = r.str();
+      e.source = r.str();
+      p.events_.push_back(std::move(e));
+    }
+    return p;
+  }
+  // one line per event, the format visualizers/visualize_profiler.py parses
+  void log(const std::string& path) const {
+    std::ofstream f(path);
+    static const char* names[] = {"COMPUTE", "COMMUNICATION", "OTHER"};
+    for (const auto& e : events()) {
+      char b[512];
+      snprintf(b, sizeof b, "[%s] %s %s start=%.3fms end=%.3fms dur=%.3fms\n", e.source.c_str(), names[(int)e.type], e.name.c_str(),
+               (e.start_ns - start_ns_) / 1e6, (e.end_ns - start_ns_) / 1e6, (e.end_ns - e.start_ns) / 1e6);
+      f << b;
+    }
+  }
+
+ private:
+  int64_t start_ns_ = 0;
+  std::vector<Event_t> events_;
+  mutable std::mutex mu_;
+};
+
+class GlobalProfiler {
+ public:
+  static Profiler& get_profiler() {
+    static Profiler* p = [] { auto* q = new Profiler(); q->init_start_time(); return q; }();
+    return *p;
+  }
+  static void init_start_time() { get_profiler().init_start_time(); }
+  static void add_event(EventType t, int64_t s, int64_t e, const std::string& name, const std::string& source) { get_profiler().add_event(t, s, e, name, source); }
+};
+
+}  // namespace tnn

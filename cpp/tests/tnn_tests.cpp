@@ -10,6 +10,7 @@
 #include <sstream>
 
 #include "runtime/archiver.hpp"
+#include "tnn/distributed.hpp"
 #include "tnn/example_models.hpp"
 #include "tnn/stepstate.hpp"
 #include "tnn/train.hpp"
@@ -474,6 +475,178 @@ TEST(training_converges_on_cpu) {
   TrainHistory h = train_model(g, train, &val, *opt, *crit, nullptr, cfg, [](const std::string&) {});
   CHECK(h.train_loss.size() == 3 && h.train_loss.back() < h.train_loss.front() * 0.8);
   CHECK(h.val_acc.back() > 0.3);
+}
+
+// ------------------------------------------------------------------------------------- distributed runtime
+TEST(message_wire_format_round_trip) {
+  Tensor t = make_tensor<float>({2, 3});
+  t->fill_random_normal(0, 1, 4);
+  Message m(CommandType::FORWARD_JOB, Job{t, 7});
+  const auto buf = m.serialize();
+  // u16 command, u32 variant index 1, u64 mb_id, u32 dtype FP32 = 5, u64 ndims, dims, raw
+  uint16_t cmd; uint32_t var; uint64_t mb; uint32_t dt;
+  std::memcpy(&cmd, buf.data(), 2); std::memcpy(&var, buf.data() + 2, 4); std::memcpy(&mb, buf.data() + 6, 8); std::memcpy(&dt, buf.data() + 14, 4);
+  CHECK(cmd == 1 && var == 1 && mb == 7 && dt == 5 && buf.size() == 2 + 4 + 8 + 4 + 8 + 16 + 24);
+  Message r = Message::deserialize(buf.data(), buf.size());
+  CHECK(r.command == CommandType::FORWARD_JOB && r.job.mb_id == 7 && max_abs_diff(*r.job.data, *t) == 0);
+  StageConfig sc;
+  sc.stage_id = 2;
+  sc.next_stage_endpoint = Endpoint::tcp("10.0.0.2", 5555);
+  sc.model_config = ExampleModels::create("mnist_cnn")->get_config().to_json();
+  const auto b2 = Message(CommandType::CONFIG_TRANSFER, sc).serialize();
+  Message r2 = Message::deserialize(b2.data(), b2.size());
+  CHECK(r2.kind == Message::STAGE && r2.stage.stage_id == 2 && r2.stage.next_stage_endpoint.port == 5555 && r2.stage.model_config == sc.model_config);
+  Profiler p;
+  p.init_start_time();
+  p.add_event(EventType::COMPUTE, 10, 20, "fwd", "w0");
+  const auto b3 = Message(CommandType::PROFILING_REPORTED, p).serialize();
+  CHECK(Message::deserialize(b3.data(), b3.size()).profiler->events().size() == 1);
+  const auto b4 = Message(CommandType::ERROR_REPORT, "boom").serialize();
+  CHECK(Message::deserialize(b4.data(), b4.size()).str == "boom");
+  // priority dequeue: FORWARD_JOB before BACKWARD_JOB before UPDATE_PARAMETERS regardless of arrival order
+  InProcessCommunicator c("c");
+  c.enqueue(Message(CommandType::UPDATE_PARAMETERS));
+  c.enqueue(Message(CommandType::BACKWARD_JOB, Job{t, 1}));
+  c.enqueue(Message(CommandType::FORWARD_JOB, Job{t, 2}));
+  Message o;
+  CHECK(c.dequeue(&o, 0) && o.command == CommandType::FORWARD_JOB);
+  CHECK(c.dequeue(&o, 0) && o.command == CommandType::BACKWARD_JOB);
+  CHECK(c.dequeue(&o, 0) && o.command == CommandType::UPDATE_PARAMETERS && !c.dequeue(&o, 0));
+}
+TEST(partitioners_cover_the_model_contiguously) {
+  auto m = ExampleModels::create("cifar100_wrn16_8");
+  const Vec<Layer*> layers = m->layers();
+  auto check = [&](Vec<SeqPartition> p, size_t n) {
+    CHECK(p.size() == n);
+    size_t cur = 0;
+    for (auto& s : p) {
+      CHECK(s.start == cur && s.length >= 1);
+      cur += s.length;
+    }
+    CHECK(cur == layers.size());
+  };
+  check(NaivePipelinePartitioner({1, 2, 1}).partition_model(layers, {64, 32, 32, 3}), 3);
+  check(WeightedPartitioner(4).partition_model(layers, {64, 32, 32, 3}), 4);
+  const auto ftd = FTDPartitioner(4).partition_model(layers, {64, 32, 32, 3});
+  check(ftd, 4);
+  // the FLOPs-aware split balances the six wide blocks instead of leaving most layers to the last stage
+  Shape s{64, 32, 32, 3};
+  std::vector<double> fl;
+  for (Layer* l : layers) { fl.push_back((double)l->forward_flops(s)); s = l->output_shape(s); }
+  double total = 0, worst = 0;
+  for (double f : fl) total += f;
+  for (auto& p : ftd) { double c = 0; for (size_t i = p.start; i < p.start + p.length; ++i) c += fl[i]; worst = std::max(worst, c); }
+  CHECK(worst < 0.45 * total);
+  auto parts = Partitioner::split(layers, ftd, "wrn");
+  CHECK(parts.size() == 4 && parts[0]->size() == ftd[0].length);
+}
+static std::vector<double> single_device_losses(const std::string& model, const Vec<std::pair<Tensor, Tensor>>& batches, size_t M, double lr) {
+  Graph g = load_or_create_model(model, "", getHost(), 123456);
+  auto opt = OptimizerFactory::create_sgd(lr, 0.9);
+  opt->attach(g.context());
+  auto crit = LossFactory::create_logsoftmax_crossentropy();
+  GraphExecutor ex(g);
+  std::vector<double> out;
+  for (auto& b : batches) {
+    Vec<Tensor> xs, ys;
+    split_microbatches(b.first, b.second, M, &xs, &ys);
+    double loss = 0;
+    for (size_t i = 0; i < xs.size(); ++i) {
+      Tensor o = ex.forward(xs[i], i);
+      Tensor stats, grad;
+      crit->loss_and_grad(o, ys[i], stats, &grad, 1.f / (float)xs.size());
+      loss += stats->data_as<float>()[0];
+      ex.backward(grad, i);
+    }
+    opt->update();
+    out.push_back(loss);
+  }
+  return out;
+}
+static void pipeline_case(bool tcp) {
+  const size_t M = 2;
+  SyntheticDataLoader data({28, 28, 1}, 10, 64, 3);
+  Vec<std::pair<Tensor, Tensor>> batches;
+  for (int i = 0; i < 3; ++i) {
+    Tensor x, y;
+    data.get_batch(16, x, y);
+    batches.emplace_back(x, y);
+  }
+  Vec<std::unique_ptr<Worker>> workers;
+  Vec<Endpoint> eps;
+  for (int i = 0; i < 2; ++i) {
+    std::unique_ptr<Communicator> c;
+    if (tcp) c = std::make_unique<TCPCommunicator>("127.0.0.1", 0, 2, nullptr, "w" + std::to_string(i));
+    else c = std::make_unique<InProcessCommunicator>("w" + std::to_string(i));
+    auto w = std::make_unique<Worker>(std::move(c), getHost(), "w" + std::to_string(i));
+    w->start(true);
+    eps.push_back(w->comm().endpoint());
+    workers.push_back(std::move(w));
+  }
+  CoordinatorConfig cc;
+  cc.model = ExampleModels::create("mnist_cnn");
+  cc.input_shape = {8, 28, 28, 1};
+  cc.optimizer_config = OptimizerFactory::create_sgd(0.05, 0.9)->get_config();
+  cc.partitioner = std::make_unique<NaivePipelinePartitioner>(Vec<size_t>{1, 2});
+  cc.worker_endpoints = eps;
+  cc.timeout_job_ms = 30000;
+  std::unique_ptr<Communicator> comm;
+  if (tcp) comm = std::make_unique<TCPCommunicator>("127.0.0.1", 0, 2, nullptr, "coord");
+  else comm = std::make_unique<InProcessCommunicator>("coord");
+  Coordinator co(std::move(cc), std::move(comm));
+  co.start();
+  auto crit = LossFactory::create_logsoftmax_crossentropy();
+  std::vector<double> losses;
+  for (auto& b : batches) {
+    Vec<Tensor> xs, ys;
+    split_microbatches(b.first, b.second, M, &xs, &ys);
+    losses.push_back(co.async_train_batch(xs, ys, *crit).first);
+    co.update_parameters();
+  }
+  // the stages are re-created from config with the reference's fixed seed (123456): compare with a single-device run whose
+  // layers were initialised the same way -- per-layer streams depend on (seed, layer name), not on the stage they live in
+  const auto ref = single_device_losses("mnist_cnn", batches, M, 0.05);
+  for (size_t i = 0; i < ref.size(); ++i) CHECK_NEAR(losses[i], ref[i], 1e-4);
+  CHECK(co.health_check().size() == 2);
+  co.barrier();
+  Profiler prof = co.fetch_profiling();
+  CHECK(!prof.events().empty());
+  const auto files = co.checkpoint("/tmp/tnn_tests_pp_ckpt");
+  CHECK(files.size() == 2);
+  co.stop();
+  for (auto& w : workers) w->stop();
+}
+TEST(in_process_pipeline_equals_single_device) { pipeline_case(false); }
+TEST(tcp_pipeline_equals_single_device) { pipeline_case(true); }
+TEST(lost_microbatch_and_worker_errors_are_detected) {
+  auto w = std::make_unique<Worker>(std::make_unique<InProcessCommunicator>("w"), getHost(), "w");
+  w->start(true);
+  int drops = 0;
+  w->fault_inject = [&](Message& m) {
+    if (m.command == CommandType::BACKWARD_JOB && drops++ == 0) throw std::runtime_error("injected fault");
+  };
+  CoordinatorConfig cc;
+  cc.model = ExampleModels::create("mnist_cnn");
+  cc.input_shape = {8, 28, 28, 1};
+  cc.optimizer_config = OptimizerFactory::create_sgd(0.05)->get_config();
+  cc.partitioner = std::make_unique<NaivePipelinePartitioner>(Vec<size_t>{1});
+  cc.worker_endpoints = {w->comm().endpoint()};
+  cc.timeout_job_ms = 3000;
+  Coordinator co(std::move(cc), std::make_unique<InProcessCommunicator>("coord"));
+  co.start();
+  SyntheticDataLoader data({28, 28, 1}, 10, 16, 3);
+  Tensor x, y;
+  data.get_batch(8, x, y);
+  auto crit = LossFactory::create_logsoftmax_crossentropy();
+  bool threw = false;
+  try {
+    co.async_train_batch({x}, {y}, *crit);
+  } catch (const DistributedError& e) {
+    threw = std::string(e.what()).find("injected fault") != std::string::npos;
+  }
+  CHECK(threw);
+  co.stop();
+  w->stop();
 }
 
 // ------------------------------------------------------------------------------------- GPU: layer parity with the CPU oracle
