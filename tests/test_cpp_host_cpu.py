@@ -234,3 +234,49 @@ def test_checkpoints_are_interchangeable_between_the_cpp_and_python_hosts(tmp_pa
     tr2 = H.Trainer("mnist_cnn", "CPU", 1, checkpoint=p2)
     np.testing.assert_allclose(tr2.predict(xs), ref, rtol=1e-4, atol=1e-4)
     np.testing.assert_array_equal(tr2.param_slab()[:tr.num_parameters()] != 0, tr.param_slab()[:tr.num_parameters()] != 0)
+
+
+def test_python_coordinator_drives_a_cpp_tcp_worker(tmp_path):
+    """Wire-format interoperability: a Python NetworkCoordinator runs a 2-stage pipeline whose second stage is the C++
+    ``tcp_worker`` executable (same Message / StageConfig / Job archiver encoding, same TCP bus framing)."""
+    _host()
+    import socket
+    import time
+
+    from tnn_b200.distributed import (CoordinatorConfig, Endpoint, NetworkCoordinator, ParallelMode, TCPWorker, split_microbatches)
+    from tnn_b200.models import ExampleModels
+    from tnn_b200.nn import LossFactory, OptimizerFactory
+    from tnn_b200.parallel import NaivePipelinePartitioner
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    proc = subprocess.Popen([os.path.join(ROOT, "cpp", "bin", "tcp_worker"), str(port)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    local = TCPWorker("127.0.0.1", 0, use_gpu=False, name="py-local")
+    try:
+        time.sleep(0.5)
+        cfgc = CoordinatorConfig(ParallelMode.PIPELINE, ExampleModels.create("mnist_cnn"), OptimizerFactory.create_sgd(0.05, 0.9), None,
+                                 NaivePipelinePartitioner([1, 1]), local_worker=local, local_worker_position=0,
+                                 worker_endpoints=[Endpoint.tcp("127.0.0.1", port)], seed=5)
+        co = NetworkCoordinator(cfgc, "127.0.0.1", 0)
+        co.start()
+        crit = LossFactory.create_logsoftmax_crossentropy()
+        g = torch.Generator().manual_seed(0)
+        x = torch.rand(16, 28, 28, 1, generator=g)
+        y = (torch.arange(16) % 10).to(torch.int32)
+        losses = []
+        for _ in range(6):
+            xs, ys = split_microbatches(x, y, 2)
+            l, _ = co.async_train_batch(xs, ys, crit)
+            co.update_parameters()
+            losses.append(l)
+        assert losses[-1] < losses[0], losses
+        status = co.health_check()
+        assert any(st["name"].startswith("tcp-worker-") for st in status)
+        co.stop()
+    finally:
+        local.stop()
+        try:
+            proc.wait(10)
+        except Exception:  # noqa: BLE001
+            proc.kill()

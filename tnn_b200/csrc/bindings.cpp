@@ -337,6 +337,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                                 const Tensor& state, bool zero_grad) {
     tnn::sgd_step_flat_dev(fp(p), fp(g), fp(mom), vp(pb), p.numel(), fp(state), zero_grad, cur_stream());
   });
+  m.def("dp_set_watchdog_ms", [](uint64_t ms) { tnn::dp_set_watchdog_ms(ms); });
   m.def("dp_fused_step", [](int world, int rank, int64_t n, int64_t chunk, std::vector<int64_t> g_peers,
                             std::vector<int64_t> p_peers, std::vector<int64_t> pb_peers,
                             std::vector<int64_t> flag_peers, int64_t g_mc, int64_t p_mc, int64_t pb_mc,

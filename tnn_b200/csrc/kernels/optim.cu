@@ -240,27 +240,49 @@ struct DpArgs {
   int use_adam;
 };
 
+// Watchdog for the cross-GPU spins: a rank that never arrives (crashed peer, diverged schedule, one rank
+// skipped a bucket) would otherwise hang every GPU of the node silently.  After kDpWatchdogNs of spinning the waiting
+// thread prints who waits for whom and traps, which surfaces on the host as a launch failure of this rank.
+__device__ unsigned long long g_dp_watchdog_ns = 20ull * 1000ull * 1000ull * 1000ull;   // 20 s; dp_set_watchdog_ms() overrides
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __noinline__ void dp_watchdog_fire(const DpArgs& a, uint32_t epoch, int peer, uint32_t seen, const char* what) {
+  printf("[tnn_b200] k_dp_step watchdog: rank %d of %d waited > %llu ms on %s (peer %d shows %u, want >= %u, bucket [%lld, %lld))\n", a.rank, a.world,
+         g_dp_watchdog_ns / 1000000ull, what, peer, seen, epoch, a.lo0, a.hi0);
+  __trap();
+}
 __device__ __forceinline__ void dp_barrier(const DpArgs& a, uint32_t epoch, uint32_t grid_target) {
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) atomicAdd(a.grid_ctr, 1u);
   if (blockIdx.x == 0) {
-    if (threadIdx.x == 0)
-      while (ld_acquire_gpu(a.grid_ctr) < grid_target) {
-      }
+    if (threadIdx.x == 0) {
+      const unsigned long long t0 = globaltimer_ns();
+      uint32_t seen;
+      while ((seen = ld_acquire_gpu(a.grid_ctr)) < grid_target)
+        if (globaltimer_ns() - t0 > g_dp_watchdog_ns) dp_watchdog_fire(a, grid_target, -1, seen, "the local grid barrier");
+    }
     __syncthreads();
     if (threadIdx.x < a.world) {
       __threadfence_system();
       st_release_sys(a.flag_peers[threadIdx.x] + a.rank, epoch);
-      while (ld_acquire_sys(a.flag_peers[a.rank] + threadIdx.x) < epoch) {
-      }
+      const unsigned long long t0 = globaltimer_ns();
+      uint32_t seen;
+      while ((seen = ld_acquire_sys(a.flag_peers[a.rank] + threadIdx.x)) < epoch)
+        if (globaltimer_ns() - t0 > g_dp_watchdog_ns) dp_watchdog_fire(a, epoch, (int)threadIdx.x, seen, "a peer's barrier flag");
     }
     __syncthreads();
     if (threadIdx.x == 0) st_release_gpu(a.go_flag, epoch);
   }
-  if (threadIdx.x == 0)
-    while (ld_acquire_gpu(a.go_flag) < epoch) {
-    }
+  if (threadIdx.x == 0) {
+    const unsigned long long t0 = globaltimer_ns();
+    uint32_t seen;
+    while ((seen = ld_acquire_gpu(a.go_flag)) < epoch)
+      if (globaltimer_ns() - t0 > g_dp_watchdog_ns + 2000000000ull) dp_watchdog_fire(a, epoch, -2, seen, "the release of block 0");
+  }
   __syncthreads();
 }
 
@@ -368,6 +390,11 @@ void dp_fused_step(int world, int rank, long long n, long long chunk, float* con
   a.use_adam = use_adam;
   k_dp_step<<<ctas, 512, 0, s>>>(a);
   TNN_CHECK_LAUNCH();
+}
+
+void dp_set_watchdog_ms(unsigned long long ms) {
+  const unsigned long long ns = ms * 1000000ull;
+  cudaMemcpyToSymbol(g_dp_watchdog_ns, &ns, sizeof(ns));
 }
 
 // Stand-alone cross-rank barrier (used by tests and by the pipeline runtime).

@@ -164,6 +164,8 @@ void dp_fused_step(int world, int rank, long long n, long long chunk, float* con
                    const float* g_mc, float* p_mc, void* pb_mc, float* m, float* v,
                    uint32_t* sync, const float* state, int use_adam, int ctas, long long lo0, long long hi0, long long st_off,
                    cudaStream_t s);
+// budget of the cross-GPU flag spins inside dp_fused_step before the kernel reports who is missing and traps (default 20 s)
+void dp_set_watchdog_ms(unsigned long long ms);
 // Graph-replayable variants: hyper-parameters come from a 16-float device "step state" that the
 // host refreshes with one small H2D copy per step (outside the captured region).
 void adam_step_flat_dev(float* p, float* g, float* m, float* v, void* p_bf16, long long n,

@@ -203,6 +203,63 @@ class FusedDataParallel:
             isinstance(opt, Adam), self.ctas, lo0, hi0, st_off)
         self.launches += 1
 
+    # ---------------------------------------------------------------- per-bucket timing / roofline (eager passes only)
+    def _timed_launch(self, b):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self._launch(b["lo"], b["hi"], b["chunk"], b["st_off"])
+        e1.record()
+        self._timing.append((b, e0, e1))
+
+    def bucket_report(self, eager_step, x, y, reps: int = 6) -> dict:
+        """Runs ``reps`` EAGER steps (``eager_step(x, y)`` = TrainStep._eager) with CUDA events around every bucket
+        kernel on the side stream and reports, max over ranks: microseconds per bucket (this includes the wait for
+        the slowest rank at the bucket's barrier), the bytes this rank moves over NVLink / HBM for it and the
+        achieved fraction of the roofline (the slower of NVLink bytes at 770 GB/s measured peer-copy bandwidth and
+        HBM bytes at the measured copy bandwidth)."""
+        import json
+        import os as _os
+        peaks = {"hbm_gbs": 6462.4}
+        try:
+            peaks.update(json.load(open(_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))), "MEASURED_PEAKS.json"))))
+        except Exception:  # noqa: BLE001
+            pass
+        self._timing = []
+        for _ in range(2):
+            eager_step(x, y)
+        torch.cuda.synchronize()
+        self._timing = []
+        for _ in range(reps):
+            eager_step(x, y)
+        torch.cuda.synchronize()
+        per = {}
+        for b, e0, e1 in self._timing:
+            per.setdefault((b["lo"], b["hi"]), []).append(e0.elapsed_time(e1) * 1e3)
+        self._timing = None
+        W = self.world
+        rows = []
+        for b in (self.buckets or [dict(lo=0, hi=self.n, chunk=self.chunk, st_off=0)]):
+            us = sorted(per.get((b["lo"], b["hi"]), [0.0]))
+            med = us[len(us) // 2]
+            t = torch.tensor([med], dtype=torch.float64, device=self.graph.device())
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            med = float(t[0])
+            mine = max(0, min(b["hi"], b["lo"] + (self.rank + 1) * b["chunk"]) - (b["lo"] + self.rank * b["chunk"]))
+            nv_in = mine * 4 if self.mc else (W - 1) * mine * 4            # gradients pulled through the switch / from W-1 peers
+            nv_out = mine * 6 if self.mc else (W - 1) * mine * 6           # fp32 + bf16 parameters pushed to every replica
+            hbm = mine * (4 + 8 + 16 + 2 + 4) + (b["hi"] - b["lo"]) * 4     # own grad read, p rw, m/v rw, bf16 w, (local copy) + grad zeroing
+            t_nv = max(nv_in, nv_out) / 770e9
+            t_hbm = hbm / (peaks["hbm_gbs"] * 1e9)
+            roof = max(t_nv, t_hbm) * 1e6
+            rows.append({"elems": b["hi"] - b["lo"], "us": med, "bytes_nvlink_in": nv_in, "bytes_nvlink_out": nv_out, "bytes_hbm": hbm,
+                         "roofline_us": roof, "frac_of_roofline": (roof / med) if med > 0 else None,
+                         "frac_of_nvlink_roofline": (t_nv * 1e6 / med) if med > 0 else None,
+                         "frac_of_hbm_roofline": (t_hbm * 1e6 / med) if med > 0 else None})
+        return {"buckets": len(rows), "path": "nvls-multimem" if self.mc else "p2p", "ctas": self.ctas, "per_bucket": rows,
+                "us_total": sum(r["us"] for r in rows), "bytes_nvlink": sum(r["bytes_nvlink_in"] + r["bytes_nvlink_out"] for r in rows),
+                "note": "eager pass, CUDA events on the side stream, median of %d, max over ranks; a bucket's time includes the wait for "
+                        "the slowest rank at its barrier" % reps}
+
     def backward_hook(self, layer_index: int):
         """Called by the top-level Sequential right after layer `layer_index` finished its backward:
         when that completes a bucket, its fused reduce+update is queued on the side stream."""
@@ -215,7 +272,10 @@ class FusedDataParallel:
                 if side_stream.has_pending(self.graph.device()):
                     self.side.wait_stream(side_stream.stream(self.graph.device()))   # the bucket's weight gradients
                 with torch.cuda.stream(self.side):
-                    self._launch(b["lo"], b["hi"], b["chunk"], b["st_off"])
+                    if getattr(self, "_timing", None) is not None:
+                        self._timed_launch(b)
+                    else:
+                        self._launch(b["lo"], b["hi"], b["chunk"], b["st_off"])
                 self._pending = True
 
     def step_overlapped_finish(self):
