@@ -286,7 +286,7 @@ __device__ __forceinline__ void dp_barrier(const DpArgs& a, uint32_t epoch, uint
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(512) k_dp_step(const DpArgs a) {
+__global__ void __launch_bounds__(256) k_dp_step(const DpArgs a) {
   const uint32_t G = gridDim.x;
   const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(a.epoch_ctr);
   const uint32_t grid_base = epoch * 2u * G;
@@ -298,46 +298,65 @@ __global__ void __launch_bounds__(512) k_dp_step(const DpArgs a) {
   AdamHyper h = hyper_from_state(a.state);
   h.grad_scale /= (float)a.world;
   const float sgd_momentum = a.state[7];
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long e = lo + i * 4;
-    float4 g;
-    if (a.g_mc) {
-      g = multimem_ld_reduce_v4(a.g_mc + e);
-    } else {
-      g = ld_peer_v4(a.g_peers[0] + e);
-      for (int r = 1; r < a.world; ++r) {
-        float4 t = ld_peer_v4(a.g_peers[r] + e);
-        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+  // The loop is LATENCY bound, not bandwidth bound: a multimem.ld_reduce through the switch (or a peer load) takes
+  // microseconds, and with one float4 in flight per thread a 3 M-element slice needed ~22 dependent round trips per
+  // thread (measured 120 us per bucket at 64 x 512 threads, inversely proportional to the CTA count).  Four
+  // independent vectors per thread are issued before any of them is consumed.
+  constexpr int U = 4;
+  const long long T = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < nv; i0 += T * U) {
+    float4 g[U], P[U], M[U], V[U];
+    long long idx[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      idx[u] = i0 + u * T;
+      if (idx[u] >= nv) continue;
+      const long long e = lo + idx[u] * 4;
+      if (a.g_mc) {
+        g[u] = multimem_ld_reduce_v4(a.g_mc + e);
+      } else {
+        g[u] = ld_peer_v4(a.g_peers[0] + e);
+        for (int r = 1; r < a.world; ++r) {
+          float4 t = ld_peer_v4(a.g_peers[r] + e);
+          g[u].x += t.x; g[u].y += t.y; g[u].z += t.z; g[u].w += t.w;
+        }
       }
+      P[u] = *reinterpret_cast<const float4*>(a.p_peers[a.rank] + e);
+      M[u] = reinterpret_cast<float4*>(a.m + a.st_off)[idx[u]];
+      if (a.use_adam) V[u] = reinterpret_cast<float4*>(a.v + a.st_off)[idx[u]];
     }
-    g.x *= h.grad_scale; g.y *= h.grad_scale; g.z *= h.grad_scale; g.w *= h.grad_scale;
-    float4 P = *reinterpret_cast<const float4*>(a.p_peers[a.rank] + e);
-    float4 M = reinterpret_cast<float4*>(a.m + a.st_off)[i];
-    if (a.use_adam) {
-      float4 V = reinterpret_cast<float4*>(a.v + a.st_off)[i];
-      adam_update(P.x, g.x, M.x, V.x, h);
-      adam_update(P.y, g.y, M.y, V.y, h);
-      adam_update(P.z, g.z, M.z, V.z, h);
-      adam_update(P.w, g.w, M.w, V.w, h);
-      reinterpret_cast<float4*>(a.v + a.st_off)[i] = V;
-    } else {
-      const float mu = sgd_momentum, lr = h.lr, wd = h.weight_decay;
-      g.x += wd * P.x; g.y += wd * P.y; g.z += wd * P.z; g.w += wd * P.w;
-      M.x = mu * M.x - lr * g.x; M.y = mu * M.y - lr * g.y;
-      M.z = mu * M.z - lr * g.z; M.w = mu * M.w - lr * g.w;
-      P.x += M.x; P.y += M.y; P.z += M.z; P.w += M.w;
-    }
-    reinterpret_cast<float4*>(a.m + a.st_off)[i] = M;
-    __nv_bfloat162 b0 = __floats2bfloat162_rn(P.x, P.y), b1 = __floats2bfloat162_rn(P.z, P.w);
-    const uint32_t u0 = *reinterpret_cast<uint32_t*>(&b0), u1 = *reinterpret_cast<uint32_t*>(&b1);
-    if (a.p_mc) {
-      multimem_st_v4(a.p_mc + e, P);
-      multimem_st_bf16x4(a.pb_mc + e, u0, u1);
-    } else {
-      for (int r = 0; r < a.world; ++r) {
-        *reinterpret_cast<float4*>(a.p_peers[r] + e) = P;
-        *reinterpret_cast<uint2*>(a.pb_peers[r] + e) = make_uint2(u0, u1);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (idx[u] >= nv) continue;
+      const long long e = lo + idx[u] * 4;
+      float4 gg = g[u];
+      gg.x *= h.grad_scale; gg.y *= h.grad_scale; gg.z *= h.grad_scale; gg.w *= h.grad_scale;
+      float4 Pu = P[u], Mu = M[u];
+      if (a.use_adam) {
+        float4 Vu = V[u];
+        adam_update(Pu.x, gg.x, Mu.x, Vu.x, h);
+        adam_update(Pu.y, gg.y, Mu.y, Vu.y, h);
+        adam_update(Pu.z, gg.z, Mu.z, Vu.z, h);
+        adam_update(Pu.w, gg.w, Mu.w, Vu.w, h);
+        reinterpret_cast<float4*>(a.v + a.st_off)[idx[u]] = Vu;
+      } else {
+        const float mu = sgd_momentum, lr = h.lr, wd = h.weight_decay;
+        gg.x += wd * Pu.x; gg.y += wd * Pu.y; gg.z += wd * Pu.z; gg.w += wd * Pu.w;
+        Mu.x = mu * Mu.x - lr * gg.x; Mu.y = mu * Mu.y - lr * gg.y;
+        Mu.z = mu * Mu.z - lr * gg.z; Mu.w = mu * Mu.w - lr * gg.w;
+        Pu.x += Mu.x; Pu.y += Mu.y; Pu.z += Mu.z; Pu.w += Mu.w;
+      }
+      reinterpret_cast<float4*>(a.m + a.st_off)[idx[u]] = Mu;
+      __nv_bfloat162 b0 = __floats2bfloat162_rn(Pu.x, Pu.y), b1 = __floats2bfloat162_rn(Pu.z, Pu.w);
+      const uint32_t u0 = *reinterpret_cast<uint32_t*>(&b0), u1 = *reinterpret_cast<uint32_t*>(&b1);
+      if (a.p_mc) {
+        multimem_st_v4(a.p_mc + e, Pu);
+        multimem_st_bf16x4(a.pb_mc + e, u0, u1);
+      } else {
+        for (int r = 0; r < a.world; ++r) {
+          *reinterpret_cast<float4*>(a.p_peers[r] + e) = Pu;
+          *reinterpret_cast<uint2*>(a.pb_peers[r] + e) = make_uint2(u0, u1);
+        }
       }
     }
   }
@@ -388,7 +407,7 @@ void dp_fused_step(int world, int rank, long long n, long long chunk, float* con
   a.epoch_ctr = sync + 2;
   a.state = state;
   a.use_adam = use_adam;
-  k_dp_step<<<ctas, 512, 0, s>>>(a);
+  k_dp_step<<<ctas, 256, 0, s>>>(a);
   TNN_CHECK_LAUNCH();
 }
 

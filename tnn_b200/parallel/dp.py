@@ -87,7 +87,7 @@ class FusedDataParallel:
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self.optimizer = optimizer
-        self.ctas = int(ctas or os.environ.get("TNN_DP_CTAS", 64))
+        self.ctas = int(ctas or os.environ.get("TNN_DP_CTAS", 64))     # x 256 threads, 4 independent vectors in flight per thread
         self.use_multicast = use_multicast
         self.graph: Graph | None = None
         self.epoch = 0
