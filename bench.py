@@ -167,7 +167,12 @@ def gpt2_block(args, impl: str, rank: int, world: int, dev) -> dict | None:
     import gpt2_lib
     import torch
     try:
-        r = gpt2_lib.tnn_gpt2(dev, iters=args.gpt2_iters) if impl == "tnn" else gpt2_lib.torch_gpt2(dev, iters=args.gpt2_iters)
+        if impl == "tnn_cpp":
+            r = gpt2_lib.tnn_gpt2_cpp(dev.index or 0, iters=args.gpt2_iters)
+        elif impl == "tnn":
+            r = gpt2_lib.tnn_gpt2(dev, iters=args.gpt2_iters)
+        else:
+            r = gpt2_lib.torch_gpt2(dev, iters=args.gpt2_iters)
     except Exception as e:  # noqa: BLE001
         r = {"error": f"{type(e).__name__}: {e}"[:300]}
     torch.cuda.synchronize()
@@ -235,7 +240,7 @@ def run_tnn_cpp(args):
     out["config"]["image"] = [32, 32, 3]
     out["config"]["seq_len"] = None
     out["config"]["clock_sampling"] = "NVML over the device-timed AND the end-to-end region of the C++ benchmark call"
-    gpt2 = gpt2_block(args, "tnn", 0, 1, dev)
+    gpt2 = gpt2_block(args, "tnn_cpp", 0, 1, dev)
     if gpt2 is not None:
         out["gpt2"] = gpt2
     emit(out)

@@ -80,6 +80,41 @@ def tnn_gpt2(dev, batch=32, seq=1024, decode_steps=64, iters=5, model="gpt2_smal
     return out
 
 
+def tnn_gpt2_cpp(gpu: int = 0, batch=32, seq=1024, decode_steps=64, iters=5, model="gpt2_small") -> dict:
+    """The same measurement through the C++ host's ``GPT2Engine`` (cpp/src/inference.cpp, bound as
+    ``tnn_b200._host.GPT2Engine``): model, KV caches, buffers, CUDA-graph decode and the CUDA-event timing all live in
+    libtnn_b200; Python only passes token arrays."""
+    import numpy as np
+    from tnn_b200 import _host
+    dev = f"GPU:{gpu}"
+    eng = _host.GPT2Engine(model, dev, 1, batch, seq, "bf16")
+    rs = np.random.RandomState(0)
+    prompt = rs.randint(0, 50257, (batch, seq)).astype(np.int32)
+    out = {"model": model, "batch": batch, "seq": seq, "decode_steps": decode_steps, "host": "cpp (libtnn_b200 GPT2Engine)"}
+    _, logits_bf16 = eng.prefill(prompt, True)
+    ms = eng.time_prefill_ms(batch, seq, iters, 2)
+    out["prefill_bf16_ms"] = ms
+    out["prefill_bf16_tok_s"] = batch * seq / ms * 1e3
+    msd = eng.time_decode_ms(batch, seq - decode_steps, decode_steps, True)
+    out["decode_ms_per_step"] = msd
+    out["decode_tok_s"] = batch / msd * 1e3
+    out["decode_dtype"] = "bf16 (cluster split-K skinny GEMMs, CUDA-graph replay)"
+    eng.enable_fp8()
+    l0 = _host.launch_count()
+    _, logits_fp8 = eng.prefill(prompt, True)
+    out["launches_prefill"] = int(_host.launch_count() - l0)
+    ms8 = eng.time_prefill_ms(batch, seq, iters, 2)
+    out["prefill_ms"] = ms8
+    out["prefill_tok_s"] = batch * seq / ms8 * 1e3
+    out["dtype"] = "fp8 (mxfp8 e4m3 + ue8m0/32 block scales on the qkv/proj/fc1/fc2 GEMMs; attention, residual stream, LM head bf16)"
+    d = np.abs(logits_fp8 - logits_bf16)
+    out["logits_max_abs_err_vs_bf16"] = float(d.max())
+    out["logits_rms_err_vs_bf16"] = float(np.sqrt((d ** 2).mean()))
+    out["logits_rms_bf16"] = float(np.sqrt((logits_bf16 ** 2).mean()))
+    out["argmax_agreement"] = float((logits_fp8.argmax(-1) == logits_bf16.argmax(-1)).mean())
+    return out
+
+
 def torch_gpt2(dev, batch=32, seq=1024, decode_steps=64, iters=5) -> dict:
     """Library arm: torch + cuBLAS + flash SDPA in bf16; the decode step is captured in a CUDA graph
     (static shapes: the position is a device tensor, attention runs over the full cache with a length mask)."""

@@ -25,6 +25,7 @@ class DenseLayer : public Layer {
   static std::unique_ptr<Layer> create_from_config(const TConfig& c);
   size_t input_features() const { return in_; }
   size_t output_features() const { return out_; }
+  bool use_bias() const { return use_bias_; }
 
  protected:
   void fill_config(TConfig& c) const override;
@@ -194,6 +195,9 @@ class LayerNormLayer : public Layer {
   Tensor backward_impl(const Tensor& dy, size_t mb, BwdAux& aux) override;
   bool fuses_bwd_extra() const override { return true; }
   static std::unique_ptr<Layer> create_from_config(const TConfig& c);
+  size_t normalized_shape() const { return C_; }
+  double epsilon() const { return eps_; }
+  bool affine() const { return affine_; }
 
  protected:
   void fill_config(TConfig& c) const override { c.set("normalized_shape", C_).set("epsilon", eps_).set("affine", affine_); }
@@ -232,6 +236,8 @@ class EmbeddingLayer : public Layer {       // ids: INT32 (or float ids as the r
   Tensor backward_impl(const Tensor& dy, size_t mb, BwdAux& aux) override;
   Shape output_shape(const Shape& s) const override { Shape o = s; o.push_back(D_); return o; }
   static std::unique_ptr<Layer> create_from_config(const TConfig& c);
+  size_t vocab_size() const { return V_; }
+  size_t embed_dim() const { return D_; }
 
  protected:
   void fill_config(TConfig& c) const override { c.set("vocab_size", V_).set("embed_dim", D_).set("padding_idx", (long)pad_); }
@@ -248,6 +254,8 @@ class PositionalEmbeddingLayer : public Layer {   // x [B, L, D] + learned table
   Tensor forward_impl(const Tensor& x, size_t mb, const FwdAux& aux) override;
   Tensor backward_impl(const Tensor& dy, size_t mb, BwdAux& aux) override;
   static std::unique_ptr<Layer> create_from_config(const TConfig& c);
+  size_t embed_dim() const { return D_; }
+  size_t seq_len() const { return L_; }
 
  protected:
   void fill_config(TConfig& c) const override { c.set("embed_dim", D_).set("seq_len", L_); }
@@ -395,6 +403,9 @@ class ResidualBlock : public Block {
   uint64_t forward_flops(const Shape& s) const override { return main_->forward_flops(s) + (shortcut_ ? shortcut_->forward_flops(s) : 0); }
   TConfig get_config() const override;
   static std::unique_ptr<Layer> create_from_config(const TConfig& c);
+  Layer* main_path() { return main_.get(); }
+  Layer* shortcut_path() { return shortcut_.get(); }
+  const std::string& activation() const { return act_; }
 
  private:
   std::unique_ptr<Layer> main_, shortcut_;
@@ -415,6 +426,9 @@ class AttentionBlock : public Block {
   bool fuses_fwd_residual() const override { return true; }
   static std::unique_ptr<Layer> create_attention(const TConfig& c);
   static std::unique_ptr<Layer> create_flash(const TConfig& c);
+  size_t embed_dim() const { return E_; }
+  size_t num_heads() const { return H_; }
+  bool is_causal() const { return causal_; }
 
  protected:
   void fill_config(TConfig& c) const override { c.set("embed_dim", E_).set("num_heads", H_).set("is_causal", causal_); }

@@ -10,6 +10,7 @@
 #include "tnn/bench.hpp"
 #include "tnn/example_models.hpp"
 #include "tnn/stepstate.hpp"
+#include "tnn/inference.hpp"
 #include "tnn/train.hpp"
 
 namespace py = pybind11;
@@ -70,6 +71,11 @@ struct PyTrainer {
   std::unique_ptr<Optimizer> opt;
   std::unique_ptr<Scheduler> sched;
   std::unique_ptr<TrainStep> step;
+};
+
+struct PyGPT2 {
+  std::unique_ptr<Layer> model;
+  std::unique_ptr<GPT2Engine> engine;
 };
 
 PYBIND11_MODULE(_host, m) {
@@ -186,5 +192,108 @@ PYBIND11_MODULE(_host, m) {
         py::array r = to_numpy(out);
         t.graph->set_training(true);
         return r;
+      });
+  // GPT-2 inference engine of the C++ host (tnn/inference.hpp): int32 token arrays in, int32 / float32 arrays out
+  py::class_<PyGPT2>(m, "GPT2Engine")
+      .def(py::init([](const std::string& model_or_config, const std::string& device, uint64_t seed, size_t max_batch, size_t max_len,
+                       const std::string& precision) {
+             auto e = std::make_unique<PyGPT2>();
+             const Device dev = parse_device(device);
+             ExampleModels::register_defaults();
+             if (!model_or_config.empty() && model_or_config[0] == '{') e->model = LayerFactory::create(TConfig::from_string(model_or_config));
+             else e->model = ExampleModels::create(model_or_config);
+             e->model->init(dev, seed);
+             e->engine = std::make_unique<GPT2Engine>(*e->model, max_batch, max_len, precision);
+             return e;
+           }), py::arg("model") = "gpt2_small", py::arg("device") = "CPU", py::arg("seed") = 1, py::arg("max_batch") = 1, py::arg("max_len") = 0,
+           py::arg("precision") = "bf16")
+      .def("prefill", [](PyGPT2& e, const py::array_t<int32_t, py::array::c_style | py::array::forcecast>& ids, bool want_logits) -> py::tuple {
+        if (ids.ndim() != 2) throw std::invalid_argument("prefill: ids must be [B, L]");
+        const size_t B = (size_t)ids.shape(0), L = (size_t)ids.shape(1);
+        std::vector<int32_t> v(ids.data(), ids.data() + B * L);
+        std::vector<float> lg;
+        std::vector<int32_t> nx;
+        {
+          py::gil_scoped_release rel;
+          nx = e.engine->prefill(v, B, L, want_logits ? &lg : nullptr);
+        }
+        py::array_t<int32_t> next((py::ssize_t)B);
+        std::memcpy(next.mutable_data(), nx.data(), B * 4);
+        if (!want_logits) return py::make_tuple(next, py::none());
+        py::array_t<float> logits({(py::ssize_t)B, (py::ssize_t)e.engine->vocab()});
+        std::memcpy(logits.mutable_data(), lg.data(), lg.size() * 4);
+        return py::make_tuple(next, logits);
+      }, py::arg("ids"), py::arg("return_logits") = false)
+      .def("decode", [](PyGPT2& e, const py::array_t<int32_t, py::array::c_style | py::array::forcecast>& tokens, bool want_logits) -> py::tuple {
+        std::vector<int32_t> v(tokens.data(), tokens.data() + tokens.size());
+        std::vector<float> lg;
+        std::vector<int32_t> nx = e.engine->decode(v, want_logits ? &lg : nullptr);
+        py::array_t<int32_t> next((py::ssize_t)nx.size());
+        std::memcpy(next.mutable_data(), nx.data(), nx.size() * 4);
+        if (!want_logits) return py::make_tuple(next, py::none());
+        py::array_t<float> logits({(py::ssize_t)nx.size(), (py::ssize_t)e.engine->vocab()});
+        std::memcpy(logits.mutable_data(), lg.data(), lg.size() * 4);
+        return py::make_tuple(next, logits);
+      }, py::arg("tokens"), py::arg("return_logits") = false)
+      .def("decode_graph", [](PyGPT2& e, const py::array_t<int32_t, py::array::c_style | py::array::forcecast>& tokens, size_t steps) {
+        std::vector<int32_t> v(tokens.data(), tokens.data() + tokens.size());
+        std::vector<int32_t> out;
+        {
+          py::gil_scoped_release rel;
+          out = e.engine->decode_graph(v, steps);
+        }
+        const size_t B = v.size(), n = B ? out.size() / B : 0;
+        py::array_t<int32_t> r({(py::ssize_t)B, (py::ssize_t)n});
+        std::memcpy(r.mutable_data(), out.data(), out.size() * 4);
+        return r;
+      })
+      .def("generate", [](PyGPT2& e, const py::array_t<int32_t, py::array::c_style | py::array::forcecast>& ids, size_t max_new, long eos) {
+        const size_t B = (size_t)ids.shape(0), L = (size_t)ids.shape(1);
+        std::vector<int32_t> v(ids.data(), ids.data() + B * L);
+        size_t n = 0;
+        std::vector<int32_t> out = e.engine->generate(v, B, L, max_new, eos, &n);
+        py::array_t<int32_t> r({(py::ssize_t)B, (py::ssize_t)n});
+        std::memcpy(r.mutable_data(), out.data(), out.size() * 4);
+        return r;
+      }, py::arg("ids"), py::arg("max_new_tokens") = 50, py::arg("eos_token") = 50256)
+      .def("full_forward_logits", [](PyGPT2& e, const py::array_t<int32_t, py::array::c_style | py::array::forcecast>& ids) {
+        const size_t B = (size_t)ids.shape(0), L = (size_t)ids.shape(1);
+        std::vector<int32_t> v(ids.data(), ids.data() + B * L);
+        std::vector<float> lg = e.engine->full_forward_logits(v, B, L);
+        py::array_t<float> r({(py::ssize_t)B, (py::ssize_t)L, (py::ssize_t)(lg.size() / (B * L))});
+        std::memcpy(r.mutable_data(), lg.data(), lg.size() * 4);
+        return r;
+      })
+      .def("enable_fp8", [](PyGPT2& e) { e.engine->enable_fp8(); })
+      .def("precision", [](PyGPT2& e) { return e.engine->precision(); })
+      .def("cur_len", [](PyGPT2& e) { return e.engine->cur_len(); })
+      .def("max_len", [](PyGPT2& e) { return e.engine->max_len(); })
+      .def("vocab", [](PyGPT2& e) { return e.engine->vocab(); })
+      .def("num_layers", [](PyGPT2& e) { return e.engine->num_layers(); })
+      .def("time_prefill_ms", [](PyGPT2& e, size_t B, size_t L, int iters, int warmup) {
+        py::gil_scoped_release rel;
+        return e.engine->time_prefill_ms(B, L, iters, warmup);
+      }, py::arg("batch"), py::arg("seq_len"), py::arg("iters") = 5, py::arg("warmup") = 2)
+      .def("time_decode_ms", [](PyGPT2& e, size_t B, size_t ctx, size_t steps, bool graph) {
+        py::gil_scoped_release rel;
+        return e.engine->time_decode_ms(B, ctx, steps, graph);
+      }, py::arg("batch"), py::arg("context"), py::arg("steps") = 16, py::arg("graph") = true)
+      .def("params", [](PyGPT2& e) {
+        py::dict d;
+        for (Layer* s : e.model->all_layers())
+          for (auto& p : s->params()) d[py::str(s->name() + "." + p.first)] = to_numpy(p.second);
+        return d;
+      })
+      .def("set_param", [](PyGPT2& e, const std::string& qualified, const py::array& v) {
+        for (Layer* s : e.model->all_layers())
+          for (auto& p : s->params())
+            if (s->name() + "." + p.first == qualified) {
+              Tensor h = from_numpy(v);
+              if (h->size() != p.second->size()) throw std::invalid_argument("set_param: size mismatch for " + qualified);
+              p.second->copy_from(*h->reshape(p.second->shape()));
+              s->mark_params_dirty();
+              return;
+            }
+        throw std::out_of_range("set_param: no parameter " + qualified);
       });
 }

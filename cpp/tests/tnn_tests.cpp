@@ -12,6 +12,9 @@
 #include "runtime/archiver.hpp"
 #include "tnn/distributed.hpp"
 #include "tnn/example_models.hpp"
+#include "tnn/hardware_info.hpp"
+#include "tnn/inference.hpp"
+#include "tnn/legacy.hpp"
 #include "tnn/stepstate.hpp"
 #include "tnn/train.hpp"
 
@@ -650,6 +653,116 @@ TEST(lost_microbatch_and_worker_errors_are_detected) {
 }
 
 // ------------------------------------------------------------------------------------- GPU: layer parity with the CPU oracle
+// ------------------------------------------------------------------------------------- GPT-2 inference engine / legacy zoo / hardware info
+static std::unique_ptr<Sequential> tiny_gpt(size_t vocab = 97, size_t E = 128, size_t H = 2, size_t layers = 2, size_t seq = 48) {
+  LayerBuilder b({seq});
+  b.embedding(vocab, E, -1, "token_embed").positional_embedding(E, seq, "pos_embed");
+  for (size_t i = 0; i < layers; ++i) b.gpt_block(E, H, 4 * E, 0.0, true, "gelu", "h" + std::to_string(i));
+  b.layernorm(1e-5, true, "ln_f").dense(vocab, true, "head");
+  return b.build_sequential("tiny_gpt");
+}
+static std::vector<int32_t> toy_ids(size_t n, size_t vocab, uint64_t seed) {
+  std::vector<int32_t> v(n);
+  for (size_t i = 0; i < n; ++i) v[i] = (int32_t)(((i + 1) * 2654435761ull + seed * 40503ull) % vocab);
+  return v;
+}
+TEST(gpt2_engine_cached_decode_equals_full_recompute_cpu) {
+  auto m = tiny_gpt();
+  m->init(getHost(), 5);
+  GPT2Engine eng(*m, 2, 0, "bf16");
+  const size_t B = 2, L = 9, V = eng.vocab();
+  std::vector<int32_t> ids = toy_ids(B * L, V, 1);
+  std::vector<float> lg;
+  std::vector<int32_t> tok = eng.prefill(ids, B, L, &lg);
+  // oracle: whole model over the whole sequence, logits of the last position
+  std::vector<float> full = eng.full_forward_logits(ids, B, L);
+  for (size_t b = 0; b < B; ++b)
+    for (size_t v = 0; v < V; ++v) CHECK_NEAR(lg[b * V + v], full[(b * L + L - 1) * V + v], 2e-4);
+  // three cached decode steps against a recompute over the grown sequence
+  std::vector<std::vector<int32_t>> rows(B);
+  for (size_t b = 0; b < B; ++b) rows[b].assign(ids.begin() + (long)(b * L), ids.begin() + (long)((b + 1) * L));
+  for (int step = 0; step < 3; ++step) {
+    for (size_t b = 0; b < B; ++b) rows[b].push_back(tok[b]);
+    tok = eng.decode(tok, &lg);
+    const size_t Ln = rows[0].size();
+    std::vector<int32_t> grown;
+    for (size_t b = 0; b < B; ++b) grown.insert(grown.end(), rows[b].begin(), rows[b].end());
+    full = eng.full_forward_logits(grown, B, Ln);
+    for (size_t b = 0; b < B; ++b) {
+      size_t arg = 0;
+      for (size_t v = 0; v < V; ++v) {
+        CHECK_NEAR(lg[b * V + v], full[(b * Ln + Ln - 1) * V + v], 3e-4);
+        if (full[(b * Ln + Ln - 1) * V + v] > full[(b * Ln + Ln - 1) * V + arg]) arg = v;
+      }
+      CHECK((size_t)tok[b] == arg);
+    }
+  }
+  CHECK(eng.cur_len() == L + 3);
+  // generate() == prefill + decode loop; decode_graph() on the CPU is that loop too
+  size_t n = 0;
+  std::vector<int32_t> gen = eng.generate(ids, B, L, 4, -1, &n);
+  CHECK(n == 4 && gen.size() == B * 4);
+  std::vector<int32_t> first = eng.prefill(ids, B, L);
+  std::vector<int32_t> rest = eng.decode_graph(first, 3);
+  for (size_t b = 0; b < B; ++b) {
+    CHECK(gen[b * 4] == first[b]);
+    for (size_t s = 0; s < 3; ++s) CHECK(gen[b * 4 + 1 + s] == rest[b * 3 + s]);
+  }
+  bool threw = false;
+  try { eng.prefill(toy_ids(3 * L, V, 2), 3, L); } catch (const std::exception&) { threw = true; }
+  CHECK(threw);                                   // batch above capacity is rejected
+}
+TEST(legacy_zoo_is_the_nchw_twin_of_the_zoo) {
+  legacy::ExampleModels::register_defaults();
+  std::unique_ptr<Sequential> nhwc = ExampleModels::create("cifar10_resnet9");
+  std::unique_ptr<Layer> nchw = legacy::to_legacy(*nhwc);
+  const std::string cfg = nchw->get_config().to_json().dump();
+  CHECK(cfg.find("legacy_conv2d") != std::string::npos && cfg.find("legacy_batchnorm") != std::string::npos);
+  CHECK(cfg.find("\"conv2d\"") == std::string::npos);
+  // same parameters, same function: copy the weights across and compare outputs on transposed inputs
+  nhwc->init(getHost(), 3);
+  nchw->init(getHost(), 4);
+  auto a = nhwc->all_layers(), b = nchw->all_layers();
+  std::map<std::string, Layer*> by_name;
+  for (Layer* l : a) by_name[l->name()] = l;
+  size_t copied = 0;
+  for (Layer* l : b) {
+    auto it = by_name.find(l->name());
+    if (it == by_name.end()) continue;
+    for (auto& kv : l->params())
+      if (it->second->has_param(kv.first) && it->second->param(kv.first)->size() == kv.second->size()) {
+        kv.second->copy_from(*it->second->param(kv.first));
+        ++copied;
+      }
+  }
+  CHECK(copied > 10);
+  nhwc->set_training(false);
+  nchw->set_training(false);
+  Tensor x = make_tensor(DType_t::FP32, {2, 32, 32, 3});
+  x->fill_random_uniform(0.0, 1.0, 5);
+  Tensor xt = make_tensor(DType_t::FP32, {2, 3, 32, 32});
+  for (size_t n = 0; n < 2; ++n)
+    for (size_t p = 0; p < 1024; ++p)
+      for (size_t c = 0; c < 3; ++c) xt->data_as<float>()[(n * 3 + c) * 1024 + p] = x->data_as<float>()[(n * 1024 + p) * 3 + c];
+  const auto y0 = to_float_vector(*nhwc->forward(x, 0)), y1 = to_float_vector(*nchw->forward(xt, 0));
+  CHECK(y0.size() == y1.size() && y0.size() == 20);
+  for (size_t i = 0; i < y0.size(); ++i) CHECK_NEAR(y0[i], y1[i], 1e-3 * std::max(1.0, std::fabs((double)y0[i])));
+  // NCHW loader adapter
+  legacy::NCHWLoader loader(std::make_unique<SyntheticDataLoader>(Shape{8, 6, 3}, 4, 16, 1));
+  Tensor bx, by;
+  CHECK(loader.get_batch(4, bx, by));
+  CHECK((bx->shape() == Shape{4, 3, 8, 6}) && (loader.get_data_shape() == Shape{3, 8, 6}));
+}
+TEST(hardware_info_reports_the_host) {
+  HardwareInfo hw;
+  CHECK(hw.logical_cores >= 1 && hw.physical_cores >= 1 && hw.total_ram_kb > 0);
+  const Json j = hw.to_json();
+  CHECK(j.at("cpu").at("logical_cores").as_int() == hw.logical_cores && j.contains("gpus") && j.contains("numa"));
+  CHECK(!hw.numa_topology().empty() && get_memory_usage_kb() > 0);
+  CHECK(!ThreadAffinity::current().empty());
+  CHECK(Json::parse(j.dump()) == j);
+}
+
 static double rel_l2(const TensorImpl& a, const TensorImpl& b) {
   const auto x = to_float_vector(a), y = to_float_vector(b);
   double num = 0, den = 0;
@@ -771,6 +884,46 @@ TEST(gpu_train_step_graph_matches_eager_and_learns) {
   const auto eager = run(false), graph = run(true);
   CHECK(eager.back() < eager.front() * 0.7 && graph.back() < graph.front() * 0.7);
   for (size_t i = 0; i < eager.size(); ++i) CHECK_NEAR(eager[i], graph[i], 0.05 * std::max(1.f, eager[i]));
+}
+
+TEST(gpu_gpt2_engine_bf16_fp8_and_graph_decode) {
+  const Device g = need_gpu();
+  auto mc = tiny_gpt(211, 128, 2, 2, 160), mg = tiny_gpt(211, 128, 2, 2, 160);
+  mc->init(getHost(), 21);
+  mg->init(g, 21);
+  {                                               // same weights on both devices
+    auto a = mc->all_layers(), b = mg->all_layers();
+    for (size_t i = 0; i < a.size(); ++i)
+      for (auto& kv : b[i]->params()) kv.second->copy_from(*a[i]->param(kv.first));
+    for (Layer* l : b) l->mark_params_dirty();
+  }
+  const size_t B = 3, L = 130, V = 211;
+  std::vector<int32_t> ids = toy_ids(B * L, V, 3);
+  GPT2Engine cpu(*mc, B), gpu(*mg, B);
+  std::vector<float> lc, lg, l8;
+  std::vector<int32_t> tc = cpu.prefill(ids, B, L, &lc), tg = gpu.prefill(ids, B, L, &lg);
+  double num = 0, den = 0;
+  for (size_t i = 0; i < lc.size(); ++i) { num += (lc[i] - lg[i]) * (lc[i] - lg[i]); den += lc[i] * lc[i]; }
+  CHECK(std::sqrt(num / den) < 4e-2);             // bf16 kernels vs the fp32 oracle
+  // eager decode == graph decode (same kernels, position from device memory)
+  std::vector<int32_t> eager_tok = tg, eager;
+  for (int s = 0; s < 5; ++s) { eager_tok = gpu.decode(eager_tok); eager.insert(eager.end(), eager_tok.begin(), eager_tok.end()); }
+  gpu.prefill(ids, B, L);
+  std::vector<int32_t> graph = gpu.decode_graph(tg, 5);
+  for (size_t b = 0; b < B; ++b)
+    for (size_t s = 0; s < 5; ++s) CHECK(graph[b * 5 + s] == eager[s * B + b]);
+  CHECK(gpu.cur_len() == L + 5);
+  // a second graph run after a new prefill replays the same captured graph
+  gpu.prefill(ids, B, L);
+  std::vector<int32_t> graph2 = gpu.decode_graph(tg, 5);
+  CHECK(graph2 == graph);
+  // block-scaled fp8 prefill against bf16
+  GPT2Engine f8(*mg, B, 0, "fp8");
+  f8.prefill(ids, B, L, &l8);
+  num = den = 0;
+  for (size_t i = 0; i < lg.size(); ++i) { num += (l8[i] - lg[i]) * (l8[i] - lg[i]); den += lg[i] * lg[i]; }
+  CHECK(std::sqrt(num / den) < 0.12);
+  CHECK(f8.precision() == "fp8");
 }
 
 int main(int argc, char** argv) {

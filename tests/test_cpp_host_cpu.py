@@ -280,3 +280,55 @@ def test_python_coordinator_drives_a_cpp_tcp_worker(tmp_path):
             proc.wait(10)
         except Exception:  # noqa: BLE001
             proc.kill()
+
+
+def test_cpp_gpt2_engine_matches_the_python_engine_and_runs_the_new_apps():
+    """The C++ GPT2Engine (KV cache, greedy arg-max) built from the PYTHON model's config with the Python weights copied in
+    produces the Python engine's logits / tokens; the small C++ example apps run."""
+    H = _host()
+    from tnn_b200.inference import GPT2InferenceEngine
+    from tnn_b200.models.zoo import _gpt2
+    from tnn_b200.nn import graph_from_sequential
+    seq = _gpt2(64, 4, 2, False, "tiny_gpt", None, seq_len=32, vocab=97, dropout=0.1)
+    g = graph_from_sequential(seq, "cpu", 3, "tiny_gpt")
+    py = GPT2InferenceEngine(g, max_batch=3)
+    cpp = H.GPT2Engine(json.dumps(seq.get_config().to_json()), "CPU", 1, 3, 0, "bf16")
+    assert cpp.num_layers() == 2 and cpp.vocab() == 97 and cpp.max_len() == 32
+    names = set(cpp.params())
+    copied = 0
+    for layer in seq.all_layers():
+        for k, v in layer.params.items():
+            q = f"{layer.name}.{k}"
+            if q in names:
+                cpp.set_param(q, v.detach().float().numpy())
+                copied += 1
+    assert copied == len(names)
+    ids = torch.randint(0, 97, (3, 9), generator=torch.Generator().manual_seed(0), dtype=torch.int32)
+    pn, pl = py.prefill(ids, return_logits=True)
+    cn, cl = cpp.prefill(ids.numpy(), True)
+    np.testing.assert_allclose(cl, pl.numpy(), rtol=2e-3, atol=2e-4)
+    assert (cn == pn.numpy()).all()
+    for _ in range(4):
+        pn, pl = py.decode(pn, return_logits=True)
+        cn, cl = cpp.decode(cn, True)
+        np.testing.assert_allclose(cl, pl.numpy(), rtol=2e-3, atol=3e-4)
+        assert (cn == pn.numpy()).all()
+    assert cpp.cur_len() == py.cur_len == 13
+    full = cpp.full_forward_logits(ids.numpy())
+    np.testing.assert_allclose(full, py.full_forward_logits(ids).numpy(), rtol=2e-3, atol=3e-4)
+    gen = cpp.generate(ids.numpy(), 5, -1)
+    assert gen.shape == (3, 5) and (gen == py.generate(ids, 5, None).numpy()).all()
+    with pytest.raises(Exception):
+        H.GPT2Engine(json.dumps(seq.get_config().to_json()), "CPU", 1, 1, 0, "fp8")      # fp8 needs a GPU
+    # example apps of the C++ host (reference examples/*.cpp)
+    bins = os.path.join(ROOT, "cpp", "bin")
+    for app in ("gpt2_inference", "inferencer", "graph_test", "msequential_example", "test_del", "device_manager_example",
+                "hardware_info_example", "legacy_trainer", "trainer", "tcp_worker", "tcp_coordinator", "bench_cpp"):
+        assert os.access(os.path.join(bins, app), os.X_OK), app
+    env = dict(os.environ, MODEL_NAME="mnist_cnn", BATCH_SIZE="16", EPOCHS="1", MAX_STEPS="3", DEVICE_TYPE="CPU")
+    for cmd, needle in ((["msequential_example"], "Example Complete"), (["test_del"], "double-ended placement ok"),
+                        (["device_manager_example"], "CPU:0"), (["graph_test", "--steps", "2"], "Loss:"),
+                        (["legacy_trainer", "--synthetic", "--samples", "64"], "final train loss"),
+                        (["inferencer", "--synthetic", "--samples", "32"], "Validation Loss")):
+        out = subprocess.run([os.path.join(bins, cmd[0])] + cmd[1:], capture_output=True, text=True, timeout=300, env=env, cwd=str(ROOT))
+        assert out.returncode == 0 and needle in out.stdout, (cmd, out.stdout[-800:], out.stderr[-800:])

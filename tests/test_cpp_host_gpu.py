@@ -83,3 +83,38 @@ def test_cpp_trainer_learns_and_bench_train_reports_a_graph_captured_step():
     out = json.loads(H.bench_train("cifar100_wrn16_8", 64, 4, 3, 0, True))
     assert out["cuda_graph"] and out["gpu_launches"] > 100 and out["value"] > 0 and out["e2e"]["value"] > 0
     assert out["e2e"]["h2d_bytes_per_step"] == 64 * 32 * 32 * 3 * 4 + 64 * 4
+
+
+def test_cpp_gpt2_engine_on_gpu_bf16_fp8_graph_decode():
+    """C++ GPT2Engine on the GPU against its own fp32 CPU oracle (same weights): bf16 prefill logits, graph decode ==
+    eager decode, block-scaled fp8 prefill within the stated tolerance of bf16."""
+    _need_gpu()
+    H = _host()
+    from tnn_b200.models.zoo import _gpt2
+    seq = _gpt2(128, 2, 2, False, "tiny_gpt", None, seq_len=192, vocab=211, dropout=0.0)
+    cj = json.dumps(seq.get_config().to_json())
+    cpu = H.GPT2Engine(cj, "CPU", 5, 4)
+    gpu = H.GPT2Engine(cj, "GPU:0", 6, 4)
+    for k, v in cpu.params().items():
+        gpu.set_param(k, v)
+    ids = np.random.RandomState(0).randint(0, 211, (4, 160)).astype(np.int32)
+    cn, cl = cpu.prefill(ids, True)
+    gn, gl = gpu.prefill(ids, True)
+    rel = np.linalg.norm(gl - cl) / np.linalg.norm(cl)
+    assert rel < 4e-2, rel
+    eager = []
+    tok = gn
+    for _ in range(6):
+        tok, _ = gpu.decode(tok)
+        eager.append(tok.copy())
+    gpu.prefill(ids)
+    graph = gpu.decode_graph(gn, 6)
+    assert (graph == np.stack(eager, 1)).all()
+    f8 = H.GPT2Engine(cj, "GPU:0", 6, 4, 0, "fp8")
+    for k, v in cpu.params().items():
+        f8.set_param(k, v)
+    f8.enable_fp8()                                   # re-quantise after the weights changed
+    _, l8 = f8.prefill(ids, True)
+    rel8 = np.linalg.norm(l8 - gl) / np.linalg.norm(gl)
+    assert rel8 < 0.12, rel8
+    assert f8.precision() == "fp8"
