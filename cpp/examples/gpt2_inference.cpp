@@ -58,6 +58,17 @@ int main(int argc, char** argv) {
       std::cout << "{\"model\": \"" << model << "\", \"batch\": " << bench_b << ", \"seq_len\": " << bench_l << ", \"precision\": \"" << precision
                 << "\", \"prefill_ms\": " << pf << ", \"prefill_tok_s\": " << (double)(bench_b * bench_l) / pf * 1e3 << ", \"decode_ms_per_step\": " << dc
                 << ", \"decode_tok_s\": " << (double)bench_b / dc * 1e3 << ", \"decode_context\": " << ctx << ", \"host\": \"cpp\"}" << std::endl;
+      const std::vector<double> prof = eng.persistent_decode_profile();
+      if (!prof.empty()) {
+        const char* names[5] = {"ln1+qkv", "attention", "out_proj", "ln2+fc1", "fc2"};
+        double sum[5] = {0, 0, 0, 0, 0};
+        const size_t nl = eng.num_layers();
+        for (size_t l = 0; l < nl; ++l)
+          for (int k = 0; k < 5; ++k) sum[k] += prof[1 + l * 5 + k];
+        std::cout << "[persistent decode, CTA 0, last step] per layer (us):";
+        for (int k = 0; k < 5; ++k) std::cout << ' ' << names[k] << ' ' << sum[k] / nl / 1e3;
+        std::cout << "; embed " << prof[0] / 1e3 << " us, head " << prof[1 + nl * 5] / 1e3 << " us, argmax " << (prof.size() > nl * 5 + 2 ? prof[nl * 5 + 2] / 1e3 : 0.0) << " us" << std::endl;
+      }
       return 0;
     }
     Tokenizer tok;

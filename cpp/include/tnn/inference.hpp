@@ -49,6 +49,12 @@ class GPT2Engine {
   size_t embed_dim() const { return E_; }
   size_t num_layers() const { return blocks_.size(); }
   const Device& device() const { return dev_; }
+  // true when decode_graph() replays the single persistent decode kernel (B <= 32, E <= 1024; TNN_DECODE_MEGA=0 disables)
+  bool uses_persistent_decode() const { return use_mega_; }
+  // logits [cur_batch, vocab] of the most recent prefill / decode / decode_graph step
+  std::vector<float> last_logits();
+  // TNN_DECODE_PROF=1: per-phase nanoseconds of CTA 0 in the last persistent decode step ({embed, [qkv, attn, out, fc1, fc2] x layers, head, argmax})
+  std::vector<double> persistent_decode_profile();
   // device-timed helpers for the bench CLIs (CUDA events on the engine's flow, after `warmup` untimed runs)
   double time_prefill_ms(size_t B, size_t L, int iters, int warmup = 2);
   double time_decode_ms(size_t B, size_t context, size_t steps, bool graph = true);
@@ -88,6 +94,14 @@ class GPT2Engine {
   Tensor q8_, q8_sf_, h8_, h8_sf_;                    // MXFP8 activations
   // device decode state
   Tensor d_tok_, d_pos_, d_step_, d_hist_;
+  // persistent whole-model decode kernel (csrc/kernels/decode_mega.cu): device array of per-layer pointers + scratch
+  Tensor mega_layers_, mega_part_, mega_cnt_, mega_bar_, mega_prof_, mega_stats_, mega_amax_;
+  std::vector<Tensor> mega_fold_;                     // LayerNorm-folded weights, column sums, biases
+  const void* mega_head_w_ = nullptr;
+  const float* mega_head_c_ = nullptr;
+  const float* mega_head_b_ = nullptr;
+  bool use_mega_ = false;
+  void build_mega();
   size_t hist_cap_ = 0, graph_batch_ = 0;
   cudaGraph_t graph_ = nullptr;
   cudaGraphExec_t graph_exec_ = nullptr;

@@ -264,6 +264,14 @@ PYBIND11_MODULE(_host, m) {
         std::memcpy(r.mutable_data(), lg.data(), lg.size() * 4);
         return r;
       })
+      .def("last_logits", [](PyGPT2& e) {
+        std::vector<float> lg = e.engine->last_logits();
+        const size_t V = e.engine->vocab();
+        py::array_t<float> r({(py::ssize_t)(lg.size() / V), (py::ssize_t)V});
+        std::memcpy(r.mutable_data(), lg.data(), lg.size() * 4);
+        return r;
+      })
+      .def("uses_persistent_decode", [](PyGPT2& e) { return e.engine->uses_persistent_decode(); })
       .def("enable_fp8", [](PyGPT2& e) { e.engine->enable_fp8(); })
       .def("precision", [](PyGPT2& e) { return e.engine->precision(); })
       .def("cur_len", [](PyGPT2& e) { return e.engine->cur_len(); })

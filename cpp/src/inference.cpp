@@ -8,6 +8,7 @@
 #include <cstring>
 
 #include "kernels/attention.cuh"
+#include "kernels/decode_mega.cuh"
 #include "kernels/mxfp8.cuh"
 #include "kernels/simt_ops.cuh"
 #include "kernels/umma_gemm.cuh"
@@ -405,8 +406,96 @@ std::vector<int32_t> GPT2Engine::decode(const std::vector<int32_t>& tokens, std:
   return finish(B, 1, logits);
 }
 
+void GPT2Engine::build_mega() {
+  // LayerNorm folding (decode_mega.cuh): W' = bf16(W * gamma), column sums of W', b' = b + W . beta -- once per engine
+  cudaStream_t s = stream();
+  mega_fold_.clear();
+  auto fold = [&](Tensor& W, const float* bias, LayerNormLayer* ln, const void*& wf, const float*& cs, const float*& bf) {
+    const size_t N = W->dimension(0), K = W->dimension(1);
+    Tensor w = make_tensor(DType_t::BF16, {N, K}, dev_), c = make_tensor(DType_t::FP32, {N}, dev_), b = make_tensor(DType_t::FP32, {N}, dev_);
+    decode_fold_ln(W->data_as<float>(), bias, ln->param("gamma")->data_as<float>(), ln->param("beta")->data_as<float>(), (int)N, (int)K, w->data(),
+                   c->data_as<float>(), b->data_as<float>(), s);
+    wf = w->data();
+    cs = c->data_as<float>();
+    bf = b->data_as<float>();
+    mega_fold_.push_back(w);
+    mega_fold_.push_back(c);
+    mega_fold_.push_back(b);
+  };
+  std::vector<DecodeLayerParams> host(blocks_.size());
+  for (size_t i = 0; i < blocks_.size(); ++i) {
+    Block& b = blocks_[i];
+    DecodeLayerParams& L = host[i];
+    fold(b.attn->param("qkv_weight"), b.attn->param("qkv_bias")->data_as<float>(), b.ln1, L.w_qkv, L.c_qkv, L.b_qkv);
+    L.w_out = b.attn->lp("out_weight")->data();
+    L.b_out = b.attn->param("out_bias")->data_as<float>();
+    fold(b.fc1->param("weight"), b.fc1->use_bias() ? b.fc1->param("bias")->data_as<float>() : nullptr, b.ln2, L.w_fc1, L.c_fc1, L.b_fc1);
+    L.w_fc2 = b.fc2->lp("weight")->data();
+    L.b_fc2 = b.fc2->use_bias() ? b.fc2->param("bias")->data_as<float>() : nullptr;
+    L.kc = b.kc->data();
+    L.vc = b.vc->data();
+    L.eps1 = (float)b.ln1->epsilon();
+    L.eps2 = (float)b.ln2->epsilon();
+  }
+  fold(head_->param("weight"), head_->use_bias() ? head_->param("bias")->data_as<float>() : nullptr, ln_f_, mega_head_w_, mega_head_c_, mega_head_b_);
+  mega_layers_ = make_tensor(DType_t::UINT8_T, {host.size() * sizeof(DecodeLayerParams)}, dev_);
+  mega_layers_->copy_from_host(host.data(), host.size() * sizeof(DecodeLayerParams));
+  mega_part_ = make_tensor(DType_t::UINT8_T, {decode_mega_part_bytes((int)max_batch_, (int)H_)}, dev_);
+  mega_cnt_ = make_tensor(DType_t::INT32_T, {max_batch_ * H_}, dev_);
+  mega_cnt_->zero();
+  mega_bar_ = make_tensor(DType_t::INT32_T, {4}, dev_);
+  mega_bar_->zero();
+  mega_stats_ = make_tensor(DType_t::FP32, {128}, dev_);
+  mega_stats_->zero();
+  mega_amax_ = make_tensor(DType_t::INT64_T, {32}, dev_);
+  mega_amax_->zero();
+  const char* pe = getenv("TNN_DECODE_PROF");
+  if (pe && atoi(pe)) {
+    mega_prof_ = make_tensor(DType_t::INT64_T, {4 + 5 * blocks_.size()}, dev_);
+    mega_prof_->zero();
+  }
+  current_flow(dev_).synchronize();
+}
+
 void GPT2Engine::decode_step_device(size_t B) {
   cudaStream_t s = stream();
+  if (use_mega_) {
+    DecodeParams p{};
+    p.layers = static_cast<const DecodeLayerParams*>(mega_layers_->data());
+    p.n_layers = (int)blocks_.size();
+    p.B = (int)B;
+    p.E = (int)E_;
+    p.H = (int)H_;
+    p.F = (int)F_;
+    p.V = (int)V_;
+    p.Lmax = (int)max_len_;
+    p.vpad = (long long)((V_ + 7) / 8 * 8);
+    p.wte = wte_->param("weight")->data_as<float>();
+    p.wpe = wpe_->param("weight")->data_as<float>();
+    p.w_head = mega_head_w_;
+    p.c_head = mega_head_c_;
+    p.b_head = mega_head_b_;
+    p.epsf = (float)ln_f_->epsilon();
+    p.tok = d_tok_->data_as<int>();
+    p.pos = d_pos_->data_as<int>();
+    p.step = d_step_->data_as<int>();
+    p.hist = d_hist_->data_as<int>();
+    p.hist_cap = (int)hist_cap_;
+    p.x = x_->data();
+    p.x2 = x2_->data();
+    p.qkv = qkv_->data();
+    p.o = o_->data();
+    p.h = h_->data();
+    p.stats = mega_stats_->data_as<float>();
+    p.amax = static_cast<unsigned long long*>(mega_amax_->data());
+    p.attn_part = static_cast<float*>(mega_part_->data());
+    p.attn_cnt = mega_cnt_->data_as<int>();
+    p.logits = logits_->data();
+    p.bar = static_cast<unsigned int*>(mega_bar_->data());
+    p.prof = mega_prof_ ? static_cast<unsigned long long*>(mega_prof_->data()) : nullptr;
+    decode_step_mega(p, s);
+    return;
+  }
   const int E = (int)E_, F = (int)F_;
   const long long tokE = (long long)E_, batE = (long long)(max_len_ * E_);
   const size_t vpad = (V_ + 7) / 8 * 8;
@@ -484,6 +573,9 @@ std::vector<int32_t> GPT2Engine::decode_graph(const std::vector<int32_t>& tokens
       b.fc2->lp("weight");
     }
     head_->lp("weight");
+    const char* env = getenv("TNN_DECODE_MEGA");
+    use_mega_ = decode_mega_supported((int)B, (int)E_, (int)H_, (int)F_) && !(env && atoi(env) == 0);
+    if (use_mega_) build_mega();
     decode_step_device(B);             // warm-up (kernel attributes, lazy state) ...
     rewind();                          // ... then undo its side effects
     TNN_CUDA(cudaStreamBeginCapture(flow.stream(), cudaStreamCaptureModeRelaxed));
@@ -541,6 +633,28 @@ std::vector<float> GPT2Engine::full_forward_logits(const std::vector<int32_t>& i
   Tensor y = model_.forward(t, 0);
   if (gpu_) current_flow(dev_).synchronize();
   return to_float_vector(*y);
+}
+
+std::vector<float> GPT2Engine::last_logits() {
+  const size_t B = cur_batch_, vpad = (V_ + 7) / 8 * 8;
+  std::vector<float> out(B * V_);
+  if (!gpu_ || !logits_) throw std::runtime_error("GPT2Engine::last_logits: GPU engine after a step only");
+  std::vector<uint16_t> raw(B * vpad);
+  current_flow(dev_).synchronize();
+  logits_->copy_to_host(raw.data(), raw.size() * 2);
+  for (size_t b = 0; b < B; ++b)
+    for (size_t v = 0; v < V_; ++v) out[b * V_ + v] = bf16_to_float(bf16_t{raw[b * vpad + v]});
+  return out;
+}
+
+std::vector<double> GPT2Engine::persistent_decode_profile() {
+  std::vector<double> out;
+  if (!mega_prof_) return out;
+  current_flow(dev_).synchronize();
+  std::vector<unsigned long long> t(mega_prof_->size());
+  mega_prof_->copy_to_host(t.data(), t.size() * 8);
+  for (size_t i = 1; i < t.size() && t[i]; ++i) out.push_back((double)(t[i] - t[i - 1]));
+  return out;
 }
 
 double GPT2Engine::time_prefill_ms(size_t B, size_t L, int iters, int warmup) {

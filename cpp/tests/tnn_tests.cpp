@@ -905,11 +905,14 @@ TEST(gpu_gpt2_engine_bf16_fp8_and_graph_decode) {
   double num = 0, den = 0;
   for (size_t i = 0; i < lc.size(); ++i) { num += (lc[i] - lg[i]) * (lc[i] - lg[i]); den += lc[i] * lc[i]; }
   CHECK(std::sqrt(num / den) < 4e-2);             // bf16 kernels vs the fp32 oracle
-  // eager decode == graph decode (same kernels, position from device memory)
+  // eager decode == graph decode of the multi-kernel path (same kernels, position from device memory)
   std::vector<int32_t> eager_tok = tg, eager;
-  for (int s = 0; s < 5; ++s) { eager_tok = gpu.decode(eager_tok); eager.insert(eager.end(), eager_tok.begin(), eager_tok.end()); }
+  std::vector<float> eager_l1;
+  for (int s = 0; s < 5; ++s) { eager_tok = gpu.decode(eager_tok, s == 0 ? &eager_l1 : nullptr); eager.insert(eager.end(), eager_tok.begin(), eager_tok.end()); }
+  setenv("TNN_DECODE_MEGA", "0", 1);
   gpu.prefill(ids, B, L);
   std::vector<int32_t> graph = gpu.decode_graph(tg, 5);
+  CHECK(!gpu.uses_persistent_decode());
   for (size_t b = 0; b < B; ++b)
     for (size_t s = 0; s < 5; ++s) CHECK(graph[b * 5 + s] == eager[s * B + b]);
   CHECK(gpu.cur_len() == L + 5);
@@ -917,6 +920,45 @@ TEST(gpu_gpt2_engine_bf16_fp8_and_graph_decode) {
   gpu.prefill(ids, B, L);
   std::vector<int32_t> graph2 = gpu.decode_graph(tg, 5);
   CHECK(graph2 == graph);
+  // the persistent whole-model decode kernel: one launch per token.  Same math, different reduction order: compare
+  // the first step's logits with the eager path, then check the bookkeeping over several steps and a re-run.
+  unsetenv("TNN_DECODE_MEGA");
+  GPT2Engine mega(*mg, B);
+  mega.prefill(ids, B, L);
+  std::vector<int32_t> m1 = mega.decode_graph(tg, 1);
+  CHECK(mega.uses_persistent_decode() && mega.cur_len() == L + 1);
+  std::vector<float> ml = mega.last_logits();
+  num = den = 0;
+  for (size_t i = 0; i < ml.size(); ++i) { num += (ml[i] - eager_l1[i]) * (ml[i] - eager_l1[i]); den += eager_l1[i] * eager_l1[i]; }
+  CHECK(std::sqrt(num / den) < 2e-2);
+  size_t agree = 0;
+  for (size_t b = 0; b < B; ++b) agree += m1[b] == eager[b];
+  CHECK(agree + 1 >= B);
+  mega.prefill(ids, B, L);
+  std::vector<int32_t> m5 = mega.decode_graph(tg, 5);
+  CHECK(mega.cur_len() == L + 5);
+  for (size_t b = 0; b < B; ++b) CHECK(m5[b * 5] == m1[b]);
+  mega.prefill(ids, B, L);
+  CHECK(mega.decode_graph(tg, 5) == m5);
+  // continuing from the cache the persistent kernel appended: eager decode of the next token agrees with a fresh run
+  std::vector<int32_t> lastcol(B);
+  for (size_t b = 0; b < B; ++b) lastcol[b] = m5[b * 5 + 4];
+  std::vector<float> cont_l;
+  mega.decode(lastcol, &cont_l);
+  {
+    std::vector<int32_t> grown;
+    for (size_t b = 0; b < B; ++b) {
+      grown.insert(grown.end(), ids.begin() + (long)(b * L), ids.begin() + (long)((b + 1) * L));
+      grown.push_back(tg[b]);
+      for (size_t s = 0; s < 5; ++s) grown.push_back(m5[b * 5 + s]);
+    }
+    std::vector<float> ref;
+    GPT2Engine fresh(*mg, B);
+    fresh.prefill(grown, B, L + 6, &ref);
+    num = den = 0;
+    for (size_t i = 0; i < ref.size(); ++i) { num += (ref[i] - cont_l[i]) * (ref[i] - cont_l[i]); den += ref[i] * ref[i]; }
+    CHECK(std::sqrt(num / den) < 3e-2);
+  }
   // block-scaled fp8 prefill against bf16
   GPT2Engine f8(*mg, B, 0, "fp8");
   f8.prefill(ids, B, L, &l8);

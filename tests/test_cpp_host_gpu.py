@@ -104,12 +104,34 @@ def test_cpp_gpt2_engine_on_gpu_bf16_fp8_graph_decode():
     assert rel < 4e-2, rel
     eager = []
     tok = gn
-    for _ in range(6):
-        tok, _ = gpu.decode(tok)
+    eager_l1 = None
+    for i in range(6):
+        tok, lg = gpu.decode(tok, i == 0)
+        eager_l1 = lg if i == 0 else eager_l1
         eager.append(tok.copy())
-    gpu.prefill(ids)
-    graph = gpu.decode_graph(gn, 6)
+    os.environ["TNN_DECODE_MEGA"] = "0"              # multi-kernel graph: the same kernels as the eager path -> identical tokens
+    try:
+        gpu.prefill(ids)
+        graph = gpu.decode_graph(gn, 6)
+        assert not gpu.uses_persistent_decode()
+    finally:
+        del os.environ["TNN_DECODE_MEGA"]
     assert (graph == np.stack(eager, 1)).all()
+    # persistent whole-model decode kernel (one launch per token): same math, different reduction order
+    mega = H.GPT2Engine(cj, "GPU:0", 6, 4)
+    for k, v in cpu.params().items():
+        mega.set_param(k, v)
+    mega.prefill(ids)
+    m1 = mega.decode_graph(gn, 1)
+    assert mega.uses_persistent_decode() and mega.cur_len() == 161
+    ml = mega.last_logits()
+    assert np.linalg.norm(ml - eager_l1) / np.linalg.norm(eager_l1) < 2e-2
+    assert (m1[:, 0] == eager[0]).mean() >= 0.75
+    mega.prefill(ids)
+    m6 = mega.decode_graph(gn, 6)
+    assert (m6[:, 0] == m1[:, 0]).all() and mega.cur_len() == 166
+    mega.prefill(ids)
+    assert (mega.decode_graph(gn, 6) == m6).all()
     f8 = H.GPT2Engine(cj, "GPU:0", 6, 4, 0, "fp8")
     for k, v in cpu.params().items():
         f8.set_param(k, v)
