@@ -18,7 +18,6 @@ static constexpr int DM_X_BYTES = 32 * DM_LDS * 2;
 static constexpr int DM_RED_BYTES = DM_WARPS * 32 * 8 * 4;
 static constexpr int DM_SMEM = DM_X_BYTES + DM_RED_BYTES;
 static constexpr int DM_UNROLL = 8;                      // 32-wide k steps in flight per lane (one round)
-static constexpr int DM_KEYS = 4;                        // keys per 8-lane group per attention step (16 per warp)
 static constexpr int DM_MAX_CHUNKS = 16;                 // sequence splits per (batch, head)
 static constexpr int DM_PART = 72;                       // floats per partial: 64 acc + m + l (+ pad)
 static constexpr int DM_D = 64;                          // head dim
@@ -76,7 +75,7 @@ __device__ __forceinline__ void dm_wait(DmBarrier& b) {
   b.pending = false;
 }
 
-__device__ __forceinline__ float dm_gelu(float v) {
+__device__ __noinline__ float dm_gelu(float v) {
   const float k0c = 0.7978845608028654f, k1c = 0.044715f;
   return 0.5f * v * (1.f + tanhf(k0c * (v + k1c * v * v * v)));
 }
@@ -95,9 +94,8 @@ struct DmGemm {
 
 // out[M, N] = act(LN?(x) . W^T + bias) + residual.  Units of NT*8 output columns are dealt round-robin to the CTAs;
 // inside a CTA the 8 warps are NT column tiles x (8 / NT) K-slices, reduced through shared memory.
-template <int NT>
-__device__ __noinline__ void dm_gemm_phase(DmBarrier& bar, uint8_t* smem, const DmGemm& g) {
-  constexpr int KS = DM_WARPS / NT;
+__device__ __noinline__ void dm_gemm_phase(DmBarrier& bar, uint8_t* smem, const DmGemm& g, const int NT) {
+  const int KS = DM_WARPS / NT;                          // NT (1 or 2) is a run-time value on purpose: ONE copy of this code (see dm_gemm)
   bf16* sx = reinterpret_cast<bf16*>(smem);
   float* red = reinterpret_cast<float*>(smem + DM_X_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -109,22 +107,21 @@ __device__ __noinline__ void dm_gemm_phase(DmBarrier& bar, uint8_t* smem, const 
   bool staged = false;
   uint4 wq[DM_UNROLL];
   // this lane's 16-byte weight loads of (unit u, K chunk k0): issued one (unit, chunk) AHEAD of the MMAs that use them
-  auto load_w = [&](int u, int k0, int rd) {
+  auto load_w = [&](int u, int k0) {
     const int nrow = u * NT * 8 + cg * 8 + (lane >> 2);
     const bool n_ok = nrow < N;
     const bf16* wrow = g.W + (long long)(n_ok ? nrow : 0) * K;
     const int kc = min(DM_KC, K - k0);
-    const int sub = ((kc + KS - 1) / KS + 31) / 32 * 32;
+    const int sub = ((kc + KS - 1) / KS + 31) / 32 * 32;           // <= 256 = DM_UNROLL steps (K chunk 1024, KS >= 4)
     const int kb = ks * sub;
 #pragma unroll
     for (int q = 0; q < DM_UNROLL; ++q) {
-      const int ko = (rd * DM_UNROLL + q) * 32;                          // offset inside this warp's K slice
-      const int kk = kb + ko + kq;
+      const int kk = kb + q * 32 + kq;
       wq[q] = make_uint4(0, 0, 0, 0);
-      if (ko < sub && n_ok && kk < kc) wq[q] = __ldg(reinterpret_cast<const uint4*>(wrow + k0 + kk));
+      if (q * 32 < sub && n_ok && kk < kc) wq[q] = __ldg(reinterpret_cast<const uint4*>(wrow + k0 + kk));
     }
   };
-  if ((int)blockIdx.x < units) load_w(blockIdx.x, 0, 0);
+  if ((int)blockIdx.x < units) load_w(blockIdx.x, 0);
   dm_wait(bar);
   for (int u = blockIdx.x; u < units; u += gridDim.x) {
     const int n_base = u * NT * 8 + cg * 8;
@@ -157,35 +154,28 @@ __device__ __noinline__ void dm_gemm_phase(DmBarrier& bar, uint8_t* smem, const 
         __syncthreads();
         staged = true;
       }
-      const int rounds = (sub + DM_UNROLL * 32 - 1) / (DM_UNROLL * 32);
-      for (int rd = 0; rd < rounds; ++rd) {
 #pragma unroll
-        for (int q = 0; q < DM_UNROLL; ++q) {
-          const int ko = (rd * DM_UNROLL + q) * 32;
-          const int kk = kb + ko + kq;
-          if (ko >= sub || kb + ko >= kc) break;
+      for (int q = 0; q < DM_UNROLL; ++q) {
+        const int kk = kb + q * 32 + kq;
+        if (q * 32 >= sub || kb + q * 32 >= kc) break;
 #pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int r0 = t * 16 + (lane >> 2);
-            const uint4 xa = *reinterpret_cast<const uint4*>(sx + r0 * DM_LDS + kk);
-            const uint4 xb = *reinterpret_cast<const uint4*>(sx + (r0 + 8) * DM_LDS + kk);
-            const uint32_t a1[4] = {xa.x, xb.x, xa.y, xb.y};
-            const uint32_t a2[4] = {xa.z, xb.z, xa.w, xb.w};
-            dm_mma(acc[t], a1, wq[q].x, wq[q].y);
-            dm_mma(acc[t], a2, wq[q].z, wq[q].w);
-          }
-        }
-        // the registers are free again: next round / next chunk / next unit's weights go in flight now
-        if (rd + 1 < rounds) load_w(u, k0, rd + 1);
-        else {
-          int nu = u, nk = k0 + DM_KC;
-          if (nk >= K) {
-            nk = 0;
-            nu = u + gridDim.x;
-          }
-          if (nu < units) load_w(nu, nk, 0);
+        for (int t = 0; t < 2; ++t) {
+          const int r0 = t * 16 + (lane >> 2);
+          const uint4 xa = *reinterpret_cast<const uint4*>(sx + r0 * DM_LDS + kk);
+          const uint4 xb = *reinterpret_cast<const uint4*>(sx + (r0 + 8) * DM_LDS + kk);
+          const uint32_t a1[4] = {xa.x, xb.x, xa.y, xb.y};
+          const uint32_t a2[4] = {xa.z, xb.z, xa.w, xb.w};
+          dm_mma(acc[t], a1, wq[q].x, wq[q].y);
+          dm_mma(acc[t], a2, wq[q].z, wq[q].w);
         }
       }
+      // the registers are free again: put the next (unit, chunk)'s weights in flight under the reduction / epilogue
+      int nu = u, nk = k0 + DM_KC;
+      if (nk >= K) {
+        nk = 0;
+        nu = u + gridDim.x;
+      }
+      if (nu < units) load_w(nu, nk);
     }
     // K-slice reduction (KS partial sums per column tile)
 #pragma unroll
@@ -194,15 +184,6 @@ __device__ __noinline__ void dm_gemm_phase(DmBarrier& bar, uint8_t* smem, const 
       for (int j = 0; j < 4; ++j) red[((ks * NT + cg) * 32 + lane) * 8 + t * 4 + j] = acc[t][j];
     __syncthreads();
     if (ks == 0) {
-#pragma unroll
-      for (int t = 0; t < 2; ++t)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float v = 0.f;
-#pragma unroll
-          for (int q = 0; q < KS; ++q) v += red[((q * NT + cg) * 32 + lane) * 8 + t * 4 + j];
-          acc[t][j] = v;
-        }
       // C fragment: rows t*16 + hh*8 + lane/4, columns n_base + (lane%4)*2 + {0,1}
       const int col = n_base + (lane & 3) * 2;
       const bool c0ok = col < N, two = col + 1 < N;
@@ -216,13 +197,21 @@ __device__ __noinline__ void dm_gemm_phase(DmBarrier& bar, uint8_t* smem, const 
         cs0 = __ldg(g.csum + col);
         if (two) cs1 = __ldg(g.csum + col + 1);
       }
-#pragma unroll
-      for (int t = 0; t < 2; ++t)
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
+      // a ROLLED loop over the lane's four (row, column pair) slots, summing the K-slice partials straight from shared
+      // memory: a quarter of the epilogue code (this kernel is instruction-fetch bound)
+#pragma unroll 1
+      for (int sl = 0; sl < 4; ++sl) {
+        {
+          const int t = sl >> 1, hh = sl & 1;
           const int row = t * 16 + hh * 8 + (lane >> 2);
           const bool rok = row < M;
-          float v0 = acc[t][hh * 2], v1 = acc[t][hh * 2 + 1];
+          float v0 = 0.f, v1 = 0.f;
+#pragma unroll 4
+          for (int q = 0; q < KS; ++q) {
+            const float2 pr = *reinterpret_cast<const float2*>(red + ((q * NT + cg) * 32 + lane) * 8 + t * 4 + hh * 2);
+            v0 += pr.x;
+            v1 += pr.y;
+          }
           if (g.csum) {                                               // LayerNorm of the input row, applied to the product
             float mean = 0.f, rstd = 0.f;
             if (rok) {
@@ -267,11 +256,12 @@ __device__ __noinline__ void dm_gemm_phase(DmBarrier& bar, uint8_t* smem, const 
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             q += __shfl_xor_sync(0xffffffffu, q, 2);
             if ((lane & 3) == 0 && rok) {
-              atomicAdd(g.stats_out + row * 2, s);
-              atomicAdd(g.stats_out + row * 2 + 1, q);
+              asm volatile("red.global.add.f32 [%0], %1;" ::"l"(g.stats_out + row * 2), "f"(s) : "memory");
+              asm volatile("red.global.add.f32 [%0], %1;" ::"l"(g.stats_out + row * 2 + 1), "f"(q) : "memory");
             }
           }
         }
+      }
       }
     }
     __syncthreads();                                                  // red is reused by the next unit
@@ -280,14 +270,15 @@ __device__ __noinline__ void dm_gemm_phase(DmBarrier& bar, uint8_t* smem, const 
 }
 
 __device__ __forceinline__ void dm_gemm(DmBarrier& bar, uint8_t* smem, const DmGemm& g) {
-  // the fewest column tiles per CTA (most K-slicing, least weight bytes per SM) that still gives every CTA at most one unit
-  const int tiles = (g.N + 7) / 8, nb = (int)gridDim.x;
-  if (tiles <= nb) dm_gemm_phase<1>(bar, smem, g);
-  else if ((tiles + 1) / 2 <= nb) dm_gemm_phase<2>(bar, smem, g);
-  else dm_gemm_phase<4>(bar, smem, g);
+  // one column tile per CTA while that still gives every CTA at most one unit; two tiles (half the x staging traffic)
+  // otherwise.  The kernel is INSTRUCTION-FETCH bound: every phase runs its code once per layer, and with two template
+  // instances of the GEMM, the attention phase and the main loop the per-layer code was ~95 KB (161 KB with a third GEMM
+  // variant: 0.89 -> 1.07 ms per token).  Hence one run-time-parameterised copy of each phase and no inlined GELU.
+  dm_gemm_phase(bar, smem, g, (g.N + 7) / 8 <= (int)gridDim.x ? 1 : 2);
 }
 
 // one online-softmax update of (m, l, acc) with up to DM_KEYS keys
+template <int DM_KEYS>
 __device__ __forceinline__ void dm_softmax_update(float& m, float& l, float (&acc)[8], const float (&s)[DM_KEYS], const uint4 (&vq)[DM_KEYS]) {
   float mn = m;
 #pragma unroll
@@ -312,6 +303,7 @@ __device__ __forceinline__ void dm_softmax_update(float& m, float& l, float (&ac
 // Attention of the current token over the cache [0, pos) plus itself.  Work item = (batch, head, sequence chunk),
 // one warp each (8 lanes per key: 4 keys per load instruction, 16 keys per step).  The warp that owns the last chunk
 // also appends this token's K / V rows to the cache.  The last warp to finish a (batch, head) merges the partials.
+template <int DM_KEYS>
 __device__ __noinline__ void dm_attention_phase(DmBarrier& bar, const DecodeParams& p, const DecodeLayerParams& L, int pos) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g4 = lane >> 3, sub = lane & 7;
@@ -365,7 +357,7 @@ __device__ __noinline__ void dm_attention_phase(DmBarrier& bar, const DecodePara
         d0 += __shfl_xor_sync(0xffffffffu, d0, 4);
         s[i] = (j0 + i * 4 + g4 < end) ? d0 : -INFINITY;
       }
-      dm_softmax_update(m, l, acc, s, vq);
+      dm_softmax_update<DM_KEYS>(m, l, acc, s, vq);
     }
     if (c == nch - 1) {                                                // the current token: from the projection, and into the cache
       const uint4 kcur = __ldcg(reinterpret_cast<const uint4*>(row + E));
@@ -382,19 +374,19 @@ __device__ __noinline__ void dm_attention_phase(DmBarrier& bar, const DecodePara
       d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
       d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
       d0 += __shfl_xor_sync(0xffffffffu, d0, 4);
-      float sc[DM_KEYS];
-      uint4 vcq[DM_KEYS];
+      if (g4 == 0) {                                                   // single-key online-softmax update
+        const float mn = fmaxf(m, d0);
+        const float a = exp2f(m - mn), e = exp2f(d0 - mn);
+        float vf[8];
+        bf8_unpack(vcur, vf);
+        l = l * a + e;
 #pragma unroll
-      for (int i = 0; i < DM_KEYS; ++i) {
-        sc[i] = -INFINITY;
-        vcq[i] = make_uint4(0, 0, 0, 0);
+        for (int d = 0; d < 8; ++d) acc[d] = acc[d] * a + e * vf[d];
+        m = mn;
       }
-      if (g4 == 0) sc[0] = d0;
-      vcq[0] = vcur;
-      dm_softmax_update(m, l, acc, sc, vcq);
     }
     // merge the 4 key groups of the warp
-#pragma unroll
+#pragma unroll 1
     for (int off = 8; off <= 16; off <<= 1) {
       const float mo = __shfl_xor_sync(0xffffffffu, m, off), lo = __shfl_xor_sync(0xffffffffu, l, off);
       const float M2 = fmaxf(m, mo);
@@ -656,7 +648,7 @@ __global__ void __launch_bounds__(DM_THREADS, 2) k_decode_mega(const DecodeParam
     }
     DM_STAMP();
     // B: o = attention(q, cache + current token); cache append
-    dm_attention_phase(bar, p, L, pos);
+    dm_attention_phase<4>(bar, p, L, pos);          // 16 keys per warp step (2 and 8 per group measured: 1.13 / 1.70 ms vs 0.89 ms per token)
     DM_STAMP();
     // C: x2 = x + o Wout^T + b  (+ row statistics of x2).  stats_x was consumed in A (every CTA passed B's barrier
     // since) and is refilled in E: clear it here.
