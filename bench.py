@@ -167,9 +167,21 @@ def gpt2_block(args, impl: str, rank: int, world: int, dev) -> dict | None:
     import gpt2_lib
     import torch
     try:
-        if impl == "tnn_cpp":
-            r = gpt2_lib.tnn_gpt2_cpp(dev.index or 0, iters=args.gpt2_iters)
-        elif impl == "tnn":
+        if impl in ("tnn_cpp", "tnn") and args.host != "python":
+            # the C++ GPT2Engine (persistent one-launch-per-token decode kernel) on this rank's GPU
+            try:
+                try:
+                    from tnn_b200 import _host  # noqa: F401  (prebuilt in-tree; ranks must not rebuild concurrently)
+                except ImportError:
+                    from tnn_b200 import build as tb
+                    tb.build_host(verbose=False)
+                r = gpt2_lib.tnn_gpt2_cpp(dev.index or 0, iters=args.gpt2_iters)
+            except Exception as e:  # noqa: BLE001
+                if impl == "tnn_cpp" or args.host == "cpp":
+                    raise
+                print(f"[bench] C++ GPT-2 engine unavailable ({type(e).__name__}: {e}); using the Python engine", file=sys.stderr)
+                r = gpt2_lib.tnn_gpt2(dev, iters=args.gpt2_iters)
+        elif impl in ("tnn_cpp", "tnn"):
             r = gpt2_lib.tnn_gpt2(dev, iters=args.gpt2_iters)
         else:
             r = gpt2_lib.torch_gpt2(dev, iters=args.gpt2_iters)

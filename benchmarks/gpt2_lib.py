@@ -98,7 +98,8 @@ def tnn_gpt2_cpp(gpu: int = 0, batch=32, seq=1024, decode_steps=64, iters=5, mod
     msd = eng.time_decode_ms(batch, seq - decode_steps, decode_steps, True)
     out["decode_ms_per_step"] = msd
     out["decode_tok_s"] = batch / msd * 1e3
-    out["decode_dtype"] = "bf16 (cluster split-K skinny GEMMs, CUDA-graph replay)"
+    out["decode_dtype"] = "bf16 (persistent whole-model decode kernel, one launch per token, CUDA-graph replay)" if eng.uses_persistent_decode() \
+        else "bf16 (cluster split-K skinny GEMMs, CUDA-graph replay)"
     eng.enable_fp8()
     l0 = _host.launch_count()
     _, logits_fp8 = eng.prefill(prompt, True)
