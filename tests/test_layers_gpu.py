@@ -40,9 +40,6 @@ def _check(make, x, tol=2e-2, train=True, int_input=False, grad_tol=6e-2):
     dg = gpu.backward(dy.cuda().bfloat16())
     if dc is not None and dg is not None:
         assert _rel(dg, dc) < tol, f"dgrad mismatch {_rel(dg, dc)}"
-    pc = dict(cpu.parameters())
-    for (n, _), lc, lg in zip(cpu.parameters(), cpu.all_layers(), gpu.all_layers()):
-        pass
     for lc, lg in zip(cpu.all_layers(), gpu.all_layers()):
         for k in lc.grads:
             gc, gg = lc.grads[k], lg.grads[k]

@@ -9,7 +9,9 @@
 
 #include "kernels/simt_ops.cuh"
 #include "kernels/umma_gemm.cuh"
-#include "runtime/runtime.hpp"
+namespace tnn {
+void runtime_bind(pybind11::module_& m);   // csrc/runtime/runtime.cpp: archiver / wire format, allocators, data loaders, tokenizer, profiler
+}
 
 namespace py = pybind11;
 using torch::Tensor;

@@ -264,7 +264,10 @@ void layernorm_fwd_mxfp8(const void* x, const void* residual, void* sum_out, lon
 // ---------------------------------------------------------------------------------------------------
 static constexpr int F8_BLOCK_M = 128;
 static constexpr int F8_BLOCK_K = 128;      // bytes == elements
-static constexpr int F8_THREADS = 192;      // warp 0 TMA, warp 1 MMA + scale copies, warps 2..5 epilogue
+static constexpr int F8_EPI_GROUPS = 3;     // epilogue warps per TMEM lane quadrant: they split the tile's 32-column chunks
+static constexpr int F8_THREADS = 64 + F8_EPI_GROUPS * 128;   // warp 0 TMA, warp 1 MMA + scale copies, warps 2.. epilogue
+// (ncu, round 2: with 4 epilogue warps the kernel was ISSUE-bound in the epilogue -- bias + GELU + re-quantisation of a
+//  128 x 192 tile is ~4 200 instructions per warp against 2 304 tensor cycles of mainloop at K = 768; tensor pipe 17 %.)
 static constexpr int F8_SF_BYTES = 3 * 512; // per stage: SFA block + two SFB blocks
 
 struct F8Params {
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(F8_THREADS)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 128);
+      mbar_init(&tmem_empty[a], F8_EPI_GROUPS * 128);
     }
     fence_mbar_init();
   }
@@ -424,9 +427,10 @@ __global__ void __launch_bounds__(F8_THREADS)
       }
     }
   } else {
-    // ----------------------------- epilogue (warps 2..5: TMEM lane quadrant = warp % 4) -----------------------------
+    // ------------- epilogue (warps 2..: TMEM lane quadrant = warp % 4, column-chunk group = (warp - 2) / 4) -------------
     const Fp8Epilogue& e = p.epi;
     const int qd = warp & 3;
+    const int cgp = (warp - 2) >> 2;
     const int row = qd * 32 + lane;
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
@@ -439,7 +443,7 @@ __global__ void __launch_bounds__(F8_THREADS)
       const int m = m0 + row;
       const bool row_ok = m < p.M;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
+      for (int c = cgp * 32; c < BLOCK_N; c += F8_EPI_GROUPS * 32) {
         const int n = n0 + c;
         if (n >= p.N) break;
         uint32_t r[32];

@@ -38,6 +38,11 @@ __device__ __forceinline__ uint32_t sk_cluster_rank() {
 __device__ __forceinline__ void sk_cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// "every CTA of the cluster has started" barrier, split so that it costs nothing: arrive at kernel entry, wait right
+// before the first distributed-shared-memory store (compute-sanitizer racecheck: a peer's shared memory must not be
+// written before that CTA is known to have entered the kernel).
+__device__ __forceinline__ void sk_cluster_arrive_entered() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+__device__ __forceinline__ void sk_cluster_wait_entered() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
 // store 4 floats into the shared memory of cluster CTA `rank` at the address that `local` has here
 __device__ __forceinline__ void sk_st_remote_v4(void* local, uint32_t rank, float a, float b, float c, float d) {
   uint32_t laddr = static_cast<uint32_t>(__cvta_generic_to_shared(local)), raddr;
@@ -55,6 +60,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32)
                   bf16* __restrict__ out, long long ldo, int M, int N, int K, int act, int ksplit) {
   // programmatic dependent launch: let the NEXT kernel of the decode chain start its own prologue now
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (ksplit > 1) sk_cluster_arrive_entered();
   extern __shared__ __align__(16) uint8_t sk_smem[];
   bf16* sx = reinterpret_cast<bf16*>(sk_smem);                                // [32][SK_KC + SK_PAD]
   float* part = reinterpret_cast<float*>(sk_smem + SK_X_BYTES);               // [ksplit][2][32][8], written by peers
@@ -148,6 +154,7 @@ __global__ void __launch_bounds__(SK_WARPS * 32)
 #pragma unroll
     for (int j = 0; j < 4; ++j) red[(((ks * 2 + cg) * 32) + lane) * 8 + t * 4 + j] = acc[t][j];
   __syncthreads();
+  if (ksplit > 1) sk_cluster_wait_entered();               // all peers are running: their shared memory may be written
   if (ks == 0) {
 #pragma unroll
     for (int t = 0; t < 2; ++t)

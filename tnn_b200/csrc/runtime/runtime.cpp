@@ -1,6 +1,9 @@
 // pybind11 surface of the C++ host runtime: archiver (wire/checkpoint format), offset
 // allocators, native data path, tokenizer, profiler event store.
-#include "runtime.hpp"
+#include <pybind11/pybind11.h>
+namespace tnn {
+void runtime_bind(pybind11::module_& m);
+}
 
 #include <pybind11/numpy.h>
 #include <pybind11/stl.h>

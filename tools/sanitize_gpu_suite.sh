@@ -12,5 +12,7 @@ for tool in memcheck racecheck synccheck; do
   timeout 900 $S --tool $tool python -m pytest tests/test_mxfp8_gpu.py -x -q -k "(quantize and 128-128) or (gemm and (128-128-128 or 256-192-256)) or (layernorm and 256)" > gpurun_out/san_${tool}_mxfp8.log 2>&1; grep -vE "^$|warnings summary|Warning|warn|Host Frame" gpurun_out/san_${tool}_mxfp8.log | head -60 >> gpurun_out/sanitizer_${tool}.txt
   echo "=== $tool: cpp/bin/tnn_tests gpu_parity_dense_conv (C++ host)" >> gpurun_out/sanitizer_${tool}.txt
   timeout 900 $S --tool $tool cpp/bin/tnn_tests gpu_parity_dense_conv 2>&1 | grep -v "Host Frame" | head -60 >> gpurun_out/sanitizer_${tool}.txt
+  echo "=== $tool: cpp/bin/tnn_tests gpu_gpt2 (C++ GPT2Engine: bf16 / MXFP8 prefill, graph decode, persistent decode kernel)" >> gpurun_out/sanitizer_${tool}.txt
+  timeout 900 $S --tool $tool cpp/bin/tnn_tests gpu_gpt2 2>&1 | grep -v "Host Frame" | head -60 >> gpurun_out/sanitizer_${tool}.txt
 done
 tail -4 gpurun_out/sanitizer_*.txt
