@@ -48,14 +48,15 @@ def test_quantize_matches_mx_rule_and_layout(rows, K, dtype):
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 128), (256, 192, 256), (300, 768, 768), (1000, 2304, 768), (513, 3072, 768),
                                    (384, 768, 3072), (64, 50257, 768), (129, 100, 384)])
-@pytest.mark.parametrize("block_n", [None, 128])
-def test_gemm_mxfp8_equals_fp32_matmul_of_dequantised_operands(M, N, K, block_n, monkeypatch):
+@pytest.mark.parametrize("block_n,pair", [(None, 0), (128, 0), (None, 1), (128, 1)])
+def test_gemm_mxfp8_equals_fp32_matmul_of_dequantised_operands(M, N, K, block_n, pair, monkeypatch):
     """The tensor-core result must equal (A_dq @ B_dq^T) computed in fp32 from the SAME quantised operands:
     any slip in the scale layout, the scale-id bytes or the tile / scale-block offsets shows up as O(1) errors."""
     from tnn_b200.ops import mxfp8
     dev = _dev()
     if block_n is not None:
         monkeypatch.setenv("TNN_FP8_BLOCK_N", str(block_n))
+    monkeypatch.setenv("TNN_FP8_PAIR", str(pair))      # 1: two-CTA clusters multicasting the shared B tile (odd tile counts included)
     g = torch.Generator(device="cpu").manual_seed(M + 3 * N + 5 * K)
     a = (torch.randn(M, K, generator=g) * torch.exp(torch.randn(M, K // 32, generator=g).repeat_interleave(32, 1))).bfloat16().to(dev)
     b = (torch.randn(N, K, generator=g) * torch.exp(torch.randn(N, K // 32, generator=g).repeat_interleave(32, 1) * 0.5)).to(dev)
