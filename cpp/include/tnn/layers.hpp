@@ -51,6 +51,12 @@ class Conv2DLayer : public Layer {
   static std::unique_ptr<Layer> create_from_config(const TConfig& c);
   size_t in_channels() const { return C_; }
   size_t out_channels() const { return K_; }
+  // the flipped dgrad weights, for the trainer's batched refresh (one launch for every convolution after the optimizer
+  // step instead of one launch per layer inside backward): null until the first backward allocated them
+  Tensor& flipped_weights() { return wt_; }
+  void mark_flipped_fresh() { wt_version_ = param_version_; }
+  size_t kernel_h() const { return R_; }
+  size_t kernel_w() const { return S_; }
 
  protected:
   void fill_config(TConfig& c) const override;

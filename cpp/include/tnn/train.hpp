@@ -54,6 +54,10 @@ class TrainStep {
 
  private:
   Tensor eager(const Tensor& x, const Tensor& y, size_t mb_id);
+  void refresh_conv_flips();               // every Conv2D's flipped dgrad weights in one kernel launch
+  Tensor flip_descs_;
+  size_t flip_count_ = 0;
+  int flip_blocks_ = 0;
   Tensor core(const Tensor& x, const Tensor& y, size_t mb_id);
   void capture(const Tensor& x, const Tensor& y);
   Graph& g_;

@@ -429,6 +429,40 @@ Tensor TrainStep::core(const Tensor& x, const Tensor& y, size_t mb) {
   exec_.backward(grad, mb);
   return stats;
 }
+void TrainStep::refresh_conv_flips() {
+  const Device& dev = g_.device();
+  if (!dev.is_gpu()) return;
+  Vec<Conv2DLayer*> convs;
+  for (Layer* top : g_.get_layers())
+    for (Layer* l : top->all_layers())
+      if (auto* c = dynamic_cast<Conv2DLayer*>(l))
+        if (c->flipped_weights()) convs.push_back(c);
+  if (convs.empty()) return;
+  if (convs.size() != flip_count_) {                       // (re)build the device descriptor table: pointers are stable
+    std::vector<ConvFlipDesc> host(convs.size());
+    int blocks = 0;
+    for (size_t i = 0; i < convs.size(); ++i) {
+      Conv2DLayer* c = convs[i];
+      ConvFlipDesc& d = host[i];
+      d.w = c->param("weight")->data_as<float>();
+      d.wt = c->flipped_weights()->data();
+      d.K = (int)c->out_channels();
+      d.R = (int)c->kernel_h();
+      d.S = (int)c->kernel_w();
+      d.C = (int)c->in_channels();
+      d.block_begin = blocks;
+      d.pad_ = 0;
+      blocks += ((d.C + 31) / 32) * ((d.K + 31) / 32) * d.R * d.S;
+    }
+    flip_descs_ = make_tensor(DType_t::UINT8_T, {host.size() * sizeof(ConvFlipDesc)}, dev);
+    flip_descs_->copy_from_host(host.data(), host.size() * sizeof(ConvFlipDesc));
+    flip_count_ = convs.size();
+    flip_blocks_ = blocks;
+  }
+  conv_weight_flip_batch(static_cast<const ConvFlipDesc*>(flip_descs_->data()), (int)flip_count_, flip_blocks_, current_flow(dev).stream());
+  for (Conv2DLayer* c : convs) c->mark_flipped_fresh();
+}
+
 Tensor TrainStep::eager(const Tensor& x, const Tensor& y, size_t mb) {
   const Device& dev = g_.device();
   Tensor dx = x->device() == dev ? x : x->to_device(dev, &exec_.workspace());
@@ -439,6 +473,7 @@ Tensor TrainStep::eager(const Tensor& x, const Tensor& y, size_t mb) {
   Tensor stats = core(dx, dy, mb);
   if (do_update) {
     opt_.update(/*external_state=*/dev.is_gpu());
+    refresh_conv_flips();
     if (sched_) sched_->step();
   }
   // the stats tensor must outlive the workspace reuse of the next step: hand back a pool-owned copy
@@ -459,6 +494,7 @@ void TrainStep::capture(const Tensor& x, const Tensor& y) {
   try {
     Tensor stats = core(sx_, sy_, 0);
     opt_.update(/*external_state=*/true);
+    refresh_conv_flips();                    // the two eager warm-up steps allocated every flipped copy: table is final here
     TNN_CUDA(cudaMemcpyAsync(sstats_->data(), stats->data(), 8, cudaMemcpyDeviceToDevice, flow.stream()));
   } catch (...) {
     cudaGraph_t dead = nullptr;

@@ -512,6 +512,45 @@ __global__ void __launch_bounds__(256)
     if (c < C && k < K) wt[(long long)c * rsk + tap_out + k] = __float2bfloat16(tile[tx][ty + i]);
   }
 }
+// Every convolution's flipped dgrad weights in ONE launch (the per-layer launches were 15 x ~6 us of latency-bound
+// kernels on the backward critical path of the WRN step): block -> (conv, c tile, k tile, tap) through the descriptors'
+// running block offsets.
+__global__ void __launch_bounds__(256) k_conv_weight_flip_batch(const ConvFlipDesc* __restrict__ descs, int n) {
+  __shared__ float tile[32][33];
+  int d = 0;
+  while (d + 1 < n && (int)blockIdx.x >= descs[d + 1].block_begin) ++d;
+  const ConvFlipDesc D = descs[d];
+  int b = blockIdx.x - D.block_begin;
+  const int ctiles = (D.C + 31) / 32, ktiles = (D.K + 31) / 32;
+  const int bx = b % ctiles;
+  b /= ctiles;
+  const int by = b % ktiles;
+  const int rs = b / ktiles;
+  const int R = D.R, S = D.S, K = D.K, C = D.C;
+  const int r = rs / S, ss = rs - r * S;
+  const int c0 = bx * 32, k0 = by * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long rsc = (long long)R * S * C, rsk = (long long)R * S * K;
+  bf16* wt = reinterpret_cast<bf16*>(D.wt);
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int k = k0 + ty + i, c = c0 + tx;
+    tile[ty + i][tx] = (k < K && c < C) ? D.w[(long long)k * rsc + (long long)rs * C + c] : 0.f;
+  }
+  __syncthreads();
+  const long long tap_out = ((long long)(R - 1 - r) * S + (S - 1 - ss)) * K;
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int c = c0 + ty + i, k = k0 + tx;
+    if (c < C && k < K) wt[(long long)c * rsk + tap_out + k] = __float2bfloat16(tile[tx][ty + i]);
+  }
+}
+void conv_weight_flip_batch(const ConvFlipDesc* descs_dev, int n, int total_blocks, cudaStream_t s) {
+  if (n <= 0 || total_blocks <= 0) return;
+  k_conv_weight_flip_batch<<<total_blocks, 256, 0, s>>>(descs_dev, n);
+  TNN_CHECK_LAUNCH();
+}
+
 void conv_weight_prep(const float* w, void* w_bf16, void* wt_bf16, int K, int R, int S, int C,
                       cudaStream_t s) {
   if (w_bf16 == nullptr && wt_bf16 != nullptr) {

@@ -106,6 +106,31 @@ __global__ void __launch_bounds__(256)
     int oh = (int)(t % p.OH);
     int n = (int)(t / p.OH);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (p.ph == 0 && p.pw == 0 && oh * p.sh + p.kh <= p.H && ow * p.sw + p.kw <= p.W && p.kw == p.W) {
+      // full-width windows without padding (global average pooling): one contiguous run of kh * W pixels, 8 loads in
+      // flight instead of a serial bounds-checked walk (WRN 8x8x512 head: 25.6 us -> a few us)
+      const uint4* src = reinterpret_cast<const uint4*>(x) + (((long long)n * p.H + (long long)oh * p.sh) * p.W) * p.C8 + c;
+      const int cnt = p.kh * p.W;
+      int q = 0;
+      for (; q + 8 <= cnt; q += 8) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = src[(long long)(q + u) * p.C8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          float f[8];
+          bf8_unpack(v[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+      }
+      for (; q < cnt; ++q) {
+        float f[8];
+        bf8_unpack(src[(long long)q * p.C8], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    } else
     for (int a = 0; a < p.kh; ++a) {
       int h = oh * p.sh - p.ph + a;
       if (h < 0 || h >= p.H) continue;
@@ -136,6 +161,12 @@ __global__ void __launch_bounds__(256)
     int h = (int)(t % p.H);
     int n = (int)(t / p.H);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (p.ph == 0 && p.pw == 0 && p.sh >= p.kh && p.sw >= p.kw) {
+      // non-overlapping windows (incl. global pooling): a pixel belongs to at most ONE window -- no 2-D search
+      const int oh = h / p.sh, ow = w / p.sw;
+      if (oh < p.OH && ow < p.OW && h - oh * p.sh < p.kh && w - ow * p.sw < p.kw)
+        bf8_unpack(reinterpret_cast<const uint4*>(dy)[(((long long)n * p.OH + oh) * p.OW + ow) * p.C8 + c], acc);
+    } else
     for (int a = 0; a < p.kh; ++a) {
       int hh = h + p.ph - a;
       if (hh < 0 || hh % p.sh) continue;

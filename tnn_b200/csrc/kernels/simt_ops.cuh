@@ -39,6 +39,15 @@ void phase_merge(const void* xp, void* x, int N, int H, int W, int C, cudaStream
 void nchw_to_nhwc(const void* x, void* y, int N, int C, int H, int W, int is_f32, cudaStream_t s);
 void nhwc_to_nchw(const void* x, void* y, int N, int C, int H, int W, int is_f32, cudaStream_t s);
 // conv weights: fp32 [K,R,S,C] -> bf16 [K,R,S,C] and bf16 [C,R,S,K] with (r,s) flipped (dgrad)
+// batched dgrad-weight flip: one descriptor per convolution, block_begin = running sum of ceil(C/32)*ceil(K/32)*R*S
+struct ConvFlipDesc {
+  const float* w;      // fp32 [K, R, S, C]
+  void* wt;            // bf16 [C, R, S, K], taps flipped
+  int K, R, S, C;
+  int block_begin;
+  int pad_;
+};
+void conv_weight_flip_batch(const ConvFlipDesc* descs_dev, int n, int total_blocks, cudaStream_t s);
 void conv_weight_prep(const float* w, void* w_bf16, void* wt_bf16, int K, int R, int S, int C,
                       cudaStream_t s);
 void philox_uniform_f32(float* x, long long n, float lo, float hi, uint64_t seed, cudaStream_t s);
