@@ -5,10 +5,13 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <fstream>
 #include <mutex>
 #include <string>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost one predictable branch unless a tool is attached
 
 #include "runtime/archiver.hpp"
 
@@ -102,6 +105,29 @@ class Profiler {
   int64_t start_ns_ = 0;
   std::vector<Event_t> events_;
   mutable std::mutex mu_;
+};
+
+// NVTX range per layer / training phase (SURVEY 5.1 target: the ranges show up in Nsight Systems / ncu --nvtx).
+// Off by default; TNN_NVTX=1 turns them on (read once).
+struct NvtxRange {
+  static bool enabled() {
+    static const bool on = [] { const char* e = getenv("TNN_NVTX"); return e && atoi(e) != 0; }();
+    return on;
+  }
+  explicit NvtxRange(const std::string& name) : active_(enabled()) {
+    if (active_) nvtxRangePushA(name.c_str());
+  }
+  NvtxRange(const std::string& prefix, const std::string& name) : active_(enabled()) {
+    if (active_) nvtxRangePushA((prefix + name).c_str());
+  }
+  ~NvtxRange() {
+    if (active_) nvtxRangePop();
+  }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+
+ private:
+  bool active_;
 };
 
 class GlobalProfiler {

@@ -8,6 +8,7 @@
 
 #include "kernels/simt_ops.cuh"
 #include "kernels/umma_gemm.cuh"
+#include "tnn/profiler.hpp"
 #include "runtime/cpu_math.hpp"
 #include "tnn/layers.hpp"
 #include "tnn/stepstate.hpp"
@@ -382,9 +383,7 @@ Tensor Conv2DLayer::forward_impl(const Tensor& xin, size_t mb, const FwdAux& aux
     const size_t ld = round8(rsc);
     Tensor col = new_tensor(DType_t::BF16, {M, ld});
     if (ld != rsc) TNN_CUDA(cudaMemsetAsync(col->data(), 0, col->nbytes(), s));
-    // anisotropic geometry: im2col takes one stride / pad; emulate by ... (isotropic only in the kernel)
-    if (sh_ != sw_ || ph_ != pw_) throw std::runtime_error(name_ + ": anisotropic stride / padding is only implemented on the CPU path");
-    im2col_nhwc(x->data(), col->data(), (long long)ld, p.N, p.H, p.W, p.C, p.R, p.S, p.stride, p.pad, p.OH, p.OW, s);
+    im2col_nhwc2(x->data(), col->data(), (long long)ld, p.N, p.H, p.W, p.C, p.R, p.S, (int)sh_, (int)sw_, (int)ph_, (int)pw_, p.OH, p.OW, s);
     Tensor wm = lp("weight");
     Tensor wpad;
     const void* wptr = wm->data();
@@ -522,7 +521,7 @@ Tensor Conv2DLayer::backward_impl(const Tensor& dyin, size_t mb, BwdAux& aux) {
       e.out_mode = OUT_BF16;
       e.ldc = (long long)ld;
       gemm_bf16(dy->data(), wptr, (int)M, (int)ld, (int)K_, (long long)K_, (long long)ld, false, true, e, 1, s);
-      col2im_nhwc(dcol->data(), (long long)ld, dx->data(), p.N, p.H, p.W, p.C, p.R, p.S, p.stride, p.pad, p.OH, p.OW, s);
+      col2im_nhwc2(dcol->data(), (long long)ld, dx->data(), p.N, p.H, p.W, p.C, p.R, p.S, (int)sh_, (int)sw_, (int)ph_, (int)pw_, p.OH, p.OW, s);
       if (aux.extra) add_bf16(dx->data(), aux.extra->data(), dx->data(), (long long)dx->size(), 0, s);
     }
   }
@@ -1030,6 +1029,7 @@ Tensor Sequential::forward_impl(const Tensor& xin, size_t mb, const FwdAux& aux)
   const size_t n = layers_.size();
   for (size_t i = 0; i < n; ++i) {
     const bool last = i + 1 == n;
+    NvtxRange range("fwd:", layers_[i]->name());
     if (last && (aux.residual || aux.act) && layers_[i]->fuses_fwd_residual()) x = layers_[i]->forward_impl(x, mb, aux);
     else x = layers_[i]->forward(x, mb);
     if (del) del->flip();            // consecutive layer outputs come from opposite ends of the workspace (sequential.cpp:33-44)
@@ -1048,6 +1048,7 @@ Tensor Sequential::backward_impl(const Tensor& dyin, size_t mb, BwdAux& aux) {
       if (backward_hook) backward_hook(k);
       continue;
     }
+    NvtxRange range("bwd:", layer->name());
     BwdAux a;
     a.colsum_in = colsum;
     a.need_dx = k > 0 || aux.need_dx;

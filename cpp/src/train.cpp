@@ -11,6 +11,7 @@
 
 #include "kernels/simt_ops.cuh"
 #include "tnn/example_models.hpp"
+#include "tnn/profiler.hpp"
 #include "tnn/stepstate.hpp"
 #include "tnn/train.hpp"
 
@@ -421,11 +422,19 @@ TrainStep::~TrainStep() {
   if (graph_) cudaGraphDestroy(graph_);
 }
 Tensor TrainStep::core(const Tensor& x, const Tensor& y, size_t mb) {
-  Tensor out = exec_.forward(x, mb);
+  Tensor out;
+  {
+    NvtxRange r("step:forward");
+    out = exec_.forward(x, mb);
+  }
   Tensor stats = make_tensor(exec_.workspace(), DType_t::FP32, {2});
   stats->zero();
   Tensor grad = make_tensor(exec_.workspace(), out->data_type(), out->shape());
-  crit_.loss_and_grad(out, y, stats, &grad, 1.f);
+  {
+    NvtxRange r("step:loss");
+    crit_.loss_and_grad(out, y, stats, &grad, 1.f);
+  }
+  NvtxRange r("step:backward");
   exec_.backward(grad, mb);
   return stats;
 }

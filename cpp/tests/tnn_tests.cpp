@@ -829,6 +829,7 @@ TEST(gpu_parity_dense_conv) {
   parity([]() -> std::unique_ptr<Layer> { return std::make_unique<Conv2DLayer>(32, 64, 1, 1, 2, 2, 0, 0, false); }, {4, 16, 16, 32}, 2e-2);
   parity([]() -> std::unique_ptr<Layer> { return std::make_unique<Conv2DLayer>(3, 16, 3, 3, 1, 1, 1, 1); }, {8, 32, 32, 3}, 2e-2);      // direct first-layer kernel
   parity([]() -> std::unique_ptr<Layer> { return std::make_unique<Conv2DLayer>(8, 16, 5, 5, 1, 1, 0, 0, false); }, {2, 12, 12, 8}, 2e-2);   // im2col path
+  parity([]() -> std::unique_ptr<Layer> { return std::make_unique<Conv2DLayer>(8, 16, 3, 2, 2, 1, 1, 0); }, {2, 13, 10, 8}, 2e-2);         // anisotropic stride / padding
 }
 TEST(gpu_parity_norms_pools_acts) {
   parity([]() -> std::unique_ptr<Layer> { return std::make_unique<BatchNormLayer>(32, 1e-5, 0.1, true, true); }, {8, 8, 8, 32}, 3e-2);

@@ -381,13 +381,18 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                            d[8], d[9], d[10], cur_stream());
   });
   m.def("im2col_nhwc", [](const Tensor& x, const Tensor& col, int64_t ldcol, std::vector<int> d) {
-    TORCH_CHECK(d.size() == 10, "dims = {N,H,W,C,R,S,stride,pad,OH,OW}");
-    tnn::im2col_nhwc(vp(x), vp(col), ldcol, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9],
-                     cur_stream());
+    TORCH_CHECK(d.size() == 10 || d.size() == 12, "dims = {N,H,W,C,R,S,stride,pad,OH,OW} or {N,H,W,C,R,S,sh,sw,ph,pw,OH,OW}");
+    if (d.size() == 12)
+      tnn::im2col_nhwc2(vp(x), vp(col), ldcol, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9], d[10], d[11], cur_stream());
+    else
+      tnn::im2col_nhwc(vp(x), vp(col), ldcol, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9], cur_stream());
   });
   m.def("col2im_nhwc", [](const Tensor& col, int64_t ldcol, const Tensor& dx, std::vector<int> d) {
-    tnn::col2im_nhwc(vp(col), ldcol, vp(dx), d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9],
-                     cur_stream());
+    TORCH_CHECK(d.size() == 10 || d.size() == 12, "dims = {N,H,W,C,R,S,stride,pad,OH,OW} or {N,H,W,C,R,S,sh,sw,ph,pw,OH,OW}");
+    if (d.size() == 12)
+      tnn::col2im_nhwc2(vp(col), ldcol, vp(dx), d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9], d[10], d[11], cur_stream());
+    else
+      tnn::col2im_nhwc(vp(col), ldcol, vp(dx), d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9], cur_stream());
   });
 
   // ------------------------------------------------------------------ embedding

@@ -10,6 +10,7 @@ namespace tnn {
 
 struct DConvP {
   int N, H, W, C, K, R, S, stride, pad, OH, OW;
+  int stride_w, pad_w1;      // im2col / col2im only: width stride (0 = same as `stride`) and width pad + 1 (0 = same as `pad`)
 };
 
 // thread = (output pixel, group of 8 output channels)
@@ -335,7 +336,8 @@ __global__ void __launch_bounds__(256)
     int oh = (int)(t % p.OH);
     int n = (int)(t / p.OH);
     int c = j % p.C, rs = j / p.C, s = rs % p.S, r = rs / p.S;
-    int h = oh * p.stride - p.pad + r, w = ow * p.stride - p.pad + s;
+    const int sw_ = p.stride_w ? p.stride_w : p.stride, pw_ = p.pad_w1 ? p.pad_w1 - 1 : p.pad;
+    int h = oh * p.stride - p.pad + r, w = ow * sw_ - pw_ + s;
     bf16 v = __float2bfloat16(0.f);
     if (h >= 0 && h < p.H && w >= 0 && w < p.W) v = x[(((long long)n * p.H + h) * p.W + w) * p.C + c];
     col[pix * ldcol + j] = v;
@@ -343,7 +345,11 @@ __global__ void __launch_bounds__(256)
 }
 void im2col_nhwc(const void* x, void* col, long long ldcol, int N, int H, int W, int C, int R, int S,
                  int stride, int pad, int OH, int OW, cudaStream_t s) {
-  DConvP p{N, H, W, C, 0, R, S, stride, pad, OH, OW};
+  im2col_nhwc2(x, col, ldcol, N, H, W, C, R, S, stride, stride, pad, pad, OH, OW, s);
+}
+void im2col_nhwc2(const void* x, void* col, long long ldcol, int N, int H, int W, int C, int R, int S, int sh, int sw,
+                  int ph, int pw, int OH, int OW, cudaStream_t s) {
+  DConvP p{N, H, W, C, 0, R, S, sh, ph, OH, OW, sw, pw + 1};
   long long total = (long long)N * OH * OW * R * S * C;
   k_im2col<<<grid_for(total, 256), 256, 0, s>>>((const bf16*)x, (bf16*)col, ldcol, p);
   TNN_CHECK_LAUNCH();
@@ -361,15 +367,16 @@ __global__ void __launch_bounds__(256)
     int h = (int)(t % p.H);
     int n = (int)(t / p.H);
     float acc = 0.f;
+    const int sw_ = p.stride_w ? p.stride_w : p.stride, pw_ = p.pad_w1 ? p.pad_w1 - 1 : p.pad;
     for (int r = 0; r < p.R; ++r) {
       int hh = h + p.pad - r;
       if (hh < 0 || hh % p.stride) continue;
       int oh = hh / p.stride;
       if (oh >= p.OH) continue;
       for (int s = 0; s < p.S; ++s) {
-        int ww = w + p.pad - s;
-        if (ww < 0 || ww % p.stride) continue;
-        int ow = ww / p.stride;
+        int ww = w + pw_ - s;
+        if (ww < 0 || ww % sw_) continue;
+        int ow = ww / sw_;
         if (ow >= p.OW) continue;
         long long pix = ((long long)n * p.OH + oh) * p.OW + ow;
         acc += __bfloat162float(col[pix * ldcol + (r * p.S + s) * p.C + c]);
@@ -380,7 +387,11 @@ __global__ void __launch_bounds__(256)
 }
 void col2im_nhwc(const void* col, long long ldcol, void* dx, int N, int H, int W, int C, int R, int S,
                  int stride, int pad, int OH, int OW, cudaStream_t s) {
-  DConvP p{N, H, W, C, 0, R, S, stride, pad, OH, OW};
+  col2im_nhwc2(col, ldcol, dx, N, H, W, C, R, S, stride, stride, pad, pad, OH, OW, s);
+}
+void col2im_nhwc2(const void* col, long long ldcol, void* dx, int N, int H, int W, int C, int R, int S, int sh, int sw,
+                  int ph, int pw, int OH, int OW, cudaStream_t s) {
+  DConvP p{N, H, W, C, 0, R, S, sh, ph, OH, OW, sw, pw + 1};
   long long total = (long long)N * H * W * C;
   k_col2im<<<grid_for(total, 256), 256, 0, s>>>((const bf16*)col, ldcol, (bf16*)dx, p);
   TNN_CHECK_LAUNCH();

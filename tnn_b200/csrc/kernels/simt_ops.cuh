@@ -201,6 +201,11 @@ void im2col_nhwc(const void* x, void* col, long long ldcol, int N, int H, int W,
                  int stride, int pad, int OH, int OW, cudaStream_t s);
 void col2im_nhwc(const void* col, long long ldcol, void* dx, int N, int H, int W, int C, int R, int S,
                  int stride, int pad, int OH, int OW, cudaStream_t s);
+// anisotropic stride / padding (height, width)
+void im2col_nhwc2(const void* x, void* col, long long ldcol, int N, int H, int W, int C, int R, int S, int sh, int sw,
+                  int ph, int pw, int OH, int OW, cudaStream_t s);
+void col2im_nhwc2(const void* col, long long ldcol, void* dx, int N, int H, int W, int C, int R, int S, int sh, int sw,
+                  int ph, int pw, int OH, int OW, cudaStream_t s);
 
 // ---- embedding & friends (embed.cu) ---------------------------------------------------
 void embedding_fwd(const int* ids, const float* table, const float* pos_table, void* y, long long T,

@@ -7,6 +7,8 @@ BN-backward+shortcut-gradient-add run as single kernels; Q/K/V are one fused GEM
 """
 from __future__ import annotations
 
+import os
+
 import math
 
 import torch
@@ -19,6 +21,9 @@ from .layer import Layer, LayerFactory, ParamDescriptor, register
 from .layers import (ActivationLayer, BatchNormLayer, Conv2DLayer, DenseLayer, DropoutLayer, LayerNormLayer, _aligned_rows,
                      _normal_init, _uniform_init, to_bf16)
 
+
+# TNN_NVTX=1: one NVTX range per layer forward / backward (shows up in Nsight Systems and `ncu --nvtx`)
+_NVTX = os.environ.get("TNN_NVTX", "0") not in ("", "0")
 
 class Block(Layer):
     """A layer that owns child layers and forwards every setter to them (block.hpp:6-71)."""
@@ -96,6 +101,16 @@ class Sequential(Block):
     def forward_impl(self, x, mb_id, last_residual=None, last_act=None):
         n = len(self.layers)
         for i, layer in enumerate(self.layers):
+            if _NVTX and x.is_cuda:
+                with torch.cuda.nvtx.range("fwd:" + layer.name):
+                    x = self._forward_one(i, n, layer, x, mb_id, last_residual, last_act)
+                continue
+            x = self._forward_one(i, n, layer, x, mb_id, last_residual, last_act)
+        return x
+
+    @staticmethod
+    def _forward_one(i, n, layer, x, mb_id, last_residual, last_act):
+        if True:
             if i == n - 1 and (last_residual is not None or last_act is not None):
                 x = layer.forward_impl(layer._migrate(x), mb_id, residual=last_residual, act=last_act) \
                     if isinstance(layer, Conv2DLayer) else layer.forward_impl(layer._migrate(x), mb_id, residual=last_residual)
@@ -123,7 +138,11 @@ class Sequential(Block):
                     if hook is not None:
                         hook(i)
                     continue
-            dy = layer.backward(dy, mb_id)
+            if _NVTX and dy.is_cuda:
+                with torch.cuda.nvtx.range("bwd:" + layer.name):
+                    dy = layer.backward(dy, mb_id)
+            else:
+                dy = layer.backward(dy, mb_id)
             if hook is not None:
                 hook(i)
         if first_extra is not None and dy is not None:

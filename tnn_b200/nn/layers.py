@@ -98,14 +98,13 @@ class DenseLayer(Layer):
         if x2.is_cuda:
             x2 = _aligned_rows(to_bf16(x2))
             M = x2.shape[0]
-            buf = torch.empty((M, _round8(N)), dtype=torch.bfloat16, device=x.device)
-            y = buf[:, :N]
             res2 = residual.reshape(-1, N) if residual is not None else None
-            if res2 is not None and (res2.stride(0) != y.stride(0)):
-                res2 = None  # strides differ: add below
+            # the epilogue reads the residual with the OUTPUT's row stride: rows are padded to 8 elements unless a
+            # residual with a different stride has to be fused (N % 8 != 0: element-wise epilogue of the same kernel)
+            ld = _round8(N) if (res2 is None or res2.stride(0) == _round8(N)) else res2.stride(0)
+            buf = torch.empty((M, ld), dtype=torch.bfloat16, device=x.device)
+            y = buf[:, :N]
             gemm_ops.linear_fwd(x2, self.lp("weight"), bias, self.activation, res2, out=y)
-            if residual is not None and res2 is None:
-                y = y + residual.reshape(-1, N)
         else:
             y = gemm_ops.linear_fwd(x2.float(), self.params["weight"], bias, self.activation, residual.reshape(-1, N) if residual is not None else None)
         if self.training:
@@ -163,10 +162,8 @@ class Conv2DLayer(Layer):
         self.kernel_h, self.kernel_w = int(kernel_h), int(kernel_w)
         self.stride_h, self.stride_w, self.pad_h, self.pad_w = int(stride_h), int(stride_w), int(pad_h), int(pad_w)
         self.use_bias = bool(use_bias)
-        if self.stride_h != self.stride_w or self.pad_h != self.pad_w:
-            self._generic = True
-        else:
-            self._generic = False
+        # anisotropic stride / padding: im2col path only (no TMA-window plan, no BatchNorm-backward fusion into the dgrad)
+        self._generic = self.stride_h != self.stride_w or self.pad_h != self.pad_w
         self._plans = {}
         self._state = conv_ops.ConvState()
         # BatchNorm statistics fusion: a consumer BatchNorm that finds this layer as the producer of
@@ -188,25 +185,16 @@ class Conv2DLayer(Layer):
         p = self._plans.get(key)
         if p is None:
             N, H, W, C = x.shape
-            if self._generic:
-                p = conv_ops.ConvPlan(N, H, W, C, self.out_channels, self.kernel_h, self.kernel_w, self.stride_h, self.pad_h)
-                p.path = "generic"
-            else:
-                p = conv_ops.make_plan(N, H, W, C, self.out_channels, self.kernel_h, self.kernel_w, self.stride_h,
-                                       self.pad_h, x.device)
+            # anisotropic stride / padding run through the im2col + tcgen05 GEMM path of the same kernels (no library call)
+            p = conv_ops.make_plan(N, H, W, C, self.out_channels, self.kernel_h, self.kernel_w, self.stride_h,
+                                   self.pad_h, x.device, stride_w=self.stride_w, pad_w=self.pad_w)
             self._plans[key] = p
         return p
 
     def forward_impl(self, x, mb_id, residual=None, act=None):
         plan = self._plan(x)
         c = self.cache(mb_id) if self.training else {}
-        if plan.path == "generic":   # anisotropic stride/pad: torch reference math (rare)
-            y = F.conv2d(x.permute(0, 3, 1, 2).float(), self.params["weight"].permute(0, 3, 1, 2),
-                         self.params.get("bias"), (self.stride_h, self.stride_w), (self.pad_h, self.pad_w))
-            y = y.permute(0, 2, 3, 1).contiguous().to(x.dtype)
-            if residual is not None:
-                y = y + residual
-        elif x.is_cuda:
+        if x.is_cuda:
             x = to_bf16(x).contiguous()
             ws = None
             if self.training and self._stats_requested and plan.path == "tma":
@@ -231,16 +219,6 @@ class Conv2DLayer(Layer):
         c = self.cache(mb_id)
         x, plan = c["x"], c["plan"]
         w = self.params["weight"]
-        if plan.path == "generic":
-            xx = x.permute(0, 3, 1, 2).float().requires_grad_(True)
-            ww = w.permute(0, 3, 1, 2).clone().requires_grad_(True)
-            y = F.conv2d(xx, ww, None, (self.stride_h, self.stride_w), (self.pad_h, self.pad_w))
-            gx, gw = torch.autograd.grad(y, (xx, ww), dy.permute(0, 3, 1, 2).float())
-            self.grads["weight"].add_(gw.permute(0, 2, 3, 1))
-            if self.use_bias:
-                self.grads["bias"].add_(dy.float().sum((0, 1, 2)))
-            dx = gx.permute(0, 2, 3, 1).contiguous().to(dy.dtype)
-            return dx + residual if residual is not None else dx
         colsum = getattr(dy, "_tnn_colsum", None)
         if dy.is_cuda:
             dy = to_bf16(dy).contiguous()

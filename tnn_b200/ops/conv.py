@@ -41,6 +41,8 @@ class ConvPlan:
     OH: int = 0
     OW: int = 0
     path: str = "ref"
+    stride_w: int = 0        # anisotropic geometry: width stride / pad (0 / -1 = same as stride / pad)
+    pad_w: int = -1
     # fprop / wgrad description
     f_geom: list = field(default_factory=list)
     f_taps: list = field(default_factory=list)
@@ -62,13 +64,19 @@ def _fprop_taps(R, S, C, stride, pad, N):
     return taps
 
 
-def make_plan(N, H, W, C, K, R, S, stride, pad, device) -> ConvPlan:
+def make_plan(N, H, W, C, K, R, S, stride, pad, device, stride_w=None, pad_w=None) -> ConvPlan:
     p = ConvPlan(N, H, W, C, K, R, S, stride, pad)
-    p.OH, p.OW = out_size(H, R, stride, pad), out_size(W, S, stride, pad)
+    aniso = (stride_w is not None and stride_w != stride) or (pad_w is not None and pad_w != pad)
+    if aniso:
+        p.stride_w, p.pad_w = int(stride_w if stride_w is not None else stride), int(pad_w if pad_w is not None else pad)
+    p.OH, p.OW = out_size(H, R, stride, pad), out_size(W, S, _sw(p), _pw(p))
     if device.type != "cuda":
         p.path = "ref"
         return p
     Cx = native.require()
+    if aniso:                       # height / width stride or padding differ: the im2col + tcgen05 GEMM path of the same kernels
+        p.path = "im2col"
+        return p
     if C < 8 and K % 8 == 0 and K * R * S * C <= 2048:
         p.path = "direct"
         return p
@@ -122,6 +130,19 @@ def make_plan(N, H, W, C, K, R, S, stride, pad, device) -> ConvPlan:
     return p
 
 
+def _sw(plan):
+    return plan.stride_w or plan.stride
+
+
+def _pw(plan):
+    return plan.pad if plan.pad_w < 0 else plan.pad_w
+
+
+def _geo12(plan, N, OH, OW):
+    """{N,H,W,C,R,S,sh,sw,ph,pw,OH,OW} for the im2col / col2im kernels (height / width stride and padding)."""
+    return [N, plan.H, plan.W, plan.C, plan.R, plan.S, plan.stride, _sw(plan), plan.pad, _pw(plan), OH, OW]
+
+
 # ------------------------------------------------------------------------------- reference
 def conv2d_fwd_ref(x, w, bias, stride, pad):
     y = F.conv2d(x.permute(0, 3, 1, 2).float(), w.permute(0, 3, 1, 2).float(), bias.float() if bias is not None else None,
@@ -159,7 +180,7 @@ def conv2d_fwd(plan: ConvPlan, x, w, w_bf16, bias, residual=None, act=None, cach
     ``stats_ws`` (tma path only): fp32 workspace the epilogue accumulates per-channel sum / sum of
     squares of y into (BatchNorm statistics fusion, finalised by ``bn_finalize_stats``)."""
     if plan.path == "ref":
-        y = conv2d_fwd_ref(x, w, bias, plan.stride, plan.pad)
+        y = conv2d_fwd_ref(x, w, bias, (plan.stride, _sw(plan)), (plan.pad, _pw(plan)))
         if residual is not None:
             y = y + residual.float()
         if act == "relu":
@@ -190,7 +211,7 @@ def conv2d_fwd(plan: ConvPlan, x, w, w_bf16, bias, residual=None, act=None, cach
     col = torch.empty((N * OH * OW, ld), device=x.device, dtype=torch.bfloat16)
     if ld != rsc:
         col.zero_()
-    Cx.im2col_nhwc(x, col, ld, [N, plan.H, plan.W, plan.C, plan.R, plan.S, plan.stride, plan.pad, OH, OW])
+    Cx.im2col_nhwc(x, col, ld, _geo12(plan, N, OH, OW))
     wm = w_bf16.reshape(K, rsc)
     if ld != rsc:
         wp = torch.zeros((K, ld), device=x.device, dtype=torch.bfloat16)
@@ -209,7 +230,7 @@ def conv2d_dgrad(plan: ConvPlan, dy, w, state: ConvState, w_version: int = 0, re
     produced this convolution's input into the epilogue -- the result is then g = mask * dx / (1-p) and
     ``bn_bwd["ws"]`` receives per-channel (sum g, sum g * xhat); keys x, pack, relu, p, seed, state, ws."""
     if plan.path == "ref":
-        dx = conv2d_dgrad_ref(dy, w, (plan.N, plan.H, plan.W, plan.C), plan.stride, plan.pad)
+        dx = conv2d_dgrad_ref(dy, w, (plan.N, plan.H, plan.W, plan.C), (plan.stride, _sw(plan)), (plan.pad, _pw(plan)))
         if residual is not None:
             dx = dx + residual.float()
         return dx.to(dy.dtype)
@@ -250,7 +271,7 @@ def conv2d_dgrad(plan: ConvPlan, dy, w, state: ConvState, w_version: int = 0, re
     dcol = torch.empty((M, ld), device=dy.device, dtype=torch.bfloat16)
     Cx.gemm(dy.reshape(M, K), wm, M, ld, K, K, ld, False, True, dcol, ld, OUT_BF16, 0, 1.0, None, None, 1)
     dx = torch.empty((N, H, W, C), device=dy.device, dtype=torch.bfloat16)
-    Cx.col2im_nhwc(dcol, ld, dx, [N, H, W, C, plan.R, plan.S, plan.stride, plan.pad, plan.OH, plan.OW])
+    Cx.col2im_nhwc(dcol, ld, dx, _geo12(plan, N, plan.OH, plan.OW))
     if residual is not None:
         Cx.add_bf16(dx, residual, dx, False)
     return dx
@@ -259,7 +280,7 @@ def conv2d_dgrad(plan: ConvPlan, dy, w, state: ConvState, w_version: int = 0, re
 def conv2d_wgrad(plan: ConvPlan, dy, x, dw, db=None, cache: dict | None = None, alpha: float = 1.0):
     """dw[K,R,S,C] (fp32) += alpha * wgrad ; db[K] += alpha * sum(dy)."""
     if plan.path == "ref":
-        dw.add_(alpha * conv2d_wgrad_ref(dy, x, (plan.K, plan.R, plan.S, plan.C), plan.stride, plan.pad))
+        dw.add_(alpha * conv2d_wgrad_ref(dy, x, (plan.K, plan.R, plan.S, plan.C), (plan.stride, _sw(plan)), (plan.pad, _pw(plan))))
         if db is not None:
             db.add_(alpha * dy.float().sum((0, 1, 2)))
         return
@@ -286,7 +307,7 @@ def conv2d_wgrad(plan: ConvPlan, dy, x, dw, db=None, cache: dict | None = None, 
             col = torch.empty((M, ld), device=x.device, dtype=torch.bfloat16)
             if ld != rsc:
                 col.zero_()
-            Cx.im2col_nhwc(x, col, ld, [N, plan.H, plan.W, plan.C, plan.R, plan.S, plan.stride, plan.pad, OH, OW])
+            Cx.im2col_nhwc(x, col, ld, _geo12(plan, N, OH, OW))
         tiles = ((K + 127) // 128) * ((rsc + 127) // 128)
         splits = max(1, min((M + 63) // 64, (2 * 148 + tiles - 1) // tiles))
         # dW[K, rsc] += dy^T[K, M] @ col[M, rsc]; N dimension limited to the real rsc columns
