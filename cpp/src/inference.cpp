@@ -216,17 +216,29 @@ void GPT2Engine::layers_gpu(size_t B, size_t L, size_t pos, bool fp8) {
         layernorm_fwd(x, nullptr, y_->data(), nullptr, T, E, g1, b1, (float)b.ln1->epsilon(), nullptr, nullptr, s);
         mxfp8_quantize_bf16(y_->data(), E, T, E, q8_->data(), E, q8_sf_->data(), s);
       }
+      // Q -> qkv_ used as a dense [T, E] buffer; K / V -> straight into the caches at [pos, pos + L) (no cache-store pass)
       Fp8Epilogue e;
-      e.out = qkv_->data();
-      e.ldc = 3 * E;
       e.bias = qkv_b;
+      e.seg_cols = E;
+      e.seg_rows = (int)L;
+      e.seg_out[0] = qkv_->data();
+      e.seg_tok[0] = E;
+      e.seg_batch[0] = (long long)L * E;
+      e.seg_out[1] = static_cast<char*>(b.kc->data()) + pos * E_ * 2;
+      e.seg_out[2] = static_cast<char*>(b.vc->data()) + pos * E_ * 2;
+      e.seg_tok[1] = e.seg_tok[2] = tokE;
+      e.seg_batch[1] = e.seg_batch[2] = batE;
       gemm_mxfp8(q8_->data(), E, q8_sf_->data(), b.qkv_q->data(), E, b.qkv_sf->data(), T, 3 * E, E, e, s);
     } else {
       layernorm_fwd(x, nullptr, y_->data(), nullptr, T, E, g1, b1, (float)b.ln1->epsilon(), nullptr, nullptr, s);
       gemm_gpu(y_->data(), E, b.attn->lp("qkv_weight")->data(), T, 3 * E, E, qkv_b, nullptr, qkv_->data(), 3 * E, ACT_NONE, s);
     }
     const char* base = static_cast<const char*>(qkv_->data());
-    if (L == 1) {
+    if (fp8) {
+      // (fp8 prefill has L > 1) queries from the dense Q buffer, keys / values of [0, pos + L) from the cache
+      attention_fwd_bf16(base, tokE, (long long)L * E, b.kc->data(), tokE, batE, b.vc->data(), tokE, batE, o_->data(), nullptr, (int)B, (int)H_, (int)L,
+                         (int)(pos + L), b.attn->is_causal() ? 1 : 0, (int)pos, s);
+    } else if (L == 1) {
       // single token per row: the decode kernel over the cache (host-known position)
       kv_cache_store_bf16(qkv_->data(), b.kc->data(), b.vc->data(), tokE, batE, (int)B, 1, E, (int)pos, s);
       attention_decode_bf16(base, 3 * E, b.kc->data(), b.vc->data(), tokE, batE, o_->data(), (int)B, (int)H_, (int)(pos + 1), s);

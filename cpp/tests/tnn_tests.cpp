@@ -967,6 +967,16 @@ TEST(gpu_gpt2_engine_bf16_fp8_and_graph_decode) {
   for (size_t i = 0; i < lg.size(); ++i) { num += (l8[i] - lg[i]) * (l8[i] - lg[i]); den += lg[i] * lg[i]; }
   CHECK(std::sqrt(num / den) < 0.12);
   CHECK(f8.precision() == "fp8");
+  // the fp8 QKV epilogue wrote K / V straight into the caches: a decode step over them must agree with the bf16 engine
+  {
+    gpu.prefill(ids, B, L);
+    std::vector<float> db, d8;
+    gpu.decode(tg, &db);
+    f8.decode(tg, &d8);
+    num = den = 0;
+    for (size_t i = 0; i < db.size(); ++i) { num += (d8[i] - db[i]) * (d8[i] - db[i]); den += db[i] * db[i]; }
+    CHECK(std::sqrt(num / den) < 0.12);
+  }
 }
 
 int main(int argc, char** argv) {

@@ -518,8 +518,15 @@ __global__ void __launch_bounds__(F8_THREADS)
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = gelu_tanh(v[j]);
         }
-        if (e.out != nullptr) {
-          bf16* o = reinterpret_cast<bf16*>(e.out) + (long long)m * e.ldc + n;
+        if (e.out != nullptr || e.seg_cols != 0) {
+          bf16* o;
+          if (e.seg_cols != 0) {
+            const int sg = n / e.seg_cols;
+            o = reinterpret_cast<bf16*>(e.seg_out[sg]) + (long long)(m / e.seg_rows) * e.seg_batch[sg] +
+                (long long)(m % e.seg_rows) * e.seg_tok[sg] + (n - sg * e.seg_cols);
+          } else {
+            o = reinterpret_cast<bf16*>(e.out) + (long long)m * e.ldc + n;
+          }
           if (full) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -667,6 +674,16 @@ void gemm_mxfp8(const void* A, long long lda, const void* sfa, const void* B, lo
   p.epi = epi;
   p.vec_ok = (epi.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(epi.out) | reinterpret_cast<uintptr_t>(epi.residual)) % 16 == 0) &&
              (reinterpret_cast<uintptr_t>(epi.bias) % 16 == 0);
+  if (epi.seg_cols != 0) {
+    const int nseg = (N + epi.seg_cols - 1) / epi.seg_cols;
+    if (epi.seg_cols % 32 != 0 || epi.seg_rows <= 0 || nseg > 3 || epi.residual != nullptr || epi.out != nullptr) {
+      fprintf(stderr, "[tnn_b200] gemm_mxfp8: segmented output needs seg_cols %% 32 == 0, <= 3 segments, no residual / plain out\n");
+      abort();
+    }
+    for (int sg = 0; sg < nseg; ++sg)
+      if (epi.seg_out[sg] == nullptr || reinterpret_cast<uintptr_t>(epi.seg_out[sg]) % 16 != 0 || epi.seg_tok[sg] % 8 != 0 || epi.seg_batch[sg] % 8 != 0)
+        p.vec_ok = 0;
+  }
   // 192-wide tiles keep two accumulators + scales inside 512 TMEM columns and divide the GPT-2 widths
   // (768, 2304, 3072); other widths take 128 when that wastes fewer columns
   const int waste192 = ((N + 191) / 192) * 192 - N, waste128 = ((N + 127) / 128) * 128 - N;

@@ -47,6 +47,14 @@ struct Fp8Epilogue {
   void* out_q = nullptr;          // e4m3 [M, N], row stride ldq bytes
   long long ldq = 0;
   void* out_sf = nullptr;         // scales of out_q in the atom layout (K' = N)
+  // optional segmented bf16 output (instead of `out`): the N columns are `seg_cols`-wide segments, segment s goes to
+  //   seg_out[s] + (m / seg_rows) * seg_batch[s] + (m % seg_rows) * seg_tok[s] + (n - s * seg_cols)      (elements)
+  // -- the fused QKV projection writes Q to its buffer and K / V straight into the KV caches at the prompt's positions
+  // (no separate cache-store pass).  seg_cols % 32 == 0; no residual with segments.
+  int seg_cols = 0, seg_rows = 0;
+  void* seg_out[3] = {nullptr, nullptr, nullptr};
+  long long seg_tok[3] = {0, 0, 0};
+  long long seg_batch[3] = {0, 0, 0};
 };
 
 // out[M, N] = act(alpha * (A . B^T) + bias + residual);  A [M, K] e4m3 (ld lda bytes) with scales sfa,
