@@ -167,6 +167,9 @@ void GPT2Engine::ensure_buffers(size_t tokens) {
     q8_sf_ = make_tensor(DType_t::UINT8_T, {(size_t)mxfp8_sf_bytes((long long)T, (long long)E_)}, dev_);
     h8_ = make_tensor(DType_t::UINT8_T, {T, F_}, dev_);
     h8_sf_ = make_tensor(DType_t::UINT8_T, {(size_t)mxfp8_sf_bytes((long long)T, (long long)F_)}, dev_);
+    // scale rows beyond the live tokens stay at 1.0 (ue8m0 byte 127): filled once here instead of a pad launch per LayerNorm
+    TNN_CUDA(cudaMemsetAsync(q8_sf_->data(), 127, q8_sf_->nbytes(), stream()));
+    TNN_CUDA(cudaMemsetAsync(h8_sf_->data(), 127, h8_sf_->nbytes(), stream()));
   }
   cap_tokens_ = T;
   if (graph_exec_) {                 // the captured graph points into the old buffers
@@ -211,7 +214,7 @@ void GPT2Engine::layers_gpu(size_t B, size_t L, size_t pos, bool fp8) {
     const float* fc2_b = b.fc2->use_bias() ? b.fc2->param("bias")->data_as<float>() : nullptr;
     // ---- attention half: x2 = x + out_proj(attn(qkv(LN(x))))
     if (fp8) {
-      if (ln8) layernorm_fwd_mxfp8(x, nullptr, nullptr, T, E, g1, b1, (float)b.ln1->epsilon(), q8_->data(), q8_sf_->data(), nullptr, s);
+      if (ln8) layernorm_fwd_mxfp8(x, nullptr, nullptr, T, E, g1, b1, (float)b.ln1->epsilon(), q8_->data(), q8_sf_->data(), nullptr, s, /*pad_scales=*/false);
       else {
         layernorm_fwd(x, nullptr, y_->data(), nullptr, T, E, g1, b1, (float)b.ln1->epsilon(), nullptr, nullptr, s);
         mxfp8_quantize_bf16(y_->data(), E, T, E, q8_->data(), E, q8_sf_->data(), s);
@@ -265,7 +268,7 @@ void GPT2Engine::layers_gpu(size_t B, size_t L, size_t pos, bool fp8) {
     }
     // ---- MLP half: x = x2 + fc2(gelu(fc1(LN(x2))))
     if (fp8) {
-      if (ln8) layernorm_fwd_mxfp8(x2, nullptr, nullptr, T, E, g2, b2, (float)b.ln2->epsilon(), q8_->data(), q8_sf_->data(), nullptr, s);
+      if (ln8) layernorm_fwd_mxfp8(x2, nullptr, nullptr, T, E, g2, b2, (float)b.ln2->epsilon(), q8_->data(), q8_sf_->data(), nullptr, s, /*pad_scales=*/false);
       else {
         layernorm_fwd(x2, nullptr, y_->data(), nullptr, T, E, g2, b2, (float)b.ln2->epsilon(), nullptr, nullptr, s);
         mxfp8_quantize_bf16(y_->data(), E, T, E, q8_->data(), E, q8_sf_->data(), s);

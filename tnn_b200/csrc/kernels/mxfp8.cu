@@ -232,7 +232,7 @@ __global__ void k_sf_pad_rows(uint8_t* sf, long long rows, long long rows_pad, i
   }
 }
 void layernorm_fwd_mxfp8(const void* x, const void* residual, void* sum_out, long long rows, int C, const float* gamma,
-                         const float* beta, float eps, void* q, void* sf, void* y_bf16, cudaStream_t s) {
+                         const float* beta, float eps, void* q, void* sf, void* y_bf16, cudaStream_t s, bool pad_scales) {
   const int wpb = 8;
   const int grid = (int)((rows + wpb - 1) / wpb);
 #define TNN_LN_FP8(V)                                                                                                  \
@@ -253,7 +253,7 @@ void layernorm_fwd_mxfp8(const void* x, const void* residual, void* sum_out, lon
 #undef TNN_LN_FP8
   TNN_CHECK_LAUNCH();
   const long long rows_pad = ((rows + 127) / 128 + 1) * 128;
-  if (rows_pad > rows) {
+  if (pad_scales && rows_pad > rows) {
     k_sf_pad_rows<<<grid_for((rows_pad - rows) * (C / 32), 256), 256, 0, s>>>(reinterpret_cast<uint8_t*>(sf), rows, rows_pad, C);
     TNN_CHECK_LAUNCH();
   }

@@ -34,7 +34,9 @@ void mxfp8_dequantize(const void* q, long long ldq, const void* sf, long long ro
 // directly as MXFP8 (q + scales) for the following GEMM; `y_bf16` (nullable) also receives the bf16 result and
 // `sum_out` (nullable) the residual stream x + residual.
 void layernorm_fwd_mxfp8(const void* x, const void* residual, void* sum_out, long long rows, int C, const float* gamma,
-                         const float* beta, float eps, void* q, void* sf, void* y_bf16, cudaStream_t s);
+                         const float* beta, float eps, void* q, void* sf, void* y_bf16, cudaStream_t s, bool pad_scales = true);
+// (pad_scales = false: the caller keeps the scale rows beyond `rows` at 1.0 (byte 127) itself, e.g. a reused buffer that was
+//  filled once -- saves one tiny launch per call)
 
 struct Fp8Epilogue {
   void* out = nullptr;            // bf16 [M, N] row stride ldc (elements); null when only the fp8 output is wanted
