@@ -113,6 +113,13 @@ def tnn_gpt2_cpp(gpu: int = 0, batch=32, seq=1024, decode_steps=64, iters=5, mod
     out["logits_rms_err_vs_bf16"] = float(np.sqrt((d ** 2).mean()))
     out["logits_rms_bf16"] = float(np.sqrt((logits_bf16 ** 2).mean()))
     out["argmax_agreement"] = float((logits_fp8.argmax(-1) == logits_bf16.argmax(-1)).mean())
+    # decode again with the fp8 engine: the persistent kernel then attends over the fp8 KV cache the fp8 prefill wrote
+    msd8 = eng.time_decode_ms(batch, seq - decode_steps, decode_steps, True)
+    if eng.uses_fp8_kv_cache():
+        out["decode_bf16_kv_ms_per_step"] = out["decode_ms_per_step"]
+        out["decode_ms_per_step"] = msd8
+        out["decode_tok_s"] = batch / msd8 * 1e3
+        out["decode_dtype"] = "bf16 weights, fp8 (e4m3 + ue8m0 per 32) KV cache; persistent whole-model decode kernel, CUDA-graph replay"
     return out
 
 

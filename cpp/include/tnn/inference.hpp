@@ -51,6 +51,7 @@ class GPT2Engine {
   const Device& device() const { return dev_; }
   // true when decode_graph() replays the single persistent decode kernel (B <= 32, E <= 1024; TNN_DECODE_MEGA=0 disables)
   bool uses_persistent_decode() const { return use_mega_; }
+  bool uses_fp8_kv_cache() const { return use_mega_ && graph_kv8_; }
   // logits [cur_batch, vocab] of the most recent prefill / decode / decode_graph step
   std::vector<float> last_logits();
   // TNN_DECODE_PROF=1: per-phase nanoseconds of CTA 0 in the last persistent decode step ({embed, [qkv, attn, out, fc1, fc2] x layers, head, argmax})
@@ -69,6 +70,7 @@ class GPT2Engine {
     Tensor kc, vc;                                   // [max_batch, max_len, E]
     // MXFP8 weights (q bytes + scale atoms)
     Tensor qkv_q, qkv_sf, out_q, out_sf, fc1_q, fc1_sf, fc2_q, fc2_sf;
+    Tensor k8, v8, ks8, vs8;                         // fp8 shadow KV cache: e4m3 [max_batch, max_len, E] + ue8m0 [.., E / 32]
   };
   void embed(const int32_t* ids_dev_or_host, size_t B, size_t L, size_t pos);
   void layers_gpu(size_t B, size_t L, size_t pos, bool fp8);
@@ -101,6 +103,10 @@ class GPT2Engine {
   const float* mega_head_c_ = nullptr;
   const float* mega_head_b_ = nullptr;
   bool use_mega_ = false;
+  // fp8 KV cache (precision "fp8" with TNN_KV_FP8=1; off by default: measured slower, see enable_fp8()): written by the fp8 QKV epilogue at prefill and by the persistent
+  // decode kernel per token; kv8_len_ = positions it covers (the bf16 caches are always complete)
+  bool kv8_enabled_ = false, graph_kv8_ = false;
+  size_t kv8_len_ = 0;
   void build_mega();
   size_t hist_cap_ = 0, graph_batch_ = 0;
   cudaGraph_t graph_ = nullptr;

@@ -272,6 +272,7 @@ PYBIND11_MODULE(_host, m) {
         return r;
       })
       .def("uses_persistent_decode", [](PyGPT2& e) { return e.engine->uses_persistent_decode(); })
+      .def("uses_fp8_kv_cache", [](PyGPT2& e) { return e.engine->uses_fp8_kv_cache(); })
       .def("enable_fp8", [](PyGPT2& e) { e.engine->enable_fp8(); })
       .def("precision", [](PyGPT2& e) { return e.engine->precision(); })
       .def("cur_len", [](PyGPT2& e) { return e.engine->cur_len(); })

@@ -142,6 +142,19 @@ void GPT2Engine::enable_fp8() {
     quant(b.fc1->param("weight"), b.fc1_q, b.fc1_sf);
     quant(b.fc2->param("weight"), b.fc2_q, b.fc2_sf);
   }
+  // fp8 shadow KV cache for the persistent decode kernel: OFF by default -- measured slower (B = 32, context ~1000: attention
+  // phase 36.8 us vs 25.3 us per layer, 1.057 vs 0.868 ms per token, and +0.3 ms of prefill for the shadow writes): the phase
+  // is instruction / latency bound (e4m3 converts, two scale-byte loads per key), not bandwidth bound.  TNN_KV_FP8=1 enables.
+  const char* kve = getenv("TNN_KV_FP8");
+  kv8_enabled_ = kve && atoi(kve) != 0 && E_ % 64 == 0;
+  if (kv8_enabled_)
+    for (auto& b : blocks_) {
+      b.k8 = make_tensor(DType_t::UINT8_T, {max_batch_, max_len_, E_}, dev_);
+      b.v8 = make_tensor(DType_t::UINT8_T, {max_batch_, max_len_, E_}, dev_);
+      b.ks8 = make_tensor(DType_t::UINT8_T, {max_batch_, max_len_, E_ / 32}, dev_);
+      b.vs8 = make_tensor(DType_t::UINT8_T, {max_batch_, max_len_, E_ / 32}, dev_);
+    }
+  kv8_len_ = 0;
   current_flow(dev_).synchronize();
   precision_ = "fp8";
   cap_tokens_ = 0;                   // the fp8 activation buffers are allocated with the next ensure_buffers()
@@ -231,6 +244,12 @@ void GPT2Engine::layers_gpu(size_t B, size_t L, size_t pos, bool fp8) {
       e.seg_out[2] = static_cast<char*>(b.vc->data()) + pos * E_ * 2;
       e.seg_tok[1] = e.seg_tok[2] = tokE;
       e.seg_batch[1] = e.seg_batch[2] = batE;
+      if (kv8_enabled_) {                                 // the fp8 shadow cache of the decode kernel, same positions
+        e.seg_q[1] = static_cast<char*>(b.k8->data()) + pos * E_;
+        e.seg_q[2] = static_cast<char*>(b.v8->data()) + pos * E_;
+        e.seg_qs[1] = static_cast<char*>(b.ks8->data()) + pos * (E_ / 32);
+        e.seg_qs[2] = static_cast<char*>(b.vs8->data()) + pos * (E_ / 32);
+      }
       gemm_mxfp8(q8_->data(), E, q8_sf_->data(), b.qkv_q->data(), E, b.qkv_sf->data(), T, 3 * E, E, e, s);
     } else {
       layernorm_fwd(x, nullptr, y_->data(), nullptr, T, E, g1, b1, (float)b.ln1->epsilon(), nullptr, nullptr, s);
@@ -400,9 +419,11 @@ std::vector<int32_t> GPT2Engine::prefill(const std::vector<int32_t>& ids, size_t
   if (gpu_) TNN_CUDA(cudaMemcpyAsync(ids_->data(), ids.data(), ids.size() * 4, cudaMemcpyHostToDevice, stream()));
   else std::memcpy(ids_->data(), ids.data(), ids.size() * 4);
   embed(nullptr, B, L, 0);
-  if (gpu_) layers_gpu(B, L, 0, precision_ == "fp8" && B * L >= 128);
+  const bool fp8_path = gpu_ && precision_ == "fp8" && B * L >= 128;
+  if (gpu_) layers_gpu(B, L, 0, fp8_path);
   else layers_cpu(B, L, 0);
   cur_len_ = L;
+  kv8_len_ = (fp8_path && kv8_enabled_) ? L : 0;
   return finish(B, L, logits);
 }
 
@@ -449,6 +470,10 @@ void GPT2Engine::build_mega() {
     L.b_fc2 = b.fc2->use_bias() ? b.fc2->param("bias")->data_as<float>() : nullptr;
     L.kc = b.kc->data();
     L.vc = b.vc->data();
+    L.k8 = b.k8 ? b.k8->data() : nullptr;
+    L.v8 = b.v8 ? b.v8->data() : nullptr;
+    L.ks8 = b.ks8 ? b.ks8->data() : nullptr;
+    L.vs8 = b.vs8 ? b.vs8->data() : nullptr;
     L.eps1 = (float)b.ln1->epsilon();
     L.eps2 = (float)b.ln2->epsilon();
   }
@@ -507,6 +532,7 @@ void GPT2Engine::decode_step_device(size_t B) {
     p.attn_cnt = mega_cnt_->data_as<int>();
     p.logits = logits_->data();
     p.bar = static_cast<unsigned int*>(mega_bar_->data());
+    p.kv_fp8 = graph_kv8_ ? 1 : 0;
     p.prof = mega_prof_ ? static_cast<unsigned long long*>(mega_prof_->data()) : nullptr;
     decode_step_mega(p, s);
     return;
@@ -558,6 +584,14 @@ std::vector<int32_t> GPT2Engine::decode_graph(const std::vector<int32_t>& tokens
   dev_.set_current();
   ensure_buffers(B);
   Flow& flow = current_flow(dev_);
+  const bool want_kv8 = kv8_enabled_ && kv8_len_ == cur_len_ && cur_len_ > 0;
+  if (graph_exec_ && want_kv8 != graph_kv8_) {            // the captured kernel variant attends over the other cache
+    cudaGraphExecDestroy(graph_exec_);
+    cudaGraphDestroy(graph_);
+    graph_exec_ = nullptr;
+    graph_ = nullptr;
+  }
+  graph_kv8_ = want_kv8;
   if (!d_tok_ || graph_batch_ != B || hist_cap_ < steps) {
     hist_cap_ = std::max<size_t>(steps, 64);
     d_tok_ = make_tensor(DType_t::INT32_T, {B}, dev_);
@@ -610,6 +644,7 @@ std::vector<int32_t> GPT2Engine::decode_graph(const std::vector<int32_t>& tokens
   TNN_CUDA(cudaMemcpyAsync(hist.data(), d_hist_->data(), hist.size() * 4, cudaMemcpyDeviceToHost, flow.stream()));
   flow.synchronize();
   cur_len_ += steps;
+  if (use_mega_ && graph_kv8_) kv8_len_ = cur_len_;       // the persistent kernel appended both caches
   for (size_t s = 0; s < steps; ++s)
     for (size_t b = 0; b < B; ++b) out[b * steps + s] = hist[s * B + b];
   return out;

@@ -977,6 +977,33 @@ TEST(gpu_gpt2_engine_bf16_fp8_and_graph_decode) {
     for (size_t i = 0; i < db.size(); ++i) { num += (d8[i] - db[i]) * (d8[i] - db[i]); den += db[i] * db[i]; }
     CHECK(std::sqrt(num / den) < 0.12);
   }
+  {
+    // persistent decode over the fp8 KV cache (opt-in: written by the QKV epilogue at prefill, appended per token)
+    setenv("TNN_KV_FP8", "1", 1);
+    GPT2Engine f8(*mg, B, 0, "fp8");
+    unsetenv("TNN_KV_FP8");
+    std::vector<float> db;
+    gpu.prefill(ids, B, L);
+    gpu.decode(tg, &db);
+    f8.prefill(ids, B, L);
+    std::vector<int32_t> g8 = f8.decode_graph(tg, 1);
+    CHECK(f8.uses_persistent_decode() && f8.uses_fp8_kv_cache() && f8.cur_len() == L + 1);
+    std::vector<float> l8kv = f8.last_logits();
+    num = den = 0;
+    for (size_t i = 0; i < db.size(); ++i) { num += (l8kv[i] - db[i]) * (l8kv[i] - db[i]); den += db[i] * db[i]; }
+    CHECK(std::sqrt(num / den) < 0.15);
+    // three more tokens through the fp8 cache, then an eager step over the (always complete) bf16 cache still works
+    std::vector<int32_t> more = f8.decode_graph(g8, 3);
+    CHECK(f8.cur_len() == L + 4 && more.size() == B * 3);
+    std::vector<int32_t> lastc(B);
+    for (size_t b = 0; b < B; ++b) lastc[b] = more[b * 3 + 2];
+    std::vector<float> cont;
+    f8.decode(lastc, &cont);
+    for (float v : cont) CHECK(std::isfinite(v));
+    // after the eager step the fp8 cache is stale: the next graph decode falls back to the bf16 cache
+    f8.decode_graph(lastc, 1);
+    CHECK(!f8.uses_fp8_kv_cache());
+  }
 }
 
 int main(int argc, char** argv) {

@@ -3,6 +3,8 @@
 // memory); what is new is everything around it: grid-wide arrive/wait barriers, weight prefetch across the barrier
 // and across work units, LayerNorm folded into weights + producer-side row statistics, split-sequence attention with
 // a last-arriver merge, fused arg-max / token bookkeeping.
+#include <cuda_fp8.h>
+
 #include "common.cuh"
 #include "decode_mega.cuh"
 
@@ -277,6 +279,33 @@ __device__ __forceinline__ void dm_gemm(DmBarrier& bar, uint8_t* smem, const DmG
   dm_gemm_phase(bar, smem, g, (g.N + 7) / 8 <= (int)gridDim.x ? 1 : 2);
 }
 
+// ---- fp8 KV cache helpers (MX rule of mxfp8.cu: e4m3 elements, one ue8m0 scale byte per 32 elements of a head row)
+__device__ __forceinline__ void dm_e4m3x8_unpack(const uint2& q, float (&f)[8]) {
+  const uint32_t w[2] = {q.x, q.y};
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const __half2_raw r = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)((w[i] >> (16 * hf)) & 0xFFFFu), __NV_E4M3);
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&r));
+      f[i * 4 + hf * 2] = t.x;
+      f[i * 4 + hf * 2 + 1] = t.y;
+    }
+}
+__device__ __forceinline__ float dm_ue8m0(unsigned int byte) { return __uint_as_float(byte << 23); }
+__device__ __forceinline__ uint32_t dm_scale_byte(float amax) {       // 2^(floor(log2 amax) - 8), clamped
+  int b = (int)((__float_as_uint(amax) >> 23) & 0xFF) - 8;
+  return (uint32_t)(b < 0 ? 0 : (b > 254 ? 254 : b));
+}
+__device__ __forceinline__ uint2 dm_pack_e4m3x8(const float (&f)[8], float inv) {
+  uint2 w;
+  w.x = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(f[0] * inv, f[1] * inv), __NV_SATFINITE, __NV_E4M3) |
+        ((uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(f[2] * inv, f[3] * inv), __NV_SATFINITE, __NV_E4M3) << 16);
+  w.y = (uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(f[4] * inv, f[5] * inv), __NV_SATFINITE, __NV_E4M3) |
+        ((uint32_t)__nv_cvt_float2_to_fp8x2(make_float2(f[6] * inv, f[7] * inv), __NV_SATFINITE, __NV_E4M3) << 16);
+  return w;
+}
+
 // one online-softmax update of (m, l, acc) with up to DM_KEYS keys
 template <int DM_KEYS>
 __device__ __forceinline__ void dm_softmax_update(float& m, float& l, float (&acc)[8], const float (&s)[DM_KEYS], const uint4 (&vq)[DM_KEYS]) {
@@ -303,7 +332,7 @@ __device__ __forceinline__ void dm_softmax_update(float& m, float& l, float (&ac
 // Attention of the current token over the cache [0, pos) plus itself.  Work item = (batch, head, sequence chunk),
 // one warp each (8 lanes per key: 4 keys per load instruction, 16 keys per step).  The warp that owns the last chunk
 // also appends this token's K / V rows to the cache.  The last warp to finish a (batch, head) merges the partials.
-template <int DM_KEYS>
+template <int DM_KEYS, bool KV8>
 __device__ __noinline__ void dm_attention_phase(DmBarrier& bar, const DecodeParams& p, const DecodeLayerParams& L, int pos) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g4 = lane >> 3, sub = lane & 7;
@@ -332,32 +361,94 @@ __device__ __noinline__ void dm_attention_phase(DmBarrier& bar, const DecodePara
     float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
     for (int d = 0; d < 8; ++d) acc[d] = 0.f;
-    for (int j0 = start; j0 < end; j0 += 4 * DM_KEYS) {             // (a second step in flight measured slower: 29 vs 25 us)
-      uint4 kq[DM_KEYS], vq[DM_KEYS];
+    if constexpr (KV8) {
+      // fp8 KV cache: 8 bytes of K and of V per lane and key (half the bytes of the bf16 cache), one scale byte per
+      // 32 elements; the K scale multiplies the partial dot product, the V scale the softmax weight
+      const int E32 = E >> 5;
+      const uint8_t* kb8 = reinterpret_cast<const uint8_t*>(L.k8) + (long long)b * p.Lmax * E + h * DM_D + sub * 8;
+      const uint8_t* vb8 = reinterpret_cast<const uint8_t*>(L.v8) + (long long)b * p.Lmax * E + h * DM_D + sub * 8;
+      const uint8_t* ks8 = reinterpret_cast<const uint8_t*>(L.ks8) + (long long)b * p.Lmax * E32 + h * 2 + (sub >> 2);
+      const uint8_t* vs8 = reinterpret_cast<const uint8_t*>(L.vs8) + (long long)b * p.Lmax * E32 + h * 2 + (sub >> 2);
+      for (int j0 = start; j0 < end; j0 += 4 * DM_KEYS) {
+        uint2 kq[DM_KEYS], vq[DM_KEYS];
+        unsigned int ksb[DM_KEYS], vsb[DM_KEYS];
 #pragma unroll
-      for (int i = 0; i < DM_KEYS; ++i) {
-        const int j = j0 + i * 4 + g4;
-        kq[i] = make_uint4(0, 0, 0, 0);
-        vq[i] = make_uint4(0, 0, 0, 0);
-        if (j < end) {
-          kq[i] = __ldcs(reinterpret_cast<const uint4*>(kb + (long long)j * E));
-          vq[i] = __ldcs(reinterpret_cast<const uint4*>(vb + (long long)j * E));
+        for (int i = 0; i < DM_KEYS; ++i) {
+          const int j = j0 + i * 4 + g4;
+          kq[i] = make_uint2(0, 0);
+          vq[i] = make_uint2(0, 0);
+          ksb[i] = 0;
+          vsb[i] = 0;
+          if (j < end) {
+            kq[i] = __ldcs(reinterpret_cast<const uint2*>(kb8 + (long long)j * E));
+            vq[i] = __ldcs(reinterpret_cast<const uint2*>(vb8 + (long long)j * E));
+            ksb[i] = __ldcs(ks8 + (long long)j * E32);
+            vsb[i] = __ldcs(vs8 + (long long)j * E32);
+          }
+        }
+        float s[DM_KEYS];
+#pragma unroll
+        for (int i = 0; i < DM_KEYS; ++i) {
+          float kf[8];
+          dm_e4m3x8_unpack(kq[i], kf);
+          float d0 = 0.f;
+#pragma unroll
+          for (int d = 0; d < 8; ++d) d0 += qf[d] * kf[d];
+          d0 *= dm_ue8m0(ksb[i]);
+          d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+          d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+          d0 += __shfl_xor_sync(0xffffffffu, d0, 4);
+          s[i] = (j0 + i * 4 + g4 < end) ? d0 : -INFINITY;
+        }
+        float mn = m;
+#pragma unroll
+        for (int i = 0; i < DM_KEYS; ++i) mn = fmaxf(mn, s[i]);
+        if (mn != -INFINITY) {
+          const float a = exp2f(m - mn);
+          l *= a;
+#pragma unroll
+          for (int d = 0; d < 8; ++d) acc[d] *= a;
+#pragma unroll
+          for (int i = 0; i < DM_KEYS; ++i) {
+            const float e = exp2f(s[i] - mn);
+            l += e;
+            const float ev = e * dm_ue8m0(vsb[i]);
+            float vf[8];
+            dm_e4m3x8_unpack(vq[i], vf);
+#pragma unroll
+            for (int d = 0; d < 8; ++d) acc[d] += ev * vf[d];
+          }
+          m = mn;
         }
       }
-      float s[DM_KEYS];
+    } else {
+    for (int j0 = start; j0 < end; j0 += 4 * DM_KEYS) {             // (a second step in flight measured slower: 29 vs 25 us)
+        uint4 kq[DM_KEYS], vq[DM_KEYS];
 #pragma unroll
-      for (int i = 0; i < DM_KEYS; ++i) {
-        float kf[8];
-        bf8_unpack(kq[i], kf);
-        float d0 = 0.f;
+        for (int i = 0; i < DM_KEYS; ++i) {
+          const int j = j0 + i * 4 + g4;
+          kq[i] = make_uint4(0, 0, 0, 0);
+          vq[i] = make_uint4(0, 0, 0, 0);
+          if (j < end) {
+            kq[i] = __ldcs(reinterpret_cast<const uint4*>(kb + (long long)j * E));
+            vq[i] = __ldcs(reinterpret_cast<const uint4*>(vb + (long long)j * E));
+          }
+        }
+        float s[DM_KEYS];
 #pragma unroll
-        for (int d = 0; d < 8; ++d) d0 += qf[d] * kf[d];
-        d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
-        d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
-        d0 += __shfl_xor_sync(0xffffffffu, d0, 4);
-        s[i] = (j0 + i * 4 + g4 < end) ? d0 : -INFINITY;
+        for (int i = 0; i < DM_KEYS; ++i) {
+          float kf[8];
+          bf8_unpack(kq[i], kf);
+          float d0 = 0.f;
+#pragma unroll
+          for (int d = 0; d < 8; ++d) d0 += qf[d] * kf[d];
+          d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+          d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+          d0 += __shfl_xor_sync(0xffffffffu, d0, 4);
+          s[i] = (j0 + i * 4 + g4 < end) ? d0 : -INFINITY;
+        }
+        dm_softmax_update<DM_KEYS>(m, l, acc, s, vq);
       }
-      dm_softmax_update<DM_KEYS>(m, l, acc, s, vq);
     }
     if (c == nch - 1) {                                                // the current token: from the projection, and into the cache
       const uint4 kcur = __ldcg(reinterpret_cast<const uint4*>(row + E));
@@ -368,6 +459,32 @@ __device__ __noinline__ void dm_attention_phase(DmBarrier& bar, const DecodePara
       }
       float kf[8];
       bf8_unpack(kcur, kf);
+      if constexpr (KV8) {                                             // the fp8 cache gets this token's rows too
+        float vf8[8];
+        bf8_unpack(vcur, vf8);
+        float ka = 0.f, va = 0.f;
+#pragma unroll
+        for (int d = 0; d < 8; ++d) {
+          ka = fmaxf(ka, fabsf(kf[d]));
+          va = fmaxf(va, fabsf(vf8[d]));
+        }
+        ka = fmaxf(ka, __shfl_xor_sync(0xffffffffu, ka, 1));
+        va = fmaxf(va, __shfl_xor_sync(0xffffffffu, va, 1));
+        ka = fmaxf(ka, __shfl_xor_sync(0xffffffffu, ka, 2));
+        va = fmaxf(va, __shfl_xor_sync(0xffffffffu, va, 2));
+        const uint32_t kb_ = dm_scale_byte(ka), vb_ = dm_scale_byte(va);
+        if (g4 == 0) {
+          const long long tokoff = (long long)b * p.Lmax + pos;
+          *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(L.k8) + tokoff * E + h * DM_D + sub * 8) =
+              dm_pack_e4m3x8(kf, __uint_as_float((uint32_t)(254 - (int)kb_) << 23));
+          *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(L.v8) + tokoff * E + h * DM_D + sub * 8) =
+              dm_pack_e4m3x8(vf8, __uint_as_float((uint32_t)(254 - (int)vb_) << 23));
+          if ((sub & 3) == 0) {
+            reinterpret_cast<uint8_t*>(L.ks8)[tokoff * (E >> 5) + h * 2 + (sub >> 2)] = (uint8_t)kb_;
+            reinterpret_cast<uint8_t*>(L.vs8)[tokoff * (E >> 5) + h * 2 + (sub >> 2)] = (uint8_t)vb_;
+          }
+        }
+      }
       float d0 = 0.f;
 #pragma unroll
       for (int d = 0; d < 8; ++d) d0 += qf[d] * kf[d];
@@ -586,6 +703,7 @@ __device__ __noinline__ void dm_head_phase(DmBarrier& bar, uint8_t* smem, const 
   dm_arrive(bar);
 }
 
+template <bool KV8>
 __global__ void __launch_bounds__(DM_THREADS, 2) k_decode_mega(const DecodeParams p) {
   extern __shared__ __align__(16) uint8_t dm_smem[];
   __shared__ float rv[DM_WARPS];
@@ -648,7 +766,7 @@ __global__ void __launch_bounds__(DM_THREADS, 2) k_decode_mega(const DecodeParam
     }
     DM_STAMP();
     // B: o = attention(q, cache + current token); cache append
-    dm_attention_phase<4>(bar, p, L, pos);          // 16 keys per warp step (2 and 8 per group measured: 1.13 / 1.70 ms vs 0.89 ms per token)
+    dm_attention_phase<4, KV8>(bar, p, L, pos);          // 16 keys per warp step (2 and 8 per group measured: 1.13 / 1.70 ms vs 0.89 ms per token)
     DM_STAMP();
     // C: x2 = x + o Wout^T + b  (+ row statistics of x2).  stats_x was consumed in A (every CTA passed B's barrier
     // since) and is refilled in E: clear it here.
@@ -731,11 +849,14 @@ void decode_fold_ln(const float* W, const float* bias, const float* gamma, const
 void decode_step_mega(const DecodeParams& p, cudaStream_t stream) {
   static int grid = 0;
   if (!grid) {
-    cudaFuncSetAttribute(k_decode_mega, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
-    int dev = 0, sms = 0, per_sm = 0;
+    cudaFuncSetAttribute(k_decode_mega<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
+    cudaFuncSetAttribute(k_decode_mega<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
+    int dev = 0, sms = 0, per_sm = 0, per_sm8 = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_mega, DM_THREADS, DM_SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_mega<false>, DM_THREADS, DM_SMEM);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm8, k_decode_mega<true>, DM_THREADS, DM_SMEM);
+    per_sm = per_sm < per_sm8 ? per_sm : per_sm8;
     if (per_sm < 1) {
       fprintf(stderr, "[tnn_b200] decode_step_mega: the kernel does not fit on an SM\n");
       abort();
@@ -746,7 +867,8 @@ void decode_step_mega(const DecodeParams& p, cudaStream_t stream) {
     if (e && atoi(e) > 0 && atoi(e) < grid) grid = atoi(e);
   }
   cudaMemsetAsync(p.bar, 0, sizeof(unsigned int), stream);
-  k_decode_mega<<<grid, DM_THREADS, DM_SMEM, stream>>>(p);
+  if (p.kv_fp8) k_decode_mega<true><<<grid, DM_THREADS, DM_SMEM, stream>>>(p);
+  else k_decode_mega<false><<<grid, DM_THREADS, DM_SMEM, stream>>>(p);
   TNN_CHECK_LAUNCH();
 }
 

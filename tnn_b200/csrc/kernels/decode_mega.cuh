@@ -21,6 +21,7 @@ struct DecodeLayerParams {
   const void* w_fc1; const float* c_fc1; const float* b_fc1;   // LN2-folded bf16 [F, E], [F], [F]
   const void* w_fc2; const float* b_fc2;                        // bf16 [E, F]
   void* kc; void* vc;                                           // bf16 KV cache [B, Lmax, E]
+  void* k8; void* v8; void* ks8; void* vs8;                     // optional fp8 shadow: e4m3 [B, Lmax, E] + ue8m0 scales [B, Lmax, E/32]
   float eps1, eps2;
 };
 
@@ -39,6 +40,7 @@ struct DecodeParams {
   void* logits;                                // bf16 [B, vpad]
   unsigned long long* amax;                    // [32] packed (ordered logit, ~column) running arg-max (zeroed once)
   unsigned int* bar;                           // grid barrier counter (zeroed by the launcher every step)
+  int kv_fp8;                                  // attend over the fp8 shadow caches (they must cover [0, pos)); both caches are appended
   unsigned long long* prof;                    // optional [4 + 5 * n_layers] %globaltimer stamps of CTA 0 at the phase ends
 };
 

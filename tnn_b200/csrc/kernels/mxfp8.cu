@@ -522,8 +522,27 @@ __global__ void __launch_bounds__(F8_THREADS)
           bf16* o;
           if (e.seg_cols != 0) {
             const int sg = n / e.seg_cols;
-            o = reinterpret_cast<bf16*>(e.seg_out[sg]) + (long long)(m / e.seg_rows) * e.seg_batch[sg] +
-                (long long)(m % e.seg_rows) * e.seg_tok[sg] + (n - sg * e.seg_cols);
+            const long long roff = (long long)(m / e.seg_rows) * e.seg_batch[sg] + (long long)(m % e.seg_rows) * e.seg_tok[sg];
+            const int nn = n - sg * e.seg_cols;
+            o = reinterpret_cast<bf16*>(e.seg_out[sg]) + roff + nn;
+            if (e.seg_q[sg] != nullptr) {                       // fp8 shadow: this thread holds exactly one 32-wide scale block
+              float amax = 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) amax = fmaxf(amax, fabsf(v[j]));
+              const uint32_t sb = mx_scale_byte(amax);
+              const float inv = mx_scale_inv(sb);
+              uint4* oq = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(e.seg_q[sg]) + roff + nn);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                uint4 w;
+                w.x = pack_e4m3x4(v[j * 16 + 0] * inv, v[j * 16 + 1] * inv, v[j * 16 + 2] * inv, v[j * 16 + 3] * inv);
+                w.y = pack_e4m3x4(v[j * 16 + 4] * inv, v[j * 16 + 5] * inv, v[j * 16 + 6] * inv, v[j * 16 + 7] * inv);
+                w.z = pack_e4m3x4(v[j * 16 + 8] * inv, v[j * 16 + 9] * inv, v[j * 16 + 10] * inv, v[j * 16 + 11] * inv);
+                w.w = pack_e4m3x4(v[j * 16 + 12] * inv, v[j * 16 + 13] * inv, v[j * 16 + 14] * inv, v[j * 16 + 15] * inv);
+                oq[j] = w;
+              }
+              reinterpret_cast<uint8_t*>(e.seg_qs[sg])[(roff >> 5) + (nn >> 5)] = (uint8_t)sb;
+            }
           } else {
             o = reinterpret_cast<bf16*>(e.out) + (long long)m * e.ldc + n;
           }
@@ -680,6 +699,12 @@ void gemm_mxfp8(const void* A, long long lda, const void* sfa, const void* B, lo
       fprintf(stderr, "[tnn_b200] gemm_mxfp8: segmented output needs seg_cols %% 32 == 0, <= 3 segments, no residual / plain out\n");
       abort();
     }
+    for (int sg = 0; sg < nseg; ++sg)
+      if (epi.seg_q[sg] != nullptr && (epi.seg_qs[sg] == nullptr || epi.seg_tok[sg] % 32 != 0 || epi.seg_batch[sg] % 32 != 0 ||
+                                       reinterpret_cast<uintptr_t>(epi.seg_q[sg]) % 16 != 0 || N % 32 != 0)) {
+        fprintf(stderr, "[tnn_b200] gemm_mxfp8: fp8 segment shadow needs scales, 32-element aligned strides and a 16-byte aligned base\n");
+        abort();
+      }
     for (int sg = 0; sg < nseg; ++sg)
       if (epi.seg_out[sg] == nullptr || reinterpret_cast<uintptr_t>(epi.seg_out[sg]) % 16 != 0 || epi.seg_tok[sg] % 8 != 0 || epi.seg_batch[sg] % 8 != 0)
         p.vec_ok = 0;

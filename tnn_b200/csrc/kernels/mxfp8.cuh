@@ -57,6 +57,10 @@ struct Fp8Epilogue {
   void* seg_out[3] = {nullptr, nullptr, nullptr};
   long long seg_tok[3] = {0, 0, 0};
   long long seg_batch[3] = {0, 0, 0};
+  // optional fp8 shadow of a segment (the fp8 KV cache of the decode kernel): e4m3 bytes at the SAME element offsets in
+  // seg_q[s], one ue8m0 scale per 32 columns at (row offset / 32 + column / 32) in seg_qs[s]  (seg_tok / seg_batch % 32 == 0)
+  void* seg_q[3] = {nullptr, nullptr, nullptr};
+  void* seg_qs[3] = {nullptr, nullptr, nullptr};
 };
 
 // out[M, N] = act(alpha * (A . B^T) + bias + residual);  A [M, K] e4m3 (ld lda bytes) with scales sfa,
