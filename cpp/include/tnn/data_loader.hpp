@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 
+#include "tnn/augmentation.hpp"
 #include "tnn/tensor.hpp"
 
 namespace tnn {
@@ -26,6 +27,9 @@ class BaseDataLoader {
   virtual size_t num_classes() const { return classes_; }
   void set_seed(uint64_t s) { rng_.seed(s); }
   void set_pinned(bool p) { pinned_ = p; }
+  // applied to every [B, H, W, C] batch this loader hands out (training loaders)
+  void set_augmentation(std::shared_ptr<Augmentation> a) { augmentation_ = std::move(a); }
+  const std::shared_ptr<Augmentation>& augmentation() const { return augmentation_; }
 
  protected:
   virtual void fill_sample(size_t index, float* dst, int32_t* label) = 0;
@@ -34,6 +38,8 @@ class BaseDataLoader {
   std::vector<uint32_t> order_;
   std::mt19937_64 rng_{12345};
   bool pinned_ = false;
+  std::shared_ptr<Augmentation> augmentation_;
+  uint64_t batches_served_ = 0;
 };
 
 // Gaussian blobs whose mean depends on the class: learnable, deterministic, no files
@@ -71,12 +77,71 @@ class MNISTDataLoader : public BaseDataLoader {
   std::vector<uint8_t> labels_;
 };
 
+// uint16 token stream (OpenWebText train.bin / val.bin, reference: open_webtext_data_loader.hpp): x [B, L] INT32 windows,
+// y [B, L] INT32 = the next tokens.  size() = number of non-overlapping windows; windows are drawn at random offsets.
+class OpenWebTextDataLoader : public BaseDataLoader {
+ public:
+  explicit OpenWebTextDataLoader(size_t seq_len = 1024) : seq_len_(seq_len) { sample_shape_ = {seq_len}; classes_ = 50257; }
+  ~OpenWebTextDataLoader() override;
+  bool load_data(const std::string& path) override;      // a .bin file
+  bool get_batch(size_t batch_size, Tensor& x, Tensor& y) override;
+  size_t num_tokens() const;
+
+ protected:
+  void fill_sample(size_t, float*, int32_t*) override {}
+  size_t seq_len_;
+  struct Impl;
+  Impl* impl_ = nullptr;
+};
+
+// Numeric CSV with a header line: the last `n_targets` columns are regression targets (reference:
+// regression_data_loader.hpp); x [B, F] FP32, y [B, n_targets] FP32
+class RegressionCSVDataLoader : public BaseDataLoader {
+ public:
+  explicit RegressionCSVDataLoader(size_t n_targets = 1, bool has_header = true) : n_targets_(n_targets), header_(has_header) {}
+  bool load_data(const std::string& path) override;
+  bool get_batch(size_t batch_size, Tensor& x, Tensor& y) override;
+  size_t num_features() const { return features_; }
+
+ protected:
+  void fill_sample(size_t, float*, int32_t*) override {}
+  size_t n_targets_, features_ = 0;
+  bool header_;
+  std::vector<float> xs_, ys_;
+};
+
+// UJIIndoorLoc-style WiFi CSV (reference: wifi_data_loader.hpp): a block of feature columns and a block of target
+// columns; regression (float targets) or classification (first target column as the class); normalize_data() z-scores
+// features (and regression targets) and keeps the statistics for de-normalisation
+class WiFiDataLoader : public BaseDataLoader {
+ public:
+  explicit WiFiDataLoader(bool is_regression = true) : regression_(is_regression) {}
+  bool load_data(const std::string& path) override { return load_data(path, 0, 0, 0, 0, true); }
+  bool load_data(const std::string& path, size_t feature_start, size_t feature_end, size_t target_start, size_t target_end, bool has_header = true);
+  bool get_batch(size_t batch_size, Tensor& x, Tensor& y) override;
+  void normalize_data();
+  bool is_normalized() const { return normalized_; }
+  const std::vector<float>& feature_means() const { return fmean_; }
+  const std::vector<float>& feature_stds() const { return fstd_; }
+  const std::vector<float>& target_means() const { return tmean_; }
+  const std::vector<float>& target_stds() const { return tstd_; }
+  size_t num_features() const { return features_; }
+  size_t num_targets() const { return targets_; }
+
+ protected:
+  void fill_sample(size_t, float*, int32_t*) override {}
+  bool regression_, normalized_ = false;
+  size_t features_ = 0, targets_ = 0;
+  std::vector<float> xs_, ys_, fmean_, fstd_, tmean_, tstd_;
+};
+
 struct DataLoaderPair {
   std::unique_ptr<BaseDataLoader> train, val;
 };
 class DataLoaderFactory {
  public:
-  // "mnist" | "cifar10" | "cifar100" | "synthetic[:H,W,C,classes,n]" ; missing files fall back to synthetic data of the named shape
+  // "mnist" | "cifar10" | "cifar100" | "openwebtext" | "regression" | "wifi" | "synthetic[:H,W,C,classes,n]"; missing image
+  // files fall back to synthetic data of the named shape
   static DataLoaderPair create(const std::string& name, const std::string& path);
 };
 

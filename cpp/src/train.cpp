@@ -10,6 +10,7 @@
 #include <sys/stat.h>
 
 #include "kernels/simt_ops.cuh"
+#include "runtime/data_loader.hpp"
 #include "tnn/example_models.hpp"
 #include "tnn/profiler.hpp"
 #include "tnn/stepstate.hpp"
@@ -196,6 +197,8 @@ bool BaseDataLoader::get_batch(size_t B, Tensor& x, Tensor& y) {
   }
   for (size_t i = 0; i < b; ++i) fill_sample(order_[cursor_ + i], x->data_as<float>() + i * per, y->data_as<int32_t>() + i);
   cursor_ += b;
+  if (augmentation_ && sample_shape_.size() == 3) augmentation_->apply(*x, batches_served_);
+  ++batches_served_;
   return true;
 }
 void BaseDataLoader::shuffle() {
@@ -266,6 +269,158 @@ void MNISTDataLoader::fill_sample(size_t index, float* dst, int32_t* label) {
   *label = labels_[index];
   for (size_t i = 0; i < 784; ++i) dst[i] = pixels_[index * 784 + i] * (1.f / 255.f);
 }
+// ---- OpenWebText token stream
+struct OpenWebTextDataLoader::Impl {
+  std::unique_ptr<TokenDataset> ds;
+};
+OpenWebTextDataLoader::~OpenWebTextDataLoader() { delete impl_; }
+bool OpenWebTextDataLoader::load_data(const std::string& path) {
+  struct stat st;
+  std::string f = path;
+  if (stat(f.c_str(), &st) != 0 || !S_ISREG(st.st_mode)) f = path + "/train.bin";
+  if (stat(f.c_str(), &st) != 0) return false;
+  if (!impl_) impl_ = new Impl();
+  impl_->ds = std::make_unique<TokenDataset>(f);
+  n_ = impl_->ds->num_tokens() / seq_len_;
+  cursor_ = 0;
+  return n_ > 0;
+}
+size_t OpenWebTextDataLoader::num_tokens() const { return impl_ && impl_->ds ? impl_->ds->num_tokens() : 0; }
+bool OpenWebTextDataLoader::get_batch(size_t B, Tensor& x, Tensor& y) {
+  if (!impl_ || !impl_->ds || cursor_ >= n_) return false;
+  const size_t b = std::min(B, n_ - cursor_);
+  IAllocator& a = pinned_ ? static_cast<IAllocator&>(DeviceAllocator::pinned()) : HostAllocator();
+  x = make_tensor(a, DType_t::INT32_T, {b, seq_len_});
+  y = make_tensor(a, DType_t::INT32_T, {b, seq_len_});
+  impl_->ds->sample((int)b, (int)seq_len_, rng_(), x->data_as<int32_t>(), y->data_as<int32_t>());
+  cursor_ += b;
+  return true;
+}
+
+// ---- numeric CSV helpers
+static bool read_csv(const std::string& path, bool header, std::vector<std::vector<float>>& rows) {
+  std::ifstream f(path);
+  if (!f) return false;
+  std::string line;
+  if (header) std::getline(f, line);
+  while (std::getline(f, line)) {
+    if (line.empty()) continue;
+    std::vector<float> r;
+    std::stringstream ss(line);
+    std::string cell;
+    while (std::getline(ss, cell, ',')) r.push_back(cell.empty() ? 0.f : (float)atof(cell.c_str()));
+    if (!r.empty()) rows.push_back(std::move(r));
+  }
+  return !rows.empty();
+}
+static bool csv_batch(size_t B, size_t& cursor, size_t n, const std::vector<uint32_t>& order, const std::vector<float>& xs, size_t F, Tensor& x,
+                      bool pinned) {
+  if (cursor >= n) return false;
+  const size_t b = std::min(B, n - cursor);
+  IAllocator& a = pinned ? static_cast<IAllocator&>(DeviceAllocator::pinned()) : HostAllocator();
+  x = make_tensor(a, DType_t::FP32, {b, F});
+  for (size_t i = 0; i < b; ++i) std::memcpy(x->data_as<float>() + i * F, xs.data() + (size_t)order[cursor + i] * F, F * sizeof(float));
+  return true;
+}
+bool RegressionCSVDataLoader::load_data(const std::string& path) {
+  std::vector<std::vector<float>> rows;
+  if (!read_csv(path, header_, rows)) return false;
+  const size_t cols = rows[0].size();
+  if (cols <= n_targets_) return false;
+  features_ = cols - n_targets_;
+  n_ = rows.size();
+  xs_.resize(n_ * features_);
+  ys_.resize(n_ * n_targets_);
+  for (size_t i = 0; i < n_; ++i) {
+    if (rows[i].size() != cols) return false;
+    std::copy(rows[i].begin(), rows[i].begin() + (long)features_, xs_.begin() + (long)(i * features_));
+    std::copy(rows[i].begin() + (long)features_, rows[i].end(), ys_.begin() + (long)(i * n_targets_));
+  }
+  sample_shape_ = {features_};
+  classes_ = n_targets_;
+  cursor_ = 0;
+  order_.clear();
+  return true;
+}
+bool RegressionCSVDataLoader::get_batch(size_t B, Tensor& x, Tensor& y) {
+  if (order_.size() != n_) {
+    order_.resize(n_);
+    std::iota(order_.begin(), order_.end(), 0u);
+  }
+  if (!csv_batch(B, cursor_, n_, order_, xs_, features_, x, pinned_)) return false;
+  size_t c2 = cursor_;
+  csv_batch(B, c2, n_, order_, ys_, n_targets_, y, pinned_);
+  cursor_ += x->dimension(0);
+  return true;
+}
+bool WiFiDataLoader::load_data(const std::string& path, size_t fs, size_t fe, size_t ts, size_t te, bool has_header) {
+  std::vector<std::vector<float>> rows;
+  if (!read_csv(path, has_header, rows)) return false;
+  const size_t cols = rows[0].size();
+  if (fe <= fs) {                                   // reference default: all but the last column
+    fs = 0;
+    fe = cols - 1;
+  }
+  if (te <= ts) {
+    ts = fe;
+    te = cols;
+  }
+  fe = std::min(fe, cols);
+  te = std::min(te, cols);
+  features_ = fe - fs;
+  targets_ = regression_ ? te - ts : 1;
+  n_ = rows.size();
+  xs_.resize(n_ * features_);
+  ys_.resize(n_ * targets_);
+  for (size_t i = 0; i < n_; ++i) {
+    if (rows[i].size() != cols) return false;
+    for (size_t c = 0; c < features_; ++c) xs_[i * features_ + c] = rows[i][fs + c];
+    for (size_t c = 0; c < targets_; ++c) ys_[i * targets_ + c] = rows[i][ts + c];
+  }
+  sample_shape_ = {features_};
+  classes_ = targets_;
+  normalized_ = false;
+  cursor_ = 0;
+  order_.clear();
+  return true;
+}
+void WiFiDataLoader::normalize_data() {
+  auto zscore = [&](std::vector<float>& v, size_t F, std::vector<float>& mean, std::vector<float>& sd) {
+    mean.assign(F, 0.f);
+    sd.assign(F, 0.f);
+    for (size_t i = 0; i < n_; ++i)
+      for (size_t c = 0; c < F; ++c) mean[c] += v[i * F + c];
+    for (size_t c = 0; c < F; ++c) mean[c] /= (float)n_;
+    for (size_t i = 0; i < n_; ++i)
+      for (size_t c = 0; c < F; ++c) sd[c] += (v[i * F + c] - mean[c]) * (v[i * F + c] - mean[c]);
+    for (size_t c = 0; c < F; ++c) sd[c] = std::max(1e-8f, std::sqrt(sd[c] / (float)n_));
+    for (size_t i = 0; i < n_; ++i)
+      for (size_t c = 0; c < F; ++c) v[i * F + c] = (v[i * F + c] - mean[c]) / sd[c];
+  };
+  if (normalized_ || n_ == 0) return;
+  zscore(xs_, features_, fmean_, fstd_);
+  if (regression_) zscore(ys_, targets_, tmean_, tstd_);
+  normalized_ = true;
+}
+bool WiFiDataLoader::get_batch(size_t B, Tensor& x, Tensor& y) {
+  if (order_.size() != n_) {
+    order_.resize(n_);
+    std::iota(order_.begin(), order_.end(), 0u);
+  }
+  if (!csv_batch(B, cursor_, n_, order_, xs_, features_, x, pinned_)) return false;
+  const size_t b = x->dimension(0);
+  IAllocator& a = pinned_ ? static_cast<IAllocator&>(DeviceAllocator::pinned()) : HostAllocator();
+  if (regression_) {
+    y = make_tensor(a, DType_t::FP32, {b, targets_});
+    for (size_t i = 0; i < b; ++i) std::memcpy(y->data_as<float>() + i * targets_, ys_.data() + (size_t)order_[cursor_ + i] * targets_, targets_ * sizeof(float));
+  } else {
+    y = make_tensor(a, DType_t::INT32_T, {b});
+    for (size_t i = 0; i < b; ++i) y->data_as<int32_t>()[i] = (int32_t)ys_[(size_t)order_[cursor_ + i]];
+  }
+  cursor_ += b;
+  return true;
+}
+
 DataLoaderPair DataLoaderFactory::create(const std::string& name, const std::string& path) {
   DataLoaderPair p;
   auto exists = [](const std::string& f) { struct stat st; return stat(f.c_str(), &st) == 0; };
@@ -297,6 +452,31 @@ DataLoaderPair DataLoaderFactory::create(const std::string& name, const std::str
     }
     p.train = std::make_unique<SyntheticDataLoader>(Shape{28, 28, 1}, 10, 4096, 1);
     p.val = std::make_unique<SyntheticDataLoader>(Shape{28, 28, 1}, 10, 512, 1);
+    return p;
+  }
+  if (name == "openwebtext" || name == "open_webtext") {
+    auto tr = std::make_unique<OpenWebTextDataLoader>(1024), va = std::make_unique<OpenWebTextDataLoader>(1024);
+    if (!tr->load_data(path + "/train.bin")) throw std::runtime_error("DataLoaderFactory: no token file " + path + "/train.bin");
+    p.train = std::move(tr);
+    if (va->load_data(path + "/val.bin")) p.val = std::move(va);
+    return p;
+  }
+  if (name == "regression" || name == "wifi" || name == "uji") {
+    const bool wifi = name != "regression";
+    auto mk = [&](const std::string& f) -> std::unique_ptr<BaseDataLoader> {
+      if (wifi) {
+        auto l = std::make_unique<WiFiDataLoader>(true);
+        if (!l->load_data(f)) return nullptr;
+        l->normalize_data();
+        return l;
+      }
+      auto l = std::make_unique<RegressionCSVDataLoader>(1);
+      if (!l->load_data(f)) return nullptr;
+      return l;
+    };
+    p.train = mk(exists(path + "/train.csv") ? path + "/train.csv" : path);
+    if (!p.train) throw std::runtime_error("DataLoaderFactory: cannot read " + path);
+    if (exists(path + "/val.csv")) p.val = mk(path + "/val.csv");
     return p;
   }
   // "synthetic[:H,W,C,classes,n]"

@@ -8,6 +8,7 @@
 #include <functional>
 #include <iostream>
 #include <sstream>
+#include <sys/stat.h>
 
 #include "runtime/archiver.hpp"
 #include "tnn/distributed.hpp"
@@ -653,6 +654,115 @@ TEST(lost_microbatch_and_worker_errors_are_detected) {
 }
 
 // ------------------------------------------------------------------------------------- GPU: layer parity with the CPU oracle
+// ------------------------------------------------------------------------------------- augmentation + file loaders
+TEST(augmentation_strategies_and_builder) {
+  auto img = [](size_t B, size_t H, size_t W, size_t C, uint64_t seed) {
+    Tensor t = make_tensor(DType_t::FP32, {B, H, W, C});
+    t->fill_random_uniform(0.0, 1.0, seed);
+    return t;
+  };
+  // flips applied twice with p = 1 are the identity; a single flip mirrors
+  Tensor x = img(2, 6, 5, 3, 1), ref = x->clone();
+  auto fl = AugmentationBuilder(3).horizontal_flip(1.0).build();
+  fl->apply(*x);
+  CHECK_NEAR(x->at<float>({0, 2, 0, 1}), ref->at<float>({0, 2, 4, 1}), 0.0);
+  fl->apply(*x);
+  for (size_t i = 0; i < x->size(); ++i) CHECK_NEAR(x->data_as<float>()[i], ref->data_as<float>()[i], 0.0);
+  auto vf = AugmentationBuilder(3).vertical_flip(1.0).build();
+  vf->apply(*x);
+  CHECK_NEAR(x->at<float>({1, 0, 3, 2}), ref->at<float>({1, 5, 3, 2}), 0.0);
+  // normalize: (x - mean) / std per channel
+  x = ref->clone();
+  AugmentationBuilder().normalize({0.5f, 0.4f, 0.3f}, {0.2f, 0.25f, 0.5f}).build()->apply(*x);
+  CHECK_NEAR(x->at<float>({0, 1, 1, 1}), (ref->at<float>({0, 1, 1, 1}) - 0.4f) / 0.25f, 1e-6);
+  // crop keeps the shape and only moves pixels; cutout zeroes a square; rotation by 0 degrees is the identity
+  x = ref->clone();
+  AugmentationBuilder(5).random_crop(1.0, 2).build()->apply(*x);
+  CHECK(x->shape() == ref->shape());
+  double zeros = 0;
+  x = ref->clone();
+  AugmentationBuilder(5).cutout(1.0, 3).build()->apply(*x);
+  for (size_t i = 0; i < x->size(); ++i) zeros += x->data_as<float>()[i] == 0.f;
+  CHECK(zeros >= 2 * 3 * 4 && zeros <= 2 * 3 * 16 + 4);            // 2 images x 3 channels x (clipped 2x2 .. 4x4 squares)
+  x = ref->clone();
+  AugmentationBuilder(5).rotation(1.0, 0.0).build()->apply(*x);
+  for (size_t i = 0; i < x->size(); ++i) CHECK_NEAR(x->data_as<float>()[i], ref->data_as<float>()[i], 1e-6);
+  // value-range strategies stay in [0, 1]; the whole chain is deterministic in (seed, batch index)
+  auto chain = [&](uint64_t seed) {
+    return AugmentationBuilder(seed).horizontal_flip(0.5).vertical_flip(0.2).rotation(0.5, 10).brightness(0.7, 0.3).contrast(0.7, 0.3).gaussian_noise(0.7, 0.1)
+        .random_crop(1.0, 2).cutout(0.5, 2).build();
+  };
+  CHECK(chain(1)->size() == 8 && chain(1)->names().front() == "horizontal_flip");
+  Tensor a = ref->clone(), b = ref->clone(), c = ref->clone();
+  chain(9)->apply(*a, 4);
+  chain(9)->apply(*b, 4);
+  chain(9)->apply(*c, 5);
+  double diff = 0;
+  for (size_t i = 0; i < a->size(); ++i) {
+    CHECK(a->data_as<float>()[i] >= 0.f && a->data_as<float>()[i] <= 1.f);
+    CHECK_NEAR(a->data_as<float>()[i], b->data_as<float>()[i], 0.0);
+    diff += std::fabs(a->data_as<float>()[i] - c->data_as<float>()[i]);
+  }
+  CHECK(diff > 1e-3);
+  // a loader applies its augmentation to every image batch
+  SyntheticDataLoader plain({8, 8, 3}, 4, 32, 1), aug({8, 8, 3}, 4, 32, 1);
+  aug.set_augmentation(AugmentationBuilder(2).horizontal_flip(1.0).build());
+  Tensor px, py, ax, ay;
+  plain.get_batch(4, px, py);
+  aug.get_batch(4, ax, ay);
+  CHECK_NEAR(ax->at<float>({1, 3, 0, 2}), px->at<float>({1, 3, 7, 2}), 0.0);
+}
+TEST(token_csv_and_wifi_loaders) {
+  const std::string dir = "/tmp/tnn_cpp_loader_test";
+  mkdir(dir.c_str(), 0755);
+  {                                               // 5000 uint16 tokens: t[i] = i % 1000
+    std::ofstream f(dir + "/train.bin", std::ios::binary);
+    for (uint32_t i = 0; i < 5000; ++i) {
+      const uint16_t t = (uint16_t)(i % 1000);
+      f.write(reinterpret_cast<const char*>(&t), 2);
+    }
+  }
+  OpenWebTextDataLoader owt(64);
+  CHECK(owt.load_data(dir + "/train.bin") && owt.num_tokens() == 5000 && owt.size() == 5000 / 64);
+  Tensor x, y;
+  CHECK(owt.get_batch(3, x, y));
+  CHECK((x->shape() == Shape{3, 64}) && x->data_type() == DType_t::INT32_T && (y->shape() == Shape{3, 64}));
+  for (size_t b = 0; b < 3; ++b)
+    for (size_t i = 0; i + 1 < 64; ++i) {
+      CHECK(y->data_as<int32_t>()[b * 64 + i] == x->data_as<int32_t>()[b * 64 + i + 1]);        // targets are the next tokens
+      CHECK((x->data_as<int32_t>()[b * 64 + i] + 1) % 1000 == x->data_as<int32_t>()[b * 64 + i + 1]);
+    }
+  DataLoaderPair p = DataLoaderFactory::create("openwebtext", dir);
+  CHECK(p.train && p.train->size() == 5000 / 1024);
+  {                                               // CSV: 3 features, 2 targets
+    std::ofstream f(dir + "/reg.csv");
+    f << "a,b,c,t0,t1\n";
+    for (int i = 0; i < 10; ++i) f << i << ',' << 2 * i << ',' << -i << ',' << 10 * i << ',' << i * i << "\n";
+  }
+  RegressionCSVDataLoader reg(2);
+  CHECK(reg.load_data(dir + "/reg.csv") && reg.size() == 10 && reg.num_features() == 3);
+  CHECK(reg.get_batch(4, x, y));
+  CHECK((x->shape() == Shape{4, 3}) && (y->shape() == Shape{4, 2}));
+  CHECK_NEAR(x->at<float>({3, 1}), 6.0, 0.0);
+  CHECK_NEAR(y->at<float>({3, 1}), 9.0, 0.0);
+  CHECK(reg.get_batch(100, x, y) && x->dimension(0) == 6 && !reg.get_batch(1, x, y));
+  WiFiDataLoader wifi(true);
+  CHECK(wifi.load_data(dir + "/reg.csv", 0, 3, 3, 5) && wifi.num_features() == 3 && wifi.num_targets() == 2);
+  wifi.normalize_data();
+  CHECK(wifi.is_normalized());
+  CHECK_NEAR(wifi.feature_means()[0], 4.5, 1e-5);
+  CHECK_NEAR(wifi.target_means()[0], 45.0, 1e-4);
+  CHECK(wifi.get_batch(10, x, y));
+  double m = 0, v = 0;
+  for (size_t i = 0; i < 10; ++i) m += x->at<float>({i, 1});
+  for (size_t i = 0; i < 10; ++i) v += x->at<float>({i, 1}) * x->at<float>({i, 1});
+  CHECK_NEAR(m / 10, 0.0, 1e-5);
+  CHECK_NEAR(v / 10, 1.0, 1e-4);
+  WiFiDataLoader cls(false);
+  CHECK(cls.load_data(dir + "/reg.csv", 0, 3, 3, 4));
+  CHECK(cls.get_batch(5, x, y) && y->data_type() == DType_t::INT32_T && y->data_as<int32_t>()[2] == 20);
+}
+
 // ------------------------------------------------------------------------------------- GPT-2 inference engine / legacy zoo / hardware info
 static std::unique_ptr<Sequential> tiny_gpt(size_t vocab = 97, size_t E = 128, size_t H = 2, size_t layers = 2, size_t seq = 48) {
   LayerBuilder b({seq});
