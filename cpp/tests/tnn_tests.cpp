@@ -2,6 +2,7 @@
 // archiver_test, device_manager_test, layer tests with CPU-vs-GPU parity, partitioner_test ...).  No network deps, so
 // the harness is 30 lines of macros instead of GoogleTest.  GPU cases skip when no device is visible.
 //   tnn_tests [filter-substring]
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -18,6 +19,7 @@
 #include "tnn/legacy.hpp"
 #include "tnn/stepstate.hpp"
 #include "tnn/train.hpp"
+#include "tnn/utils.hpp"
 
 using namespace tnn;
 
@@ -654,6 +656,44 @@ TEST(lost_microbatch_and_worker_errors_are_detected) {
 }
 
 // ------------------------------------------------------------------------------------- GPU: layer parity with the CPU oracle
+TEST(utils_threading_concurrent_map_logger) {
+  std::vector<std::atomic<int>> hits(1000);
+  parallel_for(0, 1000, [&](int64_t i) { hits[(size_t)i]++; }, 16);
+  for (auto& h : hits) CHECK(h.load() == 1);
+  std::atomic<long> sum{0};
+  parallel_for_2d(20, 30, [&](int64_t i, int64_t j) { sum += i * 30 + j; });
+  CHECK(sum.load() == 599L * 600 / 2);
+  CHECK(ThreadWrapper(2).execute([] { return thread_limit(); }) == 2 && thread_limit() == 0);
+  ConcurrentMap<std::string, int> m;
+  CHECK(m.emplace("a", 1) && !m.emplace("a", 2) && m.try_get("a").value() == 1 && !m.try_get("b").has_value());
+  parallel_for(0, 500, [&](int64_t) { m.update("n", [](int& v) { ++v; }); });
+  CHECK(m.try_get("n").value() == 500 && m.contains("n") && m.erase("a") && m.size() == 1 && m.snapshot().count("n") == 1);
+  const std::string path = "/tmp/tnn_cpp_logger_test.log", steps = "/tmp/tnn_cpp_steplog_test.jsonl";
+  std::remove(path.c_str());
+  std::remove(steps.c_str());
+  Logger log("unit", LogLevel::WARN);
+  log.set_file(path);
+  log.info("dropped");
+  log.warn("kept 1");
+  log.error("kept 2");
+  std::ifstream f(path);
+  std::string all((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+  CHECK(all.find("dropped") == std::string::npos && all.find("[warn] kept 1") != std::string::npos && all.find("[error] kept 2") != std::string::npos);
+  {
+    StepLog sl(steps);
+    Json r = Json::object();
+    r["step"] = 3;
+    r["loss"] = 0.25;
+    sl.write(r);
+  }
+  std::ifstream g(steps);
+  std::string line;
+  std::getline(g, line);
+  CHECK(Json::parse(line).at("step").as_int() == 3);
+  CHECK(get_shape_hash({2, 3, 4}) != get_shape_hash({4, 3, 2}) && get_shape_hash({2, 3}) == get_shape_hash({2, 3}));
+  CHECK(benchmark([] {}, 3, 1) >= 0.0);
+}
+
 // ------------------------------------------------------------------------------------- augmentation + file loaders
 TEST(augmentation_strategies_and_builder) {
   auto img = [](size_t B, size_t H, size_t W, size_t C, uint64_t seed) {

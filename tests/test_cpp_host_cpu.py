@@ -323,12 +323,13 @@ def test_cpp_gpt2_engine_matches_the_python_engine_and_runs_the_new_apps():
     # example apps of the C++ host (reference examples/*.cpp)
     bins = os.path.join(ROOT, "cpp", "bin")
     for app in ("gpt2_inference", "inferencer", "graph_test", "msequential_example", "test_del", "device_manager_example",
-                "hardware_info_example", "legacy_trainer", "trainer", "tcp_worker", "tcp_coordinator", "bench_cpp"):
+                "hardware_info_example", "legacy_trainer", "trainer", "tcp_worker", "tcp_coordinator", "bench_cpp", "op_bench"):
         assert os.access(os.path.join(bins, app), os.X_OK), app
     env = dict(os.environ, MODEL_NAME="mnist_cnn", BATCH_SIZE="16", EPOCHS="1", MAX_STEPS="3", DEVICE_TYPE="CPU")
     for cmd, needle in ((["msequential_example"], "Example Complete"), (["test_del"], "double-ended placement ok"),
                         (["device_manager_example"], "CPU:0"), (["graph_test", "--steps", "2"], "Loss:"),
                         (["legacy_trainer", "--synthetic", "--samples", "64"], "final train loss"),
-                        (["inferencer", "--synthetic", "--samples", "32"], "Validation Loss")):
+                        (["inferencer", "--synthetic", "--samples", "32"], "Validation Loss"),
+                        (["op_bench", "serialization", "--device", "CPU", "--iters", "2"], "serialize_GBps")):
         out = subprocess.run([os.path.join(bins, cmd[0])] + cmd[1:], capture_output=True, text=True, timeout=300, env=env, cwd=str(ROOT))
         assert out.returncode == 0 and needle in out.stdout, (cmd, out.stdout[-800:], out.stderr[-800:])
