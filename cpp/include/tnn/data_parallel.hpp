@@ -1,0 +1,52 @@
+// Data-parallel training in ONE process: a replica per GPU, a host thread per replica, and the fused data-parallel step
+// kernel (csrc/kernels/optim.cu k_dp_step) instead of "all-reduce, then optimizer": cross-GPU flag barrier -> every rank
+// reduces its 1/W slice of the gradients from all peers over NVLink peer loads -> Adam / SGD on the slice (optimizer state
+// sharded W ways) -> broadcast fp32 + bf16 parameters into every replica -> barrier -> zero the gradients.
+// (Reference: ParallelMode_t::DATA exists only as routing, SURVEY F4 -- there is no gradient reduction to mirror.)
+// The Python host runs the same kernel with one process per GPU (parallel/dp.py, NVLS multicast through symmetric memory);
+// inside one process the peers' device pointers are directly usable after cudaDeviceEnablePeerAccess.
+#pragma once
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "tnn/train.hpp"
+
+namespace tnn {
+
+class DataParallel {
+ public:
+  using ModelFactory = std::function<std::unique_ptr<Layer>()>;
+  // `world` replicas on GPU 0..world-1; the same seed initialises every replica identically
+  DataParallel(const ModelFactory& make_model, int world, uint64_t seed, const Optimizer& optimizer_proto, const std::string& loss = "logsoftmax_crossentropy",
+               bool use_graph = true);
+  ~DataParallel();
+  // xs[r] / ys[r]: replica r's batch (host, ideally pinned).  Returns {mean loss over replicas, total #correct}.
+  std::pair<double, double> step(const Vec<Tensor>& xs, const Vec<Tensor>& ys);
+  int world() const { return (int)ranks_.size(); }
+  Graph& replica(int r) { return *ranks_.at((size_t)r)->graph; }
+  size_t num_parameters() const { return n_; }
+  // max over replicas r > 0 of max |param_r - param_0| (replicas must stay bit-identical)
+  double max_replica_divergence();
+  bool captured() const;
+
+ private:
+  struct Rank {
+    Device dev{DeviceType::GPU, 0};
+    std::unique_ptr<Graph> graph;
+    std::unique_ptr<Optimizer> opt;
+    std::unique_ptr<Loss> loss;
+    std::unique_ptr<TrainStep> step;
+    Tensor m, v, flags, sync;
+  };
+  void launch_fused_step(int r);
+  std::vector<std::unique_ptr<Rank>> ranks_;
+  size_t n_ = 0, chunk_ = 0;
+  bool adam_ = true;
+  std::vector<float*> g_peers_, p_peers_;
+  std::vector<void*> pb_peers_;
+  std::vector<uint32_t*> flag_peers_;
+};
+
+}  // namespace tnn

@@ -51,6 +51,9 @@ class TrainStep {
   uint64_t replays() const { return replays_; }
   uint64_t captured_launches() const { return captured_launches_; }
   GraphExecutor& executor() { return exec_; }
+  // replaces the optimizer update of this step (eager and captured): the data-parallel trainer launches the fused
+  // cross-GPU reduce + optimizer + broadcast kernel here (data_parallel.hpp)
+  std::function<void()> update_override;
 
  private:
   Tensor eager(const Tensor& x, const Tensor& y, size_t mb_id);

@@ -1,0 +1,130 @@
+// DataParallel: see tnn/data_parallel.hpp.
+#include "tnn/data_parallel.hpp"
+
+#include <cmath>
+#include <thread>
+
+#include "kernels/simt_ops.cuh"
+#include "tnn/stepstate.hpp"
+
+namespace tnn {
+
+DataParallel::DataParallel(const ModelFactory& make_model, int world, uint64_t seed, const Optimizer& proto, const std::string& loss, bool use_graph) {
+  auto& dm = DeviceManager::getInstance();
+  if (world < 1 || world > dm.num_gpus()) throw std::invalid_argument("DataParallel: " + std::to_string(world) + " replicas requested, " + std::to_string(dm.num_gpus()) + " GPU(s) visible");
+  adam_ = proto.name() == "adam";
+  for (int r = 0; r < world; ++r) {
+    auto rk = std::make_unique<Rank>();
+    rk->dev = dm.getGPU(r);
+    rk->dev.set_current();
+    rk->graph = std::make_unique<Graph>(graph_from_sequential(make_model(), rk->dev, seed, "dp_replica" + std::to_string(r)));
+    rk->opt = proto.clone();
+    rk->loss = LossFactory::create(loss);
+    ranks_.push_back(std::move(rk));
+  }
+  n_ = ranks_[0]->graph->context().numel();
+  chunk_ = ((n_ + (size_t)world - 1) / (size_t)world + 1023) / 1024 * 1024;
+  for (int r = 0; r < world; ++r) {                       // every pair of replicas may address each other's slabs
+    TNN_CUDA(cudaSetDevice(ranks_[(size_t)r]->dev.id()));
+    for (int q = 0; q < world; ++q) {
+      if (q == r) continue;
+      const cudaError_t e = cudaDeviceEnablePeerAccess(ranks_[(size_t)q]->dev.id(), 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) throw std::runtime_error(std::string("DataParallel: no peer access ") + cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+  }
+  for (auto& rk : ranks_) {
+    Rank& k = *rk;
+    k.dev.set_current();
+    GraphContext& ctx = k.graph->context();
+    if (ctx.numel() != n_) throw std::logic_error("DataParallel: replicas differ in size");
+    k.m = make_tensor(DType_t::FP32, {chunk_}, k.dev);
+    k.m->zero();
+    if (adam_) {
+      k.v = make_tensor(DType_t::FP32, {chunk_}, k.dev);
+      k.v->zero();
+    }
+    k.flags = make_tensor(DType_t::INT32_T, {64}, k.dev);
+    k.flags->zero();
+    k.sync = make_tensor(DType_t::INT32_T, {4}, k.dev);
+    k.sync->zero();
+    g_peers_.push_back(ctx.grad_slab()->data_as<float>());
+    p_peers_.push_back(ctx.param_slab()->data_as<float>());
+    pb_peers_.push_back(ctx.lp_slab()->data());
+    flag_peers_.push_back(reinterpret_cast<uint32_t*>(k.flags->data()));
+    StepState::get(k.dev);                                  // created before the replica threads start
+    current_flow(k.dev).synchronize();
+  }
+  for (int r = 0; r < world; ++r) {
+    Rank& k = *ranks_[(size_t)r];
+    k.step = std::make_unique<TrainStep>(*k.graph, *k.loss, *k.opt, nullptr, 1, use_graph);
+    k.step->update_override = [this, r] { launch_fused_step(r); };
+  }
+}
+DataParallel::~DataParallel() {
+  for (auto& rk : ranks_) {
+    rk->dev.set_current();
+    cudaDeviceSynchronize();
+  }
+}
+
+void DataParallel::launch_fused_step(int r) {
+  Rank& k = *ranks_[(size_t)r];
+  k.dev.set_current();
+  dp_fused_step(world(), r, (long long)n_, (long long)chunk_, g_peers_.data(), p_peers_.data(), pb_peers_.data(), flag_peers_.data(), nullptr, nullptr, nullptr,
+                k.m->data_as<float>(), adam_ ? k.v->data_as<float>() : nullptr, reinterpret_cast<uint32_t*>(k.sync->data()), StepState::get(k.dev).dev(), adam_ ? 1 : 0,
+                /*ctas=*/64, 0, (long long)n_, 0, current_flow(k.dev).stream());
+  k.graph->context().mark_lp_fresh();                       // the kernel rewrote the bf16 copies of every replica
+}
+
+std::pair<double, double> DataParallel::step(const Vec<Tensor>& xs, const Vec<Tensor>& ys) {
+  const size_t W = ranks_.size();
+  if (xs.size() != W || ys.size() != W) throw std::invalid_argument("DataParallel::step: one batch per replica expected");
+  std::vector<float> loss(W, 0.f), correct(W, 0.f);
+  std::vector<std::string> errors(W);
+  std::vector<std::thread> th;
+  // one host thread per replica: the fused kernels of all replicas must be in flight together (they barrier on each
+  // other), and a replica's eager warm-up steps may synchronise its own device
+  for (size_t r = 0; r < W; ++r)
+    th.emplace_back([&, r] {
+      try {
+        Rank& k = *ranks_[r];
+        k.dev.set_current();
+        Tensor st = (*k.step)(xs[r], ys[r]);
+        float h[2];
+        st->copy_to_host(h, 8);
+        loss[r] = h[0];
+        correct[r] = h[1];
+      } catch (const std::exception& e) {
+        errors[r] = e.what();
+      }
+    });
+  for (auto& t : th) t.join();
+  for (size_t r = 0; r < W; ++r)
+    if (!errors[r].empty()) throw std::runtime_error("DataParallel replica " + std::to_string(r) + ": " + errors[r]);
+  double l = 0, c = 0;
+  for (size_t r = 0; r < W; ++r) {
+    l += loss[r];
+    c += correct[r];
+  }
+  return {l / (double)W, c};
+}
+
+double DataParallel::max_replica_divergence() {
+  ranks_[0]->dev.set_current();
+  const std::vector<float> ref = to_float_vector(*ranks_[0]->graph->context().param_slab());
+  double worst = 0;
+  for (size_t r = 1; r < ranks_.size(); ++r) {
+    ranks_[r]->dev.set_current();
+    const std::vector<float> p = to_float_vector(*ranks_[r]->graph->context().param_slab());
+    for (size_t i = 0; i < n_; ++i) worst = std::max(worst, (double)std::fabs(p[i] - ref[i]));
+  }
+  return worst;
+}
+bool DataParallel::captured() const {
+  for (auto& rk : ranks_)
+    if (!rk->step->captured()) return false;
+  return true;
+}
+
+}  // namespace tnn

@@ -661,7 +661,12 @@ Tensor TrainStep::eager(const Tensor& x, const Tensor& y, size_t mb) {
   if (dev.is_gpu()) StepState::get(dev).advance(do_update ? &opt_ : nullptr);
   Tensor stats = core(dx, dy, mb);
   if (do_update) {
-    opt_.update(/*external_state=*/dev.is_gpu());
+    if (update_override) {
+      update_override();
+      ++opt_.step_count;
+    } else {
+      opt_.update(/*external_state=*/dev.is_gpu());
+    }
     refresh_conv_flips();
     if (sched_) sched_->step();
   }
@@ -682,7 +687,8 @@ void TrainStep::capture(const Tensor& x, const Tensor& y) {
   TNN_CUDA(cudaStreamBeginCapture(flow.stream(), cudaStreamCaptureModeRelaxed));
   try {
     Tensor stats = core(sx_, sy_, 0);
-    opt_.update(/*external_state=*/true);
+    if (update_override) update_override();
+    else opt_.update(/*external_state=*/true);
     refresh_conv_flips();                    // the two eager warm-up steps allocated every flipped copy: table is final here
     TNN_CUDA(cudaMemcpyAsync(sstats_->data(), stats->data(), 8, cudaMemcpyDeviceToDevice, flow.stream()));
   } catch (...) {

@@ -12,6 +12,7 @@
 #include <sys/stat.h>
 
 #include "runtime/archiver.hpp"
+#include "tnn/data_parallel.hpp"
 #include "tnn/distributed.hpp"
 #include "tnn/example_models.hpp"
 #include "tnn/hardware_info.hpp"
@@ -1154,6 +1155,55 @@ TEST(gpu_gpt2_engine_bf16_fp8_and_graph_decode) {
     f8.decode_graph(lastc, 1);
     CHECK(!f8.uses_fp8_kv_cache());
   }
+}
+
+TEST(dp2_fused_step_matches_single_device) {
+  need_gpu();
+  if (DeviceManager::getInstance().num_gpus() < 2) throw Skip("needs 2 GPUs");
+  // BatchNorm-free model: the two-replica run on half batches must follow the single-GPU run on the full batch
+  auto make = []() -> std::unique_ptr<Layer> {
+    LayerBuilder b({8, 8, 16});
+    b.conv2d(32, 3, 3, 1, 1, 1, 1, true, "c1").activation("relu", "r1").conv2d(32, 3, 3, 2, 2, 1, 1, true, "c2").activation("relu", "r2").flatten(1, -1, "f")
+        .dense(64, true, "d1").activation("relu", "r3").dense(10, true, "head");
+    return b.build_sequential("dp_test_net");
+  };
+  const size_t B = 64;
+  SyntheticDataLoader data({8, 8, 16}, 10, 4 * B, 5);
+  data.set_pinned(true);
+  Vec<Tensor> fx, fy;
+  for (int k = 0; k < 4; ++k) {
+    Tensor x, y;
+    data.get_batch(B, x, y);
+    fx.push_back(x);
+    fy.push_back(y);
+  }
+  Adam proto(1e-3, 0.9, 0.999, 1e-8, 0.0, false);
+  std::vector<float> single;
+  {
+    Graph g = graph_from_sequential(make(), getGPU(0), 77, "single");
+    auto opt = proto.clone();
+    auto crit = LossFactory::create_logsoftmax_crossentropy();
+    TrainStep step(g, *crit, *opt, nullptr, 1, true);
+    for (int i = 0; i < 10; ++i) {
+      float h[2];
+      step(fx[(size_t)i % 4], fy[(size_t)i % 4])->copy_to_host(h, 8);
+      single.push_back(h[0]);
+    }
+  }
+  DataParallel dp(make, 2, 77, proto);
+  CHECK(dp.max_replica_divergence() == 0.0);
+  for (int i = 0; i < 10; ++i) {
+    Vec<Tensor> xs, ys;
+    for (size_t r = 0; r < 2; ++r) {
+      xs.push_back(fx[(size_t)i % 4]->slice_batch(r * B / 2, B / 2));
+      ys.push_back(fy[(size_t)i % 4]->slice_batch(r * B / 2, B / 2));
+    }
+    const auto res = dp.step(xs, ys);
+    CHECK_NEAR(res.first, single[(size_t)i], 0.03 * std::max(1.0, (double)single[(size_t)i]));
+  }
+  CHECK(dp.captured());
+  CHECK(dp.max_replica_divergence() == 0.0);          // every replica received the same broadcast parameters
+  CHECK(single.back() < single.front());
 }
 
 int main(int argc, char** argv) {

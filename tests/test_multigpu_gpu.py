@@ -38,3 +38,18 @@ def test_dp_watchdog_reports_a_missing_rank():
     """One rank skips a fused step: the others' flag spins must end in the watchdog (trap + diagnostic), not hang."""
     out = _launch("dp_watchdog_check.py", 2, 29611, timeout=300)
     assert "k_dp_step watchdog" in (out.stdout + out.stderr), (out.stdout[-2000:], out.stderr[-2000:])
+
+
+def test_cpp_host_single_process_data_parallel():
+    """C++ host: one process, a replica + host thread per GPU, the fused data-parallel kernel over peer pointers
+    (cpp/src/data_parallel.cpp): follows the single-GPU loss trajectory, replicas stay bit-identical, step is a CUDA graph;
+    and the dp_trainer CLI runs the flagship model on 2 GPUs."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from tnn_b200 import build
+    build.build_host(verbose=False)
+    out = subprocess.run([os.path.join(ROOT, "cpp", "bin", "tnn_tests"), "dp2_"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "1 passed, 0 failed, 0 skipped" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
+    cli = subprocess.run([os.path.join(ROOT, "cpp", "bin", "dp_trainer"), "--gpus", "2", "--steps", "10", "--warmup", "4"], capture_output=True,
+                         text=True, timeout=600)
+    assert cli.returncode == 0 and '"replica_divergence": 0' in cli.stdout and '"cuda_graph": true' in cli.stdout, cli.stdout[-2000:] + cli.stderr[-2000:]

@@ -472,16 +472,16 @@ void attention_fwd_bf16(const void* q, long long q_tok, long long q_batch, const
   p.O = reinterpret_cast<bf16*>(out);
   p.o_row = (long long)H * AT_D;
   p.lse = lse;
-  static bool configured = false;
+  static PerDeviceOnce configured;
   static int split = 0;
-  if (!configured) {
+  if (configured.begin()) {
     cudaFuncSetAttribute(attn_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     cudaFuncSetAttribute(attn_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     cudaFuncSetAttribute(attn_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     cudaFuncSetAttribute(attn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     const char* e = getenv("TNN_ATTN_SPLIT");
     split = (e != nullptr) ? atoi(e) : 0;
-    configured = true;
+    configured.done();
   }
   dim3 grid((Lq + AT_BM - 1) / AT_BM, H, B);
   if (split) {

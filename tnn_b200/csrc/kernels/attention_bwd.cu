@@ -373,11 +373,11 @@ void attention_bwd_bf16(const void* q, const void* k, const void* v, long long q
   p.dv = reinterpret_cast<bf16*>(dv);
   p.dkv_tok = dqkv_tok;
   p.dkv_batch = dqkv_batch;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.begin()) {
     cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
     cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
-    configured = true;
+    configured.done();
   }
   dim3 grid((L + 127) / 128, H, B);
   if (causal)

@@ -6,6 +6,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <atomic>
+#include <mutex>
+
 namespace tnn {
 
 // number of kernels launched by this library in the current process (bench.py reports it)
@@ -21,6 +24,35 @@ extern unsigned long long g_launch_count;
       abort();                                                                                \
     }                                                                                         \
   } while (0)
+
+// cudaFuncSetAttribute (dynamic shared-memory limit, carve-out) applies to ONE device.  A launcher that caches
+// "already configured" therefore caches it per device: with a per-process flag the second GPU of a single-process
+// multi-GPU run (cpp DataParallel, the in-process pipeline) launches with the default 48 KB limit and fails.
+//   static PerDeviceOnce once;  if (once.begin()) { cudaFuncSetAttribute(...); once.done(); }
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  std::mutex mu;
+  static int device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & 63;
+  }
+  // true exactly once per device; the caller holds the lock until done()
+  bool begin() {
+    const unsigned long long bit = 1ull << device();
+    if (mask.load(std::memory_order_acquire) & bit) return false;
+    mu.lock();
+    if (mask.load(std::memory_order_relaxed) & bit) {
+      mu.unlock();
+      return false;
+    }
+    return true;
+  }
+  void done() {
+    mask.fetch_or(1ull << device(), std::memory_order_release);
+    mu.unlock();
+  }
+};
 
 static constexpr int kSMs = 148;
 typedef __nv_bfloat16 bf16;

@@ -63,10 +63,11 @@ void conv_direct_fwd(const void* x, const float* w, const float* bias, void* y, 
   }
   DConvP p{N, H, W, C, K, R, S, stride, pad, OH, OW};
   size_t smem = (size_t)R * S * C * K * sizeof(float);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
+  static std::atomic<size_t> configured[64];   // per device (the attribute is per device)
+  std::atomic<size_t>& conf = configured[PerDeviceOnce::device()];
+  if (smem > 48 * 1024 && smem > conf.load()) {
     cudaFuncSetAttribute(k_conv_direct_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
+    conf.store(smem);
   }
   long long total = (long long)N * OH * OW * (K / 8);
   k_conv_direct_fwd<<<grid_for(total, 256), 256, smem, s>>>((const bf16*)x, w, bias, (bf16*)y, p);
@@ -291,10 +292,10 @@ void conv_direct_wgrad(const void* x, const void* dy, float* dw, float* dbias, i
       const int smem = (32 + K) * DT_LD * 2 + 32 * K * 4;
 #define TNN_STEM(NT_)                                                                                          \
   do {                                                                                                         \
-    static bool configured = false;                                                                            \
-    if (!configured) {                                                                                         \
+    static PerDeviceOnce configured;                                                                            \
+    if (configured.begin()) {                                                                                         \
       cudaFuncSetAttribute(k_conv_stem_wgrad<NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   \
-      configured = true;                                                                                       \
+      configured.done();                                                                                       \
     }                                                                                                          \
     k_conv_stem_wgrad<NT_><<<blocks, 256, smem, s>>>((const bf16*)x, (const bf16*)dy, dw, dbias, p);           \
   } while (0)

@@ -847,8 +847,10 @@ void decode_fold_ln(const float* W, const float* bias, const float* gamma, const
 }
 
 void decode_step_mega(const DecodeParams& p, cudaStream_t stream) {
-  static int grid = 0;
-  if (!grid) {
+  static int grids[64] = {};   // per device: the smem attribute and the occupancy are device properties
+  static PerDeviceOnce once;
+  int& grid = grids[PerDeviceOnce::device()];
+  if (once.begin()) {
     cudaFuncSetAttribute(k_decode_mega<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
     cudaFuncSetAttribute(k_decode_mega<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DM_SMEM);
     int dev = 0, sms = 0, per_sm = 0, per_sm8 = 0;
@@ -865,6 +867,7 @@ void decode_step_mega(const DecodeParams& p, cudaStream_t stream) {
     grid = sms * (per_sm > 2 ? 2 : per_sm);
     const char* e = getenv("TNN_DECODE_CTAS");
     if (e && atoi(e) > 0 && atoi(e) < grid) grid = atoi(e);
+    once.done();
   }
   cudaMemsetAsync(p.bar, 0, sizeof(unsigned int), stream);
   if (p.kv_fp8) k_decode_mega<true><<<grid, DM_THREADS, DM_SMEM, stream>>>(p);

@@ -631,15 +631,15 @@ static CUtensorMap make_u8_map(const void* ptr, long long rows, long long K, lon
 template <int BLOCK_N, int STAGES, bool PAIR>
 static void launch_mxfp8(const CUtensorMap& tmA, const CUtensorMap& tmB, const F8Params& p, cudaStream_t stream) {
   constexpr int smem_bytes = STAGES * (F8_BLOCK_M * 128 + BLOCK_N * 128 + F8_SF_BYTES) + (2 * STAGES + 4) * 8 + 16;
-  static bool attr_set = false;
+  static PerDeviceOnce attr_set;
   auto kern = umma_gemm_mxfp8_persist_kernel<BLOCK_N, STAGES, PAIR>;
-  if (!attr_set) {
+  if (attr_set.begin()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) {
       fprintf(stderr, "[tnn_b200] mxfp8 smem attribute: %s\n", cudaGetErrorString(e));
       abort();
     }
-    attr_set = true;
+    attr_set.done();
   }
   const int m_tiles = (p.M + F8_BLOCK_M - 1) / F8_BLOCK_M;
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;

@@ -421,10 +421,10 @@ void bn_train_stats(const void* x, long long M, int C, const float* gamma, const
       if (use_async) {
         constexpr int RING = 8;
         constexpr int dyn = RING * 256 * 16;                    // 32 KB
-        static bool cfg = false;
-        if (!cfg) {
+        static PerDeviceOnce cfg;
+        if (cfg.begin()) {
           cudaFuncSetAttribute(k_bn_stats_async<RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-          cfg = true;
+          cfg.done();
         }
         k_bn_stats_async<RING><<<grid, 256, dyn, s>>>((const bf16*)x, M, C, gamma, beta, eps, momentum, running_mean,
                                                       running_var, save_mean, save_invstd, scale_shift, ws,
@@ -439,10 +439,10 @@ void bn_train_stats(const void* x, long long M, int C, const float* gamma, const
       return;
     }
   }
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.begin()) {
     cudaFuncSetAttribute(k_bn_stats, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
-    configured = true;
+    configured.done();
   }
   k_bn_stats<<<bn_blocks(M, C, BN_STATS_UNROLL), 256, 256 * 8 * sizeof(float), s>>>(
       (const bf16*)x, M, C, gamma, beta, eps, momentum, running_mean, running_var, save_mean,
@@ -981,13 +981,13 @@ void bn_bwd_reduce(const void* dy, const void* x, const void* y, long long M, in
                    cudaStream_t s) {
   float ds = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   BnMaskArgs ma{beta, relu, drop_p, seed, seed_ptr, bits};
-  static bool configured = false;
-  if (!configured) {   // ncu: the default carveout admitted ONE 8 KB-smem CTA per SM (occupancy limit "shared memory")
+  static PerDeviceOnce configured;
+  if (configured.begin()) {   // ncu: the default carveout admitted ONE 8 KB-smem CTA per SM (occupancy limit "shared memory")
     cudaFuncSetAttribute(k_bn_bwd_reduce<0>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
     cudaFuncSetAttribute(k_bn_bwd_reduce<1>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
     cudaFuncSetAttribute(k_bn_bwd_reduce<2>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
     cudaFuncSetAttribute(k_bn_bwd_reduce<3>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);
-    configured = true;
+    configured.done();
   }
   const int mode = !masked ? 0 : ((bits != nullptr && (C & 7) == 0) ? 3 : (y != nullptr ? 1 : 2));
   {
@@ -1015,11 +1015,11 @@ void bn_bwd_reduce(const void* dy, const void* x, const void* y, long long M, in
       if (use_async) {
         constexpr int RING = 8;
         constexpr int dyn = RING * 2 * 256 * 16;                  // 64 KB: three CTAs per SM
-        static bool cfg = false;
-        if (!cfg) {
+        static PerDeviceOnce cfg;
+        if (cfg.begin()) {
           cudaFuncSetAttribute(k_bn_bwd_reduce_async<0, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
           cudaFuncSetAttribute(k_bn_bwd_reduce_async<3, RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
-          cfg = true;
+          cfg.done();
         }
         if (mode == 0)
           k_bn_bwd_reduce_async<0, RING><<<grid2, 256, dyn, s>>>((const bf16*)dy, (const bf16*)x, M, C, gamma, save_mean,
@@ -1418,10 +1418,10 @@ void bn_bwd_apply(const void* dy, const void* x, const void* y, const void* extr
 #define TNN_BN_APPLY_ASYNC(MODE_, EXTRA_, RING_)                                                                     \
   do {                                                                                                               \
     constexpr int dyn = RING_ * ((EXTRA_) ? 3 : 2) * 256 * 16;                                                       \
-    static bool cfg = false;                                                                                         \
-    if (!cfg) {                                                                                                      \
+    static PerDeviceOnce cfg;                                                                                         \
+    if (cfg.begin()) {                                                                                                      \
       cudaFuncSetAttribute(k_bn_bwd_apply_async<MODE_, EXTRA_, RING_>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn); \
-      cfg = true;                                                                                                    \
+      cfg.done();                                                                                                    \
     }                                                                                                                \
     k_bn_bwd_apply_async<MODE_, EXTRA_, RING_><<<grid2, 256, dyn, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)extra, \
                                                                        (bf16*)dx, M, C, save_mean, save_invstd, coef, ds, \
@@ -1458,10 +1458,10 @@ void bn_bwd_apply(const void* dy, const void* x, const void* y, const void* extr
   const size_t smem = 256 * 8 * sizeof(float);
 #define TNN_BN_APPLY(MODE_, EXTRA_)                                                                              \
   do {                                                                                                           \
-    static bool configured = false;                                                                              \
-    if (!configured) {                                                                                           \
+    static PerDeviceOnce configured;                                                                              \
+    if (configured.begin()) {                                                                                           \
       cudaFuncSetAttribute(k_bn_bwd_apply<MODE_, EXTRA_>, cudaFuncAttributePreferredSharedMemoryCarveout, 50);   \
-      configured = true;                                                                                         \
+      configured.done();                                                                                         \
     }                                                                                                            \
     k_bn_bwd_apply<MODE_, EXTRA_><<<grid, 256, smem, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y,       \
                                                           (const bf16*)extra, (bf16*)dx, M, C, save_mean,        \

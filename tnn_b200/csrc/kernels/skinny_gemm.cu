@@ -219,15 +219,15 @@ void skinny_gemm_bf16(const void* x, long long ldx, const void* w, long long ldw
     abort();
   }
   constexpr int smem = SK_X_BYTES + SK_PART_BYTES;
-  static bool configured = false;
+  static PerDeviceOnce configured;
   static int forced = -1, pdl = 1;
-  if (!configured) {
+  if (configured.begin()) {
     cudaFuncSetAttribute(k_skinny_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const char* e = getenv("TNN_SKINNY_KSPLIT");
     forced = (e != nullptr) ? atoi(e) : 0;
     const char* e2 = getenv("TNN_PDL");
     pdl = (e2 != nullptr) ? atoi(e2) : 1;
-    configured = true;
+    configured.done();
   }
   const int col_ctas = (N + SK_COLS - 1) / SK_COLS;
   // cluster size: enough CTAs for >= ~2 per SM, every rank keeps >= 128 of K

@@ -1174,10 +1174,10 @@ static void launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const KP
   constexpr int STAGES = (BLOCK_N <= 64) ? 4 : ((BLOCK_N <= 128) ? 3 : 4);
   constexpr int smem = STAGES * (BLOCK_M * 128 + BLOCK_N * 128) + 1024 + 256;
   auto kern = umma_gemm_kernel<BLOCK_N, A_MN, B_MN, CONV_A, STAGES>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.begin()) {
     set_smem(kern, smem);
-    configured = true;
+    configured.done();
   }
   kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
   ++g_launch_count;
@@ -1190,10 +1190,10 @@ static void launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const K
   constexpr int STAGES = (BLOCK_N <= 128) ? 4 : 3;
   constexpr int smem = STAGES * (BLOCK_M * 128 + (BLOCK_N / 2) * 128) + 1024 + 256;
   auto kern = umma_gemm2_kernel<BLOCK_N, CONV_A, STAGES>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.begin()) {
     set_smem(kern, smem);
-    configured = true;
+    configured.done();
   }
   kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);   // cluster dims are a kernel attribute
   ++g_launch_count;
@@ -1209,10 +1209,10 @@ static void launch_gemm2_persist_t(const CUtensorMap& tmA, const CUtensorMap& tm
   constexpr int kBarBytes = ((2 * STAGES + 4) * 8 + 4 + 127) / 128 * 128;
   constexpr int smem = STAGES * (BLOCK_M * 128 + (BLOCK_N / 2) * 128) + (TMA_STORE ? BLOCK_M * 128 : 0) + kBarBytes;
   auto kern = umma_gemm2_persist_kernel<BLOCK_N, CONV_A, STAGES, TMA_STORE>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.begin()) {
     set_smem(kern, smem);
-    configured = true;
+    configured.done();
   }
   const int num_tiles = m_tiles256 * n_tiles;
   const int max_pairs = (BLOCK_N <= 128) ? 148 : 74;   // 2 resident CTAs per SM, or 1
@@ -1304,10 +1304,10 @@ static void launch_gemm_persist_t(const CUtensorMap& tmA, const CUtensorMap& tmB
   constexpr int kBarBytes = ((2 * STAGES + 4) * 8 + 4 + 127) / 128 * 128;
   constexpr int smem = STAGES * (BLOCK_M * 128 + BLOCK_N * 128) + (TMA_STORE ? BLOCK_M * 128 : 0) + kBarBytes;
   auto kern = umma_gemm_persist_kernel<BLOCK_N, A_MN, B_MN, CONV_A, STAGES, TMA_STORE>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.begin()) {
     set_smem(kern, smem);
-    configured = true;
+    configured.done();
   }
   const int num_tiles = m_tiles * n_tiles * splits;
   const int max_ctas = (BLOCK_N <= 128) ? 2 * 148 : 148;
@@ -1598,10 +1598,10 @@ void conv_wgrad_bf16(const void* dY, long long ldy, int Kout, const void* X, con
     constexpr int STAGES = 6;
     constexpr int smem = STAGES * (2 * ATOM_BYTES + ATOM_BYTES) + 1024 + 256;
     auto kern = umma_wgrad_kernel<1, STAGES>;
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    if (configured.begin()) {
       set_smem(kern, smem);
-      configured = true;
+      configured.done();
     }
     kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p, c_tiles, dW, ldw);
     ++g_launch_count;
@@ -1610,20 +1610,20 @@ void conv_wgrad_bf16(const void* dY, long long ldy, int Kout, const void* X, con
       constexpr int STAGES = 2;
       constexpr int smem = STAGES * (2 * ATOM_BYTES + 3 * ATOM_BYTES) + 1024 + 256;
       auto kern = umma_wgrad_kernel<3, STAGES>;
-      static bool configured = false;
-      if (!configured) {
+      static PerDeviceOnce configured;
+      if (configured.begin()) {
         set_smem(kern, smem);
-        configured = true;
+        configured.done();
       }
       kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p, c_tiles, dW, ldw);
     } else {
       constexpr int STAGES = 4;
       constexpr int smem = STAGES * (2 * ATOM_BYTES + 3 * ATOM_BYTES) + 1024 + 256;
       auto kern = umma_wgrad_kernel<3, STAGES>;
-      static bool configured = false;
-      if (!configured) {
+      static PerDeviceOnce configured;
+      if (configured.begin()) {
         set_smem(kern, smem);
-        configured = true;
+        configured.done();
       }
       kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p, c_tiles, dW, ldw);
     }
