@@ -156,6 +156,12 @@ Tensor operator-(const Tensor& a, const Tensor& b);
 Tensor operator*(const Tensor& a, const Tensor& b);
 Tensor operator/(const Tensor& a, const Tensor& b);
 
+// C[M, N] = alpha * A B^T-ish for 2-D tensors of one floating dtype: a is [M, K] (or [K, M] with a_mn), b is [N, K] (or [K, N]
+// with b_mn).  GPU: BF16 -> tcgen05 kind::f16 (umma_gemm.cu), FP16 -> kind::f16 with fp16 operands, FP32 -> kind::tf32,
+// FP64 -> DFMA kernel (gemm_xt.cu); the reference picks one cuBLAS routine per dtype (src/math/cuda/cublas_gemm.cu:20-164).
+// CPU: FP32 through the packed SGEMM, the other dtypes through a double-precision loop.
+Tensor matmul(const TensorImpl& a, const TensorImpl& b, bool a_mn = false, bool b_mn = false, double alpha = 1.0);
+
 // largest |a - b| (host compare; bf16 / fp16 / fp32 / fp64)
 double max_abs_diff(const TensorImpl& a, const TensorImpl& b);
 std::vector<float> to_float_vector(const TensorImpl& t);

@@ -8,7 +8,10 @@
 #include <sstream>
 #include <unordered_map>
 
+#include "kernels/gemm_xt.cuh"
 #include "kernels/simt_ops.cuh"
+#include "kernels/umma_gemm.cuh"
+#include "runtime/cpu_math.hpp"
 #include "tnn/allocator.hpp"
 #include "tnn/device.hpp"
 #include "tnn/tensor.hpp"
@@ -530,7 +533,16 @@ static void host_set(void* p, DType_t dt, size_t i, double v) {
     default: throw std::runtime_error("host_set: dtype");
   }
 }
-static bool gpu_float(DType_t dt) { return dt == DType_t::FP32 || dt == DType_t::BF16; }
+// floating types of the templated GPU tensor ops (tensor_ops.cu) and their XtDType codes
+static bool gpu_float(DType_t dt) { return dt == DType_t::FP32 || dt == DType_t::BF16 || dt == DType_t::FP16 || dt == DType_t::FP64; }
+static int xt_code(DType_t dt) {
+  switch (dt) {
+    case DType_t::FP32: return XT_F32;
+    case DType_t::FP16: return XT_F16;
+    case DType_t::FP64: return XT_F64;
+    default: return XT_BF16;
+  }
+}
 
 void TensorImpl::fill(double v) {
   const size_t n = size();
@@ -587,9 +599,9 @@ static void binary_inplace(TensorImpl& a, const TensorImpl* b, double scalar, in
   if (b && (b->size() != a.size() || b->data_type() != a.data_type())) throw std::invalid_argument("Tensor arithmetic: shape / dtype mismatch");
   const size_t n = a.size();
   if (a.is_gpu()) {
-    if (!gpu_float(a.data_type())) throw std::runtime_error("GPU tensor arithmetic supports FP32 / BF16");
+    if (!gpu_float(a.data_type())) throw std::runtime_error("GPU tensor arithmetic supports FP32 / BF16 / FP16 / FP64");
     a.device().set_current();
-    tensor_binary(a.data(), b ? b->data() : nullptr, (float)scalar, a.data(), (long long)n, op, a.data_type() == DType_t::FP32, stream_of(a.device()));
+    tensor_binary(a.data(), b ? b->data() : nullptr, (float)scalar, a.data(), (long long)n, op, xt_code(a.data_type()), stream_of(a.device()));
     return;
   }
   for (size_t i = 0; i < n; ++i) {
@@ -639,7 +651,7 @@ static double reduce_any(const TensorImpl& t, int mode, double mu) {
   if (t.is_gpu() && gpu_float(t.data_type()) && mode <= 2) {
     t.device().set_current();
     Tensor out = make_tensor(DType_t::FP32, {1}, t.device());
-    tensor_reduce(t.data(), nullptr, (float)mu, (long long)t.size(), mode, t.data_type() == DType_t::FP32, out->data_as<float>(), stream_of(t.device()));
+    tensor_reduce(t.data(), nullptr, (float)mu, (long long)t.size(), mode, xt_code(t.data_type()), out->data_as<float>(), stream_of(t.device()));
     float h = 0;
     out->copy_to_host(&h, 4);
     return h;
@@ -715,11 +727,62 @@ Tensor dtype_cast(const TensorImpl& t, DType_t to, IAllocator* alloc) {
     cudaStream_t s = stream_of(t.device());
     if (t.data_type() == DType_t::FP32 && to == DType_t::BF16) { cast_f32_to_bf16(t.data_as<float>(), out->data(), (long long)t.size(), s); return out; }
     if (t.data_type() == DType_t::BF16 && to == DType_t::FP32) { cast_bf16_to_f32(t.data(), out->data_as<float>(), (long long)t.size(), s); return out; }
+    if (gpu_float(t.data_type()) && gpu_float(to)) {   // any pair of FP16 / BF16 / FP32 / FP64 on the device
+      tensor_cast_any(t.data(), xt_code(t.data_type()), out->data(), xt_code(to), (long long)t.size(), s);
+      return out;
+    }
     Tensor h = dtype_cast(*t.to_host(), to);
     out->copy_from(*h);
     return out;
   }
   for (size_t i = 0, n = t.size(); i < n; ++i) host_set(out->data(), to, i, host_get(t.data(), t.data_type(), i));
+  return out;
+}
+
+Tensor matmul(const TensorImpl& a, const TensorImpl& b, bool a_mn, bool b_mn, double alpha) {
+  if (a.shape().size() != 2 || b.shape().size() != 2 || a.data_type() != b.data_type() || a.device() != b.device())
+    throw std::invalid_argument("matmul: two 2-D tensors of one dtype on one device");
+  const size_t M = a_mn ? a.shape()[1] : a.shape()[0], K = a_mn ? a.shape()[0] : a.shape()[1];
+  const size_t N = b_mn ? b.shape()[1] : b.shape()[0], Kb = b_mn ? b.shape()[0] : b.shape()[1];
+  if (K != Kb) throw std::invalid_argument("matmul: inner dimensions differ");
+  const DType_t dt = a.data_type();
+  Tensor out = make_tensor(dt, {M, N}, a.device());
+  const long long lda = (long long)a.shape()[1], ldb = (long long)b.shape()[1];
+  if (a.is_gpu()) {
+    if (!gpu_float(dt)) throw std::runtime_error("matmul: GPU tensors are BF16 / FP16 / FP32 / FP64");
+    a.device().set_current();
+    cudaStream_t s = stream_of(a.device());
+    if (dt == DType_t::FP64) {
+      gemm_f64(a.data_as<double>(), b.data_as<double>(), (int)M, (int)N, (int)K, lda, ldb, a_mn, b_mn, alpha, nullptr, out->data_as<double>(),
+               (long long)N, false, s);
+    } else if (dt == DType_t::BF16) {
+      Epilogue e;
+      e.out = out->data();
+      e.ldc = (long long)N;
+      e.alpha = (float)alpha;
+      gemm_bf16(a.data(), b.data(), (int)M, (int)N, (int)K, lda, ldb, a_mn, b_mn, e, 1, s);
+    } else {
+      XtEpilogue e;
+      e.out = out->data();
+      e.ldc = (long long)N;
+      e.alpha = (float)alpha;
+      if (dt == DType_t::FP16) gemm_f16(a.data(), b.data(), (int)M, (int)N, (int)K, lda, ldb, a_mn, b_mn, e, s);
+      else gemm_tf32(a.data(), b.data(), (int)M, (int)N, (int)K, lda, ldb, a_mn, b_mn, e, s);
+    }
+    return out;
+  }
+  if (dt == DType_t::FP32) {
+    cpu_sgemm(a.data_as<float>(), b.data_as<float>(), out->data_as<float>(), (int64_t)M, (int64_t)N, (int64_t)K, a_mn, !b_mn, (float)alpha, 0.f,
+              (int64_t)lda, (int64_t)ldb, (int64_t)N);
+    return out;
+  }
+  for (size_t m = 0; m < M; ++m)
+    for (size_t n = 0; n < N; ++n) {
+      double acc = 0;
+      for (size_t k = 0; k < K; ++k)
+        acc += host_get(a.data(), dt, a_mn ? k * (size_t)lda + m : m * (size_t)lda + k) * host_get(b.data(), dt, b_mn ? k * (size_t)ldb + n : n * (size_t)ldb + k);
+      host_set(out->data(), dt, m * N + n, alpha * acc);
+    }
   return out;
 }
 

@@ -197,6 +197,28 @@ TEST(tensor_basics_cpu) {
   Tensor b = dtype_cast(*t, DType_t::BF16);
   CHECK(max_abs_diff(*b, *t) < 1e-2);
 }
+TEST(matmul_every_float_dtype_cpu) {
+  // a [5, 7] x b [4, 7]^T and the MN-major spellings of the same product, FP32 (packed SGEMM) and FP64 / FP16 / BF16 (host loop)
+  Tensor a = make_tensor<float>({5, 7}), b = make_tensor<float>({4, 7});
+  a->fill_random_uniform(-1, 1, 1);
+  b->fill_random_uniform(-1, 1, 2);
+  Tensor at = make_tensor<float>({7, 5}), bt = make_tensor<float>({7, 4});
+  for (size_t m = 0; m < 5; ++m)
+    for (size_t k = 0; k < 7; ++k) at->at<float>({k, m}) = a->at<float>({m, k});
+  for (size_t n = 0; n < 4; ++n)
+    for (size_t k = 0; k < 7; ++k) bt->at<float>({k, n}) = b->at<float>({n, k});
+  Tensor ref = matmul(*a, *b);
+  double want = 0;
+  for (size_t k = 0; k < 7; ++k) want += (double)a->at<float>({2, k}) * b->at<float>({3, k});
+  CHECK_NEAR(ref->at<float>({2, 3}), want, 1e-5);
+  CHECK(max_abs_diff(*matmul(*at, *b, true, false), *ref) < 1e-5);
+  CHECK(max_abs_diff(*matmul(*a, *bt, false, true), *ref) < 1e-5);
+  CHECK(max_abs_diff(*matmul(*at, *bt, true, true, 2.0), *(ref + ref)) < 1e-5);
+  for (DType_t dt : {DType_t::FP64, DType_t::FP16, DType_t::BF16}) {
+    Tensor y = matmul(*dtype_cast(*a, dt), *dtype_cast(*bt, dt), false, true);
+    CHECK(y->data_type() == dt && max_abs_diff(*y, *ref) < (dt == DType_t::FP64 ? 1e-6 : dt == DType_t::FP16 ? 2e-2 : 1e-1));
+  }
+}
 TEST(tensor_save_load_record) {
   Tensor t = make_tensor<float>({3, 5});
   t->fill_random_normal(0, 1, 3);
@@ -222,6 +244,33 @@ TEST(tensor_gpu_round_trip) {
   CHECK_NEAR(d->sum(), 2 * h->sum() + 1000, 1e-1);
   Tensor b = dtype_cast(*d, DType_t::BF16);
   CHECK(max_abs_diff(*b, *back) < 5e-2);
+}
+
+TEST(gpu_tensor_every_float_dtype) {
+  // FP16 / FP32 (tf32 tensor cores) / FP64 / BF16 on the device: casts, arithmetic, reductions and matmul (gemm_xt.cu)
+  const Device g = need_gpu();
+  Tensor a = make_tensor<float>({200, 136}), b = make_tensor<float>({72, 136});
+  a->fill_random_uniform(-1, 1, 5);
+  b->fill_random_uniform(-1, 1, 6);
+  Tensor ref = matmul(*a, *b);                                 // CPU fp32
+  Tensor bt = make_tensor<float>({136, 72});
+  for (size_t n = 0; n < 72; ++n)
+    for (size_t k = 0; k < 136; ++k) bt->at<float>({k, n}) = b->at<float>({n, k});
+  Tensor ad = a->to_device(g), bd = b->to_device(g), btd = bt->to_device(g);
+  for (DType_t dt : {DType_t::FP16, DType_t::FP32, DType_t::FP64, DType_t::BF16}) {
+    const double tol = dt == DType_t::FP64 ? 1e-4 : dt == DType_t::FP32 ? 2e-2 : dt == DType_t::FP16 ? 5e-2 : 3e-1;
+    Tensor x = dtype_cast(*ad, dt), w = dtype_cast(*bd, dt), wt = dtype_cast(*btd, dt);
+    CHECK(x->is_gpu() && x->data_type() == dt);
+    CHECK(max_abs_diff(*dtype_cast(*x, DType_t::FP32), *a) < (dt == DType_t::BF16 ? 1e-2 : 1e-3));      // device cast round trip
+    Tensor y = matmul(*x, *w);
+    CHECK(y->data_type() == dt && max_abs_diff(*y, *ref) < tol);
+    CHECK(max_abs_diff(*matmul(*x, *wt, false, true), *ref) < tol);                                      // MN-major B
+    Tensor s2 = x->clone();
+    s2->add(*x);
+    s2->mul_scalar(0.5);
+    CHECK(max_abs_diff(*s2, *x) < 1e-6);
+    CHECK_NEAR(x->sum(), a->sum(), dt == DType_t::FP64 || dt == DType_t::FP32 ? 5e-2 : 5.0);
+  }
 }
 
 // ------------------------------------------------------------------------------------- layers: finite differences (CPU)

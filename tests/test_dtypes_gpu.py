@@ -1,0 +1,178 @@
+"""fp16 / fp32 (tf32 tensor cores) / fp64 on the GPU: GEMMs (csrc/kernels/gemm_xt.cu), the templated tensor ops,
+casts, activations and the Dense layer's explicit IO dtype contract.
+
+Reference behaviour: include/type/type.hpp (fp16 / bf16 / fp32 / fp64 element types), src/math/cuda/cublas_gemm.cu:20-164
+(one cuBLAS call per dtype), src/nn/layers_impl/dense_layer.cpp:336-340 (DenseLayer instantiated per dtype).
+Every check is against a plain PyTorch fp32 / fp64 computation of the same op on the SAME (already rounded) inputs.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    return torch.device("cuda:0")
+
+
+def _operand(rows, k, mn, dtype, dev, g):
+    """[rows, k] logical operand stored K-major ([rows, k]) or MN-major ([k, rows])."""
+    t = torch.randn((k, rows) if mn else (rows, k), generator=g, device=dev, dtype=torch.float32)
+    t = t.to(dtype)
+    logical = (t.t() if mn else t).double()
+    return t, logical
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.float64])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 72, 136), (384, 264, 520), (64, 40, 24)])
+def test_gemm_xt_matches_fp64_reference(dtype, a_mn, b_mn, M, N, K):
+    from tnn_b200.ops import gemm as G
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(M * 7 + N * 3 + K)
+    a, la = _operand(M, K, a_mn, dtype, dev, g)
+    b, lb = _operand(N, K, b_mn, dtype, dev, g)
+    out = G.gemm_xt(a, b, a_mn, b_mn)
+    torch.cuda.synchronize()
+    ref = la @ lb.t()
+    assert out.dtype == dtype and out.shape == (M, N)
+    err = (out.double() - ref).abs().max().item()
+    bound = (la.abs() @ lb.abs().t()).max().item()          # sum |a||b| of the worst element
+    tol = {torch.float16: 2e-3, torch.float32: 1.5e-3, torch.float64: 1e-13}[dtype] * bound
+    assert err <= tol, f"{dtype} M{M} N{N} K{K} a_mn={a_mn} b_mn={b_mn}: max err {err:.3e} > {tol:.3e}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_gemm_xt_epilogue_bias_residual_act_accumulate(dtype):
+    from tnn_b200.ops import gemm as G
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(5)
+    M, N, K = 160, 200, 192
+    a = torch.randn(M, K, generator=g, device=dev).to(dtype)
+    b = (torch.randn(N, K, generator=g, device=dev) * 0.1).to(dtype)
+    bias = torch.randn(N, generator=g, device=dev)
+    res = torch.randn(M, N, generator=g, device=dev).to(dtype)
+    for act, fn in (("relu", torch.relu), ("gelu", lambda t: torch.nn.functional.gelu(t, approximate="tanh")), (None, lambda t: t)):
+        y = G.gemm_xt(a, b, bias=bias, residual=res, act=act, alpha=0.5)
+        ref = fn(0.5 * (a.double() @ b.double().t()) + bias.double() + res.double())
+        tol = 2e-2 if dtype == torch.float16 else 1e-2
+        assert (y.double() - ref).abs().max().item() < tol, act
+    # accumulate into an fp32 buffer (weight-gradient form): out += alpha * A^T-ish product
+    acc = torch.randn(M, N, generator=g, device=dev)
+    want = acc.double() + 0.25 * (a.double() @ b.double().t())
+    G.gemm_xt(a, b, out=acc, alpha=0.25, accumulate=True)
+    assert (acc.double() - want).abs().max().item() < (1e-2 if dtype == torch.float16 else 6e-3)
+    if dtype == torch.float16:
+        y32 = G.gemm_xt(a, b, out_f32=True)
+        assert y32.dtype == torch.float32
+        assert (y32.double() - a.double() @ b.double().t()).abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float64, torch.float32, torch.bfloat16])
+def test_tensor_ops_every_dtype(dtype):
+    from tnn_b200.ops import tensor_ops as T
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(11)
+    n = 4099                                                # not a multiple of any vector width
+    a = (torch.rand(n, generator=g, device=dev) + 0.5).to(dtype)
+    b = (torch.rand(n, generator=g, device=dev) + 0.5).to(dtype)
+    c = torch.randn(n, generator=g, device=dev).to(dtype)
+    ad, bd, cd = a.double(), b.double(), c.double()
+    eps = {torch.float16: 2e-3, torch.bfloat16: 1.6e-2, torch.float32: 1e-6, torch.float64: 1e-14}[dtype]
+
+    def close(got, want):
+        assert got.dtype == dtype
+        w = want.to(dtype).double()
+        assert ((got.double() - w).abs() <= eps * (1 + w.abs())).all()
+
+    close(T.add(a, b), ad + bd)
+    close(T.sub(a, b), ad - bd)
+    close(T.mul(a, b), ad * bd)
+    close(T.div(a, b), ad / bd)
+    close(T.maximum(a, b), torch.maximum(ad, bd))
+    close(T.mul(a, 3.0), ad * 3.0)
+    close(T.sqrt(a), ad.sqrt())
+    close(T.rsqrt(a), ad.rsqrt())
+    close(T.exp(c.clamp(-3, 3)), c.clamp(-3, 3).double().exp())
+    close(T.log(a), ad.log())
+    close(T.clamp(c, -0.5, 0.5), cd.clamp(-0.5, 0.5))
+    close(T.fmadd(a, b, c), ad * bd + cd)
+    s = T.sum(a)
+    assert abs(s.item() - ad.sum().item()) < 2e-3 * n * (1e-3 if dtype in (torch.float32, torch.float64) else 1)
+    d = T.dot_product(a, b)
+    assert abs(d.item() - (ad * bd).sum().item()) < 1e-3 * n
+    x = torch.randn(37, 129, generator=g, device=dev).to(dtype)
+    y = T.softmax(x)
+    ref = torch.softmax(x.double(), -1)
+    assert y.dtype == dtype and (y.double() - ref).abs().max().item() < 10 * eps
+    dy = torch.randn(37, 129, generator=g, device=dev).to(dtype)
+    dx = T.softmax_backward(y, dy)
+    yd, gd = y.double(), dy.double()
+    refdx = yd * (gd - (gd * yd).sum(-1, keepdim=True))
+    assert (dx.double() - refdx).abs().max().item() < 20 * eps
+    p = T.pad(x.reshape(1, 37, 129, 1).contiguous(), 2, 1)
+    assert p.dtype == dtype and p.shape == (1, 41, 131, 1) and torch.equal(p[0, 2:-2, 1:-1, 0], x)
+
+
+def test_cast_and_transpose_every_pair():
+    from tnn_b200.ops import tensor_ops as T
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(3)
+    src = torch.randn(1000, generator=g, device=dev, dtype=torch.float64)
+    kinds = (torch.float16, torch.bfloat16, torch.float32, torch.float64)
+    for s in kinds:
+        a = src.to(s)
+        for d in kinds:
+            got = T.cast(a, d)
+            assert got.dtype == d and torch.equal(got, a.to(d)), (s, d)
+        m = a[:999].reshape(27, 37).contiguous()
+        assert torch.equal(T.transpose_2d(m), m.t().contiguous())
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.float64])
+def test_dense_layer_explicit_io_dtype(dtype):
+    """DenseLayer with io_dtype fp16 / fp32 / fp64: forward, input gradient, weight and bias gradients."""
+    from tnn_b200.nn.layers import DenseLayer
+    dev = _dev()
+    torch.manual_seed(0)
+    lay = DenseLayer(96, 72, True, "d").set_io_dtype(dtype).init(dev, 4)
+    lay.set_training(True)
+    x = torch.randn(50, 96, device=dev).to(dtype)
+    y = lay.forward(x, 0)
+    assert y.dtype == dtype
+    w, b = lay.params["weight"].double(), lay.params["bias"].double()
+    wd = w.to(dtype).double() if dtype == torch.float16 else w
+    ref = x.double() @ wd.t() + b
+    tol = {torch.float16: 2e-2, torch.float32: 5e-3, torch.float64: 1e-6}[dtype]
+    assert (y.double() - ref).abs().max().item() < tol
+    dy = torch.randn(50, 72, device=dev).to(dtype)
+    for gname in lay.grads:
+        lay.grads[gname].zero_()
+    dx = lay.backward(dy, 0)
+    assert dx.dtype == dtype
+    assert (dx.double() - dy.double() @ wd).abs().max().item() < tol * 2
+    assert (lay.grads["weight"].double() - dy.double().t() @ x.double()).abs().max().item() < tol * 8
+    assert (lay.grads["bias"].double() - dy.double().sum(0)).abs().max().item() < tol * 4
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float64])
+def test_activation_layer_fp16_fp64(dtype):
+    from tnn_b200.nn.layers import ActivationLayer
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(2)
+    x = torch.randn(33, 65, generator=g, device=dev).to(dtype)
+    dy = torch.randn(33, 65, generator=g, device=dev).to(dtype)
+    for name in ("relu", "gelu", "tanh", "sigmoid", "softmax"):
+        lay = ActivationLayer(name).init(dev, 0)
+        lay.set_training(True)
+        y = lay.forward(x, 0)
+        dx = lay.backward(dy, 0)
+        xr = x.double().requires_grad_(True)
+        ref = {"relu": torch.relu, "gelu": lambda t: torch.nn.functional.gelu(t, approximate="tanh"), "tanh": torch.tanh,
+               "sigmoid": torch.sigmoid, "softmax": lambda t: torch.softmax(t, -1)}[name](xr)
+        ref.backward(dy.double())
+        tol = 4e-3 if dtype == torch.float16 else 1e-4            # fp64 activations evaluate in fp32 (fast tanh / exp)
+        assert y.dtype == dtype and (y.double() - ref.detach()).abs().max().item() < tol, name
+        assert dx.dtype == dtype and (dx.double() - xr.grad).abs().max().item() < 3 * tol, name

@@ -7,6 +7,7 @@
 #include <optional>
 #include <vector>
 
+#include "kernels/gemm_xt.cuh"
 #include "kernels/simt_ops.cuh"
 #include "kernels/umma_gemm.cuh"
 namespace tnn {
@@ -24,6 +25,17 @@ void mxfp8_bind(py::module_& m);      // mxfp8.cpp
 
 static cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
 static void* vp(const Tensor& t) { return t.data_ptr(); }
+// element type code of the generic tensor ops / casts / extra-dtype GEMMs (tnn::XtDType)
+static int dt_code(const Tensor& t) {
+  TORCH_CHECK(t.is_cuda(), "CUDA tensor expected");
+  switch (t.scalar_type()) {
+    case torch::kBFloat16: return tnn::XT_BF16;
+    case torch::kFloat32: return tnn::XT_F32;
+    case torch::kFloat16: return tnn::XT_F16;
+    case torch::kFloat64: return tnn::XT_F64;
+    default: TORCH_CHECK(false, "tensor ops take bf16 / fp32 / fp16 / fp64 tensors"); return 0;
+  }
+}
 static void* vp(const OptT& t) { return t.has_value() ? t->data_ptr() : nullptr; }
 static float* fp(const Tensor& t) {
   TORCH_CHECK(t.scalar_type() == torch::kFloat32, "expected fp32 tensor");
@@ -159,11 +171,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     tnn::binary_bf16(vp(a), vp(b), vp(o), a.numel(), op, cur_stream());
   });
   m.def("act_fwd", [](const Tensor& x, const Tensor& y, int kind, double slope) {
-    tnn::act_fwd(vp(x), vp(y), x.numel(), kind, (float)slope, x.scalar_type() == torch::kFloat32, cur_stream());
+    tnn::act_fwd(vp(x), vp(y), x.numel(), kind, (float)slope, dt_code(x), cur_stream());
   });
   m.def("act_bwd", [](const Tensor& x, const Tensor& dy, const Tensor& dx, int kind, double slope) {
-    tnn::act_bwd(vp(x), vp(dy), vp(dx), x.numel(), kind, (float)slope, x.scalar_type() == torch::kFloat32,
-                 cur_stream());
+    tnn::act_bwd(vp(x), vp(dy), vp(dx), x.numel(), kind, (float)slope, dt_code(x), cur_stream());
   });
   m.def("dropout_fwd", [](const Tensor& x, const Tensor& y, double p, uint64_t seed, const OptT& state,
                           const OptT& residual) {
@@ -409,11 +420,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   });
 
   // ---- generic tensor op family (tensor_ops.cu)
-  auto is32 = [](const Tensor& t) {
-    TORCH_CHECK(t.is_cuda() && (t.scalar_type() == torch::kFloat32 || t.scalar_type() == torch::kBFloat16),
-                "tensor ops take CUDA fp32 / bf16 tensors");
-    return t.scalar_type() == torch::kFloat32 ? 1 : 0;
-  };
+  auto is32 = [](const Tensor& t) { return dt_code(t); };   // XtDType code: 0 bf16, 1 fp32, 2 fp16, 3 fp64
   m.def("tensor_binary", [is32](const Tensor& a, const OptT& b, double scalar, const Tensor& out, int op) {
     tnn::tensor_binary(vp(a), vp(b), (float)scalar, vp(out), a.numel(), op, is32(a), cur_stream());
   });
@@ -450,6 +457,57 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                           (int)w.size(0), (int)x.size(1), act, static_weights ? 1 : 0, cur_stream());
   }, py::arg("x"), py::arg("w"), py::arg("bias"), py::arg("residual"), py::arg("out"), py::arg("act"),
      py::arg("static_weights") = false);
+  // ---- GEMMs / casts for fp16, fp32 (tf32 tensor cores) and fp64 (gemm_xt.cu).  a: [M,K] or (a_mn) [K,M]; b: [N,K] or (b_mn) [K,N]
+  m.def("gemm_xt", [](const Tensor& a, const Tensor& b, bool a_mn, bool b_mn, const Tensor& out, const OptT& bias, const OptT& residual,
+                      int act, double alpha, bool accumulate) {
+    TORCH_CHECK(a.is_cuda() && a.dim() == 2 && b.dim() == 2 && out.dim() == 2 && a.stride(1) == 1 && b.stride(1) == 1 && out.stride(1) == 1,
+                "gemm_xt: row-major 2-D CUDA tensors");
+    TORCH_CHECK(a.scalar_type() == b.scalar_type(), "gemm_xt: operand dtypes differ");
+    const int M = (int)(a_mn ? a.size(1) : a.size(0)), K = (int)(a_mn ? a.size(0) : a.size(1));
+    const int N = (int)(b_mn ? b.size(1) : b.size(0)), Kb = (int)(b_mn ? b.size(0) : b.size(1));
+    TORCH_CHECK(K == Kb && out.size(0) == M && out.size(1) == N, "gemm_xt: shape mismatch");
+    const int dt = dt_code(a);
+    if (dt == tnn::XT_F64) {
+      TORCH_CHECK(out.scalar_type() == torch::kFloat64 && !residual.has_value() && act == 0, "fp64 GEMM: fp64 out, no residual / activation");
+      TORCH_CHECK(!bias.has_value() || bias->scalar_type() == torch::kFloat64, "fp64 GEMM: fp64 bias");
+      tnn::gemm_f64(a.data_ptr<double>(), b.data_ptr<double>(), M, N, K, a.stride(0), b.stride(0), a_mn, b_mn, alpha,
+                    bias.has_value() ? bias->data_ptr<double>() : nullptr, out.data_ptr<double>(), out.stride(0), accumulate, cur_stream());
+      return;
+    }
+    TORCH_CHECK(dt == tnn::XT_F16 || dt == tnn::XT_F32, "gemm_xt: fp16 / fp32 / fp64 operands (bf16 goes through gemm_bf16)");
+    tnn::XtEpilogue e;
+    e.out = vp(out);
+    e.out_f32 = out.scalar_type() == torch::kFloat32;
+    TORCH_CHECK(e.out_f32 || (dt == tnn::XT_F16 && out.scalar_type() == torch::kFloat16), "gemm_xt: out is the operand type or fp32");
+    e.ldc = out.stride(0);
+    e.bias = fp(bias);
+    if (residual.has_value()) {
+      TORCH_CHECK(residual->scalar_type() == a.scalar_type() && residual->stride(1) == 1, "gemm_xt: residual has the operand type");
+      e.residual = vp(residual);
+      e.ldr = residual->stride(0);
+    }
+    e.act = act;
+    e.alpha = (float)alpha;
+    e.accumulate = accumulate ? 1 : 0;
+    if (dt == tnn::XT_F16) tnn::gemm_f16(vp(a), vp(b), M, N, K, a.stride(0), b.stride(0), a_mn, b_mn, e, cur_stream());
+    else tnn::gemm_tf32(vp(a), vp(b), M, N, K, a.stride(0), b.stride(0), a_mn, b_mn, e, cur_stream());
+  }, py::arg("a"), py::arg("b"), py::arg("a_mn"), py::arg("b_mn"), py::arg("out"), py::arg("bias") = py::none(),
+     py::arg("residual") = py::none(), py::arg("act") = 0, py::arg("alpha") = 1.0, py::arg("accumulate") = false);
+  m.def("colsum_any", [](const Tensor& x, const Tensor& out, double alpha, bool accumulate) {
+    TORCH_CHECK(x.dim() == 2 && x.stride(1) == 1 && out.numel() == x.size(1) && out.is_contiguous(), "colsum_any: x [R,C], out [C]");
+    const int dt = dt_code(x);
+    TORCH_CHECK(out.scalar_type() == (dt == tnn::XT_F64 ? torch::kFloat64 : torch::kFloat32), "colsum_any: out is fp32 (fp64 for fp64 input)");
+    tnn::colsum_any(vp(x), dt, x.size(0), (int)x.size(1), x.stride(0), alpha, vp(out), accumulate, cur_stream());
+  });
+  m.def("cast_any", [](const Tensor& src, const Tensor& dst) {
+    TORCH_CHECK(src.numel() == dst.numel() && src.is_contiguous() && dst.is_contiguous(), "cast_any: contiguous tensors of one size");
+    tnn::tensor_cast_any(vp(src), dt_code(src), vp(dst), dt_code(dst), src.numel(), cur_stream());
+  });
+  m.def("transpose_any", [](const Tensor& src, const Tensor& dst) {
+    TORCH_CHECK(src.dim() == 2 && dst.dim() == 2 && src.is_contiguous() && dst.is_contiguous() && src.size(0) == dst.size(1) &&
+                    src.size(1) == dst.size(0) && src.scalar_type() == dst.scalar_type(), "transpose_any: [R,C] -> [C,R]");
+    tnn::tensor_transpose_any(vp(src), vp(dst), dt_code(src), (int)src.size(0), (int)src.size(1), cur_stream());
+  });
   m.def("launch_count", []() { return tnn::g_launch_count; });
   tnn::attention_bind(m);
   tnn::mxfp8_bind(m);

@@ -2,6 +2,8 @@
 // Reference equivalents: src/ops/cuda/kernels.cu, src/nn/activations_impl/cuda/*.cu,
 // src/nn/layers_impl/cuda/dropout.cu, src/tensor/cuda/tensor_ops.cu -- here they are one
 // templated family, and most call sites vanish through epilogue fusion.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "simt_ops.cuh"
 
@@ -130,8 +132,14 @@ template <>
 __device__ __forceinline__ float ld1<float>(const float* p, long long i) { return p[i]; }
 template <>
 __device__ __forceinline__ float ld1<bf16>(const bf16* p, long long i) { return __bfloat162float(p[i]); }
+template <>
+__device__ __forceinline__ float ld1<__half>(const __half* p, long long i) { return __half2float(p[i]); }
+template <>
+__device__ __forceinline__ float ld1<double>(const double* p, long long i) { return (float)p[i]; }   // activations evaluate in fp32
 __device__ __forceinline__ void st1(float* p, long long i, float v) { p[i] = v; }
 __device__ __forceinline__ void st1(bf16* p, long long i, float v) { p[i] = __float2bfloat16(v); }
+__device__ __forceinline__ void st1(__half* p, long long i, float v) { p[i] = __float2half_rn(v); }
+__device__ __forceinline__ void st1(double* p, long long i, float v) { p[i] = (double)v; }
 
 template <typename T>
 __global__ void k_act_fwd(const T* __restrict__ x, T* __restrict__ y, long long n, int kind, float slope) {
@@ -170,10 +178,15 @@ __global__ void k_act_bwd_bf8(const bf16* __restrict__ x, const bf16* __restrict
     reinterpret_cast<uint4*>(dx)[i] = bf8_pack(f);
   }
 }
-void act_fwd(const void* x, void* y, long long n, int kind, float slope, int is_f32, cudaStream_t s) {
+// dt: 0 bf16, 1 fp32, 2 fp16, 3 fp64 (the XtDType codes of gemm_xt.cuh)
+void act_fwd(const void* x, void* y, long long n, int kind, float slope, int dt, cudaStream_t s) {
   if (n <= 0) return;
-  if (is_f32) {
+  if (dt == 1) {
     k_act_fwd<float><<<grid_for(n, 256), 256, 0, s>>>((const float*)x, (float*)y, n, kind, slope);
+  } else if (dt == 2) {
+    k_act_fwd<__half><<<grid_for(n, 256), 256, 0, s>>>((const __half*)x, (__half*)y, n, kind, slope);
+  } else if (dt == 3) {
+    k_act_fwd<double><<<grid_for(n, 256), 256, 0, s>>>((const double*)x, (double*)y, n, kind, slope);
   } else {
     long long nv = n / 8;
     if (nv) k_act_fwd_bf8<<<grid_for(nv, 256), 256, 0, s>>>((const bf16*)x, (bf16*)y, nv, kind, slope);
@@ -182,11 +195,15 @@ void act_fwd(const void* x, void* y, long long n, int kind, float slope, int is_
   }
   TNN_CHECK_LAUNCH();
 }
-void act_bwd(const void* x, const void* dy, void* dx, long long n, int kind, float slope, int is_f32,
+void act_bwd(const void* x, const void* dy, void* dx, long long n, int kind, float slope, int dt,
              cudaStream_t s) {
   if (n <= 0) return;
-  if (is_f32) {
+  if (dt == 1) {
     k_act_bwd<float><<<grid_for(n, 256), 256, 0, s>>>((const float*)x, (const float*)dy, (float*)dx, n, kind, slope);
+  } else if (dt == 2) {
+    k_act_bwd<__half><<<grid_for(n, 256), 256, 0, s>>>((const __half*)x, (const __half*)dy, (__half*)dx, n, kind, slope);
+  } else if (dt == 3) {
+    k_act_bwd<double><<<grid_for(n, 256), 256, 0, s>>>((const double*)x, (const double*)dy, (double*)dx, n, kind, slope);
   } else {
     long long nv = n / 8;
     if (nv)

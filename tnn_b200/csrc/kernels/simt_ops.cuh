@@ -19,7 +19,7 @@ void cast_bf16_to_f32(const void* in, float* out, long long n, cudaStream_t s);
 void add_bf16(const void* a, const void* b, void* out, long long n, int relu, cudaStream_t s);
 // N-ary elementwise on bf16 arrays: op 0 add, 1 sub, 2 mul
 void binary_bf16(const void* a, const void* b, void* out, long long n, int op, cudaStream_t s);
-void act_fwd(const void* x, void* y, long long n, int kind, float slope, int is_f32, cudaStream_t s);
+void act_fwd(const void* x, void* y, long long n, int kind, float slope, int dt, cudaStream_t s);   // dt: XtDType code
 // dx = dy * act'(x)   (x = pre-activation input)
 void act_bwd(const void* x, const void* dy, void* dx, long long n, int kind, float slope, int is_f32,
              cudaStream_t s);
@@ -59,17 +59,17 @@ void transpose_bf16(const void* x, void* y, int rows, int cols, cudaStream_t s);
 enum TensorBinaryOp : int { TOP_ADD = 0, TOP_SUB = 1, TOP_MUL = 2, TOP_DIV = 3, TOP_MIN = 4, TOP_MAX = 5, TOP_EQ = 6, TOP_GT = 7 };
 enum TensorUnaryOp : int { UOP_SQRT = 0, UOP_RSQRT = 1, UOP_RCP = 2, UOP_ABS = 3, UOP_CLAMP = 4, UOP_NEG = 5, UOP_EXP = 6, UOP_LOG = 7, UOP_SQUARE = 8 };
 // out = a (op) b  (b == nullptr: a (op) scalar); fp32 or bf16
-void tensor_binary(const void* a, const void* b, float scalar, void* out, long long n, int op, int is_f32, cudaStream_t s);
-void tensor_unary(const void* a, void* out, long long n, int op, float lo, float hi, int is_f32, cudaStream_t s);
+void tensor_binary(const void* a, const void* b, float scalar, void* out, long long n, int op, int dt, cudaStream_t s);
+void tensor_unary(const void* a, void* out, long long n, int op, float lo, float hi, int dt, cudaStream_t s);
 // op 0 fmadd a*b+c, 1 fmsub a*b-c, 2 fnmadd -(a*b)+c
-void tensor_ternary(const void* a, const void* b, const void* c, void* out, long long n, int op, int is_f32, cudaStream_t s);
+void tensor_ternary(const void* a, const void* b, const void* c, void* out, long long n, int op, int dt, cudaStream_t s);
 // mode 0 sum(a), 1 dot(a,b), 2 sum((a-mu)^2); *out (device fp32) is overwritten; finishes on the device
-void tensor_reduce(const void* a, const void* b, float mu, long long n, int mode, int is_f32, float* out, cudaStream_t s);
+void tensor_reduce(const void* a, const void* b, float mu, long long n, int mode, int dt, float* out, cudaStream_t s);
 // dst[n,h,w,c] = src[n,h+off_h,w+off_w,c] or fill outside (pad: negative offsets; crop/unpad: positive)
 void tensor_window_copy(const void* src, void* dst, int N, int SH, int SW, int DH, int DW, int C, int off_h, int off_w,
-                        float fill, int is_f32, cudaStream_t s);
-void softmax_rows(const void* x, void* y, long long rows, int C, int is_f32, cudaStream_t s);
-void softmax_rows_bwd(const void* y, const void* dy, void* dx, long long rows, int C, int is_f32, cudaStream_t s);
+                        float fill, int dt, cudaStream_t s);
+void softmax_rows(const void* x, void* y, long long rows, int C, int dt, cudaStream_t s);
+void softmax_rows_bwd(const void* y, const void* dy, void* dx, long long rows, int C, int dt, cudaStream_t s);
 void tensor_bswap(void* p, long long n_elems, int elem_size, cudaStream_t s);
 
 // ---- skinny GEMM for decode (skinny_gemm.cu): out[M<=32,N] = act(x W^T + bias (+ residual)), act 0/1 relu/2 gelu

@@ -1,12 +1,17 @@
 // Generic tensor op family: the `ops::` surface of the reference (include/ops/ops.hpp:17-835,
 // src/ops/cuda/kernels.cu:30-565, src/tensor/cuda/tensor_ops.cu:136-300) re-done for sm_100a.
-//   * one templated, 128-bit vectorised, grid-stride elementwise kernel family for fp32 and bf16
+//   * one templated, 128-bit vectorised, grid-stride elementwise kernel family for bf16, fp32, fp16 and fp64 (the `dt`
+//     argument of every entry point is an XtDType code; 0 = bf16 and 1 = fp32 keep the old `is_f32` meaning; fp64 does
+//     its arithmetic in double, the others in float)
 //     (binary, binary-with-scalar, unary, ternary fused multiply-add forms),
 //   * reductions (sum, dot, sum of squared differences) that FINISH ON THE DEVICE: warp shuffles,
 //     one fp32 atomic per block into a double-free accumulator -- no cudaMalloc, no host
 //     summation (the reference copies per-block partials to the host, kernels.cu:278-315),
 //   * pad / unpad / crop over NHWC, channel softmax, dtype casts, byte swap.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
+#include "gemm_xt.cuh"
 #include "simt_ops.cuh"
 
 namespace tnn {
@@ -16,6 +21,7 @@ struct Vec;
 template <>
 struct Vec<float> {
   static constexpr int N = 4;
+  using A = float;
   using V = float4;
   __device__ static void load(const float* p, float (&f)[4]) {
     float4 v = *reinterpret_cast<const float4*>(p);
@@ -30,12 +36,86 @@ struct Vec<float> {
 template <>
 struct Vec<bf16> {
   static constexpr int N = 8;
+  using A = float;
   __device__ static void load(const bf16* p, float (&f)[8]) { bf8_unpack(*reinterpret_cast<const uint4*>(p), f); }
   __device__ static void store(bf16* p, const float (&f)[8]) { *reinterpret_cast<uint4*>(p) = bf8_pack(f); }
   __device__ static float get(const bf16* p) { return __bfloat162float(*p); }
   __device__ static void put(bf16* p, float v) { *p = __float2bfloat16(v); }
 };
 
+template <>
+struct Vec<__half> {
+  static constexpr int N = 8;
+  using A = float;
+  __device__ static void load(const __half* p, float (&f)[8]) {
+    const uint4 q = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __half22float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+  __device__ static void store(__half* p, const float (&f)[8]) {
+    uint4 q;
+    __half2* h = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = q;
+  }
+  __device__ static float get(const __half* p) { return __half2float(*p); }
+  __device__ static void put(__half* p, float v) { *p = __float2half_rn(v); }
+};
+template <>
+struct Vec<double> {
+  static constexpr int N = 2;
+  using A = double;
+  __device__ static void load(const double* p, double (&f)[2]) {
+    const double2 v = *reinterpret_cast<const double2*>(p);
+    f[0] = v.x; f[1] = v.y;
+  }
+  __device__ static void store(double* p, const double (&f)[2]) { *reinterpret_cast<double2*>(p) = make_double2(f[0], f[1]); }
+  __device__ static double get(const double* p) { return *p; }
+  __device__ static void put(double* p, double v) { *p = v; }
+};
+
+// run BODY with T bound to the element type of dtype code `dt`
+#define TNN_DT_SWITCH(dt, ...)                         \
+  switch (dt) {                                        \
+    case XT_F32: { using T = float; __VA_ARGS__; } break;   \
+    case XT_F16: { using T = __half; __VA_ARGS__; } break;  \
+    case XT_F64: { using T = double; __VA_ARGS__; } break;  \
+    default: { using T = bf16; __VA_ARGS__; } break;        \
+  }
+
+__device__ __forceinline__ double apply_binary(int op, double a, double b) {
+  switch (op) {
+    case TOP_ADD: return a + b;
+    case TOP_SUB: return a - b;
+    case TOP_MUL: return a * b;
+    case TOP_DIV: return a / b;
+    case TOP_MIN: return fmin(a, b);
+    case TOP_MAX: return fmax(a, b);
+    case TOP_EQ: return a == b ? 1.0 : 0.0;
+    case TOP_GT: return a > b ? 1.0 : 0.0;
+    default: return a;
+  }
+}
+__device__ __forceinline__ double apply_unary(int op, double a, double lo, double hi) {
+  switch (op) {
+    case UOP_SQRT: return sqrt(a);
+    case UOP_RSQRT: return 1.0 / sqrt(a);
+    case UOP_RCP: return 1.0 / a;
+    case UOP_ABS: return fabs(a);
+    case UOP_CLAMP: return fmin(fmax(a, lo), hi);
+    case UOP_NEG: return -a;
+    case UOP_EXP: return exp(a);
+    case UOP_LOG: return log(a);
+    case UOP_SQUARE: return a * a;
+    default: return a;
+  }
+}
 __device__ __forceinline__ float apply_binary(int op, float a, float b) {
   switch (op) {
     case TOP_ADD: return a + b;
@@ -73,15 +153,16 @@ __global__ void __launch_bounds__(256)
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
   const long long nv = vec_ok ? n / N : 0;
   for (long long i = tid; i < nv; i += stride) {
-    float fa[N], fb[N], fo[N];
+    using A = typename Vec<T>::A;
+    A fa[N], fb[N], fo[N];
     Vec<T>::load(a + i * N, fa);
     if (b) Vec<T>::load(b + i * N, fb);
 #pragma unroll
-    for (int j = 0; j < N; ++j) fo[j] = apply_binary(op, fa[j], b ? fb[j] : scalar);
+    for (int j = 0; j < N; ++j) fo[j] = apply_binary(op, fa[j], b ? fb[j] : (A)scalar);
     Vec<T>::store(out + i * N, fo);
   }
   for (long long i = nv * N + tid; i < n; i += stride)
-    Vec<T>::put(out + i, apply_binary(op, Vec<T>::get(a + i), b ? Vec<T>::get(b + i) : scalar));
+    Vec<T>::put(out + i, apply_binary(op, Vec<T>::get(a + i), b ? Vec<T>::get(b + i) : (typename Vec<T>::A)scalar));
 }
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -90,13 +171,15 @@ __global__ void __launch_bounds__(256)
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
   const long long nv = vec_ok ? n / N : 0;
   for (long long i = tid; i < nv; i += stride) {
-    float fa[N], fo[N];
+    using A = typename Vec<T>::A;
+    A fa[N], fo[N];
     Vec<T>::load(a + i * N, fa);
 #pragma unroll
-    for (int j = 0; j < N; ++j) fo[j] = apply_unary(op, fa[j], lo, hi);
+    for (int j = 0; j < N; ++j) fo[j] = apply_unary(op, fa[j], (A)lo, (A)hi);
     Vec<T>::store(out + i * N, fo);
   }
-  for (long long i = nv * N + tid; i < n; i += stride) Vec<T>::put(out + i, apply_unary(op, Vec<T>::get(a + i), lo, hi));
+  for (long long i = nv * N + tid; i < n; i += stride)
+    Vec<T>::put(out + i, apply_unary(op, Vec<T>::get(a + i), (typename Vec<T>::A)lo, (typename Vec<T>::A)hi));
 }
 // fmadd: a*b + c ; fmsub: a*b - c ; fnmadd: -(a*b) + c
 template <typename T>
@@ -105,8 +188,8 @@ __global__ void __launch_bounds__(256)
               int op) {
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
   for (long long i = tid; i < n; i += stride) {
-    const float x = Vec<T>::get(a + i), y = Vec<T>::get(b + i), z = Vec<T>::get(c + i);
-    Vec<T>::put(out + i, op == 0 ? fmaf(x, y, z) : (op == 1 ? fmaf(x, y, -z) : fmaf(-x, y, z)));
+    const typename Vec<T>::A x = Vec<T>::get(a + i), y = Vec<T>::get(b + i), z = Vec<T>::get(c + i);
+    Vec<T>::put(out + i, op == 0 ? fma(x, y, z) : (op == 1 ? fma(x, y, -z) : fma(-x, y, z)));
   }
 }
 
@@ -114,30 +197,21 @@ static int vec_ok_ptrs(const void* a, const void* b, const void* c) {
   return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
 }
 
-void tensor_binary(const void* a, const void* b, float scalar, void* out, long long n, int op, int is_f32, cudaStream_t s) {
+void tensor_binary(const void* a, const void* b, float scalar, void* out, long long n, int op, int dt, cudaStream_t s) {
   if (n <= 0) return;
   const int v = vec_ok_ptrs(a, b, out);
-  if (is_f32)
-    k_binary<float><<<grid_for(n / 4 + 1, 256), 256, 0, s>>>((const float*)a, (const float*)b, scalar, (float*)out, n, op, v);
-  else
-    k_binary<bf16><<<grid_for(n / 8 + 1, 256), 256, 0, s>>>((const bf16*)a, (const bf16*)b, scalar, (bf16*)out, n, op, v);
+  TNN_DT_SWITCH(dt, k_binary<T><<<grid_for(n / Vec<T>::N + 1, 256), 256, 0, s>>>((const T*)a, (const T*)b, scalar, (T*)out, n, op, v));
   TNN_CHECK_LAUNCH();
 }
-void tensor_unary(const void* a, void* out, long long n, int op, float lo, float hi, int is_f32, cudaStream_t s) {
+void tensor_unary(const void* a, void* out, long long n, int op, float lo, float hi, int dt, cudaStream_t s) {
   if (n <= 0) return;
   const int v = vec_ok_ptrs(a, out, nullptr);
-  if (is_f32)
-    k_unary<float><<<grid_for(n / 4 + 1, 256), 256, 0, s>>>((const float*)a, (float*)out, n, op, lo, hi, v);
-  else
-    k_unary<bf16><<<grid_for(n / 8 + 1, 256), 256, 0, s>>>((const bf16*)a, (bf16*)out, n, op, lo, hi, v);
+  TNN_DT_SWITCH(dt, k_unary<T><<<grid_for(n / Vec<T>::N + 1, 256), 256, 0, s>>>((const T*)a, (T*)out, n, op, lo, hi, v));
   TNN_CHECK_LAUNCH();
 }
-void tensor_ternary(const void* a, const void* b, const void* c, void* out, long long n, int op, int is_f32, cudaStream_t s) {
+void tensor_ternary(const void* a, const void* b, const void* c, void* out, long long n, int op, int dt, cudaStream_t s) {
   if (n <= 0) return;
-  if (is_f32)
-    k_ternary<float><<<grid_for(n, 256), 256, 0, s>>>((const float*)a, (const float*)b, (const float*)c, (float*)out, n, op);
-  else
-    k_ternary<bf16><<<grid_for(n, 256), 256, 0, s>>>((const bf16*)a, (const bf16*)b, (const bf16*)c, (bf16*)out, n, op);
+  TNN_DT_SWITCH(dt, k_ternary<T><<<grid_for(n, 256), 256, 0, s>>>((const T*)a, (const T*)b, (const T*)c, (T*)out, n, op));
   TNN_CHECK_LAUNCH();
 }
 
@@ -145,14 +219,15 @@ void tensor_ternary(const void* a, const void* b, const void* c, void* out, long
 template <typename T>
 __global__ void __launch_bounds__(256)
     k_reduce(const T* __restrict__ a, const T* __restrict__ b, float mu, long long n, int mode, float* __restrict__ out) {
-  float acc = 0.f;
+  using A = typename Vec<T>::A;
+  A acc_t = 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float x = Vec<T>::get(a + i);
-    if (mode == 0) acc += x;
-    else if (mode == 1) acc += x * Vec<T>::get(b + i);
-    else acc += (x - mu) * (x - mu);
+    const A x = Vec<T>::get(a + i);
+    if (mode == 0) acc_t += x;
+    else if (mode == 1) acc_t += x * Vec<T>::get(b + i);
+    else acc_t += (x - (A)mu) * (x - (A)mu);
   }
-  acc = warp_sum(acc);
+  float acc = warp_sum((float)acc_t);
   __shared__ float part[8];
   if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -164,13 +239,10 @@ __global__ void __launch_bounds__(256)
     if (threadIdx.x == 0) atomicAdd(out, v);
   }
 }
-void tensor_reduce(const void* a, const void* b, float mu, long long n, int mode, int is_f32, float* out, cudaStream_t s) {
+void tensor_reduce(const void* a, const void* b, float mu, long long n, int mode, int dt, float* out, cudaStream_t s) {
   cudaMemsetAsync(out, 0, sizeof(float), s);
   if (n <= 0) return;
-  if (is_f32)
-    k_reduce<float><<<grid_for(n, 256, kSMs * 4), 256, 0, s>>>((const float*)a, (const float*)b, mu, n, mode, out);
-  else
-    k_reduce<bf16><<<grid_for(n, 256, kSMs * 4), 256, 0, s>>>((const bf16*)a, (const bf16*)b, mu, n, mode, out);
+  TNN_DT_SWITCH(dt, k_reduce<T><<<grid_for(n, 256, kSMs * 4), 256, 0, s>>>((const T*)a, (const T*)b, mu, n, mode, out));
   TNN_CHECK_LAUNCH();
 }
 
@@ -189,36 +261,41 @@ __global__ void __launch_bounds__(256)
     const int h = (int)(r % DH);
     const int n = (int)(r / DH);
     const int sh = h + oh, sw = w + ow;
-    float v = fill;
+    typename Vec<T>::A v = fill;
     if (sh >= 0 && sh < SH && sw >= 0 && sw < SW) v = Vec<T>::get(src + (((long long)n * SH + sh) * SW + sw) * C + c);
     Vec<T>::put(dst + i, v);
   }
 }
 void tensor_window_copy(const void* src, void* dst, int N, int SH, int SW, int DH, int DW, int C, int off_h, int off_w,
-                        float fill, int is_f32, cudaStream_t s) {
+                        float fill, int dt, cudaStream_t s) {
   const long long total = (long long)N * DH * DW * C;
   if (total <= 0) return;
-  if (is_f32)
-    k_window_copy<float><<<grid_for(total, 256), 256, 0, s>>>((const float*)src, (float*)dst, N, SH, SW, DH, DW, C, off_h, off_w, fill);
-  else
-    k_window_copy<bf16><<<grid_for(total, 256), 256, 0, s>>>((const bf16*)src, (bf16*)dst, N, SH, SW, DH, DW, C, off_h, off_w, fill);
+  TNN_DT_SWITCH(dt, k_window_copy<T><<<grid_for(total, 256), 256, 0, s>>>((const T*)src, (T*)dst, N, SH, SW, DH, DW, C, off_h, off_w, fill));
   TNN_CHECK_LAUNCH();
 }
 
 // ---- row softmax (last dim): one warp per row, fwd and bwd
+__device__ __forceinline__ float exp_t(float x) { return __expf(x); }
+__device__ __forceinline__ double exp_t(double x) { return exp(x); }
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 template <typename T>
 __global__ void __launch_bounds__(256) k_softmax_rows(const T* __restrict__ x, T* __restrict__ y, long long rows, int C) {
   const int lane = threadIdx.x & 31;
   for (long long r = blockIdx.x * 8LL + (threadIdx.x >> 5); r < rows; r += gridDim.x * 8LL) {
+    using A = typename Vec<T>::A;
     const T* xr = x + r * C;
-    float mx = -INFINITY;
-    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, Vec<T>::get(xr + c));
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-    for (int c = lane; c < C; c += 32) sum += __expf(Vec<T>::get(xr + c) - mx);
+    A mx = -INFINITY;
+    for (int c = lane; c < C; c += 32) mx = fmax(mx, (A)Vec<T>::get(xr + c));
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    A sum = 0;
+    for (int c = lane; c < C; c += 32) sum += exp_t(Vec<T>::get(xr + c) - mx);
     sum = warp_sum(sum);
-    const float inv = 1.f / sum;
-    for (int c = lane; c < C; c += 32) Vec<T>::put(y + r * C + c, __expf(Vec<T>::get(xr + c) - mx) * inv);
+    const A inv = (A)1 / sum;
+    for (int c = lane; c < C; c += 32) Vec<T>::put(y + r * C + c, exp_t(Vec<T>::get(xr + c) - mx) * inv);
   }
 }
 template <typename T>
@@ -226,27 +303,26 @@ __global__ void __launch_bounds__(256)
     k_softmax_rows_bwd(const T* __restrict__ y, const T* __restrict__ dy, T* __restrict__ dx, long long rows, int C) {
   const int lane = threadIdx.x & 31;
   for (long long r = blockIdx.x * 8LL + (threadIdx.x >> 5); r < rows; r += gridDim.x * 8LL) {
-    float dot = 0.f;
+    using A = typename Vec<T>::A;
+    A dot = 0;
     for (int c = lane; c < C; c += 32) dot += Vec<T>::get(y + r * C + c) * Vec<T>::get(dy + r * C + c);
     dot = warp_sum(dot);
     for (int c = lane; c < C; c += 32) {
-      const float yy = Vec<T>::get(y + r * C + c);
+      const A yy = Vec<T>::get(y + r * C + c);
       Vec<T>::put(dx + r * C + c, yy * (Vec<T>::get(dy + r * C + c) - dot));
     }
   }
 }
-void softmax_rows(const void* x, void* y, long long rows, int C, int is_f32, cudaStream_t s) {
+void softmax_rows(const void* x, void* y, long long rows, int C, int dt, cudaStream_t s) {
   if (rows <= 0) return;
   const int blocks = grid_for((rows + 7) / 8, 1, kSMs * 8);
-  if (is_f32) k_softmax_rows<float><<<blocks, 256, 0, s>>>((const float*)x, (float*)y, rows, C);
-  else k_softmax_rows<bf16><<<blocks, 256, 0, s>>>((const bf16*)x, (bf16*)y, rows, C);
+  TNN_DT_SWITCH(dt, k_softmax_rows<T><<<blocks, 256, 0, s>>>((const T*)x, (T*)y, rows, C));
   TNN_CHECK_LAUNCH();
 }
-void softmax_rows_bwd(const void* y, const void* dy, void* dx, long long rows, int C, int is_f32, cudaStream_t s) {
+void softmax_rows_bwd(const void* y, const void* dy, void* dx, long long rows, int C, int dt, cudaStream_t s) {
   if (rows <= 0) return;
   const int blocks = grid_for((rows + 7) / 8, 1, kSMs * 8);
-  if (is_f32) k_softmax_rows_bwd<float><<<blocks, 256, 0, s>>>((const float*)y, (const float*)dy, (float*)dx, rows, C);
-  else k_softmax_rows_bwd<bf16><<<blocks, 256, 0, s>>>((const bf16*)y, (const bf16*)dy, (bf16*)dx, rows, C);
+  TNN_DT_SWITCH(dt, k_softmax_rows_bwd<T><<<blocks, 256, 0, s>>>((const T*)y, (const T*)dy, (T*)dx, rows, C));
   TNN_CHECK_LAUNCH();
 }
 

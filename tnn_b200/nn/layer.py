@@ -153,6 +153,26 @@ class Layer:
             self._lp_version[name] = self.param_version
         return t
 
+    def lp_as(self, name: str, dtype: torch.dtype) -> torch.Tensor:
+        """Compute copy of a parameter in an explicit activation dtype (layers whose io_dtype is fp16 / fp64; fp32 is the
+        master itself, bf16 the default copy).  Same lazy refresh as ``lp``."""
+        p = self.params[name]
+        if dtype == p.dtype or not p.is_cuda:
+            return p
+        if dtype == torch.bfloat16:
+            return self.lp(name)
+        key = f"{name}@{dtype}"
+        t = self.params_lp.get(key)
+        if t is None:
+            t = torch.empty(p.shape, dtype=dtype, device=p.device)
+            self.params_lp[key] = t
+            self._lp_version[key] = -1
+        if self._lp_version.get(key, -1) != self.param_version:
+            from ..ops import native
+            native.require().cast_any(p, t)
+            self._lp_version[key] = self.param_version
+        return t
+
     def parameters(self) -> list[tuple[str, torch.Tensor]]:
         out = [(f"{self.name}.{k}", v) for k, v in self.params.items()]
         for c in self.children():

@@ -20,6 +20,7 @@ from ..core.config import TConfig
 from ..ops import conv as conv_ops
 from ..ops import gemm as gemm_ops
 from ..ops import native
+from ..ops import tensor_ops
 from .layer import Layer, ParamDescriptor, register
 
 ACT_KIND = {"none": 0, "linear": 0, "relu": 1, "leaky_relu": 2, "sigmoid": 3, "tanh": 4, "elu": 5, "gelu": 6}
@@ -48,15 +49,23 @@ def _round8(n: int) -> int:
 
 
 def to_bf16(x: torch.Tensor) -> torch.Tensor:
-    """fp32 -> bf16 on the GPU through the hand-written cast kernel (no-op when already bf16)."""
-    if x.dtype == torch.bfloat16:
+    """fp32 / fp16 / fp64 -> bf16 on the GPU through the hand-written cast kernels (no-op when already bf16)."""
+    return to_dtype(x, torch.bfloat16)
+
+
+def to_dtype(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Activation cast between bf16 / fp32 / fp16 / fp64 (csrc/kernels: cast_f32_to_bf16, cast_any)."""
+    if x.dtype == dtype:
         return x
-    if x.is_cuda and x.dtype == torch.float32:
+    if x.is_cuda and x.dtype in (torch.float32, torch.float16, torch.float64, torch.bfloat16):
         x = x.contiguous()
-        y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
-        native.require().cast_f32_to_bf16(x, y)
+        y = torch.empty(x.shape, dtype=dtype, device=x.device)
+        if x.dtype == torch.float32 and dtype == torch.bfloat16:
+            native.require().cast_f32_to_bf16(x, y)
+        else:
+            native.require().cast_any(x, y)
         return y
-    return x.to(torch.bfloat16)
+    return x.to(dtype)
 
 
 def _aligned_rows(t2d: torch.Tensor) -> torch.Tensor:
@@ -95,7 +104,14 @@ class DenseLayer(Layer):
         x2 = x.reshape(-1, shp[-1])
         N = self.output_features
         bias = self.params.get("bias")
-        if x2.is_cuda:
+        if x2.is_cuda and self.io_dtype in gemm_ops.XT_DTYPES:
+            # explicit fp16 / fp32 / fp64 IO contract (dense_layer.cpp:336-340 instantiates the layer per dtype): fp16 and
+            # fp32 (tf32) run on the tensor cores through csrc/kernels/gemm_xt.cu, fp64 on the DFMA kernel
+            dt = self.io_dtype
+            x2 = to_dtype(x2, dt)
+            res2 = to_dtype(residual.reshape(-1, N), dt) if residual is not None else None
+            y = gemm_ops.linear_fwd(x2, self.lp_as("weight", dt), bias, self.activation, res2)
+        elif x2.is_cuda:
             x2 = _aligned_rows(to_bf16(x2))
             M = x2.shape[0]
             res2 = residual.reshape(-1, N) if residual is not None else None
@@ -121,7 +137,14 @@ class DenseLayer(Layer):
         dy2 = dy.reshape(-1, N)
         if self.activation not in (None, "none", "linear"):
             raise NotImplementedError("fused-activation Dense is inference-only; use an ActivationLayer for training")
-        if dy2.is_cuda:
+        if dy2.is_cuda and self.io_dtype in gemm_ops.XT_DTYPES:
+            dt = self.io_dtype
+            dy2 = to_dtype(dy2, dt).contiguous()
+            gemm_ops.linear_wgrad(dy2, x2, self.grads["weight"])
+            if self.use_bias:
+                gemm_ops.bias_grad(dy2, self.grads["bias"])
+            dx = gemm_ops.linear_dgrad(dy2, self.lp_as("weight", dt))
+        elif dy2.is_cuda:
             dy2 = _aligned_rows(to_bf16(dy2))
             gemm_ops.linear_wgrad(dy2, x2, self.grads["weight"])
             if self.use_bias:
@@ -623,7 +646,7 @@ class ActivationLayer(Layer):
         if self.training:
             self.cache(mb_id)["x"] = x
         if self.activation == "softmax":
-            y = torch.softmax(x.float(), -1).to(x.dtype)
+            y = tensor_ops.softmax(x.contiguous()) if x.is_cuda else torch.softmax(x.float(), -1).to(x.dtype)
             if self.training:
                 self.cache(mb_id)["y"] = y
             return y
@@ -640,11 +663,13 @@ class ActivationLayer(Layer):
         c = self.cache(mb_id)
         x = c["x"]
         if self.activation == "softmax":
+            if dy.is_cuda:
+                return tensor_ops.softmax_backward(c["y"], to_dtype(dy, c["y"].dtype).contiguous())
             y = c["y"].float()
             g = dy.float()
             return (y * (g - (g * y).sum(-1, keepdim=True))).to(dy.dtype)
         if dy.is_cuda:
-            dy = dy.to(x.dtype).contiguous()
+            dy = to_dtype(dy, x.dtype).contiguous()
             dx = torch.empty_like(x)
             native.require().act_bwd(x, dy, dx, ACT_KIND[self.activation], self.slope)
             return dx

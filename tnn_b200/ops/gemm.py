@@ -47,12 +47,75 @@ def _act_ref(y: torch.Tensor, act) -> torch.Tensor:
     raise ValueError(act)
 
 
+# ------------------------------------------------------------------------------------------- fp16 / fp32 / fp64
+# The reference's DenseLayer is instantiated per IO dtype (dense_layer.cpp:336-340: fp32, fp16, bf16, fp64) and
+# picks cublasHgemm / Sgemm / Dgemm / GemmEx (src/math/cuda/cublas_gemm.cu:20-164).  Here: fp16 -> tcgen05 kind::f16
+# with fp16 operands, fp32 -> tcgen05 kind::tf32 on the untouched fp32 tensors, fp64 -> register-tiled DFMA kernel
+# (csrc/kernels/gemm_xt.cu).  bf16 (the default GPU activation type) keeps the tuned kernels below.
+XT_DTYPES = (torch.float16, torch.float32, torch.float64)
+
+
+def _xt_rows_ok(t: torch.Tensor) -> bool:
+    """TMA operands: unit inner stride, 16-byte aligned base and row pitch."""
+    return t.stride(1) == 1 and (t.stride(0) * t.element_size()) % 16 == 0 and t.data_ptr() % 16 == 0
+
+
+def _xt_operand(t: torch.Tensor) -> torch.Tensor:
+    """A 2-D view the TMA descriptors accept (copy into 16-byte padded rows only when the pitch is odd)."""
+    if t.dtype == torch.float64 or _xt_rows_ok(t):
+        return t if t.stride(1) == 1 else t.contiguous()
+    per16 = 16 // t.element_size()
+    ld = (t.shape[1] + per16 - 1) // per16 * per16
+    buf = torch.zeros((t.shape[0], ld), dtype=t.dtype, device=t.device)
+    buf[:, :t.shape[1]].copy_(t)
+    return buf[:, :t.shape[1]]
+
+
+def gemm_xt(a: torch.Tensor, b: torch.Tensor, a_mn: bool = False, b_mn: bool = False, *, out: torch.Tensor | None = None,
+            bias: torch.Tensor | None = None, residual: torch.Tensor | None = None, act=None, alpha: float = 1.0,
+            accumulate: bool = False, out_f32: bool = False) -> torch.Tensor:
+    """out[M,N] (+)= act(alpha * A B^T-ish + bias + residual) for fp16 / fp32 (tf32 tensor cores) / fp64 CUDA tensors.
+    a is [M,K] (or [K,M] with a_mn), b is [N,K] (or [K,N] with b_mn)."""
+    C = native.require()
+    a, b = _xt_operand(a), _xt_operand(b)
+    M = a.shape[1] if a_mn else a.shape[0]
+    N = b.shape[1] if b_mn else b.shape[0]
+    if out is None:
+        odt = torch.float32 if (out_f32 and a.dtype == torch.float16) else a.dtype
+        out = torch.empty((M, N), dtype=odt, device=a.device)
+    if bias is not None:
+        want = torch.float64 if a.dtype == torch.float64 else torch.float32
+        bias = bias if bias.dtype == want else bias.to(want)
+    C.gemm_xt(a, b, a_mn, b_mn, out, bias, residual, ACT[act], float(alpha), accumulate)
+    return out
+
+
+def _xt(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.dtype in XT_DTYPES and native.use_native(x)
+
+
+def _linear_fwd_xt(x, w, bias, act, residual, out, out_f32):
+    assert w.dtype == x.dtype, f"weight dtype {w.dtype} != activation dtype {x.dtype}"
+    if x.dtype == torch.float64 and (act not in (None, "none", "linear") or residual is not None):
+        y = gemm_xt(x, w, bias=bias)
+        if residual is not None:
+            y = y + residual
+        y = _act_ref(y, act)
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
+    return gemm_xt(x, w, out=out, bias=bias, residual=residual, act=act, out_f32=out_f32)
+
+
 def linear_fwd(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor | None = None, act=None,
                residual: torch.Tensor | None = None, out: torch.Tensor | None = None,
                out_f32: bool = False) -> torch.Tensor:
     """y[M,N] = act(x[M,K] @ w[N,K]^T + bias (+ residual)).  GPU: x, w bf16; bias fp32."""
     M, K = x.shape
     N = w.shape[0]
+    if _xt(x):
+        return _linear_fwd_xt(x, w, bias, act, residual, out, out_f32)
     if not native.use_native(x):
         y = x.float() @ w.float().t()
         if bias is not None:
@@ -80,6 +143,8 @@ def linear_dgrad(dy: torch.Tensor, w: torch.Tensor, out: torch.Tensor | None = N
     """dx[M,K] = dy[M,N] @ w[N,K]  (w consumed MN-major, no transpose copy)."""
     M, N = dy.shape
     K = w.shape[1]
+    if _xt(dy):
+        return gemm_xt(dy, w, False, True, out=out)          # w [N,K] read MN-major: no transpose copy
     if not native.use_native(dy):
         return (dy.float() @ w.float()).to(dy.dtype)
     C = native.require()
@@ -94,6 +159,16 @@ def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, alpha: flo
     """dw[N,K] += alpha * dy[M,N]^T @ x[M,K]  (dw fp32; both operands MN-major; split-K)."""
     M, N = dy.shape
     K = x.shape[1]
+    if _xt(dy):
+        if dy.dtype == torch.float64 and dw.dtype != torch.float64:
+            # fp64 activations over fp32 master gradients: exact fp64 product, one rounding into the fp32 accumulator
+            t = gemm_xt(dy, x, True, True, alpha=alpha)
+            t32 = torch.empty(t.shape, dtype=dw.dtype, device=t.device)
+            native.require().cast_any(t, t32)
+            native.require().tensor_binary(dw, t32, 0.0, dw, 0)
+            return
+        gemm_xt(dy, x, True, True, out=dw, alpha=alpha, accumulate=True)   # dw fp32 (fp64 for fp64 masters), both operands MN-major
+        return
     if not native.use_native(dy):
         dw.add_(alpha * (dy.float().t() @ x.float()))
         return
@@ -108,6 +183,16 @@ def linear_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, alpha: flo
 
 def bias_grad(dy: torch.Tensor, db: torch.Tensor, alpha: float = 1.0) -> None:
     """db[N] += alpha * column sums of dy[M,N]."""
+    if _xt(dy):
+        if dy.dtype == torch.float64 and db.dtype != torch.float64:
+            t = torch.empty(dy.shape[1], dtype=torch.float64, device=dy.device)
+            native.require().colsum_any(dy, t, float(alpha), False)
+            t32 = torch.empty(t.shape, dtype=db.dtype, device=t.device)
+            native.require().cast_any(t, t32)
+            native.require().tensor_binary(db, t32, 0.0, db, 0)
+            return
+        native.require().colsum_any(dy, db, float(alpha), True)
+        return
     if not native.use_native(dy):
         db.add_(alpha * dy.float().sum(0))
         return

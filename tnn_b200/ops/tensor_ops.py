@@ -18,9 +18,13 @@ _TORCH_BIN = {"add": torch.add, "sub": torch.sub, "mul": torch.mul, "div": torch
               "max": torch.maximum, "eq": lambda a, b: (a == b).to(a.dtype), "gt": lambda a, b: (a > b).to(a.dtype)}
 
 
+# element types of the templated GPU kernels (csrc/kernels/tensor_ops.cu: bf16 / fp32 / fp16 / fp64)
+_GPU_DTYPES = (torch.float32, torch.bfloat16, torch.float16, torch.float64)
+
+
 def _native_ok(*ts) -> bool:
     t0 = ts[0]
-    return t0.is_cuda and t0.dtype in (torch.float32, torch.bfloat16) and all(
+    return t0.is_cuda and t0.dtype in _GPU_DTYPES and all(
         t is None or (t.is_cuda and t.dtype == t0.dtype and t.is_contiguous() and t.shape == t0.shape) for t in ts)
 
 
@@ -184,6 +188,12 @@ def cast(a: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
             out = torch.empty(a.shape, dtype=dtype, device=a.device)
             native.require().cast_bf16_to_f32(a, out)
             return out
+        if a.dtype in _GPU_DTYPES and dtype in _GPU_DTYPES:
+            if a.dtype == dtype:
+                return a
+            out = torch.empty(a.shape, dtype=dtype, device=a.device)
+            native.require().cast_any(a, out)          # any pair of bf16 / fp32 / fp16 / fp64
+            return out
     return a.to(dtype)
 
 
@@ -244,6 +254,10 @@ def transpose_2d(x: torch.Tensor) -> torch.Tensor:
     if x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2 and x.is_contiguous():
         out = torch.empty((x.shape[1], x.shape[0]), dtype=x.dtype, device=x.device)
         native.require().transpose_bf16(x, out, x.shape[0], x.shape[1])
+        return out
+    if x.is_cuda and x.dtype in _GPU_DTYPES and x.dim() == 2 and x.is_contiguous():
+        out = torch.empty((x.shape[1], x.shape[0]), dtype=x.dtype, device=x.device)
+        native.require().transpose_any(x, out)
         return out
     return x.t().contiguous()
 
