@@ -459,3 +459,25 @@ def test_user_defined_layers_through_the_extension_bases(tmp_path):
         g.save_state(f)
     g2 = Graph.load_state(path, "cpu")
     torch.testing.assert_close(g2.get_layers()[0].layers[0].params["shift"], ss.params["shift"])
+
+
+def test_dense_fused_activation_backward_matches_autograd():
+    """Dense(activation=...) trains: dW / db / dx equal autograd of act(x W^T + b)."""
+    import torch
+    from tnn_b200.nn.layers import DenseLayer
+    for act, fn in (("relu", torch.relu), ("gelu", lambda t: torch.nn.functional.gelu(t, approximate="tanh"))):
+        lay = DenseLayer(7, 5, True, "d", activation=act).init("cpu", 3)
+        lay.set_training(True)
+        x = torch.randn(4, 7)
+        dy = torch.randn(4, 5)
+        y = lay.forward(x, 0)
+        dx = lay.backward(dy, 0)
+        xr = x.clone().requires_grad_(True)
+        w = lay.params["weight"].clone().requires_grad_(True)
+        b = lay.params["bias"].clone().requires_grad_(True)
+        ref = fn(xr @ w.t() + b)
+        ref.backward(dy)
+        assert torch.allclose(y, ref.detach(), atol=1e-5)
+        assert torch.allclose(dx, xr.grad, atol=1e-5)
+        assert torch.allclose(lay.grads["weight"], w.grad, atol=1e-5)
+        assert torch.allclose(lay.grads["bias"], b.grad, atol=1e-5)

@@ -13,6 +13,10 @@ void runtime_bind(pybind11::module_& m);
 #include <memory>
 #include <mutex>
 
+#include <cuda_runtime.h>
+
+#include <cstring>
+
 #include "allocator.hpp"
 #include "cpu_ops.hpp"
 #include "planner.hpp"
@@ -199,6 +203,72 @@ void runtime_bind(py::module_& m) {
       });
   m.attr("PACKET_HEADER_BYTES") = (int)PacketHeader::kBytes;
   m.def("host_is_little_endian", &host_is_little_endian);
+
+  // ---- CUDA-IPC device slabs: the "registered memory" of the one-sided rendezvous transport when both peers are
+  // processes on one node (distributed/rendezvous.py).  The reference registers a host slab with the NIC
+  // (include/device/ibv_allocator.hpp:31-266) and RDMA-writes into it; here the slab is cudaMalloc'd device memory,
+  // exported with cudaIpcGetMemHandle, and the peer's write is a device-to-device copy over NVLink.
+  struct DevGuard {
+    int prev = -1;
+    explicit DevGuard(int d) {
+      cudaGetDevice(&prev);
+      if (d != prev) cudaSetDevice(d);
+    }
+    ~DevGuard() {
+      int cur = -1;
+      cudaGetDevice(&cur);
+      if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+  };
+  auto ck = [](cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+  };
+  m.def("cuda_ipc_alloc", [ck](int device, size_t bytes) {
+    DevGuard g(device);
+    void* p = nullptr;
+    ck(cudaMalloc(&p, bytes), "cuda_ipc_alloc: cudaMalloc");
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+      cudaFree(p);
+      ck(e, "cuda_ipc_alloc: cudaIpcGetMemHandle");
+    }
+    return py::make_tuple((uint64_t)(uintptr_t)p, py::bytes(reinterpret_cast<const char*>(&h), sizeof(h)));
+  });
+  m.def("cuda_ipc_free", [](int device, uint64_t ptr) {
+    DevGuard g(device);
+    cudaFree(reinterpret_cast<void*>((uintptr_t)ptr));
+  });
+  m.def("cuda_ipc_open", [ck](int device, const std::string& handle) {
+    if (handle.size() != sizeof(cudaIpcMemHandle_t)) throw std::runtime_error("cuda_ipc_open: handle must be 64 bytes");
+    DevGuard g(device);
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle.data(), sizeof(h));
+    void* p = nullptr;
+    ck(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cuda_ipc_open: cudaIpcOpenMemHandle");
+    return (uint64_t)(uintptr_t)p;
+  });
+  m.def("cuda_ipc_close", [](int device, uint64_t ptr) {
+    DevGuard g(device);
+    cudaIpcCloseMemHandle(reinterpret_cast<void*>((uintptr_t)ptr));
+  });
+  // blocking device-to-device copy on a private stream of `device` (either pointer may live on a peer device)
+  m.def("cuda_copy_d2d", [ck](int device, uint64_t dst, uint64_t src, size_t bytes) {
+    if (bytes == 0) return;
+    py::gil_scoped_release nogil;
+    DevGuard g(device);
+    static std::mutex mu;
+    static cudaStream_t streams[64] = {};
+    cudaStream_t s;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      if (!streams[device & 63]) ck(cudaStreamCreateWithFlags(&streams[device & 63], cudaStreamNonBlocking), "cuda_copy_d2d: stream");
+      s = streams[device & 63];
+    }
+    ck(cudaMemcpyAsync(reinterpret_cast<void*>((uintptr_t)dst), reinterpret_cast<const void*>((uintptr_t)src), bytes, cudaMemcpyDefault, s),
+       "cuda_copy_d2d: cudaMemcpyAsync");
+    ck(cudaStreamSynchronize(s), "cuda_copy_d2d: cudaStreamSynchronize");
+  });
 
   // ---------------------------------------------------------------- CPU math / threading
   m.def("cpu_sgemm", [](int64_t a, int64_t b, int64_t c, int64_t M, int64_t N, int64_t K, bool ta, bool tb, double alpha,

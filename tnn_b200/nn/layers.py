@@ -100,6 +100,22 @@ class DenseLayer(Layer):
         return d
 
     def forward_impl(self, x, mb_id, residual=None):
+        fused = self.activation not in (None, "none", "linear")
+        if fused and self.training:
+            # training needs the PRE-activation for the backward pass: GEMM (+bias, +residual) without the activation
+            # epilogue, then the activation kernel; inference keeps the one-kernel fused epilogue
+            act, self.activation = self.activation, None
+            try:
+                z = self.forward_impl(x, mb_id, residual)
+            finally:
+                self.activation = act
+            self.cache(mb_id)["z"] = z
+            if z.is_cuda:
+                zc = z.contiguous()
+                y = torch.empty_like(zc)
+                native.require().act_fwd(zc, y, ACT_KIND[act], 1.0)
+                return y
+            return _act_ref(z.float(), act, 1.0).to(z.dtype)
         shp = x.shape
         x2 = x.reshape(-1, shp[-1])
         N = self.output_features
@@ -126,8 +142,6 @@ class DenseLayer(Layer):
         if self.training:
             c = self.cache(mb_id)
             c["x"] = x2
-            if self.activation not in (None, "none", "linear"):
-                c["y"] = y
         return y.reshape(*shp[:-1], N)
 
     def backward_impl(self, dy, mb_id):
@@ -136,7 +150,18 @@ class DenseLayer(Layer):
         N = self.output_features
         dy2 = dy.reshape(-1, N)
         if self.activation not in (None, "none", "linear"):
-            raise NotImplementedError("fused-activation Dense is inference-only; use an ActivationLayer for training")
+            z = c["z"]
+            if dy.is_cuda:
+                zc = z.contiguous()
+                g = to_dtype(dy.reshape(zc.shape), zc.dtype).contiguous()
+                dz = torch.empty_like(zc)
+                native.require().act_bwd(zc, g, dz, ACT_KIND[self.activation], 1.0)
+                dy2 = dz.reshape(-1, N)
+            else:
+                zf = z.float().detach().requires_grad_(True)
+                with torch.enable_grad():
+                    _act_ref(zf, self.activation, 1.0).backward(dy.reshape(zf.shape).float())
+                dy2 = zf.grad.reshape(-1, N)
         if dy2.is_cuda and self.io_dtype in gemm_ops.XT_DTYPES:
             dt = self.io_dtype
             dy2 = to_dtype(dy2, dt).contiguous()
