@@ -126,6 +126,52 @@ __device__ __forceinline__ float act_df(float x, int kind, float slope) {
     default: return 1.f;
   }
 }
+// fp64 tensors evaluate their activations in double precision
+__device__ __forceinline__ double act_f(double x, int kind, double slope) {
+  switch (kind) {
+    case AK_RELU: return fmax(x, 0.0);
+    case AK_LEAKY_RELU: return x > 0.0 ? x : slope * x;
+    case AK_SIGMOID: return 1.0 / (1.0 + exp(-x));
+    case AK_TANH: return tanh(x);
+    case AK_ELU: return x > 0.0 ? x : slope * (exp(x) - 1.0);
+    case AK_GELU: {
+      const double u = 0.7978845608028654 * (x + 0.044715 * x * x * x);
+      return 0.5 * x * (1.0 + tanh(u));
+    }
+    default: return x;
+  }
+}
+__device__ __forceinline__ double act_df(double x, int kind, double slope) {
+  switch (kind) {
+    case AK_RELU: return x > 0.0 ? 1.0 : 0.0;
+    case AK_LEAKY_RELU: return x > 0.0 ? 1.0 : slope;
+    case AK_SIGMOID: {
+      const double s = 1.0 / (1.0 + exp(-x));
+      return s * (1.0 - s);
+    }
+    case AK_TANH: {
+      const double t = tanh(x);
+      return 1.0 - t * t;
+    }
+    case AK_ELU: return x > 0.0 ? 1.0 : slope * exp(x);
+    case AK_GELU: {
+      const double x2 = x * x;
+      const double u = 0.7978845608028654 * (x + 0.044715 * x * x2);
+      const double t = tanh(u);
+      const double du = 0.7978845608028654 * (1.0 + 3.0 * 0.044715 * x2);
+      return 0.5 * (1.0 + t) + 0.5 * x * (1.0 - t * t) * du;
+    }
+    default: return 1.0;
+  }
+}
+__global__ void k_act_fwd_f64(const double* __restrict__ x, double* __restrict__ y, long long n, int kind, double slope) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) y[i] = act_f(x[i], kind, slope);
+}
+__global__ void k_act_bwd_f64(const double* __restrict__ x, const double* __restrict__ dy, double* __restrict__ dx, long long n, int kind,
+                              double slope) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dx[i] = dy[i] * act_df(x[i], kind, slope);
+}
 template <typename T>
 __device__ __forceinline__ float ld1(const T* p, long long i);
 template <>
@@ -134,12 +180,9 @@ template <>
 __device__ __forceinline__ float ld1<bf16>(const bf16* p, long long i) { return __bfloat162float(p[i]); }
 template <>
 __device__ __forceinline__ float ld1<__half>(const __half* p, long long i) { return __half2float(p[i]); }
-template <>
-__device__ __forceinline__ float ld1<double>(const double* p, long long i) { return (float)p[i]; }   // activations evaluate in fp32
 __device__ __forceinline__ void st1(float* p, long long i, float v) { p[i] = v; }
 __device__ __forceinline__ void st1(bf16* p, long long i, float v) { p[i] = __float2bfloat16(v); }
 __device__ __forceinline__ void st1(__half* p, long long i, float v) { p[i] = __float2half_rn(v); }
-__device__ __forceinline__ void st1(double* p, long long i, float v) { p[i] = (double)v; }
 
 template <typename T>
 __global__ void k_act_fwd(const T* __restrict__ x, T* __restrict__ y, long long n, int kind, float slope) {
@@ -186,7 +229,7 @@ void act_fwd(const void* x, void* y, long long n, int kind, float slope, int dt,
   } else if (dt == 2) {
     k_act_fwd<__half><<<grid_for(n, 256), 256, 0, s>>>((const __half*)x, (__half*)y, n, kind, slope);
   } else if (dt == 3) {
-    k_act_fwd<double><<<grid_for(n, 256), 256, 0, s>>>((const double*)x, (double*)y, n, kind, slope);
+    k_act_fwd_f64<<<grid_for(n, 256), 256, 0, s>>>((const double*)x, (double*)y, n, kind, (double)slope);
   } else {
     long long nv = n / 8;
     if (nv) k_act_fwd_bf8<<<grid_for(nv, 256), 256, 0, s>>>((const bf16*)x, (bf16*)y, nv, kind, slope);
@@ -203,7 +246,7 @@ void act_bwd(const void* x, const void* dy, void* dx, long long n, int kind, flo
   } else if (dt == 2) {
     k_act_bwd<__half><<<grid_for(n, 256), 256, 0, s>>>((const __half*)x, (const __half*)dy, (__half*)dx, n, kind, slope);
   } else if (dt == 3) {
-    k_act_bwd<double><<<grid_for(n, 256), 256, 0, s>>>((const double*)x, (const double*)dy, (double*)dx, n, kind, slope);
+    k_act_bwd_f64<<<grid_for(n, 256), 256, 0, s>>>((const double*)x, (const double*)dy, (double*)dx, n, kind, (double)slope);
   } else {
     long long nv = n / 8;
     if (nv)
