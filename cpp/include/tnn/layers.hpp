@@ -85,6 +85,9 @@ class BatchNormLayer : public Layer {
   double fused_dropout_p = 0.0;
   size_t num_features() const { return C_; }
   bool use_relu() const { return relu_; }
+  bool affine() const { return affine_; }
+  double epsilon() const { return eps_; }
+  double momentum() const { return momentum_; }
 
  protected:
   void fill_config(TConfig& c) const override;
@@ -459,7 +462,8 @@ class SDPALayer : public Layer {
 };
 
 // NCHW facade: presents an NHWC layer to NCHW tensors (legacy_conv2d / legacy_batchnorm / legacy_maxpool2d /
-// legacy_avgpool2d; legacy_dense is DenseLayer itself).  Layout conversion runs in the tiled transpose kernels.
+// legacy_avgpool2d; legacy_dense is DenseLayer itself).  Layout conversion runs in the tiled transpose kernels --
+// except legacy_batchnorm on the GPU, which is normalised in its own NCHW layout by kernels/norm_nchw.cu.
 class LegacyNCHWLayer : public Block {
  public:
   LegacyNCHWLayer(std::unique_ptr<Layer> inner, const std::string& legacy_type);
@@ -471,8 +475,11 @@ class LegacyNCHWLayer : public Block {
   TConfig get_config() const override;
 
  private:
+  Tensor bn_forward_nchw(BatchNormLayer& bn, const Tensor& x, size_t mb);
+  Tensor bn_backward_nchw(BatchNormLayer& bn, const Tensor& dy, size_t mb);
   std::unique_ptr<Layer> inner_;
   std::string legacy_type_;
+  Tensor nchw_ws_, nchw_ss_, nchw_coef_;   // persistent workspaces of the native NCHW BatchNorm kernels
 };
 
 // ---- helpers shared by layer implementations and tests

@@ -788,14 +788,71 @@ Tensor nhwc_to_nchw_tensor(const Tensor& x, IAllocator* alloc) {
 }
 LegacyNCHWLayer::LegacyNCHWLayer(std::unique_ptr<Layer> inner, const std::string& legacy_type)
     : Block(inner->name()), inner_(std::move(inner)), legacy_type_(legacy_type) {}
+// legacy_batchnorm on the GPU: normalise the [N, C, H, W] tensor in place of its layout (norm_nchw.cu): statistics,
+// finalize, apply = 3 launches; reduce, coefficients, apply = 3 launches backward; no transposes
+Tensor LegacyNCHWLayer::bn_forward_nchw(BatchNormLayer& bn, const Tensor& x, size_t mb) {
+  device_.set_current();
+  cudaStream_t s = stream();
+  const size_t N = x->shape()[0], C = x->shape()[1], HW = x->shape()[2] * x->shape()[3];
+  if (!nchw_ws_) {
+    nchw_ws_ = new_persistent(DType_t::FP64, {2 * C}, true);
+    nchw_ss_ = new_persistent(DType_t::FP32, {2 * C}, true);
+    nchw_coef_ = new_persistent(DType_t::FP32, {3 * C}, true);
+  }
+  auto& P = bn.params();
+  const float* gamma = bn.affine() ? P.at("gamma")->data_as<float>() : nullptr;
+  const float* beta = bn.affine() ? P.at("beta")->data_as<float>() : nullptr;
+  float* rmean = P.at("running_mean")->data_as<float>();
+  float* rvar = P.at("running_var")->data_as<float>();
+  const int f32 = x->data_type() == DType_t::FP32;
+  Tensor y = new_tensor(x->data_type(), x->shape());
+  const float* ss = nchw_ss_->data_as<float>();
+  if (training_) {
+    Tensor rec = new_tensor(DType_t::FP32, {4 * C});                       // mean | invstd | (scale, shift) pairs
+    float* r = rec->data_as<float>();
+    bn_nchw_train_stats(x->data(), f32, (int)N, (int)C, (int)HW, gamma, beta, (float)bn.epsilon(), (float)bn.momentum(), rmean, rvar, r, r + C,
+                        r + 2 * C, nchw_ws_->data(), s);
+    ss = r + 2 * C;
+    auto& c = cache(mb);
+    c.t["x"] = x;
+    c.t["rec"] = rec;
+  } else {
+    bn_nchw_eval_scale_shift((int)C, gamma, beta, rmean, rvar, (float)bn.epsilon(), nchw_ss_->data_as<float>(), s);
+  }
+  bn_nchw_apply(x->data(), y->data(), f32, (int)N, (int)C, (int)HW, ss, bn.use_relu() ? 1 : 0, s);
+  return y;
+}
+Tensor LegacyNCHWLayer::bn_backward_nchw(BatchNormLayer& bn, const Tensor& dy, size_t mb) {
+  device_.set_current();
+  auto& c = cache(mb);
+  Tensor x = c.t.at("x"), rec = c.t.at("rec");
+  const size_t N = x->shape()[0], C = x->shape()[1], HW = x->shape()[2] * x->shape()[3];
+  const float* r = rec->data_as<float>();
+  Tensor dx = new_tensor(x->data_type(), x->shape());
+  auto& G = bn.grads();
+  bn_nchw_backward(dy->data(), x->data(), dx->data(), x->data_type() == DType_t::FP32, (int)N, (int)C, (int)HW,
+                   bn.affine() ? bn.params().at("gamma")->data_as<float>() : nullptr, r, r + C, r + 2 * C, bn.use_relu() ? 1 : 0,
+                   bn.affine() ? G.at("gamma")->data_as<float>() : nullptr, bn.affine() ? G.at("beta")->data_as<float>() : nullptr,
+                   nchw_coef_->data_as<float>(), nchw_ws_->data(), stream());
+  clear_cache(mb);
+  return dx;
+}
 Tensor LegacyNCHWLayer::forward_impl(const Tensor& xin, size_t mb, const FwdAux&) {
   Tensor x = as_compute(xin);
   if (x->dims() != 4) return inner_->forward(x, mb);
+  if (device_.is_gpu()) {
+    auto* bn = dynamic_cast<BatchNormLayer*>(inner_.get());
+    if (bn && bn->fused_dropout_p == 0.0 && x->shape()[1] == bn->num_features()) return bn_forward_nchw(*bn, x, mb);
+  }
   Tensor y = inner_->forward(nchw_to_nhwc_tensor(x, workspace_), mb);
   return y->dims() == 4 ? nhwc_to_nchw_tensor(y, workspace_) : y;
 }
 Tensor LegacyNCHWLayer::backward_impl(const Tensor& dyin, size_t mb, BwdAux&) {
   Tensor dy = as_compute(dyin);
+  if (device_.is_gpu() && dy->dims() == 4) {
+    auto* bn = dynamic_cast<BatchNormLayer*>(inner_.get());
+    if (bn && cache(mb).get("rec")) return bn_backward_nchw(*bn, dy, mb);
+  }
   Tensor dx = inner_->backward(dy->dims() == 4 ? nchw_to_nhwc_tensor(dy, workspace_) : dy, mb);
   if (!dx) return dx;
   return dx->dims() == 4 ? nhwc_to_nchw_tensor(dx, workspace_) : dx;

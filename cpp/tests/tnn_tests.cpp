@@ -1034,6 +1034,9 @@ TEST(gpu_parity_dense_conv) {
 TEST(gpu_parity_norms_pools_acts) {
   parity([]() -> std::unique_ptr<Layer> { return std::make_unique<BatchNormLayer>(32, 1e-5, 0.1, true, true); }, {8, 8, 8, 32}, 3e-2);
   parity([]() -> std::unique_ptr<Layer> { return std::make_unique<BatchNormLayer>(64, 1e-5, 0.1, true, false); }, {4, 16, 16, 64}, 3e-2);
+  // legacy_batchnorm: NCHW in its own layout on the GPU (norm_nchw.cu), vector (H*W % 8 == 0) and scalar planes
+  parity([]() -> std::unique_ptr<Layer> { return std::make_unique<LegacyNCHWLayer>(std::make_unique<BatchNormLayer>(32, 1e-5, 0.1, true, false, "lbn"), "legacy_batchnorm"); }, {8, 32, 12, 12}, 3e-2);
+  parity([]() -> std::unique_ptr<Layer> { return std::make_unique<LegacyNCHWLayer>(std::make_unique<BatchNormLayer>(24, 1e-5, 0.1, true, false, "lbn"), "legacy_batchnorm"); }, {5, 24, 7, 7}, 3e-2);
   parity([]() -> std::unique_ptr<Layer> { return std::make_unique<LayerNormLayer>(256); }, {6, 10, 256}, 3e-2);
   parity([]() -> std::unique_ptr<Layer> { return std::make_unique<GroupNormLayer>(4, 32); }, {2, 8, 8, 32}, 3e-2);
   parity([]() -> std::unique_ptr<Layer> { return std::make_unique<MaxPool2DLayer>(2, 2); }, {2, 8, 8, 16}, 1e-2);

@@ -71,6 +71,32 @@ def test_dense_with_fused_activation_trains():
         _check(lambda: L.DenseLayer(96, 100, True, "fc", activation=act), torch.randn(64, 96), train=False)
 
 
+def test_legacy_batchnorm_runs_natively_on_nchw():
+    """legacy_batchnorm normalises the NCHW tensor in its own layout (norm_nchw.cu): 3 launches forward, 3 backward, no
+    NHWC transposes (round 1: transpose -> NHWC kernels -> transpose)."""
+    from tnn_b200.ops import native
+    _check(lambda: L.LegacyBatchNormLayer(32, 1e-5, 0.1, True, False, name="lbn"), torch.randn(8, 32, 12, 12))       # vector path
+    _check(lambda: L.LegacyBatchNormLayer(24, 1e-5, 0.1, True, False, name="lbn"), torch.randn(5, 24, 7, 7))         # H*W = 49: scalar path
+    _check(lambda: L.LegacyBatchNormLayer(16, 1e-3, 0.2, True, True, name="lbn"), torch.randn(8, 16, 8, 8), worst_element=False)
+    _check(lambda: L.LegacyBatchNormLayer(16, 1e-3, 0.2, False, False, name="lbn"), torch.randn(4, 16, 8, 8), train=False)
+    lay = L.LegacyBatchNormLayer(32, name="lbn").init("cpu", 1).to("cuda")
+    lay.set_training(True)
+    x = torch.randn(8, 32, 12, 12, device="cuda").bfloat16()
+    n0 = native.require().launch_count()
+    y = lay.forward(x, 0)
+    n1 = native.require().launch_count()
+    lay.backward(torch.randn_like(y), 0)
+    n2 = native.require().launch_count()
+    assert (n1 - n0, n2 - n1) == (3, 3), (n1 - n0, n2 - n1)
+    # running statistics follow the unbiased-variance rule of the reference
+    xf = x.float()
+    want_var = 0.9 * 1.0 + 0.1 * xf.permute(1, 0, 2, 3).reshape(32, -1).var(1, unbiased=True)
+    assert torch.allclose(lay.inner.params["running_var"], want_var, atol=2e-3)
+    # fp32 activations stay fp32
+    y32 = lay.forward(x.float(), 1)
+    assert y32.dtype == torch.float32 and _rel(y32, y) < 1e-2
+
+
 def test_conv_3x3():
     _check(lambda: L.Conv2DLayer(32, 64, 3, 3, 1, 1, 1, 1, True, "c"), torch.randn(4, 16, 16, 32))
 

@@ -493,6 +493,33 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     else tnn::gemm_tf32(vp(a), vp(b), M, N, K, a.stride(0), b.stride(0), a_mn, b_mn, e, cur_stream());
   }, py::arg("a"), py::arg("b"), py::arg("a_mn"), py::arg("b_mn"), py::arg("out"), py::arg("bias") = py::none(),
      py::arg("residual") = py::none(), py::arg("act") = 0, py::arg("alpha") = 1.0, py::arg("accumulate") = false);
+  // ---- native NCHW BatchNorm (norm_nchw.cu)
+  m.def("bn_nchw_ws_bytes", [](int C) { return (int64_t)tnn::bn_nchw_ws_bytes(C); });
+  m.def("bn_nchw_train_stats", [](const Tensor& x, const OptT& gamma, const OptT& beta, double eps, double momentum, const OptT& rmean,
+                                  const OptT& rvar, const Tensor& mean, const Tensor& invstd, const Tensor& ss, const Tensor& ws) {
+    TORCH_CHECK(x.is_cuda() && x.dim() == 4 && x.is_contiguous(), "bn_nchw: contiguous [N,C,H,W] CUDA tensor");
+    TORCH_CHECK(x.scalar_type() == torch::kFloat32 || x.scalar_type() == torch::kBFloat16, "bn_nchw: bf16 / fp32 activations");
+    const int N = (int)x.size(0), C = (int)x.size(1), HW = (int)(x.size(2) * x.size(3));
+    tnn::bn_nchw_train_stats(vp(x), x.scalar_type() == torch::kFloat32, N, C, HW, fp(gamma), fp(beta), (float)eps, (float)momentum, fp(rmean),
+                             fp(rvar), fp(mean), fp(invstd), fp(ss), ws.data_ptr(), cur_stream());
+  });
+  m.def("bn_nchw_eval_scale_shift", [](int C, const OptT& gamma, const OptT& beta, const Tensor& rmean, const Tensor& rvar, double eps,
+                                       const Tensor& ss) {
+    tnn::bn_nchw_eval_scale_shift(C, fp(gamma), fp(beta), fp(rmean), fp(rvar), (float)eps, fp(ss), cur_stream());
+  });
+  m.def("bn_nchw_apply", [](const Tensor& x, const Tensor& y, const Tensor& ss, bool relu) {
+    TORCH_CHECK(x.is_cuda() && x.dim() == 4 && x.is_contiguous() && y.is_contiguous() && x.scalar_type() == y.scalar_type(), "bn_nchw_apply");
+    tnn::bn_nchw_apply(vp(x), vp(y), x.scalar_type() == torch::kFloat32, (int)x.size(0), (int)x.size(1), (int)(x.size(2) * x.size(3)), fp(ss),
+                       relu ? 1 : 0, cur_stream());
+  });
+  m.def("bn_nchw_backward", [](const Tensor& dy, const Tensor& x, const Tensor& dx, const OptT& gamma, const Tensor& mean, const Tensor& invstd,
+                               const Tensor& ss, bool relu, const OptT& dgamma, const OptT& dbeta, const Tensor& coef, const Tensor& ws) {
+    TORCH_CHECK(x.is_cuda() && x.dim() == 4 && x.is_contiguous() && dy.is_contiguous() && dx.is_contiguous() &&
+                    dy.scalar_type() == x.scalar_type() && dx.scalar_type() == x.scalar_type(), "bn_nchw_backward");
+    tnn::bn_nchw_backward(vp(dy), vp(x), vp(dx), x.scalar_type() == torch::kFloat32, (int)x.size(0), (int)x.size(1),
+                          (int)(x.size(2) * x.size(3)), fp(gamma), fp(mean), fp(invstd), fp(ss), relu ? 1 : 0, fp(dgamma), fp(dbeta), fp(coef),
+                          ws.data_ptr(), cur_stream());
+  });
   m.def("colsum_any", [](const Tensor& x, const Tensor& out, double alpha, bool accumulate) {
     TORCH_CHECK(x.dim() == 2 && x.stride(1) == 1 && out.numel() == x.size(1) && out.is_contiguous(), "colsum_any: x [R,C], out [C]");
     const int dt = dt_code(x);

@@ -55,6 +55,19 @@ void philox_normal_f32(float* x, long long n, float mean, float std, uint64_t se
 // generic [rows, cols] transposes (bf16)
 void transpose_bf16(const void* x, void* y, int rows, int cols, cudaStream_t s);
 
+// ---- BatchNorm over NCHW tensors, native layout (norm_nchw.cu); bf16 or fp32 activations, fp32 statistics --------
+size_t bn_nchw_ws_bytes(int C);                      // fp64 (sum, sum^2) pairs; zero it once, the kernels reset it
+void bn_nchw_train_stats(const void* x, int is_f32, int N, int C, int HW, const float* gamma, const float* beta, float eps, float momentum,
+                         float* running_mean, float* running_var, float* save_mean, float* save_invstd, float* scale_shift, void* ws,
+                         cudaStream_t s);
+void bn_nchw_eval_scale_shift(int C, const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps,
+                              float* scale_shift, cudaStream_t s);
+void bn_nchw_apply(const void* x, void* y, int is_f32, int N, int C, int HW, const float* scale_shift, int relu, cudaStream_t s);
+// dx, dgamma += , dbeta += ; coef = [C][3] scratch, ws as above
+void bn_nchw_backward(const void* dy, const void* x, void* dx, int is_f32, int N, int C, int HW, const float* gamma, const float* save_mean,
+                      const float* save_invstd, const float* scale_shift, int relu, float* dgamma, float* dbeta, float* coef, void* ws,
+                      cudaStream_t s);
+
 // ---- generic tensor ops (tensor_ops.cu) -------------------------------------------
 enum TensorBinaryOp : int { TOP_ADD = 0, TOP_SUB = 1, TOP_MUL = 2, TOP_DIV = 3, TOP_MIN = 4, TOP_MAX = 5, TOP_EQ = 6, TOP_GT = 7 };
 enum TensorUnaryOp : int { UOP_SQRT = 0, UOP_RSQRT = 1, UOP_RCP = 2, UOP_ABS = 3, UOP_CLAMP = 4, UOP_NEG = 5, UOP_EXP = 6, UOP_LOG = 7, UOP_SQUARE = 8 };

@@ -1304,8 +1304,58 @@ class LegacyConv2DLayer(_NCHWFacade):
 
 @register()
 class LegacyBatchNormLayer(_NCHWFacade):
+    """BatchNorm over [N, C, H, W] (legacy_batchnorm_layer.cpp, cuda/batchnorm_nchw_ops.cu:119-550).  On the GPU the
+    NCHW tensor is normalised IN ITS OWN LAYOUT by csrc/kernels/norm_nchw.cu (per-channel plane reductions, plane-wise
+    apply; no NHWC round trip); parameters, running statistics, config and the CPU path are the inner BatchNormLayer's."""
     TYPE_NAME = "legacy_batchnorm"
     INNER = BatchNormLayer
+
+    def _native(self, x) -> bool:
+        return x.is_cuda and x.dim() == 4 and x.shape[1] == self.inner.num_features and self.inner.fused_dropout_p == 0.0 and \
+            os.environ.get("TNN_LEGACY_BN_NATIVE", "1") == "1"
+
+    def _nchw_bufs(self, dev):
+        b = getattr(self, "_nchw", None)
+        if b is None or b["ws"].device != dev:
+            C = self.inner.num_features
+            b = self._nchw = dict(ws=torch.zeros(2 * C, dtype=torch.float64, device=dev), ss=torch.zeros(2 * C, dtype=torch.float32, device=dev),
+                                  coef=torch.zeros(3 * C, dtype=torch.float32, device=dev))
+        return b
+
+    def forward_impl(self, x, mb_id):
+        if not self._native(x):
+            return super().forward_impl(x, mb_id)
+        bn, Cx = self.inner, native.require()
+        C = bn.num_features
+        x = (x if x.dtype in (torch.bfloat16, torch.float32) else to_bf16(x)).contiguous()
+        b = self._nchw_bufs(x.device)
+        gamma, beta = bn.params.get("gamma"), bn.params.get("beta")
+        if self.training:
+            rec = torch.empty(4 * C, dtype=torch.float32, device=x.device)        # mean | invstd | (scale, shift) pairs
+            ss = rec[2 * C:]
+            Cx.bn_nchw_train_stats(x, gamma, beta, bn.epsilon, bn.momentum, bn.params["running_mean"], bn.params["running_var"],
+                                   rec[:C], rec[C:2 * C], ss, b["ws"])
+            self.cache(mb_id).update(x=x, rec=rec)
+        else:
+            ss = b["ss"]
+            Cx.bn_nchw_eval_scale_shift(C, gamma, beta, bn.params["running_mean"], bn.params["running_var"], bn.epsilon, ss)
+        y = torch.empty_like(x)
+        Cx.bn_nchw_apply(x, y, ss, bn.use_relu)
+        return y
+
+    def backward_impl(self, dy, mb_id):
+        c = self.cache(mb_id)
+        if "rec" not in c:
+            return super().backward_impl(dy, mb_id)
+        bn, Cx = self.inner, native.require()
+        C = bn.num_features
+        x, rec = c["x"], c["rec"]
+        dy = to_dtype(dy, x.dtype).contiguous()
+        b = self._nchw_bufs(dy.device)
+        dx = torch.empty_like(x)
+        Cx.bn_nchw_backward(dy, x, dx, bn.params.get("gamma"), rec[:C], rec[C:2 * C], rec[2 * C:], bn.use_relu, bn.grads.get("gamma"),
+                            bn.grads.get("beta"), b["coef"], b["ws"])
+        return dx
 
 
 @register()
