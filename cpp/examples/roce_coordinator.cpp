@@ -1,0 +1,4 @@
+// roce_coordinator: see pipeline_cli.hpp (reference: examples/roce_coordinator.cpp).
+#include "pipeline_cli.hpp"
+
+int main(int argc, char** argv) { return tnn::cli::coordinator_main(argc, argv, true); }

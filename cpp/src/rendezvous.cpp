@@ -1,0 +1,390 @@
+// RoCECommunicator: the one-sided rendezvous transport of the C++ host (see tnn/distributed.hpp).  Frames are those of
+// tnn_b200/distributed/rendezvous.py: {u8 kind, u64 a, u64 b} little endian + tail.
+#include <cuda_runtime.h>
+#include <unistd.h>
+
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+
+#include "tnn/distributed.hpp"
+
+namespace tnn {
+
+namespace {
+enum : uint8_t { K_INLINE = 0, K_PREPARE = 1, K_READY = 2, K_DONE = 3, K_CANCEL = 4, K_GPREPARE = 5, K_GREADY = 6, K_GDONE = 7 };
+constexpr uint64_t kNoBlock = ~0ull;
+constexpr size_t kHdr = 17;
+
+std::string host_token() {
+  std::ifstream f("/proc/sys/kernel/random/boot_id");
+  std::string s;
+  if (f && std::getline(f, s)) {
+    while (!s.empty() && isspace((unsigned char)s.back())) s.pop_back();
+    return s;
+  }
+  char buf[256] = {};
+  gethostname(buf, sizeof(buf) - 1);
+  return buf;
+}
+std::vector<uint8_t> frame(uint8_t kind, uint64_t a, uint64_t b, const void* tail = nullptr, size_t n = 0) {
+  std::vector<uint8_t> f(kHdr + n);
+  f[0] = kind;
+  std::memcpy(&f[1], &a, 8);
+  std::memcpy(&f[9], &b, 8);
+  if (n) std::memcpy(&f[kHdr], tail, n);
+  return f;
+}
+std::string to_hex(const void* p, size_t n) {
+  static const char* d = "0123456789abcdef";
+  std::string s(2 * n, '0');
+  const uint8_t* b = static_cast<const uint8_t*>(p);
+  for (size_t i = 0; i < n; ++i) {
+    s[2 * i] = d[b[i] >> 4];
+    s[2 * i + 1] = d[b[i] & 15];
+  }
+  return s;
+}
+bool from_hex(const std::string& s, void* out, size_t n) {
+  if (s.size() != 2 * n) return false;
+  auto v = [](char c) { return c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : -1; };
+  for (size_t i = 0; i < n; ++i) {
+    const int hi = v(s[2 * i]), lo = v(s[2 * i + 1]);
+    if (hi < 0 || lo < 0) return false;
+    static_cast<uint8_t*>(out)[i] = (uint8_t)(hi * 16 + lo);
+  }
+  return true;
+}
+std::vector<std::string> split(const std::string& s, char sep) {
+  std::vector<std::string> out;
+  std::string cur;
+  for (char c : s) {
+    if (c == sep) {
+      out.push_back(cur);
+      cur.clear();
+    } else {
+      cur.push_back(c);
+    }
+  }
+  out.push_back(cur);
+  return out;
+}
+#define RDV_CUDA(call)                                                                                                \
+  do {                                                                                                                \
+    cudaError_t e_ = (call);                                                                                          \
+    if (e_ != cudaSuccess) throw DistributedError(std::string("RoCECommunicator: " #call ": ") + cudaGetErrorString(e_)); \
+  } while (0)
+}  // namespace
+
+struct RoCECommunicator::Impl {
+  size_t slab_bytes = 0, inline_bytes = 0;
+  std::string token = host_token();
+  // device slab (first fit over a sorted free list, 512-byte blocks, coalescing frees)
+  int dev = -1;
+  uint8_t* dptr = nullptr;
+  cudaIpcMemHandle_t handle{};
+  std::mutex mu;
+  std::map<uint64_t, uint64_t> free_list;                  // offset -> length
+  std::map<uint64_t, uint64_t> live;                       // offset -> length
+  std::vector<std::pair<cudaEvent_t, uint64_t>> released;  // blocks waiting for the consumer stream
+  std::map<std::string, void*> opened;                     // peer ipc handle (hex) -> mapped base
+  cudaStream_t copy_stream = nullptr;
+  struct Pending {
+    Message msg;
+    Endpoint to;
+  };
+  std::map<uint64_t, Pending> pending;
+  uint64_t next_id = 1;
+  Stats st;
+  uint64_t in_use = 0;
+
+  uint64_t alloc(uint64_t n) {
+    n = std::max<uint64_t>(512, (n + 511) / 512 * 512);
+    for (auto it = free_list.begin(); it != free_list.end(); ++it)
+      if (it->second >= n) {
+        const uint64_t off = it->first, len = it->second;
+        free_list.erase(it);
+        if (len > n) free_list[off + n] = len - n;
+        live[off] = n;
+        in_use += n;
+        st.slab_peak = std::max(st.slab_peak, in_use);
+        return off;
+      }
+    return kNoBlock;
+  }
+  void release(uint64_t off) {
+    auto it = live.find(off);
+    if (it == live.end()) return;
+    uint64_t lo = off, len = it->second;
+    in_use -= len;
+    live.erase(it);
+    auto nx = free_list.lower_bound(lo);
+    if (nx != free_list.end() && nx->first == lo + len) {
+      len += nx->second;
+      nx = free_list.erase(nx);
+    }
+    if (nx != free_list.begin()) {
+      auto pv = std::prev(nx);
+      if (pv->first + pv->second == lo) {
+        lo = pv->first;
+        len += pv->second;
+        free_list.erase(pv);
+      }
+    }
+    free_list[lo] = len;
+  }
+  void reap() {   // mu held
+    for (size_t i = 0; i < released.size();) {
+      if (released[i].first == nullptr || cudaEventQuery(released[i].first) == cudaSuccess) {
+        if (released[i].first) cudaEventDestroy(released[i].first);
+        release(released[i].second);
+        released[i] = released.back();
+        released.pop_back();
+      } else {
+        ++i;
+      }
+    }
+  }
+};
+
+RoCECommunicator::RoCECommunicator(const std::string& host, int port, int spp, const Device* land_on, const std::string& name,
+                                   size_t device_slab_bytes, size_t inline_bytes)
+    : TCPCommunicator(host, port, spp, land_on, name), impl_(std::make_unique<Impl>()) {
+  impl_->slab_bytes = device_slab_bytes;
+  impl_->inline_bytes = inline_bytes;
+}
+RoCECommunicator::~RoCECommunicator() { stop(); }
+RoCECommunicator::Stats RoCECommunicator::stats() const {
+  std::lock_guard<std::mutex> g(impl_->mu);
+  return impl_->st;
+}
+
+void RoCECommunicator::start() {
+  if (running_.exchange(true)) return;
+  Impl& I = *impl_;
+  const char* off = getenv("TNN_DEVICE_RENDEZVOUS");
+  if (has_land_ && land_.is_gpu() && I.slab_bytes > 0 && !(off && off[0] == '0')) {
+    I.dev = land_.id();
+    land_.set_current();
+    RDV_CUDA(cudaMalloc(reinterpret_cast<void**>(&I.dptr), I.slab_bytes));
+    RDV_CUDA(cudaIpcGetMemHandle(&I.handle, I.dptr));
+    RDV_CUDA(cudaStreamCreateWithFlags(&I.copy_stream, cudaStreamNonBlocking));
+    I.free_list[0] = I.slab_bytes;
+  }
+  bus_->start();
+  pump_ = std::thread([this] {
+    Impl& I = *impl_;
+    // replies go to the sender's listening address ("host:port" is how the bus names a peer); connect on first use
+    auto reply = [this](const std::string& to, const std::vector<uint8_t>& f) {
+      if (!bus_->has_peer(to)) {
+        const size_t c = to.rfind(':');
+        if (c == std::string::npos) throw DistributedError("RoCECommunicator: cannot reply to " + to);
+        bus_->connect(to.substr(0, c), atoi(to.c_str() + c + 1));
+      }
+      bus_->send(to, f.data(), f.size());
+    };
+    while (running_) {
+      std::string from;
+      std::vector<uint8_t> buf;
+      if (!bus_->recv(200, &from, &buf)) continue;
+      if (buf.size() < kHdr) continue;
+      const uint8_t kind = buf[0];
+      uint64_t a, b;
+      std::memcpy(&a, &buf[1], 8);
+      std::memcpy(&b, &buf[9], 8);
+      const uint8_t* tail = buf.data() + kHdr;
+      const size_t tn = buf.size() - kHdr;
+      try {
+        if (kind == K_INLINE) {
+          Message m = Message::deserialize(tail, tn, false, has_land_ ? &land_ : nullptr);
+          m.sender = from;
+          enqueue(std::move(m));
+        } else if (kind == K_PREPARE) {
+          // no host slab on this side: "no block" makes the peer resend the message inline
+          const std::string t = "-|";
+          const auto f = frame(K_READY, a, kNoBlock, t.data(), t.size());
+          reply(from, f);
+        } else if (kind == K_GPREPARE) {
+          const std::string ts(reinterpret_cast<const char*>(tail), tn);
+          const std::string tok = split(ts, '|')[0];
+          uint64_t off = kNoBlock;
+          if (I.dptr && tok == I.token && b <= I.slab_bytes) {
+            std::lock_guard<std::mutex> g(I.mu);
+            I.reap();
+            off = I.alloc(b);
+          }
+          std::string t;
+          if (off != kNoBlock) t = std::to_string((long long)getpid()) + "|" + std::to_string((unsigned long long)(uintptr_t)I.dptr) + "|" + to_hex(&I.handle, sizeof(I.handle));
+          const auto f = frame(K_GREADY, a, off, t.data(), t.size());
+          reply(from, f);
+        } else if (kind == K_GREADY) {
+          Impl::Pending p;
+          {
+            std::lock_guard<std::mutex> g(I.mu);
+            auto it = I.pending.find(a);
+            if (it == I.pending.end()) continue;
+            p = std::move(it->second);
+            I.pending.erase(it);
+          }
+          bool ok = false;
+          if (b != kNoBlock) {
+            try {
+              const auto parts = split(std::string(reinterpret_cast<const char*>(tail), tn), '|');
+              if (parts.size() != 3) throw DistributedError("bad G_READY tail");
+              uint8_t* base = nullptr;
+              if (atoll(parts[0].c_str()) == (long long)getpid()) {
+                base = reinterpret_cast<uint8_t*>((uintptr_t)strtoull(parts[1].c_str(), nullptr, 10));   // same process: the pointer is usable as is
+              } else {
+                std::lock_guard<std::mutex> g(I.mu);
+                auto it = I.opened.find(parts[2]);
+                if (it == I.opened.end()) {
+                  cudaIpcMemHandle_t h;
+                  if (!from_hex(parts[2], &h, sizeof(h))) throw DistributedError("bad ipc handle");
+                  void* mapped = nullptr;
+                  p.msg.job.data->device().set_current();
+                  RDV_CUDA(cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess));
+                  it = I.opened.emplace(parts[2], mapped).first;
+                }
+                base = static_cast<uint8_t*>(it->second);
+              }
+              const Tensor& t = p.msg.job.data;
+              t->device().set_current();
+              if (!I.copy_stream) RDV_CUDA(cudaStreamCreateWithFlags(&I.copy_stream, cudaStreamNonBlocking));
+              cudaStream_t cs = I.copy_stream;
+              RDV_CUDA(cudaMemcpyAsync(base + b, t->data(), t->nbytes(), cudaMemcpyDefault, cs));     // the one-sided write
+              RDV_CUDA(cudaStreamSynchronize(cs));
+              // metadata record of rendezvous.py: "<HQIIQ" + dims
+              std::vector<uint8_t> meta(26 + 8 * t->shape().size());
+              const uint16_t cmd = (uint16_t)p.msg.command;
+              const uint64_t mb = p.msg.job.mb_id, nb = t->nbytes();
+              const uint32_t dt = (uint32_t)t->data_type(), nd = (uint32_t)t->shape().size();
+              std::memcpy(&meta[0], &cmd, 2);
+              std::memcpy(&meta[2], &mb, 8);
+              std::memcpy(&meta[10], &dt, 4);
+              std::memcpy(&meta[14], &nd, 4);
+              std::memcpy(&meta[18], &nb, 8);
+              for (size_t i = 0; i < t->shape().size(); ++i) {
+                const uint64_t d = t->shape()[i];
+                std::memcpy(&meta[26 + 8 * i], &d, 8);
+              }
+              const auto f = frame(K_GDONE, a, b, meta.data(), meta.size());     // ... and its immediate
+              reply(from, f);
+              std::lock_guard<std::mutex> g(I.mu);
+              ++I.st.device_rendezvous_sent;
+              ok = true;
+            } catch (const std::exception& e) {
+              std::cerr << "[" << name_ << "] device rendezvous failed (" << e.what() << "), using the host path" << std::endl;
+              const auto f = frame(K_GDONE, a, b);                               // empty metadata = cancelled
+              reply(from, f);
+            }
+          }
+          if (!ok) {
+            {
+              std::lock_guard<std::mutex> g(I.mu);
+              ++I.st.device_fallback_host;
+            }
+            const std::vector<uint8_t> body = p.msg.serialize();
+            const auto f = frame(K_INLINE, 0, body.size(), body.data(), body.size());
+            reply(from, f);
+          }
+        } else if (kind == K_GDONE) {
+          if (!I.dptr) continue;
+          if (tn < 26) {
+            std::lock_guard<std::mutex> g(I.mu);
+            I.release(b);
+            continue;
+          }
+          uint16_t cmd;
+          uint64_t mb, nb;
+          uint32_t dt, nd;
+          std::memcpy(&cmd, tail, 2);
+          std::memcpy(&mb, tail + 2, 8);
+          std::memcpy(&dt, tail + 10, 4);
+          std::memcpy(&nd, tail + 14, 4);
+          std::memcpy(&nb, tail + 18, 8);
+          if (dt >= (uint32_t)DType_t::UNKNOWN || nd > 16 || tn < 26 + 8ull * nd) throw DistributedError("bad G_DONE metadata");
+          Shape shape;
+          for (uint32_t i = 0; i < nd; ++i) {
+            uint64_t d;
+            std::memcpy(&d, tail + 26 + 8 * i, 8);
+            shape.push_back((size_t)d);
+          }
+          // zero copy: the tensor is the slab block; when its last reference dies the block is queued for release
+          // behind an event on the consumer's current stream
+          Impl* ip = impl_.get();
+          const uint64_t off = b;
+          const Device d = land_;
+          std::shared_ptr<void> owner(static_cast<void*>(I.dptr + off), [ip, off, d](void*) {
+            cudaEvent_t ev = nullptr;
+            d.set_current();
+            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(ev, current_flow(d).stream());
+            std::lock_guard<std::mutex> g(ip->mu);
+            ip->released.emplace_back(ev, off);
+          });
+          Message m(static_cast<CommandType>(cmd), Job{make_tensor_view(I.dptr + off, (DType_t)dt, shape, land_, owner), mb});
+          m.sender = from;
+          {
+            std::lock_guard<std::mutex> g(I.mu);
+            ++I.st.device_rendezvous_received;
+          }
+          enqueue(std::move(m));
+        }
+      } catch (const std::exception& e) {
+        std::cerr << "[" << name_ << "] dropped a malformed frame from " << from << ": " << e.what() << std::endl;
+      }
+    }
+  });
+}
+
+void RoCECommunicator::stop() {
+  if (!running_.exchange(false)) return;
+  if (pump_.joinable()) pump_.join();
+  bus_->stop();
+  Impl& I = *impl_;
+  if (I.dptr) {
+    land_.set_current();
+    for (auto& o : I.opened) cudaIpcCloseMemHandle(o.second);
+    I.opened.clear();
+    for (auto& r : I.released)
+      if (r.first) cudaEventDestroy(r.first);
+    I.released.clear();
+    if (I.copy_stream) cudaStreamDestroy(I.copy_stream);
+    I.copy_stream = nullptr;
+    cudaFree(I.dptr);      // tensors that still view the slab must not outlive the communicator
+    I.dptr = nullptr;
+  }
+}
+
+void RoCECommunicator::send_remote(const Message& m, const Endpoint& to) {
+  const std::string key = to.host + ":" + std::to_string(to.port);
+  if (!bus_->has_peer(key)) bus_->connect(to.host, to.port);
+  Impl& I = *impl_;
+  const int64_t t0 = Profiler::now_ns();
+  if (m.kind == Message::JOB && m.job.data && m.job.data->is_gpu() && m.job.data->nbytes() > I.inline_bytes) {
+    // device rendezvous: announce, the pump thread does the write when the peer grants a block
+    current_flow(m.job.data->device()).synchronize();            // the producer of the tensor has finished
+    uint64_t id;
+    {
+      std::lock_guard<std::mutex> g(I.mu);
+      id = I.next_id++;
+      I.pending[id] = Impl::Pending{m, to};
+    }
+    const std::string t = I.token + "|" + std::to_string((long long)getpid());
+    const auto f = frame(K_GPREPARE, id, m.job.data->nbytes(), t.data(), t.size());
+    bus_->send(key, f.data(), f.size());
+    GlobalProfiler::add_event(EventType::COMMUNICATION, t0, Profiler::now_ns(), std::string("announce ") + command_name(m.command), name_);
+    return;
+  }
+  const std::vector<uint8_t> body = m.serialize();
+  const auto f = frame(K_INLINE, 0, body.size(), body.data(), body.size());
+  bus_->send(key, f.data(), f.size());
+  {
+    std::lock_guard<std::mutex> g(I.mu);
+    ++I.st.inline_sent;
+  }
+  GlobalProfiler::add_event(EventType::COMMUNICATION, t0, Profiler::now_ns(), std::string("send ") + command_name(m.command), name_);
+}
+
+}  // namespace tnn

@@ -596,8 +596,9 @@ TEST(partitioners_cover_the_model_contiguously) {
   auto parts = Partitioner::split(layers, ftd, "wrn");
   CHECK(parts.size() == 4 && parts[0]->size() == ftd[0].length);
 }
-static std::vector<double> single_device_losses(const std::string& model, const Vec<std::pair<Tensor, Tensor>>& batches, size_t M, double lr) {
-  Graph g = load_or_create_model(model, "", getHost(), 123456);
+static std::vector<double> single_device_losses(const std::string& model, const Vec<std::pair<Tensor, Tensor>>& batches, size_t M, double lr,
+                                                const Device& dev = getHost()) {
+  Graph g = load_or_create_model(model, "", dev, 123456);
   auto opt = OptimizerFactory::create_sgd(lr, 0.9);
   opt->attach(g.context());
   auto crit = LossFactory::create_logsoftmax_crossentropy();
@@ -610,8 +611,8 @@ static std::vector<double> single_device_losses(const std::string& model, const 
     for (size_t i = 0; i < xs.size(); ++i) {
       Tensor o = ex.forward(xs[i], i);
       Tensor stats, grad;
-      crit->loss_and_grad(o, ys[i], stats, &grad, 1.f / (float)xs.size());
-      loss += stats->data_as<float>()[0];
+      crit->loss_and_grad(o, ys[i]->device() == o->device() ? ys[i] : ys[i]->to_device(o->device()), stats, &grad, 1.f / (float)xs.size());
+      loss += (stats->is_gpu() ? stats->to_host() : stats)->data_as<float>()[0];
       ex.backward(grad, i);
     }
     opt->update();
@@ -619,7 +620,9 @@ static std::vector<double> single_device_losses(const std::string& model, const 
   }
   return out;
 }
-static void pipeline_case(bool tcp) {
+// transport: 0 in-process, 1 TCP bus, 2 one-sided rendezvous (RoCECommunicator); `dev`: where the stages run
+static void pipeline_case(int transport, const Device& dev = getHost(), double tol = 1e-4) {
+  const bool tcp = transport != 0;
   const size_t M = 2;
   SyntheticDataLoader data({28, 28, 1}, 10, 64, 3);
   Vec<std::pair<Tensor, Tensor>> batches;
@@ -632,9 +635,10 @@ static void pipeline_case(bool tcp) {
   Vec<Endpoint> eps;
   for (int i = 0; i < 2; ++i) {
     std::unique_ptr<Communicator> c;
-    if (tcp) c = std::make_unique<TCPCommunicator>("127.0.0.1", 0, 2, nullptr, "w" + std::to_string(i));
+    if (transport == 2) c = std::make_unique<RoCECommunicator>("127.0.0.1", 0, 2, &dev, "w" + std::to_string(i), 32u << 20, 1024);   // stage-0 activations are exactly 16 KiB
+    else if (tcp) c = std::make_unique<TCPCommunicator>("127.0.0.1", 0, 2, &dev, "w" + std::to_string(i));
     else c = std::make_unique<InProcessCommunicator>("w" + std::to_string(i));
-    auto w = std::make_unique<Worker>(std::move(c), getHost(), "w" + std::to_string(i));
+    auto w = std::make_unique<Worker>(std::move(c), dev, "w" + std::to_string(i));
     w->start(true);
     eps.push_back(w->comm().endpoint());
     workers.push_back(std::move(w));
@@ -647,7 +651,8 @@ static void pipeline_case(bool tcp) {
   cc.worker_endpoints = eps;
   cc.timeout_job_ms = 30000;
   std::unique_ptr<Communicator> comm;
-  if (tcp) comm = std::make_unique<TCPCommunicator>("127.0.0.1", 0, 2, nullptr, "coord");
+  if (transport == 2) comm = std::make_unique<RoCECommunicator>("127.0.0.1", 0, 2, dev.is_gpu() ? &dev : nullptr, "coord", 32u << 20);
+  else if (tcp) comm = std::make_unique<TCPCommunicator>("127.0.0.1", 0, 2, nullptr, "coord");
   else comm = std::make_unique<InProcessCommunicator>("coord");
   Coordinator co(std::move(cc), std::move(comm));
   co.start();
@@ -661,8 +666,24 @@ static void pipeline_case(bool tcp) {
   }
   // the stages are re-created from config with the reference's fixed seed (123456): compare with a single-device run whose
   // layers were initialised the same way -- per-layer streams depend on (seed, layer name), not on the stage they live in
-  const auto ref = single_device_losses("mnist_cnn", batches, M, 0.05);
-  for (size_t i = 0; i < ref.size(); ++i) CHECK_NEAR(losses[i], ref[i], 1e-4);
+  // (on the GPU the reference run is a GPU run too: dropout masks come from the device Philox stream, keyed by seed / layer / micro-batch)
+  const auto ref = single_device_losses("mnist_cnn", batches, M, 0.05, dev);
+  {
+    std::string all;
+    for (size_t i = 0; i < ref.size(); ++i) all += " " + std::to_string(losses[i]) + "/" + std::to_string(ref[i]);
+    for (size_t i = 0; i < ref.size(); ++i)
+      if (!(std::fabs(losses[i] - ref[i]) <= tol)) throw std::runtime_error("pipeline losses differ from the single-device run (pipeline/reference):" + all);
+  }
+  if (transport == 2 && dev.is_gpu()) {
+    // activations and gradients crossed through the device slabs, not through host staging
+    for (auto& w : workers) {
+      const auto st = static_cast<RoCECommunicator&>(w->comm()).stats();
+      if (!(st.device_rendezvous_sent > 0 && st.device_rendezvous_received > 0 && st.device_fallback_host == 0))
+        throw std::runtime_error(w->comm().name() + ": device rendezvous sent " + std::to_string(st.device_rendezvous_sent) + " received " +
+                                 std::to_string(st.device_rendezvous_received) + " host fallbacks " + std::to_string(st.device_fallback_host) +
+                                 " inline " + std::to_string(st.inline_sent));
+    }
+  }
   CHECK(co.health_check().size() == 2);
   co.barrier();
   Profiler prof = co.fetch_profiling();
@@ -672,8 +693,9 @@ static void pipeline_case(bool tcp) {
   co.stop();
   for (auto& w : workers) w->stop();
 }
-TEST(in_process_pipeline_equals_single_device) { pipeline_case(false); }
-TEST(tcp_pipeline_equals_single_device) { pipeline_case(true); }
+TEST(in_process_pipeline_equals_single_device) { pipeline_case(0); }
+TEST(tcp_pipeline_equals_single_device) { pipeline_case(1); }
+TEST(roce_pipeline_equals_single_device) { pipeline_case(2); }
 TEST(lost_microbatch_and_worker_errors_are_detected) {
   auto w = std::make_unique<Worker>(std::make_unique<InProcessCommunicator>("w"), getHost(), "w");
   w->start(true);
@@ -1209,6 +1231,15 @@ TEST(gpu_gpt2_engine_bf16_fp8_and_graph_decode) {
   }
 }
 
+TEST(gpu_pipeline_in_process_and_tcp_equal_single_device) {
+  pipeline_case(0, need_gpu(), 5e-2);      // device tensors by reference
+  pipeline_case(1, need_gpu(), 5e-2);      // host-staged through the TCP bus
+}
+TEST(gpu_roce_pipeline_moves_activations_device_to_device) {
+  // two stages on the GPU behind RoCECommunicators: activations / gradients are written device to device into the
+  // peer's registered device slab (same process: the slab pointer; other processes: its CUDA-IPC handle)
+  pipeline_case(2, need_gpu(), 5e-2);
+}
 TEST(dp2_fused_step_matches_single_device) {
   need_gpu();
   if (DeviceManager::getInstance().num_gpus() < 2) throw Skip("needs 2 GPUs");

@@ -282,6 +282,54 @@ def test_python_coordinator_drives_a_cpp_tcp_worker(tmp_path):
             proc.kill()
 
 
+def test_python_roce_coordinator_drives_a_cpp_roce_worker():
+    """Frame-level interoperability of the rendezvous transport: the Python ``RoCECoordinator`` runs a 2-stage pipeline whose
+    second stage is the C++ ``roce_worker`` (cpp/src/rendezvous.cpp).  On CPU every message ends up INLINE: the C++ side
+    answers a Python PREPARE with "no block", which makes the sender fall back to the inline frame."""
+    _host()
+    import socket
+    import time
+
+    from tnn_b200.distributed import CoordinatorConfig, Endpoint, ParallelMode, RoCECoordinator, RoCEWorker, split_microbatches
+    from tnn_b200.models import ExampleModels
+    from tnn_b200.nn import LossFactory, OptimizerFactory
+    from tnn_b200.parallel import NaivePipelinePartitioner
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    proc = subprocess.Popen([os.path.join(ROOT, "cpp", "bin", "roce_worker"), str(port)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    local = RoCEWorker("127.0.0.1", 0, use_gpu=False, name="py-local", slab_bytes=8 << 20)
+    try:
+        time.sleep(0.5)
+        cfgc = CoordinatorConfig(ParallelMode.PIPELINE, ExampleModels.create("mnist_cnn"), OptimizerFactory.create_sgd(0.05, 0.9), None,
+                                 NaivePipelinePartitioner([1, 1]), local_worker=local, local_worker_position=0,
+                                 worker_endpoints=[Endpoint.roce("127.0.0.1", port)], seed=5)
+        co = RoCECoordinator(cfgc, "127.0.0.1", 0, slab_bytes=8 << 20)
+        co.start()
+        crit = LossFactory.create_logsoftmax_crossentropy()
+        g = torch.Generator().manual_seed(0)
+        x = torch.rand(16, 28, 28, 1, generator=g)
+        y = (torch.arange(16) % 10).to(torch.int32)
+        losses = []
+        for _ in range(6):
+            xs, ys = split_microbatches(x, y, 2)
+            l, _ = co.async_train_batch(xs, ys, crit)
+            co.update_parameters()
+            losses.append(l)
+        assert losses[-1] < losses[0], losses
+        assert any(st["name"].startswith("roce-worker-") for st in co.health_check())
+        st = local.comm.stats()
+        assert st["fallback_inline"] > 0 and st["received_messages"] > 0, st      # activations > 16 KiB: PREPARE -> "no block" -> inline
+        co.stop()
+    finally:
+        local.stop()
+        try:
+            proc.wait(10)
+        except Exception:  # noqa: BLE001
+            proc.kill()
+
+
 def test_cpp_gpt2_engine_matches_the_python_engine_and_runs_the_new_apps():
     """The C++ GPT2Engine (KV cache, greedy arg-max) built from the PYTHON model's config with the Python weights copied in
     produces the Python engine's logits / tokens; the small C++ example apps run."""
@@ -323,7 +371,8 @@ def test_cpp_gpt2_engine_matches_the_python_engine_and_runs_the_new_apps():
     # example apps of the C++ host (reference examples/*.cpp)
     bins = os.path.join(ROOT, "cpp", "bin")
     for app in ("gpt2_inference", "inferencer", "graph_test", "msequential_example", "test_del", "device_manager_example",
-                "hardware_info_example", "legacy_trainer", "trainer", "tcp_worker", "tcp_coordinator", "bench_cpp", "op_bench"):
+                "hardware_info_example", "legacy_trainer", "trainer", "tcp_worker", "tcp_coordinator", "roce_worker", "roce_coordinator",
+                "dp_trainer", "bench_cpp", "op_bench"):
         assert os.access(os.path.join(bins, app), os.X_OK), app
     env = dict(os.environ, MODEL_NAME="mnist_cnn", BATCH_SIZE="16", EPOCHS="1", MAX_STEPS="3", DEVICE_TYPE="CPU")
     for cmd, needle in ((["msequential_example"], "Example Complete"), (["test_del"], "double-ended placement ok"),

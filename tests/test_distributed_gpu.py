@@ -207,3 +207,56 @@ def test_roce_pipeline_on_gpus_moves_activations_device_to_device():
         proc.join(20)
         if proc.is_alive():
             proc.terminate()
+
+
+def test_python_gpu_stage_and_cpp_roce_worker_exchange_device_tensors():
+    """Mixed hosts on one node: stage 0 is a Python ``RoCEWorker`` on the GPU, stage 1 the C++ ``roce_worker --gpu``
+    (cpp/src/rendezvous.cpp).  Activations go Python -> C++ and gradients C++ -> Python through the device rendezvous of
+    both implementations (same frames, same metadata record, CUDA-IPC handles exchanged between the processes)."""
+    _need_gpu()
+    import socket
+    import subprocess
+    import time
+
+    from tnn_b200.distributed import CoordinatorConfig, Endpoint, ParallelMode, RoCECoordinator, RoCEWorker, split_microbatches
+    from tnn_b200.models import ExampleModels
+    from tnn_b200.nn import LossFactory, OptimizerFactory
+    from tnn_b200.parallel import NaivePipelinePartitioner
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "cpp", "bin", "roce_worker")
+    if not os.access(exe, os.X_OK):
+        pytest.skip("C++ host not built")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    child_dev = 1 if torch.cuda.device_count() > 1 else 0
+    proc = subprocess.Popen([exe, str(port), "--gpu", str(child_dev)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    local = RoCEWorker("127.0.0.1", 0, use_gpu=True, gpu_index=0, name="py-gpu", slab_bytes=8 << 20)
+    try:
+        time.sleep(2.0)
+        cfgc = CoordinatorConfig(ParallelMode.PIPELINE, ExampleModels.create("mnist_cnn"), OptimizerFactory.create_sgd(0.05, 0.9), None,
+                                 NaivePipelinePartitioner([1, 1]), local_worker=local, local_worker_position=0,
+                                 worker_endpoints=[Endpoint.roce("127.0.0.1", port)], seed=5)
+        co = RoCECoordinator(cfgc, "127.0.0.1", 0, slab_bytes=8 << 20)
+        co.start()
+        crit = LossFactory.create_logsoftmax_crossentropy()
+        g = torch.Generator().manual_seed(0)
+        x = torch.rand(64, 28, 28, 1, generator=g)
+        y = (torch.arange(64) % 10).to(torch.int32)
+        losses = []
+        for _ in range(6):
+            xs, ys = split_microbatches(x, y, 2)
+            l, _ = co.async_train_batch(xs, ys, crit)
+            co.update_parameters()
+            losses.append(l)
+        assert losses[-1] < losses[0], losses
+        st = local.comm.stats()
+        assert st["device_rendezvous_sent"] >= 12 and st["device_rendezvous_received"] >= 12 and st["device_fallback_host"] == 0, st
+        co.stop()
+    finally:
+        local.stop()
+        try:
+            proc.wait(15)
+        except Exception:  # noqa: BLE001
+            proc.kill()

@@ -143,7 +143,8 @@ def build_host(force: bool = False, verbose: bool = True) -> dict:
     for d in (obj_dir, lib_dir, bin_dir):
         d.mkdir(parents=True, exist_ok=True)
     hdr = hashlib.sha256()
-    for h in sorted(list((CPP / "include").rglob("*.hpp")) + list(CSRC.rglob("*.hpp")) + list(CSRC.rglob("*.cuh"))):
+    for h in sorted(list((CPP / "include").rglob("*.hpp")) + list((CPP / "examples").glob("*.hpp")) + list(CSRC.rglob("*.hpp")) +
+                    list(CSRC.rglob("*.cuh"))):
         hdr.update(h.read_bytes())
     gxx = ["g++", "-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", f"-I{CPP / 'include'}", f"-I{CSRC}",
            f"-I{cuda}/include", "-pthread"]
