@@ -84,7 +84,7 @@ PYBIND11_MODULE(_host, m) {
   m.def("registered_layer_types", [] { return LayerFactory::registered_types(); });
   m.def("available_models", [] { return ExampleModels::available_models(); });
   m.def("model_config", [](const std::string& name) { return ExampleModels::create(name)->get_config().dump(-1); });
-  m.def("launch_count", [] { return (unsigned long long)g_launch_count; });
+  m.def("launch_count", [] { return (unsigned long long)g_launch_count.load(); });
   // the flagship benchmark, in process (bench.py --host cpp); returns the JSON line as a string
   m.def("bench_train", [](const std::string& model, size_t batch, int steps, int warmup, int gpu, bool use_graph) {
     Json j;

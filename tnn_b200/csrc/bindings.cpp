@@ -535,7 +535,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                     src.size(1) == dst.size(0) && src.scalar_type() == dst.scalar_type(), "transpose_any: [R,C] -> [C,R]");
     tnn::tensor_transpose_any(vp(src), vp(dst), dt_code(src), (int)src.size(0), (int)src.size(1), cur_stream());
   });
-  m.def("launch_count", []() { return tnn::g_launch_count; });
+  m.def("launch_count", []() { return (unsigned long long)tnn::g_launch_count.load(); });
   tnn::attention_bind(m);
   tnn::mxfp8_bind(m);
   tnn::runtime_bind(m);

@@ -12,7 +12,7 @@
 namespace tnn {
 
 // number of kernels launched by this library in the current process (bench.py reports it)
-extern unsigned long long g_launch_count;
+extern std::atomic<unsigned long long> g_launch_count;   // atomic: the C++ data-parallel host launches from one thread per GPU
 
 #define TNN_CHECK_LAUNCH()                                                                    \
   do {                                                                                        \

@@ -9,7 +9,7 @@
 
 namespace tnn {
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 // ---------------------------------------------------------------- casts
 __global__ void k_cast_f32_bf16(const float* __restrict__ in, bf16* __restrict__ out, long long n) {

@@ -5,9 +5,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 namespace tnn {
 
-extern unsigned long long g_launch_count;
+extern std::atomic<unsigned long long> g_launch_count;
 
 // ---- elementwise (elementwise.cu) ------------------------------------------------
 enum ActKind : int {

@@ -30,7 +30,7 @@
 
 namespace tnn {
 using namespace sm100;
-extern unsigned long long g_launch_count;
+extern std::atomic<unsigned long long> g_launch_count;
 
 #define TNN_CUDA_CHECK(x)                                                              \
   do {                                                                                 \
