@@ -176,3 +176,51 @@ def test_activation_layer_fp16_fp64(dtype):
         tol = 4e-3 if dtype == torch.float16 else 1e-12           # fp64 activations evaluate in double precision
         assert y.dtype == dtype and (y.double() - ref.detach()).abs().max().item() < tol, name
         assert dx.dtype == dtype and (dx.double() - xr.grad).abs().max().item() < 3 * tol, name
+
+
+@pytest.mark.parametrize("causal", [True, False])
+@pytest.mark.parametrize("B,L,H", [(2, 128, 2), (1, 200, 3), (1, 1024, 2)])
+def test_fp16_attention_kernels_match_fp32_reference(B, L, H, causal):
+    """The fused tcgen05 attention forward / backward with fp16 operands (the dtype the reference's flash attention
+    requires, cudnn_flash_attention_ops.cu:123) against the fp32 formula."""
+    from tnn_b200.ops import attention as A
+    dev = _dev()
+    torch.manual_seed(4)
+    qkv = (torch.randn(B, L, 3, H, 64, device=dev) * 0.8).half()
+    do = (torch.randn(B, L, H * 64, device=dev) * 0.5).half()
+    o, lse = A.attention_fwd(qkv, causal)
+    assert o.dtype == torch.float16 and o.shape == (B, L, H * 64)
+    ref_in = qkv.float().requires_grad_(True)
+    oref, lref = A.attention_ref(ref_in[:, :, 0], ref_in[:, :, 1], ref_in[:, :, 2], causal)
+
+    def rel(a, b):
+        return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+    assert rel(o.reshape(B, L, H, 64), oref.detach()) < 5e-3                    # fp16: 11-bit mantissa (bf16 bound is 2e-2)
+    assert (lse - lref.detach()).abs().max().item() < 5e-3
+    got = A.attention_bwd(qkv, do, o, lse, causal)
+    (oref.reshape(B, L, H * 64) * do.float()).sum().backward()
+    assert got.dtype == torch.float16 and got.shape == qkv.shape
+    for i, name in enumerate(("dq", "dk", "dv")):
+        assert rel(got[:, :, i], ref_in.grad[:, :, i]) < 8e-3, name
+
+
+def test_attention_block_fp16_io_dtype_trains():
+    """AttentionBlock / FlashAttentionBlock with io_dtype fp16: fp16 projections (gemm_xt) + fp16 attention, parity with CPU."""
+    from tnn_b200.nn import FlashAttentionBlock
+    dev = _dev()
+    torch.manual_seed(5)
+    cpu = FlashAttentionBlock(128, 2, True, "fa").init("cpu", 7)
+    gpu = FlashAttentionBlock(128, 2, True, "fa").set_io_dtype(torch.float16).init("cpu", 7).to(dev)
+    cpu.set_training(True), gpu.set_training(True)
+    x = torch.randn(2, 96, 128).half().float()
+    dy = torch.randn(2, 96, 128).half().float()
+    yc = cpu.forward(x, 0)
+    yg = gpu.forward(x.to(dev).half(), 0)
+    assert yg.dtype == torch.float16
+    assert ((yg.float().cpu() - yc).norm() / yc.norm()).item() < 5e-3
+    dc = cpu.backward(dy, 0)
+    dg = gpu.backward(dy.to(dev).half(), 0)
+    assert dg.dtype == torch.float16 and ((dg.float().cpu() - dc).norm() / dc.norm()).item() < 1e-2
+    for k in cpu.grads:
+        assert ((gpu.grads[k].cpu() - cpu.grads[k]).norm() / (cpu.grads[k].norm() + 1e-12)).item() < 2e-2, k

@@ -10,7 +10,8 @@ using torch::Tensor;
 namespace tnn {
 
 static void check_head_view(const Tensor& t, const char* name) {
-  TORCH_CHECK(t.is_cuda() && t.scalar_type() == torch::kBFloat16, name, ": expected a CUDA bf16 tensor");
+  TORCH_CHECK(t.is_cuda() && (t.scalar_type() == torch::kBFloat16 || t.scalar_type() == torch::kFloat16), name,
+              ": expected a CUDA bf16 / fp16 tensor");
   TORCH_CHECK(t.dim() == 4 && t.size(3) == 64 && t.stride(3) == 1 && t.stride(2) == 64, name,
               ": expected a [B, L, H, 64] view with contiguous heads");
 }
@@ -23,8 +24,10 @@ void attention_bind(py::module_& m) {
     check_head_view(v, "v");
     const int B = (int)q.size(0), Lq = (int)q.size(1), H = (int)q.size(2), Lk = (int)k.size(1);
     TORCH_CHECK(k.size(0) == B && v.size(0) == B && k.size(2) == H && v.size(2) == H && v.size(1) == Lk, "q/k/v shape mismatch");
-    TORCH_CHECK(out.is_cuda() && out.scalar_type() == torch::kBFloat16 && out.is_contiguous() &&
-                    out.numel() == (int64_t)B * Lq * H * 64, "out must be contiguous bf16 [B, Lq, H*64]");
+    const bool f16 = q.scalar_type() == torch::kFloat16;       // fp16 q / k / v / out: the kind::f16 fp16 operand format
+    TORCH_CHECK(k.scalar_type() == q.scalar_type() && v.scalar_type() == q.scalar_type(), "q / k / v dtypes differ");
+    TORCH_CHECK(out.is_cuda() && out.scalar_type() == q.scalar_type() && out.is_contiguous() &&
+                    out.numel() == (int64_t)B * Lq * H * 64, "out must be contiguous [B, Lq, H*64] of the q dtype");
     float* lp = nullptr;
     if (lse.has_value()) {
       TORCH_CHECK(lse->scalar_type() == torch::kFloat32 && lse->is_contiguous() && lse->numel() == (int64_t)B * H * Lq,
@@ -33,18 +36,20 @@ void attention_bind(py::module_& m) {
     }
     attention_fwd_bf16(q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0), v.data_ptr(),
                        v.stride(1), v.stride(0), out.data_ptr(), lp, B, H, Lq, Lk, causal ? 1 : 0, (int)q_offset,
-                       at::cuda::getCurrentCUDAStream().stream());
+                       at::cuda::getCurrentCUDAStream().stream(), f16 ? 1 : 0);
   });
   m.def("attention_bwd", [](const Tensor& qkv, const Tensor& dout, const Tensor& out, const Tensor& lse,
                             const Tensor& dqkv, const Tensor& delta, const Tensor& dq_acc, bool causal) {
-    TORCH_CHECK(qkv.is_cuda() && qkv.scalar_type() == torch::kBFloat16 && qkv.dim() == 5 && qkv.size(2) == 3 &&
-                    qkv.size(4) == 64 && qkv.is_contiguous(), "qkv must be contiguous bf16 [B, L, 3, H, 64]");
-    TORCH_CHECK(dqkv.is_cuda() && dqkv.scalar_type() == torch::kBFloat16 && dqkv.is_contiguous() &&
+    const bool f16 = qkv.scalar_type() == torch::kFloat16;
+    const auto dt16 = qkv.scalar_type();
+    TORCH_CHECK(qkv.is_cuda() && (f16 || dt16 == torch::kBFloat16) && qkv.dim() == 5 && qkv.size(2) == 3 &&
+                    qkv.size(4) == 64 && qkv.is_contiguous(), "qkv must be contiguous bf16 / fp16 [B, L, 3, H, 64]");
+    TORCH_CHECK(dqkv.is_cuda() && dqkv.scalar_type() == dt16 && dqkv.is_contiguous() &&
                     dqkv.sizes() == qkv.sizes(), "dqkv must match qkv");
     const int B = (int)qkv.size(0), L = (int)qkv.size(1), H = (int)qkv.size(3);
     const int64_t E = (int64_t)H * 64, n = (int64_t)B * L * E;
-    TORCH_CHECK(dout.scalar_type() == torch::kBFloat16 && dout.is_contiguous() && dout.numel() == n, "dout: contiguous bf16 [B, L, H*64]");
-    TORCH_CHECK(out.scalar_type() == torch::kBFloat16 && out.is_contiguous() && out.numel() == n, "out: contiguous bf16 [B, L, H*64]");
+    TORCH_CHECK(dout.scalar_type() == dt16 && dout.is_contiguous() && dout.numel() == n, "dout: contiguous [B, L, H*64] of the qkv dtype");
+    TORCH_CHECK(out.scalar_type() == dt16 && out.is_contiguous() && out.numel() == n, "out: contiguous [B, L, H*64] of the qkv dtype");
     TORCH_CHECK(lse.scalar_type() == torch::kFloat32 && lse.is_contiguous() && lse.numel() == (int64_t)B * H * L, "lse: fp32 [B, H, L]");
     TORCH_CHECK(delta.scalar_type() == torch::kFloat32 && delta.is_contiguous() && delta.numel() == (int64_t)B * H * L, "delta: fp32 [B, H, L]");
     TORCH_CHECK(dq_acc.scalar_type() == torch::kFloat32 && dq_acc.is_contiguous() && dq_acc.numel() == n, "dq_acc: fp32 [B, L, H*64]");
@@ -53,7 +58,7 @@ void attention_bind(py::module_& m) {
     attention_bwd_bf16(base, base + E, base + 2 * E, 3 * E, (int64_t)L * 3 * E, dout.data_ptr(), out.data_ptr(),
                        lse.data_ptr<float>(), delta.data_ptr<float>(), dq_acc.data_ptr<float>(), dbase, dbase + E,
                        dbase + 2 * E, 3 * E, (int64_t)L * 3 * E, B, H, L, causal ? 1 : 0,
-                       at::cuda::getCurrentCUDAStream().stream());
+                       at::cuda::getCurrentCUDAStream().stream(), f16 ? 1 : 0);
   });
   m.def("attention_decode", [](const Tensor& q, const Tensor& kc, const Tensor& vc, const Tensor& out, int64_t len) {
     TORCH_CHECK(q.is_cuda() && q.scalar_type() == torch::kBFloat16, "q: CUDA bf16");

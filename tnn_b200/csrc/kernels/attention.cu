@@ -57,7 +57,7 @@ struct AttnParams {
 // L=4096: 0.374 vs 0.327 ms -- halving the per-thread softmax work does NOT help, the per-tile chain
 // S-MMA -> softmax -> PV-MMA -> O update inside a CTA is the bound (two CTAs per SM interleave only two such
 // chains).  The fix is a two-tile ping-pong per CTA, not more softmax threads; kept for that experiment.
-template <bool CAUSAL, bool SPLIT>
+template <bool CAUSAL, bool SPLIT, bool F16>
 __global__ void __launch_bounds__(SPLIT ? 320 : AT_THREADS, 2)
     attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -129,8 +129,8 @@ __global__ void __launch_bounds__(SPLIT ? 320 : AT_THREADS, 2)
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0u, 0u);   // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0u, 1u);   // P (K-major) x V (MN-major)
+      constexpr uint32_t idesc_s = make_idesc_16<F16>(128, 128, 0u, 0u);   // Q (K-major) x K (K-major)
+      constexpr uint32_t idesc_pv = make_idesc_16<F16>(128, 64, 0u, 1u);   // P (K-major) x V (MN-major)
       mbar_wait(q_full, 0);
       const uint32_t q_addr = smem_u32(sQ);
       const uint32_t p_addr = smem_u32(sP);
@@ -207,10 +207,10 @@ __global__ void __launch_bounds__(SPLIT ? 320 : AT_THREADS, 2)
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               uint4 v;
-              v.x = pack_bf16(pr[t * 8 + 0], pr[t * 8 + 1]);
-              v.y = pack_bf16(pr[t * 8 + 2], pr[t * 8 + 3]);
-              v.z = pack_bf16(pr[t * 8 + 4], pr[t * 8 + 5]);
-              v.w = pack_bf16(pr[t * 8 + 6], pr[t * 8 + 7]);
+              v.x = pack16<F16>(pr[t * 8 + 0], pr[t * 8 + 1]);
+              v.y = pack16<F16>(pr[t * 8 + 2], pr[t * 8 + 3]);
+              v.z = pack16<F16>(pr[t * 8 + 4], pr[t * 8 + 5]);
+              v.w = pack16<F16>(pr[t * 8 + 6], pr[t * 8 + 7]);
               *reinterpret_cast<uint4*>(prow + (((cc0 + t) ^ sw) << 4)) = v;
             }
 #pragma unroll
@@ -272,10 +272,10 @@ __global__ void __launch_bounds__(SPLIT ? 320 : AT_THREADS, 2)
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         uint4 v;
-        v.x = pack_bf16(o[t * 8 + 0] * inv, o[t * 8 + 1] * inv);
-        v.y = pack_bf16(o[t * 8 + 2] * inv, o[t * 8 + 3] * inv);
-        v.z = pack_bf16(o[t * 8 + 4] * inv, o[t * 8 + 5] * inv);
-        v.w = pack_bf16(o[t * 8 + 6] * inv, o[t * 8 + 7] * inv);
+        v.x = pack16<F16>(o[t * 8 + 0] * inv, o[t * 8 + 1] * inv);
+        v.y = pack16<F16>(o[t * 8 + 2] * inv, o[t * 8 + 3] * inv);
+        v.z = pack16<F16>(o[t * 8 + 4] * inv, o[t * 8 + 5] * inv);
+        v.w = pack16<F16>(o[t * 8 + 6] * inv, o[t * 8 + 7] * inv);
         reinterpret_cast<uint4*>(dst)[t] = v;
       }
       if (half == 0 && p.lse != nullptr)
@@ -334,10 +334,10 @@ __global__ void __launch_bounds__(SPLIT ? 320 : AT_THREADS, 2)
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               uint4 v;
-              v.x = pack_bf16(pr[t * 8 + 0], pr[t * 8 + 1]);
-              v.y = pack_bf16(pr[t * 8 + 2], pr[t * 8 + 3]);
-              v.z = pack_bf16(pr[t * 8 + 4], pr[t * 8 + 5]);
-              v.w = pack_bf16(pr[t * 8 + 6], pr[t * 8 + 7]);
+              v.x = pack16<F16>(pr[t * 8 + 0], pr[t * 8 + 1]);
+              v.y = pack16<F16>(pr[t * 8 + 2], pr[t * 8 + 3]);
+              v.z = pack16<F16>(pr[t * 8 + 4], pr[t * 8 + 5]);
+              v.w = pack16<F16>(pr[t * 8 + 6], pr[t * 8 + 7]);
               *reinterpret_cast<uint4*>(atom + (((cc0 + t) ^ sw) << 4)) = v;
             }
 #pragma unroll
@@ -395,10 +395,10 @@ __global__ void __launch_bounds__(SPLIT ? 320 : AT_THREADS, 2)
 #pragma unroll
       for (int t = 0; t < AT_D / 8; ++t) {
         uint4 v;
-        v.x = pack_bf16(o[t * 8 + 0] * inv, o[t * 8 + 1] * inv);
-        v.y = pack_bf16(o[t * 8 + 2] * inv, o[t * 8 + 3] * inv);
-        v.z = pack_bf16(o[t * 8 + 4] * inv, o[t * 8 + 5] * inv);
-        v.w = pack_bf16(o[t * 8 + 6] * inv, o[t * 8 + 7] * inv);
+        v.x = pack16<F16>(o[t * 8 + 0] * inv, o[t * 8 + 1] * inv);
+        v.y = pack16<F16>(o[t * 8 + 2] * inv, o[t * 8 + 3] * inv);
+        v.z = pack16<F16>(o[t * 8 + 4] * inv, o[t * 8 + 5] * inv);
+        v.w = pack16<F16>(o[t * 8 + 6] * inv, o[t * 8 + 7] * inv);
         reinterpret_cast<uint4*>(dst)[t] = v;
       }
       if (p.lse != nullptr)
@@ -431,13 +431,13 @@ static PFN_cuTensorMapEncodeTiled_v12000 attn_encode_fn() {
 }
 
 // [B, L, H, 64] view with arbitrary token / batch strides (elements): dims {64, H, L, B}.
-CUtensorMap make_head_map(const void* ptr, int B, int L, int H, long long tok_stride, long long batch_stride) {
+CUtensorMap make_head_map(const void* ptr, int B, int L, int H, long long tok_stride, long long batch_stride, int f16) {
   CUtensorMap m;
   cuuint64_t dims[4] = {(cuuint64_t)AT_D, (cuuint64_t)H, (cuuint64_t)L, (cuuint64_t)B};
   cuuint64_t str[3] = {(cuuint64_t)AT_D * 2, (cuuint64_t)tok_stride * 2, (cuuint64_t)batch_stride * 2};
   cuuint32_t box[4] = {64, 1, 128, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = attn_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, str, box, es,
+  CUresult r = attn_encode_fn()(&m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, str, box, es,
                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -450,7 +450,7 @@ CUtensorMap make_head_map(const void* ptr, int B, int L, int H, long long tok_st
 
 void attention_fwd_bf16(const void* q, long long q_tok, long long q_batch, const void* k, long long k_tok,
                         long long k_batch, const void* v, long long v_tok, long long v_batch, void* out,
-                        float* lse, int B, int H, int Lq, int Lk, int causal, int q_offset, cudaStream_t stream) {
+                        float* lse, int B, int H, int Lq, int Lk, int causal, int q_offset, cudaStream_t stream, int f16) {
   if (B <= 0 || H <= 0 || Lq <= 0 || Lk <= 0) return;
   if ((q_tok % 8) || (k_tok % 8) || (v_tok % 8) || (q_batch % 8) || (k_batch % 8) || (v_batch % 8) ||
       (reinterpret_cast<uintptr_t>(q) & 15) || (reinterpret_cast<uintptr_t>(k) & 15) ||
@@ -458,9 +458,9 @@ void attention_fwd_bf16(const void* q, long long q_tok, long long q_batch, const
     fprintf(stderr, "[tnn_b200] attention_fwd_bf16: operands must be 16-byte aligned (strides %% 8 == 0)\n");
     abort();
   }
-  CUtensorMap tmQ = make_head_map(q, B, Lq, H, q_tok, q_batch);
-  CUtensorMap tmK = make_head_map(k, B, Lk, H, k_tok, k_batch);
-  CUtensorMap tmV = make_head_map(v, B, Lk, H, v_tok, v_batch);
+  CUtensorMap tmQ = make_head_map(q, B, Lq, H, q_tok, q_batch, f16);
+  CUtensorMap tmK = make_head_map(k, B, Lk, H, k_tok, k_batch, f16);
+  CUtensorMap tmV = make_head_map(v, B, Lk, H, v_tok, v_batch, f16);
   AttnParams p{};
   p.B = B;
   p.H = H;
@@ -475,24 +475,31 @@ void attention_fwd_bf16(const void* q, long long q_tok, long long q_batch, const
   static PerDeviceOnce configured;
   static int split = 0;
   if (configured.begin()) {
-    cudaFuncSetAttribute(attn_fwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-    cudaFuncSetAttribute(attn_fwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-    cudaFuncSetAttribute(attn_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
-    cudaFuncSetAttribute(attn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    cudaFuncSetAttribute(attn_fwd_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    cudaFuncSetAttribute(attn_fwd_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    cudaFuncSetAttribute(attn_fwd_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    cudaFuncSetAttribute(attn_fwd_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    cudaFuncSetAttribute(attn_fwd_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+    cudaFuncSetAttribute(attn_fwd_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
     const char* e = getenv("TNN_ATTN_SPLIT");
     split = (e != nullptr) ? atoi(e) : 0;
     configured.done();
   }
   dim3 grid((Lq + AT_BM - 1) / AT_BM, H, B);
-  if (split) {
+  if (f16) {     // fp16 operands and output (the reference's flash attention is fp16-only): same kernel, other operand format
     if (causal)
-      attn_fwd_kernel<true, true><<<grid, 320, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
+      attn_fwd_kernel<true, false, true><<<grid, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
     else
-      attn_fwd_kernel<false, true><<<grid, 320, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
+      attn_fwd_kernel<false, false, true><<<grid, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
+  } else if (split) {
+    if (causal)
+      attn_fwd_kernel<true, true, false><<<grid, 320, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
+    else
+      attn_fwd_kernel<false, true, false><<<grid, 320, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
   } else if (causal)
-    attn_fwd_kernel<true, false><<<grid, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
+    attn_fwd_kernel<true, false, false><<<grid, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
   else
-    attn_fwd_kernel<false, false><<<grid, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
+    attn_fwd_kernel<false, false, false><<<grid, AT_THREADS, AT_SMEM, stream>>>(tmQ, tmK, tmV, p);
   TNN_CHECK_LAUNCH();
 }
 

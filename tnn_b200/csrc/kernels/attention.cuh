@@ -9,7 +9,7 @@ namespace tnn {
 // out: bf16 [B, Lq, H*64]; lse: fp32 [B, H, Lq] or null.  q_offset = absolute position of query 0.
 void attention_fwd_bf16(const void* q, long long q_tok, long long q_batch, const void* k, long long k_tok,
                         long long k_batch, const void* v, long long v_tok, long long v_batch, void* out,
-                        float* lse, int B, int H, int Lq, int Lk, int causal, int q_offset, cudaStream_t stream);
+                        float* lse, int B, int H, int Lq, int Lk, int causal, int q_offset, cudaStream_t stream, int f16 = 0);   // f16: fp16 q / k / v / out
 
 // Flash-attention backward (attention_bwd.cu).  q/k/v: bf16 [B, L, H, 64] views sharing one token /
 // batch stride (the packed projection); dout/out: contiguous bf16 [B, L, H*64]; lse: fp32 [B, H, L] from
@@ -18,7 +18,7 @@ void attention_fwd_bf16(const void* q, long long q_tok, long long q_batch, const
 void attention_bwd_bf16(const void* q, const void* k, const void* v, long long qkv_tok, long long qkv_batch,
                         const void* dout, const void* out, const float* lse, float* delta, float* dq_acc, void* dq,
                         void* dk, void* dv, long long dqkv_tok, long long dqkv_batch, int B, int H, int L, int causal,
-                        cudaStream_t stream);
+                        cudaStream_t stream, int f16 = 0);                          // f16: every 16-bit tensor is fp16
 
 // Single-token decode: q bf16 [B, H*64] (batch stride q_batch), caches [B, Lmax, H, 64], attends to
 // the first `len` cached positions.  out: bf16 [B, H*64].

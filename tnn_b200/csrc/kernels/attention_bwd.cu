@@ -31,7 +31,7 @@
 namespace tnn {
 using namespace sm100;
 
-CUtensorMap make_head_map(const void* ptr, int B, int L, int H, long long tok_stride, long long batch_stride);
+CUtensorMap make_head_map(const void* ptr, int B, int L, int H, long long tok_stride, long long batch_stride, int f16);
 
 static constexpr int AB_TILE = 128 * 128;     // bytes of one [128 rows][64 bf16] tile
 static constexpr int AB_THREADS = 320;
@@ -50,7 +50,7 @@ struct AttnBwdParams {
   long long dkv_tok, dkv_batch;
 };
 
-template <bool CAUSAL>
+template <bool CAUSAL, bool F16>
 __global__ void __launch_bounds__(AB_THREADS, 1)
     attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
@@ -125,9 +125,9 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0u, 0u);    // K-major x K-major
-      constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, 1u, 1u);     // MN-major A (transposed tile) x MN-major B
-      constexpr uint32_t idesc_q = make_idesc_bf16(128, 64, 0u, 1u);     // K-major A x MN-major B
+      constexpr uint32_t idesc_s = make_idesc_16<F16>(128, 128, 0u, 0u);    // K-major x K-major
+      constexpr uint32_t idesc_t = make_idesc_16<F16>(128, 64, 1u, 1u);     // MN-major A (transposed tile) x MN-major B
+      constexpr uint32_t idesc_q = make_idesc_16<F16>(128, 64, 0u, 1u);     // K-major A x MN-major B
       const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
       const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
       mbar_wait(kv_full, 0);
@@ -232,14 +232,14 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           uint4 v, w;
-          v.x = pack_bf16(pr[t * 8 + 0], pr[t * 8 + 1]);
-          v.y = pack_bf16(pr[t * 8 + 2], pr[t * 8 + 3]);
-          v.z = pack_bf16(pr[t * 8 + 4], pr[t * 8 + 5]);
-          v.w = pack_bf16(pr[t * 8 + 6], pr[t * 8 + 7]);
-          w.x = pack_bf16(ds[t * 8 + 0], ds[t * 8 + 1]);
-          w.y = pack_bf16(ds[t * 8 + 2], ds[t * 8 + 3]);
-          w.z = pack_bf16(ds[t * 8 + 4], ds[t * 8 + 5]);
-          w.w = pack_bf16(ds[t * 8 + 6], ds[t * 8 + 7]);
+          v.x = pack16<F16>(pr[t * 8 + 0], pr[t * 8 + 1]);
+          v.y = pack16<F16>(pr[t * 8 + 2], pr[t * 8 + 3]);
+          v.z = pack16<F16>(pr[t * 8 + 4], pr[t * 8 + 5]);
+          v.w = pack16<F16>(pr[t * 8 + 6], pr[t * 8 + 7]);
+          w.x = pack16<F16>(ds[t * 8 + 0], ds[t * 8 + 1]);
+          w.y = pack16<F16>(ds[t * 8 + 2], ds[t * 8 + 3]);
+          w.z = pack16<F16>(ds[t * 8 + 4], ds[t * 8 + 5]);
+          w.w = pack16<F16>(ds[t * 8 + 6], ds[t * 8 + 7]);
           const int off = ((cc0 + t) ^ sw) << 4;
           *reinterpret_cast<uint4*>(prow + off) = v;
           *reinterpret_cast<uint4*>(dsrow + off) = w;
@@ -269,14 +269,14 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           uint4 a, c;
-          a.x = pack_bf16(__uint_as_float(rk[8 * t + 0]), __uint_as_float(rk[8 * t + 1]));
-          a.y = pack_bf16(__uint_as_float(rk[8 * t + 2]), __uint_as_float(rk[8 * t + 3]));
-          a.z = pack_bf16(__uint_as_float(rk[8 * t + 4]), __uint_as_float(rk[8 * t + 5]));
-          a.w = pack_bf16(__uint_as_float(rk[8 * t + 6]), __uint_as_float(rk[8 * t + 7]));
-          c.x = pack_bf16(__uint_as_float(rv[8 * t + 0]), __uint_as_float(rv[8 * t + 1]));
-          c.y = pack_bf16(__uint_as_float(rv[8 * t + 2]), __uint_as_float(rv[8 * t + 3]));
-          c.z = pack_bf16(__uint_as_float(rv[8 * t + 4]), __uint_as_float(rv[8 * t + 5]));
-          c.w = pack_bf16(__uint_as_float(rv[8 * t + 6]), __uint_as_float(rv[8 * t + 7]));
+          a.x = pack16<F16>(__uint_as_float(rk[8 * t + 0]), __uint_as_float(rk[8 * t + 1]));
+          a.y = pack16<F16>(__uint_as_float(rk[8 * t + 2]), __uint_as_float(rk[8 * t + 3]));
+          a.z = pack16<F16>(__uint_as_float(rk[8 * t + 4]), __uint_as_float(rk[8 * t + 5]));
+          a.w = pack16<F16>(__uint_as_float(rk[8 * t + 6]), __uint_as_float(rk[8 * t + 7]));
+          c.x = pack16<F16>(__uint_as_float(rv[8 * t + 0]), __uint_as_float(rv[8 * t + 1]));
+          c.y = pack16<F16>(__uint_as_float(rv[8 * t + 2]), __uint_as_float(rv[8 * t + 3]));
+          c.z = pack16<F16>(__uint_as_float(rv[8 * t + 4]), __uint_as_float(rv[8 * t + 5]));
+          c.w = pack16<F16>(__uint_as_float(rv[8 * t + 6]), __uint_as_float(rv[8 * t + 7]));
           dk[t] = a;
           dv[t] = c;
         }
@@ -290,6 +290,21 @@ __global__ void __launch_bounds__(AB_THREADS, 1)
 }
 
 // delta[b, h, l] = sum_d dO[b, l, h, d] * O[b, l, h, d]; 8 lanes per (b, l, h), 16-byte loads
+template <bool F16>
+__device__ __forceinline__ void unpack16x8(const uint4& q, float (&f)[8]) {
+  if constexpr (F16) {
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __half22float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  } else {
+    bf8_unpack(q, f);
+  }
+}
+template <bool F16>
 __global__ void __launch_bounds__(256)
     k_attn_delta(const bf16* __restrict__ dO, const bf16* __restrict__ O, float* __restrict__ delta, long long rows,
                  int H, int L) {
@@ -298,8 +313,8 @@ __global__ void __launch_bounds__(256)
   float s = 0.f;
   if (head_row < rows) {
     float a[8], c[8];
-    bf8_unpack(__ldg(reinterpret_cast<const uint4*>(dO) + gid), a);
-    bf8_unpack(__ldg(reinterpret_cast<const uint4*>(O) + gid), c);
+    unpack16x8<F16>(__ldg(reinterpret_cast<const uint4*>(dO) + gid), a);
+    unpack16x8<F16>(__ldg(reinterpret_cast<const uint4*>(O) + gid), c);
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += a[i] * c[i];
   }
@@ -315,7 +330,8 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-// dq_acc fp32 [B, L, H*64] -> bf16 view with token / batch strides
+// dq_acc fp32 [B, L, H*64] -> bf16 / fp16 view with token / batch strides
+template <bool F16>
 __global__ void __launch_bounds__(256)
     k_attn_dq_store(const float* __restrict__ acc, bf16* __restrict__ dq, long long n_vec, int E8, int L,
                     long long tok, long long batch) {
@@ -328,17 +344,17 @@ __global__ void __launch_bounds__(256)
   const float4 lo = __ldg(reinterpret_cast<const float4*>(acc) + gid * 2);
   const float4 hi = __ldg(reinterpret_cast<const float4*>(acc) + gid * 2 + 1);
   uint4 v;
-  v.x = pack_bf16(lo.x, lo.y);
-  v.y = pack_bf16(lo.z, lo.w);
-  v.z = pack_bf16(hi.x, hi.y);
-  v.w = pack_bf16(hi.z, hi.w);
+  v.x = pack16<F16>(lo.x, lo.y);
+  v.y = pack16<F16>(lo.z, lo.w);
+  v.z = pack16<F16>(hi.x, hi.y);
+  v.w = pack16<F16>(hi.z, hi.w);
   *reinterpret_cast<uint4*>(dq + b * batch + (long long)l * tok + (long long)c * 8) = v;
 }
 
 void attention_bwd_bf16(const void* q, const void* k, const void* v, long long qkv_tok, long long qkv_batch,
                         const void* dout, const void* out, const float* lse, float* delta, float* dq_acc, void* dq,
                         void* dk, void* dv, long long dqkv_tok, long long dqkv_batch, int B, int H, int L, int causal,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, int f16) {
   if (B <= 0 || H <= 0 || L <= 0) return;
   if ((qkv_tok % 8) || (qkv_batch % 8) || (dqkv_tok % 8) || (dqkv_batch % 8) ||
       ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
@@ -351,15 +367,19 @@ void attention_bwd_bf16(const void* q, const void* k, const void* v, long long q
   {
     const long long rows = (long long)B * L * H;
     const long long threads = rows * 8;
-    k_attn_delta<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
-        reinterpret_cast<const bf16*>(dout), reinterpret_cast<const bf16*>(out), delta, rows, H, L);
+    if (f16)
+      k_attn_delta<true><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(dout),
+                                                                                reinterpret_cast<const bf16*>(out), delta, rows, H, L);
+    else
+      k_attn_delta<false><<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(dout),
+                                                                                 reinterpret_cast<const bf16*>(out), delta, rows, H, L);
     TNN_CHECK_LAUNCH();
   }
   cudaMemsetAsync(dq_acc, 0, sizeof(float) * (size_t)B * L * E, stream);
-  CUtensorMap tmQ = make_head_map(q, B, L, H, qkv_tok, qkv_batch);
-  CUtensorMap tmK = make_head_map(k, B, L, H, qkv_tok, qkv_batch);
-  CUtensorMap tmV = make_head_map(v, B, L, H, qkv_tok, qkv_batch);
-  CUtensorMap tmdO = make_head_map(dout, B, L, H, E, (long long)L * E);
+  CUtensorMap tmQ = make_head_map(q, B, L, H, qkv_tok, qkv_batch, f16);
+  CUtensorMap tmK = make_head_map(k, B, L, H, qkv_tok, qkv_batch, f16);
+  CUtensorMap tmV = make_head_map(v, B, L, H, qkv_tok, qkv_batch, f16);
+  CUtensorMap tmdO = make_head_map(dout, B, L, H, E, (long long)L * E, f16);
   AttnBwdParams p{};
   p.B = B;
   p.H = H;
@@ -375,20 +395,29 @@ void attention_bwd_bf16(const void* q, const void* k, const void* v, long long q
   p.dkv_batch = dqkv_batch;
   static PerDeviceOnce configured;
   if (configured.begin()) {
-    cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
-    cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+    cudaFuncSetAttribute(attn_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+    cudaFuncSetAttribute(attn_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+    cudaFuncSetAttribute(attn_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+    cudaFuncSetAttribute(attn_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
     configured.done();
   }
   dim3 grid((L + 127) / 128, H, B);
-  if (causal)
-    attn_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, p);
+  if (f16) {
+    if (causal) attn_bwd_kernel<true, true><<<grid, AB_THREADS, AB_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, p);
+    else attn_bwd_kernel<false, true><<<grid, AB_THREADS, AB_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, p);
+  } else if (causal)
+    attn_bwd_kernel<true, false><<<grid, AB_THREADS, AB_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, p);
   else
-    attn_bwd_kernel<false><<<grid, AB_THREADS, AB_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, p);
+    attn_bwd_kernel<false, false><<<grid, AB_THREADS, AB_SMEM, stream>>>(tmQ, tmK, tmV, tmdO, p);
   TNN_CHECK_LAUNCH();
   {
     const long long n_vec = (long long)B * L * E / 8;
-    k_attn_dq_store<<<(unsigned)((n_vec + 255) / 256), 256, 0, stream>>>(dq_acc, reinterpret_cast<bf16*>(dq), n_vec,
-                                                                        (int)(E / 8), L, dqkv_tok, dqkv_batch);
+    if (f16)
+      k_attn_dq_store<true><<<(unsigned)((n_vec + 255) / 256), 256, 0, stream>>>(dq_acc, reinterpret_cast<bf16*>(dq), n_vec, (int)(E / 8), L,
+                                                                                dqkv_tok, dqkv_batch);
+    else
+      k_attn_dq_store<false><<<(unsigned)((n_vec + 255) / 256), 256, 0, stream>>>(dq_acc, reinterpret_cast<bf16*>(dq), n_vec, (int)(E / 8), L,
+                                                                                 dqkv_tok, dqkv_batch);
     TNN_CHECK_LAUNCH();
   }
 }

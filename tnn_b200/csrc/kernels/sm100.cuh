@@ -8,6 +8,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -300,6 +301,21 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// 16-bit element type chosen at compile time: bf16 (F16 = false) or fp16 -- same tcgen05 kind::f16 instruction, the
+// operand format field of the instruction descriptor and the register packing are all that differ
+template <bool F16>
+__host__ __device__ constexpr uint32_t make_idesc_16(uint32_t M, uint32_t N, uint32_t a_mn_major, uint32_t b_mn_major) {
+  return F16 ? (make_idesc_bf16(M, N, a_mn_major, b_mn_major) & ~((1u << 7) | (1u << 10))) : make_idesc_bf16(M, N, a_mn_major, b_mn_major);
+}
+template <bool F16>
+__device__ __forceinline__ uint32_t pack16(float lo, float hi) {
+  if constexpr (F16) {
+    __half2 v = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+  } else {
+    return pack_bf16(lo, hi);
+  }
 }
 __device__ __forceinline__ float gelu_tanh(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;

@@ -19,7 +19,7 @@ from ..ops import gemm as gemm_ops
 from ..ops import native
 from .layer import Layer, LayerFactory, ParamDescriptor, register
 from .layers import (ActivationLayer, BatchNormLayer, Conv2DLayer, DenseLayer, DropoutLayer, LayerNormLayer, _aligned_rows,
-                     _normal_init, _uniform_init, to_bf16)
+                     _normal_init, _uniform_init, to_bf16, to_dtype)
 
 
 # TNN_NVTX=1: one NVTX range per layer forward / backward (shows up in Nsight Systems and `ncu --nvtx`)
@@ -357,7 +357,13 @@ class AttentionBlock(Block):
         B, L, E = x.shape
         H, D = self.num_heads, self.head_dim
         x2 = x.reshape(B * L, E)
-        if x.is_cuda:
+        # io_dtype fp16 (what the reference's flash attention requires, flash_attention_block.cpp:96-97): projections on the
+        # fp16 tcgen05 GEMM, the fused attention kernel with fp16 operands; default = bf16, the tuned path
+        f16 = x.is_cuda and self.io_dtype == torch.float16 and D == 64 and kv_cache is None
+        if f16:
+            x2 = to_dtype(x2, torch.float16)
+            qkv = gemm_ops.linear_fwd(x2, self.lp_as("qkv_weight", torch.float16), self.params["qkv_bias"])
+        elif x.is_cuda:
             x2 = _aligned_rows(to_bf16(x2))
             qkv = gemm_ops.linear_fwd(x2, self.lp("qkv_weight"), self.params["qkv_bias"])
         else:
@@ -366,7 +372,10 @@ class AttentionBlock(Block):
         o, lse = attn_ops.attention_fwd(qkv, self.is_causal, kv_cache=kv_cache, pos=pos)   # [B, L, H*D]
         o2 = o.reshape(B * L, E)
         res2 = residual.reshape(B * L, E) if residual is not None else None
-        if x.is_cuda:
+        if f16:
+            y = gemm_ops.linear_fwd(o2, self.lp_as("out_weight", torch.float16), self.params["out_bias"],
+                                    residual=to_dtype(res2, torch.float16) if res2 is not None else None)
+        elif x.is_cuda:
             y = gemm_ops.linear_fwd(o2, self.lp("out_weight"), self.params["out_bias"], residual=res2)
         else:
             y = gemm_ops.linear_fwd(o2, self.params["out_weight"], self.params["out_bias"], residual=res2)
@@ -391,20 +400,27 @@ class AttentionBlock(Block):
         E = self.embed_dim
         dy2 = dy.reshape(B * L, E)
         cuda = dy.is_cuda
-        if cuda:
+        f16 = cuda and qkv.dtype == torch.float16
+        if f16:
+            dy2 = to_dtype(dy2, torch.float16).contiguous()
+        elif cuda:
             dy2 = _aligned_rows(to_bf16(dy2))
         else:
             dy2 = dy2.float()
+
+        def w(name):
+            return self.lp_as(name, torch.float16) if f16 else (self.lp(name) if cuda else self.params[name])
+
         gemm_ops.linear_wgrad(dy2, o2, self.grads["out_weight"])
         gemm_ops.bias_grad(dy2, self.grads["out_bias"])
-        do = gemm_ops.linear_dgrad(dy2, self.lp("out_weight") if cuda else self.params["out_weight"])
+        do = gemm_ops.linear_dgrad(dy2, w("out_weight"))
         dqkv = attn_ops.attention_bwd(qkv, do.reshape(B, L, E), c["o"].reshape(B, L, E), c["lse"], self.is_causal)
         dqkv2 = dqkv.reshape(B * L, 3 * E)
-        if cuda:
+        if cuda and not f16:
             dqkv2 = _aligned_rows(dqkv2)
         gemm_ops.linear_wgrad(dqkv2, x2, self.grads["qkv_weight"])
         gemm_ops.bias_grad(dqkv2, self.grads["qkv_bias"])
-        dx = gemm_ops.linear_dgrad(dqkv2, self.lp("qkv_weight") if cuda else self.params["qkv_weight"])
+        dx = gemm_ops.linear_dgrad(dqkv2, w("qkv_weight"))
         return dx.reshape(B, L, E)
 
     def forward_flops(self, s):
@@ -424,8 +440,8 @@ class AttentionBlock(Block):
 
 @register()
 class FlashAttentionBlock(AttentionBlock):
-    """Same math; the reference's flash variant forces fp16 through cuDNN SDPA
-    (flash_attention_block.cpp:96-97) -- here both names run the same bf16 fused kernel."""
+    """Same math; the reference's flash variant forces fp16 through cuDNN SDPA (flash_attention_block.cpp:96-97).  Here both
+    names run the same fused tcgen05 kernel: bf16 by default, fp16 operands end to end when ``set_io_dtype(torch.float16)``."""
     TYPE_NAME = "flash_attention_block"
     FLASH = True
 

@@ -22,6 +22,9 @@ import torch
 from . import native
 
 
+_KERNEL_DTYPES = (torch.bfloat16, torch.float16)      # element types of the fused tcgen05 attention kernels
+
+
 class KVCache:
     """Per-layer key/value cache [B, Lmax, H, D] (bf16) for incremental decoding."""
 
@@ -63,8 +66,11 @@ def attention_fwd(qkv: torch.Tensor, causal: bool, kv_cache: KVCache | None = No
         k, v = kv_cache.k[:, :pos + L], kv_cache.v[:, :pos + L]
     if qkv.is_cuda:
         Cx = native.require()
-        if hasattr(Cx, "attention_fwd") and D == 64 and qkv.dtype == torch.bfloat16:
-            o = torch.empty((B, L, H * D), device=qkv.device, dtype=torch.bfloat16)
+        if hasattr(Cx, "attention_fwd") and D == 64 and qkv.dtype in _KERNEL_DTYPES and \
+                (qkv.dtype == torch.bfloat16 or not (L == 1 and kv_cache is not None)):
+            # bf16, or fp16 (the reference's flash attention is fp16-only, cudnn_flash_attention_ops.cu:123): the same
+            # tcgen05 kernel with the fp16 operand format; the decode / KV-cache kernels are bf16
+            o = torch.empty((B, L, H * D), device=qkv.device, dtype=qkv.dtype)
             lse = torch.empty((B, H, L), device=qkv.device, dtype=torch.float32)
             if L == 1 and kv_cache is not None:
                 Cx.attention_decode(q.contiguous(), kv_cache.k, kv_cache.v, o, pos + 1)
@@ -78,13 +84,13 @@ def attention_fwd(qkv: torch.Tensor, causal: bool, kv_cache: KVCache | None = No
 def attention_bwd(qkv: torch.Tensor, do: torch.Tensor, o: torch.Tensor, lse: torch.Tensor, causal: bool):
     """dqkv [B, L, 3, H, D] from do [B, L, H*D]; P is recomputed from the saved lse."""
     B, L, _, H, D = qkv.shape
-    if qkv.is_cuda and D == 64 and qkv.dtype == torch.bfloat16 and os.environ.get("TNN_ATTN_BWD_KERNEL", "1") != "0":
+    if qkv.is_cuda and D == 64 and qkv.dtype in _KERNEL_DTYPES and os.environ.get("TNN_ATTN_BWD_KERNEL", "1") != "0":
         # tcgen05 flash backward (csrc/kernels/attention_bwd.cu): five MMAs per (key tile, query tile)
         Cx = native.require()
         dqkv = torch.empty_like(qkv, memory_format=torch.contiguous_format)
         delta = torch.empty((B, H, L), device=qkv.device, dtype=torch.float32)
         dq_acc = torch.empty((B, L, H * D), device=qkv.device, dtype=torch.float32)
-        Cx.attention_bwd(qkv.contiguous(), do.reshape(B, L, H * D).to(torch.bfloat16).contiguous(),
+        Cx.attention_bwd(qkv.contiguous(), do.reshape(B, L, H * D).to(qkv.dtype).contiguous(),
                          o.reshape(B, L, H * D).contiguous(), lse.contiguous(), dqkv, delta, dq_acc, bool(causal))
         return dqkv
     q, k, v = (qkv[:, :, i].float().permute(0, 2, 1, 3) for i in range(3))   # [B,H,L,D]
