@@ -224,3 +224,59 @@ def test_attention_block_fp16_io_dtype_trains():
     assert dg.dtype == torch.float16 and ((dg.float().cpu() - dc).norm() / dc.norm()).item() < 1e-2
     for k in cpu.grads:
         assert ((gpu.grads[k].cpu() - cpu.grads[k]).norm() / (cpu.grads[k].norm() + 1e-12)).item() < 2e-2, k
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32, torch.float64])
+def test_layernorm_explicit_io_dtype(dtype):
+    """LayerNormLayer with io_dtype fp16 / fp32 / fp64 (any-dtype warp-per-row kernels): forward with the fused residual add,
+    backward with the fused extra gradient, dgamma / dbeta -- against autograd in fp64."""
+    from tnn_b200.nn.layers import LayerNormLayer
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(8)
+    lay = LayerNormLayer(200, 1e-5, True, "ln").set_io_dtype(dtype).init(dev, 2)
+    lay.params["gamma"].copy_(torch.rand(200, generator=g, device=dev) + 0.5)
+    lay.params["beta"].copy_(torch.randn(200, generator=g, device=dev))
+    lay.set_training(True)
+    x = torch.randn(37, 200, generator=g, device=dev).to(dtype)
+    res = torch.randn(37, 200, generator=g, device=dev).to(dtype)
+    dy = torch.randn(37, 200, generator=g, device=dev).to(dtype)
+    extra = torch.randn(37, 200, generator=g, device=dev).to(dtype)
+    y = lay.forward_impl(x, 0, residual=res)
+    assert y.dtype == dtype
+    xr = (x.double() + res.double()).to(dtype).double().requires_grad_(True)     # the layer stores the sum in the io dtype
+    gam = lay.params["gamma"].double().clone().requires_grad_(True)
+    bet = lay.params["beta"].double().clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (200,), gam, bet, 1e-5)
+    tol = {torch.float16: 4e-3, torch.float32: 2e-5, torch.float64: 2e-6}[dtype]      # statistics are kept in fp32
+    assert (y.double() - ref.detach()).abs().max().item() < tol * 4
+    for k in lay.grads:
+        lay.grads[k].zero_()
+    dx = lay.backward_impl(dy, 0, extra=extra)
+    ref.backward(dy.double())
+    assert dx.dtype == dtype and (dx.double() - (xr.grad + extra.double())).abs().max().item() < tol * 8
+    assert (lay.grads["gamma"].double() - gam.grad).abs().max().item() < tol * 40
+    assert (lay.grads["beta"].double() - bet.grad).abs().max().item() < tol * 40
+
+
+def test_tiny_gpt2_runs_in_fp16_end_to_end():
+    """A 2-layer GPT-2 (head_dim 64) with io_dtype fp16 on every layer: embeddings -> LayerNorm (any-dtype kernel) -> fp16 QKV /
+    attention / projection -> fp16 MLP -> LM head; forward logits and parameter gradients against the CPU fp32 run."""
+    from tnn_b200.models.zoo import _gpt2
+    dev = _dev()
+    cpu = _gpt2(128, 2, 2, True, "tiny", None, seq_len=64, vocab=97, dropout=0.0).init("cpu", 11)
+    gpu = _gpt2(128, 2, 2, True, "tiny", torch.float16, seq_len=64, vocab=97, dropout=0.0).init("cpu", 11).to(dev)
+    cpu.set_training(True), gpu.set_training(True)
+    ids = (torch.arange(3 * 64).reshape(3, 64) * 7 % 97).to(torch.int32)
+    yc = cpu.forward(ids, 0)
+    yg = gpu.forward(ids.to(dev), 0)
+    assert yg.dtype == torch.float16 and yg.shape == yc.shape
+    assert ((yg.float().cpu() - yc).norm() / yc.norm()).item() < 2e-2
+    dy = torch.randn_like(yc) * 0.1
+    cpu.backward(dy, 0)
+    gpu.backward(dy.to(dev).half(), 0)
+    worst = 0.0
+    for lc, lg in zip(cpu.all_layers(), gpu.all_layers()):
+        for k, gc in lc.grads.items():
+            if gc.norm() > 1e-6:
+                worst = max(worst, ((lg.grads[k].cpu() - gc).norm() / gc.norm()).item())
+    assert worst < 6e-2, worst

@@ -520,6 +520,19 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                           (int)(x.size(2) * x.size(3)), fp(gamma), fp(mean), fp(invstd), fp(ss), relu ? 1 : 0, fp(dgamma), fp(dbeta), fp(coef),
                           ws.data_ptr(), cur_stream());
   });
+  m.def("layernorm_fwd_any", [](const Tensor& x, const OptT& residual, const Tensor& y, const OptT& sum_out, int64_t rows, int C,
+                                const OptT& gamma, const OptT& beta, double eps, const Tensor& mean, const Tensor& rstd) {
+    TORCH_CHECK(x.is_contiguous() && y.is_contiguous() && y.scalar_type() == x.scalar_type(), "layernorm_fwd_any: contiguous tensors of one dtype");
+    tnn::layernorm_fwd_any(vp(x), vp(residual), vp(y), vp(sum_out), dt_code(x), rows, C, fp(gamma), fp(beta), (float)eps, fp(mean), fp(rstd),
+                           cur_stream());
+  });
+  m.def("layernorm_bwd_any", [](const Tensor& dy, const Tensor& x, int64_t rows, int C, const OptT& gamma, const Tensor& mean, const Tensor& rstd,
+                                const Tensor& dx, const OptT& dgamma, const OptT& dbeta, const OptT& extra) {
+    TORCH_CHECK(dy.is_contiguous() && x.is_contiguous() && dx.is_contiguous() && dy.scalar_type() == x.scalar_type() &&
+                    dx.scalar_type() == x.scalar_type(), "layernorm_bwd_any: contiguous tensors of one dtype");
+    tnn::layernorm_bwd_any(vp(dy), vp(x), dt_code(x), rows, C, fp(gamma), fp(mean), fp(rstd), vp(dx), fp(dgamma), fp(dbeta), vp(extra),
+                           cur_stream());
+  });
   m.def("colsum_any", [](const Tensor& x, const Tensor& out, double alpha, bool accumulate) {
     TORCH_CHECK(x.dim() == 2 && x.stride(1) == 1 && out.numel() == x.size(1) && out.is_contiguous(), "colsum_any: x [R,C], out [C]");
     const int dt = dt_code(x);

@@ -490,7 +490,96 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ------------------------------------------------------------------------------------------------ LayerNorm, any dtype
+// One warp per row (fp32 statistics, two-pass variance over registers-free strided loads): the fp16 / fp32 / fp64
+// counterpart of the bf16 warp-per-row kernels in norm.cu.  y = (x (+ residual) - mean) * rstd * gamma + beta.
+__global__ void __launch_bounds__(256)
+    k_layernorm_fwd_any(const void* __restrict__ x, const void* __restrict__ residual, void* __restrict__ y, void* __restrict__ sum_out, int dt,
+                        long long rows, int C, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                        float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int lane = threadIdx.x & 31;
+  for (long long r = blockIdx.x * 8LL + (threadIdx.x >> 5); r < rows; r += gridDim.x * 8LL) {
+    const long long base = r * C;
+    double s = 0.0;
+    for (int c = lane; c < C; c += 32) {
+      double v = cv_get(x, dt, base + c);
+      if (residual) {
+        v += cv_get(residual, dt, base + c);
+        if (sum_out) cv_put(sum_out, dt, base + c, v);
+      }
+      s += v;
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const double mean = s / C;
+    double q = 0.0;
+    const void* src = (residual && sum_out) ? sum_out : x;        // the stored sum is what backward sees
+    for (int c = lane; c < C; c += 32) {
+      double v = cv_get(src, dt, base + c);
+      if (residual && !sum_out) v += cv_get(residual, dt, base + c);
+      q += (v - mean) * (v - mean);
+    }
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const double rstd = 1.0 / sqrt(q / C + (double)eps);
+    if (lane == 0) {
+      mean_out[r] = (float)mean;
+      rstd_out[r] = (float)rstd;
+    }
+    for (int c = lane; c < C; c += 32) {
+      double v = cv_get(src, dt, base + c);
+      if (residual && !sum_out) v += cv_get(residual, dt, base + c);
+      double o = (v - mean) * rstd;
+      if (gamma) o = o * gamma[c] + (beta ? beta[c] : 0.f);
+      cv_put(y, dt, base + c, o);
+    }
+  }
+}
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma; dgamma / dbeta through fp32 atomics (one per warp and column)
+__global__ void __launch_bounds__(256)
+    k_layernorm_bwd_any(const void* __restrict__ dy, const void* __restrict__ x, int dt, long long rows, int C, const float* __restrict__ gamma,
+                        const float* __restrict__ mean, const float* __restrict__ rstd, void* __restrict__ dx, float* __restrict__ dgamma,
+                        float* __restrict__ dbeta, const void* __restrict__ extra) {
+  const int lane = threadIdx.x & 31;
+  for (long long r = blockIdx.x * 8LL + (threadIdx.x >> 5); r < rows; r += gridDim.x * 8LL) {
+    const long long base = r * C;
+    const double mu = mean[r], is = rstd[r];
+    double sg = 0.0, sgx = 0.0;
+    for (int c = lane; c < C; c += 32) {
+      const double d = cv_get(dy, dt, base + c), xh = (cv_get(x, dt, base + c) - mu) * is;
+      const double g = gamma ? d * gamma[c] : d;
+      sg += g;
+      sgx += g * xh;
+      if (dgamma) atomicAdd(dgamma + c, (float)(d * xh));
+      if (dbeta) atomicAdd(dbeta + c, (float)d);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      sg += __shfl_xor_sync(0xffffffffu, sg, o);
+      sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
+    }
+    const double mg = sg / C, mgx = sgx / C;
+    for (int c = lane; c < C; c += 32) {
+      const double d = cv_get(dy, dt, base + c), xh = (cv_get(x, dt, base + c) - mu) * is;
+      const double g = gamma ? d * gamma[c] : d;
+      double v = is * (g - mg - xh * mgx);
+      if (extra) v += cv_get(extra, dt, base + c);
+      cv_put(dx, dt, base + c, v);
+    }
+  }
+}
+
 }  // namespace
+
+void layernorm_fwd_any(const void* x, const void* residual, void* y, void* sum_out, int dt, long long rows, int C, const float* gamma,
+                       const float* beta, float eps, float* mean, float* rstd, cudaStream_t stream) {
+  if (rows <= 0 || C <= 0) return;
+  k_layernorm_fwd_any<<<grid_for((rows + 7) / 8, 1, kSMs * 8), 256, 0, stream>>>(x, residual, y, sum_out, dt, rows, C, gamma, beta, eps, mean, rstd);
+  TNN_CHECK_LAUNCH();
+}
+void layernorm_bwd_any(const void* dy, const void* x, int dt, long long rows, int C, const float* gamma, const float* mean, const float* rstd,
+                       void* dx, float* dgamma, float* dbeta, const void* extra, cudaStream_t stream) {
+  if (rows <= 0 || C <= 0) return;
+  k_layernorm_bwd_any<<<grid_for((rows + 7) / 8, 1, kSMs * 8), 256, 0, stream>>>(dy, x, dt, rows, C, gamma, mean, rstd, dx, dgamma, dbeta, extra);
+  TNN_CHECK_LAUNCH();
+}
 
 void colsum_any(const void* x, int dt, long long rows, int cols, long long ld, double alpha, void* out, bool accumulate, cudaStream_t stream) {
   if (cols <= 0) return;

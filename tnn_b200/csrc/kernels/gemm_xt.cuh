@@ -31,6 +31,12 @@ void gemm_f64(const double* A, const double* B, int M, int N, int K, long long l
 
 // out[cols] (= or +=) alpha * column sums of x[rows, cols] (row stride ld); out is fp32 (fp64 for fp64 input)
 void colsum_any(const void* x, int dt, long long rows, int cols, long long ld, double alpha, void* out, bool accumulate, cudaStream_t stream);
+// LayerNorm for fp16 / fp32 / fp64 rows (bf16 has the tuned kernels of norm.cu): optional residual add (sum_out keeps x + residual
+// for the backward pass), fp32 gamma / beta / statistics; backward adds `extra` (same dtype) to dx and accumulates dgamma / dbeta
+void layernorm_fwd_any(const void* x, const void* residual, void* y, void* sum_out, int dt, long long rows, int C, const float* gamma,
+                       const float* beta, float eps, float* mean, float* rstd, cudaStream_t stream);
+void layernorm_bwd_any(const void* dy, const void* x, int dt, long long rows, int C, const float* gamma, const float* mean, const float* rstd,
+                       void* dx, float* dgamma, float* dbeta, const void* extra, cudaStream_t stream);
 void tensor_cast_any(const void* src, int src_dt, void* dst, int dst_dt, long long n, cudaStream_t stream);
 // dst[c, r] = src[r, c]; src_ld / dst_ld = elements between rows (0: dense)
 void tensor_transpose_any(const void* src, void* dst, int dt, int rows, int cols, cudaStream_t stream, long long src_ld = 0,

@@ -17,6 +17,7 @@ from ..core.config import TConfig
 from ..ops import attention as attn_ops
 from ..ops import gemm as gemm_ops
 from ..ops import native
+from ..ops import tensor_ops
 from .layer import Layer, LayerFactory, ParamDescriptor, register
 from .layers import (ActivationLayer, BatchNormLayer, Conv2DLayer, DenseLayer, DropoutLayer, LayerNormLayer, _aligned_rows,
                      _normal_init, _uniform_init, to_bf16, to_dtype)
@@ -181,6 +182,14 @@ def _add(a, b, relu=False):
     if a.is_cuda and a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.shape == b.shape:
         o = torch.empty_like(a)
         native.require().add_bf16(a.contiguous(), b.contiguous(), o, relu)
+        return o
+    if a.is_cuda and a.shape == b.shape and a.dtype in (torch.float16, torch.float32, torch.float64, torch.bfloat16):
+        # other float dtypes (explicit io dtype): the templated tensor-op kernels, not a library add
+        o = tensor_ops.add(a.contiguous(), to_dtype(b, a.dtype).contiguous())
+        if relu:
+            y = torch.empty_like(o)
+            native.require().act_fwd(o, y, 1, 0.0)
+            return y
         return o
     o = a + b
     return torch.relu(o) if relu else o

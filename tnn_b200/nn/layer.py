@@ -58,7 +58,10 @@ class Layer:
         return self
 
     def set_io_dtype(self, dt):
+        """Activation dtype contract of this layer and every child (layer.hpp:65-70).  None = fp32 on CPU, bf16 on CUDA."""
         self.io_dtype = dt
+        for c in self.children():
+            c.set_io_dtype(dt)
         return self
 
     def children(self) -> list["Layer"]:

@@ -723,6 +723,8 @@ def _residual_add(x, residual):
         o = torch.empty_like(x)
         native.require().add_bf16(x.contiguous(), residual.contiguous(), o, False)
         return o
+    if x.is_cuda and x.shape == residual.shape and x.dtype in (torch.float16, torch.float32, torch.float64, torch.bfloat16):
+        return tensor_ops.add(x.contiguous(), to_dtype(residual, x.dtype).contiguous())
     return x + residual.to(x.dtype)
 
 
@@ -887,6 +889,9 @@ class _NAry(Layer):
                 o = torch.empty_like(out)
                 native.require().binary_bf16(out.contiguous(), t.contiguous(), o, self.OP)
                 out = o
+            elif out.is_cuda and out.shape == t.shape and out.dtype in (torch.float16, torch.float32, torch.float64, torch.bfloat16):
+                f = (tensor_ops.add, tensor_ops.sub, tensor_ops.mul)[self.OP]
+                out = f(out.contiguous(), to_dtype(t, out.dtype).contiguous())
             else:
                 out = out + t if self.OP == 0 else (out - t if self.OP == 1 else out * t)
         return out
@@ -980,14 +985,20 @@ class LayerNormLayer(Layer):
         gamma, beta = self.params.get("gamma"), self.params.get("beta")
         if x.is_cuda:
             Cx = native.require()
-            x = to_bf16(x).contiguous()
+            # explicit fp16 / fp32 / fp64 io dtype: the any-dtype warp-per-row kernel (gemm_xt.cu); default bf16: norm.cu
+            xt = self.io_dtype in gemm_ops.XT_DTYPES
+            x = (to_dtype(x, self.io_dtype) if xt else to_bf16(x)).contiguous()
             rows = x.numel() // C
             y = torch.empty_like(x)
             s = torch.empty_like(x) if residual is not None else None
             mean = torch.empty(rows, dtype=torch.float32, device=x.device)
             rstd = torch.empty_like(mean)
-            Cx.layernorm_fwd(x, residual.contiguous() if residual is not None else None, y, s, rows, C, gamma, beta,
-                             self.epsilon, mean, rstd)
+            if xt:
+                Cx.layernorm_fwd_any(x, to_dtype(residual, x.dtype).contiguous() if residual is not None else None, y, s, rows, C, gamma, beta,
+                                     self.epsilon, mean, rstd)
+            else:
+                Cx.layernorm_fwd(x, residual.contiguous() if residual is not None else None, y, s, rows, C, gamma, beta,
+                                 self.epsilon, mean, rstd)
             xin = s if s is not None else x
             if self.training:
                 self.cache(mb_id).update(x=xin, mean=mean, rstd=rstd)
@@ -1012,6 +1023,16 @@ class LayerNormLayer(Layer):
         c = self.cache(mb_id)
         C = self.normalized_shape
         gamma = self.params.get("gamma")
+        if dy.is_cuda and c["x"].dtype in gemm_ops.XT_DTYPES:
+            Cx = native.require()
+            dy = to_dtype(dy, c["x"].dtype).contiguous()
+            dx = torch.empty_like(dy)
+            ex = to_dtype(extra, dy.dtype).contiguous() if extra is not None and extra.shape == dy.shape else None
+            Cx.layernorm_bwd_any(dy, c["x"], dy.numel() // C, C, gamma, c["mean"], c["rstd"], dx, self.grads.get("gamma"),
+                                 self.grads.get("beta"), ex)
+            if extra is not None and ex is None:
+                dx = dx + extra.to(dx.dtype)
+            return dx
         if dy.is_cuda:
             Cx = native.require()
             dy = to_bf16(dy).contiguous()
