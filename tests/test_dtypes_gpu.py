@@ -280,3 +280,29 @@ def test_tiny_gpt2_runs_in_fp16_end_to_end():
             if gc.norm() > 1e-6:
                 worst = max(worst, ((lg.grads[k].cpu() - gc).norm() / gc.norm()).item())
     assert worst < 6e-2, worst
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+@pytest.mark.parametrize("cfg", [(8, 16, 3, 3, 1, 1, 1, 1, (2, 10, 10, 8)), (3, 8, 5, 5, 2, 2, 2, 2, (2, 11, 11, 3)), (16, 24, 3, 2, 2, 1, 1, 0, (3, 9, 8, 16))])
+def test_conv2d_explicit_io_dtype(dtype, cfg):
+    """Conv2DLayer with io_dtype fp16 / fp32: im2col + the fp16 / tf32 tcgen05 GEMM (forward, dgrad through col2im, wgrad with fp32
+    accumulation, bias gradient) against the CPU fp32 layer; padded (R*S*C % 8 != 0) and anisotropic geometries included."""
+    from tnn_b200.nn.layers import Conv2DLayer
+    dev = _dev()
+    cin, cout, kh, kw, sh, sw, ph, pw, shape = cfg
+    cpu = Conv2DLayer(cin, cout, kh, kw, sh, sw, ph, pw, True, "c").init("cpu", 5)
+    gpu = Conv2DLayer(cin, cout, kh, kw, sh, sw, ph, pw, True, "c").set_io_dtype(dtype).init("cpu", 5).to(dev)
+    cpu.set_training(True), gpu.set_training(True)
+    torch.manual_seed(9)
+    x = torch.randn(*shape).half().float()
+    yc = cpu.forward(x, 0)
+    yg = gpu.forward(x.to(dev).to(dtype), 0)
+    assert yg.dtype == dtype and yg.shape == yc.shape
+    tol = 4e-3 if dtype == torch.float16 else 2e-3
+    assert ((yg.float().cpu() - yc).norm() / yc.norm()).item() < tol
+    dy = torch.randn_like(yc).half().float()
+    dc = cpu.backward(dy, 0)
+    dg = gpu.backward(dy.to(dev).to(dtype), 0)
+    assert dg.dtype == dtype and ((dg.float().cpu() - dc).norm() / dc.norm()).item() < 2 * tol
+    for k in cpu.grads:
+        assert ((gpu.grads[k].cpu() - cpu.grads[k]).norm() / cpu.grads[k].norm()).item() < 2 * tol, k

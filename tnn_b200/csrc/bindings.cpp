@@ -23,6 +23,14 @@ void attention_bind(py::module_& m);  // attention.cpp
 void mxfp8_bind(py::module_& m);      // mxfp8.cpp
 }
 
+static int dt_code(const Tensor& t);
+// element type of an im2col / col2im pair: bf16 (default), fp32 or fp16 -- both tensors must agree
+static int conv_dt(const Tensor& a, const Tensor& b) {
+  TORCH_CHECK(a.scalar_type() == b.scalar_type(), "im2col / col2im: source and destination dtypes differ");
+  const int dt = dt_code(a);
+  TORCH_CHECK(dt != tnn::XT_F64, "im2col / col2im: bf16 / fp32 / fp16");
+  return dt;
+}
 static cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
 static void* vp(const Tensor& t) { return t.data_ptr(); }
 // element type code of the generic tensor ops / casts / extra-dtype GEMMs (tnn::XtDType)
@@ -394,14 +402,16 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("im2col_nhwc", [](const Tensor& x, const Tensor& col, int64_t ldcol, std::vector<int> d) {
     TORCH_CHECK(d.size() == 10 || d.size() == 12, "dims = {N,H,W,C,R,S,stride,pad,OH,OW} or {N,H,W,C,R,S,sh,sw,ph,pw,OH,OW}");
     if (d.size() == 12)
-      tnn::im2col_nhwc2(vp(x), vp(col), ldcol, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9], d[10], d[11], cur_stream());
+      tnn::im2col_nhwc2(vp(x), vp(col), ldcol, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9], d[10], d[11], cur_stream(),
+                        conv_dt(x, col));
     else
       tnn::im2col_nhwc(vp(x), vp(col), ldcol, d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9], cur_stream());
   });
   m.def("col2im_nhwc", [](const Tensor& col, int64_t ldcol, const Tensor& dx, std::vector<int> d) {
     TORCH_CHECK(d.size() == 10 || d.size() == 12, "dims = {N,H,W,C,R,S,stride,pad,OH,OW} or {N,H,W,C,R,S,sh,sw,ph,pw,OH,OW}");
     if (d.size() == 12)
-      tnn::col2im_nhwc2(vp(col), ldcol, vp(dx), d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9], d[10], d[11], cur_stream());
+      tnn::col2im_nhwc2(vp(col), ldcol, vp(dx), d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9], d[10], d[11], cur_stream(),
+                        conv_dt(col, dx));
     else
       tnn::col2im_nhwc(vp(col), ldcol, vp(dx), d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8], d[9], cur_stream());
   });

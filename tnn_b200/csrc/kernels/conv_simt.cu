@@ -3,6 +3,8 @@
 //    tensor map and has K = R*S*C_in <= 75, far below one UMMA tile)
 //  * im2col / col2im for geometries outside the TMA window path (odd widths, 5x5/7x7,
 //    stride > 2); the GEMM itself still runs on tcgen05.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "simt_ops.cuh"
 
@@ -324,8 +326,17 @@ void conv_direct_wgrad(const void* x, const void* dy, float* dw, float* dbias, i
 }
 
 // --------------------------------------------------------------------------- im2col / col2im
+// templated on the element type: bf16 (the conv paths outside the TMA-window kernels), fp16 and fp32 (convolutions with an
+// explicit io dtype: im2col + the fp16 / tf32 tcgen05 GEMMs of gemm_xt.cu)
+__device__ __forceinline__ float cs_get(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ float cs_get(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ float cs_get(const float* p) { return *p; }
+__device__ __forceinline__ void cs_put(bf16* p, float v) { *p = __float2bfloat16(v); }
+__device__ __forceinline__ void cs_put(__half* p, float v) { *p = __float2half_rn(v); }
+__device__ __forceinline__ void cs_put(float* p, float v) { *p = v; }
+template <typename T>
 __global__ void __launch_bounds__(256)
-    k_im2col(const bf16* __restrict__ x, bf16* __restrict__ col, long long ldcol, DConvP p) {
+    k_im2col(const T* __restrict__ x, T* __restrict__ col, long long ldcol, DConvP p) {
   const int rsc = p.R * p.S * p.C;
   const long long total = (long long)p.N * p.OH * p.OW * rsc;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -339,7 +350,8 @@ __global__ void __launch_bounds__(256)
     int c = j % p.C, rs = j / p.C, s = rs % p.S, r = rs / p.S;
     const int sw_ = p.stride_w ? p.stride_w : p.stride, pw_ = p.pad_w1 ? p.pad_w1 - 1 : p.pad;
     int h = oh * p.stride - p.pad + r, w = ow * sw_ - pw_ + s;
-    bf16 v = __float2bfloat16(0.f);
+    T v;
+    cs_put(&v, 0.f);
     if (h >= 0 && h < p.H && w >= 0 && w < p.W) v = x[(((long long)n * p.H + h) * p.W + w) * p.C + c];
     col[pix * ldcol + j] = v;
   }
@@ -349,15 +361,18 @@ void im2col_nhwc(const void* x, void* col, long long ldcol, int N, int H, int W,
   im2col_nhwc2(x, col, ldcol, N, H, W, C, R, S, stride, stride, pad, pad, OH, OW, s);
 }
 void im2col_nhwc2(const void* x, void* col, long long ldcol, int N, int H, int W, int C, int R, int S, int sh, int sw,
-                  int ph, int pw, int OH, int OW, cudaStream_t s) {
+                  int ph, int pw, int OH, int OW, cudaStream_t s, int dt) {
   DConvP p{N, H, W, C, 0, R, S, sh, ph, OH, OW, sw, pw + 1};
   long long total = (long long)N * OH * OW * R * S * C;
-  k_im2col<<<grid_for(total, 256), 256, 0, s>>>((const bf16*)x, (bf16*)col, ldcol, p);
+  if (dt == 1) k_im2col<float><<<grid_for(total, 256), 256, 0, s>>>((const float*)x, (float*)col, ldcol, p);
+  else if (dt == 2) k_im2col<__half><<<grid_for(total, 256), 256, 0, s>>>((const __half*)x, (__half*)col, ldcol, p);
+  else k_im2col<bf16><<<grid_for(total, 256), 256, 0, s>>>((const bf16*)x, (bf16*)col, ldcol, p);
   TNN_CHECK_LAUNCH();
 }
 // gather formulation: one thread per input element sums the col entries that map onto it
+template <typename T>
 __global__ void __launch_bounds__(256)
-    k_col2im(const bf16* __restrict__ col, long long ldcol, bf16* __restrict__ dx, DConvP p) {
+    k_col2im(const T* __restrict__ col, long long ldcol, T* __restrict__ dx, DConvP p) {
   const long long total = (long long)p.N * p.H * p.W * p.C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -380,10 +395,10 @@ __global__ void __launch_bounds__(256)
         int ow = ww / sw_;
         if (ow >= p.OW) continue;
         long long pix = ((long long)n * p.OH + oh) * p.OW + ow;
-        acc += __bfloat162float(col[pix * ldcol + (r * p.S + s) * p.C + c]);
+        acc += cs_get(col + pix * ldcol + (r * p.S + s) * p.C + c);
       }
     }
-    dx[i] = __float2bfloat16(acc);
+    cs_put(dx + i, acc);
   }
 }
 void col2im_nhwc(const void* col, long long ldcol, void* dx, int N, int H, int W, int C, int R, int S,
@@ -391,10 +406,12 @@ void col2im_nhwc(const void* col, long long ldcol, void* dx, int N, int H, int W
   col2im_nhwc2(col, ldcol, dx, N, H, W, C, R, S, stride, stride, pad, pad, OH, OW, s);
 }
 void col2im_nhwc2(const void* col, long long ldcol, void* dx, int N, int H, int W, int C, int R, int S, int sh, int sw,
-                  int ph, int pw, int OH, int OW, cudaStream_t s) {
+                  int ph, int pw, int OH, int OW, cudaStream_t s, int dt) {
   DConvP p{N, H, W, C, 0, R, S, sh, ph, OH, OW, sw, pw + 1};
   long long total = (long long)N * H * W * C;
-  k_col2im<<<grid_for(total, 256), 256, 0, s>>>((const bf16*)col, ldcol, (bf16*)dx, p);
+  if (dt == 1) k_col2im<float><<<grid_for(total, 256), 256, 0, s>>>((const float*)col, ldcol, (float*)dx, p);
+  else if (dt == 2) k_col2im<__half><<<grid_for(total, 256), 256, 0, s>>>((const __half*)col, ldcol, (__half*)dx, p);
+  else k_col2im<bf16><<<grid_for(total, 256), 256, 0, s>>>((const bf16*)col, ldcol, (bf16*)dx, p);
   TNN_CHECK_LAUNCH();
 }
 

@@ -217,10 +217,11 @@ void im2col_nhwc(const void* x, void* col, long long ldcol, int N, int H, int W,
 void col2im_nhwc(const void* col, long long ldcol, void* dx, int N, int H, int W, int C, int R, int S,
                  int stride, int pad, int OH, int OW, cudaStream_t s);
 // anisotropic stride / padding (height, width)
+// dt: element type code (0 bf16, 1 fp32, 2 fp16)
 void im2col_nhwc2(const void* x, void* col, long long ldcol, int N, int H, int W, int C, int R, int S, int sh, int sw,
-                  int ph, int pw, int OH, int OW, cudaStream_t s);
+                  int ph, int pw, int OH, int OW, cudaStream_t s, int dt = 0);
 void col2im_nhwc2(const void* col, long long ldcol, void* dx, int N, int H, int W, int C, int R, int S, int sh, int sw,
-                  int ph, int pw, int OH, int OW, cudaStream_t s);
+                  int ph, int pw, int OH, int OW, cudaStream_t s, int dt = 0);
 
 // ---- embedding & friends (embed.cu) ---------------------------------------------------
 void embedding_fwd(const int* ids, const float* table, const float* pos_table, void* y, long long T,

@@ -239,7 +239,67 @@ class Conv2DLayer(Layer):
             self._plans[key] = p
         return p
 
+    # ---- explicit fp16 / fp32 io dtype: im2col + the fp16 / tf32 tcgen05 GEMMs of gemm_xt.cu (the reference instantiates
+    # its conv layer per dtype over cuDNN, conv2d_layer.cpp; bf16 -- the default -- runs the TMA-window implicit GEMM)
+    def _xt_geo(self, x):
+        N, H, W, C = x.shape
+        OH = conv_ops.out_size(H, self.kernel_h, self.stride_h, self.pad_h)
+        OW = conv_ops.out_size(W, self.kernel_w, self.stride_w, self.pad_w)
+        geo = [N, H, W, C, self.kernel_h, self.kernel_w, self.stride_h, self.stride_w, self.pad_h, self.pad_w, OH, OW]
+        rsc = self.kernel_h * self.kernel_w * C
+        per16 = 16 // x.element_size()
+        return geo, N * OH * OW, rsc, (rsc + per16 - 1) // per16 * per16, OH, OW
+
+    def _xt_weight(self, dt, rsc, ld):
+        """[K, ld] weight matrix in the io dtype, rows padded with zeros to the 16-byte pitch the TMA descriptors need."""
+        w = self.lp_as("weight", dt).reshape(self.out_channels, rsc)
+        if ld == rsc:
+            return w
+        key = f"weight@{dt}@pad"
+        wp = self.params_lp.get(key)
+        if wp is None or self._lp_version.get(key, -1) != self.param_version:
+            wp = self.params_lp[key] = torch.zeros((self.out_channels, ld), dtype=dt, device=w.device)
+            wp[:, :rsc].copy_(w)
+            self._lp_version[key] = self.param_version
+        return wp
+
+    def _forward_xt(self, x, mb_id, residual, act):
+        Cx, dt = native.require(), self.io_dtype
+        x = to_dtype(x, dt).contiguous()
+        geo, M, rsc, ld, OH, OW = self._xt_geo(x)
+        col = torch.zeros((M, ld), dtype=dt, device=x.device) if ld != rsc else torch.empty((M, ld), dtype=dt, device=x.device)
+        Cx.im2col_nhwc(x, col, ld, geo)
+        res2 = to_dtype(residual, dt).reshape(M, self.out_channels).contiguous() if residual is not None else None
+        y = gemm_ops.gemm_xt(col, self._xt_weight(dt, rsc, ld), bias=self.params.get("bias"), residual=res2, act=act)
+        if self.training:
+            self.cache(mb_id).update(x=x, col=col, xt=(geo, M, rsc, ld))
+        return y.reshape(x.shape[0], OH, OW, self.out_channels)
+
+    def _backward_xt(self, dy, mb_id, need_dx):
+        Cx = native.require()
+        c = self.cache(mb_id)
+        x, col = c["x"], c["col"]
+        geo, M, rsc, ld = c["xt"]
+        dt = x.dtype
+        dy2 = to_dtype(dy, dt).reshape(M, self.out_channels).contiguous()
+        gw = self.grads["weight"].reshape(self.out_channels, rsc)
+        if ld == rsc:
+            gemm_ops.gemm_xt(dy2, col, True, True, out=gw, accumulate=True)              # dW[K, RSC] += dy^T col, fp32 accumulation
+        else:
+            t = gemm_ops.gemm_xt(dy2, col, True, True, out_f32=True)
+            tensor_ops.add(gw, t[:, :rsc].contiguous(), out=gw)
+        if self.grads.get("bias") is not None:
+            Cx.colsum_any(dy2, self.grads["bias"], 1.0, True)
+        if not need_dx:
+            return None
+        dcol = gemm_ops.gemm_xt(dy2, self._xt_weight(dt, rsc, ld), False, True)         # [M, ld] = dy W
+        dx = torch.empty_like(x)
+        Cx.col2im_nhwc(dcol, ld, dx, geo)
+        return dx
+
     def forward_impl(self, x, mb_id, residual=None, act=None):
+        if x.is_cuda and self.io_dtype in (torch.float16, torch.float32):
+            return self._forward_xt(x, mb_id, residual, act)
         plan = self._plan(x)
         c = self.cache(mb_id) if self.training else {}
         if x.is_cuda:
@@ -265,6 +325,11 @@ class Conv2DLayer(Layer):
 
     def backward_impl(self, dy, mb_id, residual=None, need_dx=True):
         c = self.cache(mb_id)
+        if "xt" in c:
+            dx = self._backward_xt(dy, mb_id, need_dx)
+            if dx is not None and residual is not None:
+                dx = tensor_ops.add(dx, to_dtype(residual, dx.dtype).contiguous())
+            return dx
         x, plan = c["x"], c["plan"]
         w = self.params["weight"]
         colsum = getattr(dy, "_tnn_colsum", None)
