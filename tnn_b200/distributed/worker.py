@@ -87,6 +87,10 @@ class Worker:
         return self
 
     def run(self):
+        # the kernels of this repo launch on the CURRENT device's stream: a worker that owns cuda:1 must make it current in
+        # the thread that runs its loop (the device is per thread in the CUDA runtime)
+        if torch.device(self.device).type == "cuda":
+            torch.cuda.set_device(self.device)
         while not self.should_stop:
             msg = self.comm.dequeue_input_message(timeout=0.25)
             if msg is None:

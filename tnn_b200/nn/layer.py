@@ -189,7 +189,16 @@ class Layer:
             c.zero_grads()
 
     # ------------------------------------------------------------------ execution
+    def _foreign_device(self) -> bool:
+        """True when this layer lives on a CUDA device that is not the calling thread's current one (the hand-written kernels
+        launch on the current device's stream, so the call is wrapped in a device guard)."""
+        d = self.device
+        return d.type == "cuda" and d.index is not None and torch.cuda.current_device() != d.index
+
     def forward(self, inputs, mb_id: int = 0):
+        if self._foreign_device():
+            with torch.cuda.device(self.device):
+                return self.forward(inputs, mb_id)
         if isinstance(inputs, (list, tuple)):
             inputs = [self._migrate(t) for t in inputs]
             if len(inputs) == 1 and not self.MULTI_INPUT:
@@ -198,6 +207,9 @@ class Layer:
         return self.forward_impl(self._migrate(inputs), mb_id)
 
     def backward(self, grads, mb_id: int = 0):
+        if self._foreign_device():
+            with torch.cuda.device(self.device):
+                return self.backward(grads, mb_id)
         if isinstance(grads, (list, tuple)) and len(grads) == 1 and not self.MULTI_OUTPUT:
             grads = grads[0]
         if isinstance(grads, (list, tuple)):
