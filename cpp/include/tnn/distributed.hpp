@@ -160,7 +160,7 @@ class RoCECommunicator : public TCPCommunicator {
   void send_remote(const Message& m, const Endpoint& to) override;
 
  private:
-  std::unique_ptr<Impl> impl_;
+  std::shared_ptr<Impl> impl_;      // shared with the deleters of delivered tensors (they may outlive the communicator)
 };
 
 // ------------------------------------------------------------------------------------- partitioners

@@ -151,7 +151,7 @@ struct RoCECommunicator::Impl {
 
 RoCECommunicator::RoCECommunicator(const std::string& host, int port, int spp, const Device* land_on, const std::string& name,
                                    size_t device_slab_bytes, size_t inline_bytes)
-    : TCPCommunicator(host, port, spp, land_on, name), impl_(std::make_unique<Impl>()) {
+    : TCPCommunicator(host, port, spp, land_on, name), impl_(std::make_shared<Impl>()) {
   impl_->slab_bytes = device_slab_bytes;
   impl_->inline_bytes = inline_bytes;
 }
@@ -313,15 +313,18 @@ void RoCECommunicator::start() {
           }
           // zero copy: the tensor is the slab block; when its last reference dies the block is queued for release
           // behind an event on the consumer's current stream
-          Impl* ip = impl_.get();
+          std::shared_ptr<Impl> ip = impl_;          // keeps the bookkeeping alive for tensors that outlive the communicator
           const uint64_t off = b;
           const Device d = land_;
           std::shared_ptr<void> owner(static_cast<void*>(I.dptr + off), [ip, off, d](void*) {
             cudaEvent_t ev = nullptr;
-            d.set_current();
-            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(ev, current_flow(d).stream());
+            if (ip->dptr) {                          // slab still registered: release behind the consumer's stream
+              d.set_current();
+              if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(ev, current_flow(d).stream());
+            }
             std::lock_guard<std::mutex> g(ip->mu);
-            ip->released.emplace_back(ev, off);
+            if (ip->dptr) ip->released.emplace_back(ev, off);
+            else if (ev) cudaEventDestroy(ev);
           });
           Message m(static_cast<CommandType>(cmd), Job{make_tensor_view(I.dptr + off, (DType_t)dt, shape, land_, owner), mb});
           m.sender = from;
@@ -347,12 +350,13 @@ void RoCECommunicator::stop() {
     land_.set_current();
     for (auto& o : I.opened) cudaIpcCloseMemHandle(o.second);
     I.opened.clear();
+    std::lock_guard<std::mutex> g(I.mu);
     for (auto& r : I.released)
       if (r.first) cudaEventDestroy(r.first);
     I.released.clear();
     if (I.copy_stream) cudaStreamDestroy(I.copy_stream);
     I.copy_stream = nullptr;
-    cudaFree(I.dptr);      // tensors that still view the slab must not outlive the communicator
+    cudaFree(I.dptr);      // tensors that still view the slab must not be USED after the communicator stopped
     I.dptr = nullptr;
   }
 }
