@@ -135,8 +135,9 @@ class TCPCommunicator : public Communicator {
 
 // One-sided rendezvous transport (the RoCE backend of the reference, include/distributed/roce_communicator.hpp:39-391,
 // on one node): frame-compatible with tnn_b200/distributed/rendezvous.py, so Python and C++ peers interoperate.
-//   * control and host messages: INLINE frames on the TCP bus (a Python peer's PREPARE is answered "no block", which
-//     makes it resend inline -- the protocol's own fallback);
+//   * small / control messages: INLINE frames on the TCP bus; large host messages: PREPARE(len) -> READY_TO_WRITE(offset,
+//     segment) -> the sender memcpy's the serialised message into the receiver's registered shared-memory slab -> DONE
+//     (at most 16 in flight per peer, PREPAREs queue while the slab is full, inline fallback across hosts);
 //   * GPU jobs: DEVICE rendezvous.  Every communicator that lands on a GPU registers a device slab (cudaMalloc +
 //     cudaIpcGetMemHandle); G_PREPARE(nbytes) -> G_READY(offset, ipc handle) -> the sender copies the tensor device to
 //     device straight into the peer's block (NVLink between the GPUs of a node; the GPUDirect-RDMA write of the
@@ -145,13 +146,15 @@ class TCPCommunicator : public Communicator {
 class RoCECommunicator : public TCPCommunicator {
  public:
   RoCECommunicator(const std::string& host = "127.0.0.1", int port = 0, int sockets_per_peer = 4, const Device* land_on = nullptr,
-                   const std::string& name = "roce", size_t device_slab_bytes = 256u << 20, size_t inline_bytes = 16u << 10);
+                   const std::string& name = "roce", size_t device_slab_bytes = 256u << 20, size_t inline_bytes = 16u << 10,
+                   size_t host_slab_bytes = 64u << 20);
   ~RoCECommunicator() override;
   void start() override;
   void stop() override;
   Endpoint endpoint() override { return Endpoint::roce(host_, bus_->port()); }
   struct Stats {
     uint64_t inline_sent = 0, device_rendezvous_sent = 0, device_rendezvous_received = 0, device_fallback_host = 0, slab_peak = 0;
+    uint64_t rendezvous_sent = 0, rendezvous_received = 0, fallback_inline = 0, host_slab_peak = 0;     // host (shared-memory) slab
   };
   Stats stats() const;
   struct Impl;

@@ -1,6 +1,9 @@
 // RoCECommunicator: the one-sided rendezvous transport of the C++ host (see tnn/distributed.hpp).  Frames are those of
 // tnn_b200/distributed/rendezvous.py: {u8 kind, u64 a, u64 b} little endian + tail.
 #include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include <cstring>
@@ -78,9 +81,99 @@ std::vector<std::string> split(const std::string& s, char sep) {
   } while (0)
 }  // namespace
 
+namespace {
+// first fit over a sorted free list, `align`-byte blocks, coalescing frees (the IbvAllocator role: one registered range)
+struct SlabRange {
+  std::map<uint64_t, uint64_t> free_list, live;            // offset -> length
+  uint64_t in_use = 0, peak = 0, align = 512;
+  void reset(uint64_t bytes) {
+    free_list.clear();
+    live.clear();
+    in_use = 0;
+    if (bytes) free_list[0] = bytes;
+  }
+  uint64_t alloc(uint64_t n) {
+    n = std::max<uint64_t>(align, (n + align - 1) / align * align);
+    for (auto it = free_list.begin(); it != free_list.end(); ++it)
+      if (it->second >= n) {
+        const uint64_t off = it->first, len = it->second;
+        free_list.erase(it);
+        if (len > n) free_list[off + n] = len - n;
+        live[off] = n;
+        in_use += n;
+        peak = std::max(peak, in_use);
+        return off;
+      }
+    return kNoBlock;
+  }
+  void release(uint64_t off) {
+    auto it = live.find(off);
+    if (it == live.end()) return;
+    uint64_t lo = off, len = it->second;
+    in_use -= len;
+    live.erase(it);
+    auto nx = free_list.lower_bound(lo);
+    if (nx != free_list.end() && nx->first == lo + len) {
+      len += nx->second;
+      nx = free_list.erase(nx);
+    }
+    if (nx != free_list.begin()) {
+      auto pv = std::prev(nx);
+      if (pv->first + pv->second == lo) {
+        lo = pv->first;
+        len += pv->second;
+        free_list.erase(pv);
+      }
+    }
+    free_list[lo] = len;
+  }
+};
+// a POSIX shared-memory segment under /dev/shm (the creator unlinks it)
+struct ShmSegment {
+  std::string name;
+  uint8_t* base = nullptr;
+  size_t bytes = 0;
+  bool created = false;
+  bool open(const std::string& n, size_t size, bool create) {
+    name = n;
+    created = create;
+    const std::string path = "/dev/shm/" + n;
+    const int fd = ::open(path.c_str(), create ? (O_CREAT | O_EXCL | O_RDWR) : O_RDWR, 0600);
+    if (fd < 0) return false;
+    if (create && ftruncate(fd, (off_t)size) != 0) {
+      ::close(fd);
+      return false;
+    }
+    struct stat st;
+    if (fstat(fd, &st) != 0) {
+      ::close(fd);
+      return false;
+    }
+    bytes = (size_t)st.st_size;
+    void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    ::close(fd);
+    if (p == MAP_FAILED) return false;
+    base = static_cast<uint8_t*>(p);
+    return true;
+  }
+  void close() {
+    if (base) munmap(base, bytes);
+    base = nullptr;
+    if (created && !name.empty()) unlink(("/dev/shm/" + name).c_str());
+    created = false;
+  }
+};
+}  // namespace
+
 struct RoCECommunicator::Impl {
-  size_t slab_bytes = 0, inline_bytes = 0;
+  size_t slab_bytes = 0, inline_bytes = 0, host_slab_bytes = 64u << 20;
   std::string token = host_token();
+  // host slab: a shared-memory segment peers on this node write CPU messages into (PREPARE / READY_TO_WRITE / write / DONE)
+  ShmSegment shm;
+  SlabRange hslab;
+  std::map<std::string, ShmSegment> peer_shm;               // segment name -> mapping
+  std::map<uint64_t, std::pair<std::vector<uint8_t>, std::string>> pending_host;   // id -> (serialised message, peer key)
+  std::vector<std::tuple<std::string, uint64_t, uint64_t>> waiting;                // PREPAREs that did not fit yet
   // device slab (first fit over a sorted free list, 512-byte blocks, coalescing frees)
   int dev = -1;
   uint8_t* dptr = nullptr;
@@ -150,15 +243,18 @@ struct RoCECommunicator::Impl {
 };
 
 RoCECommunicator::RoCECommunicator(const std::string& host, int port, int spp, const Device* land_on, const std::string& name,
-                                   size_t device_slab_bytes, size_t inline_bytes)
+                                   size_t device_slab_bytes, size_t inline_bytes, size_t host_slab_bytes)
     : TCPCommunicator(host, port, spp, land_on, name), impl_(std::make_shared<Impl>()) {
   impl_->slab_bytes = device_slab_bytes;
   impl_->inline_bytes = inline_bytes;
+  impl_->host_slab_bytes = host_slab_bytes;
 }
 RoCECommunicator::~RoCECommunicator() { stop(); }
 RoCECommunicator::Stats RoCECommunicator::stats() const {
   std::lock_guard<std::mutex> g(impl_->mu);
-  return impl_->st;
+  Stats s = impl_->st;
+  s.host_slab_peak = impl_->hslab.peak;
+  return s;
 }
 
 void RoCECommunicator::start() {
@@ -172,6 +268,15 @@ void RoCECommunicator::start() {
     RDV_CUDA(cudaIpcGetMemHandle(&I.handle, I.dptr));
     RDV_CUDA(cudaStreamCreateWithFlags(&I.copy_stream, cudaStreamNonBlocking));
     I.free_list[0] = I.slab_bytes;
+  }
+  if (I.host_slab_bytes > 0) {
+    static std::atomic<unsigned> serial{0};
+    char nm[64];
+    snprintf(nm, sizeof(nm), "tnn_%08x%04x%04x", (unsigned)getpid(), serial.fetch_add(1) & 0xffffu, (unsigned)(Profiler::now_ns() & 0xffff));
+    if (I.shm.open(nm, I.host_slab_bytes, true)) {
+      I.hslab.align = 256;
+      I.hslab.reset(I.host_slab_bytes);
+    }
   }
   bus_->start();
   pump_ = std::thread([this] {
@@ -202,10 +307,94 @@ void RoCECommunicator::start() {
           m.sender = from;
           enqueue(std::move(m));
         } else if (kind == K_PREPARE) {
-          // no host slab on this side: "no block" makes the peer resend the message inline
-          const std::string t = "-|";
-          const auto f = frame(K_READY, a, kNoBlock, t.data(), t.size());
-          reply(from, f);
+          // grant a block of the registered shared-memory slab (same host), queue the request while the slab is full, or
+          // answer "no block" (other host / larger than the slab / no slab): the peer then resends the message inline
+          const std::string tok(reinterpret_cast<const char*>(tail), tn);
+          auto grant = [&](const std::string& to, uint64_t mid, uint64_t len) -> bool {
+            uint64_t off = kNoBlock;
+            const bool can = I.shm.base && tok == I.token && len <= I.host_slab_bytes;
+            if (can) {
+              std::lock_guard<std::mutex> g(I.mu);
+              off = I.hslab.alloc(len);
+              if (off == kNoBlock) return false;
+            }
+            const std::string t = can ? I.token + "|" + I.shm.name : std::string("-|");
+            reply(to, frame(K_READY, mid, off, t.data(), t.size()));
+            return true;
+          };
+          if (!grant(from, a, b)) {
+            std::lock_guard<std::mutex> g(I.mu);
+            I.waiting.emplace_back(from, a, b);
+          }
+        } else if (kind == K_READY) {
+          std::pair<std::vector<uint8_t>, std::string> item;
+          {
+            std::lock_guard<std::mutex> g(I.mu);
+            auto it = I.pending_host.find(a);
+            if (it == I.pending_host.end()) continue;
+            item = std::move(it->second);
+            I.pending_host.erase(it);
+          }
+          bool ok = false;
+          if (b != kNoBlock) {
+            const auto parts = split(std::string(reinterpret_cast<const char*>(tail), tn), '|');
+            if (parts.size() == 2 && parts[0] == I.token) {
+              ShmSegment* seg = nullptr;
+              {
+                std::lock_guard<std::mutex> g(I.mu);
+                auto it = I.peer_shm.find(parts[1]);
+                if (it == I.peer_shm.end()) {
+                  ShmSegment sg;
+                  if (sg.open(parts[1], 0, false)) it = I.peer_shm.emplace(parts[1], sg).first;
+                }
+                if (it != I.peer_shm.end()) seg = &it->second;
+              }
+              if (seg && b + item.first.size() <= seg->bytes) {
+                std::memcpy(seg->base + b, item.first.data(), item.first.size());        // the one-sided write
+                const uint64_t len = item.first.size();
+                reply(from, frame(K_DONE, a, b, &len, 8));                                 // ... and its immediate
+                std::lock_guard<std::mutex> g(I.mu);
+                ++I.st.rendezvous_sent;
+                ok = true;
+              }
+            }
+            if (!ok) reply(from, frame(K_CANCEL, a, b));
+          }
+          if (!ok) {
+            reply(from, frame(K_INLINE, 0, item.first.size(), item.first.data(), item.first.size()));
+            std::lock_guard<std::mutex> g(I.mu);
+            ++I.st.fallback_inline;
+          }
+        } else if (kind == K_DONE || kind == K_CANCEL) {
+          if (kind == K_DONE && I.shm.base && tn >= 8) {
+            uint64_t len;
+            std::memcpy(&len, tail, 8);
+            if (b + len <= I.shm.bytes) {
+              Message m = Message::deserialize(I.shm.base + b, (size_t)len, false, has_land_ ? &land_ : nullptr);
+              m.sender = from;
+              enqueue(std::move(m));
+            }
+          }
+          std::vector<std::tuple<std::string, uint64_t, uint64_t>> retry;
+          {
+            std::lock_guard<std::mutex> g(I.mu);
+            if (b != kNoBlock) I.hslab.release(b);
+            if (kind == K_DONE) ++I.st.rendezvous_received;
+            retry.swap(I.waiting);
+          }
+          for (auto& w : retry) {                          // blocks were freed: serve the PREPAREs that waited
+            uint64_t off;
+            {
+              std::lock_guard<std::mutex> g(I.mu);
+              off = I.hslab.alloc(std::get<2>(w));
+              if (off == kNoBlock) {
+                I.waiting.push_back(w);
+                continue;
+              }
+            }
+            const std::string t = I.token + "|" + I.shm.name;
+            reply(std::get<0>(w), frame(K_READY, std::get<1>(w), off, t.data(), t.size()));
+          }
         } else if (kind == K_GPREPARE) {
           const std::string ts(reinterpret_cast<const char*>(tail), tn);
           const std::string tok = split(ts, '|')[0];
@@ -346,6 +535,12 @@ void RoCECommunicator::stop() {
   if (pump_.joinable()) pump_.join();
   bus_->stop();
   Impl& I = *impl_;
+  {
+    std::lock_guard<std::mutex> g(I.mu);
+    for (auto& ps : I.peer_shm) ps.second.close();
+    I.peer_shm.clear();
+    I.shm.close();
+  }
   if (I.dptr) {
     land_.set_current();
     for (auto& o : I.opened) cudaIpcCloseMemHandle(o.second);
@@ -381,7 +576,21 @@ void RoCECommunicator::send_remote(const Message& m, const Endpoint& to) {
     GlobalProfiler::add_event(EventType::COMMUNICATION, t0, Profiler::now_ns(), std::string("announce ") + command_name(m.command), name_);
     return;
   }
-  const std::vector<uint8_t> body = m.serialize();
+  std::vector<uint8_t> body = m.serialize();
+  if (body.size() > I.inline_bytes && I.shm.base) {
+    // large host message: announce it; the pump thread writes it into the block the peer grants (or falls back inline)
+    uint64_t id;
+    const uint64_t len = body.size();
+    {
+      std::lock_guard<std::mutex> g(I.mu);
+      id = I.next_id++;
+      I.pending_host[id] = std::make_pair(std::move(body), key);
+    }
+    const auto f = frame(K_PREPARE, id, len, I.token.data(), I.token.size());
+    bus_->send(key, f.data(), f.size());
+    GlobalProfiler::add_event(EventType::COMMUNICATION, t0, Profiler::now_ns(), std::string("announce ") + command_name(m.command), name_);
+    return;
+  }
   const auto f = frame(K_INLINE, 0, body.size(), body.data(), body.size());
   bus_->send(key, f.data(), f.size());
   {

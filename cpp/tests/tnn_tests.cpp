@@ -696,6 +696,46 @@ static void pipeline_case(int transport, const Device& dev = getHost(), double t
 TEST(in_process_pipeline_equals_single_device) { pipeline_case(0); }
 TEST(tcp_pipeline_equals_single_device) { pipeline_case(1); }
 TEST(roce_pipeline_equals_single_device) { pipeline_case(2); }
+TEST(roce_host_slab_rendezvous_and_fallbacks) {
+  // CPU tensors between two RoCECommunicators of one node: small -> inline frame, large -> PREPARE / READY_TO_WRITE / write
+  // into the peer's shared-memory slab / DONE, larger than the slab -> inline fallback, more than the slab holds at once ->
+  // the late PREPAREs wait for frees
+  RoCECommunicator a("127.0.0.1", 0, 2, nullptr, "a", 0, 16u << 10, 4u << 20), b("127.0.0.1", 0, 2, nullptr, "b", 0, 16u << 10, 4u << 20);
+  a.start();
+  b.start();
+  a.connect(b.endpoint());
+  auto make = [](size_t n, uint64_t seed) {
+    Tensor t = make_tensor<float>({n});
+    t->fill_random_uniform(-1, 1, seed);
+    return t;
+  };
+  Tensor small = make(16, 1), big = make(1u << 18, 2), huge = make(5u << 18, 3);        // 64 B, 1 MiB, 5 MiB
+  const Tensor ts[3] = {small, big, huge};
+  for (int i = 0; i < 3; ++i) a.send_message(Message(CommandType::FORWARD_JOB, Job{ts[i], (uint64_t)i}), b.endpoint());
+  for (int i = 0; i < 3; ++i) {
+    Message m;
+    CHECK(b.dequeue(&m, 30000));
+    CHECK(m.command == CommandType::FORWARD_JOB && m.job.mb_id < 3 && max_abs_diff(*m.job.data, *ts[m.job.mb_id]) == 0);
+  }
+  auto sa = a.stats(), sb = b.stats();
+  CHECK(sa.inline_sent == 1 && sa.rendezvous_sent == 1 && sa.fallback_inline == 1);
+  CHECK(sb.rendezvous_received == 1 && sb.host_slab_peak >= (1u << 20));
+  b.send_message(Message(CommandType::BACKWARD_JOB, Job{big, 9}), a.endpoint());                // the other direction
+  Message back;
+  CHECK(a.dequeue(&back, 30000) && back.job.mb_id == 9 && max_abs_diff(*back.job.data, *big) == 0);
+  for (int i = 0; i < 12; ++i) a.send_message(Message(CommandType::FORWARD_JOB, Job{big, (uint64_t)(100 + i)}), b.endpoint());
+  std::vector<uint64_t> ids;
+  for (int i = 0; i < 12; ++i) {
+    Message m;
+    CHECK(b.dequeue(&m, 30000));
+    ids.push_back(m.job.mb_id);
+  }
+  std::sort(ids.begin(), ids.end());
+  for (int i = 0; i < 12; ++i) CHECK(ids[i] == (uint64_t)(100 + i));
+  CHECK(b.stats().rendezvous_received == 13 && b.stats().host_slab_peak <= (4u << 20));
+  a.stop();
+  b.stop();
+}
 TEST(lost_microbatch_and_worker_errors_are_detected) {
   auto w = std::make_unique<Worker>(std::make_unique<InProcessCommunicator>("w"), getHost(), "w");
   w->start(true);

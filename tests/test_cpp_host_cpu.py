@@ -284,8 +284,8 @@ def test_python_coordinator_drives_a_cpp_tcp_worker(tmp_path):
 
 def test_python_roce_coordinator_drives_a_cpp_roce_worker():
     """Frame-level interoperability of the rendezvous transport: the Python ``RoCECoordinator`` runs a 2-stage pipeline whose
-    second stage is the C++ ``roce_worker`` (cpp/src/rendezvous.cpp).  On CPU every message ends up INLINE: the C++ side
-    answers a Python PREPARE with "no block", which makes the sender fall back to the inline frame."""
+    second stage is the C++ ``roce_worker`` (cpp/src/rendezvous.cpp).  On CPU the activations / gradients (> 16 KiB) cross
+    through the registered shared-memory slabs of the two implementations in both directions."""
     _host()
     import socket
     import time
@@ -320,7 +320,8 @@ def test_python_roce_coordinator_drives_a_cpp_roce_worker():
         assert losses[-1] < losses[0], losses
         assert any(st["name"].startswith("roce-worker-") for st in co.health_check())
         st = local.comm.stats()
-        assert st["fallback_inline"] > 0 and st["received_messages"] > 0, st      # activations > 16 KiB: PREPARE -> "no block" -> inline
+        # Python -> C++ activations written into the C++ worker's slab, C++ -> Python gradients into the Python slab
+        assert st["rendezvous_sent"] >= 12 and st["rendezvous_received"] >= 12 and st["fallback_inline"] == 0, st
         co.stop()
     finally:
         local.stop()
