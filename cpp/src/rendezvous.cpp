@@ -366,13 +366,19 @@ void RoCECommunicator::start() {
             ++I.st.fallback_inline;
           }
         } else if (kind == K_DONE || kind == K_CANCEL) {
+          Message m;
+          bool have = false;
           if (kind == K_DONE && I.shm.base && tn >= 8) {
             uint64_t len;
             std::memcpy(&len, tail, 8);
             if (b + len <= I.shm.bytes) {
-              Message m = Message::deserialize(I.shm.base + b, (size_t)len, false, has_land_ ? &land_ : nullptr);
-              m.sender = from;
-              enqueue(std::move(m));
+              try {
+                m = Message::deserialize(I.shm.base + b, (size_t)len, false, has_land_ ? &land_ : nullptr);   // copies out of the slab
+                m.sender = from;
+                have = true;
+              } catch (const std::exception& e) {           // the block is released below either way
+                std::cerr << "[" << name_ << "] dropped a malformed slab message from " << from << ": " << e.what() << std::endl;
+              }
             }
           }
           std::vector<std::tuple<std::string, uint64_t, uint64_t>> retry;
@@ -382,6 +388,7 @@ void RoCECommunicator::start() {
             if (kind == K_DONE) ++I.st.rendezvous_received;
             retry.swap(I.waiting);
           }
+          if (have) enqueue(std::move(m));                  // counters and the block are settled before the consumer sees it
           for (auto& w : retry) {                          // blocks were freed: serve the PREPAREs that waited
             uint64_t off;
             {
