@@ -27,11 +27,25 @@ struct Event_t {
 class Profiler {
  public:
   Profiler() = default;
-  Profiler(const Profiler& o) : start_ns_(o.start_ns_), events_(o.events_) {}
+  // copies take the SOURCE's lock: the global profiler is copied into a PROFILING_REPORTED message while other workers of
+  // the same process keep adding events (found by tools/tsan_cpp_host.sh)
+  Profiler(const Profiler& o) {
+    std::lock_guard<std::mutex> g(o.mu_);
+    start_ns_ = o.start_ns_;
+    events_ = o.events_;
+  }
   Profiler& operator=(const Profiler& o) {
     if (this != &o) {
-      start_ns_ = o.start_ns_;
-      events_ = o.events_;
+      std::vector<Event_t> ev;
+      int64_t st;
+      {
+        std::lock_guard<std::mutex> g(o.mu_);
+        ev = o.events_;
+        st = o.start_ns_;
+      }
+      std::lock_guard<std::mutex> g(mu_);
+      start_ns_ = st;
+      events_ = std::move(ev);
     }
     return *this;
   }
