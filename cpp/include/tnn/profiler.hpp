@@ -28,7 +28,7 @@ class Profiler {
  public:
   Profiler() = default;
   // copies take the SOURCE's lock: the global profiler is copied into a PROFILING_REPORTED message while other workers of
-  // the same process keep adding events (found by tools/tsan_cpp_host.sh)
+  // the same process keep adding events (found by tools/sanitize_cpp_host.sh)
   Profiler(const Profiler& o) {
     std::lock_guard<std::mutex> g(o.mu_);
     start_ns_ = o.start_ns_;
