@@ -15,6 +15,7 @@
 #include "tnn/data_parallel.hpp"
 #include "tnn/distributed.hpp"
 #include "tnn/example_models.hpp"
+#include "tnn/matrix.hpp"
 #include "tnn/hardware_info.hpp"
 #include "tnn/inference.hpp"
 #include "tnn/legacy.hpp"
@@ -218,6 +219,56 @@ TEST(matmul_every_float_dtype_cpu) {
     Tensor y = matmul(*dtype_cast(*a, dt), *dtype_cast(*bt, dt), false, true);
     CHECK(y->data_type() == dt && max_abs_diff(*y, *ref) < (dt == DType_t::FP64 ? 1e-6 : dt == DType_t::FP16 ? 2e-2 : 1e-1));
   }
+}
+TEST(legacy_matrix_value_semantics) {
+  // the legacy 2-D value type (include/matrix/matrix.hpp of the reference): deep copies, +, -, scalar * and /, product, reshape / resize
+  Matrix<float> a(2, 3), b(2, 3);
+  for (size_t r = 0; r < 2; ++r)
+    for (size_t c = 0; c < 3; ++c) {
+      a(r, c) = (float)(r * 3 + c);
+      b(r, c) = 1.f;
+    }
+  Matrix<float> s = a + b, d = a - b, k = a * 2.f, h = a / 2.f, k2 = 3.f * a;
+  CHECK_NEAR(s(1, 2), 6.0, 0);
+  CHECK_NEAR(d(0, 0), -1.0, 0);
+  CHECK_NEAR(k(1, 1), 8.0, 0);
+  CHECK_NEAR(h(1, 0), 1.5, 0);
+  CHECK_NEAR(k2(0, 2), 6.0, 0);
+  Matrix<float> copy = a;                                     // value semantics: the copy owns its storage
+  copy(0, 0) = 42.f;
+  CHECK_NEAR(a(0, 0), 0.0, 0);
+  a += b;
+  a -= b;
+  CHECK_NEAR(a(1, 2), 5.0, 0);
+  Matrix<float> bt(3, 2);
+  for (size_t r = 0; r < 3; ++r)
+    for (size_t c = 0; c < 2; ++c) bt(r, c) = (float)(r + c);
+  Matrix<float> p = a * bt;                                   // [2, 3] x [3, 2]
+  CHECK(p.rows() == 2 && p.cols() == 2);
+  CHECK_NEAR(p(0, 0), 0 * 0 + 1 * 1 + 2 * 2, 1e-5);
+  CHECK_NEAR(p(1, 1), 3 * 1 + 4 * 2 + 5 * 3, 1e-5);
+  Matrix<float> r = a.reshape(3, 2);
+  CHECK(r.rows() == 3 && r(2, 1) == 5.f);
+  bool threw = false;
+  try { a.reshape(4, 2); } catch (const std::invalid_argument&) { threw = true; }
+  CHECK(threw);
+  threw = false;
+  try { a + bt; } catch (const std::invalid_argument&) { threw = true; }
+  CHECK(threw);
+  threw = false;
+  try { a / 0.f; } catch (const std::invalid_argument&) { threw = true; }
+  CHECK(threw);
+  a.resize(4, 4);
+  CHECK(a.rows() == 4 && a.size() == 16 && a(3, 3) == 0.f);
+  Matrix<float> e;
+  CHECK(e.rows() == 0 && e.size() == 0 && (e + e).size() == 0);
+  Matrix<double> dd(2, 2);
+  dd.fill(0.5);
+  Matrix<double> pd = dd * dd;
+  CHECK_NEAR(pd(1, 1), 0.5, 1e-12);
+  Matrix<float> u(8, 8);
+  u.fill_random_uniform(0.25f, 7);
+  CHECK(u.tensor()->min() >= -0.25 && u.tensor()->max() <= 0.25);
 }
 TEST(tensor_save_load_record) {
   Tensor t = make_tensor<float>({3, 5});
