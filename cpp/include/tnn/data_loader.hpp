@@ -135,6 +135,41 @@ class WiFiDataLoader : public BaseDataLoader {
   std::vector<float> xs_, ys_, fmean_, fstd_, tmean_, tstd_;
 };
 
+// Directory trees of JPEG images or their decoded caches (reference: image_data_loader.hpp + stb_image, tiny_imagenet_data_loader.hpp,
+// imagenet100_data_loader.hpp; Python host: data/loaders.py::ImageFolderDataLoader -- same layouts, same cache files).
+//   * `<path>/<split>_x.npy` (uint8 [N, S, S, 3]) + `<split>_y.npy` (int32 [N]): memory mapped, no decoding;
+//   * otherwise the tree: TinyImageNet (`train/<wnid>/images/*.JPEG`, `val/images` + `val/val_annotations.txt`, `wnids.txt`) or
+//     class-per-directory (`train/<class>/*`, `val/<class>/*`: ImageNet-100), decoded per batch on the thread pool by the
+//     baseline JPEG decoder of tnn/jpeg.hpp and resized (bilinear) to size x size.
+class ImageFolderDataLoader : public BaseDataLoader {
+ public:
+  ImageFolderDataLoader(size_t size, size_t classes, bool train) : train_(train) { sample_shape_ = {size, size, 3}; classes_ = classes; }
+  ~ImageFolderDataLoader() override;
+  bool load_data(const std::string& path) override;           // the dataset root
+  bool get_batch(size_t batch_size, Tensor& x, Tensor& y) override;
+  const std::vector<std::string>& class_names() const { return names_; }
+  bool uses_cache() const { return cache_x_ != nullptr; }
+
+ protected:
+  void fill_sample(size_t index, float* dst, int32_t* label) override;
+  bool train_;
+  std::vector<std::string> files_, names_;
+  std::vector<int32_t> labels_;
+  const uint8_t* cache_x_ = nullptr;       // mapped <split>_x.npy payload
+  const int32_t* cache_y_ = nullptr;
+  void* map_x_ = nullptr;
+  void* map_y_ = nullptr;
+  size_t map_x_bytes_ = 0, map_y_bytes_ = 0;
+};
+class TinyImageNetDataLoader : public ImageFolderDataLoader {
+ public:
+  explicit TinyImageNetDataLoader(bool train = true) : ImageFolderDataLoader(64, 200, train) {}
+};
+class ImageNet100DataLoader : public ImageFolderDataLoader {
+ public:
+  explicit ImageNet100DataLoader(bool train = true, size_t size = 224) : ImageFolderDataLoader(size, 100, train) {}
+};
+
 struct DataLoaderPair {
   std::unique_ptr<BaseDataLoader> train, val;
 };

@@ -461,6 +461,18 @@ DataLoaderPair DataLoaderFactory::create(const std::string& name, const std::str
     if (va->load_data(path + "/val.bin")) p.val = std::move(va);
     return p;
   }
+  if (name == "tiny_imagenet" || name == "imagenet100") {
+    const bool tiny = name == "tiny_imagenet";
+    auto mk = [&](bool train) -> std::unique_ptr<ImageFolderDataLoader> {
+      if (tiny) return std::make_unique<TinyImageNetDataLoader>(train);
+      return std::make_unique<ImageNet100DataLoader>(train);
+    };
+    auto tr = mk(true), va = mk(false);
+    if (!tr->load_data(path)) throw std::runtime_error("DataLoaderFactory: no image tree or .npy cache under " + path);
+    p.train = std::move(tr);
+    if (va->load_data(path)) p.val = std::move(va);
+    return p;
+  }
   if (name == "regression" || name == "wifi" || name == "uji") {
     const bool wifi = name != "regression";
     auto mk = [&](const std::string& f) -> std::unique_ptr<BaseDataLoader> {

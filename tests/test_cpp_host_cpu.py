@@ -383,3 +383,80 @@ def test_cpp_gpt2_engine_matches_the_python_engine_and_runs_the_new_apps():
                         (["op_bench", "serialization", "--device", "CPU", "--iters", "2"], "serialize_GBps")):
         out = subprocess.run([os.path.join(bins, cmd[0])] + cmd[1:], capture_output=True, text=True, timeout=300, env=env, cwd=str(ROOT))
         assert out.returncode == 0 and needle in out.stdout, (cmd, out.stdout[-800:], out.stderr[-800:])
+
+
+def test_cpp_jpeg_decoder_and_image_tree_loaders(tmp_path):
+    """The C++ host's own baseline JPEG decoder (cpp/include/tnn/jpeg.hpp) against libjpeg (PIL) on 4:4:4 / 4:2:2 / 4:2:0, odd
+    sizes, grayscale, restart markers; progressive files are refused; the TinyImageNet-layout and class-per-directory loaders
+    return the batches of the Python ImageFolderDataLoader, from the JPEG tree and from the .npy cache it writes."""
+    import numpy as np
+    Image = pytest.importorskip("PIL.Image")
+    from tnn_b200.data.loaders import ImageFolderDataLoader
+    exe = os.path.join(ROOT, "cpp", "bin", "jpeg_decode")
+    rng = np.random.default_rng(0)
+
+    def picture(h, w):
+        y, x = np.mgrid[0:h, 0:w]
+        img = np.stack([128 + 100 * np.sin(x / 7.0) * np.cos(y / 9.0), 128 + 90 * np.cos(x / 5.0 + y / 11.0), 60 + 1.5 * x + 0.8 * y], -1)
+        return np.clip(img + rng.normal(0, 6, img.shape), 0, 255).astype(np.uint8)
+
+    cases = [(64, 64, 0, 95, {}), (37, 53, 1, 60, {}), (100, 81, 2, 85, {}), (72, 88, 2, 85, dict(restart_marker_blocks=4))]
+    for i, (h, w, sub, q, extra) in enumerate(cases):
+        f = str(tmp_path / f"c{i}.jpg")
+        Image.fromarray(picture(h, w)).save(f, quality=q, subsampling=sub, **extra)
+        r = subprocess.run([exe, f, f + ".rgb"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        W, H = map(int, r.stdout.split())
+        got = np.fromfile(f + ".rgb", dtype=np.uint8).reshape(H, W, 3).astype(int)
+        ref = np.asarray(Image.open(f).convert("RGB")).astype(int)
+        assert np.abs(got - ref).max() <= 4 and np.abs(got - ref).mean() < 0.2, (h, w, sub, q)
+    g = str(tmp_path / "gray.jpg")
+    Image.fromarray(picture(40, 40)).convert("L").save(g, quality=90)
+    assert subprocess.run([exe, g, g + ".rgb"], capture_output=True).returncode == 0
+    gg = np.fromfile(g + ".rgb", dtype=np.uint8).reshape(40, 40, 3)
+    assert (gg[..., 0] == gg[..., 1]).all() and np.abs(gg[..., 0].astype(int) - np.asarray(Image.open(g)).astype(int)).max() <= 2
+    p = str(tmp_path / "prog.jpg")
+    Image.fromarray(picture(32, 32)).save(p, progressive=True)
+    r = subprocess.run([exe, p, p + ".rgb"], capture_output=True, text=True)
+    assert r.returncode == 1 and "progressive" in r.stderr
+
+    # TinyImageNet layout: train/<wnid>/images/*.JPEG, val/images + val_annotations.txt, wnids.txt
+    root = tmp_path / "tiny"
+    wnids = ["n001", "n002", "n003"]
+    (root / "val" / "images").mkdir(parents=True)
+    (root / "wnids.txt").write_text("\n".join(wnids) + "\n")
+    ann = []
+    for ci, wn in enumerate(wnids):
+        d = root / "train" / wn / "images"
+        d.mkdir(parents=True)
+        for k in range(3):
+            Image.fromarray(picture(64, 64)).save(str(d / f"{wn}_{k}.JPEG"), quality=92, subsampling=ci % 3)
+        Image.fromarray(picture(64, 64)).save(str(root / "val" / "images" / f"val_{ci}.JPEG"), quality=92)
+        ann.append(f"val_{ci}.JPEG\t{wn}\t0\t0\t63\t63")
+    (root / "val" / "val_annotations.txt").write_text("\n".join(ann) + "\n")
+    for split, n in (("train", 9), ("val", 3)):
+        out = str(tmp_path / f"{split}.f32")
+        r = subprocess.run([exe, "--loader", str(root), "tiny_imagenet", split, "16", out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        vals = list(map(int, r.stdout.split()))
+        assert vals[0] == n and vals[1] == 3 and vals[2] == 0
+        py = ImageFolderDataLoader(64, 200).load_data(str(root), split == "train")
+        xb, yb = py.get_batch(16)
+        assert vals[3:] == yb.tolist()
+        x = np.fromfile(out, dtype=np.float32).reshape(n, 64, 64, 3)
+        assert np.abs(x - xb.numpy()).max() <= 4.5 / 255
+    # the decoded cache the Python host writes is read back by the C++ loader without decoding
+    ImageFolderDataLoader(64, 200).cache(str(root), True)
+    out = str(tmp_path / "cache.f32")
+    r = subprocess.run([exe, "--loader", str(root), "tiny_imagenet", "train", "4", out], capture_output=True, text=True)
+    assert r.returncode == 0 and list(map(int, r.stdout.split()))[:3] == [9, 0, 1], (r.stdout, r.stderr)
+    xb, _ = ImageFolderDataLoader(64, 200).load_data(str(root), True).get_batch(4)
+    assert np.array_equal(np.fromfile(out, dtype=np.float32).reshape(4, 64, 64, 3), xb.numpy())
+    # class-per-directory layout with a resize (ImageNet-100 style)
+    root2 = tmp_path / "inet"
+    for cname in ("cat", "dog"):
+        (root2 / "train" / cname).mkdir(parents=True)
+        for k in range(2):
+            Image.fromarray(picture(48, 40)).save(str(root2 / "train" / cname / f"{k}.jpg"), quality=90)
+    r = subprocess.run([exe, "--loader", str(root2), "imagenet100", "train", "8", str(tmp_path / "i.f32")], capture_output=True, text=True)
+    assert r.returncode == 0 and list(map(int, r.stdout.split())) == [4, 2, 0, 0, 0, 1, 1], (r.stdout, r.stderr)
