@@ -223,6 +223,7 @@ inline bool decode(const uint8_t* data, size_t n, Image* out, std::string* err) 
       W = u16(pos + 5);
       const int nc = seg[5];
       if (W <= 0 || H <= 0 || (nc != 1 && nc != 3) || sl < 6 + 3 * nc) return fail("unsupported frame header (components: " + std::to_string(nc) + ")");
+      if ((long long)W * H > 100ll * 1000 * 1000) return fail("image larger than 100 megapixels");     // a damaged header must not allocate gigabytes
       comps.resize(nc);
       for (int k = 0; k < nc; ++k) {
         comps[k].id = seg[6 + 3 * k];
