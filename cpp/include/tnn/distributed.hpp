@@ -230,6 +230,11 @@ class Worker {
   void set_config(const StageConfig& cfg); // rebuild the stage from JSON (worker.hpp:98-130)
   Graph* graph() { return graph_.get(); }
   std::function<void(Message&)> fault_inject;     // tests: drop / delay / throw
+  // Directories a peer may name in SAVE_TO_FILE / LOAD_PARAMS / CHECKPOINT_REQUEST (the bus is unauthenticated): the working
+  // directory, the system temp directory and TNN_WORKER_IO_ROOT (':'-separated), as in the Python worker.  Throws on a path
+  // that resolves (symlinks and ".." included) outside every root.
+  std::string checked_path(const std::string& path) const;
+  const std::vector<std::string>& io_roots() const { return io_roots_; }
 
  private:
   void process(Message& m);
@@ -246,6 +251,7 @@ class Worker {
   std::atomic<bool> stop_{false};
   uint64_t jobs_ = 0;
   int64_t busy_ns_ = 0;
+  std::vector<std::string> io_roots_;
 };
 
 // ------------------------------------------------------------------------------------- coordinator

@@ -1,5 +1,6 @@
 // Distributed runtime: messages, communicators, partitioners, worker, coordinator, distributed trainer.
 #include <chrono>
+#include <filesystem>
 #include <iostream>
 #include <sstream>
 
@@ -315,7 +316,37 @@ Vec<SeqPartition> FTDPartitioner::partition_model(const Vec<Layer*>& layers, con
 }
 
 // ===================================================================================== worker
-Worker::Worker(std::unique_ptr<Communicator> comm, const Device& dev, const std::string& name) : comm_(std::move(comm)), dev_(dev), name_(name) {}
+Worker::Worker(std::unique_ptr<Communicator> comm, const Device& dev, const std::string& name) : comm_(std::move(comm)), dev_(dev), name_(name) {
+  namespace fs = std::filesystem;
+  std::error_code ec;
+  auto add_root = [&](const fs::path& p) {
+    if (p.empty()) return;
+    fs::path r = fs::weakly_canonical(p, ec);
+    if (!ec && !r.empty()) io_roots_.push_back(r.string());
+  };
+  add_root(fs::current_path(ec));
+  add_root(fs::temp_directory_path(ec));
+  if (const char* extra = std::getenv("TNN_WORKER_IO_ROOT")) {
+    std::stringstream ss(extra);
+    std::string item;
+    while (std::getline(ss, item, ':')) add_root(item);
+  }
+}
+std::string Worker::checked_path(const std::string& path) const {
+  namespace fs = std::filesystem;
+  std::error_code ec;
+  // weakly_canonical resolves symlinks of the existing prefix and normalises "." / ".." of the rest
+  const std::string real = fs::weakly_canonical(fs::absolute(path, ec), ec).string();
+  if (!ec)
+    for (const std::string& root : io_roots_) {
+      std::string r = root;
+      while (r.size() > 1 && r.back() == '/') r.pop_back();
+      if (real == r || (real.size() > r.size() && real.compare(0, r.size(), r) == 0 && (r == "/" || real[r.size()] == '/'))) return real;
+    }
+  std::string roots;
+  for (const std::string& r : io_roots_) roots += (roots.empty() ? "" : ", ") + r;
+  throw std::runtime_error("worker " + name_ + ": path '" + path + "' is outside the allowed I/O roots [" + roots + "] (extend with TNN_WORKER_IO_ROOT)");
+}
 Worker::~Worker() { stop(); }
 void Worker::start(bool background) {
   comm_->start();
@@ -427,10 +458,11 @@ void Worker::process(Message& m) {
       for (const auto& e : GlobalProfiler::get_profiler().events()) std::cout << "[" << name_ << "] " << e.name << " " << (e.end_ns - e.start_ns) / 1e6 << " ms\n";
       reply(Message(CommandType::PROFILING_PRINTED, true));
       break;
-    case CommandType::SAVE_TO_FILE: graph_->save_state(m.str + ".stage" + std::to_string(cfg_.stage_id)); break;
+    case CommandType::SAVE_TO_FILE: graph_->save_state(checked_path(m.str + ".stage" + std::to_string(cfg_.stage_id))); break;
     case CommandType::LOAD_PARAMS: {
-      std::ifstream f(m.str, std::ios::binary);
-      if (!f) throw std::runtime_error("cannot open " + m.str);
+      const std::string path = checked_path(m.str);
+      std::ifstream f(path, std::ios::binary);
+      if (!f) throw std::runtime_error("cannot open " + path);
       std::stringstream ss;
       ss << f.rdbuf();
       const std::string data = ss.str();
@@ -466,7 +498,7 @@ void Worker::process(Message& m) {
       break;
     }
     case CommandType::CHECKPOINT_REQUEST: {
-      const std::string p = m.str + ".stage" + std::to_string(cfg_.stage_id);
+      const std::string p = checked_path(m.str + ".stage" + std::to_string(cfg_.stage_id));
       save_checkpoint(*graph_, p, opt_.get(), sched_.get(), opt_ ? opt_->step_count : 0);
       reply(Message(CommandType::CHECKPOINT_COMPLETE, p));
       break;

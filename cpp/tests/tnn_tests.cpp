@@ -744,6 +744,26 @@ static void pipeline_case(int transport, const Device& dev = getHost(), double t
   co.stop();
   for (auto& w : workers) w->stop();
 }
+TEST(worker_refuses_paths_outside_its_io_roots) {
+  // SAVE_TO_FILE / LOAD_PARAMS / CHECKPOINT_REQUEST arrive over an unauthenticated bus: only the working directory, the
+  // temp directory and TNN_WORKER_IO_ROOT may be named
+  Worker w(std::make_unique<InProcessCommunicator>("w"), getHost(), "w");
+  CHECK(w.io_roots().size() >= 2);
+  CHECK(w.checked_path("/tmp/tnn_tests_ok/model.stage0").rfind("/tmp/", 0) == 0 || w.checked_path("/tmp/tnn_tests_ok/model.stage0").find("tnn_tests_ok") != std::string::npos);
+  CHECK(!w.checked_path("relative_snapshot").empty());
+  auto refused = [&](const std::string& p) {
+    try {
+      w.checked_path(p);
+    } catch (const std::runtime_error&) {
+      return true;
+    }
+    return false;
+  };
+  CHECK(refused("/etc/passwd"));
+  CHECK(refused("/tmp/../etc/cron.d/x"));
+  CHECK(refused("../../../../../../etc/shadow"));
+  CHECK(refused("/tmpfoo/model"));                      // a root is a directory prefix, not a string prefix
+}
 TEST(in_process_pipeline_equals_single_device) { pipeline_case(0); }
 TEST(tcp_pipeline_equals_single_device) { pipeline_case(1); }
 TEST(roce_pipeline_equals_single_device) { pipeline_case(2); }

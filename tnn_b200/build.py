@@ -167,8 +167,10 @@ def build_host(force: bool = False, verbose: bool = True) -> dict:
     lib = lib_dir / "libtnn_b200.so"
     lib_objs = [obj_dir / (s.stem + ".o") for s in sorted((CPP / "src").glob("*.cpp"))]
     cu_objs = sorted(BUILD.glob("*.cu.o"))
-    newest_cu = max(o.stat().st_mtime for o in cu_objs)
-    if rebuilt or not lib.exists() or lib.stat().st_mtime < newest_cu:
+    # link decisions look at the objects' mtimes, not only at "compiled in this call": an interrupted build leaves fresh
+    # objects (with their stamps) next to a stale library / executable
+    newest_in = max(o.stat().st_mtime for o in cu_objs + lib_objs)
+    if rebuilt or not lib.exists() or lib.stat().st_mtime < newest_in:
         link = ["g++", "-shared", "-o", str(lib), *map(str, lib_objs), *map(str, cu_objs), f"-L{cuda}/lib64", "-lcudart",
                 f"-Wl,-rpath,{cuda}/lib64", "-pthread", "-ldl"]
         r = subprocess.run(link, capture_output=True, text=True)
@@ -185,7 +187,7 @@ def build_host(force: bool = False, verbose: bool = True) -> dict:
     bcmd = gxx + [f"-I{pybind11.get_include()}", f"-I{sysconfig.get_paths()['include']}", "-fvisibility=hidden"]
     bstamp = hashlib.sha256(bsrc.read_bytes() + hdr.hexdigest().encode() + _flag_sig(bcmd).encode()).hexdigest()
     _, bdid, _ = _compile_one(bsrc, bcmd, bobj, bstamp)
-    if bdid or rebuilt or not host_so.exists():
+    if bdid or rebuilt or not host_so.exists() or host_so.stat().st_mtime < max(bobj.stat().st_mtime, lib.stat().st_mtime):
         link = ["g++", "-shared", "-o", str(host_so), str(bobj), f"-L{lib_dir}", "-ltnn_b200", f"-L{cuda}/lib64", "-lcudart",
                 "-Wl,-rpath,$ORIGIN/../cpp/lib", f"-Wl,-rpath,{cuda}/lib64", "-pthread"]
         r = subprocess.run(link, capture_output=True, text=True)
@@ -196,7 +198,7 @@ def build_host(force: bool = False, verbose: bool = True) -> dict:
     exes = {"_host": host_so}
     for s in sorted((CPP / "examples").glob("*.cpp")) + sorted((CPP / "tests").glob("*.cpp")):
         exe = bin_dir / s.stem
-        if rebuilt or not exe.exists():
+        if rebuilt or not exe.exists() or exe.stat().st_mtime < max((obj_dir / (s.stem + ".o")).stat().st_mtime, lib.stat().st_mtime):
             link = ["g++", "-o", str(exe), str(obj_dir / (s.stem + ".o")), f"-L{lib_dir}", "-ltnn_b200", f"-L{cuda}/lib64", "-lcudart",
                     "-Wl,-rpath,$ORIGIN/../lib", f"-Wl,-rpath,{cuda}/lib64", "-pthread"]
             r = subprocess.run(link, capture_output=True, text=True)
