@@ -15,6 +15,7 @@
 #include <mutex>
 #include <vector>
 
+#include "runtime/symmetric_memory.hpp"
 #include "tnn/device.hpp"
 
 namespace tnn {
@@ -130,6 +131,29 @@ class DELAllocatorV2 : public IAllocator {
   std::map<void*, Block> live_;
   std::mutex mu_;
   size_t in_use_ = 0, reserved_ = 0, peak_ = 0;
+};
+
+// One rank's view of a SymmetricMemory group (runtime/symmetric_memory.hpp: cuMemCreate + peer mappings + NVLS multicast
+// window): blocks come out of the rank's slab, so peer(p, q) / multicast(p) translate a block to the same offset in rank
+// q's slab / in the switch-reduced window.  This is the reference's "registered slab" allocator (ibv_allocator.hpp) with
+// NVLink instead of a NIC on the other side.
+class SymmetricAllocator : public IAllocator {
+ public:
+  SymmetricAllocator(std::shared_ptr<SymmetricMemory> group, int rank) : group_(std::move(group)), rank_(rank), dev_(DeviceType::GPU, group_->device_of(rank)) {}
+  void* allocate(size_t bytes) override { return group_->allocate(rank_, bytes); }
+  void deallocate(void* p) override { group_->deallocate(rank_, p); }
+  const Device& device() const override { return dev_; }
+  size_t bytes_in_use() const override { return group_->free_list(rank_).in_use(); }
+  size_t bytes_reserved() const override { return group_->bytes(); }
+  int rank() const { return rank_; }
+  SymmetricMemory& group() { return *group_; }
+  void* peer(const void* p, int other) const { return group_->peer(rank_, p, other); }
+  void* multicast(const void* p) const { return group_->multicast(rank_, p); }      // nullptr without NVLS
+
+ private:
+  std::shared_ptr<SymmetricMemory> group_;
+  int rank_;
+  Device dev_;
 };
 
 }  // namespace tnn

@@ -5,6 +5,10 @@
 // (Reference: ParallelMode_t::DATA exists only as routing, SURVEY F4 -- there is no gradient reduction to mirror.)
 // The Python host runs the same kernel with one process per GPU (parallel/dp.py, NVLS multicast through symmetric memory);
 // inside one process the peers' device pointers are directly usable after cudaDeviceEnablePeerAccess.
+// TNN_DP_NVLS=1 (or symmetric = true) puts every replica's parameter / gradient / bf16 slabs and flag words into the
+// framework's own SymmetricMemory group (cuMemCreate + peer mappings + cuMulticast window, runtime/symmetric_memory.hpp):
+// the kernel then pulls the gradient SUM from the switch (multimem.ld_reduce) and broadcasts the new parameters with
+// multimem.st instead of W - 1 peer loads / stores per element.
 #pragma once
 #include <functional>
 #include <memory>
@@ -20,11 +24,13 @@ class DataParallel {
   using ModelFactory = std::function<std::unique_ptr<Layer>()>;
   // `world` replicas on GPU 0..world-1; the same seed initialises every replica identically
   DataParallel(const ModelFactory& make_model, int world, uint64_t seed, const Optimizer& optimizer_proto, const std::string& loss = "logsoftmax_crossentropy",
-               bool use_graph = true);
+               bool use_graph = true, int symmetric = -1 /* -1: TNN_DP_NVLS, 0: plain peer memory, 1: SymmetricMemory (+ NVLS) */);
   ~DataParallel();
   // xs[r] / ys[r]: replica r's batch (host, ideally pinned).  Returns {mean loss over replicas, total #correct}.
   std::pair<double, double> step(const Vec<Tensor>& xs, const Vec<Tensor>& ys);
   int world() const { return (int)ranks_.size(); }
+  bool symmetric() const { return symm_ != nullptr; }               // slabs live in the own VMM group
+  bool multicast() const { return g_mc_ != nullptr; }               // ... and the NVLS window is bound
   Graph& replica(int r) { return *ranks_.at((size_t)r)->graph; }
   size_t num_parameters() const { return n_; }
   // max over replicas r > 0 of max |param_r - param_0| (replicas must stay bit-identical)
@@ -41,6 +47,12 @@ class DataParallel {
     Tensor m, v, flags, sync;
   };
   void launch_fused_step(int r);
+  // declared before ranks_: the replicas' slabs are freed through these allocators
+  std::shared_ptr<SymmetricMemory> symm_;
+  std::vector<std::unique_ptr<SymmetricAllocator>> symm_alloc_;
+  const float* g_mc_ = nullptr;
+  float* p_mc_ = nullptr;
+  void* pb_mc_ = nullptr;
   std::vector<std::unique_ptr<Rank>> ranks_;
   size_t n_ = 0, chunk_ = 0;
   bool adam_ = true;

@@ -71,7 +71,11 @@ class GraphBuilder {
 
 class GraphContext {
  public:
-  GraphContext(const Vec<Layer*>& layers, const Device& dev);
+  // `slabs`: where the four slabs come from (default: the device allocator).  A SymmetricAllocator puts them into
+  // peer-addressable / switch-reducible memory (data_parallel.hpp); the allocation order is params, grads, buffers, bf16.
+  GraphContext(const Vec<Layer*>& layers, const Device& dev, IAllocator* slabs = nullptr);
+  // bytes the slabs of these layers take from `slabs` (each rounded up to 256 bytes): sizes a symmetric slab up front
+  static size_t slab_bytes(const Vec<Layer*>& layers, bool gpu);
   const Device& device() const { return dev_; }
   Tensor& param_slab() { return param_slab_; }
   Tensor& grad_slab() { return grad_slab_; }
@@ -104,7 +108,7 @@ class GraphContext {
 
 class Graph {
  public:
-  Graph(GraphBuilder&& b, const Device& dev, uint64_t seed);
+  Graph(GraphBuilder&& b, const Device& dev, uint64_t seed, IAllocator* slabs = nullptr);
   Graph(Graph&&) = default;
   const std::string& name() const { return name_; }
   void set_name(const std::string& n) { name_ = n; }
@@ -157,6 +161,6 @@ class GraphExecutor {
 };
 
 // input -> [model] -> output, the shape every zoo model uses (example_models.hpp:49-84)
-Graph graph_from_sequential(std::unique_ptr<Layer> model, const Device& dev, uint64_t seed = 0, const std::string& name = "");
+Graph graph_from_sequential(std::unique_ptr<Layer> model, const Device& dev, uint64_t seed = 0, const std::string& name = "", IAllocator* slabs = nullptr);
 
 }  // namespace tnn

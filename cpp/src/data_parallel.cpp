@@ -9,15 +9,30 @@
 
 namespace tnn {
 
-DataParallel::DataParallel(const ModelFactory& make_model, int world, uint64_t seed, const Optimizer& proto, const std::string& loss, bool use_graph) {
+DataParallel::DataParallel(const ModelFactory& make_model, int world, uint64_t seed, const Optimizer& proto, const std::string& loss, bool use_graph, int symmetric) {
   auto& dm = DeviceManager::getInstance();
   if (world < 1 || world > dm.num_gpus()) throw std::invalid_argument("DataParallel: " + std::to_string(world) + " replicas requested, " + std::to_string(dm.num_gpus()) + " GPU(s) visible");
   adam_ = proto.name() == "adam";
+  if (symmetric < 0) {
+    const char* e = std::getenv("TNN_DP_NVLS");
+    symmetric = e && e[0] == '1';
+  }
+  constexpr size_t kFlagWords = 64;
+  if (symmetric && world > 1) {
+    // one VMM slab per replica, sized for its four parameter slabs + the flag words; explicitly requested, so a box that
+    // cannot provide it is an error, not a silent fall-back to peer loads
+    std::vector<int> devs;
+    for (int r = 0; r < world; ++r) devs.push_back(dm.getGPU(r).id());
+    const std::unique_ptr<Layer> probe = make_model();
+    const size_t need = GraphContext::slab_bytes(probe->all_layers(), true) + 4096;
+    symm_ = std::make_shared<SymmetricMemory>(devs, need, /*want_multicast=*/true);
+    for (int r = 0; r < world; ++r) symm_alloc_.push_back(std::make_unique<SymmetricAllocator>(symm_, r));
+  }
   for (int r = 0; r < world; ++r) {
     auto rk = std::make_unique<Rank>();
     rk->dev = dm.getGPU(r);
     rk->dev.set_current();
-    rk->graph = std::make_unique<Graph>(graph_from_sequential(make_model(), rk->dev, seed, "dp_replica" + std::to_string(r)));
+    rk->graph = std::make_unique<Graph>(graph_from_sequential(make_model(), rk->dev, seed, "dp_replica" + std::to_string(r), symm_ ? symm_alloc_[(size_t)r].get() : nullptr));
     rk->opt = proto.clone();
     rk->loss = LossFactory::create(loss);
     ranks_.push_back(std::move(rk));
@@ -44,7 +59,7 @@ DataParallel::DataParallel(const ModelFactory& make_model, int world, uint64_t s
       k.v = make_tensor(DType_t::FP32, {chunk_}, k.dev);
       k.v->zero();
     }
-    k.flags = make_tensor(DType_t::INT32_T, {64}, k.dev);
+    k.flags = symm_ ? make_tensor(*symm_alloc_[g_peers_.size()], DType_t::INT32_T, {kFlagWords}) : make_tensor(DType_t::INT32_T, {kFlagWords}, k.dev);
     k.flags->zero();
     k.sync = make_tensor(DType_t::INT32_T, {4}, k.dev);
     k.sync->zero();
@@ -54,6 +69,18 @@ DataParallel::DataParallel(const ModelFactory& make_model, int world, uint64_t s
     flag_peers_.push_back(reinterpret_cast<uint32_t*>(k.flags->data()));
     StepState::get(k.dev);                                  // created before the replica threads start
     current_flow(k.dev).synchronize();
+  }
+  if (symm_) {
+    // "symmetric" = one offset addresses the same slab in every replica (and in the multicast window)
+    for (int r = 1; r < world; ++r)
+      if (symm_->offset_of(r, g_peers_[(size_t)r]) != symm_->offset_of(0, g_peers_[0]) || symm_->offset_of(r, p_peers_[(size_t)r]) != symm_->offset_of(0, p_peers_[0]) ||
+          symm_->offset_of(r, pb_peers_[(size_t)r]) != symm_->offset_of(0, pb_peers_[0]))
+        throw std::logic_error("DataParallel: replicas allocated their slabs at different offsets of the symmetric group");
+    if (symm_->has_multicast()) {
+      g_mc_ = static_cast<const float*>(symm_->multicast(0, g_peers_[0]));
+      p_mc_ = static_cast<float*>(symm_->multicast(0, p_peers_[0]));
+      pb_mc_ = symm_->multicast(0, pb_peers_[0]);
+    }
   }
   for (int r = 0; r < world; ++r) {
     Rank& k = *ranks_[(size_t)r];
@@ -71,7 +98,7 @@ DataParallel::~DataParallel() {
 void DataParallel::launch_fused_step(int r) {
   Rank& k = *ranks_[(size_t)r];
   k.dev.set_current();
-  dp_fused_step(world(), r, (long long)n_, (long long)chunk_, g_peers_.data(), p_peers_.data(), pb_peers_.data(), flag_peers_.data(), nullptr, nullptr, nullptr,
+  dp_fused_step(world(), r, (long long)n_, (long long)chunk_, g_peers_.data(), p_peers_.data(), pb_peers_.data(), flag_peers_.data(), g_mc_, p_mc_, pb_mc_,
                 k.m->data_as<float>(), adam_ ? k.v->data_as<float>() : nullptr, reinterpret_cast<uint32_t*>(k.sync->data()), StepState::get(k.dev).dev(), adam_ ? 1 : 0,
                 /*ctas=*/64, 0, (long long)n_, 0, current_flow(k.dev).stream());
   k.graph->context().mark_lp_fresh();                       // the kernel rewrote the bf16 copies of every replica

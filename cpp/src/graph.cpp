@@ -65,10 +65,13 @@ Vec<Edge> GraphBuilder::topo_sort() const {
   return order;
 }
 Graph GraphBuilder::compile(const Device& dev, uint64_t seed) { return Graph(std::move(*this), dev, seed); }
-Graph GraphBuilder::compile(IAllocator& allocator, uint64_t seed) { return Graph(std::move(*this), allocator.device(), seed); }
+// the reference signature (graph_builder.hpp compile(allocator)): the parameter / gradient slabs come from `allocator`
+Graph GraphBuilder::compile(IAllocator& allocator, uint64_t seed) { return Graph(std::move(*this), allocator.device(), seed, &allocator); }
 
 // ===================================================================================== context
-GraphContext::GraphContext(const Vec<Layer*>& layers, const Device& dev) : dev_(dev), layers_(layers) {
+GraphContext::GraphContext(const Vec<Layer*>& layers, const Device& dev, IAllocator* slabs) : dev_(dev), layers_(layers) {
+  if (slabs && slabs->device() != dev) throw std::invalid_argument("GraphContext: the slab allocator serves " + slabs->device().name() + ", the graph lives on " + dev.name());
+  auto slab = [&](DType_t dt, size_t n) { return slabs ? make_tensor(*slabs, dt, {n}) : make_tensor(dt, {n}, dev); };
   size_t off = 0, boff = 0;
   auto aligned = [](size_t n) { return (n + ALIGN_ELEMS - 1) / ALIGN_ELEMS * ALIGN_ELEMS; };
   for (Layer* l : layers)
@@ -84,14 +87,14 @@ GraphContext::GraphContext(const Vec<Layer*>& layers, const Device& dev) : dev_(
     }
   numel_ = off;
   const size_t pn = std::max(off, ALIGN_ELEMS), bn = std::max(boff, ALIGN_ELEMS);
-  param_slab_ = make_tensor(DType_t::FP32, {pn}, dev);
-  grad_slab_ = make_tensor(DType_t::FP32, {pn}, dev);
-  buffer_slab_ = make_tensor(DType_t::FP32, {bn}, dev);
+  param_slab_ = slab(DType_t::FP32, pn);
+  grad_slab_ = slab(DType_t::FP32, pn);
+  buffer_slab_ = slab(DType_t::FP32, bn);
   param_slab_->zero();
   grad_slab_->zero();
   buffer_slab_->zero();
   if (dev.is_gpu()) {
-    lp_slab_ = make_tensor(DType_t::BF16, {pn}, dev);
+    lp_slab_ = slab(DType_t::BF16, pn);
     lp_slab_->zero();
   }
   for (const auto& e : entries_) {
@@ -112,6 +115,15 @@ GraphContext::GraphContext(const Vec<Layer*>& layers, const Device& dev) : dev_(
     }
   }
   refresh_lp();
+}
+size_t GraphContext::slab_bytes(const Vec<Layer*>& layers, bool gpu) {
+  size_t off = 0, boff = 0;
+  auto aligned = [](size_t n) { return (n + ALIGN_ELEMS - 1) / ALIGN_ELEMS * ALIGN_ELEMS; };
+  for (Layer* l : layers)
+    for (const auto& d : l->param_descriptors()) (d.trainable ? off : boff) += aligned(shape_numel(d.shape));
+  const size_t pn = std::max(off, ALIGN_ELEMS), bn = std::max(boff, ALIGN_ELEMS);
+  auto r256 = [](size_t b) { return (b + 255) / 256 * 256; };
+  return 2 * r256(pn * 4) + r256(bn * 4) + (gpu ? r256(pn * 2) : 0);
 }
 size_t GraphContext::num_parameters() const {
   size_t n = 0;
@@ -148,7 +160,7 @@ Vec<std::pair<std::string, Tensor>> GraphContext::parameters() const {
 }
 
 // ===================================================================================== graph
-Graph::Graph(GraphBuilder&& b, const Device& dev, uint64_t seed) : name_(b.name_), dev_(dev) {
+Graph::Graph(GraphBuilder&& b, const Device& dev, uint64_t seed, IAllocator* slabs) : name_(b.name_), dev_(dev) {
   edges_ = b.topo_sort();
   io_nodes_ = std::move(b.io_nodes_);
   op_nodes_ = std::move(b.op_nodes_);
@@ -158,7 +170,7 @@ Graph::Graph(GraphBuilder&& b, const Device& dev, uint64_t seed) : name_(b.name_
     auto all = n->layer()->all_layers();
     flat.insert(flat.end(), all.begin(), all.end());
   }
-  ctx_ = std::make_unique<GraphContext>(flat, dev);
+  ctx_ = std::make_unique<GraphContext>(flat, dev, slabs);
 }
 void Graph::set_training(bool f) {
   for (auto& n : op_nodes_) n->layer()->set_training(f);
@@ -276,13 +288,13 @@ Graph Graph::load_state(const std::string& path, const Device& dev, std::map<std
   return load_state(f, dev, tensors, meta);
 }
 
-Graph graph_from_sequential(std::unique_ptr<Layer> model, const Device& dev, uint64_t seed, const std::string& name) {
+Graph graph_from_sequential(std::unique_ptr<Layer> model, const Device& dev, uint64_t seed, const std::string& name, IAllocator* slabs) {
   GraphBuilder b(name.empty() ? model->name() : name);
   b.io("input");
   b.io("output");
   OpNode& n = b.add_layer(std::move(model), "model");
   b.add_edge({"input"}, {"output"}, n);
-  return b.compile(dev, seed);
+  return Graph(std::move(b), dev, seed, slabs);
 }
 
 // ===================================================================================== executor

@@ -12,13 +12,14 @@
 #include <map>
 #include <sstream>
 
+#include "runtime/symmetric_memory.hpp"
 #include "tnn/distributed.hpp"
 
 namespace tnn {
 
 namespace {
 enum : uint8_t { K_INLINE = 0, K_PREPARE = 1, K_READY = 2, K_DONE = 3, K_CANCEL = 4, K_GPREPARE = 5, K_GREADY = 6, K_GDONE = 7 };
-constexpr uint64_t kNoBlock = ~0ull;
+constexpr uint64_t kNoBlock = OffsetFreeList::kNone;
 constexpr size_t kHdr = 17;
 
 std::string host_token() {
@@ -82,52 +83,6 @@ std::vector<std::string> split(const std::string& s, char sep) {
 }  // namespace
 
 namespace {
-// first fit over a sorted free list, `align`-byte blocks, coalescing frees (the IbvAllocator role: one registered range)
-struct SlabRange {
-  std::map<uint64_t, uint64_t> free_list, live;            // offset -> length
-  uint64_t in_use = 0, peak = 0, align = 512;
-  void reset(uint64_t bytes) {
-    free_list.clear();
-    live.clear();
-    in_use = 0;
-    if (bytes) free_list[0] = bytes;
-  }
-  uint64_t alloc(uint64_t n) {
-    n = std::max<uint64_t>(align, (n + align - 1) / align * align);
-    for (auto it = free_list.begin(); it != free_list.end(); ++it)
-      if (it->second >= n) {
-        const uint64_t off = it->first, len = it->second;
-        free_list.erase(it);
-        if (len > n) free_list[off + n] = len - n;
-        live[off] = n;
-        in_use += n;
-        peak = std::max(peak, in_use);
-        return off;
-      }
-    return kNoBlock;
-  }
-  void release(uint64_t off) {
-    auto it = live.find(off);
-    if (it == live.end()) return;
-    uint64_t lo = off, len = it->second;
-    in_use -= len;
-    live.erase(it);
-    auto nx = free_list.lower_bound(lo);
-    if (nx != free_list.end() && nx->first == lo + len) {
-      len += nx->second;
-      nx = free_list.erase(nx);
-    }
-    if (nx != free_list.begin()) {
-      auto pv = std::prev(nx);
-      if (pv->first + pv->second == lo) {
-        lo = pv->first;
-        len += pv->second;
-        free_list.erase(pv);
-      }
-    }
-    free_list[lo] = len;
-  }
-};
 // a POSIX shared-memory segment under /dev/shm (the creator unlinks it)
 struct ShmSegment {
   std::string name;
@@ -170,17 +125,16 @@ struct RoCECommunicator::Impl {
   std::string token = host_token();
   // host slab: a shared-memory segment peers on this node write CPU messages into (PREPARE / READY_TO_WRITE / write / DONE)
   ShmSegment shm;
-  SlabRange hslab;
+  OffsetFreeList hslab{0, 256};              // best fit + coalescing (the IbvAllocator role: one registered range)
   std::map<std::string, ShmSegment> peer_shm;               // segment name -> mapping
   std::map<uint64_t, std::pair<std::vector<uint8_t>, std::string>> pending_host;   // id -> (serialised message, peer key)
   std::vector<std::tuple<std::string, uint64_t, uint64_t>> waiting;                // PREPAREs that did not fit yet
-  // device slab (first fit over a sorted free list, 512-byte blocks, coalescing frees)
+  // device slab (OffsetFreeList, 512-byte blocks)
   int dev = -1;
   uint8_t* dptr = nullptr;
   cudaIpcMemHandle_t handle{};
   std::mutex mu;
-  std::map<uint64_t, uint64_t> free_list;                  // offset -> length
-  std::map<uint64_t, uint64_t> live;                       // offset -> length
+  OffsetFreeList dslab{0, 512};
   std::vector<std::pair<cudaEvent_t, uint64_t>> released;  // blocks waiting for the consumer stream
   std::map<std::string, void*> opened;                     // peer ipc handle (hex) -> mapped base
   cudaStream_t copy_stream = nullptr;
@@ -191,43 +145,13 @@ struct RoCECommunicator::Impl {
   std::map<uint64_t, Pending> pending;
   uint64_t next_id = 1;
   Stats st;
-  uint64_t in_use = 0;
 
   uint64_t alloc(uint64_t n) {
-    n = std::max<uint64_t>(512, (n + 511) / 512 * 512);
-    for (auto it = free_list.begin(); it != free_list.end(); ++it)
-      if (it->second >= n) {
-        const uint64_t off = it->first, len = it->second;
-        free_list.erase(it);
-        if (len > n) free_list[off + n] = len - n;
-        live[off] = n;
-        in_use += n;
-        st.slab_peak = std::max(st.slab_peak, in_use);
-        return off;
-      }
-    return kNoBlock;
+    const uint64_t off = dslab.allocate(n);
+    st.slab_peak = std::max<uint64_t>(st.slab_peak, dslab.peak());
+    return off;
   }
-  void release(uint64_t off) {
-    auto it = live.find(off);
-    if (it == live.end()) return;
-    uint64_t lo = off, len = it->second;
-    in_use -= len;
-    live.erase(it);
-    auto nx = free_list.lower_bound(lo);
-    if (nx != free_list.end() && nx->first == lo + len) {
-      len += nx->second;
-      nx = free_list.erase(nx);
-    }
-    if (nx != free_list.begin()) {
-      auto pv = std::prev(nx);
-      if (pv->first + pv->second == lo) {
-        lo = pv->first;
-        len += pv->second;
-        free_list.erase(pv);
-      }
-    }
-    free_list[lo] = len;
-  }
+  void release(uint64_t off) { dslab.release(off); }
   void reap() {   // mu held
     for (size_t i = 0; i < released.size();) {
       if (released[i].first == nullptr || cudaEventQuery(released[i].first) == cudaSuccess) {
@@ -253,7 +177,7 @@ RoCECommunicator::~RoCECommunicator() { stop(); }
 RoCECommunicator::Stats RoCECommunicator::stats() const {
   std::lock_guard<std::mutex> g(impl_->mu);
   Stats s = impl_->st;
-  s.host_slab_peak = impl_->hslab.peak;
+  s.host_slab_peak = impl_->hslab.peak();
   return s;
 }
 
@@ -267,14 +191,13 @@ void RoCECommunicator::start() {
     RDV_CUDA(cudaMalloc(reinterpret_cast<void**>(&I.dptr), I.slab_bytes));
     RDV_CUDA(cudaIpcGetMemHandle(&I.handle, I.dptr));
     RDV_CUDA(cudaStreamCreateWithFlags(&I.copy_stream, cudaStreamNonBlocking));
-    I.free_list[0] = I.slab_bytes;
+    I.dslab.reset(I.slab_bytes);
   }
   if (I.host_slab_bytes > 0) {
     static std::atomic<unsigned> serial{0};
     char nm[64];
     snprintf(nm, sizeof(nm), "tnn_%08x%04x%04x", (unsigned)getpid(), serial.fetch_add(1) & 0xffffu, (unsigned)(Profiler::now_ns() & 0xffff));
     if (I.shm.open(nm, I.host_slab_bytes, true)) {
-      I.hslab.align = 256;
       I.hslab.reset(I.host_slab_bytes);
     }
   }
@@ -315,7 +238,7 @@ void RoCECommunicator::start() {
             const bool can = I.shm.base && tok == I.token && len <= I.host_slab_bytes;
             if (can) {
               std::lock_guard<std::mutex> g(I.mu);
-              off = I.hslab.alloc(len);
+              off = I.hslab.allocate(len);
               if (off == kNoBlock) return false;
             }
             const std::string t = can ? I.token + "|" + I.shm.name : std::string("-|");
@@ -393,7 +316,7 @@ void RoCECommunicator::start() {
             uint64_t off;
             {
               std::lock_guard<std::mutex> g(I.mu);
-              off = I.hslab.alloc(std::get<2>(w));
+              off = I.hslab.allocate(std::get<2>(w));
               if (off == kNoBlock) {
                 I.waiting.push_back(w);
                 continue;

@@ -988,3 +988,51 @@ def test_checkpoint_header_is_the_reference_graph_schema(tmp_path):
     p2.write_bytes(json.dumps(flat).encode() + blob[len(json.dumps(golden, indent=4).encode()):])
     g3 = Graph.load_state(str(p2), "cpu")
     torch.testing.assert_close(GraphExecutor(g3).forward({"input": x})["output"], y)
+
+
+def test_symmetric_memory_host_side_pieces(tmp_path):
+    """csrc/runtime/symmetric_memory.hpp without a GPU: the offset free list (best fit, coalescing, refused double frees),
+    descriptors crossing a process boundary through FdMailbox (the carrier of cuMemExportToShareableHandle's POSIX fds),
+    and probe() naming the reason the VMM group is unavailable on a CPU box."""
+    import os
+
+    from tnn_b200.ops import native
+    Cx = native.require()
+    fl = Cx.OffsetFreeList(1 << 16, 256)
+    a, b, c = fl.allocate(100), fl.allocate(1000), fl.allocate(100)
+    assert (a, b, c) == (0, 256, 1280) and fl.block_size(b) == 1024 and fl.in_use == 256 + 1024 + 256
+    assert fl.release(b) and not fl.release(b)
+    assert fl.allocate(512) == 256                      # best fit: the 1 KB hole, not the tail
+    assert fl.allocate(1 << 20) is None
+    for off in (a, 256, c):
+        assert fl.release(off)
+    assert fl.num_free_ranges == 1 and fl.largest_free == 1 << 16 and fl.peak >= 1536
+
+    d = str(tmp_path)
+    pid = os.fork()
+    if pid == 0:                                        # child: gets the write end of a pipe through the mailbox
+        rc = 1
+        try:
+            box = Cx.FdMailbox(d, "child.sock")
+            tag, fd = box.recv(20000)
+            if tag == 42 and fd >= 0:
+                os.write(fd, b"via scm_rights")
+                os.close(fd)
+                rc = 0
+        finally:
+            os._exit(rc)
+    r, w = os.pipe()
+    box = Cx.FdMailbox(d, "parent.sock")
+    box.send(os.path.join(d, "child.sock"), 42, w, 20000)   # retried until the child has bound
+    os.close(w)
+    assert os.read(r, 64) == b"via scm_rights"
+    os.close(r)
+    assert os.waitpid(pid, 0)[1] == 0
+    with pytest.raises(RuntimeError, match="timed out"):
+        box.recv(50)
+
+    if not torch.cuda.is_available():
+        sup = Cx.SymmetricMemory.probe([0, 1])
+        assert not sup["vmm"] and not sup["multicast"] and sup["why"]
+        with pytest.raises(RuntimeError, match="SymmetricMemory"):
+            Cx.SymmetricMemory([0, 1], 1 << 20)

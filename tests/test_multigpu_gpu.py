@@ -53,3 +53,18 @@ def test_cpp_host_single_process_data_parallel():
     cli = subprocess.run([os.path.join(ROOT, "cpp", "bin", "dp_trainer"), "--gpus", "2", "--steps", "10", "--warmup", "4"], capture_output=True,
                          text=True, timeout=600)
     assert cli.returncode == 0 and '"replica_divergence": 0' in cli.stdout and '"cuda_graph": true' in cli.stdout, cli.stdout[-2000:] + cli.stderr[-2000:]
+
+
+def test_own_symmetric_memory_group_opt_in():
+    """The framework's own VMM / NVLS group (csrc/runtime/symmetric_memory.hpp) under the fused data-parallel step, in both
+    hosts: one process per GPU (handles as POSIX fds over Unix sockets) and one process for all GPUs.  Written after the
+    round's GPU budget was spent, so it has not run on hardware yet: opt-in with TNN_TEST_NVLS=1."""
+    if os.environ.get("TNN_TEST_NVLS") != "1":
+        pytest.skip("opt-in: TNN_TEST_NVLS=1 (not yet run on hardware)")
+    out = _launch("dp_check.py", 2, 29577, env={"TNN_DP_OWN_SYMM": "1"})
+    assert out.returncode == 0 and "DP_CHECK PASS" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
+    from tnn_b200 import build
+    build.build_host(verbose=False)
+    cpp = subprocess.run([os.path.join(ROOT, "cpp", "bin", "tnn_tests"), "symmetric_memory"], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, TNN_TEST_NVLS="1"))
+    assert cpp.returncode == 0 and " 0 failed" in cpp.stdout, cpp.stdout[-3000:] + cpp.stderr[-2000:]

@@ -23,6 +23,7 @@ void runtime_bind(pybind11::module_& m);
 #include "archiver.hpp"
 #include "cpu_math.hpp"
 #include "data_loader.hpp"
+#include "symmetric_memory.hpp"
 #include "tcp_bus.hpp"
 #include "tokenizer.hpp"
 
@@ -252,6 +253,62 @@ void runtime_bind(py::module_& m) {
     DevGuard g(device);
     cudaIpcCloseMemHandle(reinterpret_cast<void*>((uintptr_t)ptr));
   });
+  // ---- the framework's own symmetric NVLink memory (symmetric_memory.hpp): cuMemCreate slabs mapped into every rank,
+  // an NVLS multicast window over them, handles exchanged as file descriptors.  parallel/dp.py uses it with TNN_DP_OWN_SYMM=1.
+  py::class_<OffsetFreeList>(m, "OffsetFreeList")
+      .def(py::init<uint64_t, uint64_t>(), py::arg("bytes"), py::arg("align") = 256)
+      .def("allocate", [](OffsetFreeList& f, uint64_t n) -> py::object {
+        const uint64_t off = f.allocate(n);
+        if (off == OffsetFreeList::kNone) return py::none();
+        return py::int_(off);
+      })
+      .def("release", &OffsetFreeList::release)
+      .def("block_size", &OffsetFreeList::block_size)
+      .def_property_readonly("in_use", &OffsetFreeList::in_use)
+      .def_property_readonly("peak", &OffsetFreeList::peak)
+      .def_property_readonly("capacity", &OffsetFreeList::capacity)
+      .def_property_readonly("largest_free", &OffsetFreeList::largest_free)
+      .def_property_readonly("num_free_ranges", &OffsetFreeList::num_free_ranges);
+  py::class_<FdMailbox>(m, "FdMailbox")
+      .def(py::init<const std::string&, const std::string&>(), py::arg("dir"), py::arg("name"))
+      .def_property_readonly("path", &FdMailbox::path)
+      .def("send", [](const FdMailbox& b, const std::string& to, uint64_t tag, int fd, int timeout_ms) {
+        py::gil_scoped_release nogil;
+        b.send(to, tag, fd, timeout_ms);
+      }, py::arg("to"), py::arg("tag"), py::arg("fd") = -1, py::arg("timeout_ms") = 30000)
+      .def("recv", [](const FdMailbox& b, int timeout_ms) {
+        int fd = -1;
+        uint64_t tag;
+        {
+          py::gil_scoped_release nogil;
+          tag = b.recv(&fd, timeout_ms);
+        }
+        return py::make_tuple(tag, fd);
+      }, py::arg("timeout_ms") = 30000);
+  py::class_<SymmetricMemory>(m, "SymmetricMemory")
+      .def_static("probe", [](const std::vector<int>& devices) {
+        const auto s = SymmetricMemory::probe(devices);
+        py::dict d;
+        d["vmm"] = s.vmm;
+        d["multicast"] = s.multicast;
+        d["why"] = s.why;
+        return d;
+      })
+      .def_static("rendezvous", [](int rank, int world, int device, size_t bytes, const std::string& dir, bool want_multicast, int timeout_ms) {
+        py::gil_scoped_release nogil;
+        return SymmetricMemory::rendezvous(rank, world, device, bytes, dir, want_multicast, timeout_ms);
+      }, py::arg("rank"), py::arg("world"), py::arg("device"), py::arg("bytes"), py::arg("dir"), py::arg("want_multicast") = true, py::arg("timeout_ms") = 60000)
+      .def(py::init([](const std::vector<int>& devices, size_t bytes, bool want_multicast) { return std::make_unique<SymmetricMemory>(devices, bytes, want_multicast); }),
+           py::arg("devices"), py::arg("bytes"), py::arg("want_multicast") = true)
+      .def_property_readonly("world", &SymmetricMemory::world)
+      .def_property_readonly("my_rank", &SymmetricMemory::my_rank)
+      .def_property_readonly("bytes", &SymmetricMemory::bytes)
+      .def_property_readonly("granularity", &SymmetricMemory::granularity)
+      .def_property_readonly("has_multicast", &SymmetricMemory::has_multicast)
+      .def("base", [](const SymmetricMemory& s, int rank) { return (uint64_t)(uintptr_t)s.base(rank); })
+      .def_property_readonly("multicast_base", [](const SymmetricMemory& s) { return (uint64_t)(uintptr_t)s.multicast_base(); })
+      .def("allocate", [](SymmetricMemory& s, int rank, size_t n) { return (uint64_t)(uintptr_t)s.allocate(rank, n); })
+      .def("deallocate", [](SymmetricMemory& s, int rank, uint64_t p) { s.deallocate(rank, reinterpret_cast<void*>((uintptr_t)p)); });
   // blocking device-to-device copy on a private stream of `device` (either pointer may live on a peer device)
   m.def("cuda_copy_d2d", [ck](int device, uint64_t dst, uint64_t src, size_t bytes) {
     if (bytes == 0) return;

@@ -112,9 +112,18 @@ class FusedDataParallel:
         self.off_lp = self.off_g + npad * 4
         self.off_flag = (self.off_lp + npad * 2 + 255) // 256 * 256
         total = self.off_flag + self.FLAG_BYTES
-        self.buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
-        self.buf.zero_()
-        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.own_symm = os.environ.get("TNN_DP_OWN_SYMM", "0") == "1"
+        if self.own_symm:
+            # the framework's own group (csrc/runtime/symmetric_memory.hpp): cuMemCreate slab per rank, POSIX-fd handles
+            # over Unix sockets, NVLS multicast window created by rank 0.  Opt-in: it has not run on hardware yet.
+            self.buf, ptrs, mc = self._own_symmetric(total, device)
+            self.hdl = None
+        else:
+            self.buf = symm_mem.empty(total, dtype=torch.uint8, device=device)
+            self.buf.zero_()
+            self.hdl = symm_mem.rendezvous(self.buf, self.group)
+            ptrs = list(self.hdl.buffer_ptrs)
+            mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
         f32 = lambda off, cnt: self.buf[off:off + cnt * 4].view(torch.float32)  # noqa: E731
         self._p, self._g = f32(self.off_p, npad), f32(self.off_g, npad)
         self._lp = self.buf[self.off_lp:self.off_lp + npad * 2].view(torch.bfloat16)
@@ -126,12 +135,10 @@ class FusedDataParallel:
             return t[:numel] if numel != t.numel() else t
 
         self.graph = graph_from_sequential(seq, device, seed, name, alloc_fn=alloc)
-        ptrs = list(self.hdl.buffer_ptrs)
         self.g_peers = [p + self.off_g for p in ptrs]
         self.p_peers = [p + self.off_p for p in ptrs]
         self.pb_peers = [p + self.off_lp for p in ptrs]
         self.flag_peers = [p + self.off_flag for p in ptrs]
-        mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)
         want_mc = self.use_multicast if self.use_multicast is not None else os.environ.get("TNN_DP_MULTICAST", "1") == "1"
         self.mc = mc if (mc and want_mc) else 0
         self.sync = torch.zeros(4, dtype=torch.int32, device=device)
@@ -149,6 +156,34 @@ class FusedDataParallel:
             self.broadcast_parameters(0)      # unseeded replicas would start (and stay) different
             torch.cuda.synchronize(device)
         return self.graph
+
+    def _own_symmetric(self, total: int, device):
+        """(uint8 tensor over this rank's slab, [base pointer of every rank], multicast base or 0)."""
+        import tempfile
+
+        Cx = native.require()
+        box = [tempfile.mkdtemp(prefix="tnn_symm_") if self.rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(self.group, 0), group=self.group)
+        mem = Cx.SymmetricMemory.rendezvous(self.rank, self.world, device.index if device.index is not None else torch.cuda.current_device(),
+                                            total, box[0], True, 60000)
+        self._own_mem = mem                               # owns the mappings: must outlive every view
+        if self.rank == 0:
+            try:
+                os.rmdir(box[0])                          # every mailbox unlinked itself after the last phase
+            except OSError:
+                pass
+
+        class _Slab:                                      # zero-copy view; keeps `mem` alive through the tensor
+            def __init__(s):
+                s._keep = mem
+                s.__cuda_array_interface__ = {"shape": (total,), "typestr": "|u1", "data": (mem.base(self.rank), False), "version": 3,
+                                              "strides": None}
+
+        buf = torch.as_tensor(_Slab(), device=device)
+        buf.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)                          # nobody reads a peer's slab before it was cleared
+        return buf, [mem.base(r) for r in range(self.world)], int(mem.multicast_base) if mem.has_multicast else 0
 
     # ---------------------------------------------------------------- gradient buckets
     def _plan_buckets(self, seq):
