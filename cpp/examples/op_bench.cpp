@@ -1,11 +1,12 @@
-// op_bench: operator micro-benchmarks of the C++ host (reference: benchmarks/{dense,conv2d,batchnorm,attention,copy,
-// grad_clear,serialization}_benchmark.cpp).  Times forward (+ backward) of one layer with CUDA events on the layer's
+// op_bench: operator micro-benchmarks of the C++ host (reference: benchmarks/{gemm,dense,conv2d,batchnorm,attention,copy,
+// grad_clear,serialization,tcp_communicator,roce_communicator,pipeline}_benchmark.cpp).  Times forward (+ backward) of one layer with CUDA events on the layer's
 // flow (wall clock on the CPU), prints one JSON line per case.
-//   op_bench [dense|conv2d|batchnorm|attention|copy|grad_clear|serialization|all] [--device CPU|GPU:i] [--iters N]
+//   op_bench [gemm|dense|conv2d|batchnorm|attention|copy|grad_clear|serialization|tcp|roce|pipeline|all] [--device CPU|GPU:i] [--iters N]
 #include <chrono>
 #include <cstring>
 #include <iostream>
 #include <sstream>
+#include <thread>
 
 #include "tnn/distributed.hpp"
 #include "tnn/example_models.hpp"
@@ -58,6 +59,116 @@ int main(int argc, char** argv) {
     const Device dev = device.empty() ? (dm.has_gpu() ? dm.getGPU(0) : dm.getHost()) : dm.getDevice(device);
     const bool big = dev.is_gpu();
     auto want = [&](const char* n) { return what == "all" || what == n; };
+    if (want("gemm")) {
+      // gemm_benchmark.cpp: C[M,N] = A[M,K] x B[K,N] per dtype through tnn::matmul (tcgen05 kernels on the GPU, packed AVX2 on the CPU)
+      const size_t M = big ? 4096 : 256, N = big ? 4096 : 256, K = big ? 4096 : 256;
+      for (DType_t dt : big ? std::vector<DType_t>{DType_t::BF16, DType_t::FP16, DType_t::FP32} : std::vector<DType_t>{DType_t::FP32}) {
+        Tensor a = make_tensor(DType_t::FP32, {M, K}), b = make_tensor(DType_t::FP32, {K, N});
+        a->fill_random_normal(0.0, 1.0, 1);
+        b->fill_random_normal(0.0, 1.0, 2);
+        if (dev.is_gpu()) {
+          a = a->to_device(dev);
+          b = b->to_device(dev);
+        }
+        if (dt != DType_t::FP32) {
+          a = dtype_cast(*a, dt);
+          b = dtype_cast(*b, dt);
+        }
+        Tensor c;
+        const double ms = time_ms(dev, iters, [&] { c = matmul(*a, *b); });
+        std::cout << "{\"bench\": \"gemm\", \"dtype\": \"" << dtype_to_string(dt) << "\", \"shape\": \"" << M << "x" << N << "x" << K << "\", \"device\": \"" << dev.name()
+                  << "\", \"ms\": " << ms << ", \"tflops\": " << 2.0 * M * N * K / ms / 1e9 << "}" << std::endl;
+      }
+    }
+    for (const char* transport : {"tcp", "roce"}) {
+      if (!want(transport)) continue;
+      // tcp_communicator_benchmark.cpp / roce_communicator_benchmark.cpp: two endpoints bounce FORWARD_JOB messages for a
+      // fixed number of round trips; bandwidth = payload bytes received / elapsed (both endpoints in this process, loopback)
+      const bool roce = !strcmp(transport, "roce");
+      auto make = [&](const char* nm) -> std::unique_ptr<Communicator> {
+        if (roce) return std::make_unique<RoCECommunicator>("127.0.0.1", 0, 4, nullptr, nm);
+        return std::make_unique<TCPCommunicator>("127.0.0.1", 0, 4, nullptr, nm);
+      };
+      auto a = make("bench_a"), b = make("bench_b");
+      a->start();
+      b->start();
+      a->connect(b->endpoint());
+      b->connect(a->endpoint());
+      const size_t n = big ? (size_t)(32u << 20) : (size_t)(1u << 20);       // fp32 elements: 128 MiB (the reference's message) / 4 MiB
+      Tensor t = make_tensor(DType_t::FP32, {n});
+      t->fill_random_uniform(-1.0, 1.0, 5);
+      const int trips = std::max(2, iters);
+      std::thread echo([&] {
+        Message m;
+        for (int i = 0; i < trips; ++i) {
+          if (!b->dequeue(&m, 60000, {CommandType::FORWARD_JOB})) return;
+          b->send_message(m, a->endpoint());
+        }
+      });
+      const auto t0 = std::chrono::steady_clock::now();
+      bool ok = true;
+      for (int i = 0; i < trips && ok; ++i) {
+        a->send_message(Message(CommandType::FORWARD_JOB, Job{t, (uint64_t)i}), b->endpoint());
+        Message back;
+        ok = a->dequeue(&back, 60000, {CommandType::FORWARD_JOB}) && back.job.data->size() == n;
+      }
+      const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      echo.join();
+      a->stop();
+      b->stop();
+      if (!ok) throw std::runtime_error(std::string(transport) + " ping-pong: message lost");
+      std::cout << "{\"bench\": \"" << transport << "_communicator\", \"message_MB\": " << n * 4.0 / (1 << 20) << ", \"round_trips\": " << trips << ", \"seconds\": " << sec
+                << ", \"MBps_per_direction\": " << trips * n * 4.0 / sec / 1e6 << "}" << std::endl;
+    }
+    if (want("pipeline")) {
+      // pipeline_benchmark.cpp: a two-stage in-process pipeline (coordinator + two workers) against the same model on one device
+      ExampleModels::register_defaults();
+      const char* model = big ? "cifar10_resnet9" : "mnist_cnn";
+      const Shape in = big ? Shape{32, 32, 3} : Shape{28, 28, 1};
+      const size_t B = big ? 256 : 32, M = 4;
+      SyntheticDataLoader data(in, 10, 4 * B, 5);
+      Tensor x, y;
+      data.get_batch(B, x, y);
+      Vec<std::unique_ptr<Worker>> workers;
+      Vec<Endpoint> eps;
+      for (int i = 0; i < 2; ++i) {
+        workers.push_back(std::make_unique<Worker>(std::make_unique<InProcessCommunicator>("w" + std::to_string(i)), dev, "w" + std::to_string(i)));
+        workers.back()->start(true);
+        eps.push_back(workers.back()->comm().endpoint());
+      }
+      CoordinatorConfig cc;
+      cc.model = ExampleModels::create(model);
+      Shape full{B / M};
+      full.insert(full.end(), in.begin(), in.end());
+      cc.input_shape = full;
+      cc.optimizer_config = OptimizerFactory::create_sgd(0.01, 0.9)->get_config();
+      cc.partitioner = std::make_unique<NaivePipelinePartitioner>(Vec<size_t>{1, 1});
+      cc.worker_endpoints = eps;
+      Coordinator co(std::move(cc), std::make_unique<InProcessCommunicator>("coord"));
+      co.start();
+      auto crit = LossFactory::create_logsoftmax_crossentropy();
+      Vec<Tensor> xs, ys;
+      split_microbatches(x, y, M, &xs, &ys);
+      auto one = [&] {
+        co.async_train_batch(xs, ys, *crit);
+        co.update_parameters();
+      };
+      for (int i = 0; i < 2; ++i) one();
+      const double pp_ms = benchmark(one, iters, 0);
+      co.stop();
+      for (auto& w : workers) w->stop();
+      Graph g = load_or_create_model(model, "", dev, 1);
+      auto opt = OptimizerFactory::create_sgd(0.01, 0.9);
+      TrainStep step(g, *crit, *opt, nullptr, 1, false);
+      for (int i = 0; i < 2; ++i) step(x, y);
+      const double one_ms = benchmark([&] {
+        Tensor st = step(x, y);
+        float h[2];
+        st->copy_to_host(h, 8);
+      }, iters, 0);
+      std::cout << "{\"bench\": \"pipeline\", \"model\": \"" << model << "\", \"device\": \"" << dev.name() << "\", \"batch\": " << B << ", \"microbatches\": " << M
+                << ", \"two_stage_ms\": " << pp_ms << ", \"single_device_ms\": " << one_ms << "}" << std::endl;
+    }
     if (want("dense")) {
       layer_case("dense", big ? "4096x4096x4096" : "256x512x512", std::make_unique<DenseLayer>(big ? 4096 : 512, big ? 4096 : 512), big ? Shape{4096, 4096} : Shape{256, 512}, dev, iters);
       if (big) layer_case("dense", "gpt2_fc1_32768x768x3072", std::make_unique<DenseLayer>(768, 3072), {32768, 768}, dev, iters);

@@ -380,7 +380,11 @@ def test_cpp_gpt2_engine_matches_the_python_engine_and_runs_the_new_apps():
                         (["device_manager_example"], "CPU:0"), (["graph_test", "--steps", "2"], "Loss:"),
                         (["legacy_trainer", "--synthetic", "--samples", "64"], "final train loss"),
                         (["inferencer", "--synthetic", "--samples", "32"], "Validation Loss"),
-                        (["op_bench", "serialization", "--device", "CPU", "--iters", "2"], "serialize_GBps")):
+                        (["op_bench", "serialization", "--device", "CPU", "--iters", "2"], "serialize_GBps"),
+                        (["op_bench", "gemm", "--device", "CPU", "--iters", "2"], '"tflops"'),
+                        (["op_bench", "tcp", "--device", "CPU", "--iters", "2"], "MBps_per_direction"),
+                        (["op_bench", "roce", "--device", "CPU", "--iters", "2"], "MBps_per_direction"),
+                        (["op_bench", "pipeline", "--device", "CPU", "--iters", "2"], "two_stage_ms")):
         out = subprocess.run([os.path.join(bins, cmd[0])] + cmd[1:], capture_output=True, text=True, timeout=300, env=env, cwd=str(ROOT))
         assert out.returncode == 0 and needle in out.stdout, (cmd, out.stdout[-800:], out.stderr[-800:])
 
