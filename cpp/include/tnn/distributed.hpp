@@ -14,6 +14,7 @@
 #include <thread>
 
 #include "runtime/tcp_bus.hpp"
+#include "tnn/common.hpp"
 #include "tnn/profiler.hpp"
 #include "tnn/train.hpp"
 
@@ -234,6 +235,8 @@ class Worker {
   // directory, the system temp directory and TNN_WORKER_IO_ROOT (':'-separated), as in the Python worker.  Throws on a path
   // that resolves (symlinks and ".." included) outside every root.
   std::string checked_path(const std::string& path) const;
+  // the stage's LoadTracker record (load_tracker.hpp:10-21): what REPORT_LOAD answers with
+  LoadTracker load_tracker() const;
   const std::vector<std::string>& io_roots() const { return io_roots_; }
 
  private:
@@ -249,8 +252,10 @@ class Worker {
   StageConfig cfg_;
   std::thread thread_;
   std::atomic<bool> stop_{false};
-  uint64_t jobs_ = 0;
-  int64_t busy_ns_ = 0;
+  uint64_t jobs_ = 0, fwd_jobs_ = 0, bwd_jobs_ = 0;
+  int64_t busy_ns_ = 0, fwd_ns_ = 0, bwd_ns_ = 0;
+  double cpu_t0_ = 0;                                 // process CPU seconds / wall clock at construction
+  std::chrono::steady_clock::time_point wall_t0_ = std::chrono::steady_clock::now();
   std::vector<std::string> io_roots_;
 };
 
@@ -286,6 +291,8 @@ class Coordinator {
   void print_profiling();
   void clear_profiling();
   Vec<Json> health_check(int timeout_ms = 5000);
+  // REPORT_LOAD -> one record per stage: {stage, jobs, avg_forward_backward_ms} + the LoadTracker fields
+  Vec<Json> report_load(int timeout_ms = 10000);
   void barrier(int timeout_ms = 30000);
   Vec<std::string> checkpoint(const std::string& path, int timeout_ms = 60000);
   size_t num_stages() const { return stages_.size(); }

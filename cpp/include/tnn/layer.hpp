@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "tnn/config.hpp"
+#include "tnn/profiler.hpp"
 #include "tnn/tensor.hpp"
 
 namespace tnn {
@@ -166,5 +167,34 @@ class LayerFactory {
 std::function<void(TensorImpl&, uint64_t)> uniform_init(double bound);
 std::function<void(TensorImpl&, uint64_t)> const_init(double v);
 std::function<void(TensorImpl&, uint64_t)> normal_init(double stddev);
+
+// Scope that charges its wall time to a layer in the LayerProfiler (one relaxed load when profiling is off).
+struct LayerTimer {
+  LayerTimer(const std::string& layer, const Device& dev, bool backward) : active_(LayerProfiler::instance().enabled()) {
+    if (!active_) return;
+    name_ = &layer;
+    dev_ = dev;
+    backward_ = backward;
+    if (dev_.is_gpu()) current_flow(dev_).synchronize();             // work queued by the previous layer is not this layer's time
+    t0_ = std::chrono::steady_clock::now();
+  }
+  ~LayerTimer() {
+    if (!active_) return;
+    try {
+      if (dev_.is_gpu()) current_flow(dev_).synchronize();
+    } catch (...) {                                                   // a failed launch surfaces at the caller's next CUDA call
+    }
+    LayerProfiler::instance().add(*name_, backward_, std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0_).count());
+  }
+  LayerTimer(const LayerTimer&) = delete;
+  LayerTimer& operator=(const LayerTimer&) = delete;
+
+ private:
+  bool active_;
+  bool backward_ = false;
+  const std::string* name_ = nullptr;
+  Device dev_;
+  std::chrono::steady_clock::time_point t0_;
+};
 
 }  // namespace tnn

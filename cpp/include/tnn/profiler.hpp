@@ -3,6 +3,7 @@
 // Byte-compatible with the Python host's ProfilerCore (tnn_b200/csrc/runtime/runtime.cpp).
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdint>
 #include <cstdlib>
@@ -142,6 +143,78 @@ struct NvtxRange {
 
  private:
   bool active_;
+};
+
+// Per-layer timing of the single-process trainer (TrainingConfig::profiler_type / print_layer_profiling; the reference
+// declares both, include/nn/train.hpp:31,54-56, and leaves the timing unimplemented).  Sequential records the wall time of
+// every child's forward / backward (LayerTimer, layer.hpp: the layer's flow is synchronised at the end of the scope, so a
+// profiled run executes eagerly and serialised -- like the reference's Debug build, src/nn/layer.cpp:49-51).  Times of
+// blocks include their children.  NORMAL: the table is printed and cleared at every progress interval; CUMULATIVE: it
+// accumulates over the run and is printed once at the end.
+class LayerProfiler {
+ public:
+  struct Row {
+    std::string name;
+    int64_t fwd_ns = 0, bwd_ns = 0;
+    uint64_t fwd_calls = 0, bwd_calls = 0;
+  };
+  static LayerProfiler& instance() {
+    static LayerProfiler* p = new LayerProfiler();
+    return *p;
+  }
+  void enable(bool on) { enabled_.store(on, std::memory_order_relaxed); }
+  bool enabled() const { return enabled_.load(std::memory_order_relaxed); }
+  void add(const std::string& layer, bool backward, int64_t ns) {
+    std::lock_guard<std::mutex> g(mu_);
+    size_t i = 0;
+    for (; i < rows_.size(); ++i)
+      if (rows_[i].name == layer) break;
+    if (i == rows_.size()) {
+      rows_.emplace_back();
+      rows_.back().name = layer;
+    }
+    Row& r = rows_[i];
+    if (backward) {
+      r.bwd_ns += ns;
+      ++r.bwd_calls;
+    } else {
+      r.fwd_ns += ns;
+      ++r.fwd_calls;
+    }
+  }
+  std::vector<Row> rows() const {                       // in first-execution order
+    std::lock_guard<std::mutex> g(mu_);
+    return rows_;
+  }
+  void reset() {
+    std::lock_guard<std::mutex> g(mu_);
+    rows_.clear();
+  }
+  std::string table(const std::string& title) const {
+    const std::vector<Row> rs = rows();
+    size_t w = 5;
+    for (const auto& r : rs) w = std::max(w, r.name.size());
+    std::string out = title + "\n";
+    char b[512];
+    snprintf(b, sizeof b, "  %-*s %12s %12s %9s %9s %12s %12s\n", (int)w, "layer", "fwd ms", "bwd ms", "fwd calls", "bwd calls", "fwd ms/call", "bwd ms/call");
+    out += b;
+    double tf = 0, tb = 0;
+    for (const auto& r : rs) {
+      const double f = r.fwd_ns / 1e6, k = r.bwd_ns / 1e6;
+      snprintf(b, sizeof b, "  %-*s %12.3f %12.3f %9llu %9llu %12.4f %12.4f\n", (int)w, r.name.c_str(), f, k, (unsigned long long)r.fwd_calls, (unsigned long long)r.bwd_calls,
+               r.fwd_calls ? f / (double)r.fwd_calls : 0.0, r.bwd_calls ? k / (double)r.bwd_calls : 0.0);
+      out += b;
+      tf += f;
+      tb += k;
+    }
+    snprintf(b, sizeof b, "  %-*s %12.3f %12.3f   (blocks include their children)", (int)w, "sum", tf, tb);
+    return out + b;
+  }
+
+ private:
+  std::atomic<bool> enabled_{false};
+  mutable std::mutex mu_;
+  std::vector<Row> rows_;
 };
 
 class GlobalProfiler {

@@ -82,6 +82,8 @@ struct TrainHistory {
 };
 // (mean loss, accuracy) over the loader
 std::pair<double, double> validate_model(Graph& g, BaseDataLoader& loader, Loss& criterion, const TrainingConfig& cfg);
+// the table TrainingConfig::print_layer_memory_usage prints before and after training
+std::string layer_memory_table(Graph& g, GraphExecutor& exec);
 TrainHistory train_model(Graph& g, BaseDataLoader& train, BaseDataLoader* val, Optimizer& opt, Loss& criterion, Scheduler* sched,
                          const TrainingConfig& cfg, const std::function<void(const std::string&)>& log = nullptr);
 // model file (reference format) + trailer with optimizer moments / step / scheduler position

@@ -316,6 +316,10 @@ Vec<SeqPartition> FTDPartitioner::partition_model(const Vec<Layer*>& layers, con
 }
 
 // ===================================================================================== worker
+static double process_cpu_seconds() {
+  timespec ts{};
+  return clock_gettime(CLOCK_PROCESS_CPUTIME_ID, &ts) == 0 ? (double)ts.tv_sec + ts.tv_nsec * 1e-9 : -1.0;
+}
 Worker::Worker(std::unique_ptr<Communicator> comm, const Device& dev, const std::string& name) : comm_(std::move(comm)), dev_(dev), name_(name) {
   namespace fs = std::filesystem;
   std::error_code ec;
@@ -324,6 +328,7 @@ Worker::Worker(std::unique_ptr<Communicator> comm, const Device& dev, const std:
     fs::path r = fs::weakly_canonical(p, ec);
     if (!ec && !r.empty()) io_roots_.push_back(r.string());
   };
+  cpu_t0_ = std::max(0.0, process_cpu_seconds());
   add_root(fs::current_path(ec));
   add_root(fs::temp_directory_path(ec));
   if (const char* extra = std::getenv("TNN_WORKER_IO_ROOT")) {
@@ -331,6 +336,26 @@ Worker::Worker(std::unique_ptr<Communicator> comm, const Device& dev, const std:
     std::string item;
     while (std::getline(ss, item, ':')) add_root(item);
   }
+}
+LoadTracker Worker::load_tracker() const {
+  LoadTracker t;
+  t.avg_forward_time_ = (float)(fwd_ns_ / 1e6 / (double)std::max<uint64_t>(fwd_jobs_, 1));
+  t.avg_backward_time_ = (float)(bwd_ns_ / 1e6 / (double)std::max<uint64_t>(bwd_jobs_, 1));
+  const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall_t0_).count(), cpu = process_cpu_seconds();
+  t.avg_cpu_utilization_ = (cpu >= 0 && wall > 0) ? (float)((cpu - cpu_t0_) / wall) : -1.f;
+  {
+    std::ifstream f("/proc/self/status");               // VmHWM: peak resident set
+    std::string line;
+    while (std::getline(f, line))
+      if (line.rfind("VmHWM:", 0) == 0) t.max_memory_usage_ = (float)(atol(line.c_str() + 6) / 1024.0);
+  }
+  if (dev_.is_gpu()) {
+    size_t free_b = 0, total_b = 0;
+    dev_.set_current();
+    if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) t.max_device_memory_usage_ = (float)((total_b - free_b) / 1048576.0);
+    else cudaGetLastError();
+  }
+  return t;
 }
 std::string Worker::checked_path(const std::string& path) const {
   namespace fs = std::filesystem;
@@ -407,6 +432,8 @@ void Worker::process(Message& m) {
       const int64_t t1 = Profiler::now_ns();
       GlobalProfiler::add_event(EventType::COMPUTE, t0, t1, "forward mb " + std::to_string(m.job.mb_id), name_);
       busy_ns_ += t1 - t0;
+      fwd_ns_ += t1 - t0;
+      ++fwd_jobs_;
       ++jobs_;
       reply(Message(CommandType::FORWARD_JOB, Job{y, m.job.mb_id}), cfg_.next_stage_endpoint ? &cfg_.next_stage_endpoint : nullptr);
       break;
@@ -419,6 +446,8 @@ void Worker::process(Message& m) {
       const int64_t t1 = Profiler::now_ns();
       GlobalProfiler::add_event(EventType::COMPUTE, t0, t1, "backward mb " + std::to_string(m.job.mb_id), name_);
       busy_ns_ += t1 - t0;
+      bwd_ns_ += t1 - t0;
+      ++bwd_jobs_;
       if (cfg_.prev_stage_endpoint && dx) reply(Message(CommandType::BACKWARD_JOB, Job{dx, m.job.mb_id}), &cfg_.prev_stage_endpoint);
       else reply(Message(CommandType::BACKWARD_COMPLETE));
       break;
@@ -512,6 +541,8 @@ void Worker::process(Message& m) {
       s["stage"] = cfg_.stage_id;
       s["avg_forward_backward_ms"] = busy_ns_ / 1e6 / (double)std::max<uint64_t>(jobs_, 1);
       s["jobs"] = (long long)jobs_;
+      const Json lt = load_tracker().to_json();
+      for (const auto& kv : lt.members()) s[kv.first] = kv.second;
       reply(Message(CommandType::LOAD_REPORT, s.dump()));
       break;
     }
@@ -672,6 +703,13 @@ Vec<Json> Coordinator::health_check(int timeout_ms) {
   broadcast(Message(CommandType::HEALTH_CHECK));
   Vec<Json> out;
   for (auto& m : join(CommandType::STATUS_RESPONSE, stages_.size(), timeout_ms, "health_check")) out.push_back(Json::parse(m.str));
+  return out;
+}
+Vec<Json> Coordinator::report_load(int timeout_ms) {
+  broadcast(Message(CommandType::REPORT_LOAD));
+  Vec<Json> out;
+  for (auto& m : join(CommandType::LOAD_REPORT, stages_.size(), timeout_ms, "report_load")) out.push_back(Json::parse(m.str));
+  std::sort(out.begin(), out.end(), [](const Json& a, const Json& b) { return a.value("stage", 0) < b.value("stage", 0); });
   return out;
 }
 void Coordinator::barrier(int timeout_ms) {

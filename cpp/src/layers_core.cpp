@@ -1030,6 +1030,7 @@ Tensor Sequential::forward_impl(const Tensor& xin, size_t mb, const FwdAux& aux)
   for (size_t i = 0; i < n; ++i) {
     const bool last = i + 1 == n;
     NvtxRange range("fwd:", layers_[i]->name());
+    LayerTimer timer(layers_[i]->name(), device_, false);
     if (last && (aux.residual || aux.act) && layers_[i]->fuses_fwd_residual()) x = layers_[i]->forward_impl(x, mb, aux);
     else x = layers_[i]->forward(x, mb);
     if (del) del->flip();            // consecutive layer outputs come from opposite ends of the workspace (sequential.cpp:33-44)
@@ -1049,6 +1050,7 @@ Tensor Sequential::backward_impl(const Tensor& dyin, size_t mb, BwdAux& aux) {
       continue;
     }
     NvtxRange range("bwd:", layer->name());
+    LayerTimer timer(layer->name(), device_, true);
     BwdAux a;
     a.colsum_in = colsum;
     a.need_dx = k > 0 || aux.need_dx;

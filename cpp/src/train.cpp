@@ -11,7 +11,9 @@
 
 #include "kernels/simt_ops.cuh"
 #include "runtime/data_loader.hpp"
+#include "tnn/common.hpp"
 #include "tnn/example_models.hpp"
+#include "tnn/hardware_info.hpp"
 #include "tnn/profiler.hpp"
 #include "tnn/stepstate.hpp"
 #include "tnn/train.hpp"
@@ -800,6 +802,39 @@ Graph load_checkpoint(const std::string& path, const Device& dev, Optimizer* opt
   if (sched && meta.is_object()) sched->set_step_index((uint64_t)meta.value("sched.step", (int64_t)0));
   return g;
 }
+std::string layer_memory_table(Graph& g, GraphExecutor& exec) {
+  // TrainingConfig::print_layer_memory_usage: parameter bytes per leaf layer (fp32 master + gradient, + the bf16 copy on the
+  // GPU) and the executor's activation workspace (in use now / peak / reserved slabs)
+  std::string out = "layer memory usage:\n";
+  char b[512];
+  const bool gpu = g.device().is_gpu();
+  size_t total = 0, w = 5;
+  Vec<Layer*> leaves;
+  for (Layer* top : g.get_layers())
+    for (Layer* l : top->all_layers())
+      if (!l->param_descriptors().empty()) {
+        leaves.push_back(l);
+        w = std::max(w, l->name().size());
+      }
+  snprintf(b, sizeof b, "  %-*s %-18s %14s %14s\n", (int)w, "layer", "type", "parameters", "bytes");
+  out += b;
+  for (Layer* l : leaves) {
+    size_t n = 0, bytes = 0;
+    for (const auto& d : l->param_descriptors()) {
+      const size_t k = shape_numel(d.shape);
+      n += k;
+      bytes += k * 4 + (d.trainable ? k * 4 + (gpu ? k * 2 : 0) : 0);
+    }
+    total += bytes;
+    snprintf(b, sizeof b, "  %-*s %-18s %14zu %14zu\n", (int)w, l->name().c_str(), l->type().c_str(), n, bytes);
+    out += b;
+  }
+  DELAllocatorV2& ws = exec.workspace();
+  snprintf(b, sizeof b, "  parameters + gradients%s: %.2f MB; activation workspace: %.2f MB in use, %.2f MB peak, %.2f MB reserved in %zu slab(s); process RSS %.1f MB",
+           gpu ? " + bf16 copies" : "", total / 1048576.0, ws.bytes_in_use() / 1048576.0, ws.peak_in_use() / 1048576.0, ws.bytes_reserved() / 1048576.0, ws.num_slabs(),
+           get_memory_usage_kb() / 1024.0);
+  return out + b;
+}
 TrainHistory train_model(Graph& g, BaseDataLoader& train, BaseDataLoader* val, Optimizer& opt, Loss& criterion, Scheduler* sched,
                          const TrainingConfig& cfg, const std::function<void(const std::string&)>& log_in) {
   auto log = log_in ? log_in : [](const std::string& s) { std::cout << s << std::endl; };
@@ -807,7 +842,22 @@ TrainHistory train_model(Graph& g, BaseDataLoader& train, BaseDataLoader* val, O
   g.set_training(true);
   train.set_pinned(dev.is_gpu());
   if (val) val->set_pinned(dev.is_gpu());
-  TrainStep step(g, criterion, opt, sched, cfg.gradient_accumulation_steps, true);
+  // per-layer timing synchronises inside the step, so a profiled run is eager (no CUDA-graph capture)
+  const ProfilerType ptype = string_to_profiler_type(cfg.profiler_type);
+  const bool layer_prof = cfg.print_layer_profiling && ptype != ProfilerType::NONE;
+  LayerProfiler& lprof = LayerProfiler::instance();
+  if (layer_prof) {
+    lprof.reset();
+    lprof.enable(true);
+  }
+  struct ProfOff {
+    bool on;
+    ~ProfOff() {
+      if (on) LayerProfiler::instance().enable(false);
+    }
+  } prof_off{layer_prof};
+  TrainStep step(g, criterion, opt, sched, cfg.gradient_accumulation_steps, /*use_graph=*/!layer_prof);
+  if (cfg.print_layer_memory_usage) log(layer_memory_table(g, step.executor()));
   TrainHistory hist;
   double best_acc = -1;
   uint64_t global_step = 0;
@@ -856,6 +906,10 @@ TrainHistory train_model(Graph& g, BaseDataLoader& train, BaseDataLoader* val, O
         snprintf(b, sizeof b, "epoch %zu step %llu: loss %.4f acc %.2f%% %.2f ms/step lr %.2e", epoch + 1, (unsigned long long)global_step,
                  loss_sum / (double)std::max<size_t>(batches, 1), 100.0 * correct / (double)std::max<size_t>(seen, 1), ms, opt.get_learning_rate());
         log(b);
+        if (layer_prof && ptype == ProfilerType::NORMAL) {
+          log(lprof.table("layer profile of the last " + std::to_string(cfg.progress_print_interval) + " step(s):"));
+          lprof.reset();
+        }
       }
       if (cfg.max_steps > 0 && (long)global_step >= cfg.max_steps) break;
     }
@@ -883,6 +937,8 @@ TrainHistory train_model(Graph& g, BaseDataLoader& train, BaseDataLoader* val, O
     }
   }
   if (dev.is_gpu()) current_flow(dev).synchronize();
+  if (layer_prof && ptype == ProfilerType::CUMULATIVE) log(lprof.table("cumulative layer profile of " + std::to_string(global_step) + " step(s):"));
+  if (cfg.print_layer_memory_usage) log(layer_memory_table(g, step.executor()));
   return hist;
 }
 

@@ -15,6 +15,7 @@
 #include <unistd.h>
 
 #include "runtime/archiver.hpp"
+#include "tnn/common.hpp"
 #include "tnn/data_parallel.hpp"
 #include "tnn/distributed.hpp"
 #include "tnn/example_models.hpp"
@@ -127,6 +128,107 @@ TEST(archiver_byte_layout) {
     bad.prim<uint64_t>();
   } catch (const std::out_of_range&) { threw = true; }
   CHECK(threw);
+}
+
+// ------------------------------------------------------------------------------------- common value types
+TEST(common_variant_blob_endian_dispatch) {
+  using V = Variant<std::monostate, bool, std::string, int64_t>;
+  static_assert(V::index_of<std::string>() == 2 && V::size() == 4, "index_of follows the declaration order (the wire index)");
+  V v;
+  CHECK(v.index() == 0 && v.is<std::monostate>());
+  v = std::string("payload");
+  CHECK(v.index() == 2 && v.is<std::string>() && v.get<std::string>() == "payload" && v.get_if<bool>() == nullptr);
+  bool threw = false;
+  try {
+    v.get<int64_t>();
+  } catch (const std::runtime_error&) {
+    threw = true;
+  }
+  CHECK(threw);
+  v.set_index(3);                                       // read side: index first, then the value is filled in
+  CHECK(v.is<int64_t>() && v.get<int64_t>() == 0);
+  v.get<int64_t>() = 41;
+  CHECK(v.visit([](auto& x) -> int64_t {
+    if constexpr (std::is_same_v<std::decay_t<decltype(x)>, int64_t>) return x + 1;
+    else return -1;
+  }) == 42);
+  V w = v;
+  CHECK(w == v);
+  threw = false;
+  try {
+    v.set_index(9);
+  } catch (const std::out_of_range&) {
+    threw = true;
+  }
+  CHECK(threw);
+
+  float data[4] = {1, 2, 3, 4};
+  auto blob = make_blob(data, 4);
+  CHECK(blob.count == 4 && blob.bytes() == 16 && !blob.device.is_gpu() && blob.ptr[2] == 3.f);
+
+  CHECK(bswap<uint32_t>(0x11223344u) == 0x44332211u && bswap<uint16_t>(0xABCD) == 0xCDAB && bswap<uint8_t>(7) == 7);
+  uint32_t words[2] = {0x01020304u, 0xA0B0C0D0u};
+  bswap_buffer(words, 2, 4);
+  CHECK(words[0] == 0x04030201u && words[1] == 0xD0C0B0A0u);
+  CHECK(host_endianness() == (host_is_little_endian() ? Endianness::LITTLE : Endianness::BIG));
+
+  size_t sz = 0;
+  TNN_DISPATCH_DTYPE(DType_t::BF16, T, sz = sizeof(T));
+  CHECK(sz == 2);
+  TNN_DISPATCH_ANY_DTYPE(DType_t::INT64_T, T, sz = sizeof(T));
+  CHECK(sz == 8);
+  CHECK(dispatch_float_dtype(DType_t::FP64, [](auto t) { return sizeof(t); }) == 8);
+  threw = false;
+  try {
+    dispatch_float_dtype(DType_t::INT32_T, [](auto) { return 0; });
+  } catch (const std::runtime_error&) {
+    threw = true;
+  }
+  CHECK(threw);
+  CHECK(string_to_profiler_type("cumulative") == ProfilerType::CUMULATIVE && std::string(profiler_type_to_string(ProfilerType::NORMAL)) == "NORMAL");
+  LoadTracker lt;
+  lt.avg_forward_time_ = 1.5f;
+  lt.max_memory_usage_ = 123.f;
+  const LoadTracker back = LoadTracker::from_json(Json::parse(lt.to_json().dump()));
+  CHECK(back.avg_forward_time_ == 1.5f && back.max_memory_usage_ == 123.f && back.avg_cpu_utilization_ == -1.f);
+}
+TEST(trainer_layer_profiler_and_memory_table) {
+  // TrainingConfig::profiler_type / print_layer_profiling / print_layer_memory_usage
+  ExampleModels::register_defaults();
+  Graph g = load_or_create_model("mnist_cnn", "", getHost(), 11);
+  auto opt = OptimizerFactory::create_sgd(0.01, 0.9);
+  auto crit = LossFactory::create_logsoftmax_crossentropy();
+  SyntheticDataLoader train({28, 28, 1}, 10, 64, 5);
+  for (const char* mode : {"NORMAL", "CUMULATIVE"}) {
+    TrainingConfig cfg;
+    cfg.epochs = 1;
+    cfg.batch_size = 16;
+    cfg.progress_print_interval = 2;
+    cfg.profiler_type = mode;
+    cfg.print_layer_profiling = true;
+    cfg.print_layer_memory_usage = true;
+    cfg.snapshot_dir = "/tmp/tnn_tests_snap";
+    std::vector<std::string> lines;
+    train_model(g, train, nullptr, *opt, *crit, nullptr, cfg, [&](const std::string& s) { lines.push_back(s); });
+    size_t tables = 0, mem = 0;
+    for (const auto& l : lines) {
+      if (l.find("layer profile") != std::string::npos) {
+        ++tables;
+        CHECK(l.find("fwd ms") != std::string::npos && l.find("sum") != std::string::npos);
+      }
+      if (l.rfind("layer memory usage:", 0) == 0) {
+        ++mem;
+        CHECK(l.find("activation workspace") != std::string::npos && l.find("parameters") != std::string::npos);
+      }
+    }
+    CHECK(mem == 2);
+    CHECK(tables == (std::string(mode) == "NORMAL" ? 2u : 1u));     // 4 steps, interval 2 -> two interval tables; one cumulative table
+    CHECK(!LayerProfiler::instance().enabled());                    // switched off again when training returns
+  }
+  // a cumulative table has every top-level layer with 4 forward and 4 backward calls
+  const auto rows = LayerProfiler::instance().rows();
+  CHECK(!rows.empty());
+  for (const auto& r : rows) CHECK(r.fwd_calls == 4 && r.bwd_calls == 4 && r.fwd_ns > 0);
 }
 
 // ------------------------------------------------------------------------------------- allocators
@@ -835,6 +937,15 @@ static void pipeline_case(int transport, const Device& dev = getHost(), double t
     }
   }
   CHECK(co.health_check().size() == 2);
+  {
+    const auto loads = co.report_load();                // LoadTracker record per stage (load_tracker.hpp)
+    CHECK(loads.size() == 2 && loads[0].value("stage", -1) == 0 && loads[1].value("stage", -1) == 1);
+    for (const auto& l : loads) {
+      const LoadTracker t = LoadTracker::from_json(l);
+      CHECK(t.avg_forward_time_ > 0 && t.avg_backward_time_ > 0 && t.max_memory_usage_ > 1 && t.avg_cpu_utilization_ >= 0);
+      CHECK(l.value("jobs", 0) > 0);
+    }
+  }
   co.barrier();
   Profiler prof = co.fetch_profiling();
   CHECK(!prof.events().empty());
