@@ -2,6 +2,7 @@
 // applied in order to NHWC float batches on the host, each with its own probability, deterministic per (seed, batch,
 // sample).  BaseDataLoader::set_augmentation() applies one to every training batch.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <memory>
@@ -161,6 +162,19 @@ class Augmentation {
  public:
   explicit Augmentation(uint64_t seed = 0) : seed_(seed) {}
   void add(std::unique_ptr<AugmentationStrategy> s) { strategies_.push_back(std::move(s)); }
+  // strategy management of the reference (augmentation.hpp:67-97): add_augmentation / remove_augmentation(index | name) / clear_augmentations
+  void add_augmentation(std::unique_ptr<AugmentationStrategy> s) { add(std::move(s)); }
+  void remove_augmentation(size_t index) {
+    if (index >= strategies_.size()) throw std::out_of_range("Augmentation: no strategy at index " + std::to_string(index));
+    strategies_.erase(strategies_.begin() + (std::ptrdiff_t)index);
+  }
+  // removes every strategy with that name; returns how many were removed
+  size_t remove_augmentation(const std::string& name) {
+    const size_t before = strategies_.size();
+    strategies_.erase(std::remove_if(strategies_.begin(), strategies_.end(), [&](const std::unique_ptr<AugmentationStrategy>& s) { return s->name() == name; }), strategies_.end());
+    return before - strategies_.size();
+  }
+  void clear_augmentations() { strategies_.clear(); }
   size_t size() const { return strategies_.size(); }
   std::vector<std::string> names() const {
     std::vector<std::string> n;
@@ -195,6 +209,8 @@ class AugmentationBuilder {
   AugmentationBuilder& random_crop(double p = 1.0, size_t padding = 4) { aug_->add(std::make_unique<RandomCrop>(p, padding)); return *this; }
   AugmentationBuilder& cutout(double p = 0.5, size_t size = 8) { aug_->add(std::make_unique<Cutout>(p, size)); return *this; }
   AugmentationBuilder& normalize(std::vector<float> mean, std::vector<float> stdv) { aug_->add(std::make_unique<Normalize>(std::move(mean), std::move(stdv))); return *this; }
+  // any user strategy (docs/USAGE.md "custom augmentation"): applied in sequence with the built-in ones
+  AugmentationBuilder& custom_augmentation(std::unique_ptr<AugmentationStrategy> s) { aug_->add(std::move(s)); return *this; }
   std::shared_ptr<Augmentation> build() { return aug_; }
 
  private:

@@ -120,3 +120,14 @@ def test_torch_pipeline_baseline_matches_single_stage(tmp_path):
     l2 = json.loads([l for l in two.stdout.splitlines() if l.startswith("{")][-1])
     assert l2["n_gpus"] == 2 and l2["config"]["parallelism"] == "pp2" and len(l1["losses"]) == 3
     assert all(abs(a - b) < 1e-4 for a, b in zip(l1["losses"], l2["losses"]))
+
+
+def test_usage_tours_run():
+    """docs/USAGE.md quotes these two programs: tensors, LayerBuilder / TrainStep, augmentation (custom strategy, removal by
+    name / index) and an in-process two-stage pipeline, in both hosts."""
+    out = _run("examples/usage_tour.py", "--device", "cpu")
+    assert "usage tour complete" in out and "after removals: 3 strategies" in out and "pipeline batch 2" in out
+    from tnn_b200 import build
+    build.build_host(verbose=False)
+    cpp = subprocess.run([os.path.join(ROOT, "cpp", "bin", "usage_tour"), "--device", "CPU"], capture_output=True, text=True, timeout=300)
+    assert cpp.returncode == 0 and "usage tour complete" in cpp.stdout and "after removals: 3 strategies" in cpp.stdout, cpp.stdout[-1500:] + cpp.stderr[-1500:]

@@ -176,6 +176,29 @@ class Augmentation:
         self.strategies.append(s)
         return self
 
+    # strategy management of the reference (include/data_augmentation/augmentation.hpp:67-97)
+    add_augmentation = add
+
+    def remove_augmentation(self, which) -> int:
+        """Remove by index (int) or by strategy name (str: every strategy of that name); returns how many were removed."""
+        if isinstance(which, int):
+            if not 0 <= which < len(self.strategies):
+                raise IndexError(f"no strategy at index {which}")
+            del self.strategies[which]
+            return 1
+        before = len(self.strategies)
+        self.strategies = [s for s in self.strategies if s.name != which]
+        return before - len(self.strategies)
+
+    def clear_augmentations(self):
+        self.strategies.clear()
+
+    def size(self) -> int:
+        return len(self.strategies)
+
+    def names(self) -> list[str]:
+        return [s.name for s in self.strategies]
+
     def native_params(self) -> dict:
         d = {}
         for s in self.strategies:
@@ -223,6 +246,10 @@ class AugmentationBuilder:
 
     def normalize(self, mean, std):
         self.aug.add(Normalize(mean, std)); return self
+
+    def custom_augmentation(self, strategy: AugmentationStrategy):
+        """Any user strategy (a subclass of AugmentationStrategy with ``apply(x, gen)``), applied in sequence with the others."""
+        self.aug.add(strategy); return self
 
     def build(self) -> Augmentation:
         return self.aug
