@@ -23,7 +23,10 @@ if __name__ == "__main__":
     dev = torch.device("cuda", local) if cuda else torch.device("cpu")
     if cuda:
         torch.cuda.set_device(local)
-    dist.init_process_group("nccl" if cuda else "gloo")
+    # a collective stuck longer than this aborts the communicator (torch's NCCL watchdog); the engine's own host-side stall
+    # watchdog is TNN_PP_WATCHDOG_SEC (parallel/pipeline.py)
+    import datetime
+    dist.init_process_group("nccl" if cuda else "gloo", timeout=datetime.timedelta(seconds=float(os.environ.get("TNN_PP_TIMEOUT_SEC", "600"))))
     B, M = 256, 8
     model = ExampleModels.create(os.environ.get("MODEL_NAME", "cifar100_wrn16_8"))
     pp = PipelineParallel(model, FTDPartitioner(world, (B // M, 32, 32, 3)), OptimizerFactory.create_adam(1e-3, 0.9, 0.999, 1e-3, 3e-4),

@@ -460,6 +460,69 @@ def test_1f1b_pipeline_engine_equals_single_device(world, M):
     assert nbytes > 0
 
 
+def _pp_stall_rank(rank, world, port, out_q):
+    import torch.distributed as dist
+    torch.set_num_threads(1)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from tnn_b200.parallel.pipeline import PipelineParallel
+    x, y = _batches(1)[0]
+    B, M = x.shape[0], 2
+    pp = PipelineParallel(_model(), NaivePipelinePartitioner([1] * world), OptimizerFactory.create_sgd(0.05, 0.9),
+                          LossFactory.create_logsoftmax_crossentropy(), M, (B // M, 8, 8, 4), "cpu", seed=1, stall_timeout=5.0)
+    dist.barrier()                                        # process start-up skew is not a stall
+    pp.train_batch(x, y)                                  # one healthy batch: the watchdog stays quiet
+    assert not pp.watchdog.fired
+    out_q.put(("healthy", rank))
+    if rank == 1:
+        time.sleep(30)                                    # the last stage leaves the schedule (killed by the parent)
+        return
+    pp.train_batch(x, y)                                  # stage 0 now waits for a gradient that never comes
+    out_q.put(("returned", rank))                         # not reached: the watchdog ends the process with code 86
+
+
+def test_1f1b_engine_stall_watchdog_ends_a_rank_whose_neighbour_left():
+    """a stage whose neighbour died must not sit in its receive forever -- the host-side stall watchdog names the
+    step it is stuck in and exits with its code, which lets a launcher take the job down."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 22000 + (os.getpid() % 10000)
+    procs = [ctx.Process(target=_pp_stall_rank, args=(r, 2, port, q), daemon=True) for r in range(2)]
+    for p in procs:
+        p.start()
+    try:
+        assert sorted(q.get(timeout=120) for _ in range(2)) == [("healthy", 0), ("healthy", 1)]
+        procs[0].join(30)
+        assert procs[0].exitcode == 86, procs[0].exitcode
+        assert q.empty()
+    finally:
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+            p.join(10)
+
+
+def test_stall_watchdog_unit():
+    from tnn_b200.parallel.pipeline import StallWatchdog
+    hits = []
+    w = StallWatchdog(0.2, "unit", on_stall=hits.append)
+    w.enter("step a")
+    time.sleep(0.1)
+    w.progress(("p2p", "forward mb", 1, "", "recv<-prev"))     # progress re-arms the budget
+    time.sleep(0.15)
+    assert not hits
+    w.leave()
+    time.sleep(0.4)
+    assert not hits                                           # disarmed outside a schedule
+    w.enter(("p2p", "forward mb", 3, "", "recv<-prev"))
+    time.sleep(0.6)
+    assert len(hits) == 1 and "no progress for 0 s in p2p forward mb 3 recv<-prev" in hits[0] and w.fired
+    off = StallWatchdog(0, "off", on_stall=hits.append)      # 0 disables: no thread at all
+    off.enter("x")
+    assert off._thread is None
+
+
 def test_env_fault_injection_drop_and_delay(monkeypatch):
     monkeypatch.setenv("TNN_FAULT_INJECT", "0:FORWARD_JOB:drop:2")
     w = InProcessWorker("cpu", "w0")

@@ -22,10 +22,23 @@ graph's static input buffer, the graph's output buffer is what ``ncclSend`` read
 one memory pool and are captured -- and always replayed -- in schedule order, so a unit's scratch
 memory can be reused by later units while the per-microbatch layer caches stay alive between a
 forward and its backward.  ``TNN_PP_GRAPH=0`` keeps the eager path.
+
+Failure detection (the reference's un-timed ``cv.wait`` deadlocks on a lost microbatch,
+coordinator.hpp:182-184): a neighbour that died or fell out of the schedule leaves this rank waiting in a
+send / receive forever.  Two layers catch that.  (1) Device side: torch's NCCL watchdog aborts the communicator
+when a collective exceeds the process group's ``timeout`` -- pass one to ``init_process_group`` (the examples
+use ``TNN_PP_TIMEOUT_SEC``, default 600).  (2) Host side: ``StallWatchdog`` below notices when THIS rank has sat in
+one schedule step for ``stall_timeout`` seconds (``TNN_PP_WATCHDOG_SEC``, default 600, 0 = off), prints which
+unit it is stuck in (phase, micro-batch, peer rank) and ends the process with exit code 86, so that a launcher
+(torchrun) tears the job down instead of leaving N - 1 GPUs spinning.  The watchdog is a plain Python thread that
+only reads a timestamp: it makes no CUDA or NCCL call of its own (safe next to stream capture).
 """
 from __future__ import annotations
 
 import os
+import sys
+import threading
+import time
 
 import torch
 import torch.distributed as dist
@@ -38,10 +51,60 @@ from ..nn.optimizers import Optimizer, OptimizerFactory
 from .partitioner import Partitioner, flatten_pipeline_layers
 
 
+class StallWatchdog:
+    """Ends the process when the owner reports no progress for ``timeout`` seconds while it is inside a schedule.
+
+    ``enter(what)`` / ``progress(what)`` stamp the current position, ``leave()`` disarms; ``on_stall(message)`` defaults to
+    printing the message and ``os._exit(86)`` (a hung rank cannot be recovered in-process: its peers are blocked in
+    their own sends / receives and the launcher must take the job down)."""
+
+    EXIT_CODE = 86
+
+    def __init__(self, timeout: float, name: str, on_stall=None):
+        self.timeout, self.name = float(timeout), name
+        self.on_stall = on_stall or self._die
+        self._lock = threading.Lock()
+        self._since: float | None = None
+        self._what = ""
+        self._stop = threading.Event()
+        self.fired = False
+        self._thread = None
+        if self.timeout > 0:
+            self._thread = threading.Thread(target=self._run, name=f"{name}-stall-watchdog", daemon=True)
+            self._thread.start()
+
+    def enter(self, what):
+        with self._lock:
+            self._since, self._what = time.monotonic(), what
+
+    progress = enter
+
+    def leave(self):
+        with self._lock:
+            self._since = None
+
+    def close(self):
+        self._stop.set()
+
+    def _die(self, message: str):
+        print(message, file=sys.stderr, flush=True)
+        os._exit(self.EXIT_CODE)
+
+    def _run(self):
+        while not self._stop.wait(min(1.0, max(0.05, self.timeout / 4))):
+            with self._lock:
+                since, what = self._since, self._what
+            if since is not None and time.monotonic() - since > self.timeout:
+                self.fired = True
+                self.on_stall(f"[{self.name}] pipeline stall watchdog: no progress for {self.timeout:.0f} s in {' '.join(str(w) for w in what if w != '') if isinstance(what, tuple) else what}; a neighbouring stage "
+                              f"died or left the schedule (TNN_PP_WATCHDOG_SEC changes the budget, 0 disables)")
+                return
+
+
 class PipelineParallel:
     def __init__(self, model: Sequential, partitioner: Partitioner, optimizer: Optimizer, criterion: Loss,
                  num_microbatches: int, microbatch_shape: tuple, device, seed: int = 123456, group=None,
-                 scheduler_factory=None):
+                 scheduler_factory=None, stall_timeout: float | None = None, on_stall=None):
         assert dist.is_initialized(), "init torch.distributed first (nccl on GPUs, gloo on CPU)"
         self.group = group or dist.group.WORLD
         self.rank = dist.get_rank(self.group)
@@ -85,6 +148,9 @@ class PipelineParallel:
         self._gstats = torch.zeros(2, dtype=torch.float32, device=self.device)
         self._stat_scale = torch.tensor([1.0 / self.M, 1.0], dtype=torch.float32).to(self.device)
         self.graph_replays = 0
+        if stall_timeout is None:
+            stall_timeout = float(os.environ.get("TNN_PP_WATCHDOG_SEC", "600"))
+        self.watchdog = StallWatchdog(stall_timeout, f"stage {self.rank}/{self.world}", on_stall)
 
     # ------------------------------------------------------------------ p2p helpers
     def _ops(self, send_next=None, send_prev=None, recv_prev=False, recv_next=False):
@@ -100,6 +166,10 @@ class PipelineParallel:
             rn = self._recv_buf("next", self._bwd_i, self.out_shape)
             ops.append(dist.P2POp(dist.irecv, rn, self.next, self.group))
         if ops:
+            # a tuple, formatted only if the watchdog fires (this runs once per p2p group on the hot path)
+            self.watchdog.progress(("p2p", "forward mb", self._fwd_i, "backward mb", self._bwd_i, "send->next" if send_next is not None else "",
+                                    "send->prev" if send_prev is not None else "", "recv<-prev" if recv_prev else "", "recv<-next" if recv_next else "",
+                                    "prev/next rank", self.prev, self.next))
             for t in (send_next, send_prev):
                 if t is not None:
                     self.p2p_bytes += t.numel() * t.element_size()
@@ -180,6 +250,7 @@ class PipelineParallel:
         """1F1B over ``M`` microbatches.  ``x`` is consumed on the first stage, ``y`` on the last.
         Returns the device tensor [mean loss, #correct] (meaningful on the last stage)."""
         M, S, r = self.M, self.world, self.rank
+        self.watchdog.enter(f"train_batch {self.steps} (start)")
         xs = list(torch.tensor_split(x.to(self.device, non_blocking=True), M, 0)) if self.is_first else None
         ys = list(torch.tensor_split(y.to(self.device, non_blocking=True), M, 0)) if self.is_last else None
         if self.device.type == "cuda":
@@ -239,10 +310,12 @@ class PipelineParallel:
             if self.scheduler is not None:
                 self.scheduler.step()
         self.steps += 1
+        self.watchdog.leave()
         return stats.clone() if self._graph_mode else stats
 
     def eval_batch(self, x, y):
         self.graph.set_training(False)
+        self.watchdog.enter("eval_batch")
         inp, _ = self._ops(recv_prev=not self.is_first)
         out = self.stage.forward(x.to(self.device) if self.is_first else inp, 0)
         stats = torch.zeros(2, dtype=torch.float32, device=self.device)
@@ -252,6 +325,7 @@ class PipelineParallel:
         else:
             self._ops(send_next=self._boundary(out))
         self.graph.set_training(True)
+        self.watchdog.leave()
         return stats
 
     def broadcast_stats(self, stats: torch.Tensor) -> torch.Tensor:
