@@ -131,3 +131,41 @@ def test_usage_tours_run():
     build.build_host(verbose=False)
     cpp = subprocess.run([os.path.join(ROOT, "cpp", "bin", "usage_tour"), "--device", "CPU"], capture_output=True, text=True, timeout=300)
     assert cpp.returncode == 0 and "usage tour complete" in cpp.stdout and "after removals: 3 strategies" in cpp.stdout, cpp.stdout[-1500:] + cpp.stderr[-1500:]
+
+
+def test_vocab_export_and_corpus_preparation_tools(tmp_path):
+    """tools/export_vocab.py + tools/prepare_openwebtext.py (the reference's python/export_vocab.py and python/openwebtext.py
+    without tiktoken / datasets): a Hugging-Face style byte-level vocab.json becomes vocab.bin, text + jsonl documents become
+    uint16 train.bin / val.bin with an end-of-text token after every document, and the OpenWebText loader reads them."""
+    import json
+
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        from export_vocab import bytes_to_unicode
+    finally:
+        sys.path.pop(0)
+    u = bytes_to_unicode()
+    assert len(u) == 256 and len(set(u.values())) == 256 and u[ord("A")] == "A" and u[ord(" ")] == "Ġ"
+    toks = [u[b] for b in range(256)] + [u[ord("t")] + u[ord("h")], u[ord(" ")] + u[ord("t")] + u[ord("h")], u[ord("e")] + u[ord("r")], "<|endoftext|>"]
+    (tmp_path / "vocab.json").write_text(json.dumps({t: i for i, t in enumerate(toks)}))
+    (tmp_path / "a.txt").write_text("the other weather, then there")
+    (tmp_path / "b.jsonl").write_text(json.dumps({"text": "hello the world"}) + "\n" + json.dumps({"text": "another one"}) + "\n")
+    out = tmp_path / "out"
+    assert "wrote 260 tokens" in _run("tools/export_vocab.py", "--from", "vocab-json", str(tmp_path / "vocab.json"), "--out", str(out / "vocab.bin"))
+    rep = json.loads(_run("tools/prepare_openwebtext.py", str(tmp_path / "a.txt"), str(tmp_path / "b.jsonl"), "--vocab", str(out / "vocab.bin"),
+                          "--out", str(out), "--val-fraction", "0.5").splitlines()[-1])
+    assert rep["documents"] == 3 and rep["eot"] == 259 and rep["val_tokens"] > 0 and rep["train_tokens"] > 0
+    from tnn_b200.data import Tokenizer
+    from tnn_b200.data.loaders import OpenWebTextDataLoader
+    tok = Tokenizer(str(out / "vocab.bin"))
+    ids = np.concatenate([np.fromfile(out / f"{s}.bin", dtype=np.uint16) for s in ("train", "val")]).tolist()
+    assert ids.count(259) == 3                                         # one end-of-text per document
+    text = tok.decode(ids)
+    for doc in ("the other weather, then there", "hello the world", "another one"):
+        assert doc + "<|endoftext|>" in text
+    assert 257 in ids and 258 in ids                                   # the merges were used (" th", "er")
+    dl = OpenWebTextDataLoader(seq_len=4).load_data(str(out))
+    x, y = dl.get_batch(2)
+    assert x.shape == (2, 4) and bool((x[:, 1:] == y[:, :-1]).all())
+    assert "wrote 257 tokens" in _run("tools/export_vocab.py", "--from", "byte-fallback", "--out", str(out / "bytes.bin"))
