@@ -10,6 +10,7 @@
 #include <iostream>
 #include <sstream>
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <sys/wait.h>
 #include <unistd.h>
@@ -296,6 +297,276 @@ TEST(fd_mailbox_passes_descriptors_between_processes) {
     timed_out = true;
   }
   CHECK(timed_out);
+}
+// ---- a memfd-backed stand-in for the CUDA VMM / multicast driver calls: "physical allocations" are memfds, exporting one
+// dup()s its descriptor, mapping is mmap(MAP_SHARED) into a reserved range.  With it the whole SymmetricMemory group protocol
+// (sizes, mappings, symmetric offsets, descriptor exchange between processes, phase ordering, teardown) runs on a CPU box;
+// what stays unverified without a GPU is only that the real driver accepts the same call sequence.
+namespace fake_vmm {
+struct Handle {
+  int fd = -1;
+  size_t size = 0;
+  bool multicast = false;
+  int devices_added = 0, binds = 0;
+};
+static std::mutex mu;
+static std::map<CUmemGenericAllocationHandle, Handle> handles;
+static std::map<CUdeviceptr, size_t> reserved;
+static uint64_t next_handle = 1;
+static int access_calls = 0;
+static CUmemGenericAllocationHandle add(int fd, size_t size, bool mc) {
+  std::lock_guard<std::mutex> g(mu);
+  Handle h;
+  h.fd = fd;
+  h.size = size;
+  h.multicast = mc;
+  handles[next_handle] = h;
+  return next_handle++;
+}
+static int new_memfd(size_t size) {
+  const int fd = memfd_create("tnn_fake_vmm", MFD_CLOEXEC);
+  if (fd >= 0 && ftruncate(fd, (off_t)size) != 0) {
+    close(fd);
+    return -1;
+  }
+  return fd;
+}
+static const VmmDriver& table(int device_count) {
+  static VmmDriver d;
+  d.fake_device_count = device_count;
+  d.GetErrorString = [](CUresult, const char** s) -> CUresult {
+    *s = "fake driver error";
+    return CUDA_SUCCESS;
+  };
+  d.DeviceGet = [](CUdevice* dev, int ordinal) -> CUresult {
+    *dev = ordinal;
+    return CUDA_SUCCESS;
+  };
+  d.DeviceGetAttribute = [](int* v, CUdevice_attribute, CUdevice) -> CUresult {
+    *v = 1;
+    return CUDA_SUCCESS;
+  };
+  d.MemGetAllocationGranularity = [](size_t* g, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) -> CUresult {
+    *g = 64 << 10;
+    return CUDA_SUCCESS;
+  };
+  d.MulticastGetGranularity = [](size_t* g, const CUmulticastObjectProp*, CUmulticastGranularity_flags) -> CUresult {
+    *g = 128 << 10;
+    return CUDA_SUCCESS;
+  };
+  d.MemCreate = [](CUmemGenericAllocationHandle* h, size_t size, const CUmemAllocationProp* p, unsigned long long) -> CUresult {
+    if (p->requestedHandleTypes != CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR || size % (64 << 10)) return CUDA_ERROR_INVALID_VALUE;
+    const int fd = new_memfd(size);
+    if (fd < 0) return CUDA_ERROR_OUT_OF_MEMORY;
+    *h = add(fd, size, false);
+    return CUDA_SUCCESS;
+  };
+  d.MulticastCreate = [](CUmemGenericAllocationHandle* h, const CUmulticastObjectProp* p) -> CUresult {
+    if (p->numDevices < 2 || p->size % (128 << 10)) return CUDA_ERROR_INVALID_VALUE;
+    const int fd = new_memfd(p->size);
+    if (fd < 0) return CUDA_ERROR_OUT_OF_MEMORY;
+    *h = add(fd, p->size, true);
+    return CUDA_SUCCESS;
+  };
+  d.MemRelease = [](CUmemGenericAllocationHandle h) -> CUresult {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = handles.find(h);
+    if (it == handles.end()) return CUDA_ERROR_INVALID_VALUE;
+    close(it->second.fd);
+    handles.erase(it);
+    return CUDA_SUCCESS;
+  };
+  d.MemExportToShareableHandle = [](void* out, CUmemGenericAllocationHandle h, CUmemAllocationHandleType, unsigned long long) -> CUresult {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = handles.find(h);
+    if (it == handles.end()) return CUDA_ERROR_INVALID_VALUE;
+    *static_cast<int*>(out) = dup(it->second.fd);
+    return CUDA_SUCCESS;
+  };
+  d.MemImportFromShareableHandle = [](CUmemGenericAllocationHandle* h, void* os_handle, CUmemAllocationHandleType) -> CUresult {
+    const int fd = dup((int)(uintptr_t)os_handle);      // the caller closes its descriptor afterwards, like with the real driver
+    struct stat st {};
+    if (fd < 0 || fstat(fd, &st) != 0) return CUDA_ERROR_INVALID_VALUE;
+    *h = add(fd, (size_t)st.st_size, false);
+    return CUDA_SUCCESS;
+  };
+  d.MemAddressReserve = [](CUdeviceptr* ptr, size_t size, size_t, CUdeviceptr, unsigned long long) -> CUresult {
+    void* p = mmap(nullptr, size, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return CUDA_ERROR_OUT_OF_MEMORY;
+    std::lock_guard<std::mutex> g(mu);
+    reserved[(CUdeviceptr)(uintptr_t)p] = size;
+    *ptr = (CUdeviceptr)(uintptr_t)p;
+    return CUDA_SUCCESS;
+  };
+  d.MemAddressFree = [](CUdeviceptr ptr, size_t size) -> CUresult {
+    std::lock_guard<std::mutex> g(mu);
+    if (!reserved.erase(ptr)) return CUDA_ERROR_INVALID_VALUE;
+    munmap(reinterpret_cast<void*>((uintptr_t)ptr), size);
+    return CUDA_SUCCESS;
+  };
+  d.MemMap = [](CUdeviceptr ptr, size_t size, size_t offset, CUmemGenericAllocationHandle h, unsigned long long) -> CUresult {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = handles.find(h);
+    if (it == handles.end() || offset != 0 || size > it->second.size || !reserved.count(ptr)) return CUDA_ERROR_INVALID_VALUE;
+    void* p = mmap(reinterpret_cast<void*>((uintptr_t)ptr), size, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_FIXED, it->second.fd, 0);
+    return p == MAP_FAILED ? CUDA_ERROR_OUT_OF_MEMORY : CUDA_SUCCESS;
+  };
+  d.MemUnmap = [](CUdeviceptr ptr, size_t size) -> CUresult {
+    void* p = mmap(reinterpret_cast<void*>((uintptr_t)ptr), size, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_FIXED, -1, 0);
+    return p == MAP_FAILED ? CUDA_ERROR_INVALID_VALUE : CUDA_SUCCESS;
+  };
+  d.MemSetAccess = [](CUdeviceptr, size_t, const CUmemAccessDesc* desc, size_t count) -> CUresult {
+    if (!desc || count == 0) return CUDA_ERROR_INVALID_VALUE;
+    ++access_calls;
+    return CUDA_SUCCESS;
+  };
+  d.MulticastAddDevice = [](CUmemGenericAllocationHandle h, CUdevice) -> CUresult {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = handles.find(h);
+    if (it == handles.end()) return CUDA_ERROR_INVALID_VALUE;
+    ++it->second.devices_added;
+    return CUDA_SUCCESS;
+  };
+  d.MulticastBindMem = [](CUmemGenericAllocationHandle mc, size_t mc_off, CUmemGenericAllocationHandle mem, size_t mem_off, size_t size, unsigned long long) -> CUresult {
+    std::lock_guard<std::mutex> g(mu);
+    auto a = handles.find(mc), b = handles.find(mem);
+    if (a == handles.end() || b == handles.end() || mc_off || mem_off || size > a->second.size || size > b->second.size) return CUDA_ERROR_INVALID_VALUE;
+    if (a->second.devices_added == 0) return CUDA_ERROR_INVALID_VALUE;         // bind before add
+    ++a->second.binds;
+    return CUDA_SUCCESS;
+  };
+  d.MulticastUnbind = [](CUmemGenericAllocationHandle, CUdevice, size_t, size_t) -> CUresult { return CUDA_SUCCESS; };
+  return d;
+}
+struct Install {
+  explicit Install(int devices) { VmmDriver::install_for_testing(&table(devices)); }
+  ~Install() { VmmDriver::install_for_testing(nullptr); }
+};
+}  // namespace fake_vmm
+
+TEST(symmetric_memory_group_in_one_process_over_a_fake_driver) {
+  if (DeviceManager::getInstance().has_gpu()) throw Skip("GPU present: the real driver is used");
+  fake_vmm::Install fake(4);
+  {
+    const auto sup = SymmetricMemory::probe({0, 1, 2});
+    CHECK(sup.vmm && sup.multicast);
+    CHECK(!SymmetricMemory::probe({0}).multicast && !SymmetricMemory::probe({0, 7}).vmm);
+    auto group = std::make_shared<SymmetricMemory>(std::vector<int>{0, 1, 2}, (size_t)300 << 10, true);
+    CHECK(group->world() == 3 && group->my_rank() == -1 && group->granularity() == (128u << 10) && group->bytes() == (384u << 10));
+    CHECK(group->has_multicast() && fake_vmm::handles.size() == 4);       // three slabs + the multicast object
+    for (const auto& kv : fake_vmm::handles)
+      if (kv.second.multicast) CHECK(kv.second.devices_added == 3 && kv.second.binds == 3);
+    std::vector<std::unique_ptr<SymmetricAllocator>> al;
+    std::vector<int*> blk, blk2;
+    for (int r = 0; r < 3; ++r) {
+      al.push_back(std::make_unique<SymmetricAllocator>(group, r));
+      CHECK(al.back()->device() == Device(DeviceType::GPU, r));
+      blk.push_back(static_cast<int*>(al.back()->allocate(1000)));
+      blk2.push_back(static_cast<int*>(al.back()->allocate(5000)));
+    }
+    for (int r = 0; r < 3; ++r) {
+      CHECK(group->offset_of(r, blk[(size_t)r]) == 0 && group->offset_of(r, blk2[(size_t)r]) == 1024);     // symmetric offsets
+      blk2[(size_t)r][7] = 100 + r;
+    }
+    // rank 0's view of rank 2's block is rank 2's block
+    CHECK(static_cast<int*>(al[0]->peer(blk2[0], 2)) == blk2[2] && static_cast<int*>(al[0]->peer(blk2[0], 2))[7] == 102);
+    CHECK(al[1]->multicast(blk2[1]) == static_cast<char*>(group->multicast_base()) + 1024);
+    bool threw = false;
+    try {
+      group->offset_of(0, blk[1]);                        // another rank's pointer
+    } catch (const std::out_of_range&) {
+      threw = true;
+    }
+    CHECK(threw);
+    threw = false;
+    try {
+      al[0]->allocate(group->bytes());                    // larger than what is left
+    } catch (const std::bad_alloc&) {
+      threw = true;
+    }
+    CHECK(threw);
+    CHECK(al[0]->bytes_in_use() == 1024 + 5120 && al[0]->bytes_reserved() == group->bytes());
+    const int fd = group->export_fd(1);
+    CHECK(fd >= 0);
+    close(fd);
+    for (int r = 0; r < 3; ++r) {
+      al[(size_t)r]->deallocate(blk[(size_t)r]);
+      al[(size_t)r]->deallocate(blk2[(size_t)r]);
+    }
+    CHECK(group->free_list(2).in_use() == 0 && group->free_list(2).num_free_ranges() == 1);
+    // a model's parameter slabs inside the group (what DataParallel does with TNN_DP_NVLS=1)
+    LayerBuilder lb({16});
+    lb.dense(8, true, "d");
+    CHECK(GraphContext::slab_bytes(lb.build_sequential("m")->all_layers(), true) < group->bytes());
+  }
+  CHECK(fake_vmm::handles.empty() && fake_vmm::reserved.empty());         // teardown released every handle and range
+}
+TEST(symmetric_memory_rendezvous_between_processes_over_a_fake_driver) {
+  if (DeviceManager::getInstance().has_gpu()) throw Skip("GPU present: the real driver is used");
+  // three processes, one rank each: physical handles and the multicast handle cross as SCM_RIGHTS descriptors; because the
+  // fake "allocations" are memfds the slabs really are shared, so every rank can check what its peers wrote
+  char tmpl[] = "/tmp/tnn_symm_XXXXXX";
+  CHECK(mkdtemp(tmpl) != nullptr);
+  const std::string dir = tmpl;
+  const int W = 3;
+  fake_vmm::Install fake(1);
+  std::vector<pid_t> kids;
+  for (int r = 0; r < W; ++r) {
+    const pid_t pid = fork();
+    if (pid == 0) {
+      int rc = 1;
+      try {
+        if (r == 1) usleep(200 * 1000);                 // a late rank: the others retry their sends / hold early datagrams
+        auto m = SymmetricMemory::rendezvous(r, W, /*device=*/0, (size_t)100 << 10, dir, true, 20000);
+        rc = 2;
+        if (m->world() == W && m->my_rank() == r && m->has_multicast() && m->bytes() == (128u << 10)) {
+          int* mine = static_cast<int*>(m->allocate(r, 4096));
+          rc = 3;
+          if (m->offset_of(r, mine) == 0) {
+            mine[0] = 1000 + r;
+            __sync_synchronize();
+            FdMailbox box(dir, "t." + std::to_string(r));
+            for (int q = 0; q < W; ++q)
+              if (q != r) box.send(dir + "/t." + std::to_string(q), (uint64_t)r, -1, 20000);
+            for (int i = 0; i < W - 1; ++i) {
+              int f = -1;
+              box.recv(&f, 20000);
+            }
+            rc = 0;
+            for (int q = 0; q < W; ++q)
+              if (static_cast<int*>(m->peer(r, mine, q))[0] != 1000 + q) rc = 4;          // peers' writes through MY mappings
+            if (m->multicast(r, mine) != m->multicast_base()) rc = 5;
+            bool refused = false;
+            try {
+              m->allocate((r + 1) % W, 16);             // only the local rank allocates in a multi-process group
+            } catch (const std::invalid_argument&) {
+              refused = true;
+            }
+            if (!refused) rc = 6;
+            // nobody unmaps before everybody has checked
+            for (int q = 0; q < W; ++q)
+              if (q != r) box.send(dir + "/t." + std::to_string(q), 100 + (uint64_t)r, -1, 20000);
+            for (int i = 0; i < W - 1; ++i) {
+              int f = -1;
+              box.recv(&f, 20000);
+            }
+          }
+        }
+      } catch (const std::exception& e) {
+        fprintf(stderr, "rank %d: %s\n", r, e.what());
+        rc = 9;
+      }
+      _exit(rc);
+    }
+    kids.push_back(pid);
+  }
+  for (int r = 0; r < W; ++r) {
+    int st = 0;
+    waitpid(kids[(size_t)r], &st, 0);
+    if (!(WIFEXITED(st) && WEXITSTATUS(st) == 0)) throw std::runtime_error("rank " + std::to_string(r) + " exited with " + std::to_string(WIFEXITED(st) ? WEXITSTATUS(st) : -1));
+  }
+  // every mailbox unlinked itself
+  CHECK(rmdir(dir.c_str()) == 0);
 }
 TEST(symmetric_memory_reports_unsupported_on_a_cpu_box) {
   if (DeviceManager::getInstance().has_gpu()) throw Skip("GPU present");

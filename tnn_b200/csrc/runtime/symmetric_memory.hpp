@@ -236,11 +236,18 @@ struct VmmDriver {
   decltype(&cuDeviceGet) DeviceGet = nullptr;
   decltype(&cuGetErrorString) GetErrorString = nullptr;
   std::string why;                                     // empty: every entry point resolved
+  // A table installed by install_for_testing() stands in for the driver (tests/ use a memfd-backed one: "physical
+  // allocations" are memfds, "mapping" is mmap, so the whole group protocol runs on a CPU box).  `device_count` > 0 then
+  // replaces cudaGetDeviceCount and the CUDA runtime calls (context creation, device synchronise) are skipped.
+  int fake_device_count = 0;
 
   static const VmmDriver& get() {
+    if (const VmmDriver* t = testing_slot()) return *t;
     static const VmmDriver d = load();
     return d;
   }
+  static void install_for_testing(const VmmDriver* table) { testing_slot() = table; }
+  bool fake() const { return fake_device_count > 0; }
   bool ok() const { return why.empty(); }
   std::string err(CUresult r) const {
     const char* s = nullptr;
@@ -249,6 +256,10 @@ struct VmmDriver {
   }
 
  private:
+  static const VmmDriver*& testing_slot() {
+    static const VmmDriver* t = nullptr;
+    return t;
+  }
   template <class F>
   static bool one(const char* name, F* out, std::string* why) {
     void* p = nullptr;
@@ -305,8 +316,8 @@ class SymmetricMemory {
       s.why = D.why;
       return s;
     }
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    int n = D.fake_device_count;
+    if (!D.fake() && (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)) {
       cudaGetLastError();
       s.why = "no CUDA device";
       return s;
@@ -430,6 +441,7 @@ class SymmetricMemory {
     if (r != CUDA_SUCCESS) throw std::runtime_error(std::string("SymmetricMemory: ") + what + ": " + D().err(r));
   }
   static void make_context(int dev) {
+    if (D().fake()) return;
     if (cudaSetDevice(dev) != cudaSuccess || cudaFree(nullptr) != cudaSuccess) {
       const std::string e = cudaGetErrorString(cudaGetLastError());
       throw std::runtime_error("SymmetricMemory: cannot initialise device " + std::to_string(dev) + ": " + e);
@@ -521,10 +533,11 @@ class SymmetricMemory {
   }
   void destroy() {
     if (!D().ok()) return;
-    for (int d : local_devices_safe()) {
-      cudaSetDevice(d);
-      cudaDeviceSynchronize();
-    }
+    if (!D().fake())
+      for (int d : local_devices_safe()) {
+        cudaSetDevice(d);
+        cudaDeviceSynchronize();
+      }
     unmap(mc_va_);
     if (mc_handle_) {
       for (size_t r = 0; r < phys_.size(); ++r)
@@ -538,7 +551,7 @@ class SymmetricMemory {
         D().MemRelease(h);
         h = 0;
       }
-    cudaGetLastError();
+    if (!D().fake()) cudaGetLastError();
   }
   std::vector<int> local_devices_safe() const {
     if (my_rank_ < 0) return devices_;
