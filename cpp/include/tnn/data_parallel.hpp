@@ -19,6 +19,12 @@
 
 namespace tnn {
 
+// Shard layout of the fused step: rank r owns elements [r * chunk, min(n, (r + 1) * chunk)) of a flat state vector.
+// gather: W shard buffers (each >= its owned length) -> one vector of `total` (>= n) elements, zero beyond n;
+// scatter: the inverse, every shard buffer `chunk` long and zero padded.  (Host-side helpers of save / load_checkpoint.)
+std::vector<float> dp_gather_shards(const std::vector<std::vector<float>>& shards, size_t n, size_t chunk, size_t total);
+std::vector<std::vector<float>> dp_scatter_shards(const std::vector<float>& full, size_t n, size_t chunk, size_t world);
+
 class DataParallel {
  public:
   using ModelFactory = std::function<std::unique_ptr<Layer>()>;
@@ -36,6 +42,13 @@ class DataParallel {
   // max over replicas r > 0 of max |param_r - param_0| (replicas must stay bit-identical)
   double max_replica_divergence();
   bool captured() const;
+  // Checkpoint / resume.  The file is an ordinary model checkpoint (replica 0's graph + the "opt.*" trailer of
+  // save_checkpoint, train.hpp): the optimizer moments, which live sharded W ways across the replicas, are gathered into
+  // full-length tensors on save and scattered to whatever world size loads them, so a file written by W replicas resumes on
+  // W' replicas or on one GPU (load_checkpoint) and the other way round.  Replicas must be idle (between step() calls).
+  void save_checkpoint(const std::string& path);
+  void load_checkpoint(const std::string& path);
+  uint64_t step_count() const;
 
  private:
   struct Rank {

@@ -148,6 +148,86 @@ double DataParallel::max_replica_divergence() {
   }
   return worst;
 }
+std::vector<float> dp_gather_shards(const std::vector<std::vector<float>>& shards, size_t n, size_t chunk, size_t total) {
+  if (total < n) throw std::invalid_argument("dp_gather_shards: total < n");
+  std::vector<float> full(total, 0.f);
+  for (size_t r = 0; r < shards.size(); ++r) {
+    const size_t lo = r * chunk, hi = std::min(n, lo + chunk);
+    if (lo >= hi) continue;
+    if (shards[r].size() < hi - lo) throw std::invalid_argument("dp_gather_shards: shard " + std::to_string(r) + " is shorter than the range it owns");
+    std::copy(shards[r].begin(), shards[r].begin() + (std::ptrdiff_t)(hi - lo), full.begin() + (std::ptrdiff_t)lo);
+  }
+  return full;
+}
+std::vector<std::vector<float>> dp_scatter_shards(const std::vector<float>& full, size_t n, size_t chunk, size_t world) {
+  if (full.size() < n || chunk * world < n) throw std::invalid_argument("dp_scatter_shards: the shards do not cover n");
+  std::vector<std::vector<float>> shards(world, std::vector<float>(chunk, 0.f));
+  for (size_t r = 0; r < world; ++r) {
+    const size_t lo = r * chunk, hi = std::min(n, lo + chunk);
+    if (lo < hi) std::copy(full.begin() + (std::ptrdiff_t)lo, full.begin() + (std::ptrdiff_t)hi, shards[r].begin());
+  }
+  return shards;
+}
+uint64_t DataParallel::step_count() const { return ranks_[0]->opt->step_count; }
+void DataParallel::save_checkpoint(const std::string& path) {
+  const size_t W = ranks_.size();
+  std::vector<std::vector<float>> ms(W), vs(W);
+  for (size_t r = 0; r < W; ++r) {
+    Rank& k = *ranks_[r];
+    k.dev.set_current();
+    current_flow(k.dev).synchronize();
+    ms[r] = to_float_vector(*k.m);
+    if (adam_) vs[r] = to_float_vector(*k.v);
+  }
+  GraphContext& ctx = ranks_[0]->graph->context();
+  const size_t total = ctx.param_slab()->size();
+  std::map<std::string, Tensor> tensors;
+  // the names a single-device optimizer uses for the same state (Adam: m, v; SGD: velocity)
+  tensors[adam_ ? "opt.m" : "opt.velocity"] = make_tensor_from(dp_gather_shards(ms, n_, chunk_, total), {total});
+  if (adam_) tensors["opt.v"] = make_tensor_from(dp_gather_shards(vs, n_, chunk_, total), {total});
+  Optimizer& opt = *ranks_[0]->opt;
+  Json meta = Json::object();
+  meta["step"] = (long long)opt.step_count;
+  meta["opt.config"] = opt.get_config().to_json();
+  meta["opt.step"] = (long long)opt.step_count;
+  meta["opt.lr"] = opt.get_learning_rate();
+  meta["dp.world"] = (long long)W;
+  ranks_[0]->dev.set_current();
+  ranks_[0]->graph->save_state(path, &tensors, &meta);
+}
+void DataParallel::load_checkpoint(const std::string& path) {
+  std::map<std::string, Tensor> tensors;
+  Json meta;
+  Graph host = Graph::load_state(path, getHost(), &tensors, &meta);
+  GraphContext& src = host.context();
+  if (src.numel() != n_) throw std::runtime_error("DataParallel::load_checkpoint: " + path + " holds " + std::to_string(src.numel()) + " parameters, the replicas " + std::to_string(n_));
+  auto full = [&](const char* a, const char* b) -> std::vector<float> {
+    auto it = tensors.find(a);
+    if (it == tensors.end() && b) it = tensors.find(b);
+    if (it == tensors.end()) return std::vector<float>(n_, 0.f);        // a checkpoint without optimizer state: fresh moments
+    std::vector<float> v = to_float_vector(*it->second);
+    if (v.size() < n_) throw std::runtime_error(std::string("DataParallel::load_checkpoint: optimizer tensor ") + a + " is too short");
+    return v;
+  };
+  const auto ms = dp_scatter_shards(adam_ ? full("opt.m", nullptr) : full("opt.velocity", "opt.m"), n_, chunk_, ranks_.size());
+  const auto vs = adam_ ? dp_scatter_shards(full("opt.v", nullptr), n_, chunk_, ranks_.size()) : std::vector<std::vector<float>>();
+  for (size_t r = 0; r < ranks_.size(); ++r) {
+    Rank& k = *ranks_[r];
+    k.dev.set_current();
+    GraphContext& ctx = k.graph->context();
+    ctx.param_slab()->copy_from(*src.param_slab());
+    ctx.buffer_slab()->copy_from(*src.buffer_slab());
+    ctx.grad_slab()->zero();
+    ctx.refresh_lp();
+    k.m->copy_from_host(ms[r].data(), ms[r].size() * 4);
+    if (adam_) k.v->copy_from_host(vs[r].data(), vs[r].size() * 4);
+    if (meta.is_object()) {
+      k.opt->step_count = (uint64_t)meta.value("opt.step", (int64_t)0);
+      k.opt->set_learning_rate(meta.value("opt.lr", k.opt->get_learning_rate()));
+    }
+    current_flow(k.dev).synchronize();
+  }
+}
 bool DataParallel::captured() const {
   for (auto& rk : ranks_)
     if (!rk->step->captured()) return false;

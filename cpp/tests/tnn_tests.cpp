@@ -1883,6 +1883,96 @@ static void dp2_case(int symmetric) {
   CHECK(single.back() < single.front());
 }
 TEST(dp2_fused_step_matches_single_device) { dp2_case(0); }
+TEST(data_parallel_shard_layout_gather_scatter) {
+  // host-side layout of the sharded optimizer state (DataParallel::save_checkpoint / load_checkpoint): n = 10 elements,
+  // 3 ranks, chunk 4 -> rank 2 owns only [8, 10); the gathered vector is padded to the slab size
+  const size_t n = 10, chunk = 4, total = 16;
+  std::vector<std::vector<float>> shards = {{0, 1, 2, 3}, {4, 5, 6, 7}, {8, 9, -1, -1}};
+  const auto full = dp_gather_shards(shards, n, chunk, total);
+  CHECK(full.size() == total);
+  for (size_t i = 0; i < total; ++i) CHECK(full[i] == (i < n ? (float)i : 0.f));          // rank 2's padding is not state
+  // the same state on 2 ranks (chunk 8) and back on 3
+  const auto two = dp_scatter_shards(full, n, 8, 2);
+  CHECK(two.size() == 2 && two[0].size() == 8 && two[1][0] == 8.f && two[1][1] == 9.f && two[1][2] == 0.f);
+  CHECK(dp_gather_shards(two, n, 8, total) == full);
+  const auto three = dp_scatter_shards(full, n, chunk, 3);
+  CHECK(three[2][0] == 8.f && three[2][1] == 9.f && three[2][2] == 0.f && three[0] == shards[0] && three[1] == shards[1]);
+  bool threw = false;
+  try {
+    dp_scatter_shards(full, n, 4, 2);                   // 2 x 4 < 10
+  } catch (const std::invalid_argument&) {
+    threw = true;
+  }
+  CHECK(threw);
+  threw = false;
+  try {
+    dp_gather_shards({{0, 1}, {4, 5, 6, 7}, {8, 9}}, n, chunk, total);      // rank 0's buffer is shorter than its range
+  } catch (const std::invalid_argument&) {
+    threw = true;
+  }
+  CHECK(threw);
+}
+TEST(data_parallel_checkpoint_resumes_sharded_and_single) {
+  // written after the round's GPU budget was spent: not yet run on hardware (needs 2 GPUs; the driver's GPU tier has one)
+  need_gpu();
+  if (DeviceManager::getInstance().num_gpus() < 2) throw Skip("needs 2 GPUs");
+  auto make = []() -> std::unique_ptr<Layer> {
+    LayerBuilder b({8, 8, 16});
+    b.conv2d(32, 3, 3, 1, 1, 1, 1, true, "c1").activation("relu", "r1").flatten(1, -1, "f").dense(10, true, "head");
+    return b.build_sequential("dp_ckpt_net");
+  };
+  const size_t B = 32;
+  SyntheticDataLoader data({8, 8, 16}, 10, 2 * B, 5);
+  data.set_pinned(true);
+  Tensor x, y;
+  data.get_batch(B, x, y);
+  auto halves = [&](Vec<Tensor>* xs, Vec<Tensor>* ys) {
+    for (size_t r = 0; r < 2; ++r) {
+      xs->push_back(x->slice_batch(r * B / 2, B / 2));
+      ys->push_back(y->slice_batch(r * B / 2, B / 2));
+    }
+  };
+  Adam proto(1e-3, 0.9, 0.999, 1e-8, 0.0, false);
+  const std::string path = "/tmp/tnn_tests_dp_ckpt";
+  std::vector<double> cont;
+  {
+    DataParallel dp(make, 2, 5, proto);
+    for (int i = 0; i < 6; ++i) {
+      Vec<Tensor> xs, ys;
+      halves(&xs, &ys);
+      dp.step(xs, ys);
+    }
+    dp.save_checkpoint(path);
+    CHECK(dp.step_count() == 6);
+    for (int i = 0; i < 3; ++i) {
+      Vec<Tensor> xs, ys;
+      halves(&xs, &ys);
+      cont.push_back(dp.step(xs, ys).first);
+    }
+  }
+  {
+    DataParallel dp(make, 2, 99, proto);               // different seed: everything must come from the file
+    dp.load_checkpoint(path);
+    CHECK(dp.step_count() == 6 && dp.max_replica_divergence() == 0.0);
+    for (int i = 0; i < 3; ++i) {
+      Vec<Tensor> xs, ys;
+      halves(&xs, &ys);
+      CHECK_NEAR(dp.step(xs, ys).first, cont[(size_t)i], 2e-3 * std::max(1.0, cont[(size_t)i]));
+    }
+  }
+  {
+    // the same file resumes single-GPU training: full-length moments, the single-device optimizer's tensor names
+    auto opt = proto.clone();
+    uint64_t step_no = 0;
+    Graph g = load_checkpoint(path, getGPU(0), opt.get(), nullptr, &step_no);
+    CHECK(step_no == 6 && opt->step_count == 6);
+    auto crit = LossFactory::create_logsoftmax_crossentropy();
+    TrainStep step(g, *crit, *opt, nullptr, 1, false);
+    float h[2];
+    step(x, y)->copy_to_host(h, 8);
+    CHECK_NEAR(h[0], cont[0], 0.03 * std::max(1.0, cont[0]));
+  }
+}
 // The two cases below exercise the framework's own VMM / multicast group on real GPUs.  They were written after the
 // round's GPU budget was spent and have not run on hardware yet, so they are opt-in (TNN_TEST_NVLS=1) instead of being able
 // to turn the round-end GPU suite red.

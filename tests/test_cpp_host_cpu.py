@@ -464,3 +464,20 @@ def test_cpp_jpeg_decoder_and_image_tree_loaders(tmp_path):
             Image.fromarray(picture(48, 40)).save(str(root2 / "train" / cname / f"{k}.jpg"), quality=90)
     r = subprocess.run([exe, "--loader", str(root2), "imagenet100", "train", "8", str(tmp_path / "i.f32")], capture_output=True, text=True)
     assert r.returncode == 0 and list(map(int, r.stdout.split())) == [4, 2, 0, 0, 0, 1, 1], (r.stdout, r.stderr)
+
+
+def test_tnn_tests_name_filters_used_by_the_gpu_suite_select_only_plain_gpu_cases():
+    """tests/test_cpp_host_gpu.py runs ``tnn_tests gpu`` and requires "0 skipped"; tests/test_multigpu_gpu.py runs ``tnn_tests dp2_``
+    and requires exactly one case.  A new case whose NAME happens to contain one of those substrings but skips for another
+    reason (opt-in, needs 2 GPUs) would turn those suites red on the GPU box: every case the filters select must be one that
+    skips only for lack of a GPU."""
+    if torch.cuda.is_available():
+        pytest.skip("CPU-side check of the skip reasons")
+    _host()
+    exe = os.path.join(ROOT, "cpp", "bin", "tnn_tests")
+    out = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=300).stdout
+    skipped = [l for l in out.splitlines() if l.startswith("[ SKIPPED ]")]
+    assert skipped and all(l.rstrip().endswith("(no GPU)") for l in skipped), skipped
+    assert "0 passed, 0 failed" in out
+    out = subprocess.run([exe, "dp2_"], capture_output=True, text=True, timeout=300).stdout
+    assert "0 passed, 0 failed, 1 skipped" in out and "(no GPU)" in out, out
