@@ -2,6 +2,7 @@
 // reduce + optimizer + broadcast kernel per step).  The reference has no data-parallel trainer; this is the
 // C++ counterpart of examples/dp_train.py / bench.py --gpus N.
 //   dp_trainer [--model cifar100_wrn16_8] [--gpus N] [--batch 256 (per GPU)] [--steps 40] [--warmup 8] [--no-graph]
+//              [--resume FILE] [--save FILE]     checkpoint with the sharded optimizer state gathered (any world size resumes it)
 #include <chrono>
 #include <cstring>
 #include <iostream>
@@ -16,6 +17,7 @@ int main(int argc, char** argv) {
   int gpus = 0, steps = 40, warmup = 8;
   size_t batch = 256;
   bool use_graph = true;
+  std::string resume, save;
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "--model") && i + 1 < argc) model = argv[++i];
     else if (!strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = atoi(argv[++i]);
@@ -23,6 +25,8 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "--steps") && i + 1 < argc) steps = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--warmup") && i + 1 < argc) warmup = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--no-graph")) use_graph = false;
+    else if (!strcmp(argv[i], "--resume") && i + 1 < argc) resume = argv[++i];
+    else if (!strcmp(argv[i], "--save") && i + 1 < argc) save = argv[++i];
   }
   try {
     ExampleModels::register_defaults();
@@ -32,6 +36,10 @@ int main(int argc, char** argv) {
     Adam proto(1e-3, 0.9, 0.999, 1e-3, 3e-4, false);
     DataParallel dp([&]() -> std::unique_ptr<Layer> { return ExampleModels::create(model); }, gpus, 1234, proto, "logsoftmax_crossentropy", use_graph);
     std::cout << "[dp_trainer] " << model << ": " << dp.num_parameters() << " parameters x " << gpus << " replicas" << std::endl;
+    if (!resume.empty()) {
+      dp.load_checkpoint(resume);
+      std::cout << "[dp_trainer] resumed " << resume << " at optimizer step " << dp.step_count() << std::endl;
+    }
     const Shape in = ExampleModels::input_shape(model);
     const size_t classes = ExampleModels::num_classes(model);
     Vec<std::unique_ptr<SyntheticDataLoader>> loaders;
@@ -55,6 +63,10 @@ int main(int argc, char** argv) {
     std::cout << "{\"bench\": \"dp_trainer\", \"model\": \"" << model << "\", \"n_gpus\": " << gpus << ", \"per_gpu_batch\": " << batch << ", \"ms_per_step\": " << ms
               << ", \"img_s\": " << (double)(batch * (size_t)gpus) / ms * 1e3 << ", \"final_loss\": " << loss << ", \"cuda_graph\": " << (dp.captured() ? "true" : "false")
               << ", \"replica_divergence\": " << dp.max_replica_divergence() << ", \"timing\": \"wall clock incl. H2D of every batch and the loss read-back\"}" << std::endl;
+    if (!save.empty()) {
+      dp.save_checkpoint(save);
+      std::cout << "[dp_trainer] saved " << save << " at optimizer step " << dp.step_count() << std::endl;
+    }
     return 0;
   } catch (const std::exception& e) {
     std::cerr << "[dp_trainer] error: " << e.what() << std::endl;
