@@ -13,6 +13,7 @@
 #include <mutex>
 #include <optional>
 #include <sstream>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -109,9 +110,22 @@ enum class LogLevel : int { TRACE = 0, DEBUG, INFO, WARN, ERROR, OFF };
 class Logger {
  public:
   explicit Logger(std::string name = "tnn", LogLevel level = LogLevel::INFO) : name_(std::move(name)), level_(level) {}
+  // the process-wide logger starts at the level named by LOG_LEVEL (TRACE | DEBUG | INFO | WARN | ERROR; the key of the
+  // reference's .env.example that none of its C++ reads), INFO otherwise
   static Logger& global() {
-    static Logger* l = new Logger();
+    static Logger* l = new Logger("tnn", level_from_string(std::getenv("LOG_LEVEL"), LogLevel::INFO));
     return *l;
+  }
+  static LogLevel level_from_string(const char* s, LogLevel fallback) {
+    if (!s) return fallback;
+    std::string u(s);
+    for (auto& c : u) c = (char)toupper((unsigned char)c);
+    if (u == "TRACE") return LogLevel::TRACE;
+    if (u == "DEBUG") return LogLevel::DEBUG;
+    if (u == "INFO") return LogLevel::INFO;
+    if (u == "WARN" || u == "WARNING") return LogLevel::WARN;
+    if (u == "ERROR" || u == "ERR") return LogLevel::ERROR;
+    return fallback;
   }
   void set_level(LogLevel l) { level_ = l; }
   LogLevel level() const { return level_; }

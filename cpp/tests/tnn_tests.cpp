@@ -132,6 +132,10 @@ TEST(archiver_byte_layout) {
 }
 
 // ------------------------------------------------------------------------------------- common value types
+TEST(logger_level_names) {
+  CHECK(Logger::level_from_string("debug", LogLevel::INFO) == LogLevel::DEBUG && Logger::level_from_string("WARNING", LogLevel::INFO) == LogLevel::WARN);
+  CHECK(Logger::level_from_string(nullptr, LogLevel::ERROR) == LogLevel::ERROR && Logger::level_from_string("loud", LogLevel::INFO) == LogLevel::INFO);
+}
 TEST(common_variant_blob_endian_dispatch) {
   using V = Variant<std::monostate, bool, std::string, int64_t>;
   static_assert(V::index_of<std::string>() == 2 && V::size() == 4, "index_of follows the declaration order (the wire index)");
