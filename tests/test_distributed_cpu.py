@@ -700,3 +700,46 @@ def test_tcp_bus_rejects_hostile_packets_and_worker_rejects_foreign_paths(tmp_pa
         w._checked_path("/etc/passwd")
     with pytest.raises(PermissionError):
         w._checked_path(os.path.join(str(tmp_path), *[".."] * 12, "etc", "shadow"))
+
+
+def test_fused_dp_build_graph_wires_peer_and_multicast_pointers(monkeypatch):
+    """FusedDataParallel.build_graph on its default path (torch symmetric memory) with the allocation / rendezvous calls
+    replaced by host stand-ins: slab layout, the peer pointer tables and the multicast base the kernel launch receives.  (The
+    kernel itself needs GPUs: tests/dp_check.py.)"""
+    import types
+
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm_mem
+    from tnn_b200.nn.optimizers import Adam
+    from tnn_b200.parallel.dp import FusedDataParallel
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(24000 + os.getpid() % 20000))
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        made = {}
+
+        def fake_empty(n, dtype, device):
+            made["buf"] = torch.empty(n, dtype=dtype)
+            return made["buf"]
+
+        def fake_rendezvous(buf, group):
+            assert buf is made["buf"]
+            return types.SimpleNamespace(buffer_ptrs=[buf.data_ptr()], multicast_ptr=0x7000_0000_0000)
+
+        monkeypatch.setattr(symm_mem, "empty", fake_empty)
+        monkeypatch.setattr(symm_mem, "rendezvous", fake_rendezvous)
+        monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+        monkeypatch.delenv("TNN_DP_OWN_SYMM", raising=False)
+        dp = FusedDataParallel(Adam(1e-3), use_multicast=True)
+        g = dp.build_graph(_model(), torch.device("cpu"), seed=3)
+        n = g.context().numel
+        base = made["buf"].data_ptr()
+        assert dp.n == n and dp.chunk % 1024 == 0 and dp.chunk >= n and not dp.own_symm and dp.hdl is not None
+        npad = dp.chunk * dp.world
+        assert (dp.off_p, dp.off_g, dp.off_lp) == (0, npad * 4, npad * 8) and dp.off_flag % 256 == 0
+        assert dp.p_peers == [base] and dp.g_peers == [base + dp.off_g] and dp.pb_peers == [base + dp.off_lp] and dp.flag_peers == [base + dp.off_flag]
+        assert dp.mc == 0x7000_0000_0000
+        # the graph's slabs ARE views of the symmetric buffer
+        assert g.context().param_slab.data_ptr() == base and g.context().grad_slab.data_ptr() == base + dp.off_g
+        assert dp.m.numel() >= dp.chunk and dp.v is not None and dp.optimizer.ctx is g.context()
+    finally:
+        dist.destroy_process_group()
