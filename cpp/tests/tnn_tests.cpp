@@ -318,6 +318,7 @@ static std::map<CUmemGenericAllocationHandle, Handle> handles;
 static std::map<CUdeviceptr, size_t> reserved;
 static uint64_t next_handle = 1;
 static int access_calls = 0;
+static bool refuse_multicast = false;                   // the object cannot be created although the devices advertise support
 static CUmemGenericAllocationHandle add(int fd, size_t size, bool mc) {
   std::lock_guard<std::mutex> g(mu);
   Handle h;
@@ -367,6 +368,7 @@ static const VmmDriver& table(int device_count) {
   };
   d.MulticastCreate = [](CUmemGenericAllocationHandle* h, const CUmulticastObjectProp* p) -> CUresult {
     if (p->numDevices < 2 || p->size % (128 << 10)) return CUDA_ERROR_INVALID_VALUE;
+    if (refuse_multicast) return CUDA_ERROR_NOT_SUPPORTED;
     const int fd = new_memfd(p->size);
     if (fd < 0) return CUDA_ERROR_OUT_OF_MEMORY;
     *h = add(fd, p->size, true);
@@ -504,6 +506,16 @@ TEST(symmetric_memory_group_in_one_process_over_a_fake_driver) {
     CHECK(GraphContext::slab_bytes(lb.build_sequential("m")->all_layers(), true) < group->bytes());
   }
   CHECK(fake_vmm::handles.empty() && fake_vmm::reserved.empty());         // teardown released every handle and range
+  {
+    // the window is refused at creation: the group still forms, on peer mappings alone
+    fake_vmm::refuse_multicast = true;
+    SymmetricMemory group({0, 1}, (size_t)64 << 10, true);
+    fake_vmm::refuse_multicast = false;
+    CHECK(!group.has_multicast() && group.multicast_base() == nullptr && group.multicast_error().find("cuMulticastCreate") != std::string::npos);
+    int* a = static_cast<int*>(group.allocate(0, 64));
+    CHECK(group.multicast(0, a) == nullptr && group.peer(0, a, 1) == group.base(1) && fake_vmm::handles.size() == 2);
+  }
+  CHECK(fake_vmm::handles.empty() && fake_vmm::reserved.empty());
 }
 TEST(symmetric_memory_rendezvous_between_processes_over_a_fake_driver) {
   if (DeviceManager::getInstance().has_gpu()) throw Skip("GPU present: the real driver is used");

@@ -369,11 +369,22 @@ class SymmetricMemory {
       }
       for (int r = 0; r < W; ++r) va_[(size_t)r] = map_handle(phys_[(size_t)r]);
       if (mc) {
-        CUmulticastObjectProp mp = multicast_prop();
-        check(D().MulticastCreate(&mc_handle_, &mp), "cuMulticastCreate");
-        for (int r = 0; r < W; ++r) check(D().MulticastAddDevice(mc_handle_, cu_device(devices_[(size_t)r])), "cuMulticastAddDevice");
-        for (int r = 0; r < W; ++r) check(D().MulticastBindMem(mc_handle_, 0, phys_[(size_t)r], 0, bytes_, 0), "cuMulticastBindMem");
-        mc_va_ = map_handle(mc_handle_);
+        // the multicast window is an optimisation: a box that advertises it but refuses the object (fabric manager down,
+        // NVLS disabled) still gets the peer mappings, and the kernels take their peer-load path (has_multicast() == false)
+        try {
+          CUmulticastObjectProp mp = multicast_prop();
+          check(D().MulticastCreate(&mc_handle_, &mp), "cuMulticastCreate");
+          for (int r = 0; r < W; ++r) check(D().MulticastAddDevice(mc_handle_, cu_device(devices_[(size_t)r])), "cuMulticastAddDevice");
+          for (int r = 0; r < W; ++r) check(D().MulticastBindMem(mc_handle_, 0, phys_[(size_t)r], 0, bytes_, 0), "cuMulticastBindMem");
+          mc_va_ = map_handle(mc_handle_);
+        } catch (const std::exception& e) {
+          multicast_error_ = e.what();
+          unmap(mc_va_);
+          if (mc_handle_) {
+            D().MemRelease(mc_handle_);
+            mc_handle_ = 0;
+          }
+        }
       }
     } catch (...) {
       destroy();
@@ -401,6 +412,7 @@ class SymmetricMemory {
   size_t bytes() const { return bytes_; }                                // per rank, rounded up to the mapping granularity
   size_t granularity() const { return gran_; }
   bool has_multicast() const { return mc_va_ != 0; }
+  const std::string& multicast_error() const { return multicast_error_; }   // why a requested window is missing ("" otherwise)
   void* base(int rank) const { return reinterpret_cast<void*>(va_.at((size_t)rank)); }
   void* multicast_base() const { return reinterpret_cast<void*>(mc_va_); }
   int device_of(int rank) const { return devices_.at((size_t)rank); }
@@ -718,6 +730,7 @@ class SymmetricMemory {
   std::vector<CUdeviceptr> va_;
   CUmemGenericAllocationHandle mc_handle_ = 0;
   CUdeviceptr mc_va_ = 0;
+  std::string multicast_error_;
   std::vector<std::unique_ptr<OffsetFreeList>> lists_;
   std::mutex mu_;
 };
